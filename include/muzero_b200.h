@@ -1,0 +1,189 @@
+/*
+ * muzero_b200 — C ABI of the B200-native MuZero search-and-inference engine.
+ *
+ * Drop-in boundary for the self-play hot path of michaelnny/muzero.  The
+ * reference has no FFI; its boundary is three Python call signatures
+ *   muzero/mcts.py:302-312      uct_search(...)
+ *   muzero/network.py:62-84     MuZeroNet.initial_inference(x)
+ *   muzero/network.py:86-111    MuZeroNet.recurrent_inference(hidden, action)
+ * which muzero_b200/{mcts,network}.py keep; those modules call ONLY the entry
+ * points below (ctypes, raw device pointers + the current CUDA stream).  Each
+ * entry point cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative MZ_E* code otherwise and
+ *     never throws; mz_last_error() gives the thread-local message;
+ *   - every pointer marked "dev" is device memory owned by the caller; the
+ *     library allocates no device memory: pools and nets live inside an arena
+ *     the caller allocates (size from mz_*_arena_bytes) and keeps alive;
+ *   - kernels are enqueued on `stream` (a cudaStream_t) and nothing
+ *     synchronises except where stated, so a whole simulation loop can be
+ *     captured into a CUDA graph;
+ *   - a handle is not thread-safe.
+ */
+#ifndef MUZERO_B200_H
+#define MUZERO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MZ_OK            0
+#define MZ_EINVAL       -1   /* bad argument                                  */
+#define MZ_ECUDA        -2   /* CUDA runtime error (message has the detail)   */
+#define MZ_ENOMEM       -3   /* arena too small                               */
+#define MZ_ESTATE       -4   /* call out of order (e.g. expand before select) */
+
+typedef struct mz_pool mz_pool;   /* node pool + per-tree search state for B trees */
+typedef struct mz_net  mz_net;    /* repacked network weights + launch plan        */
+typedef void* mz_stream;          /* cudaStream_t                                  */
+
+const char* mz_last_error(void);
+int mz_version(void);
+/* sm count and compute capability of `device`; fails on anything but sm_100. */
+int mz_device_check(int device, int* sm_count, int* cc);
+
+/* ------------------------------------------------------------------------
+ * Search pool  (replaces Node / MinMaxStats objects, mcts.py:33-217)
+ * ---------------------------------------------------------------------- */
+typedef struct mz_pool_config {
+  int32_t num_trees;          /* B                                                    */
+  int32_t num_actions;        /* A                                                    */
+  int32_t num_simulations;    /* S; a tree has exactly S+1 expanded nodes; S <= 65534 */
+  int32_t hidden_bytes;       /* bytes of one node's hidden-state slot (multiple of 16) */
+  int32_t is_board_game;      /* config.is_board_game   (mcts.py:147-155,169-171)     */
+  int32_t has_known_bounds;   /* config.known_bounds is not None (mcts.py:36-38)      */
+  double  bound_min, bound_max;
+  double  discount;           /* config.discount                                      */
+} mz_pool_config;
+
+/* buffers inside the arena that tests / the host wrapper may look at */
+enum mz_view {
+  MZ_VIEW_EDGES = 0,     /* [B, S+1, A] 16-byte records {f64 W, f32 reward, u16 N, u16 child(0xFFFF=none)} */
+  MZ_VIEW_PRIOR,         /* f64 [B, A]   the one prior every node of a tree uses (mcts.py:386)             */
+  MZ_VIEW_ROOT_W,        /* f64 [B]                                                                          */
+  MZ_VIEW_ROOT_N,        /* i32 [B]                                                                          */
+  MZ_VIEW_MINMAX,        /* f64 [B, 2]   (min, max)                                                          */
+  MZ_VIEW_COUNT,         /* i32 [B]      expanded nodes so far                                               */
+  MZ_VIEW_LEAF_PARENT,   /* i32 [B]      node the last select stopped at                                     */
+  MZ_VIEW_LEAF_ACTION,   /* i32 [B]                                                                          */
+  MZ_VIEW_LEAF_DEPTH,    /* i32 [B]      depth of the leaf about to be created (>= 1)                        */
+  MZ_VIEW_SRC_SLOT,      /* i32 [B]      tree*(S+1)+leaf_parent : hidden slot to read                        */
+  MZ_VIEW_DST_SLOT,      /* i32 [B]      tree*(S+1)+count       : hidden slot to write                       */
+  MZ_VIEW_PATH,          /* u32 [B, S+1] edge index (node*A+action) per level of the last select             */
+  MZ_VIEW_NODE_PARENT,   /* i32 [B, S+1] parent node of each expanded node (-1 for the root)                 */
+  MZ_VIEW_NODE_MOVE,     /* i32 [B, S+1] action that led to each expanded node                               */
+  MZ_VIEW_RNG_KEY,       /* u32 [B, 624] MT19937 state (numpy legacy stream)                                 */
+  MZ_VIEW_RNG_POS,       /* i32 [B]                                                                          */
+  MZ_VIEW_HIDDEN,        /* u8  [B, S+1, hidden_bytes]                                                       */
+  MZ_VIEW_REWARD,        /* f32 [B]      scratch the network writes, expand_backup reads                     */
+  MZ_VIEW_VALUE,         /* f32 [B]                                                                          */
+  MZ_VIEW_ERROR,         /* i32 [1]      sticky device-side error bits (MZ_DEVERR_*)                         */
+  MZ_VIEW_STATS,         /* u64 [4]      {sum of select depths, select calls*B, tie-break draws, mt twists}  */
+  MZ_VIEW__COUNT
+};
+#define MZ_DEVERR_POOL_FULL   1   /* more than S expansions                       */
+#define MZ_DEVERR_NAN_POLICY  2   /* visit policy has NaN (all visits masked)     */
+
+int mz_pool_arena_bytes(const mz_pool_config* cfg, size_t* bytes);
+/* pb_c_table_host: float64[S+2], (log((n+base+1)/base)+init)*sqrt(n) computed by the
+ * caller with CPython math exactly as mcts.py:193-195 does; copied synchronously. */
+int mz_pool_create(const mz_pool_config* cfg, const double* pb_c_table_host,
+                   void* arena_dev, size_t arena_bytes, mz_pool** out);
+int mz_pool_destroy(mz_pool* pool);
+int mz_pool_view(mz_pool* pool, int which, void** dev_ptr, size_t* bytes);
+
+/* np.random.seed(seed[t]) for every tree (init_genrand), on device. */
+int mz_rng_seed(mz_pool* pool, const uint32_t* seeds_dev, mz_stream stream);
+
+/* Dirichlet(alpha) noise from each tree's MT19937 stream with numpy's legacy
+ * gamma sampler (mcts.py:244-245).  Same algorithm and draws as numpy; log/pow
+ * are CUDA's, so samples agree with numpy to a few ulp, not bit-for-bit —
+ * parity tests inject numpy's own noise through mz_search_reset instead. */
+int mz_dirichlet(mz_pool* pool, double alpha, double* noise_out_dev /* [B,A] */, mz_stream stream);
+
+/* Root preparation: Dirichlet mix, illegal-action masking + renormalisation,
+ * root expansion, MinMaxStats reset.  Replaces mcts.py:353-367 (+244-246, 283-299).
+ *   pi_probs    f32 [B,A]  softmax output of initial_inference
+ *   noise       f64 [B,A]  or NULL (deterministic / alpha == 0: prior stays float32)
+ *   eps         config.root_exploration_eps
+ *   mask        u8  [B,A]  or NULL (actions_mask is None)
+ *   players     i32 [B,2]  (current_player, opponent_player) or NULL (= (1,1))
+ *   root_reward f32 [B]    or NULL (= 0, network.py:77)                         */
+int mz_search_reset(mz_pool* pool, const float* pi_probs, const double* noise, double eps,
+                    const uint8_t* mask, const int32_t* players, const float* root_reward,
+                    mz_stream stream);
+
+/* One warp per tree: pUCT descent with min-max normalised Q, float32 scores,
+ * MT19937 tie-breaks, until an unexpanded child.  Replaces the select loop
+ * mcts.py:372-379 and Node.best_child/child_Q/child_U (mcts.py:104-127,159-200).
+ * Results land in the LEAF_* / SRC_SLOT / DST_SLOT / PATH views. */
+int mz_select(mz_pool* pool, mz_stream stream);
+
+/* Expand the selected leaf with (reward, value) of recurrent_inference and back
+ * the value up to the root.  Replaces Node.expand (mcts.py:75-102, called at
+ * mcts.py:386) and Node.backup (mcts.py:129-157).  reward/value: f32 [B] dev,
+ * or NULL to use the pool's REWARD / VALUE scratch. */
+int mz_expand_backup(mz_pool* pool, const float* reward, const float* value, mz_stream stream);
+
+/* Visit counts -> masked policy -> action.  Replaces mcts.py:392-407 and
+ * generate_play_policy (mcts.py:250-280).
+ *   mask         u8  [B,A] or NULL
+ *   temperature  f64 [B]
+ *   deterministic  argmax(visits) instead of sampling
+ *   action i32 [B], pi f64 [B,A], root_value f64 [B], visits i32 [B,A] (nullable) */
+int mz_root_policy(mz_pool* pool, const uint8_t* mask, const double* temperature, int deterministic,
+                   int32_t* action, double* pi, double* root_value, int32_t* visits, mz_stream stream);
+
+/* ------------------------------------------------------------------------
+ * Networks  (replace MuZeroNet.initial_inference / recurrent_inference,
+ *            network.py:62-111, with util.py:31-36 and util.py:70-93 fused in)
+ * ---------------------------------------------------------------------- */
+enum mz_net_kind { MZ_NET_MLP = 0, MZ_NET_BOARD = 1, MZ_NET_ATARI = 2 };
+
+typedef struct mz_net_config {
+  int32_t kind;              /* mz_net_kind                                              */
+  int32_t in_channels, in_h, in_w;   /* observation shape (MLP: flattened = c*h*w)       */
+  int32_t num_actions;
+  int32_t num_planes;        /* MLP width / conv channels                                */
+  int32_t num_res_blocks;    /* conv nets                                                */
+  int32_t hidden_dim;        /* MLP hidden-state size                                    */
+  int32_t value_support, reward_support;   /* 1 = scalar head (network.py:126-134)       */
+} mz_net_config;
+
+/* bytes of one hidden-state slot in the layout the net's kernels use */
+int mz_net_hidden_bytes(const mz_net_config* cfg, int32_t* bytes);
+int mz_net_arena_bytes(const mz_net_config* cfg, int32_t max_batch, size_t* bytes);
+/* weights: array of `num_weights` device pointers to float32 tensors in the
+ * reference's state_dict order and PyTorch layouts (see muzero_b200/network.py);
+ * they are repacked (transposed / BatchNorm folded / converted) into the arena
+ * synchronously, so the caller may free them afterwards. */
+int mz_net_create(const mz_net_config* cfg, const float* const* weights, int32_t num_weights,
+                  int32_t max_batch, void* arena_dev, size_t arena_bytes, mz_net** out);
+int mz_net_destroy(mz_net* net);
+
+/* initial_inference for `batch` observations (network.py:62-84).
+ *   obs        f32 [batch, c*h*w]
+ *   hidden_out slot array; row i goes to slot dst_index[i] (or i when NULL)
+ *   pi_probs   f32 [batch, A] softmax;  value f32 [batch] (support -> scalar applied) */
+int mz_net_initial(mz_net* net, int32_t batch, const float* obs, void* hidden_out,
+                   const int32_t* dst_index, float* pi_probs, float* value, mz_stream stream);
+
+/* recurrent_inference (network.py:86-111): row i reads slot src_index[i] of
+ * hidden_in, applies action[i], writes slot dst_index[i] of hidden_out.
+ * pi_probs may be NULL: the search never uses it (mcts.py:386 passes the root
+ * prior to every expansion), so the policy head is skipped. */
+int mz_net_recurrent(mz_net* net, int32_t batch, const void* hidden_in, const int32_t* src_index,
+                     const int32_t* action, void* hidden_out, const int32_t* dst_index,
+                     float* reward, float* value, float* pi_probs, mz_stream stream);
+
+/* number of kernels the library has launched since load (bench's gpu_launches) */
+uint64_t mz_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MUZERO_B200_H */
