@@ -1,0 +1,78 @@
+// Shared declarations of the muzero_b200 library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/muzero_b200.h"
+
+namespace mz {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define MZ_CHECK_ARG(cond, ...)            \
+  do {                                     \
+    if (!(cond)) {                         \
+      mz::set_error(__VA_ARGS__);          \
+      return MZ_EINVAL;                    \
+    }                                      \
+  } while (0)
+
+#define MZ_CUDA(call)                                                                  \
+  do {                                                                                 \
+    cudaError_t e__ = (call);                                                          \
+    if (e__ != cudaSuccess) {                                                          \
+      mz::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+                    __LINE__);                                                         \
+      return MZ_ECUDA;                                                                 \
+    }                                                                                  \
+  } while (0)
+
+#define MZ_LAUNCH_CHECK(name)                                                         \
+  do {                                                                                \
+    cudaError_t e__ = cudaGetLastError();                                             \
+    if (e__ != cudaSuccess) {                                                         \
+      mz::set_error("launch of %s failed: %s", name, cudaGetErrorString(e__));        \
+      return MZ_ECUDA;                                                                \
+    }                                                                                 \
+    mz::count_launch();                                                               \
+  } while (0)
+
+constexpr int kWarp = 32;
+constexpr uint16_t kNoChild = 0xFFFF;
+
+// One (node, action) edge of a tree: the statistics of the child that action
+// leads to, stored in the PARENT's row so a warp reads a node's A children
+// with one coalesced 16-byte-per-lane load.  Unvisited child = all zero with
+// child == kNoChild (the reference creates such children eagerly, mcts.py:98-100;
+// N=0, W=0, reward=0 makes lazy creation observationally identical).
+struct __align__(16) Edge {
+  double W;        // total value      (Node.W, float64 in the reference)
+  float reward;    // Node.reward      (float32-representable, network.py:107)
+  uint16_t N;      // Node.N
+  uint16_t child;  // node index of the expanded child, kNoChild if not expanded
+};
+static_assert(sizeof(Edge) == 16, "Edge must be 16 bytes");
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace mz
+
+// Search pool: every pointer aims into the caller's arena.
+struct mz_pool {
+  mz_pool_config cfg;
+  int B, A, S, max_nodes;
+  void* arena;
+  size_t arena_bytes;
+  void* view_ptr[MZ_VIEW__COUNT];
+  size_t view_bytes[MZ_VIEW__COUNT];
+  double* pb_c_table;  // dev f64 [S+2]
+  uint8_t* same_player;  // dev u8 [B]: current_player == opponent_player
+  double* root_reward;   // dev f64 [B]
+  uint8_t* f32_prior;    // dev u8 [B]: prior is float32 (no-noise path)
+  int selected;          // host-side call-order check
+};

@@ -1,0 +1,795 @@
+// Batched MCTS over a GPU-resident struct-of-arrays node pool: one warp per tree.
+//
+// Bit-exactness contract: every float64 operation
+// of the reference's CPython arithmetic is issued as a separate IEEE
+// round-to-nearest instruction (__dadd_rn/__dmul_rn/__ddiv_rn — never
+// contracted into FMA), float32 score arithmetic uses __fmul_rn/__fadd_rn, the
+// pb_c term comes from a host table computed with CPython math, tie-breaks
+// consume numpy's legacy MT19937 stream with numpy's masked rejection.
+#include "common.cuh"
+
+namespace mz {
+
+struct PoolDev {
+  int B, A, S, max_nodes;
+  int board;
+  double discount, dp;
+  Edge* edges;
+  double* prior;
+  double* rootW;
+  int* rootN;
+  double* minmax;
+  int* count;
+  int *leaf_parent, *leaf_action, *leaf_depth, *src_slot, *dst_slot;
+  uint32_t* path;
+  int *node_parent, *node_move;
+  uint32_t* rng_key;
+  int* rng_pos;
+  float *reward, *value;
+  int* error;
+  unsigned long long* stats;
+  const double* T;
+  uint8_t* same_player;
+  double* root_reward;
+  uint8_t* f32_prior;
+  double bound_min, bound_max;
+  int has_bounds;
+};
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kTreesPerBlock = 4;  // 128 threads
+
+// ---------------------------------------------------------------------------
+// numpy legacy MT19937, one stream per tree, driven by a whole warp
+// ---------------------------------------------------------------------------
+struct WarpRng {
+  uint32_t* key;
+  int pos;
+  int lane;
+  unsigned long long draws, twists;
+
+  __device__ void load(uint32_t* k, const int* pos_ptr, int ln) {
+    key = k; pos = *pos_ptr; lane = ln; draws = 0; twists = 0;
+  }
+  __device__ void store(int* pos_ptr) const {
+    if (lane == 0) *pos_ptr = pos;
+  }
+  // genrand regeneration: chunks of 32 consecutive words in ascending order;
+  // inside a chunk every lane reads its three inputs before any lane writes, which
+  // reproduces the sequential recurrence (k[i+1] old, k[i+397 mod 624] new iff < i).
+  __device__ void twist() {
+    __syncwarp();
+    for (int c = 0; c < 20; ++c) {
+      const int i = c * 32 + lane;
+      uint32_t a = 0, b = 0, s = 0;
+      if (i < 624) {
+        a = key[i];
+        b = key[(i + 1) % 624];
+        s = key[(i + 397) % 624];
+      }
+      __syncwarp();
+      if (i < 624) {
+        const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+        key[i] = s ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      }
+      __syncwarp();
+    }
+    pos = 0;
+    ++twists;
+  }
+  __device__ uint32_t next_u32() {
+    if (pos >= 624) twist();
+    uint32_t y = key[pos];
+    ++pos;
+    ++draws;
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+  }
+  // random_sample(): (a >> 5, b >> 6) -> 53-bit double
+  __device__ double next_double() {
+    const uint32_t a = next_u32() >> 5, b = next_u32() >> 6;
+    return __ddiv_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)b), 9007199254740992.0);
+  }
+  // randint(0, k) of RandomState.choice: masked rejection on 32-bit draws, no draw for k == 1
+  __device__ uint32_t bounded(uint32_t k) {
+    const uint32_t rng = k - 1;
+    if (rng == 0) return 0;
+    uint32_t mask = rng;
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    uint32_t v;
+    do { v = next_u32() & mask; } while (v > rng);
+    return v;
+  }
+};
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_max_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_min_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+
+__device__ __forceinline__ Edge load_edge(const Edge* p) {
+  const int4 r = *reinterpret_cast<const int4*>(p);
+  Edge e;
+  e.W = __hiloint2double(r.y, r.x);
+  e.reward = __int_as_float(r.z);
+  e.N = (uint16_t)((uint32_t)r.w & 0xffffu);
+  e.child = (uint16_t)((uint32_t)r.w >> 16);
+  return e;
+}
+__device__ __forceinline__ void store_edge(Edge* p, double W, float reward, uint32_t N, uint32_t child) {
+  int4 r;
+  r.x = __double2loint(W);
+  r.y = __double2hiint(W);
+  r.z = __float_as_int(reward);
+  r.w = (int)((N & 0xffffu) | (child << 16));
+  *reinterpret_cast<int4*>(p) = r;
+}
+
+// ---------------------------------------------------------------------------
+// numpy pairwise summation (np.sum of a contiguous 1-D array), sequential
+// ---------------------------------------------------------------------------
+template <typename T> struct Add;
+template <> struct Add<float>  { static __device__ float  f(float a, float b)   { return __fadd_rn(a, b); } };
+template <> struct Add<double> { static __device__ double f(double a, double b) { return __dadd_rn(a, b); } };
+
+// `a` holds doubles; on the float32 path they are exactly float32 values and T = float.
+template <typename T>
+__device__ T pairwise_sum(const double* a, int n) {
+  if (n < 8) {
+    T res = (T)(-0.0);
+    for (int i = 0; i < n; ++i) res = Add<T>::f(res, (T)a[i]);
+    return res;
+  }
+  if (n <= 128) {
+    T r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = (T)a[j];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = Add<T>::f(r[j], (T)a[i + j]);
+    }
+    T res = Add<T>::f(Add<T>::f(Add<T>::f(r[0], r[1]), Add<T>::f(r[2], r[3])),
+                      Add<T>::f(Add<T>::f(r[4], r[5]), Add<T>::f(r[6], r[7])));
+    for (; i < n; ++i) res = Add<T>::f(res, (T)a[i]);
+    return res;
+  }
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  return Add<T>::f(pairwise_sum<T>(a, n2), pairwise_sum<T>(a + n2, n - n2));
+}
+
+// ---------------------------------------------------------------------------
+// mz_rng_seed: init_genrand(seed) per tree
+// ---------------------------------------------------------------------------
+__global__ void rng_seed_kernel(PoolDev p, const uint32_t* __restrict__ seeds) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= p.B) return;
+  uint32_t* key = p.rng_key + (size_t)t * 624;
+  uint32_t s = seeds[t];
+  for (int i = 0; i < 624; ++i) {
+    key[i] = s;
+    s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)i + 1u;
+  }
+  p.rng_pos[t] = 624;
+}
+
+// ---------------------------------------------------------------------------
+// mz_search_reset
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTreesPerBlock * 32)
+reset_kernel(PoolDev p, const float* __restrict__ pi, const double* __restrict__ noise, double eps,
+             float one_minus_eps_f32, const uint8_t* __restrict__ mask, const int32_t* __restrict__ players,
+             const float* __restrict__ root_reward) {
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (t >= p.B) return;
+  const int A = p.A;
+  double* P = p.prior + (size_t)t * A;
+  const bool f32p = (noise == nullptr);
+
+  for (int a = lane; a < A; a += 32) {
+    const float pf = pi[(size_t)t * A + a];
+    double pd;
+    if (f32p) {
+      pd = (double)pf;
+    } else {
+      // (1 - eps) * prob is a float32 product (weak python scalar); eps * noise is float64
+      pd = __dadd_rn((double)__fmul_rn(one_minus_eps_f32, pf), __dmul_rn(eps, noise[(size_t)t * A + a]));
+    }
+    if (mask != nullptr && mask[(size_t)t * A + a] == 0) pd = 0.0;
+    P[a] = pd;
+  }
+  __syncwarp();
+  if (mask != nullptr) {
+    // sequential on every lane (identical results), cheaper than a broadcast for A <= a few hundred
+    if (f32p) {
+      const float s = pairwise_sum<float>(P, A);
+      __syncwarp();
+      if (s > 0.0f)
+        for (int a = lane; a < A; a += 32) P[a] = (double)__fdiv_rn((float)P[a], s);
+    } else {
+      const double s = pairwise_sum<double>(P, A);
+      __syncwarp();
+      if (s > 0.0)
+        for (int a = lane; a < A; a += 32) P[a] = __ddiv_rn(P[a], s);
+    }
+  }
+  // root expansion: row 0 zeroed, no children yet
+  Edge* row = p.edges + (size_t)t * p.max_nodes * A;
+  for (int a = lane; a < A; a += 32) store_edge(row + a, 0.0, 0.0f, 0u, kNoChild);
+  if (lane == 0) {
+    p.rootW[t] = 0.0;
+    p.rootN[t] = 0;
+    p.minmax[2 * t] = p.has_bounds ? p.bound_min : __longlong_as_double(0x7ff0000000000000LL);
+    p.minmax[2 * t + 1] = p.has_bounds ? p.bound_max : __longlong_as_double(0xfff0000000000000LL);
+    p.count[t] = 1;
+    p.node_parent[(size_t)t * p.max_nodes] = -1;
+    p.node_move[(size_t)t * p.max_nodes] = -1;
+    p.same_player[t] = (players == nullptr) ? 1 : (players[2 * t] == players[2 * t + 1]);
+    p.root_reward[t] = (root_reward == nullptr) ? 0.0 : (double)root_reward[t];
+    p.f32_prior[t] = f32p ? 1 : 0;
+    p.leaf_depth[t] = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// mz_select
+// ---------------------------------------------------------------------------
+extern __shared__ __align__(16) unsigned char smem_raw[];
+
+__global__ void __launch_bounds__(kTreesPerBlock * 32)
+select_kernel(PoolDev p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * kTreesPerBlock + warp;
+  if (t >= p.B) return;
+  const int A = p.A;
+  float* sc = reinterpret_cast<float*>(smem_raw) + (size_t)warp * ((A + 3) & ~3);
+
+  const Edge* tree = p.edges + (size_t)t * p.max_nodes * A;
+  const double* __restrict__ P = p.prior + (size_t)t * A;
+  const double lo = p.minmax[2 * t], hi = p.minmax[2 * t + 1];
+  const bool norm = hi > lo;
+  const double range = __dsub_rn(hi, lo);
+  const bool f32p = p.f32_prior[t] != 0;
+  const double dp = p.dp;
+  uint32_t* pth = p.path + (size_t)t * p.max_nodes;
+
+  WarpRng rng;
+  rng.load(p.rng_key + (size_t)t * 624, p.rng_pos + t, lane);
+
+  int n = 0, Nn = p.rootN[t], depth = 0, act = 0;
+  while (true) {
+    const double tN = p.T[Nn];
+    const Edge* row = tree + (size_t)n * A;
+    float best = -INFINITY;
+    for (int a = lane; a < A; a += 32) {
+      const Edge e = load_edge(row + a);
+      const int cn = e.N;
+      const double y = __ddiv_rn(tN, (double)(cn + 1));
+      const double pa = P[a];
+      const float u = f32p ? __fmul_rn((float)pa, __double2float_rn(y)) : __double2float_rn(__dmul_rn(pa, y));
+      float q = 0.0f;
+      if (cn > 0) {
+        double v = __dadd_rn((double)e.reward, __dmul_rn(dp, __ddiv_rn(e.W, (double)cn)));
+        if (norm) v = __ddiv_rn(__dsub_rn(v, lo), range);
+        q = __double2float_rn(v);
+      }
+      const float s = __fadd_rn(q, u);
+      sc[a] = s;
+      best = fmaxf(best, s);
+    }
+    best = warp_max(best);
+    __syncwarp();
+    // ties, ascending action order (np.where(ucb == ucb.max())[0])
+    int k = 0, first = -1;
+    for (int a0 = 0; a0 < A; a0 += 32) {
+      const int a = a0 + lane;
+      const unsigned b = __ballot_sync(kFull, a < A && sc[a] == best);
+      if (first < 0 && b) first = a0 + __ffs(b) - 1;
+      k += __popc(b);
+    }
+    act = first;
+    if (k > 1) {
+      int r = (int)rng.bounded((uint32_t)k);
+      for (int a0 = 0; a0 < A; a0 += 32) {
+        const int a = a0 + lane;
+        const unsigned b = __ballot_sync(kFull, a < A && sc[a] == best);
+        const int c = __popc(b);
+        if (r < c) {
+          unsigned bb = b;
+          for (int q = 0; q < r; ++q) bb &= bb - 1;   // drop the r lowest ties
+          act = a0 + __ffs(bb) - 1;
+          break;
+        }
+        r -= c;
+      }
+    }
+    __syncwarp();
+    const Edge e = load_edge(row + act);
+    if (lane == 0) pth[depth] = (uint32_t)(n * A + act);
+    ++depth;
+    if (e.child == kNoChild) break;
+    n = e.child;
+    Nn = e.N;
+  }
+  rng.store(p.rng_pos + t);
+  if (lane == 0) {
+    p.leaf_parent[t] = n;
+    p.leaf_action[t] = act;
+    p.leaf_depth[t] = depth;
+    p.src_slot[t] = t * p.max_nodes + n;
+    const int c = p.count[t];
+    p.dst_slot[t] = t * p.max_nodes + (c < p.max_nodes ? c : p.max_nodes - 1);
+    atomicAdd(p.stats + 0, (unsigned long long)depth);
+    atomicAdd(p.stats + 1, 1ULL);
+    if (rng.draws) atomicAdd(p.stats + 2, rng.draws);
+    if (rng.twists) atomicAdd(p.stats + 3, rng.twists);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// mz_expand_backup
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTreesPerBlock * 32)
+expand_backup_kernel(PoolDev p, const float* __restrict__ reward_in, const float* __restrict__ value_in) {
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (t >= p.B) return;
+  const int A = p.A;
+  const int depth = p.leaf_depth[t];
+  const int c = p.count[t];
+  if (depth <= 0) return;                // no select since the last reset/expand
+  if (c >= p.max_nodes) {
+    if (lane == 0) atomicOr(p.error, MZ_DEVERR_POOL_FULL);
+    return;
+  }
+  Edge* tree = p.edges + (size_t)t * p.max_nodes * A;
+  const uint32_t* pth = p.path + (size_t)t * p.max_nodes;
+
+  // expand: fresh all-zero row for the new node
+  Edge* crow = tree + (size_t)c * A;
+  for (int a = lane; a < A; a += 32) store_edge(crow + a, 0.0, 0.0f, 0u, kNoChild);
+
+  const float rew = reward_in[t];
+  double value = (double)value_in[t];
+  const bool same_pl = p.same_player[t] != 0;
+  const bool board = p.board != 0;
+  const double discount = p.discount;
+  double lo = p.minmax[2 * t], hi = p.minmax[2 * t + 1];
+
+  const int total = depth + 1;           // leaf ... root
+  for (int base = 0; base < total; base += 32) {
+    const int i = base + lane;           // 0 = new leaf, depth = root
+    const bool active = i < total;
+    const int level = depth - i;
+    double W = 0.0, R = 0.0;
+    uint32_t N = 0, child = kNoChild;
+    Edge* ep = nullptr;
+    if (active) {
+      if (level > 0) {
+        ep = tree + pth[level - 1];
+        if (i == 0) { R = (double)rew; child = (uint32_t)c; }
+        else { const Edge e = load_edge(ep); W = e.W; R = (double)e.reward; N = e.N; child = e.child; }
+      } else {
+        W = p.rootW[t]; N = (uint32_t)p.rootN[t]; R = p.root_reward[t];
+      }
+    }
+    // Node.player_id == leaf player  <=>  same parity of depth (players swap every level, mcts.py:379)
+    const bool same = same_pl || ((i & 1) == 0);
+    const double Rs = (board && same) ? -R : R;
+    // serial part of Node.backup: value <- (+-reward) + discount * value, leaf to root
+    double myval = 0.0;
+    const int cnt = min(32, total - base);
+    for (int j = 0; j < cnt; ++j) {
+      const double Rj = __shfl_sync(kFull, Rs, j);
+      if (lane == j) myval = value;
+      value = __dadd_rn(Rj, __dmul_rn(discount, value));
+    }
+    double mm_hi = -INFINITY, mm_lo = INFINITY;
+    if (active) {
+      const double Wn = __dadd_rn(W, same ? myval : -myval);
+      const uint32_t Nn = N + 1;
+      const double q = __ddiv_rn(Wn, (double)Nn);
+      const double mm = __dadd_rn(R, __dmul_rn(discount, board ? -q : q));
+      mm_hi = mm; mm_lo = mm;
+      if (level > 0) store_edge(ep, Wn, (float)R, Nn, child);
+      else { p.rootW[t] = Wn; p.rootN[t] = (int)Nn; }
+    }
+    hi = fmax(hi, warp_max_d(mm_hi));
+    lo = fmin(lo, warp_min_d(mm_lo));
+  }
+  if (lane == 0) {
+    p.minmax[2 * t] = lo;
+    p.minmax[2 * t + 1] = hi;
+    p.count[t] = c + 1;
+    p.node_parent[(size_t)t * p.max_nodes + c] = p.leaf_parent[t];
+    p.node_move[(size_t)t * p.max_nodes + c] = p.leaf_action[t];
+    p.leaf_depth[t] = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// mz_root_policy
+// ---------------------------------------------------------------------------
+// v ** e for integral e in [1,5], correctly rounded (what a faithful pow returns)
+__device__ double pow_int_exact(uint32_t v, int e) {
+  unsigned __int128 pw = 1;
+  for (int i = 0; i < e; ++i) pw *= (unsigned __int128)v;
+  const unsigned long long hi64 = (unsigned long long)(pw >> 64), lo64 = (unsigned long long)pw;
+  if (hi64 == 0 && lo64 < (1ULL << 53)) return (double)lo64;
+  const int msb = hi64 ? 127 - __clzll((long long)hi64) : 63 - __clzll((long long)lo64);
+  const int shift = msb - 52;
+  unsigned long long mant = (unsigned long long)(pw >> shift);
+  const unsigned __int128 rem = pw & ((((unsigned __int128)1) << shift) - 1);
+  const unsigned __int128 half = ((unsigned __int128)1) << (shift - 1);
+  if (rem > half || (rem == half && (mant & 1ULL))) ++mant;
+  return ldexp((double)mant, shift);
+}
+
+__global__ void __launch_bounds__(kTreesPerBlock * 32)
+root_policy_kernel(PoolDev p, const uint8_t* __restrict__ mask, const double* __restrict__ temperature,
+                   int deterministic, int32_t* __restrict__ action, double* __restrict__ pi_out,
+                   double* __restrict__ root_value, int32_t* __restrict__ visits_out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * kTreesPerBlock + warp;
+  if (t >= p.B) return;
+  const int A = p.A;
+  double* x = reinterpret_cast<double*>(smem_raw) + (size_t)warp * A;
+  const Edge* row = p.edges + (size_t)t * p.max_nodes * A;
+  const double T = temperature[t];
+
+  int best_v = -1, best_a = 0;
+  long long isum = 0;
+  double e = 1.0;
+  bool e_int = true;
+  if (T > 0.0) {
+    e = __ddiv_rn(1.0, T);
+    e = (e < 5.0) ? e : 5.0;     // min(5.0, 1/T)
+    e = (1.0 > e) ? 1.0 : e;     // max(1.0, .)
+    e_int = (e == floor(e));
+  }
+  for (int a0 = 0; a0 < A; a0 += 32) {
+    const int a = a0 + lane;
+    int v = -1;
+    if (a < A) {
+      v = load_edge(row + a).N;
+      if (mask != nullptr && mask[(size_t)t * A + a] == 0) v = 0;
+      if (visits_out) visits_out[(size_t)t * A + a] = v;
+      x[a] = (T > 0.0) ? (e_int ? pow_int_exact((uint32_t)v, (int)e) : pow((double)v, e)) : (double)v;
+      isum += v;
+    }
+    // first maximum of the visit counts (np.argmax)
+    int bv = v, ba = a;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int ov = __shfl_xor_sync(kFull, bv, o), oa = __shfl_xor_sync(kFull, ba, o);
+      if (ov > bv || (ov == bv && oa < ba)) { bv = ov; ba = oa; }
+    }
+    if (bv > best_v) { best_v = bv; best_a = ba; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) isum += __shfl_xor_sync(kFull, isum, o);
+  __syncwarp();
+  const double s = (T > 0.0) ? pairwise_sum<double>(x, A) : (double)isum;
+  __syncwarp();
+  bool has_nan = false;
+  for (int a = lane; a < A; a += 32) {
+    const double pr = __ddiv_rn(x[a], s);
+    x[a] = pr;
+    pi_out[(size_t)t * A + a] = pr;
+    has_nan |= (pr != pr);
+  }
+  has_nan = __any_sync(kFull, has_nan);
+  __syncwarp();
+  int act = best_a;
+  if (!deterministic) {
+    if (has_nan) {
+      if (lane == 0) atomicOr(p.error, MZ_DEVERR_NAN_POLICY);
+      act = -1;
+    } else {
+      // np.random.choice(A, p=pi): cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(cdf, u, 'right')
+      WarpRng rng;
+      rng.load(p.rng_key + (size_t)t * 624, p.rng_pos + t, lane);
+      const double u = rng.next_double();
+      rng.store(p.rng_pos + t);
+      double acc = 0.0;
+      for (int a = 0; a < A; ++a) acc = __dadd_rn(acc, x[a]);
+      const double last = acc;
+      acc = 0.0;
+      int idx = 0;
+      for (int a = 0; a < A; ++a) {
+        acc = __dadd_rn(acc, x[a]);
+        if (__ddiv_rn(acc, last) <= u) idx = a + 1; else break;
+      }
+      act = idx;
+    }
+  }
+  if (lane == 0) {
+    action[t] = act;
+    const int rn = p.rootN[t];
+    root_value[t] = rn > 0 ? __ddiv_rn(p.rootW[t], (double)rn) : 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// mz_dirichlet: numpy legacy_standard_gamma / dirichlet on the tree's stream
+// ---------------------------------------------------------------------------
+__device__ double legacy_gamma(WarpRng& rng, double shape) {
+  if (shape == 1.0) return -log(__dsub_rn(1.0, rng.next_double()));
+  if (shape == 0.0) return 0.0;
+  while (true) {
+    const double u = rng.next_double();
+    const double v = -log(__dsub_rn(1.0, rng.next_double()));
+    if (u <= __dsub_rn(1.0, shape)) {
+      const double xx = pow(u, __ddiv_rn(1.0, shape));
+      if (xx <= v) return xx;
+    } else {
+      const double y = -log(__ddiv_rn(__dsub_rn(1.0, u), shape));
+      const double xx = pow(__dadd_rn(__dsub_rn(1.0, shape), __dmul_rn(shape, y)), __ddiv_rn(1.0, shape));
+      if (xx <= __dadd_rn(v, y)) return xx;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kTreesPerBlock * 32)
+dirichlet_kernel(PoolDev p, double alpha, double* __restrict__ out) {
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (t >= p.B) return;
+  WarpRng rng;
+  rng.load(p.rng_key + (size_t)t * 624, p.rng_pos + t, lane);
+  double* o = out + (size_t)t * p.A;
+  double acc = 0.0;
+  for (int a = 0; a < p.A; ++a) {          // every lane runs the identical sequential sampler
+    const double g = legacy_gamma(rng, alpha);
+    acc = __dadd_rn(acc, g);
+    if (lane == 0) o[a] = g;
+  }
+  __syncwarp();
+  const double inv = __ddiv_rn(1.0, acc);
+  for (int a = lane; a < p.A; a += 32) o[a] = __dmul_rn(o[a], inv);
+  rng.store(p.rng_pos + t);
+}
+
+}  // namespace mz
+
+// ===========================================================================
+// host side of the C ABI
+// ===========================================================================
+using namespace mz;
+
+namespace {
+
+struct Carve {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    const size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  }
+};
+
+void layout(const mz_pool_config& c, size_t* offs, size_t* sizes, size_t* extra_offs, size_t* total) {
+  const size_t B = c.num_trees, A = c.num_actions, n = (size_t)c.num_simulations + 1;
+  Carve cv;
+  auto put = [&](int which, size_t bytes) { offs[which] = cv.take(bytes); sizes[which] = bytes; };
+  put(MZ_VIEW_EDGES, B * n * A * sizeof(Edge));
+  put(MZ_VIEW_PRIOR, B * A * 8);
+  put(MZ_VIEW_ROOT_W, B * 8);
+  put(MZ_VIEW_ROOT_N, B * 4);
+  put(MZ_VIEW_MINMAX, B * 16);
+  put(MZ_VIEW_COUNT, B * 4);
+  put(MZ_VIEW_LEAF_PARENT, B * 4);
+  put(MZ_VIEW_LEAF_ACTION, B * 4);
+  put(MZ_VIEW_LEAF_DEPTH, B * 4);
+  put(MZ_VIEW_SRC_SLOT, B * 4);
+  put(MZ_VIEW_DST_SLOT, B * 4);
+  put(MZ_VIEW_PATH, B * n * 4);
+  put(MZ_VIEW_NODE_PARENT, B * n * 4);
+  put(MZ_VIEW_NODE_MOVE, B * n * 4);
+  put(MZ_VIEW_RNG_KEY, B * 624 * 4);
+  put(MZ_VIEW_RNG_POS, B * 4);
+  put(MZ_VIEW_HIDDEN, B * n * (size_t)c.hidden_bytes);
+  put(MZ_VIEW_REWARD, B * 4);
+  put(MZ_VIEW_VALUE, B * 4);
+  put(MZ_VIEW_ERROR, 4);
+  put(MZ_VIEW_STATS, 4 * 8);
+  extra_offs[0] = cv.take((size_t)(c.num_simulations + 2) * 8);  // pb_c table
+  extra_offs[1] = cv.take(B);                                     // same_player
+  extra_offs[2] = cv.take(B * 8);                                 // root_reward
+  extra_offs[3] = cv.take(B);                                     // f32_prior
+  *total = cv.off;
+}
+
+int check_cfg(const mz_pool_config* c) {
+  MZ_CHECK_ARG(c != nullptr, "config is NULL");
+  MZ_CHECK_ARG(c->num_trees > 0, "num_trees must be positive, got %d", c->num_trees);
+  MZ_CHECK_ARG(c->num_actions > 0 && c->num_actions <= 65535, "num_actions out of range: %d", c->num_actions);
+  MZ_CHECK_ARG(c->num_simulations > 0 && c->num_simulations <= 65534,
+               "num_simulations must be in [1, 65534], got %d", c->num_simulations);
+  MZ_CHECK_ARG(c->hidden_bytes >= 0 && c->hidden_bytes % 16 == 0, "hidden_bytes must be a multiple of 16, got %d",
+               c->hidden_bytes);
+  MZ_CHECK_ARG((size_t)c->num_trees * (c->num_simulations + 1) < (size_t)1 << 31, "too many node slots");
+  MZ_CHECK_ARG((size_t)(c->num_simulations + 1) * c->num_actions < (size_t)1 << 32, "tree too large for u32 edge ids");
+  if (c->is_board_game)  // mcts.py:349-350
+    MZ_CHECK_ARG(c->discount == 1.0, "board games require discount == 1.0 (mcts.py:349), got %g", c->discount);
+  return MZ_OK;
+}
+
+PoolDev dev_of(const mz_pool* h) {
+  PoolDev d;
+  d.B = h->B; d.A = h->A; d.S = h->S; d.max_nodes = h->max_nodes;
+  d.board = h->cfg.is_board_game;
+  d.discount = h->cfg.discount;
+  d.dp = h->cfg.discount * (h->cfg.is_board_game ? -1.0 : 1.0);   // mcts.py:169-174: discount * p
+  d.edges = (Edge*)h->view_ptr[MZ_VIEW_EDGES];
+  d.prior = (double*)h->view_ptr[MZ_VIEW_PRIOR];
+  d.rootW = (double*)h->view_ptr[MZ_VIEW_ROOT_W];
+  d.rootN = (int*)h->view_ptr[MZ_VIEW_ROOT_N];
+  d.minmax = (double*)h->view_ptr[MZ_VIEW_MINMAX];
+  d.count = (int*)h->view_ptr[MZ_VIEW_COUNT];
+  d.leaf_parent = (int*)h->view_ptr[MZ_VIEW_LEAF_PARENT];
+  d.leaf_action = (int*)h->view_ptr[MZ_VIEW_LEAF_ACTION];
+  d.leaf_depth = (int*)h->view_ptr[MZ_VIEW_LEAF_DEPTH];
+  d.src_slot = (int*)h->view_ptr[MZ_VIEW_SRC_SLOT];
+  d.dst_slot = (int*)h->view_ptr[MZ_VIEW_DST_SLOT];
+  d.path = (uint32_t*)h->view_ptr[MZ_VIEW_PATH];
+  d.node_parent = (int*)h->view_ptr[MZ_VIEW_NODE_PARENT];
+  d.node_move = (int*)h->view_ptr[MZ_VIEW_NODE_MOVE];
+  d.rng_key = (uint32_t*)h->view_ptr[MZ_VIEW_RNG_KEY];
+  d.rng_pos = (int*)h->view_ptr[MZ_VIEW_RNG_POS];
+  d.reward = (float*)h->view_ptr[MZ_VIEW_REWARD];
+  d.value = (float*)h->view_ptr[MZ_VIEW_VALUE];
+  d.error = (int*)h->view_ptr[MZ_VIEW_ERROR];
+  d.stats = (unsigned long long*)h->view_ptr[MZ_VIEW_STATS];
+  d.T = h->pb_c_table;
+  d.same_player = h->same_player;
+  d.root_reward = h->root_reward;
+  d.f32_prior = h->f32_prior;
+  d.bound_min = h->cfg.bound_min; d.bound_max = h->cfg.bound_max;
+  d.has_bounds = h->cfg.has_known_bounds;
+  return d;
+}
+
+inline int tree_blocks(int B) { return (B + kTreesPerBlock - 1) / kTreesPerBlock; }
+
+}  // namespace
+
+extern "C" int mz_pool_arena_bytes(const mz_pool_config* cfg, size_t* bytes) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  MZ_CHECK_ARG(bytes != nullptr, "bytes is NULL");
+  size_t offs[MZ_VIEW__COUNT], sizes[MZ_VIEW__COUNT], extra[4];
+  layout(*cfg, offs, sizes, extra, bytes);
+  return MZ_OK;
+}
+
+extern "C" int mz_pool_create(const mz_pool_config* cfg, const double* pb_c_table_host, void* arena_dev,
+                              size_t arena_bytes, mz_pool** out) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  MZ_CHECK_ARG(pb_c_table_host && arena_dev && out, "NULL argument");
+  MZ_CHECK_ARG(((uintptr_t)arena_dev & 255) == 0, "arena must be 256-byte aligned");
+  size_t offs[MZ_VIEW__COUNT], sizes[MZ_VIEW__COUNT], extra[4], total;
+  layout(*cfg, offs, sizes, extra, &total);
+  if (arena_bytes < total) {
+    set_error("arena too small: %zu < %zu", arena_bytes, total);
+    return MZ_ENOMEM;
+  }
+  mz_pool* h = new mz_pool();
+  h->cfg = *cfg;
+  h->B = cfg->num_trees; h->A = cfg->num_actions; h->S = cfg->num_simulations; h->max_nodes = h->S + 1;
+  h->arena = arena_dev; h->arena_bytes = arena_bytes;
+  char* base = (char*)arena_dev;
+  for (int i = 0; i < MZ_VIEW__COUNT; ++i) { h->view_ptr[i] = base + offs[i]; h->view_bytes[i] = sizes[i]; }
+  h->pb_c_table = (double*)(base + extra[0]);
+  h->same_player = (uint8_t*)(base + extra[1]);
+  h->root_reward = (double*)(base + extra[2]);
+  h->f32_prior = (uint8_t*)(base + extra[3]);
+  h->selected = 0;
+  cudaError_t e = cudaMemcpy(h->pb_c_table, pb_c_table_host, (size_t)(h->S + 2) * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(h->view_ptr[MZ_VIEW_ERROR], 0, 4);
+  if (e == cudaSuccess) e = cudaMemset(h->view_ptr[MZ_VIEW_STATS], 0, 32);
+  if (e == cudaSuccess) e = cudaMemset(h->view_ptr[MZ_VIEW_LEAF_DEPTH], 0, sizes[MZ_VIEW_LEAF_DEPTH]);
+  if (e == cudaSuccess) e = cudaMemset(h->view_ptr[MZ_VIEW_RNG_KEY], 0, sizes[MZ_VIEW_RNG_KEY]);
+  if (e == cudaSuccess) e = cudaMemset(h->view_ptr[MZ_VIEW_RNG_POS], 0, sizes[MZ_VIEW_RNG_POS]);
+  if (e != cudaSuccess) {
+    set_error("pool initialisation failed: %s", cudaGetErrorString(e));
+    delete h;
+    return MZ_ECUDA;
+  }
+  *out = h;
+  return MZ_OK;
+}
+
+extern "C" int mz_pool_destroy(mz_pool* pool) {
+  delete pool;
+  return MZ_OK;
+}
+
+extern "C" int mz_pool_view(mz_pool* pool, int which, void** dev_ptr, size_t* bytes) {
+  MZ_CHECK_ARG(pool && dev_ptr && bytes, "NULL argument");
+  MZ_CHECK_ARG(which >= 0 && which < MZ_VIEW__COUNT, "unknown view %d", which);
+  *dev_ptr = pool->view_ptr[which];
+  *bytes = pool->view_bytes[which];
+  return MZ_OK;
+}
+
+extern "C" int mz_rng_seed(mz_pool* pool, const uint32_t* seeds_dev, mz_stream stream) {
+  MZ_CHECK_ARG(pool && seeds_dev, "NULL argument");
+  rng_seed_kernel<<<(pool->B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dev_of(pool), seeds_dev);
+  MZ_LAUNCH_CHECK("rng_seed_kernel");
+  return MZ_OK;
+}
+
+extern "C" int mz_dirichlet(mz_pool* pool, double alpha, double* noise_out_dev, mz_stream stream) {
+  MZ_CHECK_ARG(pool && noise_out_dev, "NULL argument");
+  // mcts.py:241-242 restricts alpha to [0, 1]; numpy rejects alpha <= 0
+  MZ_CHECK_ARG(alpha > 0.0 && alpha <= 1.0, "Expect `alpha` to be a float in the range (0.0, 1.0], got %g", alpha);
+  dirichlet_kernel<<<tree_blocks(pool->B), kTreesPerBlock * 32, 0, (cudaStream_t)stream>>>(dev_of(pool), alpha,
+                                                                                          noise_out_dev);
+  MZ_LAUNCH_CHECK("dirichlet_kernel");
+  return MZ_OK;
+}
+
+extern "C" int mz_search_reset(mz_pool* pool, const float* pi_probs, const double* noise, double eps,
+                               const uint8_t* mask, const int32_t* players, const float* root_reward,
+                               mz_stream stream) {
+  MZ_CHECK_ARG(pool && pi_probs, "NULL argument");
+  // mcts.py:239-240
+  MZ_CHECK_ARG(eps >= 0.0 && eps <= 1.0, "Expect `eps` to be a float in the range [0.0, 1.0], got %g", eps);
+  const float ome = (float)(1.0 - eps);
+  reset_kernel<<<tree_blocks(pool->B), kTreesPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      dev_of(pool), pi_probs, noise, eps, ome, mask, players, root_reward);
+  MZ_LAUNCH_CHECK("reset_kernel");
+  pool->selected = 0;
+  return MZ_OK;
+}
+
+extern "C" int mz_select(mz_pool* pool, mz_stream stream) {
+  MZ_CHECK_ARG(pool, "NULL argument");
+  const size_t smem = (size_t)kTreesPerBlock * ((pool->A + 3) & ~3) * sizeof(float);
+  select_kernel<<<tree_blocks(pool->B), kTreesPerBlock * 32, smem, (cudaStream_t)stream>>>(dev_of(pool));
+  MZ_LAUNCH_CHECK("select_kernel");
+  pool->selected = 1;
+  return MZ_OK;
+}
+
+extern "C" int mz_expand_backup(mz_pool* pool, const float* reward, const float* value, mz_stream stream) {
+  MZ_CHECK_ARG(pool, "NULL argument");
+  if (!pool->selected) {
+    set_error("mz_expand_backup called without a preceding mz_select");
+    return MZ_ESTATE;
+  }
+  const PoolDev d = dev_of(pool);
+  expand_backup_kernel<<<tree_blocks(pool->B), kTreesPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      d, reward ? reward : d.reward, value ? value : d.value);
+  MZ_LAUNCH_CHECK("expand_backup_kernel");
+  pool->selected = 0;
+  return MZ_OK;
+}
+
+extern "C" int mz_root_policy(mz_pool* pool, const uint8_t* mask, const double* temperature, int deterministic,
+                              int32_t* action, double* pi, double* root_value, int32_t* visits, mz_stream stream) {
+  MZ_CHECK_ARG(pool && temperature && action && pi && root_value, "NULL argument");
+  const size_t smem = (size_t)kTreesPerBlock * pool->A * sizeof(double);
+  root_policy_kernel<<<tree_blocks(pool->B), kTreesPerBlock * 32, smem, (cudaStream_t)stream>>>(
+      dev_of(pool), mask, temperature, deterministic, action, pi, root_value, visits);
+  MZ_LAUNCH_CHECK("root_policy_kernel");
+  return MZ_OK;
+}

@@ -1,0 +1,71 @@
+// C ABI of the network handles: dispatch on the network family.
+#include "net.cuh"
+
+using namespace mz;
+
+extern "C" int mz_net_hidden_bytes(const mz_net_config* cfg, int32_t* bytes) {
+  MZ_CHECK_ARG(cfg && bytes, "NULL argument");
+  switch (cfg->kind) {
+    case MZ_NET_MLP: return mlp_hidden_bytes(*cfg, bytes);
+    case MZ_NET_BOARD:
+    case MZ_NET_ATARI: return conv_hidden_bytes(*cfg, bytes);
+  }
+  set_error("unknown network kind %d", cfg->kind);
+  return MZ_EINVAL;
+}
+
+extern "C" int mz_net_arena_bytes(const mz_net_config* cfg, int32_t max_batch, size_t* bytes) {
+  MZ_CHECK_ARG(cfg && bytes, "NULL argument");
+  MZ_CHECK_ARG(max_batch > 0, "max_batch must be positive");
+  switch (cfg->kind) {
+    case MZ_NET_MLP: return mlp_arena_bytes(*cfg, bytes);
+    case MZ_NET_BOARD:
+    case MZ_NET_ATARI: return conv_arena_bytes(*cfg, max_batch, bytes);
+  }
+  set_error("unknown network kind %d", cfg->kind);
+  return MZ_EINVAL;
+}
+
+extern "C" int mz_net_create(const mz_net_config* cfg, const float* const* weights, int32_t num_weights,
+                             int32_t max_batch, void* arena_dev, size_t arena_bytes, mz_net** out) {
+  MZ_CHECK_ARG(cfg && weights && arena_dev && out, "NULL argument");
+  MZ_CHECK_ARG(max_batch > 0, "max_batch must be positive");
+  MZ_CHECK_ARG(((uintptr_t)arena_dev & 255) == 0, "arena must be 256-byte aligned");
+  for (int i = 0; i < num_weights; ++i) MZ_CHECK_ARG(weights[i] != nullptr, "weights[%d] is NULL", i);
+  NetImpl* impl = nullptr;
+  int rc;
+  switch (cfg->kind) {
+    case MZ_NET_MLP: rc = mlp_create(*cfg, weights, num_weights, arena_dev, arena_bytes, &impl); break;
+    case MZ_NET_BOARD:
+    case MZ_NET_ATARI: rc = conv_create(*cfg, weights, num_weights, max_batch, arena_dev, arena_bytes, &impl); break;
+    default: set_error("unknown network kind %d", cfg->kind); return MZ_EINVAL;
+  }
+  if (rc) return rc;
+  mz_net* h = new mz_net();
+  h->cfg = *cfg;
+  h->max_batch = max_batch;
+  h->impl = impl;
+  *out = h;
+  return MZ_OK;
+}
+
+extern "C" int mz_net_destroy(mz_net* net) {
+  if (net) { delete net->impl; delete net; }
+  return MZ_OK;
+}
+
+extern "C" int mz_net_initial(mz_net* net, int32_t batch, const float* obs, void* hidden_out,
+                              const int32_t* dst_index, float* pi_probs, float* value, mz_stream stream) {
+  MZ_CHECK_ARG(net && obs && hidden_out && value, "NULL argument");
+  MZ_CHECK_ARG(batch > 0 && batch <= net->max_batch, "batch %d outside (0, %d]", batch, net->max_batch);
+  return net->impl->initial(batch, obs, hidden_out, dst_index, pi_probs, value, (cudaStream_t)stream);
+}
+
+extern "C" int mz_net_recurrent(mz_net* net, int32_t batch, const void* hidden_in, const int32_t* src_index,
+                                const int32_t* action, void* hidden_out, const int32_t* dst_index, float* reward,
+                                float* value, float* pi_probs, mz_stream stream) {
+  MZ_CHECK_ARG(net && hidden_in && action && hidden_out && reward && value, "NULL argument");
+  MZ_CHECK_ARG(batch > 0 && batch <= net->max_batch, "batch %d outside (0, %d]", batch, net->max_batch);
+  return net->impl->recurrent(batch, hidden_in, src_index, action, hidden_out, dst_index, reward, value, pi_probs,
+                              (cudaStream_t)stream);
+}

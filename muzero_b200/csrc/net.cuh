@@ -1,0 +1,31 @@
+// Internal interface every network family implements behind the mz_net handle.
+#pragma once
+#include "common.cuh"
+
+namespace mz {
+
+struct NetImpl {
+  virtual ~NetImpl() {}
+  virtual int initial(int batch, const float* obs, void* hidden_out, const int32_t* dst_index, float* pi_probs,
+                      float* value, cudaStream_t st) = 0;
+  virtual int recurrent(int batch, const void* hidden_in, const int32_t* src_index, const int32_t* action,
+                        void* hidden_out, const int32_t* dst_index, float* reward, float* value, float* pi_probs,
+                        cudaStream_t st) = 0;
+};
+
+int mlp_hidden_bytes(const mz_net_config& c, int32_t* bytes);
+int mlp_arena_bytes(const mz_net_config& c, size_t* bytes);
+int mlp_create(const mz_net_config& c, const float* const* w, int nw, void* arena, size_t arena_bytes, NetImpl** out);
+
+int conv_hidden_bytes(const mz_net_config& c, int32_t* bytes);
+int conv_arena_bytes(const mz_net_config& c, int max_batch, size_t* bytes);
+int conv_create(const mz_net_config& c, const float* const* w, int nw, int max_batch, void* arena,
+                size_t arena_bytes, NetImpl** out);
+
+}  // namespace mz
+
+struct mz_net {
+  mz_net_config cfg;
+  int max_batch;
+  mz::NetImpl* impl;
+};

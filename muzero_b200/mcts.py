@@ -1,0 +1,402 @@
+"""Batched GPU tree search: drop-in ``uct_search`` plus ``uct_search_batch``.
+
+Reference interface mirrored here (michaelnny/muzero, muzero/mcts.py):
+  mcts.py:302-407  uct_search(state, network, device, config, temperature, actions_mask,
+                              current_player, opponent_player, deterministic=False)
+                   -> (action: int, pi: float64[A], root value: float)
+
+All tree arithmetic happens in the CUDA kernels of csrc/mcts.cu behind the C
+ABI (include/muzero_b200.h).  This module only validates arguments the way the
+reference does, draws the Dirichlet noise from numpy when bit-exact stream
+continuity with ``np.random`` is requested, and sequences the launches.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from .network import MuZeroNet
+
+
+def pb_c_table(num_simulations: int, pb_c_base: float, pb_c_init: float) -> np.ndarray:
+    """The exploration factor of mcts.py:193-195 for every parent visit count,
+    evaluated with CPython ``math`` exactly as the reference evaluates it."""
+    return np.array([(math.log((n + pb_c_base + 1) / pb_c_base) + pb_c_init) * math.sqrt(n)
+                     for n in range(num_simulations + 2)], dtype=np.float64)
+
+
+class SearchPool:
+    """GPU-resident node pool + search state for ``num_trees`` independent trees.
+
+    Replaces the ``Node`` / ``MinMaxStats`` object graph of mcts.py:33-217 with
+    the struct-of-arrays arena described in DESIGN.md.
+    """
+
+    def __init__(self, num_trees: int, num_actions: int, config, hidden_bytes: int,
+                 device: Union[str, torch.device] = 'cuda') -> None:
+        if config.is_board_game:
+            assert config.discount == 1.0            # mcts.py:349-350
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise RuntimeError('SearchPool lives on a CUDA device (no CPU fallback)')
+        if self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
+        self.B, self.A, self.S = int(num_trees), int(num_actions), int(config.num_simulations)
+        self.hidden_bytes = int(hidden_bytes)
+        kb = config.known_bounds
+        self.cfg = _lib.PoolConfig(
+            num_trees=self.B, num_actions=self.A, num_simulations=self.S, hidden_bytes=self.hidden_bytes,
+            is_board_game=int(bool(config.is_board_game)), has_known_bounds=int(kb is not None),
+            bound_min=float(kb.min) if kb is not None else 0.0, bound_max=float(kb.max) if kb is not None else 0.0,
+            discount=float(config.discount))
+        lib = _lib.lib()
+        nbytes = C.c_size_t()
+        _lib.check(lib.mz_pool_arena_bytes(C.byref(self.cfg), C.byref(nbytes)))
+        with torch.cuda.device(self.device):
+            self.arena = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=self.device)
+            self._base = (self.arena.data_ptr() + 255) // 256 * 256
+            table = pb_c_table(self.S, config.pb_c_base, config.pb_c_init)
+            self.handle = C.c_void_p()
+            _lib.check(lib.mz_pool_create(C.byref(self.cfg), table.ctypes.data_as(C.POINTER(C.c_double)),
+                                          self._base, nbytes.value, C.byref(self.handle)))
+        self.arena_bytes = nbytes.value
+        self._views = {}
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None):
+                _lib.lib().mz_pool_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # -- typed views into the arena ------------------------------------------
+    _VIEW_TYPES = {
+        'EDGES': (torch.uint8, 16), 'PRIOR': (torch.float64, None), 'ROOT_W': (torch.float64, None),
+        'ROOT_N': (torch.int32, None), 'MINMAX': (torch.float64, 2), 'COUNT': (torch.int32, None),
+        'LEAF_PARENT': (torch.int32, None), 'LEAF_ACTION': (torch.int32, None), 'LEAF_DEPTH': (torch.int32, None),
+        'SRC_SLOT': (torch.int32, None), 'DST_SLOT': (torch.int32, None), 'PATH': (torch.int32, None),
+        'NODE_PARENT': (torch.int32, None), 'NODE_MOVE': (torch.int32, None), 'RNG_KEY': (torch.int32, 624),
+        'RNG_POS': (torch.int32, None), 'HIDDEN': (torch.uint8, None), 'REWARD': (torch.float32, None),
+        'VALUE': (torch.float32, None), 'ERROR': (torch.int32, None), 'STATS': (torch.int64, None),
+    }
+
+    def view(self, name: str) -> torch.Tensor:
+        """Zero-copy tensor over one of the pool's buffers (see enum mz_view)."""
+        if name not in self._views:
+            p, n = C.c_void_p(), C.c_size_t()
+            _lib.check(_lib.lib().mz_pool_view(self.handle, _lib.VIEW[name], C.byref(p), C.byref(n)))
+            off = p.value - self.arena.data_ptr()
+            dt, _ = self._VIEW_TYPES[name]
+            self._views[name] = self.arena[off:off + n.value].view(dt)
+        return self._views[name]
+
+    @property
+    def hidden(self) -> torch.Tensor:
+        """[B*(S+1), hidden_bytes] uint8 slot array."""
+        return self.view('HIDDEN').view(self.B * (self.S + 1), max(self.hidden_bytes, 1)) \
+            if self.hidden_bytes else self.view('HIDDEN')
+
+    def _call(self, fn, *args):
+        with torch.cuda.device(self.device):
+            _lib.check(fn(self.handle, *args, _lib.current_stream()))
+
+    # -- RNG -------------------------------------------------------------------
+    def seed(self, seeds) -> None:
+        """``np.random.seed(seeds[t])`` for each tree, done on the device."""
+        s = torch.as_tensor(np.asarray(seeds, dtype=np.uint32).astype(np.int64), device=self.device).to(torch.int32)
+        assert s.shape == (self.B,)
+        self._call(_lib.lib().mz_rng_seed, _lib.ptr(s.contiguous()))
+
+    def set_rng_states(self, states: Sequence) -> None:
+        """Load numpy legacy states (``RandomState.get_state()`` tuples), one per tree."""
+        keys = np.stack([np.asarray(st[1], dtype=np.uint32) for st in states]).view(np.int32)
+        pos = np.array([st[2] for st in states], dtype=np.int32)
+        self.view('RNG_KEY').view(self.B, 624).copy_(torch.from_numpy(keys))
+        self.view('RNG_POS').copy_(torch.from_numpy(pos))
+
+    def get_rng_states(self):
+        keys = self.view('RNG_KEY').view(self.B, 624).cpu().numpy().view(np.uint32)
+        pos = self.view('RNG_POS').cpu().numpy()
+        return [('MT19937', keys[t].copy(), int(pos[t]), 0, 0.0) for t in range(self.B)]
+
+    def dirichlet(self, alpha: float) -> torch.Tensor:
+        out = torch.empty((self.B, self.A), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().mz_dirichlet(self.handle, float(alpha), _lib.ptr(out), _lib.current_stream()))
+        return out
+
+    # -- search steps ------------------------------------------------------------
+    def reset(self, pi_probs: torch.Tensor, noise: Optional[torch.Tensor], eps: float,
+              mask: Optional[torch.Tensor], players: Optional[torch.Tensor],
+              root_reward: Optional[torch.Tensor] = None) -> None:
+        assert pi_probs.dtype == torch.float32 and pi_probs.shape == (self.B, self.A)
+        if mask is not None:
+            assert mask.shape == pi_probs.shape          # mcts.py:293
+        self._call(_lib.lib().mz_search_reset, _lib.ptr(pi_probs), _lib.ptr(noise), float(eps), _lib.ptr(mask),
+                   _lib.ptr(players), _lib.ptr(root_reward))
+
+    def select(self) -> None:
+        self._call(_lib.lib().mz_select)
+
+    def expand_backup(self, reward: Optional[torch.Tensor] = None, value: Optional[torch.Tensor] = None) -> None:
+        self._call(_lib.lib().mz_expand_backup, _lib.ptr(reward), _lib.ptr(value))
+
+    def root_policy(self, mask: Optional[torch.Tensor], temperature: torch.Tensor, deterministic: bool):
+        dev = self.device
+        action = torch.empty(self.B, dtype=torch.int32, device=dev)
+        pi = torch.empty((self.B, self.A), dtype=torch.float64, device=dev)
+        rootv = torch.empty(self.B, dtype=torch.float64, device=dev)
+        visits = torch.empty((self.B, self.A), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().mz_root_policy(self.handle, _lib.ptr(mask), _lib.ptr(temperature),
+                                                 int(bool(deterministic)), _lib.ptr(action), _lib.ptr(pi),
+                                                 _lib.ptr(rootv), _lib.ptr(visits), _lib.current_stream()))
+        return action, pi, rootv, visits
+
+    def check_errors(self) -> None:
+        """Synchronising read of the sticky device error word."""
+        e = int(self.view('ERROR').cpu()[0])
+        if e:
+            self.view('ERROR').zero_()
+        if e & _lib.MZ_DEVERR_POOL_FULL:
+            raise RuntimeError('Node already expanded.')          # mcts.py:90-91: more expansions than slots
+        if e & _lib.MZ_DEVERR_NAN_POLICY:
+            raise ValueError('probabilities contain NaN')           # what np.random.choice raises (mcts.py:404)
+
+    # -- debug / parity ------------------------------------------------------------
+    def dump_tree(self, t: int) -> dict:
+        """Host copy of tree ``t`` as node-indexed arrays (expansion order), the
+        same shape as ``oracle.mcts_oracle.SearchTrace``."""
+        A, n = self.A, self.S + 1
+        count = int(self.view('COUNT')[t].cpu())
+        edges = self.view('EDGES').view(self.B, n * A * 16)[t].cpu().numpy()
+        rec = edges.view(np.dtype([('W', '<f8'), ('R', '<f4'), ('N', '<u2'), ('child', '<u2')])).reshape(n, A)
+        parent = self.view('NODE_PARENT').view(self.B, n)[t].cpu().numpy()[:count].copy()
+        move = self.view('NODE_MOVE').view(self.B, n)[t].cpu().numpy()[:count].copy()
+        N = np.zeros(count, np.int32); W = np.zeros(count, np.float64); R = np.zeros(count, np.float64)
+        N[0] = int(self.view('ROOT_N')[t].cpu()); W[0] = float(self.view('ROOT_W')[t].cpu())
+        for i in range(1, count):
+            e = rec[parent[i], move[i]]
+            assert e['child'] == i, (i, e)
+            N[i], W[i], R[i] = e['N'], e['W'], e['R']
+        children = np.where(rec['child'][:count] == 0xFFFF, -1, rec['child'][:count].astype(np.int32))
+        mm = self.view('MINMAX').view(self.B, 2)[t].cpu().numpy()
+        return dict(num_nodes=count, N=N, W=W, R=R, parent=parent, move=move, children=children,
+                    prior=self.view('PRIOR').view(self.B, A)[t].cpu().numpy().copy(), minmax=(mm[0], mm[1]))
+
+
+# ---------------------------------------------------------------------------
+# argument checks shared by both entry points (same messages as the reference)
+# ---------------------------------------------------------------------------
+def _check_temperature(temperature) -> None:
+    # generate_play_policy, mcts.py:268-269
+    if not isinstance(temperature, float) or not 0.0 <= temperature <= 1.0:
+        raise ValueError(f'Expect `temperature` to be float type in the range [0.0, 1.0], got {temperature}')
+
+
+def _noise_enabled(config, deterministic: bool) -> bool:
+    use = (not deterministic) and config.root_dirichlet_alpha > 0.0 and config.root_exploration_eps > 0.0  # mcts.py:361
+    if use:
+        eps, alpha = config.root_exploration_eps, config.root_dirichlet_alpha
+        if not isinstance(eps, float) or not 0.0 <= eps <= 1.0:           # mcts.py:239-240
+            raise ValueError(f'Expect `eps` to be a float in the range [0.0, 1.0], got {eps}')
+        if not isinstance(alpha, float) or not 0.0 <= alpha <= 1.0:       # mcts.py:241-242
+            raise ValueError(f'Expect `alpha` to be a float in the range [0.0, 1.0], got {alpha}')
+    return use
+
+
+_POOLS = {}
+
+
+def _pool_for(B, A, config, hidden_bytes, device) -> SearchPool:
+    kb = config.known_bounds
+    key = (B, A, config.num_simulations, hidden_bytes, str(device), bool(config.is_board_game),
+           None if kb is None else (float(kb.min), float(kb.max)), float(config.discount),
+           float(config.pb_c_base), float(config.pb_c_init))
+    if key not in _POOLS:
+        if len(_POOLS) >= 4:
+            _POOLS.pop(next(iter(_POOLS)))
+        _POOLS[key] = SearchPool(B, A, config, hidden_bytes, device)
+    return _POOLS[key]
+
+
+def clear_pools() -> None:
+    _POOLS.clear()
+
+
+# ---------------------------------------------------------------------------
+# batched entry point (additive API)
+# ---------------------------------------------------------------------------
+@torch.no_grad()
+def uct_search_batch(states, network: MuZeroNet, config, temperature, actions_mask, current_player, opponent_player,
+                     deterministic: bool = False, rng=None, noise=None, pool: Optional[SearchPool] = None,
+                     return_pool: bool = False):
+    """``uct_search`` for B independent trees at once, everything on the GPU.
+
+    states          [B, *obs] array/tensor
+    temperature     float or float64[B]
+    actions_mask    bool[B, A] or None
+    current_player / opponent_player   int or int[B]
+    rng             None: each tree continues its device-resident MT19937 stream
+                    (seed it with ``pool.seed``) and, when noise is on, the
+                    Dirichlet sample is drawn on the device;
+                    list of B ``np.random.RandomState``: numpy-exact mode — the
+                    Dirichlet sample is drawn by numpy from each stream, the
+                    stream is continued on the device for tie-breaks and the final
+                    draw, and written back, i.e. tree t consumes its stream exactly
+                    as the reference ``uct_search`` would.
+    noise           optional float64[B, A] pre-drawn Dirichlet samples (overrides both).
+
+    Returns (actions int32[B], pi float64[B, A], root_values float64[B]) as CUDA tensors.
+    """
+    dev = next(network.parameters()).device
+    states = torch.as_tensor(states)
+    B = states.shape[0]
+    A = network.num_actions
+    if config.is_board_game:
+        assert config.discount == 1.0
+    temps = np.full(B, temperature, dtype=np.float64) if np.isscalar(temperature) else \
+        np.asarray(temperature, dtype=np.float64)
+    if np.isscalar(temperature):
+        _check_temperature(temperature)
+    elif not ((temps >= 0.0) & (temps <= 1.0)).all():
+        raise ValueError(f'Expect `temperature` to be float type in the range [0.0, 1.0], got {temperature}')
+    use_noise = _noise_enabled(config, deterministic)
+
+    if pool is None:
+        pool = _pool_for(B, A, config, network.hidden_bytes, dev)
+    S = pool.S
+
+    mask_d = None
+    if actions_mask is not None:
+        m = torch.as_tensor(np.asarray(actions_mask)) if not torch.is_tensor(actions_mask) else actions_mask
+        assert tuple(m.shape) == (B, A)                                   # mcts.py:293
+        mask_d = m.to(device=dev, dtype=torch.uint8).contiguous()
+    cur = np.broadcast_to(np.asarray(current_player, dtype=np.int32), (B,))
+    opp = np.broadcast_to(np.asarray(opponent_player, dtype=np.int32), (B,))
+    players_d = torch.from_numpy(np.stack([cur, opp], axis=1).copy()).to(dev)
+    temps_d = torch.from_numpy(temps).to(dev)
+
+    # root: representation + prediction straight into slot 0 of every tree (mcts.py:355-356)
+    root_slots = torch.arange(B, dtype=torch.int32, device=dev) * (S + 1)
+    _, pi0, _ = network.initial_inference_batch(states.to(dev), hidden_out=pool.hidden, dst_index=root_slots)
+
+    noise_d = None
+    if use_noise:
+        if noise is not None:
+            noise_d = torch.as_tensor(np.asarray(noise, dtype=np.float64)).to(dev).contiguous()
+        elif rng is not None:
+            alphas = np.ones(A, dtype=np.float32) * config.root_dirichlet_alpha   # np.ones_like(prob) * alpha
+            noise_d = torch.from_numpy(np.stack([r.dirichlet(alphas) for r in rng])).to(dev)
+    if rng is not None:
+        pool.set_rng_states([r.get_state() for r in rng])
+    if use_noise and noise_d is None:
+        noise_d = pool.dirichlet(float(np.float32(config.root_dirichlet_alpha)))   # alphas are float32 in the reference
+
+    pool.reset(pi0, noise_d, config.root_exploration_eps if use_noise else 0.0, mask_d, players_d)
+    reward, value = pool.view('REWARD'), pool.view('VALUE')
+    src, dst, act = pool.view('SRC_SLOT'), pool.view('DST_SLOT'), pool.view('LEAF_ACTION')
+    hidden = pool.hidden
+    lib = _lib.lib()
+    eng = network.engine(B)
+    with torch.cuda.device(dev):
+        stream = _lib.current_stream()
+        for _ in range(S):
+            _lib.check(lib.mz_select(pool.handle, stream))
+            _lib.check(lib.mz_net_recurrent(eng['handle'], B, hidden.data_ptr(), src.data_ptr(), act.data_ptr(),
+                                            hidden.data_ptr(), dst.data_ptr(), reward.data_ptr(), value.data_ptr(),
+                                            None, stream))
+            _lib.check(lib.mz_expand_backup(pool.handle, None, None, stream))
+    action, pi, rootv, _ = pool.root_policy(mask_d, temps_d, deterministic)
+    if rng is not None:
+        for r, st in zip(rng, pool.get_rng_states()):
+            old = r.get_state()
+            r.set_state(('MT19937', st[1], st[2], old[3], old[4]))
+    if return_pool:
+        return action, pi, rootv, pool
+    return action, pi, rootv
+
+
+# ---------------------------------------------------------------------------
+# the reference's entry point
+# ---------------------------------------------------------------------------
+class _GlobalNumpyStream:
+    """Adapter giving ``np.random``'s global stream the RandomState methods used above."""
+    dirichlet = staticmethod(lambda a: np.random.dirichlet(a))
+    get_state = staticmethod(lambda: np.random.get_state())
+    set_state = staticmethod(lambda s: np.random.set_state(s))
+
+
+@torch.no_grad()
+def uct_search(state: np.ndarray, network, device, config, temperature: float, actions_mask: np.ndarray,
+               current_player: int, opponent_player: int, deterministic: bool = False) -> Tuple[int, np.ndarray, float]:
+    """Drop-in for ``muzero.mcts.uct_search`` (mcts.py:302-407), one tree on the GPU.
+
+    Consumes ``np.random``'s global MT19937 stream exactly like the reference
+    (Dirichlet sample, tie-breaks, final action draw) and leaves it where the
+    reference would.  ``network`` is either a ``muzero_b200`` network (inference in
+    the CUDA engine) or any object with the reference's ``initial_inference`` /
+    ``recurrent_inference`` methods (then only the tree runs on the GPU and the
+    network is called once per simulation, like the reference does).
+    """
+    _check_temperature(temperature)
+    dev = torch.device(device)
+    mask = None if actions_mask is None else np.asarray(actions_mask)[None, :]
+    if isinstance(network, MuZeroNet):
+        a, pi, q = uct_search_batch(np.asarray(state)[None, ...], network, config, temperature, mask,
+                                    current_player, opponent_player, deterministic, rng=[_GlobalNumpyStream])
+        return int(a[0].cpu()), pi[0].cpu().numpy(), float(q[0].cpu())
+    return _uct_search_external(state, network, dev, config, temperature, actions_mask, current_player,
+                                opponent_player, deterministic)
+
+
+def _uct_search_external(state, network, dev, config, temperature, actions_mask, current_player, opponent_player,
+                         deterministic):
+    """Tree on the GPU, network = caller's object (batch-1 calls on ``dev``'s side)."""
+    if config.is_board_game:
+        assert config.discount == 1.0
+    gpu = dev if dev.type == 'cuda' else torch.device('cuda', torch.cuda.current_device())
+    st = torch.from_numpy(np.asarray(state)).to(device=dev, dtype=torch.float32)
+    out0 = network.initial_inference(st[None, ...])
+    prior = np.asarray(out0.pi_probs)
+    if not isinstance(prior, np.ndarray) or prior.ndim != 1 or prior.dtype not in (np.float32, np.float64):
+        raise ValueError(f'Expect `prior` to be a 1D float numpy.array, got {prior}')      # mcts.py:92-93
+    A = prior.shape[0]
+    use_noise = _noise_enabled(config, deterministic)
+    noise_d = None
+    if use_noise:
+        noise_d = torch.from_numpy(np.random.dirichlet(np.ones_like(prior) * config.root_dirichlet_alpha)[None]).to(gpu)
+    mask_d = None
+    if actions_mask is not None:
+        assert np.asarray(actions_mask).shape == prior.shape                            # mcts.py:293
+        mask_d = torch.from_numpy(np.asarray(actions_mask, dtype=np.uint8)[None].copy()).to(gpu)
+    pool = _pool_for(1, A, config, 0, gpu)
+    pool.set_rng_states([np.random.get_state()])
+    players = torch.tensor([[current_player, opponent_player]], dtype=torch.int32, device=gpu)
+    rr = torch.tensor([float(out0.reward)], dtype=torch.float32, device=gpu)
+    pool.reset(torch.from_numpy(prior.astype(np.float32))[None].to(gpu).contiguous(), noise_d,
+               config.root_exploration_eps if use_noise else 0.0, mask_d, players, rr)
+    hidden = {0: out0.hidden_state}
+    rv = torch.empty(2, dtype=torch.float32, device=gpu)
+    for i in range(config.num_simulations):
+        pool.select()
+        par = int(pool.view('LEAF_PARENT')[0].cpu())
+        a = int(pool.view('LEAF_ACTION')[0].cpu())
+        h = torch.from_numpy(np.asarray(hidden[par])).to(device=dev, dtype=torch.float32)
+        o = network.recurrent_inference(h[None, ...], torch.tensor([[a]], dtype=torch.long, device=dev))
+        hidden[i + 1] = o.hidden_state
+        rv.copy_(torch.tensor([float(o.reward), float(o.value)], dtype=torch.float32))
+        pool.expand_backup(rv[0:1], rv[1:2])
+    temps = torch.tensor([temperature], dtype=torch.float64, device=gpu)
+    action, pi, rootv, _ = pool.root_policy(mask_d, temps, deterministic)
+    pool.check_errors()
+    stt = pool.get_rng_states()[0]
+    old = np.random.get_state()
+    np.random.set_state(('MT19937', stt[1], stt[2], old[3], old[4]))
+    return int(action[0].cpu()), pi[0].cpu().numpy(), float(rootv[0].cpu())

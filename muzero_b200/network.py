@@ -1,0 +1,426 @@
+"""MuZero networks: the reference's constructors, state_dict keys and
+``initial_inference`` / ``recurrent_inference`` signatures, with inference
+running through the hand-written sm_100a kernels behind the C ABI.
+
+Reference interface mirrored here (michaelnny/muzero):
+  network.py:25-30    NetworkOutputs
+  network.py:49-137   MuZeroNet (initial_inference / recurrent_inference)
+  network.py:236-267  MuZeroMLPNet(input_shape, num_actions, num_planes, value_support_size,
+                                   reward_support_size, hidden_dim)
+  network.py:501-537  MuZeroAtariNet(input_shape, num_actions, num_res_blocks, num_planes,
+                                     value_support_size, reward_support_size)
+  network.py:540-574  MuZeroBoardGameNet(input_shape, num_actions, num_res_blocks, num_planes)
+
+The torch modules below exist to (a) own the parameters under the reference's
+state_dict key names, so its checkpoints load unchanged and autograd training
+(``represent`` / ``dynamics`` / ``prediction``) works, and (b) be the source the
+engine repacks its weights from.  Inference never runs through them: there is
+no eager fallback — without CUDA and the built library the inference methods
+raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import NamedTuple, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import _lib
+
+
+class NetworkOutputs(NamedTuple):
+    hidden_state: np.ndarray
+    reward: float
+    pi_probs: np.ndarray
+    value: float
+
+
+# ---------------------------------------------------------------------------
+# parameter containers (attribute names == reference state_dict keys)
+# ---------------------------------------------------------------------------
+def _two_layer(i: int, h: int, o: int) -> nn.Sequential:
+    return nn.Sequential(nn.Linear(i, h), nn.ReLU(), nn.Linear(h, o))
+
+
+def _conv3(i: int, o: int, stride: int = 1) -> nn.Conv2d:
+    return nn.Conv2d(i, o, kernel_size=3, stride=stride, padding=1, bias=False)
+
+
+def _conv_bn_relu(i: int, o: int) -> nn.Sequential:
+    return nn.Sequential(_conv3(i, o), nn.BatchNorm2d(o), nn.ReLU())
+
+
+def _head(planes: int, mid: int, hw: int, out: int) -> nn.Sequential:
+    return nn.Sequential(nn.Conv2d(planes, mid, kernel_size=1, stride=1, bias=False), nn.BatchNorm2d(mid),
+                         nn.ReLU(), nn.Flatten(), nn.Linear(mid * hw, out))
+
+
+class _Holder(nn.Module):
+    """Plain namespace module; children are attached by the builders below."""
+
+
+class ResNetBlock(nn.Module):
+    def __init__(self, planes: int) -> None:
+        super().__init__()
+        self.conv_block1 = _conv_bn_relu(planes, planes)
+        self.conv_block2 = nn.Sequential(_conv3(planes, planes), nn.BatchNorm2d(planes))
+
+    def forward(self, x):
+        return F.relu(self.conv_block2(self.conv_block1(x)) + x)
+
+
+def _tower(planes: int, n: int) -> nn.Sequential:
+    return nn.Sequential(*[ResNetBlock(planes) for _ in range(n)])
+
+
+def _kaiming(net: nn.Module) -> None:
+    """network.py:33-46, same module traversal order (so the same seed gives the same weights)."""
+    for m in net.modules():
+        if isinstance(m, (nn.Conv2d, nn.Linear)):
+            nn.init.kaiming_normal_(m.weight, nonlinearity='relu')
+            if m.bias is not None:
+                nn.init.zeros_(m.bias)
+
+
+def action_planes(action: torch.Tensor, num_actions: int, h: int, w: int) -> torch.Tensor:
+    """The action encoding the reference's DynamicsConvNet actually feeds its first conv
+    (network.py:440-444).  With the [B, 1] action every caller passes (mcts.py:383-384,
+    pipeline.py:581) the one-hot is [B, 1, A]; ``repeat_interleave(h*w, dim=1)`` then ``reshape``
+    to [B, A, h, w] yields a comb, not constant planes: flat element f of the A*h*w block is 1
+    iff f % A == action.  Bit-for-bit the same tensor, built directly."""
+    b = action.shape[0]
+    f = torch.arange(num_actions * h * w, device=action.device)
+    return ((f % num_actions)[None, :] == action.reshape(b, 1).long()).to(torch.float32).reshape(b, num_actions, h, w)
+
+
+def normalize_hidden_state(h: torch.Tensor) -> torch.Tensor:
+    """util.py:31-36 (torch, used by the autograd/training path only)."""
+    lo = h.min(dim=1, keepdim=True)[0]
+    hi = h.max(dim=1, keepdim=True)[0]
+    return (h - lo) / (hi - lo + 1e-8)
+
+
+# ---------------------------------------------------------------------------
+# engine-backed base class
+# ---------------------------------------------------------------------------
+class MuZeroNet(nn.Module):
+    kind = None            # _lib.MZ_NET_*
+    hidden_shape: Tuple[int, ...] = ()
+
+    def __init__(self, num_actions: int, value_support_size: int = 31, reward_support_size: int = 31) -> None:
+        super().__init__()
+        self.num_actions = num_actions
+        self.value_support_size = value_support_size
+        self.reward_support_size = reward_support_size
+        self._eng = None          # (handle, arena tensor, version stamp, device, max_batch)
+
+    @property
+    def mse_loss_for_value(self):
+        return self.value_support_size == 1
+
+    @property
+    def mse_loss_for_reward(self):
+        return self.reward_support_size == 1
+
+    # -- engine -------------------------------------------------------------
+    def _net_config(self) -> _lib.NetConfig:
+        raise NotImplementedError
+
+    def _stamp(self):
+        return (tuple(p._version for p in self.parameters()), tuple(b._version for b in self.buffers()),
+                self.training)
+
+    def engine(self, max_batch: int = 1):
+        """The ``mz_net`` handle for the current weights (rebuilt when they changed)."""
+        dev = next(self.parameters()).device
+        if dev.type != 'cuda':
+            raise RuntimeError('muzero_b200 inference runs on CUDA only (no CPU fallback): move the network to a '
+                               'cuda device first')
+        stamp = self._stamp()
+        e = self._eng
+        if e is not None and e['stamp'] == stamp and e['device'] == dev and e['max_batch'] >= max_batch:
+            return e
+        self.release_engine()
+        lib = _lib.lib()
+        with torch.cuda.device(dev):
+            _lib.check(lib.mz_device_check(dev.index or 0, None, None))
+            cfg = self._net_config()
+            nbytes = C.c_size_t()
+            _lib.check(lib.mz_net_arena_bytes(C.byref(cfg), max_batch, C.byref(nbytes)))
+            arena = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=dev)
+            base = (arena.data_ptr() + 255) // 256 * 256
+            tensors = [t.detach().to(torch.float32).contiguous() for t in self._engine_tensors()]
+            ptrs = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+            handle = C.c_void_p()
+            torch.cuda.synchronize(dev)
+            _lib.check(lib.mz_net_create(C.byref(cfg), ptrs, len(tensors), max_batch, base, nbytes.value,
+                                         C.byref(handle)))
+            hb = C.c_int32()
+            _lib.check(lib.mz_net_hidden_bytes(C.byref(cfg), C.byref(hb)))
+        self._eng = dict(handle=handle, arena=arena, stamp=stamp, device=dev, max_batch=max_batch,
+                         hidden_bytes=hb.value)
+        return self._eng
+
+    def release_engine(self) -> None:
+        if self._eng is not None:
+            _lib.lib().mz_net_destroy(self._eng['handle'])
+            self._eng = None
+
+    def __del__(self):
+        try:
+            self.release_engine()
+        except Exception:
+            pass
+
+    def _engine_tensors(self):
+        """float32 tensors handed to mz_net_create, in state_dict order."""
+        return [v for k, v in self.state_dict().items() if not k.endswith('num_batches_tracked')]
+
+    @property
+    def hidden_bytes(self) -> int:
+        cfg = self._net_config()
+        hb = C.c_int32()
+        _lib.check(_lib.lib().mz_net_hidden_bytes(C.byref(cfg), C.byref(hb)))
+        return hb.value
+
+    # -- batched device API (additive) ---------------------------------------
+    def new_hidden(self, n: int) -> torch.Tensor:
+        """Uninitialised array of ``n`` hidden-state slots in the engine's layout."""
+        dev = next(self.parameters()).device
+        return torch.zeros((n, self.hidden_bytes), dtype=torch.uint8, device=dev)
+
+    @torch.no_grad()
+    def initial_inference_batch(self, obs: torch.Tensor, hidden_out: Optional[torch.Tensor] = None,
+                                dst_index: Optional[torch.Tensor] = None):
+        """``initial_inference`` for a batch, all outputs stay on the device.
+
+        Returns (hidden slots [u8, engine layout], pi_probs f32[B,A], value f32[B])."""
+        b = obs.shape[0]
+        e = self.engine(b)
+        dev = e['device']
+        obs = obs.to(device=dev, dtype=torch.float32).reshape(b, -1).contiguous()
+        if hidden_out is None:
+            hidden_out = self.new_hidden(b)
+        pi = torch.empty((b, self.num_actions), dtype=torch.float32, device=dev)
+        value = torch.empty((b,), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().mz_net_initial(e['handle'], b, _lib.ptr(obs), _lib.ptr(hidden_out),
+                                                 _lib.ptr(dst_index), _lib.ptr(pi), _lib.ptr(value),
+                                                 _lib.current_stream()))
+        return hidden_out, pi, value
+
+    @torch.no_grad()
+    def recurrent_inference_batch(self, hidden_in: torch.Tensor, action: torch.Tensor,
+                                  src_index: Optional[torch.Tensor] = None,
+                                  hidden_out: Optional[torch.Tensor] = None,
+                                  dst_index: Optional[torch.Tensor] = None, want_policy: bool = True):
+        """``recurrent_inference`` for a batch of (slot, action) pairs on the device.
+
+        Returns (hidden slots, reward f32[B], pi_probs f32[B,A] or None, value f32[B])."""
+        b = action.shape[0]
+        e = self.engine(b)
+        dev = e['device']
+        action = action.to(device=dev, dtype=torch.int32).reshape(b).contiguous()
+        if hidden_out is None:
+            hidden_out = self.new_hidden(b)
+        reward = torch.empty((b,), dtype=torch.float32, device=dev)
+        value = torch.empty((b,), dtype=torch.float32, device=dev)
+        pi = torch.empty((b, self.num_actions), dtype=torch.float32, device=dev) if want_policy else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().mz_net_recurrent(e['handle'], b, _lib.ptr(hidden_in), _lib.ptr(src_index),
+                                                   _lib.ptr(action), _lib.ptr(hidden_out), _lib.ptr(dst_index),
+                                                   _lib.ptr(reward), _lib.ptr(value), _lib.ptr(pi),
+                                                   _lib.current_stream()))
+        return hidden_out, reward, pi, value
+
+    # -- engine layout <-> reference layout ----------------------------------
+    def hidden_to_reference(self, slots: torch.Tensor) -> torch.Tensor:
+        """Engine slots [n, hidden_bytes] -> float32 [n, *hidden_shape] (reference layout)."""
+        raise NotImplementedError
+
+    def hidden_from_reference(self, h: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError
+
+    # -- the reference's single-observation API (network.py:62-111) ----------
+    @torch.no_grad()
+    def initial_inference(self, x: torch.Tensor) -> NetworkOutputs:
+        hidden, pi, value = self.initial_inference_batch(x)
+        h = self.hidden_to_reference(hidden)[0]
+        return NetworkOutputs(hidden_state=h.cpu().numpy(), reward=0.0, pi_probs=pi[0].cpu().numpy(),
+                              value=value[0].cpu().item())
+
+    @torch.no_grad()
+    def recurrent_inference(self, hidden_state: torch.Tensor, action: torch.Tensor) -> NetworkOutputs:
+        dev = next(self.parameters()).device
+        slots = self.hidden_from_reference(hidden_state.to(device=dev, dtype=torch.float32))
+        hidden, reward, pi, value = self.recurrent_inference_batch(slots, action.reshape(-1))
+        h = self.hidden_to_reference(hidden)[0]
+        return NetworkOutputs(hidden_state=h.cpu().numpy(), reward=reward[0].cpu().item(),
+                              pi_probs=pi[0].cpu().numpy(), value=value[0].cpu().item())
+
+    # -- autograd path for training (network.py:113-124) ---------------------
+    def represent(self, x: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError
+
+    def dynamics(self, hidden_state: torch.Tensor, action: torch.Tensor):
+        raise NotImplementedError
+
+    def prediction(self, hidden_state: torch.Tensor):
+        raise NotImplementedError
+
+
+# ---------------------------------------------------------------------------
+# MLP family (network.py:140-267)
+# ---------------------------------------------------------------------------
+class MuZeroMLPNet(MuZeroNet):
+    kind = _lib.MZ_NET_MLP
+
+    def __init__(self, input_shape: Tuple, num_actions: int, num_planes: int = 256, value_support_size: int = 31,
+                 reward_support_size: int = 31, hidden_dim: int = 64) -> None:
+        super().__init__(num_actions, value_support_size, reward_support_size)
+        self.input_shape = tuple(input_shape)
+        self.num_planes, self.hidden_dim = num_planes, hidden_dim
+        self.hidden_shape = (hidden_dim,)
+        # construction order == network.py:249-253 so equal seeds give equal weights
+        self.represent_net = _Holder()
+        self.represent_net.net = _two_layer(math.prod(input_shape), num_planes, hidden_dim)
+        self.dynamics_net = _Holder()
+        self.dynamics_net.transition_net = _two_layer(hidden_dim + num_actions, num_planes, hidden_dim)
+        self.dynamics_net.reward_net = _two_layer(hidden_dim, num_planes, reward_support_size)
+        self.prediction_net = _Holder()
+        self.prediction_net.policy_net = _two_layer(hidden_dim, num_planes, num_actions)
+        self.prediction_net.value_net = _two_layer(hidden_dim, num_planes, value_support_size)
+
+    def _net_config(self) -> _lib.NetConfig:
+        return _lib.NetConfig(kind=self.kind, in_channels=math.prod(self.input_shape), in_h=1, in_w=1,
+                              num_actions=self.num_actions, num_planes=self.num_planes, num_res_blocks=0,
+                              hidden_dim=self.hidden_dim, value_support=self.value_support_size,
+                              reward_support=self.reward_support_size)
+
+    def hidden_to_reference(self, slots):
+        return slots.view(torch.float32).reshape(slots.shape[0], self.hidden_dim)
+
+    def hidden_from_reference(self, h):
+        return h.reshape(-1, self.hidden_dim).contiguous().view(torch.uint8)
+
+    def represent(self, x):
+        return normalize_hidden_state(self.represent_net.net(x.reshape(x.shape[0], -1)))
+
+    def dynamics(self, hidden_state, action):
+        onehot = torch.zeros((hidden_state.shape[0], self.num_actions), dtype=torch.float32,
+                             device=hidden_state.device).scatter_(1, action, 1.0)
+        h = self.dynamics_net.transition_net(torch.cat([hidden_state, onehot], dim=1))
+        return normalize_hidden_state(h), self.dynamics_net.reward_net(h)
+
+    def prediction(self, hidden_state):
+        return self.prediction_net.policy_net(hidden_state), self.prediction_net.value_net(hidden_state)
+
+
+# ---------------------------------------------------------------------------
+# ResNet families (network.py:273-574)
+# ---------------------------------------------------------------------------
+class _ConvNet(MuZeroNet):
+    latent_hw: Tuple[int, int] = (0, 0)
+
+    def _build_dyn_pred(self, planes, blocks, h, w, num_actions, reward_support, value_support):
+        self.dynamics_net = _Holder()
+        self.dynamics_net.num_actions = num_actions
+        self.dynamics_net.conv_block = _conv_bn_relu(planes + num_actions, planes)
+        self.dynamics_net.res_blocks = _tower(planes, blocks)
+        self.dynamics_net.reward_head = _head(planes, 1, h * w, reward_support)
+        self.prediction_net = _Holder()
+        self.prediction_net.res_blocks = _tower(planes, blocks)
+        self.prediction_net.policy_net = _head(planes, 2, h * w, num_actions)
+        self.prediction_net.value_net = _head(planes, 1, h * w, value_support)
+
+    def _net_config(self) -> _lib.NetConfig:
+        c, h, w = self.input_shape
+        return _lib.NetConfig(kind=self.kind, in_channels=c, in_h=h, in_w=w, num_actions=self.num_actions,
+                              num_planes=self.num_planes, num_res_blocks=self.num_res_blocks, hidden_dim=0,
+                              value_support=self.value_support_size, reward_support=self.reward_support_size)
+
+    def _engine_tensors(self):
+        if self.training:
+            raise RuntimeError('engine inference folds BatchNorm running statistics: call .eval() first '
+                               '(self-play always does, pipeline.py:79-80)')
+        return super()._engine_tensors()
+
+    # engine layout: bf16, channel-last, zero-padded grid (see csrc/conv.cu)
+    def hidden_to_reference(self, slots):
+        h, w = self.latent_hw
+        c = self.num_planes
+        x = slots.view(torch.bfloat16).reshape(slots.shape[0], h + 1, w + 1, c)[:, :h, :w, :]
+        return x.permute(0, 3, 1, 2).to(torch.float32).contiguous()
+
+    def hidden_from_reference(self, hid):
+        h, w = self.latent_hw
+        c = self.num_planes
+        hid = hid.reshape(-1, c, h, w)
+        out = torch.zeros((hid.shape[0], h + 1, w + 1, c), dtype=torch.bfloat16, device=hid.device)
+        out[:, :h, :w, :] = hid.permute(0, 2, 3, 1).to(torch.bfloat16)
+        return out.reshape(hid.shape[0], -1).view(torch.uint8)
+
+    def dynamics(self, hidden_state, action):
+        b, c, h, w = hidden_state.shape
+        planes = action_planes(action, self.num_actions, h, w).to(hidden_state.dtype)
+        x = torch.cat([hidden_state, planes], dim=1)
+        hs = self.dynamics_net.res_blocks(self.dynamics_net.conv_block(x))
+        return normalize_hidden_state(hs), self.dynamics_net.reward_head(hs)
+
+    def prediction(self, hidden_state):
+        f = self.prediction_net.res_blocks(hidden_state)
+        return self.prediction_net.policy_net(f), self.prediction_net.value_net(f)
+
+
+class MuZeroBoardGameNet(_ConvNet):
+    kind = _lib.MZ_NET_BOARD
+
+    def __init__(self, input_shape: tuple, num_actions: int, num_res_blocks: int = 16, num_planes: int = 256) -> None:
+        super().__init__(num_actions, 1, 1)
+        c, h, w = input_shape
+        self.input_shape = tuple(input_shape)
+        self.num_planes, self.num_res_blocks = num_planes, num_res_blocks
+        self.latent_hw = (h, w)
+        self.hidden_shape = (num_planes, h, w)
+        self.represent_net = _Holder()
+        self.represent_net.conv_block = _conv_bn_relu(c, num_planes)
+        self.represent_net.res_blocks = _tower(num_planes, num_res_blocks)
+        self._build_dyn_pred(num_planes, num_res_blocks, h, w, num_actions, 1, 1)
+        _kaiming(self)
+
+    def represent(self, x):
+        return normalize_hidden_state(self.represent_net.res_blocks(self.represent_net.conv_block(x)))
+
+
+class MuZeroAtariNet(_ConvNet):
+    kind = _lib.MZ_NET_ATARI
+
+    def __init__(self, input_shape: tuple, num_actions: int, num_res_blocks: int = 16, num_planes: int = 256,
+                 value_support_size: int = 601, reward_support_size: int = 601) -> None:
+        super().__init__(num_actions, value_support_size, reward_support_size)
+        c, h, w = input_shape
+        self.input_shape = tuple(input_shape)
+        self.num_planes, self.num_res_blocks = num_planes, num_res_blocks
+        self.latent_hw = (6, 6)              # hard-wired downstream of the representation, network.py:516-519
+        self.hidden_shape = (num_planes, 6, 6)
+        r = self.represent_net = _Holder()
+        r.conv_1 = _conv3(c, 128, stride=2)                       # 96 -> 48
+        r.res_blocks_1 = _tower(128, 2)
+        r.conv_2 = _conv3(128, num_planes, stride=2)              # 48 -> 24
+        r.res_blocks_2 = _tower(num_planes, 2)
+        r.avg_pool_1 = nn.AvgPool2d(kernel_size=3, stride=2, padding=1)   # 24 -> 12
+        r.res_blocks_3 = _tower(num_planes, 2)
+        r.avg_pool_2 = nn.AvgPool2d(kernel_size=3, stride=2, padding=1)   # 12 -> 6
+        self._build_dyn_pred(num_planes, num_res_blocks, 6, 6, num_actions, reward_support_size, value_support_size)
+        _kaiming(self)
+
+    def represent(self, x):
+        r = self.represent_net
+        x = r.res_blocks_1(F.relu(r.conv_1(x)))
+        x = r.res_blocks_2(F.relu(r.conv_2(x)))
+        x = r.res_blocks_3(r.avg_pool_1(x))
+        return normalize_hidden_state(r.avg_pool_2(x))
