@@ -1,0 +1,461 @@
+#!/usr/bin/env python
+"""Benchmark of the self-play hot path: MCTS simulations/sec, network evaluation included.
+
+    python bench.py --gpus N --steps K --warmup W [--workload tictactoe|cartpole|gomoku|atari]
+    python bench.py --impl reference ...        # the CPU arm (oracle port of the reference path)
+
+A "step" is ONE batched search: B trees x S simulations, from observations to
+(action, pi, root value): initial inference, Dirichlet noise, S x (select, recurrent
+inference, expand+backup), visit policy and action sampling all inside the timed region.
+`value` keeps the inputs resident in HBM; `e2e` goes through the public
+``uct_search_batch`` with HOST (pinned) observations/masks and reads the results back.
+Under torchrun (N > 1) every rank searches its own B trees (games shard across GPUs with no
+collective, weak scaling), time is the max over ranks, value the whole-job aggregate.
+One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+METRIC = 'mcts_simulations_per_sec_net_eval_incl'
+UNIT = 'simulations/s'
+
+
+# ---------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------
+def workload_spec(name: str, trees: int | None):
+    import muzero_b200 as mz
+    if name == 'tictactoe':       # BASELINE.json configs[1]
+        cfg = mz.make_tictactoe_config(use_tensorboard=False)
+        spec = dict(kind='mlp', ckpt='tictactoe', net_kw=dict(input_shape=(9, 3, 3), num_actions=10, num_planes=256,
+                    value_support_size=1, reward_support_size=1, hidden_dim=64), trees=4096, board=True,
+                    label='Tic-Tac-Toe 3x3 MLP MuZero from checkpoint TicTacToe_train_steps_35000')
+    elif name == 'cartpole':      # configs[0]
+        cfg = mz.make_classic_config(use_tensorboard=False)
+        spec = dict(kind='mlp', ckpt='cartpole', net_kw=dict(input_shape=(4, 5), num_actions=2, num_planes=512,
+                    value_support_size=31, reward_support_size=31, hidden_dim=64), trees=16384, board=False,
+                    label='CartPole-v1 MLP MuZero from checkpoint CartPole-v1_train_steps_44800')
+    elif name == 'gomoku':        # configs[2]
+        cfg = mz.make_gomoku_config(use_tensorboard=False)
+        spec = dict(kind='board', ckpt=None, net_kw=dict(input_shape=(9, 9, 9), num_actions=82, num_res_blocks=8,
+                    num_planes=128), trees=2048, board=True, label='Gomoku 9x9 ResNet(128x8) MuZero, random init seed 0')
+    elif name == 'atari':         # configs[3]
+        cfg = mz.make_atari_config(use_tensorboard=False)
+        cfg.num_simulations = 50
+        spec = dict(kind='atari', ckpt=None, net_kw=dict(input_shape=(16, 96, 96), num_actions=18, num_res_blocks=8,
+                    num_planes=128, value_support_size=61, reward_support_size=61), trees=1024, board=False,
+                    label='Atari-shaped 16x96x96 ResNet(128x8) MuZero, random init seed 0, 50 sims')
+    else:
+        raise SystemExit(f'unknown workload {name}')
+    if trees:
+        spec['trees'] = trees
+    spec['name'], spec['cfg'] = name, cfg
+    return spec
+
+
+def state_dict_for(spec):
+    import torch
+    import muzero_b200 as mz
+    if spec['ckpt']:
+        return {k: torch.from_numpy(v) for k, v in np.load(os.path.join(GOLDEN, f"ckpt_{spec['ckpt']}.npz")).items()}
+    torch.manual_seed(0)
+    cls = mz.MuZeroBoardGameNet if spec['kind'] == 'board' else mz.MuZeroAtariNet
+    return cls(**spec['net_kw']).eval().state_dict()
+
+
+def synthetic_inputs(spec, B: int, seed: int):
+    """Observations / masks / players of each config's shape (no envs, no ROMs)."""
+    gen = np.random.RandomState(seed)
+    shape, A = spec['net_kw']['input_shape'], spec['net_kw']['num_actions']
+    if spec['name'] in ('tictactoe', 'gomoku'):
+        c, h, w = shape
+        n_hist = (c - 1) // 2
+        obs = np.zeros((B, c, h, w), dtype=np.int8)
+        mask = np.ones((B, A), dtype=bool)
+        max_moves = 6 if spec['name'] == 'tictactoe' else 40
+        cur = np.ones(B, dtype=np.int32)
+        for b in range(B):
+            k = gen.randint(0, max_moves + 1)
+            cells = gen.permutation(h * w)[:k]
+            boards = np.zeros((k + 1, 2, h * w), dtype=np.int8)
+            for i, cell in enumerate(cells):
+                boards[i + 1] = boards[i]
+                boards[i + 1, i % 2, cell] = 1
+            me = k % 2                                # side to move
+            for t in range(n_hist):                   # most recent first: [mine_t, theirs_t] * history, then colour
+                bd = boards[max(k - t, 0)]
+                obs[b, 2 * t] = bd[me].reshape(h, w)
+                obs[b, 2 * t + 1] = bd[1 - me].reshape(h, w)
+            obs[b, c - 1] = 1 if me == 0 else 0
+            mask[b, :h * w] = boards[k].sum(0) == 0
+            mask[b, h * w:] = True                    # resign
+            cur[b] = 1 + me
+        return obs, mask, cur, (3 - cur).astype(np.int32)
+    if spec['name'] == 'cartpole':
+        obs = gen.standard_normal((B,) + shape).astype(np.float32)
+        obs[:, :, -1] = (gen.randint(0, 2, size=(B, shape[0])) + 1) / 2.0
+    else:
+        obs = gen.randint(0, 256, size=(B,) + shape).astype(np.float32)
+        half = shape[0] // 2
+        obs[:, half:] = ((gen.randint(0, A, size=(B, shape[0] - half, 1, 1)) + 1) / A).astype(np.float32)
+    one = np.ones(B, dtype=np.int32)
+    return obs, np.ones((B, A), dtype=bool), one, one
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, uuid: str):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', uuid, f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        busy = [s for s, p in zip(sm, power) if p >= 0.5 * max(power)] or sm
+        return {'sm_mhz': statistics.median(busy), 'sm_max_mhz': max(mx), 'reasons': sorted(reasons),
+                'samples': len(sm), 'power_w_max': max(power)}
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path, one tree per process at a time
+# ---------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_worker_init(name, trees):
+    import torch
+    torch.set_num_threads(1)
+    from oracle.network_oracle import OracleNet
+    spec = workload_spec(name, trees)
+    sd = state_dict_for(spec)
+    kw = spec['net_kw']
+    _W['spec'] = spec
+    _W['net'] = OracleNet(spec['kind'], sd, kw['num_actions'], kw.get('value_support_size', 1),
+                          kw.get('reward_support_size', 1), kw.get('num_res_blocks', 0))
+
+
+def _cpu_worker_run(args):
+    """Run `n` single-tree searches (reference structure: batch-1 network call per simulation)."""
+    wid, n, seed = args
+    from oracle import mcts_oracle as orc
+    spec = _W['spec']
+    obs, mask, cur, opp = synthetic_inputs(spec, n, seed + wid)
+    rs = np.random.RandomState(1234 + wid)
+    t0 = time.perf_counter()
+    for i in range(n):
+        orc.uct_search(obs[i], _W['net'], 'cpu', spec['cfg'], 1.0, mask[i], int(cur[i]), int(opp[i]), False, rng=rs)
+    return n * spec['cfg'].num_simulations, time.perf_counter() - t0
+
+
+class CpuArm:
+    def __init__(self, name, trees, procs):
+        import multiprocessing as mp
+        self.procs = procs
+        self.pool = mp.get_context('spawn').Pool(procs, initializer=_cpu_worker_init, initargs=(name, trees))
+
+    def step(self, searches_per_proc, seed):
+        t0 = time.perf_counter()
+        out = self.pool.map(_cpu_worker_run, [(w, searches_per_proc, seed) for w in range(self.procs)])
+        wall = time.perf_counter() - t0
+        return sum(o[0] for o in out), wall
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_searches_per_step(name):
+    return {'tictactoe': 40, 'cartpole': 12, 'gomoku': 1, 'atari': 1}[name]
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    spec = workload_spec(args.workload, args.trees)
+    procs = min(os.cpu_count() or 1, args.cpu_procs)
+    arm = CpuArm(args.workload, args.trees, procs)
+    n = cpu_searches_per_step(args.workload)
+    for w in range(args.warmup):
+        arm.step(max(1, n // 4), 10_000 + w)
+    sims, wall = 0, 0.0
+    for k in range(args.steps):
+        s, t = arm.step(n, 20_000 + k)
+        sims += s; wall += t
+    arm.close()
+    value = sims / wall
+    sample = f'{procs} processes x {n} single-tree searches x {spec["cfg"].num_simulations} sims per step, {args.steps} steps'
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1000.0 * wall / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': spec['label'], 'trees': spec['trees'], 'simulations': spec['cfg'].num_simulations},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': procs, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def algorithmic_bytes_per_launch(kernel, spec, B, A, S, mean_depth, hidden_bytes, noise):
+    """SURVEY.md section 8(d) per-tree-per-simulation figures x B trees (one launch = one simulation of B trees)."""
+    d = mean_depth
+    if kernel == 'select':
+        per = d * (16 * A + 4) + (8 if noise else 4) * A
+    elif kernel == 'expand_backup':
+        per = 32 * (d + 1) + 16 * A + 32
+    else:   # recurrent inference: read parent state once, write child state once, + action
+        per = 2 * hidden_bytes + 4
+    return per * B
+
+
+def run_engine_arm(args):
+    import torch
+    import torch.distributed as dist
+    import muzero_b200 as mz
+    from muzero_b200 import _lib
+    from muzero_b200.mcts import SearchPlan
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    spec = workload_spec(args.workload, args.trees)
+    cfg, B, A, S = spec['cfg'], spec['trees'], spec['net_kw']['num_actions'], spec['cfg'].num_simulations
+    cls = {'mlp': mz.MuZeroMLPNet, 'board': mz.MuZeroBoardGameNet, 'atari': mz.MuZeroAtariNet}[spec['kind']]
+    net = cls(**spec['net_kw'])
+    net.load_state_dict(state_dict_for(spec))
+    net = net.to(dev).eval()
+    plan = SearchPlan(net, cfg, B)
+    pool = plan.pool
+    pool.seed(1234 + rank * B + np.arange(B))
+
+    obs, mask, cur, opp = synthetic_inputs(spec, B, 99 + rank)
+    obs_h = torch.from_numpy(obs).pin_memory()
+    mask_h = torch.from_numpy(mask).pin_memory()
+    # inputs resident in HBM for `value`
+    plan.obs.copy_(obs_h.reshape(B, -1)); plan.mask.copy_(mask_h)
+    plan.players.copy_(torch.from_numpy(np.stack([cur, opp], 1)))
+    plan.temps.fill_(1.0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def step_device():
+        plan.run('device', True, False)
+
+    out_h = [torch.empty(B, dtype=torch.int32).pin_memory(), torch.empty((B, A), dtype=torch.float64).pin_memory(),
+             torch.empty(B, dtype=torch.float64).pin_memory()]
+
+    def step_e2e():
+        a, pi, q = mz.uct_search_batch(obs_h, net, cfg, 1.0, mask_h, cur, opp, plan=plan)
+        out_h[0].copy_(a, non_blocking=True); out_h[1].copy_(pi, non_blocking=True); out_h[2].copy_(q, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def timed(fn, steps):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for e0, e1 in ev:
+            flush.zero_()                      # L2 flush between timed iterations (not timed)
+            e0.record(); fn(); e1.record()
+        barrier()
+        ms = sum(e0.elapsed_time(e1) for e0, e1 in ev) / steps
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    for _ in range(2):
+        step_e2e()
+    torch.cuda.synchronize()
+    pool.check_errors()
+    stats0 = pool.view('STATS').cpu().numpy().copy()
+
+    uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    sampler = ClockSampler(uuid if uuid.startswith('GPU-') else 'GPU-' + uuid) if rank == 0 else None
+    ms_dev = timed(step_device, args.steps)
+    stats1 = pool.view('STATS').cpu().numpy().copy()
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    pool.check_errors()
+
+    mean_depth = float(stats1[0] - stats0[0]) / max(1.0, float(stats1[1] - stats0[1]))
+    value = world * B * S / (ms_dev / 1000.0)
+    e2e_value = world * B * S / (ms_e2e / 1000.0)
+    h2d = obs_h.numel() * obs_h.element_size() + mask_h.numel() + 2 * 4 * B + 8 * B
+    d2h = sum(t.numel() * t.element_size() for t in out_h)
+
+    # ---- per-kernel timing (eager launches, CUDA events on the launching stream) -> roofline
+    lib = _lib.lib()
+    eng = net.engine(B)
+    hidden = pool.hidden.data_ptr() if pool.hidden_bytes else None
+    names = ['select', 'recurrent', 'expand_backup']
+    tot = {n: 0.0 for n in names}
+    reps = max(1, min(args.steps, 3))
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream().cuda_stream
+        for _ in range(reps):
+            plan.use_graph = False
+            # root part eagerly, then instrumented simulation loop
+            _lib.check(lib.mz_net_initial(eng['handle'], B, plan.obs.data_ptr(), hidden, plan.root_slots.data_ptr(),
+                                          plan.pi0.data_ptr(), plan.v0.data_ptr(), stream))
+            _lib.check(lib.mz_dirichlet(pool.handle, float(np.float32(cfg.root_dirichlet_alpha)),
+                                        plan.noise.data_ptr(), stream))
+            _lib.check(lib.mz_search_reset(pool.handle, plan.pi0.data_ptr(), plan.noise.data_ptr(),
+                                           float(cfg.root_exploration_eps), plan.mask.data_ptr(),
+                                           plan.players.data_ptr(), None, stream))
+            evs = []
+            for _s in range(S):
+                e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                e[0].record()
+                _lib.check(lib.mz_select(pool.handle, stream)); e[1].record()
+                _lib.check(lib.mz_net_recurrent(eng['handle'], B, hidden, pool.view('SRC_SLOT').data_ptr(),
+                                                pool.view('LEAF_ACTION').data_ptr(), hidden,
+                                                pool.view('DST_SLOT').data_ptr(), pool.view('REWARD').data_ptr(),
+                                                pool.view('VALUE').data_ptr(), None, stream)); e[2].record()
+                _lib.check(lib.mz_expand_backup(pool.handle, None, None, stream)); e[3].record()
+                evs.append(e)
+            torch.cuda.synchronize()
+            for e in evs:
+                for i, n in enumerate(names):
+                    tot[n] += e[i].elapsed_time(e[i + 1])
+            plan.use_graph = True
+    launches = reps * S
+    avg_ms = {n: tot[n] / launches for n in names}
+    share = {n: tot[n] / sum(tot.values()) for n in names}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    tf_peak = float(peaks.get('bf16_tflops', 1590.0))
+    peak_src = 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback (B200_PROFILING.md)'
+    dominant = max(names, key=lambda n: tot[n])
+    noise_on = True
+    roof = {}
+    for n in names:
+        ab = algorithmic_bytes_per_launch(n, spec, B, A, S, mean_depth, pool.hidden_bytes, noise_on)
+        roof[n] = {'bound': 'hbm', 'achieved': ab / (avg_ms[n] * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+                   'avg_launch_us': avg_ms[n] * 1e3, 'share_of_sim_loop': share[n], 'algorithmic_bytes': ab}
+        roof[n]['frac'] = roof[n]['achieved'] / hbm_peak
+    flops = {'tictactoe': 175104, 'cartpole': 395264, 'gomoku': 803712780, 'atari': 351896688}[spec['name']]
+    if spec['kind'] != 'mlp':
+        ach = flops * B / (avg_ms['recurrent'] * 1e-3) / 1e12
+        roof['recurrent'].update({'bound': 'tensor', 'achieved': ach, 'peak': tf_peak, 'unit': 'TFLOP/s',
+                                  'frac': ach / tf_peak, 'reference_graph_flops': flops * B})
+    roofline = dict(roof[dominant])
+    roofline.update({'kernel': dominant, 'traffic': None, 'peak_source': peak_src})
+
+    result = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+        'ms_per_step': ms_dev, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64 tree statistics / f32 scores; network ' + ('f32' if spec['kind'] == 'mlp' else 'bf16 x bf16 -> f32'),
+        'data': 'synthetic',
+        'config': {'workload': spec['label'], 'trees_per_gpu': B, 'simulations': S, 'num_actions': A,
+                   'l2': 'flushed between timed iterations (256 MiB write)', 'mean_select_depth': mean_depth,
+                   'parallelism': f'games sharded over {world} GPU(s), no collective'},
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': int(h2d),
+                'd2h_bytes_per_step': int(d2h)},
+        'gpu_launches': int(plan.launches_per_search * args.steps * 2),
+        'clocks': clocks,
+        'roofline': roofline,
+        'kernels': roof,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        del flush
+        result['cpu_baseline'] = cpu_baseline_sample(args, spec)
+    if rank == 0:
+        print(json.dumps(result))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline_sample(args, spec):
+    procs = min(os.cpu_count() or 1, args.cpu_procs)
+    arm = CpuArm(args.workload, args.trees, procs)
+    n = cpu_searches_per_step(args.workload)
+    arm.step(max(1, n // 4), 1)
+    sims, wall = arm.step(n, 2)
+    arm.close()
+    return {'value': sims / wall, 'unit': UNIT, 'cores': procs, 'kind': 'port',
+            'sample': f'{procs} processes x {n} single-tree searches x {spec["cfg"].num_simulations} sims '
+                      f'(oracle port of uct_search + fp32 torch network, 1 thread per process)'}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--workload', default=os.environ.get('MZ_BENCH_WORKLOAD', 'tictactoe'))
+    ap.add_argument('--trees', type=int, default=None, help='trees per GPU (default: the config size)')
+    ap.add_argument('--impl', default='engine', choices=['engine', 'reference'])
+    ap.add_argument('--cpu-procs', type=int, default=int(os.environ.get('MZ_BENCH_CPU_PROCS', '64')))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference_arm(args)
+    else:
+        run_engine_arm(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -76,6 +76,7 @@ enum mz_view {
   MZ_VIEW_PATH,          /* u32 [B, S+1] edge index (node*A+action) per level of the last select             */
   MZ_VIEW_NODE_PARENT,   /* i32 [B, S+1] parent node of each expanded node (-1 for the root)                 */
   MZ_VIEW_NODE_MOVE,     /* i32 [B, S+1] action that led to each expanded node                               */
+  MZ_VIEW_NODE_VALUE,    /* f32 [B, S+1] value the network gave each node when it was expanded (debug/replay) */
   MZ_VIEW_RNG_KEY,       /* u32 [B, 624] MT19937 state (numpy legacy stream)                                 */
   MZ_VIEW_RNG_POS,       /* i32 [B]                                                                          */
   MZ_VIEW_HIDDEN,        /* u8  [B, S+1, hidden_bytes]                                                       */

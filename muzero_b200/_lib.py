@@ -17,7 +17,7 @@ MZ_DEVERR_POOL_FULL, MZ_DEVERR_NAN_POLICY = 1, 2
 MZ_NET_MLP, MZ_NET_BOARD, MZ_NET_ATARI = 0, 1, 2
 
 VIEWS = ['EDGES', 'PRIOR', 'ROOT_W', 'ROOT_N', 'MINMAX', 'COUNT', 'LEAF_PARENT', 'LEAF_ACTION', 'LEAF_DEPTH',
-         'SRC_SLOT', 'DST_SLOT', 'PATH', 'NODE_PARENT', 'NODE_MOVE', 'RNG_KEY', 'RNG_POS', 'HIDDEN', 'REWARD',
+         'SRC_SLOT', 'DST_SLOT', 'PATH', 'NODE_PARENT', 'NODE_MOVE', 'NODE_VALUE', 'RNG_KEY', 'RNG_POS', 'HIDDEN', 'REWARD',
          'VALUE', 'ERROR', 'STATS']
 VIEW = {name: i for i, name in enumerate(VIEWS)}
 

@@ -23,6 +23,7 @@ struct PoolDev {
   int *leaf_parent, *leaf_action, *leaf_depth, *src_slot, *dst_slot;
   uint32_t* path;
   int *node_parent, *node_move;
+  float* node_value;
   uint32_t* rng_key;
   int* rng_pos;
   float *reward, *value;
@@ -419,6 +420,7 @@ expand_backup_kernel(PoolDev p, const float* __restrict__ reward_in, const float
     p.count[t] = c + 1;
     p.node_parent[(size_t)t * p.max_nodes + c] = p.leaf_parent[t];
     p.node_move[(size_t)t * p.max_nodes + c] = p.leaf_action[t];
+    p.node_value[(size_t)t * p.max_nodes + c] = value_in[t];
     p.leaf_depth[t] = 0;
   }
 }
@@ -602,6 +604,7 @@ void layout(const mz_pool_config& c, size_t* offs, size_t* sizes, size_t* extra_
   put(MZ_VIEW_PATH, B * n * 4);
   put(MZ_VIEW_NODE_PARENT, B * n * 4);
   put(MZ_VIEW_NODE_MOVE, B * n * 4);
+  put(MZ_VIEW_NODE_VALUE, B * n * 4);
   put(MZ_VIEW_RNG_KEY, B * 624 * 4);
   put(MZ_VIEW_RNG_POS, B * 4);
   put(MZ_VIEW_HIDDEN, B * n * (size_t)c.hidden_bytes);
@@ -651,6 +654,7 @@ PoolDev dev_of(const mz_pool* h) {
   d.path = (uint32_t*)h->view_ptr[MZ_VIEW_PATH];
   d.node_parent = (int*)h->view_ptr[MZ_VIEW_NODE_PARENT];
   d.node_move = (int*)h->view_ptr[MZ_VIEW_NODE_MOVE];
+  d.node_value = (float*)h->view_ptr[MZ_VIEW_NODE_VALUE];
   d.rng_key = (uint32_t*)h->view_ptr[MZ_VIEW_RNG_KEY];
   d.rng_pos = (int*)h->view_ptr[MZ_VIEW_RNG_POS];
   d.reward = (float*)h->view_ptr[MZ_VIEW_REWARD];

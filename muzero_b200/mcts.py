@@ -81,7 +81,8 @@ class SearchPool:
         'ROOT_N': (torch.int32, None), 'MINMAX': (torch.float64, 2), 'COUNT': (torch.int32, None),
         'LEAF_PARENT': (torch.int32, None), 'LEAF_ACTION': (torch.int32, None), 'LEAF_DEPTH': (torch.int32, None),
         'SRC_SLOT': (torch.int32, None), 'DST_SLOT': (torch.int32, None), 'PATH': (torch.int32, None),
-        'NODE_PARENT': (torch.int32, None), 'NODE_MOVE': (torch.int32, None), 'RNG_KEY': (torch.int32, 624),
+        'NODE_PARENT': (torch.int32, None), 'NODE_MOVE': (torch.int32, None), 'NODE_VALUE': (torch.float32, None),
+        'RNG_KEY': (torch.int32, 624),
         'RNG_POS': (torch.int32, None), 'HIDDEN': (torch.uint8, None), 'REWARD': (torch.float32, None),
         'VALUE': (torch.float32, None), 'ERROR': (torch.int32, None), 'STATS': (torch.int64, None),
     }
@@ -187,7 +188,8 @@ class SearchPool:
             N[i], W[i], R[i] = e['N'], e['W'], e['R']
         children = np.where(rec['child'][:count] == 0xFFFF, -1, rec['child'][:count].astype(np.int32))
         mm = self.view('MINMAX').view(self.B, 2)[t].cpu().numpy()
-        return dict(num_nodes=count, N=N, W=W, R=R, parent=parent, move=move, children=children,
+        value = self.view('NODE_VALUE').view(self.B, n)[t].cpu().numpy()[:count].copy()
+        return dict(num_nodes=count, N=N, W=W, R=R, parent=parent, move=move, children=children, value=value,
                     prior=self.view('PRIOR').view(self.B, A)[t].cpu().numpy().copy(), minmax=(mm[0], mm[1]))
 
 
@@ -233,19 +235,133 @@ def clear_pools() -> None:
 # ---------------------------------------------------------------------------
 # batched entry point (additive API)
 # ---------------------------------------------------------------------------
+class SearchPlan:
+    """One batched search = ONE CUDA-graph replay.
+
+    Holds the node pool, static input/output buffers and, per variant
+    (noise source, mask present, deterministic), a captured graph of
+        initial_inference -> [device Dirichlet] -> reset -> S x (select, recurrent_inference,
+        expand+backup) -> root policy
+    so a search costs one graph launch instead of 3*S+3 kernel launches from Python.
+    """
+
+    def __init__(self, network: MuZeroNet, config, num_trees: int, pool: Optional[SearchPool] = None) -> None:
+        self.network, self.config = network, config
+        self.dev = next(network.parameters()).device
+        self.B, self.A, self.S = int(num_trees), network.num_actions, int(config.num_simulations)
+        self.pool = pool if pool is not None else SearchPool(self.B, self.A, config, network.hidden_bytes, self.dev)
+        assert self.pool.B == self.B and self.pool.A == self.A and self.pool.S == self.S
+        B, A, dev = self.B, self.A, self.dev
+        obs_elems = int(np.prod(network.input_shape))
+        self.obs = torch.zeros((B, obs_elems), dtype=torch.float32, device=dev)
+        self.mask = torch.ones((B, A), dtype=torch.uint8, device=dev)
+        self.players = torch.ones((B, 2), dtype=torch.int32, device=dev)
+        self.temps = torch.ones(B, dtype=torch.float64, device=dev)
+        self.noise = torch.zeros((B, A), dtype=torch.float64, device=dev)
+        self.pi0 = torch.empty((B, A), dtype=torch.float32, device=dev)
+        self.v0 = torch.empty(B, dtype=torch.float32, device=dev)
+        self.root_slots = (torch.arange(B, dtype=torch.int32, device=dev) * (self.S + 1)).contiguous()
+        self.action = torch.empty(B, dtype=torch.int32, device=dev)
+        self.pi = torch.empty((B, A), dtype=torch.float64, device=dev)
+        self.root_value = torch.empty(B, dtype=torch.float64, device=dev)
+        self.visits = torch.empty((B, A), dtype=torch.int32, device=dev)
+        self._graphs = {}
+        self._eng = None
+        self.launches_per_search = 0
+        self.use_graph = True
+
+    def _enqueue(self, noise_mode: str, has_mask: bool, deterministic: bool) -> None:
+        """Enqueue one whole search on the current stream (pure C-ABI calls, static pointers)."""
+        lib, pool, cfg = _lib.lib(), self.pool, self.config
+        eng = self.network.engine(self.B)
+        stream = _lib.current_stream()
+        hidden = pool.hidden.data_ptr() if pool.hidden_bytes else None
+        mask_p = self.mask.data_ptr() if has_mask else None
+        _lib.check(lib.mz_net_initial(eng['handle'], self.B, self.obs.data_ptr(), hidden, self.root_slots.data_ptr(),
+                                      self.pi0.data_ptr(), self.v0.data_ptr(), stream))
+        noise_p, eps = None, 0.0
+        if noise_mode != 'none':
+            eps = cfg.root_exploration_eps
+            noise_p = self.noise.data_ptr()
+            if noise_mode == 'device':       # alphas are float32 in the reference (np.ones_like(prob) * alpha)
+                _lib.check(lib.mz_dirichlet(pool.handle, float(np.float32(cfg.root_dirichlet_alpha)), noise_p, stream))
+        _lib.check(lib.mz_search_reset(pool.handle, self.pi0.data_ptr(), noise_p, float(eps), mask_p,
+                                       self.players.data_ptr(), None, stream))
+        src, dst, act = (pool.view(k).data_ptr() for k in ('SRC_SLOT', 'DST_SLOT', 'LEAF_ACTION'))
+        rew, val = pool.view('REWARD').data_ptr(), pool.view('VALUE').data_ptr()
+        for _ in range(self.S):
+            _lib.check(lib.mz_select(pool.handle, stream))
+            # pi_probs = NULL: the search never reads the recurrent policy (mcts.py:386)
+            _lib.check(lib.mz_net_recurrent(eng['handle'], self.B, hidden, src, act, hidden, dst, rew, val, None,
+                                            stream))
+            _lib.check(lib.mz_expand_backup(pool.handle, None, None, stream))
+        _lib.check(lib.mz_root_policy(pool.handle, mask_p, self.temps.data_ptr(), int(deterministic),
+                                      self.action.data_ptr(), self.pi.data_ptr(), self.root_value.data_ptr(),
+                                      self.visits.data_ptr(), stream))
+
+    def run(self, noise_mode: str = 'device', has_mask: bool = True, deterministic: bool = False) -> None:
+        """Execute one search over the current contents of the static input buffers."""
+        eng = self.network.engine(self.B)
+        if eng is not self._eng:                 # weights changed -> engine rebuilt -> old graphs are stale
+            self._graphs.clear()
+            self._eng = eng
+        with torch.cuda.device(self.dev):
+            if not self.use_graph:
+                self._enqueue(noise_mode, has_mask, deterministic)
+                return
+            key = (noise_mode, has_mask, deterministic)
+            g = self._graphs.get(key)
+            if g is None:
+                lib = _lib.lib()
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):     # eager warm-up: lazy module/attribute setup must not be captured
+                    n0 = lib.mz_launch_count()
+                    self._enqueue(noise_mode, has_mask, deterministic)
+                    self.launches_per_search = int(lib.mz_launch_count() - n0)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                # that eager pass WAS this call's search (capture below records, it does not execute)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue(noise_mode, has_mask, deterministic)
+                self._graphs[key] = g
+                return
+            g.replay()
+
+
+_PLANS = {}
+
+
+def _plan_for(network, config, B) -> SearchPlan:
+    kb = config.known_bounds
+    key = (id(network), B, config.num_simulations, bool(config.is_board_game),
+           None if kb is None else (float(kb.min), float(kb.max)), float(config.discount),
+           float(config.pb_c_base), float(config.pb_c_init), float(config.root_dirichlet_alpha),
+           float(config.root_exploration_eps))
+    if key in _PLANS and _PLANS[key].network is not network:      # id() reused after garbage collection
+        del _PLANS[key]
+    if key not in _PLANS:
+        if len(_PLANS) >= 4:
+            _PLANS.pop(next(iter(_PLANS)))
+        _PLANS[key] = SearchPlan(network, config, B)
+    plan = _PLANS[key]
+    plan.config = config
+    return plan
+
+
 @torch.no_grad()
 def uct_search_batch(states, network: MuZeroNet, config, temperature, actions_mask, current_player, opponent_player,
-                     deterministic: bool = False, rng=None, noise=None, pool: Optional[SearchPool] = None,
-                     return_pool: bool = False):
+                     deterministic: bool = False, rng=None, noise=None, plan: Optional[SearchPlan] = None):
     """``uct_search`` for B independent trees at once, everything on the GPU.
 
-    states          [B, *obs] array/tensor
+    states          [B, *obs] array/tensor (host or device)
     temperature     float or float64[B]
     actions_mask    bool[B, A] or None
     current_player / opponent_player   int or int[B]
     rng             None: each tree continues its device-resident MT19937 stream
-                    (seed it with ``pool.seed``) and, when noise is on, the
-                    Dirichlet sample is drawn on the device;
+                    (seed it with ``plan.pool.seed``) and, when noise is on, the
+                    Dirichlet sample is drawn on the device from that stream;
                     list of B ``np.random.RandomState``: numpy-exact mode — the
                     Dirichlet sample is drawn by numpy from each stream, the
                     stream is continued on the device for tie-breaks and the final
@@ -255,72 +371,52 @@ def uct_search_batch(states, network: MuZeroNet, config, temperature, actions_ma
 
     Returns (actions int32[B], pi float64[B, A], root_values float64[B]) as CUDA tensors.
     """
-    dev = next(network.parameters()).device
-    states = torch.as_tensor(states)
+    states = torch.as_tensor(states) if not torch.is_tensor(states) else states
     B = states.shape[0]
-    A = network.num_actions
     if config.is_board_game:
-        assert config.discount == 1.0
-    temps = np.full(B, temperature, dtype=np.float64) if np.isscalar(temperature) else \
-        np.asarray(temperature, dtype=np.float64)
+        assert config.discount == 1.0                                     # mcts.py:349-350
     if np.isscalar(temperature):
         _check_temperature(temperature)
-    elif not ((temps >= 0.0) & (temps <= 1.0)).all():
-        raise ValueError(f'Expect `temperature` to be float type in the range [0.0, 1.0], got {temperature}')
+        temps = np.full(B, temperature, dtype=np.float64)
+    else:
+        temps = np.asarray(temperature, dtype=np.float64)
+        if temps.shape != (B,) or not ((temps >= 0.0) & (temps <= 1.0)).all():
+            raise ValueError(f'Expect `temperature` to be float type in the range [0.0, 1.0], got {temperature}')
     use_noise = _noise_enabled(config, deterministic)
+    if plan is None:
+        plan = _plan_for(network, config, B)
+    A, dev, pool = plan.A, plan.dev, plan.pool
 
-    if pool is None:
-        pool = _pool_for(B, A, config, network.hidden_bytes, dev)
-    S = pool.S
-
-    mask_d = None
-    if actions_mask is not None:
-        m = torch.as_tensor(np.asarray(actions_mask)) if not torch.is_tensor(actions_mask) else actions_mask
+    plan.obs.copy_(states.reshape(B, -1), non_blocking=True)
+    has_mask = actions_mask is not None
+    if has_mask:
+        m = actions_mask if torch.is_tensor(actions_mask) else torch.from_numpy(np.asarray(actions_mask, dtype=np.bool_))
         assert tuple(m.shape) == (B, A)                                   # mcts.py:293
-        mask_d = m.to(device=dev, dtype=torch.uint8).contiguous()
+        plan.mask.copy_(m, non_blocking=True)
     cur = np.broadcast_to(np.asarray(current_player, dtype=np.int32), (B,))
     opp = np.broadcast_to(np.asarray(opponent_player, dtype=np.int32), (B,))
-    players_d = torch.from_numpy(np.stack([cur, opp], axis=1).copy()).to(dev)
-    temps_d = torch.from_numpy(temps).to(dev)
+    plan.players.copy_(torch.from_numpy(np.stack([cur, opp], axis=1)))
+    plan.temps.copy_(torch.from_numpy(temps))
 
-    # root: representation + prediction straight into slot 0 of every tree (mcts.py:355-356)
-    root_slots = torch.arange(B, dtype=torch.int32, device=dev) * (S + 1)
-    _, pi0, _ = network.initial_inference_batch(states.to(dev), hidden_out=pool.hidden, dst_index=root_slots)
-
-    noise_d = None
+    noise_mode = 'none'
     if use_noise:
+        noise_mode = 'device'
         if noise is not None:
-            noise_d = torch.as_tensor(np.asarray(noise, dtype=np.float64)).to(dev).contiguous()
+            plan.noise.copy_(torch.as_tensor(np.asarray(noise, dtype=np.float64)))
+            noise_mode = 'given'
         elif rng is not None:
             alphas = np.ones(A, dtype=np.float32) * config.root_dirichlet_alpha   # np.ones_like(prob) * alpha
-            noise_d = torch.from_numpy(np.stack([r.dirichlet(alphas) for r in rng])).to(dev)
-    if rng is not None:
-        pool.set_rng_states([r.get_state() for r in rng])
-    if use_noise and noise_d is None:
-        noise_d = pool.dirichlet(float(np.float32(config.root_dirichlet_alpha)))   # alphas are float32 in the reference
-
-    pool.reset(pi0, noise_d, config.root_exploration_eps if use_noise else 0.0, mask_d, players_d)
-    reward, value = pool.view('REWARD'), pool.view('VALUE')
-    src, dst, act = pool.view('SRC_SLOT'), pool.view('DST_SLOT'), pool.view('LEAF_ACTION')
-    hidden = pool.hidden
-    lib = _lib.lib()
-    eng = network.engine(B)
-    with torch.cuda.device(dev):
-        stream = _lib.current_stream()
-        for _ in range(S):
-            _lib.check(lib.mz_select(pool.handle, stream))
-            _lib.check(lib.mz_net_recurrent(eng['handle'], B, hidden.data_ptr(), src.data_ptr(), act.data_ptr(),
-                                            hidden.data_ptr(), dst.data_ptr(), reward.data_ptr(), value.data_ptr(),
-                                            None, stream))
-            _lib.check(lib.mz_expand_backup(pool.handle, None, None, stream))
-    action, pi, rootv, _ = pool.root_policy(mask_d, temps_d, deterministic)
+            plan.noise.copy_(torch.from_numpy(np.stack([r.dirichlet(alphas) for r in rng])))
+            noise_mode = 'given'
+    states_in = [r.get_state() for r in rng] if rng is not None else None
+    if states_in is not None:
+        pool.set_rng_states(states_in)
+    plan.run(noise_mode, has_mask, deterministic)
     if rng is not None:
         for r, st in zip(rng, pool.get_rng_states()):
             old = r.get_state()
             r.set_state(('MT19937', st[1], st[2], old[3], old[4]))
-    if return_pool:
-        return action, pi, rootv, pool
-    return action, pi, rootv
+    return plan.action.clone(), plan.pi.clone(), plan.root_value.clone()
 
 
 # ---------------------------------------------------------------------------
@@ -351,6 +447,7 @@ def uct_search(state: np.ndarray, network, device, config, temperature: float, a
     if isinstance(network, MuZeroNet):
         a, pi, q = uct_search_batch(np.asarray(state)[None, ...], network, config, temperature, mask,
                                     current_player, opponent_player, deterministic, rng=[_GlobalNumpyStream])
+        _plan_for(network, config, 1).pool.check_errors()
         return int(a[0].cpu()), pi[0].cpu().numpy(), float(q[0].cpu())
     return _uct_search_external(state, network, dev, config, temperature, actions_mask, current_player,
                                 opponent_player, deterministic)

@@ -146,9 +146,6 @@ def test_search_with_engine_network_replays_bit_exact_in_oracle(name, B, determi
     rec_p = torch.empty((S, B), dtype=torch.int32, device=dev); rec_a = torch.empty((S, B), dtype=torch.int32, device=dev)
     for i in range(S):
         pool.select()
-        net.recurrent_inference_batch(pool.hidden, pool.view('LEAF_ACTION'), src_index=pool.view('SRC_SLOT'),
-                                      hidden_out=pool.hidden, dst_index=pool.view('DST_SLOT'), want_policy=False)
-        # the public loop writes straight into the pool's scratch; here: recompute into recordable buffers
         _, r, _, v = net.recurrent_inference_batch(pool.hidden, pool.view('LEAF_ACTION'),
                                                    src_index=pool.view('SRC_SLOT'), hidden_out=pool.hidden,
                                                    dst_index=pool.view('DST_SLOT'), want_policy=False)
