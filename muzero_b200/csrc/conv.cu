@@ -1,6 +1,745 @@
+// ResNet towers of MuZeroBoardGameNet / MuZeroAtariNet (network.py:273-574) on the
+// Blackwell tensor cores.
+//
+// Data layout ("padded grid, channel-last"): a board's activation is
+//   [PB = (H+1)*(W+1) positions][C channels] bf16,   position p = y*(W+1) + x,
+// where column x == W and row y == H are a zero halo SHARED with the next row /
+// the next board.  Flattening boards back to back (P = b*PB + p) makes every 3x3
+// tap a constant row offset: tap (ky,kx) of output position P reads input position
+// P + (ky-1)*(W+1) + (kx-1).  A hidden-state slot of the search pool is one such
+// board (PB*C*2 bytes); halo entries are never read (the loader zero-fills them by
+// predicate) and never written.
+//
+// Kernel: implicit GEMM, M = positions, N = C_out, K = 9 taps x C_in.
+//   - the activation tile (256 positions + halo) is staged ONCE in shared memory in
+//     the no-swizzle K-major core-matrix layout; the 9 taps are 9 descriptor start
+//     addresses on that one tile (umma.cuh) -> activations are read once per layer;
+//   - folded conv+BatchNorm weights stream through a 4-stage mbarrier ring of 1-D bulk
+//     copies (TMA), pre-packed on the host side of mz_net_create in exactly the
+//     shared-memory layout;
+//   - tcgen05.mma (M=128, N=C_out, K=16) accumulates in TMEM, two 128-row accumulators
+//     per tile, double-buffered across tiles so that epilogue(i-1) and load(i+1)
+//     overlap mma(i);
+//   - warp roles: warp 0 weight producer, warp 1 MMA issuer (+TMEM owner), warps 2-5
+//     activation loaders + epilogue (bias / action-bias table / residual / ReLU /
+//     per-pixel channel min-max normalisation of util.py:31-36 fused here).
 #include "net.cuh"
+#include "umma.cuh"
+
 namespace mz {
-int conv_hidden_bytes(const mz_net_config&, int32_t*) { set_error("conv nets not built yet"); return MZ_EINVAL; }
-int conv_arena_bytes(const mz_net_config&, int, size_t*) { set_error("conv nets not built yet"); return MZ_EINVAL; }
-int conv_create(const mz_net_config&, const float* const*, int, int, void*, size_t, NetImpl**) { set_error("conv nets not built yet"); return MZ_EINVAL; }
+using namespace umma;
+
+constexpr int kConvThreads = 192;
+constexpr int kWorkers = 128;
+constexpr int kTileM = 256;     // positions per tile (two M=128 accumulators)
+constexpr int kStages = 4;
+
+struct ConvParams {
+  const __nv_bfloat16* in;        // [.. boards ..][PB][Cin_pad]
+  const int32_t* in_index;        // board b lives in slot in_index[b] (nullptr: b)
+  const __nv_bfloat16* w;         // packed [9][chunks][chunk_g][N][8]
+  const float* bias;              // [N]
+  const float* tab;               // [A][PB][N] per-action bias (dynamics conv0) or nullptr
+  const int32_t* action;          // [B]
+  const __nv_bfloat16* residual;  // contiguous [Ptot][N] or nullptr
+  __nv_bfloat16* out;             // contiguous [Ptot][N] (relu'd) or nullptr
+  __nv_bfloat16* out_norm;        // contiguous, min-max normalised, or nullptr
+  __nv_bfloat16* out_slots;       // indexed slots, normalised, or nullptr
+  const int32_t* out_index;
+  int Ptot, PB, Wp, W, H, B;
+  int cg;                         // input channel groups of 8 (Cin_pad / 8), even
+  int N;                          // output channels (multiple of 32, <= 128)
+  int relu;
+  int num_tiles;
+  int TP;                         // tile positions incl. halo, odd
+};
+
+__device__ __forceinline__ void split_pos(int P, const ConvParams& p, int& b, int& q, bool& halo) {
+  b = P / p.PB;
+  q = P - b * p.PB;
+  const int y = q / p.Wp, x = q - y * p.Wp;
+  halo = (x == p.W) || (y == p.H);
 }
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int halo = p.Wp + 1;
+  const int TP = p.TP;
+  const int chunk_g = p.cg < 8 ? p.cg : 8;              // channel groups per weight stage
+  const int chunks_tap = p.cg / chunk_g;                // weight stages per tap
+  const uint32_t stage_bytes = (uint32_t)chunk_g * p.N * 16;
+  const uint32_t a_bytes = (uint32_t)p.cg * TP * 16;
+
+  unsigned char* sA = smem;                                              // [2][cg][TP][16]
+  unsigned char* sW = smem + (((size_t)2 * a_bytes + 127) & ~(size_t)127);   // [kStages][stage_bytes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)kStages * stage_bytes);
+  uint64_t* w_full = bars;                 // [kStages]
+  uint64_t* w_empty = bars + kStages;      // [kStages]
+  uint64_t* a_full = bars + 2 * kStages;   // [2]
+  uint64_t* mma_done = a_full + 2;         // [2]
+  uint64_t* acc_empty = mma_done + 2;      // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_bias = reinterpret_cast<float*>(tmem_holder + 2);            // [N]
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&a_full[b], kWorkers); mbar_init(&mma_done[b], 1); mbar_init(&acc_empty[b], kWorkers); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_holder, 512);
+  if (tid < p.N) s_bias[tid] = p.bias[tid];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_holder;
+
+  const int n_my = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) {
+    // ------------------------------------------------ weight producer
+    if (lane == 0) {
+      const int per_tile = 9 * chunks_tap;
+      uint32_t it = 0;
+      for (int i = 0; i < n_my; ++i) {
+        for (int c = 0; c < per_tile; ++c, ++it) {
+          const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+          mbar_wait(&w_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&w_full[s], stage_bytes);
+          bulk_g2s(sW + (size_t)s * stage_bytes, reinterpret_cast<const unsigned char*>(p.w) + (size_t)c * stage_bytes,
+                   stage_bytes, &w_full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc_bf16(128, (uint32_t)p.N);
+      const uint32_t a_lbo = (uint32_t)TP * 16, b_lbo = (uint32_t)p.N * 16;
+      uint32_t it = 0;
+      for (int i = 0; i < n_my; ++i) {
+        const int buf = i & 1;
+        const uint32_t uph = (i >> 1) & 1;
+        mbar_wait(&acc_empty[buf], uph ^ 1);
+        mbar_wait(&a_full[buf], uph);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(sA) + (uint32_t)buf * a_bytes;
+        uint32_t first = 1;
+        for (int tap = 0; tap < 9; ++tap) {
+          const int shift = (tap / 3 - 1) * p.Wp + (tap % 3 - 1);
+          for (int ch = 0; ch < chunks_tap; ++ch, ++it) {
+            const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+            mbar_wait(&w_full[s], ph);
+            tc_fence_after();
+            const uint32_t w_base = smem_u32(sW) + s * stage_bytes;
+            for (int ks = 0; ks < chunk_g / 2; ++ks) {
+              const uint32_t g = (uint32_t)(ch * chunk_g + 2 * ks);
+              const uint64_t bdesc = smem_desc(w_base + (uint32_t)(2 * ks) * b_lbo, b_lbo, 128);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const uint32_t a_addr = a_base + ((uint32_t)(j * 128 + halo + shift) + g * (uint32_t)TP) * 16;
+                mma_bf16(tmem + (uint32_t)(buf * 256 + j * 128), smem_desc(a_addr, a_lbo, 128), bdesc, idesc, first ^ 1);
+              }
+              first = 0;
+            }
+            commit(&w_empty[s]);
+          }
+        }
+        commit(&mma_done[buf]);
+      }
+    }
+  } else {
+    // ------------------------------------------------ workers: activation loads + epilogue
+    const int wt = tid - 64;                 // 0..127
+    const int quad = warp & 3;               // TMEM lane quadrant this warp may read
+    const int cpp = p.cg;                    // 16-byte chunks per position
+    const int cin = p.cg * 8;
+
+    auto load_tile = [&](int tile, int buf) {
+      const int m0 = tile * kTileM;
+      unsigned char* dst = sA + (size_t)buf * a_bytes;
+      const int total = (kTileM + 2 * halo) * cpp;
+      for (int idx = wt; idx < total; idx += kWorkers) {
+        const int q = idx / cpp, g = idx - q * cpp;
+        const int P = m0 - halo + q;
+        int4 v = make_int4(0, 0, 0, 0);
+        if (P >= 0 && P < p.Ptot) {
+          int b, pos; bool hl;
+          split_pos(P, p, b, pos, hl);
+          if (!hl) {
+            const size_t board = p.in_index ? (size_t)p.in_index[b] : (size_t)b;
+            v = *reinterpret_cast<const int4*>(p.in + (board * p.PB + pos) * cin + g * 8);
+          }
+        }
+        *reinterpret_cast<int4*>(dst + ((size_t)g * TP + q) * 16) = v;
+      }
+      fence_proxy_async();
+      mbar_arrive(&a_full[buf]);
+    };
+
+    auto epilogue = [&](int k) {
+      const int buf = k & 1;
+      const uint32_t ph = (k >> 1) & 1;
+      const int tile = (int)blockIdx.x + k * (int)gridDim.x;
+      mbar_wait(&mma_done[buf], ph);
+      tc_fence_after();
+      const bool norm = (p.out_norm != nullptr) || (p.out_slots != nullptr);
+      for (int j = 0; j < 2; ++j) {
+        const int P = tile * kTileM + j * 128 + quad * 32 + lane;
+        int b = 0, pos = 0; bool hl = true;
+        if (P < p.Ptot) split_pos(P, p, b, pos, hl);
+        const bool valid = !hl;
+        const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256 + j * 128);
+        const float* tab = (p.tab && valid) ? p.tab + ((size_t)p.action[b] * p.PB + pos) * p.N : nullptr;
+        const __nv_bfloat16* res = (p.residual && valid) ? p.residual + (size_t)P * p.N : nullptr;
+        float mn = INFINITY, mx = -INFINITY;
+        for (int pass = 0; pass < (norm ? 2 : 1); ++pass) {
+          float inv = 0.0f;
+          if (pass == 1) inv = 1.0f / ((mx - mn) + 1e-8f);
+          for (int c0 = 0; c0 < p.N; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(taddr + c0, r);          // .sync.aligned: the whole warp executes it, valid row or not
+            tmem_ld_wait();
+            if (valid) {
+            float v[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]) + s_bias[c0 + e];
+            if (tab) {
+#pragma unroll
+              for (int e = 0; e < 32; e += 4) {
+                const float4 t4 = *reinterpret_cast<const float4*>(tab + c0 + e);
+                v[e] += t4.x; v[e + 1] += t4.y; v[e + 2] += t4.z; v[e + 3] += t4.w;
+              }
+            }
+            if (res) {
+#pragma unroll
+              for (int e = 0; e < 32; e += 8) {
+                const int4 r4 = *reinterpret_cast<const int4*>(res + c0 + e);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r4);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const float2 f = __bfloat1622float2(h[u]);
+                  v[e + 2 * u] += f.x; v[e + 2 * u + 1] += f.y;
+                }
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.0f);
+            }
+            if (pass == 0) {
+              if (norm) {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) { mn = fminf(mn, v[e]); mx = fmaxf(mx, v[e]); }
+              }
+              if (p.out) {
+                int4* o = reinterpret_cast<int4*>(p.out + (size_t)P * p.N + c0);
+#pragma unroll
+                for (int e = 0; e < 32; e += 8)
+                  o[e / 8] = make_int4((int)pack2(v[e], v[e + 1]), (int)pack2(v[e + 2], v[e + 3]),
+                                       (int)pack2(v[e + 4], v[e + 5]), (int)pack2(v[e + 6], v[e + 7]));
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) v[e] = (v[e] - mn) * inv;
+              int4 o4[4];
+#pragma unroll
+              for (int e = 0; e < 32; e += 8)
+                o4[e / 8] = make_int4((int)pack2(v[e], v[e + 1]), (int)pack2(v[e + 2], v[e + 3]),
+                                      (int)pack2(v[e + 4], v[e + 5]), (int)pack2(v[e + 6], v[e + 7]));
+              if (p.out_norm) {
+                int4* o = reinterpret_cast<int4*>(p.out_norm + (size_t)P * p.N + c0);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) o[u] = o4[u];
+              }
+              if (p.out_slots) {
+                const size_t board = p.out_index ? (size_t)p.out_index[b] : (size_t)b;
+                int4* o = reinterpret_cast<int4*>(p.out_slots + (board * p.PB + pos) * p.N + c0);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) o[u] = o4[u];
+              }
+            }
+            }  // valid
+            __syncwarp();
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[buf]);
+    };
+
+    if (n_my > 0) load_tile((int)blockIdx.x, 0);
+    for (int i = 0; i < n_my; ++i) {
+      if (i >= 1) epilogue(i - 1);
+      if (i + 1 < n_my) load_tile((int)blockIdx.x + (i + 1) * (int)gridDim.x, (i + 1) & 1);
+    }
+    if (n_my > 0) epilogue(n_my - 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------
+// small SIMT kernels: observation packing, heads, weight repacking
+// ---------------------------------------------------------------------------
+// obs f32 [B][C][H][W] -> bf16 padded grid [B][PB][cpad]
+__global__ void pack_obs_kernel(const float* __restrict__ obs, __nv_bfloat16* __restrict__ out, int B, int C, int H,
+                                int W, int cpad) {
+  const int Wp = W + 1, PB = (H + 1) * Wp;
+  const size_t n = (size_t)B * PB * cpad;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cpad);
+    const size_t r = i / cpad;
+    const int pos = (int)(r % PB), b = (int)(r / PB);
+    const int y = pos / Wp, x = pos % Wp;
+    float v = 0.0f;
+    if (c < C && y < H && x < W) v = obs[(((size_t)b * C + c) * H + y) * W + x];
+    out[i] = __float2bfloat16(v);
+  }
+}
+
+// 1x1 conv (C -> mid, BatchNorm folded) + ReLU + Flatten + Linear(mid*hw -> out) and the output
+// transform: 0 = raw scalar (support 1), 1 = support->scalar (util.py:70-93), 2 = softmax.
+// One CTA of 128 threads per board.
+struct HeadParams {
+  const __nv_bfloat16* act;   // contiguous [B][PB][C]
+  const float* w1;            // [mid][C]  (scaled)
+  const float* b1;            // [mid]
+  const float* w2;            // [out][mid*hw]
+  const float* b2;            // [out]
+  float* dst;                 // [B] or [B][out]
+  int C, H, W, mid, out, kind;
+};
+
+__device__ __forceinline__ float signed_parabolic_f(float x) {
+  const float eps = 1e-3f;
+  float z = __fadd_rn(1.0f, __fmul_rn(0.004f, __fadd_rn(1.001f, fabsf(x))));
+  z = __fsqrt_rn(z);
+  z = __fdiv_rn(__fdiv_rn(z, 2.0f), eps);
+  z = __fsub_rn(z, 500.0f);
+  const float r = __fsub_rn(__fmul_rn(z, z), 1.0f);
+  return x > 0.0f ? r : (x < 0.0f ? -r : 0.0f);
+}
+
+__global__ void __launch_bounds__(128) head_kernel(const HeadParams p) {
+  extern __shared__ float hs[];            // f[mid*hw] | logits[out]
+  const int hw = p.H * p.W, Wp = p.W + 1, PB = (p.H + 1) * Wp;
+  float* f = hs;
+  float* lg = hs + p.mid * hw;
+  const int b = blockIdx.x;
+  const __nv_bfloat16* a = p.act + (size_t)b * PB * p.C;
+  for (int i = threadIdx.x; i < p.mid * hw; i += blockDim.x) {
+    const int m = i / hw, q = i % hw;
+    const int y = q / p.W, x = q % p.W;
+    const __nv_bfloat16* row = a + (size_t)(y * Wp + x) * p.C;
+    const float* w = p.w1 + (size_t)m * p.C;
+    float acc = 0.0f;
+    for (int c = 0; c < p.C; c += 8) {
+      const int4 r4 = *reinterpret_cast<const int4*>(row + c);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r4);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float2 v = __bfloat1622float2(h[u]);
+        acc = fmaf(v.x, w[c + 2 * u], acc);
+        acc = fmaf(v.y, w[c + 2 * u + 1], acc);
+      }
+    }
+    f[i] = fmaxf(acc + p.b1[m], 0.0f);     // index m*hw + y*W + x == nn.Flatten order
+  }
+  __syncthreads();
+  const int K = p.mid * hw;
+  for (int o = threadIdx.x; o < p.out; o += blockDim.x) {
+    const float* w = p.w2 + (size_t)o * K;
+    float acc = p.b2[o];
+    for (int k = 0; k < K; ++k) acc = fmaf(f[k], w[k], acc);
+    lg[o] = acc;
+  }
+  __syncthreads();
+  if (p.kind == 0) {
+    if (threadIdx.x == 0) p.dst[b] = lg[0];
+    return;
+  }
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    float m = -INFINITY;
+    for (int i = lane; i < p.out; i += 32) m = fmaxf(m, lg[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float den = 0.0f, num = 0.0f;
+    const int maxv = (p.out - 1) / 2;
+    const float step = p.out > 1 ? (float)(2 * maxv) / (float)(p.out - 1) : 0.0f;
+    for (int i = lane; i < p.out; i += 32) {
+      const float e = expf(lg[i] - m);
+      den += e;
+      num += e * ((float)(-maxv) + step * (float)i);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      den += __shfl_xor_sync(0xffffffffu, den, o);
+      num += __shfl_xor_sync(0xffffffffu, num, o);
+    }
+    if (p.kind == 1) {
+      if (lane == 0) p.dst[b] = signed_parabolic_f(num / den);
+    } else {
+      for (int i = lane; i < p.out; i += 32) p.dst[(size_t)b * p.out + i] = expf(lg[i] - m) / den;
+    }
+  }
+}
+
+// BatchNorm (eval) folded into the preceding bias-free conv: scale = gamma / sqrt(var + eps)
+__global__ void bn_fold_kernel(const float* g, const float* beta, const float* mean, const float* var, float* scale,
+                               float* bias, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float s = g[i] / sqrtf(var[i] + 1e-5f);
+    scale[i] = s;
+    bias[i] = beta[i] - mean[i] * s;
+  }
+}
+
+// conv weight [N][cin_total][3][3] (first `cin` input channels) * scale[n] -> packed bf16
+// [9 taps][chunks][chunk_g][N][8]
+__global__ void pack_conv_kernel(const float* __restrict__ w, const float* __restrict__ scale,
+                                 __nv_bfloat16* __restrict__ out, int N, int cin, int cin_total, int cg) {
+  const int chunk_g = cg < 8 ? cg : 8;
+  const size_t total = (size_t)9 * cg * N * 8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int e = (int)(i % 8);
+    size_t r = i / 8;
+    const int n = (int)(r % N); r /= N;
+    const int gl = (int)(r % chunk_g); r /= chunk_g;
+    const int ch = (int)(r % (cg / chunk_g));
+    const int tap = (int)(r / (cg / chunk_g));
+    const int c = (ch * chunk_g + gl) * 8 + e;
+    float v = 0.0f;
+    if (c < cin) v = w[(((size_t)n * cin_total + c) * 3 + tap / 3) * 3 + tap % 3] * scale[n];
+    out[i] = __float2bfloat16(v);
+  }
+}
+
+// 1x1 head conv weight [mid][C][1][1] * scale[mid] -> f32 [mid][C]
+__global__ void scale_rows_kernel(const float* w, const float* scale, float* out, int rows, int cols) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows * cols) out[i] = w[i] * scale[i / cols];
+}
+
+// per-action bias table of the dynamics' first conv: the A extra input planes are a fixed
+// 0/1 pattern per action (QUIRK C, network.py:440-444: flat element f of the [A*h*w] block is
+// 1 iff f % A == action), so their contribution is tab[a][pos][n] = scale[n] * sum over
+// (plane c, tap) of w[n][C + c][tap] * E_a[c][y+ky-1][x+kx-1].
+__global__ void action_table_kernel(const float* __restrict__ w, const float* __restrict__ scale,
+                                    float* __restrict__ tab, int A, int C, int N, int H, int W) {
+  const int Wp = W + 1, PB = (H + 1) * Wp, hw = H * W;
+  const size_t total = (size_t)A * PB * N;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i % N);
+    const int pos = (int)((i / N) % PB);
+    const int a = (int)(i / ((size_t)N * PB));
+    const int y = pos / Wp, x = pos % Wp;
+    float acc = 0.0f;
+    if (y < H && x < W) {
+      for (int c = 0; c < A; ++c)
+        for (int ky = 0; ky < 3; ++ky)
+          for (int kx = 0; kx < 3; ++kx) {
+            const int yy = y + ky - 1, xx = x + kx - 1;
+            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+            const int fidx = c * hw + yy * W + xx;
+            if (fidx % A == a) acc += w[(((size_t)n * (C + A) + C + c) * 3 + ky) * 3 + kx];
+          }
+      acc *= scale[n];
+    }
+    tab[i] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+struct ConvLayer {
+  const __nv_bfloat16* w;
+  const float* bias;
+  int cg;
+};
+struct Head {
+  const float *w1, *b1, *w2, *b2;
+  int mid, out, kind;
+};
+
+struct ConvNet : NetImpl {
+  mz_net_config cfg;
+  int H, W, Wp, PB, C, A, blocks, max_batch, num_sms;
+  int in_cg;                       // channel groups of the packed observation
+  ConvLayer rep0, dyn0;
+  ConvLayer rep_blocks[64], dyn_blocks[64], pred_blocks[64];   // 2 per block
+  const float* tab;
+  Head h_reward, h_policy, h_value;
+  __nv_bfloat16 *xobs, *b0, *b1, *b2, *b3;
+
+  int launch_conv(const ConvLayer& L, const __nv_bfloat16* in, const int32_t* in_index, int batch, const float* tab_,
+                  const int32_t* action, const __nv_bfloat16* residual, __nv_bfloat16* out, __nv_bfloat16* out_norm,
+                  __nv_bfloat16* out_slots, const int32_t* out_index, cudaStream_t st) {
+    ConvParams p;
+    p.in = in; p.in_index = in_index; p.w = L.w; p.bias = L.bias; p.tab = tab_; p.action = action;
+    p.residual = residual; p.out = out; p.out_norm = out_norm; p.out_slots = out_slots; p.out_index = out_index;
+    p.Ptot = batch * PB; p.PB = PB; p.Wp = Wp; p.W = W; p.H = H; p.B = batch;
+    p.cg = L.cg; p.N = C; p.relu = 1;
+    p.num_tiles = (p.Ptot + kTileM - 1) / kTileM;
+    p.TP = (kTileM + 2 * (Wp + 1)) | 1;
+    const size_t smem = conv_smem(L.cg);
+    const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    conv3x3_kernel<<<grid, kConvThreads, smem, st>>>(p);
+    MZ_LAUNCH_CHECK("conv3x3_kernel");
+    return MZ_OK;
+  }
+  size_t conv_smem(int cg) const {
+    const int TP = (kTileM + 2 * (Wp + 1)) | 1;
+    const int chunk_g = cg < 8 ? cg : 8;
+    size_t a = (((size_t)2 * cg * TP * 16) + 127) & ~(size_t)127;
+    return a + (size_t)kStages * chunk_g * C * 16 + 16 * 8 + 16 + (size_t)C * 4 + 64;
+  }
+  int launch_head(const Head& h, const __nv_bfloat16* act, int batch, float* dst, cudaStream_t st) {
+    HeadParams p;
+    p.act = act; p.w1 = h.w1; p.b1 = h.b1; p.w2 = h.w2; p.b2 = h.b2; p.dst = dst;
+    p.C = C; p.H = H; p.W = W; p.mid = h.mid; p.out = h.out; p.kind = h.kind;
+    const size_t smem = ((size_t)h.mid * H * W + h.out) * 4;
+    head_kernel<<<batch, 128, smem, st>>>(p);
+    MZ_LAUNCH_CHECK("head_kernel");
+    return MZ_OK;
+  }
+
+  // [first conv] -> residual blocks; the LAST layer optionally also emits the min-max normalised
+  // state (contiguous copy and/or indexed slots).  *final_buf = buffer holding the raw (ReLU'd)
+  // tower output, unless want_raw is false and the last layer normalises (then it is not written).
+  int tower(const ConvLayer* first, const ConvLayer* blk, const __nv_bfloat16* in, const int32_t* in_index,
+            const float* tab_, const int32_t* action, int batch, bool want_raw, __nv_bfloat16* norm_out,
+            __nv_bfloat16* slots, const int32_t* out_index, cudaStream_t st, __nv_bfloat16** final_buf) {
+    const __nv_bfloat16* cur = in;
+    const int32_t* cur_index = in_index;
+    __nv_bfloat16* pp[2] = {b0, b1};
+    int which = 0, rc;
+    const bool normalise = (norm_out != nullptr) || (slots != nullptr);
+    if (first) {
+      const bool last = (blocks == 0);
+      __nv_bfloat16* dst = pp[which];
+      rc = launch_conv(*first, cur, cur_index, batch, tab_, action, nullptr,
+                       (last && normalise && !want_raw) ? nullptr : dst, last ? norm_out : nullptr,
+                       last ? slots : nullptr, out_index, st);
+      if (rc) return rc;
+      cur = dst; cur_index = nullptr; which ^= 1;
+    }
+    for (int i = 0; i < blocks; ++i) {
+      const bool last = (i == blocks - 1);
+      rc = launch_conv(blk[2 * i], cur, cur_index, batch, nullptr, nullptr, nullptr, b2, nullptr, nullptr, nullptr, st);
+      if (rc) return rc;
+      if (cur_index != nullptr) { set_error("internal: residual input must be contiguous"); return MZ_EINVAL; }
+      __nv_bfloat16* dst = pp[which];
+      if (dst == cur) dst = pp[which ^ 1];
+      rc = launch_conv(blk[2 * i + 1], b2, nullptr, batch, nullptr, nullptr, cur,
+                       (last && normalise && !want_raw) ? nullptr : dst, last ? norm_out : nullptr,
+                       last ? slots : nullptr, out_index, st);
+      if (rc) return rc;
+      cur = dst; which ^= 1;
+    }
+    *final_buf = const_cast<__nv_bfloat16*>(cur);
+    return MZ_OK;
+  }
+
+  int initial(int batch, const float* obs, void* hidden_out, const int32_t* dst_index, float* pi_probs, float* value,
+              cudaStream_t st) override {
+    pack_obs_kernel<<<num_sms * 4, 256, 0, st>>>(obs, xobs, batch, cfg.in_channels, H, W, in_cg * 8);
+    MZ_LAUNCH_CHECK("pack_obs_kernel");
+    __nv_bfloat16* fin;
+    // representation: raw output is not needed, normalised goes to b3 (for the prediction tower) and the slots
+    int rc = tower(&rep0, rep_blocks, xobs, nullptr, nullptr, nullptr, batch, false, b3, (__nv_bfloat16*)hidden_out,
+                   dst_index, st, &fin);
+    if (rc) return rc;
+    return predict(batch, pi_probs, value, st);
+  }
+
+  int predict(int batch, float* pi_probs, float* value, cudaStream_t st) {
+    __nv_bfloat16* fin;
+    int rc = tower(nullptr, pred_blocks, b3, nullptr, nullptr, nullptr, batch, true, nullptr, nullptr, nullptr, st, &fin);
+    if (rc) return rc;
+    if (pi_probs) {
+      rc = launch_head(h_policy, fin, batch, pi_probs, st);
+      if (rc) return rc;
+    }
+    return launch_head(h_value, fin, batch, value, st);
+  }
+
+  int recurrent(int batch, const void* hidden_in, const int32_t* src_index, const int32_t* action, void* hidden_out,
+                const int32_t* dst_index, float* reward_out, float* value_out, float* pi_probs,
+                cudaStream_t st) override {
+    __nv_bfloat16* fin;
+    // dynamics: raw output (for the reward head) in a ping-pong buffer, normalised copy in b3 + the slots
+    int rc = tower(&dyn0, dyn_blocks, (const __nv_bfloat16*)hidden_in, src_index, tab, action, batch, true, b3,
+                   (__nv_bfloat16*)hidden_out, dst_index, st, &fin);
+    if (rc) return rc;
+    rc = launch_head(h_reward, fin, batch, reward_out, st);     // reward head reads the UN-normalised state
+    if (rc) return rc;
+    return predict(batch, pi_probs, value_out, st);
+  }
+};
+
+static int conv_geometry(const mz_net_config& c, int* H, int* W) {
+  MZ_CHECK_ARG(c.num_planes == 32 || c.num_planes == 64 || c.num_planes == 128,
+               "conv nets need num_planes in {32, 64, 128}, got %d", c.num_planes);
+  MZ_CHECK_ARG(c.in_channels > 0 && c.in_channels <= 64, "conv nets take 1..64 observation planes, got %d",
+               c.in_channels);
+  MZ_CHECK_ARG(c.num_res_blocks >= 0 && c.num_res_blocks <= 32, "num_res_blocks out of range");
+  if (c.kind == MZ_NET_BOARD) { *H = c.in_h; *W = c.in_w; }
+  else { *H = 6; *W = 6; }                    // network.py:516-519 hard-wires the 6x6 latent
+  MZ_CHECK_ARG(*H > 0 && *W > 0 && *W <= 40, "unsupported board size %dx%d", *H, *W);
+  if (c.kind == MZ_NET_ATARI) {
+    set_error("MuZeroAtariNet's strided representation tower is not built yet");
+    return MZ_EINVAL;
+  }
+  return MZ_OK;
+}
+
+int conv_hidden_bytes(const mz_net_config& c, int32_t* bytes) {
+  int H, W;
+  int rc = conv_geometry(c, &H, &W);
+  if (rc) return rc;
+  *bytes = (H + 1) * (W + 1) * c.num_planes * 2;
+  return MZ_OK;
+}
+
+static size_t conv_w_bytes(int cg, int N) { return align_up((size_t)9 * cg * N * 16, 256); }
+static int obs_cg(int cin) { return ((cin + 15) / 16) * 2; }
+
+int conv_arena_bytes(const mz_net_config& c, int max_batch, size_t* bytes) {
+  int H, W;
+  int rc = conv_geometry(c, &H, &W);
+  if (rc) return rc;
+  const int N = c.num_planes, PB = (H + 1) * (W + 1), A = c.num_actions, hw = H * W;
+  size_t t = 0;
+  const int nconv_main = 1 + 6 * c.num_res_blocks;            // dyn0 + 2 per block x 3 towers
+  t += conv_w_bytes(obs_cg(c.in_channels), N) + (size_t)nconv_main * conv_w_bytes(N / 8, N);
+  t += (size_t)(2 + 6 * c.num_res_blocks) * 2 * align_up((size_t)N * 4, 256);          // scale + bias per conv
+  t += align_up((size_t)A * PB * N * 4, 256);                                           // action table
+  t += 3 * (align_up((size_t)2 * N * 4, 256) + 2 * 256 + 256);                          // head 1x1 weights/bias/scale
+  t += align_up((size_t)c.reward_support * hw * 4, 256) + align_up((size_t)A * 2 * hw * 4, 256) +
+       align_up((size_t)c.value_support * hw * 4, 256) + 3 * align_up((size_t)(A + c.value_support + c.reward_support) * 4, 256);
+  t += align_up((size_t)max_batch * PB * obs_cg(c.in_channels) * 16, 256);              // packed observations
+  t += 4 * align_up((size_t)max_batch * PB * N * 2, 256);                               // b0..b3
+  *bytes = t + 4096;
+  return MZ_OK;
+}
+
+int conv_create(const mz_net_config& c, const float* const* w, int nw, int max_batch, void* arena, size_t arena_bytes,
+                NetImpl** out) {
+  int H, W;
+  int rc = conv_geometry(c, &H, &W);
+  if (rc) return rc;
+  const int N = c.num_planes, A = c.num_actions, hw = H * W, blocks = c.num_res_blocks;
+  const int expect = (5 + 10 * blocks) + (5 + 10 * blocks + 7) + (10 * blocks + 14);
+  MZ_CHECK_ARG(nw == expect, "MuZeroBoardGameNet with %d blocks has %d state_dict tensors, got %d", blocks, expect, nw);
+  size_t need;
+  conv_arena_bytes(c, max_batch, &need);
+  if (arena_bytes < need) { set_error("net arena too small: %zu < %zu", arena_bytes, need); return MZ_ENOMEM; }
+
+  ConvNet* net = new ConvNet();
+  net->cfg = c; net->H = H; net->W = W; net->Wp = W + 1; net->PB = (H + 1) * (W + 1); net->C = N; net->A = A;
+  net->blocks = blocks; net->max_batch = max_batch;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&net->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  net->in_cg = obs_cg(c.in_channels);
+
+  char* p = (char*)arena;
+  auto take = [&](size_t bytes) { char* r = p; p += align_up(bytes, 256); return r; };
+  int cur = 0;
+  auto next = [&]() { return w[cur++]; };
+
+  // conv (no bias) + BatchNorm -> packed bf16 weights + fp32 bias; optional action table
+  auto fold_conv = [&](int cin, int cin_total, int cg, ConvLayer* L, float** scale_out) -> int {
+    const float* cw = next();
+    const float *g = next(), *beta = next(), *mean = next(), *var = next();
+    float* scale = (float*)take((size_t)N * 4);
+    float* bias = (float*)take((size_t)N * 4);
+    bn_fold_kernel<<<(N + 127) / 128, 128>>>(g, beta, mean, var, scale, bias, N);
+    MZ_LAUNCH_CHECK("bn_fold_kernel");
+    __nv_bfloat16* wp = (__nv_bfloat16*)take((size_t)9 * cg * N * 16);
+    pack_conv_kernel<<<256, 256>>>(cw, scale, wp, N, cin, cin_total, cg);
+    MZ_LAUNCH_CHECK("pack_conv_kernel");
+    L->w = wp; L->bias = bias; L->cg = cg;
+    if (scale_out) *scale_out = scale;
+    (void)cw;
+    return MZ_OK;
+  };
+  auto fold_head = [&](int mid, int outn, int kind, Head* h) -> int {
+    const float* cw = next();
+    const float *g = next(), *beta = next(), *mean = next(), *var = next();
+    float* scale = (float*)take(256);
+    float* bias = (float*)take(256);
+    bn_fold_kernel<<<1, 32>>>(g, beta, mean, var, scale, bias, mid);
+    MZ_LAUNCH_CHECK("bn_fold_kernel");
+    float* w1 = (float*)take((size_t)mid * N * 4);
+    scale_rows_kernel<<<(mid * N + 255) / 256, 256>>>(cw, scale, w1, mid, N);
+    MZ_LAUNCH_CHECK("scale_rows_kernel");
+    const float* lw = next();
+    const float* lb = next();
+    float* w2 = (float*)take((size_t)outn * mid * hw * 4);
+    float* b2 = (float*)take((size_t)outn * 4);
+    MZ_CUDA(cudaMemcpy(w2, lw, (size_t)outn * mid * hw * 4, cudaMemcpyDeviceToDevice));
+    MZ_CUDA(cudaMemcpy(b2, lb, (size_t)outn * 4, cudaMemcpyDeviceToDevice));
+    h->w1 = w1; h->b1 = bias; h->w2 = w2; h->b2 = b2; h->mid = mid; h->out = outn; h->kind = kind;
+    return MZ_OK;
+  };
+#define MZ_TRY(x) do { int rc__ = (x); if (rc__) { delete net; return rc__; } } while (0)
+
+  // representation (network.py:356-393)
+  MZ_TRY(fold_conv(c.in_channels, c.in_channels, net->in_cg, &net->rep0, nullptr));
+  for (int i = 0; i < 2 * blocks; ++i) MZ_TRY(fold_conv(N, N, N / 8, &net->rep_blocks[i], nullptr));
+  // dynamics (network.py:396-449): first conv sees C + A channels; the A action planes become a table
+  {
+    const float* dyn_w = w[cur];
+    float* scale = nullptr;
+    MZ_TRY(fold_conv(N, N + A, N / 8, &net->dyn0, &scale));
+    float* tab = (float*)take((size_t)A * net->PB * N * 4);
+    action_table_kernel<<<512, 256>>>(dyn_w, scale, tab, A, N, N, H, W);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("action_table_kernel: %s", cudaGetErrorString(e)); delete net; return MZ_ECUDA; }
+    count_launch();
+    net->tab = tab;
+  }
+  for (int i = 0; i < 2 * blocks; ++i) MZ_TRY(fold_conv(N, N, N / 8, &net->dyn_blocks[i], nullptr));
+  MZ_TRY(fold_head(1, c.reward_support, c.reward_support == 1 ? 0 : 1, &net->h_reward));
+  // prediction (network.py:452-498)
+  for (int i = 0; i < 2 * blocks; ++i) MZ_TRY(fold_conv(N, N, N / 8, &net->pred_blocks[i], nullptr));
+  MZ_TRY(fold_head(2, A, 2, &net->h_policy));
+  MZ_TRY(fold_head(1, c.value_support, c.value_support == 1 ? 0 : 1, &net->h_value));
+#undef MZ_TRY
+  net->xobs = (__nv_bfloat16*)take((size_t)max_batch * net->PB * net->in_cg * 16);
+  const size_t act_bytes = (size_t)max_batch * net->PB * N * 2;
+  net->b0 = (__nv_bfloat16*)take(act_bytes);
+  net->b1 = (__nv_bfloat16*)take(act_bytes);
+  net->b2 = (__nv_bfloat16*)take(act_bytes);
+  net->b3 = (__nv_bfloat16*)take(act_bytes);
+  if ((size_t)(p - (char*)arena) > arena_bytes) {
+    set_error("internal: net arena overrun (%zu > %zu)", (size_t)(p - (char*)arena), arena_bytes);
+    delete net;
+    return MZ_ENOMEM;
+  }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { set_error("weight repacking failed: %s", cudaGetErrorString(e)); delete net; return MZ_ECUDA; }
+  const size_t smem_max = net->conv_smem(N / 8) > net->conv_smem(net->in_cg) ? net->conv_smem(N / 8) : net->conv_smem(net->in_cg);
+  if (smem_max > 227 * 1024) {
+    set_error("conv tile needs %zu bytes of shared memory (board too wide)", smem_max);
+    delete net;
+    return MZ_EINVAL;
+  }
+  e = cudaFuncSetAttribute(conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); delete net; return MZ_ECUDA; }
+  *out = net;
+  return MZ_OK;
+}
+
+}  // namespace mz

@@ -160,3 +160,16 @@ class OracleNet:
     def recurrent_inference(self, hidden_state, action):
         h, r, pi, v = self.recurrent_batch(hidden_state, action)
         return NetworkOutputs(h.squeeze(0).numpy(), r.squeeze(0).item(), pi.squeeze(0).numpy(), v.squeeze(0).item())
+
+
+def randomize_batchnorm(net, seed: int) -> None:
+    """Give every BatchNorm2d of a torch module non-trivial, reproducible statistics and affine
+    parameters (module traversal order).  tests/golden/make_golden_nets.py used exactly this
+    recipe on the reference modules before recording their outputs."""
+    g = torch.Generator().manual_seed(seed)
+    for m in list(net.modules()):
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.num_features, generator=g) * 0.5 + 0.75)
+            m.weight.data.copy_(torch.rand(m.num_features, generator=g) * 0.5 + 0.75)
+            m.bias.data.copy_(torch.randn(m.num_features, generator=g) * 0.1)

@@ -34,7 +34,7 @@ sys.dont_write_bytecode = True
 from muzero import network as ref_net                    # noqa: E402  (the reference)
 
 import muzero_b200.network as my_net                     # noqa: E402
-from oracle.network_oracle import OracleNet              # noqa: E402
+from oracle.network_oracle import OracleNet, randomize_batchnorm   # noqa: E402
 
 CKPT = '/root/reference/saved_checkpoints'
 MLPS = {
@@ -117,14 +117,8 @@ def main():
         torch.manual_seed(seed); ref = rcls(**kw).eval()
         torch.manual_seed(seed); mine = mcls(**kw).eval()
         check_module_parity(ref, mine, name)
-        # non-trivial BatchNorm statistics, deterministic, reproduced by the test from the same recipe
-        g = torch.Generator().manual_seed(1000 + seed)
-        for m in list(ref.modules()):
-            if isinstance(m, torch.nn.BatchNorm2d):
-                m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
-                m.running_var.copy_(torch.rand(m.num_features, generator=g) * 0.5 + 0.75)
-                m.weight.data.copy_(torch.rand(m.num_features, generator=g) * 0.5 + 0.75)
-                m.bias.data.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+        # non-trivial BatchNorm statistics, deterministic, reproduced by the tests from the same recipe
+        randomize_batchnorm(ref, 1000 + seed)
         sd = ref.state_dict()
         orc = OracleNet(kind, sd, kw['num_actions'], kw.get('value_support_size', 1),
                         kw.get('reward_support_size', 1), kw['num_res_blocks'])

@@ -1,0 +1,151 @@
+"""GPU tests of the tcgen05 ResNet towers (bf16 x bf16 -> fp32) against the fp32 torch
+restatement of the reference and the reference's own recorded outputs.
+
+Stated tolerance (bf16 activations between layers, fp32 accumulation, fp32 heads):
+  hidden state (min-max normalised to [0,1]):  |err| <= 0.03 for an 8-block tower, 0.02 shallow
+  policy probabilities:                        |err| <= 0.03
+  value / reward (scalar heads):               |err| <= 0.03 * max(1, |ref|_max)
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, bits
+from oracle import mcts_oracle as orc
+from oracle.network_oracle import OracleNet, randomize_batchnorm
+from oracle.stubnet import ReplayStub
+
+pytestmark = pytest.mark.gpu
+
+
+def build_board(input_shape, num_actions, blocks, planes, seed):
+    import muzero_b200 as mz
+    torch.manual_seed(seed)
+    net = mz.MuZeroBoardGameNet(input_shape, num_actions, blocks, planes).eval()
+    randomize_batchnorm(net, 1000 + seed)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    onet = OracleNet('board', sd, num_actions, 1, 1, blocks)
+    return net.cuda(), onet
+
+
+def report(name, got, ref, tol):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    err = np.abs(got - ref)
+    scale = max(1.0, float(np.abs(ref).max()))
+    print(f'{name}: max|err|={err.max():.4g} mean|err|={err.mean():.4g} ref|max|={np.abs(ref).max():.4g} '
+          f'(tol {tol * scale:.4g})')
+    assert np.isfinite(got).all(), f'{name}: non-finite output'
+    assert err.max() <= tol * scale, f'{name}: max err {err.max():.4g} > {tol * scale:.4g} at {np.unravel_index(err.argmax(), err.shape)}'
+
+
+@pytest.mark.parametrize('shape,A,planes', [((3, 3, 3), 10, 32), ((9, 5, 5), 26, 64), ((9, 9, 9), 82, 128),
+                                            ((17, 15, 15), 226, 128)])
+@pytest.mark.parametrize('batch', [1, 7, 300])
+def test_single_conv_layers_blocks0(shape, A, planes, batch):
+    """num_res_blocks = 0 isolates ONE tensor-core conv per function: the representation
+    conv (few input planes), the dynamics conv (C planes + per-action bias table, QUIRK C)
+    and the 1x1-conv heads."""
+    net, onet = build_board(shape, A, 0, planes, seed=batch)
+    gen = np.random.RandomState(batch)
+    obs = gen.randint(0, 2, size=(batch,) + shape).astype(np.float32)
+    hid, pi, v = net.initial_inference_batch(torch.from_numpy(obs).cuda())
+    h_ref, pi_ref, v_ref = onet.initial_batch(obs)
+    report('rep hidden', net.hidden_to_reference(hid).cpu().numpy(), h_ref.numpy(), 0.02)
+    report('pi0', pi.cpu().numpy(), pi_ref.numpy(), 0.03)
+    report('v0', v.cpu().numpy(), v_ref.numpy(), 0.03)
+    act = gen.randint(0, A, size=batch)
+    src = torch.arange(batch - 1, -1, -1, dtype=torch.int32).cuda()
+    dst = (torch.arange(batch, dtype=torch.int32) * 2 + 1).cuda()
+    out = net.new_hidden(2 * batch + 1)
+    slots_in = net.hidden_from_reference(h_ref.cuda())
+    _, r, pi2, v2 = net.recurrent_inference_batch(slots_in, torch.from_numpy(act).cuda(), src_index=src, hidden_out=out,
+                                                  dst_index=dst)
+    h2_ref, r_ref, pi2_ref, v2_ref = onet.recurrent_batch(h_ref.flip(0), act)
+    report('dyn hidden', net.hidden_to_reference(out)[1::2].cpu().numpy(), h2_ref.numpy(), 0.02)
+    report('reward', r.cpu().numpy(), r_ref.numpy(), 0.03)
+    report('v1', v2.cpu().numpy(), v2_ref.numpy(), 0.03)
+    report('pi1', pi2.cpu().numpy(), pi2_ref.numpy(), 0.03)
+    assert (out.view(torch.bfloat16)[0::2] == 0).all()        # untouched slots stay untouched
+
+
+@pytest.mark.parametrize('name,kind,kw,seed', [
+    ('board_small', 'board', dict(input_shape=(5, 5, 5), num_actions=26, num_res_blocks=2, num_planes=32), 3),
+    ('gomoku', 'board', dict(input_shape=(9, 9, 9), num_actions=82, num_res_blocks=8, num_planes=128), 0),
+])
+def test_towers_vs_reference_recording(name, kind, kw, seed):
+    """Single-item reference API against the reference's own recorded outputs
+    (tests/golden/net_golden.npz; the recording stores hidden states as float16)."""
+    net, onet = build_board(kw['input_shape'], kw['num_actions'], kw['num_res_blocks'], kw['num_planes'], seed)
+    z = np.load(os.path.join(GOLDEN, 'net_golden.npz'))
+    tol_h = 0.03
+    for j in range(2):
+        g = {k: z[f'{name}_{j}_{k}'] for k in ('obs', 'actions', 'h0', 'pi0', 'v0', 'h', 'r', 'v', 'pi')}
+        o = net.initial_inference(torch.from_numpy(g['obs'])[None].cuda())
+        assert o.hidden_state.shape == g['h0'].shape and o.hidden_state.dtype == np.float32
+        assert isinstance(o.value, float) and o.reward == 0.0
+        report(f'{name}/{j} h0', o.hidden_state, g['h0'].astype(np.float32), tol_h)
+        report(f'{name}/{j} pi0', o.pi_probs, g['pi0'], 0.03)
+        report(f'{name}/{j} v0', o.value, g['v0'], 0.03)
+        h = g['h0'].astype(np.float32)
+        for i, a in enumerate(g['actions']):
+            o = net.recurrent_inference(torch.from_numpy(h)[None].cuda(), torch.tensor([[int(a)]]).cuda())
+            report(f'{name}/{j} h[{i}]', o.hidden_state, g['h'][i].astype(np.float32), tol_h)
+            report(f'{name}/{j} r[{i}]', o.reward, g['r'][i], 0.03)
+            report(f'{name}/{j} v[{i}]', o.value, g['v'][i], 0.03)
+            report(f'{name}/{j} pi[{i}]', o.pi_probs, g['pi'][i], 0.03)
+            h = g['h'][i].astype(np.float32)
+
+
+@pytest.mark.parametrize('batch', [5, 129, 2048])
+def test_gomoku_batched_vs_torch_fp32(batch):
+    net, onet = build_board((9, 9, 9), 82, 8, 128, seed=0)
+    gen = np.random.RandomState(batch)
+    nref = min(batch, 24)                                  # torch-CPU fp32 reference on a subset of rows
+    obs = gen.randint(0, 2, size=(batch, 9, 9, 9)).astype(np.float32)
+    hid, pi, v = net.initial_inference_batch(torch.from_numpy(obs).cuda())
+    rows = np.sort(gen.choice(batch, size=nref, replace=False))
+    h_ref, pi_ref, v_ref = onet.initial_batch(obs[rows])
+    report('h0', net.hidden_to_reference(hid)[rows].cpu().numpy(), h_ref.numpy(), 0.03)
+    report('pi0', pi[rows].cpu().numpy(), pi_ref.numpy(), 0.03)
+    report('v0', v[rows].cpu().numpy(), v_ref.numpy(), 0.03)
+    act = gen.randint(0, 82, size=batch)
+    _, r, pi2, v2 = net.recurrent_inference_batch(hid, torch.from_numpy(act).cuda())
+    h2_ref, r_ref, pi2_ref, v2_ref = onet.recurrent_batch(h_ref, act[rows])
+    report('r', r[rows].cpu().numpy(), r_ref.numpy(), 0.03)
+    report('v1', v2[rows].cpu().numpy(), v2_ref.numpy(), 0.03)
+    report('pi1', pi2[rows].cpu().numpy(), pi2_ref.numpy(), 0.03)
+
+
+def test_gomoku_search_replays_bit_exact_in_oracle():
+    """Whole batched Gomoku search on the GPU with the tensor-core network; every tree, fed the
+    per-node (reward, value) the engine produced, is rebuilt bit-for-bit by the CPU oracle."""
+    import muzero_b200 as mz
+    net, onet = build_board((9, 9, 9), 82, 2, 32, seed=1)
+    cfg = mz.make_gomoku_config(use_tensorboard=False)
+    cfg.num_simulations = 60
+    B, A, S = 48, 82, 60
+    gen = np.random.RandomState(5)
+    obs = gen.randint(0, 2, size=(B, 9, 9, 9)).astype(np.int8)
+    mask = gen.rand(B, A) < 0.8
+    mask[:, -1] = True
+    streams = [np.random.RandomState(300 + t) for t in range(B)]
+    plan = mz.mcts.SearchPlan(net, cfg, B)
+    action, pi, rootv = mz.uct_search_batch(obs, net, cfg, 1.0, mask, 1, 2, rng=streams, plan=plan)
+    plan.pool.check_errors()
+    pi0 = plan.pi0.cpu().numpy()
+    for t in range(0, B, 4):
+        d = plan.pool.dump_tree(t)
+        rs = np.random.RandomState(300 + t)
+        stub = ReplayStub(pi0[t], d['R'][1:].astype(np.float32), d['value'][1:], d['parent'], d['move'])
+        a_o, pi_o, q_o, tr = orc.uct_search(obs[t].astype(np.float32), stub, 'cpu', cfg, 1.0, mask[t], 1, 2, False,
+                                            rng=rs, return_trace=True)
+        assert np.array_equal(tr.N, d['N']) and np.array_equal(bits(tr.W), bits(d['W']))
+        assert a_o == int(action[t]) and np.array_equal(bits(pi_o), bits(pi[t].cpu().numpy()))
+        assert bits(q_o)[0] == bits(rootv[t].item())[0]
+        assert rs.get_state()[2] == streams[t].get_state()[2]
+    # second search through the captured CUDA graph gives the same answer as the eager first one
+    streams2 = [np.random.RandomState(300 + t) for t in range(B)]
+    a2, pi2, q2 = mz.uct_search_batch(obs, net, cfg, 1.0, mask, 1, 2, rng=streams2, plan=plan)
+    assert torch.equal(a2, action) and torch.equal(pi2, pi) and torch.equal(q2, rootv)
