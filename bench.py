@@ -349,8 +349,10 @@ def run_engine_arm(args):
     names = ['select', 'recurrent', 'expand_backup']
     tot = {n: 0.0 for n in names}
     reps = max(1, min(args.steps, 3))
+    import ctypes as C
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.mz_net_profile_begin(eng['handle']))
         for _ in range(reps):
             plan.use_graph = False
             # root part eagerly, then instrumented simulation loop
@@ -377,6 +379,9 @@ def run_engine_arm(args):
                 for i, n in enumerate(names):
                     tot[n] += e[i].elapsed_time(e[i + 1])
             plan.use_graph = True
+        prof_ms = (C.c_double * 4)()
+        prof_n = (C.c_int64 * 4)()
+        _lib.check(lib.mz_net_profile_end(eng['handle'], prof_ms, prof_n))
     launches = reps * S
     avg_ms = {n: tot[n] / launches for n in names}
     share = {n: tot[n] / sum(tot.values()) for n in names}
@@ -403,11 +408,32 @@ def run_engine_arm(args):
                                   'frac': ach / tf_peak, 'reference_graph_flops': flops * B})
     roofline = dict(roof[dominant])
     roofline.update({'kernel': dominant, 'traffic': None, 'peak_source': peak_src})
+    if spec['kind'] != 'mlp' and prof_n[0] > 0:
+        # the dominant KERNEL is the tcgen05 3x3 convolution (33 launches per recurrent inference):
+        # algorithmic flops per launch = the reference graph's 128->128 3x3 conv over the H*W real
+        # positions of B boards; executed = the same over the (H+1)*(W+1) padded grid.
+        c, h, w = spec['net_kw']['input_shape']
+        hh, ww = (h, w) if spec['kind'] == 'board' else (6, 6)
+        planes = spec['net_kw']['num_planes']
+        per_pos = 2.0 * planes * planes * 9
+        conv_ms = prof_ms[0] / prof_n[0]
+        # initial-inference convs are inside the profile too (same shapes except the first layer)
+        alg = per_pos * hh * ww * B
+        exe = per_pos * (hh + 1) * (ww + 1) * B
+        ach = alg / (conv_ms * 1e-3) / 1e12
+        roofline = {'kernel': 'conv3x3_kernel (tcgen05.mma M128 N128 K16, TMEM accumulators)', 'bound': 'tensor',
+                    'achieved': ach, 'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': ach / tf_peak, 'traffic': None,
+                    'avg_launch_us': conv_ms * 1e3, 'launches_timed': int(prof_n[0]),
+                    'algorithmic_flops_per_launch': alg, 'executed_flops_per_launch': exe,
+                    'executed_tflops': exe / (conv_ms * 1e-3) / 1e12,
+                    'share_of_recurrent_inference': prof_ms[0] / max(1e-9, prof_ms[0] + prof_ms[1] + prof_ms[2]),
+                    'share_of_sim_loop': prof_ms[0] / max(1e-9, sum(tot.values())), 'peak_source': peak_src}
+        roof['head_kernel'] = {'avg_launch_us': 1e3 * prof_ms[1] / max(1, prof_n[1]), 'launches_timed': int(prof_n[1])}
 
     result = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
         'ms_per_step': ms_dev, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f64 tree statistics / f32 scores; network ' + ('f32' if spec['kind'] == 'mlp' else 'bf16 x bf16 -> f32'),
+        'dtype': 'f64 tree statistics / f32 scores; network ' + ('f32' if spec['kind'] == 'mlp' else 'fp16 x fp16 -> f32 (tcgen05)'),
         'data': 'synthetic',
         'config': {'workload': spec['label'], 'trees_per_gpu': B, 'simulations': S, 'num_actions': A,
                    'l2': 'flushed between timed iterations (256 MiB write)', 'mean_select_depth': mean_depth,

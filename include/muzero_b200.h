@@ -181,6 +181,13 @@ int mz_net_recurrent(mz_net* net, int32_t batch, const void* hidden_in, const in
                      const int32_t* action, void* hidden_out, const int32_t* dst_index,
                      float* reward, float* value, float* pi_probs, mz_stream stream);
 
+/* Per-kernel device timing of a net's launches (measurement aid for bench.py's roofline):
+ * between begin and end every kernel the net launches EAGERLY is bracketed by CUDA events on
+ * its stream; end synchronises and returns milliseconds and launch counts per kernel class
+ * {0: conv3x3 (tcgen05), 1: heads, 2: observation packing, 3: fused MLP}. */
+int mz_net_profile_begin(mz_net* net);
+int mz_net_profile_end(mz_net* net, double* ms_by_class /* [4] */, int64_t* launches_by_class /* [4] */);
+
 /* number of kernels the library has launched since load (bench's gpu_launches) */
 uint64_t mz_launch_count(void);
 

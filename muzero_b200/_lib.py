@@ -57,6 +57,8 @@ PROTOTYPES = {
     'mz_net_destroy': (C.c_int, [_P]),
     'mz_net_initial': (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P]),
     'mz_net_recurrent': (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'mz_net_profile_begin': (C.c_int, [_P]),
+    'mz_net_profile_end': (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     'mz_launch_count': (C.c_uint64, []),
 }
 

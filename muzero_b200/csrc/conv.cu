@@ -1,8 +1,8 @@
 // ResNet towers of MuZeroBoardGameNet / MuZeroAtariNet (network.py:273-574) on the
-// Blackwell tensor cores.
+// Blackwell tensor cores (fp16 x fp16 -> fp32).
 //
 // Data layout ("padded grid, channel-last"): a board's activation is
-//   [PB = (H+1)*(W+1) positions][C channels] bf16,   position p = y*(W+1) + x,
+//   [PB = (H+1)*(W+1) positions][C channels] fp16,   position p = y*(W+1) + x,
 // where column x == W and row y == H are a zero halo SHARED with the next row /
 // the next board.  Flattening boards back to back (P = b*PB + p) makes every 3x3
 // tap a constant row offset: tap (ky,kx) of output position P reads input position
@@ -25,9 +25,16 @@
 //     per-pixel channel min-max normalisation of util.py:31-36 fused here).
 #include "net.cuh"
 #include "umma.cuh"
+#include <cuda_fp16.h>
 
 namespace mz {
 using namespace umma;
+
+// Activations and folded weights are IEEE fp16 (10-bit mantissa; the hidden state is min-max
+// normalised to [0,1] and BatchNorm keeps tower activations O(1..100), far inside fp16 range;
+// conversions saturate instead of overflowing).  Same tensor-core rate as bf16, 8x finer rounding.
+typedef __half act_t;
+typedef __half2 act2_t;
 
 constexpr int kConvThreads = 192;
 constexpr int kWorkers = 128;
@@ -35,16 +42,16 @@ constexpr int kTileM = 256;     // positions per tile (two M=128 accumulators)
 constexpr int kStages = 4;
 
 struct ConvParams {
-  const __nv_bfloat16* in;        // [.. boards ..][PB][Cin_pad]
+  const act_t* in;        // [.. boards ..][PB][Cin_pad]
   const int32_t* in_index;        // board b lives in slot in_index[b] (nullptr: b)
-  const __nv_bfloat16* w;         // packed [9][chunks][chunk_g][N][8]
+  const act_t* w;         // packed [9][chunks][chunk_g][N][8]
   const float* bias;              // [N]
   const float* tab;               // [A][PB][N] per-action bias (dynamics conv0) or nullptr
   const int32_t* action;          // [B]
-  const __nv_bfloat16* residual;  // contiguous [Ptot][N] or nullptr
-  __nv_bfloat16* out;             // contiguous [Ptot][N] (relu'd) or nullptr
-  __nv_bfloat16* out_norm;        // contiguous, min-max normalised, or nullptr
-  __nv_bfloat16* out_slots;       // indexed slots, normalised, or nullptr
+  const act_t* residual;  // contiguous [Ptot][N] or nullptr
+  act_t* out;             // contiguous [Ptot][N] (relu'd) or nullptr
+  act_t* out_norm;        // contiguous, min-max normalised, or nullptr
+  act_t* out_slots;       // indexed slots, normalised, or nullptr
   const int32_t* out_index;
   int Ptot, PB, Wp, W, H, B;
   int cg;                         // input channel groups of 8 (Cin_pad / 8), even
@@ -62,7 +69,7 @@ __device__ __forceinline__ void split_pos(int P, const ConvParams& p, int& b, in
 }
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  act2_t t = __floats2half2_rn(fminf(fmaxf(a, -65504.0f), 65504.0f), fminf(fmaxf(b, -65504.0f), 65504.0f));
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
@@ -119,7 +126,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = instr_desc_bf16(128, (uint32_t)p.N);
+      const uint32_t idesc = instr_desc_f16(128, (uint32_t)p.N);
       const uint32_t a_lbo = (uint32_t)TP * 16, b_lbo = (uint32_t)p.N * 16;
       uint32_t it = 0;
       for (int i = 0; i < n_my; ++i) {
@@ -196,7 +203,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
         const bool valid = !hl;
         const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256 + j * 128);
         const float* tab = (p.tab && valid) ? p.tab + ((size_t)p.action[b] * p.PB + pos) * p.N : nullptr;
-        const __nv_bfloat16* res = (p.residual && valid) ? p.residual + (size_t)P * p.N : nullptr;
+        const act_t* res = (p.residual && valid) ? p.residual + (size_t)P * p.N : nullptr;
         float mn = INFINITY, mx = -INFINITY;
         for (int pass = 0; pass < (norm ? 2 : 1); ++pass) {
           float inv = 0.0f;
@@ -220,10 +227,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
 #pragma unroll
               for (int e = 0; e < 32; e += 8) {
                 const int4 r4 = *reinterpret_cast<const int4*>(res + c0 + e);
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r4);
+                const act2_t* h = reinterpret_cast<const act2_t*>(&r4);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                  const float2 f = __bfloat1622float2(h[u]);
+                  const float2 f = __half22float2(h[u]);
                   v[e + 2 * u] += f.x; v[e + 2 * u + 1] += f.y;
                 }
               }
@@ -289,7 +296,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
 // small SIMT kernels: observation packing, heads, weight repacking
 // ---------------------------------------------------------------------------
 // obs f32 [B][C][H][W] -> bf16 padded grid [B][PB][cpad]
-__global__ void pack_obs_kernel(const float* __restrict__ obs, __nv_bfloat16* __restrict__ out, int B, int C, int H,
+__global__ void pack_obs_kernel(const float* __restrict__ obs, act_t* __restrict__ out, int B, int C, int H,
                                 int W, int cpad) {
   const int Wp = W + 1, PB = (H + 1) * Wp;
   const size_t n = (size_t)B * PB * cpad;
@@ -300,7 +307,7 @@ __global__ void pack_obs_kernel(const float* __restrict__ obs, __nv_bfloat16* __
     const int y = pos / Wp, x = pos % Wp;
     float v = 0.0f;
     if (c < C && y < H && x < W) v = obs[(((size_t)b * C + c) * H + y) * W + x];
-    out[i] = __float2bfloat16(v);
+    out[i] = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
   }
 }
 
@@ -308,7 +315,7 @@ __global__ void pack_obs_kernel(const float* __restrict__ obs, __nv_bfloat16* __
 // transform: 0 = raw scalar (support 1), 1 = support->scalar (util.py:70-93), 2 = softmax.
 // One CTA of 128 threads per board.
 struct HeadParams {
-  const __nv_bfloat16* act;   // contiguous [B][PB][C]
+  const act_t* act;   // contiguous [B][PB][C]
   const float* w1;            // [mid][C]  (scaled)
   const float* b1;            // [mid]
   const float* w2;            // [out][mid*hw]
@@ -333,19 +340,19 @@ __global__ void __launch_bounds__(128) head_kernel(const HeadParams p) {
   float* f = hs;
   float* lg = hs + p.mid * hw;
   const int b = blockIdx.x;
-  const __nv_bfloat16* a = p.act + (size_t)b * PB * p.C;
+  const act_t* a = p.act + (size_t)b * PB * p.C;
   for (int i = threadIdx.x; i < p.mid * hw; i += blockDim.x) {
     const int m = i / hw, q = i % hw;
     const int y = q / p.W, x = q % p.W;
-    const __nv_bfloat16* row = a + (size_t)(y * Wp + x) * p.C;
+    const act_t* row = a + (size_t)(y * Wp + x) * p.C;
     const float* w = p.w1 + (size_t)m * p.C;
     float acc = 0.0f;
     for (int c = 0; c < p.C; c += 8) {
       const int4 r4 = *reinterpret_cast<const int4*>(row + c);
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r4);
+      const act2_t* h = reinterpret_cast<const act2_t*>(&r4);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const float2 v = __bfloat1622float2(h[u]);
+        const float2 v = __half22float2(h[u]);
         acc = fmaf(v.x, w[c + 2 * u], acc);
         acc = fmaf(v.y, w[c + 2 * u + 1], acc);
       }
@@ -406,7 +413,7 @@ __global__ void bn_fold_kernel(const float* g, const float* beta, const float* m
 // conv weight [N][cin_total][3][3] (first `cin` input channels) * scale[n] -> packed bf16
 // [9 taps][chunks][chunk_g][N][8]
 __global__ void pack_conv_kernel(const float* __restrict__ w, const float* __restrict__ scale,
-                                 __nv_bfloat16* __restrict__ out, int N, int cin, int cin_total, int cg) {
+                                 act_t* __restrict__ out, int N, int cin, int cin_total, int cg) {
   const int chunk_g = cg < 8 ? cg : 8;
   const size_t total = (size_t)9 * cg * N * 8;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -419,7 +426,7 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, const float* __res
     const int c = (ch * chunk_g + gl) * 8 + e;
     float v = 0.0f;
     if (c < cin) v = w[(((size_t)n * cin_total + c) * 3 + tap / 3) * 3 + tap % 3] * scale[n];
-    out[i] = __float2bfloat16(v);
+    out[i] = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
   }
 }
 
@@ -462,7 +469,7 @@ __global__ void action_table_kernel(const float* __restrict__ w, const float* __
 // host side
 // ---------------------------------------------------------------------------
 struct ConvLayer {
-  const __nv_bfloat16* w;
+  const act_t* w;
   const float* bias;
   int cg;
 };
@@ -479,11 +486,11 @@ struct ConvNet : NetImpl {
   ConvLayer rep_blocks[64], dyn_blocks[64], pred_blocks[64];   // 2 per block
   const float* tab;
   Head h_reward, h_policy, h_value;
-  __nv_bfloat16 *xobs, *b0, *b1, *b2, *b3;
+  act_t *xobs, *b0, *b1, *b2, *b3;
 
-  int launch_conv(const ConvLayer& L, const __nv_bfloat16* in, const int32_t* in_index, int batch, const float* tab_,
-                  const int32_t* action, const __nv_bfloat16* residual, __nv_bfloat16* out, __nv_bfloat16* out_norm,
-                  __nv_bfloat16* out_slots, const int32_t* out_index, cudaStream_t st) {
+  int launch_conv(const ConvLayer& L, const act_t* in, const int32_t* in_index, int batch, const float* tab_,
+                  const int32_t* action, const act_t* residual, act_t* out, act_t* out_norm,
+                  act_t* out_slots, const int32_t* out_index, cudaStream_t st) {
     ConvParams p;
     p.in = in; p.in_index = in_index; p.w = L.w; p.bias = L.bias; p.tab = tab_; p.action = action;
     p.residual = residual; p.out = out; p.out_norm = out_norm; p.out_slots = out_slots; p.out_index = out_index;
@@ -493,7 +500,9 @@ struct ConvNet : NetImpl {
     p.TP = (kTileM + 2 * (Wp + 1)) | 1;
     const size_t smem = conv_smem(L.cg);
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    prof_mark(kProfConv, st);
     conv3x3_kernel<<<grid, kConvThreads, smem, st>>>(p);
+    prof_mark(-1, st);
     MZ_LAUNCH_CHECK("conv3x3_kernel");
     return MZ_OK;
   }
@@ -503,12 +512,14 @@ struct ConvNet : NetImpl {
     size_t a = (((size_t)2 * cg * TP * 16) + 127) & ~(size_t)127;
     return a + (size_t)kStages * chunk_g * C * 16 + 16 * 8 + 16 + (size_t)C * 4 + 64;
   }
-  int launch_head(const Head& h, const __nv_bfloat16* act, int batch, float* dst, cudaStream_t st) {
+  int launch_head(const Head& h, const act_t* act, int batch, float* dst, cudaStream_t st) {
     HeadParams p;
     p.act = act; p.w1 = h.w1; p.b1 = h.b1; p.w2 = h.w2; p.b2 = h.b2; p.dst = dst;
     p.C = C; p.H = H; p.W = W; p.mid = h.mid; p.out = h.out; p.kind = h.kind;
     const size_t smem = ((size_t)h.mid * H * W + h.out) * 4;
+    prof_mark(kProfHead, st);
     head_kernel<<<batch, 128, smem, st>>>(p);
+    prof_mark(-1, st);
     MZ_LAUNCH_CHECK("head_kernel");
     return MZ_OK;
   }
@@ -516,17 +527,17 @@ struct ConvNet : NetImpl {
   // [first conv] -> residual blocks; the LAST layer optionally also emits the min-max normalised
   // state (contiguous copy and/or indexed slots).  *final_buf = buffer holding the raw (ReLU'd)
   // tower output, unless want_raw is false and the last layer normalises (then it is not written).
-  int tower(const ConvLayer* first, const ConvLayer* blk, const __nv_bfloat16* in, const int32_t* in_index,
-            const float* tab_, const int32_t* action, int batch, bool want_raw, __nv_bfloat16* norm_out,
-            __nv_bfloat16* slots, const int32_t* out_index, cudaStream_t st, __nv_bfloat16** final_buf) {
-    const __nv_bfloat16* cur = in;
+  int tower(const ConvLayer* first, const ConvLayer* blk, const act_t* in, const int32_t* in_index,
+            const float* tab_, const int32_t* action, int batch, bool want_raw, act_t* norm_out,
+            act_t* slots, const int32_t* out_index, cudaStream_t st, act_t** final_buf) {
+    const act_t* cur = in;
     const int32_t* cur_index = in_index;
-    __nv_bfloat16* pp[2] = {b0, b1};
+    act_t* pp[2] = {b0, b1};
     int which = 0, rc;
     const bool normalise = (norm_out != nullptr) || (slots != nullptr);
     if (first) {
       const bool last = (blocks == 0);
-      __nv_bfloat16* dst = pp[which];
+      act_t* dst = pp[which];
       rc = launch_conv(*first, cur, cur_index, batch, tab_, action, nullptr,
                        (last && normalise && !want_raw) ? nullptr : dst, last ? norm_out : nullptr,
                        last ? slots : nullptr, out_index, st);
@@ -538,7 +549,7 @@ struct ConvNet : NetImpl {
       rc = launch_conv(blk[2 * i], cur, cur_index, batch, nullptr, nullptr, nullptr, b2, nullptr, nullptr, nullptr, st);
       if (rc) return rc;
       if (cur_index != nullptr) { set_error("internal: residual input must be contiguous"); return MZ_EINVAL; }
-      __nv_bfloat16* dst = pp[which];
+      act_t* dst = pp[which];
       if (dst == cur) dst = pp[which ^ 1];
       rc = launch_conv(blk[2 * i + 1], b2, nullptr, batch, nullptr, nullptr, cur,
                        (last && normalise && !want_raw) ? nullptr : dst, last ? norm_out : nullptr,
@@ -546,24 +557,26 @@ struct ConvNet : NetImpl {
       if (rc) return rc;
       cur = dst; which ^= 1;
     }
-    *final_buf = const_cast<__nv_bfloat16*>(cur);
+    *final_buf = const_cast<act_t*>(cur);
     return MZ_OK;
   }
 
   int initial(int batch, const float* obs, void* hidden_out, const int32_t* dst_index, float* pi_probs, float* value,
               cudaStream_t st) override {
+    prof_mark(kProfPack, st);
     pack_obs_kernel<<<num_sms * 4, 256, 0, st>>>(obs, xobs, batch, cfg.in_channels, H, W, in_cg * 8);
+    prof_mark(-1, st);
     MZ_LAUNCH_CHECK("pack_obs_kernel");
-    __nv_bfloat16* fin;
+    act_t* fin;
     // representation: raw output is not needed, normalised goes to b3 (for the prediction tower) and the slots
-    int rc = tower(&rep0, rep_blocks, xobs, nullptr, nullptr, nullptr, batch, false, b3, (__nv_bfloat16*)hidden_out,
+    int rc = tower(&rep0, rep_blocks, xobs, nullptr, nullptr, nullptr, batch, false, b3, (act_t*)hidden_out,
                    dst_index, st, &fin);
     if (rc) return rc;
     return predict(batch, pi_probs, value, st);
   }
 
   int predict(int batch, float* pi_probs, float* value, cudaStream_t st) {
-    __nv_bfloat16* fin;
+    act_t* fin;
     int rc = tower(nullptr, pred_blocks, b3, nullptr, nullptr, nullptr, batch, true, nullptr, nullptr, nullptr, st, &fin);
     if (rc) return rc;
     if (pi_probs) {
@@ -576,10 +589,10 @@ struct ConvNet : NetImpl {
   int recurrent(int batch, const void* hidden_in, const int32_t* src_index, const int32_t* action, void* hidden_out,
                 const int32_t* dst_index, float* reward_out, float* value_out, float* pi_probs,
                 cudaStream_t st) override {
-    __nv_bfloat16* fin;
+    act_t* fin;
     // dynamics: raw output (for the reward head) in a ping-pong buffer, normalised copy in b3 + the slots
-    int rc = tower(&dyn0, dyn_blocks, (const __nv_bfloat16*)hidden_in, src_index, tab, action, batch, true, b3,
-                   (__nv_bfloat16*)hidden_out, dst_index, st, &fin);
+    int rc = tower(&dyn0, dyn_blocks, (const act_t*)hidden_in, src_index, tab, action, batch, true, b3,
+                   (act_t*)hidden_out, dst_index, st, &fin);
     if (rc) return rc;
     rc = launch_head(h_reward, fin, batch, reward_out, st);     // reward head reads the UN-normalised state
     if (rc) return rc;
@@ -666,7 +679,7 @@ int conv_create(const mz_net_config& c, const float* const* w, int nw, int max_b
     float* bias = (float*)take((size_t)N * 4);
     bn_fold_kernel<<<(N + 127) / 128, 128>>>(g, beta, mean, var, scale, bias, N);
     MZ_LAUNCH_CHECK("bn_fold_kernel");
-    __nv_bfloat16* wp = (__nv_bfloat16*)take((size_t)9 * cg * N * 16);
+    act_t* wp = (act_t*)take((size_t)9 * cg * N * 16);
     pack_conv_kernel<<<256, 256>>>(cw, scale, wp, N, cin, cin_total, cg);
     MZ_LAUNCH_CHECK("pack_conv_kernel");
     L->w = wp; L->bias = bias; L->cg = cg;
@@ -717,12 +730,12 @@ int conv_create(const mz_net_config& c, const float* const* w, int nw, int max_b
   MZ_TRY(fold_head(2, A, 2, &net->h_policy));
   MZ_TRY(fold_head(1, c.value_support, c.value_support == 1 ? 0 : 1, &net->h_value));
 #undef MZ_TRY
-  net->xobs = (__nv_bfloat16*)take((size_t)max_batch * net->PB * net->in_cg * 16);
+  net->xobs = (act_t*)take((size_t)max_batch * net->PB * net->in_cg * 16);
   const size_t act_bytes = (size_t)max_batch * net->PB * N * 2;
-  net->b0 = (__nv_bfloat16*)take(act_bytes);
-  net->b1 = (__nv_bfloat16*)take(act_bytes);
-  net->b2 = (__nv_bfloat16*)take(act_bytes);
-  net->b3 = (__nv_bfloat16*)take(act_bytes);
+  net->b0 = (act_t*)take(act_bytes);
+  net->b1 = (act_t*)take(act_bytes);
+  net->b2 = (act_t*)take(act_bytes);
+  net->b3 = (act_t*)take(act_bytes);
   if ((size_t)(p - (char*)arena) > arena_bytes) {
     set_error("internal: net arena overrun (%zu > %zu)", (size_t)(p - (char*)arena), arena_bytes);
     delete net;

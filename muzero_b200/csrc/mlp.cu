@@ -288,15 +288,19 @@ struct MlpNet : NetImpl {
 
   int initial(int batch, const float* obs, void* hidden_out, const int32_t* dst_index, float* pi_probs,
               float* value, cudaStream_t st) override {
+    prof_mark(kProfMlp, st);
     mlp_initial_kernel<<<(batch + kRows - 1) / kRows, kThreads, smem, st>>>(d, batch, obs, (float*)hidden_out,
                                                                            dst_index, pi_probs, value);
+    prof_mark(-1, st);
     MZ_LAUNCH_CHECK("mlp_initial_kernel");
     return MZ_OK;
   }
   int recurrent(int batch, const void* hidden_in, const int32_t* src_index, const int32_t* action, void* hidden_out,
                 const int32_t* dst_index, float* reward, float* value, float* pi_probs, cudaStream_t st) override {
+    prof_mark(kProfMlp, st);
     mlp_recurrent_kernel<<<(batch + kRows - 1) / kRows, kThreads, smem, st>>>(
         d, batch, (const float*)hidden_in, src_index, action, (float*)hidden_out, dst_index, reward, value, pi_probs);
+    prof_mark(-1, st);
     MZ_LAUNCH_CHECK("mlp_recurrent_kernel");
     return MZ_OK;
   }

@@ -69,3 +69,31 @@ extern "C" int mz_net_recurrent(mz_net* net, int32_t batch, const void* hidden_i
   return net->impl->recurrent(batch, hidden_in, src_index, action, hidden_out, dst_index, reward, value, pi_probs,
                               (cudaStream_t)stream);
 }
+
+extern "C" int mz_net_profile_begin(mz_net* net) {
+  MZ_CHECK_ARG(net, "NULL argument");
+  NetImpl* n = net->impl;
+  for (cudaEvent_t e : n->prof_ev) cudaEventDestroy(e);
+  n->prof_ev.clear();
+  n->prof_cls.clear();
+  n->profiling = true;
+  return MZ_OK;
+}
+
+extern "C" int mz_net_profile_end(mz_net* net, double* ms_by_class, int64_t* launches_by_class) {
+  MZ_CHECK_ARG(net && ms_by_class && launches_by_class, "NULL argument");
+  NetImpl* n = net->impl;
+  n->profiling = false;
+  MZ_CUDA(cudaDeviceSynchronize());
+  for (int c = 0; c < kProfClasses; ++c) { ms_by_class[c] = 0.0; launches_by_class[c] = 0; }
+  for (size_t i = 0; i < n->prof_cls.size(); ++i) {
+    float ms = 0.0f;
+    MZ_CUDA(cudaEventElapsedTime(&ms, n->prof_ev[2 * i], n->prof_ev[2 * i + 1]));
+    ms_by_class[n->prof_cls[i]] += ms;
+    launches_by_class[n->prof_cls[i]] += 1;
+  }
+  for (cudaEvent_t e : n->prof_ev) cudaEventDestroy(e);
+  n->prof_ev.clear();
+  n->prof_cls.clear();
+  return MZ_OK;
+}

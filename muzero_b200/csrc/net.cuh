@@ -1,11 +1,29 @@
 // Internal interface every network family implements behind the mz_net handle.
 #pragma once
 #include "common.cuh"
+#include <vector>
 
 namespace mz {
 
+// Optional per-kernel timing (mz_net_profile_begin/end): CUDA events recorded on the launching
+// stream around every kernel the net launches, summed per kernel class.  Eager launches only.
+enum ProfClass { kProfConv = 0, kProfHead = 1, kProfPack = 2, kProfMlp = 3, kProfClasses = 4 };
+
 struct NetImpl {
-  virtual ~NetImpl() {}
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_ev;     // pairs (begin, end)
+  std::vector<int> prof_cls;
+  void prof_mark(int cls, cudaStream_t st) {
+    if (!profiling) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    prof_ev.push_back(e);
+    if (cls >= 0) prof_cls.push_back(cls);
+  }
+  virtual ~NetImpl() {
+    for (cudaEvent_t e : prof_ev) cudaEventDestroy(e);
+  }
   virtual int initial(int batch, const float* obs, void* hidden_out, const int32_t* dst_index, float* pi_probs,
                       float* value, cudaStream_t st) = 0;
   virtual int recurrent(int batch, const void* hidden_in, const int32_t* src_index, const int32_t* action,

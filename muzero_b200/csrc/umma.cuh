@@ -94,6 +94,10 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
 __host__ __device__ constexpr uint32_t instr_desc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
+// same with FP16 x FP16 operands (a_format = b_format = 0)
+__host__ __device__ constexpr uint32_t instr_desc_f16(uint32_t M, uint32_t N) {
+  return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 
 // D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread on behalf of the CTA
 __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
