@@ -73,6 +73,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+template <int kN>
 __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -167,110 +168,131 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
     const int cpp = p.cg;                    // 16-byte chunks per position
     const int cin = p.cg * 8;
 
-    auto load_tile = [&](int tile, int buf) {
+    // Activation tile -> shared memory with cp.async (LDGSTS): every 16-byte chunk of the tile is
+    // in flight at once (no register staging, zero-fill for halo / out-of-range positions), so
+    // the load costs one memory latency instead of one per chunk.  Thread -> fixed channel group
+    // g, positions q0, q0+step, ...: consecutive threads read one position's contiguous channels.
+    const int ld_g = wt % cpp, ld_q0 = wt / cpp, ld_step = kWorkers / cpp;
+    auto issue_load = [&](int tile, int buf) {
       const int m0 = tile * kTileM;
-      unsigned char* dst = sA + (size_t)buf * a_bytes;
-      const int total = (kTileM + 2 * halo) * cpp;
-      for (int idx = wt; idx < total; idx += kWorkers) {
-        const int q = idx / cpp, g = idx - q * cpp;
+      const uint32_t dst = smem_u32(sA) + (uint32_t)buf * a_bytes + (uint32_t)ld_g * TP * 16;
+      const int nq = kTileM + 2 * halo;
+      for (int q = ld_q0; q < nq; q += ld_step) {
         const int P = m0 - halo + q;
-        int4 v = make_int4(0, 0, 0, 0);
+        const act_t* src = p.in;
+        uint32_t nbytes = 0;
         if (P >= 0 && P < p.Ptot) {
           int b, pos; bool hl;
           split_pos(P, p, b, pos, hl);
           if (!hl) {
             const size_t board = p.in_index ? (size_t)p.in_index[b] : (size_t)b;
-            v = *reinterpret_cast<const int4*>(p.in + (board * p.PB + pos) * cin + g * 8);
+            src = p.in + (board * p.PB + pos) * cin + ld_g * 8;
+            nbytes = 16;
           }
         }
-        *reinterpret_cast<int4*>(dst + ((size_t)g * TP + q) * 16) = v;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)q * 16), "l"(src), "r"(nbytes)
+                     : "memory");
       }
+    };
+    auto finish_load = [&](int buf) {
+      asm volatile("cp.async.wait_all;" ::: "memory");
       fence_proxy_async();
       mbar_arrive(&a_full[buf]);
+    };
+    auto wait_acc = [&](int k) {
+      mbar_wait(&mma_done[k & 1], (uint32_t)((k >> 1) & 1));
+      tc_fence_after();
     };
 
     auto epilogue = [&](int k) {
       const int buf = k & 1;
-      const uint32_t ph = (k >> 1) & 1;
       const int tile = (int)blockIdx.x + k * (int)gridDim.x;
-      mbar_wait(&mma_done[buf], ph);
-      tc_fence_after();
       const bool norm = (p.out_norm != nullptr) || (p.out_slots != nullptr);
+#pragma unroll 1
       for (int j = 0; j < 2; ++j) {
         const int P = tile * kTileM + j * 128 + quad * 32 + lane;
         int b = 0, pos = 0; bool hl = true;
         if (P < p.Ptot) split_pos(P, p, b, pos, hl);
         const bool valid = !hl;
         const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256 + j * 128);
-        const float* tab = (p.tab && valid) ? p.tab + ((size_t)p.action[b] * p.PB + pos) * p.N : nullptr;
-        const act_t* res = (p.residual && valid) ? p.residual + (size_t)P * p.N : nullptr;
+        const float* tab = (p.tab && valid) ? p.tab + ((size_t)p.action[b] * p.PB + pos) * kN : nullptr;
+        // the whole residual row is requested up front: one memory latency per row, not per chunk
+        int4 rres[kN / 8];
+        const bool has_res = (p.residual != nullptr) && valid;
+        if (has_res) {
+          const int4* rp = reinterpret_cast<const int4*>(p.residual + (size_t)P * kN);
+#pragma unroll
+          for (int u = 0; u < kN / 8; ++u) rres[u] = rp[u];
+        } else {
+#pragma unroll
+          for (int u = 0; u < kN / 8; ++u) rres[u] = make_int4(0, 0, 0, 0);
+        }
         float mn = INFINITY, mx = -INFINITY;
+#pragma unroll 1
         for (int pass = 0; pass < (norm ? 2 : 1); ++pass) {
           float inv = 0.0f;
           if (pass == 1) inv = 1.0f / ((mx - mn) + 1e-8f);
-          for (int c0 = 0; c0 < p.N; c0 += 32) {
+#pragma unroll
+          for (int c0 = 0; c0 < kN; c0 += 32) {
             uint32_t r[32];
             tmem_ld32(taddr + c0, r);          // .sync.aligned: the whole warp executes it, valid row or not
             tmem_ld_wait();
             if (valid) {
-            float v[32];
+              float v[32];
 #pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]) + s_bias[c0 + e];
-            if (tab) {
+              for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]) + s_bias[c0 + e];
+              if (tab) {
 #pragma unroll
-              for (int e = 0; e < 32; e += 4) {
-                const float4 t4 = *reinterpret_cast<const float4*>(tab + c0 + e);
-                v[e] += t4.x; v[e + 1] += t4.y; v[e + 2] += t4.z; v[e + 3] += t4.w;
+                for (int e = 0; e < 32; e += 4) {
+                  const float4 t4 = *reinterpret_cast<const float4*>(tab + c0 + e);
+                  v[e] += t4.x; v[e + 1] += t4.y; v[e + 2] += t4.z; v[e + 3] += t4.w;
+                }
               }
-            }
-            if (res) {
 #pragma unroll
               for (int e = 0; e < 32; e += 8) {
-                const int4 r4 = *reinterpret_cast<const int4*>(res + c0 + e);
-                const act2_t* h = reinterpret_cast<const act2_t*>(&r4);
+                const act2_t* h = reinterpret_cast<const act2_t*>(&rres[(c0 + e) / 8]);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                   const float2 f = __half22float2(h[u]);
                   v[e + 2 * u] += f.x; v[e + 2 * u + 1] += f.y;
                 }
               }
-            }
-            if (p.relu) {
+              if (p.relu) {
 #pragma unroll
-              for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.0f);
-            }
-            if (pass == 0) {
-              if (norm) {
-#pragma unroll
-                for (int e = 0; e < 32; ++e) { mn = fminf(mn, v[e]); mx = fmaxf(mx, v[e]); }
+                for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.0f);
               }
-              if (p.out) {
-                int4* o = reinterpret_cast<int4*>(p.out + (size_t)P * p.N + c0);
+              if (pass == 0) {
+                if (norm) {
+#pragma unroll
+                  for (int e = 0; e < 32; ++e) { mn = fminf(mn, v[e]); mx = fmaxf(mx, v[e]); }
+                }
+                if (p.out) {
+                  int4* o = reinterpret_cast<int4*>(p.out + (size_t)P * kN + c0);
+#pragma unroll
+                  for (int e = 0; e < 32; e += 8)
+                    o[e / 8] = make_int4((int)pack2(v[e], v[e + 1]), (int)pack2(v[e + 2], v[e + 3]),
+                                         (int)pack2(v[e + 4], v[e + 5]), (int)pack2(v[e + 6], v[e + 7]));
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) v[e] = (v[e] - mn) * inv;
+                int4 o4[4];
 #pragma unroll
                 for (int e = 0; e < 32; e += 8)
-                  o[e / 8] = make_int4((int)pack2(v[e], v[e + 1]), (int)pack2(v[e + 2], v[e + 3]),
-                                       (int)pack2(v[e + 4], v[e + 5]), (int)pack2(v[e + 6], v[e + 7]));
+                  o4[e / 8] = make_int4((int)pack2(v[e], v[e + 1]), (int)pack2(v[e + 2], v[e + 3]),
+                                        (int)pack2(v[e + 4], v[e + 5]), (int)pack2(v[e + 6], v[e + 7]));
+                if (p.out_norm) {
+                  int4* o = reinterpret_cast<int4*>(p.out_norm + (size_t)P * kN + c0);
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) o[u] = o4[u];
+                }
+                if (p.out_slots) {
+                  const size_t board = p.out_index ? (size_t)p.out_index[b] : (size_t)b;
+                  int4* o = reinterpret_cast<int4*>(p.out_slots + (board * p.PB + pos) * kN + c0);
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) o[u] = o4[u];
+                }
               }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 32; ++e) v[e] = (v[e] - mn) * inv;
-              int4 o4[4];
-#pragma unroll
-              for (int e = 0; e < 32; e += 8)
-                o4[e / 8] = make_int4((int)pack2(v[e], v[e + 1]), (int)pack2(v[e + 2], v[e + 3]),
-                                      (int)pack2(v[e + 4], v[e + 5]), (int)pack2(v[e + 6], v[e + 7]));
-              if (p.out_norm) {
-                int4* o = reinterpret_cast<int4*>(p.out_norm + (size_t)P * p.N + c0);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) o[u] = o4[u];
-              }
-              if (p.out_slots) {
-                const size_t board = p.out_index ? (size_t)p.out_index[b] : (size_t)b;
-                int4* o = reinterpret_cast<int4*>(p.out_slots + (board * p.PB + pos) * p.N + c0);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) o[u] = o4[u];
-              }
-            }
             }  // valid
             __syncwarp();
           }
@@ -280,12 +302,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
       mbar_arrive(&acc_empty[buf]);
     };
 
-    if (n_my > 0) load_tile((int)blockIdx.x, 0);
+    // while the tensor core works on tile i: drain tile i-1's accumulators and fetch tile i+1
+    if (n_my > 0) { issue_load((int)blockIdx.x, 0); finish_load(0); }
     for (int i = 0; i < n_my; ++i) {
+      const bool have_next = i + 1 < n_my;
+      if (i >= 1) wait_acc(i - 1);          // MMAs of tile i-1 done: its accumulators are ready and its
+                                            // activation buffer (the one tile i+1 goes to) is free
+      if (have_next) issue_load((int)blockIdx.x + (i + 1) * (int)gridDim.x, (i + 1) & 1);
       if (i >= 1) epilogue(i - 1);
-      if (i + 1 < n_my) load_tile((int)blockIdx.x + (i + 1) * (int)gridDim.x, (i + 1) & 1);
+      if (have_next) finish_load((i + 1) & 1);
     }
-    if (n_my > 0) epilogue(n_my - 1);
+    if (n_my > 0) { wait_acc(n_my - 1); epilogue(n_my - 1); }
   }
   tc_fence_before();
   __syncthreads();
@@ -501,7 +528,9 @@ struct ConvNet : NetImpl {
     const size_t smem = conv_smem(L.cg);
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
     prof_mark(kProfConv, st);
-    conv3x3_kernel<<<grid, kConvThreads, smem, st>>>(p);
+    if (C == 128) conv3x3_kernel<128><<<grid, kConvThreads, smem, st>>>(p);
+    else if (C == 64) conv3x3_kernel<64><<<grid, kConvThreads, smem, st>>>(p);
+    else conv3x3_kernel<32><<<grid, kConvThreads, smem, st>>>(p);
     prof_mark(-1, st);
     MZ_LAUNCH_CHECK("conv3x3_kernel");
     return MZ_OK;
@@ -749,7 +778,9 @@ int conv_create(const mz_net_config& c, const float* const* w, int nw, int max_b
     delete net;
     return MZ_EINVAL;
   }
-  e = cudaFuncSetAttribute(conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+  e = cudaFuncSetAttribute(conv3x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
   if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); delete net; return MZ_ECUDA; }
   *out = net;
   return MZ_OK;
