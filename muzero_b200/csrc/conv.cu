@@ -21,8 +21,8 @@
 //     per tile, double-buffered across tiles so that epilogue(i-1) and load(i+1)
 //     overlap mma(i);
 //   - warp roles: warp 0 weight producer, warp 1 MMA issuer (+TMEM owner), warps 2-5
-//     activation loaders + epilogue (bias / action-bias table / residual / ReLU /
-//     per-pixel channel min-max normalisation of util.py:31-36 fused here).
+//     epilogue (bias / action-bias table / residual / ReLU / per-pixel channel min-max
+//     normalisation of util.py:31-36 fused here), warps 6-9 activation loaders (cp.async).
 #include "net.cuh"
 #include "umma.cuh"
 #include <cuda_fp16.h>
@@ -36,7 +36,7 @@ using namespace umma;
 typedef __half act_t;
 typedef __half2 act2_t;
 
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 320;   // producer, MMA, 4 epilogue warps, 4 loader warps
 constexpr int kWorkers = 128;
 constexpr int kTileM = 256;     // positions per tile (two M=128 accumulators)
 constexpr int kStages = 4;
@@ -69,7 +69,7 @@ __device__ __forceinline__ void split_pos(int P, const ConvParams& p, int& b, in
 }
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
-  act2_t t = __floats2half2_rn(fminf(fmaxf(a, -65504.0f), 65504.0f), fminf(fmaxf(b, -65504.0f), 65504.0f));
+  act2_t t = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
@@ -93,7 +93,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
   uint64_t* mma_done = a_full + 2;         // [2]
   uint64_t* acc_empty = mma_done + 2;      // [2]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* s_bias = reinterpret_cast<float*>(tmem_holder + 2);            // [N]
+  float* s_bias = reinterpret_cast<float*>(tmem_holder + 4);            // [N], 16-byte aligned
+  int* s_row = reinterpret_cast<int*>(s_bias + p.N);                    // [TP] source row per tile position
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
@@ -161,53 +162,55 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
         commit(&mma_done[buf]);
       }
     }
-  } else {
-    // ------------------------------------------------ workers: activation loads + epilogue
-    const int wt = tid - 64;                 // 0..127
-    const int quad = warp & 3;               // TMEM lane quadrant this warp may read
+  } else if (warp >= 6) {
+    // ------------------------------------------------ loaders (warps 6-9): activation tile -> smem
+    // cp.async (LDGSTS): every 16-byte chunk of the tile is in flight at once, zero-fill for halo /
+    // out-of-range positions.  Per tile the 128 threads first resolve each tile position to its
+    // source row (board slot * PB + position, or -1) into a small smem table, so the chunk loop
+    // carries no integer divisions.  Thread -> fixed channel group g, positions q0, q0+step, ...
+    const int lt = tid - 192;                // 0..127
     const int cpp = p.cg;                    // 16-byte chunks per position
     const int cin = p.cg * 8;
-
-    // Activation tile -> shared memory with cp.async (LDGSTS): every 16-byte chunk of the tile is
-    // in flight at once (no register staging, zero-fill for halo / out-of-range positions), so
-    // the load costs one memory latency instead of one per chunk.  Thread -> fixed channel group
-    // g, positions q0, q0+step, ...: consecutive threads read one position's contiguous channels.
-    const int ld_g = wt % cpp, ld_q0 = wt / cpp, ld_step = kWorkers / cpp;
-    auto issue_load = [&](int tile, int buf) {
-      const int m0 = tile * kTileM;
-      const uint32_t dst = smem_u32(sA) + (uint32_t)buf * a_bytes + (uint32_t)ld_g * TP * 16;
-      const int nq = kTileM + 2 * halo;
-      for (int q = ld_q0; q < nq; q += ld_step) {
+    const int ld_g = lt % cpp, ld_q0 = lt / cpp, ld_step = kWorkers / cpp;
+    const int nq = kTileM + 2 * halo;
+    for (int i = 0; i < n_my; ++i) {
+      const int buf = i & 1;
+      const int m0 = ((int)blockIdx.x + i * (int)gridDim.x) * kTileM;
+      for (int q = lt; q < nq; q += kWorkers) {
         const int P = m0 - halo + q;
-        const act_t* src = p.in;
-        uint32_t nbytes = 0;
+        int row = -1;
         if (P >= 0 && P < p.Ptot) {
           int b, pos; bool hl;
           split_pos(P, p, b, pos, hl);
-          if (!hl) {
-            const size_t board = p.in_index ? (size_t)p.in_index[b] : (size_t)b;
-            src = p.in + (board * p.PB + pos) * cin + ld_g * 8;
-            nbytes = 16;
-          }
+          if (!hl) row = (p.in_index ? p.in_index[b] : b) * p.PB + pos;
         }
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)q * 16), "l"(src), "r"(nbytes)
+        s_row[q] = row;
+      }
+      // the buffer was last read by the MMAs of tile i-2
+      if (i >= 2) mbar_wait(&mma_done[buf], (uint32_t)(((i - 2) >> 1) & 1));
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const uint32_t dst = smem_u32(sA) + (uint32_t)buf * a_bytes + (uint32_t)ld_g * TP * 16;
+      for (int q = ld_q0; q < nq; q += ld_step) {
+        const int row = s_row[q];
+        const act_t* src = row >= 0 ? p.in + ((size_t)row * cin + ld_g * 8) : p.in;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)q * 16), "l"(src),
+                     "r"(row >= 0 ? 16u : 0u)
                      : "memory");
       }
-    };
-    auto finish_load = [&](int buf) {
       asm volatile("cp.async.wait_all;" ::: "memory");
       fence_proxy_async();
       mbar_arrive(&a_full[buf]);
-    };
-    auto wait_acc = [&](int k) {
-      mbar_wait(&mma_done[k & 1], (uint32_t)((k >> 1) & 1));
-      tc_fence_after();
-    };
-
-    auto epilogue = [&](int k) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");      // table is rewritten next iteration
+    }
+  } else {
+    // ------------------------------------------------ epilogue (warps 2-5): TMEM -> registers -> global
+    const int quad = warp & 3;               // TMEM lane quadrant this warp may read
+    const bool norm = (p.out_norm != nullptr) || (p.out_slots != nullptr);
+    for (int k = 0; k < n_my; ++k) {
       const int buf = k & 1;
       const int tile = (int)blockIdx.x + k * (int)gridDim.x;
-      const bool norm = (p.out_norm != nullptr) || (p.out_slots != nullptr);
+      mbar_wait(&mma_done[buf], (uint32_t)((k >> 1) & 1));
+      tc_fence_after();
 #pragma unroll 1
       for (int j = 0; j < 2; ++j) {
         const int P = tile * kTileM + j * 128 + quad * 32 + lane;
@@ -216,31 +219,30 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
         const bool valid = !hl;
         const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256 + j * 128);
         const float* tab = (p.tab && valid) ? p.tab + ((size_t)p.action[b] * p.PB + pos) * kN : nullptr;
-        // the whole residual row is requested up front: one memory latency per row, not per chunk
-        int4 rres[kN / 8];
         const bool has_res = (p.residual != nullptr) && valid;
-        if (has_res) {
-          const int4* rp = reinterpret_cast<const int4*>(p.residual + (size_t)P * kN);
-#pragma unroll
-          for (int u = 0; u < kN / 8; ++u) rres[u] = rp[u];
-        } else {
-#pragma unroll
-          for (int u = 0; u < kN / 8; ++u) rres[u] = make_int4(0, 0, 0, 0);
-        }
+        const int4* rp = reinterpret_cast<const int4*>(p.residual + (size_t)(has_res ? P : 0) * kN);
         float mn = INFINITY, mx = -INFINITY;
 #pragma unroll 1
         for (int pass = 0; pass < (norm ? 2 : 1); ++pass) {
           float inv = 0.0f;
           if (pass == 1) inv = 1.0f / ((mx - mn) + 1e-8f);
-#pragma unroll
+#pragma unroll 1
           for (int c0 = 0; c0 < kN; c0 += 32) {
+            // this chunk's residual (4 x 16 B) is requested before the TMEM load so both latencies overlap
+            int4 rres[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) rres[u] = has_res ? rp[c0 / 8 + u] : make_int4(0, 0, 0, 0);
             uint32_t r[32];
             tmem_ld32(taddr + c0, r);          // .sync.aligned: the whole warp executes it, valid row or not
             tmem_ld_wait();
             if (valid) {
               float v[32];
 #pragma unroll
-              for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]) + s_bias[c0 + e];
+              for (int e = 0; e < 32; e += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + e);
+                v[e] = __uint_as_float(r[e]) + b4.x; v[e + 1] = __uint_as_float(r[e + 1]) + b4.y;
+                v[e + 2] = __uint_as_float(r[e + 2]) + b4.z; v[e + 3] = __uint_as_float(r[e + 3]) + b4.w;
+              }
               if (tab) {
 #pragma unroll
                 for (int e = 0; e < 32; e += 4) {
@@ -250,17 +252,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
               }
 #pragma unroll
               for (int e = 0; e < 32; e += 8) {
-                const act2_t* h = reinterpret_cast<const act2_t*>(&rres[(c0 + e) / 8]);
+                const act2_t* h = reinterpret_cast<const act2_t*>(&rres[e / 8]);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                   const float2 f = __half22float2(h[u]);
                   v[e + 2 * u] += f.x; v[e + 2 * u + 1] += f.y;
                 }
               }
-              if (p.relu) {
+              // ReLU (every conv of these nets is followed by one) and fp16 saturation in one clamp
 #pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.0f);
-              }
+              for (int e = 0; e < 32; ++e) v[e] = fminf(fmaxf(v[e], 0.0f), 65504.0f);
               if (pass == 0) {
                 if (norm) {
 #pragma unroll
@@ -300,19 +301,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[buf]);
-    };
-
-    // while the tensor core works on tile i: drain tile i-1's accumulators and fetch tile i+1
-    if (n_my > 0) { issue_load((int)blockIdx.x, 0); finish_load(0); }
-    for (int i = 0; i < n_my; ++i) {
-      const bool have_next = i + 1 < n_my;
-      if (i >= 1) wait_acc(i - 1);          // MMAs of tile i-1 done: its accumulators are ready and its
-                                            // activation buffer (the one tile i+1 goes to) is free
-      if (have_next) issue_load((int)blockIdx.x + (i + 1) * (int)gridDim.x, (i + 1) & 1);
-      if (i >= 1) epilogue(i - 1);
-      if (have_next) finish_load((i + 1) & 1);
     }
-    if (n_my > 0) { wait_acc(n_my - 1); epilogue(n_my - 1); }
   }
   tc_fence_before();
   __syncthreads();
@@ -539,7 +528,7 @@ struct ConvNet : NetImpl {
     const int TP = (kTileM + 2 * (Wp + 1)) | 1;
     const int chunk_g = cg < 8 ? cg : 8;
     size_t a = (((size_t)2 * cg * TP * 16) + 127) & ~(size_t)127;
-    return a + (size_t)kStages * chunk_g * C * 16 + 16 * 8 + 16 + (size_t)C * 4 + 64;
+    return a + (size_t)kStages * chunk_g * C * 16 + 16 * 8 + 16 + (size_t)C * 4 + (size_t)TP * 4 + 64;
   }
   int launch_head(const Head& h, const act_t* act, int batch, float* dst, cudaStream_t st) {
     HeadParams p;
