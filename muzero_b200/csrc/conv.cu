@@ -128,8 +128,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer
     if (lane == 0) {
+      // One thread feeds the tensor core, so the per-MMA instruction count matters (a single
+      // thread issues ~1 dependent instruction per 4-5 cycles; an MMA lasts 64): descriptors are
+      // built once and only their 14-bit start-address field (16-byte units) is stepped.
       const uint32_t idesc = instr_desc_f16(128, (uint32_t)p.N);
-      const uint32_t a_lbo = (uint32_t)TP * 16, b_lbo = (uint32_t)p.N * 16;
+      const uint64_t a_tmpl = smem_desc(0, (uint32_t)TP * 16, 128);
+      const uint64_t b_tmpl = smem_desc(0, (uint32_t)p.N * 16, 128);
+      const uint32_t a_hi = (uint32_t)(a_tmpl >> 32), a_lo0 = (uint32_t)a_tmpl;
+      const uint32_t b_hi = (uint32_t)(b_tmpl >> 32), b_lo0 = (uint32_t)b_tmpl;
+      const uint32_t a_kstep = 2u * (uint32_t)TP, b_kstep = 2u * (uint32_t)p.N;   // 16-byte units per K=16 step
+      const uint32_t sA16 = smem_u32(sA) >> 4, sW16 = smem_u32(sW) >> 4, stage16 = stage_bytes >> 4;
+      const int ksteps = chunk_g / 2;
+      auto desc64 = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
       uint32_t it = 0;
       for (int i = 0; i < n_my; ++i) {
         const int buf = i & 1;
@@ -137,24 +147,25 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
         mbar_wait(&acc_empty[buf], uph ^ 1);
         mbar_wait(&a_full[buf], uph);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(sA) + (uint32_t)buf * a_bytes;
-        uint32_t first = 1;
+        const uint32_t a_tile = a_lo0 + sA16 + (uint32_t)buf * (a_bytes >> 4) + (uint32_t)halo;
+        const uint32_t d0 = tmem + (uint32_t)(buf * 256), d1 = d0 + 128;
+        uint32_t acc = 0;
         for (int tap = 0; tap < 9; ++tap) {
           const int shift = (tap / 3 - 1) * p.Wp + (tap % 3 - 1);
+          uint32_t a_lo = a_tile + (uint32_t)shift;        // wraps correctly: shift may be negative
           for (int ch = 0; ch < chunks_tap; ++ch, ++it) {
             const uint32_t s = it % kStages, ph = (it / kStages) & 1;
             mbar_wait(&w_full[s], ph);
             tc_fence_after();
-            const uint32_t w_base = smem_u32(sW) + s * stage_bytes;
-            for (int ks = 0; ks < chunk_g / 2; ++ks) {
-              const uint32_t g = (uint32_t)(ch * chunk_g + 2 * ks);
-              const uint64_t bdesc = smem_desc(w_base + (uint32_t)(2 * ks) * b_lbo, b_lbo, 128);
-#pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                const uint32_t a_addr = a_base + ((uint32_t)(j * 128 + halo + shift) + g * (uint32_t)TP) * 16;
-                mma_bf16(tmem + (uint32_t)(buf * 256 + j * 128), smem_desc(a_addr, a_lbo, 128), bdesc, idesc, first ^ 1);
-              }
-              first = 0;
+            uint32_t b_lo = b_lo0 + sW16 + s * stage16;
+#pragma unroll 4
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint64_t bd = desc64(b_lo, b_hi);
+              mma_bf16(d0, desc64(a_lo, a_hi), bd, idesc, acc);
+              mma_bf16(d1, desc64(a_lo + 128u, a_hi), bd, idesc, acc);
+              acc = 1;
+              a_lo += a_kstep;
+              b_lo += b_kstep;
             }
             commit(&w_empty[s]);
           }
