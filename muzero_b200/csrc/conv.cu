@@ -26,6 +26,7 @@
 #include "net.cuh"
 #include "umma.cuh"
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 namespace mz {
 using namespace umma;
@@ -59,6 +60,7 @@ struct ConvParams {
   int relu;
   int num_tiles;
   int TP;                         // tile positions incl. halo, odd
+  long long* dbg;                 // optional per-CTA role timing (MZ_CONV_DEBUG), else nullptr
 };
 
 __device__ __forceinline__ void split_pos(int P, const ConvParams& p, int& b, int& q, bool& halo) {
@@ -115,15 +117,20 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
     if (lane == 0) {
       const int per_tile = 9 * chunks_tap;
       uint32_t it = 0;
+      long long t_wait = 0;
+      const long long t_begin = clock64();
       for (int i = 0; i < n_my; ++i) {
         for (int c = 0; c < per_tile; ++c, ++it) {
           const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+          const long long tw = clock64();
           mbar_wait(&w_empty[s], ph ^ 1);
+          t_wait += clock64() - tw;
           mbar_arrive_expect_tx(&w_full[s], stage_bytes);
           bulk_g2s(sW + (size_t)s * stage_bytes, reinterpret_cast<const unsigned char*>(p.w) + (size_t)c * stage_bytes,
                    stage_bytes, &w_full[s]);
         }
       }
+      if (p.dbg) { p.dbg[blockIdx.x * 16 + 0] = clock64() - t_begin; p.dbg[blockIdx.x * 16 + 1] = t_wait; }
     }
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer
@@ -141,11 +148,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
       const int ksteps = chunk_g / 2;
       auto desc64 = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
       uint32_t it = 0;
+      long long t_acc = 0, t_a = 0, t_w = 0;
+      const long long t_begin = clock64();
       for (int i = 0; i < n_my; ++i) {
         const int buf = i & 1;
         const uint32_t uph = (i >> 1) & 1;
+        long long tw = clock64();
         mbar_wait(&acc_empty[buf], uph ^ 1);
+        long long tw2 = clock64();
+        t_acc += tw2 - tw;
         mbar_wait(&a_full[buf], uph);
+        t_a += clock64() - tw2;
         tc_fence_after();
         const uint32_t a_tile = a_lo0 + sA16 + (uint32_t)buf * (a_bytes >> 4) + (uint32_t)halo;
         const uint32_t d0 = tmem + (uint32_t)(buf * 256), d1 = d0 + 128;
@@ -155,7 +168,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
           uint32_t a_lo = a_tile + (uint32_t)shift;        // wraps correctly: shift may be negative
           for (int ch = 0; ch < chunks_tap; ++ch, ++it) {
             const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+            tw = clock64();
             mbar_wait(&w_full[s], ph);
+            t_w += clock64() - tw;
             tc_fence_after();
             uint32_t b_lo = b_lo0 + sW16 + s * stage16;
 #pragma unroll 4
@@ -172,6 +187,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
         }
         commit(&mma_done[buf]);
       }
+      if (p.dbg) {
+        long long* d = p.dbg + blockIdx.x * 16;
+        d[2] = clock64() - t_begin; d[3] = t_acc; d[4] = t_a; d[5] = t_w; d[6] = n_my;
+      }
     }
   } else if (warp >= 6) {
     // ------------------------------------------------ loaders (warps 6-9): activation tile -> smem
@@ -184,6 +203,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
     const int cin = p.cg * 8;
     const int ld_g = lt % cpp, ld_q0 = lt / cpp, ld_step = kWorkers / cpp;
     const int nq = kTileM + 2 * halo;
+    long long t_wait = 0, t_cp = 0;
+    const long long t_begin = clock64();
     for (int i = 0; i < n_my; ++i) {
       const int buf = i & 1;
       const int m0 = ((int)blockIdx.x + i * (int)gridDim.x) * kTileM;
@@ -198,8 +219,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
         s_row[q] = row;
       }
       // the buffer was last read by the MMAs of tile i-2
+      long long tw = clock64();
       if (i >= 2) mbar_wait(&mma_done[buf], (uint32_t)(((i - 2) >> 1) & 1));
+      t_wait += clock64() - tw;
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      tw = clock64();
       const uint32_t dst = smem_u32(sA) + (uint32_t)buf * a_bytes + (uint32_t)ld_g * TP * 16;
       for (int q = ld_q0; q < nq; q += ld_step) {
         const int row = s_row[q];
@@ -211,16 +235,25 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
       asm volatile("cp.async.wait_all;" ::: "memory");
       fence_proxy_async();
       mbar_arrive(&a_full[buf]);
+      t_cp += clock64() - tw;
       asm volatile("bar.sync 1, 128;" ::: "memory");      // table is rewritten next iteration
+    }
+    if (p.dbg && lt == 0) {
+      long long* d = p.dbg + blockIdx.x * 16;
+      d[7] = clock64() - t_begin; d[8] = t_wait; d[9] = t_cp;
     }
   } else {
     // ------------------------------------------------ epilogue (warps 2-5): TMEM -> registers -> global
     const int quad = warp & 3;               // TMEM lane quadrant this warp may read
     const bool norm = (p.out_norm != nullptr) || (p.out_slots != nullptr);
+    long long t_wait = 0;
+    const long long t_begin = clock64();
     for (int k = 0; k < n_my; ++k) {
       const int buf = k & 1;
       const int tile = (int)blockIdx.x + k * (int)gridDim.x;
+      const long long tw = clock64();
       mbar_wait(&mma_done[buf], (uint32_t)((k >> 1) & 1));
+      t_wait += clock64() - tw;
       tc_fence_after();
 #pragma unroll 1
       for (int j = 0; j < 2; ++j) {
@@ -312,6 +345,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[buf]);
+    }
+    if (p.dbg && tid == 64) {
+      long long* d = p.dbg + blockIdx.x * 16;
+      d[10] = clock64() - t_begin; d[11] = t_wait;
     }
   }
   tc_fence_before();
@@ -527,12 +564,26 @@ struct ConvNet : NetImpl {
     p.TP = (kTileM + 2 * (Wp + 1)) | 1;
     const size_t smem = conv_smem(L.cg);
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    p.dbg = nullptr;
+    static const bool debug = getenv("MZ_CONV_DEBUG") != nullptr;
+    if (debug) cudaMalloc(&p.dbg, (size_t)grid * 16 * sizeof(long long));
     prof_mark(kProfConv, st);
     if (C == 128) conv3x3_kernel<128><<<grid, kConvThreads, smem, st>>>(p);
     else if (C == 64) conv3x3_kernel<64><<<grid, kConvThreads, smem, st>>>(p);
     else conv3x3_kernel<32><<<grid, kConvThreads, smem, st>>>(p);
     prof_mark(-1, st);
     MZ_LAUNCH_CHECK("conv3x3_kernel");
+    if (debug) {   // measurement aid: per-role cycle accounting, averaged over CTAs
+      cudaDeviceSynchronize();
+      std::vector<long long> h((size_t)grid * 16);
+      cudaMemcpy(h.data(), p.dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+      cudaFree(p.dbg);
+      double a[16] = {0};
+      for (int c = 0; c < grid; ++c) for (int k = 0; k < 16; ++k) a[k] += (double)h[(size_t)c * 16 + k] / grid;
+      fprintf(stderr, "[conv dbg] cg=%d tiles/cta=%.1f | producer total %.0f wait_empty %.0f | mma total %.0f wait_acc %.0f "
+              "wait_a %.0f wait_w %.0f | loader total %.0f wait_mma %.0f copy %.0f | epilogue total %.0f wait_mma %.0f\n",
+              L.cg, a[6], a[0], a[1], a[2], a[3], a[4], a[5], a[7], a[8], a[9], a[10], a[11]);
+    }
     return MZ_OK;
   }
   size_t conv_smem(int cg) const {
