@@ -40,7 +40,7 @@ typedef __half2 act2_t;
 constexpr int kConvThreads = 320;   // producer, MMA, 4 epilogue warps, 4 loader warps
 constexpr int kWorkers = 128;
 constexpr int kTileM = 256;     // positions per tile (two M=128 accumulators)
-constexpr int kStages = 4;
+constexpr int kMaxStages = 6;
 
 struct ConvParams {
   const act_t* in;        // [.. boards ..][PB][Cin_pad]
@@ -60,6 +60,7 @@ struct ConvParams {
   int relu;
   int num_tiles;
   int TP;                         // tile positions incl. halo, odd
+  int stages;                     // weight ring depth (as many as shared memory allows, <= kMaxStages)
   long long* dbg;                 // optional per-CTA role timing (MZ_CONV_DEBUG), else nullptr
 };
 
@@ -88,10 +89,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
 
   unsigned char* sA = smem;                                              // [2][cg][TP][16]
   unsigned char* sW = smem + (((size_t)2 * a_bytes + 127) & ~(size_t)127);   // [kStages][stage_bytes]
+  const uint32_t kStages = (uint32_t)p.stages;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)kStages * stage_bytes);
   uint64_t* w_full = bars;                 // [kStages]
-  uint64_t* w_empty = bars + kStages;      // [kStages]
-  uint64_t* a_full = bars + 2 * kStages;   // [2]
+  uint64_t* w_empty = bars + kMaxStages;   // [kStages]
+  uint64_t* a_full = bars + 2 * kMaxStages;   // [2]
   uint64_t* mma_done = a_full + 2;         // [2]
   uint64_t* acc_empty = mma_done + 2;      // [2]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
   int* s_row = reinterpret_cast<int*>(s_bias + p.N);                    // [TP] source row per tile position
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (uint32_t s = 0; s < kStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&a_full[b], kWorkers); mbar_init(&mma_done[b], 1); mbar_init(&acc_empty[b], kWorkers); }
     fence_mbar_init();
   }
@@ -251,10 +253,73 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
     for (int k = 0; k < n_my; ++k) {
       const int buf = k & 1;
       const int tile = (int)blockIdx.x + k * (int)gridDim.x;
+      // Fast path (30 of the 33 convs of a recurrent inference: plain conv+bias(+residual)+ReLU):
+      // the 2 rows x kN/32 column chunks of this thread form one unrolled sequence, and the
+      // residual of step t+2 is requested at step t (the first two before the MMAs even finish),
+      // so its global-memory latency never sits on the critical path.
+      constexpr int NC = kN / 32, STEPS = 2 * NC;
+      const bool fast = !norm && p.tab == nullptr && p.out != nullptr;
+      int Pj[2] = {0, 0};
+      bool vj[2] = {false, false};
+      const int4* rpj[2] = {nullptr, nullptr};
+      int4 ring[3][4];
+      auto fetch = [&](int t, int4 (&dst)[4]) {
+        const int4* src = rpj[t / NC];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dst[u] = src ? src[(t % NC) * 4 + u] : make_int4(0, 0, 0, 0);
+      };
+      if (fast) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          Pj[j] = tile * kTileM + j * 128 + quad * 32 + lane;
+          int b = 0, pos = 0; bool hl = true;
+          if (Pj[j] < p.Ptot) split_pos(Pj[j], p, b, pos, hl);
+          vj[j] = !hl;
+          if (vj[j] && p.residual) rpj[j] = reinterpret_cast<const int4*>(p.residual + (size_t)Pj[j] * kN);
+        }
+        fetch(0, ring[0]);
+        fetch(1, ring[1]);
+      }
       const long long tw = clock64();
       mbar_wait(&mma_done[buf], (uint32_t)((k >> 1) & 1));
       t_wait += clock64() - tw;
       tc_fence_after();
+      if (fast) {
+#pragma unroll
+        for (int t = 0; t < STEPS; ++t) {
+          const int j = t / NC, c0 = (t % NC) * 32;
+          if (t + 2 < STEPS) fetch(t + 2, ring[(t + 2) % 3]);
+          uint32_t r[32];
+          tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256 + j * 128 + c0), r);
+          tmem_ld_wait();
+          if (vj[j]) {
+            float v[32];
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + e);
+              v[e] = __uint_as_float(r[e]) + b4.x; v[e + 1] = __uint_as_float(r[e + 1]) + b4.y;
+              v[e + 2] = __uint_as_float(r[e + 2]) + b4.z; v[e + 3] = __uint_as_float(r[e + 3]) + b4.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 32; e += 8) {
+              const act2_t* h = reinterpret_cast<const act2_t*>(&ring[t % 3][e / 8]);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float2 f = __half22float2(h[u]);
+                v[e + 2 * u] += f.x; v[e + 2 * u + 1] += f.y;
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = fminf(fmaxf(v[e], 0.0f), 65504.0f);
+            int4* o = reinterpret_cast<int4*>(p.out + (size_t)Pj[j] * kN + c0);
+#pragma unroll
+            for (int e = 0; e < 32; e += 8)
+              o[e / 8] = make_int4((int)pack2(v[e], v[e + 1]), (int)pack2(v[e + 2], v[e + 3]),
+                                   (int)pack2(v[e + 4], v[e + 5]), (int)pack2(v[e + 6], v[e + 7]));
+          }
+          __syncwarp();
+        }
+      } else {
 #pragma unroll 1
       for (int j = 0; j < 2; ++j) {
         const int P = tile * kTileM + j * 128 + quad * 32 + lane;
@@ -343,6 +408,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
           }
         }
       }
+      }  // generic path
       tc_fence_before();
       mbar_arrive(&acc_empty[buf]);
     }
@@ -562,6 +628,7 @@ struct ConvNet : NetImpl {
     p.cg = L.cg; p.N = C; p.relu = 1;
     p.num_tiles = (p.Ptot + kTileM - 1) / kTileM;
     p.TP = (kTileM + 2 * (Wp + 1)) | 1;
+    p.stages = conv_stages(L.cg);
     const size_t smem = conv_smem(L.cg);
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
     p.dbg = nullptr;
@@ -586,11 +653,20 @@ struct ConvNet : NetImpl {
     }
     return MZ_OK;
   }
-  size_t conv_smem(int cg) const {
+  size_t conv_fixed_smem(int cg) const {
     const int TP = (kTileM + 2 * (Wp + 1)) | 1;
-    const int chunk_g = cg < 8 ? cg : 8;
     size_t a = (((size_t)2 * cg * TP * 16) + 127) & ~(size_t)127;
-    return a + (size_t)kStages * chunk_g * C * 16 + 16 * 8 + 16 + (size_t)C * 4 + (size_t)TP * 4 + 64;
+    return a + (2 * kMaxStages + 6) * 8 + 16 + (size_t)C * 4 + (size_t)TP * 4 + 64;
+  }
+  int conv_stages(int cg) const {
+    const int chunk_g = cg < 8 ? cg : 8;
+    const size_t stage = (size_t)chunk_g * C * 16;
+    int s = (int)((227 * 1024 - conv_fixed_smem(cg)) / stage);
+    return s > kMaxStages ? kMaxStages : s;
+  }
+  size_t conv_smem(int cg) const {
+    const int chunk_g = cg < 8 ? cg : 8;
+    return conv_fixed_smem(cg) + (size_t)conv_stages(cg) * chunk_g * C * 16;
   }
   int launch_head(const Head& h, const act_t* act, int batch, float* dst, cudaStream_t st) {
     HeadParams p;
@@ -824,7 +900,7 @@ int conv_create(const mz_net_config& c, const float* const* w, int nw, int max_b
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { set_error("weight repacking failed: %s", cudaGetErrorString(e)); delete net; return MZ_ECUDA; }
   const size_t smem_max = net->conv_smem(N / 8) > net->conv_smem(net->in_cg) ? net->conv_smem(N / 8) : net->conv_smem(net->in_cg);
-  if (smem_max > 227 * 1024) {
+  if (smem_max > 227 * 1024 || net->conv_stages(N / 8) < 2 || net->conv_stages(net->in_cg) < 2) {
     set_error("conv tile needs %zu bytes of shared memory (board too wide)", smem_max);
     delete net;
     return MZ_EINVAL;

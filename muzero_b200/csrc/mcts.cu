@@ -253,13 +253,45 @@ reset_kernel(PoolDev p, const float* __restrict__ pi, const double* __restrict__
 // ---------------------------------------------------------------------------
 extern __shared__ __align__(16) unsigned char smem_raw[];
 
+// order-preserving map float -> uint32 (so the warp maximum is one redux.sync instruction)
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// pUCT score of one child, bit-for-bit Node.child_Q + Node.child_U (mcts.py:159-200)
+__device__ __forceinline__ float puct_score(double eW, float eR, int cn, double pa, double tN, bool f32p, double dp,
+                                            bool norm, double lo, double range) {
+  const double y = __ddiv_rn(tN, (double)(cn + 1));
+  const float u = f32p ? __fmul_rn((float)pa, __double2float_rn(y)) : __double2float_rn(__dmul_rn(pa, y));
+  float q = 0.0f;
+  if (cn > 0) {
+    double v = __dadd_rn((double)eR, __dmul_rn(dp, __ddiv_rn(eW, (double)cn)));
+    if (norm) v = __ddiv_rn(__dsub_rn(v, lo), range);
+    q = __double2float_rn(v);
+  }
+  return __fadd_rn(q, u);
+}
+
+// NCH = number of 32-action chunks held in registers (A <= 32*NCH); NCH == 0: any A, scores staged
+// in shared memory.  The register path keeps a node's whole child row, the tree's prior and the
+// scores in registers, takes the chosen child's record by shuffle instead of re-reading it, looks
+// the pb_c factor up in shared memory, and prefetches the row of the most-visited child (the one
+// pUCT most often descends into) while the float64 divisions of the current level are in flight.
+template <int NCH>
 __global__ void __launch_bounds__(kTreesPerBlock * 32)
 select_kernel(PoolDev p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * kTreesPerBlock + warp;
-  if (t >= p.B) return;
   const int A = p.A;
-  float* sc = reinterpret_cast<float*>(smem_raw) + (size_t)warp * ((A + 3) & ~3);
+  double* sT = reinterpret_cast<double*>(smem_raw);                       // [S+2] pb_c table
+  float* sc = reinterpret_cast<float*>(sT + (p.S + 2)) + (size_t)warp * ((A + 3) & ~3);
+  for (int i = threadIdx.x; i < p.S + 2; i += blockDim.x) sT[i] = p.T[i];
+  __syncthreads();
+  if (t >= p.B) return;
 
   const Edge* tree = p.edges + (size_t)t * p.max_nodes * A;
   const double* __restrict__ P = p.prior + (size_t)t * A;
@@ -273,60 +305,122 @@ select_kernel(PoolDev p) {
   WarpRng rng;
   rng.load(p.rng_key + (size_t)t * 624, p.rng_pos + t, lane);
 
+  double pr[NCH > 0 ? NCH : 1];
+  if (NCH > 0) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) pr[c] = (c * 32 + lane < A) ? P[c * 32 + lane] : 0.0;
+  }
+
   int n = 0, Nn = p.rootN[t], depth = 0, act = 0;
   while (true) {
-    const double tN = p.T[Nn];
+    const double tN = sT[Nn];
     const Edge* row = tree + (size_t)n * A;
-    float best = -INFINITY;
-    for (int a = lane; a < A; a += 32) {
-      const Edge e = load_edge(row + a);
-      const int cn = e.N;
-      const double y = __ddiv_rn(tN, (double)(cn + 1));
-      const double pa = P[a];
-      const float u = f32p ? __fmul_rn((float)pa, __double2float_rn(y)) : __double2float_rn(__dmul_rn(pa, y));
-      float q = 0.0f;
-      if (cn > 0) {
-        double v = __dadd_rn((double)e.reward, __dmul_rn(dp, __ddiv_rn(e.W, (double)cn)));
-        if (norm) v = __ddiv_rn(__dsub_rn(v, lo), range);
-        q = __double2float_rn(v);
+    uint32_t nc_sel;      // (child << 16 | N) of the chosen edge
+    if constexpr (NCH > 0) {
+      constexpr int NC = NCH > 0 ? NCH : 1;
+      // child records in registers: W, reward, packed (child << 16 | N)
+      double eW[NC];
+      float eR[NC];
+      uint32_t eNC[NC];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int a = c * 32 + lane;
+        int4 r4 = make_int4(0, 0, 0, (int)((uint32_t)kNoChild << 16));
+        if (a < A) r4 = *reinterpret_cast<const int4*>(row + a);
+        eW[c] = __hiloint2double(r4.y, r4.x);
+        eR[c] = __int_as_float(r4.z);
+        eNC[c] = (uint32_t)r4.w;
       }
-      const float s = __fadd_rn(q, u);
-      sc[a] = s;
-      best = fmaxf(best, s);
-    }
-    best = warp_max(best);
-    __syncwarp();
-    // ties, ascending action order (np.where(ucb == ucb.max())[0])
-    int k = 0, first = -1;
-    for (int a0 = 0; a0 < A; a0 += 32) {
-      const int a = a0 + lane;
-      const unsigned b = __ballot_sync(kFull, a < A && sc[a] == best);
-      if (first < 0 && b) first = a0 + __ffs(b) - 1;
-      k += __popc(b);
-    }
-    act = first;
-    if (k > 1) {
-      int r = (int)rng.bounded((uint32_t)k);
+      // most-visited expanded child -> prefetch its row into L2 (it is the likeliest next node)
+      uint32_t top = 0;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c)
+        if ((eNC[c] >> 16) != kNoChild) top = max(top, (eNC[c] << 16) | (eNC[c] >> 16));
+      top = __reduce_max_sync(kFull, top);
+      if (top != 0) {
+        const char* nxt = reinterpret_cast<const char*>(tree + (size_t)(top & 0xffffu) * A);
+        if (lane * 128 < A * 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + lane * 128));
+      }
+      float s[NC];
+      uint32_t key = 0;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        s[c] = puct_score(eW[c], eR[c], (int)(eNC[c] & 0xffffu), pr[c], tN, f32p, dp, norm, lo, range);
+        if (c * 32 + lane < A) key = max(key, f2ord(s[c]));
+      }
+      const float best = ord2f(__reduce_max_sync(kFull, key));
+      // ties, ascending action order (np.where(ucb == ucb.max())[0])
+      unsigned tb[NC];
+      int k = 0;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        tb[c] = __ballot_sync(kFull, (c * 32 + lane < A) && s[c] == best);
+        k += __popc(tb[c]);
+      }
+      int r = (k > 1) ? (int)rng.bounded((uint32_t)k) : 0;
+      act = 0;
+      bool found = false;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int cnt = __popc(tb[c]);
+        if (!found) {
+          if (r < cnt) {
+            unsigned bb = tb[c];
+            for (int q = 0; q < r; ++q) bb &= bb - 1;       // drop the r lowest ties
+            act = c * 32 + __ffs(bb) - 1;
+            found = true;
+          } else {
+            r -= cnt;
+          }
+        }
+      }
+      uint32_t mine = 0;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c)
+        if ((act >> 5) == c) mine = eNC[c];
+      nc_sel = __shfl_sync(kFull, mine, act & 31);
+    } else {
+      float bestl = -INFINITY;
+      for (int a = lane; a < A; a += 32) {
+        const Edge e = load_edge(row + a);
+        const float s = puct_score(e.W, e.reward, (int)e.N, P[a], tN, f32p, dp, norm, lo, range);
+        sc[a] = s;
+        bestl = fmaxf(bestl, s);
+      }
+      const float best = warp_max(bestl);
+      __syncwarp();
+      int k = 0, first = -1;
       for (int a0 = 0; a0 < A; a0 += 32) {
         const int a = a0 + lane;
         const unsigned b = __ballot_sync(kFull, a < A && sc[a] == best);
-        const int c = __popc(b);
-        if (r < c) {
-          unsigned bb = b;
-          for (int q = 0; q < r; ++q) bb &= bb - 1;   // drop the r lowest ties
-          act = a0 + __ffs(bb) - 1;
-          break;
-        }
-        r -= c;
+        if (first < 0 && b) first = a0 + __ffs(b) - 1;
+        k += __popc(b);
       }
+      act = first;
+      if (k > 1) {
+        int r = (int)rng.bounded((uint32_t)k);
+        for (int a0 = 0; a0 < A; a0 += 32) {
+          const int a = a0 + lane;
+          const unsigned b = __ballot_sync(kFull, a < A && sc[a] == best);
+          const int c = __popc(b);
+          if (r < c) {
+            unsigned bb = b;
+            for (int q = 0; q < r; ++q) bb &= bb - 1;
+            act = a0 + __ffs(bb) - 1;
+            break;
+          }
+          r -= c;
+        }
+      }
+      __syncwarp();
+      const Edge e = load_edge(row + act);
+      nc_sel = ((uint32_t)e.child << 16) | e.N;
     }
-    __syncwarp();
-    const Edge e = load_edge(row + act);
     if (lane == 0) pth[depth] = (uint32_t)(n * A + act);
     ++depth;
-    if (e.child == kNoChild) break;
-    n = e.child;
-    Nn = e.N;
+    if ((nc_sel >> 16) == kNoChild) break;
+    n = (int)(nc_sel >> 16);
+    Nn = (int)(nc_sel & 0xffffu);
   }
   rng.store(p.rng_pos + t);
   if (lane == 0) {
@@ -629,6 +723,7 @@ int check_cfg(const mz_pool_config* c) {
                c->hidden_bytes);
   MZ_CHECK_ARG((size_t)c->num_trees * (c->num_simulations + 1) < (size_t)1 << 31, "too many node slots");
   MZ_CHECK_ARG((size_t)(c->num_simulations + 1) * c->num_actions < (size_t)1 << 32, "tree too large for u32 edge ids");
+  MZ_CHECK_ARG(c->num_simulations <= 4000, "num_simulations > 4000 not supported (pb_c table lives in shared memory)");
   if (c->is_board_game)  // mcts.py:349-350
     MZ_CHECK_ARG(c->discount == 1.0, "board games require discount == 1.0 (mcts.py:349), got %g", c->discount);
   return MZ_OK;
@@ -767,8 +862,16 @@ extern "C" int mz_search_reset(mz_pool* pool, const float* pi_probs, const doubl
 
 extern "C" int mz_select(mz_pool* pool, mz_stream stream) {
   MZ_CHECK_ARG(pool, "NULL argument");
-  const size_t smem = (size_t)kTreesPerBlock * ((pool->A + 3) & ~3) * sizeof(float);
-  select_kernel<<<tree_blocks(pool->B), kTreesPerBlock * 32, smem, (cudaStream_t)stream>>>(dev_of(pool));
+  const int A = pool->A;
+  const size_t smem = (size_t)(pool->S + 2) * 8 + (A > 128 ? (size_t)kTreesPerBlock * ((A + 3) & ~3) * sizeof(float) : 0);
+  const dim3 grid(tree_blocks(pool->B)), block(kTreesPerBlock * 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  const PoolDev d = dev_of(pool);
+  if (A <= 32) select_kernel<1><<<grid, block, smem, st>>>(d);
+  else if (A <= 64) select_kernel<2><<<grid, block, smem, st>>>(d);
+  else if (A <= 96) select_kernel<3><<<grid, block, smem, st>>>(d);
+  else if (A <= 128) select_kernel<4><<<grid, block, smem, st>>>(d);
+  else select_kernel<0><<<grid, block, smem, st>>>(d);
   MZ_LAUNCH_CHECK("select_kernel");
   pool->selected = 1;
   return MZ_OK;

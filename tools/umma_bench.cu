@@ -1,7 +1,8 @@
-// Micro-benchmark: cycles per tcgen05.mma (M=128, K=16, fp16) issued back to back from shared
-// memory operands in the no-swizzle K-major layout, as a function of N and of the K-direction
-// strides (LBO) of A and B.  Answers: is the operand fetch bank-conflict bound?
-// usage: umma_bench N a_rows b_rows [grid] [iters] [extra_smem_writer]
+// Micro-benchmark: cycles per tcgen05.mma (K=16, fp16) issued back to back from shared-memory
+// operands in the no-swizzle K-major layout, with optional competing shared-memory store
+// traffic, for cta_group::1 (M=128 per SM) and cta_group::2 (M=256 over an SM pair, each SM
+// holding half of B).  Answers: what bounds the MMA rate inside conv.cu?
+// usage: umma_bench N a_rows b_rows [grid] [iters] [writer_warps 0..3] [two_cta 0|1]
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>
@@ -9,67 +10,121 @@
 
 using namespace mz::umma;
 
+__device__ __forceinline__ void mma2(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <bool kTwo>
 __global__ void __launch_bounds__(128) bench(int N, int a_rows, int b_rows, int iters, long long* out, int writer) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base;
+  __shared__ volatile int stop;
   const int tid = threadIdx.x, warp = tid >> 5;
+  uint32_t rank = 0;
+  if (kTwo) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
   unsigned char* sA = smem;
   unsigned char* sB = smem + 16 * a_rows * 16;
   for (int i = tid; i < (16 * a_rows + 8 * b_rows) * 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
-  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
-  if (warp == 0) tmem_alloc(&tmem_base, 512);
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); stop = 0; }
+  if (warp == 0) {
+    if (kTwo) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      tmem_alloc(&tmem_base, 512);
+    }
+  }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
+  if (kTwo) cluster_sync();
   tc_fence_after();
   const uint32_t tm = tmem_base;
   if (tid == 0) {
-    const uint32_t idesc = instr_desc_f16(128, N);
-    const uint64_t at = smem_desc(smem_u32(sA) + 11 * 16, a_rows * 16, 128);
-    const uint64_t bt = smem_desc(smem_u32(sB), b_rows * 16, 128);
-    const long long t0 = clock64();
-    for (int it = 0; it < iters; ++it) {
+    long long t0 = 0, t1 = 0;
+    if (!kTwo || rank == 0) {
+      const uint32_t idesc = instr_desc_f16(kTwo ? 256 : 128, N);
+      const uint64_t at = smem_desc(smem_u32(sA) + 11 * 16, a_rows * 16, 128);
+      const uint64_t bt = smem_desc(smem_u32(sB), b_rows * 16, 128);
+      t0 = clock64();
+      for (int it = 0; it < iters; ++it) {
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        mma_bf16(tm, at + (uint64_t)(2 * ks * a_rows), bt + (uint64_t)(2 * ks * b_rows), idesc, 1);
-        if (N <= 128) mma_bf16(tm + 256, at + 128 + (uint64_t)(2 * ks * a_rows), bt + (uint64_t)(2 * ks * b_rows), idesc, 1);
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t a = at + (uint64_t)(2 * ks * a_rows), b = bt + (uint64_t)(2 * ks * b_rows);
+          if (kTwo) { mma2(tm, a, b, idesc, 1); mma2(tm + 256, a + 128, b, idesc, 1); }
+          else { mma_bf16(tm, a, b, idesc, 1); mma_bf16(tm + 256, a + 128, b, idesc, 1); }
+        }
       }
+      if (kTwo)
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                         smem_u32(&bar)), "h"((unsigned short)3) : "memory");
+      else
+        commit(&bar);
     }
-    commit(&bar);
     mbar_wait(&bar, 0);
-    const long long t1 = clock64();
+    t1 = clock64();
     out[blockIdx.x] = t1 - t0;
-  } else if (writer && warp >= 2) {
-    // competing shared-memory store traffic (what cp.async / TMA fills do in the real kernel)
-    const uint32_t w = smem_u32(sB + 8 * b_rows * 16);
-    for (int it = 0; it < iters * writer; ++it)
-      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(w + (uint32_t)((tid - 64) + 64 * (it & 31)) * 16), "r"(it)
-                   : "memory");
+    stop = 1;
+  } else if (warp >= 1 && warp <= writer) {
+    // competing shared-memory store traffic (what the TMA weight fills / cp.async tile fills do)
+    const uint32_t w = smem_u32(sB + 8 * b_rows * 16) + (uint32_t)(tid - 32) * 16;
+    int it = 0;
+    while (!stop) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(w + (uint32_t)(((it + u) & 7) * 96 * 16)), "r"(it) : "memory");
+      it += 8;
+    }
+    if (tid == 32) out[gridDim.x + blockIdx.x] = (long long)it * 16 * 32 * writer;   // bytes stored by this CTA
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tm, 512);
+  if (kTwo) cluster_sync();
+  if (warp == 0) {
+    if (kTwo) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512) : "memory");
+    else tmem_dealloc(tm, 512);
+  }
 }
 
 int main(int argc, char** argv) {
   const int N = argc > 1 ? atoi(argv[1]) : 128, a_rows = argc > 2 ? atoi(argv[2]) : 279, b_rows = argc > 3 ? atoi(argv[3]) : N;
   const int grid = argc > 4 ? atoi(argv[4]) : 1, iters = argc > 5 ? atoi(argv[5]) : 2000, writer = argc > 6 ? atoi(argv[6]) : 0;
+  const int two = argc > 7 ? atoi(argv[7]) : 0;
   long long* d;
-  cudaMalloc(&d, grid * sizeof(long long));
-  const int smem = 16 * a_rows * 16 + 8 * b_rows * 16 + 64 * 32 * 16 + 1024;
-  cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  bench<<<grid, 128, smem>>>(N, a_rows, b_rows, iters, d, writer);
-  cudaError_t e = cudaDeviceSynchronize();
+  cudaMalloc(&d, 2 * grid * sizeof(long long));
+  cudaMemset(d, 0, 2 * grid * sizeof(long long));
+  const int smem = 16 * a_rows * 16 + 8 * b_rows * 16 + 8 * 96 * 16 + 1024;
+  cudaError_t e;
+  if (two) {
+    cudaFuncSetAttribute(bench<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, bench<true>, N, a_rows, b_rows, iters, d, writer);
+    if (e != cudaSuccess) { printf("launch error %s\n", cudaGetErrorString(e)); return 1; }
+  } else {
+    cudaFuncSetAttribute(bench<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    bench<false><<<grid, 128, smem>>>(N, a_rows, b_rows, iters, d, writer);
+  }
+  e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
-  long long h[256];
-  cudaMemcpy(h, d, grid * sizeof(long long), cudaMemcpyDeviceToHost);
-  const int per_it = (N <= 128) ? 8 : 4;
-  double mx = 0;
-  for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
-  const double cyc = mx / ((double)iters * per_it);
-  printf("N=%d a_rows=%d (LBO %d B, mod128=%d) b_rows=%d (LBO %d B, mod128=%d) grid=%d writer=%d: %.1f cycles/MMA, "
-         "%.0f flop/cycle/SM (ideal 8192)\n", N, a_rows, a_rows * 16, (a_rows * 16) % 128, b_rows, b_rows * 16,
-         (b_rows * 16) % 128, grid, writer, cyc, 2.0 * 128 * N * 16 / cyc);
+  long long h[1024];
+  cudaMemcpy(h, d, 2 * grid * sizeof(long long), cudaMemcpyDeviceToHost);
+  double mx = 0, wbytes = 0;
+  for (int i = 0; i < grid; ++i) { if (two && (i & 1)) continue; mx = h[i] > mx ? h[i] : mx; }
+  for (int i = 0; i < grid; ++i) wbytes += (double)h[grid + i] / grid;
+  const double cyc = mx / ((double)iters * 8);
+  const double flop = 2.0 * 128 * N * 16;     // per SM per MMA (a 2-SM MMA does this much on each SM)
+  printf("cta_group::%d N=%d A-LBO %d B b_rows=%d grid=%d writer_warps=%d: %.1f cycles/MMA, %.0f flop/cycle/SM (ideal 8192), "
+         "competing stores %.1f B/cycle/SM\n", two ? 2 : 1, N, a_rows * 16, b_rows, grid, writer, cyc, flop / cyc, wbytes / mx);
   return 0;
 }
