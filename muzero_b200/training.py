@@ -1,0 +1,185 @@
+"""K-step-unroll training step, data-parallel over NCCL (BASELINE.json config 5).
+
+Reference semantics mirrored here (michaelnny/muzero):
+  pipeline.py:541-612  calc_loss(network, device, transitions, weights) -> (loss, priorities)
+  pipeline.py:615-629  loss_func
+  util.py:20-22,48-59,96-116  signed_hyperbolic, transform_to_2hot, scalar_to_categorical_probabilities
+  pipeline.py:232-257  one learner iteration: zero_grad, calc_loss, backward, [clip], Adam step, LR step
+  replay.py:27-32      Transition(state, action, pi_prob, value, reward)
+
+The reference has ONE learner on one device; here every rank computes the loss of its shard of the replay batch and
+the gradients are averaged with ONE flat-bucket all-reduce (the whole model, 29 MB fp32 for the Gomoku net, is a single
+latency-bound NVLink transfer), then every rank applies the identical Adam step, so weights stay in sync and the
+self-play engine on the same rank sees them without a broadcast.  Forward/backward run through PyTorch autograd over
+the same parameters the inference engine repacks (SURVEY.md §8 e/f-2: fused fwd/bwd kernels are "next").
+
+BatchNorm note: like the reference's `network.train()` (pipeline.py:218) each rank uses ITS shard's batch statistics;
+DP therefore equals "mean of per-shard reference gradients", not the full-batch gradient, for the ResNets (MLP nets
+have no BatchNorm and match the single-process full-batch step up to float reassociation).
+"""
+from __future__ import annotations
+
+from typing import NamedTuple, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from .network import MuZeroNet
+
+
+class Transition(NamedTuple):
+    state: Optional[np.ndarray]
+    action: Optional[np.ndarray]
+    pi_prob: Optional[np.ndarray]
+    value: Optional[np.ndarray]
+    reward: Optional[np.ndarray]
+
+
+def signed_hyperbolic(x: torch.Tensor, eps: float = 1e-3) -> torch.Tensor:
+    return torch.sign(x) * (torch.sqrt(torch.abs(x) + 1) - 1) + eps * x
+
+
+def signed_parabolic(x: torch.Tensor, eps: float = 1e-3) -> torch.Tensor:
+    z = torch.sqrt(1 + 4 * eps * (eps + 1 + torch.abs(x))) / 2 / eps - 1 / 2 / eps
+    return torch.sign(x) * (torch.square(z) - 1)
+
+
+def transform_to_2hot(scalar: torch.Tensor, min_value: float, max_value: float, num_bins: int) -> torch.Tensor:
+    """util.py:48-59."""
+    scalar = torch.clamp(scalar, min_value, max_value)
+    scalar_bin = (scalar - min_value) / (max_value - min_value) * (num_bins - 1)
+    lower, upper = torch.floor(scalar_bin), torch.ceil(scalar_bin)
+    lower_value = (lower / (num_bins - 1.0)) * (max_value - min_value) + min_value
+    upper_value = (upper / (num_bins - 1.0)) * (max_value - min_value) + min_value
+    p_lower = (upper_value - scalar) / (upper_value - lower_value + 1e-5)
+    p_upper = 1 - p_lower
+    return F.one_hot(lower.long(), num_bins) * p_lower.unsqueeze(-1) + F.one_hot(upper.long(), num_bins) * p_upper.unsqueeze(-1)
+
+
+def scalar_to_categorical_probabilities(x: torch.Tensor, support_size: int) -> torch.Tensor:
+    """util.py:96-116."""
+    hi = (support_size - 1) // 2
+    return transform_to_2hot(signed_hyperbolic(x), -hi, hi, support_size)
+
+
+def logits_to_transformed_expected_value(logits: torch.Tensor, support_size: int) -> torch.Tensor:
+    """util.py:70-93 (support created on the logits' device, unlike util.py:64)."""
+    hi = (support_size - 1) // 2
+    probs = torch.softmax(logits, dim=-1)
+    support = torch.linspace(-hi, hi, support_size, device=logits.device).expand_as(probs)
+    return signed_parabolic(torch.sum(probs * support, dim=-1, keepdim=True))
+
+
+def loss_func(prediction: torch.Tensor, target: torch.Tensor, mse: bool = False) -> torch.Tensor:
+    """pipeline.py:615-629."""
+    assert prediction.shape == target.shape
+    if mse:
+        return F.mse_loss(prediction, target, reduction='none')
+    assert prediction.dim() == 2
+    return F.cross_entropy(prediction, target, reduction='none')
+
+
+def calc_loss(network: MuZeroNet, device, transitions: Transition, weights: torch.Tensor):
+    """pipeline.py:541-612: representation, then T unrolled (prediction, dynamics) steps with the
+    0.5 gradient scale on the hidden state and the 1/T scale on the loss."""
+    state = torch.as_tensor(transitions.state).to(device=device, dtype=torch.float32, non_blocking=True)
+    action = torch.as_tensor(transitions.action).to(device=device, dtype=torch.long, non_blocking=True)
+    target_value_scalar = torch.as_tensor(transitions.value).to(device=device, dtype=torch.float32, non_blocking=True)
+    target_reward_scalar = torch.as_tensor(transitions.reward).to(device=device, dtype=torch.float32, non_blocking=True)
+    target_pi_prob = torch.as_tensor(transitions.pi_prob).to(device=device, dtype=torch.float32, non_blocking=True)
+
+    target_value = target_value_scalar if network.mse_loss_for_value else \
+        scalar_to_categorical_probabilities(target_value_scalar, network.value_support_size)
+    target_reward = target_reward_scalar if network.mse_loss_for_reward else \
+        scalar_to_categorical_probabilities(target_reward_scalar, network.reward_support_size)
+
+    B, T = action.shape
+    reward_loss, value_loss, policy_loss = 0, 0, 0
+    pred_values = []
+    hidden_state = network.represent(state)
+    for t in range(T):
+        pred_pi_logits, pred_value = network.prediction(hidden_state)
+        hidden_state, pred_reward = network.dynamics(hidden_state, action[:, t].unsqueeze(1))
+        hidden_state.register_hook(lambda grad: grad * 0.5)
+        value_loss = value_loss + loss_func(pred_value.squeeze(), target_value[:, t], network.mse_loss_for_value)
+        reward_loss = reward_loss + loss_func(pred_reward.squeeze(), target_reward[:, t], network.mse_loss_for_reward)
+        policy_loss = policy_loss + loss_func(pred_pi_logits, target_pi_prob[:, t])
+        pred_values.append(pred_value.detach())
+    loss = reward_loss + value_loss + policy_loss
+    loss = torch.mean(loss * weights.detach())
+    loss_scale = 1.0 / T
+    loss.register_hook(lambda grad: grad * loss_scale)
+    with torch.no_grad():
+        pv = torch.stack(pred_values, dim=1)
+        pv_scalar = pv.squeeze(-1) if network.mse_loss_for_value else \
+            logits_to_transformed_expected_value(pv, network.value_support_size).squeeze(-1)
+        priorities = (pv_scalar[:, 0] - target_value_scalar[:, 0]).abs().cpu().numpy()
+    return loss, priorities
+
+
+class DataParallelLearner:
+    """One learner iteration of pipeline.py:232-257 on every rank, gradients averaged by one all-reduce."""
+
+    def __init__(self, network: MuZeroNet, config, device, process_group=None) -> None:
+        self.network, self.config, self.device = network, config, torch.device(device)
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        params = [p for p in network.parameters() if p.requires_grad]
+        # one flat gradient bucket; every .grad is a view into it -> the all-reduce needs no packing copies
+        self.flat_grad = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=self.device)
+        off = 0
+        for p in params:
+            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.params = params
+        # gomoku/run_training.py:110 / classic: Adam(lr_init, weight_decay), MultiStepLR(milestones, lr_decay_rate)
+        self.optimizer = torch.optim.Adam(params, lr=config.lr_init, weight_decay=config.weight_decay)
+        self.lr_scheduler = torch.optim.lr_scheduler.MultiStepLR(self.optimizer, milestones=list(config.lr_milestones),
+                                                                 gamma=config.lr_decay_rate)
+        self.train_steps = 0
+        self.last_allreduce_ms = None
+
+    def step(self, transitions: Transition, weights, time_allreduce: bool = False) -> Tuple[float, np.ndarray]:
+        self.network.train()
+        self.flat_grad.zero_()                                  # optimizer.zero_grad() that keeps the views
+        w = torch.as_tensor(weights).to(device=self.device, dtype=torch.float32)
+        loss, priorities = calc_loss(self.network, self.device, transitions, w)
+        loss.backward()
+        if self.world > 1:
+            if time_allreduce and self.device.type == 'cuda':
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat_grad.div_(self.world)
+            if time_allreduce and self.device.type == 'cuda':
+                e1.record()
+                torch.cuda.synchronize(self.device)
+                self.last_allreduce_ms = e0.elapsed_time(e1)
+        if self.config.clip_grad:
+            torch.nn.utils.clip_grad_norm_(self.params, self.config.max_grad_norm)
+        self.optimizer.step()
+        self.lr_scheduler.step()
+        self.train_steps += 1
+        return float(loss.detach()), priorities
+
+    def state_dict(self):
+        """Same keys as the reference's checkpoints (pipeline.py:224-230)."""
+        return {'network': self.network.state_dict(), 'optimizer': self.optimizer.state_dict(),
+                'lr_scheduler': self.lr_scheduler.state_dict(), 'train_steps': self.train_steps}
+
+
+def synthetic_transitions(network: MuZeroNet, batch: int, unroll: int, seed: int) -> Tuple[Transition, np.ndarray]:
+    """A replay batch of config 5's shapes: state int8/float32 [B,*obs], action [B,T],
+    value/reward float32 [B,T], pi float32 [B,T,A], importance weights float32 [B]."""
+    gen = np.random.RandomState(seed)
+    A = network.num_actions
+    shape = tuple(network.input_shape)
+    state = gen.randint(0, 2, size=(batch,) + shape).astype(np.float32)
+    action = gen.randint(0, A, size=(batch, unroll)).astype(np.int64)
+    value = gen.choice([-1.0, 0.0, 1.0], size=(batch, unroll)).astype(np.float32)
+    reward = (gen.standard_normal((batch, unroll)) * 0.1).astype(np.float32)
+    pi = gen.dirichlet(np.ones(A), size=(batch, unroll)).astype(np.float32)
+    weights = gen.uniform(0.5, 1.0, size=batch).astype(np.float32)
+    return Transition(state=state, action=action, pi_prob=pi, value=value, reward=reward), weights
