@@ -212,7 +212,7 @@ class CpuArm:
 
 
 def cpu_searches_per_step(name):
-    return {'tictactoe': 40, 'cartpole': 12, 'gomoku': 1, 'atari': 1}[name]
+    return {'tictactoe': 40, 'cartpole': 12, 'gomoku': 1, 'atari': 2}[name]
 
 
 def run_reference_arm(args):
@@ -445,6 +445,11 @@ def run_engine_arm(args):
         'roofline': roofline,
         'kernels': roof,
     }
+    if not args.no_train_step:
+        try:
+            result['train_step'] = train_step_sample(net, spec, dev, world)
+        except Exception as exc:                      # never lose the search line to the secondary measurement
+            result['train_step'] = {'error': repr(exc)[:200]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         del flush
         result['cpu_baseline'] = cpu_baseline_sample(args, spec)
@@ -452,6 +457,50 @@ def run_engine_arm(args):
         print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()
+
+
+def train_step_sample(net, spec, dev, world, batch=128, unroll=5, warmup=2, steps=3):
+    """BASELINE.json config 5's second half: the K=5-unroll training step, data-parallel, one flat
+    NCCL all-reduce of the gradients (PyTorch autograd forward/backward)."""
+    import copy
+    import torch
+    import torch.distributed as dist
+    import muzero_b200 as mz
+    from muzero_b200.training import DataParallelLearner, synthetic_transitions
+    cls = type(net)
+    twin = cls(**spec['net_kw']).to(dev)
+    twin.load_state_dict(net.state_dict())
+    learner = DataParallelLearner(twin, spec['cfg'], dev)
+    rank = dist.get_rank() if world > 1 else 0
+    tr, w = synthetic_transitions(twin, batch, unroll, seed=500 + rank)
+    for _ in range(warmup):
+        learner.step(tr, w)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ar = []
+    if world > 1:
+        dist.barrier()
+    e0.record()
+    for _ in range(steps):
+        loss, _ = learner.step(tr, w, time_allreduce=world > 1)
+        if learner.last_allreduce_ms is not None:
+            ar.append(learner.last_allreduce_ms)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    nbytes = learner.flat_grad.numel() * 4
+    out = {'ms_per_step': float(ms.item()), 'batch_per_gpu': batch, 'unroll_steps': unroll, 'loss': loss,
+           'samples_per_s': world * batch / (float(ms.item()) / 1e3), 'grad_bytes': nbytes,
+           'impl': 'PyTorch autograd fwd/bwd + one flat NCCL all-reduce + Adam'}
+    if ar:
+        a = sum(ar) / len(ar)
+        out['allreduce_ms'] = a
+        out['allreduce_bus_gbs'] = 2.0 * (world - 1) / world * nbytes / (a * 1e-3) / 1e9
+    del learner, twin
+    torch.cuda.empty_cache()
+    return out
 
 
 def cpu_baseline_sample(args, spec):
@@ -471,11 +520,12 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--workload', default=os.environ.get('MZ_BENCH_WORKLOAD', 'tictactoe'))
+    ap.add_argument('--workload', default=os.environ.get('MZ_BENCH_WORKLOAD', 'gomoku'))
     ap.add_argument('--trees', type=int, default=None, help='trees per GPU (default: the config size)')
     ap.add_argument('--impl', default='engine', choices=['engine', 'reference'])
     ap.add_argument('--cpu-procs', type=int, default=int(os.environ.get('MZ_BENCH_CPU_PROCS', '64')))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-train-step', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)
