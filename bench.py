@@ -232,14 +232,14 @@ def run_reference_arm(args):
     arm.close()
     value = sims / wall
     sample = f'{procs} processes x {n} single-tree searches x {spec["cfg"].num_simulations} sims per step, {args.steps} steps'
-    print(json.dumps({
+    emit({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1000.0 * wall / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': spec['label'], 'trees': spec['trees'], 'simulations': spec['cfg'].num_simulations},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': procs, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-    }))
+    })
 
 
 # ---------------------------------------------------------------------------
@@ -454,7 +454,7 @@ def run_engine_arm(args):
         del flush
         result['cpu_baseline'] = cpu_baseline_sample(args, spec)
     if rank == 0:
-        print(json.dumps(result))
+        emit(result)
     if world > 1:
         dist.destroy_process_group()
 
@@ -515,7 +515,25 @@ def cpu_baseline_sample(args, spec):
                       f'(oracle port of uct_search + fp32 torch network, 1 thread per process)'}
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj) -> None:
+    """The ONE JSON line goes to the real stdout; everything else any library prints (NCCL's version
+    banner goes to fd 1) was diverted to stderr by main()."""
+    line = json.dumps(obj) + '\n'
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line)
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line.encode())
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
