@@ -596,6 +596,146 @@ __global__ void action_table_kernel(const float* __restrict__ w, const float* __
 }
 
 // ---------------------------------------------------------------------------
+// MuZeroAtariNet representation extras (network.py:312-353): two stride-2 3x3 convs (no
+// BatchNorm, ReLU) and two 3x3/stride-2 average pools.  These run once per search (not per
+// simulation) and are plain SIMT kernels; the 3x3 stride-1 residual blocks between them go
+// through the tcgen05 kernel above at 48x48 / 24x24 / 12x12.
+// ---------------------------------------------------------------------------
+// out[b][oy][ox][co] = relu(sum_{ky,kx,ci} in[b][2oy+ky-1][2ox+kx-1][ci] * w[ky*3+kx][ci][co]), Co = 128.
+// Tile: 64 output positions x 128 output channels per CTA, K in chunks of 16 input channels.
+__global__ void __launch_bounds__(256) conv3x3_s2_kernel(const act_t* __restrict__ in, const act_t* __restrict__ w,
+                                                         act_t* __restrict__ out, int B, int Hi, int Wi, int Ci) {
+  constexpr int Co = 128, TPOS = 64, KC = 16;
+  const int Ho = Hi / 2, Wo = Wi / 2, Wpi = Wi + 1, PBi = (Hi + 1) * Wpi, Wpo = Wo + 1, PBo = (Ho + 1) * Wpo;
+  __shared__ float As[KC][TPOS + 4];
+  __shared__ float Ws[KC][Co];
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const long long total = (long long)B * Ho * Wo;
+  const long long p0 = (long long)blockIdx.x * TPOS;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  // this thread's load assignment: position lp (0..63), half hp (0/1) of the 16-channel chunk
+  const int lp = tid >> 1, hp = tid & 1;
+  const long long gp = p0 + lp;
+  int lb = 0, loy = 0, lox = 0;
+  const bool lvalid = (tid < 128) && gp < total;
+  if (lvalid) { lb = (int)(gp / (Ho * Wo)); const int r = (int)(gp % (Ho * Wo)); loy = r / Wo; lox = r % Wo; }
+  for (int tap = 0; tap < 9; ++tap) {
+    const int iy = 2 * loy + tap / 3 - 1, ix = 2 * lox + tap % 3 - 1;
+    const bool inb = lvalid && iy >= 0 && iy < Hi && ix >= 0 && ix < Wi;
+    const act_t* src = in + ((size_t)lb * PBi + (size_t)(inb ? iy * Wpi + ix : 0)) * Ci;
+    for (int c0 = 0; c0 < Ci; c0 += KC) {
+      if (tid < 128) {
+        int4 v = make_int4(0, 0, 0, 0);
+        if (inb) v = *reinterpret_cast<const int4*>(src + c0 + hp * 8);
+        const act2_t* h = reinterpret_cast<const act2_t*>(&v);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float2 f = __half22float2(h[u]);
+          As[hp * 8 + 2 * u][lp] = f.x;
+          As[hp * 8 + 2 * u + 1][lp] = f.y;
+        }
+      }
+      {
+        const int4 v = reinterpret_cast<const int4*>(w + ((size_t)tap * Ci + c0) * Co)[tid];   // 16 x 128 halfs
+        const act2_t* h = reinterpret_cast<const act2_t*>(&v);
+        const int k = tid >> 4, c = (tid & 15) * 8;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float2 f = __half22float2(h[u]);
+          Ws[k][c + 2 * u] = f.x;
+          Ws[k][c + 2 * u + 1] = f.y;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        float a[8], b[4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = As[k][ty * 8 + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = Ws[k][tx * 4 + j];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long long g = p0 + ty * 8 + i;
+    if (g >= total) continue;
+    const int b = (int)(g / (Ho * Wo)), r = (int)(g % (Ho * Wo)), oy = r / Wo, ox = r % Wo;
+    act_t* o = out + ((size_t)b * PBo + (size_t)oy * Wpo + ox) * Co + tx * 4;
+    uint2 pk;
+    pk.x = pack2(fminf(fmaxf(acc[i][0], 0.0f), 65504.0f), fminf(fmaxf(acc[i][1], 0.0f), 65504.0f));
+    pk.y = pack2(fminf(fmaxf(acc[i][2], 0.0f), 65504.0f), fminf(fmaxf(acc[i][3], 0.0f), 65504.0f));
+    *reinterpret_cast<uint2*>(o) = pk;
+  }
+}
+
+// AvgPool2d(3, stride 2, padding 1), count_include_pad (divide by 9), C = 128: one warp per output
+// position, 4 channels per lane.  Optionally min-max normalises over the channels (util.py:31-36) and
+// also writes the result to indexed hidden-state slots.
+__global__ void __launch_bounds__(256) avgpool_kernel(const act_t* __restrict__ in, act_t* __restrict__ out,
+                                                      act_t* __restrict__ slots, const int32_t* __restrict__ out_index,
+                                                      int B, int Hi, int Wi, int normalise) {
+  constexpr int C = 128;
+  const int Ho = Hi / 2, Wo = Wi / 2, Wpi = Wi + 1, PBi = (Hi + 1) * Wpi, Wpo = Wo + 1, PBo = (Ho + 1) * Wpo;
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)B * Ho * Wo;
+  for (long long g = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); g < total; g += (long long)gridDim.x * 8) {
+    const int b = (int)(g / (Ho * Wo)), r = (int)(g % (Ho * Wo)), oy = r / Wo, ox = r % Wo;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        const int iy = 2 * oy + ky - 1, ix = 2 * ox + kx - 1;
+        if (iy < 0 || iy >= Hi || ix < 0 || ix >= Wi) continue;
+        const uint2 v = *reinterpret_cast<const uint2*>(in + ((size_t)b * PBi + (size_t)iy * Wpi + ix) * C + lane * 4);
+        const float2 f0 = __half22float2(*reinterpret_cast<const act2_t*>(&v.x));
+        const float2 f1 = __half22float2(*reinterpret_cast<const act2_t*>(&v.y));
+        s[0] += f0.x; s[1] += f0.y; s[2] += f1.x; s[3] += f1.y;
+      }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[j] *= (1.0f / 9.0f);
+    if (normalise) {
+      float mn = fminf(fminf(s[0], s[1]), fminf(s[2], s[3])), mx = fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3]));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      }
+      const float inv = 1.0f / ((mx - mn) + 1e-8f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[j] = (s[j] - mn) * inv;
+    }
+    uint2 pk;
+    pk.x = pack2(s[0], s[1]);
+    pk.y = pack2(s[2], s[3]);
+    const size_t pos = (size_t)oy * Wpo + ox;
+    if (out) *reinterpret_cast<uint2*>(out + ((size_t)b * PBo + pos) * C + lane * 4) = pk;
+    if (slots) {
+      const size_t board = out_index ? (size_t)out_index[b] : (size_t)b;
+      *reinterpret_cast<uint2*>(slots + (board * PBo + pos) * C + lane * 4) = pk;
+    }
+  }
+}
+
+// stride-2 conv weight [Co][Ci][3][3] fp32 -> fp16 [9][Ci_pad][Co]
+__global__ void pack_s2_kernel(const float* __restrict__ w, act_t* __restrict__ out, int Co, int Ci, int Ci_pad) {
+  const size_t total = (size_t)9 * Ci_pad * Co;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Co), ci = (int)((i / Co) % Ci_pad), tap = (int)(i / ((size_t)Co * Ci_pad));
+    out[i] = __float2half_rn(ci < Ci ? w[(((size_t)co * Ci + ci) * 3 + tap / 3) * 3 + tap % 3] : 0.0f);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 struct ConvLayer {
@@ -607,29 +747,60 @@ struct Head {
   const float *w1, *b1, *w2, *b2;
   int mid, out, kind;
 };
+struct Geo {
+  int H, W;
+  int Wp() const { return W + 1; }
+  int PB() const { return (H + 1) * (W + 1); }
+};
 
 struct ConvNet : NetImpl {
   mz_net_config cfg;
-  int H, W, Wp, PB, C, A, blocks, max_batch, num_sms;
-  int in_cg;                       // channel groups of the packed observation
+  Geo lat;                          // latent grid: the board (board games) or 6x6 (Atari)
+  int C, A, blocks, max_batch, num_sms;
+  bool atari;
+  int in_cg;                        // channel groups of the packed observation
   ConvLayer rep0, dyn0;
   ConvLayer rep_blocks[64], dyn_blocks[64], pred_blocks[64];   // 2 per block
+  // Atari representation: conv_1 (s2) -> 2 blocks @48 -> conv_2 (s2) -> 2 blocks @24 -> pool -> 2 blocks @12 -> pool
+  const act_t *s2_w1, *s2_w2;
+  ConvLayer at_blocks[3][4];
   const float* tab;
   Head h_reward, h_policy, h_value;
   act_t *xobs, *b0, *b1, *b2, *b3;
 
-  int launch_conv(const ConvLayer& L, const act_t* in, const int32_t* in_index, int batch, const float* tab_,
-                  const int32_t* action, const act_t* residual, act_t* out, act_t* out_norm,
+  static int tp_of(const Geo& g) { return (kTileM + 2 * (g.Wp() + 1)) | 1; }
+  size_t conv_fixed_smem(const Geo& g, int cg) const {
+    const int TP = tp_of(g);
+    size_t a = (((size_t)2 * cg * TP * 16) + 127) & ~(size_t)127;
+    return a + (2 * kMaxStages + 6) * 8 + 16 + (size_t)C * 4 + (size_t)TP * 4 + 64;
+  }
+  int conv_stages(const Geo& g, int cg) const {
+    const int chunk_g = cg < 8 ? cg : 8;
+    const size_t stage = (size_t)chunk_g * C * 16;
+    const size_t fixed = conv_fixed_smem(g, cg);
+    if (fixed + 2 * stage > 227 * 1024) return 0;
+    int s = (int)((227 * 1024 - fixed) / stage);
+    return s > kMaxStages ? kMaxStages : s;
+  }
+  size_t conv_smem(const Geo& g, int cg) const {
+    const int chunk_g = cg < 8 ? cg : 8;
+    return conv_fixed_smem(g, cg) + (size_t)conv_stages(g, cg) * chunk_g * C * 16;
+  }
+
+  int launch_conv(const ConvLayer& L, const Geo& g, const act_t* in, const int32_t* in_index, int batch,
+                  const float* tab_, const int32_t* action, const act_t* residual, act_t* out, act_t* out_norm,
                   act_t* out_slots, const int32_t* out_index, cudaStream_t st) {
     ConvParams p;
     p.in = in; p.in_index = in_index; p.w = L.w; p.bias = L.bias; p.tab = tab_; p.action = action;
     p.residual = residual; p.out = out; p.out_norm = out_norm; p.out_slots = out_slots; p.out_index = out_index;
-    p.Ptot = batch * PB; p.PB = PB; p.Wp = Wp; p.W = W; p.H = H; p.B = batch;
+    p.PB = g.PB(); p.Wp = g.Wp(); p.W = g.W; p.H = g.H; p.B = batch;
+    p.Ptot = batch * p.PB;
     p.cg = L.cg; p.N = C; p.relu = 1;
     p.num_tiles = (p.Ptot + kTileM - 1) / kTileM;
-    p.TP = (kTileM + 2 * (Wp + 1)) | 1;
-    p.stages = conv_stages(L.cg);
-    const size_t smem = conv_smem(L.cg);
+    p.TP = tp_of(g);
+    p.stages = conv_stages(g, L.cg);
+    if (p.stages < 2) { set_error("conv tile does not fit shared memory for a %dx%d grid", g.H, g.W); return MZ_EINVAL; }
+    const size_t smem = conv_smem(g, L.cg);
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
     p.dbg = nullptr;
     static const bool debug = getenv("MZ_CONV_DEBUG") != nullptr;
@@ -647,32 +818,17 @@ struct ConvNet : NetImpl {
       cudaFree(p.dbg);
       double a[16] = {0};
       for (int c = 0; c < grid; ++c) for (int k = 0; k < 16; ++k) a[k] += (double)h[(size_t)c * 16 + k] / grid;
-      fprintf(stderr, "[conv dbg] cg=%d tiles/cta=%.1f | producer total %.0f wait_empty %.0f | mma total %.0f wait_acc %.0f "
+      fprintf(stderr, "[conv dbg] %dx%d cg=%d tiles/cta=%.1f | producer total %.0f wait_empty %.0f | mma total %.0f wait_acc %.0f "
               "wait_a %.0f wait_w %.0f | loader total %.0f wait_mma %.0f copy %.0f | epilogue total %.0f wait_mma %.0f\n",
-              L.cg, a[6], a[0], a[1], a[2], a[3], a[4], a[5], a[7], a[8], a[9], a[10], a[11]);
+              g.H, g.W, L.cg, a[6], a[0], a[1], a[2], a[3], a[4], a[5], a[7], a[8], a[9], a[10], a[11]);
     }
     return MZ_OK;
-  }
-  size_t conv_fixed_smem(int cg) const {
-    const int TP = (kTileM + 2 * (Wp + 1)) | 1;
-    size_t a = (((size_t)2 * cg * TP * 16) + 127) & ~(size_t)127;
-    return a + (2 * kMaxStages + 6) * 8 + 16 + (size_t)C * 4 + (size_t)TP * 4 + 64;
-  }
-  int conv_stages(int cg) const {
-    const int chunk_g = cg < 8 ? cg : 8;
-    const size_t stage = (size_t)chunk_g * C * 16;
-    int s = (int)((227 * 1024 - conv_fixed_smem(cg)) / stage);
-    return s > kMaxStages ? kMaxStages : s;
-  }
-  size_t conv_smem(int cg) const {
-    const int chunk_g = cg < 8 ? cg : 8;
-    return conv_fixed_smem(cg) + (size_t)conv_stages(cg) * chunk_g * C * 16;
   }
   int launch_head(const Head& h, const act_t* act, int batch, float* dst, cudaStream_t st) {
     HeadParams p;
     p.act = act; p.w1 = h.w1; p.b1 = h.b1; p.w2 = h.w2; p.b2 = h.b2; p.dst = dst;
-    p.C = C; p.H = H; p.W = W; p.mid = h.mid; p.out = h.out; p.kind = h.kind;
-    const size_t smem = ((size_t)h.mid * H * W + h.out) * 4;
+    p.C = C; p.H = lat.H; p.W = lat.W; p.mid = h.mid; p.out = h.out; p.kind = h.kind;
+    const size_t smem = ((size_t)h.mid * lat.H * lat.W + h.out) * 4;
     prof_mark(kProfHead, st);
     head_kernel<<<batch, 128, smem, st>>>(p);
     prof_mark(-1, st);
@@ -680,34 +836,34 @@ struct ConvNet : NetImpl {
     return MZ_OK;
   }
 
-  // [first conv] -> residual blocks; the LAST layer optionally also emits the min-max normalised
-  // state (contiguous copy and/or indexed slots).  *final_buf = buffer holding the raw (ReLU'd)
-  // tower output, unless want_raw is false and the last layer normalises (then it is not written).
-  int tower(const ConvLayer* first, const ConvLayer* blk, const act_t* in, const int32_t* in_index,
-            const float* tab_, const int32_t* action, int batch, bool want_raw, act_t* norm_out,
-            act_t* slots, const int32_t* out_index, cudaStream_t st, act_t** final_buf) {
+  // [first conv] -> nblk residual blocks on grid g; the LAST layer optionally also emits the min-max
+  // normalised state (contiguous copy and/or indexed slots).  *final_buf = buffer holding the raw
+  // (ReLU'd) tower output, unless want_raw is false and the last layer normalises.
+  int tower(const ConvLayer* first, const ConvLayer* blk, int nblk, const Geo& g, const act_t* in,
+            const int32_t* in_index, const float* tab_, const int32_t* action, int batch, bool want_raw,
+            act_t* norm_out, act_t* slots, const int32_t* out_index, cudaStream_t st, act_t** final_buf) {
     const act_t* cur = in;
     const int32_t* cur_index = in_index;
     act_t* pp[2] = {b0, b1};
-    int which = 0, rc;
+    int which = (in == b0) ? 1 : 0, rc;
     const bool normalise = (norm_out != nullptr) || (slots != nullptr);
     if (first) {
-      const bool last = (blocks == 0);
+      const bool last = (nblk == 0);
       act_t* dst = pp[which];
-      rc = launch_conv(*first, cur, cur_index, batch, tab_, action, nullptr,
+      rc = launch_conv(*first, g, cur, cur_index, batch, tab_, action, nullptr,
                        (last && normalise && !want_raw) ? nullptr : dst, last ? norm_out : nullptr,
                        last ? slots : nullptr, out_index, st);
       if (rc) return rc;
       cur = dst; cur_index = nullptr; which ^= 1;
     }
-    for (int i = 0; i < blocks; ++i) {
-      const bool last = (i == blocks - 1);
-      rc = launch_conv(blk[2 * i], cur, cur_index, batch, nullptr, nullptr, nullptr, b2, nullptr, nullptr, nullptr, st);
+    for (int i = 0; i < nblk; ++i) {
+      const bool last = (i == nblk - 1);
+      rc = launch_conv(blk[2 * i], g, cur, cur_index, batch, nullptr, nullptr, nullptr, b2, nullptr, nullptr, nullptr, st);
       if (rc) return rc;
       if (cur_index != nullptr) { set_error("internal: residual input must be contiguous"); return MZ_EINVAL; }
       act_t* dst = pp[which];
       if (dst == cur) dst = pp[which ^ 1];
-      rc = launch_conv(blk[2 * i + 1], b2, nullptr, batch, nullptr, nullptr, cur,
+      rc = launch_conv(blk[2 * i + 1], g, b2, nullptr, batch, nullptr, nullptr, cur,
                        (last && normalise && !want_raw) ? nullptr : dst, last ? norm_out : nullptr,
                        last ? slots : nullptr, out_index, st);
       if (rc) return rc;
@@ -717,23 +873,68 @@ struct ConvNet : NetImpl {
     return MZ_OK;
   }
 
-  int initial(int batch, const float* obs, void* hidden_out, const int32_t* dst_index, float* pi_probs, float* value,
-              cudaStream_t st) override {
+  int represent_atari(int batch, const float* obs, act_t* slots, const int32_t* dst_index, cudaStream_t st) {
+    const int Hin = cfg.in_h, Win = cfg.in_w;
     prof_mark(kProfPack, st);
-    pack_obs_kernel<<<num_sms * 4, 256, 0, st>>>(obs, xobs, batch, cfg.in_channels, H, W, in_cg * 8);
+    pack_obs_kernel<<<num_sms * 8, 256, 0, st>>>(obs, xobs, batch, cfg.in_channels, Hin, Win, 16);
     prof_mark(-1, st);
     MZ_LAUNCH_CHECK("pack_obs_kernel");
+    Geo g1{Hin / 2, Win / 2}, g2{Hin / 4, Win / 4}, g3{Hin / 8, Win / 8};
+    auto s2 = [&](const act_t* in, const act_t* w, act_t* out, int Hi, int Wi, int Ci) -> int {
+      const long long total = (long long)batch * (Hi / 2) * (Wi / 2);
+      prof_mark(kProfPack, st);
+      conv3x3_s2_kernel<<<(unsigned)((total + 63) / 64), 256, 0, st>>>(in, w, out, batch, Hi, Wi, Ci);
+      prof_mark(-1, st);
+      MZ_LAUNCH_CHECK("conv3x3_s2_kernel");
+      return MZ_OK;
+    };
+    auto pool = [&](const act_t* in, act_t* out, act_t* sl, const int32_t* idx, int Hi, int Wi, int norm) -> int {
+      prof_mark(kProfPack, st);
+      avgpool_kernel<<<num_sms * 8, 256, 0, st>>>(in, out, sl, idx, batch, Hi, Wi, norm);
+      prof_mark(-1, st);
+      MZ_LAUNCH_CHECK("avgpool_kernel");
+      return MZ_OK;
+    };
     act_t* fin;
-    // representation: raw output is not needed, normalised goes to b3 (for the prediction tower) and the slots
-    int rc = tower(&rep0, rep_blocks, xobs, nullptr, nullptr, nullptr, batch, false, b3, (act_t*)hidden_out,
-                   dst_index, st, &fin);
+    int rc;
+    // halo entries of b0..b3 are never read, so grids of different sizes can reuse the same buffers
+    if ((rc = s2(xobs, s2_w1, b0, Hin, Win, 16))) return rc;                                   // relu(conv_1)
+    if ((rc = tower(nullptr, at_blocks[0], 2, g1, b0, nullptr, nullptr, nullptr, batch, true, nullptr, nullptr,
+                    nullptr, st, &fin))) return rc;
+    act_t* nxt = (fin == b0) ? b1 : b0;
+    if ((rc = s2(fin, s2_w2, nxt, g1.H, g1.W, C))) return rc;                                  // relu(conv_2)
+    if ((rc = tower(nullptr, at_blocks[1], 2, g2, nxt, nullptr, nullptr, nullptr, batch, true, nullptr, nullptr,
+                    nullptr, st, &fin))) return rc;
+    nxt = (fin == b0) ? b1 : b0;
+    if ((rc = pool(fin, nxt, nullptr, nullptr, g2.H, g2.W, 0))) return rc;                     // avg_pool_1
+    if ((rc = tower(nullptr, at_blocks[2], 2, g3, nxt, nullptr, nullptr, nullptr, batch, true, nullptr, nullptr,
+                    nullptr, st, &fin))) return rc;
+    return pool(fin, b3, slots, dst_index, g3.H, g3.W, 1);                                     // avg_pool_2 + normalise
+  }
+
+  int initial(int batch, const float* obs, void* hidden_out, const int32_t* dst_index, float* pi_probs, float* value,
+              cudaStream_t st) override {
+    int rc;
+    if (atari) {
+      rc = represent_atari(batch, obs, (act_t*)hidden_out, dst_index, st);
+    } else {
+      prof_mark(kProfPack, st);
+      pack_obs_kernel<<<num_sms * 4, 256, 0, st>>>(obs, xobs, batch, cfg.in_channels, lat.H, lat.W, in_cg * 8);
+      prof_mark(-1, st);
+      MZ_LAUNCH_CHECK("pack_obs_kernel");
+      act_t* fin;
+      // representation: raw output is not needed, normalised goes to b3 (for the prediction tower) and the slots
+      rc = tower(&rep0, rep_blocks, blocks, lat, xobs, nullptr, nullptr, nullptr, batch, false, b3,
+                 (act_t*)hidden_out, dst_index, st, &fin);
+    }
     if (rc) return rc;
     return predict(batch, pi_probs, value, st);
   }
 
   int predict(int batch, float* pi_probs, float* value, cudaStream_t st) {
     act_t* fin;
-    int rc = tower(nullptr, pred_blocks, b3, nullptr, nullptr, nullptr, batch, true, nullptr, nullptr, nullptr, st, &fin);
+    int rc = tower(nullptr, pred_blocks, blocks, lat, b3, nullptr, nullptr, nullptr, batch, true, nullptr, nullptr,
+                   nullptr, st, &fin);
     if (rc) return rc;
     if (pi_probs) {
       rc = launch_head(h_policy, fin, batch, pi_probs, st);
@@ -747,7 +948,7 @@ struct ConvNet : NetImpl {
                 cudaStream_t st) override {
     act_t* fin;
     // dynamics: raw output (for the reward head) in a ping-pong buffer, normalised copy in b3 + the slots
-    int rc = tower(&dyn0, dyn_blocks, (const act_t*)hidden_in, src_index, tab, action, batch, true, b3,
+    int rc = tower(&dyn0, dyn_blocks, blocks, lat, (const act_t*)hidden_in, src_index, tab, action, batch, true, b3,
                    (act_t*)hidden_out, dst_index, st, &fin);
     if (rc) return rc;
     rc = launch_head(h_reward, fin, batch, reward_out, st);     // reward head reads the UN-normalised state
@@ -759,15 +960,21 @@ struct ConvNet : NetImpl {
 static int conv_geometry(const mz_net_config& c, int* H, int* W) {
   MZ_CHECK_ARG(c.num_planes == 32 || c.num_planes == 64 || c.num_planes == 128,
                "conv nets need num_planes in {32, 64, 128}, got %d", c.num_planes);
-  MZ_CHECK_ARG(c.in_channels > 0 && c.in_channels <= 64, "conv nets take 1..64 observation planes, got %d",
-               c.in_channels);
   MZ_CHECK_ARG(c.num_res_blocks >= 0 && c.num_res_blocks <= 32, "num_res_blocks out of range");
-  if (c.kind == MZ_NET_BOARD) { *H = c.in_h; *W = c.in_w; }
-  else { *H = 6; *W = 6; }                    // network.py:516-519 hard-wires the 6x6 latent
-  MZ_CHECK_ARG(*H > 0 && *W > 0 && *W <= 40, "unsupported board size %dx%d", *H, *W);
-  if (c.kind == MZ_NET_ATARI) {
-    set_error("MuZeroAtariNet's strided representation tower is not built yet");
-    return MZ_EINVAL;
+  if (c.kind == MZ_NET_BOARD) {
+    MZ_CHECK_ARG(c.in_channels > 0 && c.in_channels <= 64, "board nets take 1..64 observation planes, got %d",
+                 c.in_channels);
+    *H = c.in_h; *W = c.in_w;
+    MZ_CHECK_ARG(*H > 0 && *W > 0 && *W <= 40, "unsupported board size %dx%d", *H, *W);
+  } else {
+    // network.py:516-519 hard-wires the 6x6 latent, i.e. 96x96 frames (gym_env.py:373-374); the first
+    // residual stage is 128 wide whatever num_planes says (network.py:324-327)
+    MZ_CHECK_ARG(c.in_h == 96 && c.in_w == 96, "MuZeroAtariNet needs 96x96 observations (6x6 latent), got %dx%d",
+                 c.in_h, c.in_w);
+    MZ_CHECK_ARG(c.num_planes == 128, "MuZeroAtariNet is built for num_planes == 128, got %d", c.num_planes);
+    MZ_CHECK_ARG(c.in_channels > 0 && c.in_channels <= 16, "MuZeroAtariNet takes 1..16 stacked planes, got %d",
+                 c.in_channels);
+    *H = 6; *W = 6;
   }
   return MZ_OK;
 }
@@ -787,18 +994,23 @@ int conv_arena_bytes(const mz_net_config& c, int max_batch, size_t* bytes) {
   int H, W;
   int rc = conv_geometry(c, &H, &W);
   if (rc) return rc;
+  const bool atari = c.kind == MZ_NET_ATARI;
   const int N = c.num_planes, PB = (H + 1) * (W + 1), A = c.num_actions, hw = H * W;
   size_t t = 0;
-  const int nconv_main = 1 + 6 * c.num_res_blocks;            // dyn0 + 2 per block x 3 towers
+  const int nconv_main = 1 + 6 * c.num_res_blocks + (atari ? 12 : 0);   // dyn0 + 2 per block x 3 towers (+ Atari rep)
   t += conv_w_bytes(obs_cg(c.in_channels), N) + (size_t)nconv_main * conv_w_bytes(N / 8, N);
-  t += (size_t)(2 + 6 * c.num_res_blocks) * 2 * align_up((size_t)N * 4, 256);          // scale + bias per conv
+  t += (size_t)(2 + 6 * c.num_res_blocks + 12) * 2 * align_up((size_t)N * 4, 256);     // scale + bias per conv
+  t += 2 * align_up((size_t)9 * 128 * 128 * 2, 256);                                    // stride-2 conv weights
   t += align_up((size_t)A * PB * N * 4, 256);                                           // action table
   t += 3 * (align_up((size_t)2 * N * 4, 256) + 2 * 256 + 256);                          // head 1x1 weights/bias/scale
   t += align_up((size_t)c.reward_support * hw * 4, 256) + align_up((size_t)A * 2 * hw * 4, 256) +
        align_up((size_t)c.value_support * hw * 4, 256) + 3 * align_up((size_t)(A + c.value_support + c.reward_support) * 4, 256);
-  t += align_up((size_t)max_batch * PB * obs_cg(c.in_channels) * 16, 256);              // packed observations
-  t += 4 * align_up((size_t)max_batch * PB * N * 2, 256);                               // b0..b3
-  *bytes = t + 4096;
+  const size_t big_pb = atari ? (size_t)(c.in_h / 2 + 1) * (c.in_w / 2 + 1) : (size_t)PB;   // largest activation grid
+  const size_t obs_pb = atari ? (size_t)(c.in_h + 1) * (c.in_w + 1) : (size_t)PB;
+  t += align_up((size_t)max_batch * obs_pb * (atari ? 2 : obs_cg(c.in_channels)) * 16, 256);   // packed observations
+  t += 3 * align_up((size_t)max_batch * big_pb * N * 2, 256);                            // b0..b2
+  t += align_up((size_t)max_batch * PB * N * 2, 256);                                    // b3 (latent grid only)
+  *bytes = t + 8192;
   return MZ_OK;
 }
 
@@ -807,27 +1019,31 @@ int conv_create(const mz_net_config& c, const float* const* w, int nw, int max_b
   int H, W;
   int rc = conv_geometry(c, &H, &W);
   if (rc) return rc;
+  const bool atari = c.kind == MZ_NET_ATARI;
   const int N = c.num_planes, A = c.num_actions, hw = H * W, blocks = c.num_res_blocks;
-  const int expect = (5 + 10 * blocks) + (5 + 10 * blocks + 7) + (10 * blocks + 14);
-  MZ_CHECK_ARG(nw == expect, "MuZeroBoardGameNet with %d blocks has %d state_dict tensors, got %d", blocks, expect, nw);
+  const int rep_tensors = atari ? (1 + 20 + 1 + 20 + 20) : (5 + 10 * blocks);
+  const int expect = rep_tensors + (5 + 10 * blocks + 7) + (10 * blocks + 14);
+  MZ_CHECK_ARG(nw == expect, "%s with %d blocks has %d state_dict tensors, got %d",
+               atari ? "MuZeroAtariNet" : "MuZeroBoardGameNet", blocks, expect, nw);
   size_t need;
   conv_arena_bytes(c, max_batch, &need);
   if (arena_bytes < need) { set_error("net arena too small: %zu < %zu", arena_bytes, need); return MZ_ENOMEM; }
 
   ConvNet* net = new ConvNet();
-  net->cfg = c; net->H = H; net->W = W; net->Wp = W + 1; net->PB = (H + 1) * (W + 1); net->C = N; net->A = A;
+  net->cfg = c; net->lat = Geo{H, W}; net->C = N; net->A = A; net->atari = atari;
   net->blocks = blocks; net->max_batch = max_batch;
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&net->num_sms, cudaDevAttrMultiProcessorCount, dev);
   net->in_cg = obs_cg(c.in_channels);
+  const int PB = net->lat.PB();
 
   char* p = (char*)arena;
   auto take = [&](size_t bytes) { char* r = p; p += align_up(bytes, 256); return r; };
   int cur = 0;
   auto next = [&]() { return w[cur++]; };
 
-  // conv (no bias) + BatchNorm -> packed bf16 weights + fp32 bias; optional action table
+  // conv (no bias) + BatchNorm -> packed fp16 weights + fp32 bias
   auto fold_conv = [&](int cin, int cin_total, int cg, ConvLayer* L, float** scale_out) -> int {
     const float* cw = next();
     const float *g = next(), *beta = next(), *mean = next(), *var = next();
@@ -840,7 +1056,15 @@ int conv_create(const mz_net_config& c, const float* const* w, int nw, int max_b
     MZ_LAUNCH_CHECK("pack_conv_kernel");
     L->w = wp; L->bias = bias; L->cg = cg;
     if (scale_out) *scale_out = scale;
-    (void)cw;
+    return MZ_OK;
+  };
+  auto pack_s2 = [&](int cin, const act_t** dst) -> int {
+    const float* cw = next();
+    const int cpad = (cin + 15) / 16 * 16;
+    act_t* wp = (act_t*)take((size_t)9 * cpad * 128 * 2);
+    pack_s2_kernel<<<256, 256>>>(cw, wp, 128, cin, cpad);
+    MZ_LAUNCH_CHECK("pack_s2_kernel");
+    *dst = wp;
     return MZ_OK;
   };
   auto fold_head = [&](int mid, int outn, int kind, Head* h) -> int {
@@ -864,15 +1088,24 @@ int conv_create(const mz_net_config& c, const float* const* w, int nw, int max_b
   };
 #define MZ_TRY(x) do { int rc__ = (x); if (rc__) { delete net; return rc__; } } while (0)
 
-  // representation (network.py:356-393)
-  MZ_TRY(fold_conv(c.in_channels, c.in_channels, net->in_cg, &net->rep0, nullptr));
-  for (int i = 0; i < 2 * blocks; ++i) MZ_TRY(fold_conv(N, N, N / 8, &net->rep_blocks[i], nullptr));
+  if (atari) {
+    // representation (network.py:312-353): conv_1, res_blocks_1 x2, conv_2, res_blocks_2 x2, res_blocks_3 x2
+    MZ_TRY(pack_s2(c.in_channels, &net->s2_w1));
+    for (int i = 0; i < 4; ++i) MZ_TRY(fold_conv(N, N, N / 8, &net->at_blocks[0][i], nullptr));
+    MZ_TRY(pack_s2(128, &net->s2_w2));
+    for (int i = 0; i < 4; ++i) MZ_TRY(fold_conv(N, N, N / 8, &net->at_blocks[1][i], nullptr));
+    for (int i = 0; i < 4; ++i) MZ_TRY(fold_conv(N, N, N / 8, &net->at_blocks[2][i], nullptr));
+  } else {
+    // representation (network.py:356-393)
+    MZ_TRY(fold_conv(c.in_channels, c.in_channels, net->in_cg, &net->rep0, nullptr));
+    for (int i = 0; i < 2 * blocks; ++i) MZ_TRY(fold_conv(N, N, N / 8, &net->rep_blocks[i], nullptr));
+  }
   // dynamics (network.py:396-449): first conv sees C + A channels; the A action planes become a table
   {
     const float* dyn_w = w[cur];
     float* scale = nullptr;
     MZ_TRY(fold_conv(N, N + A, N / 8, &net->dyn0, &scale));
-    float* tab = (float*)take((size_t)A * net->PB * N * 4);
+    float* tab = (float*)take((size_t)A * PB * N * 4);
     action_table_kernel<<<512, 256>>>(dyn_w, scale, tab, A, N, N, H, W);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("action_table_kernel: %s", cudaGetErrorString(e)); delete net; return MZ_ECUDA; }
@@ -886,12 +1119,14 @@ int conv_create(const mz_net_config& c, const float* const* w, int nw, int max_b
   MZ_TRY(fold_head(2, A, 2, &net->h_policy));
   MZ_TRY(fold_head(1, c.value_support, c.value_support == 1 ? 0 : 1, &net->h_value));
 #undef MZ_TRY
-  net->xobs = (act_t*)take((size_t)max_batch * net->PB * net->in_cg * 16);
-  const size_t act_bytes = (size_t)max_batch * net->PB * N * 2;
+  const size_t big_pb = atari ? (size_t)(c.in_h / 2 + 1) * (c.in_w / 2 + 1) : (size_t)PB;
+  const size_t obs_pb = atari ? (size_t)(c.in_h + 1) * (c.in_w + 1) : (size_t)PB;
+  net->xobs = (act_t*)take((size_t)max_batch * obs_pb * (atari ? 2 : net->in_cg) * 16);
+  const size_t act_bytes = (size_t)max_batch * big_pb * N * 2;
   net->b0 = (act_t*)take(act_bytes);
   net->b1 = (act_t*)take(act_bytes);
   net->b2 = (act_t*)take(act_bytes);
-  net->b3 = (act_t*)take(act_bytes);
+  net->b3 = (act_t*)take((size_t)max_batch * PB * N * 2);
   if ((size_t)(p - (char*)arena) > arena_bytes) {
     set_error("internal: net arena overrun (%zu > %zu)", (size_t)(p - (char*)arena), arena_bytes);
     delete net;
@@ -899,15 +1134,16 @@ int conv_create(const mz_net_config& c, const float* const* w, int nw, int max_b
   }
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { set_error("weight repacking failed: %s", cudaGetErrorString(e)); delete net; return MZ_ECUDA; }
-  const size_t smem_max = net->conv_smem(N / 8) > net->conv_smem(net->in_cg) ? net->conv_smem(N / 8) : net->conv_smem(net->in_cg);
-  if (smem_max > 227 * 1024 || net->conv_stages(N / 8) < 2 || net->conv_stages(net->in_cg) < 2) {
-    set_error("conv tile needs %zu bytes of shared memory (board too wide)", smem_max);
+  if (net->conv_stages(net->lat, N / 8) < 2 || (!atari && net->conv_stages(net->lat, net->in_cg) < 2) ||
+      (atari && net->conv_stages(Geo{c.in_h / 2, c.in_w / 2}, N / 8) < 2)) {
+    set_error("conv tile does not fit shared memory (grid too wide)");
     delete net;
     return MZ_EINVAL;
   }
-  e = cudaFuncSetAttribute(conv3x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+  const int smem_max = 227 * 1024;
+  e = cudaFuncSetAttribute(conv3x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
   if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); delete net; return MZ_ECUDA; }
   *out = net;
   return MZ_OK;

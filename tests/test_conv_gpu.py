@@ -149,3 +149,59 @@ def test_gomoku_search_replays_bit_exact_in_oracle():
     streams2 = [np.random.RandomState(300 + t) for t in range(B)]
     a2, pi2, q2 = mz.uct_search_batch(obs, net, cfg, 1.0, mask, 1, 2, rng=streams2, plan=plan)
     assert torch.equal(a2, action) and torch.equal(pi2, pi) and torch.equal(q2, rootv)
+
+
+def build_atari(kw, seed):
+    import muzero_b200 as mz
+    torch.manual_seed(seed)
+    net = mz.MuZeroAtariNet(**kw).eval()
+    randomize_batchnorm(net, 1000 + seed)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    onet = OracleNet('atari', sd, kw['num_actions'], kw['value_support_size'], kw['reward_support_size'],
+                     kw['num_res_blocks'])
+    return net.cuda(), onet
+
+
+ATARI_SMALL = dict(input_shape=(4, 96, 96), num_actions=6, num_res_blocks=2, num_planes=128, value_support_size=21,
+                   reward_support_size=21)
+
+
+def test_atari_net_vs_reference_recording():
+    """MuZeroAtariNet: strided representation (SIMT stride-2 convs + avg pools around tcgen05 residual
+    blocks at 48x48 / 24x24 / 12x12), 6x6 latent towers, support heads; against the reference's recording."""
+    net, onet = build_atari(ATARI_SMALL, 5)
+    z = np.load(os.path.join(GOLDEN, 'net_golden.npz'))
+    for j in range(2):
+        g = {k: z[f'atari_small_{j}_{k}'] for k in ('obs', 'actions', 'h0', 'pi0', 'v0', 'h', 'r', 'v', 'pi')}
+        o = net.initial_inference(torch.from_numpy(g['obs'])[None].cuda())
+        assert o.hidden_state.shape == (128, 6, 6)
+        report(f'atari/{j} h0', o.hidden_state, g['h0'].astype(np.float32), 0.03)
+        report(f'atari/{j} pi0', o.pi_probs, g['pi0'], 0.03)
+        report(f'atari/{j} v0', o.value, g['v0'], 0.03)
+        h = g['h0'].astype(np.float32)
+        for i, a in enumerate(g['actions']):
+            o = net.recurrent_inference(torch.from_numpy(h)[None].cuda(), torch.tensor([[int(a)]]).cuda())
+            report(f'atari/{j} h[{i}]', o.hidden_state, g['h'][i].astype(np.float32), 0.03)
+            report(f'atari/{j} r[{i}]', o.reward, g['r'][i], 0.03)
+            report(f'atari/{j} v[{i}]', o.value, g['v'][i], 0.03)
+            report(f'atari/{j} pi[{i}]', o.pi_probs, g['pi'][i], 0.03)
+            h = g['h'][i].astype(np.float32)
+
+
+def test_atari_batched_vs_torch_fp32():
+    net, onet = build_atari(ATARI_SMALL, 5)
+    gen = np.random.RandomState(3)
+    B = 5
+    obs = gen.randint(0, 256, size=(B, 4, 96, 96)).astype(np.float32)
+    obs[:, 2:] = ((gen.randint(0, 6, size=(B, 2, 1, 1)) + 1) / 6).astype(np.float32)
+    hid, pi, v = net.initial_inference_batch(torch.from_numpy(obs).cuda())
+    h_ref, pi_ref, v_ref = onet.initial_batch(obs)
+    report('atari h0', net.hidden_to_reference(hid).cpu().numpy(), h_ref.numpy(), 0.03)
+    report('atari pi0', pi.cpu().numpy(), pi_ref.numpy(), 0.03)
+    report('atari v0', v.cpu().numpy(), v_ref.numpy(), 0.03)
+    act = gen.randint(0, 6, size=B)
+    _, r, pi2, v2 = net.recurrent_inference_batch(net.hidden_from_reference(h_ref.cuda()), torch.from_numpy(act).cuda())
+    _, r_ref, pi2_ref, v2_ref = onet.recurrent_batch(h_ref, act)
+    report('atari r', r.cpu().numpy(), r_ref.numpy(), 0.03)
+    report('atari v1', v2.cpu().numpy(), v2_ref.numpy(), 0.03)
+    report('atari pi1', pi2.cpu().numpy(), pi2_ref.numpy(), 0.03)
