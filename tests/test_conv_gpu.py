@@ -1,10 +1,10 @@
 """GPU tests of the tcgen05 ResNet towers (bf16 x bf16 -> fp32) against the fp32 torch
 restatement of the reference and the reference's own recorded outputs.
 
-Stated tolerance (bf16 activations between layers, fp32 accumulation, fp32 heads):
-  hidden state (min-max normalised to [0,1]):  |err| <= 0.03 for an 8-block tower, 0.02 shallow
-  policy probabilities:                        |err| <= 0.03
-  value / reward (scalar heads):               |err| <= 0.03 * max(1, |ref|_max)
+Stated tolerance (fp16 activations and weights, fp32 accumulation in TMEM, fp32 heads):
+  hidden state (min-max normalised to [0,1]):  |err| <= 0.005   (measured <= 0.002)
+  policy probabilities:                        |err| <= 0.02    (measured <= 0.0096 on random-init nets with |logit| ~ 40)
+  value / reward:                              |err| <= 0.02 * max(1, |ref|_max)   (measured <= 0.014)
 """
 import os
 
@@ -18,6 +18,8 @@ from oracle.network_oracle import OracleNet, randomize_batchnorm
 from oracle.stubnet import ReplayStub
 
 pytestmark = pytest.mark.gpu
+TOL_H = 0.005      # hidden state, normalised to [0, 1]
+TOL_PV = 0.02      # policy probabilities (absolute); value / reward (relative to max(1, |ref|max))
 
 
 def build_board(input_shape, num_actions, blocks, planes, seed):
@@ -52,9 +54,9 @@ def test_single_conv_layers_blocks0(shape, A, planes, batch):
     obs = gen.randint(0, 2, size=(batch,) + shape).astype(np.float32)
     hid, pi, v = net.initial_inference_batch(torch.from_numpy(obs).cuda())
     h_ref, pi_ref, v_ref = onet.initial_batch(obs)
-    report('rep hidden', net.hidden_to_reference(hid).cpu().numpy(), h_ref.numpy(), 0.02)
-    report('pi0', pi.cpu().numpy(), pi_ref.numpy(), 0.03)
-    report('v0', v.cpu().numpy(), v_ref.numpy(), 0.03)
+    report('rep hidden', net.hidden_to_reference(hid).cpu().numpy(), h_ref.numpy(), TOL_H)
+    report('pi0', pi.cpu().numpy(), pi_ref.numpy(), TOL_PV)
+    report('v0', v.cpu().numpy(), v_ref.numpy(), TOL_PV)
     act = gen.randint(0, A, size=batch)
     src = torch.arange(batch - 1, -1, -1, dtype=torch.int32).cuda()
     dst = (torch.arange(batch, dtype=torch.int32) * 2 + 1).cuda()
@@ -63,10 +65,10 @@ def test_single_conv_layers_blocks0(shape, A, planes, batch):
     _, r, pi2, v2 = net.recurrent_inference_batch(slots_in, torch.from_numpy(act).cuda(), src_index=src, hidden_out=out,
                                                   dst_index=dst)
     h2_ref, r_ref, pi2_ref, v2_ref = onet.recurrent_batch(h_ref.flip(0), act)
-    report('dyn hidden', net.hidden_to_reference(out)[1::2].cpu().numpy(), h2_ref.numpy(), 0.02)
-    report('reward', r.cpu().numpy(), r_ref.numpy(), 0.03)
-    report('v1', v2.cpu().numpy(), v2_ref.numpy(), 0.03)
-    report('pi1', pi2.cpu().numpy(), pi2_ref.numpy(), 0.03)
+    report('dyn hidden', net.hidden_to_reference(out)[1::2].cpu().numpy(), h2_ref.numpy(), TOL_H)
+    report('reward', r.cpu().numpy(), r_ref.numpy(), TOL_PV)
+    report('v1', v2.cpu().numpy(), v2_ref.numpy(), TOL_PV)
+    report('pi1', pi2.cpu().numpy(), pi2_ref.numpy(), TOL_PV)
     assert (out.view(torch.float16)[0::2] == 0).all()        # untouched slots stay untouched
 
 
@@ -79,22 +81,22 @@ def test_towers_vs_reference_recording(name, kind, kw, seed):
     (tests/golden/net_golden.npz; the recording stores hidden states as float16)."""
     net, onet = build_board(kw['input_shape'], kw['num_actions'], kw['num_res_blocks'], kw['num_planes'], seed)
     z = np.load(os.path.join(GOLDEN, 'net_golden.npz'))
-    tol_h = 0.03
+    tol_h = TOL_H
     for j in range(2):
         g = {k: z[f'{name}_{j}_{k}'] for k in ('obs', 'actions', 'h0', 'pi0', 'v0', 'h', 'r', 'v', 'pi')}
         o = net.initial_inference(torch.from_numpy(g['obs'])[None].cuda())
         assert o.hidden_state.shape == g['h0'].shape and o.hidden_state.dtype == np.float32
         assert isinstance(o.value, float) and o.reward == 0.0
-        report(f'{name}/{j} h0', o.hidden_state, g['h0'].astype(np.float32), tol_h)
-        report(f'{name}/{j} pi0', o.pi_probs, g['pi0'], 0.03)
-        report(f'{name}/{j} v0', o.value, g['v0'], 0.03)
+        report(f'{name}/{j} h0', o.hidden_state, g['h0'].astype(np.float32), TOL_H)
+        report(f'{name}/{j} pi0', o.pi_probs, g['pi0'], TOL_PV)
+        report(f'{name}/{j} v0', o.value, g['v0'], TOL_PV)
         h = g['h0'].astype(np.float32)
         for i, a in enumerate(g['actions']):
             o = net.recurrent_inference(torch.from_numpy(h)[None].cuda(), torch.tensor([[int(a)]]).cuda())
-            report(f'{name}/{j} h[{i}]', o.hidden_state, g['h'][i].astype(np.float32), tol_h)
-            report(f'{name}/{j} r[{i}]', o.reward, g['r'][i], 0.03)
-            report(f'{name}/{j} v[{i}]', o.value, g['v'][i], 0.03)
-            report(f'{name}/{j} pi[{i}]', o.pi_probs, g['pi'][i], 0.03)
+            report(f'{name}/{j} h[{i}]', o.hidden_state, g['h'][i].astype(np.float32), TOL_H)
+            report(f'{name}/{j} r[{i}]', o.reward, g['r'][i], TOL_PV)
+            report(f'{name}/{j} v[{i}]', o.value, g['v'][i], TOL_PV)
+            report(f'{name}/{j} pi[{i}]', o.pi_probs, g['pi'][i], TOL_PV)
             h = g['h'][i].astype(np.float32)
 
 
@@ -107,15 +109,15 @@ def test_gomoku_batched_vs_torch_fp32(batch):
     hid, pi, v = net.initial_inference_batch(torch.from_numpy(obs).cuda())
     rows = np.sort(gen.choice(batch, size=nref, replace=False))
     h_ref, pi_ref, v_ref = onet.initial_batch(obs[rows])
-    report('h0', net.hidden_to_reference(hid)[rows].cpu().numpy(), h_ref.numpy(), 0.03)
-    report('pi0', pi[rows].cpu().numpy(), pi_ref.numpy(), 0.03)
-    report('v0', v[rows].cpu().numpy(), v_ref.numpy(), 0.03)
+    report('h0', net.hidden_to_reference(hid)[rows].cpu().numpy(), h_ref.numpy(), TOL_H)
+    report('pi0', pi[rows].cpu().numpy(), pi_ref.numpy(), TOL_PV)
+    report('v0', v[rows].cpu().numpy(), v_ref.numpy(), TOL_PV)
     act = gen.randint(0, 82, size=batch)
     _, r, pi2, v2 = net.recurrent_inference_batch(hid, torch.from_numpy(act).cuda())
     h2_ref, r_ref, pi2_ref, v2_ref = onet.recurrent_batch(h_ref, act[rows])
-    report('r', r[rows].cpu().numpy(), r_ref.numpy(), 0.03)
-    report('v1', v2[rows].cpu().numpy(), v2_ref.numpy(), 0.03)
-    report('pi1', pi2[rows].cpu().numpy(), pi2_ref.numpy(), 0.03)
+    report('r', r[rows].cpu().numpy(), r_ref.numpy(), TOL_PV)
+    report('v1', v2[rows].cpu().numpy(), v2_ref.numpy(), TOL_PV)
+    report('pi1', pi2[rows].cpu().numpy(), pi2_ref.numpy(), TOL_PV)
 
 
 def test_gomoku_search_replays_bit_exact_in_oracle():
@@ -175,16 +177,16 @@ def test_atari_net_vs_reference_recording():
         g = {k: z[f'atari_small_{j}_{k}'] for k in ('obs', 'actions', 'h0', 'pi0', 'v0', 'h', 'r', 'v', 'pi')}
         o = net.initial_inference(torch.from_numpy(g['obs'])[None].cuda())
         assert o.hidden_state.shape == (128, 6, 6)
-        report(f'atari/{j} h0', o.hidden_state, g['h0'].astype(np.float32), 0.03)
-        report(f'atari/{j} pi0', o.pi_probs, g['pi0'], 0.03)
-        report(f'atari/{j} v0', o.value, g['v0'], 0.03)
+        report(f'atari/{j} h0', o.hidden_state, g['h0'].astype(np.float32), TOL_H)
+        report(f'atari/{j} pi0', o.pi_probs, g['pi0'], TOL_PV)
+        report(f'atari/{j} v0', o.value, g['v0'], TOL_PV)
         h = g['h0'].astype(np.float32)
         for i, a in enumerate(g['actions']):
             o = net.recurrent_inference(torch.from_numpy(h)[None].cuda(), torch.tensor([[int(a)]]).cuda())
-            report(f'atari/{j} h[{i}]', o.hidden_state, g['h'][i].astype(np.float32), 0.03)
-            report(f'atari/{j} r[{i}]', o.reward, g['r'][i], 0.03)
-            report(f'atari/{j} v[{i}]', o.value, g['v'][i], 0.03)
-            report(f'atari/{j} pi[{i}]', o.pi_probs, g['pi'][i], 0.03)
+            report(f'atari/{j} h[{i}]', o.hidden_state, g['h'][i].astype(np.float32), TOL_H)
+            report(f'atari/{j} r[{i}]', o.reward, g['r'][i], TOL_PV)
+            report(f'atari/{j} v[{i}]', o.value, g['v'][i], TOL_PV)
+            report(f'atari/{j} pi[{i}]', o.pi_probs, g['pi'][i], TOL_PV)
             h = g['h'][i].astype(np.float32)
 
 
@@ -196,12 +198,12 @@ def test_atari_batched_vs_torch_fp32():
     obs[:, 2:] = ((gen.randint(0, 6, size=(B, 2, 1, 1)) + 1) / 6).astype(np.float32)
     hid, pi, v = net.initial_inference_batch(torch.from_numpy(obs).cuda())
     h_ref, pi_ref, v_ref = onet.initial_batch(obs)
-    report('atari h0', net.hidden_to_reference(hid).cpu().numpy(), h_ref.numpy(), 0.03)
-    report('atari pi0', pi.cpu().numpy(), pi_ref.numpy(), 0.03)
-    report('atari v0', v.cpu().numpy(), v_ref.numpy(), 0.03)
+    report('atari h0', net.hidden_to_reference(hid).cpu().numpy(), h_ref.numpy(), TOL_H)
+    report('atari pi0', pi.cpu().numpy(), pi_ref.numpy(), TOL_PV)
+    report('atari v0', v.cpu().numpy(), v_ref.numpy(), TOL_PV)
     act = gen.randint(0, 6, size=B)
     _, r, pi2, v2 = net.recurrent_inference_batch(net.hidden_from_reference(h_ref.cuda()), torch.from_numpy(act).cuda())
     _, r_ref, pi2_ref, v2_ref = onet.recurrent_batch(h_ref, act)
-    report('atari r', r.cpu().numpy(), r_ref.numpy(), 0.03)
-    report('atari v1', v2.cpu().numpy(), v2_ref.numpy(), 0.03)
-    report('atari pi1', pi2.cpu().numpy(), pi2_ref.numpy(), 0.03)
+    report('atari r', r.cpu().numpy(), r_ref.numpy(), TOL_PV)
+    report('atari v1', v2.cpu().numpy(), v2_ref.numpy(), TOL_PV)
+    report('atari pi1', pi2.cpu().numpy(), pi2_ref.numpy(), TOL_PV)
