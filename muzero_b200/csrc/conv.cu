@@ -42,7 +42,12 @@ constexpr int kWorkers = 128;
 constexpr int kTileM = 256;     // positions per tile (two M=128 accumulators)
 constexpr int kMaxStages = 6;
 
-struct ConvParams {
+constexpr int kMaxLayers = 34;   // one launch runs up to a whole recurrent inference: 1 + 16 + 16 convs
+
+// One convolution layer of a launch.  Layers of a launch share geometry, channel counts and the
+// persistent CTAs; layer l+1's tile t starts as soon as tiles t-1, t, t+1 of layer l are published
+// (per-tile flags in global memory), so there is no per-layer launch, prologue or tail.
+struct LayerDesc {
   const act_t* in;        // [.. boards ..][PB][Cin_pad]
   const int32_t* in_index;        // board b lives in slot in_index[b] (nullptr: b)
   const act_t* w;         // packed [9][chunks][chunk_g][N][8]
@@ -54,6 +59,16 @@ struct ConvParams {
   act_t* out_norm;        // contiguous, min-max normalised, or nullptr
   act_t* out_slots;       // indexed slots, normalised, or nullptr
   const int32_t* out_index;
+  int dep;                        // input is produced by the previous layer of this launch
+  int pad_;
+};
+
+struct ConvParams {
+  LayerDesc L[kMaxLayers];
+  int num_layers;
+  int rot;                        // tile t of layer l belongs to CTA (t + l*rot) % grid: rotates who gets the odd tile
+  unsigned int* flags;            // [num_layers][num_tiles], zeroed before the launch (nullptr for one layer)
+  int* err;                       // dependency wait timed out (should never happen)
   int Ptot, PB, Wp, W, H, B;
   int cg;                         // input channel groups of 8 (Cin_pad / 8), even
   int N;                          // output channels (multiple of 32, <= 128)
@@ -76,8 +91,17 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 template <int kN>
-__global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvParams p) {
+__global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int halo = p.Wp + 1;
@@ -106,13 +130,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_holder, 512);
-  if (tid < p.N) s_bias[tid] = p.bias[tid];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_holder;
 
-  const int n_my = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // every role walks the same (layer, tile) item sequence of this CTA
+  const int G = (int)gridDim.x;
+  auto first_tile = [&](int l) { int t0 = ((int)blockIdx.x - l * p.rot) % G; return t0 < 0 ? t0 + G : t0; };
 
   if (warp == 0) {
     // ------------------------------------------------ weight producer
@@ -121,15 +146,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
       uint32_t it = 0;
       long long t_wait = 0;
       const long long t_begin = clock64();
-      for (int i = 0; i < n_my; ++i) {
-        for (int c = 0; c < per_tile; ++c, ++it) {
-          const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-          const long long tw = clock64();
-          mbar_wait(&w_empty[s], ph ^ 1);
-          t_wait += clock64() - tw;
-          mbar_arrive_expect_tx(&w_full[s], stage_bytes);
-          bulk_g2s(sW + (size_t)s * stage_bytes, reinterpret_cast<const unsigned char*>(p.w) + (size_t)c * stage_bytes,
-                   stage_bytes, &w_full[s]);
+      for (int l = 0; l < p.num_layers; ++l) {
+        const unsigned char* wl = reinterpret_cast<const unsigned char*>(p.L[l].w);
+        for (int tile = first_tile(l); tile < p.num_tiles; tile += G) {
+          for (int c = 0; c < per_tile; ++c, ++it) {
+            const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+            const long long tw = clock64();
+            mbar_wait(&w_empty[s], ph ^ 1);
+            t_wait += clock64() - tw;
+            mbar_arrive_expect_tx(&w_full[s], stage_bytes);
+            bulk_g2s(sW + (size_t)s * stage_bytes, wl + (size_t)c * stage_bytes, stage_bytes, &w_full[s]);
+          }
         }
       }
       if (p.dbg) { p.dbg[blockIdx.x * 16 + 0] = clock64() - t_begin; p.dbg[blockIdx.x * 16 + 1] = t_wait; }
@@ -152,7 +179,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
       uint32_t it = 0;
       long long t_acc = 0, t_a = 0, t_w = 0;
       const long long t_begin = clock64();
-      for (int i = 0; i < n_my; ++i) {
+      int i = 0;
+      for (int l = 0; l < p.num_layers; ++l)
+      for (int tile = first_tile(l); tile < p.num_tiles; tile += G, ++i) {
         const int buf = i & 1;
         const uint32_t uph = (i >> 1) & 1;
         long long tw = clock64();
@@ -191,7 +220,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
       }
       if (p.dbg) {
         long long* d = p.dbg + blockIdx.x * 16;
-        d[2] = clock64() - t_begin; d[3] = t_acc; d[4] = t_a; d[5] = t_w; d[6] = n_my;
+        d[2] = clock64() - t_begin; d[3] = t_acc; d[4] = t_a; d[5] = t_w; d[6] = i;
       }
     }
   } else if (warp >= 6) {
@@ -207,18 +236,33 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
     const int nq = kTileM + 2 * halo;
     long long t_wait = 0, t_cp = 0;
     const long long t_begin = clock64();
-    for (int i = 0; i < n_my; ++i) {
+    int i = 0;
+    for (int l = 0; l < p.num_layers; ++l)
+    for (int tile = first_tile(l); tile < p.num_tiles; tile += G, ++i) {
+      const LayerDesc& L = p.L[l];
       const int buf = i & 1;
-      const int m0 = ((int)blockIdx.x + i * (int)gridDim.x) * kTileM;
+      const int m0 = tile * kTileM;
       for (int q = lt; q < nq; q += kWorkers) {
         const int P = m0 - halo + q;
         int row = -1;
         if (P >= 0 && P < p.Ptot) {
           int b, pos; bool hl;
           split_pos(P, p, b, pos, hl);
-          if (!hl) row = (p.in_index ? p.in_index[b] : b) * p.PB + pos;
+          if (!hl) row = (L.in_index ? L.in_index[b] : b) * p.PB + pos;
         }
         s_row[q] = row;
+      }
+      // dataflow dependency: the three tiles of the previous layer whose rows this tile reads
+      if (L.dep && lt == 0) {
+        const unsigned* f = p.flags + (size_t)(l - 1) * p.num_tiles;
+        for (int tt = max(tile - 1, 0); tt <= min(tile + 1, p.num_tiles - 1); ++tt) {
+          unsigned spins = 0;
+          while (ld_acquire(f + tt) == 0u) {
+            ++spins;
+            if ((spins & 0xffffu) == 0 && p.err && *reinterpret_cast<volatile int*>(p.err)) break;   // sticky bail-out
+            if (spins > (1u << 26)) { if (p.err) atomicExch(p.err, 1); break; }
+          }
+        }
       }
       // the buffer was last read by the MMAs of tile i-2
       long long tw = clock64();
@@ -229,7 +273,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
       const uint32_t dst = smem_u32(sA) + (uint32_t)buf * a_bytes + (uint32_t)ld_g * TP * 16;
       for (int q = ld_q0; q < nq; q += ld_step) {
         const int row = s_row[q];
-        const act_t* src = row >= 0 ? p.in + ((size_t)row * cin + ld_g * 8) : p.in;
+        const act_t* src = row >= 0 ? L.in + ((size_t)row * cin + ld_g * 8) : L.in;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)q * 16), "l"(src),
                      "r"(row >= 0 ? 16u : 0u)
                      : "memory");
@@ -247,18 +291,26 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
   } else {
     // ------------------------------------------------ epilogue (warps 2-5): TMEM -> registers -> global
     const int quad = warp & 3;               // TMEM lane quadrant this warp may read
-    const bool norm = (p.out_norm != nullptr) || (p.out_slots != nullptr);
     long long t_wait = 0;
     const long long t_begin = clock64();
-    for (int k = 0; k < n_my; ++k) {
+    int k = 0, bias_layer = -1;
+    for (int l = 0; l < p.num_layers; ++l)
+    for (int tile = first_tile(l); tile < p.num_tiles; tile += G, ++k) {
+      const LayerDesc& L = p.L[l];
+      const bool norm = (L.out_norm != nullptr) || (L.out_slots != nullptr);
       const int buf = k & 1;
-      const int tile = (int)blockIdx.x + k * (int)gridDim.x;
+      if (bias_layer != l) {               // new layer: swap the bias vector in shared memory
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (tid - 64 < kN) s_bias[tid - 64] = L.bias[tid - 64];
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        bias_layer = l;
+      }
       // Fast path (30 of the 33 convs of a recurrent inference: plain conv+bias(+residual)+ReLU):
       // the 2 rows x kN/32 column chunks of this thread form one unrolled sequence, and the
       // residual of step t+2 is requested at step t (the first two before the MMAs even finish),
       // so its global-memory latency never sits on the critical path.
       constexpr int NC = kN / 32, STEPS = 2 * NC;
-      const bool fast = !norm && p.tab == nullptr && p.out != nullptr;
+      const bool fast = !norm && L.tab == nullptr && L.out != nullptr;
       int Pj[2] = {0, 0};
       bool vj[2] = {false, false};
       const int4* rpj[2] = {nullptr, nullptr};
@@ -266,7 +318,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
       auto fetch = [&](int t, int4 (&dst)[4]) {
         const int4* src = rpj[t / NC];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) dst[u] = src ? src[(t % NC) * 4 + u] : make_int4(0, 0, 0, 0);
+        for (int u = 0; u < 4; ++u) dst[u] = src ? __ldcg(src + (t % NC) * 4 + u) : make_int4(0, 0, 0, 0);
       };
       if (fast) {
 #pragma unroll
@@ -275,7 +327,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
           int b = 0, pos = 0; bool hl = true;
           if (Pj[j] < p.Ptot) split_pos(Pj[j], p, b, pos, hl);
           vj[j] = !hl;
-          if (vj[j] && p.residual) rpj[j] = reinterpret_cast<const int4*>(p.residual + (size_t)Pj[j] * kN);
+          if (vj[j] && L.residual) rpj[j] = reinterpret_cast<const int4*>(L.residual + (size_t)Pj[j] * kN);
         }
         fetch(0, ring[0]);
         fetch(1, ring[1]);
@@ -311,7 +363,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
             }
 #pragma unroll
             for (int e = 0; e < 32; ++e) v[e] = fminf(fmaxf(v[e], 0.0f), 65504.0f);
-            int4* o = reinterpret_cast<int4*>(p.out + (size_t)Pj[j] * kN + c0);
+            int4* o = reinterpret_cast<int4*>(L.out + (size_t)Pj[j] * kN + c0);
 #pragma unroll
             for (int e = 0; e < 32; e += 8)
               o[e / 8] = make_int4((int)pack2(v[e], v[e + 1]), (int)pack2(v[e + 2], v[e + 3]),
@@ -327,9 +379,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
         if (P < p.Ptot) split_pos(P, p, b, pos, hl);
         const bool valid = !hl;
         const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256 + j * 128);
-        const float* tab = (p.tab && valid) ? p.tab + ((size_t)p.action[b] * p.PB + pos) * kN : nullptr;
-        const bool has_res = (p.residual != nullptr) && valid;
-        const int4* rp = reinterpret_cast<const int4*>(p.residual + (size_t)(has_res ? P : 0) * kN);
+        const float* tab = (L.tab && valid) ? L.tab + ((size_t)L.action[b] * p.PB + pos) * kN : nullptr;
+        const bool has_res = (L.residual != nullptr) && valid;
+        const int4* rp = reinterpret_cast<const int4*>(L.residual + (size_t)(has_res ? P : 0) * kN);
         float mn = INFINITY, mx = -INFINITY;
 #pragma unroll 1
         for (int pass = 0; pass < (norm ? 2 : 1); ++pass) {
@@ -340,7 +392,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
             // this chunk's residual (4 x 16 B) is requested before the TMEM load so both latencies overlap
             int4 rres[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) rres[u] = has_res ? rp[c0 / 8 + u] : make_int4(0, 0, 0, 0);
+            for (int u = 0; u < 4; ++u) rres[u] = has_res ? __ldcg(rp + c0 / 8 + u) : make_int4(0, 0, 0, 0);
             uint32_t r[32];
             tmem_ld32(taddr + c0, r);          // .sync.aligned: the whole warp executes it, valid row or not
             tmem_ld_wait();
@@ -376,8 +428,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
 #pragma unroll
                   for (int e = 0; e < 32; ++e) { mn = fminf(mn, v[e]); mx = fmaxf(mx, v[e]); }
                 }
-                if (p.out) {
-                  int4* o = reinterpret_cast<int4*>(p.out + (size_t)P * kN + c0);
+                if (L.out) {
+                  int4* o = reinterpret_cast<int4*>(L.out + (size_t)P * kN + c0);
 #pragma unroll
                   for (int e = 0; e < 32; e += 8)
                     o[e / 8] = make_int4((int)pack2(v[e], v[e + 1]), (int)pack2(v[e + 2], v[e + 3]),
@@ -391,14 +443,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
                 for (int e = 0; e < 32; e += 8)
                   o4[e / 8] = make_int4((int)pack2(v[e], v[e + 1]), (int)pack2(v[e + 2], v[e + 3]),
                                         (int)pack2(v[e + 4], v[e + 5]), (int)pack2(v[e + 6], v[e + 7]));
-                if (p.out_norm) {
-                  int4* o = reinterpret_cast<int4*>(p.out_norm + (size_t)P * kN + c0);
+                if (L.out_norm) {
+                  int4* o = reinterpret_cast<int4*>(L.out_norm + (size_t)P * kN + c0);
 #pragma unroll
                   for (int u = 0; u < 4; ++u) o[u] = o4[u];
                 }
-                if (p.out_slots) {
-                  const size_t board = p.out_index ? (size_t)p.out_index[b] : (size_t)b;
-                  int4* o = reinterpret_cast<int4*>(p.out_slots + (board * p.PB + pos) * kN + c0);
+                if (L.out_slots) {
+                  const size_t board = L.out_index ? (size_t)L.out_index[b] : (size_t)b;
+                  int4* o = reinterpret_cast<int4*>(L.out_slots + (board * p.PB + pos) * kN + c0);
 #pragma unroll
                   for (int u = 0; u < 4; ++u) o[u] = o4[u];
                 }
@@ -411,6 +463,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const ConvPara
       }  // generic path
       tc_fence_before();
       mbar_arrive(&acc_empty[buf]);
+      if (p.flags) {                       // publish the tile: stores fenced by every thread, then one release
+        __threadfence();
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (tid == 64) st_release(p.flags + (size_t)l * p.num_tiles + tile, 1u);
+      }
     }
     if (p.dbg && tid == 64) {
       long long* d = p.dbg + blockIdx.x * 16;
@@ -766,7 +823,10 @@ struct ConvNet : NetImpl {
   ConvLayer at_blocks[3][4];
   const float* tab;
   Head h_reward, h_policy, h_value;
-  act_t *xobs, *b0, *b1, *b2, *b3;
+  act_t *xobs, *b0, *b1, *b2, *b3, *b4;
+  unsigned* flags;
+  size_t flags_cap;
+  int* err_flag;
 
   static int tp_of(const Geo& g) { return (kTileM + 2 * (g.Wp() + 1)) | 1; }
   size_t conv_fixed_smem(const Geo& g, int cg) const {
@@ -787,29 +847,61 @@ struct ConvNet : NetImpl {
     return conv_fixed_smem(g, cg) + (size_t)conv_stages(g, cg) * chunk_g * C * 16;
   }
 
-  int launch_conv(const ConvLayer& L, const Geo& g, const act_t* in, const int32_t* in_index, int batch,
-                  const float* tab_, const int32_t* action, const act_t* residual, act_t* out, act_t* out_norm,
-                  act_t* out_slots, const int32_t* out_index, cudaStream_t st) {
-    ConvParams p;
-    p.in = in; p.in_index = in_index; p.w = L.w; p.bias = L.bias; p.tab = tab_; p.action = action;
-    p.residual = residual; p.out = out; p.out_norm = out_norm; p.out_slots = out_slots; p.out_index = out_index;
+  // ---- layer batching: consecutive convs on the same grid become ONE dataflow launch ----
+  ConvParams pend;                 // layers collected so far
+  Geo pend_geo{0, 0};
+  int pend_cg = 0, pend_batch = 0;
+
+  int add_layer(const ConvLayer& L, const Geo& g, const act_t* in, const int32_t* in_index, int batch,
+                const float* tab_, const int32_t* action, const act_t* residual, act_t* out, act_t* out_norm,
+                act_t* out_slots, const int32_t* out_index, cudaStream_t st) {
+    if (pend.num_layers > 0 && (pend_cg != L.cg || pend_geo.H != g.H || pend_geo.W != g.W || pend_batch != batch ||
+                                pend.num_layers == kMaxLayers)) {
+      int rc = flush(st);
+      if (rc) return rc;
+    }
+    LayerDesc& d = pend.L[pend.num_layers];
+    d.in = in; d.in_index = in_index; d.w = L.w; d.bias = L.bias; d.tab = tab_; d.action = action;
+    d.residual = residual; d.out = out; d.out_norm = out_norm; d.out_slots = out_slots; d.out_index = out_index;
+    d.dep = pend.num_layers > 0 ? 1 : 0;
+    d.pad_ = 0;
+    pend_geo = g; pend_cg = L.cg; pend_batch = batch;
+    ++pend.num_layers;
+    return MZ_OK;
+  }
+
+  int flush(cudaStream_t st) {
+    if (pend.num_layers == 0) return MZ_OK;
+    ConvParams& p = pend;
+    const Geo g = pend_geo;
+    const int batch = pend_batch, cg = pend_cg, nl = p.num_layers;
     p.PB = g.PB(); p.Wp = g.Wp(); p.W = g.W; p.H = g.H; p.B = batch;
     p.Ptot = batch * p.PB;
-    p.cg = L.cg; p.N = C; p.relu = 1;
+    p.cg = cg; p.N = C; p.relu = 1;
     p.num_tiles = (p.Ptot + kTileM - 1) / kTileM;
     p.TP = tp_of(g);
-    p.stages = conv_stages(g, L.cg);
-    if (p.stages < 2) { set_error("conv tile does not fit shared memory for a %dx%d grid", g.H, g.W); return MZ_EINVAL; }
-    const size_t smem = conv_smem(g, L.cg);
+    p.stages = conv_stages(g, cg);
+    p.err = err_flag;
+    if (p.stages < 2) { pend.num_layers = 0; set_error("conv tile does not fit shared memory for a %dx%d grid", g.H, g.W); return MZ_EINVAL; }
+    const size_t smem = conv_smem(g, cg);
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    p.rot = nl > 1 ? p.num_tiles % grid : 0;
+    p.flags = nullptr;
+    if (nl > 1) {
+      if ((size_t)nl * p.num_tiles > flags_cap) { pend.num_layers = 0; set_error("internal: flag buffer too small"); return MZ_EINVAL; }
+      p.flags = flags;
+      cudaError_t e = cudaMemsetAsync(flags, 0, (size_t)nl * p.num_tiles * sizeof(unsigned), st);
+      if (e != cudaSuccess) { pend.num_layers = 0; set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return MZ_ECUDA; }
+    }
     p.dbg = nullptr;
     static const bool debug = getenv("MZ_CONV_DEBUG") != nullptr;
     if (debug) cudaMalloc(&p.dbg, (size_t)grid * 16 * sizeof(long long));
-    prof_mark(kProfConv, st);
+    prof_mark(kProfConv, st, nl);
     if (C == 128) conv3x3_kernel<128><<<grid, kConvThreads, smem, st>>>(p);
     else if (C == 64) conv3x3_kernel<64><<<grid, kConvThreads, smem, st>>>(p);
     else conv3x3_kernel<32><<<grid, kConvThreads, smem, st>>>(p);
     prof_mark(-1, st);
+    pend.num_layers = 0;
     MZ_LAUNCH_CHECK("conv3x3_kernel");
     if (debug) {   // measurement aid: per-role cycle accounting, averaged over CTAs
       cudaDeviceSynchronize();
@@ -818,9 +910,9 @@ struct ConvNet : NetImpl {
       cudaFree(p.dbg);
       double a[16] = {0};
       for (int c = 0; c < grid; ++c) for (int k = 0; k < 16; ++k) a[k] += (double)h[(size_t)c * 16 + k] / grid;
-      fprintf(stderr, "[conv dbg] %dx%d cg=%d tiles/cta=%.1f | producer total %.0f wait_empty %.0f | mma total %.0f wait_acc %.0f "
+      fprintf(stderr, "[conv dbg] %dx%d cg=%d layers=%d items/cta=%.1f | producer total %.0f wait_empty %.0f | mma total %.0f wait_acc %.0f "
               "wait_a %.0f wait_w %.0f | loader total %.0f wait_mma %.0f copy %.0f | epilogue total %.0f wait_mma %.0f\n",
-              g.H, g.W, L.cg, a[6], a[0], a[1], a[2], a[3], a[4], a[5], a[7], a[8], a[9], a[10], a[11]);
+              g.H, g.W, cg, nl, a[6], a[0], a[1], a[2], a[3], a[4], a[5], a[7], a[8], a[9], a[10], a[11]);
     }
     return MZ_OK;
   }
@@ -841,7 +933,8 @@ struct ConvNet : NetImpl {
   // (ReLU'd) tower output, unless want_raw is false and the last layer normalises.
   int tower(const ConvLayer* first, const ConvLayer* blk, int nblk, const Geo& g, const act_t* in,
             const int32_t* in_index, const float* tab_, const int32_t* action, int batch, bool want_raw,
-            act_t* norm_out, act_t* slots, const int32_t* out_index, cudaStream_t st, act_t** final_buf) {
+            act_t* norm_out, act_t* slots, const int32_t* out_index, cudaStream_t st, act_t** final_buf,
+            act_t* raw_dst = nullptr) {
     const act_t* cur = in;
     const int32_t* cur_index = in_index;
     act_t* pp[2] = {b0, b1};
@@ -849,8 +942,8 @@ struct ConvNet : NetImpl {
     const bool normalise = (norm_out != nullptr) || (slots != nullptr);
     if (first) {
       const bool last = (nblk == 0);
-      act_t* dst = pp[which];
-      rc = launch_conv(*first, g, cur, cur_index, batch, tab_, action, nullptr,
+      act_t* dst = (last && raw_dst) ? raw_dst : pp[which];
+      rc = add_layer(*first, g, cur, cur_index, batch, tab_, action, nullptr,
                        (last && normalise && !want_raw) ? nullptr : dst, last ? norm_out : nullptr,
                        last ? slots : nullptr, out_index, st);
       if (rc) return rc;
@@ -858,12 +951,13 @@ struct ConvNet : NetImpl {
     }
     for (int i = 0; i < nblk; ++i) {
       const bool last = (i == nblk - 1);
-      rc = launch_conv(blk[2 * i], g, cur, cur_index, batch, nullptr, nullptr, nullptr, b2, nullptr, nullptr, nullptr, st);
+      rc = add_layer(blk[2 * i], g, cur, cur_index, batch, nullptr, nullptr, nullptr, b2, nullptr, nullptr, nullptr, st);
       if (rc) return rc;
       if (cur_index != nullptr) { set_error("internal: residual input must be contiguous"); return MZ_EINVAL; }
       act_t* dst = pp[which];
       if (dst == cur) dst = pp[which ^ 1];
-      rc = launch_conv(blk[2 * i + 1], g, b2, nullptr, batch, nullptr, nullptr, cur,
+      if (last && raw_dst) dst = raw_dst;
+      rc = add_layer(blk[2 * i + 1], g, b2, nullptr, batch, nullptr, nullptr, cur,
                        (last && normalise && !want_raw) ? nullptr : dst, last ? norm_out : nullptr,
                        last ? slots : nullptr, out_index, st);
       if (rc) return rc;
@@ -901,14 +995,17 @@ struct ConvNet : NetImpl {
     if ((rc = s2(xobs, s2_w1, b0, Hin, Win, 16))) return rc;                                   // relu(conv_1)
     if ((rc = tower(nullptr, at_blocks[0], 2, g1, b0, nullptr, nullptr, nullptr, batch, true, nullptr, nullptr,
                     nullptr, st, &fin))) return rc;
+    if ((rc = flush(st))) return rc;
     act_t* nxt = (fin == b0) ? b1 : b0;
     if ((rc = s2(fin, s2_w2, nxt, g1.H, g1.W, C))) return rc;                                  // relu(conv_2)
     if ((rc = tower(nullptr, at_blocks[1], 2, g2, nxt, nullptr, nullptr, nullptr, batch, true, nullptr, nullptr,
                     nullptr, st, &fin))) return rc;
+    if ((rc = flush(st))) return rc;
     nxt = (fin == b0) ? b1 : b0;
     if ((rc = pool(fin, nxt, nullptr, nullptr, g2.H, g2.W, 0))) return rc;                     // avg_pool_1
     if ((rc = tower(nullptr, at_blocks[2], 2, g3, nxt, nullptr, nullptr, nullptr, batch, true, nullptr, nullptr,
                     nullptr, st, &fin))) return rc;
+    if ((rc = flush(st))) return rc;
     return pool(fin, b3, slots, dst_index, g3.H, g3.W, 1);                                     // avg_pool_2 + normalise
   }
 
@@ -936,6 +1033,7 @@ struct ConvNet : NetImpl {
     int rc = tower(nullptr, pred_blocks, blocks, lat, b3, nullptr, nullptr, nullptr, batch, true, nullptr, nullptr,
                    nullptr, st, &fin);
     if (rc) return rc;
+    if ((rc = flush(st))) return rc;
     if (pi_probs) {
       rc = launch_head(h_policy, fin, batch, pi_probs, st);
       if (rc) return rc;
@@ -948,12 +1046,14 @@ struct ConvNet : NetImpl {
                 cudaStream_t st) override {
     act_t* fin;
     // dynamics: raw output (for the reward head) in a ping-pong buffer, normalised copy in b3 + the slots
+    // The dynamics tower and the prediction tower run as ONE launch; the dynamics' raw output goes to b4,
+    // which the prediction tower never touches, so the reward head can read it afterwards.
     int rc = tower(&dyn0, dyn_blocks, blocks, lat, (const act_t*)hidden_in, src_index, tab, action, batch, true, b3,
-                   (act_t*)hidden_out, dst_index, st, &fin);
+                   (act_t*)hidden_out, dst_index, st, &fin, b4);
     if (rc) return rc;
-    rc = launch_head(h_reward, fin, batch, reward_out, st);     // reward head reads the UN-normalised state
+    rc = predict(batch, pi_probs, value_out, st);
     if (rc) return rc;
-    return predict(batch, pi_probs, value_out, st);
+    return launch_head(h_reward, fin, batch, reward_out, st);   // reward head reads the UN-normalised state
   }
 };
 
@@ -1009,7 +1109,8 @@ int conv_arena_bytes(const mz_net_config& c, int max_batch, size_t* bytes) {
   const size_t obs_pb = atari ? (size_t)(c.in_h + 1) * (c.in_w + 1) : (size_t)PB;
   t += align_up((size_t)max_batch * obs_pb * (atari ? 2 : obs_cg(c.in_channels)) * 16, 256);   // packed observations
   t += 3 * align_up((size_t)max_batch * big_pb * N * 2, 256);                            // b0..b2
-  t += align_up((size_t)max_batch * PB * N * 2, 256);                                    // b3 (latent grid only)
+  t += 2 * align_up((size_t)max_batch * PB * N * 2, 256);                                // b3, b4 (latent grid only)
+  t += align_up((size_t)kMaxLayers * (((size_t)max_batch * big_pb + kTileM - 1) / kTileM) * 4, 256) + 256;   // tile flags
   *bytes = t + 8192;
   return MZ_OK;
 }
@@ -1127,6 +1228,12 @@ int conv_create(const mz_net_config& c, const float* const* w, int nw, int max_b
   net->b1 = (act_t*)take(act_bytes);
   net->b2 = (act_t*)take(act_bytes);
   net->b3 = (act_t*)take((size_t)max_batch * PB * N * 2);
+  net->b4 = (act_t*)take((size_t)max_batch * PB * N * 2);
+  net->flags_cap = (size_t)kMaxLayers * (((size_t)max_batch * big_pb + kTileM - 1) / kTileM);
+  net->flags = (unsigned*)take(net->flags_cap * 4);
+  net->err_flag = (int*)take(256);
+  cudaMemset(net->err_flag, 0, 4);
+  net->pend.num_layers = 0;
   if ((size_t)(p - (char*)arena) > arena_bytes) {
     set_error("internal: net arena overrun (%zu > %zu)", (size_t)(p - (char*)arena), arena_bytes);
     delete net;

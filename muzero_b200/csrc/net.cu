@@ -76,6 +76,7 @@ extern "C" int mz_net_profile_begin(mz_net* net) {
   for (cudaEvent_t e : n->prof_ev) cudaEventDestroy(e);
   n->prof_ev.clear();
   n->prof_cls.clear();
+  n->prof_weight.clear();
   n->profiling = true;
   return MZ_OK;
 }
@@ -90,10 +91,11 @@ extern "C" int mz_net_profile_end(mz_net* net, double* ms_by_class, int64_t* lau
     float ms = 0.0f;
     MZ_CUDA(cudaEventElapsedTime(&ms, n->prof_ev[2 * i], n->prof_ev[2 * i + 1]));
     ms_by_class[n->prof_cls[i]] += ms;
-    launches_by_class[n->prof_cls[i]] += 1;
+    launches_by_class[n->prof_cls[i]] += n->prof_weight[i];
   }
   for (cudaEvent_t e : n->prof_ev) cudaEventDestroy(e);
   n->prof_ev.clear();
   n->prof_cls.clear();
+  n->prof_weight.clear();
   return MZ_OK;
 }

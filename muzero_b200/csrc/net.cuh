@@ -12,14 +12,14 @@ enum ProfClass { kProfConv = 0, kProfHead = 1, kProfPack = 2, kProfMlp = 3, kPro
 struct NetImpl {
   bool profiling = false;
   std::vector<cudaEvent_t> prof_ev;     // pairs (begin, end)
-  std::vector<int> prof_cls;
-  void prof_mark(int cls, cudaStream_t st) {
+  std::vector<int> prof_cls, prof_weight;   // weight: how many layers one launch covers
+  void prof_mark(int cls, cudaStream_t st, int weight = 1) {
     if (!profiling) return;
     cudaEvent_t e;
     cudaEventCreate(&e);
     cudaEventRecord(e, st);
     prof_ev.push_back(e);
-    if (cls >= 0) prof_cls.push_back(cls);
+    if (cls >= 0) { prof_cls.push_back(cls); prof_weight.push_back(weight); }
   }
   virtual ~NetImpl() {
     for (cudaEvent_t e : prof_ev) cudaEventDestroy(e);
