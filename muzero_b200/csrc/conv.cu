@@ -242,22 +242,47 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
       const LayerDesc& L = p.L[l];
       const int buf = i & 1;
       const int m0 = tile * kTileM;
-      for (int q = lt; q < nq; q += kWorkers) {
-        const int P = m0 - halo + q;
-        int row = -1;
-        if (P >= 0 && P < p.Ptot) {
-          int b, pos; bool hl;
-          split_pos(P, p, b, pos, hl);
-          if (!hl) row = (L.in_index ? L.in_index[b] : b) * p.PB + pos;
+      // source row of every tile position: the divisions first, then the (independent) slot-index loads,
+      // so the loads overlap instead of forming a chain of L2 round trips
+      {
+        int qq[3], bb[3], pp_[3];
+        bool ok[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          qq[u] = lt + u * kWorkers;
+          const int P = m0 - halo + qq[u];
+          ok[u] = false; bb[u] = 0; pp_[u] = 0;
+          if (qq[u] < nq && P >= 0 && P < p.Ptot) {
+            bool hl;
+            split_pos(P, p, bb[u], pp_[u], hl);
+            ok[u] = !hl;
+          }
         }
-        s_row[q] = row;
+        int slot[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) slot[u] = (ok[u] && L.in_index) ? L.in_index[bb[u]] : bb[u];
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+          if (qq[u] < nq) s_row[qq[u]] = ok[u] ? slot[u] * p.PB + pp_[u] : -1;
+        for (int q = lt + 3 * kWorkers; q < nq; q += kWorkers) {      // wide grids: more than 384 tile positions
+          const int P = m0 - halo + q;
+          int row = -1;
+          if (P >= 0 && P < p.Ptot) {
+            int b, pos; bool hl;
+            split_pos(P, p, b, pos, hl);
+            if (!hl) row = (L.in_index ? L.in_index[b] : b) * p.PB + pos;
+          }
+          s_row[q] = row;
+        }
       }
-      // dataflow dependency: the three tiles of the previous layer whose rows this tile reads
-      if (L.dep && lt == 0) {
-        const unsigned* f = p.flags + (size_t)(l - 1) * p.num_tiles;
-        for (int tt = max(tile - 1, 0); tt <= min(tile + 1, p.num_tiles - 1); ++tt) {
+      // dataflow dependency: the three tiles of the previous layer whose rows this tile reads (polled by
+      // three different threads so the L2 round trips overlap)
+      if (L.dep && lt < 3) {
+        const int tt = tile - 1 + lt;
+        if (tt >= 0 && tt < p.num_tiles) {
+          const unsigned* f = p.flags + (size_t)(l - 1) * p.num_tiles + tt;
           unsigned spins = 0;
-          while (ld_acquire(f + tt) == 0u) {
+          while (ld_acquire(f) == 0u) {
             ++spins;
             if ((spins & 0xffffu) == 0 && p.err && *reinterpret_cast<volatile int*>(p.err)) break;   // sticky bail-out
             if (spins > (1u << 26)) { if (p.err) atomicExch(p.err, 1); break; }
