@@ -163,10 +163,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      // One thread feeds the tensor core, so the per-MMA instruction count matters (a single
-      // thread issues ~1 dependent instruction per 4-5 cycles; an MMA lasts 64): descriptors are
-      // built once and only their 14-bit start-address field (16-byte units) is stepped.
+    {
+      // One thread feeds the tensor core, so the issue path must cost well under the 64 cycles an MMA
+      // lasts.  The WHOLE warp walks the loop (all values warp-uniform, so descriptors live in uniform
+      // registers and are stepped with uniform ALU ops instead of per-MMA vector->uniform moves) and
+      // only lane 0 is predicated onto the tcgen05 instructions.  Descriptors are built once; only
+      // their 14-bit start-address field (16-byte units) is stepped.
+      const bool issuer = (lane == 0);
       const uint32_t idesc = instr_desc_f16(128, (uint32_t)p.N);
       const uint64_t a_tmpl = smem_desc(0, (uint32_t)TP * 16, 128);
       const uint64_t b_tmpl = smem_desc(0, (uint32_t)p.N * 16, 128);
@@ -184,12 +187,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
       for (int tile = first_tile(l); tile < p.num_tiles; tile += G, ++i) {
         const int buf = i & 1;
         const uint32_t uph = (i >> 1) & 1;
-        long long tw = clock64();
+        long long tw = p.dbg ? clock64() : 0;
         mbar_wait(&acc_empty[buf], uph ^ 1);
-        long long tw2 = clock64();
+        long long tw2 = p.dbg ? clock64() : 0;
         t_acc += tw2 - tw;
         mbar_wait(&a_full[buf], uph);
-        t_a += clock64() - tw2;
+        if (p.dbg) t_a += clock64() - tw2;
         tc_fence_after();
         const uint32_t a_tile = a_lo0 + sA16 + (uint32_t)buf * (a_bytes >> 4) + (uint32_t)halo;
         const uint32_t d0 = tmem + (uint32_t)(buf * 256), d1 = d0 + 128;
@@ -199,26 +202,30 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
           uint32_t a_lo = a_tile + (uint32_t)shift;        // wraps correctly: shift may be negative
           for (int ch = 0; ch < chunks_tap; ++ch, ++it) {
             const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-            tw = clock64();
+            if (p.dbg) tw = clock64();
             mbar_wait(&w_full[s], ph);
-            t_w += clock64() - tw;
+            if (p.dbg) t_w += clock64() - tw;
             tc_fence_after();
             uint32_t b_lo = b_lo0 + sW16 + s * stage16;
 #pragma unroll 4
             for (int ks = 0; ks < ksteps; ++ks) {
               const uint64_t bd = desc64(b_lo, b_hi);
-              mma_bf16(d0, desc64(a_lo, a_hi), bd, idesc, acc);
-              mma_bf16(d1, desc64(a_lo + 128u, a_hi), bd, idesc, acc);
+              if (issuer) {
+                mma_bf16(d0, desc64(a_lo, a_hi), bd, idesc, acc);
+                mma_bf16(d1, desc64(a_lo + 128u, a_hi), bd, idesc, acc);
+              }
               acc = 1;
               a_lo += a_kstep;
               b_lo += b_kstep;
             }
-            commit(&w_empty[s]);
+            if (issuer) commit(&w_empty[s]);
+            __syncwarp();
           }
         }
-        commit(&mma_done[buf]);
+        if (issuer) commit(&mma_done[buf]);
+        __syncwarp();
       }
-      if (p.dbg) {
+      if (p.dbg && issuer) {
         long long* d = p.dbg + blockIdx.x * 16;
         d[2] = clock64() - t_begin; d[3] = t_acc; d[4] = t_a; d[5] = t_w; d[6] = i;
       }

@@ -2,7 +2,7 @@
 // operands in the no-swizzle K-major layout, with optional competing shared-memory store
 // traffic, for cta_group::1 (M=128 per SM) and cta_group::2 (M=256 over an SM pair, each SM
 // holding half of B).  Answers: what bounds the MMA rate inside conv.cu?
-// usage: umma_bench N a_rows b_rows [grid] [iters] [writer_warps 0..3] [two_cta 0|1]
+// usage: umma_bench N a_rows b_rows [grid] [iters] [writer_warps 0..3] [two_cta 0|1] [data 0=zeros|1=random]
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>
@@ -20,7 +20,7 @@ __device__ __forceinline__ void cluster_sync() {
 }
 
 template <bool kTwo>
-__global__ void __launch_bounds__(128) bench(int N, int a_rows, int b_rows, int iters, long long* out, int writer) {
+__global__ void __launch_bounds__(128) bench(int N, int a_rows, int b_rows, int iters, long long* out, int writer, int data) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base;
@@ -30,7 +30,17 @@ __global__ void __launch_bounds__(128) bench(int N, int a_rows, int b_rows, int 
   if (kTwo) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
   unsigned char* sA = smem;
   unsigned char* sB = smem + 16 * a_rows * 16;
-  for (int i = tid; i < (16 * a_rows + 8 * b_rows) * 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  // operand data: zeros (data == 0) or pseudo-random fp16 in [-1, 1) (data == 1): tensor-core power depends on it
+  for (int i = tid; i < (16 * a_rows + 8 * b_rows) * 4; i += 128) {
+    uint32_t v = 0;
+    if (data) {
+      uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u;
+      h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+      const uint32_t lo = 0x3800u | (h & 0x83ffu), hi = 0x3800u | ((h >> 16) & 0x83ffu);   // +-[0.5, 1)
+      v = lo | (hi << 16);
+    }
+    reinterpret_cast<uint32_t*>(smem)[i] = v;
+  }
   if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); stop = 0; }
   if (warp == 0) {
     if (kTwo) {
@@ -96,6 +106,7 @@ int main(int argc, char** argv) {
   const int N = argc > 1 ? atoi(argv[1]) : 128, a_rows = argc > 2 ? atoi(argv[2]) : 279, b_rows = argc > 3 ? atoi(argv[3]) : N;
   const int grid = argc > 4 ? atoi(argv[4]) : 1, iters = argc > 5 ? atoi(argv[5]) : 2000, writer = argc > 6 ? atoi(argv[6]) : 0;
   const int two = argc > 7 ? atoi(argv[7]) : 0;
+  const int data = argc > 8 ? atoi(argv[8]) : 0;
   long long* d;
   cudaMalloc(&d, 2 * grid * sizeof(long long));
   cudaMemset(d, 0, 2 * grid * sizeof(long long));
@@ -109,11 +120,11 @@ int main(int argc, char** argv) {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, bench<true>, N, a_rows, b_rows, iters, d, writer);
+    e = cudaLaunchKernelEx(&cfg, bench<true>, N, a_rows, b_rows, iters, d, writer, data);
     if (e != cudaSuccess) { printf("launch error %s\n", cudaGetErrorString(e)); return 1; }
   } else {
     cudaFuncSetAttribute(bench<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    bench<false><<<grid, 128, smem>>>(N, a_rows, b_rows, iters, d, writer);
+    bench<false><<<grid, 128, smem>>>(N, a_rows, b_rows, iters, d, writer, data);
   }
   e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
@@ -124,7 +135,7 @@ int main(int argc, char** argv) {
   for (int i = 0; i < grid; ++i) wbytes += (double)h[grid + i] / grid;
   const double cyc = mx / ((double)iters * 8);
   const double flop = 2.0 * 128 * N * 16;     // per SM per MMA (a 2-SM MMA does this much on each SM)
-  printf("cta_group::%d N=%d A-LBO %d B b_rows=%d grid=%d writer_warps=%d: %.1f cycles/MMA, %.0f flop/cycle/SM (ideal 8192), "
-         "competing stores %.1f B/cycle/SM\n", two ? 2 : 1, N, a_rows * 16, b_rows, grid, writer, cyc, flop / cyc, wbytes / mx);
+  printf("data=%s cta_group::%d N=%d A-LBO %d B b_rows=%d grid=%d writer_warps=%d: %.1f cycles/MMA, %.0f flop/cycle/SM (ideal 8192), "
+         "competing stores %.1f B/cycle/SM\n", data ? "random" : "zeros", two ? 2 : 1, N, a_rows * 16, b_rows, grid, writer, cyc, flop / cyc, wbytes / mx);
   return 0;
 }
