@@ -77,6 +77,7 @@ struct ConvParams {
   int TP;                         // tile positions incl. halo, odd
   int stages;                     // weight ring depth (as many as shared memory allows, <= kMaxStages)
   long long* dbg;                 // optional per-CTA role timing (MZ_CONV_DEBUG), else nullptr
+  int ablate;                     // debug only (MZ_CONV_ABLATE): 1 skip epilogue work, 2 skip tile loads, 4 skip weight copies
 };
 
 __device__ __forceinline__ void split_pos(int P, const ConvParams& p, int& b, int& q, bool& halo) {
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
             const long long tw = clock64();
             mbar_wait(&w_empty[s], ph ^ 1);
             t_wait += clock64() - tw;
+            if (p.ablate & 4) { mbar_arrive(&w_full[s]); continue; }
             mbar_arrive_expect_tx(&w_full[s], stage_bytes);
             bulk_g2s(sW + (size_t)s * stage_bytes, wl + (size_t)c * stage_bytes, stage_bytes, &w_full[s]);
           }
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
       const int ksteps = chunk_g / 2;
       auto desc64 = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
       uint32_t it = 0;
-      long long t_acc = 0, t_a = 0, t_w = 0;
+      long long t_acc = 0, t_a = 0, t_w = 0, t_issue = 0, t_commit = 0;
       const long long t_begin = clock64();
       int i = 0;
       for (int l = 0; l < p.num_layers; ++l)
@@ -207,6 +209,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
             if (p.dbg) t_w += clock64() - tw;
             tc_fence_after();
             uint32_t b_lo = b_lo0 + sW16 + s * stage16;
+            const long long ti = p.dbg ? clock64() : 0;
 #pragma unroll 4
             for (int ks = 0; ks < ksteps; ++ks) {
               const uint64_t bd = desc64(b_lo, b_hi);
@@ -218,8 +221,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
               a_lo += a_kstep;
               b_lo += b_kstep;
             }
+            const long long tc = p.dbg ? clock64() : 0;
             if (issuer) commit(&w_empty[s]);
             __syncwarp();
+            if (p.dbg) { t_issue += tc - ti; t_commit += clock64() - tc; }
           }
         }
         if (issuer) commit(&mma_done[buf]);
@@ -227,7 +232,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
       }
       if (p.dbg && issuer) {
         long long* d = p.dbg + blockIdx.x * 16;
-        d[2] = clock64() - t_begin; d[3] = t_acc; d[4] = t_a; d[5] = t_w; d[6] = i;
+        d[2] = clock64() - t_begin; d[3] = t_acc; d[4] = t_a; d[5] = t_w; d[6] = i; d[12] = t_issue; d[13] = t_commit;
       }
     }
   } else if (warp >= 6) {
@@ -303,7 +308,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
       asm volatile("bar.sync 1, 128;" ::: "memory");
       tw = clock64();
       const uint32_t dst = smem_u32(sA) + (uint32_t)buf * a_bytes + (uint32_t)ld_g * TP * 16;
-      for (int q = ld_q0; q < nq; q += ld_step) {
+      for (int q = ld_q0; q < nq && !(p.ablate & 2); q += ld_step) {
         const int row = s_row[q];
         const act_t* src = row >= 0 ? L.in + ((size_t)row * cin + ld_g * 8) : L.in;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)q * 16), "l"(src),
@@ -368,7 +373,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
       mbar_wait(&mma_done[buf], (uint32_t)((k >> 1) & 1));
       t_wait += clock64() - tw;
       tc_fence_after();
-      if (fast) {
+      if (p.ablate & 1) {
+      } else if (fast) {
 #pragma unroll
         for (int t = 0; t < STEPS; ++t) {
           const int j = t / NC, c0 = (t % NC) * 32;
@@ -926,6 +932,8 @@ struct ConvNet : NetImpl {
       if (e != cudaSuccess) { pend.num_layers = 0; set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return MZ_ECUDA; }
     }
     p.dbg = nullptr;
+    static const int ablate = getenv("MZ_CONV_ABLATE") ? atoi(getenv("MZ_CONV_ABLATE")) : 0;
+    p.ablate = ablate;
     static const bool debug = getenv("MZ_CONV_DEBUG") != nullptr;
     if (debug) cudaMalloc(&p.dbg, (size_t)grid * 16 * sizeof(long long));
     prof_mark(kProfConv, st, nl);
@@ -943,8 +951,8 @@ struct ConvNet : NetImpl {
       double a[16] = {0};
       for (int c = 0; c < grid; ++c) for (int k = 0; k < 16; ++k) a[k] += (double)h[(size_t)c * 16 + k] / grid;
       fprintf(stderr, "[conv dbg] %dx%d cg=%d layers=%d items/cta=%.1f | producer total %.0f wait_empty %.0f | mma total %.0f wait_acc %.0f "
-              "wait_a %.0f wait_w %.0f | loader total %.0f wait_mma %.0f copy %.0f | epilogue total %.0f wait_mma %.0f\n",
-              g.H, g.W, cg, nl, a[6], a[0], a[1], a[2], a[3], a[4], a[5], a[7], a[8], a[9], a[10], a[11]);
+              "wait_a %.0f wait_w %.0f issue %.0f commit %.0f | loader total %.0f wait_mma %.0f copy %.0f | epilogue total %.0f wait_mma %.0f\n",
+              g.H, g.W, cg, nl, a[6], a[0], a[1], a[2], a[3], a[4], a[5], a[12], a[13], a[7], a[8], a[9], a[10], a[11]);
     }
     return MZ_OK;
   }
