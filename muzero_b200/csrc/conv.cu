@@ -181,50 +181,76 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
       const uint32_t sA16 = smem_u32(sA) >> 4, sW16 = smem_u32(sW) >> 4, stage16 = stage_bytes >> 4;
       const int ksteps = chunk_g / 2;
       auto desc64 = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
-      uint32_t it = 0;
+      // The tensor core only queues a couple of MMAs, so whatever the issuing thread does between two
+      // stages (barrier poll, fence, commit, bookkeeping) beyond ~2 MMA times shows up as a bubble: the
+      // stage ring is walked with incremental counters (no div/mod), tap shifts are stepped, and the
+      // debug clocks are skipped by a uniform branch when profiling is off.
+      uint32_t st = 0, st_ph = 0;                 // weight ring slot and its phase parity
+      uint32_t b_slot = b_lo0 + sW16;             // descriptor low word of ring slot `st`
+      const uint32_t b_first = b_slot;
       long long t_acc = 0, t_a = 0, t_w = 0, t_issue = 0, t_commit = 0;
+      const bool prof = p.dbg != nullptr;
       const long long t_begin = clock64();
       int i = 0;
       for (int l = 0; l < p.num_layers; ++l)
       for (int tile = first_tile(l); tile < p.num_tiles; tile += G, ++i) {
         const int buf = i & 1;
         const uint32_t uph = (i >> 1) & 1;
-        long long tw = p.dbg ? clock64() : 0;
+        long long tw = prof ? clock64() : 0;
         mbar_wait(&acc_empty[buf], uph ^ 1);
-        long long tw2 = p.dbg ? clock64() : 0;
+        long long tw2 = prof ? clock64() : 0;
         t_acc += tw2 - tw;
         mbar_wait(&a_full[buf], uph);
-        if (p.dbg) t_a += clock64() - tw2;
+        if (prof) t_a += clock64() - tw2;
         tc_fence_after();
         const uint32_t a_tile = a_lo0 + sA16 + (uint32_t)buf * (a_bytes >> 4) + (uint32_t)halo;
         const uint32_t d0 = tmem + (uint32_t)(buf * 256), d1 = d0 + 128;
         uint32_t acc = 0;
+        int shift = -p.Wp - 1;                    // tap (0,0); then +1, +1, +(Wp-2), ...
         for (int tap = 0; tap < 9; ++tap) {
-          const int shift = (tap / 3 - 1) * p.Wp + (tap % 3 - 1);
           uint32_t a_lo = a_tile + (uint32_t)shift;        // wraps correctly: shift may be negative
-          for (int ch = 0; ch < chunks_tap; ++ch, ++it) {
-            const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-            if (p.dbg) tw = clock64();
-            mbar_wait(&w_full[s], ph);
-            if (p.dbg) t_w += clock64() - tw;
+          shift += (tap == 2 || tap == 5) ? p.Wp - 2 : 1;
+          for (int ch = 0; ch < chunks_tap; ++ch) {
+            if (prof) tw = clock64();
+            mbar_wait(&w_full[st], st_ph);
+            if (prof) t_w += clock64() - tw;
             tc_fence_after();
-            uint32_t b_lo = b_lo0 + sW16 + s * stage16;
-            const long long ti = p.dbg ? clock64() : 0;
-#pragma unroll 4
-            for (int ks = 0; ks < ksteps; ++ks) {
-              const uint64_t bd = desc64(b_lo, b_hi);
+            uint32_t b_lo = b_slot;
+            const long long ti = prof ? clock64() : 0;
+            if (ksteps == 4) {
+              // the common case (64-channel stage) fully unrolled: the eight descriptors are formed (and
+              // moved to uniform registers) ahead of the eight back-to-back MMAs
+              uint32_t al[4], bl[4];
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) { al[ks] = a_lo + (uint32_t)ks * a_kstep; bl[ks] = b_lo + (uint32_t)ks * b_kstep; }
               if (issuer) {
-                mma_bf16(d0, desc64(a_lo, a_hi), bd, idesc, acc);
-                mma_bf16(d1, desc64(a_lo + 128u, a_hi), bd, idesc, acc);
+                mma_bf16(d0, desc64(al[0], a_hi), desc64(bl[0], b_hi), idesc, acc);
+                mma_bf16(d1, desc64(al[0] + 128u, a_hi), desc64(bl[0], b_hi), idesc, acc);
+#pragma unroll
+                for (int ks = 1; ks < 4; ++ks) {
+                  mma_bf16(d0, desc64(al[ks], a_hi), desc64(bl[ks], b_hi), idesc, 1u);
+                  mma_bf16(d1, desc64(al[ks] + 128u, a_hi), desc64(bl[ks], b_hi), idesc, 1u);
+                }
               }
               acc = 1;
-              a_lo += a_kstep;
-              b_lo += b_kstep;
+              a_lo += 4u * a_kstep;
+            } else {
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint64_t bd = desc64(b_lo, b_hi);
+                if (issuer) {
+                  mma_bf16(d0, desc64(a_lo, a_hi), bd, idesc, acc);
+                  mma_bf16(d1, desc64(a_lo + 128u, a_hi), bd, idesc, acc);
+                }
+                acc = 1;
+                a_lo += a_kstep;
+                b_lo += b_kstep;
+              }
             }
-            const long long tc = p.dbg ? clock64() : 0;
-            if (issuer) commit(&w_empty[s]);
-            __syncwarp();
-            if (p.dbg) { t_issue += tc - ti; t_commit += clock64() - tc; }
+            const long long tc = prof ? clock64() : 0;
+            if (issuer) commit(&w_empty[st]);
+            if (prof) { t_issue += tc - ti; t_commit += clock64() - tc; }
+            ++st; b_slot += stage16;
+            if (st == kStages) { st = 0; st_ph ^= 1; b_slot = b_first; }
           }
         }
         if (issuer) commit(&mma_done[buf]);
