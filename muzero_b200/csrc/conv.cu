@@ -37,7 +37,7 @@ using namespace umma;
 typedef __half act_t;
 typedef __half2 act2_t;
 
-constexpr int kConvThreads = 320;   // producer, MMA, 4 epilogue warps, 4 loader warps
+constexpr int kConvThreads = 352;   // producer, MMA issuer 0, 4 epilogue warps, 4 loader warps, MMA issuer 1
 constexpr int kWorkers = 128;
 constexpr int kTileM = 256;     // positions per tile (two M=128 accumulators)
 constexpr int kMaxStages = 6;
@@ -77,7 +77,7 @@ struct ConvParams {
   int TP;                         // tile positions incl. halo, odd
   int stages;                     // weight ring depth (as many as shared memory allows, <= kMaxStages)
   long long* dbg;                 // optional per-CTA role timing (MZ_CONV_DEBUG), else nullptr
-  int ablate;                     // debug only (MZ_CONV_ABLATE): 1 skip epilogue work, 2 skip tile loads, 4 skip weight copies
+  int ablate;                     // debug only (MZ_CONV_ABLATE): 1 skip epilogue work, 2 skip tile loads, 4 skip weight copies, 8 no w_full wait, 16 no w_empty commit/wait (use with 4), 32 no per-stage fence, 64 only the MMA warp runs, 256 coarse debug timing only, 512 epilogue without global loads/stores
 };
 
 __device__ __forceinline__ void split_pos(int P, const ConvParams& p, int& b, int& q, bool& halo) {
@@ -126,8 +126,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
   int* s_row = reinterpret_cast<int*>(s_bias + p.N);                    // [TP] source row per tile position
 
   if (tid == 0) {
-    for (uint32_t s = 0; s < kStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&a_full[b], kWorkers); mbar_init(&mma_done[b], 1); mbar_init(&acc_empty[b], kWorkers); }
+    for (uint32_t s = 0; s < kStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 2); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&a_full[b], kWorkers); mbar_init(&mma_done[b], 2); mbar_init(&acc_empty[b], kWorkers); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_holder, 512);
@@ -140,7 +140,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
   const int G = (int)gridDim.x;
   auto first_tile = [&](int l) { int t0 = ((int)blockIdx.x - l * p.rot) % G; return t0 < 0 ? t0 + G : t0; };
 
-  if (warp == 0) {
+  if ((p.ablate & 64) && warp != 1 && warp != 10) {
+    // debug: only the MMA warp runs
+  } else if (warp == 0) {
     // ------------------------------------------------ weight producer
     if (lane == 0) {
       const int per_tile = 9 * chunks_tap;
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
           for (int c = 0; c < per_tile; ++c, ++it) {
             const uint32_t s = it % kStages, ph = (it / kStages) & 1;
             const long long tw = clock64();
-            mbar_wait(&w_empty[s], ph ^ 1);
+            if (!(p.ablate & 16)) mbar_wait(&w_empty[s], ph ^ 1);
             t_wait += clock64() - tw;
             if (p.ablate & 4) { mbar_arrive(&w_full[s]); continue; }
             mbar_arrive_expect_tx(&w_full[s], stage_bytes);
@@ -163,15 +165,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
       }
       if (p.dbg) { p.dbg[blockIdx.x * 16 + 0] = clock64() - t_begin; p.dbg[blockIdx.x * 16 + 1] = t_wait; }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer
+  } else if (warp == 1 || warp == 10) {
+    // ------------------------------------------------ MMA issuers: warp 1 drives accumulator 0 (tile rows 0-127),
+    // warp 10 accumulator 1 (rows 128-255); a stage / a tile is released when BOTH have committed
     {
       // One thread feeds the tensor core, so the issue path must cost well under the 64 cycles an MMA
       // lasts.  The WHOLE warp walks the loop (all values warp-uniform, so descriptors live in uniform
       // registers and are stepped with uniform ALU ops instead of per-MMA vector->uniform moves) and
       // only lane 0 is predicated onto the tcgen05 instructions.  Descriptors are built once; only
       // their 14-bit start-address field (16-byte units) is stepped.
-      const bool issuer = (lane == 0);
+      const bool issuer = (lane == 0) && warp == 1;
+      const uint32_t mhalf = warp == 1 ? 0u : 1u;
       const uint32_t idesc = instr_desc_f16(128, (uint32_t)p.N);
       const uint64_t a_tmpl = smem_desc(0, (uint32_t)TP * 16, 128);
       const uint64_t b_tmpl = smem_desc(0, (uint32_t)p.N * 16, 128);
@@ -189,7 +193,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
       uint32_t b_slot = b_lo0 + sW16;             // descriptor low word of ring slot `st`
       const uint32_t b_first = b_slot;
       long long t_acc = 0, t_a = 0, t_w = 0, t_issue = 0, t_commit = 0;
-      const bool prof = p.dbg != nullptr;
+      const bool prof = p.dbg != nullptr && !(p.ablate & 256);
       const long long t_begin = clock64();
       int i = 0;
       for (int l = 0; l < p.num_layers; ++l)
@@ -197,14 +201,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
         const int buf = i & 1;
         const uint32_t uph = (i >> 1) & 1;
         long long tw = prof ? clock64() : 0;
-        mbar_wait(&acc_empty[buf], uph ^ 1);
+        if (!(p.ablate & 64)) mbar_wait(&acc_empty[buf], uph ^ 1);
         long long tw2 = prof ? clock64() : 0;
         t_acc += tw2 - tw;
-        mbar_wait(&a_full[buf], uph);
+        if (!(p.ablate & 64)) mbar_wait(&a_full[buf], uph);
         if (prof) t_a += clock64() - tw2;
         tc_fence_after();
-        const uint32_t a_tile = a_lo0 + sA16 + (uint32_t)buf * (a_bytes >> 4) + (uint32_t)halo;
-        const uint32_t d0 = tmem + (uint32_t)(buf * 256), d1 = d0 + 128;
+        const uint32_t a_tile = a_lo0 + sA16 + (uint32_t)buf * (a_bytes >> 4) + (uint32_t)halo + 128u * mhalf;
+        const uint32_t dacc = tmem + (uint32_t)(buf * 256) + 128u * mhalf;
         uint32_t acc = 0;
         int shift = -p.Wp - 1;                    // tap (0,0); then +1, +1, +(Wp-2), ...
         for (int tap = 0; tap < 9; ++tap) {
@@ -212,9 +216,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
           shift += (tap == 2 || tap == 5) ? p.Wp - 2 : 1;
           for (int ch = 0; ch < chunks_tap; ++ch) {
             if (prof) tw = clock64();
-            mbar_wait(&w_full[st], st_ph);
+            if (!(p.ablate & 8)) mbar_wait(&w_full[st], st_ph);
             if (prof) t_w += clock64() - tw;
-            tc_fence_after();
+            if (!(p.ablate & 32)) tc_fence_after();
             uint32_t b_lo = b_slot;
             const long long ti = prof ? clock64() : 0;
             if (ksteps == 4) {
@@ -223,45 +227,35 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
               uint32_t al[4], bl[4];
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) { al[ks] = a_lo + (uint32_t)ks * a_kstep; bl[ks] = b_lo + (uint32_t)ks * b_kstep; }
-              if (issuer) {
-                mma_bf16(d0, desc64(al[0], a_hi), desc64(bl[0], b_hi), idesc, acc);
-                mma_bf16(d1, desc64(al[0] + 128u, a_hi), desc64(bl[0], b_hi), idesc, acc);
+              mma_f16_elect(dacc, desc64(al[0], a_hi), desc64(bl[0], b_hi), idesc, acc);
 #pragma unroll
-                for (int ks = 1; ks < 4; ++ks) {
-                  mma_bf16(d0, desc64(al[ks], a_hi), desc64(bl[ks], b_hi), idesc, 1u);
-                  mma_bf16(d1, desc64(al[ks] + 128u, a_hi), desc64(bl[ks], b_hi), idesc, 1u);
-                }
-              }
+              for (int ks = 1; ks < 4; ++ks) mma_f16_elect(dacc, desc64(al[ks], a_hi), desc64(bl[ks], b_hi), idesc, 1u);
               acc = 1;
               a_lo += 4u * a_kstep;
             } else {
               for (int ks = 0; ks < ksteps; ++ks) {
                 const uint64_t bd = desc64(b_lo, b_hi);
-                if (issuer) {
-                  mma_bf16(d0, desc64(a_lo, a_hi), bd, idesc, acc);
-                  mma_bf16(d1, desc64(a_lo + 128u, a_hi), bd, idesc, acc);
-                }
+                mma_f16_elect(dacc, desc64(a_lo, a_hi), bd, idesc, acc);
                 acc = 1;
                 a_lo += a_kstep;
                 b_lo += b_kstep;
               }
             }
             const long long tc = prof ? clock64() : 0;
-            if (issuer) commit(&w_empty[st]);
+            if (!(p.ablate & 16)) commit_elect(&w_empty[st]);
             if (prof) { t_issue += tc - ti; t_commit += clock64() - tc; }
             ++st; b_slot += stage16;
             if (st == kStages) { st = 0; st_ph ^= 1; b_slot = b_first; }
           }
         }
-        if (issuer) commit(&mma_done[buf]);
-        __syncwarp();
+        commit_elect(&mma_done[buf]);
       }
       if (p.dbg && issuer) {
         long long* d = p.dbg + blockIdx.x * 16;
         d[2] = clock64() - t_begin; d[3] = t_acc; d[4] = t_a; d[5] = t_w; d[6] = i; d[12] = t_issue; d[13] = t_commit;
       }
     }
-  } else if (warp >= 6) {
+  } else if (warp >= 6) {   // warps 6-9
     // ------------------------------------------------ loaders (warps 6-9): activation tile -> smem
     // cp.async (LDGSTS): every 16-byte chunk of the tile is in flight at once, zero-fill for halo /
     // out-of-range positions.  Per tile the 128 threads first resolve each tile position to its
@@ -390,7 +384,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
           int b = 0, pos = 0; bool hl = true;
           if (Pj[j] < p.Ptot) split_pos(Pj[j], p, b, pos, hl);
           vj[j] = !hl;
-          if (vj[j] && L.residual) rpj[j] = reinterpret_cast<const int4*>(L.residual + (size_t)Pj[j] * kN);
+          if (vj[j] && L.residual && !(p.ablate & 512)) rpj[j] = reinterpret_cast<const int4*>(L.residual + (size_t)Pj[j] * kN);
         }
         fetch(0, ring[0]);
         fetch(1, ring[1]);
@@ -428,10 +422,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
 #pragma unroll
             for (int e = 0; e < 32; ++e) v[e] = fminf(fmaxf(v[e], 0.0f), 65504.0f);
             int4* o = reinterpret_cast<int4*>(L.out + (size_t)Pj[j] * kN + c0);
+            if (!(p.ablate & 512) || v[0] == 12345.678f) {
 #pragma unroll
             for (int e = 0; e < 32; e += 8)
               o[e / 8] = make_int4((int)pack2(v[e], v[e + 1]), (int)pack2(v[e + 2], v[e + 3]),
                                    (int)pack2(v[e + 4], v[e + 5]), (int)pack2(v[e + 6], v[e + 7]));
+            }
           }
           __syncwarp();
         }

@@ -2,7 +2,7 @@
 // operands in the no-swizzle K-major layout, with optional competing shared-memory store
 // traffic, for cta_group::1 (M=128 per SM) and cta_group::2 (M=256 over an SM pair, each SM
 // holding half of B).  Answers: what bounds the MMA rate inside conv.cu?
-// usage: umma_bench N a_rows b_rows [grid] [iters] [writer_warps 0..3] [two_cta 0|1] [data 0=zeros|1=random]
+// usage: umma_bench N a_rows b_rows [grid] [iters] [writer_warps 0..3] [two_cta 0|1] [data 0=zeros|1=random] [spinner_warps 0..8]
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>
@@ -20,9 +20,10 @@ __device__ __forceinline__ void cluster_sync() {
 }
 
 template <bool kTwo>
-__global__ void __launch_bounds__(128) bench(int N, int a_rows, int b_rows, int iters, long long* out, int writer, int data) {
+__global__ void __launch_bounds__(384) bench(int N, int a_rows, int b_rows, int iters, long long* out, int writer, int data) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bar2;   // never completes: spinner warps poll it like idle pipeline roles do
   __shared__ uint32_t tmem_base;
   __shared__ volatile int stop;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -31,7 +32,7 @@ __global__ void __launch_bounds__(128) bench(int N, int a_rows, int b_rows, int 
   unsigned char* sA = smem;
   unsigned char* sB = smem + 16 * a_rows * 16;
   // operand data: zeros (data == 0) or pseudo-random fp16 in [-1, 1) (data == 1): tensor-core power depends on it
-  for (int i = tid; i < (16 * a_rows + 8 * b_rows) * 4; i += 128) {
+  for (int i = tid; i < (16 * a_rows + 8 * b_rows) * 4; i += blockDim.x) {
     uint32_t v = 0;
     if (data) {
       uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u;
@@ -41,7 +42,7 @@ __global__ void __launch_bounds__(128) bench(int N, int a_rows, int b_rows, int 
     }
     reinterpret_cast<uint32_t*>(smem)[i] = v;
   }
-  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); stop = 0; }
+  if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1); fence_mbar_init(); stop = 0; }
   if (warp == 0) {
     if (kTwo) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512) : "memory");
@@ -92,6 +93,8 @@ __global__ void __launch_bounds__(128) bench(int N, int a_rows, int b_rows, int 
       it += 8;
     }
     if (tid == 32) out[gridDim.x + blockIdx.x] = (long long)it * 16 * 32 * writer;   // bytes stored by this CTA
+  } else if (warp >= 4) {
+    while (!stop) { if (mbar_try_wait(&bar2, 0)) break; }
   }
   tc_fence_before();
   __syncthreads();
@@ -107,6 +110,8 @@ int main(int argc, char** argv) {
   const int grid = argc > 4 ? atoi(argv[4]) : 1, iters = argc > 5 ? atoi(argv[5]) : 2000, writer = argc > 6 ? atoi(argv[6]) : 0;
   const int two = argc > 7 ? atoi(argv[7]) : 0;
   const int data = argc > 8 ? atoi(argv[8]) : 0;
+  const int spin = argc > 9 ? atoi(argv[9]) : 0;
+  const int threads = 128 + 32 * spin;
   long long* d;
   cudaMalloc(&d, 2 * grid * sizeof(long long));
   cudaMemset(d, 0, 2 * grid * sizeof(long long));
@@ -115,7 +120,7 @@ int main(int argc, char** argv) {
   if (two) {
     cudaFuncSetAttribute(bench<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -124,7 +129,7 @@ int main(int argc, char** argv) {
     if (e != cudaSuccess) { printf("launch error %s\n", cudaGetErrorString(e)); return 1; }
   } else {
     cudaFuncSetAttribute(bench<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    bench<false><<<grid, 128, smem>>>(N, a_rows, b_rows, iters, d, writer, data);
+    bench<false><<<grid, threads, smem>>>(N, a_rows, b_rows, iters, d, writer, data);
   }
   e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
@@ -135,7 +140,7 @@ int main(int argc, char** argv) {
   for (int i = 0; i < grid; ++i) wbytes += (double)h[grid + i] / grid;
   const double cyc = mx / ((double)iters * 8);
   const double flop = 2.0 * 128 * N * 16;     // per SM per MMA (a 2-SM MMA does this much on each SM)
-  printf("data=%s cta_group::%d N=%d A-LBO %d B b_rows=%d grid=%d writer_warps=%d: %.1f cycles/MMA, %.0f flop/cycle/SM (ideal 8192), "
-         "competing stores %.1f B/cycle/SM\n", data ? "random" : "zeros", two ? 2 : 1, N, a_rows * 16, b_rows, grid, writer, cyc, flop / cyc, wbytes / mx);
+  printf("spin=%d data=%s cta_group::%d N=%d A-LBO %d B b_rows=%d grid=%d writer_warps=%d: %.1f cycles/MMA, %.0f flop/cycle/SM (ideal 8192), "
+         "competing stores %.1f B/cycle/SM\n", spin, data ? "random" : "zeros", two ? 2 : 1, N, a_rows * 16, b_rows, grid, writer, cyc, flop / cyc, wbytes / mx);
   return 0;
 }
