@@ -1,28 +1,32 @@
 // ResNet towers of MuZeroBoardGameNet / MuZeroAtariNet (network.py:273-574) on the
 // Blackwell tensor cores (fp16 x fp16 -> fp32).
 //
-// Data layout ("padded grid, channel-last"): a board's activation is
-//   [PB = (H+1)*(W+1) positions][C channels] fp16,   position p = y*(W+1) + x,
-// where column x == W and row y == H are a zero halo SHARED with the next row /
-// the next board.  Flattening boards back to back (P = b*PB + p) makes every 3x3
-// tap a constant row offset: tap (ky,kx) of output position P reads input position
-// P + (ky-1)*(W+1) + (kx-1).  A hidden-state slot of the search pool is one such
-// board (PB*C*2 bytes); halo entries are never read (the loader zero-fills them by
-// predicate) and never written.
+// Data layout ("padded grid, channel-group planes"): a board is a grid of
+//   PB = (H+1)*(W+1) positions,  position q = y*(W+1) + x,
+// where column x == W and row y == H are a ZERO halo shared with the next row / the next
+// board.  Flattening boards back to back (row P = b*PB + q) makes every 3x3 tap a constant row
+// offset: tap (ky,kx) of output row P reads input row P + (ky-1)*(W+1) + (kx-1).
+// An activation tensor is stored as C/8 PLANES of [rows][8 channels] fp16 (16 bytes per row):
+//   contiguous buffer:  element (P, c) at ((c/8) * plane_rows + P) * 8 + c%8
+//   hidden-state slot:  element (q, c) of slot s at ((s * C/8 + c/8) * PB + q) * 8 + c%8
+// which is exactly the no-swizzle K-major core-matrix layout tcgen05.mma reads from shared
+// memory, so (a) a tile of 256 rows + halo is ONE contiguous run per plane and is fetched by
+// 1-D bulk copies (TMA) with no per-element work, (b) the epilogue's stores (lane = row, 16
+// bytes per plane) are fully coalesced.  Every writer of an activation buffer writes ZEROS at
+// halo positions; rows past the last board are never read by a valid output.
 //
-// Kernel: implicit GEMM, M = positions, N = C_out, K = 9 taps x C_in.
-//   - the activation tile (256 positions + halo) is staged ONCE in shared memory in
-//     the no-swizzle K-major core-matrix layout; the 9 taps are 9 descriptor start
-//     addresses on that one tile (umma.cuh) -> activations are read once per layer;
-//   - folded conv+BatchNorm weights stream through a 4-stage mbarrier ring of 1-D bulk
-//     copies (TMA), pre-packed on the host side of mz_net_create in exactly the
-//     shared-memory layout;
+// Kernel: implicit GEMM, M = rows, N = C_out, K = 9 taps x C_in.
+//   - the activation tile (256 rows + halo) is staged ONCE in shared memory; the 9 taps are 9
+//     descriptor start addresses on that one tile (umma.cuh) -> activations are read once;
+//   - folded conv+BatchNorm weights stream through an mbarrier ring of 1-D bulk copies,
+//     pre-packed on the host side of mz_net_create in exactly the shared-memory layout;
 //   - tcgen05.mma (M=128, N=C_out, K=16) accumulates in TMEM, two 128-row accumulators
 //     per tile, double-buffered across tiles so that epilogue(i-1) and load(i+1)
 //     overlap mma(i);
-//   - warp roles: warp 0 weight producer, warp 1 MMA issuer (+TMEM owner), warps 2-5
-//     epilogue (bias / action-bias table / residual / ReLU / per-pixel channel min-max
-//     normalisation of util.py:31-36 fused here), warps 6-9 activation loaders (cp.async).
+//   - warp roles: warp 0 weight producer, warps 1 and 3 MMA issuers (one per accumulator half:
+//     a single warp cannot issue an M128 N128 MMA every 64 cycles), warp 2 tile loader (TMA),
+//     warps 4-11 epilogue (bias / action-bias table / residual / ReLU / per-pixel channel
+//     min-max normalisation of util.py:31-36 fused here).
 #include "net.cuh"
 #include "umma.cuh"
 #include <cuda_fp16.h>
@@ -37,10 +41,11 @@ using namespace umma;
 typedef __half act_t;
 typedef __half2 act2_t;
 
-constexpr int kConvThreads = 352;   // producer, MMA issuer 0, 4 epilogue warps, 4 loader warps, MMA issuer 1
-constexpr int kWorkers = 128;
-constexpr int kTileM = 256;     // positions per tile (two M=128 accumulators)
+constexpr int kConvThreads = 384;   // w0 weights, w1 MMA (rows 0-127), w2 tile loader, w3 MMA (rows 128-255), w4-11 epilogue
+constexpr int kEpiThreads = 256;
+constexpr int kTileM = 256;     // rows per tile (two M=128 accumulators)
 constexpr int kMaxStages = 6;
+constexpr int kPlaneSlack = 64; // rows allocated past the last tile of every plane (>= the widest halo)
 
 constexpr int kMaxLayers = 34;   // one launch runs up to a whole recurrent inference: 1 + 16 + 16 convs
 
@@ -48,19 +53,19 @@ constexpr int kMaxLayers = 34;   // one launch runs up to a whole recurrent infe
 // persistent CTAs; layer l+1's tile t starts as soon as tiles t-1, t, t+1 of layer l are published
 // (per-tile flags in global memory), so there is no per-layer launch, prologue or tail.
 struct LayerDesc {
-  const act_t* in;        // [.. boards ..][PB][Cin_pad]
-  const int32_t* in_index;        // board b lives in slot in_index[b] (nullptr: b)
+  const act_t* in;        // planes [Cin/8][plane_rows][8], or the slot array when in_slots is set
+  const int32_t* in_index;        // slot input: board b lives in slot in_index[b] (nullptr: slot b)
   const act_t* w;         // packed [9][chunks][chunk_g][N][8]
   const float* bias;              // [N]
-  const float* tab;               // [A][PB][N] per-action bias (dynamics conv0) or nullptr
+  const float* tab;               // [A][N/8][PB][8] per-action bias (dynamics conv0) or nullptr
   const int32_t* action;          // [B]
-  const act_t* residual;  // contiguous [Ptot][N] or nullptr
-  act_t* out;             // contiguous [Ptot][N] (relu'd) or nullptr
-  act_t* out_norm;        // contiguous, min-max normalised, or nullptr
+  const act_t* residual;  // contiguous planes or nullptr
+  act_t* out;             // contiguous planes (relu'd) or nullptr
+  act_t* out_norm;        // contiguous planes, min-max normalised, or nullptr
   act_t* out_slots;       // indexed slots, normalised, or nullptr
   const int32_t* out_index;
   int dep;                        // input is produced by the previous layer of this launch
-  int pad_;
+  int in_slots;                   // input is an array of hidden-state slots, not a contiguous buffer
 };
 
 struct ConvParams {
@@ -70,14 +75,15 @@ struct ConvParams {
   unsigned int* flags;            // [num_layers][num_tiles], zeroed before the launch (nullptr for one layer)
   int* err;                       // dependency wait timed out (should never happen)
   int Ptot, PB, Wp, W, H, B;
+  int plane_rows;                 // rows per plane of the contiguous buffers of this launch
   int cg;                         // input channel groups of 8 (Cin_pad / 8), even
   int N;                          // output channels (multiple of 32, <= 128)
   int relu;
   int num_tiles;
-  int TP;                         // tile positions incl. halo, odd
+  int TP;                         // tile rows incl. halo, odd
   int stages;                     // weight ring depth (as many as shared memory allows, <= kMaxStages)
   long long* dbg;                 // optional per-CTA role timing (MZ_CONV_DEBUG), else nullptr
-  int ablate;                     // debug only (MZ_CONV_ABLATE): 1 skip epilogue work, 2 skip tile loads, 4 skip weight copies, 8 no w_full wait, 16 no w_empty commit/wait (use with 4), 32 no per-stage fence, 64 only the MMA warp runs, 256 coarse debug timing only, 512 epilogue without global loads/stores
+  int ablate;                     // debug only (MZ_CONV_ABLATE): 1 skip epilogue work, 2 skip tile loads, 4 skip weight copies, 512 epilogue without global loads/stores
 };
 
 __device__ __forceinline__ void split_pos(int P, const ConvParams& p, int& b, int& q, bool& halo) {
@@ -99,6 +105,29 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
 }
 __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// bias + residual + ReLU (+ fp16 saturation) of 32 accumulator columns -> four 16-byte plane rows
+__device__ __forceinline__ void finish32(const uint32_t (&r)[32], const float* s_bias_c0, const int4 (&res)[4],
+                                         float (&v)[32]) {
+#pragma unroll
+  for (int e = 0; e < 32; e += 4) {
+    const float4 b4 = *reinterpret_cast<const float4*>(s_bias_c0 + e);
+    v[e] = __uint_as_float(r[e]) + b4.x; v[e + 1] = __uint_as_float(r[e + 1]) + b4.y;
+    v[e + 2] = __uint_as_float(r[e + 2]) + b4.z; v[e + 3] = __uint_as_float(r[e + 3]) + b4.w;
+  }
+#pragma unroll
+  for (int e = 0; e < 32; e += 8) {
+    const act2_t* h = reinterpret_cast<const act2_t*>(&res[e / 8]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float2 f = __half22float2(h[u]);
+      v[e + 2 * u] += f.x; v[e + 2 * u + 1] += f.y;
+    }
+  }
+}
+__device__ __forceinline__ int4 pack8(const float* v) {
+  return make_int4((int)pack2(v[0], v[1]), (int)pack2(v[2], v[3]), (int)pack2(v[4], v[5]), (int)pack2(v[6], v[7]));
 }
 
 template <int kN>
@@ -123,11 +152,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
   uint64_t* acc_empty = mma_done + 2;      // [2]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* s_bias = reinterpret_cast<float*>(tmem_holder + 4);            // [N], 16-byte aligned
-  int* s_row = reinterpret_cast<int*>(s_bias + p.N);                    // [TP] source row per tile position
+  float2* s_mm = reinterpret_cast<float2*>(s_bias + p.N);               // [2][128] partial (min, max) per row
 
   if (tid == 0) {
     for (uint32_t s = 0; s < kStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 2); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&a_full[b], kWorkers); mbar_init(&mma_done[b], 2); mbar_init(&acc_empty[b], kWorkers); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&a_full[b], 1); mbar_init(&mma_done[b], 2); mbar_init(&acc_empty[b], kEpiThreads); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_holder, 512);
@@ -139,10 +168,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
   // every role walks the same (layer, tile) item sequence of this CTA
   const int G = (int)gridDim.x;
   auto first_tile = [&](int l) { int t0 = ((int)blockIdx.x - l * p.rot) % G; return t0 < 0 ? t0 + G : t0; };
+  const bool dbg = p.dbg != nullptr;
 
-  if ((p.ablate & 64) && warp != 1 && warp != 10) {
-    // debug: only the MMA warp runs
-  } else if (warp == 0) {
+  if (warp == 0) {
     // ------------------------------------------------ weight producer
     if (lane == 0) {
       const int per_tile = 9 * chunks_tap;
@@ -154,200 +182,176 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
         for (int tile = first_tile(l); tile < p.num_tiles; tile += G) {
           for (int c = 0; c < per_tile; ++c, ++it) {
             const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-            const long long tw = clock64();
-            if (!(p.ablate & 16)) mbar_wait(&w_empty[s], ph ^ 1);
-            t_wait += clock64() - tw;
+            const long long tw = dbg ? clock64() : 0;
+            mbar_wait(&w_empty[s], ph ^ 1);
+            if (dbg) t_wait += clock64() - tw;
             if (p.ablate & 4) { mbar_arrive(&w_full[s]); continue; }
             mbar_arrive_expect_tx(&w_full[s], stage_bytes);
             bulk_g2s(sW + (size_t)s * stage_bytes, wl + (size_t)c * stage_bytes, stage_bytes, &w_full[s]);
           }
         }
       }
-      if (p.dbg) { p.dbg[blockIdx.x * 16 + 0] = clock64() - t_begin; p.dbg[blockIdx.x * 16 + 1] = t_wait; }
+      if (dbg) { p.dbg[blockIdx.x * 16 + 0] = clock64() - t_begin; p.dbg[blockIdx.x * 16 + 1] = t_wait; }
     }
-  } else if (warp == 1 || warp == 10) {
+  } else if (warp == 1 || warp == 3) {
     // ------------------------------------------------ MMA issuers: warp 1 drives accumulator 0 (tile rows 0-127),
-    // warp 10 accumulator 1 (rows 128-255); a stage / a tile is released when BOTH have committed
-    {
-      // One thread feeds the tensor core, so the issue path must cost well under the 64 cycles an MMA
-      // lasts.  The WHOLE warp walks the loop (all values warp-uniform, so descriptors live in uniform
-      // registers and are stepped with uniform ALU ops instead of per-MMA vector->uniform moves) and
-      // only lane 0 is predicated onto the tcgen05 instructions.  Descriptors are built once; only
-      // their 14-bit start-address field (16-byte units) is stepped.
-      const bool issuer = (lane == 0) && warp == 1;
-      const uint32_t mhalf = warp == 1 ? 0u : 1u;
-      const uint32_t idesc = instr_desc_f16(128, (uint32_t)p.N);
-      const uint64_t a_tmpl = smem_desc(0, (uint32_t)TP * 16, 128);
-      const uint64_t b_tmpl = smem_desc(0, (uint32_t)p.N * 16, 128);
-      const uint32_t a_hi = (uint32_t)(a_tmpl >> 32), a_lo0 = (uint32_t)a_tmpl;
-      const uint32_t b_hi = (uint32_t)(b_tmpl >> 32), b_lo0 = (uint32_t)b_tmpl;
-      const uint32_t a_kstep = 2u * (uint32_t)TP, b_kstep = 2u * (uint32_t)p.N;   // 16-byte units per K=16 step
-      const uint32_t sA16 = smem_u32(sA) >> 4, sW16 = smem_u32(sW) >> 4, stage16 = stage_bytes >> 4;
-      const int ksteps = chunk_g / 2;
-      auto desc64 = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
-      // The tensor core only queues a couple of MMAs, so whatever the issuing thread does between two
-      // stages (barrier poll, fence, commit, bookkeeping) beyond ~2 MMA times shows up as a bubble: the
-      // stage ring is walked with incremental counters (no div/mod), tap shifts are stepped, and the
-      // debug clocks are skipped by a uniform branch when profiling is off.
-      uint32_t st = 0, st_ph = 0;                 // weight ring slot and its phase parity
-      uint32_t b_slot = b_lo0 + sW16;             // descriptor low word of ring slot `st`
-      const uint32_t b_first = b_slot;
-      long long t_acc = 0, t_a = 0, t_w = 0, t_issue = 0, t_commit = 0;
-      const bool prof = p.dbg != nullptr && !(p.ablate & 256);
-      const long long t_begin = clock64();
-      int i = 0;
-      for (int l = 0; l < p.num_layers; ++l)
-      for (int tile = first_tile(l); tile < p.num_tiles; tile += G, ++i) {
-        const int buf = i & 1;
-        const uint32_t uph = (i >> 1) & 1;
-        long long tw = prof ? clock64() : 0;
-        if (!(p.ablate & 64)) mbar_wait(&acc_empty[buf], uph ^ 1);
-        long long tw2 = prof ? clock64() : 0;
-        t_acc += tw2 - tw;
-        if (!(p.ablate & 64)) mbar_wait(&a_full[buf], uph);
-        if (prof) t_a += clock64() - tw2;
-        tc_fence_after();
-        const uint32_t a_tile = a_lo0 + sA16 + (uint32_t)buf * (a_bytes >> 4) + (uint32_t)halo + 128u * mhalf;
-        const uint32_t dacc = tmem + (uint32_t)(buf * 256) + 128u * mhalf;
-        uint32_t acc = 0;
-        int shift = -p.Wp - 1;                    // tap (0,0); then +1, +1, +(Wp-2), ...
-        for (int tap = 0; tap < 9; ++tap) {
-          uint32_t a_lo = a_tile + (uint32_t)shift;        // wraps correctly: shift may be negative
-          shift += (tap == 2 || tap == 5) ? p.Wp - 2 : 1;
-          for (int ch = 0; ch < chunks_tap; ++ch) {
-            if (prof) tw = clock64();
-            if (!(p.ablate & 8)) mbar_wait(&w_full[st], st_ph);
-            if (prof) t_w += clock64() - tw;
-            if (!(p.ablate & 32)) tc_fence_after();
-            uint32_t b_lo = b_slot;
-            const long long ti = prof ? clock64() : 0;
-            if (ksteps == 4) {
-              // the common case (64-channel stage) fully unrolled: the eight descriptors are formed (and
-              // moved to uniform registers) ahead of the eight back-to-back MMAs
-              uint32_t al[4], bl[4];
+    // warp 3 accumulator 1 (rows 128-255); a weight stage / a tile is released when BOTH have committed.
+    // The WHOLE warp walks the loop and one lane is elected inside each tcgen05 asm statement, so
+    // ptxas emits straight-line predicated UTCHMMAs (an `if (lane == 0)` around them costs a convergence
+    // loop per MMA, ~100 cycles).  Descriptors are built once; only their 14-bit start-address field
+    // (16-byte units) is stepped.
+    const uint32_t mhalf = warp == 1 ? 0u : 1u;
+    const uint32_t idesc = instr_desc_f16(128, (uint32_t)p.N);
+    const uint64_t a_tmpl = smem_desc(0, (uint32_t)TP * 16, 128);
+    const uint64_t b_tmpl = smem_desc(0, (uint32_t)p.N * 16, 128);
+    const uint32_t a_hi = (uint32_t)(a_tmpl >> 32), a_lo0 = (uint32_t)a_tmpl;
+    const uint32_t b_hi = (uint32_t)(b_tmpl >> 32), b_lo0 = (uint32_t)b_tmpl;
+    const uint32_t a_kstep = 2u * (uint32_t)TP, b_kstep = 2u * (uint32_t)p.N;   // 16-byte units per K=16 step
+    const uint32_t sA16 = smem_u32(sA) >> 4, sW16 = smem_u32(sW) >> 4, stage16 = stage_bytes >> 4;
+    const int ksteps = chunk_g / 2;
+    auto desc64 = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
+    uint32_t st = 0, st_ph = 0;                 // weight ring slot and its phase parity
+    uint32_t b_slot = b_lo0 + sW16;             // descriptor low word of ring slot `st`
+    const uint32_t b_first = b_slot;
+    long long t_acc = 0, t_a = 0;
+    const long long t_begin = clock64();
+    int i = 0;
+    for (int l = 0; l < p.num_layers; ++l)
+    for (int tile = first_tile(l); tile < p.num_tiles; tile += G, ++i) {
+      const int buf = i & 1;
+      const uint32_t uph = (i >> 1) & 1;
+      long long tw = dbg ? clock64() : 0;
+      mbar_wait(&acc_empty[buf], uph ^ 1);
+      long long tw2 = dbg ? clock64() : 0;
+      t_acc += tw2 - tw;
+      mbar_wait(&a_full[buf], uph);
+      if (dbg) t_a += clock64() - tw2;
+      tc_fence_after();
+      const uint32_t a_tile = a_lo0 + sA16 + (uint32_t)buf * (a_bytes >> 4) + (uint32_t)halo + 128u * mhalf;
+      const uint32_t dacc = tmem + (uint32_t)(buf * 256) + 128u * mhalf;
+      uint32_t acc = 0;
+      int shift = -p.Wp - 1;                    // tap (0,0); then +1, +1, +(Wp-2), ...
+      for (int tap = 0; tap < 9; ++tap) {
+        uint32_t a_lo = a_tile + (uint32_t)shift;        // wraps correctly: shift may be negative
+        shift += (tap == 2 || tap == 5) ? p.Wp - 2 : 1;
+        for (int ch = 0; ch < chunks_tap; ++ch) {
+          mbar_wait(&w_full[st], st_ph);
+          tc_fence_after();
+          uint32_t b_lo = b_slot;
+          if (ksteps == 4) {
+            // the common case (64-channel stage) fully unrolled
+            uint32_t al[4], bl[4];
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) { al[ks] = a_lo + (uint32_t)ks * a_kstep; bl[ks] = b_lo + (uint32_t)ks * b_kstep; }
-              mma_f16_elect(dacc, desc64(al[0], a_hi), desc64(bl[0], b_hi), idesc, acc);
+            for (int ks = 0; ks < 4; ++ks) { al[ks] = a_lo + (uint32_t)ks * a_kstep; bl[ks] = b_lo + (uint32_t)ks * b_kstep; }
+            mma_f16_elect(dacc, desc64(al[0], a_hi), desc64(bl[0], b_hi), idesc, acc);
 #pragma unroll
-              for (int ks = 1; ks < 4; ++ks) mma_f16_elect(dacc, desc64(al[ks], a_hi), desc64(bl[ks], b_hi), idesc, 1u);
+            for (int ks = 1; ks < 4; ++ks) mma_f16_elect(dacc, desc64(al[ks], a_hi), desc64(bl[ks], b_hi), idesc, 1u);
+            acc = 1;
+            a_lo += 4u * a_kstep;
+          } else {
+            for (int ks = 0; ks < ksteps; ++ks) {
+              mma_f16_elect(dacc, desc64(a_lo, a_hi), desc64(b_lo, b_hi), idesc, acc);
               acc = 1;
-              a_lo += 4u * a_kstep;
-            } else {
-              for (int ks = 0; ks < ksteps; ++ks) {
-                const uint64_t bd = desc64(b_lo, b_hi);
-                mma_f16_elect(dacc, desc64(a_lo, a_hi), bd, idesc, acc);
-                acc = 1;
-                a_lo += a_kstep;
-                b_lo += b_kstep;
-              }
+              a_lo += a_kstep;
+              b_lo += b_kstep;
             }
-            const long long tc = prof ? clock64() : 0;
-            if (!(p.ablate & 16)) commit_elect(&w_empty[st]);
-            if (prof) { t_issue += tc - ti; t_commit += clock64() - tc; }
-            ++st; b_slot += stage16;
-            if (st == kStages) { st = 0; st_ph ^= 1; b_slot = b_first; }
           }
+          commit_elect(&w_empty[st]);
+          ++st; b_slot += stage16;
+          if (st == kStages) { st = 0; st_ph ^= 1; b_slot = b_first; }
         }
-        commit_elect(&mma_done[buf]);
       }
-      if (p.dbg && issuer) {
-        long long* d = p.dbg + blockIdx.x * 16;
-        d[2] = clock64() - t_begin; d[3] = t_acc; d[4] = t_a; d[5] = t_w; d[6] = i; d[12] = t_issue; d[13] = t_commit;
-      }
+      commit_elect(&mma_done[buf]);
     }
-  } else if (warp >= 6) {   // warps 6-9
-    // ------------------------------------------------ loaders (warps 6-9): activation tile -> smem
-    // cp.async (LDGSTS): every 16-byte chunk of the tile is in flight at once, zero-fill for halo /
-    // out-of-range positions.  Per tile the 128 threads first resolve each tile position to its
-    // source row (board slot * PB + position, or -1) into a small smem table, so the chunk loop
-    // carries no integer divisions.  Thread -> fixed channel group g, positions q0, q0+step, ...
-    const int lt = tid - 192;                // 0..127
-    const int cpp = p.cg;                    // 16-byte chunks per position
-    const int cin = p.cg * 8;
-    const int ld_g = lt % cpp, ld_q0 = lt / cpp, ld_step = kWorkers / cpp;
-    const int nq = kTileM + 2 * halo;
-    long long t_wait = 0, t_cp = 0;
+    if (dbg && lane == 0 && warp == 1) {
+      long long* d = p.dbg + blockIdx.x * 16;
+      d[2] = clock64() - t_begin; d[3] = t_acc; d[4] = t_a; d[6] = i;
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------ tile loader: activation rows -> shared memory by bulk copies.
+    // A tile's rows are one contiguous run per channel-group plane (or one run per board and plane when the
+    // input lives in indexed hidden-state slots), already in the shared-memory layout.
+    const int cg = p.cg;
+    long long t_wait = 0, t_dep = 0;
     const long long t_begin = clock64();
     int i = 0;
     for (int l = 0; l < p.num_layers; ++l)
     for (int tile = first_tile(l); tile < p.num_tiles; tile += G, ++i) {
       const LayerDesc& L = p.L[l];
       const int buf = i & 1;
-      const int m0 = tile * kTileM;
-      // source row of every tile position: the divisions first, then the (independent) slot-index loads,
-      // so the loads overlap instead of forming a chain of L2 round trips
-      {
-        int qq[3], bb[3], pp_[3];
-        bool ok[3];
-#pragma unroll
-        for (int u = 0; u < 3; ++u) {
-          qq[u] = lt + u * kWorkers;
-          const int P = m0 - halo + qq[u];
-          ok[u] = false; bb[u] = 0; pp_[u] = 0;
-          if (qq[u] < nq && P >= 0 && P < p.Ptot) {
-            bool hl;
-            split_pos(P, p, bb[u], pp_[u], hl);
-            ok[u] = !hl;
+      const int r0 = tile * kTileM - halo, r1 = r0 + kTileM + 2 * halo;     // tile rows [r0, r1)
+      // dataflow dependency: the three tiles of the previous layer whose rows this tile reads
+      long long tw = dbg ? clock64() : 0;
+      if (L.dep) {
+        if (lane < 3) {
+          const int tt = tile - 1 + lane;
+          if (tt >= 0 && tt < p.num_tiles) {
+            const unsigned* f = p.flags + (size_t)(l - 1) * p.num_tiles + tt;
+            unsigned spins = 0;
+            while (ld_acquire(f) == 0u) {
+              ++spins;
+              if ((spins & 0xffffu) == 0 && p.err && *reinterpret_cast<volatile int*>(p.err)) break;   // sticky bail-out
+              if (spins > (1u << 26)) { if (p.err) atomicExch(p.err, 1); break; }
+            }
           }
         }
-        int slot[3];
-#pragma unroll
-        for (int u = 0; u < 3; ++u) slot[u] = (ok[u] && L.in_index) ? L.in_index[bb[u]] : bb[u];
-#pragma unroll
-        for (int u = 0; u < 3; ++u)
-          if (qq[u] < nq) s_row[qq[u]] = ok[u] ? slot[u] * p.PB + pp_[u] : -1;
-        for (int q = lt + 3 * kWorkers; q < nq; q += kWorkers) {      // wide grids: more than 384 tile positions
-          const int P = m0 - halo + q;
-          int row = -1;
-          if (P >= 0 && P < p.Ptot) {
-            int b, pos; bool hl;
-            split_pos(P, p, b, pos, hl);
-            if (!hl) row = (L.in_index ? L.in_index[b] : b) * p.PB + pos;
-          }
-          s_row[q] = row;
-        }
+        __syncwarp();
+        asm volatile("fence.proxy.async;" ::: "memory");   // other CTAs' (generic-proxy) stores -> our async-proxy reads
       }
-      // dataflow dependency: the three tiles of the previous layer whose rows this tile reads (polled by
-      // three different threads so the L2 round trips overlap)
-      if (L.dep && lt < 3) {
-        const int tt = tile - 1 + lt;
-        if (tt >= 0 && tt < p.num_tiles) {
-          const unsigned* f = p.flags + (size_t)(l - 1) * p.num_tiles + tt;
-          unsigned spins = 0;
-          while (ld_acquire(f) == 0u) {
-            ++spins;
-            if ((spins & 0xffffu) == 0 && p.err && *reinterpret_cast<volatile int*>(p.err)) break;   // sticky bail-out
-            if (spins > (1u << 26)) { if (p.err) atomicExch(p.err, 1); break; }
-          }
-        }
-      }
+      long long tw2 = dbg ? clock64() : 0;
+      t_dep += tw2 - tw;
       // the buffer was last read by the MMAs of tile i-2
-      long long tw = clock64();
       if (i >= 2) mbar_wait(&mma_done[buf], (uint32_t)(((i - 2) >> 1) & 1));
-      t_wait += clock64() - tw;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      tw = clock64();
-      const uint32_t dst = smem_u32(sA) + (uint32_t)buf * a_bytes + (uint32_t)ld_g * TP * 16;
-      for (int q = ld_q0; q < nq && !(p.ablate & 2); q += ld_step) {
-        const int row = s_row[q];
-        const act_t* src = row >= 0 ? L.in + ((size_t)row * cin + ld_g * 8) : L.in;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)q * 16), "l"(src),
-                     "r"(row >= 0 ? 16u : 0u)
-                     : "memory");
+      if (dbg) t_wait += clock64() - tw2;
+      const uint32_t dst0 = smem_u32(sA) + (uint32_t)buf * a_bytes;
+      const int lo = r0 > 0 ? r0 : 0;
+      int hi = L.in_slots ? p.Ptot : p.plane_rows;
+      hi = r1 < hi ? r1 : hi;
+      if (r0 < 0) {
+        // rows before the first board are read by valid outputs (top-left taps of board 0): zeros
+        const int nz = -r0;
+        for (int k = lane; k < nz * cg; k += 32) {
+          const int g = k / nz, q = k - g * nz;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst0 + (uint32_t)(g * TP + q) * 16), "r"(0) : "memory");
+        }
+        fence_proxy_async();
       }
-      asm volatile("cp.async.wait_all;" ::: "memory");
-      fence_proxy_async();
-      mbar_arrive(&a_full[buf]);
-      t_cp += clock64() - tw;
-      asm volatile("bar.sync 1, 128;" ::: "memory");      // table is rewritten next iteration
+      __syncwarp();
+      if (p.ablate & 2) {
+        if (lane == 0) mbar_arrive(&a_full[buf]);
+      } else {
+        if (lane == 0) mbar_arrive_expect_tx(&a_full[buf], (uint32_t)(hi - lo) * 16u * (uint32_t)cg);
+        __syncwarp();
+        if (!L.in_slots) {
+          for (int g = lane; g < cg; g += 32)
+            bulk_g2s_u32(dst0 + (uint32_t)(g * TP + (lo - r0)) * 16, L.in + ((size_t)g * p.plane_rows + lo) * 8,
+                         (uint32_t)(hi - lo) * 16u, &a_full[buf]);
+        } else {
+          const int b_lo = lo / p.PB, nb = (hi - 1) / p.PB - b_lo + 1;
+          for (int k = lane; k < nb * cg; k += 32) {
+            const int bi = k / cg, g = k - bi * cg, b = b_lo + bi;
+            const int s0 = b * p.PB > lo ? b * p.PB : lo, s1 = (b + 1) * p.PB < hi ? (b + 1) * p.PB : hi;
+            const size_t slot = L.in_index ? (size_t)L.in_index[b] : (size_t)b;
+            bulk_g2s_u32(dst0 + (uint32_t)(g * TP + (s0 - r0)) * 16,
+                         L.in + ((slot * cg + g) * p.PB + (size_t)(s0 - b * p.PB)) * 8, (uint32_t)(s1 - s0) * 16u,
+                         &a_full[buf]);
+          }
+        }
+      }
     }
-    if (p.dbg && lt == 0) {
+    if (dbg && lane == 0) {
       long long* d = p.dbg + blockIdx.x * 16;
-      d[7] = clock64() - t_begin; d[8] = t_wait; d[9] = t_cp;
+      d[7] = clock64() - t_begin; d[8] = t_wait; d[9] = t_dep;
     }
-  } else {
-    // ------------------------------------------------ epilogue (warps 2-5): TMEM -> registers -> global
-    const int quad = warp & 3;               // TMEM lane quadrant this warp may read
+  } else if (warp >= 4) {
+    // ------------------------------------------------ epilogue (warps 4-11): TMEM -> registers -> global
+    // warp w reads TMEM lanes 32*(w%4).. (its rows) and one half of the output columns
+    const int quad = warp & 3, chalf = (warp - 4) >> 2;
+    const int et = tid - 128;                // 0..255
+    constexpr int NC = kN / 32;              // 32-column chunks of the accumulator
+    constexpr int NCW = NC >= 2 ? NC / 2 : 1;     // chunks per warp
+    const bool has_cols = chalf * NCW < NC;
+    const size_t PR = (size_t)p.plane_rows;
     long long t_wait = 0;
     const long long t_begin = clock64();
     int k = 0, bias_layer = -1;
@@ -357,179 +361,155 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
       const bool norm = (L.out_norm != nullptr) || (L.out_slots != nullptr);
       const int buf = k & 1;
       if (bias_layer != l) {               // new layer: swap the bias vector in shared memory
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-        if (tid - 64 < kN) s_bias[tid - 64] = L.bias[tid - 64];
-        asm volatile("bar.sync 2, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et < kN) s_bias[et] = L.bias[et];
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         bias_layer = l;
       }
-      // Fast path (30 of the 33 convs of a recurrent inference: plain conv+bias(+residual)+ReLU):
-      // the 2 rows x kN/32 column chunks of this thread form one unrolled sequence, and the
-      // residual of step t+2 is requested at step t (the first two before the MMAs even finish),
-      // so its global-memory latency never sits on the critical path.
-      constexpr int NC = kN / 32, STEPS = 2 * NC;
       const bool fast = !norm && L.tab == nullptr && L.out != nullptr;
-      int Pj[2] = {0, 0};
-      bool vj[2] = {false, false};
-      const int4* rpj[2] = {nullptr, nullptr};
-      int4 ring[3][4];
-      auto fetch = [&](int t, int4 (&dst)[4]) {
-        const int4* src = rpj[t / NC];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) dst[u] = src ? __ldcg(src + (t % NC) * 4 + u) : make_int4(0, 0, 0, 0);
-      };
+      const uint32_t tbase = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256);
       if (fast) {
+        // Plain conv + bias (+ residual) + ReLU (30 of the 33 convs of a recurrent inference).  The steps of
+        // this warp (2 row halves x NCW column chunks) form one unrolled sequence and the residual of step
+        // t+2 is requested at step t (the first two before the MMAs even finish).
+        constexpr int STEPS = 2 * NCW;
+        int Pj[2];
+        bool vj[2], inr[2];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           Pj[j] = tile * kTileM + j * 128 + quad * 32 + lane;
           int b = 0, pos = 0; bool hl = true;
-          if (Pj[j] < p.Ptot) split_pos(Pj[j], p, b, pos, hl);
+          inr[j] = Pj[j] < p.Ptot;
+          if (inr[j]) split_pos(Pj[j], p, b, pos, hl);
           vj[j] = !hl;
-          if (vj[j] && L.residual && !(p.ablate & 512)) rpj[j] = reinterpret_cast<const int4*>(L.residual + (size_t)Pj[j] * kN);
         }
-        fetch(0, ring[0]);
-        fetch(1, ring[1]);
-      }
-      const long long tw = clock64();
-      mbar_wait(&mma_done[buf], (uint32_t)((k >> 1) & 1));
-      t_wait += clock64() - tw;
-      tc_fence_after();
-      if (p.ablate & 1) {
-      } else if (fast) {
+        const int4* resp = reinterpret_cast<const int4*>(L.residual);
+        const bool has_res = resp != nullptr && !(p.ablate & 512);
+        int4 ring[3][4];
+        auto fetch = [&](int t, int4 (&dst)[4]) {
+          const int j = t / NCW, g0 = (chalf * NCW + t % NCW) * 4;
+          const bool ld = has_res && vj[j];
 #pragma unroll
-        for (int t = 0; t < STEPS; ++t) {
-          const int j = t / NC, c0 = (t % NC) * 32;
-          if (t + 2 < STEPS) fetch(t + 2, ring[(t + 2) % 3]);
-          uint32_t r[32];
-          tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256 + j * 128 + c0), r);
-          tmem_ld_wait();
-          if (vj[j]) {
+          for (int u = 0; u < 4; ++u) dst[u] = ld ? __ldcg(resp + (size_t)(g0 + u) * PR + Pj[j]) : make_int4(0, 0, 0, 0);
+        };
+        if (has_cols) {
+          fetch(0, ring[0]);
+          if (STEPS > 1) fetch(1, ring[1]);
+        }
+        const long long tw = dbg ? clock64() : 0;
+        mbar_wait(&mma_done[buf], (uint32_t)((k >> 1) & 1));
+        if (dbg) t_wait += clock64() - tw;
+        tc_fence_after();
+        if (has_cols && !(p.ablate & 1)) {
+          int4* outp = reinterpret_cast<int4*>(L.out);
+#pragma unroll
+          for (int t = 0; t < STEPS; ++t) {
+            const int j = t / NCW, c = chalf * NCW + t % NCW, c0 = c * 32;
+            if (t + 2 < STEPS) fetch(t + 2, ring[(t + 2) % 3]);
+            uint32_t r[32];
+            tmem_ld32(tbase + (uint32_t)(j * 128 + c0), r);
+            tmem_ld_wait();
             float v[32];
+            finish32(r, s_bias + c0, ring[t % 3], v);
+            // ReLU (every conv of these nets is followed by one) and fp16 saturation in one clamp; halo rows are ZERO
+            const float top = vj[j] ? 65504.0f : 0.0f;
 #pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + e);
-              v[e] = __uint_as_float(r[e]) + b4.x; v[e + 1] = __uint_as_float(r[e + 1]) + b4.y;
-              v[e + 2] = __uint_as_float(r[e + 2]) + b4.z; v[e + 3] = __uint_as_float(r[e + 3]) + b4.w;
-            }
+            for (int e = 0; e < 32; ++e) v[e] = fminf(fmaxf(v[e], 0.0f), top);
+            if (inr[j] && !(p.ablate & 512)) {
 #pragma unroll
-            for (int e = 0; e < 32; e += 8) {
-              const act2_t* h = reinterpret_cast<const act2_t*>(&ring[t % 3][e / 8]);
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const float2 f = __half22float2(h[u]);
-                v[e + 2 * u] += f.x; v[e + 2 * u + 1] += f.y;
-              }
-            }
-#pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = fminf(fmaxf(v[e], 0.0f), 65504.0f);
-            int4* o = reinterpret_cast<int4*>(L.out + (size_t)Pj[j] * kN + c0);
-            if (!(p.ablate & 512) || v[0] == 12345.678f) {
-#pragma unroll
-            for (int e = 0; e < 32; e += 8)
-              o[e / 8] = make_int4((int)pack2(v[e], v[e + 1]), (int)pack2(v[e + 2], v[e + 3]),
-                                   (int)pack2(v[e + 4], v[e + 5]), (int)pack2(v[e + 6], v[e + 7]));
+              for (int u = 0; u < 4; ++u) outp[(size_t)(c * 4 + u) * PR + Pj[j]] = pack8(v + 8 * u);
             }
           }
-          __syncwarp();
         }
       } else {
+        const long long tw = dbg ? clock64() : 0;
+        mbar_wait(&mma_done[buf], (uint32_t)((k >> 1) & 1));
+        if (dbg) t_wait += clock64() - tw;
+        tc_fence_after();
 #pragma unroll 1
-      for (int j = 0; j < 2; ++j) {
-        const int P = tile * kTileM + j * 128 + quad * 32 + lane;
-        int b = 0, pos = 0; bool hl = true;
-        if (P < p.Ptot) split_pos(P, p, b, pos, hl);
-        const bool valid = !hl;
-        const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256 + j * 128);
-        const float* tab = (L.tab && valid) ? L.tab + ((size_t)L.action[b] * p.PB + pos) * kN : nullptr;
-        const bool has_res = (L.residual != nullptr) && valid;
-        const int4* rp = reinterpret_cast<const int4*>(L.residual + (size_t)(has_res ? P : 0) * kN);
-        float mn = INFINITY, mx = -INFINITY;
-#pragma unroll 1
-        for (int pass = 0; pass < (norm ? 2 : 1); ++pass) {
-          float inv = 0.0f;
-          if (pass == 1) inv = 1.0f / ((mx - mn) + 1e-8f);
-#pragma unroll 1
-          for (int c0 = 0; c0 < kN; c0 += 32) {
-            // this chunk's residual (4 x 16 B) is requested before the TMEM load so both latencies overlap
-            int4 rres[4];
+        for (int j = 0; j < 2 && !(p.ablate & 1); ++j) {
+          const int P = tile * kTileM + j * 128 + quad * 32 + lane;
+          int b = 0, pos = 0; bool hl = true;
+          const bool inrange = P < p.Ptot;
+          if (inrange) split_pos(P, p, b, pos, hl);
+          const bool valid = !hl;
+          const float top = valid ? 65504.0f : 0.0f;
+          const float* tab = (L.tab && valid) ? L.tab + ((size_t)L.action[b] * (kN / 8) * p.PB + pos) * 8 : nullptr;
+          const int4* resp = (L.residual && valid) ? reinterpret_cast<const int4*>(L.residual) + P : nullptr;
+          float v[NCW][32];
+          float mn = INFINITY, mx = -INFINITY;
+          if (has_cols) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) rres[u] = has_res ? __ldcg(rp + c0 / 8 + u) : make_int4(0, 0, 0, 0);
-            uint32_t r[32];
-            tmem_ld32(taddr + c0, r);          // .sync.aligned: the whole warp executes it, valid row or not
-            tmem_ld_wait();
-            if (valid) {
-              float v[32];
+            for (int cc = 0; cc < NCW; ++cc) {
+              const int c = chalf * NCW + cc, c0 = c * 32;
+              int4 rres[4];
 #pragma unroll
-              for (int e = 0; e < 32; e += 4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + e);
-                v[e] = __uint_as_float(r[e]) + b4.x; v[e + 1] = __uint_as_float(r[e + 1]) + b4.y;
-                v[e + 2] = __uint_as_float(r[e + 2]) + b4.z; v[e + 3] = __uint_as_float(r[e + 3]) + b4.w;
-              }
+              for (int u = 0; u < 4; ++u) rres[u] = resp ? __ldcg(resp + (size_t)(c * 4 + u) * PR) : make_int4(0, 0, 0, 0);
+              uint32_t r[32];
+              tmem_ld32(tbase + (uint32_t)(j * 128 + c0), r);
+              tmem_ld_wait();
+              finish32(r, s_bias + c0, rres, v[cc]);
               if (tab) {
 #pragma unroll
-                for (int e = 0; e < 32; e += 4) {
-                  const float4 t4 = *reinterpret_cast<const float4*>(tab + c0 + e);
-                  v[e] += t4.x; v[e + 1] += t4.y; v[e + 2] += t4.z; v[e + 3] += t4.w;
+                for (int u = 0; u < 4; ++u) {
+                  const float4* t4 = reinterpret_cast<const float4*>(tab + (size_t)(c * 4 + u) * p.PB * 8);
+                  const float4 ta = t4[0], tb = t4[1];
+                  v[cc][8 * u] += ta.x; v[cc][8 * u + 1] += ta.y; v[cc][8 * u + 2] += ta.z; v[cc][8 * u + 3] += ta.w;
+                  v[cc][8 * u + 4] += tb.x; v[cc][8 * u + 5] += tb.y; v[cc][8 * u + 6] += tb.z; v[cc][8 * u + 7] += tb.w;
                 }
               }
 #pragma unroll
-              for (int e = 0; e < 32; e += 8) {
-                const act2_t* h = reinterpret_cast<const act2_t*>(&rres[e / 8]);
+              for (int e = 0; e < 32; ++e) {
+                v[cc][e] = fminf(fmaxf(v[cc][e], 0.0f), top);
+                mn = fminf(mn, v[cc][e]); mx = fmaxf(mx, v[cc][e]);
+              }
+              if (L.out && inrange) {
+                int4* o = reinterpret_cast<int4*>(L.out) + P;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) o[(size_t)(c * 4 + u) * PR] = pack8(v[cc] + 8 * u);
+              }
+            }
+          }
+          if (norm) {
+            // min/max over ALL channels of the row: combine with the warp holding the other column half
+            s_mm[chalf * 128 + quad * 32 + lane] = make_float2(mn, mx);
+            asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");
+            const float2 o = s_mm[(chalf ^ 1) * 128 + quad * 32 + lane];
+            asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");
+            mn = fminf(mn, o.x); mx = fmaxf(mx, o.y);
+            const float inv = valid ? 1.0f / ((mx - mn) + 1e-8f) : 0.0f;
+            if (has_cols && inrange) {
+              int4* on = L.out_norm ? reinterpret_cast<int4*>(L.out_norm) + P : nullptr;
+              int4* os = nullptr;
+              if (L.out_slots) {
+                const size_t slot = L.out_index ? (size_t)L.out_index[b] : (size_t)b;
+                os = reinterpret_cast<int4*>(L.out_slots) + slot * (kN / 8) * p.PB + pos;
+              }
+#pragma unroll
+              for (int cc = 0; cc < NCW; ++cc) {
+                const int c = chalf * NCW + cc;
+#pragma unroll
+                for (int e = 0; e < 32; ++e) v[cc][e] = (v[cc][e] - mn) * inv;
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                  const float2 f = __half22float2(h[u]);
-                  v[e + 2 * u] += f.x; v[e + 2 * u + 1] += f.y;
+                  const int4 o4 = pack8(v[cc] + 8 * u);
+                  if (on) on[(size_t)(c * 4 + u) * PR] = o4;
+                  if (os) os[(size_t)(c * 4 + u) * p.PB] = o4;
                 }
               }
-              // ReLU (every conv of these nets is followed by one) and fp16 saturation in one clamp
-#pragma unroll
-              for (int e = 0; e < 32; ++e) v[e] = fminf(fmaxf(v[e], 0.0f), 65504.0f);
-              if (pass == 0) {
-                if (norm) {
-#pragma unroll
-                  for (int e = 0; e < 32; ++e) { mn = fminf(mn, v[e]); mx = fmaxf(mx, v[e]); }
-                }
-                if (L.out) {
-                  int4* o = reinterpret_cast<int4*>(L.out + (size_t)P * kN + c0);
-#pragma unroll
-                  for (int e = 0; e < 32; e += 8)
-                    o[e / 8] = make_int4((int)pack2(v[e], v[e + 1]), (int)pack2(v[e + 2], v[e + 3]),
-                                         (int)pack2(v[e + 4], v[e + 5]), (int)pack2(v[e + 6], v[e + 7]));
-                }
-              } else {
-#pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] = (v[e] - mn) * inv;
-                int4 o4[4];
-#pragma unroll
-                for (int e = 0; e < 32; e += 8)
-                  o4[e / 8] = make_int4((int)pack2(v[e], v[e + 1]), (int)pack2(v[e + 2], v[e + 3]),
-                                        (int)pack2(v[e + 4], v[e + 5]), (int)pack2(v[e + 6], v[e + 7]));
-                if (L.out_norm) {
-                  int4* o = reinterpret_cast<int4*>(L.out_norm + (size_t)P * kN + c0);
-#pragma unroll
-                  for (int u = 0; u < 4; ++u) o[u] = o4[u];
-                }
-                if (L.out_slots) {
-                  const size_t board = L.out_index ? (size_t)L.out_index[b] : (size_t)b;
-                  int4* o = reinterpret_cast<int4*>(L.out_slots + (board * p.PB + pos) * kN + c0);
-#pragma unroll
-                  for (int u = 0; u < 4; ++u) o[u] = o4[u];
-                }
-              }
-            }  // valid
-            __syncwarp();
+            }
           }
         }
       }
-      }  // generic path
       tc_fence_before();
       mbar_arrive(&acc_empty[buf]);
       if (p.flags) {                       // publish the tile: stores fenced by every thread, then one release
         __threadfence();
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-        if (tid == 64) st_release(p.flags + (size_t)l * p.num_tiles + tile, 1u);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et == 0) st_release(p.flags + (size_t)l * p.num_tiles + tile, 1u);
       }
     }
-    if (p.dbg && tid == 64) {
+    if (dbg && et == 0) {
       long long* d = p.dbg + blockIdx.x * 16;
       d[10] = clock64() - t_begin; d[11] = t_wait;
     }
@@ -542,19 +522,35 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
 // ---------------------------------------------------------------------------
 // small SIMT kernels: observation packing, heads, weight repacking
 // ---------------------------------------------------------------------------
-// obs f32 [B][C][H][W] -> bf16 padded grid [B][PB][cpad]
+// obs f32 [B][C][H][W] -> fp16 planes [cpad/8][plane_rows][8] (zeros at halo positions and padded channels)
 __global__ void pack_obs_kernel(const float* __restrict__ obs, act_t* __restrict__ out, int B, int C, int H,
-                                int W, int cpad) {
+                                int W, int cpad, int plane_rows) {
   const int Wp = W + 1, PB = (H + 1) * Wp;
   const size_t n = (size_t)B * PB * cpad;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cpad);
-    const size_t r = i / cpad;
-    const int pos = (int)(r % PB), b = (int)(r / PB);
+    const int e = (int)(i % 8);
+    const size_t r = i / 8;
+    const size_t P = r % ((size_t)B * PB);
+    const int g = (int)(r / ((size_t)B * PB));
+    const int c = g * 8 + e;
+    const int pos = (int)(P % PB), b = (int)(P / PB);
     const int y = pos / Wp, x = pos % Wp;
     float v = 0.0f;
     if (c < C && y < H && x < W) v = obs[(((size_t)b * C + c) * H + y) * W + x];
-    out[i] = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
+    out[((size_t)g * plane_rows + P) * 8 + e] = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
+  }
+}
+
+// zeros at the halo positions of a planar buffer (after the SIMT kernels that only write real positions)
+__global__ void zero_halo_kernel(act_t* __restrict__ buf, int B, int H, int W, int cg, int plane_rows) {
+  const int Wp = W + 1, PB = (H + 1) * Wp, nh = H + Wp;       // halo positions per board: column W of rows 0..H-1, row H
+  const size_t n = (size_t)cg * B * nh;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % nh);
+    const size_t r = i / nh;
+    const int b = (int)(r % B), g = (int)(r / B);
+    const int pos = k < H ? k * Wp + W : H * Wp + (k - H);
+    reinterpret_cast<int4*>(buf)[(size_t)g * plane_rows + (size_t)b * PB + pos] = make_int4(0, 0, 0, 0);
   }
 }
 
@@ -562,7 +558,8 @@ __global__ void pack_obs_kernel(const float* __restrict__ obs, act_t* __restrict
 // transform: 0 = raw scalar (support 1), 1 = support->scalar (util.py:70-93), 2 = softmax.
 // One CTA of 128 threads per board.
 struct HeadParams {
-  const act_t* act;   // contiguous [B][PB][C]
+  const act_t* act;   // contiguous planes [C/8][plane_rows][8]
+  int plane_rows;
   const float* w1;            // [mid][C]  (scaled)
   const float* b1;            // [mid]
   const float* w2;            // [out][mid*hw]
@@ -587,15 +584,15 @@ __global__ void __launch_bounds__(128) head_kernel(const HeadParams p) {
   float* f = hs;
   float* lg = hs + p.mid * hw;
   const int b = blockIdx.x;
-  const act_t* a = p.act + (size_t)b * PB * p.C;
+  const int4* a = reinterpret_cast<const int4*>(p.act) + (size_t)b * PB;
   for (int i = threadIdx.x; i < p.mid * hw; i += blockDim.x) {
     const int m = i / hw, q = i % hw;
     const int y = q / p.W, x = q % p.W;
-    const act_t* row = a + (size_t)(y * Wp + x) * p.C;
+    const int4* row = a + (y * Wp + x);
     const float* w = p.w1 + (size_t)m * p.C;
     float acc = 0.0f;
     for (int c = 0; c < p.C; c += 8) {
-      const int4 r4 = *reinterpret_cast<const int4*>(row + c);
+      const int4 r4 = row[(size_t)(c / 8) * p.plane_rows];
       const act2_t* h = reinterpret_cast<const act2_t*>(&r4);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -692,9 +689,12 @@ __global__ void action_table_kernel(const float* __restrict__ w, const float* __
   const int Wp = W + 1, PB = (H + 1) * Wp, hw = H * W;
   const size_t total = (size_t)A * PB * N;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int n = (int)(i % N);
-    const int pos = (int)((i / N) % PB);
+    // table layout [A][N/8][PB][8]: the epilogue (lane = row) reads 32 contiguous bytes per channel group
+    const int e = (int)(i % 8);
+    const int pos = (int)((i / 8) % PB);
+    const int g = (int)((i / ((size_t)8 * PB)) % (N / 8));
     const int a = (int)(i / ((size_t)N * PB));
+    const int n = g * 8 + e;
     const int y = pos / Wp, x = pos % Wp;
     float acc = 0.0f;
     if (y < H && x < W) {
@@ -721,7 +721,8 @@ __global__ void action_table_kernel(const float* __restrict__ w, const float* __
 // out[b][oy][ox][co] = relu(sum_{ky,kx,ci} in[b][2oy+ky-1][2ox+kx-1][ci] * w[ky*3+kx][ci][co]), Co = 128.
 // Tile: 64 output positions x 128 output channels per CTA, K in chunks of 16 input channels.
 __global__ void __launch_bounds__(256) conv3x3_s2_kernel(const act_t* __restrict__ in, const act_t* __restrict__ w,
-                                                         act_t* __restrict__ out, int B, int Hi, int Wi, int Ci) {
+                                                         act_t* __restrict__ out, int B, int Hi, int Wi, int Ci,
+                                                         int rows_in, int rows_out) {
   constexpr int Co = 128, TPOS = 64, KC = 16;
   const int Ho = Hi / 2, Wo = Wi / 2, Wpi = Wi + 1, PBi = (Hi + 1) * Wpi, Wpo = Wo + 1, PBo = (Ho + 1) * Wpo;
   __shared__ float As[KC][TPOS + 4];
@@ -743,11 +744,11 @@ __global__ void __launch_bounds__(256) conv3x3_s2_kernel(const act_t* __restrict
   for (int tap = 0; tap < 9; ++tap) {
     const int iy = 2 * loy + tap / 3 - 1, ix = 2 * lox + tap % 3 - 1;
     const bool inb = lvalid && iy >= 0 && iy < Hi && ix >= 0 && ix < Wi;
-    const act_t* src = in + ((size_t)lb * PBi + (size_t)(inb ? iy * Wpi + ix : 0)) * Ci;
+    const int4* src = reinterpret_cast<const int4*>(in) + ((size_t)lb * PBi + (size_t)(inb ? iy * Wpi + ix : 0));
     for (int c0 = 0; c0 < Ci; c0 += KC) {
       if (tid < 128) {
         int4 v = make_int4(0, 0, 0, 0);
-        if (inb) v = *reinterpret_cast<const int4*>(src + c0 + hp * 8);
+        if (inb) v = src[(size_t)(c0 / 8 + hp) * rows_in];
         const act2_t* h = reinterpret_cast<const act2_t*>(&v);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -788,7 +789,7 @@ __global__ void __launch_bounds__(256) conv3x3_s2_kernel(const act_t* __restrict
     const long long g = p0 + ty * 8 + i;
     if (g >= total) continue;
     const int b = (int)(g / (Ho * Wo)), r = (int)(g % (Ho * Wo)), oy = r / Wo, ox = r % Wo;
-    act_t* o = out + ((size_t)b * PBo + (size_t)oy * Wpo + ox) * Co + tx * 4;
+    act_t* o = out + ((size_t)(tx / 2) * rows_out + (size_t)b * PBo + (size_t)oy * Wpo + ox) * 8 + (tx & 1) * 4;
     uint2 pk;
     pk.x = pack2(fminf(fmaxf(acc[i][0], 0.0f), 65504.0f), fminf(fmaxf(acc[i][1], 0.0f), 65504.0f));
     pk.y = pack2(fminf(fmaxf(acc[i][2], 0.0f), 65504.0f), fminf(fmaxf(acc[i][3], 0.0f), 65504.0f));
@@ -801,44 +802,46 @@ __global__ void __launch_bounds__(256) conv3x3_s2_kernel(const act_t* __restrict
 // also writes the result to indexed hidden-state slots.
 __global__ void __launch_bounds__(256) avgpool_kernel(const act_t* __restrict__ in, act_t* __restrict__ out,
                                                       act_t* __restrict__ slots, const int32_t* __restrict__ out_index,
-                                                      int B, int Hi, int Wi, int normalise) {
+                                                      int B, int Hi, int Wi, int normalise, int rows_in, int rows_out) {
   constexpr int C = 128;
   const int Ho = Hi / 2, Wo = Wi / 2, Wpi = Wi + 1, PBi = (Hi + 1) * Wpi, Wpo = Wo + 1, PBo = (Ho + 1) * Wpo;
   const int lane = threadIdx.x & 31;
-  const long long total = (long long)B * Ho * Wo;
-  for (long long g = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); g < total; g += (long long)gridDim.x * 8) {
-    const int b = (int)(g / (Ho * Wo)), r = (int)(g % (Ho * Wo)), oy = r / Wo, ox = r % Wo;
+  const int g = lane >> 1, off = (lane & 1) * 4;      // channel-group plane and offset of this lane's 4 channels
+  const long long total = (long long)B * PBo;         // halo positions included: they are written as zeros
+  for (long long i = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); i < total; i += (long long)gridDim.x * 8) {
+    const int b = (int)(i / PBo), pos = (int)(i % PBo), oy = pos / Wpo, ox = pos % Wpo;
     float s[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int ky = 0; ky < 3; ++ky)
-      for (int kx = 0; kx < 3; ++kx) {
-        const int iy = 2 * oy + ky - 1, ix = 2 * ox + kx - 1;
-        if (iy < 0 || iy >= Hi || ix < 0 || ix >= Wi) continue;
-        const uint2 v = *reinterpret_cast<const uint2*>(in + ((size_t)b * PBi + (size_t)iy * Wpi + ix) * C + lane * 4);
-        const float2 f0 = __half22float2(*reinterpret_cast<const act2_t*>(&v.x));
-        const float2 f1 = __half22float2(*reinterpret_cast<const act2_t*>(&v.y));
-        s[0] += f0.x; s[1] += f0.y; s[2] += f1.x; s[3] += f1.y;
+    if (oy < Ho && ox < Wo) {
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {
+          const int iy = 2 * oy + ky - 1, ix = 2 * ox + kx - 1;
+          if (iy < 0 || iy >= Hi || ix < 0 || ix >= Wi) continue;
+          const uint2 v = *reinterpret_cast<const uint2*>(in + ((size_t)g * rows_in + (size_t)b * PBi + (size_t)iy * Wpi + ix) * 8 + off);
+          const float2 f0 = __half22float2(*reinterpret_cast<const act2_t*>(&v.x));
+          const float2 f1 = __half22float2(*reinterpret_cast<const act2_t*>(&v.y));
+          s[0] += f0.x; s[1] += f0.y; s[2] += f1.x; s[3] += f1.y;
+        }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[j] *= (1.0f / 9.0f);
+      if (normalise) {
+        float mn = fminf(fminf(s[0], s[1]), fminf(s[2], s[3])), mx = fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        const float inv = 1.0f / ((mx - mn) + 1e-8f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[j] = (s[j] - mn) * inv;
       }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) s[j] *= (1.0f / 9.0f);
-    if (normalise) {
-      float mn = fminf(fminf(s[0], s[1]), fminf(s[2], s[3])), mx = fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3]));
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      }
-      const float inv = 1.0f / ((mx - mn) + 1e-8f);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) s[j] = (s[j] - mn) * inv;
     }
     uint2 pk;
     pk.x = pack2(s[0], s[1]);
     pk.y = pack2(s[2], s[3]);
-    const size_t pos = (size_t)oy * Wpo + ox;
-    if (out) *reinterpret_cast<uint2*>(out + ((size_t)b * PBo + pos) * C + lane * 4) = pk;
+    if (out) *reinterpret_cast<uint2*>(out + ((size_t)g * rows_out + (size_t)b * PBo + pos) * 8 + off) = pk;
     if (slots) {
       const size_t board = out_index ? (size_t)out_index[b] : (size_t)b;
-      *reinterpret_cast<uint2*>(slots + (board * PBo + pos) * C + lane * 4) = pk;
+      *reinterpret_cast<uint2*>(slots + ((board * (C / 8) + g) * PBo + pos) * 8 + off) = pk;
     }
   }
 }
@@ -889,10 +892,14 @@ struct ConvNet : NetImpl {
   int* err_flag;
 
   static int tp_of(const Geo& g) { return (kTileM + 2 * (g.Wp() + 1)) | 1; }
+  // rows of one channel-group plane of a contiguous activation buffer holding `batch` boards of grid g
+  static int plane_rows_of(const Geo& g, int batch) {
+    return (batch * g.PB() + kTileM - 1) / kTileM * kTileM + kPlaneSlack;
+  }
   size_t conv_fixed_smem(const Geo& g, int cg) const {
     const int TP = tp_of(g);
     size_t a = (((size_t)2 * cg * TP * 16) + 127) & ~(size_t)127;
-    return a + (2 * kMaxStages + 6) * 8 + 16 + (size_t)C * 4 + (size_t)TP * 4 + 64;
+    return a + (2 * kMaxStages + 6) * 8 + 16 + (size_t)C * 4 + 2048 + 64;
   }
   int conv_stages(const Geo& g, int cg) const {
     const int chunk_g = cg < 8 ? cg : 8;
@@ -912,7 +919,7 @@ struct ConvNet : NetImpl {
   Geo pend_geo{0, 0};
   int pend_cg = 0, pend_batch = 0;
 
-  int add_layer(const ConvLayer& L, const Geo& g, const act_t* in, const int32_t* in_index, int batch,
+  int add_layer(const ConvLayer& L, const Geo& g, const act_t* in, const int32_t* in_index, bool in_slots, int batch,
                 const float* tab_, const int32_t* action, const act_t* residual, act_t* out, act_t* out_norm,
                 act_t* out_slots, const int32_t* out_index, cudaStream_t st) {
     if (pend.num_layers > 0 && (pend_cg != L.cg || pend_geo.H != g.H || pend_geo.W != g.W || pend_batch != batch ||
@@ -924,7 +931,7 @@ struct ConvNet : NetImpl {
     d.in = in; d.in_index = in_index; d.w = L.w; d.bias = L.bias; d.tab = tab_; d.action = action;
     d.residual = residual; d.out = out; d.out_norm = out_norm; d.out_slots = out_slots; d.out_index = out_index;
     d.dep = pend.num_layers > 0 ? 1 : 0;
-    d.pad_ = 0;
+    d.in_slots = in_slots ? 1 : 0;
     pend_geo = g; pend_cg = L.cg; pend_batch = batch;
     ++pend.num_layers;
     return MZ_OK;
@@ -937,6 +944,7 @@ struct ConvNet : NetImpl {
     const int batch = pend_batch, cg = pend_cg, nl = p.num_layers;
     p.PB = g.PB(); p.Wp = g.Wp(); p.W = g.W; p.H = g.H; p.B = batch;
     p.Ptot = batch * p.PB;
+    p.plane_rows = plane_rows_of(g, batch);
     p.cg = cg; p.N = C; p.relu = 1;
     p.num_tiles = (p.Ptot + kTileM - 1) / kTileM;
     p.TP = tp_of(g);
@@ -973,14 +981,15 @@ struct ConvNet : NetImpl {
       double a[16] = {0};
       for (int c = 0; c < grid; ++c) for (int k = 0; k < 16; ++k) a[k] += (double)h[(size_t)c * 16 + k] / grid;
       fprintf(stderr, "[conv dbg] %dx%d cg=%d layers=%d items/cta=%.1f | producer total %.0f wait_empty %.0f | mma total %.0f wait_acc %.0f "
-              "wait_a %.0f wait_w %.0f issue %.0f commit %.0f | loader total %.0f wait_mma %.0f copy %.0f | epilogue total %.0f wait_mma %.0f\n",
-              g.H, g.W, cg, nl, a[6], a[0], a[1], a[2], a[3], a[4], a[5], a[12], a[13], a[7], a[8], a[9], a[10], a[11]);
+              "wait_a %.0f | loader total %.0f wait_mma %.0f wait_dep %.0f | epilogue total %.0f wait_mma %.0f\n",
+              g.H, g.W, cg, nl, a[6], a[0], a[1], a[2], a[3], a[4], a[7], a[8], a[9], a[10], a[11]);
     }
     return MZ_OK;
   }
   int launch_head(const Head& h, const act_t* act, int batch, float* dst, cudaStream_t st) {
     HeadParams p;
     p.act = act; p.w1 = h.w1; p.b1 = h.b1; p.w2 = h.w2; p.b2 = h.b2; p.dst = dst;
+    p.plane_rows = plane_rows_of(lat, batch);
     p.C = C; p.H = lat.H; p.W = lat.W; p.mid = h.mid; p.out = h.out; p.kind = h.kind;
     const size_t smem = ((size_t)h.mid * lat.H * lat.W + h.out) * 4;
     prof_mark(kProfHead, st);
@@ -994,32 +1003,33 @@ struct ConvNet : NetImpl {
   // normalised state (contiguous copy and/or indexed slots).  *final_buf = buffer holding the raw
   // (ReLU'd) tower output, unless want_raw is false and the last layer normalises.
   int tower(const ConvLayer* first, const ConvLayer* blk, int nblk, const Geo& g, const act_t* in,
-            const int32_t* in_index, const float* tab_, const int32_t* action, int batch, bool want_raw,
+            const int32_t* in_index, bool in_slots, const float* tab_, const int32_t* action, int batch, bool want_raw,
             act_t* norm_out, act_t* slots, const int32_t* out_index, cudaStream_t st, act_t** final_buf,
             act_t* raw_dst = nullptr) {
     const act_t* cur = in;
     const int32_t* cur_index = in_index;
+    bool cur_slots = in_slots;
     act_t* pp[2] = {b0, b1};
     int which = (in == b0) ? 1 : 0, rc;
     const bool normalise = (norm_out != nullptr) || (slots != nullptr);
     if (first) {
       const bool last = (nblk == 0);
       act_t* dst = (last && raw_dst) ? raw_dst : pp[which];
-      rc = add_layer(*first, g, cur, cur_index, batch, tab_, action, nullptr,
+      rc = add_layer(*first, g, cur, cur_index, cur_slots, batch, tab_, action, nullptr,
                        (last && normalise && !want_raw) ? nullptr : dst, last ? norm_out : nullptr,
                        last ? slots : nullptr, out_index, st);
       if (rc) return rc;
-      cur = dst; cur_index = nullptr; which ^= 1;
+      cur = dst; cur_index = nullptr; cur_slots = false; which ^= 1;
     }
     for (int i = 0; i < nblk; ++i) {
       const bool last = (i == nblk - 1);
-      rc = add_layer(blk[2 * i], g, cur, cur_index, batch, nullptr, nullptr, nullptr, b2, nullptr, nullptr, nullptr, st);
+      rc = add_layer(blk[2 * i], g, cur, cur_index, cur_slots, batch, nullptr, nullptr, nullptr, b2, nullptr, nullptr, nullptr, st);
       if (rc) return rc;
-      if (cur_index != nullptr) { set_error("internal: residual input must be contiguous"); return MZ_EINVAL; }
+      if (cur_slots) { set_error("internal: residual input must be contiguous"); return MZ_EINVAL; }
       act_t* dst = pp[which];
       if (dst == cur) dst = pp[which ^ 1];
       if (last && raw_dst) dst = raw_dst;
-      rc = add_layer(blk[2 * i + 1], g, b2, nullptr, batch, nullptr, nullptr, cur,
+      rc = add_layer(blk[2 * i + 1], g, b2, nullptr, false, batch, nullptr, nullptr, cur,
                        (last && normalise && !want_raw) ? nullptr : dst, last ? norm_out : nullptr,
                        last ? slots : nullptr, out_index, st);
       if (rc) return rc;
@@ -1031,44 +1041,49 @@ struct ConvNet : NetImpl {
 
   int represent_atari(int batch, const float* obs, act_t* slots, const int32_t* dst_index, cudaStream_t st) {
     const int Hin = cfg.in_h, Win = cfg.in_w;
+    const Geo g0{Hin, Win}, g1{Hin / 2, Win / 2}, g2{Hin / 4, Win / 4}, g3{Hin / 8, Win / 8};
     prof_mark(kProfPack, st);
-    pack_obs_kernel<<<num_sms * 8, 256, 0, st>>>(obs, xobs, batch, cfg.in_channels, Hin, Win, 16);
+    pack_obs_kernel<<<num_sms * 8, 256, 0, st>>>(obs, xobs, batch, cfg.in_channels, Hin, Win, 16, plane_rows_of(g0, batch));
     prof_mark(-1, st);
     MZ_LAUNCH_CHECK("pack_obs_kernel");
-    Geo g1{Hin / 2, Win / 2}, g2{Hin / 4, Win / 4}, g3{Hin / 8, Win / 8};
-    auto s2 = [&](const act_t* in, const act_t* w, act_t* out, int Hi, int Wi, int Ci) -> int {
-      const long long total = (long long)batch * (Hi / 2) * (Wi / 2);
+    // stride-2 conv: writes the real positions of the half-size grid, then the halo is zeroed
+    auto s2 = [&](const act_t* in, const act_t* w, act_t* out, const Geo& gi, const Geo& go, int Ci) -> int {
+      const long long total = (long long)batch * go.H * go.W;
       prof_mark(kProfPack, st);
-      conv3x3_s2_kernel<<<(unsigned)((total + 63) / 64), 256, 0, st>>>(in, w, out, batch, Hi, Wi, Ci);
-      prof_mark(-1, st);
+      conv3x3_s2_kernel<<<(unsigned)((total + 63) / 64), 256, 0, st>>>(in, w, out, batch, gi.H, gi.W, Ci,
+                                                                        plane_rows_of(gi, batch), plane_rows_of(go, batch));
       MZ_LAUNCH_CHECK("conv3x3_s2_kernel");
+      zero_halo_kernel<<<num_sms * 4, 256, 0, st>>>(out, batch, go.H, go.W, C / 8, plane_rows_of(go, batch));
+      prof_mark(-1, st);
+      MZ_LAUNCH_CHECK("zero_halo_kernel");
       return MZ_OK;
     };
-    auto pool = [&](const act_t* in, act_t* out, act_t* sl, const int32_t* idx, int Hi, int Wi, int norm) -> int {
+    auto pool = [&](const act_t* in, act_t* out, act_t* sl, const int32_t* idx, const Geo& gi, const Geo& go, int norm) -> int {
       prof_mark(kProfPack, st);
-      avgpool_kernel<<<num_sms * 8, 256, 0, st>>>(in, out, sl, idx, batch, Hi, Wi, norm);
+      avgpool_kernel<<<num_sms * 8, 256, 0, st>>>(in, out, sl, idx, batch, gi.H, gi.W, norm, plane_rows_of(gi, batch),
+                                                  plane_rows_of(go, batch));
       prof_mark(-1, st);
       MZ_LAUNCH_CHECK("avgpool_kernel");
       return MZ_OK;
     };
     act_t* fin;
     int rc;
-    // halo entries of b0..b3 are never read, so grids of different sizes can reuse the same buffers
-    if ((rc = s2(xobs, s2_w1, b0, Hin, Win, 16))) return rc;                                   // relu(conv_1)
-    if ((rc = tower(nullptr, at_blocks[0], 2, g1, b0, nullptr, nullptr, nullptr, batch, true, nullptr, nullptr,
+    // every writer rewrites the halo of the grid it produces, so grids of different sizes can reuse the same buffers
+    if ((rc = s2(xobs, s2_w1, b0, g0, g1, 16))) return rc;                                     // relu(conv_1)
+    if ((rc = tower(nullptr, at_blocks[0], 2, g1, b0, nullptr, false, nullptr, nullptr, batch, true, nullptr, nullptr,
                     nullptr, st, &fin))) return rc;
     if ((rc = flush(st))) return rc;
     act_t* nxt = (fin == b0) ? b1 : b0;
-    if ((rc = s2(fin, s2_w2, nxt, g1.H, g1.W, C))) return rc;                                  // relu(conv_2)
-    if ((rc = tower(nullptr, at_blocks[1], 2, g2, nxt, nullptr, nullptr, nullptr, batch, true, nullptr, nullptr,
+    if ((rc = s2(fin, s2_w2, nxt, g1, g2, C))) return rc;                                      // relu(conv_2)
+    if ((rc = tower(nullptr, at_blocks[1], 2, g2, nxt, nullptr, false, nullptr, nullptr, batch, true, nullptr, nullptr,
                     nullptr, st, &fin))) return rc;
     if ((rc = flush(st))) return rc;
     nxt = (fin == b0) ? b1 : b0;
-    if ((rc = pool(fin, nxt, nullptr, nullptr, g2.H, g2.W, 0))) return rc;                     // avg_pool_1
-    if ((rc = tower(nullptr, at_blocks[2], 2, g3, nxt, nullptr, nullptr, nullptr, batch, true, nullptr, nullptr,
+    if ((rc = pool(fin, nxt, nullptr, nullptr, g2, g3, 0))) return rc;                         // avg_pool_1
+    if ((rc = tower(nullptr, at_blocks[2], 2, g3, nxt, nullptr, false, nullptr, nullptr, batch, true, nullptr, nullptr,
                     nullptr, st, &fin))) return rc;
     if ((rc = flush(st))) return rc;
-    return pool(fin, b3, slots, dst_index, g3.H, g3.W, 1);                                     // avg_pool_2 + normalise
+    return pool(fin, b3, slots, dst_index, g3, lat, 1);                                        // avg_pool_2 + normalise
   }
 
   int initial(int batch, const float* obs, void* hidden_out, const int32_t* dst_index, float* pi_probs, float* value,
@@ -1078,12 +1093,13 @@ struct ConvNet : NetImpl {
       rc = represent_atari(batch, obs, (act_t*)hidden_out, dst_index, st);
     } else {
       prof_mark(kProfPack, st);
-      pack_obs_kernel<<<num_sms * 4, 256, 0, st>>>(obs, xobs, batch, cfg.in_channels, lat.H, lat.W, in_cg * 8);
+      pack_obs_kernel<<<num_sms * 4, 256, 0, st>>>(obs, xobs, batch, cfg.in_channels, lat.H, lat.W, in_cg * 8,
+                                                   plane_rows_of(lat, batch));
       prof_mark(-1, st);
       MZ_LAUNCH_CHECK("pack_obs_kernel");
       act_t* fin;
       // representation: raw output is not needed, normalised goes to b3 (for the prediction tower) and the slots
-      rc = tower(&rep0, rep_blocks, blocks, lat, xobs, nullptr, nullptr, nullptr, batch, false, b3,
+      rc = tower(&rep0, rep_blocks, blocks, lat, xobs, nullptr, false, nullptr, nullptr, batch, false, b3,
                  (act_t*)hidden_out, dst_index, st, &fin);
     }
     if (rc) return rc;
@@ -1092,7 +1108,7 @@ struct ConvNet : NetImpl {
 
   int predict(int batch, float* pi_probs, float* value, cudaStream_t st) {
     act_t* fin;
-    int rc = tower(nullptr, pred_blocks, blocks, lat, b3, nullptr, nullptr, nullptr, batch, true, nullptr, nullptr,
+    int rc = tower(nullptr, pred_blocks, blocks, lat, b3, nullptr, false, nullptr, nullptr, batch, true, nullptr, nullptr,
                    nullptr, st, &fin);
     if (rc) return rc;
     if ((rc = flush(st))) return rc;
@@ -1110,7 +1126,7 @@ struct ConvNet : NetImpl {
     // dynamics: raw output (for the reward head) in a ping-pong buffer, normalised copy in b3 + the slots
     // The dynamics tower and the prediction tower run as ONE launch; the dynamics' raw output goes to b4,
     // which the prediction tower never touches, so the reward head can read it afterwards.
-    int rc = tower(&dyn0, dyn_blocks, blocks, lat, (const act_t*)hidden_in, src_index, tab, action, batch, true, b3,
+    int rc = tower(&dyn0, dyn_blocks, blocks, lat, (const act_t*)hidden_in, src_index, true, tab, action, batch, true, b3,
                    (act_t*)hidden_out, dst_index, st, &fin, b4);
     if (rc) return rc;
     rc = predict(batch, pi_probs, value_out, st);
@@ -1169,9 +1185,10 @@ int conv_arena_bytes(const mz_net_config& c, int max_batch, size_t* bytes) {
        align_up((size_t)c.value_support * hw * 4, 256) + 3 * align_up((size_t)(A + c.value_support + c.reward_support) * 4, 256);
   const size_t big_pb = atari ? (size_t)(c.in_h / 2 + 1) * (c.in_w / 2 + 1) : (size_t)PB;   // largest activation grid
   const size_t obs_pb = atari ? (size_t)(c.in_h + 1) * (c.in_w + 1) : (size_t)PB;
-  t += align_up((size_t)max_batch * obs_pb * (atari ? 2 : obs_cg(c.in_channels)) * 16, 256);   // packed observations
-  t += 3 * align_up((size_t)max_batch * big_pb * N * 2, 256);                            // b0..b2
-  t += 2 * align_up((size_t)max_batch * PB * N * 2, 256);                                // b3, b4 (latent grid only)
+  auto rows = [&](size_t pb) { return ((size_t)max_batch * pb + kTileM - 1) / kTileM * kTileM + kPlaneSlack; };
+  t += align_up(rows(obs_pb) * (atari ? 2 : obs_cg(c.in_channels)) * 16, 256);           // packed observations
+  t += 3 * align_up(rows(big_pb) * N * 2, 256);                                          // b0..b2
+  t += 2 * align_up(rows(PB) * N * 2, 256);                                              // b3, b4 (latent grid only)
   t += align_up((size_t)kMaxLayers * (((size_t)max_batch * big_pb + kTileM - 1) / kTileM) * 4, 256) + 256;   // tile flags
   *bytes = t + 8192;
   return MZ_OK;
@@ -1284,13 +1301,14 @@ int conv_create(const mz_net_config& c, const float* const* w, int nw, int max_b
 #undef MZ_TRY
   const size_t big_pb = atari ? (size_t)(c.in_h / 2 + 1) * (c.in_w / 2 + 1) : (size_t)PB;
   const size_t obs_pb = atari ? (size_t)(c.in_h + 1) * (c.in_w + 1) : (size_t)PB;
-  net->xobs = (act_t*)take((size_t)max_batch * obs_pb * (atari ? 2 : net->in_cg) * 16);
-  const size_t act_bytes = (size_t)max_batch * big_pb * N * 2;
+  auto rows = [&](size_t pb) { return ((size_t)max_batch * pb + kTileM - 1) / kTileM * kTileM + kPlaneSlack; };
+  net->xobs = (act_t*)take(rows(obs_pb) * (atari ? 2 : net->in_cg) * 16);
+  const size_t act_bytes = rows(big_pb) * N * 2;
   net->b0 = (act_t*)take(act_bytes);
   net->b1 = (act_t*)take(act_bytes);
   net->b2 = (act_t*)take(act_bytes);
-  net->b3 = (act_t*)take((size_t)max_batch * PB * N * 2);
-  net->b4 = (act_t*)take((size_t)max_batch * PB * N * 2);
+  net->b3 = (act_t*)take(rows(PB) * N * 2);
+  net->b4 = (act_t*)take(rows(PB) * N * 2);
   net->flags_cap = (size_t)kMaxLayers * (((size_t)max_batch * big_pb + kTileM - 1) / kTileM);
   net->flags = (unsigned*)take(net->flags_cap * 4);
   net->err_flag = (int*)take(256);

@@ -349,19 +349,19 @@ class _ConvNet(MuZeroNet):
                                '(self-play always does, pipeline.py:79-80)')
         return super()._engine_tensors()
 
-    # engine layout: fp16, channel-last, zero-padded grid (see csrc/conv.cu)
+    # engine layout: fp16 planes of 8 channels over the zero-padded grid, [C/8][(H+1)*(W+1)][8] (see csrc/conv.cu)
     def hidden_to_reference(self, slots):
         h, w = self.latent_hw
         c = self.num_planes
-        x = slots.view(torch.float16).reshape(slots.shape[0], h + 1, w + 1, c)[:, :h, :w, :]
-        return x.permute(0, 3, 1, 2).to(torch.float32).contiguous()
+        x = slots.view(torch.float16).reshape(slots.shape[0], c // 8, h + 1, w + 1, 8)[:, :, :h, :w, :]
+        return x.permute(0, 1, 4, 2, 3).reshape(slots.shape[0], c, h, w).to(torch.float32).contiguous()
 
     def hidden_from_reference(self, hid):
         h, w = self.latent_hw
         c = self.num_planes
-        hid = hid.reshape(-1, c, h, w)
-        out = torch.zeros((hid.shape[0], h + 1, w + 1, c), dtype=torch.float16, device=hid.device)
-        out[:, :h, :w, :] = hid.permute(0, 2, 3, 1).to(torch.float16)
+        hid = hid.reshape(-1, c // 8, 8, h, w)
+        out = torch.zeros((hid.shape[0], c // 8, h + 1, w + 1, 8), dtype=torch.float16, device=hid.device)
+        out[:, :, :h, :w, :] = hid.permute(0, 1, 3, 4, 2).to(torch.float16)
         return out.reshape(hid.shape[0], -1).view(torch.uint8)
 
     def dynamics(self, hidden_state, action):
