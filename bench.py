@@ -262,7 +262,7 @@ def run_engine_arm(args):
     import torch.distributed as dist
     import muzero_b200 as mz
     from muzero_b200 import _lib
-    from muzero_b200.mcts import SearchPlan
+    from muzero_b200.mcts import PipelinedSearchPlan, SearchPlan
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -283,9 +283,12 @@ def run_engine_arm(args):
     net = cls(**spec['net_kw'])
     net.load_state_dict(state_dict_for(spec))
     net = net.to(dev).eval()
-    plan = SearchPlan(net, cfg, B)
+    # conv nets: two half-batches interleaved on two streams (tree kernels of one overlap the tower of the other)
+    parts = args.parts if args.parts else (2 if spec['kind'] != 'mlp' and B % 2 == 0 else 1)
+    plan = PipelinedSearchPlan(net, cfg, B, parts) if parts > 1 else SearchPlan(net, cfg, B)
     pool = plan.pool
     pool.seed(1234 + rank * B + np.arange(B))
+    read_stats = (lambda: pool.stats()) if parts > 1 else (lambda: pool.view('STATS').cpu().numpy().copy())
 
     obs, mask, cur, opp = synthetic_inputs(spec, B, 99 + rank)
     obs_h = torch.from_numpy(obs).pin_memory()
@@ -326,12 +329,12 @@ def run_engine_arm(args):
         step_e2e()
     torch.cuda.synchronize()
     pool.check_errors()
-    stats0 = pool.view('STATS').cpu().numpy().copy()
+    stats0 = read_stats()
 
     uuid = str(torch.cuda.get_device_properties(dev).uuid)
     sampler = ClockSampler(uuid if uuid.startswith('GPU-') else 'GPU-' + uuid) if rank == 0 else None
     ms_dev = timed(step_device, args.steps)
-    stats1 = pool.view('STATS').cpu().numpy().copy()
+    stats1 = read_stats()
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     pool.check_errors()
@@ -342,10 +345,13 @@ def run_engine_arm(args):
     h2d = obs_h.numel() * obs_h.element_size() + mask_h.numel() + 2 * 4 * B + 8 * B
     d2h = sum(t.numel() * t.element_size() for t in out_h)
 
-    # ---- per-kernel timing (eager launches, CUDA events on the launching stream) -> roofline
+    # ---- per-kernel timing (eager launches, CUDA events on the launching stream) -> roofline.
+    # With a pipelined plan the kernels run on sub-batches of B / parts trees: part 0 is timed as it runs there.
     lib = _lib.lib()
-    eng = net.engine(B)
-    hidden = pool.hidden.data_ptr() if pool.hidden_bytes else None
+    pplan = plan.parts[0] if parts > 1 else plan
+    ppool, Bp = pplan.pool, pplan.B
+    eng = net.engine(Bp, pplan.instance)
+    hidden = ppool.hidden.data_ptr() if ppool.hidden_bytes else None
     names = ['select', 'recurrent', 'expand_backup']
     tot = {n: 0.0 for n in names}
     reps = max(1, min(args.steps, 3))
@@ -354,31 +360,29 @@ def run_engine_arm(args):
         stream = torch.cuda.current_stream().cuda_stream
         _lib.check(lib.mz_net_profile_begin(eng['handle']))
         for _ in range(reps):
-            plan.use_graph = False
             # root part eagerly, then instrumented simulation loop
-            _lib.check(lib.mz_net_initial(eng['handle'], B, plan.obs.data_ptr(), hidden, plan.root_slots.data_ptr(),
-                                          plan.pi0.data_ptr(), plan.v0.data_ptr(), stream))
-            _lib.check(lib.mz_dirichlet(pool.handle, float(np.float32(cfg.root_dirichlet_alpha)),
-                                        plan.noise.data_ptr(), stream))
-            _lib.check(lib.mz_search_reset(pool.handle, plan.pi0.data_ptr(), plan.noise.data_ptr(),
-                                           float(cfg.root_exploration_eps), plan.mask.data_ptr(),
-                                           plan.players.data_ptr(), None, stream))
+            _lib.check(lib.mz_net_initial(eng['handle'], Bp, pplan.obs.data_ptr(), hidden, pplan.root_slots.data_ptr(),
+                                          pplan.pi0.data_ptr(), pplan.v0.data_ptr(), stream))
+            _lib.check(lib.mz_dirichlet(ppool.handle, float(np.float32(cfg.root_dirichlet_alpha)),
+                                        pplan.noise.data_ptr(), stream))
+            _lib.check(lib.mz_search_reset(ppool.handle, pplan.pi0.data_ptr(), pplan.noise.data_ptr(),
+                                           float(cfg.root_exploration_eps), pplan.mask.data_ptr(),
+                                           pplan.players.data_ptr(), None, stream))
             evs = []
             for _s in range(S):
                 e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
                 e[0].record()
-                _lib.check(lib.mz_select(pool.handle, stream)); e[1].record()
-                _lib.check(lib.mz_net_recurrent(eng['handle'], B, hidden, pool.view('SRC_SLOT').data_ptr(),
-                                                pool.view('LEAF_ACTION').data_ptr(), hidden,
-                                                pool.view('DST_SLOT').data_ptr(), pool.view('REWARD').data_ptr(),
-                                                pool.view('VALUE').data_ptr(), None, stream)); e[2].record()
-                _lib.check(lib.mz_expand_backup(pool.handle, None, None, stream)); e[3].record()
+                _lib.check(lib.mz_select(ppool.handle, stream)); e[1].record()
+                _lib.check(lib.mz_net_recurrent(eng['handle'], Bp, hidden, ppool.view('SRC_SLOT').data_ptr(),
+                                                ppool.view('LEAF_ACTION').data_ptr(), hidden,
+                                                ppool.view('DST_SLOT').data_ptr(), ppool.view('REWARD').data_ptr(),
+                                                ppool.view('VALUE').data_ptr(), None, stream)); e[2].record()
+                _lib.check(lib.mz_expand_backup(ppool.handle, None, None, stream)); e[3].record()
                 evs.append(e)
             torch.cuda.synchronize()
             for e in evs:
                 for i, n in enumerate(names):
                     tot[n] += e[i].elapsed_time(e[i + 1])
-            plan.use_graph = True
         prof_ms = (C.c_double * 4)()
         prof_n = (C.c_int64 * 4)()
         _lib.check(lib.mz_net_profile_end(eng['handle'], prof_ms, prof_n))
@@ -397,15 +401,15 @@ def run_engine_arm(args):
     noise_on = True
     roof = {}
     for n in names:
-        ab = algorithmic_bytes_per_launch(n, spec, B, A, S, mean_depth, pool.hidden_bytes, noise_on)
+        ab = algorithmic_bytes_per_launch(n, spec, Bp, A, S, mean_depth, pool.hidden_bytes, noise_on)
         roof[n] = {'bound': 'hbm', 'achieved': ab / (avg_ms[n] * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
                    'avg_launch_us': avg_ms[n] * 1e3, 'share_of_sim_loop': share[n], 'algorithmic_bytes': ab}
         roof[n]['frac'] = roof[n]['achieved'] / hbm_peak
     flops = {'tictactoe': 175104, 'cartpole': 395264, 'gomoku': 803712780, 'atari': 351896688}[spec['name']]
     if spec['kind'] != 'mlp':
-        ach = flops * B / (avg_ms['recurrent'] * 1e-3) / 1e12
+        ach = flops * Bp / (avg_ms['recurrent'] * 1e-3) / 1e12
         roof['recurrent'].update({'bound': 'tensor', 'achieved': ach, 'peak': tf_peak, 'unit': 'TFLOP/s',
-                                  'frac': ach / tf_peak, 'reference_graph_flops': flops * B})
+                                  'frac': ach / tf_peak, 'reference_graph_flops': flops * Bp})
     roofline = dict(roof[dominant])
     roofline.update({'kernel': dominant, 'traffic': None, 'peak_source': peak_src})
     if spec['kind'] != 'mlp' and prof_n[0] > 0:
@@ -418,8 +422,8 @@ def run_engine_arm(args):
         per_pos = 2.0 * planes * planes * 9
         conv_ms = prof_ms[0] / prof_n[0]
         # initial-inference convs are inside the profile too (same shapes except the first layer)
-        alg = per_pos * hh * ww * B
-        exe = per_pos * (hh + 1) * (ww + 1) * B
+        alg = per_pos * hh * ww * Bp
+        exe = per_pos * (hh + 1) * (ww + 1) * Bp
         ach = alg / (conv_ms * 1e-3) / 1e12
         roofline = {'kernel': 'conv3x3_kernel (tcgen05.mma M128 N128 K16, TMEM accumulators)', 'bound': 'tensor',
                     'achieved': ach, 'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': ach / tf_peak, 'traffic': None,
@@ -436,6 +440,7 @@ def run_engine_arm(args):
         'dtype': 'f64 tree statistics / f32 scores; network ' + ('f32' if spec['kind'] == 'mlp' else 'fp16 x fp16 -> f32 (tcgen05)'),
         'data': 'synthetic',
         'config': {'workload': spec['label'], 'trees_per_gpu': B, 'simulations': S, 'num_actions': A,
+                   'pipeline_parts': parts, 'trees_per_kernel_launch': Bp,
                    'l2': 'flushed between timed iterations (256 MiB write)', 'mean_select_depth': mean_depth,
                    'parallelism': f'games sharded over {world} GPU(s), no collective'},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': int(h2d),
@@ -542,6 +547,7 @@ def main():
     ap.add_argument('--trees', type=int, default=None, help='trees per GPU (default: the config size)')
     ap.add_argument('--impl', default='engine', choices=['engine', 'reference'])
     ap.add_argument('--cpu-procs', type=int, default=int(os.environ.get('MZ_BENCH_CPU_PROCS', '64')))
+    ap.add_argument('--parts', type=int, default=0, help='sub-batches in flight per GPU (0: 2 for conv nets, 1 for MLPs)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-train-step', action='store_true')
     args = ap.parse_args()

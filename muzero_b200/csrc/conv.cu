@@ -131,7 +131,7 @@ __device__ __forceinline__ int4 pack8(const float* v) {
 }
 
 template <int kN>
-__global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int halo = p.Wp + 1;
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
       if (fast) {
         // Plain conv + bias (+ residual) + ReLU (30 of the 33 convs of a recurrent inference).  The steps of
         // this warp (2 row halves x NCW column chunks) form one unrolled sequence and the residual of step
-        // t+2 is requested at step t (the first two before the MMAs even finish).
+        // t+1 is requested at step t (the first before the MMAs even finish).
         constexpr int STEPS = 2 * NCW;
         int Pj[2];
         bool vj[2], inr[2];
@@ -385,17 +385,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
         }
         const int4* resp = reinterpret_cast<const int4*>(L.residual);
         const bool has_res = resp != nullptr && !(p.ablate & 512);
-        int4 ring[3][4];
+        int4 ring[2][4];
         auto fetch = [&](int t, int4 (&dst)[4]) {
           const int j = t / NCW, g0 = (chalf * NCW + t % NCW) * 4;
           const bool ld = has_res && vj[j];
 #pragma unroll
           for (int u = 0; u < 4; ++u) dst[u] = ld ? __ldcg(resp + (size_t)(g0 + u) * PR + Pj[j]) : make_int4(0, 0, 0, 0);
         };
-        if (has_cols) {
-          fetch(0, ring[0]);
-          if (STEPS > 1) fetch(1, ring[1]);
-        }
+        if (has_cols) fetch(0, ring[0]);
         const long long tw = dbg ? clock64() : 0;
         mbar_wait(&mma_done[buf], (uint32_t)((k >> 1) & 1));
         if (dbg) t_wait += clock64() - tw;
@@ -405,12 +402,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
 #pragma unroll
           for (int t = 0; t < STEPS; ++t) {
             const int j = t / NCW, c = chalf * NCW + t % NCW, c0 = c * 32;
-            if (t + 2 < STEPS) fetch(t + 2, ring[(t + 2) % 3]);
+            if (t + 1 < STEPS) fetch(t + 1, ring[(t + 1) & 1]);
             uint32_t r[32];
             tmem_ld32(tbase + (uint32_t)(j * 128 + c0), r);
             tmem_ld_wait();
             float v[32];
-            finish32(r, s_bias + c0, ring[t % 3], v);
+            finish32(r, s_bias + c0, ring[t & 1], v);
             // ReLU (every conv of these nets is followed by one) and fp16 saturation in one clamp; halo rows are ZERO
             const float top = vj[j] ? 65504.0f : 0.0f;
 #pragma unroll
@@ -436,37 +433,41 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
           const float top = valid ? 65504.0f : 0.0f;
           const float* tab = (L.tab && valid) ? L.tab + ((size_t)L.action[b] * (kN / 8) * p.PB + pos) * 8 : nullptr;
           const int4* resp = (L.residual && valid) ? reinterpret_cast<const int4*>(L.residual) + P : nullptr;
-          float v[NCW][32];
+          // conv + bias (+ table) (+ residual) + ReLU of one 32-column chunk of this row (one chunk live at a
+          // time keeps the register count of the whole kernel low; the normalising layers read TMEM twice)
+          auto chunk = [&](int c, float (&v)[32]) {
+            int4 rres[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) rres[u] = resp ? __ldcg(resp + (size_t)(c * 4 + u) * PR) : make_int4(0, 0, 0, 0);
+            uint32_t r[32];
+            tmem_ld32(tbase + (uint32_t)(j * 128 + c * 32), r);
+            tmem_ld_wait();
+            finish32(r, s_bias + c * 32, rres, v);
+            if (tab) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float4* t4 = reinterpret_cast<const float4*>(tab + (size_t)(c * 4 + u) * p.PB * 8);
+                const float4 ta = t4[0], tb = t4[1];
+                v[8 * u] += ta.x; v[8 * u + 1] += ta.y; v[8 * u + 2] += ta.z; v[8 * u + 3] += ta.w;
+                v[8 * u + 4] += tb.x; v[8 * u + 5] += tb.y; v[8 * u + 6] += tb.z; v[8 * u + 7] += tb.w;
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = fminf(fmaxf(v[e], 0.0f), top);
+          };
           float mn = INFINITY, mx = -INFINITY;
           if (has_cols) {
-#pragma unroll
+#pragma unroll 1
             for (int cc = 0; cc < NCW; ++cc) {
-              const int c = chalf * NCW + cc, c0 = c * 32;
-              int4 rres[4];
+              const int c = chalf * NCW + cc;
+              float v[32];
+              chunk(c, v);
 #pragma unroll
-              for (int u = 0; u < 4; ++u) rres[u] = resp ? __ldcg(resp + (size_t)(c * 4 + u) * PR) : make_int4(0, 0, 0, 0);
-              uint32_t r[32];
-              tmem_ld32(tbase + (uint32_t)(j * 128 + c0), r);
-              tmem_ld_wait();
-              finish32(r, s_bias + c0, rres, v[cc]);
-              if (tab) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const float4* t4 = reinterpret_cast<const float4*>(tab + (size_t)(c * 4 + u) * p.PB * 8);
-                  const float4 ta = t4[0], tb = t4[1];
-                  v[cc][8 * u] += ta.x; v[cc][8 * u + 1] += ta.y; v[cc][8 * u + 2] += ta.z; v[cc][8 * u + 3] += ta.w;
-                  v[cc][8 * u + 4] += tb.x; v[cc][8 * u + 5] += tb.y; v[cc][8 * u + 6] += tb.z; v[cc][8 * u + 7] += tb.w;
-                }
-              }
-#pragma unroll
-              for (int e = 0; e < 32; ++e) {
-                v[cc][e] = fminf(fmaxf(v[cc][e], 0.0f), top);
-                mn = fminf(mn, v[cc][e]); mx = fmaxf(mx, v[cc][e]);
-              }
+              for (int e = 0; e < 32; ++e) { mn = fminf(mn, v[e]); mx = fmaxf(mx, v[e]); }
               if (L.out && inrange) {
                 int4* o = reinterpret_cast<int4*>(L.out) + P;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) o[(size_t)(c * 4 + u) * PR] = pack8(v[cc] + 8 * u);
+                for (int u = 0; u < 4; ++u) o[(size_t)(c * 4 + u) * PR] = pack8(v + 8 * u);
               }
             }
           }
@@ -478,21 +479,23 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_kernel(const __grid_c
             asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");
             mn = fminf(mn, o.x); mx = fmaxf(mx, o.y);
             const float inv = valid ? 1.0f / ((mx - mn) + 1e-8f) : 0.0f;
-            if (has_cols && inrange) {
-              int4* on = L.out_norm ? reinterpret_cast<int4*>(L.out_norm) + P : nullptr;
+            if (has_cols) {             // warp-uniform: the TMEM loads inside chunk() are warp-collective
+              int4* on = (L.out_norm && inrange) ? reinterpret_cast<int4*>(L.out_norm) + P : nullptr;
               int4* os = nullptr;
-              if (L.out_slots) {
+              if (L.out_slots && inrange) {
                 const size_t slot = L.out_index ? (size_t)L.out_index[b] : (size_t)b;
                 os = reinterpret_cast<int4*>(L.out_slots) + slot * (kN / 8) * p.PB + pos;
               }
-#pragma unroll
+#pragma unroll 1
               for (int cc = 0; cc < NCW; ++cc) {
                 const int c = chalf * NCW + cc;
+                float v[32];
+                chunk(c, v);
 #pragma unroll
-                for (int e = 0; e < 32; ++e) v[cc][e] = (v[cc][e] - mn) * inv;
+                for (int e = 0; e < 32; ++e) v[e] = (v[e] - mn) * inv;
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                  const int4 o4 = pack8(v[cc] + 8 * u);
+                  const int4 o4 = pack8(v + 8 * u);
                   if (on) on[(size_t)(c * 4 + u) * PR] = o4;
                   if (os) os[(size_t)(c * 4 + u) * p.PB] = o4;
                 }
@@ -578,7 +581,14 @@ __device__ __forceinline__ float signed_parabolic_f(float x) {
   return x > 0.0f ? r : (x < 0.0f ? -r : 0.0f);
 }
 
-__global__ void __launch_bounds__(128) head_kernel(const HeadParams p) {
+constexpr int kMaxHeads = 3;
+struct HeadsParams {
+  HeadParams h[kMaxHeads];
+};
+
+// grid (boards, heads): all heads of one inference in ONE launch
+__global__ void __launch_bounds__(128) head_kernel(const __grid_constant__ HeadsParams hp) {
+  const HeadParams& p = hp.h[blockIdx.y];
   extern __shared__ float hs[];            // f[mid*hw] | logits[out]
   const int hw = p.H * p.W, Wp = p.W + 1, PB = (p.H + 1) * Wp;
   float* f = hs;
@@ -605,11 +615,17 @@ __global__ void __launch_bounds__(128) head_kernel(const HeadParams p) {
   }
   __syncthreads();
   const int K = p.mid * hw;
-  for (int o = threadIdx.x; o < p.out; o += blockDim.x) {
-    const float* w = p.w2 + (size_t)o * K;
-    float acc = p.b2[o];
-    for (int k = 0; k < K; ++k) acc = fmaf(f[k], w[k], acc);
-    lg[o] = acc;
+  {
+    // Linear(mid*hw -> out): one warp per output, lanes split K (coalesced weight rows)
+    const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31;
+    for (int o = wid; o < p.out; o += 4) {
+      const float* w = p.w2 + (size_t)o * K;
+      float acc = 0.0f;
+      for (int k = ln; k < K; k += 32) acc = fmaf(f[k], w[k], acc);
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+      if (ln == 0) lg[o] = acc + p.b2[o];
+    }
   }
   __syncthreads();
   if (p.kind == 0) {
@@ -986,15 +1002,25 @@ struct ConvNet : NetImpl {
     }
     return MZ_OK;
   }
-  int launch_head(const Head& h, const act_t* act, int batch, float* dst, cudaStream_t st) {
-    HeadParams p;
+  // heads of one inference, launched together
+  HeadsParams pend_heads;
+  int num_pend_heads = 0;
+  size_t pend_heads_smem = 0;
+  void add_head(const Head& h, const act_t* act, int batch, float* dst) {
+    HeadParams& p = pend_heads.h[num_pend_heads++];
     p.act = act; p.w1 = h.w1; p.b1 = h.b1; p.w2 = h.w2; p.b2 = h.b2; p.dst = dst;
     p.plane_rows = plane_rows_of(lat, batch);
     p.C = C; p.H = lat.H; p.W = lat.W; p.mid = h.mid; p.out = h.out; p.kind = h.kind;
     const size_t smem = ((size_t)h.mid * lat.H * lat.W + h.out) * 4;
+    if (smem > pend_heads_smem) pend_heads_smem = smem;
+  }
+  int launch_heads(int batch, cudaStream_t st) {
+    if (num_pend_heads == 0) return MZ_OK;
     prof_mark(kProfHead, st);
-    head_kernel<<<batch, 128, smem, st>>>(p);
+    head_kernel<<<dim3(batch, num_pend_heads), 128, pend_heads_smem, st>>>(pend_heads);
     prof_mark(-1, st);
+    num_pend_heads = 0;
+    pend_heads_smem = 0;
     MZ_LAUNCH_CHECK("head_kernel");
     return MZ_OK;
   }
@@ -1103,7 +1129,8 @@ struct ConvNet : NetImpl {
                  (act_t*)hidden_out, dst_index, st, &fin);
     }
     if (rc) return rc;
-    return predict(batch, pi_probs, value, st);
+    if ((rc = predict(batch, pi_probs, value, st))) return rc;
+    return launch_heads(batch, st);
   }
 
   int predict(int batch, float* pi_probs, float* value, cudaStream_t st) {
@@ -1112,11 +1139,9 @@ struct ConvNet : NetImpl {
                    nullptr, st, &fin);
     if (rc) return rc;
     if ((rc = flush(st))) return rc;
-    if (pi_probs) {
-      rc = launch_head(h_policy, fin, batch, pi_probs, st);
-      if (rc) return rc;
-    }
-    return launch_head(h_value, fin, batch, value, st);
+    if (pi_probs) add_head(h_policy, fin, batch, pi_probs);
+    add_head(h_value, fin, batch, value);
+    return MZ_OK;     // the caller launches the collected heads
   }
 
   int recurrent(int batch, const void* hidden_in, const int32_t* src_index, const int32_t* action, void* hidden_out,
@@ -1131,7 +1156,8 @@ struct ConvNet : NetImpl {
     if (rc) return rc;
     rc = predict(batch, pi_probs, value_out, st);
     if (rc) return rc;
-    return launch_head(h_reward, fin, batch, reward_out, st);   // reward head reads the UN-normalised state
+    add_head(h_reward, fin, batch, reward_out);                 // reward head reads the UN-normalised state
+    return launch_heads(batch, st);
   }
 };
 

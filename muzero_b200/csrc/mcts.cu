@@ -345,7 +345,16 @@ select_kernel(PoolDev p) {
       uint32_t key = 0;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
-        s[c] = puct_score(eW[c], eR[c], (int)(eNC[c] & 0xffffu), pr[c], tN, f32p, dp, norm, lo, range);
+        const int cn = (int)(eNC[c] & 0xffffu);
+        if (__any_sync(kFull, cn > 0)) {
+          s[c] = puct_score(eW[c], eR[c], cn, pr[c], tN, f32p, dp, norm, lo, range);
+        } else {
+          // no visited child among these 32 actions (the common case deep in a tree): y = tN / 1 = tN exactly
+          // and q = 0, so the three float64 divisions of puct_score -- the select kernel is bound by the
+          // FP64 pipe, not by memory -- are skipped for the whole chunk; same bits as the general path
+          const float u = f32p ? __fmul_rn((float)pr[c], __double2float_rn(tN)) : __double2float_rn(__dmul_rn(pr[c], tN));
+          s[c] = __fadd_rn(0.0f, u);
+        }
         if (c * 32 + lane < A) key = max(key, f2ord(s[c]));
       }
       const float best = ord2f(__reduce_max_sync(kFull, key));

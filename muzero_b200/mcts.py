@@ -245,26 +245,31 @@ class SearchPlan:
     so a search costs one graph launch instead of 3*S+3 kernel launches from Python.
     """
 
-    def __init__(self, network: MuZeroNet, config, num_trees: int, pool: Optional[SearchPool] = None) -> None:
+    def __init__(self, network: MuZeroNet, config, num_trees: int, pool: Optional[SearchPool] = None,
+                 instance: int = 0, buffers: Optional[dict] = None) -> None:
         self.network, self.config = network, config
+        self.instance = int(instance)            # which engine instance of the network this plan drives
         self.dev = next(network.parameters()).device
         self.B, self.A, self.S = int(num_trees), network.num_actions, int(config.num_simulations)
         self.pool = pool if pool is not None else SearchPool(self.B, self.A, config, network.hidden_bytes, self.dev)
         assert self.pool.B == self.B and self.pool.A == self.A and self.pool.S == self.S
         B, A, dev = self.B, self.A, self.dev
         obs_elems = int(np.prod(network.input_shape))
-        self.obs = torch.zeros((B, obs_elems), dtype=torch.float32, device=dev)
-        self.mask = torch.ones((B, A), dtype=torch.uint8, device=dev)
-        self.players = torch.ones((B, 2), dtype=torch.int32, device=dev)
-        self.temps = torch.ones(B, dtype=torch.float64, device=dev)
-        self.noise = torch.zeros((B, A), dtype=torch.float64, device=dev)
-        self.pi0 = torch.empty((B, A), dtype=torch.float32, device=dev)
-        self.v0 = torch.empty(B, dtype=torch.float32, device=dev)
+        spec = dict(obs=((B, obs_elems), torch.float32, 0), mask=((B, A), torch.uint8, 1),
+                    players=((B, 2), torch.int32, 1), temps=((B,), torch.float64, 1), noise=((B, A), torch.float64, 0),
+                    pi0=((B, A), torch.float32, None), v0=((B,), torch.float32, None),
+                    action=((B,), torch.int32, None), pi=((B, A), torch.float64, None),
+                    root_value=((B,), torch.float64, None), visits=((B, A), torch.int32, None))
+        for name, (shape, dt, fill) in spec.items():
+            if buffers is not None:              # views into a larger plan's static buffers (PipelinedSearchPlan)
+                t = buffers[name]
+                assert tuple(t.shape) == shape and t.dtype == dt and t.is_contiguous()
+            elif fill is None:
+                t = torch.empty(shape, dtype=dt, device=dev)
+            else:
+                t = torch.full(shape, fill, dtype=dt, device=dev)
+            setattr(self, name, t)
         self.root_slots = (torch.arange(B, dtype=torch.int32, device=dev) * (self.S + 1)).contiguous()
-        self.action = torch.empty(B, dtype=torch.int32, device=dev)
-        self.pi = torch.empty((B, A), dtype=torch.float64, device=dev)
-        self.root_value = torch.empty(B, dtype=torch.float64, device=dev)
-        self.visits = torch.empty((B, A), dtype=torch.int32, device=dev)
         self._graphs = {}
         self._eng = None
         self.launches_per_search = 0
@@ -273,7 +278,7 @@ class SearchPlan:
     def _enqueue(self, noise_mode: str, has_mask: bool, deterministic: bool) -> None:
         """Enqueue one whole search on the current stream (pure C-ABI calls, static pointers)."""
         lib, pool, cfg = _lib.lib(), self.pool, self.config
-        eng = self.network.engine(self.B)
+        eng = self.network.engine(self.B, self.instance)
         stream = _lib.current_stream()
         hidden = pool.hidden.data_ptr() if pool.hidden_bytes else None
         mask_p = self.mask.data_ptr() if has_mask else None
@@ -301,7 +306,7 @@ class SearchPlan:
 
     def run(self, noise_mode: str = 'device', has_mask: bool = True, deterministic: bool = False) -> None:
         """Execute one search over the current contents of the static input buffers."""
-        eng = self.network.engine(self.B)
+        eng = self.network.engine(self.B, self.instance)
         if eng is not self._eng:                 # weights changed -> engine rebuilt -> old graphs are stale
             self._graphs.clear()
             self._eng = eng
@@ -325,6 +330,130 @@ class SearchPlan:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     self._enqueue(noise_mode, has_mask, deterministic)
+                self._graphs[key] = g
+                return
+            g.replay()
+
+
+class _PoolGroup:
+    """The pools of a PipelinedSearchPlan seen as one pool of B trees (tree t lives in part t // (B / parts))."""
+
+    def __init__(self, pools) -> None:
+        self.pools = list(pools)
+        self.B = sum(p.B for p in self.pools)
+        self.A, self.S, self.hidden_bytes = self.pools[0].A, self.pools[0].S, self.pools[0].hidden_bytes
+
+    def _split(self, seq):
+        out, o = [], 0
+        for p in self.pools:
+            out.append(seq[o:o + p.B])
+            o += p.B
+        return out
+
+    def seed(self, seeds) -> None:
+        for p, s in zip(self.pools, self._split(np.asarray(seeds))):
+            p.seed(s)
+
+    def set_rng_states(self, states) -> None:
+        for p, s in zip(self.pools, self._split(list(states))):
+            p.set_rng_states(s)
+
+    def get_rng_states(self):
+        return [st for p in self.pools for st in p.get_rng_states()]
+
+    def check_errors(self) -> None:
+        for p in self.pools:
+            p.check_errors()
+
+    def stats(self) -> np.ndarray:
+        return sum(p.view('STATS').cpu().numpy().astype(np.int64) for p in self.pools)
+
+    def dump_tree(self, t: int) -> dict:
+        per = self.pools[0].B
+        return self.pools[t // per].dump_tree(t % per)
+
+
+class PipelinedSearchPlan:
+    """B trees searched as ``parts`` independent sub-batches whose launch chains are interleaved on separate
+    streams inside ONE CUDA graph.
+
+    Trees never interact, so the result is bit-identical to one SearchPlan over all B trees.  What changes is
+    the schedule: a simulation is select -> recurrent inference (a persistent kernel that fills every SM) ->
+    heads -> expand+backup, and the tree kernels are latency-bound on the deepest tree (a warp per tree, ~2000
+    cycles per level) while all other SMs idle.  With two sub-batches in flight the tree kernels of one overlap
+    the tensor-core tower of the other (the conv kernel leaves room for one small CTA per SM).  Each part has
+    its own node pool and its own engine instance (activation buffers); weights are shared read-only.
+    """
+
+    def __init__(self, network: MuZeroNet, config, num_trees: int, parts: int = 2) -> None:
+        assert parts >= 1 and num_trees % parts == 0, 'num_trees must be a multiple of parts'
+        self.network, self.config = network, config
+        self.dev = next(network.parameters()).device
+        self.B, self.A, self.S = int(num_trees), network.num_actions, int(config.num_simulations)
+        B, A, dev, per = self.B, self.A, self.dev, int(num_trees) // parts
+        obs_elems = int(np.prod(network.input_shape))
+        self.obs = torch.zeros((B, obs_elems), dtype=torch.float32, device=dev)
+        self.mask = torch.ones((B, A), dtype=torch.uint8, device=dev)
+        self.players = torch.ones((B, 2), dtype=torch.int32, device=dev)
+        self.temps = torch.ones(B, dtype=torch.float64, device=dev)
+        self.noise = torch.zeros((B, A), dtype=torch.float64, device=dev)
+        self.pi0 = torch.empty((B, A), dtype=torch.float32, device=dev)
+        self.v0 = torch.empty(B, dtype=torch.float32, device=dev)
+        self.action = torch.empty(B, dtype=torch.int32, device=dev)
+        self.pi = torch.empty((B, A), dtype=torch.float64, device=dev)
+        self.root_value = torch.empty(B, dtype=torch.float64, device=dev)
+        self.visits = torch.empty((B, A), dtype=torch.int32, device=dev)
+        names = ('obs', 'mask', 'players', 'temps', 'noise', 'pi0', 'v0', 'action', 'pi', 'root_value', 'visits')
+        self.parts = [SearchPlan(network, config, per, instance=i,
+                                 buffers={n: getattr(self, n)[i * per:(i + 1) * per] for n in names})
+                      for i in range(parts)]
+        self.pool = _PoolGroup([p.pool for p in self.parts])
+        self._streams = [torch.cuda.Stream(device=dev) for _ in range(parts - 1)]
+        self._graphs = {}
+        self._engs = None
+        self.use_graph = True
+
+    @property
+    def launches_per_search(self) -> int:
+        return sum(p.launches_per_search for p in self.parts)
+
+    def _enqueue_all(self, noise_mode, has_mask, deterministic) -> None:
+        """Fork one stream per extra part off the current stream, enqueue every part, join."""
+        main = torch.cuda.current_stream()
+        for s in self._streams:
+            s.wait_stream(main)
+        self.parts[0]._enqueue(noise_mode, has_mask, deterministic)
+        for part, s in zip(self.parts[1:], self._streams):
+            with torch.cuda.stream(s):
+                part._enqueue(noise_mode, has_mask, deterministic)
+        for s in self._streams:
+            main.wait_stream(s)
+
+    def run(self, noise_mode: str = 'device', has_mask: bool = True, deterministic: bool = False) -> None:
+        engs = [p.network.engine(p.B, p.instance) for p in self.parts]
+        if self._engs is None or any(a is not b for a, b in zip(engs, self._engs)):
+            self._graphs.clear()                 # weights changed -> engines rebuilt -> old graphs are stale
+            self._engs = engs
+        with torch.cuda.device(self.dev):
+            if not self.use_graph:
+                self._enqueue_all(noise_mode, has_mask, deterministic)
+                return
+            key = (noise_mode, has_mask, deterministic)
+            g = self._graphs.get(key)
+            if g is None:
+                lib = _lib.lib()
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):     # eager warm-up (this call's search), one part after the other
+                    for part in self.parts:
+                        n0 = lib.mz_launch_count()
+                        part._enqueue(noise_mode, has_mask, deterministic)
+                        part.launches_per_search = int(lib.mz_launch_count() - n0)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue_all(noise_mode, has_mask, deterministic)
                 self._graphs[key] = g
                 return
             g.replay()

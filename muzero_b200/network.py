@@ -116,7 +116,7 @@ class MuZeroNet(nn.Module):
         self.num_actions = num_actions
         self.value_support_size = value_support_size
         self.reward_support_size = reward_support_size
-        self._eng = None          # (handle, arena tensor, version stamp, device, max_batch)
+        self._engs = {}           # instance -> dict(handle, arena tensor, version stamp, device, max_batch)
 
     @property
     def mse_loss_for_value(self):
@@ -134,17 +134,20 @@ class MuZeroNet(nn.Module):
         return (tuple(p._version for p in self.parameters()), tuple(b._version for b in self.buffers()),
                 self.training)
 
-    def engine(self, max_batch: int = 1):
-        """The ``mz_net`` handle for the current weights (rebuilt when they changed)."""
+    def engine(self, max_batch: int = 1, instance: int = 0):
+        """The ``mz_net`` handle for the current weights (rebuilt when they changed).
+
+        ``instance`` selects one of several independent engines over the same weights (each owns its
+        activation buffers), so that two searches can be in flight at once (mcts.PipelinedSearchPlan)."""
         dev = next(self.parameters()).device
         if dev.type != 'cuda':
             raise RuntimeError('muzero_b200 inference runs on CUDA only (no CPU fallback): move the network to a '
                                'cuda device first')
         stamp = self._stamp()
-        e = self._eng
+        e = self._engs.get(instance)
         if e is not None and e['stamp'] == stamp and e['device'] == dev and e['max_batch'] >= max_batch:
             return e
-        self.release_engine()
+        self.release_engine(instance)
         lib = _lib.lib()
         with torch.cuda.device(dev):
             _lib.check(lib.mz_device_check(dev.index or 0, None, None))
@@ -161,14 +164,15 @@ class MuZeroNet(nn.Module):
                                          C.byref(handle)))
             hb = C.c_int32()
             _lib.check(lib.mz_net_hidden_bytes(C.byref(cfg), C.byref(hb)))
-        self._eng = dict(handle=handle, arena=arena, stamp=stamp, device=dev, max_batch=max_batch,
-                         hidden_bytes=hb.value)
-        return self._eng
+        self._engs[instance] = dict(handle=handle, arena=arena, stamp=stamp, device=dev, max_batch=max_batch,
+                                    hidden_bytes=hb.value)
+        return self._engs[instance]
 
-    def release_engine(self) -> None:
-        if self._eng is not None:
-            _lib.lib().mz_net_destroy(self._eng['handle'])
-            self._eng = None
+    def release_engine(self, instance: Optional[int] = None) -> None:
+        for k in ([instance] if instance is not None else list(self._engs)):
+            e = self._engs.pop(k, None)
+            if e is not None:
+                _lib.lib().mz_net_destroy(e['handle'])
 
     def __del__(self):
         try:

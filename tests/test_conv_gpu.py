@@ -153,6 +153,41 @@ def test_gomoku_search_replays_bit_exact_in_oracle():
     assert torch.equal(a2, action) and torch.equal(pi2, pi) and torch.equal(q2, rootv)
 
 
+def test_pipelined_plan_is_bit_identical_to_single_plan():
+    """Two half-batches interleaved on two streams in one CUDA graph (PipelinedSearchPlan) give exactly the
+    trees, actions, policies, root values and RNG positions of one SearchPlan over the whole batch: trees
+    are independent and a network row does not depend on which other rows share its launch."""
+    import muzero_b200 as mz
+    net, _ = build_board((9, 9, 9), 82, 2, 32, seed=1)
+    cfg = mz.make_gomoku_config(use_tensorboard=False)
+    cfg.num_simulations = 40
+    B, A = 64, 82
+    gen = np.random.RandomState(11)
+    obs = gen.randint(0, 2, size=(B, 9, 9, 9)).astype(np.int8)
+    mask = gen.rand(B, A) < 0.8
+    mask[:, -1] = True
+    out = []
+    for plan in (mz.mcts.SearchPlan(net, cfg, B), mz.mcts.PipelinedSearchPlan(net, cfg, B, parts=2)):
+        res = []
+        for rep in range(3):                       # eager warm-up pass, graph capture, graph replay
+            streams = [np.random.RandomState(900 + t) for t in range(B)]
+            a, pi, q = mz.uct_search_batch(obs, net, cfg, 1.0, mask, 1, 2, rng=streams, plan=plan)
+            plan.pool.check_errors()
+            res.append((a.cpu().numpy(), pi.cpu().numpy(), q.cpu().numpy(), [s.get_state()[2] for s in streams],
+                        [plan.pool.dump_tree(t) for t in (0, 31, 32, 63)]))
+        for r in res[1:]:
+            assert np.array_equal(r[0], res[0][0]) and np.array_equal(bits(r[1]), bits(res[0][1]))
+        out.append(res[-1])
+    single, piped = out
+    assert np.array_equal(single[0], piped[0])
+    assert np.array_equal(bits(single[1]), bits(piped[1])) and np.array_equal(bits(single[2]), bits(piped[2]))
+    assert single[3] == piped[3]
+    for d0, d1 in zip(single[4], piped[4]):
+        assert np.array_equal(d0['N'], d1['N']) and np.array_equal(bits(d0['W']), bits(d1['W']))
+        assert np.array_equal(d0['parent'], d1['parent']) and np.array_equal(d0['move'], d1['move'])
+        assert np.array_equal(d0['value'][1:], d1['value'][1:])          # slot 0 (the root) is never written
+
+
 def build_atari(kw, seed):
     import muzero_b200 as mz
     torch.manual_seed(seed)
