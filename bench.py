@@ -284,7 +284,12 @@ def run_engine_arm(args):
     net.load_state_dict(state_dict_for(spec))
     net = net.to(dev).eval()
     # conv nets: two half-batches interleaved on two streams (tree kernels of one overlap the tower of the other)
-    parts = args.parts if args.parts else (2 if spec['kind'] != 'mlp' and B % 2 == 0 else 1)
+    parts = args.parts
+    if not parts:
+        parts = 1
+        if spec['kind'] != 'mlp' and B % 2 == 0:
+            hh, ww = net.latent_hw
+            parts = 2 if (B // 2) * (hh + 1) * (ww + 1) >= 2 * 148 * 256 else 1
     plan = PipelinedSearchPlan(net, cfg, B, parts) if parts > 1 else SearchPlan(net, cfg, B)
     pool = plan.pool
     pool.seed(1234 + rank * B + np.arange(B))
@@ -383,8 +388,8 @@ def run_engine_arm(args):
             for e in evs:
                 for i, n in enumerate(names):
                     tot[n] += e[i].elapsed_time(e[i + 1])
-        prof_ms = (C.c_double * 4)()
-        prof_n = (C.c_int64 * 4)()
+        prof_ms = (C.c_double * 5)()
+        prof_n = (C.c_int64 * 5)()
         _lib.check(lib.mz_net_profile_end(eng['handle'], prof_ms, prof_n))
     launches = reps * S
     avg_ms = {n: tot[n] / launches for n in names}
@@ -413,23 +418,32 @@ def run_engine_arm(args):
     roofline = dict(roof[dominant])
     roofline.update({'kernel': dominant, 'traffic': None, 'peak_source': peak_src})
     if spec['kind'] != 'mlp' and prof_n[0] > 0:
-        # the dominant KERNEL is the tcgen05 3x3 convolution (33 launches per recurrent inference):
-        # algorithmic flops per launch = the reference graph's 128->128 3x3 conv over the H*W real
-        # positions of B boards; executed = the same over the (H+1)*(W+1) padded grid.
+        # the dominant KERNEL is the tcgen05 3x3 convolution.  One launch runs a whole tower pair as a dataflow
+        # of layers (33 convs for a recurrent inference): algorithmic flops per layer = the reference graph's
+        # 128->128 3x3 conv over the H*W real positions of the boards of one launch; executed = the same over
+        # the (H+1)*(W+1) padded grid.  Launch duration: CUDA events around every eager launch.
         c, h, w = spec['net_kw']['input_shape']
         hh, ww = (h, w) if spec['kind'] == 'board' else (6, 6)
         planes = spec['net_kw']['num_planes']
         per_pos = 2.0 * planes * planes * 9
-        conv_ms = prof_ms[0] / prof_n[0]
-        # initial-inference convs are inside the profile too (same shapes except the first layer)
-        alg = per_pos * hh * ww * Bp
-        exe = per_pos * (hh + 1) * (ww + 1) * Bp
-        ach = alg / (conv_ms * 1e-3) / 1e12
-        roofline = {'kernel': 'conv3x3_kernel (tcgen05.mma M128 N128 K16, TMEM accumulators)', 'bound': 'tensor',
-                    'achieved': ach, 'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': ach / tf_peak, 'traffic': None,
-                    'avg_launch_us': conv_ms * 1e3, 'launches_timed': int(prof_n[0]),
+        layers_per_launch = prof_n[0] / max(1, prof_n[4])
+        launch_ms = prof_ms[0] / max(1, prof_n[4])
+        alg = per_pos * hh * ww * Bp * layers_per_launch
+        exe = per_pos * (hh + 1) * (ww + 1) * Bp * layers_per_launch
+        ach = alg / (launch_ms * 1e-3) / 1e12
+        traffic = None
+        try:     # dram bytes of one launch from the committed ncu --set full capture of the same kernel
+            tj = json.load(open(os.path.join(ROOT, 'profiles', 'conv_traffic.json')))
+            if tj.get('workload') == spec['name'] and tj.get('trees_per_launch') == Bp:
+                traffic = tj['dram_bytes_per_launch']
+        except Exception:
+            pass
+        roofline = {'kernel': 'conv3x3_kernel (tcgen05.mma M128 N128 K16, TMEM accumulators, TMA tile loads)',
+                    'bound': 'tensor', 'achieved': ach, 'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': ach / tf_peak,
+                    'traffic': traffic, 'avg_launch_us': launch_ms * 1e3, 'launches_timed': int(prof_n[4]),
+                    'conv_layers_per_launch': layers_per_launch,
                     'algorithmic_flops_per_launch': alg, 'executed_flops_per_launch': exe,
-                    'executed_tflops': exe / (conv_ms * 1e-3) / 1e12,
+                    'executed_tflops': exe / (launch_ms * 1e-3) / 1e12,
                     'share_of_recurrent_inference': prof_ms[0] / max(1e-9, prof_ms[0] + prof_ms[1] + prof_ms[2]),
                     'share_of_sim_loop': prof_ms[0] / max(1e-9, sum(tot.values())), 'peak_source': peak_src}
         roof['head_kernel'] = {'avg_launch_us': 1e3 * prof_ms[1] / max(1, prof_n[1]), 'launches_timed': int(prof_n[1])}

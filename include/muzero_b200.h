@@ -183,10 +183,11 @@ int mz_net_recurrent(mz_net* net, int32_t batch, const void* hidden_in, const in
 
 /* Per-kernel device timing of a net's launches (measurement aid for bench.py's roofline):
  * between begin and end every kernel the net launches EAGERLY is bracketed by CUDA events on
- * its stream; end synchronises and returns milliseconds and launch counts per kernel class
- * {0: conv3x3 (tcgen05), 1: heads, 2: observation packing, 3: fused MLP}. */
+ * its stream; end synchronises and returns milliseconds and counts per kernel class
+ * {0: conv3x3 (tcgen05; counted in conv LAYERS, one launch runs many), 1: heads, 2: observation packing,
+ *  3: fused MLP, 4: conv3x3 again, counted in kernel LAUNCHES (same milliseconds as class 0)}. */
 int mz_net_profile_begin(mz_net* net);
-int mz_net_profile_end(mz_net* net, double* ms_by_class /* [4] */, int64_t* launches_by_class /* [4] */);
+int mz_net_profile_end(mz_net* net, double* ms_by_class /* [5] */, int64_t* launches_by_class /* [5] */);
 
 /* number of kernels the library has launched since load (bench's gpu_launches) */
 uint64_t mz_launch_count(void);

@@ -983,9 +983,22 @@ struct ConvNet : NetImpl {
     static const bool debug = getenv("MZ_CONV_DEBUG") != nullptr;
     if (debug) cudaMalloc(&p.dbg, (size_t)grid * 16 * sizeof(long long));
     prof_mark(kProfConv, st, nl);
-    if (C == 128) conv3x3_kernel<128><<<grid, kConvThreads, smem, st>>>(p);
-    else if (C == 64) conv3x3_kernel<64><<<grid, kConvThreads, smem, st>>>(p);
-    else conv3x3_kernel<32><<<grid, kConvThreads, smem, st>>>(p);
+    {
+      // Layers of a launch wait on each other's tiles, so every CTA must be resident: a cooperative launch
+      // makes the hardware place the grid all at once (two such grids of different streams could otherwise
+      // each grab part of the SMs and wait for the rest forever).
+      cudaLaunchConfig_t lc = {};
+      lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(kConvThreads); lc.dynamicSmemBytes = smem; lc.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeCooperative;
+      at[0].val.cooperative = nl > 1 ? 1 : 0;
+      lc.attrs = at; lc.numAttrs = 1;
+      cudaError_t le;
+      if (C == 128) le = cudaLaunchKernelEx(&lc, conv3x3_kernel<128>, p);
+      else if (C == 64) le = cudaLaunchKernelEx(&lc, conv3x3_kernel<64>, p);
+      else le = cudaLaunchKernelEx(&lc, conv3x3_kernel<32>, p);
+      if (le != cudaSuccess) { pend.num_layers = 0; set_error("conv3x3_kernel launch: %s", cudaGetErrorString(le)); cudaGetLastError(); return MZ_ECUDA; }
+    }
     prof_mark(-1, st);
     pend.num_layers = 0;
     MZ_LAUNCH_CHECK("conv3x3_kernel");
@@ -1357,6 +1370,7 @@ int conv_create(const mz_net_config& c, const float* const* w, int nw, int max_b
   e = cudaFuncSetAttribute(conv3x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(head_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); delete net; return MZ_ECUDA; }
   *out = net;
   return MZ_OK;

@@ -795,6 +795,19 @@ extern "C" int mz_pool_create(const mz_pool_config* cfg, const double* pb_c_tabl
   MZ_CHECK_ARG(((uintptr_t)arena_dev & 255) == 0, "arena must be 256-byte aligned");
   size_t offs[MZ_VIEW__COUNT], sizes[MZ_VIEW__COUNT], extra[4], total;
   layout(*cfg, offs, sizes, extra, &total);
+  {
+    // The per-simulation tree kernels must be able to share an SM with the persistent conv kernel of ANOTHER
+    // sub-batch (PipelinedSearchPlan), which runs with the maximum shared-memory carve-out; a kernel that
+    // prefers a different L1/shared split cannot be co-resident with it.
+    const int mx = (int)cudaSharedmemCarveoutMaxShared;
+    cudaFuncSetAttribute(select_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(select_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(select_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(select_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(select_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(expand_backup_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaGetLastError();
+  }
   if (arena_bytes < total) {
     set_error("arena too small: %zu < %zu", arena_bytes, total);
     return MZ_ENOMEM;

@@ -92,6 +92,7 @@ extern "C" int mz_net_profile_end(mz_net* net, double* ms_by_class, int64_t* lau
     MZ_CUDA(cudaEventElapsedTime(&ms, n->prof_ev[2 * i], n->prof_ev[2 * i + 1]));
     ms_by_class[n->prof_cls[i]] += ms;
     launches_by_class[n->prof_cls[i]] += n->prof_weight[i];
+    if (n->prof_cls[i] == kProfConv) { ms_by_class[kProfConvLaunches] += ms; launches_by_class[kProfConvLaunches] += 1; }
   }
   for (cudaEvent_t e : n->prof_ev) cudaEventDestroy(e);
   n->prof_ev.clear();

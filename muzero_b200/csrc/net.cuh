@@ -7,7 +7,7 @@ namespace mz {
 
 // Optional per-kernel timing (mz_net_profile_begin/end): CUDA events recorded on the launching
 // stream around every kernel the net launches, summed per kernel class.  Eager launches only.
-enum ProfClass { kProfConv = 0, kProfHead = 1, kProfPack = 2, kProfMlp = 3, kProfClasses = 4 };
+enum ProfClass { kProfConv = 0, kProfHead = 1, kProfPack = 2, kProfMlp = 3, kProfConvLaunches = 4, kProfClasses = 5 };
 
 struct NetImpl {
   bool profiling = false;

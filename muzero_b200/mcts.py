@@ -473,7 +473,12 @@ def _plan_for(network, config, B) -> SearchPlan:
     if key not in _PLANS:
         if len(_PLANS) >= 4:
             _PLANS.pop(next(iter(_PLANS)))
-        _PLANS[key] = SearchPlan(network, config, B)
+        # large conv-net batches: two sub-batches in flight (each still fills the GPU's tile grid)
+        pipelined = False
+        if network.kind != _lib.MZ_NET_MLP and B % 2 == 0:
+            h, w = network.latent_hw
+            pipelined = (B // 2) * (h + 1) * (w + 1) >= 2 * 148 * 256        # >= two 256-row tiles per SM and part
+        _PLANS[key] = PipelinedSearchPlan(network, config, B, 2) if pipelined else SearchPlan(network, config, B)
     plan = _PLANS[key]
     plan.config = config
     return plan
