@@ -8,8 +8,12 @@
 // is launch/latency bound, so the design goal is ONE launch per network call.
 #include "common.cuh"
 #include "net.cuh"
+#include "umma.cuh"
+#include <cuda_fp16.h>
+#include <cstdlib>
 
 namespace mz {
+using namespace umma;
 
 constexpr int kRows = 32;
 constexpr int kThreads = 256;
@@ -281,10 +285,302 @@ __global__ void transpose_kernel(const float* __restrict__ w, float* __restrict_
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// tcgen05 path of recurrent_inference (the per-simulation call of the search)
+// ---------------------------------------------------------------------------
+// One CTA owns tiles of 128 rows (trees) and runs the whole chain for a tile on the tensor
+// cores with every activation staying on chip:
+//   transition: [h(64) | onehot(a)] -> P -> 64     reward: h_raw -> P -> Sr     value: h' -> P -> Sv   [policy]
+// Each two-layer net is processed in chunks of 256 hidden units:
+//   D1[128 x 256] = A_in[128 x 64] . W1c^T      (4 MMAs  M128 N256 K16, fp32 in TMEM columns 0..255)
+//   epilogue 1: + bias (+ the action's weight column, a [A][P] fp32 table) , ReLU, fp16 -> A_mid (smem, K-major)
+//   D2[128 x N2] (+)= A_mid[128 x 256] . W2c^T  (16 MMAs M128 N{32,64,..} K16, TMEM columns 256..)
+// followed by the net's own epilogue 2 (min-max normalisation of util.py:31-36, support -> scalar of
+// util.py:70-93, softmax).  Operands are fp16 (the hidden state is normalised to [0,1]), accumulation fp32.
+// Weights are pre-packed per (net, chunk, layer) block in exactly the shared-memory core-matrix layout and
+// streamed by a producer warp with 1-D bulk copies (TMA) through a 3-slot mbarrier ring, so the next block
+// loads while the current one is multiplied.
+
+constexpr int kTcRows = 128;          // rows per tile == compute threads
+constexpr int kTcThreads = 160;       // 4 compute warps + 1 producer warp
+constexpr int kTcChunk = 256;         // hidden units per chunk
+constexpr int kTcSlots = 3;           // weight ring
+constexpr int kTcSlotBytes = 32768;
+constexpr int kTcMaxBlocks = 16;
+
+struct MlpTcParams {
+  const unsigned char* wpack;
+  uint32_t blk_off[kTcMaxBlocks], blk_bytes[kTcMaxBlocks];
+  int nblk, nnets, chunks;
+  int P, A, Apad, Sr, Sv;
+  const float* tabA;                  // [A][P]: first-layer weight column of each action (network.py:191-193)
+  const float* b1[4];
+  const float* b2[4];
+  int batch;
+  const float* hidden_in; const int32_t* src_index; const int32_t* action;
+  float* hidden_out; const int32_t* dst_index; float* reward; float* value; float* pi;
+};
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 t = __floats2half2_rn(fminf(fmaxf(a, -65504.0f), 65504.0f), fminf(fmaxf(b, -65504.0f), 65504.0f));
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// softmax expectation over a support of S <= 32 logits held by one thread, then the inverse value transform
+__device__ __forceinline__ float support_scalar_regs(const float (&l)[32], int S) {
+  if (S == 1) return l[0];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) if (i < S) m = fmaxf(m, l[i]);
+  const int maxv = (S - 1) / 2;
+  const float step = (float)(2 * maxv) / (float)(S - 1);
+  float den = 0.0f, num = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if (i < S) {
+      const float e = expf(l[i] - m);
+      den += e;
+      num += e * ((float)(-maxv) + step * (float)i);
+    }
+  return signed_parabolic(num / den);
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) mlp_recurrent_tc_kernel(const __grid_constant__ MlpTcParams p) {
+  extern __shared__ __align__(1024) unsigned char tsm[];
+  unsigned char* sIn = tsm;                       // [8][128][16]  h_in   (fp16, K-major core matrices)
+  unsigned char* sRaw = sIn + 16384;              // h_raw
+  unsigned char* sNorm = sRaw + 16384;            // h' (normalised)
+  unsigned char* sMid = sNorm + 16384;            // [32][128][16] hidden chunk
+  unsigned char* sW = sMid + 65536;               // [kTcSlots][32 KB]
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(sW + kTcSlots * kTcSlotBytes);
+  uint64_t* w_empty = w_full + kTcSlots;
+  uint64_t* bar_mma = w_empty + kTcSlots;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar_mma + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < kTcSlots; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    mbar_init(bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_holder, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_holder;
+  const int ntiles = (p.batch + kTcRows - 1) / kTcRows;
+
+  if (warp == 4) {
+    // ------------------------------------------------ weight producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+        for (int b = 0; b < p.nblk; ++b, ++it) {
+          const uint32_t s = it % kTcSlots, ph = (it / kTcSlots) & 1;
+          mbar_wait(&w_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&w_full[s], p.blk_bytes[b]);
+          bulk_g2s(sW + (size_t)s * kTcSlotBytes, p.wpack + p.blk_off[b], p.blk_bytes[b], &w_full[s]);
+        }
+    }
+  } else {
+    // ------------------------------------------------ compute: thread = row of the tile
+    const int row = tid;
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);          // this warp's TMEM lanes
+    const uint32_t sIn_a = smem_u32(sIn), sRaw_a = smem_u32(sRaw), sNorm_a = smem_u32(sNorm), sMid_a = smem_u32(sMid);
+    uint32_t wit = 0, mma_ph = 0;
+    auto bar128 = []() { asm volatile("bar.sync 1, 128;" ::: "memory"); };
+    // tid 0 issues `n` K-steps of D(+)= A.B^T on the weight block at the head of the ring, then every thread
+    // waits for them (one mbarrier, alternating phase)
+    auto mma_group = [&](uint32_t a_addr, int ksteps, uint32_t dcol, uint32_t N, bool accumulate) {
+      if (tid == 0) {
+        const uint32_t s = wit % kTcSlots, ph = (wit / kTcSlots) & 1;
+        mbar_wait(&w_full[s], ph);
+        tc_fence_after();
+        const uint32_t idesc = instr_desc_f16(128, N);
+        const uint32_t b_addr = smem_u32(sW) + s * kTcSlotBytes;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t ad = smem_desc(a_addr + (uint32_t)ks * 4096u, 2048, 128);
+          const uint64_t bd = smem_desc(b_addr + (uint32_t)ks * 32u * N, N * 16, 128);
+          mma_bf16(tmem + dcol, ad, bd, idesc, (accumulate || ks > 0) ? 1u : 0u);
+        }
+        commit(&w_empty[s]);
+        commit(bar_mma);
+      }
+      ++wit;
+      mbar_wait(bar_mma, mma_ph);
+      mma_ph ^= 1;
+      tc_fence_after();
+    };
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int grow = tile * kTcRows + row;
+      const bool live = grow < p.batch;
+      // leaf gather: parent hidden state by slot index -> fp16 operand tile
+      {
+        const size_t slot = live ? (p.src_index ? (size_t)p.src_index[grow] : (size_t)grow) : 0;
+        const float4* src = reinterpret_cast<const float4*>(p.hidden_in + slot * 64);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+          if (live) { a = src[2 * g]; b = src[2 * g + 1]; }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sIn_a + (uint32_t)(g * 128 + row) * 16),
+                       "r"(pack_h2(a.x, a.y)), "r"(pack_h2(a.z, a.w)), "r"(pack_h2(b.x, b.y)), "r"(pack_h2(b.z, b.w)) : "memory");
+        }
+      }
+      int act = live ? p.action[grow] : 0;
+      act = min(max(act, 0), p.A - 1);
+      fence_proxy_async();
+      tc_fence_before();
+      bar128();
+
+      for (int net = 0; net < p.nnets; ++net) {
+        const uint32_t a_in = net == 0 ? sIn_a : (net == 1 ? sRaw_a : sNorm_a);
+        const uint32_t N2 = net == 0 ? 64u : (net == 3 ? (uint32_t)p.Apad : 32u);
+        const float* b1 = p.b1[net];
+        const float* tab = net == 0 ? p.tabA + (size_t)act * p.P : nullptr;
+        for (int c = 0; c < p.chunks; ++c) {
+          mma_group(a_in, 4, 0u, 256u, false);                        // D1 = A_in . W1c^T
+          // epilogue 1: bias (+ action column) + ReLU -> fp16 hidden chunk in shared memory
+#pragma unroll 1
+          for (int q = 0; q < 8; ++q) {
+            uint32_t r[32];
+            tmem_ld32(trow + (uint32_t)(q * 32), r);
+            tmem_ld_wait();
+            const int col0 = c * kTcChunk + q * 32;
+            float v[32];
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(b1 + col0 + e));
+              v[e] = __uint_as_float(r[e]) + b4.x; v[e + 1] = __uint_as_float(r[e + 1]) + b4.y;
+              v[e + 2] = __uint_as_float(r[e + 2]) + b4.z; v[e + 3] = __uint_as_float(r[e + 3]) + b4.w;
+            }
+            if (tab) {
+#pragma unroll
+              for (int e = 0; e < 32; e += 4) {
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(tab + col0 + e));
+                v[e] += t4.x; v[e + 1] += t4.y; v[e + 2] += t4.z; v[e + 3] += t4.w;
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float* w = v + 8 * u;
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sMid_a + (uint32_t)((q * 4 + u) * 128 + row) * 16),
+                           "r"(pack_h2(fmaxf(w[0], 0.f), fmaxf(w[1], 0.f))), "r"(pack_h2(fmaxf(w[2], 0.f), fmaxf(w[3], 0.f))),
+                           "r"(pack_h2(fmaxf(w[4], 0.f), fmaxf(w[5], 0.f))), "r"(pack_h2(fmaxf(w[6], 0.f), fmaxf(w[7], 0.f))) : "memory");
+            }
+          }
+          fence_proxy_async();
+          tc_fence_before();
+          bar128();
+          mma_group(sMid_a, 16, 256u, N2, c > 0);                     // D2 (+)= A_mid . W2c^T
+        }
+        // epilogue 2
+        const float* b2 = p.b2[net];
+        if (net == 0) {
+          // transition output: h_raw (for the reward net) and its min-max normalisation (util.py:31-36)
+          float h[64];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            uint32_t r[32];
+            tmem_ld32(trow + 256u + (uint32_t)(q * 32), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) h[q * 32 + e] = __uint_as_float(r[e]) + __ldg(b2 + q * 32 + e);
+          }
+          float mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+          for (int e = 0; e < 64; ++e) { mn = fminf(mn, h[e]); mx = fmaxf(mx, h[e]); }
+          const float den = __fadd_rn(__fsub_rn(mx, mn), 1e-8f);
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sRaw_a + (uint32_t)(g * 128 + row) * 16),
+                         "r"(pack_h2(h[8 * g], h[8 * g + 1])), "r"(pack_h2(h[8 * g + 2], h[8 * g + 3])),
+                         "r"(pack_h2(h[8 * g + 4], h[8 * g + 5])), "r"(pack_h2(h[8 * g + 6], h[8 * g + 7])) : "memory");
+#pragma unroll
+          for (int e = 0; e < 64; ++e) h[e] = __fdiv_rn(__fsub_rn(h[e], mn), den);
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sNorm_a + (uint32_t)(g * 128 + row) * 16),
+                         "r"(pack_h2(h[8 * g], h[8 * g + 1])), "r"(pack_h2(h[8 * g + 2], h[8 * g + 3])),
+                         "r"(pack_h2(h[8 * g + 4], h[8 * g + 5])), "r"(pack_h2(h[8 * g + 6], h[8 * g + 7])) : "memory");
+          if (live) {
+            const size_t slot = p.dst_index ? (size_t)p.dst_index[grow] : (size_t)grow;
+            float4* dst = reinterpret_cast<float4*>(p.hidden_out + slot * 64);
+#pragma unroll
+            for (int g = 0; g < 16; ++g) dst[g] = make_float4(h[4 * g], h[4 * g + 1], h[4 * g + 2], h[4 * g + 3]);
+          }
+        } else if (net == 1 || net == 2) {
+          uint32_t r[32];
+          tmem_ld32(trow + 256u, r);
+          tmem_ld_wait();
+          const int S = net == 1 ? p.Sr : p.Sv;
+          float l[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) l[e] = __uint_as_float(r[e]) + (e < S ? __ldg(b2 + e) : 0.0f);
+          const float out = support_scalar_regs(l, S);
+          if (live) (net == 1 ? p.reward : p.value)[grow] = out;
+        } else {
+          // policy: softmax over A logits spread over Apad TMEM columns (three passes over TMEM)
+          float m = -INFINITY, den = 0.0f;
+          for (int pass = 0; pass < 3; ++pass)
+            for (int q = 0; q * 32 < p.Apad; ++q) {
+              uint32_t r[32];
+              tmem_ld32(trow + 256u + (uint32_t)(q * 32), r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {
+                const int a = q * 32 + e;
+                if (a < p.A) {
+                  const float lg = __uint_as_float(r[e]) + __ldg(b2 + a);
+                  if (pass == 0) m = fmaxf(m, lg);
+                  else if (pass == 1) den += expf(lg - m);
+                  else if (live) p.pi[(size_t)grow * p.A + a] = expf(lg - m) / den;
+                }
+              }
+            }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        bar128();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// W [out x in_total] fp32 (row-major, PyTorch Linear.weight) -> fp16 block [K/8][N][8]:
+// rows n0 .. n0+N-1 (zero beyond `out`), input columns k0 .. k0+K-1
+__global__ void pack_linear_kernel(const float* __restrict__ w, __half* __restrict__ dst, int out, int in_total, int n0,
+                                   int N, int k0, int K) {
+  const int total = K * N;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int e = i % 8, n = (i / 8) % N, g = i / (8 * N);
+    const int k = k0 + g * 8 + e, row = n0 + n;
+    const float v = (row < out) ? w[(size_t)row * in_total + k] : 0.0f;
+    dst[i] = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
+  }
+}
+// tab[a][p] = W1[p][HD + a]
+__global__ void action_column_kernel(const float* __restrict__ w, float* __restrict__ tab, int P, int HD, int A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < A * P) {
+    const int a = i / P, pp = i % P;
+    tab[i] = w[(size_t)pp * (HD + A) + HD + a];
+  }
+}
+
+
 // ---------------------------------------------------------------------------
 struct MlpNet : NetImpl {
   MlpDev d;
   size_t smem;
+  bool tc = false;                  // tcgen05 recurrent path available for these dimensions
+  MlpTcParams tcp;
+  int tc_blocks_no_policy = 0, tc_blocks_policy = 0, num_sms = 148;
+  size_t tc_smem = 0;
 
   int initial(int batch, const float* obs, void* hidden_out, const int32_t* dst_index, float* pi_probs,
               float* value, cudaStream_t st) override {
@@ -297,6 +593,19 @@ struct MlpNet : NetImpl {
   }
   int recurrent(int batch, const void* hidden_in, const int32_t* src_index, const int32_t* action, void* hidden_out,
                 const int32_t* dst_index, float* reward, float* value, float* pi_probs, cudaStream_t st) override {
+    if (tc && (pi_probs == nullptr || tc_blocks_policy > 0)) {
+      MlpTcParams q = tcp;
+      q.batch = batch; q.hidden_in = (const float*)hidden_in; q.src_index = src_index; q.action = action;
+      q.hidden_out = (float*)hidden_out; q.dst_index = dst_index; q.reward = reward; q.value = value; q.pi = pi_probs;
+      q.nnets = pi_probs ? 4 : 3;
+      q.nblk = pi_probs ? tc_blocks_policy : tc_blocks_no_policy;
+      const int ntiles = (batch + kTcRows - 1) / kTcRows;
+      prof_mark(kProfMlp, st);
+      mlp_recurrent_tc_kernel<<<ntiles < num_sms ? ntiles : num_sms, kTcThreads, tc_smem, st>>>(q);
+      prof_mark(-1, st);
+      MZ_LAUNCH_CHECK("mlp_recurrent_tc_kernel");
+      return MZ_OK;
+    }
     prof_mark(kProfMlp, st);
     mlp_recurrent_kernel<<<(batch + kRows - 1) / kRows, kThreads, smem, st>>>(
         d, batch, (const float*)hidden_in, src_index, action, (float*)hidden_out, dst_index, reward, value, pi_probs);
@@ -343,6 +652,9 @@ int mlp_arena_bytes(const mz_net_config& c, size_t* bytes) {
   mlp_shapes(c, in_dim, sh);
   size_t tot = 0;
   for (int i = 0; i < 20; ++i) tot += 2 * align_up((size_t)sh[i][0] * sh[i][1] * 4, 256);   // [out,in] + transposed
+  // tcgen05 recurrent path: packed fp16 weight blocks (4 nets x chunks x 2 layers, <= 32 KB each) + action table
+  tot += (size_t)4 * ((c.num_planes + kTcChunk - 1) / kTcChunk) * 2 * kTcSlotBytes +
+         align_up((size_t)c.num_actions * c.num_planes * 4, 256) + 1024;
   *bytes = tot;
   return MZ_OK;
 }
@@ -381,6 +693,56 @@ int mlp_create(const mz_net_config& c, const float* const* w, int nw, void* aren
   d.rew1_wt = tr[8];  d.rew1_b = orig[9];  d.rew2_wt = tr[10]; d.rew2_w = orig[10]; d.rew2_b = orig[11];
   d.pol1_wt = tr[12]; d.pol1_b = orig[13]; d.pol2_wt = tr[14]; d.pol2_w = orig[14]; d.pol2_b = orig[15];
   d.val1_wt = tr[16]; d.val1_b = orig[17]; d.val2_wt = tr[18]; d.val2_w = orig[18]; d.val2_b = orig[19];
+  // ---- tcgen05 recurrent path (hidden 64, hidden layers in chunks of 256, supports and actions that fit one block)
+  {
+    const int P = d.P, A = d.A;
+    const int apad = (A + 15) / 16 * 16;
+    const char* simt = getenv("MZ_MLP_SIMT");
+    net->tc = d.HD == 64 && P % kTcChunk == 0 && P <= 2048 && d.Sr <= 32 && d.Sv <= 32 && !(simt && simt[0] == '1');
+    if (net->tc) {
+      const int chunks = P / kTcChunk;
+      const bool pol = apad <= 64 && 4 * chunks * 2 <= kTcMaxBlocks;
+      p = (char*)align_up((size_t)p, 1024);
+      unsigned char* wp = (unsigned char*)p;
+      MlpTcParams& q = net->tcp;
+      memset(&q, 0, sizeof(q));
+      q.wpack = wp; q.chunks = chunks; q.P = P; q.A = A; q.Apad = apad; q.Sr = d.Sr; q.Sv = d.Sv;
+      const int w1_idx[4] = {4, 8, 16, 12}, in_tot[4] = {d.HD + A, d.HD, d.HD, d.HD};
+      const int n2[4] = {64, 32, 32, apad}, out2[4] = {d.HD, d.Sr, d.Sv, A};
+      size_t off = 0;
+      int nb = 0;
+      for (int net_i = 0; net_i < (pol ? 4 : 3); ++net_i) {
+        q.b1[net_i] = orig[w1_idx[net_i] + 1];
+        q.b2[net_i] = orig[w1_idx[net_i] + 3];
+        for (int ch = 0; ch < chunks; ++ch) {
+          // layer 1 block: rows ch*256.., K = 64
+          pack_linear_kernel<<<64, 256>>>(orig[w1_idx[net_i]], (__half*)(wp + off), P, in_tot[net_i], ch * kTcChunk,
+                                          kTcChunk, 0, 64);
+          MZ_LAUNCH_CHECK("pack_linear_kernel");
+          q.blk_off[nb] = (uint32_t)off; q.blk_bytes[nb] = 64 * kTcChunk * 2; off += kTcSlotBytes; ++nb;
+          // layer 2 block: N2 rows (zero-padded), input columns ch*256..
+          pack_linear_kernel<<<64, 256>>>(orig[w1_idx[net_i] + 2], (__half*)(wp + off), out2[net_i], P, 0, n2[net_i],
+                                          ch * kTcChunk, kTcChunk);
+          MZ_LAUNCH_CHECK("pack_linear_kernel");
+          q.blk_off[nb] = (uint32_t)off; q.blk_bytes[nb] = (uint32_t)(kTcChunk * n2[net_i] * 2); off += kTcSlotBytes; ++nb;
+        }
+        if (net_i == 2) net->tc_blocks_no_policy = nb;
+      }
+      net->tc_blocks_policy = pol ? nb : 0;
+      p += off;
+      float* tab = (float*)p; p += align_up((size_t)A * P * 4, 256);
+      action_column_kernel<<<(A * P + 255) / 256, 256>>>(orig[4], tab, P, d.HD, A);
+      MZ_LAUNCH_CHECK("action_column_kernel");
+      q.tabA = tab;
+      MZ_CUDA(cudaDeviceSynchronize());
+      if ((size_t)(p - (char*)arena) > arena_bytes) { set_error("internal: MLP arena overrun"); delete net; return MZ_ENOMEM; }
+      net->tc_smem = 3 * 16384 + 65536 + (size_t)kTcSlots * kTcSlotBytes + 256;
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&net->num_sms, cudaDevAttrMultiProcessorCount, dev);
+      MZ_CUDA(cudaFuncSetAttribute(mlp_recurrent_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)net->tc_smem));
+    }
+  }
   net->smem = smem_bytes(d);
   if (net->smem > 227 * 1024) {
     set_error("MLP too wide for the fused kernel: needs %zu bytes of shared memory", net->smem);

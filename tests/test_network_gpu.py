@@ -22,8 +22,20 @@ MLPS = {
     'lunarlander': dict(input_shape=(4, 9), num_actions=4, num_planes=512, value_support_size=31,
                         reward_support_size=31, hidden_dim=64),
 }
-# fp32 SIMT kernels vs fp32 torch: only the summation order differs
+# initial_inference: fp32 SIMT kernels vs fp32 torch, only the summation order differs
 MLP_TOL = dict(rtol=2e-4, atol=2e-4)
+# recurrent_inference: tcgen05 path, fp16 operands (hidden state in [0,1], trained weights) with fp32 accumulation.
+# Stated tolerance: |err| <= 5e-3 * max(1, |ref|max) on hidden state, reward and value (measured on the three
+# checkpoints at batch 4096: hidden <= 1.4e-3, reward / value <= 2.4e-3 of scale), <= 1e-2 on policy probabilities
+# (measured <= 2.3e-3).
+TC_TOL, TC_TOL_PI = 5e-3, 1e-2
+
+
+def close_tc(got, ref, tol=TC_TOL, scale=None):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    scale = max(1.0, float(np.abs(ref).max())) if scale is None else scale
+    err = float(np.abs(got - ref).max())
+    assert np.isfinite(got).all() and err <= tol * scale, f'max err {err:.4g} > {tol * scale:.4g}'
 
 
 def load_mlp(name):
@@ -55,10 +67,10 @@ def test_mlp_single_item_api_vs_reference_recording(name):
         for i, a in enumerate(g['actions']):
             # feed the REFERENCE's hidden state so errors do not compound along the chain
             o = net.recurrent_inference(torch.from_numpy(h)[None].cuda(), torch.tensor([[int(a)]]).cuda())
-            np.testing.assert_allclose(o.hidden_state, g['h'][i], **MLP_TOL)
-            np.testing.assert_allclose(o.reward, g['r'][i], **MLP_TOL)
-            np.testing.assert_allclose(o.value, g['v'][i], **MLP_TOL)
-            np.testing.assert_allclose(o.pi_probs, g['pi'][i], **MLP_TOL)
+            close_tc(o.hidden_state, g['h'][i])
+            close_tc(o.reward, g['r'][i])
+            close_tc(o.value, g['v'][i])
+            close_tc(o.pi_probs, g['pi'][i], TC_TOL_PI)
             h = g['h'][i]
 
 
@@ -82,15 +94,17 @@ def test_mlp_batched_vs_torch_fp32(name, batch):
     _, reward, pi2, value2 = net.recurrent_inference_batch(slots_in, torch.from_numpy(act).cuda(), src_index=src,
                                                            hidden_out=out, dst_index=dst)
     h2_ref, r_ref, pi2_ref, v2_ref = onet.recurrent_batch(h_ref.flip(0), act)
-    np.testing.assert_allclose(net.hidden_to_reference(out)[::2].cpu().numpy(), h2_ref.numpy(), **MLP_TOL)
-    np.testing.assert_allclose(reward.cpu().numpy(), r_ref.numpy(), **MLP_TOL)
-    np.testing.assert_allclose(value2.cpu().numpy(), v2_ref.numpy(), **MLP_TOL)
-    np.testing.assert_allclose(pi2.cpu().numpy(), pi2_ref.numpy(), **MLP_TOL)
+    close_tc(net.hidden_to_reference(out)[::2].cpu().numpy(), h2_ref.numpy())
+    close_tc(reward.cpu().numpy(), r_ref.numpy())
+    close_tc(value2.cpu().numpy(), v2_ref.numpy())
+    close_tc(pi2.cpu().numpy(), pi2_ref.numpy(), TC_TOL_PI)
     assert (net.hidden_to_reference(out)[1::2] == 0).all()          # untouched slots stay untouched
     # policy head skipped (what the search asks for): same reward/value
     _, reward3, pi3, value3 = net.recurrent_inference_batch(slots_in, torch.from_numpy(act).cuda(), src_index=src,
                                                             want_policy=False)
     assert pi3 is None and torch.equal(reward3, reward) and torch.equal(value3, value2)
+    # the fp32 SIMT kernel (MZ_MLP_SIMT=1 selects it for every call) stays within the fp32 tolerance: covered by
+    # initial_inference above, which always runs on it
 
 
 def test_engine_tracks_weight_updates():
@@ -175,9 +189,10 @@ def test_search_with_engine_network_replays_bit_exact_in_oracle(name, B, determi
     hid = net.hidden_to_reference(pool.hidden.view(B, S + 1, -1)[t]).cpu()
     for i in range(0, S, 5):
         h_ref, r_ref, _, v_ref = onet.recurrent_batch(hid[rec_p[i, t]][None], np.array([rec_a[i, t]]))
-        np.testing.assert_allclose(rec_r[i, t], r_ref.numpy()[0], **MLP_TOL)
-        np.testing.assert_allclose(rec_v[i, t], v_ref.numpy()[0], **MLP_TOL)
-        np.testing.assert_allclose(hid[i + 1].numpy(), h_ref.numpy()[0], **MLP_TOL)
+        scale = max(1.0, float(np.abs(rec_v[:, t]).max()), float(np.abs(rec_r[:, t]).max()))
+        close_tc(rec_r[i, t], r_ref.numpy()[0], scale=scale)
+        close_tc(rec_v[i, t], v_ref.numpy()[0], scale=scale)
+        close_tc(hid[i + 1].numpy(), h_ref.numpy()[0])
 
 
 def test_public_batch_entry_point_matches_manual_loop():
