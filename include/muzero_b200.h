@@ -189,6 +189,48 @@ int mz_net_recurrent(mz_net* net, int32_t batch, const void* hidden_in, const in
 int mz_net_profile_begin(mz_net* net);
 int mz_net_profile_end(mz_net* net, double* ms_by_class /* [5] */, int64_t* launches_by_class /* [5] */);
 
+/* ------------------------------------------------------------------------
+ * Callers of the search path, device-resident (f-1, f-3)
+ * ---------------------------------------------------------------------- */
+/* Batched board-game environments: replace BoardGameEnv.reset / step / observation
+ * (games/env.py:100-154, 242-271) with the last-move win check of games/gomoku.py:72-116 and
+ * games/tictactoe.py:33-77.  num_actions = board_size^2 + 1 (the last action resigns).
+ * Players: 1 = black (moves first), 2 = white.  Observations are written as float32
+ * [G, 2*stack_history+1, N, N] from the side to move: [X_t, Y_t, X_t-1, Y_t-1, ..., colour]. */
+typedef struct mz_env mz_env;
+int mz_env_arena_bytes(int32_t games, int32_t board_size, int32_t stack_history, size_t* bytes);
+int mz_env_create(int32_t games, int32_t board_size, int32_t stack_history, int32_t num_to_win, void* arena_dev,
+                  size_t arena_bytes, mz_env** out);
+int mz_env_destroy(mz_env* env);
+/* views: 0 board i8[G,N*N], 1 history i8[G,2,stack,N*N], 2 mask u8[G,A], 3 player i32[G], 4 steps i32[G],
+ *        5 winner i32[G], 6 done u8[G], 7 error i32[1] (bit 0: an illegal action was submitted)            */
+int mz_env_view(mz_env* env, int32_t which, void** ptr, size_t* bytes);
+/* reset the games with which[g] != 0 (all when NULL); obs may be NULL */
+int mz_env_reset(mz_env* env, const uint8_t* which /* [G] */, float* obs, mz_stream stream);
+/* one move per unfinished game: reward f64[G] and done u8[G] of THIS move, mover i32[G] = who played it,
+ * obs = the next observation; finished games are left untouched (reward 0, done 1) */
+int mz_env_step(mz_env* env, const int32_t* action /* [G] */, double* reward, uint8_t* done, int32_t* mover,
+                float* obs, mz_stream stream);
+
+/* Trajectories [G, max_len] (lengths i32[G]) -> training targets.  float64 in the reference's operation order:
+ * targets and priorities are bit-identical to compute_n_step_target (pipeline.py:632-671; pow_table[i] =
+ * discount**i evaluated by the caller with CPython floats, i = 0..td_steps), compute_mc_return_target
+ * (pipeline.py:674-706) and priorities = |root_value - target| (pipeline.py:128,152).                       */
+int mz_targets_nstep(int32_t games, int32_t max_len, const int32_t* lengths, const double* rewards,
+                     const double* root_values, int32_t td_steps, const double* pow_table_dev, double* targets,
+                     double* priorities /* nullable */, mz_stream stream);
+int mz_targets_mc(int32_t games, int32_t max_len, const int32_t* lengths, const double* rewards,
+                  const int32_t* player_ids, const double* root_values /* nullable with priorities */,
+                  double* targets, double* priorities /* nullable */, mz_stream stream);
+/* make_unroll_sequence (pipeline.py:709-767): per (game, step) the next unroll_steps actions / rewards / targets /
+ * search policies with absorbing padding (action 0, reward 0, value 0, uniform policy).  Outputs are laid out
+ * [G, max_len, unroll_steps(, A)]; valid u8[G, max_len] marks real steps.  Actions stay int32 (the reference's
+ * int8 cast wraps for more than 127 actions, pipeline.py:753).                                               */
+int mz_unroll_sequences(int32_t games, int32_t max_len, int32_t unroll_steps, int32_t num_actions,
+                        const int32_t* lengths, const int32_t* actions, const double* rewards, const double* targets,
+                        const float* pi /* [G,max_len,A] */, int32_t* out_action, float* out_reward, float* out_value,
+                        float* out_pi, uint8_t* valid /* nullable */, mz_stream stream);
+
 /* number of kernels the library has launched since load (bench's gpu_launches) */
 uint64_t mz_launch_count(void);
 

@@ -59,6 +59,16 @@ PROTOTYPES = {
     'mz_net_recurrent': (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'mz_net_profile_begin': (C.c_int, [_P]),
     'mz_net_profile_end': (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    'mz_env_arena_bytes': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
+    'mz_env_create': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.c_size_t, C.POINTER(_P)]),
+    'mz_env_destroy': (C.c_int, [_P]),
+    'mz_env_view': (C.c_int, [_P, C.c_int32, C.POINTER(_P), C.POINTER(C.c_size_t)]),
+    'mz_env_reset': (C.c_int, [_P, _P, _P, _P]),
+    'mz_env_step': (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    'mz_targets_nstep': (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
+    'mz_targets_mc': (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
+    'mz_unroll_sequences': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                      _P, _P]),
     'mz_launch_count': (C.c_uint64, []),
 }
 
