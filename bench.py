@@ -470,6 +470,11 @@ def run_engine_arm(args):
             result['train_step'] = train_step_sample(net, spec, dev, world)
         except Exception as exc:                      # never lose the search line to the secondary measurement
             result['train_step'] = {'error': repr(exc)[:200]}
+    if spec['name'] in ('gomoku', 'tictactoe') and not args.no_self_play:
+        try:
+            result['self_play'] = self_play_sample(net, spec, dev, rank)
+        except Exception as exc:
+            result['self_play'] = {'error': repr(exc)[:200]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         del flush
         result['cpu_baseline'] = cpu_baseline_sample(args, spec)
@@ -523,6 +528,38 @@ def train_step_sample(net, spec, dev, world, batch=128, unroll=5, warmup=2, step
     return out
 
 
+def self_play_sample(net, spec, dev, rank, moves=3):
+    """SURVEY 8f rows f-1/f-3 on top of the search: B concurrent games on the device (batched env step, trajectory
+    buffers, MC-return targets + unroll windows for finished games), a few moves timed end to end."""
+    import torch
+    import muzero_b200 as mz
+    c, h, w = spec['net_kw']['input_shape']
+    num_to_win = 3 if spec['name'] == 'tictactoe' else 5
+    env = mz.BatchedBoardEnv(spec['trees'], h, num_to_win, (c - 1) // 2, device=dev)
+    loop = mz.BoardSelfPlay(net, spec['cfg'], env, seed=777 + rank)
+    loop.play_move()                                   # plan creation + graph capture
+    loop.play_move()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    samples = 0
+    for _ in range(moves):
+        out = loop.play_move()
+        samples += 0 if out is None else int(out.state.shape[0])
+    e1.record()
+    torch.cuda.synchronize(dev)
+    env.check_errors()
+    ms = e0.elapsed_time(e1) / moves
+    S = spec['cfg'].num_simulations
+    res = {'ms_per_move': ms, 'games_in_flight': spec['trees'], 'moves_per_s': spec['trees'] / (ms / 1e3),
+           'simulations_per_s': spec['trees'] * S / (ms / 1e3), 'samples_emitted': samples,
+           'impl': 'uct_search_batch + env_step_kernel + target/unroll kernels, one D2H flag read per move'}
+    del loop, env
+    mz.mcts._PLANS.clear()
+    torch.cuda.empty_cache()
+    return res
+
+
 def cpu_baseline_sample(args, spec):
     procs = min(os.cpu_count() or 1, args.cpu_procs)
     arm = CpuArm(args.workload, args.trees, procs)
@@ -565,6 +602,7 @@ def main():
     ap.add_argument('--parts', type=int, default=0, help='sub-batches in flight per GPU (0: 2 for conv nets, 1 for MLPs)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-train-step', action='store_true')
+    ap.add_argument('--no-self-play', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)

@@ -12,6 +12,6 @@ for a in ${ABLATES:-0 1 2 4 7 512}; do
   MZ_CONV_ABLATE=$a MZ_CONV_DEBUG=1 timeout 120 python tools/profile_target.py gomoku 2 2>&1 | grep "conv dbg" | tail -1
 done
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
-timeout 600 python bench.py --steps 3 --warmup 3 --no-train-step --no-cpu-baseline
+timeout 600 python bench.py --steps 3 --warmup 3 --no-train-step --no-cpu-baseline --no-self-play
 } > $L 2>&1
 cat $L
