@@ -169,7 +169,8 @@ class BoardSelfPlay:
         assert config.is_board_game
         from .mcts import _plan_for
         self.net, self.cfg, self.env = network, config, env
-        _plan_for(network, config, env.G).pool.seed(seed + np.arange(env.G))     # one MT19937 stream per game slot
+        self._plan = _plan_for(network, config, env.G)
+        self._plan.pool.seed(seed + np.arange(env.G))     # one MT19937 stream per game slot
         G, A, dev = env.G, env.num_actions, env.device
         self.Tmax = env.N * env.N + 1
         self.train_steps = train_steps
@@ -192,6 +193,9 @@ class BoardSelfPlay:
         temps = np.array([cfg.visit_softmax_temperature_fn(int(s), self.train_steps) for s in self.steps], np.float64)
         cur = (1 + (self.steps % 2)).astype(np.int32)                   # black moves first, players alternate
         action, pi, root_value = mz.uct_search_batch(env.obs, self.net, cfg, temps, env.actions_mask, cur, 3 - cur)
+        # the reference's actor dies with ValueError('probabilities contain NaN') when every visit of a search went
+        # below an illegal first pick (mcts.py:404); same here, before the bad action reaches the environment
+        self._plan.pool.check_errors()
         t = torch.from_numpy(self.steps).to(env.device)
         self.t_obs[self._rows, t] = env.obs.to(torch.int8)
         self.t_action[self._rows, t] = action

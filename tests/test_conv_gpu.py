@@ -153,6 +153,51 @@ def test_gomoku_search_replays_bit_exact_in_oracle():
     assert torch.equal(a2, action) and torch.equal(pi2, pi) and torch.equal(q2, rootv)
 
 
+def test_gomoku_15x15_wide_board_and_226_actions():
+    """The reference's class-default Gomoku (15x15, 8 history planes -> 17 observation planes, 226 actions,
+    games/gomoku.py:31-36): wider halo / tile geometry in the conv kernel, the A > 128 path of the select kernel,
+    a 226-row action table.  Network vs fp32 torch, and a batched search replayed bit-exactly in the oracle."""
+    import muzero_b200 as mz
+    net, onet = build_board((17, 15, 15), 226, 2, 64, seed=3)
+    gen = np.random.RandomState(15)
+    B, A = 40, 226
+    obs = gen.randint(0, 2, size=(B, 17, 15, 15)).astype(np.float32)
+    hid, pi, v = net.initial_inference_batch(torch.from_numpy(obs).cuda())
+    h_ref, pi_ref, v_ref = onet.initial_batch(obs)
+    report('15x15 h0', net.hidden_to_reference(hid).cpu().numpy(), h_ref.numpy(), TOL_H)
+    report('15x15 pi0', pi.cpu().numpy(), pi_ref.numpy(), TOL_PV)
+    report('15x15 v0', v.cpu().numpy(), v_ref.numpy(), TOL_PV)
+    act = gen.randint(0, A, size=B)
+    hid2, r, pi2, v2 = net.recurrent_inference_batch(hid, torch.from_numpy(act).cuda())
+    h2_ref, r_ref, pi2_ref, v2_ref = onet.recurrent_batch(h_ref, act)
+    report('15x15 h1', net.hidden_to_reference(hid2).cpu().numpy(), h2_ref.numpy(), TOL_H)
+    report('15x15 r', r.cpu().numpy(), r_ref.numpy(), TOL_PV)
+    report('15x15 v1', v2.cpu().numpy(), v2_ref.numpy(), TOL_PV)
+    report('15x15 pi1', pi2.cpu().numpy(), pi2_ref.numpy(), TOL_PV)
+
+    cfg = mz.make_gomoku_config(use_tensorboard=False)
+    cfg.num_simulations = 40
+    # every action legal: with illegal actions a random-init net at A = 226 reproduces the reference's own
+    # pathology (the first simulation ties over ALL actions, mcts.py:104-127 with N_root = 0; a tree whose first
+    # pick is illegal can spend every visit below it, and generate_play_policy then divides 0 by 0 ->
+    # ValueError('probabilities contain NaN'), covered by test_error_paths_match_reference_exceptions)
+    mask = np.ones((B, A), dtype=bool)
+    streams = [np.random.RandomState(500 + t) for t in range(B)]
+    plan = mz.mcts.SearchPlan(net, cfg, B)
+    action, pi, rootv = mz.uct_search_batch(obs, net, cfg, 1.0, mask, 1, 2, rng=streams, plan=plan)
+    plan.pool.check_errors()
+    pi0 = plan.pi0.cpu().numpy()
+    for t in range(0, B, 5):
+        d = plan.pool.dump_tree(t)
+        rs = np.random.RandomState(500 + t)
+        stub = ReplayStub(pi0[t], d['R'][1:].astype(np.float32), d['value'][1:], d['parent'], d['move'])
+        a_o, pi_o, q_o, tr = orc.uct_search(obs[t], stub, 'cpu', cfg, 1.0, mask[t], 1, 2, False, rng=rs,
+                                            return_trace=True)
+        assert np.array_equal(tr.N, d['N']) and np.array_equal(bits(tr.W), bits(d['W']))
+        assert a_o == int(action[t]) and np.array_equal(bits(pi_o), bits(pi[t].cpu().numpy()))
+        assert bits(q_o)[0] == bits(rootv[t].item())[0] and rs.get_state()[2] == streams[t].get_state()[2]
+
+
 def test_pipelined_plan_is_bit_identical_to_single_plan():
     """Two half-batches interleaved on two streams in one CUDA graph (PipelinedSearchPlan) give exactly the
     trees, actions, policies, root values and RNG positions of one SearchPlan over the whole batch: trees
