@@ -284,13 +284,11 @@ def run_engine_arm(args):
     net.load_state_dict(state_dict_for(spec))
     net = net.to(dev).eval()
     # conv nets: two half-batches interleaved on two streams (tree kernels of one overlap the tower of the other)
-    parts = args.parts
-    if not parts:
-        parts = 1
-        if spec['kind'] != 'mlp' and B % 2 == 0:
-            hh, ww = net.latent_hw
-            parts = 2 if (B // 2) * (hh + 1) * (ww + 1) >= 2 * 148 * 256 else 1
-    plan = PipelinedSearchPlan(net, cfg, B, parts) if parts > 1 else SearchPlan(net, cfg, B)
+    from muzero_b200.mcts import pipeline_shape
+    parts, cta_limit = pipeline_shape(net, B)
+    if args.parts:
+        parts, cta_limit = args.parts, args.cta_limit
+    plan = PipelinedSearchPlan(net, cfg, B, parts, cta_limit) if parts > 1 else SearchPlan(net, cfg, B)
     pool = plan.pool
     pool.seed(1234 + rank * B + np.arange(B))
     read_stats = (lambda: pool.stats()) if parts > 1 else (lambda: pool.view('STATS').cpu().numpy().copy())
@@ -455,7 +453,7 @@ def run_engine_arm(args):
                  (' for recurrent inference, f32 SIMT for the root inference' if spec['kind'] == 'mlp' else ''),
         'data': 'synthetic',
         'config': {'workload': spec['label'], 'trees_per_gpu': B, 'simulations': S, 'num_actions': A,
-                   'pipeline_parts': parts, 'trees_per_kernel_launch': Bp,
+                   'pipeline_parts': parts, 'trees_per_kernel_launch': Bp, 'ctas_per_tower_launch': cta_limit or 148,
                    'l2': 'flushed between timed iterations (256 MiB write)', 'mean_select_depth': mean_depth,
                    'parallelism': f'games sharded over {world} GPU(s), no collective'},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': int(h2d),
@@ -600,6 +598,7 @@ def main():
     ap.add_argument('--impl', default='engine', choices=['engine', 'reference'])
     ap.add_argument('--cpu-procs', type=int, default=int(os.environ.get('MZ_BENCH_CPU_PROCS', '64')))
     ap.add_argument('--parts', type=int, default=0, help='sub-batches in flight per GPU (0: 2 for conv nets, 1 for MLPs)')
+    ap.add_argument('--cta-limit', type=int, default=0, help='with --parts: SMs per tower launch (0: all)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-train-step', action='store_true')
     ap.add_argument('--no-self-play', action='store_true')

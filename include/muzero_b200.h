@@ -181,6 +181,11 @@ int mz_net_recurrent(mz_net* net, int32_t batch, const void* hidden_in, const in
                      const int32_t* action, void* hidden_out, const int32_t* dst_index,
                      float* reward, float* value, float* pi_probs, mz_stream stream);
 
+/* Cap the grid of the net's persistent kernels (0 = one CTA per SM).  Two engines that are driven from two
+ * streams (sub-batches of one search) can each be given half of the SMs so that their towers run side by side:
+ * small batches are bound by the layer-to-layer tile dependencies, not by SM count. */
+int mz_net_set_cta_limit(mz_net* net, int32_t max_ctas);
+
 /* Per-kernel device timing of a net's launches (measurement aid for bench.py's roofline):
  * between begin and end every kernel the net launches EAGERLY is bracketed by CUDA events on
  * its stream; end synchronises and returns milliseconds and counts per kernel class

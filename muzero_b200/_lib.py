@@ -57,6 +57,7 @@ PROTOTYPES = {
     'mz_net_destroy': (C.c_int, [_P]),
     'mz_net_initial': (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P]),
     'mz_net_recurrent': (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'mz_net_set_cta_limit': (C.c_int, [_P, C.c_int32]),
     'mz_net_profile_begin': (C.c_int, [_P]),
     'mz_net_profile_end': (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     'mz_env_arena_bytes': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),

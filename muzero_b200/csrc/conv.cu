@@ -968,7 +968,8 @@ struct ConvNet : NetImpl {
     p.err = err_flag;
     if (p.stages < 2) { pend.num_layers = 0; set_error("conv tile does not fit shared memory for a %dx%d grid", g.H, g.W); return MZ_EINVAL; }
     const size_t smem = conv_smem(g, cg);
-    const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    const int sm_cap = (cta_limit > 0 && cta_limit < num_sms) ? cta_limit : num_sms;
+    const int grid = p.num_tiles < sm_cap ? p.num_tiles : sm_cap;
     p.rot = nl > 1 ? p.num_tiles % grid : 0;
     p.flags = nullptr;
     if (nl > 1) {

@@ -70,6 +70,12 @@ extern "C" int mz_net_recurrent(mz_net* net, int32_t batch, const void* hidden_i
                               (cudaStream_t)stream);
 }
 
+extern "C" int mz_net_set_cta_limit(mz_net* net, int32_t max_ctas) {
+  MZ_CHECK_ARG(net && max_ctas >= 0, "bad argument");
+  net->impl->cta_limit = max_ctas;
+  return MZ_OK;
+}
+
 extern "C" int mz_net_profile_begin(mz_net* net) {
   MZ_CHECK_ARG(net, "NULL argument");
   NetImpl* n = net->impl;

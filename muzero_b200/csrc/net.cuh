@@ -11,6 +11,7 @@ enum ProfClass { kProfConv = 0, kProfHead = 1, kProfPack = 2, kProfMlp = 3, kPro
 
 struct NetImpl {
   bool profiling = false;
+  int cta_limit = 0;                    // persistent kernels use at most this many CTAs (0: one per SM)
   std::vector<cudaEvent_t> prof_ev;     // pairs (begin, end)
   std::vector<int> prof_cls, prof_weight;   // weight: how many layers one launch covers
   void prof_mark(int cls, cudaStream_t st, int weight = 1) {

@@ -249,6 +249,7 @@ class SearchPlan:
                  instance: int = 0, buffers: Optional[dict] = None) -> None:
         self.network, self.config = network, config
         self.instance = int(instance)            # which engine instance of the network this plan drives
+        self.cta_limit = 0                       # SMs the tower kernels of this plan may use (0: all)
         self.dev = next(network.parameters()).device
         self.B, self.A, self.S = int(num_trees), network.num_actions, int(config.num_simulations)
         self.pool = pool if pool is not None else SearchPool(self.B, self.A, config, network.hidden_bytes, self.dev)
@@ -279,6 +280,7 @@ class SearchPlan:
         """Enqueue one whole search on the current stream (pure C-ABI calls, static pointers)."""
         lib, pool, cfg = _lib.lib(), self.pool, self.config
         eng = self.network.engine(self.B, self.instance)
+        _lib.check(lib.mz_net_set_cta_limit(eng['handle'], self.cta_limit))     # engines are shared between plans
         stream = _lib.current_stream()
         hidden = pool.hidden.data_ptr() if pool.hidden_bytes else None
         mask_p = self.mask.data_ptr() if has_mask else None
@@ -385,9 +387,12 @@ class PipelinedSearchPlan:
     its own node pool and its own engine instance (activation buffers); weights are shared read-only.
     """
 
-    def __init__(self, network: MuZeroNet, config, num_trees: int, parts: int = 2) -> None:
+    def __init__(self, network: MuZeroNet, config, num_trees: int, parts: int = 2, cta_limit: int = 0) -> None:
         assert parts >= 1 and num_trees % parts == 0, 'num_trees must be a multiple of parts'
         self.network, self.config = network, config
+        # cta_limit > 0: every part's persistent tower kernel uses at most that many SMs, so the towers of the
+        # parts run SIDE BY SIDE (small batches: a tower is bound by tile dependencies between layers, not by SMs)
+        self.cta_limit = int(cta_limit)
         self.dev = next(network.parameters()).device
         self.B, self.A, self.S = int(num_trees), network.num_actions, int(config.num_simulations)
         B, A, dev, per = self.B, self.A, self.dev, int(num_trees) // parts
@@ -407,6 +412,8 @@ class PipelinedSearchPlan:
         self.parts = [SearchPlan(network, config, per, instance=i,
                                  buffers={n: getattr(self, n)[i * per:(i + 1) * per] for n in names})
                       for i in range(parts)]
+        for part in self.parts:
+            part.cta_limit = self.cta_limit
         self.pool = _PoolGroup([p.pool for p in self.parts])
         self._streams = [torch.cuda.Stream(device=dev) for _ in range(parts - 1)]
         self._graphs = {}
@@ -462,6 +469,22 @@ class PipelinedSearchPlan:
 _PLANS = {}
 
 
+def pipeline_shape(network, B: int):
+    """(parts, cta_limit) of the plan uct_search_batch builds for B trees of this network.
+
+    Conv nets with large batches (>= two 256-row tiles per SM and part): two sub-batches that each use the whole GPU,
+    so the tree kernels of one overlap the tower of the other.  Smaller batches run as one plan: giving two
+    sub-batches half of the SMs each (cta_limit = 74, towers side by side) was measured on the Atari-shaped config
+    (1024 trees, 196 tiles per layer) and changes nothing -- a tower launch there is bound by the tile dependencies
+    between layers (~1.3 tiles per CTA and layer), whatever the number of SMs."""
+    if network.kind == _lib.MZ_NET_MLP or B % 2:
+        return 1, 0
+    h, w = network.latent_hw
+    if (B // 2) * (h + 1) * (w + 1) >= 2 * 148 * 256:
+        return 2, 0
+    return 1, 0
+
+
 def _plan_for(network, config, B) -> SearchPlan:
     kb = config.known_bounds
     key = (id(network), B, config.num_simulations, bool(config.is_board_game),
@@ -474,11 +497,9 @@ def _plan_for(network, config, B) -> SearchPlan:
         if len(_PLANS) >= 4:
             _PLANS.pop(next(iter(_PLANS)))
         # large conv-net batches: two sub-batches in flight (each still fills the GPU's tile grid)
-        pipelined = False
-        if network.kind != _lib.MZ_NET_MLP and B % 2 == 0:
-            h, w = network.latent_hw
-            pipelined = (B // 2) * (h + 1) * (w + 1) >= 2 * 148 * 256        # >= two 256-row tiles per SM and part
-        _PLANS[key] = PipelinedSearchPlan(network, config, B, 2) if pipelined else SearchPlan(network, config, B)
+        parts, limit = pipeline_shape(network, B)
+        _PLANS[key] = PipelinedSearchPlan(network, config, B, parts, limit) if parts > 1 else \
+            SearchPlan(network, config, B)
     plan = _PLANS[key]
     plan.config = config
     return plan
