@@ -76,6 +76,8 @@ struct ConvParams {
   int* err;                       // dependency wait timed out (should never happen)
   int Ptot, PB, Wp, W, H, B;
   int plane_rows;                 // rows per plane of the contiguous buffers of this launch
+  int sub;                        // stride-2 layer: only rows with even (y, x) are stored, on the half-size grid
+  int out_plane_rows, out_PB, out_Wp;   // geometry of the output buffer when sub is set
   int cg;                         // input channel groups of 8 (Cin_pad / 8), even
   int N;                          // output channels (multiple of 32, <= 128)
   int relu;
@@ -374,7 +376,8 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
         // t+1 is requested at step t (the first before the MMAs even finish).
         constexpr int STEPS = 2 * NCW;
         int Pj[2];
-        bool vj[2], inr[2];
+        size_t Dj[2];                        // destination row of the output buffer
+        bool vj[2], inr[2];                  // real (non-halo) row / row that is stored at all
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           Pj[j] = tile * kTileM + j * 128 + quad * 32 + lane;
@@ -382,7 +385,16 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
           inr[j] = Pj[j] < p.Ptot;
           if (inr[j]) split_pos(Pj[j], p, b, pos, hl);
           vj[j] = !hl;
+          Dj[j] = (size_t)Pj[j];
+          if (p.sub) {
+            // stride-2 convolution (padding 1) == the stride-1 result at the even positions: store those rows
+            // on the half-size grid, drop the rest (the destination's halo is zeroed by the caller)
+            const int y = pos / p.Wp, x = pos - y * p.Wp;
+            inr[j] = vj[j] && !((y | x) & 1);
+            Dj[j] = (size_t)b * p.out_PB + (size_t)(y >> 1) * p.out_Wp + (x >> 1);
+          }
         }
+        const size_t PRo = p.sub ? (size_t)p.out_plane_rows : PR;
         const int4* resp = reinterpret_cast<const int4*>(L.residual);
         const bool has_res = resp != nullptr && !(p.ablate & 512);
         int4 ring[2][4];
@@ -414,7 +426,7 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
             for (int e = 0; e < 32; ++e) v[e] = fminf(fmaxf(v[e], 0.0f), top);
             if (inr[j] && !(p.ablate & 512)) {
 #pragma unroll
-              for (int u = 0; u < 4; ++u) outp[(size_t)(c * 4 + u) * PR + Pj[j]] = pack8(v + 8 * u);
+              for (int u = 0; u < 4; ++u) outp[(size_t)(c * 4 + u) * PRo + Dj[j]] = pack8(v + 8 * u);
             }
           }
         }
@@ -528,19 +540,23 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
 // obs f32 [B][C][H][W] -> fp16 planes [cpad/8][plane_rows][8] (zeros at halo positions and padded channels)
 __global__ void pack_obs_kernel(const float* __restrict__ obs, act_t* __restrict__ out, int B, int C, int H,
                                 int W, int cpad, int plane_rows) {
+  // one thread per (channel group, row): 8 plane reads that are each coalesced across the threads of a warp
+  // (consecutive x), one 16-byte store
   const int Wp = W + 1, PB = (H + 1) * Wp;
-  const size_t n = (size_t)B * PB * cpad;
+  const size_t rows = (size_t)B * PB, n = rows * (cpad / 8);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const int e = (int)(i % 8);
-    const size_t r = i / 8;
-    const size_t P = r % ((size_t)B * PB);
-    const int g = (int)(r / ((size_t)B * PB));
-    const int c = g * 8 + e;
+    const size_t P = i % rows;
+    const int g = (int)(i / rows);
     const int pos = (int)(P % PB), b = (int)(P / PB);
     const int y = pos / Wp, x = pos % Wp;
-    float v = 0.0f;
-    if (c < C && y < H && x < W) v = obs[(((size_t)b * C + c) * H + y) * W + x];
-    out[((size_t)g * plane_rows + P) * 8 + e] = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = g * 8 + e;
+      v[e] = (c < C && y < H && x < W) ? obs[(((size_t)b * C + c) * H + y) * W + x] : 0.0f;
+      v[e] = fminf(fmaxf(v[e], -65504.0f), 65504.0f);
+    }
+    reinterpret_cast<int4*>(out)[(size_t)g * plane_rows + P] = pack8(v);
   }
 }
 
@@ -730,89 +746,11 @@ __global__ void action_table_kernel(const float* __restrict__ w, const float* __
 
 // ---------------------------------------------------------------------------
 // MuZeroAtariNet representation extras (network.py:312-353): two stride-2 3x3 convs (no
-// BatchNorm, ReLU) and two 3x3/stride-2 average pools.  These run once per search (not per
-// simulation) and are plain SIMT kernels; the 3x3 stride-1 residual blocks between them go
-// through the tcgen05 kernel above at 48x48 / 24x24 / 12x12.
+// BatchNorm, ReLU) and two 3x3/stride-2 average pools, once per search.  The stride-2 convs run on
+// the tcgen05 kernel above as stride-1 convs whose epilogue keeps the even positions (4x the
+// flops, still 3-4x faster than a SIMT kernel); the pools are plain SIMT kernels; the residual
+// blocks between them go through the tcgen05 kernel at 48x48 / 24x24 / 12x12.
 // ---------------------------------------------------------------------------
-// out[b][oy][ox][co] = relu(sum_{ky,kx,ci} in[b][2oy+ky-1][2ox+kx-1][ci] * w[ky*3+kx][ci][co]), Co = 128.
-// Tile: 64 output positions x 128 output channels per CTA, K in chunks of 16 input channels.
-__global__ void __launch_bounds__(256) conv3x3_s2_kernel(const act_t* __restrict__ in, const act_t* __restrict__ w,
-                                                         act_t* __restrict__ out, int B, int Hi, int Wi, int Ci,
-                                                         int rows_in, int rows_out) {
-  constexpr int Co = 128, TPOS = 64, KC = 16;
-  const int Ho = Hi / 2, Wo = Wi / 2, Wpi = Wi + 1, PBi = (Hi + 1) * Wpi, Wpo = Wo + 1, PBo = (Ho + 1) * Wpo;
-  __shared__ float As[KC][TPOS + 4];
-  __shared__ float Ws[KC][Co];
-  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  const long long total = (long long)B * Ho * Wo;
-  const long long p0 = (long long)blockIdx.x * TPOS;
-  float acc[8][4];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
-  // this thread's load assignment: position lp (0..63), half hp (0/1) of the 16-channel chunk
-  const int lp = tid >> 1, hp = tid & 1;
-  const long long gp = p0 + lp;
-  int lb = 0, loy = 0, lox = 0;
-  const bool lvalid = (tid < 128) && gp < total;
-  if (lvalid) { lb = (int)(gp / (Ho * Wo)); const int r = (int)(gp % (Ho * Wo)); loy = r / Wo; lox = r % Wo; }
-  for (int tap = 0; tap < 9; ++tap) {
-    const int iy = 2 * loy + tap / 3 - 1, ix = 2 * lox + tap % 3 - 1;
-    const bool inb = lvalid && iy >= 0 && iy < Hi && ix >= 0 && ix < Wi;
-    const int4* src = reinterpret_cast<const int4*>(in) + ((size_t)lb * PBi + (size_t)(inb ? iy * Wpi + ix : 0));
-    for (int c0 = 0; c0 < Ci; c0 += KC) {
-      if (tid < 128) {
-        int4 v = make_int4(0, 0, 0, 0);
-        if (inb) v = src[(size_t)(c0 / 8 + hp) * rows_in];
-        const act2_t* h = reinterpret_cast<const act2_t*>(&v);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float2 f = __half22float2(h[u]);
-          As[hp * 8 + 2 * u][lp] = f.x;
-          As[hp * 8 + 2 * u + 1][lp] = f.y;
-        }
-      }
-      {
-        const int4 v = reinterpret_cast<const int4*>(w + ((size_t)tap * Ci + c0) * Co)[tid];   // 16 x 128 halfs
-        const act2_t* h = reinterpret_cast<const act2_t*>(&v);
-        const int k = tid >> 4, c = (tid & 15) * 8;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float2 f = __half22float2(h[u]);
-          Ws[k][c + 2 * u] = f.x;
-          Ws[k][c + 2 * u + 1] = f.y;
-        }
-      }
-      __syncthreads();
-#pragma unroll
-      for (int k = 0; k < KC; ++k) {
-        float a[8], b[4];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = As[k][ty * 8 + i];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = Ws[k][tx * 4 + j];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-      }
-      __syncthreads();
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const long long g = p0 + ty * 8 + i;
-    if (g >= total) continue;
-    const int b = (int)(g / (Ho * Wo)), r = (int)(g % (Ho * Wo)), oy = r / Wo, ox = r % Wo;
-    act_t* o = out + ((size_t)(tx / 2) * rows_out + (size_t)b * PBo + (size_t)oy * Wpo + ox) * 8 + (tx & 1) * 4;
-    uint2 pk;
-    pk.x = pack2(fminf(fmaxf(acc[i][0], 0.0f), 65504.0f), fminf(fmaxf(acc[i][1], 0.0f), 65504.0f));
-    pk.y = pack2(fminf(fmaxf(acc[i][2], 0.0f), 65504.0f), fminf(fmaxf(acc[i][3], 0.0f), 65504.0f));
-    *reinterpret_cast<uint2*>(o) = pk;
-  }
-}
-
 // AvgPool2d(3, stride 2, padding 1), count_include_pad (divide by 9), C = 128: one warp per output
 // position, 4 channels per lane.  Optionally min-max normalises over the channels (util.py:31-36) and
 // also writes the result to indexed hidden-state slots.
@@ -862,15 +800,6 @@ __global__ void __launch_bounds__(256) avgpool_kernel(const act_t* __restrict__ 
   }
 }
 
-// stride-2 conv weight [Co][Ci][3][3] fp32 -> fp16 [9][Ci_pad][Co]
-__global__ void pack_s2_kernel(const float* __restrict__ w, act_t* __restrict__ out, int Co, int Ci, int Ci_pad) {
-  const size_t total = (size_t)9 * Ci_pad * Co;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int co = (int)(i % Co), ci = (int)((i / Co) % Ci_pad), tap = (int)(i / ((size_t)Co * Ci_pad));
-    out[i] = __float2half_rn(ci < Ci ? w[(((size_t)co * Ci + ci) * 3 + tap / 3) * 3 + tap % 3] : 0.0f);
-  }
-}
-
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
@@ -898,7 +827,7 @@ struct ConvNet : NetImpl {
   ConvLayer rep0, dyn0;
   ConvLayer rep_blocks[64], dyn_blocks[64], pred_blocks[64];   // 2 per block
   // Atari representation: conv_1 (s2) -> 2 blocks @48 -> conv_2 (s2) -> 2 blocks @24 -> pool -> 2 blocks @12 -> pool
-  const act_t *s2_w1, *s2_w2;
+  ConvLayer s2_1, s2_2;             // the two stride-2 convs (no BatchNorm): stride-1 on tcgen05, even rows kept
   ConvLayer at_blocks[3][4];
   const float* tab;
   Head h_reward, h_policy, h_value;
@@ -934,6 +863,7 @@ struct ConvNet : NetImpl {
   ConvParams pend;                 // layers collected so far
   Geo pend_geo{0, 0};
   int pend_cg = 0, pend_batch = 0;
+  bool pend_sub = false;           // the (single) pending layer is a stride-2 conv writing the half-size grid
 
   int add_layer(const ConvLayer& L, const Geo& g, const act_t* in, const int32_t* in_index, bool in_slots, int batch,
                 const float* tab_, const int32_t* action, const act_t* residual, act_t* out, act_t* out_norm,
@@ -961,6 +891,12 @@ struct ConvNet : NetImpl {
     p.PB = g.PB(); p.Wp = g.Wp(); p.W = g.W; p.H = g.H; p.B = batch;
     p.Ptot = batch * p.PB;
     p.plane_rows = plane_rows_of(g, batch);
+    p.sub = pend_sub ? 1 : 0;
+    {
+      const Geo go{g.H / 2, g.W / 2};
+      p.out_plane_rows = plane_rows_of(go, batch); p.out_PB = go.PB(); p.out_Wp = go.Wp();
+    }
+    pend_sub = false;
     p.cg = cg; p.N = C; p.relu = 1;
     p.num_tiles = (p.Ptot + kTileM - 1) / kTileM;
     p.TP = tp_of(g);
@@ -1086,13 +1022,16 @@ struct ConvNet : NetImpl {
     pack_obs_kernel<<<num_sms * 8, 256, 0, st>>>(obs, xobs, batch, cfg.in_channels, Hin, Win, 16, plane_rows_of(g0, batch));
     prof_mark(-1, st);
     MZ_LAUNCH_CHECK("pack_obs_kernel");
-    // stride-2 conv: writes the real positions of the half-size grid, then the halo is zeroed
-    auto s2 = [&](const act_t* in, const act_t* w, act_t* out, const Geo& gi, const Geo& go, int Ci) -> int {
-      const long long total = (long long)batch * go.H * go.W;
+    // stride-2 conv + ReLU: one tcgen05 launch at the input resolution whose epilogue stores the even positions on
+    // the half-size grid; then the halo of that grid is zeroed
+    auto s2 = [&](const ConvLayer& L, const act_t* in, act_t* out, const Geo& gi, const Geo& go) -> int {
+      int rc2 = flush(st);
+      if (rc2) return rc2;
+      rc2 = add_layer(L, gi, in, nullptr, false, batch, nullptr, nullptr, nullptr, out, nullptr, nullptr, nullptr, st);
+      if (rc2) return rc2;
+      pend_sub = true;
+      if ((rc2 = flush(st))) return rc2;
       prof_mark(kProfPack, st);
-      conv3x3_s2_kernel<<<(unsigned)((total + 63) / 64), 256, 0, st>>>(in, w, out, batch, gi.H, gi.W, Ci,
-                                                                        plane_rows_of(gi, batch), plane_rows_of(go, batch));
-      MZ_LAUNCH_CHECK("conv3x3_s2_kernel");
       zero_halo_kernel<<<num_sms * 4, 256, 0, st>>>(out, batch, go.H, go.W, C / 8, plane_rows_of(go, batch));
       prof_mark(-1, st);
       MZ_LAUNCH_CHECK("zero_halo_kernel");
@@ -1109,12 +1048,12 @@ struct ConvNet : NetImpl {
     act_t* fin;
     int rc;
     // every writer rewrites the halo of the grid it produces, so grids of different sizes can reuse the same buffers
-    if ((rc = s2(xobs, s2_w1, b0, g0, g1, 16))) return rc;                                     // relu(conv_1)
+    if ((rc = s2(s2_1, xobs, b0, g0, g1))) return rc;                                          // relu(conv_1)
     if ((rc = tower(nullptr, at_blocks[0], 2, g1, b0, nullptr, false, nullptr, nullptr, batch, true, nullptr, nullptr,
                     nullptr, st, &fin))) return rc;
     if ((rc = flush(st))) return rc;
     act_t* nxt = (fin == b0) ? b1 : b0;
-    if ((rc = s2(fin, s2_w2, nxt, g1, g2, C))) return rc;                                      // relu(conv_2)
+    if ((rc = s2(s2_2, fin, nxt, g1, g2))) return rc;                                          // relu(conv_2)
     if ((rc = tower(nullptr, at_blocks[1], 2, g2, nxt, nullptr, false, nullptr, nullptr, batch, true, nullptr, nullptr,
                     nullptr, st, &fin))) return rc;
     if ((rc = flush(st))) return rc;
@@ -1278,13 +1217,20 @@ int conv_create(const mz_net_config& c, const float* const* w, int nw, int max_b
     if (scale_out) *scale_out = scale;
     return MZ_OK;
   };
-  auto pack_s2 = [&](int cin, const act_t** dst) -> int {
+  // conv without BatchNorm or bias (the Atari stride-2 convs): scale 1, bias 0
+  float* ones = (float*)take((size_t)N * 4);
+  float* zeros = (float*)take((size_t)N * 4);
+  {
+    std::vector<float> h1((size_t)N, 1.0f);
+    MZ_CUDA(cudaMemcpy(ones, h1.data(), (size_t)N * 4, cudaMemcpyHostToDevice));
+    MZ_CUDA(cudaMemset(zeros, 0, (size_t)N * 4));
+  }
+  auto plain_conv = [&](int cin, int cg, ConvLayer* L) -> int {
     const float* cw = next();
-    const int cpad = (cin + 15) / 16 * 16;
-    act_t* wp = (act_t*)take((size_t)9 * cpad * 128 * 2);
-    pack_s2_kernel<<<256, 256>>>(cw, wp, 128, cin, cpad);
-    MZ_LAUNCH_CHECK("pack_s2_kernel");
-    *dst = wp;
+    act_t* wp = (act_t*)take((size_t)9 * cg * N * 16);
+    pack_conv_kernel<<<256, 256>>>(cw, ones, wp, N, cin, cin, cg);
+    MZ_LAUNCH_CHECK("pack_conv_kernel");
+    L->w = wp; L->bias = zeros; L->cg = cg;
     return MZ_OK;
   };
   auto fold_head = [&](int mid, int outn, int kind, Head* h) -> int {
@@ -1310,9 +1256,9 @@ int conv_create(const mz_net_config& c, const float* const* w, int nw, int max_b
 
   if (atari) {
     // representation (network.py:312-353): conv_1, res_blocks_1 x2, conv_2, res_blocks_2 x2, res_blocks_3 x2
-    MZ_TRY(pack_s2(c.in_channels, &net->s2_w1));
+    MZ_TRY(plain_conv(c.in_channels, 2, &net->s2_1));
     for (int i = 0; i < 4; ++i) MZ_TRY(fold_conv(N, N, N / 8, &net->at_blocks[0][i], nullptr));
-    MZ_TRY(pack_s2(128, &net->s2_w2));
+    MZ_TRY(plain_conv(128, N / 8, &net->s2_2));
     for (int i = 0; i < 4; ++i) MZ_TRY(fold_conv(N, N, N / 8, &net->at_blocks[1][i], nullptr));
     for (int i = 0; i < 4; ++i) MZ_TRY(fold_conv(N, N, N / 8, &net->at_blocks[2][i], nullptr));
   } else {
@@ -1362,7 +1308,7 @@ int conv_create(const mz_net_config& c, const float* const* w, int nw, int max_b
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { set_error("weight repacking failed: %s", cudaGetErrorString(e)); delete net; return MZ_ECUDA; }
   if (net->conv_stages(net->lat, N / 8) < 2 || (!atari && net->conv_stages(net->lat, net->in_cg) < 2) ||
-      (atari && net->conv_stages(Geo{c.in_h / 2, c.in_w / 2}, N / 8) < 2)) {
+      (atari && (net->conv_stages(Geo{c.in_h / 2, c.in_w / 2}, N / 8) < 2 || net->conv_stages(Geo{c.in_h, c.in_w}, 2) < 2))) {
     set_error("conv tile does not fit shared memory (grid too wide)");
     delete net;
     return MZ_EINVAL;
