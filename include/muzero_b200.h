@@ -130,6 +130,10 @@ int mz_select(mz_pool* pool, mz_stream stream);
  * or NULL to use the pool's REWARD / VALUE scratch. */
 int mz_expand_backup(mz_pool* pool, const float* reward, const float* value, mz_stream stream);
 
+/* mz_expand_backup of this simulation followed by mz_select of the next one, in one launch (same results as
+ * the two calls; saves a launch per simulation). */
+int mz_expand_backup_select(mz_pool* pool, const float* reward, const float* value, mz_stream stream);
+
 /* Visit counts -> masked policy -> action.  Replaces mcts.py:392-407 and
  * generate_play_policy (mcts.py:250-280).
  *   mask         u8  [B,A] or NULL

@@ -49,6 +49,7 @@ PROTOTYPES = {
     'mz_search_reset': (C.c_int, [_P, _P, _P, C.c_double, _P, _P, _P, _P]),
     'mz_select': (C.c_int, [_P, _P]),
     'mz_expand_backup': (C.c_int, [_P, _P, _P, _P]),
+    'mz_expand_backup_select': (C.c_int, [_P, _P, _P, _P]),
     'mz_root_policy': (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, _P, _P]),
     'mz_net_hidden_bytes': (C.c_int, [C.POINTER(NetConfig), C.POINTER(C.c_int32)]),
     'mz_net_arena_bytes': (C.c_int, [C.POINTER(NetConfig), C.c_int32, C.POINTER(C.c_size_t)]),

@@ -282,17 +282,8 @@ __device__ __forceinline__ float puct_score(double eW, float eR, int cn, double 
 // the pb_c factor up in shared memory, and prefetches the row of the most-visited child (the one
 // pUCT most often descends into) while the float64 divisions of the current level are in flight.
 template <int NCH>
-__global__ void __launch_bounds__(kTreesPerBlock * 32)
-select_kernel(PoolDev p) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t = blockIdx.x * kTreesPerBlock + warp;
+__device__ __forceinline__ void select_tree(const PoolDev& p, const int t, const int lane, const double* sT, float* sc) {
   const int A = p.A;
-  double* sT = reinterpret_cast<double*>(smem_raw);                       // [S+2] pb_c table
-  float* sc = reinterpret_cast<float*>(sT + (p.S + 2)) + (size_t)warp * ((A + 3) & ~3);
-  for (int i = threadIdx.x; i < p.S + 2; i += blockDim.x) sT[i] = p.T[i];
-  __syncthreads();
-  if (t >= p.B) return;
-
   const Edge* tree = p.edges + (size_t)t * p.max_nodes * A;
   const double* __restrict__ P = p.prior + (size_t)t * A;
   const double lo = p.minmax[2 * t], hi = p.minmax[2 * t + 1];
@@ -446,14 +437,25 @@ select_kernel(PoolDev p) {
   }
 }
 
+template <int NCH>
+__global__ void __launch_bounds__(kTreesPerBlock * 32)
+select_kernel(PoolDev p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * kTreesPerBlock + warp;
+  double* sT = reinterpret_cast<double*>(smem_raw);                       // [S+2] pb_c table
+  float* sc = reinterpret_cast<float*>(sT + (p.S + 2)) + (size_t)warp * ((p.A + 3) & ~3);
+  for (int i = threadIdx.x; i < p.S + 2; i += blockDim.x) sT[i] = p.T[i];
+  __syncthreads();
+  if (t >= p.B) return;
+  select_tree<NCH>(p, t, lane, sT, sc);
+}
+
 // ---------------------------------------------------------------------------
 // mz_expand_backup
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTreesPerBlock * 32)
-expand_backup_kernel(PoolDev p, const float* __restrict__ reward_in, const float* __restrict__ value_in) {
-  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (t >= p.B) return;
+__device__ __forceinline__ void expand_backup_tree(const PoolDev& p, const int t, const int lane,
+                                                   const float* __restrict__ reward_in,
+                                                   const float* __restrict__ value_in) {
   const int A = p.A;
   const int depth = p.leaf_depth[t];
   const int c = p.count[t];
@@ -526,6 +528,33 @@ expand_backup_kernel(PoolDev p, const float* __restrict__ reward_in, const float
     p.node_value[(size_t)t * p.max_nodes + c] = value_in[t];
     p.leaf_depth[t] = 0;
   }
+}
+
+__global__ void __launch_bounds__(kTreesPerBlock * 32)
+expand_backup_kernel(PoolDev p, const float* __restrict__ reward_in, const float* __restrict__ value_in) {
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (t >= p.B) return;
+  expand_backup_tree(p, t, lane, reward_in, value_in);
+}
+
+// expand+backup of simulation s and select of simulation s+1 in ONE launch: both are warp-per-tree and touch only
+// their own tree, so the second half simply runs on the statistics the first half just wrote (ordered by
+// __syncwarp).  Saves a launch and a cold pass over the path per simulation -- what the MLP configurations, whose
+// whole simulation lasts ~50 us, are bound by.
+template <int NCH>
+__global__ void __launch_bounds__(kTreesPerBlock * 32)
+backup_select_kernel(PoolDev p, const float* __restrict__ reward_in, const float* __restrict__ value_in) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * kTreesPerBlock + warp;
+  double* sT = reinterpret_cast<double*>(smem_raw);
+  float* sc = reinterpret_cast<float*>(sT + (p.S + 2)) + (size_t)warp * ((p.A + 3) & ~3);
+  for (int i = threadIdx.x; i < p.S + 2; i += blockDim.x) sT[i] = p.T[i];
+  __syncthreads();
+  if (t >= p.B) return;
+  expand_backup_tree(p, t, lane, reward_in, value_in);
+  __syncwarp();
+  select_tree<NCH>(p, t, lane, sT, sc);
 }
 
 // ---------------------------------------------------------------------------
@@ -806,6 +835,11 @@ extern "C" int mz_pool_create(const mz_pool_config* cfg, const double* pb_c_tabl
     cudaFuncSetAttribute(select_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(select_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(expand_backup_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(backup_select_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(backup_select_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(backup_select_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(backup_select_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(backup_select_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaGetLastError();
   }
   if (arena_bytes < total) {
@@ -895,6 +929,29 @@ extern "C" int mz_select(mz_pool* pool, mz_stream stream) {
   else if (A <= 128) select_kernel<4><<<grid, block, smem, st>>>(d);
   else select_kernel<0><<<grid, block, smem, st>>>(d);
   MZ_LAUNCH_CHECK("select_kernel");
+  pool->selected = 1;
+  return MZ_OK;
+}
+
+extern "C" int mz_expand_backup_select(mz_pool* pool, const float* reward, const float* value, mz_stream stream) {
+  MZ_CHECK_ARG(pool, "NULL argument");
+  if (!pool->selected) {
+    set_error("mz_expand_backup_select called without a preceding mz_select");
+    return MZ_ESTATE;
+  }
+  const int A = pool->A;
+  const size_t smem = (size_t)(pool->S + 2) * 8 + (A > 128 ? (size_t)kTreesPerBlock * ((A + 3) & ~3) * sizeof(float) : 0);
+  const dim3 grid(tree_blocks(pool->B)), block(kTreesPerBlock * 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  const PoolDev d = dev_of(pool);
+  const float* r = reward ? reward : d.reward;
+  const float* v = value ? value : d.value;
+  if (A <= 32) backup_select_kernel<1><<<grid, block, smem, st>>>(d, r, v);
+  else if (A <= 64) backup_select_kernel<2><<<grid, block, smem, st>>>(d, r, v);
+  else if (A <= 96) backup_select_kernel<3><<<grid, block, smem, st>>>(d, r, v);
+  else if (A <= 128) backup_select_kernel<4><<<grid, block, smem, st>>>(d, r, v);
+  else backup_select_kernel<0><<<grid, block, smem, st>>>(d, r, v);
+  MZ_LAUNCH_CHECK("backup_select_kernel");
   pool->selected = 1;
   return MZ_OK;
 }
