@@ -686,7 +686,7 @@ __global__ void bn_fold_kernel(const float* g, const float* beta, const float* m
   }
 }
 
-// conv weight [N][cin_total][3][3] (first `cin` input channels) * scale[n] -> packed bf16
+// conv weight [N][cin_total][3][3] (first `cin` input channels) * scale[n] -> packed fp16
 // [9 taps][chunks][chunk_g][N][8]
 __global__ void pack_conv_kernel(const float* __restrict__ w, const float* __restrict__ scale,
                                  act_t* __restrict__ out, int N, int cin, int cin_total, int cg) {

@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_recurrent_tc_kernel(const _
         for (int ks = 0; ks < ksteps; ++ks) {
           const uint64_t ad = smem_desc(a_addr + (uint32_t)ks * 4096u, 2048, 128);
           const uint64_t bd = smem_desc(b_addr + (uint32_t)ks * 32u * N, N * 16, 128);
-          mma_bf16(tmem + dcol, ad, bd, idesc, (accumulate || ks > 0) ? 1u : 0u);
+          mma_f16(tmem + dcol, ad, bd, idesc, (accumulate || ks > 0) ? 1u : 0u);
         }
         commit(&w_empty[s]);
         commit(bar_mma);

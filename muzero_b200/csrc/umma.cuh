@@ -4,7 +4,7 @@
 //
 // Operand layout used throughout this library: K-major, NO swizzle ("interleave").
 // A tile is a set of 8x16-byte "core matrices": 8 consecutive rows (M or N index)
-// of 8 bf16 (16 bytes) each, rows 16 bytes apart.  The descriptor carries
+// of 8 16-bit elements (16 bytes) each, rows 16 bytes apart.  The descriptor carries
 //   SBO = byte distance between consecutive 8-row groups        (M/N direction)
 //   LBO = byte distance between consecutive 16-byte K chunks    (K direction)
 // and a start address that only needs 16-byte alignment, which is what lets a
@@ -100,7 +100,7 @@ __host__ __device__ constexpr uint32_t instr_desc_f16(uint32_t M, uint32_t N) {
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread on behalf of the CTA
-__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                          uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -110,7 +110,7 @@ __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64
       : "memory");
 }
 // The same, executed by a WHOLE converged warp: one lane is elected inside the asm statement.  With the
-// election here (instead of an `if (lane == 0)` around mma_bf16) ptxas emits a predicated UTCHMMA with no
+// election here (instead of an `if (lane == 0)` around mma_f16) ptxas emits a predicated UTCHMMA with no
 // per-MMA convergence loop (ELECT / R2UR.BROADCAST / BRA.U.ANY), which otherwise costs ~100 cycles per MMA
 // on the single issuing warp -- more than the 64 cycles an M128 N128 K16 MMA lasts.
 __device__ __forceinline__ void mma_f16_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,

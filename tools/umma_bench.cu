@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(384) bench(int N, int a_rows, int b_rows, int 
         for (int ks = 0; ks < 4; ++ks) {
           const uint64_t a = at + (uint64_t)(2 * ks * a_rows), b = bt + (uint64_t)(2 * ks * b_rows);
           if (kTwo) { mma2(tm, a, b, idesc, 1); mma2(tm + 256, a + 128, b, idesc, 1); }
-          else { mma_bf16(tm, a, b, idesc, 1); mma_bf16(tm + 256, a + 128, b, idesc, 1); }
+          else { mma_f16(tm, a, b, idesc, 1); mma_f16(tm + 256, a + 128, b, idesc, 1); }
         }
       }
       if (kTwo)

@@ -57,8 +57,8 @@ __global__ void __launch_bounds__(128) bench(int iters, int a_rows, long long* o
             uint32_t a_lo = a0 + (uint32_t)((tap / 3 - 1) * 10 + (tap % 3 - 1));
             uint32_t b_lo = b0;
             for (int ks = 0; ks < 4; ++ks) {
-              mma_bf16(tm, d64(a_lo, a_hi), d64(b_lo, b_hi), idesc, 1);
-              mma_bf16(tm + 128, d64(a_lo + 128, a_hi), d64(b_lo, b_hi), idesc, 1);
+              mma_f16(tm, d64(a_lo, a_hi), d64(b_lo, b_hi), idesc, 1);
+              mma_f16(tm + 128, d64(a_lo + 128, a_hi), d64(b_lo, b_hi), idesc, 1);
               a_lo += 2 * a_rows; b_lo += 256;
             }
           }

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(128) probe(const __nv_bfloat16* A, const __nv_
       uint64_t da, db;
       if (mode & 1) { da = smem_desc(a0, 128, AROWS * 16); db = smem_desc(b0, 128, N * 16); }
       else          { da = smem_desc(a0, AROWS * 16, 128); db = smem_desc(b0, N * 16, 128); }
-      mma_bf16(tm, da, db, idesc, k > 0);
+      mma_f16(tm, da, db, idesc, k > 0);
     }
     commit(&bar_mma);
   }
