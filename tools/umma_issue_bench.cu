@@ -10,7 +10,7 @@
 #include "../muzero_b200/csrc/umma.cuh"
 using namespace mz::umma;
 
-__device__ __forceinline__ void mma_elect(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+__device__ __forceinline__ void bench_mma_elect(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p, q;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -19,7 +19,7 @@ __device__ __forceinline__ void mma_elect(uint32_t d, uint64_t a, uint64_t b, ui
       ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc)
       : "memory");
 }
-__device__ __forceinline__ void commit_elect(uint64_t* bar) {
+__device__ __forceinline__ void bench_commit_elect(uint64_t* bar) {
   asm volatile(
       "{\n\t.reg .pred q;\n\t"
       "elect.sync _|q, 0xffffffff;\n\t"
@@ -80,13 +80,13 @@ __global__ void __launch_bounds__(128) bench(int iters, int a_rows, long long* o
           uint32_t b_lo = b0;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            mma_elect(tm, d64(a_lo, a_hi), d64(b_lo, b_hi), idesc, 1);
-            mma_elect(tm + 128, d64(a_lo + 128, a_hi), d64(b_lo, b_hi), idesc, 1);
+            bench_mma_elect(tm, d64(a_lo, a_hi), d64(b_lo, b_hi), idesc, 1);
+            bench_mma_elect(tm + 128, d64(a_lo + 128, a_hi), d64(b_lo, b_hi), idesc, 1);
             a_lo += arows2; b_lo += 256;
           }
         }
       }
-      commit_elect(&bar);
+      bench_commit_elect(&bar);
       mbar_wait(&bar, 0);
       if (lane == 0) out[blockIdx.x] = clock64() - t0;
     }
