@@ -190,7 +190,10 @@ class BoardSelfPlay:
         """Search + one move in every game; returns the samples of the games that just ended (or None)."""
         import muzero_b200 as mz
         env, cfg, G = self.env, self.cfg, self.env.G
-        temps = np.array([cfg.visit_softmax_temperature_fn(int(s), self.train_steps) for s in self.steps], np.float64)
+        # config.visit_softmax_temperature_fn(steps, train_steps) per game (pipeline.py:100): one call per distinct
+        # move number instead of one per game
+        uniq, inv = np.unique(self.steps, return_inverse=True)
+        temps = np.array([cfg.visit_softmax_temperature_fn(int(s), self.train_steps) for s in uniq], np.float64)[inv]
         cur = (1 + (self.steps % 2)).astype(np.int32)                   # black moves first, players alternate
         action, pi, root_value = mz.uct_search_batch(env.obs, self.net, cfg, temps, env.actions_mask, cur, 3 - cur)
         # the reference's actor dies with ValueError('probabilities contain NaN') when every visit of a search went
