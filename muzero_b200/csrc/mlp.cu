@@ -314,6 +314,7 @@ struct MlpTcParams {
   uint32_t blk_off[kTcMaxBlocks], blk_bytes[kTcMaxBlocks];
   int nblk, nnets, chunks;
   int P, A, Apad, Sr, Sv;
+  int tab_in_smem;                    // the [A][P] action table fits beside the tiles in shared memory
   const float* tabA;                  // [A][P]: first-layer weight column of each action (network.py:191-193)
   const float* b1[4];
   const float* b2[4];
@@ -357,7 +358,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_recurrent_tc_kernel(const _
   uint64_t* w_empty = w_full + kTcSlots;
   uint64_t* bar_mma = w_empty + kTcSlots;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar_mma + 1);
+  float* sB1 = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_holder + 4) + 15) & ~(uintptr_t)15);   // [4][P] first-layer biases
+  float* sTab = sB1 + 4 * p.P;                                      // [A][P] action columns (when they fit)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // first-layer biases and the action table are read by every row of every tile: stage them once per CTA
+  // (from global they cost an exposed L2 round trip per 32-column chunk of every epilogue)
+  for (int i = tid; i < p.nnets * p.P; i += kTcThreads) sB1[i] = p.b1[i / p.P][i % p.P];
+  if (p.tab_in_smem)
+    for (int i = tid; i < p.A * p.P; i += kTcThreads) sTab[i] = p.tabA[i];
 
   if (tid == 0) {
     for (int s = 0; s < kTcSlots; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
@@ -437,8 +445,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_recurrent_tc_kernel(const _
       for (int net = 0; net < p.nnets; ++net) {
         const uint32_t a_in = net == 0 ? sIn_a : (net == 1 ? sRaw_a : sNorm_a);
         const uint32_t N2 = net == 0 ? 64u : (net == 3 ? (uint32_t)p.Apad : 32u);
-        const float* b1 = p.b1[net];
-        const float* tab = net == 0 ? p.tabA + (size_t)act * p.P : nullptr;
+        const float* b1 = sB1 + net * p.P;
+        const float* tab = net == 0 ? (p.tab_in_smem ? sTab : p.tabA) + (size_t)act * p.P : nullptr;
         for (int c = 0; c < p.chunks; ++c) {
           mma_group(a_in, 4, 0u, 256u, false);                        // D1 = A_in . W1c^T
           // epilogue 1: bias (+ action column) + ReLU -> fp16 hidden chunk in shared memory
@@ -451,14 +459,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_recurrent_tc_kernel(const _
             float v[32];
 #pragma unroll
             for (int e = 0; e < 32; e += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(b1 + col0 + e));
+              const float4 b4 = *reinterpret_cast<const float4*>(b1 + col0 + e);
               v[e] = __uint_as_float(r[e]) + b4.x; v[e + 1] = __uint_as_float(r[e + 1]) + b4.y;
               v[e + 2] = __uint_as_float(r[e + 2]) + b4.z; v[e + 3] = __uint_as_float(r[e + 3]) + b4.w;
             }
             if (tab) {
 #pragma unroll
               for (int e = 0; e < 32; e += 4) {
-                const float4 t4 = __ldg(reinterpret_cast<const float4*>(tab + col0 + e));
+                const float4 t4 = *reinterpret_cast<const float4*>(tab + col0 + e);
                 v[e] += t4.x; v[e + 1] += t4.y; v[e + 2] += t4.z; v[e + 3] += t4.w;
               }
             }
@@ -736,7 +744,9 @@ int mlp_create(const mz_net_config& c, const float* const* w, int nw, void* aren
       q.tabA = tab;
       MZ_CUDA(cudaDeviceSynchronize());
       if ((size_t)(p - (char*)arena) > arena_bytes) { set_error("internal: MLP arena overrun"); delete net; return MZ_ENOMEM; }
-      net->tc_smem = 3 * 16384 + 65536 + (size_t)kTcSlots * kTcSlotBytes + 256;
+      net->tc_smem = 3 * 16384 + 65536 + (size_t)kTcSlots * kTcSlotBytes + 256 + (size_t)4 * P * 4;
+      q.tab_in_smem = net->tc_smem + (size_t)A * P * 4 <= 227 * 1024 ? 1 : 0;
+      if (q.tab_in_smem) net->tc_smem += (size_t)A * P * 4;
       int dev = 0;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&net->num_sms, cudaDevAttrMultiProcessorCount, dev);
