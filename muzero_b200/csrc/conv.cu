@@ -128,6 +128,16 @@ __device__ __forceinline__ void finish32(const uint32_t (&r)[32], const float* s
     }
   }
 }
+// ReLU + fp16 saturation + pack of two floats in ONE conversion (cvt.rn.relu.satfinite.f16x2.f32 d, hi, lo)
+__device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ int4 pack8_relu(const float* v) {
+  return make_int4((int)pack2_relu(v[0], v[1]), (int)pack2_relu(v[2], v[3]), (int)pack2_relu(v[4], v[5]),
+                   (int)pack2_relu(v[6], v[7]));
+}
 __device__ __forceinline__ int4 pack8(const float* v) {
   return make_int4((int)pack2(v[0], v[1]), (int)pack2(v[2], v[3]), (int)pack2(v[4], v[5]), (int)pack2(v[6], v[7]));
 }
@@ -153,8 +163,8 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
   uint64_t* mma_done = a_full + 2;         // [2]
   uint64_t* acc_empty = mma_done + 2;      // [2]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* s_bias = reinterpret_cast<float*>(tmem_holder + 4);            // [N], 16-byte aligned
-  float2* s_mm = reinterpret_cast<float2*>(s_bias + p.N);               // [2][128] partial (min, max) per row
+  float* s_bias = reinterpret_cast<float*>(tmem_holder + 4);            // [4][N] bias of layer l in slot l & 3, 16-byte aligned
+  float2* s_mm = reinterpret_cast<float2*>(s_bias + 4 * p.N);           // [2][128] partial (min, max) per row
 
   if (tid == 0) {
     for (uint32_t s = 0; s < kStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 2); }
@@ -276,7 +286,7 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
     const int cg = p.cg;
     long long t_wait = 0, t_dep = 0;
     const long long t_begin = clock64();
-    int i = 0;
+    int i = 0, bias_layer = -1;
     for (int l = 0; l < p.num_layers; ++l)
     for (int tile = first_tile(l); tile < p.num_tiles; tile += G, ++i) {
       const LayerDesc& L = p.L[l];
@@ -305,6 +315,13 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
       // the buffer was last read by the MMAs of tile i-2
       if (i >= 2) mbar_wait(&mma_done[buf], (uint32_t)(((i - 2) >> 1) & 1));
       if (dbg) t_wait += clock64() - tw2;
+      // this layer's bias vector -> slot l & 3 (the epilogue is at most two items behind, so a slot is not reused
+      // while it is read; the write is ordered before the epilogue's reads by a_full -> MMA -> mma_done)
+      if (l != bias_layer) {
+        for (int c4 = lane; c4 * 4 < kN; c4 += 32)
+          *reinterpret_cast<float4*>(s_bias + (l & 3) * kN + c4 * 4) = __ldg(reinterpret_cast<const float4*>(L.bias) + c4);
+        bias_layer = l;
+      }
       const uint32_t dst0 = smem_u32(sA) + (uint32_t)buf * a_bytes;
       const int lo = r0 > 0 ? r0 : 0;
       int hi = L.in_slots ? p.Ptot : p.plane_rows;
@@ -356,24 +373,19 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
     const size_t PR = (size_t)p.plane_rows;
     long long t_wait = 0;
     const long long t_begin = clock64();
-    int k = 0, bias_layer = -1;
+    int k = 0;
     for (int l = 0; l < p.num_layers; ++l)
     for (int tile = first_tile(l); tile < p.num_tiles; tile += G, ++k) {
       const LayerDesc& L = p.L[l];
       const bool norm = (L.out_norm != nullptr) || (L.out_slots != nullptr);
       const int buf = k & 1;
-      if (bias_layer != l) {               // new layer: swap the bias vector in shared memory
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (et < kN) s_bias[et] = L.bias[et];
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        bias_layer = l;
-      }
+      const float* s_bias_l = s_bias + (l & 3) * kN;
       const bool fast = !norm && L.tab == nullptr && L.out != nullptr;
       const uint32_t tbase = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256);
       if (fast) {
         // Plain conv + bias (+ residual) + ReLU (30 of the 33 convs of a recurrent inference).  The steps of
         // this warp (2 row halves x NCW column chunks) form one unrolled sequence and the residual of step
-        // t+1 is requested at step t (the first before the MMAs even finish).
+        // t+2 is requested at step t (the first two before the MMAs even finish).
         constexpr int STEPS = 2 * NCW;
         int Pj[2];
         size_t Dj[2];                        // destination row of the output buffer
@@ -397,14 +409,17 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
         const size_t PRo = p.sub ? (size_t)p.out_plane_rows : PR;
         const int4* resp = reinterpret_cast<const int4*>(L.residual);
         const bool has_res = resp != nullptr && !(p.ablate & 512);
-        int4 ring[2][4];
+        int4 ring[3][4];
         auto fetch = [&](int t, int4 (&dst)[4]) {
           const int j = t / NCW, g0 = (chalf * NCW + t % NCW) * 4;
           const bool ld = has_res && vj[j];
 #pragma unroll
           for (int u = 0; u < 4; ++u) dst[u] = ld ? __ldcg(resp + (size_t)(g0 + u) * PR + Pj[j]) : make_int4(0, 0, 0, 0);
         };
-        if (has_cols) fetch(0, ring[0]);
+        if (has_cols) {
+          fetch(0, ring[0]);
+          if (STEPS > 1) fetch(1, ring[1]);
+        }
         const long long tw = dbg ? clock64() : 0;
         mbar_wait(&mma_done[buf], (uint32_t)((k >> 1) & 1));
         if (dbg) t_wait += clock64() - tw;
@@ -414,19 +429,20 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
 #pragma unroll
           for (int t = 0; t < STEPS; ++t) {
             const int j = t / NCW, c = chalf * NCW + t % NCW, c0 = c * 32;
-            if (t + 1 < STEPS) fetch(t + 1, ring[(t + 1) & 1]);
+            if (t + 2 < STEPS) fetch(t + 2, ring[(t + 2) % 3]);
             uint32_t r[32];
             tmem_ld32(tbase + (uint32_t)(j * 128 + c0), r);
             tmem_ld_wait();
             float v[32];
-            finish32(r, s_bias + c0, ring[t & 1], v);
-            // ReLU (every conv of these nets is followed by one) and fp16 saturation in one clamp; halo rows are ZERO
-            const float top = vj[j] ? 65504.0f : 0.0f;
-#pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = fminf(fmaxf(v[e], 0.0f), top);
+            finish32(r, s_bias_l + c0, ring[t % 3], v);
+            // ReLU (every conv of these nets is followed by one) and fp16 saturation ride on the fp32 -> fp16
+            // conversion; halo rows are stored as ZERO
             if (inr[j] && !(p.ablate & 512)) {
 #pragma unroll
-              for (int u = 0; u < 4; ++u) outp[(size_t)(c * 4 + u) * PRo + Dj[j]] = pack8(v + 8 * u);
+              for (int u = 0; u < 4; ++u) {
+                const int4 o4 = pack8_relu(v + 8 * u);
+                outp[(size_t)(c * 4 + u) * PRo + Dj[j]] = vj[j] ? o4 : make_int4(0, 0, 0, 0);
+              }
             }
           }
         }
@@ -454,7 +470,7 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
             uint32_t r[32];
             tmem_ld32(tbase + (uint32_t)(j * 128 + c * 32), r);
             tmem_ld_wait();
-            finish32(r, s_bias + c * 32, rres, v);
+            finish32(r, s_bias_l + c * 32, rres, v);
             if (tab) {
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
@@ -518,8 +534,9 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[buf]);
-      if (p.flags) {                       // publish the tile: stores fenced by every thread, then one release
-        __threadfence();
+      if (p.flags) {
+        // publish the tile: the barrier orders every epilogue thread's stores before thread 0, whose gpu-scope
+        // release is cumulative over them (the CUTLASS semaphore pattern) -- no per-thread MEMBAR on the chain
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (et == 0) st_release(p.flags + (size_t)l * p.num_tiles + tile, 1u);
       }
@@ -844,7 +861,7 @@ struct ConvNet : NetImpl {
   size_t conv_fixed_smem(const Geo& g, int cg) const {
     const int TP = tp_of(g);
     size_t a = (((size_t)2 * cg * TP * 16) + 127) & ~(size_t)127;
-    return a + (2 * kMaxStages + 6) * 8 + 16 + (size_t)C * 4 + 2048 + 64;
+    return a + (2 * kMaxStages + 6) * 8 + 16 + (size_t)4 * C * 4 + 2048 + 64;
   }
   int conv_stages(const Geo& g, int cg) const {
     const int chunk_g = cg < 8 ? cg : 8;
