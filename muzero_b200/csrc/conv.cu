@@ -142,8 +142,14 @@ __device__ __forceinline__ int4 pack8(const float* v) {
   return make_int4((int)pack2(v[0], v[1]), (int)pack2(v[2], v[3]), (int)pack2(v[4], v[5]), (int)pack2(v[6], v[7]));
 }
 
-template <int kN>
+// kRows = 256: a tile is two 128-row accumulators, one per MMA warp (the throughput configuration).
+// kRows = 128: a tile is ONE 128-row block whose K range is split between the two MMA warps (weight stages
+// alternate between them; each accumulates into its own TMEM accumulator and the epilogue adds the two in a
+// fixed order, so results stay deterministic).  Half the MMA time per tile: for launches with few tiles per SM
+// the layer-to-layer dependency chain (load -> MMA -> epilogue -> publish) is the bound, not throughput.
+template <int kN, int kRows>
 __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvParams p) {
+  constexpr bool kSplitK = (kRows == 128);
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int halo = p.Wp + 1;
@@ -167,7 +173,7 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
   float2* s_mm = reinterpret_cast<float2*>(s_bias + 4 * p.N);           // [2][128] partial (min, max) per row
 
   if (tid == 0) {
-    for (uint32_t s = 0; s < kStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 2); }
+    for (uint32_t s = 0; s < kStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], kSplitK ? 1 : 2); }
     for (int b = 0; b < 2; ++b) { mbar_init(&a_full[b], 1); mbar_init(&mma_done[b], 2); mbar_init(&acc_empty[b], kEpiThreads); }
     fence_mbar_init();
   }
@@ -239,14 +245,21 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
       mbar_wait(&a_full[buf], uph);
       if (dbg) t_a += clock64() - tw2;
       tc_fence_after();
-      const uint32_t a_tile = a_lo0 + sA16 + (uint32_t)buf * (a_bytes >> 4) + (uint32_t)halo + 128u * mhalf;
+      const uint32_t a_tile = a_lo0 + sA16 + (uint32_t)buf * (a_bytes >> 4) + (uint32_t)halo + (kSplitK ? 0u : 128u * mhalf);
       const uint32_t dacc = tmem + (uint32_t)(buf * 256) + 128u * mhalf;
       uint32_t acc = 0;
+      uint32_t stage_no = 0;                    // weight stage within the tile (split-K: stage s belongs to warp s & 1)
       int shift = -p.Wp - 1;                    // tap (0,0); then +1, +1, +(Wp-2), ...
       for (int tap = 0; tap < 9; ++tap) {
         uint32_t a_lo = a_tile + (uint32_t)shift;        // wraps correctly: shift may be negative
         shift += (tap == 2 || tap == 5) ? p.Wp - 2 : 1;
-        for (int ch = 0; ch < chunks_tap; ++ch) {
+        for (int ch = 0; ch < chunks_tap; ++ch, ++stage_no) {
+          if (kSplitK && (stage_no & 1u) != mhalf) {     // the other warp's stage: just step the ring and the K offset
+            a_lo += (uint32_t)ksteps * a_kstep;
+            ++st; b_slot += stage16;
+            if (st == kStages) { st = 0; st_ph ^= 1; b_slot = b_first; }
+            continue;
+          }
           mbar_wait(&w_full[st], st_ph);
           tc_fence_after();
           uint32_t b_lo = b_slot;
@@ -291,7 +304,7 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
     for (int tile = first_tile(l); tile < p.num_tiles; tile += G, ++i) {
       const LayerDesc& L = p.L[l];
       const int buf = i & 1;
-      const int r0 = tile * kTileM - halo, r1 = r0 + kTileM + 2 * halo;     // tile rows [r0, r1)
+      const int r0 = tile * kRows - halo, r1 = r0 + kRows + 2 * halo;       // tile rows [r0, r1)
       // dataflow dependency: the three tiles of the previous layer whose rows this tile reads
       long long tw = dbg ? clock64() : 0;
       if (L.dep) {
@@ -386,13 +399,14 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
         // Plain conv + bias (+ residual) + ReLU (30 of the 33 convs of a recurrent inference).  The steps of
         // this warp (2 row halves x NCW column chunks) form one unrolled sequence and the residual of step
         // t+2 is requested at step t (the first two before the MMAs even finish).
-        constexpr int STEPS = 2 * NCW;
+        constexpr int NJ = kRows / 128;      // 128-row blocks of a tile
+        constexpr int STEPS = NJ * NCW;
         int Pj[2];
         size_t Dj[2];                        // destination row of the output buffer
         bool vj[2], inr[2];                  // real (non-halo) row / row that is stored at all
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          Pj[j] = tile * kTileM + j * 128 + quad * 32 + lane;
+        for (int j = 0; j < NJ; ++j) {
+          Pj[j] = tile * kRows + j * 128 + quad * 32 + lane;
           int b = 0, pos = 0; bool hl = true;
           inr[j] = Pj[j] < p.Ptot;
           if (inr[j]) split_pos(Pj[j], p, b, pos, hl);
@@ -432,7 +446,15 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
             if (t + 2 < STEPS) fetch(t + 2, ring[(t + 2) % 3]);
             uint32_t r[32];
             tmem_ld32(tbase + (uint32_t)(j * 128 + c0), r);
-            tmem_ld_wait();
+            if (kSplitK) {                     // second half of the K range lives in the other accumulator
+              uint32_t r2[32];
+              tmem_ld32(tbase + (uint32_t)(128 + c0), r2);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__fadd_rn(__uint_as_float(r[e]), __uint_as_float(r2[e])));
+            } else {
+              tmem_ld_wait();
+            }
             float v[32];
             finish32(r, s_bias_l + c0, ring[t % 3], v);
             // ReLU (every conv of these nets is followed by one) and fp16 saturation ride on the fp32 -> fp16
@@ -452,8 +474,8 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
         if (dbg) t_wait += clock64() - tw;
         tc_fence_after();
 #pragma unroll 1
-        for (int j = 0; j < 2 && !(p.ablate & 1); ++j) {
-          const int P = tile * kTileM + j * 128 + quad * 32 + lane;
+        for (int j = 0; j < kRows / 128 && !(p.ablate & 1); ++j) {
+          const int P = tile * kRows + j * 128 + quad * 32 + lane;
           int b = 0, pos = 0; bool hl = true;
           const bool inrange = P < p.Ptot;
           if (inrange) split_pos(P, p, b, pos, hl);
@@ -469,7 +491,15 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
             for (int u = 0; u < 4; ++u) rres[u] = resp ? __ldcg(resp + (size_t)(c * 4 + u) * PR) : make_int4(0, 0, 0, 0);
             uint32_t r[32];
             tmem_ld32(tbase + (uint32_t)(j * 128 + c * 32), r);
-            tmem_ld_wait();
+            if (kSplitK) {
+              uint32_t r2[32];
+              tmem_ld32(tbase + (uint32_t)(128 + c * 32), r2);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__fadd_rn(__uint_as_float(r[e]), __uint_as_float(r2[e])));
+            } else {
+              tmem_ld_wait();
+            }
             finish32(r, s_bias_l + c * 32, rres, v);
             if (tab) {
 #pragma unroll
@@ -853,27 +883,27 @@ struct ConvNet : NetImpl {
   size_t flags_cap;
   int* err_flag;
 
-  static int tp_of(const Geo& g) { return (kTileM + 2 * (g.Wp() + 1)) | 1; }
+  static int tp_of(const Geo& g, int rows = kTileM) { return (rows + 2 * (g.Wp() + 1)) | 1; }
   // rows of one channel-group plane of a contiguous activation buffer holding `batch` boards of grid g
   static int plane_rows_of(const Geo& g, int batch) {
     return (batch * g.PB() + kTileM - 1) / kTileM * kTileM + kPlaneSlack;
   }
-  size_t conv_fixed_smem(const Geo& g, int cg) const {
-    const int TP = tp_of(g);
+  size_t conv_fixed_smem(const Geo& g, int cg, int rows = kTileM) const {
+    const int TP = tp_of(g, rows);
     size_t a = (((size_t)2 * cg * TP * 16) + 127) & ~(size_t)127;
     return a + (2 * kMaxStages + 6) * 8 + 16 + (size_t)4 * C * 4 + 2048 + 64;
   }
-  int conv_stages(const Geo& g, int cg) const {
+  int conv_stages(const Geo& g, int cg, int rows = kTileM) const {
     const int chunk_g = cg < 8 ? cg : 8;
     const size_t stage = (size_t)chunk_g * C * 16;
-    const size_t fixed = conv_fixed_smem(g, cg);
+    const size_t fixed = conv_fixed_smem(g, cg, rows);
     if (fixed + 2 * stage > 227 * 1024) return 0;
     int s = (int)((227 * 1024 - fixed) / stage);
     return s > kMaxStages ? kMaxStages : s;
   }
-  size_t conv_smem(const Geo& g, int cg) const {
+  size_t conv_smem(const Geo& g, int cg, int rows = kTileM) const {
     const int chunk_g = cg < 8 ? cg : 8;
-    return conv_fixed_smem(g, cg) + (size_t)conv_stages(g, cg) * chunk_g * C * 16;
+    return conv_fixed_smem(g, cg, rows) + (size_t)conv_stages(g, cg, rows) * chunk_g * C * 16;
   }
 
   // ---- layer batching: consecutive convs on the same grid become ONE dataflow launch ----
@@ -915,12 +945,19 @@ struct ConvNet : NetImpl {
     }
     pend_sub = false;
     p.cg = cg; p.N = C; p.relu = 1;
-    p.num_tiles = (p.Ptot + kTileM - 1) / kTileM;
-    p.TP = tp_of(g);
-    p.stages = conv_stages(g, cg);
+    // Few tiles per SM (small batches / small grids): a multi-layer launch is bound by the dependency chain between
+    // layers, so use 128-row tiles whose K range is split over the two MMA warps (half the MMA time per tile).
+    // Otherwise 256-row tiles (half the weight traffic per row).
+    const char* force_env = getenv("MZ_CONV_TILE_ROWS");          // tests force either variant at any size
+    const int force_rows = force_env ? atoi(force_env) : 0;
+    int rows = (nl > 1 && (p.Ptot + kTileM - 1) / kTileM < 2 * num_sms) ? 128 : kTileM;
+    if (force_rows == 128 || force_rows == 256) rows = force_rows;
+    p.num_tiles = (p.Ptot + rows - 1) / rows;
+    p.TP = tp_of(g, rows);
+    p.stages = conv_stages(g, cg, rows);
     p.err = err_flag;
     if (p.stages < 2) { pend.num_layers = 0; set_error("conv tile does not fit shared memory for a %dx%d grid", g.H, g.W); return MZ_EINVAL; }
-    const size_t smem = conv_smem(g, cg);
+    const size_t smem = conv_smem(g, cg, rows);
     const int sm_cap = (cta_limit > 0 && cta_limit < num_sms) ? cta_limit : num_sms;
     const int grid = p.num_tiles < sm_cap ? p.num_tiles : sm_cap;
     p.rot = nl > 1 ? p.num_tiles % grid : 0;
@@ -948,9 +985,15 @@ struct ConvNet : NetImpl {
       at[0].val.cooperative = nl > 1 ? 1 : 0;
       lc.attrs = at; lc.numAttrs = 1;
       cudaError_t le;
-      if (C == 128) le = cudaLaunchKernelEx(&lc, conv3x3_kernel<128>, p);
-      else if (C == 64) le = cudaLaunchKernelEx(&lc, conv3x3_kernel<64>, p);
-      else le = cudaLaunchKernelEx(&lc, conv3x3_kernel<32>, p);
+      if (rows == 256) {
+        if (C == 128) le = cudaLaunchKernelEx(&lc, conv3x3_kernel<128, 256>, p);
+        else if (C == 64) le = cudaLaunchKernelEx(&lc, conv3x3_kernel<64, 256>, p);
+        else le = cudaLaunchKernelEx(&lc, conv3x3_kernel<32, 256>, p);
+      } else {
+        if (C == 128) le = cudaLaunchKernelEx(&lc, conv3x3_kernel<128, 128>, p);
+        else if (C == 64) le = cudaLaunchKernelEx(&lc, conv3x3_kernel<64, 128>, p);
+        else le = cudaLaunchKernelEx(&lc, conv3x3_kernel<32, 128>, p);
+      }
       if (le != cudaSuccess) { pend.num_layers = 0; set_error("conv3x3_kernel launch: %s", cudaGetErrorString(le)); cudaGetLastError(); return MZ_ECUDA; }
     }
     prof_mark(-1, st);
@@ -1185,7 +1228,7 @@ int conv_arena_bytes(const mz_net_config& c, int max_batch, size_t* bytes) {
   t += align_up(rows(obs_pb) * (atari ? 2 : obs_cg(c.in_channels)) * 16, 256);           // packed observations
   t += 3 * align_up(rows(big_pb) * N * 2, 256);                                          // b0..b2
   t += 2 * align_up(rows(PB) * N * 2, 256);                                              // b3, b4 (latent grid only)
-  t += align_up((size_t)kMaxLayers * (((size_t)max_batch * big_pb + kTileM - 1) / kTileM) * 4, 256) + 256;   // tile flags
+  t += align_up((size_t)kMaxLayers * (((size_t)max_batch * big_pb + 127) / 128) * 4, 256) + 256;   // tile flags (128-row tiles)
   *bytes = t + 8192;
   return MZ_OK;
 }
@@ -1312,7 +1355,7 @@ int conv_create(const mz_net_config& c, const float* const* w, int nw, int max_b
   net->b2 = (act_t*)take(act_bytes);
   net->b3 = (act_t*)take(rows(PB) * N * 2);
   net->b4 = (act_t*)take(rows(PB) * N * 2);
-  net->flags_cap = (size_t)kMaxLayers * (((size_t)max_batch * big_pb + kTileM - 1) / kTileM);
+  net->flags_cap = (size_t)kMaxLayers * (((size_t)max_batch * big_pb + 127) / 128);
   net->flags = (unsigned*)take(net->flags_cap * 4);
   net->err_flag = (int*)take(256);
   cudaMemset(net->err_flag, 0, 4);
@@ -1331,9 +1374,12 @@ int conv_create(const mz_net_config& c, const float* const* w, int nw, int max_b
     return MZ_EINVAL;
   }
   const int smem_max = 227 * 1024;
-  e = cudaFuncSetAttribute(conv3x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+  e = cudaFuncSetAttribute(conv3x3_kernel<128, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_kernel<64, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_kernel<32, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_kernel<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_kernel<64, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_kernel<32, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(head_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); delete net; return MZ_ECUDA; }
   *out = net;

@@ -72,11 +72,22 @@ def test_single_conv_layers_blocks0(shape, A, planes, batch):
     assert (out.view(torch.float16)[0::2] == 0).all()        # untouched slots stay untouched
 
 
+@pytest.fixture(params=['auto', '128', '256'])
+def tile_rows(request, monkeypatch):
+    """The conv kernel has a 256-row-tile (throughput) and a 128-row split-K (latency) variant, chosen from the
+    number of tiles per SM; MZ_CONV_TILE_ROWS forces one so that both are exercised at test sizes."""
+    if request.param == 'auto':
+        monkeypatch.delenv('MZ_CONV_TILE_ROWS', raising=False)
+    else:
+        monkeypatch.setenv('MZ_CONV_TILE_ROWS', request.param)
+    return request.param
+
+
 @pytest.mark.parametrize('name,kind,kw,seed', [
     ('board_small', 'board', dict(input_shape=(5, 5, 5), num_actions=26, num_res_blocks=2, num_planes=32), 3),
     ('gomoku', 'board', dict(input_shape=(9, 9, 9), num_actions=82, num_res_blocks=8, num_planes=128), 0),
 ])
-def test_towers_vs_reference_recording(name, kind, kw, seed):
+def test_towers_vs_reference_recording(name, kind, kw, seed, tile_rows):
     """Single-item reference API against the reference's own recorded outputs
     (tests/golden/net_golden.npz; the recording stores hidden states as float16)."""
     net, onet = build_board(kw['input_shape'], kw['num_actions'], kw['num_res_blocks'], kw['num_planes'], seed)
@@ -120,7 +131,7 @@ def test_gomoku_batched_vs_torch_fp32(batch):
     report('pi1', pi2[rows].cpu().numpy(), pi2_ref.numpy(), TOL_PV)
 
 
-def test_gomoku_search_replays_bit_exact_in_oracle():
+def test_gomoku_search_replays_bit_exact_in_oracle(tile_rows):
     """Whole batched Gomoku search on the GPU with the tensor-core network; every tree, fed the
     per-node (reward, value) the engine produced, is rebuilt bit-for-bit by the CPU oracle."""
     import muzero_b200 as mz
@@ -248,7 +259,7 @@ ATARI_SMALL = dict(input_shape=(4, 96, 96), num_actions=6, num_res_blocks=2, num
                    reward_support_size=21)
 
 
-def test_atari_net_vs_reference_recording():
+def test_atari_net_vs_reference_recording(tile_rows):
     """MuZeroAtariNet: strided representation (SIMT stride-2 convs + avg pools around tcgen05 residual
     blocks at 48x48 / 24x24 / 12x12), 6x6 latent towers, support heads; against the reference's recording."""
     net, onet = build_atari(ATARI_SMALL, 5)
