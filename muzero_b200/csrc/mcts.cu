@@ -276,19 +276,85 @@ __device__ __forceinline__ float puct_score(double eW, float eR, int cn, double 
   return __fadd_rn(q, u);
 }
 
+// Correctly rounded float64 division without the ~35-instruction IEEE division sequence: with y = RN(1/b),
+//   q0 = RN(a*y);  r0 = a - b*q0 (one FMA, exact);  q1 = RN(q0 + r0*y)
+// q1 == RN(a/b) for every integer divisor b < 2^16 (a quotient by a small integer is never closer than 2^-17 ulp to a
+// rounding boundary, the error of q0 + r0*y before rounding is ~2^-53 ulp); for an arbitrary divisor a second
+// correction step makes it Markstein's sequence (correct unless b's significand is all ones).  Operands outside a
+// +-2^400 exponent window (and zeros, infinities, NaNs) take the IEEE path.  tools/fastdiv_check.c searches 6e8
+// operand pairs for a mismatch (none).  The select kernel executes ~300 instructions per level with the IEEE
+// divisions and is bound by exactly that dependent chain.
+// out of line on purpose: inlined, ptxas if-converts the IEEE sequence back into the hot path
+__device__ __noinline__ double ieee_div_cold(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ bool fastdiv_window(double a) {
+  const uint32_t e = ((uint32_t)__double2hiint(a) >> 20) & 0x7ffu;
+  return e - 623u <= 800u;
+}
+__device__ __forceinline__ double div_by_count(double a, int b, double y) {
+  const double db = (double)b;
+  const double q0 = __dmul_rn(a, y);
+  const double r0 = __fma_rn(-db, q0, a);
+  const double q1 = __fma_rn(r0, y, q0);
+  if (fastdiv_window(a)) return q1;
+  return ieee_div_cold(a, db);
+}
+__device__ __forceinline__ double div_by_range(double a, double b, double y, bool b_ok) {
+  const double q0 = __dmul_rn(a, y);
+  const double r0 = __fma_rn(-b, q0, a);
+  const double q1 = __fma_rn(r0, y, q0);
+  const double r1 = __fma_rn(-b, q1, a);
+  const double q2 = __fma_rn(r1, y, q1);
+  if (b_ok && fastdiv_window(a)) return q2;
+  return ieee_div_cold(a, b);
+}
+struct RangeDiv {
+  double lo, range, rrange;
+  bool norm, ok;
+  __device__ void init(double lo_, double hi_) {
+    lo = lo_;
+    norm = hi_ > lo_;
+    range = __dsub_rn(hi_, lo_);
+    rrange = norm ? __ddiv_rn(1.0, range) : 0.0;
+    const uint32_t mh = (uint32_t)__double2hiint(range) & 0xfffffu, ml = (uint32_t)__double2loint(range);
+    ok = norm && fastdiv_window(range) && !(mh == 0xfffffu && ml == 0xffffffffu);
+  }
+};
+// same bits as puct_score; sR[n] = RN(1/n)
+__device__ __forceinline__ float puct_score_fast(double eW, float eR, int cn, double pa, double tN, bool f32p, double dp,
+                                                 const RangeDiv& rd, const double* sR) {
+  const double y = div_by_count(tN, cn + 1, sR[cn + 1]);
+  const float u = f32p ? __fmul_rn((float)pa, __double2float_rn(y)) : __double2float_rn(__dmul_rn(pa, y));
+  float q = 0.0f;
+  if (cn > 0) {
+    double v = __dadd_rn((double)eR, __dmul_rn(dp, div_by_count(eW, cn, sR[cn])));
+    if (rd.norm) v = div_by_range(__dsub_rn(v, rd.lo), rd.range, rd.rrange, rd.ok);
+    q = __double2float_rn(v);
+  }
+  return __fadd_rn(q, u);
+}
+
+// child record `a` of a row as raw words {W lo, W hi, reward, child << 16 | N}; the empty record past the last action
+__device__ __forceinline__ int4 load_rec(const Edge* row, int a, int A) {
+  int4 r = make_int4(0, 0, 0, (int)((uint32_t)kNoChild << 16));
+  if (a < A) r = *reinterpret_cast<const int4*>(row + a);
+  return r;
+}
+
 // NCH = number of 32-action chunks held in registers (A <= 32*NCH); NCH == 0: any A, scores staged
 // in shared memory.  The register path keeps a node's whole child row, the tree's prior and the
 // scores in registers, takes the chosen child's record by shuffle instead of re-reading it, looks
-// the pb_c factor up in shared memory, and prefetches the row of the most-visited child (the one
-// pUCT most often descends into) while the float64 divisions of the current level are in flight.
+// the pb_c factor and the reciprocals of the visit counts up in shared memory, and loads the row of
+// the most-visited child (the one pUCT most often descends into) SPECULATIVELY into registers before
+// the scores of the current level are computed: when the descent does go there -- the common case --
+// the next level starts without a memory round trip.
 template <int NCH>
-__device__ __forceinline__ void select_tree(const PoolDev& p, const int t, const int lane, const double* sT, float* sc) {
+__device__ __forceinline__ void select_tree(const PoolDev& p, const int t, const int lane, const double* sT,
+                                            const double* sR, float* sc) {
   const int A = p.A;
   const Edge* tree = p.edges + (size_t)t * p.max_nodes * A;
   const double* __restrict__ P = p.prior + (size_t)t * A;
-  const double lo = p.minmax[2 * t], hi = p.minmax[2 * t + 1];
-  const bool norm = hi > lo;
-  const double range = __dsub_rn(hi, lo);
+  RangeDiv rd;
+  rd.init(p.minmax[2 * t], p.minmax[2 * t + 1]);
   const bool f32p = p.f32_prior[t] != 0;
   const double dp = p.dp;
   uint32_t* pth = p.path + (size_t)t * p.max_nodes;
@@ -296,10 +362,16 @@ __device__ __forceinline__ void select_tree(const PoolDev& p, const int t, const
   WarpRng rng;
   rng.load(p.rng_key + (size_t)t * 624, p.rng_pos + t, lane);
 
-  double pr[NCH > 0 ? NCH : 1];
+  constexpr int NC = NCH > 0 ? NCH : 1;
+  double pr[NC];
+  int4 cur[NC];            // child records of the current node: {W lo, W hi, reward, child << 16 | N}
   if (NCH > 0) {
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) pr[c] = (c * 32 + lane < A) ? P[c * 32 + lane] : 0.0;
+    for (int c = 0; c < NCH; ++c) {
+      const int a = c * 32 + lane;
+      pr[c] = (a < A) ? P[a] : 0.0;
+      cur[c] = load_rec(tree, a, A);
+    }
   }
 
   int n = 0, Nn = p.rootN[t], depth = 0, act = 0;
@@ -308,41 +380,35 @@ __device__ __forceinline__ void select_tree(const PoolDev& p, const int t, const
     const Edge* row = tree + (size_t)n * A;
     uint32_t nc_sel;      // (child << 16 | N) of the chosen edge
     if constexpr (NCH > 0) {
-      constexpr int NC = NCH > 0 ? NCH : 1;
-      // child records in registers: W, reward, packed (child << 16 | N)
-      double eW[NC];
-      float eR[NC];
-      uint32_t eNC[NC];
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const int a = c * 32 + lane;
-        int4 r4 = make_int4(0, 0, 0, (int)((uint32_t)kNoChild << 16));
-        if (a < A) r4 = *reinterpret_cast<const int4*>(row + a);
-        eW[c] = __hiloint2double(r4.y, r4.x);
-        eR[c] = __int_as_float(r4.z);
-        eNC[c] = (uint32_t)r4.w;
-      }
-      // most-visited expanded child -> prefetch its row into L2 (it is the likeliest next node)
+      // most-visited expanded child: its row is the likeliest next one
       uint32_t top = 0;
 #pragma unroll
-      for (int c = 0; c < NCH; ++c)
-        if ((eNC[c] >> 16) != kNoChild) top = max(top, (eNC[c] << 16) | (eNC[c] >> 16));
+      for (int c = 0; c < NCH; ++c) {
+        const uint32_t nc = (uint32_t)cur[c].w;
+        if ((nc >> 16) != kNoChild) top = max(top, (nc << 16) | (nc >> 16));
+      }
       top = __reduce_max_sync(kFull, top);
-      if (top != 0) {
-        const char* nxt = reinterpret_cast<const char*>(tree + (size_t)(top & 0xffffu) * A);
-        if (lane * 128 < A * 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + lane * 128));
+      int4 nxt[NC];
+      const int spec = (top != 0) ? (int)(top & 0xffffu) : -1;
+      if (spec >= 0) {
+        const Edge* srow = tree + (size_t)spec * A;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int a = c * 32 + lane;
+          nxt[c] = load_rec(srow, a, A);
+        }
       }
       float s[NC];
       uint32_t key = 0;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
-        const int cn = (int)(eNC[c] & 0xffffu);
+        const int cn = (int)((uint32_t)cur[c].w & 0xffffu);
         if (__any_sync(kFull, cn > 0)) {
-          s[c] = puct_score(eW[c], eR[c], cn, pr[c], tN, f32p, dp, norm, lo, range);
+          s[c] = puct_score_fast(__hiloint2double(cur[c].y, cur[c].x), __int_as_float(cur[c].z), cn, pr[c], tN, f32p,
+                                 dp, rd, sR);
         } else {
           // no visited child among these 32 actions (the common case deep in a tree): y = tN / 1 = tN exactly
-          // and q = 0, so the three float64 divisions of puct_score -- the select kernel is bound by the
-          // FP64 pipe, not by memory -- are skipped for the whole chunk; same bits as the general path
+          // and q = 0: same bits as the general path without its float64 chain
           const float u = f32p ? __fmul_rn((float)pr[c], __double2float_rn(tN)) : __double2float_rn(__dmul_rn(pr[c], tN));
           s[c] = __fadd_rn(0.0f, u);
         }
@@ -374,16 +440,33 @@ __device__ __forceinline__ void select_tree(const PoolDev& p, const int t, const
           }
         }
       }
-      uint32_t mine = 0;
+      // the chosen record from its owner lane: one shuffle per chunk (independent, so one shuffle latency), then a
+      // warp-uniform pick -- indexing cur[] with act >> 5 would move the whole row to local memory
+      nc_sel = 0;
 #pragma unroll
-      for (int c = 0; c < NCH; ++c)
-        if ((act >> 5) == c) mine = eNC[c];
-      nc_sel = __shfl_sync(kFull, mine, act & 31);
+      for (int c = 0; c < NCH; ++c) {
+        const uint32_t w = __shfl_sync(kFull, (uint32_t)cur[c].w, act & 31);
+        nc_sel = ((act >> 5) == c) ? w : nc_sel;
+      }
+      const int child = (int)(nc_sel >> 16);
+      if (child != (int)kNoChild) {
+        if (child == spec) {
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) cur[c] = nxt[c];
+        } else {
+          const Edge* crow = tree + (size_t)child * A;
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            const int a = c * 32 + lane;
+            cur[c] = load_rec(crow, a, A);
+          }
+        }
+      }
     } else {
       float bestl = -INFINITY;
       for (int a = lane; a < A; a += 32) {
         const Edge e = load_edge(row + a);
-        const float s = puct_score(e.W, e.reward, (int)e.N, P[a], tN, f32p, dp, norm, lo, range);
+        const float s = puct_score(e.W, e.reward, (int)e.N, P[a], tN, f32p, dp, rd.norm, rd.lo, rd.range);
         sc[a] = s;
         bestl = fmaxf(bestl, s);
       }
@@ -443,11 +526,15 @@ select_kernel(PoolDev p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * kTreesPerBlock + warp;
   double* sT = reinterpret_cast<double*>(smem_raw);                       // [S+2] pb_c table
-  float* sc = reinterpret_cast<float*>(sT + (p.S + 2)) + (size_t)warp * ((p.A + 3) & ~3);
-  for (int i = threadIdx.x; i < p.S + 2; i += blockDim.x) sT[i] = p.T[i];
+  double* sR = sT + (p.S + 2);                                            // [S+2] RN(1/n)
+  float* sc = reinterpret_cast<float*>(sR + (p.S + 2)) + (size_t)warp * ((p.A + 3) & ~3);
+  for (int i = threadIdx.x; i < p.S + 2; i += blockDim.x) {
+    sT[i] = p.T[i];
+    sR[i] = __ddiv_rn(1.0, (double)max(i, 1));
+  }
   __syncthreads();
   if (t >= p.B) return;
-  select_tree<NCH>(p, t, lane, sT, sc);
+  select_tree<NCH>(p, t, lane, sT, sR, sc);
 }
 
 // ---------------------------------------------------------------------------
@@ -548,13 +635,17 @@ backup_select_kernel(PoolDev p, const float* __restrict__ reward_in, const float
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * kTreesPerBlock + warp;
   double* sT = reinterpret_cast<double*>(smem_raw);
-  float* sc = reinterpret_cast<float*>(sT + (p.S + 2)) + (size_t)warp * ((p.A + 3) & ~3);
-  for (int i = threadIdx.x; i < p.S + 2; i += blockDim.x) sT[i] = p.T[i];
+  double* sR = sT + (p.S + 2);
+  float* sc = reinterpret_cast<float*>(sR + (p.S + 2)) + (size_t)warp * ((p.A + 3) & ~3);
+  for (int i = threadIdx.x; i < p.S + 2; i += blockDim.x) {
+    sT[i] = p.T[i];
+    sR[i] = __ddiv_rn(1.0, (double)max(i, 1));
+  }
   __syncthreads();
   if (t >= p.B) return;
   expand_backup_tree(p, t, lane, reward_in, value_in);
   __syncwarp();
-  select_tree<NCH>(p, t, lane, sT, sc);
+  select_tree<NCH>(p, t, lane, sT, sR, sc);
 }
 
 // ---------------------------------------------------------------------------
@@ -919,7 +1010,7 @@ extern "C" int mz_search_reset(mz_pool* pool, const float* pi_probs, const doubl
 extern "C" int mz_select(mz_pool* pool, mz_stream stream) {
   MZ_CHECK_ARG(pool, "NULL argument");
   const int A = pool->A;
-  const size_t smem = (size_t)(pool->S + 2) * 8 + (A > 128 ? (size_t)kTreesPerBlock * ((A + 3) & ~3) * sizeof(float) : 0);
+  const size_t smem = (size_t)(pool->S + 2) * 16 + (A > 128 ? (size_t)kTreesPerBlock * ((A + 3) & ~3) * sizeof(float) : 0);
   const dim3 grid(tree_blocks(pool->B)), block(kTreesPerBlock * 32);
   cudaStream_t st = (cudaStream_t)stream;
   const PoolDev d = dev_of(pool);
@@ -940,7 +1031,7 @@ extern "C" int mz_expand_backup_select(mz_pool* pool, const float* reward, const
     return MZ_ESTATE;
   }
   const int A = pool->A;
-  const size_t smem = (size_t)(pool->S + 2) * 8 + (A > 128 ? (size_t)kTreesPerBlock * ((A + 3) & ~3) * sizeof(float) : 0);
+  const size_t smem = (size_t)(pool->S + 2) * 16 + (A > 128 ? (size_t)kTreesPerBlock * ((A + 3) & ~3) * sizeof(float) : 0);
   const dim3 grid(tree_blocks(pool->B)), block(kTreesPerBlock * 32);
   cudaStream_t st = (cudaStream_t)stream;
   const PoolDev d = dev_of(pool);
