@@ -453,7 +453,9 @@ def run_engine_arm(args):
                  (' for recurrent inference, f32 SIMT for the root inference' if spec['kind'] == 'mlp' else ''),
         'data': 'synthetic',
         'config': {'workload': spec['label'], 'trees_per_gpu': B, 'simulations': S, 'num_actions': A,
-                   'pipeline_parts': parts, 'trees_per_kernel_launch': Bp, 'ctas_per_tower_launch': cta_limit or 148,
+                   'pipeline_parts': parts, 'trees_per_kernel_launch': Bp,
+                   'ctas_per_tower_launch': getattr(plan, 'cta_limit', 0) or cta_limit or 148,
+                   'ctas_per_tree_kernel_launch': getattr(plan, 'tree_ctas', 0) or 'one warp per tree, all SMs',
                    'l2': 'flushed between timed iterations (256 MiB write)', 'mean_select_depth': mean_depth,
                    'parallelism': f'games sharded over {world} GPU(s), no collective'},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': int(h2d),

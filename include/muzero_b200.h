@@ -83,7 +83,8 @@ enum mz_view {
   MZ_VIEW_REWARD,        /* f32 [B]      scratch the network writes, expand_backup reads                     */
   MZ_VIEW_VALUE,         /* f32 [B]                                                                          */
   MZ_VIEW_ERROR,         /* i32 [1]      sticky device-side error bits (MZ_DEVERR_*)                         */
-  MZ_VIEW_STATS,         /* u64 [4]      {sum of select depths, select calls*B, tie-break draws, mt twists}  */
+  MZ_VIEW_STATS,         /* u64 [8]      {sum of select depths, select calls*B, tie-break draws, mt twists, then (MZ_TREE_TIMING only) min / max block start and max block end of the fused tree kernel, ns} */
+  MZ_VIEW_QCACHE,        /* f32 [B, S+1, A] Node.child_Q of every edge (float32, min-max normalised) as the next select reads it; 0 for unvisited edges; refreshed by expand_backup */
   MZ_VIEW__COUNT
 };
 #define MZ_DEVERR_POOL_FULL   1   /* more than S expansions                       */
@@ -95,6 +96,12 @@ int mz_pool_arena_bytes(const mz_pool_config* cfg, size_t* bytes);
 int mz_pool_create(const mz_pool_config* cfg, const double* pb_c_table_host,
                    void* arena_dev, size_t arena_bytes, mz_pool** out);
 int mz_pool_destroy(mz_pool* pool);
+/* Scheduling knob for pipelined sub-batches (no effect on results): num_ctas > 0 makes mz_expand_backup_select run as
+ * that many persistent 1024-thread CTAs that pull trees off a counter and request more shared memory than is left
+ * beside a persistent conv CTA, so the tree kernel of one sub-batch occupies `num_ctas` SMs of its own while the other
+ * sub-batch's tower (capped to the remaining SMs with mz_net_set_cta_limit) runs undisturbed.  0 = warp-per-tree grid
+ * over all SMs. */
+int mz_pool_set_tree_ctas(mz_pool* pool, int num_ctas);
 int mz_pool_view(mz_pool* pool, int which, void** dev_ptr, size_t* bytes);
 
 /* np.random.seed(seed[t]) for every tree (init_genrand), on device. */

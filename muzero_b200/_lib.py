@@ -18,7 +18,7 @@ MZ_NET_MLP, MZ_NET_BOARD, MZ_NET_ATARI = 0, 1, 2
 
 VIEWS = ['EDGES', 'PRIOR', 'ROOT_W', 'ROOT_N', 'MINMAX', 'COUNT', 'LEAF_PARENT', 'LEAF_ACTION', 'LEAF_DEPTH',
          'SRC_SLOT', 'DST_SLOT', 'PATH', 'NODE_PARENT', 'NODE_MOVE', 'NODE_VALUE', 'RNG_KEY', 'RNG_POS', 'HIDDEN', 'REWARD',
-         'VALUE', 'ERROR', 'STATS']
+         'VALUE', 'ERROR', 'STATS', 'QCACHE']
 VIEW = {name: i for i, name in enumerate(VIEWS)}
 
 
@@ -43,6 +43,7 @@ PROTOTYPES = {
     'mz_pool_arena_bytes': (C.c_int, [C.POINTER(PoolConfig), C.POINTER(C.c_size_t)]),
     'mz_pool_create': (C.c_int, [C.POINTER(PoolConfig), C.POINTER(C.c_double), _P, C.c_size_t, C.POINTER(_P)]),
     'mz_pool_destroy': (C.c_int, [_P]),
+    'mz_pool_set_tree_ctas': (C.c_int, [_P, C.c_int]),
     'mz_pool_view': (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     'mz_rng_seed': (C.c_int, [_P, _P, _P]),
     'mz_dirichlet': (C.c_int, [_P, C.c_double, _P, _P]),

@@ -74,5 +74,7 @@ struct mz_pool {
   uint8_t* same_player;  // dev u8 [B]: current_player == opponent_player
   double* root_reward;   // dev f64 [B]
   uint8_t* f32_prior;    // dev u8 [B]: prior is float32 (no-noise path)
+  unsigned* work;        // dev u32 [2]: work counters of the confined tree kernel
+  int tree_ctas;         // > 0: the fused tree kernel runs as that many persistent CTAs (mz_pool_set_tree_ctas)
   int selected;          // host-side call-order check
 };

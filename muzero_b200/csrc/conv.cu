@@ -147,6 +147,19 @@ __device__ __forceinline__ int4 pack8(const float* v) {
 // alternate between them; each accumulates into its own TMEM accumulator and the epilogue adds the two in a
 // fixed order, so results stay deterministic).  Half the MMA time per tile: for launches with few tiles per SM
 // the layer-to-layer dependency chain (load -> MMA -> epilogue -> publish) is the bound, not throughput.
+// 64-thread named barrier 2 + quad with an IMMEDIATE id: with the id in a register ptxas must assume all 16
+// hardware barriers are in use ("used 16 barriers"), and an SM whose 16 barriers are taken by the persistent conv CTA
+// cannot host any other CTA that uses __syncthreads() -- the tree kernels of the other sub-batch then wait for
+// the whole tower instead of running beside it (tools/coresident_probe.py).
+__device__ __forceinline__ void quad_bar_sync(int quad) {
+  switch (quad) {
+    case 0: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 5, 64;" ::: "memory"); break;
+  }
+}
+
 template <int kN, int kRows>
 __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvParams p) {
   constexpr bool kSplitK = (kRows == 128);
@@ -532,9 +545,9 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
           if (norm) {
             // min/max over ALL channels of the row: combine with the warp holding the other column half
             s_mm[chalf * 128 + quad * 32 + lane] = make_float2(mn, mx);
-            asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");
+            quad_bar_sync(quad);
             const float2 o = s_mm[(chalf ^ 1) * 128 + quad * 32 + lane];
-            asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");
+            quad_bar_sync(quad);
             mn = fminf(mn, o.x); mx = fmaxf(mx, o.y);
             const float inv = valid ? 1.0f / ((mx - mn) + 1e-8f) : 0.0f;
             if (has_cols) {             // warp-uniform: the TMEM loads inside chunk() are warp-collective
@@ -899,6 +912,8 @@ struct ConvNet : NetImpl {
     const size_t fixed = conv_fixed_smem(g, cg, rows);
     if (fixed + 2 * stage > 227 * 1024) return 0;
     int s = (int)((227 * 1024 - fixed) / stage);
+    static const int cap = getenv("MZ_CONV_MAX_STAGES") ? atoi(getenv("MZ_CONV_MAX_STAGES")) : kMaxStages;
+    if (s > cap && cap >= 2) s = cap;
     return s > kMaxStages ? kMaxStages : s;
   }
   size_t conv_smem(const Geo& g, int cg, int rows = kTileM) const {
@@ -982,7 +997,8 @@ struct ConvNet : NetImpl {
       lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(kConvThreads); lc.dynamicSmemBytes = smem; lc.stream = st;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeCooperative;
-      at[0].val.cooperative = nl > 1 ? 1 : 0;
+      static const bool noncoop = getenv("MZ_CONV_NONCOOP") != nullptr;     // scheduling experiments only
+      at[0].val.cooperative = (nl > 1 && !noncoop) ? 1 : 0;
       lc.attrs = at; lc.numAttrs = 1;
       cudaError_t le;
       if (rows == 256) {

@@ -7,6 +7,7 @@
 // pb_c term comes from a host table computed with CPython math, tie-breaks
 // consume numpy's legacy MT19937 stream with numpy's masked rejection.
 #include "common.cuh"
+#include <vector>
 
 namespace mz {
 
@@ -15,6 +16,7 @@ struct PoolDev {
   int board;
   double discount, dp;
   Edge* edges;
+  float* qcache;     // f32 [B][max_nodes][A]: Node.child_Q of every edge as select reads it (0 for unvisited edges)
   double* prior;
   double* rootW;
   int* rootN;
@@ -35,9 +37,16 @@ struct PoolDev {
   uint8_t* f32_prior;
   double bound_min, bound_max;
   int has_bounds;
+  unsigned* work;   // {next tree, finished CTAs} of the confined tree kernel
+  int timing;   // MZ_TREE_TIMING: stats[4..6] = min / max block start and max block end of the tree kernels (%globaltimer)
 };
 
 constexpr unsigned kFull = 0xffffffffu;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 constexpr int kTreesPerBlock = 4;  // 128 threads
 
 // ---------------------------------------------------------------------------
@@ -232,7 +241,8 @@ reset_kernel(PoolDev p, const float* __restrict__ pi, const double* __restrict__
   }
   // root expansion: row 0 zeroed, no children yet
   Edge* row = p.edges + (size_t)t * p.max_nodes * A;
-  for (int a = lane; a < A; a += 32) store_edge(row + a, 0.0, 0.0f, 0u, kNoChild);
+  float* qrow = p.qcache + (size_t)t * p.max_nodes * A;
+  for (int a = lane; a < A; a += 32) { store_edge(row + a, 0.0, 0.0f, 0u, kNoChild); qrow[a] = 0.0f; }
   if (lane == 0) {
     p.rootW[t] = 0.0;
     p.rootN[t] = 0;
@@ -276,14 +286,26 @@ __device__ __forceinline__ float puct_score(double eW, float eR, int cn, double 
   return __fadd_rn(q, u);
 }
 
+// Node.child_Q of one edge (mcts.py:159-178) exactly as puct_score computes it, IEEE divisions: evaluated by the
+// BACKUP (off the descent's dependent chain, lanes in parallel) and cached as float32 per edge.  The value depends on
+// the edge's own (W, N, reward) and on the tree's min-max bounds, so the backup refreshes the edges of its path, or
+// every visited edge of the tree when it moved a bound.  Why: while the conv tower of the other sub-batch runs
+// tcgen05.mma on the same SM, FP64 throughput collapses (a dependent DFMA chain is 9.5x slower, measured by
+// tools/coresident_probe.py), so the descent keeps as little float64 arithmetic as bit-exactness allows.
+__device__ __forceinline__ float child_q(double W, float R, uint32_t N, double dp, bool norm, double lo, double range) {
+  if (N == 0) return 0.0f;
+  double v = __dadd_rn((double)R, __dmul_rn(dp, __ddiv_rn(W, (double)N)));
+  if (norm) v = __ddiv_rn(__dsub_rn(v, lo), range);
+  return __double2float_rn(v);
+}
+
 // Correctly rounded float64 division without the ~35-instruction IEEE division sequence: with y = RN(1/b),
 //   q0 = RN(a*y);  r0 = a - b*q0 (one FMA, exact);  q1 = RN(q0 + r0*y)
 // q1 == RN(a/b) for every integer divisor b < 2^16 (a quotient by a small integer is never closer than 2^-17 ulp to a
-// rounding boundary, the error of q0 + r0*y before rounding is ~2^-53 ulp); for an arbitrary divisor a second
-// correction step makes it Markstein's sequence (correct unless b's significand is all ones).  Operands outside a
-// +-2^400 exponent window (and zeros, infinities, NaNs) take the IEEE path.  tools/fastdiv_check.c searches 6e8
-// operand pairs for a mismatch (none).  The select kernel executes ~300 instructions per level with the IEEE
-// divisions and is bound by exactly that dependent chain.
+// rounding boundary, the error of q0 + r0*y before rounding is ~2^-53 ulp).  Operands outside a +-2^400 exponent
+// window (and zeros, infinities, NaNs) take the IEEE path.  tools/fastdiv_check.c searches 2e8 operand pairs over all
+// 65535 divisors for a mismatch (none; tests/test_abi.py runs a 5 % sample).  Used for y = T[N] / (n + 1) on the
+// descent's dependent chain; everything else that divides (child_Q) runs in the backup with IEEE divisions.
 // out of line on purpose: inlined, ptxas if-converts the IEEE sequence back into the hot path
 __device__ __noinline__ double ieee_div_cold(double a, double b) { return __ddiv_rn(a, b); }
 __device__ __forceinline__ bool fastdiv_window(double a) {
@@ -298,45 +320,10 @@ __device__ __forceinline__ double div_by_count(double a, int b, double y) {
   if (fastdiv_window(a)) return q1;
   return ieee_div_cold(a, db);
 }
-__device__ __forceinline__ double div_by_range(double a, double b, double y, bool b_ok) {
-  const double q0 = __dmul_rn(a, y);
-  const double r0 = __fma_rn(-b, q0, a);
-  const double q1 = __fma_rn(r0, y, q0);
-  const double r1 = __fma_rn(-b, q1, a);
-  const double q2 = __fma_rn(r1, y, q1);
-  if (b_ok && fastdiv_window(a)) return q2;
-  return ieee_div_cold(a, b);
-}
-struct RangeDiv {
-  double lo, range, rrange;
-  bool norm, ok;
-  __device__ void init(double lo_, double hi_) {
-    lo = lo_;
-    norm = hi_ > lo_;
-    range = __dsub_rn(hi_, lo_);
-    rrange = norm ? __ddiv_rn(1.0, range) : 0.0;
-    const uint32_t mh = (uint32_t)__double2hiint(range) & 0xfffffu, ml = (uint32_t)__double2loint(range);
-    ok = norm && fastdiv_window(range) && !(mh == 0xfffffu && ml == 0xffffffffu);
-  }
-};
-// same bits as puct_score; sR[n] = RN(1/n)
-__device__ __forceinline__ float puct_score_fast(double eW, float eR, int cn, double pa, double tN, bool f32p, double dp,
-                                                 const RangeDiv& rd, const double* sR) {
-  const double y = div_by_count(tN, cn + 1, sR[cn + 1]);
-  const float u = f32p ? __fmul_rn((float)pa, __double2float_rn(y)) : __double2float_rn(__dmul_rn(pa, y));
-  float q = 0.0f;
-  if (cn > 0) {
-    double v = __dadd_rn((double)eR, __dmul_rn(dp, div_by_count(eW, cn, sR[cn])));
-    if (rd.norm) v = div_by_range(__dsub_rn(v, rd.lo), rd.range, rd.rrange, rd.ok);
-    q = __double2float_rn(v);
-  }
-  return __fadd_rn(q, u);
-}
-
-// child record `a` of a row as raw words {W lo, W hi, reward, child << 16 | N}; the empty record past the last action
-__device__ __forceinline__ int4 load_rec(const Edge* row, int a, int A) {
-  int4 r = make_int4(0, 0, 0, (int)((uint32_t)kNoChild << 16));
-  if (a < A) r = *reinterpret_cast<const int4*>(row + a);
+// (child << 16 | N) of child record `a` of a row -- all the descent needs of a record; "no child" past the last action
+__device__ __forceinline__ uint32_t load_nc(const Edge* row, int a, int A) {
+  uint32_t r = (uint32_t)kNoChild << 16;
+  if (a < A) r = reinterpret_cast<const uint32_t*>(row + a)[3];
   return r;
 }
 
@@ -352,9 +339,13 @@ __device__ __forceinline__ void select_tree(const PoolDev& p, const int t, const
                                             const double* sR, float* sc) {
   const int A = p.A;
   const Edge* tree = p.edges + (size_t)t * p.max_nodes * A;
+  const float* qtree = p.qcache + (size_t)t * p.max_nodes * A;
   const double* __restrict__ P = p.prior + (size_t)t * A;
-  RangeDiv rd;
-  rd.init(p.minmax[2 * t], p.minmax[2 * t + 1]);
+  struct { double lo, range; bool norm; } rd = {0.0, 0.0, false};    // generic path only (scores computed in place)
+  if (NCH == 0) {
+    const double lo_ = p.minmax[2 * t], hi_ = p.minmax[2 * t + 1];
+    rd.lo = lo_; rd.norm = hi_ > lo_; rd.range = __dsub_rn(hi_, lo_);
+  }
   const bool f32p = p.f32_prior[t] != 0;
   const double dp = p.dp;
   uint32_t* pth = p.path + (size_t)t * p.max_nodes;
@@ -364,13 +355,17 @@ __device__ __forceinline__ void select_tree(const PoolDev& p, const int t, const
 
   constexpr int NC = NCH > 0 ? NCH : 1;
   double pr[NC];
-  int4 cur[NC];            // child records of the current node: {W lo, W hi, reward, child << 16 | N}
+  float prf[NC];
+  uint32_t cur[NC];        // (child << 16 | N) of the current node's edges
+  float curq[NC];          // their cached child_Q
   if (NCH > 0) {
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int a = c * 32 + lane;
       pr[c] = (a < A) ? P[a] : 0.0;
-      cur[c] = load_rec(tree, a, A);
+      prf[c] = (float)pr[c];
+      cur[c] = load_nc(tree, a, A);
+      curq[c] = (a < A) ? qtree[a] : 0.0f;
     }
   }
 
@@ -383,35 +378,39 @@ __device__ __forceinline__ void select_tree(const PoolDev& p, const int t, const
       // most-visited expanded child: its row is the likeliest next one
       uint32_t top = 0;
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const uint32_t nc = (uint32_t)cur[c].w;
-        if ((nc >> 16) != kNoChild) top = max(top, (nc << 16) | (nc >> 16));
-      }
+      for (int c = 0; c < NCH; ++c)
+        if ((cur[c] >> 16) != kNoChild) top = max(top, (cur[c] << 16) | (cur[c] >> 16));
       top = __reduce_max_sync(kFull, top);
-      int4 nxt[NC];
+      uint32_t nxt[NC];
+      float nxtq[NC];
       const int spec = (top != 0) ? (int)(top & 0xffffu) : -1;
       if (spec >= 0) {
         const Edge* srow = tree + (size_t)spec * A;
+        const float* sq = qtree + (size_t)spec * A;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           const int a = c * 32 + lane;
-          nxt[c] = load_rec(srow, a, A);
+          nxt[c] = load_nc(srow, a, A);
+          nxtq[c] = (a < A) ? sq[a] : 0.0f;
         }
       }
+      // pUCT score = cached child_Q + child_U; the only float64 work left on the chain is y = tN / (cn + 1) for
+      // chunks with a visited child and the float64-prior product
+      const float tNf = __double2float_rn(tN);
       float s[NC];
       uint32_t key = 0;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
-        const int cn = (int)((uint32_t)cur[c].w & 0xffffu);
+        const int cn = (int)(cur[c] & 0xffffu);
+        float u;
         if (__any_sync(kFull, cn > 0)) {
-          s[c] = puct_score_fast(__hiloint2double(cur[c].y, cur[c].x), __int_as_float(cur[c].z), cn, pr[c], tN, f32p,
-                                 dp, rd, sR);
+          const double y = div_by_count(tN, cn + 1, __ldg(sR + cn + 1));
+          u = f32p ? __fmul_rn(prf[c], __double2float_rn(y)) : __double2float_rn(__dmul_rn(pr[c], y));
         } else {
           // no visited child among these 32 actions (the common case deep in a tree): y = tN / 1 = tN exactly
-          // and q = 0: same bits as the general path without its float64 chain
-          const float u = f32p ? __fmul_rn((float)pr[c], __double2float_rn(tN)) : __double2float_rn(__dmul_rn(pr[c], tN));
-          s[c] = __fadd_rn(0.0f, u);
+          u = f32p ? __fmul_rn(prf[c], tNf) : __double2float_rn(__dmul_rn(pr[c], tN));
         }
+        s[c] = __fadd_rn(curq[c], u);
         if (c * 32 + lane < A) key = max(key, f2ord(s[c]));
       }
       const float best = ord2f(__reduce_max_sync(kFull, key));
@@ -445,20 +444,22 @@ __device__ __forceinline__ void select_tree(const PoolDev& p, const int t, const
       nc_sel = 0;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
-        const uint32_t w = __shfl_sync(kFull, (uint32_t)cur[c].w, act & 31);
+        const uint32_t w = __shfl_sync(kFull, cur[c], act & 31);
         nc_sel = ((act >> 5) == c) ? w : nc_sel;
       }
       const int child = (int)(nc_sel >> 16);
       if (child != (int)kNoChild) {
         if (child == spec) {
 #pragma unroll
-          for (int c = 0; c < NCH; ++c) cur[c] = nxt[c];
+          for (int c = 0; c < NCH; ++c) { cur[c] = nxt[c]; curq[c] = nxtq[c]; }
         } else {
           const Edge* crow = tree + (size_t)child * A;
+          const float* cq = qtree + (size_t)child * A;
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
             const int a = c * 32 + lane;
-            cur[c] = load_rec(crow, a, A);
+            cur[c] = load_nc(crow, a, A);
+            curq[c] = (a < A) ? cq[a] : 0.0f;
           }
         }
       }
@@ -526,12 +527,11 @@ select_kernel(PoolDev p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * kTreesPerBlock + warp;
   double* sT = reinterpret_cast<double*>(smem_raw);                       // [S+2] pb_c table
-  double* sR = sT + (p.S + 2);                                            // [S+2] RN(1/n)
-  float* sc = reinterpret_cast<float*>(sR + (p.S + 2)) + (size_t)warp * ((p.A + 3) & ~3);
-  for (int i = threadIdx.x; i < p.S + 2; i += blockDim.x) {
-    sT[i] = p.T[i];
-    sR[i] = __ddiv_rn(1.0, (double)max(i, 1));
-  }
+  // RN(1/n): read through L1 (__ldg), not staged -- 3.2 KB of shared memory per CTA would no longer fit beside the
+  // persistent conv kernel of the other sub-batch (228 KB - 223.75 KB - two 1 KB reservations)
+  const double* sR = p.T + (p.S + 2);
+  float* sc = reinterpret_cast<float*>(sT + (p.S + 2)) + (size_t)warp * ((p.A + 3) & ~3);
+  for (int i = threadIdx.x; i < p.S + 2; i += blockDim.x) sT[i] = p.T[i];
   __syncthreads();
   if (t >= p.B) return;
   select_tree<NCH>(p, t, lane, sT, sR, sc);
@@ -556,7 +556,8 @@ __device__ __forceinline__ void expand_backup_tree(const PoolDev& p, const int t
 
   // expand: fresh all-zero row for the new node
   Edge* crow = tree + (size_t)c * A;
-  for (int a = lane; a < A; a += 32) store_edge(crow + a, 0.0, 0.0f, 0u, kNoChild);
+  float* qtree = p.qcache + (size_t)t * p.max_nodes * A;
+  for (int a = lane; a < A; a += 32) { store_edge(crow + a, 0.0, 0.0f, 0u, kNoChild); qtree[(size_t)c * A + a] = 0.0f; }
 
   const float rew = reward_in[t];
   double value = (double)value_in[t];
@@ -564,6 +565,7 @@ __device__ __forceinline__ void expand_backup_tree(const PoolDev& p, const int t
   const bool board = p.board != 0;
   const double discount = p.discount;
   double lo = p.minmax[2 * t], hi = p.minmax[2 * t + 1];
+  const double lo0 = lo, hi0 = hi;
 
   const int total = depth + 1;           // leaf ... root
   for (int base = 0; base < total; base += 32) {
@@ -606,14 +608,39 @@ __device__ __forceinline__ void expand_backup_tree(const PoolDev& p, const int t
     hi = fmax(hi, warp_max_d(mm_hi));
     lo = fmin(lo, warp_min_d(mm_lo));
   }
+  int* npar = p.node_parent + (size_t)t * p.max_nodes;
+  int* nmov = p.node_move + (size_t)t * p.max_nodes;
   if (lane == 0) {
     p.minmax[2 * t] = lo;
     p.minmax[2 * t + 1] = hi;
     p.count[t] = c + 1;
-    p.node_parent[(size_t)t * p.max_nodes + c] = p.leaf_parent[t];
-    p.node_move[(size_t)t * p.max_nodes + c] = p.leaf_action[t];
+    npar[c] = p.leaf_parent[t];
+    nmov[c] = p.leaf_action[t];
     p.node_value[(size_t)t * p.max_nodes + c] = value_in[t];
     p.leaf_depth[t] = 0;
+  }
+  __syncwarp();                          // the records and the node list written above -> every lane
+  // child_Q cache for the next descents, under the bounds they will see (the ones just stored)
+  {
+    const bool norm = hi > lo;
+    const double range = __dsub_rn(hi, lo);
+    const double dpq = p.dp;
+    const bool moved = __double_as_longlong(lo) != __double_as_longlong(lo0) ||
+                       __double_as_longlong(hi) != __double_as_longlong(hi0);
+    if (moved) {
+      // a bound moved: every cached value of this tree is stale.  Visited edges == expanded nodes 1..c
+      for (int k = 1 + lane; k <= c; k += 32) {
+        const uint32_t e = (uint32_t)npar[k] * (uint32_t)A + (uint32_t)nmov[k];
+        const Edge r = load_edge(tree + e);
+        qtree[e] = child_q(r.W, r.reward, r.N, dpq, norm, lo, range);
+      }
+    } else {
+      for (int k = lane; k < depth; k += 32) {
+        const uint32_t e = pth[k];
+        const Edge r = load_edge(tree + e);
+        qtree[e] = child_q(r.W, r.reward, r.N, dpq, norm, lo, range);
+      }
+    }
   }
 }
 
@@ -635,17 +662,58 @@ backup_select_kernel(PoolDev p, const float* __restrict__ reward_in, const float
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * kTreesPerBlock + warp;
   double* sT = reinterpret_cast<double*>(smem_raw);
-  double* sR = sT + (p.S + 2);
-  float* sc = reinterpret_cast<float*>(sR + (p.S + 2)) + (size_t)warp * ((p.A + 3) & ~3);
-  for (int i = threadIdx.x; i < p.S + 2; i += blockDim.x) {
-    sT[i] = p.T[i];
-    sR[i] = __ddiv_rn(1.0, (double)max(i, 1));
-  }
+  const double* sR = p.T + (p.S + 2);
+  float* sc = reinterpret_cast<float*>(sT + (p.S + 2)) + (size_t)warp * ((p.A + 3) & ~3);
+  for (int i = threadIdx.x; i < p.S + 2; i += blockDim.x) sT[i] = p.T[i];
   __syncthreads();
   if (t >= p.B) return;
+  if (p.timing && threadIdx.x == 0) {
+    const unsigned long long t0 = globaltimer_ns();
+    atomicMin(p.stats + 4, t0);
+    atomicMax(p.stats + 5, t0);
+  }
   expand_backup_tree(p, t, lane, reward_in, value_in);
   __syncwarp();
   select_tree<NCH>(p, t, lane, sT, sR, sc);
+  if (p.timing && lane == 0) atomicMax(p.stats + 6, globaltimer_ns());
+}
+
+// The same, CONFINED to a few SMs: `gridDim.x` CTAs of 32 warps pull trees off a counter.  For PipelinedSearchPlan,
+// where the tree kernels of one sub-batch are meant to run in the shadow of the other sub-batch's conv tower.
+// Spread over all SMs (one small CTA beside every persistent conv CTA) they do start there, but a latency-bound warp
+// beside the tower's warps runs 2-10x slower per instruction (FP64 9.5x) AND slows the tower's MMA issue by ~25 %
+// (tools/coresident_probe.py) -- worse than not overlapping at all.  So the tower is launched on
+// num_sms - gridDim.x SMs and this kernel asks for more shared memory than is left beside a conv CTA: its CTAs can
+// only land on the SMs the tower leaves free, and at most gridDim.x SMs are ever withheld from the (cooperative)
+// tower launch of the other sub-batch.
+constexpr int kConfinedThreads = 1024;
+constexpr int kConfinedSmem = 40 * 1024;
+template <int NCH>
+__global__ void __launch_bounds__(kConfinedThreads)
+backup_select_confined_kernel(PoolDev p, const float* __restrict__ reward_in, const float* __restrict__ value_in) {
+  const int lane = threadIdx.x & 31;
+  double* sT = reinterpret_cast<double*>(smem_raw);
+  const double* sR = p.T + (p.S + 2);
+  for (int i = threadIdx.x; i < p.S + 2; i += blockDim.x) sT[i] = p.T[i];
+  __syncthreads();
+  while (true) {
+    unsigned t = 0;
+    if (lane == 0) t = atomicAdd(p.work, 1u);
+    t = __shfl_sync(kFull, t, 0);
+    if (t >= (unsigned)p.B) break;
+    expand_backup_tree(p, (int)t, lane, reward_in, value_in);
+    __syncwarp();
+    select_tree<NCH>(p, (int)t, lane, sT, sR, nullptr);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(p.work + 1, 1u) == gridDim.x - 1) {   // last CTA out: every CTA has left its loop
+      p.work[0] = 0;
+      p.work[1] = 0;
+      __threadfence();
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -834,11 +902,13 @@ void layout(const mz_pool_config& c, size_t* offs, size_t* sizes, size_t* extra_
   put(MZ_VIEW_REWARD, B * 4);
   put(MZ_VIEW_VALUE, B * 4);
   put(MZ_VIEW_ERROR, 4);
-  put(MZ_VIEW_STATS, 4 * 8);
-  extra_offs[0] = cv.take((size_t)(c.num_simulations + 2) * 8);  // pb_c table
+  put(MZ_VIEW_STATS, 8 * 8);
+  put(MZ_VIEW_QCACHE, B * n * A * 4);
+  extra_offs[0] = cv.take((size_t)(c.num_simulations + 2) * 16); // pb_c table, then RN(1/n)
   extra_offs[1] = cv.take(B);                                     // same_player
   extra_offs[2] = cv.take(B * 8);                                 // root_reward
   extra_offs[3] = cv.take(B);                                     // f32_prior
+  extra_offs[4] = cv.take(16);                                    // work counters of the confined tree kernel
   *total = cv.off;
 }
 
@@ -865,6 +935,7 @@ PoolDev dev_of(const mz_pool* h) {
   d.discount = h->cfg.discount;
   d.dp = h->cfg.discount * (h->cfg.is_board_game ? -1.0 : 1.0);   // mcts.py:169-174: discount * p
   d.edges = (Edge*)h->view_ptr[MZ_VIEW_EDGES];
+  d.qcache = (float*)h->view_ptr[MZ_VIEW_QCACHE];
   d.prior = (double*)h->view_ptr[MZ_VIEW_PRIOR];
   d.rootW = (double*)h->view_ptr[MZ_VIEW_ROOT_W];
   d.rootN = (int*)h->view_ptr[MZ_VIEW_ROOT_N];
@@ -889,8 +960,11 @@ PoolDev dev_of(const mz_pool* h) {
   d.same_player = h->same_player;
   d.root_reward = h->root_reward;
   d.f32_prior = h->f32_prior;
+  d.work = h->work;
   d.bound_min = h->cfg.bound_min; d.bound_max = h->cfg.bound_max;
   d.has_bounds = h->cfg.has_known_bounds;
+  static const int timing = getenv("MZ_TREE_TIMING") != nullptr;
+  d.timing = timing;
   return d;
 }
 
@@ -902,7 +976,7 @@ extern "C" int mz_pool_arena_bytes(const mz_pool_config* cfg, size_t* bytes) {
   int rc = check_cfg(cfg);
   if (rc) return rc;
   MZ_CHECK_ARG(bytes != nullptr, "bytes is NULL");
-  size_t offs[MZ_VIEW__COUNT], sizes[MZ_VIEW__COUNT], extra[4];
+  size_t offs[MZ_VIEW__COUNT], sizes[MZ_VIEW__COUNT], extra[5];
   layout(*cfg, offs, sizes, extra, bytes);
   return MZ_OK;
 }
@@ -913,7 +987,7 @@ extern "C" int mz_pool_create(const mz_pool_config* cfg, const double* pb_c_tabl
   if (rc) return rc;
   MZ_CHECK_ARG(pb_c_table_host && arena_dev && out, "NULL argument");
   MZ_CHECK_ARG(((uintptr_t)arena_dev & 255) == 0, "arena must be 256-byte aligned");
-  size_t offs[MZ_VIEW__COUNT], sizes[MZ_VIEW__COUNT], extra[4], total;
+  size_t offs[MZ_VIEW__COUNT], sizes[MZ_VIEW__COUNT], extra[5], total;
   layout(*cfg, offs, sizes, extra, &total);
   {
     // The per-simulation tree kernels must be able to share an SM with the persistent conv kernel of ANOTHER
@@ -931,6 +1005,10 @@ extern "C" int mz_pool_create(const mz_pool_config* cfg, const double* pb_c_tabl
     cudaFuncSetAttribute(backup_select_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(backup_select_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(backup_select_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(backup_select_confined_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(backup_select_confined_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(backup_select_confined_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(backup_select_confined_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaGetLastError();
   }
   if (arena_bytes < total) {
@@ -947,10 +1025,19 @@ extern "C" int mz_pool_create(const mz_pool_config* cfg, const double* pb_c_tabl
   h->same_player = (uint8_t*)(base + extra[1]);
   h->root_reward = (double*)(base + extra[2]);
   h->f32_prior = (uint8_t*)(base + extra[3]);
+  h->work = (unsigned*)(base + extra[4]);
+  h->tree_ctas = 0;
   h->selected = 0;
   cudaError_t e = cudaMemcpy(h->pb_c_table, pb_c_table_host, (size_t)(h->S + 2) * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    // correctly rounded reciprocals of the visit counts (host IEEE division) for div_by_count
+    std::vector<double> rcp((size_t)h->S + 2);
+    for (int i = 0; i < h->S + 2; ++i) rcp[i] = 1.0 / (double)(i > 0 ? i : 1);
+    e = cudaMemcpy(h->pb_c_table + (h->S + 2), rcp.data(), rcp.size() * 8, cudaMemcpyHostToDevice);
+  }
+  if (e == cudaSuccess) e = cudaMemset(h->work, 0, 16);
   if (e == cudaSuccess) e = cudaMemset(h->view_ptr[MZ_VIEW_ERROR], 0, 4);
-  if (e == cudaSuccess) e = cudaMemset(h->view_ptr[MZ_VIEW_STATS], 0, 32);
+  if (e == cudaSuccess) e = cudaMemset(h->view_ptr[MZ_VIEW_STATS], 0, 64);
   if (e == cudaSuccess) e = cudaMemset(h->view_ptr[MZ_VIEW_LEAF_DEPTH], 0, sizes[MZ_VIEW_LEAF_DEPTH]);
   if (e == cudaSuccess) e = cudaMemset(h->view_ptr[MZ_VIEW_RNG_KEY], 0, sizes[MZ_VIEW_RNG_KEY]);
   if (e == cudaSuccess) e = cudaMemset(h->view_ptr[MZ_VIEW_RNG_POS], 0, sizes[MZ_VIEW_RNG_POS]);
@@ -960,6 +1047,14 @@ extern "C" int mz_pool_create(const mz_pool_config* cfg, const double* pb_c_tabl
     return MZ_ECUDA;
   }
   *out = h;
+  return MZ_OK;
+}
+
+extern "C" int mz_pool_set_tree_ctas(mz_pool* pool, int num_ctas) {
+  MZ_CHECK_ARG(pool, "NULL argument");
+  MZ_CHECK_ARG(num_ctas >= 0 && num_ctas <= 64, "num_ctas out of range: %d", num_ctas);
+  MZ_CHECK_ARG((size_t)(pool->S + 2) * 8 <= (size_t)kConfinedSmem, "pb_c table does not fit the confined kernel");
+  pool->tree_ctas = num_ctas;
   return MZ_OK;
 }
 
@@ -1010,7 +1105,7 @@ extern "C" int mz_search_reset(mz_pool* pool, const float* pi_probs, const doubl
 extern "C" int mz_select(mz_pool* pool, mz_stream stream) {
   MZ_CHECK_ARG(pool, "NULL argument");
   const int A = pool->A;
-  const size_t smem = (size_t)(pool->S + 2) * 16 + (A > 128 ? (size_t)kTreesPerBlock * ((A + 3) & ~3) * sizeof(float) : 0);
+  const size_t smem = (size_t)(pool->S + 2) * 8 + (A > 128 ? (size_t)kTreesPerBlock * ((A + 3) & ~3) * sizeof(float) : 0);
   const dim3 grid(tree_blocks(pool->B)), block(kTreesPerBlock * 32);
   cudaStream_t st = (cudaStream_t)stream;
   const PoolDev d = dev_of(pool);
@@ -1031,12 +1126,22 @@ extern "C" int mz_expand_backup_select(mz_pool* pool, const float* reward, const
     return MZ_ESTATE;
   }
   const int A = pool->A;
-  const size_t smem = (size_t)(pool->S + 2) * 16 + (A > 128 ? (size_t)kTreesPerBlock * ((A + 3) & ~3) * sizeof(float) : 0);
+  const size_t smem = (size_t)(pool->S + 2) * 8 + (A > 128 ? (size_t)kTreesPerBlock * ((A + 3) & ~3) * sizeof(float) : 0);
   const dim3 grid(tree_blocks(pool->B)), block(kTreesPerBlock * 32);
   cudaStream_t st = (cudaStream_t)stream;
   const PoolDev d = dev_of(pool);
   const float* r = reward ? reward : d.reward;
   const float* v = value ? value : d.value;
+  if (pool->tree_ctas > 0 && A <= 128) {
+    const dim3 cgrid(pool->tree_ctas), cblock(kConfinedThreads);
+    if (A <= 32) backup_select_confined_kernel<1><<<cgrid, cblock, kConfinedSmem, st>>>(d, r, v);
+    else if (A <= 64) backup_select_confined_kernel<2><<<cgrid, cblock, kConfinedSmem, st>>>(d, r, v);
+    else if (A <= 96) backup_select_confined_kernel<3><<<cgrid, cblock, kConfinedSmem, st>>>(d, r, v);
+    else backup_select_confined_kernel<4><<<cgrid, cblock, kConfinedSmem, st>>>(d, r, v);
+    MZ_LAUNCH_CHECK("backup_select_confined_kernel");
+    pool->selected = 1;
+    return MZ_OK;
+  }
   if (A <= 32) backup_select_kernel<1><<<grid, block, smem, st>>>(d, r, v);
   else if (A <= 64) backup_select_kernel<2><<<grid, block, smem, st>>>(d, r, v);
   else if (A <= 96) backup_select_kernel<3><<<grid, block, smem, st>>>(d, r, v);

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -85,6 +86,7 @@ class SearchPool:
         'RNG_KEY': (torch.int32, 624),
         'RNG_POS': (torch.int32, None), 'HIDDEN': (torch.uint8, None), 'REWARD': (torch.float32, None),
         'VALUE': (torch.float32, None), 'ERROR': (torch.int32, None), 'STATS': (torch.int64, None),
+        'QCACHE': (torch.float32, None),
     }
 
     def view(self, name: str) -> torch.Tensor:
@@ -390,7 +392,8 @@ class PipelinedSearchPlan:
     its own node pool and its own engine instance (activation buffers); weights are shared read-only.
     """
 
-    def __init__(self, network: MuZeroNet, config, num_trees: int, parts: int = 2, cta_limit: int = 0) -> None:
+    def __init__(self, network: MuZeroNet, config, num_trees: int, parts: int = 2, cta_limit: int = 0,
+                 tree_ctas: Optional[int] = None) -> None:
         assert parts >= 1 and num_trees % parts == 0, 'num_trees must be a multiple of parts'
         self.network, self.config = network, config
         # cta_limit > 0: every part's persistent tower kernel uses at most that many SMs, so the towers of the
@@ -415,6 +418,18 @@ class PipelinedSearchPlan:
         self.parts = [SearchPlan(network, config, per, instance=i,
                                  buffers={n: getattr(self, n)[i * per:(i + 1) * per] for n in names})
                       for i in range(parts)]
+        # Large conv-net sub-batches that each fill the GPU (cta_limit == 0): the fused tree kernel of a part runs as
+        # `tree_ctas` persistent CTAs on SMs of its own and the towers get the rest (see mz_pool_set_tree_ctas) --
+        # a tree warp beside the tower's warps is several times slower AND slows the tower.
+        env = os.environ.get('MZ_TREE_CTAS')
+        self.tree_ctas = int(env) if env is not None else (4 if tree_ctas is None else int(tree_ctas))
+        if parts < 2 or self.cta_limit or network.kind == _lib.MZ_NET_MLP or A > 128:
+            self.tree_ctas = 0
+        if self.tree_ctas:
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            self.cta_limit = sms - self.tree_ctas
+            for part in self.parts:
+                _lib.check(_lib.lib().mz_pool_set_tree_ctas(part.pool.handle, self.tree_ctas))
         for part in self.parts:
             part.cta_limit = self.cta_limit
         self.pool = _PoolGroup([p.pool for p in self.parts])

@@ -129,3 +129,18 @@ def test_product_never_imports_the_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), f'{f} imports the oracle'
+
+
+def test_fma_division_sequence_is_correctly_rounded(tmp_path):
+    """div_by_count of csrc/mcts.cu (reciprocal + one FMA correction) == IEEE division for every visit count:
+    compiled and searched on the CPU (tools/fastdiv_check.c, 5 % of the full search)."""
+    import shutil
+    import subprocess
+    if shutil.which('gcc') is None or 'fma' not in open('/proc/cpuinfo').read():
+        pytest.skip('needs gcc and a CPU with FMA')
+    exe = str(tmp_path / 'fastdiv_check')
+    subprocess.run(['gcc', '-O2', '-mfma', '-ffp-contract=off', '-o', exe, os.path.join(ROOT, 'tools', 'fastdiv_check.c'),
+                    '-lm'], check=True)
+    r = subprocess.run([exe, '5'], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout
+    assert ' 0 mismatches' in r.stdout

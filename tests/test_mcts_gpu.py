@@ -324,3 +324,59 @@ def test_error_paths_match_reference_exceptions():
     pool.root_policy(none, torch.ones(2, dtype=torch.float64, device=dev), False)
     with pytest.raises(ValueError, match='NaN'):
         pool.check_errors()
+
+
+@pytest.mark.parametrize('A,S,board,bounds', [(2, 50, False, False), (10, 25, True, True), (40, 60, False, True),
+                                              (82, 120, True, True), (120, 40, False, False)],
+                         ids=['A2', 'A10', 'A40', 'A82', 'A120'])
+def test_fused_and_confined_tree_kernels_equal_the_separate_launches(A, S, board, bounds):
+    """mz_expand_backup_select (one warp per tree over all SMs) and its confined form (mz_pool_set_tree_ctas: a few
+    persistent CTAs pulling trees off a counter) against mz_expand_backup + mz_select, which the lock-step tests pin
+    to the oracle: every byte of the search state, the child_Q cache and the RNG streams included."""
+    import muzero_b200 as mz
+    from muzero_b200 import _lib
+    dev = _dev()
+    lib = _lib.lib()
+    B = 300
+    gen = np.random.RandomState(A * 1000 + S)
+    cfg = mz.MuZeroConfig(discount=1.0 if board else 0.997, dirichlet_alpha=0.25, num_simulations=S, batch_size=1,
+                          td_steps=0, lr_init=0.0, lr_milestones=[], visit_softmax_temperature_fn=None,
+                          known_bounds=mz.KnownBounds(-1, 1) if bounds else None, is_board_game=board)
+    pi0 = gen.dirichlet(np.ones(A), size=B).astype(np.float32)
+    pi0[::3] = 1.0 / A                                    # tie-heavy trees: the RNG streams matter
+    noise = gen.dirichlet(np.ones(A) * 0.25, size=B)
+    players = np.stack([np.ones(B), 2 * np.ones(B) if board else np.ones(B)], 1).astype(np.int32)
+    rewards = (gen.standard_normal((S, B)) * (0.0 if board else 0.5)).astype(np.float32)
+    values = np.tanh(gen.standard_normal((S, B))).astype(np.float32) * (1.0 if bounds else 3.0)
+    values[:, ::5] = np.round(values[:, ::5])              # exact zeros / +-1: W == 0 takes the IEEE division path
+
+    def run(mode):
+        pool = mz.SearchPool(B, A, cfg, 0, dev)
+        pool.seed(77 + np.arange(B))
+        pool.reset(torch.from_numpy(pi0).to(dev), torch.from_numpy(noise).to(dev), 0.25, None,
+                   torch.from_numpy(players).to(dev))
+        if mode == 'confined':
+            _lib.check(lib.mz_pool_set_tree_ctas(pool.handle, 3))
+        st = _lib.current_stream()
+        pool.select()
+        for i in range(S):
+            r, v = torch.from_numpy(rewards[i]).to(dev), torch.from_numpy(values[i]).to(dev)
+            if mode == 'separate':
+                pool.expand_backup(r, v)
+                if i + 1 < S:
+                    pool.select()
+            elif i + 1 < S:
+                _lib.check(lib.mz_expand_backup_select(pool.handle, r.data_ptr(), v.data_ptr(), st))
+            else:
+                pool.expand_backup(r, v)
+            torch.cuda.synchronize()
+        pool.check_errors()
+        names = ('EDGES', 'QCACHE', 'MINMAX', 'ROOT_W', 'ROOT_N', 'COUNT', 'NODE_PARENT', 'NODE_MOVE', 'RNG_KEY',
+                 'RNG_POS', 'PRIOR')
+        return {k: pool.view(k).cpu().numpy().view(np.uint8).copy() for k in names}
+
+    want = run('separate')
+    for mode in ('fused', 'confined'):
+        got = run(mode)
+        for k in want:
+            assert np.array_equal(want[k], got[k]), f'{mode}: {k} differs'

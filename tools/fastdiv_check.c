@@ -1,19 +1,19 @@
-// CPU proof-by-search for the FMA division sequences of the select kernel (mcts.cu: div_by_count / div_by_range).
+// CPU proof-by-search for the FMA division sequence of the select kernel (mcts.cu: div_by_count).
 //
 //   q0 = RN(a * y)            y = RN(1 / b)
 //   r0 = RN(a - b * q0)       (fma, exact)
 //   q1 = RN(q0 + r0 * y)      (fma)
-//  [r1 = RN(a - b * q1);  q2 = RN(q1 + r1 * y)]     second step only for arbitrary b
 //
-// must equal the IEEE quotient RN(a / b) bit for bit: (1) for every integer divisor 1..65535 (visit counts) with one
-// correction step, (2) for arbitrary positive doubles (hi - lo of MinMaxStats) with two.  Markstein's theorem covers
-// (2) when b's significand is not all ones; (1) follows because a / b with a small integer b is never closer than
-// 2^-17 ulp to a rounding boundary.  This program searches for counterexamples anyway.
+// must equal the IEEE quotient RN(a / b) bit for bit for every integer divisor 1..65535 (visit counts): a / b with a
+// small integer b is never closer than 2^-17 ulp to a rounding boundary, the error of q0 + r0 * y before its rounding
+// is ~2^-53 ulp.  This program searches for counterexamples anyway (random numerators of many significand patterns
+// inside the kernel's +-2^400 exponent window, and small integer numerators).
 //
-//   gcc -O2 -mfma -o /tmp/fastdiv_check tools/fastdiv_check.c -lm && /tmp/fastdiv_check
+//   gcc -O2 -mfma -ffp-contract=off -o /tmp/fastdiv_check tools/fastdiv_check.c -lm && /tmp/fastdiv_check [percent]
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 static uint64_t s[2] = {0x9E3779B97F4A7C15ull, 0xD1B54A32D192ED03ull};
@@ -32,12 +32,6 @@ static inline double div1(double a, double b, double y) {
   const double r0 = __builtin_fma(-b, q0, a);
   return __builtin_fma(r0, y, q0);
 }
-static inline double div2(double a, double b, double y) {
-  const double q1 = div1(a, b, y);
-  const double r1 = __builtin_fma(-b, q1, a);
-  return __builtin_fma(r1, y, q1);
-}
-
 // random double with biased exponent in [elo, ehi], random sign, significand drawn from a mix of patterns
 static double rand_double(int elo, int ehi) {
   uint64_t m = rnd() & 0xFFFFFFFFFFFFFull;
@@ -52,12 +46,14 @@ static double rand_double(int elo, int ehi) {
   return bits2d(((rnd() & 1) << 63) | (e << 52) | m);
 }
 
-int main(void) {
-  unsigned long long bad1 = 0, bad2 = 0, n1 = 0, n2 = 0;
+int main(int argc, char** argv) {
+  // optional argument: scale in percent of the full search (tests run 5)
+  const long pct = argc > 1 ? atol(argv[1]) : 100;
+  unsigned long long bad1 = 0, n1 = 0;
   // (1) integer divisors
   for (int b = 1; b <= 65535; ++b) {
     const double db = (double)b, y = 1.0 / db;
-    for (int i = 0; i < 3000; ++i) {
+    for (long i = 0; i < 30 * pct; ++i) {
       const double a = rand_double(1023 - 400, 1023 + 400);
       const double want = a / db, got = div1(a, db, y);
       ++n1;
@@ -74,20 +70,6 @@ int main(void) {
       if (d2bits(want) != d2bits(got)) { if (bad1 < 10) printf("int/int mismatch %d / %d\n", a, b); ++bad1; }
     }
   }
-  // (2) arbitrary divisors, exponents within the guarded window of the kernel
-  for (long i = 0; i < 400000000L; ++i) {
-    double b = fabs(rand_double(1023 - 400, 1023 + 400));
-    if ((d2bits(b) & 0xFFFFFFFFFFFFFull) == 0xFFFFFFFFFFFFFull) continue;    // kernel takes the IEEE path
-    const double a = rand_double(1023 - 400, 1023 + 400);
-    const double y = 1.0 / b;
-    const double want = a / b, got = div2(a, b, y);
-    ++n2;
-    if (d2bits(want) != d2bits(got)) {
-      if (bad2 < 10) printf("range divisor mismatch: %a / %a: %a vs %a\n", a, b, want, got);
-      ++bad2;
-    }
-  }
   printf("integer divisors: %llu checked, %llu mismatches\n", n1, bad1);
-  printf("arbitrary divisors (two steps): %llu checked, %llu mismatches\n", n2, bad2);
-  return (bad1 || bad2) ? 1 : 0;
+  return bad1 ? 1 : 0;
 }
