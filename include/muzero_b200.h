@@ -247,6 +247,30 @@ int mz_unroll_sequences(int32_t games, int32_t max_len, int32_t unroll_steps, in
                         const float* pi /* [G,max_len,A] */, int32_t* out_action, float* out_reward, float* out_value,
                         float* out_pi, uint8_t* valid /* nullable */, mz_stream stream);
 
+/* ---- device-resident replay (reference: muzero/replay.py:38-142) ---------------------------------
+ * The caller (muzero_b200/replay.py) owns every buffer; rng_key u32[624] / rng_pos i32[1] are numpy legacy MT19937
+ * states on the device (same format as MZ_VIEW_RNG_KEY / MZ_VIEW_RNG_POS).                                        */
+/* PrioritizedReplay.sample with priority_exponent == 0 (replay.py:89-91): out_index[k] = trunc(size * u_k) for
+ * consecutive doubles of the replay's OWN stream, out_weight[k] = 1.                                               */
+int mz_replay_sample_uniform(int64_t size, int32_t batch, uint32_t* rng_key, int32_t* rng_pos, int64_t* out_index,
+                             float* out_weight, mz_stream stream);
+/* PrioritizedReplay.sample with priority_exponent != 0 (replay.py:93-100): float32 priorities ** exponent / their
+ * float32 pairwise sum, np.random.choice(p=...) on the stream passed in (the reference draws from the GLOBAL numpy
+ * stream here), importance weights ((1/size) / p[idx]) ** importance_exponent / max.  scratch_probs: f32[size + 1],
+ * scratch_cdf: f64[size].  Bit-exact for exponents 1, 2 and 0.5 (numpy's exact paths), powf otherwise.              */
+int mz_replay_sample_prioritized(int64_t size, int32_t batch, const float* priorities, float priority_exponent,
+                                 float importance_exponent, uint32_t* rng_key, int32_t* rng_pos, float* scratch_probs,
+                                 double* scratch_cdf, int64_t* out_index, float* out_weight, mz_stream stream);
+/* PrioritizedReplay.add for n items at once (replay.py:70-79): storage[(start + i) % capacity] = rows[i]            */
+int mz_replay_scatter(const void* rows, void* storage, int64_t n, int64_t row_bytes, int64_t start, int64_t capacity,
+                      mz_stream stream);
+/* PrioritizedReplay.get + the np.stack of sample (replay.py:81-83,102-104): rows[i] = storage[index[i]]            */
+int mz_replay_gather(const void* storage, const int64_t* index, void* rows, int64_t n, int64_t row_bytes,
+                     mz_stream stream);
+/* PrioritizedReplay.update_priorities (replay.py:107-114): in order, later duplicates win                          */
+int mz_replay_update_priorities(float* priorities, const int64_t* index, const float* values, int32_t n,
+                                mz_stream stream);
+
 /* number of kernels the library has launched since load (bench's gpu_launches) */
 uint64_t mz_launch_count(void);
 

@@ -49,6 +49,11 @@ PROTOTYPES = {
     'mz_dirichlet': (C.c_int, [_P, C.c_double, _P, _P]),
     'mz_search_reset': (C.c_int, [_P, _P, _P, C.c_double, _P, _P, _P, _P]),
     'mz_select': (C.c_int, [_P, _P]),
+    'mz_replay_sample_uniform': (C.c_int, [C.c_int64, C.c_int32, _P, _P, _P, _P, _P]),
+    'mz_replay_sample_prioritized': (C.c_int, [C.c_int64, C.c_int32, _P, C.c_float, C.c_float, _P, _P, _P, _P, _P, _P, _P]),
+    'mz_replay_scatter': (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P]),
+    'mz_replay_gather': (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, _P]),
+    'mz_replay_update_priorities': (C.c_int, [_P, _P, _P, C.c_int32, _P]),
     'mz_expand_backup': (C.c_int, [_P, _P, _P, _P]),
     'mz_expand_backup_select': (C.c_int, [_P, _P, _P, _P]),
     'mz_root_policy': (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, _P, _P]),
