@@ -497,33 +497,48 @@ def train_step_sample(net, spec, dev, world, batch=128, unroll=5, warmup=2, step
     twin.load_state_dict(net.state_dict())
     learner = DataParallelLearner(twin, spec['cfg'], dev)
     rank = dist.get_rank() if world > 1 else 0
-    tr, w = synthetic_transitions(twin, batch, unroll, seed=500 + rank)
+    # batches come out of the device-resident replay: 64 batches' worth of synthetic transitions,
+    # uniform sampling like every run_training.py of the reference, sample + gather inside the timed step
+    from muzero_b200.replay import DeviceReplay
+    replay = DeviceReplay(64 * batch, 0.0, 0.0, np.random.RandomState(900 + rank), device=dev)
+    for k in range(64):
+        tr_k, _ = synthetic_transitions(twin, batch, unroll, seed=500 + 64 * rank + k)
+        replay.add_batch(tr_k, np.ones(batch, np.float32))
     for _ in range(warmup):
+        tr, idx, w = replay.sample(batch)
         learner.step(tr, w)
     torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ar = []
     if world > 1:
         dist.barrier()
     e0.record()
     for _ in range(steps):
-        loss, _ = learner.step(tr, w, time_allreduce=world > 1)
+        s0.record()
+        tr, idx, w = replay.sample(batch)
+        s1.record()
+        loss, prio = learner.step(tr, w, time_allreduce=world > 1)
+        replay.update_priorities(idx, prio)
         if learner.last_allreduce_ms is not None:
             ar.append(learner.last_allreduce_ms)
     e1.record()
     torch.cuda.synchronize(dev)
+    sample_ms = s0.elapsed_time(s1)
     ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     nbytes = learner.flat_grad.numel() * 4
     out = {'ms_per_step': float(ms.item()), 'batch_per_gpu': batch, 'unroll_steps': unroll, 'loss': loss,
            'samples_per_s': world * batch / (float(ms.item()) / 1e3), 'grad_bytes': nbytes,
-           'impl': 'PyTorch autograd fwd/bwd + one flat NCCL all-reduce + Adam'}
+           'replay_sample_ms': sample_ms, 'replay_items': replay.size,
+           'impl': 'DeviceReplay.sample (sampling + gather kernels) -> PyTorch autograd fwd/bwd + one flat NCCL '
+                   'all-reduce + Adam -> update_priorities'}
     if ar:
         a = sum(ar) / len(ar)
         out['allreduce_ms'] = a
         out['allreduce_bus_gbs'] = 2.0 * (world - 1) / world * nbytes / (a * 1e-3) / 1e9
-    del learner, twin
+    del learner, twin, replay
     torch.cuda.empty_cache()
     return out
 

@@ -19,6 +19,8 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python tools/profile_target.py gomoku 3 1024 > $O/${TAG}_ncu_launch.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv3x3 -s 2 -c 1 -f -o $O/${TAG}_conv_full \
     python tools/profile_target.py gomoku 2 1024 > $O/${TAG}_ncu_full.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:backup_select_kernel -s 150 -c 1 -f -o $O/${TAG}_select_full \
+    python tools/profile_target.py gomoku 200 1024 > $O/${TAG}_ncu_select.log 2>&1
 tail -3 $O/${TAG}_pytest_gpu.log
 cat $O/${TAG}_bench_gomoku.json
 tail -3 $O/${TAG}_bench_gomoku.err
