@@ -484,7 +484,7 @@ def run_engine_arm(args):
         dist.destroy_process_group()
 
 
-def train_step_sample(net, spec, dev, world, batch=128, unroll=5, warmup=2, steps=3):
+def train_step_sample(net, spec, dev, world, batch=128, unroll=5, warmup=6, steps=5):
     """BASELINE.json config 5's second half: the K=5-unroll training step, data-parallel, one flat
     NCCL all-reduce of the gradients (PyTorch autograd forward/backward)."""
     import copy
@@ -518,13 +518,20 @@ def train_step_sample(net, spec, dev, world, batch=128, unroll=5, warmup=2, step
         s0.record()
         tr, idx, w = replay.sample(batch)
         s1.record()
-        loss, prio = learner.step(tr, w, time_allreduce=world > 1)
+        loss, prio = learner.step(tr, w)
         replay.update_priorities(idx, prio)
-        if learner.last_allreduce_ms is not None:
-            ar.append(learner.last_allreduce_ms)
     e1.record()
     torch.cuda.synchronize(dev)
     sample_ms = s0.elapsed_time(s1)
+    if world > 1:                        # the gradient all-reduce on its own (inside the step it is part of the graph)
+        for i in range(8):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            dist.all_reduce(learner.flat_grad, op=dist.ReduceOp.SUM)
+            a1.record()
+            torch.cuda.synchronize(dev)
+            if i >= 3:
+                ar.append(a0.elapsed_time(a1))
     ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -532,8 +539,9 @@ def train_step_sample(net, spec, dev, world, batch=128, unroll=5, warmup=2, step
     out = {'ms_per_step': float(ms.item()), 'batch_per_gpu': batch, 'unroll_steps': unroll, 'loss': loss,
            'samples_per_s': world * batch / (float(ms.item()) / 1e3), 'grad_bytes': nbytes,
            'replay_sample_ms': sample_ms, 'replay_items': replay.size,
-           'impl': 'DeviceReplay.sample (sampling + gather kernels) -> PyTorch autograd fwd/bwd + one flat NCCL '
-                   'all-reduce + Adam -> update_priorities'}
+           'cuda_graph': bool(learner.use_graph and learner._graph is not None),
+           'impl': 'DeviceReplay.sample (sampling + gather kernels) -> ONE CUDA graph of the PyTorch autograd fwd/bwd, '
+                   'the flat NCCL all-reduce and Adam -> update_priorities'}
     if ar:
         a = sum(ar) / len(ar)
         out['allreduce_ms'] = a

@@ -9,8 +9,9 @@ from .config import (KnownBounds, MuZeroConfig, make_atari_config, make_classic_
 from .network import MuZeroAtariNet, MuZeroBoardGameNet, MuZeroMLPNet, MuZeroNet, NetworkOutputs
 from .mcts import SearchPool, uct_search, uct_search_batch
 from .selfplay import BatchedBoardEnv, BoardSelfPlay, mc_return_targets, n_step_targets, unroll_sequences
+from .replay import DeviceReplay
 
 __all__ = ['KnownBounds', 'MuZeroConfig', 'make_atari_config', 'make_classic_config', 'make_gomoku_config',
            'make_tictactoe_config', 'MuZeroAtariNet', 'MuZeroBoardGameNet', 'MuZeroMLPNet', 'MuZeroNet',
            'NetworkOutputs', 'SearchPool', 'uct_search', 'uct_search_batch', 'BatchedBoardEnv', 'BoardSelfPlay',
-           'mc_return_targets', 'n_step_targets', 'unroll_sequences']
+           'mc_return_targets', 'n_step_targets', 'unroll_sequences', 'DeviceReplay']

@@ -29,6 +29,14 @@ import torch.nn.functional as F
 from .network import MuZeroNet
 
 
+class _nullcontext:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
 class Transition(NamedTuple):
     state: Optional[np.ndarray]
     action: Optional[np.ndarray]
@@ -81,15 +89,11 @@ def loss_func(prediction: torch.Tensor, target: torch.Tensor, mse: bool = False)
     return F.cross_entropy(prediction, target, reduction='none')
 
 
-def calc_loss(network: MuZeroNet, device, transitions: Transition, weights: torch.Tensor):
-    """pipeline.py:541-612: representation, then T unrolled (prediction, dynamics) steps with the
-    0.5 gradient scale on the hidden state and the 1/T scale on the loss."""
-    state = torch.as_tensor(transitions.state).to(device=device, dtype=torch.float32, non_blocking=True)
-    action = torch.as_tensor(transitions.action).to(device=device, dtype=torch.long, non_blocking=True)
-    target_value_scalar = torch.as_tensor(transitions.value).to(device=device, dtype=torch.float32, non_blocking=True)
-    target_reward_scalar = torch.as_tensor(transitions.reward).to(device=device, dtype=torch.float32, non_blocking=True)
-    target_pi_prob = torch.as_tensor(transitions.pi_prob).to(device=device, dtype=torch.float32, non_blocking=True)
-
+def calc_loss_tensors(network: MuZeroNet, state, action, target_value_scalar, target_reward_scalar, target_pi_prob,
+                      weights):
+    """pipeline.py:541-612 on device tensors, no host synchronisation (so a whole training step can be captured in a
+    CUDA graph): representation, then T unrolled (prediction, dynamics) steps with the 0.5 gradient scale on the
+    hidden state and the 1/T scale on the loss.  Returns (loss, priorities tensor [B])."""
     target_value = target_value_scalar if network.mse_loss_for_value else \
         scalar_to_categorical_probabilities(target_value_scalar, network.value_support_size)
     target_reward = target_reward_scalar if network.mse_loss_for_reward else \
@@ -115,14 +119,33 @@ def calc_loss(network: MuZeroNet, device, transitions: Transition, weights: torc
         pv = torch.stack(pred_values, dim=1)
         pv_scalar = pv.squeeze(-1) if network.mse_loss_for_value else \
             logits_to_transformed_expected_value(pv, network.value_support_size).squeeze(-1)
-        priorities = (pv_scalar[:, 0] - target_value_scalar[:, 0]).abs().cpu().numpy()
+        priorities = (pv_scalar[:, 0] - target_value_scalar[:, 0]).abs()
     return loss, priorities
 
 
-class DataParallelLearner:
-    """One learner iteration of pipeline.py:232-257 on every rank, gradients averaged by one all-reduce."""
+def _to_device(transitions: Transition, device):
+    return (torch.as_tensor(transitions.state).to(device=device, dtype=torch.float32, non_blocking=True),
+            torch.as_tensor(transitions.action).to(device=device, dtype=torch.long, non_blocking=True),
+            torch.as_tensor(transitions.value).to(device=device, dtype=torch.float32, non_blocking=True),
+            torch.as_tensor(transitions.reward).to(device=device, dtype=torch.float32, non_blocking=True),
+            torch.as_tensor(transitions.pi_prob).to(device=device, dtype=torch.float32, non_blocking=True))
 
-    def __init__(self, network: MuZeroNet, config, device, process_group=None) -> None:
+
+def calc_loss(network: MuZeroNet, device, transitions: Transition, weights: torch.Tensor):
+    """pipeline.py:541-612 with the reference's signature: (loss, priorities as a host array)."""
+    loss, priorities = calc_loss_tensors(network, *_to_device(transitions, device), weights)
+    return loss, priorities.cpu().numpy()
+
+
+class DataParallelLearner:
+    """One learner iteration of pipeline.py:232-257 on every rank, gradients averaged by one all-reduce.
+
+    On a CUDA device the whole iteration (zero grads, K-step unroll forward, backward, all-reduce, clip, Adam) is
+    captured in ONE CUDA graph after three eager iterations and replayed from static input buffers: at batch 128 the
+    ~3000 small kernels of the unroll are launch-bound when issued from Python.  ``use_graph=False`` keeps every
+    iteration eager; a capture that fails (e.g. a collective backend that cannot be captured) falls back to eager."""
+
+    def __init__(self, network: MuZeroNet, config, device, process_group=None, use_graph: bool = True) -> None:
         self.network, self.config, self.device = network, config, torch.device(device)
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
@@ -134,18 +157,26 @@ class DataParallelLearner:
             p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
             off += p.numel()
         self.params = params
-        # gomoku/run_training.py:110 / classic: Adam(lr_init, weight_decay), MultiStepLR(milestones, lr_decay_rate)
-        self.optimizer = torch.optim.Adam(params, lr=config.lr_init, weight_decay=config.weight_decay)
+        self.use_graph = bool(use_graph) and self.device.type == 'cuda'
+        # gomoku/run_training.py:110 / classic: Adam(lr_init, weight_decay), MultiStepLR(milestones, lr_decay_rate).
+        # Graph mode: step counters and the learning rate live on the device so that a replay sees their updates.
+        # (On CUDA the optimizer is the capturable flavour whether or not the graph is used, so that eager and
+        # replayed iterations run the same arithmetic.)
+        on_cuda = self.device.type == 'cuda'
+        lr = torch.tensor(float(config.lr_init), device=self.device) if on_cuda else config.lr_init
+        self.optimizer = torch.optim.Adam(params, lr=lr, weight_decay=config.weight_decay, capturable=on_cuda)
         self.lr_scheduler = torch.optim.lr_scheduler.MultiStepLR(self.optimizer, milestones=list(config.lr_milestones),
                                                                  gamma=config.lr_decay_rate)
         self.train_steps = 0
         self.last_allreduce_ms = None
+        self._graph = None
+        self._static = None
+        self._eager_left = 3
 
-    def step(self, transitions: Transition, weights, time_allreduce: bool = False) -> Tuple[float, np.ndarray]:
-        self.network.train()
+    def _iteration(self, state, action, value, reward, pi, w, time_allreduce: bool = False):
+        """zero grads -> loss -> backward -> all-reduce -> clip -> Adam; device tensors in and out."""
         self.flat_grad.zero_()                                  # optimizer.zero_grad() that keeps the views
-        w = torch.as_tensor(weights).to(device=self.device, dtype=torch.float32)
-        loss, priorities = calc_loss(self.network, self.device, transitions, w)
+        loss, priorities = calc_loss_tensors(self.network, state, action, value, reward, pi, w)
         loss.backward()
         if self.world > 1:
             if time_allreduce and self.device.type == 'cuda':
@@ -160,9 +191,43 @@ class DataParallelLearner:
         if self.config.clip_grad:
             torch.nn.utils.clip_grad_norm_(self.params, self.config.max_grad_norm)
         self.optimizer.step()
+        return loss.detach(), priorities
+
+    def _graphed(self, inputs):
+        if self._static is None or any(a.shape != b.shape for a, b in zip(self._static, inputs)):
+            self._static = [torch.empty_like(t) for t in inputs]
+            self._graph = None
+        for dst, src in zip(self._static, inputs):
+            dst.copy_(src, non_blocking=True)
+        if self._graph is None:
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._out = self._iteration(*self._static)
+                self._graph = g
+            except Exception as exc:                            # noqa: BLE001 - any capture failure -> eager for good
+                import warnings
+                warnings.warn(f'training-step graph capture failed ({exc!r}); continuing eagerly')
+                self.use_graph = False
+                torch.cuda.synchronize(self.device)
+                self.flat_grad.zero_()
+                return self._iteration(*inputs)
+        self._graph.replay()
+        return self._out
+
+    def step(self, transitions: Transition, weights, time_allreduce: bool = False) -> Tuple[float, np.ndarray]:
+        self.network.train()
+        with torch.cuda.device(self.device) if self.device.type == 'cuda' else _nullcontext():
+            w = torch.as_tensor(weights).to(device=self.device, dtype=torch.float32)
+            inputs = _to_device(transitions, self.device) + (w,)
+            if self.use_graph and not time_allreduce and self._eager_left <= 0:
+                loss, priorities = self._graphed(inputs)
+            else:
+                self._eager_left -= 1
+                loss, priorities = self._iteration(*inputs, time_allreduce=time_allreduce)
         self.lr_scheduler.step()
         self.train_steps += 1
-        return float(loss.detach()), priorities
+        return float(loss), priorities.cpu().numpy()
 
     def state_dict(self):
         """Same keys as the reference's checkpoints (pipeline.py:224-230)."""
