@@ -303,7 +303,9 @@ __global__ void transpose_kernel(const float* __restrict__ w, float* __restrict_
 // loads while the current one is multiplied.
 
 constexpr int kTcRows = 128;          // rows per tile == compute threads
-constexpr int kTcThreads = 160;       // 4 compute warps + 1 producer warp
+constexpr int kTcCompute = 256;       // 8 compute warps: warps 0-3 own the tile's rows (thread = row), warps 4-7 share
+                                      // their TMEM lane quadrants and take half of the first-layer epilogue's columns
+constexpr int kTcThreads = 288;       // + 1 producer warp
 constexpr int kTcChunk = 256;         // hidden units per chunk
 constexpr int kTcSlots = 3;           // weight ring
 constexpr int kTcSlotBytes = 32768;
@@ -321,6 +323,7 @@ struct MlpTcParams {
   int batch;
   const float* hidden_in; const int32_t* src_index; const int32_t* action;
   float* hidden_out; const int32_t* dst_index; float* reward; float* value; float* pi;
+  long long* dbg;                     // MZ_MLP_DEBUG: clock64 stamps of CTA 0 / thread 0 (measurement aid)
 };
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
@@ -347,6 +350,21 @@ __device__ __forceinline__ float support_scalar_regs(const float (&l)[32], int S
   return signed_parabolic(num / den);
 }
 
+// leaf gather: parent hidden state of row `row` of tile `tile` by slot index -> fp16 operand tile in shared memory
+__device__ __forceinline__ void gather_tile(const MlpTcParams& p, int tile, int row, uint32_t sIn_a) {
+  const int grow = tile * kTcRows + row;
+  const bool live = grow < p.batch;
+  const size_t slot = live ? (p.src_index ? (size_t)p.src_index[grow] : (size_t)grow) : 0;
+  const float4* src = reinterpret_cast<const float4*>(p.hidden_in + slot * 64);
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (live) { a = src[2 * g]; b = src[2 * g + 1]; }
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sIn_a + (uint32_t)(g * 128 + row) * 16),
+                 "r"(pack_h2(a.x, a.y)), "r"(pack_h2(a.z, a.w)), "r"(pack_h2(b.x, b.y)), "r"(pack_h2(b.z, b.w)) : "memory");
+  }
+}
+
 __global__ void __launch_bounds__(kTcThreads, 1) mlp_recurrent_tc_kernel(const __grid_constant__ MlpTcParams p) {
   extern __shared__ __align__(1024) unsigned char tsm[];
   unsigned char* sIn = tsm;                       // [8][128][16]  h_in   (fp16, K-major core matrices)
@@ -361,11 +379,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_recurrent_tc_kernel(const _
   float* sB1 = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_holder + 4) + 15) & ~(uintptr_t)15);   // [4][P] first-layer biases
   float* sTab = sB1 + 4 * p.P;                                      // [A][P] action columns (when they fit)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int dbg_n = 0;
+  auto stamp = [&]() { if (p.dbg && blockIdx.x == 0 && tid == 0 && dbg_n < 60) p.dbg[dbg_n++] = clock64(); };
+  stamp();
+  // the first tile's leaf gather (two dependent global round trips) overlaps the staging below and the TMEM allocation
+  if (tid < 128 && (int)blockIdx.x * kTcRows < p.batch) gather_tile(p, (int)blockIdx.x, tid, smem_u32(sIn));
   // first-layer biases and the action table are read by every row of every tile: stage them once per CTA
   // (from global they cost an exposed L2 round trip per 32-column chunk of every epilogue)
   for (int i = tid; i < p.nnets * p.P; i += kTcThreads) sB1[i] = p.b1[i / p.P][i % p.P];
+  // rows of the table are padded by 4 floats: rows of a warp pick different actions, and with a stride of P floats
+  // (a multiple of 32 banks) every action's column c sits in the same bank -- a 10-way conflict per float4
+  const int tabP = p.P + 4;
   if (p.tab_in_smem)
-    for (int i = tid; i < p.A * p.P; i += kTcThreads) sTab[i] = p.tabA[i];
+    for (int i = tid; i < p.A * p.P; i += kTcThreads) sTab[(i / p.P) * tabP + i % p.P] = p.tabA[i];
 
   if (tid == 0) {
     for (int s = 0; s < kTcSlots; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
@@ -378,8 +404,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_recurrent_tc_kernel(const _
   tc_fence_after();
   const uint32_t tmem = *tmem_holder;
   const int ntiles = (p.batch + kTcRows - 1) / kTcRows;
+  stamp();
 
-  if (warp == 4) {
+  if (warp == kTcCompute / 32) {
     // ------------------------------------------------ weight producer
     if (lane == 0) {
       uint32_t it = 0;
@@ -392,12 +419,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_recurrent_tc_kernel(const _
         }
     }
   } else {
-    // ------------------------------------------------ compute: thread = row of the tile
-    const int row = tid;
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);          // this warp's TMEM lanes
+    // ------------------------------------------------ compute: thread (warps 0-3) = row of the tile; warps 4-7 help
+    // with epilogue 1, the longest serial piece of a tile (256 columns per row): a warp can only read the TMEM lanes
+    // of its quadrant (warp % 4), so warp w + 4 takes columns 128..255 of the rows warp w owns
+    const int row = tid & 127;
+    const bool owner = tid < 128;
+    const int qbeg = owner ? 0 : 4;
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);    // this warp's TMEM lanes
     const uint32_t sIn_a = smem_u32(sIn), sRaw_a = smem_u32(sRaw), sNorm_a = smem_u32(sNorm), sMid_a = smem_u32(sMid);
     uint32_t wit = 0, mma_ph = 0;
-    auto bar128 = []() { asm volatile("bar.sync 1, 128;" ::: "memory"); };
+    auto bar128 = []() { asm volatile("bar.sync 1, 256;" ::: "memory"); };   // all compute warps
     // tid 0 issues `n` K-steps of D(+)= A.B^T on the weight block at the head of the ring, then every thread
     // waits for them (one mbarrier, alternating phase)
     auto mma_group = [&](uint32_t a_addr, int ksteps, uint32_t dcol, uint32_t N, bool accumulate) {
@@ -424,34 +455,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_recurrent_tc_kernel(const _
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int grow = tile * kTcRows + row;
       const bool live = grow < p.batch;
-      // leaf gather: parent hidden state by slot index -> fp16 operand tile
-      {
-        const size_t slot = live ? (p.src_index ? (size_t)p.src_index[grow] : (size_t)grow) : 0;
-        const float4* src = reinterpret_cast<const float4*>(p.hidden_in + slot * 64);
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-          if (live) { a = src[2 * g]; b = src[2 * g + 1]; }
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sIn_a + (uint32_t)(g * 128 + row) * 16),
-                       "r"(pack_h2(a.x, a.y)), "r"(pack_h2(a.z, a.w)), "r"(pack_h2(b.x, b.y)), "r"(pack_h2(b.z, b.w)) : "memory");
-        }
-      }
+      // leaf gather (the CTA's first tile was gathered before the prologue barrier)
+      if (owner && tile != (int)blockIdx.x) gather_tile(p, tile, row, sIn_a);
       int act = live ? p.action[grow] : 0;
       act = min(max(act, 0), p.A - 1);
       fence_proxy_async();
       tc_fence_before();
       bar128();
+      stamp();
 
       for (int net = 0; net < p.nnets; ++net) {
         const uint32_t a_in = net == 0 ? sIn_a : (net == 1 ? sRaw_a : sNorm_a);
         const uint32_t N2 = net == 0 ? 64u : (net == 3 ? (uint32_t)p.Apad : 32u);
         const float* b1 = sB1 + net * p.P;
-        const float* tab = net == 0 ? (p.tab_in_smem ? sTab : p.tabA) + (size_t)act * p.P : nullptr;
+        const float* tab = net == 0 ? (p.tab_in_smem ? sTab + (size_t)act * tabP : p.tabA + (size_t)act * p.P) : nullptr;
         for (int c = 0; c < p.chunks; ++c) {
           mma_group(a_in, 4, 0u, 256u, false);                        // D1 = A_in . W1c^T
+          stamp();
           // epilogue 1: bias (+ action column) + ReLU -> fp16 hidden chunk in shared memory
 #pragma unroll 1
-          for (int q = 0; q < 8; ++q) {
+          for (int q = qbeg; q < qbeg + 4; ++q) {
             uint32_t r[32];
             tmem_ld32(trow + (uint32_t)(q * 32), r);
             tmem_ld_wait();
@@ -481,11 +504,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_recurrent_tc_kernel(const _
           fence_proxy_async();
           tc_fence_before();
           bar128();
+          stamp();
           mma_group(sMid_a, 16, 256u, N2, c > 0);                     // D2 (+)= A_mid . W2c^T
+          stamp();
         }
         // epilogue 2
         const float* b2 = p.b2[net];
-        if (net == 0) {
+        if (!owner) {
+          // helpers have no part in the second-layer epilogues
+        } else if (net == 0) {
           // transition output: h_raw (for the reward net) and its min-max normalisation (util.py:31-36)
           float h[64];
 #pragma unroll
@@ -496,28 +523,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_recurrent_tc_kernel(const _
 #pragma unroll
             for (int e = 0; e < 32; ++e) h[q * 32 + e] = __uint_as_float(r[e]) + __ldg(b2 + q * 32 + e);
           }
+          stamp();
           float mn = INFINITY, mx = -INFINITY;
 #pragma unroll
           for (int e = 0; e < 64; ++e) { mn = fminf(mn, h[e]); mx = fmaxf(mx, h[e]); }
-          const float den = __fadd_rn(__fsub_rn(mx, mn), 1e-8f);
+          // (h - min) * (1 / den): 64 IEEE divisions per row serialise behind their slow-path checks (measured 10 k
+          // cycles of a 42 k-cycle tile with only the four row-owner warps active); the product differs from the
+          // quotient by at most 1 ulp of fp32, three orders of magnitude below the fp16 operand rounding
+          const float inv = __fdiv_rn(1.0f, __fadd_rn(__fsub_rn(mx, mn), 1e-8f));
 #pragma unroll
           for (int g = 0; g < 8; ++g)
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sRaw_a + (uint32_t)(g * 128 + row) * 16),
                          "r"(pack_h2(h[8 * g], h[8 * g + 1])), "r"(pack_h2(h[8 * g + 2], h[8 * g + 3])),
                          "r"(pack_h2(h[8 * g + 4], h[8 * g + 5])), "r"(pack_h2(h[8 * g + 6], h[8 * g + 7])) : "memory");
 #pragma unroll
-          for (int e = 0; e < 64; ++e) h[e] = __fdiv_rn(__fsub_rn(h[e], mn), den);
+          for (int e = 0; e < 64; ++e) h[e] = __fmul_rn(__fsub_rn(h[e], mn), inv);
 #pragma unroll
           for (int g = 0; g < 8; ++g)
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sNorm_a + (uint32_t)(g * 128 + row) * 16),
                          "r"(pack_h2(h[8 * g], h[8 * g + 1])), "r"(pack_h2(h[8 * g + 2], h[8 * g + 3])),
                          "r"(pack_h2(h[8 * g + 4], h[8 * g + 5])), "r"(pack_h2(h[8 * g + 6], h[8 * g + 7])) : "memory");
+          stamp();
           if (live) {
             const size_t slot = p.dst_index ? (size_t)p.dst_index[grow] : (size_t)grow;
             float4* dst = reinterpret_cast<float4*>(p.hidden_out + slot * 64);
 #pragma unroll
             for (int g = 0; g < 16; ++g) dst[g] = make_float4(h[4 * g], h[4 * g + 1], h[4 * g + 2], h[4 * g + 3]);
           }
+          stamp();
         } else if (net == 1 || net == 2) {
           uint32_t r[32];
           tmem_ld32(trow + 256u, r);
@@ -551,11 +584,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_recurrent_tc_kernel(const _
         fence_proxy_async();
         tc_fence_before();
         bar128();
+        stamp();
       }
     }
   }
   tc_fence_before();
   __syncthreads();
+  stamp();
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
@@ -608,10 +643,22 @@ struct MlpNet : NetImpl {
       q.nnets = pi_probs ? 4 : 3;
       q.nblk = pi_probs ? tc_blocks_policy : tc_blocks_no_policy;
       const int ntiles = (batch + kTcRows - 1) / kTcRows;
+      static const bool debug = getenv("MZ_MLP_DEBUG") != nullptr;
+      q.dbg = nullptr;
+      if (debug) { cudaMalloc(&q.dbg, 64 * sizeof(long long)); cudaMemset(q.dbg, 0, 64 * sizeof(long long)); }
       prof_mark(kProfMlp, st);
       mlp_recurrent_tc_kernel<<<ntiles < num_sms ? ntiles : num_sms, kTcThreads, tc_smem, st>>>(q);
       prof_mark(-1, st);
       MZ_LAUNCH_CHECK("mlp_recurrent_tc_kernel");
+      if (debug) {   // measurement aid: cycle stamps of CTA 0 (start, prologue, gather, then per net: MMA1, epi1, MMA2, epi2; end)
+        cudaDeviceSynchronize();
+        long long h[64];
+        cudaMemcpy(h, q.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        cudaFree(q.dbg);
+        fprintf(stderr, "[mlp dbg] cycles since start:");
+        for (int i = 1; i < 64 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[0]);
+        fprintf(stderr, "\n");
+      }
       return MZ_OK;
     }
     prof_mark(kProfMlp, st);
@@ -745,8 +792,8 @@ int mlp_create(const mz_net_config& c, const float* const* w, int nw, void* aren
       MZ_CUDA(cudaDeviceSynchronize());
       if ((size_t)(p - (char*)arena) > arena_bytes) { set_error("internal: MLP arena overrun"); delete net; return MZ_ENOMEM; }
       net->tc_smem = 3 * 16384 + 65536 + (size_t)kTcSlots * kTcSlotBytes + 256 + (size_t)4 * P * 4;
-      q.tab_in_smem = net->tc_smem + (size_t)A * P * 4 <= 227 * 1024 ? 1 : 0;
-      if (q.tab_in_smem) net->tc_smem += (size_t)A * P * 4;
+      q.tab_in_smem = net->tc_smem + (size_t)A * (P + 4) * 4 <= 227 * 1024 ? 1 : 0;
+      if (q.tab_in_smem) net->tc_smem += (size_t)A * (P + 4) * 4;
       int dev = 0;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&net->num_sms, cudaDevAttrMultiProcessorCount, dev);
