@@ -427,7 +427,8 @@ def run_engine_arm(args):
         layers_per_launch = prof_n[0] / max(1, prof_n[4])
         launch_ms = prof_ms[0] / max(1, prof_n[4])
         alg = per_pos * hh * ww * Bp * layers_per_launch
-        exe = per_pos * (hh + 1) * (ww + 1) * Bp * layers_per_launch
+        pad = net.grid_pad          # 0: no halo rows (edge taps masked in the MMA), 1: padded (H+1)(W+1) grid
+        exe = per_pos * (hh + pad) * (ww + pad) * Bp * layers_per_launch
         ach = alg / (launch_ms * 1e-3) / 1e12
         traffic = None
         try:     # dram bytes of one launch from the committed ncu --set full capture of the same kernel

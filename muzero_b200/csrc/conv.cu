@@ -85,6 +85,7 @@ struct ConvParams {
   int TP;                         // tile rows incl. halo, odd
   int stages;                     // weight ring depth (as many as shared memory allows, <= kMaxStages)
   long long* dbg;                 // optional per-CTA role timing (MZ_CONV_DEBUG), else nullptr
+  int masked;                     // halo-free grid: edge taps are masked per output row (disable-output-lane)
   int ablate;                     // debug only (MZ_CONV_ABLATE): 1 skip epilogue work, 2 skip tile loads, 4 skip weight copies, 512 epilogue without global loads/stores
 };
 
@@ -160,6 +161,8 @@ __device__ __forceinline__ void quad_bar_sync(int quad) {
   }
 }
 
+__device__ __constant__ int kTapOrder[9] = {4, 0, 1, 2, 3, 5, 6, 7, 8};
+
 template <int kN, int kRows>
 __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvParams p) {
   constexpr bool kSplitK = (kRows == 128);
@@ -184,6 +187,7 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* s_bias = reinterpret_cast<float*>(tmem_holder + 4);            // [4][N] bias of layer l in slot l & 3, 16-byte aligned
   float2* s_mm = reinterpret_cast<float2*>(s_bias + 4 * p.N);           // [2][128] partial (min, max) per row
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_mm + 2 * 128);       // [2 tiles][2 halves][left,right,top,bottom][4] edge rows
 
   if (tid == 0) {
     for (uint32_t s = 0; s < kStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], kSplitK ? 1 : 2); }
@@ -218,7 +222,10 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
             if (dbg) t_wait += clock64() - tw;
             if (p.ablate & 4) { mbar_arrive(&w_full[s]); continue; }
             mbar_arrive_expect_tx(&w_full[s], stage_bytes);
-            bulk_g2s(sW + (size_t)s * stage_bytes, wl + (size_t)c * stage_bytes, stage_bytes, &w_full[s]);
+            // taps are consumed centre first (kTapOrder): the centre tap is the one no edge mask applies to, so it is
+            // the MMA that initialises every row of the accumulator
+            const int ti = c / chunks_tap, src_stage = kTapOrder[ti] * chunks_tap + (c - ti * chunks_tap);
+            bulk_g2s(sW + (size_t)s * stage_bytes, wl + (size_t)src_stage * stage_bytes, stage_bytes, &w_full[s]);
           }
         }
       }
@@ -262,10 +269,21 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
       const uint32_t dacc = tmem + (uint32_t)(buf * 256) + 128u * mhalf;
       uint32_t acc = 0;
       uint32_t stage_no = 0;                    // weight stage within the tile (split-K: stage s belongs to warp s & 1)
-      int shift = -p.Wp - 1;                    // tap (0,0); then +1, +1, +(Wp-2), ...
-      for (int tap = 0; tap < 9; ++tap) {
-        uint32_t a_lo = a_tile + (uint32_t)shift;        // wraps correctly: shift may be negative
-        shift += (tap == 2 || tap == 5) ? p.Wp - 2 : 1;
+      // rows of this accumulator that sit on a board edge (left / right column, top / bottom row), from the loader
+      uint4 eL = make_uint4(0, 0, 0, 0), eR = eL, eT = eL, eB = eL;
+      if (p.masked) {
+        const uint4* em = reinterpret_cast<const uint4*>(s_mask + (buf * 2 + (kSplitK ? 0 : (int)mhalf)) * 16);
+        eL = em[0]; eR = em[1]; eT = em[2]; eB = em[3];
+      }
+      for (int ti = 0; ti < 9; ++ti) {
+        const int tap = ti == 0 ? 4 : (ti <= 4 ? ti - 1 : ti);          // kTapOrder: centre first
+        const int ky = tap / 3, kx = tap - 3 * ky;
+        uint32_t a_lo = a_tile + (uint32_t)((ky - 1) * p.Wp + (kx - 1));   // wraps correctly: the shift may be negative
+        // output rows whose (y + ky - 1, x + kx - 1) neighbour is across a board edge take no part in this tap
+        const uint32_t m0 = (kx == 0 ? eL.x : 0u) | (kx == 2 ? eR.x : 0u) | (ky == 0 ? eT.x : 0u) | (ky == 2 ? eB.x : 0u);
+        const uint32_t m1 = (kx == 0 ? eL.y : 0u) | (kx == 2 ? eR.y : 0u) | (ky == 0 ? eT.y : 0u) | (ky == 2 ? eB.y : 0u);
+        const uint32_t m2 = (kx == 0 ? eL.z : 0u) | (kx == 2 ? eR.z : 0u) | (ky == 0 ? eT.z : 0u) | (ky == 2 ? eB.z : 0u);
+        const uint32_t m3 = (kx == 0 ? eL.w : 0u) | (kx == 2 ? eR.w : 0u) | (ky == 0 ? eT.w : 0u) | (ky == 2 ? eB.w : 0u);
         for (int ch = 0; ch < chunks_tap; ++ch, ++stage_no) {
           if (kSplitK && (stage_no & 1u) != mhalf) {     // the other warp's stage: just step the ring and the K offset
             a_lo += (uint32_t)ksteps * a_kstep;
@@ -281,14 +299,15 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
             uint32_t al[4], bl[4];
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) { al[ks] = a_lo + (uint32_t)ks * a_kstep; bl[ks] = b_lo + (uint32_t)ks * b_kstep; }
-            mma_f16_elect(dacc, desc64(al[0], a_hi), desc64(bl[0], b_hi), idesc, acc);
+            mma_f16_elect_masked(dacc, desc64(al[0], a_hi), desc64(bl[0], b_hi), idesc, acc, m0, m1, m2, m3);
 #pragma unroll
-            for (int ks = 1; ks < 4; ++ks) mma_f16_elect(dacc, desc64(al[ks], a_hi), desc64(bl[ks], b_hi), idesc, 1u);
+            for (int ks = 1; ks < 4; ++ks)
+              mma_f16_elect_masked(dacc, desc64(al[ks], a_hi), desc64(bl[ks], b_hi), idesc, 1u, m0, m1, m2, m3);
             acc = 1;
             a_lo += 4u * a_kstep;
           } else {
             for (int ks = 0; ks < ksteps; ++ks) {
-              mma_f16_elect(dacc, desc64(a_lo, a_hi), desc64(b_lo, b_hi), idesc, acc);
+              mma_f16_elect_masked(dacc, desc64(a_lo, a_hi), desc64(b_lo, b_hi), idesc, acc, m0, m1, m2, m3);
               acc = 1;
               a_lo += a_kstep;
               b_lo += b_kstep;
@@ -347,6 +366,20 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
         for (int c4 = lane; c4 * 4 < kN; c4 += 32)
           *reinterpret_cast<float4*>(s_bias + (l & 3) * kN + c4 * 4) = __ldg(reinterpret_cast<const float4*>(L.bias) + c4);
         bias_layer = l;
+      }
+      if (p.masked) {
+        // which rows of this tile are a board's left / right column or top / bottom row: one ballot per 32 rows
+        for (int h = 0; h < kRows / 128; ++h)
+          for (int w = 0; w < 4; ++w) {
+            const int P = tile * kRows + h * 128 + w * 32 + lane;
+            const int q = P % p.PB, y = q / p.Wp, x = q - y * p.Wp;
+            const unsigned mL = __ballot_sync(0xffffffffu, x == 0), mR = __ballot_sync(0xffffffffu, x == p.W - 1);
+            const unsigned mT = __ballot_sync(0xffffffffu, y == 0), mB = __ballot_sync(0xffffffffu, y == p.H - 1);
+            if (lane == 0) {
+              uint32_t* m = s_mask + (buf * 2 + h) * 16;
+              m[w] = mL; m[4 + w] = mR; m[8 + w] = mT; m[12 + w] = mB;
+            }
+          }
       }
       const uint32_t dst0 = smem_u32(sA) + (uint32_t)buf * a_bytes;
       const int lo = r0 > 0 ? r0 : 0;
@@ -599,10 +632,10 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
 // ---------------------------------------------------------------------------
 // obs f32 [B][C][H][W] -> fp16 planes [cpad/8][plane_rows][8] (zeros at halo positions and padded channels)
 __global__ void pack_obs_kernel(const float* __restrict__ obs, act_t* __restrict__ out, int B, int C, int H,
-                                int W, int cpad, int plane_rows) {
+                                int W, int cpad, int plane_rows, int pad) {
   // one thread per (channel group, row): 8 plane reads that are each coalesced across the threads of a warp
   // (consecutive x), one 16-byte store
-  const int Wp = W + 1, PB = (H + 1) * Wp;
+  const int Wp = W + pad, PB = (H + pad) * Wp;
   const size_t rows = (size_t)B * PB, n = rows * (cpad / 8);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const size_t P = i % rows;
@@ -622,7 +655,7 @@ __global__ void pack_obs_kernel(const float* __restrict__ obs, act_t* __restrict
 
 // zeros at the halo positions of a planar buffer (after the SIMT kernels that only write real positions)
 __global__ void zero_halo_kernel(act_t* __restrict__ buf, int B, int H, int W, int cg, int plane_rows) {
-  const int Wp = W + 1, PB = (H + 1) * Wp, nh = H + Wp;       // halo positions per board: column W of rows 0..H-1, row H
+  const int Wp = W + 1, PB = (H + 1) * Wp, nh = H + Wp;       // (padded layout only)       // halo positions per board: column W of rows 0..H-1, row H
   const size_t n = (size_t)cg * B * nh;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int k = (int)(i % nh);
@@ -644,7 +677,7 @@ struct HeadParams {
   const float* w2;            // [out][mid*hw]
   const float* b2;            // [out]
   float* dst;                 // [B] or [B][out]
-  int C, H, W, mid, out, kind;
+  int C, H, W, pad, mid, out, kind;
 };
 
 __device__ __forceinline__ float signed_parabolic_f(float x) {
@@ -666,7 +699,7 @@ struct HeadsParams {
 __global__ void __launch_bounds__(128) head_kernel(const __grid_constant__ HeadsParams hp) {
   const HeadParams& p = hp.h[blockIdx.y];
   extern __shared__ float hs[];            // f[mid*hw] | logits[out]
-  const int hw = p.H * p.W, Wp = p.W + 1, PB = (p.H + 1) * Wp;
+  const int hw = p.H * p.W, Wp = p.W + p.pad, PB = (p.H + p.pad) * Wp;
   float* f = hs;
   float* lg = hs + p.mid * hw;
   const int b = blockIdx.x;
@@ -777,8 +810,8 @@ __global__ void scale_rows_kernel(const float* w, const float* scale, float* out
 // 1 iff f % A == action), so their contribution is tab[a][pos][n] = scale[n] * sum over
 // (plane c, tap) of w[n][C + c][tap] * E_a[c][y+ky-1][x+kx-1].
 __global__ void action_table_kernel(const float* __restrict__ w, const float* __restrict__ scale,
-                                    float* __restrict__ tab, int A, int C, int N, int H, int W) {
-  const int Wp = W + 1, PB = (H + 1) * Wp, hw = H * W;
+                                    float* __restrict__ tab, int A, int C, int N, int H, int W, int pad) {
+  const int Wp = W + pad, PB = (H + pad) * Wp, hw = H * W;
   const size_t total = (size_t)A * PB * N;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     // table layout [A][N/8][PB][8]: the epilogue (lane = row) reads 32 contiguous bytes per channel group
@@ -816,9 +849,10 @@ __global__ void action_table_kernel(const float* __restrict__ w, const float* __
 // also writes the result to indexed hidden-state slots.
 __global__ void __launch_bounds__(256) avgpool_kernel(const act_t* __restrict__ in, act_t* __restrict__ out,
                                                       act_t* __restrict__ slots, const int32_t* __restrict__ out_index,
-                                                      int B, int Hi, int Wi, int normalise, int rows_in, int rows_out) {
+                                                      int B, int Hi, int Wi, int normalise, int rows_in, int rows_out,
+                                                      int pad) {
   constexpr int C = 128;
-  const int Ho = Hi / 2, Wo = Wi / 2, Wpi = Wi + 1, PBi = (Hi + 1) * Wpi, Wpo = Wo + 1, PBo = (Ho + 1) * Wpo;
+  const int Ho = Hi / 2, Wo = Wi / 2, Wpi = Wi + pad, PBi = (Hi + pad) * Wpi, Wpo = Wo + pad, PBo = (Ho + pad) * Wpo;
   const int lane = threadIdx.x & 31;
   const int g = lane >> 1, off = (lane & 1) * 4;      // channel-group plane and offset of this lane's 4 channels
   const long long total = (long long)B * PBo;         // halo positions included: they are written as zeros
@@ -872,10 +906,18 @@ struct Head {
   const float *w1, *b1, *w2, *b2;
   int mid, out, kind;
 };
+// Grid padding.  0 (default): boards are stored without halo, H*W rows each, and the conv kernel masks the taps that
+// would reach over a board edge with tcgen05.mma's disable-output-lane vector (no MMA row is spent on padding).
+// 1: the first layout of this kernel -- one zero column / row shared between neighbours, (H+1)*(W+1) rows per board,
+// every tap unmasked (19 % of the rows of a 9x9 board, 27 % of a 6x6 latent, are halo).  MZ_CONV_PAD=1 selects it.
+static int grid_pad() {
+  static const int pad = getenv("MZ_CONV_PAD") ? (atoi(getenv("MZ_CONV_PAD")) != 0) : 0;
+  return pad;
+}
 struct Geo {
   int H, W;
-  int Wp() const { return W + 1; }
-  int PB() const { return (H + 1) * (W + 1); }
+  int Wp() const { return W + grid_pad(); }
+  int PB() const { return (H + grid_pad()) * (W + grid_pad()); }
 };
 
 struct ConvNet : NetImpl {
@@ -904,7 +946,7 @@ struct ConvNet : NetImpl {
   size_t conv_fixed_smem(const Geo& g, int cg, int rows = kTileM) const {
     const int TP = tp_of(g, rows);
     size_t a = (((size_t)2 * cg * TP * 16) + 127) & ~(size_t)127;
-    return a + (2 * kMaxStages + 6) * 8 + 16 + (size_t)4 * C * 4 + 2048 + 64;
+    return a + (2 * kMaxStages + 6) * 8 + 16 + (size_t)4 * C * 4 + 2048 + 256 + 64;
   }
   int conv_stages(const Geo& g, int cg, int rows = kTileM) const {
     const int chunk_g = cg < 8 ? cg : 8;
@@ -967,6 +1009,10 @@ struct ConvNet : NetImpl {
     const int force_rows = force_env ? atoi(force_env) : 0;
     int rows = (nl > 1 && (p.Ptot + kTileM - 1) / kTileM < 2 * num_sms) ? 128 : kTileM;
     if (force_rows == 128 || force_rows == 256) rows = force_rows;
+    p.masked = grid_pad() == 0;
+    // split-K tiles give the second MMA warp the odd weight stages; with one stage per tap its first MMA would be a
+    // masked (non-centre) tap and could not initialise its accumulator
+    if (p.masked && cg <= 8) rows = kTileM;
     p.num_tiles = (p.Ptot + rows - 1) / rows;
     p.TP = tp_of(g, rows);
     p.stages = conv_stages(g, cg, rows);
@@ -1036,7 +1082,7 @@ struct ConvNet : NetImpl {
     HeadParams& p = pend_heads.h[num_pend_heads++];
     p.act = act; p.w1 = h.w1; p.b1 = h.b1; p.w2 = h.w2; p.b2 = h.b2; p.dst = dst;
     p.plane_rows = plane_rows_of(lat, batch);
-    p.C = C; p.H = lat.H; p.W = lat.W; p.mid = h.mid; p.out = h.out; p.kind = h.kind;
+    p.C = C; p.H = lat.H; p.W = lat.W; p.pad = grid_pad(); p.mid = h.mid; p.out = h.out; p.kind = h.kind;
     const size_t smem = ((size_t)h.mid * lat.H * lat.W + h.out) * 4;
     if (smem > pend_heads_smem) pend_heads_smem = smem;
   }
@@ -1095,7 +1141,7 @@ struct ConvNet : NetImpl {
     const int Hin = cfg.in_h, Win = cfg.in_w;
     const Geo g0{Hin, Win}, g1{Hin / 2, Win / 2}, g2{Hin / 4, Win / 4}, g3{Hin / 8, Win / 8};
     prof_mark(kProfPack, st);
-    pack_obs_kernel<<<num_sms * 8, 256, 0, st>>>(obs, xobs, batch, cfg.in_channels, Hin, Win, 16, plane_rows_of(g0, batch));
+    pack_obs_kernel<<<num_sms * 8, 256, 0, st>>>(obs, xobs, batch, cfg.in_channels, Hin, Win, 16, plane_rows_of(g0, batch), grid_pad());
     prof_mark(-1, st);
     MZ_LAUNCH_CHECK("pack_obs_kernel");
     // stride-2 conv + ReLU: one tcgen05 launch at the input resolution whose epilogue stores the even positions on
@@ -1107,16 +1153,18 @@ struct ConvNet : NetImpl {
       if (rc2) return rc2;
       pend_sub = true;
       if ((rc2 = flush(st))) return rc2;
-      prof_mark(kProfPack, st);
-      zero_halo_kernel<<<num_sms * 4, 256, 0, st>>>(out, batch, go.H, go.W, C / 8, plane_rows_of(go, batch));
-      prof_mark(-1, st);
-      MZ_LAUNCH_CHECK("zero_halo_kernel");
+      if (grid_pad()) {
+        prof_mark(kProfPack, st);
+        zero_halo_kernel<<<num_sms * 4, 256, 0, st>>>(out, batch, go.H, go.W, C / 8, plane_rows_of(go, batch));
+        prof_mark(-1, st);
+        MZ_LAUNCH_CHECK("zero_halo_kernel");
+      }
       return MZ_OK;
     };
     auto pool = [&](const act_t* in, act_t* out, act_t* sl, const int32_t* idx, const Geo& gi, const Geo& go, int norm) -> int {
       prof_mark(kProfPack, st);
       avgpool_kernel<<<num_sms * 8, 256, 0, st>>>(in, out, sl, idx, batch, gi.H, gi.W, norm, plane_rows_of(gi, batch),
-                                                  plane_rows_of(go, batch));
+                                                  plane_rows_of(go, batch), grid_pad());
       prof_mark(-1, st);
       MZ_LAUNCH_CHECK("avgpool_kernel");
       return MZ_OK;
@@ -1149,7 +1197,7 @@ struct ConvNet : NetImpl {
     } else {
       prof_mark(kProfPack, st);
       pack_obs_kernel<<<num_sms * 4, 256, 0, st>>>(obs, xobs, batch, cfg.in_channels, lat.H, lat.W, in_cg * 8,
-                                                   plane_rows_of(lat, batch));
+                                                   plane_rows_of(lat, batch), grid_pad());
       prof_mark(-1, st);
       MZ_LAUNCH_CHECK("pack_obs_kernel");
       act_t* fin;
@@ -1216,7 +1264,7 @@ int conv_hidden_bytes(const mz_net_config& c, int32_t* bytes) {
   int H, W;
   int rc = conv_geometry(c, &H, &W);
   if (rc) return rc;
-  *bytes = (H + 1) * (W + 1) * c.num_planes * 2;
+  *bytes = (H + grid_pad()) * (W + grid_pad()) * c.num_planes * 2;
   return MZ_OK;
 }
 
@@ -1348,7 +1396,7 @@ int conv_create(const mz_net_config& c, const float* const* w, int nw, int max_b
     float* scale = nullptr;
     MZ_TRY(fold_conv(N, N + A, N / 8, &net->dyn0, &scale));
     float* tab = (float*)take((size_t)A * PB * N * 4);
-    action_table_kernel<<<512, 256>>>(dyn_w, scale, tab, A, N, N, H, W);
+    action_table_kernel<<<512, 256>>>(dyn_w, scale, tab, A, N, N, H, W, grid_pad());
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("action_table_kernel: %s", cudaGetErrorString(e)); delete net; return MZ_ECUDA; }
     count_launch();

@@ -123,6 +123,20 @@ __device__ __forceinline__ void mma_f16_elect(uint32_t d_tmem, uint64_t adesc, u
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// the same with the disable-output-lane vector: bit j of word i keeps TMEM lane 32*i + j (row 32*i + j of D) from
+// being written by this MMA.  conv3x3 uses it to drop, per tap, the output rows whose neighbour lies across a board edge
+// (halo-free activation layout).
+__device__ __forceinline__ void mma_f16_elect_masked(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                     uint32_t accumulate, uint32_t m0, uint32_t m1, uint32_t m2,
+                                                     uint32_t m3) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
+      : "memory");
+}
 __device__ __forceinline__ void commit_elect(uint64_t* bar) {
   asm volatile(
       "{\n\t.reg .pred q;\n\t"

@@ -357,14 +357,23 @@ class _ConvNet(MuZeroNet):
     def hidden_to_reference(self, slots):
         h, w = self.latent_hw
         c = self.num_planes
-        x = slots.view(torch.float16).reshape(slots.shape[0], c // 8, h + 1, w + 1, 8)[:, :, :h, :w, :]
+        pad = self.grid_pad
+        x = slots.view(torch.float16).reshape(slots.shape[0], c // 8, h + pad, w + pad, 8)[:, :, :h, :w, :]
         return x.permute(0, 1, 4, 2, 3).reshape(slots.shape[0], c, h, w).to(torch.float32).contiguous()
+
+    @property
+    def grid_pad(self) -> int:
+        """0: boards stored without halo (the conv kernel masks the edge taps); 1: the padded (H+1)x(W+1) layout
+        (MZ_CONV_PAD=1).  Read off the engine's slot size so that this module never disagrees with the library."""
+        h, w = self.latent_hw
+        return 1 if self.hidden_bytes == (h + 1) * (w + 1) * self.num_planes * 2 else 0
 
     def hidden_from_reference(self, hid):
         h, w = self.latent_hw
         c = self.num_planes
         hid = hid.reshape(-1, c // 8, 8, h, w)
-        out = torch.zeros((hid.shape[0], c // 8, h + 1, w + 1, 8), dtype=torch.float16, device=hid.device)
+        pad = self.grid_pad
+        out = torch.zeros((hid.shape[0], c // 8, h + pad, w + pad, 8), dtype=torch.float16, device=hid.device)
         out[:, :, :h, :w, :] = hid.permute(0, 1, 3, 4, 2).to(torch.float16)
         return out.reshape(hid.shape[0], -1).view(torch.uint8)
 
