@@ -1,19 +1,23 @@
 // ResNet towers of MuZeroBoardGameNet / MuZeroAtariNet (network.py:273-574) on the
 // Blackwell tensor cores (fp16 x fp16 -> fp32).
 //
-// Data layout ("padded grid, channel-group planes"): a board is a grid of
-//   PB = (H+1)*(W+1) positions,  position q = y*(W+1) + x,
-// where column x == W and row y == H are a ZERO halo shared with the next row / the next
-// board.  Flattening boards back to back (row P = b*PB + q) makes every 3x3 tap a constant row
-// offset: tap (ky,kx) of output row P reads input row P + (ky-1)*(W+1) + (kx-1).
+// Data layout ("channel-group planes"): a board is a grid of
+//   PB = (H+pad)*(W+pad) positions,  position q = y*(W+pad) + x,          pad = grid_pad(), 0 by default.
+// Flattening boards back to back (row P = b*PB + q) makes every 3x3 tap a constant row offset: tap (ky,kx) of
+// output row P reads input row P + (ky-1)*(W+pad) + (kx-1).
+//   pad == 0: no row is padding; a tap whose neighbour lies across a board edge is switched off for that output row
+//             by the disable-output-lane vector of the tap's tcgen05.mma (edge masks per tile from the loader warp,
+//             centre tap first so that it initialises the accumulator).
+//   pad == 1 (MZ_CONV_PAD=1, the first version): column x == W and row y == H are a ZERO halo shared with the next
+//             row / the next board, every tap is unmasked, every writer of an activation buffer writes zeros at halo
+//             positions.  19 % (9x9) / 27 % (6x6) of all MMA rows are halo.
 // An activation tensor is stored as C/8 PLANES of [rows][8 channels] fp16 (16 bytes per row):
 //   contiguous buffer:  element (P, c) at ((c/8) * plane_rows + P) * 8 + c%8
 //   hidden-state slot:  element (q, c) of slot s at ((s * C/8 + c/8) * PB + q) * 8 + c%8
 // which is exactly the no-swizzle K-major core-matrix layout tcgen05.mma reads from shared
-// memory, so (a) a tile of 256 rows + halo is ONE contiguous run per plane and is fetched by
+// memory, so (a) a tile of 256 rows + W+1 rows either side is ONE contiguous run per plane and is fetched by
 // 1-D bulk copies (TMA) with no per-element work, (b) the epilogue's stores (lane = row, 16
-// bytes per plane) are fully coalesced.  Every writer of an activation buffer writes ZEROS at
-// halo positions; rows past the last board are never read by a valid output.
+// bytes per plane) are fully coalesced.  Rows past the last board are never read by a valid output.
 //
 // Kernel: implicit GEMM, M = rows, N = C_out, K = 9 taps x C_in.
 //   - the activation tile (256 rows + halo) is staged ONCE in shared memory; the 9 taps are 9

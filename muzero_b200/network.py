@@ -353,7 +353,7 @@ class _ConvNet(MuZeroNet):
                                '(self-play always does, pipeline.py:79-80)')
         return super()._engine_tensors()
 
-    # engine layout: fp16 planes of 8 channels over the zero-padded grid, [C/8][(H+1)*(W+1)][8] (see csrc/conv.cu)
+    # engine layout: fp16 planes of 8 channels, [C/8][(H+pad)*(W+pad)][8], pad = grid_pad (see csrc/conv.cu)
     def hidden_to_reference(self, slots):
         h, w = self.latent_hw
         c = self.num_planes
