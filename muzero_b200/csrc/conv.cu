@@ -303,10 +303,9 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
             uint32_t al[4], bl[4];
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) { al[ks] = a_lo + (uint32_t)ks * a_kstep; bl[ks] = b_lo + (uint32_t)ks * b_kstep; }
-            mma_f16_elect_masked(dacc, desc64(al[0], a_hi), desc64(bl[0], b_hi), idesc, acc, m0, m1, m2, m3);
-#pragma unroll
-            for (int ks = 1; ks < 4; ++ks)
-              mma_f16_elect_masked(dacc, desc64(al[ks], a_hi), desc64(bl[ks], b_hi), idesc, 1u, m0, m1, m2, m3);
+            mma4_f16_elect_masked(dacc, desc64(al[0], a_hi), desc64(al[1], a_hi), desc64(al[2], a_hi), desc64(al[3], a_hi),
+                                  desc64(bl[0], b_hi), desc64(bl[1], b_hi), desc64(bl[2], b_hi), desc64(bl[3], b_hi), idesc,
+                                  acc, m0, m1, m2, m3);
             acc = 1;
             a_lo += 4u * a_kstep;
           } else {

@@ -137,6 +137,28 @@ __device__ __forceinline__ void mma_f16_elect_masked(uint32_t d_tmem, uint64_t a
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
       : "memory");
 }
+// four K-steps under ONE election: ptxas moves every register operand of an elected tcgen05.mma into uniform
+// registers (R2UR.BROADCAST) once per asm statement, so issuing the four MMAs of a 64-channel weight stage from one
+// statement pays for the election, the accumulator address, the instruction descriptor and the lane masks once
+// instead of four times (the issue loop, not the tensor pipe, bounds the halo-free conv kernel: 158 cycles per MMA
+// and warp measured against the 128 the pipe needs).
+__device__ __forceinline__ void mma4_f16_elect_masked(uint32_t d_tmem, uint64_t a0, uint64_t a1, uint64_t a2, uint64_t a3,
+                                                      uint64_t b0, uint64_t b1, uint64_t b2, uint64_t b3, uint32_t idesc,
+                                                      uint32_t accumulate, uint32_t m0, uint32_t m1, uint32_t m2,
+                                                      uint32_t m3) {
+  asm volatile(
+      "{\n\t.reg .pred p, q, t;\n\t"
+      "setp.ne.b32 p, %10, 0;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %5, %9, {%11, %12, %13, %14}, p;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %6, %9, {%11, %12, %13, %14}, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %3, %7, %9, {%11, %12, %13, %14}, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %4, %8, %9, {%11, %12, %13, %14}, t;\n\t}"
+      ::"r"(d_tmem), "l"(a0), "l"(a1), "l"(a2), "l"(a3), "l"(b0), "l"(b1), "l"(b2), "l"(b3), "r"(idesc),
+        "r"(accumulate), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
+      : "memory");
+}
 __device__ __forceinline__ void commit_elect(uint64_t* bar) {
   asm volatile(
       "{\n\t.reg .pred q;\n\t"
