@@ -69,6 +69,7 @@ struct LayerDesc {
   act_t* out_slots;       // indexed slots, normalised, or nullptr
   const int32_t* out_index;
   int dep;                        // input is produced by the previous layer of this launch
+  int fwd;                        // resident launches: 1 = the next layer reads this layer's `out`, 2 = its `out_norm`
   int in_slots;                   // input is an array of hidden-state slots, not a contiguous buffer
 };
 
@@ -89,6 +90,8 @@ struct ConvParams {
   int TP;                         // tile rows incl. halo, odd
   int stages;                     // weight ring depth (as many as shared memory allows, <= kMaxStages)
   long long* dbg;                 // optional per-CTA role timing (MZ_CONV_DEBUG), else nullptr
+  int tile_stride;                // rows between the starts of consecutive tiles: kRows, or (resident) whole boards
+  int resident;                   // every CTA owns ONE board-aligned tile for all layers; activations stay in shared memory
   int masked;                     // halo-free grid: edge taps are masked per output row (disable-output-lane)
   int ablate;                     // debug only (MZ_CONV_ABLATE): 1 skip epilogue work, 2 skip tile loads, 4 skip weight copies, 512 epilogue without global loads/stores
 };
@@ -165,6 +168,10 @@ __device__ __forceinline__ void quad_bar_sync(int quad) {
   }
 }
 
+__device__ __forceinline__ void st_tile(uint32_t addr, const int4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 __device__ __constant__ int kTapOrder[9] = {4, 0, 1, 2, 3, 5, 6, 7, 8};
 
 template <int kN, int kRows>
@@ -188,14 +195,18 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
   uint64_t* a_full = bars + 2 * kMaxStages;   // [2]
   uint64_t* mma_done = a_full + 2;         // [2]
   uint64_t* acc_empty = mma_done + 2;      // [2]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* a_ready = acc_empty + 2;       // [2] resident launches: the epilogue has written the next layer's tile
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(a_ready + 2);
   float* s_bias = reinterpret_cast<float*>(tmem_holder + 4);            // [4][N] bias of layer l in slot l & 3, 16-byte aligned
   float2* s_mm = reinterpret_cast<float2*>(s_bias + 4 * p.N);           // [2][128] partial (min, max) per row
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_mm + 2 * 128);       // [2 tiles][2 halves][left,right,top,bottom][4] edge rows
 
   if (tid == 0) {
     for (uint32_t s = 0; s < kStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], kSplitK ? 1 : 2); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&a_full[b], 1); mbar_init(&mma_done[b], 2); mbar_init(&acc_empty[b], kEpiThreads); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&a_full[b], 1); mbar_init(&mma_done[b], 2); mbar_init(&acc_empty[b], kEpiThreads);
+      mbar_init(&a_ready[b], kEpiThreads);
+    }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_holder, 512);
@@ -267,6 +278,8 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
       long long tw2 = dbg ? clock64() : 0;
       t_acc += tw2 - tw;
       mbar_wait(&a_full[buf], uph);
+      // resident launch (item i == layer i): the tile of layer i >= 1 was written by the epilogue of layer i - 1
+      if (p.resident && i > 0) mbar_wait(&a_ready[buf], (uint32_t)(((i >> 1) - (buf == 0 ? 1 : 0)) & 1));
       if (dbg) t_a += clock64() - tw2;
       tc_fence_after();
       const uint32_t a_tile = a_lo0 + sA16 + (uint32_t)buf * (a_bytes >> 4) + (uint32_t)halo + (kSplitK ? 0u : 128u * mhalf);
@@ -339,10 +352,11 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
     for (int tile = first_tile(l); tile < p.num_tiles; tile += G, ++i) {
       const LayerDesc& L = p.L[l];
       const int buf = i & 1;
-      const int r0 = tile * kRows - halo, r1 = r0 + kRows + 2 * halo;       // tile rows [r0, r1)
+      const int r0 = tile * p.tile_stride - halo, r1 = r0 + kRows + 2 * halo;       // tile rows [r0, r1)
+      const bool handed_over = p.resident && l > 0;     // the epilogue of layer l - 1 writes this tile into shared memory
       // dataflow dependency: the three tiles of the previous layer whose rows this tile reads
       long long tw = dbg ? clock64() : 0;
-      if (L.dep) {
+      if (L.dep && !p.resident) {
         if (lane < 3) {
           const int tt = tile - 1 + lane;
           if (tt >= 0 && tt < p.num_tiles) {
@@ -374,7 +388,7 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
         // which rows of this tile are a board's left / right column or top / bottom row: one ballot per 32 rows
         for (int h = 0; h < kRows / 128; ++h)
           for (int w = 0; w < 4; ++w) {
-            const int P = tile * kRows + h * 128 + w * 32 + lane;
+            const int P = tile * p.tile_stride + h * 128 + w * 32 + lane;
             const int q = P % p.PB, y = q / p.Wp, x = q - y * p.Wp;
             const unsigned mL = __ballot_sync(0xffffffffu, x == 0), mR = __ballot_sync(0xffffffffu, x == p.W - 1);
             const unsigned mT = __ballot_sync(0xffffffffu, y == 0), mB = __ballot_sync(0xffffffffu, y == p.H - 1);
@@ -385,10 +399,17 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
           }
       }
       const uint32_t dst0 = smem_u32(sA) + (uint32_t)buf * a_bytes;
-      const int lo = r0 > 0 ? r0 : 0;
+      if (handed_over) {          // nothing to load: bias and masks are staged, tell the MMA warps
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[buf]);
+        continue;
+      }
+      // resident: exactly the tile's own boards (every tap that leaves them is masked); else the tile and its halo
+      const int lo = p.resident ? tile * p.tile_stride : (r0 > 0 ? r0 : 0);
       int hi = L.in_slots ? p.Ptot : p.plane_rows;
-      hi = r1 < hi ? r1 : hi;
-      if (r0 < 0) {
+      if (p.resident) { const int e = lo + p.tile_stride; hi = e < p.Ptot ? e : p.Ptot; }
+      else hi = r1 < hi ? r1 : hi;
+      if (r0 < 0 && !p.resident) {
         // rows before the first board are read by valid outputs (top-left taps of board 0): zeros
         const int nz = -r0;
         for (int k = lane; k < nz * cg; k += 32) {
@@ -443,6 +464,10 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
       const int buf = k & 1;
       const float* s_bias_l = s_bias + (l & 3) * kN;
       const bool fast = !norm && L.tab == nullptr && L.out != nullptr;
+      // resident launch: this layer's output rows also go straight into the OTHER tile buffer in shared memory, in the
+      // operand layout ([channel group][row][16 B], rows offset by the halo), where the next layer's MMAs read them
+      const int hand = (p.resident && l + 1 < p.num_layers) ? L.fwd : 0;
+      const uint32_t next_a = smem_u32(sA) + (uint32_t)(buf ^ 1) * a_bytes + (uint32_t)halo * 16;
       const uint32_t tbase = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256);
       if (fast) {
         // Plain conv + bias (+ residual) + ReLU (30 of the 33 convs of a recurrent inference).  The steps of
@@ -455,9 +480,9 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
         bool vj[2], inr[2];                  // real (non-halo) row / row that is stored at all
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-          Pj[j] = tile * kRows + j * 128 + quad * 32 + lane;
+          Pj[j] = tile * p.tile_stride + j * 128 + quad * 32 + lane;
           int b = 0, pos = 0; bool hl = true;
-          inr[j] = Pj[j] < p.Ptot;
+          inr[j] = Pj[j] < p.Ptot && j * 128 + quad * 32 + lane < p.tile_stride;
           if (inr[j]) split_pos(Pj[j], p, b, pos, hl);
           vj[j] = !hl;
           Dj[j] = (size_t)Pj[j];
@@ -515,6 +540,11 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
                 outp[(size_t)(c * 4 + u) * PRo + Dj[j]] = vj[j] ? o4 : make_int4(0, 0, 0, 0);
               }
             }
+            if (hand == 1) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) st_tile(next_a + (uint32_t)((c * 4 + u) * TP + j * 128 + quad * 32 + lane) * 16,
+                                                   pack8_relu(v + 8 * u));
+            }
           }
         }
       } else {
@@ -524,9 +554,9 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
         tc_fence_after();
 #pragma unroll 1
         for (int j = 0; j < kRows / 128 && !(p.ablate & 1); ++j) {
-          const int P = tile * kRows + j * 128 + quad * 32 + lane;
+          const int P = tile * p.tile_stride + j * 128 + quad * 32 + lane;
           int b = 0, pos = 0; bool hl = true;
-          const bool inrange = P < p.Ptot;
+          const bool inrange = P < p.Ptot && j * 128 + quad * 32 + lane < p.tile_stride;
           if (inrange) split_pos(P, p, b, pos, hl);
           const bool valid = !hl;
           const float top = valid ? 65504.0f : 0.0f;
@@ -576,6 +606,11 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
 #pragma unroll
                 for (int u = 0; u < 4; ++u) o[(size_t)(c * 4 + u) * PR] = pack8(v + 8 * u);
               }
+              if (hand == 1) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) st_tile(next_a + (uint32_t)((c * 4 + u) * TP + j * 128 + quad * 32 + lane) * 16,
+                                                     pack8(v + 8 * u));
+              }
             }
           }
           if (norm) {
@@ -605,11 +640,16 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
                   const int4 o4 = pack8(v + 8 * u);
                   if (on) on[(size_t)(c * 4 + u) * PR] = o4;
                   if (os) os[(size_t)(c * 4 + u) * p.PB] = o4;
+                  if (hand == 2) st_tile(next_a + (uint32_t)((c * 4 + u) * TP + j * 128 + quad * 32 + lane) * 16, o4);
                 }
               }
             }
           }
         }
+      }
+      if (hand) {
+        fence_proxy_async();               // generic-proxy st.shared -> the MMAs' async-proxy reads
+        mbar_arrive(&a_ready[buf ^ 1]);
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[buf]);
@@ -949,7 +989,7 @@ struct ConvNet : NetImpl {
   size_t conv_fixed_smem(const Geo& g, int cg, int rows = kTileM) const {
     const int TP = tp_of(g, rows);
     size_t a = (((size_t)2 * cg * TP * 16) + 127) & ~(size_t)127;
-    return a + (2 * kMaxStages + 6) * 8 + 16 + (size_t)4 * C * 4 + 2048 + 256 + 64;
+    return a + (2 * kMaxStages + 8) * 8 + 16 + (size_t)4 * C * 4 + 2048 + 256 + 64;
   }
   int conv_stages(const Geo& g, int cg, int rows = kTileM) const {
     const int chunk_g = cg < 8 ? cg : 8;
@@ -984,6 +1024,7 @@ struct ConvNet : NetImpl {
     d.in = in; d.in_index = in_index; d.w = L.w; d.bias = L.bias; d.tab = tab_; d.action = action;
     d.residual = residual; d.out = out; d.out_norm = out_norm; d.out_slots = out_slots; d.out_index = out_index;
     d.dep = pend.num_layers > 0 ? 1 : 0;
+    d.fwd = 0;
     d.in_slots = in_slots ? 1 : 0;
     pend_geo = g; pend_cg = L.cg; pend_batch = batch;
     ++pend.num_layers;
@@ -1016,7 +1057,37 @@ struct ConvNet : NetImpl {
     // split-K tiles give the second MMA warp the odd weight stages; with one stage per tap its first MMA would be a
     // masked (non-centre) tap and could not initialise its accumulator
     if (p.masked && cg <= 8) rows = kTileM;
-    p.num_tiles = (p.Ptot + rows - 1) / rows;
+    // RESIDENT launch: when every CTA can own one tile of whole boards for all layers, nothing a tile needs comes from
+    // another tile (the halo-free layout masks every tap that leaves a board), so the layers of a tower hand their
+    // activations over in shared memory -- no tile flags, no tile loads, no waiting for neighbours after layer 0.
+    // This is the regime of small batches and small grids (single-tree searches, the 6x6 Atari latent), where a
+    // launch is bound by the chain flag -> load -> MMA -> epilogue -> publish of every layer, not by throughput.
+    const int sm_cap0 = (cta_limit > 0 && cta_limit < num_sms) ? cta_limit : num_sms;
+    p.resident = 0;
+    p.tile_stride = rows;
+    static const bool no_resident = getenv("MZ_CONV_NO_RESIDENT") != nullptr;
+    if (p.masked && nl > 1 && !p.sub && !no_resident) {
+      bool chain = true;
+      for (int i = 0; i + 1 < nl && chain; ++i) {
+        LayerDesc& a = pend.L[i];
+        const LayerDesc& b = pend.L[i + 1];
+        a.fwd = (b.in_slots == 0 && b.in == a.out && a.out) ? 1 : ((b.in_slots == 0 && b.in == a.out_norm && a.out_norm) ? 2 : 0);
+        chain = a.fwd != 0;
+      }
+      if (chain) {
+        const int cand[2] = {128, kTileM};
+        for (int ci = 0; ci < 2 && !p.resident; ++ci) {
+          const int rr = cand[ci];
+          if (force_rows && force_rows != rr) continue;
+          if (rr == 128 && cg <= 8) continue;
+          const int bpt = rr / p.PB;                               // whole boards per tile
+          if (bpt < 1) continue;
+          if ((batch + bpt - 1) / bpt > sm_cap0) continue;
+          p.resident = 1; rows = rr; p.tile_stride = bpt * p.PB;
+        }
+      }
+    }
+    p.num_tiles = p.resident ? (p.Ptot + p.tile_stride - 1) / p.tile_stride : (p.Ptot + rows - 1) / rows;
     p.TP = tp_of(g, rows);
     p.stages = conv_stages(g, cg, rows);
     p.err = err_flag;
@@ -1026,7 +1097,7 @@ struct ConvNet : NetImpl {
     const int grid = p.num_tiles < sm_cap ? p.num_tiles : sm_cap;
     p.rot = nl > 1 ? p.num_tiles % grid : 0;
     p.flags = nullptr;
-    if (nl > 1) {
+    if (nl > 1 && !p.resident) {
       if ((size_t)nl * p.num_tiles > flags_cap) { pend.num_layers = 0; set_error("internal: flag buffer too small"); return MZ_EINVAL; }
       p.flags = flags;
       cudaError_t e = cudaMemsetAsync(flags, 0, (size_t)nl * p.num_tiles * sizeof(unsigned), st);
