@@ -613,6 +613,210 @@ backup_select_kernel(PoolDev p, const float* __restrict__ reward_in, const float
   if (p.timing && lane == 0) atomicMax(p.stats + 6, globaltimer_ns());
 }
 
+// ---------------------------------------------------------------------------
+// Tiny action spaces (A <= kThreadA: CartPole 2, LunarLander 4): ONE THREAD per tree.  A warp per tree keeps 2 of 32
+// lanes busy there and needs as many warps as trees (16 384 for config 1: two waves of latency-bound warps); a thread
+// per tree needs 512.  Same arithmetic, instruction for instruction (puct via the child_Q cache, div_by_count,
+// child_q, the backup recurrence), same MT19937 stream (sequential twist), same memory -- only the work split differs,
+// and the lock-step / golden tests with A = 2 and A = 4 run through these kernels.
+// ---------------------------------------------------------------------------
+constexpr int kThreadA = 4;
+constexpr int kThreadBlock = 64;
+
+__device__ __forceinline__ void select_tree_thread(const PoolDev& p, const int t, const double* sT, const double* sR,
+                                                   const unsigned member) {
+  const int A = p.A;
+  const Edge* tree = p.edges + (size_t)t * p.max_nodes * A;
+  const float* qtree = p.qcache + (size_t)t * p.max_nodes * A;
+  const double* __restrict__ P = p.prior + (size_t)t * A;
+  const bool f32p = p.f32_prior[t] != 0;
+  uint32_t* pth = p.path + (size_t)t * p.max_nodes;
+  ThreadRng rng;
+  rng.load(p.rng_key + (size_t)t * 624, p.rng_pos + t);
+  double pr[kThreadA];
+  float prf[kThreadA];
+#pragma unroll
+  for (int a = 0; a < kThreadA; ++a) { pr[a] = a < A ? P[a] : 0.0; prf[a] = (float)pr[a]; }
+
+  int n = 0, Nn = p.rootN[t], depth = 0, act = 0;
+  while (true) {
+    const double tN = sT[Nn];
+    const float tNf = __double2float_rn(tN);
+    uint32_t nc[kThreadA], key = 0;
+    float s[kThreadA];
+#pragma unroll
+    for (int a = 0; a < kThreadA; ++a) {
+      nc[a] = (uint32_t)kNoChild << 16;
+      s[a] = 0.0f;
+      if (a < A) {
+        nc[a] = reinterpret_cast<const uint32_t*>(tree + (size_t)n * A + a)[3];
+        const float q = qtree[(size_t)n * A + a];
+        const int cn = (int)(nc[a] & 0xffffu);
+        float u;
+        if (cn > 0) {
+          const double y = div_by_count(tN, cn + 1, __ldg(sR + cn + 1));
+          u = f32p ? __fmul_rn(prf[a], __double2float_rn(y)) : __double2float_rn(__dmul_rn(pr[a], y));
+        } else {
+          u = f32p ? __fmul_rn(prf[a], tNf) : __double2float_rn(__dmul_rn(pr[a], tN));
+        }
+        s[a] = __fadd_rn(q, u);
+        key = max(key, f2ord(s[a]));
+      }
+    }
+    const float best = ord2f(key);
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < kThreadA; ++a) k += (a < A && s[a] == best) ? 1 : 0;
+    int r = (k > 1) ? (int)rng.bounded((uint32_t)k) : 0;
+    act = 0;
+    bool found = false;
+#pragma unroll
+    for (int a = 0; a < kThreadA; ++a)
+      if (!found && a < A && s[a] == best) {
+        if (r == 0) { act = a; found = true; }
+        --r;
+      }
+    uint32_t nc_sel = nc[0];
+#pragma unroll
+    for (int a = 1; a < kThreadA; ++a) nc_sel = (act == a) ? nc[a] : nc_sel;
+    pth[depth] = (uint32_t)(n * A + act);
+    ++depth;
+    if ((nc_sel >> 16) == kNoChild) break;
+    n = (int)(nc_sel >> 16);
+    Nn = (int)(nc_sel & 0xffffu);
+  }
+  rng.store(p.rng_pos + t);
+  p.leaf_parent[t] = n;
+  p.leaf_action[t] = act;
+  p.leaf_depth[t] = depth;
+  p.src_slot[t] = t * p.max_nodes + n;
+  const int c = p.count[t];
+  p.dst_slot[t] = t * p.max_nodes + (c < p.max_nodes ? c : p.max_nodes - 1);
+  // statistics: one atomic per warp and counter (`member` = the lanes of this warp that own a tree)
+  __syncwarp(member);
+  const unsigned d = __reduce_add_sync(member, (unsigned)depth);
+  const unsigned dr = __reduce_add_sync(member, (unsigned)rng.draws);
+  const unsigned tw = __reduce_add_sync(member, (unsigned)rng.twists);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(p.stats + 0, (unsigned long long)d);
+    atomicAdd(p.stats + 1, (unsigned long long)__popc(member));
+    if (dr) atomicAdd(p.stats + 2, (unsigned long long)dr);
+    if (tw) atomicAdd(p.stats + 3, (unsigned long long)tw);
+  }
+}
+
+__device__ __forceinline__ void expand_backup_tree_thread(const PoolDev& p, const int t,
+                                                          const float* __restrict__ reward_in,
+                                                          const float* __restrict__ value_in) {
+  const int A = p.A;
+  const int depth = p.leaf_depth[t];
+  const int c = p.count[t];
+  if (depth <= 0) return;
+  if (c >= p.max_nodes) { atomicOr(p.error, MZ_DEVERR_POOL_FULL); return; }
+  Edge* tree = p.edges + (size_t)t * p.max_nodes * A;
+  float* qtree = p.qcache + (size_t)t * p.max_nodes * A;
+  const uint32_t* pth = p.path + (size_t)t * p.max_nodes;
+  for (int a = 0; a < A; ++a) { store_edge(tree + (size_t)c * A + a, 0.0, 0.0f, 0u, kNoChild); qtree[(size_t)c * A + a] = 0.0f; }
+
+  const float rew = reward_in[t];
+  double value = (double)value_in[t];
+  const bool same_pl = p.same_player[t] != 0;
+  const bool board = p.board != 0;
+  const double discount = p.discount;
+  double lo = p.minmax[2 * t], hi = p.minmax[2 * t + 1];
+  const double lo0 = lo, hi0 = hi;
+  // leaf -> root in chunks of 8 levels: the 8 path entries, then the 8 edge records, are loaded back to back (one
+  // memory round trip each instead of one per level), then the value recurrence runs over them in order
+  constexpr int CH = 8;
+  for (int base = 0; base <= depth; base += CH) {          // i = 0: new leaf ... i = depth: root
+    uint32_t eid[CH];
+    int4 raw[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      const int level = depth - (base + j);
+      eid[j] = level > 0 ? pth[level - 1] : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      const int i = base + j, level = depth - i;
+      raw[j] = (i > 0 && level > 0) ? *reinterpret_cast<const int4*>(tree + eid[j]) : make_int4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      const int i = base + j, level = depth - i;
+      if (i > depth) break;
+      double W = 0.0, R = 0.0;
+      uint32_t N = 0, child = kNoChild;
+      if (level > 0) {
+        if (i == 0) { R = (double)rew; child = (uint32_t)c; }
+        else {
+          W = __hiloint2double(raw[j].y, raw[j].x); R = (double)__int_as_float(raw[j].z);
+          N = (uint32_t)raw[j].w & 0xffffu; child = (uint32_t)raw[j].w >> 16;
+        }
+      } else {
+        W = p.rootW[t]; N = (uint32_t)p.rootN[t]; R = p.root_reward[t];
+      }
+      const bool same = same_pl || ((i & 1) == 0);
+      const double Rs = (board && same) ? -R : R;
+      const double myval = value;
+      value = __dadd_rn(Rs, __dmul_rn(discount, value));
+      const double Wn = __dadd_rn(W, same ? myval : -myval);
+      const uint32_t Nn = N + 1;
+      const double q = __ddiv_rn(Wn, (double)Nn);
+      const double mm = __dadd_rn(R, __dmul_rn(discount, board ? -q : q));
+      hi = fmax(hi, mm);
+      lo = fmin(lo, mm);
+      if (level > 0) store_edge(tree + eid[j], Wn, (float)R, Nn, child);
+      else { p.rootW[t] = Wn; p.rootN[t] = (int)Nn; }
+    }
+  }
+  int* npar = p.node_parent + (size_t)t * p.max_nodes;
+  int* nmov = p.node_move + (size_t)t * p.max_nodes;
+  p.minmax[2 * t] = lo;
+  p.minmax[2 * t + 1] = hi;
+  p.count[t] = c + 1;
+  npar[c] = p.leaf_parent[t];
+  nmov[c] = p.leaf_action[t];
+  p.node_value[(size_t)t * p.max_nodes + c] = value_in[t];
+  p.leaf_depth[t] = 0;
+  const bool norm = hi > lo;
+  const double range = __dsub_rn(hi, lo);
+  const bool moved = __double_as_longlong(lo) != __double_as_longlong(lo0) ||
+                     __double_as_longlong(hi) != __double_as_longlong(hi0);
+  // child_Q cache: all visited edges (nodes 1..c) when a bound moved, else the path; same chunking
+  const int cnt = moved ? c : depth;
+  for (int base = 0; base < cnt; base += CH) {
+    uint32_t eid[CH];
+    int4 raw[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      const int k = base + j;
+      eid[j] = k < cnt ? (moved ? (uint32_t)npar[k + 1] * (uint32_t)A + (uint32_t)nmov[k + 1] : pth[k]) : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < CH; ++j) raw[j] = (base + j < cnt) ? *reinterpret_cast<const int4*>(tree + eid[j]) : make_int4(0, 0, 0, 0);
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+      if (base + j < cnt)
+        qtree[eid[j]] = child_q(__hiloint2double(raw[j].y, raw[j].x), __int_as_float(raw[j].z),
+                                (uint32_t)raw[j].w & 0xffffu, p.dp, norm, lo, range);
+  }
+}
+
+// mode: 1 select, 2 expand+backup, 3 expand+backup then select
+__global__ void __launch_bounds__(kThreadBlock)
+tree_thread_kernel(PoolDev p, const float* __restrict__ reward_in, const float* __restrict__ value_in, int mode) {
+  double* sT = reinterpret_cast<double*>(smem_raw);
+  const double* sR = p.T + (p.S + 2);
+  for (int i = threadIdx.x; i < p.S + 2; i += blockDim.x) sT[i] = p.T[i];
+  __syncthreads();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned member = __ballot_sync(kFull, t < p.B);
+  if (t >= p.B) return;
+  if (mode & 2) expand_backup_tree_thread(p, t, reward_in, value_in);
+  if (mode & 1) select_tree_thread(p, t, sT, sR, member);
+}
+
 // The same, CONFINED to a few SMs: `gridDim.x` CTAs of 32 warps pull trees off a counter.  For PipelinedSearchPlan,
 // where the tree kernels of one sub-batch are meant to run in the shadow of the other sub-batch's conv tower.
 // Spread over all SMs (one small CTA beside every persistent conv CTA) they do start there, but a latency-bound warp
@@ -904,6 +1108,13 @@ PoolDev dev_of(const mz_pool* h) {
 }
 
 inline int tree_blocks(int B) { return (B + kTreesPerBlock - 1) / kTreesPerBlock; }
+// thread-per-tree kernels: tiny action spaces and enough trees to fill warps (MZ_TREE_THREAD=0/1 overrides)
+inline bool use_thread_kernels(const mz_pool* pool) {
+  static const int force = getenv("MZ_TREE_THREAD") ? atoi(getenv("MZ_TREE_THREAD")) : -1;
+  if (pool->A > kThreadA) return false;
+  if (force >= 0) return force != 0;
+  return pool->B >= 512;
+}
 
 }  // namespace
 
@@ -1044,6 +1255,13 @@ extern "C" int mz_select(mz_pool* pool, mz_stream stream) {
   const dim3 grid(tree_blocks(pool->B)), block(kTreesPerBlock * 32);
   cudaStream_t st = (cudaStream_t)stream;
   const PoolDev d = dev_of(pool);
+  if (use_thread_kernels(pool)) {
+    tree_thread_kernel<<<(pool->B + kThreadBlock - 1) / kThreadBlock, kThreadBlock, (size_t)(pool->S + 2) * 8, st>>>(
+        d, nullptr, nullptr, 1);
+    MZ_LAUNCH_CHECK("tree_thread_kernel");
+    pool->selected = 1;
+    return MZ_OK;
+  }
   if (A <= 32) select_kernel<1><<<grid, block, smem, st>>>(d);
   else if (A <= 64) select_kernel<2><<<grid, block, smem, st>>>(d);
   else if (A <= 96) select_kernel<3><<<grid, block, smem, st>>>(d);
@@ -1067,6 +1285,13 @@ extern "C" int mz_expand_backup_select(mz_pool* pool, const float* reward, const
   const PoolDev d = dev_of(pool);
   const float* r = reward ? reward : d.reward;
   const float* v = value ? value : d.value;
+  if (use_thread_kernels(pool)) {
+    tree_thread_kernel<<<(pool->B + kThreadBlock - 1) / kThreadBlock, kThreadBlock, (size_t)(pool->S + 2) * 8, st>>>(
+        d, r, v, 3);
+    MZ_LAUNCH_CHECK("tree_thread_kernel");
+    pool->selected = 1;
+    return MZ_OK;
+  }
   if (pool->tree_ctas > 0 && A <= 128) {
     const dim3 cgrid(pool->tree_ctas), cblock(kConfinedThreads);
     if (A <= 32) backup_select_confined_kernel<1><<<cgrid, cblock, kConfinedSmem, st>>>(d, r, v);
@@ -1094,6 +1319,13 @@ extern "C" int mz_expand_backup(mz_pool* pool, const float* reward, const float*
     return MZ_ESTATE;
   }
   const PoolDev d = dev_of(pool);
+  if (use_thread_kernels(pool)) {
+    tree_thread_kernel<<<(pool->B + kThreadBlock - 1) / kThreadBlock, kThreadBlock, (size_t)(pool->S + 2) * 8,
+                         (cudaStream_t)stream>>>(d, reward ? reward : d.reward, value ? value : d.value, 2);
+    MZ_LAUNCH_CHECK("tree_thread_kernel");
+    pool->selected = 0;
+    return MZ_OK;
+  }
   expand_backup_kernel<<<tree_blocks(pool->B), kTreesPerBlock * 32, 0, (cudaStream_t)stream>>>(
       d, reward ? reward : d.reward, value ? value : d.value);
   MZ_LAUNCH_CHECK("expand_backup_kernel");

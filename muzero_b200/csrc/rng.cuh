@@ -71,4 +71,50 @@ struct WarpRng {
 };
 
 
+// The same stream driven by ONE thread (thread-per-tree kernels for tiny action spaces): sequential genrand twist.
+struct ThreadRng {
+  uint32_t* key;
+  int pos;
+  unsigned long long draws, twists;
+
+  __device__ void load(uint32_t* k, const int* pos_ptr) { key = k; pos = *pos_ptr; draws = 0; twists = 0; }
+  __device__ void store(int* pos_ptr) const { *pos_ptr = pos; }
+  __device__ void twist() {
+    const uint32_t kUp = 0x80000000u, kLo = 0x7fffffffu, kMat = 0x9908b0dfu;
+    int kk = 0;
+    for (; kk < 624 - 397; ++kk) {
+      const uint32_t y = (key[kk] & kUp) | (key[kk + 1] & kLo);
+      key[kk] = key[kk + 397] ^ (y >> 1) ^ ((y & 1u) ? kMat : 0u);
+    }
+    for (; kk < 623; ++kk) {
+      const uint32_t y = (key[kk] & kUp) | (key[kk + 1] & kLo);
+      key[kk] = key[kk + (397 - 624)] ^ (y >> 1) ^ ((y & 1u) ? kMat : 0u);
+    }
+    const uint32_t y = (key[623] & kUp) | (key[0] & kLo);
+    key[623] = key[396] ^ (y >> 1) ^ ((y & 1u) ? kMat : 0u);
+    pos = 0;
+    ++twists;
+  }
+  __device__ uint32_t next_u32() {
+    if (pos >= 624) twist();
+    uint32_t y = key[pos];
+    ++pos;
+    ++draws;
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+  }
+  __device__ uint32_t bounded(uint32_t k) {
+    const uint32_t rng = k - 1;
+    if (rng == 0) return 0;
+    uint32_t mask = rng;
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    uint32_t v;
+    do { v = next_u32() & mask; } while (v > rng);
+    return v;
+  }
+};
+
 }  // namespace mz
