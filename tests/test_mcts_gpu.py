@@ -170,7 +170,14 @@ def _lockstep(B, A, S, board, bounds, discount, alpha, noise_on, seed, quantise=
          uniform_prior=True, temperature=0.1),
     dict(B=4, A=226, S=40, board=True, bounds=True, discount=1.0, alpha=0.03, noise_on=True, seed=6),
     dict(B=5, A=1, S=10, board=False, bounds=False, discount=0.9, alpha=0.25, noise_on=False, seed=7),
-], ids=['ttt', 'cartpole', 'gomoku', 'atari', 'ties', 'gomoku15', 'single-action'])
+    # >= 512 trees with <= 4 actions: the thread-per-tree kernels (no bounds: the child_Q cache is refreshed wholesale;
+    # uniform prior + coarse values: ties, i.e. the sequential MT19937 path)
+    dict(B=520, A=2, S=14, board=False, bounds=False, discount=0.997, alpha=0.25, noise_on=True, seed=8,
+         reward_scale=1.0),
+    dict(B=512, A=4, S=12, board=True, bounds=True, discount=1.0, alpha=0.25, noise_on=False, seed=9, quantise=2,
+         uniform_prior=True),
+], ids=['ttt', 'cartpole', 'gomoku', 'atari', 'ties', 'gomoku15', 'single-action', 'thread-per-tree-A2',
+        'thread-per-tree-A4-ties'])
 def test_batched_trees_lockstep_with_oracle(kw):
     _lockstep(**kw)
 
