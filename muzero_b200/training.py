@@ -21,6 +21,8 @@ from __future__ import annotations
 
 from typing import NamedTuple, Optional, Tuple
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -147,6 +149,13 @@ class DataParallelLearner:
 
     def __init__(self, network: MuZeroNet, config, device, process_group=None, use_graph: bool = True) -> None:
         self.network, self.config, self.device = network, config, torch.device(device)
+        # conv nets on CUDA train with NHWC weights / activations: same fp32 (TF32) cuDNN arithmetic without the layout
+        # transposes around every convolution (24.8 -> 20.7 ms per 128 x K=5 Gomoku step).  state_dict shapes, the
+        # engine's weight packing and checkpoints are unaffected (memory format only).  MZ_TRAIN_CHANNELS_LAST=0: NCHW.
+        self.channels_last = (os.environ.get('MZ_TRAIN_CHANNELS_LAST', '1') != '0' and self.device.type == 'cuda'
+                              and getattr(network, 'latent_hw', (0, 0)) != (0, 0))
+        if self.channels_last:
+            network.to(memory_format=torch.channels_last)
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         params = [p for p in network.parameters() if p.requires_grad]
@@ -154,7 +163,8 @@ class DataParallelLearner:
         self.flat_grad = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=self.device)
         off = 0
         for p in params:
-            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+            # same strides as the parameter (NHWC conv weights are a dense permutation): autograd accumulates in place
+            p.grad = self.flat_grad[off:off + p.numel()].as_strided(p.size(), p.stride())
             off += p.numel()
         self.params = params
         self.use_graph = bool(use_graph) and self.device.type == 'cuda'
@@ -220,6 +230,8 @@ class DataParallelLearner:
         with torch.cuda.device(self.device) if self.device.type == 'cuda' else _nullcontext():
             w = torch.as_tensor(weights).to(device=self.device, dtype=torch.float32)
             inputs = _to_device(transitions, self.device) + (w,)
+            if self.channels_last and inputs[0].dim() == 4:
+                inputs = (inputs[0].contiguous(memory_format=torch.channels_last),) + inputs[1:]
             if self.use_graph and not time_allreduce and self._eager_left <= 0:
                 loss, priorities = self._graphed(inputs)
             else:
