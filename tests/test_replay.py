@@ -174,38 +174,3 @@ def test_self_play_samples_flow_into_replay_and_the_learner():
     rep.update_priorities(idx, prio)
     net.eval()
     sp.play_move()                      # the actor searches with the refreshed weights (engine rebuilt)
-
-
-@pytest.mark.gpu
-def test_graphed_training_step_equals_the_eager_one():
-    """DataParallelLearner replays one CUDA graph per iteration after three eager ones.  Compared step by step with a
-    learner that stays eager, both started from the same weights and Adam state at every iteration (free-running
-    trajectories drift apart within a few steps even between two eager learners: cuDNN's backward kernels accumulate
-    with atomics and Adam turns the noise of a near-zero gradient into a +-lr step)."""
-    import copy
-    import muzero_b200 as mz
-    from muzero_b200.training import DataParallelLearner, synthetic_transitions
-    torch.manual_seed(0)
-    net_a = mz.MuZeroBoardGameNet((5, 5, 5), 26, 2, 16).cuda()
-    net_b = copy.deepcopy(net_a)
-    cfg = mz.config.make_gomoku_config(num_training_steps=10, batch_size=16)
-    cfg.lr_milestones = [4]                                      # the schedule must reach the replayed graph
-    la = DataParallelLearner(net_a, cfg, 'cuda', use_graph=True)
-    lb = DataParallelLearner(net_b, cfg, 'cuda', use_graph=False)
-    for it in range(8):
-        tr, w = synthetic_transitions(net_a, 16, 5, seed=it)
-        net_b.load_state_dict(net_a.state_dict())
-        for sa, sb in zip(la.optimizer.state.values(), lb.optimizer.state.values()):
-            for k in sa:
-                sb[k].copy_(sa[k])
-        loss_a, pa = la.step(tr, w)
-        loss_b, pb = lb.step(tr, w)
-        assert abs(loss_a - loss_b) <= 1e-6 * max(1.0, abs(loss_b)), (it, loss_a, loss_b)
-        np.testing.assert_allclose(pa, pb, rtol=1e-5, atol=1e-6)
-        gmax = float(lb.flat_grad.abs().max())
-        assert float((la.flat_grad - lb.flat_grad).abs().max()) <= 1e-5 * gmax
-        for (k, a), (_, b) in zip(net_a.state_dict().items(), net_b.state_dict().items()):
-            assert float((a.float() - b.float()).abs().max()) <= 1e-6, (it, k)
-        assert abs(float(la.optimizer.param_groups[0]['lr']) - float(lb.optimizer.param_groups[0]['lr'])) < 1e-12
-    assert la._graph is not None and lb._graph is None
-    assert abs(float(la.optimizer.param_groups[0]['lr']) - cfg.lr_init * cfg.lr_decay_rate) < 1e-9
