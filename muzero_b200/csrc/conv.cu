@@ -91,6 +91,8 @@ struct ConvParams {
   int stages;                     // weight ring depth (as many as shared memory allows, <= kMaxStages)
   long long* dbg;                 // optional per-CTA role timing (MZ_CONV_DEBUG), else nullptr
   int tile_stride;                // rows between the starts of consecutive tiles: kRows, or (resident) whole boards
+  int khalf;                      // resident 256-row launches with two 64-channel K chunks: the K loop runs chunk by chunk
+                                  // and the epilogue hands the low / high 64 channels of the next tile over separately
   int resident;                   // every CTA owns ONE board-aligned tile for all layers; activations stay in shared memory
   int masked;                     // halo-free grid: edge taps are masked per output row (disable-output-lane)
   int ablate;                     // debug only (MZ_CONV_ABLATE): 1 skip epilogue work, 2 skip tile loads, 4 skip weight copies, 512 epilogue without global loads/stores
@@ -195,8 +197,9 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
   uint64_t* a_full = bars + 2 * kMaxStages;   // [2]
   uint64_t* mma_done = a_full + 2;         // [2]
   uint64_t* acc_empty = mma_done + 2;      // [2]
-  uint64_t* a_ready = acc_empty + 2;       // [2] resident launches: the epilogue has written the next layer's tile
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(a_ready + 2);
+  uint64_t* a_ready = acc_empty + 2;       // [2 tiles][low, high channels] resident launches: the epilogue has written
+                                           // that half of the next layer's tile
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(a_ready + 4);
   float* s_bias = reinterpret_cast<float*>(tmem_holder + 4);            // [4][N] bias of layer l in slot l & 3, 16-byte aligned
   float2* s_mm = reinterpret_cast<float2*>(s_bias + 4 * p.N);           // [2][128] partial (min, max) per row
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_mm + 2 * 128);       // [2 tiles][2 halves][left,right,top,bottom][4] edge rows
@@ -205,7 +208,7 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
     for (uint32_t s = 0; s < kStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], kSplitK ? 1 : 2); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&a_full[b], 1); mbar_init(&mma_done[b], 2); mbar_init(&acc_empty[b], kEpiThreads);
-      mbar_init(&a_ready[b], kEpiThreads);
+      mbar_init(&a_ready[2 * b], kEpiThreads); mbar_init(&a_ready[2 * b + 1], kEpiThreads);
     }
     fence_mbar_init();
   }
@@ -239,7 +242,9 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
             mbar_arrive_expect_tx(&w_full[s], stage_bytes);
             // taps are consumed centre first (kTapOrder): the centre tap is the one no edge mask applies to, so it is
             // the MMA that initialises every row of the accumulator
-            const int ti = c / chunks_tap, src_stage = kTapOrder[ti] * chunks_tap + (c - ti * chunks_tap);
+            // (khalf: all taps of the low 64 input channels first, then the high ones -- the order the MMA warps use)
+            const int ti = p.khalf ? c % 9 : c / chunks_tap, chs = p.khalf ? c / 9 : c - ti * chunks_tap;
+            const int src_stage = kTapOrder[ti] * chunks_tap + chs;
             bulk_g2s(sW + (size_t)s * stage_bytes, wl + (size_t)src_stage * stage_bytes, stage_bytes, &w_full[s]);
           }
         }
@@ -279,7 +284,11 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
       t_acc += tw2 - tw;
       mbar_wait(&a_full[buf], uph);
       // resident launch (item i == layer i): the tile of layer i >= 1 was written by the epilogue of layer i - 1
-      if (p.resident && i > 0) mbar_wait(&a_ready[buf], (uint32_t)(((i >> 1) - (buf == 0 ? 1 : 0)) & 1));
+      const uint32_t rdy_ph = (uint32_t)(((i >> 1) - (buf == 0 ? 1 : 0)) & 1);
+      if (p.resident && i > 0) {
+        mbar_wait(&a_ready[2 * buf], rdy_ph);                         // low 64 channels of the tile
+        if (!p.khalf) mbar_wait(&a_ready[2 * buf + 1], rdy_ph);       // khalf: the high half is awaited before its K chunk
+      }
       if (dbg) t_a += clock64() - tw2;
       tc_fence_after();
       const uint32_t a_tile = a_lo0 + sA16 + (uint32_t)buf * (a_bytes >> 4) + (uint32_t)halo + (kSplitK ? 0u : 128u * mhalf);
@@ -292,46 +301,58 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
         const uint4* em = reinterpret_cast<const uint4*>(s_mask + (buf * 2 + (kSplitK ? 0 : (int)mhalf)) * 16);
         eL = em[0]; eR = em[1]; eT = em[2]; eB = em[3];
       }
-      for (int ti = 0; ti < 9; ++ti) {
-        const int tap = ti == 0 ? 4 : (ti <= 4 ? ti - 1 : ti);          // kTapOrder: centre first
-        const int ky = tap / 3, kx = tap - 3 * ky;
-        uint32_t a_lo = a_tile + (uint32_t)((ky - 1) * p.Wp + (kx - 1));   // wraps correctly: the shift may be negative
-        // output rows whose (y + ky - 1, x + kx - 1) neighbour is across a board edge take no part in this tap
-        const uint32_t m0 = (kx == 0 ? eL.x : 0u) | (kx == 2 ? eR.x : 0u) | (ky == 0 ? eT.x : 0u) | (ky == 2 ? eB.x : 0u);
-        const uint32_t m1 = (kx == 0 ? eL.y : 0u) | (kx == 2 ? eR.y : 0u) | (ky == 0 ? eT.y : 0u) | (ky == 2 ? eB.y : 0u);
-        const uint32_t m2 = (kx == 0 ? eL.z : 0u) | (kx == 2 ? eR.z : 0u) | (ky == 0 ? eT.z : 0u) | (ky == 2 ? eB.z : 0u);
-        const uint32_t m3 = (kx == 0 ? eL.w : 0u) | (kx == 2 ? eR.w : 0u) | (ky == 0 ? eT.w : 0u) | (ky == 2 ? eB.w : 0u);
-        for (int ch = 0; ch < chunks_tap; ++ch, ++stage_no) {
-          if (kSplitK && (stage_no & 1u) != mhalf) {     // the other warp's stage: just step the ring and the K offset
-            a_lo += (uint32_t)ksteps * a_kstep;
-            ++st; b_slot += stage16;
-            if (st == kStages) { st = 0; st_ph ^= 1; b_slot = b_first; }
-            continue;
-          }
-          mbar_wait(&w_full[st], st_ph);
-          tc_fence_after();
-          uint32_t b_lo = b_slot;
-          if (ksteps == 4) {
-            // the common case (64-channel stage) fully unrolled
-            uint32_t al[4], bl[4];
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) { al[ks] = a_lo + (uint32_t)ks * a_kstep; bl[ks] = b_lo + (uint32_t)ks * b_kstep; }
-            mma4_f16_elect_masked(dacc, desc64(al[0], a_hi), desc64(al[1], a_hi), desc64(al[2], a_hi), desc64(al[3], a_hi),
-                                  desc64(bl[0], b_hi), desc64(bl[1], b_hi), desc64(bl[2], b_hi), desc64(bl[3], b_hi), idesc,
-                                  acc, m0, m1, m2, m3);
-            acc = 1;
-            a_lo += 4u * a_kstep;
-          } else {
-            for (int ks = 0; ks < ksteps; ++ks) {
-              mma_f16_elect_masked(dacc, desc64(a_lo, a_hi), desc64(b_lo, b_hi), idesc, acc, m0, m1, m2, m3);
-              acc = 1;
-              a_lo += a_kstep;
-              b_lo += b_kstep;
-            }
-          }
-          commit_elect(&w_empty[st]);
+      // one weight stage (a 64-channel K chunk of one tap): wait for it, issue its MMAs, release it, step the ring
+      auto run_stage = [&](uint32_t a_lo, uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
+        if (kSplitK && (stage_no & 1u) != mhalf) {       // the other warp's stage: just step the ring
+          ++stage_no;
           ++st; b_slot += stage16;
           if (st == kStages) { st = 0; st_ph ^= 1; b_slot = b_first; }
+          return;
+        }
+        ++stage_no;
+        mbar_wait(&w_full[st], st_ph);
+        tc_fence_after();
+        uint32_t b_lo = b_slot;
+        if (ksteps == 4) {
+          // the common case (64-channel stage) fully unrolled
+          uint32_t al[4], bl[4];
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) { al[ks] = a_lo + (uint32_t)ks * a_kstep; bl[ks] = b_lo + (uint32_t)ks * b_kstep; }
+          mma4_f16_elect_masked(dacc, desc64(al[0], a_hi), desc64(al[1], a_hi), desc64(al[2], a_hi), desc64(al[3], a_hi),
+                                desc64(bl[0], b_hi), desc64(bl[1], b_hi), desc64(bl[2], b_hi), desc64(bl[3], b_hi), idesc,
+                                acc, m0, m1, m2, m3);
+          acc = 1;
+        } else {
+          for (int ks = 0; ks < ksteps; ++ks) {
+            mma_f16_elect_masked(dacc, desc64(a_lo, a_hi), desc64(b_lo, b_hi), idesc, acc, m0, m1, m2, m3);
+            acc = 1;
+            a_lo += a_kstep;
+            b_lo += b_kstep;
+          }
+        }
+        commit_elect(&w_empty[st]);
+        ++st; b_slot += stage16;
+        if (st == kStages) { st = 0; st_ph ^= 1; b_slot = b_first; }
+      };
+      // taps centre first (kTapOrder); K chunks inside a tap -- or, khalf, all taps of the low 64 input channels, then
+      // (once the epilogue of the previous layer has handed them over) all taps of the high 64
+      const int outer = p.khalf ? 2 : 1;
+      for (int ko = 0; ko < outer; ++ko) {
+        if (p.khalf && ko == 1 && i > 0) { mbar_wait(&a_ready[2 * buf + 1], rdy_ph); tc_fence_after(); }
+        for (int ti = 0; ti < 9; ++ti) {
+          const int tap = ti == 0 ? 4 : (ti <= 4 ? ti - 1 : ti);
+          const int ky = tap / 3, kx = tap - 3 * ky;
+          const uint32_t a_tap = a_tile + (uint32_t)((ky - 1) * p.Wp + (kx - 1));   // wraps correctly: the shift may be negative
+          // output rows whose (y + ky - 1, x + kx - 1) neighbour is across a board edge take no part in this tap
+          const uint32_t m0 = (kx == 0 ? eL.x : 0u) | (kx == 2 ? eR.x : 0u) | (ky == 0 ? eT.x : 0u) | (ky == 2 ? eB.x : 0u);
+          const uint32_t m1 = (kx == 0 ? eL.y : 0u) | (kx == 2 ? eR.y : 0u) | (ky == 0 ? eT.y : 0u) | (ky == 2 ? eB.y : 0u);
+          const uint32_t m2 = (kx == 0 ? eL.z : 0u) | (kx == 2 ? eR.z : 0u) | (ky == 0 ? eT.z : 0u) | (ky == 2 ? eB.z : 0u);
+          const uint32_t m3 = (kx == 0 ? eL.w : 0u) | (kx == 2 ? eR.w : 0u) | (ky == 0 ? eT.w : 0u) | (ky == 2 ? eB.w : 0u);
+          if (p.khalf) {
+            run_stage(a_tap + (uint32_t)(ko * ksteps) * a_kstep, m0, m1, m2, m3);
+          } else {
+            for (int ch = 0; ch < chunks_tap; ++ch) run_stage(a_tap + (uint32_t)(ch * ksteps) * a_kstep, m0, m1, m2, m3);
+          }
         }
       }
       commit_elect(&mma_done[buf]);
@@ -467,6 +488,7 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
       // resident launch: this layer's output rows also go straight into the OTHER tile buffer in shared memory, in the
       // operand layout ([channel group][row][16 B], rows offset by the halo), where the next layer's MMAs read them
       const int hand = (p.resident && l + 1 < p.num_layers) ? L.fwd : 0;
+      bool lo_done = false;
       const uint32_t next_a = smem_u32(sA) + (uint32_t)(buf ^ 1) * a_bytes + (uint32_t)halo * 16;
       const uint32_t tbase = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256);
       if (fast) {
@@ -498,11 +520,18 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
         const int4* resp = reinterpret_cast<const int4*>(L.residual);
         const bool has_res = resp != nullptr && !(p.ablate & 512);
         int4 ring[3][4];
+        // step t of this warp -> (row half j, 32-column chunk c).  khalf: low 64 channels (chunks 0, 1 across the two
+        // column-half warps) of every row first, so that they can be handed to the next layer's first K chunk early
+        const bool kh = p.khalf && NCW == 2;
+        auto jof = [&](int t) { return kh ? t % NJ : t / NCW; };
+        auto cof = [&](int t) { return kh ? 2 * (t / NJ) + chalf : chalf * NCW + t % NCW; };
+        // j is a run-time value under khalf: select, do not index (indexing would move the arrays to local memory)
+        auto pick = [&](const auto (&arr)[2], int j) { return (NJ > 1 && j) ? arr[NJ - 1] : arr[0]; };
         auto fetch = [&](int t, int4 (&dst)[4]) {
-          const int j = t / NCW, g0 = (chalf * NCW + t % NCW) * 4;
-          const bool ld = has_res && vj[j];
+          const int j = jof(t), g0 = cof(t) * 4;
+          const bool ld = has_res && pick(vj, j);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) dst[u] = ld ? __ldcg(resp + (size_t)(g0 + u) * PR + Pj[j]) : make_int4(0, 0, 0, 0);
+          for (int u = 0; u < 4; ++u) dst[u] = ld ? __ldcg(resp + (size_t)(g0 + u) * PR + pick(Pj, j)) : make_int4(0, 0, 0, 0);
         };
         if (has_cols) {
           fetch(0, ring[0]);
@@ -516,7 +545,7 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
           int4* outp = reinterpret_cast<int4*>(L.out);
 #pragma unroll
           for (int t = 0; t < STEPS; ++t) {
-            const int j = t / NCW, c = chalf * NCW + t % NCW, c0 = c * 32;
+            const int j = jof(t), c = cof(t), c0 = c * 32;
             if (t + 2 < STEPS) fetch(t + 2, ring[(t + 2) % 3]);
             uint32_t r[32];
             tmem_ld32(tbase + (uint32_t)(j * 128 + c0), r);
@@ -533,17 +562,22 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
             finish32(r, s_bias_l + c0, ring[t % 3], v);
             // ReLU (every conv of these nets is followed by one) and fp16 saturation ride on the fp32 -> fp16
             // conversion; halo rows are stored as ZERO
-            if (inr[j] && !(p.ablate & 512)) {
+            if (pick(inr, j) && !(p.ablate & 512)) {
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
                 const int4 o4 = pack8_relu(v + 8 * u);
-                outp[(size_t)(c * 4 + u) * PRo + Dj[j]] = vj[j] ? o4 : make_int4(0, 0, 0, 0);
+                outp[(size_t)(c * 4 + u) * PRo + pick(Dj, j)] = pick(vj, j) ? o4 : make_int4(0, 0, 0, 0);
               }
             }
             if (hand == 1) {
 #pragma unroll
               for (int u = 0; u < 4; ++u) st_tile(next_a + (uint32_t)((c * 4 + u) * TP + j * 128 + quad * 32 + lane) * 16,
                                                    pack8_relu(v + 8 * u));
+              if (kh && t + 1 == NJ) {           // channels 0-63 of every row of this thread are in place
+                fence_proxy_async();
+                mbar_arrive(&a_ready[2 * (buf ^ 1)]);
+                lo_done = true;
+              }
             }
           }
         }
@@ -649,7 +683,8 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
       }
       if (hand) {
         fence_proxy_async();               // generic-proxy st.shared -> the MMAs' async-proxy reads
-        mbar_arrive(&a_ready[buf ^ 1]);
+        if (!lo_done) mbar_arrive(&a_ready[2 * (buf ^ 1)]);
+        mbar_arrive(&a_ready[2 * (buf ^ 1) + 1]);
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[buf]);
@@ -989,7 +1024,7 @@ struct ConvNet : NetImpl {
   size_t conv_fixed_smem(const Geo& g, int cg, int rows = kTileM) const {
     const int TP = tp_of(g, rows);
     size_t a = (((size_t)2 * cg * TP * 16) + 127) & ~(size_t)127;
-    return a + (2 * kMaxStages + 8) * 8 + 16 + (size_t)4 * C * 4 + 2048 + 256 + 64;
+    return a + (2 * kMaxStages + 10) * 8 + 16 + (size_t)4 * C * 4 + 2048 + 256 + 64;
   }
   int conv_stages(const Geo& g, int cg, int rows = kTileM) const {
     const int chunk_g = cg < 8 ? cg : 8;
@@ -1064,6 +1099,7 @@ struct ConvNet : NetImpl {
     // launch is bound by the chain flag -> load -> MMA -> epilogue -> publish of every layer, not by throughput.
     const int sm_cap0 = (cta_limit > 0 && cta_limit < num_sms) ? cta_limit : num_sms;
     p.resident = 0;
+    p.khalf = 0;
     p.tile_stride = rows;
     static const bool no_resident = getenv("MZ_CONV_NO_RESIDENT") != nullptr;
     if (p.masked && nl > 1 && !p.sub && !no_resident) {
@@ -1084,6 +1120,8 @@ struct ConvNet : NetImpl {
           if (bpt < 1) continue;
           if ((batch + bpt - 1) / bpt > sm_cap0) continue;
           p.resident = 1; rows = rr; p.tile_stride = bpt * p.PB;
+          static const bool no_khalf = getenv("MZ_CONV_NO_KHALF") != nullptr;
+          p.khalf = (rr == kTileM && cg == 16 && !no_khalf) ? 1 : 0;
         }
       }
     }
