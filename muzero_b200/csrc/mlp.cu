@@ -315,6 +315,8 @@ struct MlpTcParams {
   const unsigned char* wpack;
   uint32_t blk_off[kTcMaxBlocks], blk_bytes[kTcMaxBlocks];
   int nblk, nnets, chunks;
+  int nsplit;                         // 2: two CTAs per tile -- both run the transition net, one adds the reward net, the other
+                                      // the value (and policy) net; 1: one CTA runs all nets of its tiles
   int P, A, Apad, Sr, Sv;
   int tab_in_smem;                    // the [A][P] action table fits beside the tiles in shared memory
   const float* tabA;                  // [A][P]: first-layer weight column of each action (network.py:191-193)
@@ -383,7 +385,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_recurrent_tc_kernel(const _
   auto stamp = [&]() { if (p.dbg && blockIdx.x == 0 && tid == 0 && dbg_n < 60) p.dbg[dbg_n++] = clock64(); };
   stamp();
   // the first tile's leaf gather (two dependent global round trips) overlaps the staging below and the TMEM allocation
-  if (tid < 128 && (int)blockIdx.x * kTcRows < p.batch) gather_tile(p, (int)blockIdx.x, tid, smem_u32(sIn));
+  const int nsplit = p.nsplit, part = (int)blockIdx.x % nsplit;
+  // the nets this CTA runs, in order: everything, or transition + its share of the heads
+  uint32_t net_list = 0;              // 4 bits per entry (an indexed array would live in local memory)
+  int nn = 0;
+  for (int n = 0; n < p.nnets; ++n)
+    if (nsplit == 1 || n == 0 || (n == 1) == (part == 0)) net_list |= (uint32_t)n << (4 * nn++);
+  auto net_at = [&](int ni) { return (int)((net_list >> (4 * ni)) & 15u); };
+  const int bpn = 2 * p.chunks;       // weight blocks per net
+  const int first_tile = (int)blockIdx.x / nsplit, tile_step = (int)gridDim.x / nsplit;
+  if (tid < 128 && first_tile * kTcRows < p.batch) gather_tile(p, first_tile, tid, smem_u32(sIn));
   // first-layer biases and the action table are read by every row of every tile: stage them once per CTA
   // (from global they cost an exposed L2 round trip per 32-column chunk of every epilogue)
   for (int i = tid; i < p.nnets * p.P; i += kTcThreads) sB1[i] = p.b1[i / p.P][i % p.P];
@@ -410,13 +421,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_recurrent_tc_kernel(const _
     // ------------------------------------------------ weight producer
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-        for (int b = 0; b < p.nblk; ++b, ++it) {
-          const uint32_t s = it % kTcSlots, ph = (it / kTcSlots) & 1;
-          mbar_wait(&w_empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&w_full[s], p.blk_bytes[b]);
-          bulk_g2s(sW + (size_t)s * kTcSlotBytes, p.wpack + p.blk_off[b], p.blk_bytes[b], &w_full[s]);
-        }
+      for (int tile = first_tile; tile < ntiles; tile += tile_step)
+        for (int ni = 0; ni < nn; ++ni)
+          for (int b = net_at(ni) * bpn; b < (net_at(ni) + 1) * bpn; ++b, ++it) {
+            const uint32_t s = it % kTcSlots, ph = (it / kTcSlots) & 1;
+            mbar_wait(&w_empty[s], ph ^ 1);
+            mbar_arrive_expect_tx(&w_full[s], p.blk_bytes[b]);
+            bulk_g2s(sW + (size_t)s * kTcSlotBytes, p.wpack + p.blk_off[b], p.blk_bytes[b], &w_full[s]);
+          }
     }
   } else {
     // ------------------------------------------------ compute: thread (warps 0-3) = row of the tile; warps 4-7 help
@@ -452,11 +464,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_recurrent_tc_kernel(const _
       tc_fence_after();
     };
 
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int tile = first_tile; tile < ntiles; tile += tile_step) {
       const int grow = tile * kTcRows + row;
       const bool live = grow < p.batch;
       // leaf gather (the CTA's first tile was gathered before the prologue barrier)
-      if (owner && tile != (int)blockIdx.x) gather_tile(p, tile, row, sIn_a);
+      if (owner && tile != first_tile) gather_tile(p, tile, row, sIn_a);
       int act = live ? p.action[grow] : 0;
       act = min(max(act, 0), p.A - 1);
       fence_proxy_async();
@@ -464,7 +476,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_recurrent_tc_kernel(const _
       bar128();
       stamp();
 
-      for (int net = 0; net < p.nnets; ++net) {
+      for (int ni = 0; ni < nn; ++ni) {
+        const int net = net_at(ni);
         const uint32_t a_in = net == 0 ? sIn_a : (net == 1 ? sRaw_a : sNorm_a);
         const uint32_t N2 = net == 0 ? 64u : (net == 3 ? (uint32_t)p.Apad : 32u);
         const float* b1 = sB1 + net * p.P;
@@ -544,7 +557,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_recurrent_tc_kernel(const _
                          "r"(pack_h2(h[8 * g], h[8 * g + 1])), "r"(pack_h2(h[8 * g + 2], h[8 * g + 3])),
                          "r"(pack_h2(h[8 * g + 4], h[8 * g + 5])), "r"(pack_h2(h[8 * g + 6], h[8 * g + 7])) : "memory");
           stamp();
-          if (live) {
+          if (live && part == 0) {
             const size_t slot = p.dst_index ? (size_t)p.dst_index[grow] : (size_t)grow;
             float4* dst = reinterpret_cast<float4*>(p.hidden_out + slot * 64);
 #pragma unroll
@@ -643,11 +656,14 @@ struct MlpNet : NetImpl {
       q.nnets = pi_probs ? 4 : 3;
       q.nblk = pi_probs ? tc_blocks_policy : tc_blocks_no_policy;
       const int ntiles = (batch + kTcRows - 1) / kTcRows;
+      // few tiles: two CTAs per tile share the heads (the four nets of a tile otherwise run back to back on one SM)
+      static const bool no_split = getenv("MZ_MLP_NO_SPLIT") != nullptr;
+      q.nsplit = (!no_split && 2 * ntiles <= num_sms) ? 2 : 1;
       static const bool debug = getenv("MZ_MLP_DEBUG") != nullptr;
       q.dbg = nullptr;
       if (debug) { cudaMalloc(&q.dbg, 64 * sizeof(long long)); cudaMemset(q.dbg, 0, 64 * sizeof(long long)); }
       prof_mark(kProfMlp, st);
-      mlp_recurrent_tc_kernel<<<ntiles < num_sms ? ntiles : num_sms, kTcThreads, tc_smem, st>>>(q);
+      mlp_recurrent_tc_kernel<<<q.nsplit == 2 ? 2 * ntiles : (ntiles < num_sms ? ntiles : num_sms), kTcThreads, tc_smem, st>>>(q);
       prof_mark(-1, st);
       MZ_LAUNCH_CHECK("mlp_recurrent_tc_kernel");
       if (debug) {   // measurement aid: cycle stamps of CTA 0 (start, prologue, gather, then per net: MMA1, epi1, MMA2, epi2; end)
