@@ -70,6 +70,7 @@ struct LayerDesc {
   const int32_t* out_index;
   int dep;                        // input is produced by the previous layer of this launch
   int fwd;                        // resident launches: 1 = the next layer reads this layer's `out`, 2 = its `out_norm`
+  int res_layer;                  // layer of THIS launch that writes the residual buffer (-1: an earlier launch did)
   int in_slots;                   // input is an array of hidden-state slots, not a contiguous buffer
 };
 
@@ -205,6 +206,7 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_mm + 2 * 128);       // [2 tiles][2 halves][left,right,top,bottom][4] edge rows
 
   if (tid == 0) {
+    tmem_holder[2] = 0;
     for (uint32_t s = 0; s < kStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], kSplitK ? 1 : 2); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&a_full[b], 1); mbar_init(&mma_done[b], 2); mbar_init(&acc_empty[b], kEpiThreads);
@@ -217,6 +219,9 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_holder;
+  // tmem_holder[2]: number of items whose RESIDUAL producer (layer res_layer, same tile, possibly another CTA) the
+  // weight-producer lane has seen published (dataflow launches); read by the epilogue before it requests residual rows
+  const uint32_t s_res_a = smem_u32(tmem_holder + 2);
 
   // every role walks the same (layer, tile) item sequence of this CTA
   const int G = (int)gridDim.x;
@@ -227,12 +232,29 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
     // ------------------------------------------------ weight producer
     if (lane == 0) {
       const int per_tile = 9 * chunks_tap;
-      uint32_t it = 0;
+      uint32_t it = 0, res_items = 0;
       long long t_wait = 0;
       const long long t_begin = clock64();
       for (int l = 0; l < p.num_layers; ++l) {
         const unsigned char* wl = reinterpret_cast<const unsigned char*>(p.L[l].w);
         for (int tile = first_tile(l); tile < p.num_tiles; tile += G) {
+          if (!p.resident && p.flags) {
+            // The epilogue prefetches this item's residual rows (written by layer res_layer, same tile, in general by
+            // ANOTHER CTA two layers ago) before its MMAs finish, i.e. possibly before this CTA's loader has acquired
+            // the item's dependency flags -- nothing would order that write before the prefetch.  This lane, which
+            // runs a few weight stages ahead of everything else, acquires the producer's flag (it is practically
+            // always set already: 0 misses in 10^4 items measured) and publishes an item counter at CTA scope.
+            const LayerDesc& Lr = p.L[l];
+            if (Lr.residual && Lr.res_layer >= 0) {
+              const unsigned* f = p.flags + (size_t)Lr.res_layer * p.num_tiles + tile;
+              unsigned spins = 0;
+              while (ld_acquire(f) == 0u) {
+                if (++spins > (1u << 26)) { if (p.err) atomicExch(p.err, 1); break; }
+              }
+            }
+            ++res_items;
+            asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(s_res_a), "r"(res_items) : "memory");
+          }
           for (int c = 0; c < per_tile; ++c, ++it) {
             const uint32_t s = it % kStages, ph = (it / kStages) & 1;
             const long long tw = dbg ? clock64() : 0;
@@ -533,6 +555,11 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
 #pragma unroll
           for (int u = 0; u < 4; ++u) dst[u] = ld ? __ldcg(resp + (size_t)(g0 + u) * PR + pick(Pj, j)) : make_int4(0, 0, 0, 0);
         };
+        if (!p.resident && has_res && p.flags && L.res_layer >= 0) {
+          // ordered behind the residual producer's flag, see the weight-producer warp (a counter that is ahead of us)
+          uint32_t seen;
+          do { asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(seen) : "r"(s_res_a) : "memory"); } while (seen < (uint32_t)(k + 1));
+        }
         if (has_cols) {
           fetch(0, ring[0]);
           if (STEPS > 1) fetch(1, ring[1]);
@@ -1060,6 +1087,7 @@ struct ConvNet : NetImpl {
     d.residual = residual; d.out = out; d.out_norm = out_norm; d.out_slots = out_slots; d.out_index = out_index;
     d.dep = pend.num_layers > 0 ? 1 : 0;
     d.fwd = 0;
+    d.res_layer = -1;
     d.in_slots = in_slots ? 1 : 0;
     pend_geo = g; pend_cg = L.cg; pend_batch = batch;
     ++pend.num_layers;
@@ -1088,6 +1116,12 @@ struct ConvNet : NetImpl {
     const int force_rows = force_env ? atoi(force_env) : 0;
     int rows = (nl > 1 && (p.Ptot + kTileM - 1) / kTileM < 2 * num_sms) ? 128 : kTileM;
     if (force_rows == 128 || force_rows == 256) rows = force_rows;
+    for (int i = 0; i < nl; ++i) {          // which layer of this launch produces layer i's residual buffer
+      pend.L[i].res_layer = -1;
+      if (pend.L[i].residual)
+        for (int j = i - 1; j >= 0; --j)
+          if (pend.L[j].out == pend.L[i].residual || pend.L[j].out_norm == pend.L[i].residual) { pend.L[i].res_layer = j; break; }
+    }
     p.masked = grid_pad() == 0;
     // split-K tiles give the second MMA warp the odd weight stages; with one stage per tap its first MMA would be a
     // masked (non-centre) tap and could not initialise its accumulator
