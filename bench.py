@@ -215,11 +215,22 @@ def cpu_searches_per_step(name):
     return {'tictactoe': 40, 'cartpole': 12, 'gomoku': 1, 'atari': 2}[name]
 
 
+def bench_config(spec, trees_per_gpu, world, strong):
+    """The `config` object of the JSON line: ONE definition for both arms, so that the driver's same_config check
+    compares like with like.  Engine-side scheduling detail lives under `schedule`, not here."""
+    return {'workload': spec['label'], 'trees_per_gpu': int(trees_per_gpu), 'simulations': int(spec['cfg'].num_simulations),
+            'num_actions': int(spec['net_kw']['num_actions']),
+            'l2': 'flushed between timed iterations (256 MiB write)',
+            'parallelism': ('2048 games split over' if strong else 'games sharded over') + f' {world} GPU(s), no collective'}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     spec = workload_spec(args.workload, args.trees)
+    if args.strong:
+        spec['trees'] = max(1, spec['trees'] // max(1, args.gpus))
     procs = min(os.cpu_count() or 1, args.cpu_procs)
     arm = CpuArm(args.workload, args.trees, procs)
     n = cpu_searches_per_step(args.workload)
@@ -234,9 +245,10 @@ def run_reference_arm(args):
     sample = f'{procs} processes x {n} single-tree searches x {spec["cfg"].num_simulations} sims per step, {args.steps} steps'
     emit({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': 1000.0 * wall / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'warmup': args.warmup, 'ms_per_step': 1000.0 * wall / args.steps, 'higher_is_better': True,
+        'scaling': 'strong' if args.strong else 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': spec['label'], 'trees': spec['trees'], 'simulations': spec['cfg'].num_simulations},
+        'config': bench_config(spec, spec['trees'], args.gpus, bool(args.strong)),
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': procs, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     })
@@ -257,42 +269,25 @@ def algorithmic_bytes_per_launch(kernel, spec, B, A, S, mean_depth, hidden_bytes
     return per * B
 
 
-def run_engine_arm(args):
+def build_search(spec, dev, rank=0, parts=0, cta_limit=0):
+    """Network, search plan and synthetic inputs exactly as the bench runs them (tests/test_bench_parity_gpu.py builds
+    its plan through this function, so what is parity-checked IS what is timed)."""
     import torch
-    import torch.distributed as dist
     import muzero_b200 as mz
-    from muzero_b200 import _lib
-    from muzero_b200.mcts import PipelinedSearchPlan, SearchPlan
-
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    spec = workload_spec(args.workload, args.trees)
-    cfg, B, A, S = spec['cfg'], spec['trees'], spec['net_kw']['num_actions'], spec['cfg'].num_simulations
+    from muzero_b200.mcts import PipelinedSearchPlan, SearchPlan, pipeline_shape
+    cfg, B = spec['cfg'], spec['trees']
     cls = {'mlp': mz.MuZeroMLPNet, 'board': mz.MuZeroBoardGameNet, 'atari': mz.MuZeroAtariNet}[spec['kind']]
     net = cls(**spec['net_kw'])
     net.load_state_dict(state_dict_for(spec))
     net = net.to(dev).eval()
-    # conv nets: two half-batches interleaved on two streams (tree kernels of one overlap the tower of the other)
-    from muzero_b200.mcts import pipeline_shape
-    parts, cta_limit = pipeline_shape(net, B)
-    if args.parts:
-        parts, cta_limit = args.parts, args.cta_limit
+    # conv nets with enough rows: two half-batches interleaved on two streams (tree kernels of one overlap the tower
+    # of the other)
+    auto_parts, auto_limit = pipeline_shape(net, B)
+    if not parts:
+        parts, cta_limit = auto_parts, auto_limit
     plan = PipelinedSearchPlan(net, cfg, B, parts, cta_limit) if parts > 1 else SearchPlan(net, cfg, B)
-    pool = plan.pool
-    pool.seed(1234 + rank * B + np.arange(B))
-    read_stats = (lambda: pool.stats()) if parts > 1 else (lambda: pool.view('STATS').cpu().numpy().copy())
-
+    seeds = 1234 + rank * B + np.arange(B)
+    plan.pool.seed(seeds)
     obs, mask, cur, opp = synthetic_inputs(spec, B, 99 + rank)
     obs_h = torch.from_numpy(obs).pin_memory()
     mask_h = torch.from_numpy(mask).pin_memory()
@@ -300,6 +295,30 @@ def run_engine_arm(args):
     plan.obs.copy_(obs_h.reshape(B, -1)); plan.mask.copy_(mask_h)
     plan.players.copy_(torch.from_numpy(np.stack([cur, opp], 1)))
     plan.temps.fill_(1.0)
+    return dict(net=net, plan=plan, parts=parts, cta_limit=cta_limit, obs=obs, mask=mask, cur=cur, opp=opp,
+                obs_h=obs_h, mask_h=mask_h, seeds=seeds)
+
+
+def measure_workload(spec, args, dev, world, rank, steps, warmup, min_seconds=0.0, parts=0, cta_limit=0,
+                     kernel_timing=True):
+    """One workload on this rank's GPU: device-timed `value`, `e2e` through uct_search_batch with host buffers,
+    clocks sampled during the timed region, per-kernel roofline (eager launches bracketed by CUDA events)."""
+    import torch
+    import torch.distributed as dist
+    import muzero_b200 as mz
+    from muzero_b200 import _lib
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cfg, B, A, S = spec['cfg'], spec['trees'], spec['net_kw']['num_actions'], spec['cfg'].num_simulations
+    built = build_search(spec, dev, rank, parts, cta_limit)
+    net, plan, parts, cta_limit = built['net'], built['plan'], built['parts'], built['cta_limit']
+    obs_h, mask_h, cur, opp = built['obs_h'], built['mask_h'], built['cur'], built['opp']
+    pool = plan.pool
+    read_stats = (lambda: pool.stats()) if parts > 1 else (lambda: pool.view('STATS').cpu().numpy().copy())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
     def step_device():
@@ -326,19 +345,30 @@ def run_engine_arm(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for _ in range(max(args.warmup, 3)):
+    warmup = max(warmup, 3)
+    t0 = time.perf_counter()
+    for _ in range(warmup):
         step_device()
+    torch.cuda.synchronize()
     for _ in range(2):
         step_e2e()
     torch.cuda.synchronize()
     pool.check_errors()
+    if min_seconds > 0:
+        # short workloads (a Tic-Tac-Toe search lasts a millisecond): enough steps that nvidia-smi, sampling every
+        # 100 ms, sees the timed region at least ten times.  Same count on every rank.
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); step_device(); step_device(); e1.record()
+        torch.cuda.synchronize()
+        est = max(1e-4, e0.elapsed_time(e1) / 2e3 + 1e-3)            # + the L2 flush between steps
+        steps = int(min(5000, max(steps, min_seconds / est)))
     stats0 = read_stats()
 
     uuid = str(torch.cuda.get_device_properties(dev).uuid)
     sampler = ClockSampler(uuid if uuid.startswith('GPU-') else 'GPU-' + uuid) if rank == 0 else None
-    ms_dev = timed(step_device, args.steps)
+    ms_dev = timed(step_device, steps)
     stats1 = read_stats()
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = timed(step_e2e, steps)
     clocks = sampler.stop() if rank == 0 else None
     pool.check_errors()
 
@@ -348,16 +378,46 @@ def run_engine_arm(args):
     h2d = obs_h.numel() * obs_h.element_size() + mask_h.numel() + 2 * 4 * B + 8 * B
     d2h = sum(t.numel() * t.element_size() for t in out_h)
 
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    tf_peak = float(peaks.get('bf16_tflops', 1590.0))
+    tf_sustained = float(peaks.get('bf16_tflops_sustained', tf_peak))
+    peak_src = 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback (B200_PROFILING.md)'
+    pplan = plan.parts[0] if parts > 1 else plan
+    Bp = pplan.B
+    result = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps, 'warmup': warmup,
+        'ms_per_step': ms_dev, 'higher_is_better': True, 'scaling': 'strong' if args.strong else 'weak',
+        'vs_baseline': None,
+        'dtype': 'f64 tree statistics / f32 scores; network fp16 x fp16 -> f32 (tcgen05)' +
+                 (' for recurrent inference, f32 SIMT for the root inference' if spec['kind'] == 'mlp' else ''),
+        'data': 'synthetic',
+        'config': bench_config(spec, B, world, bool(args.strong)),
+        'schedule': {'pipeline_parts': parts, 'trees_per_kernel_launch': Bp,
+                     'ctas_per_tower_launch': getattr(plan, 'cta_limit', 0) or cta_limit or 148,
+                     'ctas_per_tree_kernel_launch': getattr(plan, 'tree_ctas', 0) or 'one warp per tree, all SMs',
+                     'mean_select_depth': mean_depth},
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': int(h2d),
+                'd2h_bytes_per_step': int(d2h)},
+        'gpu_launches': int(plan.launches_per_search * steps * 2),
+        'clocks': clocks,
+    }
+    if not kernel_timing:
+        return result, built
+
     # ---- per-kernel timing (eager launches, CUDA events on the launching stream) -> roofline.
     # With a pipelined plan the kernels run on sub-batches of B / parts trees: part 0 is timed as it runs there.
     lib = _lib.lib()
-    pplan = plan.parts[0] if parts > 1 else plan
-    ppool, Bp = pplan.pool, pplan.B
+    ppool = pplan.pool
     eng = net.engine(Bp, pplan.instance)
     hidden = ppool.hidden.data_ptr() if ppool.hidden_bytes else None
     names = ['select', 'recurrent', 'expand_backup']
     tot = {n: 0.0 for n in names}
-    reps = max(1, min(args.steps, 3))
+    reps = max(1, min(steps, 3))
     import ctypes as C
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream().cuda_stream
@@ -392,34 +452,24 @@ def run_engine_arm(args):
     launches = reps * S
     avg_ms = {n: tot[n] / launches for n in names}
     share = {n: tot[n] / sum(tot.values()) for n in names}
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
-    tf_peak = float(peaks.get('bf16_tflops', 1590.0))
-    peak_src = 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback (B200_PROFILING.md)'
     dominant = max(names, key=lambda n: tot[n])
-    noise_on = True
     roof = {}
     for n in names:
-        ab = algorithmic_bytes_per_launch(n, spec, Bp, A, S, mean_depth, pool.hidden_bytes, noise_on)
+        ab = algorithmic_bytes_per_launch(n, spec, Bp, A, S, mean_depth, pool.hidden_bytes, True)
         roof[n] = {'bound': 'hbm', 'achieved': ab / (avg_ms[n] * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
                    'avg_launch_us': avg_ms[n] * 1e3, 'share_of_sim_loop': share[n], 'algorithmic_bytes': ab}
         roof[n]['frac'] = roof[n]['achieved'] / hbm_peak
     flops = {'tictactoe': 175104, 'cartpole': 395264, 'gomoku': 803712780, 'atari': 351896688}[spec['name']]
-    if True:     # every network family runs recurrent inference on the tensor cores
-        ach = flops * Bp / (avg_ms['recurrent'] * 1e-3) / 1e12
-        roof['recurrent'].update({'bound': 'tensor', 'achieved': ach, 'peak': tf_peak, 'unit': 'TFLOP/s',
-                                  'frac': ach / tf_peak, 'reference_graph_flops': flops * Bp})
+    ach = flops * Bp / (avg_ms['recurrent'] * 1e-3) / 1e12        # every family runs recurrent inference on tcgen05
+    roof['recurrent'].update({'bound': 'tensor', 'achieved': ach, 'peak': tf_peak, 'unit': 'TFLOP/s',
+                              'frac': ach / tf_peak, 'reference_graph_flops': flops * Bp})
     roofline = dict(roof[dominant])
     roofline.update({'kernel': dominant, 'traffic': None, 'peak_source': peak_src})
     if spec['kind'] != 'mlp' and prof_n[0] > 0:
         # the dominant KERNEL is the tcgen05 3x3 convolution.  One launch runs a whole tower pair as a dataflow
         # of layers (33 convs for a recurrent inference): algorithmic flops per layer = the reference graph's
-        # 128->128 3x3 conv over the H*W real positions of the boards of one launch; executed = the same over
-        # the (H+1)*(W+1) padded grid.  Launch duration: CUDA events around every eager launch.
+        # CxC 3x3 conv over the H*W real positions of the boards of one launch.  Launch duration: CUDA events around
+        # every eager launch.
         c, h, w = spec['net_kw']['input_shape']
         hh, ww = (h, w) if spec['kind'] == 'board' else (6, 6)
         planes = spec['net_kw']['num_planes']
@@ -439,6 +489,9 @@ def run_engine_arm(args):
             pass
         roofline = {'kernel': 'conv3x3_kernel (tcgen05.mma M128 N128 K16, TMEM accumulators, TMA tile loads)',
                     'bound': 'tensor', 'achieved': ach, 'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': ach / tf_peak,
+                    'peak_regime': 'burst (cuBLAS bf16 8192^3 best of 10); the kernel is timed inside the eager '
+                                   'simulation loop of a long step, where the sustained figure applies',
+                    'frac_of_sustained_peak': ach / tf_sustained, 'sustained_peak': tf_sustained,
                     'traffic': traffic, 'avg_launch_us': launch_ms * 1e3, 'launches_timed': int(prof_n[4]),
                     'conv_layers_per_launch': layers_per_launch,
                     'algorithmic_flops_per_launch': alg, 'executed_flops_per_launch': exe,
@@ -446,26 +499,42 @@ def run_engine_arm(args):
                     'share_of_recurrent_inference': prof_ms[0] / max(1e-9, prof_ms[0] + prof_ms[1] + prof_ms[2]),
                     'share_of_sim_loop': prof_ms[0] / max(1e-9, sum(tot.values())), 'peak_source': peak_src}
         roof['head_kernel'] = {'avg_launch_us': 1e3 * prof_ms[1] / max(1, prof_n[1]), 'launches_timed': int(prof_n[1])}
+    result['roofline'] = roofline
+    result['kernels'] = roof
+    del flush
+    return result, built
 
-    result = {
-        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
-        'ms_per_step': ms_dev, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f64 tree statistics / f32 scores; network fp16 x fp16 -> f32 (tcgen05)' +
-                 (' for recurrent inference, f32 SIMT for the root inference' if spec['kind'] == 'mlp' else ''),
-        'data': 'synthetic',
-        'config': {'workload': spec['label'], 'trees_per_gpu': B, 'simulations': S, 'num_actions': A,
-                   'pipeline_parts': parts, 'trees_per_kernel_launch': Bp,
-                   'ctas_per_tower_launch': getattr(plan, 'cta_limit', 0) or cta_limit or 148,
-                   'ctas_per_tree_kernel_launch': getattr(plan, 'tree_ctas', 0) or 'one warp per tree, all SMs',
-                   'l2': 'flushed between timed iterations (256 MiB write)', 'mean_select_depth': mean_depth,
-                   'parallelism': f'games sharded over {world} GPU(s), no collective'},
-        'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': int(h2d),
-                'd2h_bytes_per_step': int(d2h)},
-        'gpu_launches': int(plan.launches_per_search * args.steps * 2),
-        'clocks': clocks,
-        'roofline': roofline,
-        'kernels': roof,
-    }
+
+def release(built):
+    """Drop a workload's plan, pools and engines before the next one is built."""
+    import gc
+    import torch
+    import muzero_b200 as mz
+    built['net'].release_engine()
+    built.clear()
+    mz.mcts._PLANS.clear()
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
+def run_engine_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    spec = workload_spec(args.workload, args.trees)
+    if args.strong:                       # SURVEY 8d: the configuration's trees in TOTAL, split over the ranks
+        spec['trees'] = max(1, spec['trees'] // world)
+    result, built = measure_workload(spec, args, dev, world, rank, args.steps, args.warmup, parts=args.parts,
+                                     cta_limit=args.cta_limit)
+    net = built['net']
     if not args.no_train_step:
         try:
             result['train_step'] = train_step_sample(net, spec, dev, world)
@@ -476,8 +545,34 @@ def run_engine_arm(args):
             result['self_play'] = self_play_sample(net, spec, dev, rank)
         except Exception as exc:
             result['self_play'] = {'error': repr(exc)[:200]}
+    release(built)
+    if world > 1 and not args.strong and not args.no_configs and spec['name'] == 'gomoku':
+        # the same configuration split over the ranks (SURVEY 8d "2048 total"): the latency regime of the design
+        try:
+            s2 = workload_spec(args.workload, max(1, spec['trees'] // world))
+            r2, b2 = measure_workload(s2, args, dev, world, rank, max(3, args.steps // 2), 3, kernel_timing=False)
+            result['strong_scaling'] = {'trees_total': s2['trees'] * world, 'trees_per_gpu': s2['trees'],
+                                        'value': r2['value'], 'ms_per_step': r2['ms_per_step'], 'unit': UNIT,
+                                        'e2e': r2['e2e'], 'schedule': r2['schedule'],
+                                        'speedup_vs_one_gpu_weak_step': result['ms_per_step'] / r2['ms_per_step']}
+            release(b2)
+        except Exception as exc:
+            result['strong_scaling'] = {'error': repr(exc)[:200]}
+    if not args.no_configs and spec['name'] == 'gomoku' and not args.strong:
+        # short sub-runs of the other BASELINE.json configurations, so that the driver's line carries every config
+        # (each with its own clocks record of >= 10 samples, e2e and per-kernel roofline)
+        result['configs'] = {}
+        for name in ('cartpole', 'tictactoe', 'atari'):
+            try:
+                s_i = workload_spec(name, None)
+                r_i, b_i = measure_workload(s_i, args, dev, world, rank, 5, 3, min_seconds=1.5)
+                release(b_i)
+                for k in ('metric', 'unit', 'higher_is_better', 'vs_baseline', 'data'):
+                    r_i.pop(k, None)
+                result['configs'][name] = r_i
+            except Exception as exc:
+                result['configs'][name] = {'error': repr(exc)[:300]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        del flush
         result['cpu_baseline'] = cpu_baseline_sample(args, spec)
     if rank == 0:
         emit(result)
@@ -494,10 +589,33 @@ def train_step_sample(net, spec, dev, world, batch=128, unroll=5, warmup=6, step
     import muzero_b200 as mz
     from muzero_b200.training import DataParallelLearner, synthetic_transitions
     cls = type(net)
+    rank = dist.get_rank() if world > 1 else 0
+    local_ms = None
+    if world > 1:
+        # the same step WITHOUT the collective (what one GPU does on its own), on this box, right before the
+        # data-parallel one: ms_local / ms_dp is the step's own weak-scaling efficiency
+        twin0 = cls(**spec['net_kw']).to(dev)
+        twin0.load_state_dict(net.state_dict())
+        solo = DataParallelLearner(twin0, spec['cfg'], dev, data_parallel=False)
+        tr0, w0 = synthetic_transitions(twin0, batch, unroll, seed=400 + rank)
+        for _ in range(warmup):
+            solo.step(tr0, w0)
+        torch.cuda.synchronize(dev)
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        l0.record()
+        for _ in range(steps):
+            solo.step(tr0, w0)
+        l1.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([l0.elapsed_time(l1) / steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        local_ms = float(t.item())
+        del solo, twin0
+        torch.cuda.empty_cache()
     twin = cls(**spec['net_kw']).to(dev)
     twin.load_state_dict(net.state_dict())
     learner = DataParallelLearner(twin, spec['cfg'], dev)
-    rank = dist.get_rank() if world > 1 else 0
     # batches come out of the device-resident replay: 64 batches' worth of synthetic transitions,
     # uniform sampling like every run_training.py of the reference, sample + gather inside the timed step
     from muzero_b200.replay import DeviceReplay
@@ -524,6 +642,18 @@ def train_step_sample(net, spec, dev, world, batch=128, unroll=5, warmup=6, step
     e1.record()
     torch.cuda.synchronize(dev)
     sample_ms = s0.elapsed_time(s1)
+    dp_only_ms = None
+    if world > 1:                        # the data-parallel learner step on its own (fixed batch, no replay calls)
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        d0.record()
+        for _ in range(steps):
+            learner.step(tr, w)
+        d1.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([d0.elapsed_time(d1) / steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dp_only_ms = float(t.item())
     if world > 1:                        # the gradient all-reduce on its own (inside the step it is part of the graph)
         for i in range(8):
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -543,6 +673,10 @@ def train_step_sample(net, spec, dev, world, batch=128, unroll=5, warmup=6, step
            'cuda_graph': bool(learner.use_graph and learner._graph is not None),
            'impl': 'DeviceReplay.sample (sampling + gather kernels) -> ONE CUDA graph of the PyTorch autograd fwd/bwd, '
                    'the flat NCCL all-reduce and Adam -> update_priorities'}
+    if local_ms is not None:
+        out['ms_per_learner_step_no_collective'] = local_ms
+        out['ms_per_learner_step_data_parallel'] = dp_only_ms
+        out['efficiency'] = local_ms / dp_only_ms
     if ar:
         a = sum(ar) / len(ar)
         out['allreduce_ms'] = a
@@ -628,6 +762,9 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-train-step', action='store_true')
     ap.add_argument('--no-self-play', action='store_true')
+    ap.add_argument('--no-configs', action='store_true', help='skip the sub-runs of the other configurations')
+    ap.add_argument('--strong', action='store_true',
+                    help="strong scaling: the configuration's trees in total, split over the ranks")
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)

@@ -67,6 +67,11 @@ class SearchPool:
                                           self._base, nbytes.value, C.byref(self.handle)))
         self.arena_bytes = nbytes.value
         self._views = {}
+        # mz_pool_create zeroes the MT19937 states, and an all-zero state emits 0 forever (NaN Dirichlet noise, a
+        # degenerate tie-break).  Every new pool therefore starts from OS entropy -- NOT from np.random, whose global
+        # stream the drop-in uct_search must leave exactly where the reference would.  seed() / set_rng_states()
+        # replace these streams when a reproducible search is wanted.
+        self.seed(np.random.SeedSequence().generate_state(self.B, dtype=np.uint32))
 
     def __del__(self):
         try:

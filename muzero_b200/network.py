@@ -117,6 +117,7 @@ class MuZeroNet(nn.Module):
         self.value_support_size = value_support_size
         self.reward_support_size = reward_support_size
         self._engs = {}           # instance -> dict(handle, arena tensor, version stamp, device, max_batch)
+        self._weight_epoch = 0    # bumped by mark_weights_updated(): updates the version counters cannot see
 
     @property
     def mse_loss_for_value(self):
@@ -130,9 +131,17 @@ class MuZeroNet(nn.Module):
     def _net_config(self) -> _lib.NetConfig:
         raise NotImplementedError
 
+    def mark_weights_updated(self) -> None:
+        """Tell the engine that parameters / buffers changed behind autograd's back.
+
+        ``_stamp`` reads the tensors' ``_version`` counters, which a CUDA-graph replay (the graphed training
+        step of ``training.DataParallelLearner``) or a raw-pointer write never advances: without this call the
+        next search would keep the engine (and the captured search graphs) packed from the old weights."""
+        self._weight_epoch += 1
+
     def _stamp(self):
         return (tuple(p._version for p in self.parameters()), tuple(b._version for b in self.buffers()),
-                self.training)
+                self.training, self._weight_epoch)
 
     def engine(self, max_batch: int = 1, instance: int = 0):
         """The ``mz_net`` handle for the current weights (rebuilt when they changed).

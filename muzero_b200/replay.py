@@ -14,8 +14,9 @@ of them in host RAM; 1e6 Gomoku samples are 0.73 GB of int8 here), ``add_batch``
 self-play kernels emit (``selfplay.Samples``), ``sample`` returns device tensors that ``training.calc_loss`` consumes
 without a host round trip, and the index stream is produced by ``csrc/replay.cu`` from numpy's legacy MT19937 state
 kept on the device: the uniform path continues the replay's own ``random_state`` exactly like
-``RandomState.uniform`` (replay.py:90), the prioritized path continues the stream handed to ``global_state``
-(the reference calls the GLOBAL ``np.random.choice`` there, replay.py:96).  ``get_state()['random_state']`` returns
+``RandomState.uniform`` (replay.py:90), the prioritized path draws from numpy's live GLOBAL stream like the reference's
+``np.random.choice`` (replay.py:96) -- loaded to the device and written back around every ``sample`` -- or, when
+``global_state`` is given, from that private stream kept on the device.  ``get_state()['random_state']`` returns
 the stream so that a host ``RandomState`` can carry on from it.
 """
 from __future__ import annotations
@@ -71,7 +72,12 @@ class DeviceReplay:
         with torch.cuda.device(self.device):
             self._priorities = torch.zeros(self._capacity, dtype=torch.float32, device=self.device)
             self._own = _DeviceStream(random_state, self.device)
-            # replay.py:96 draws from numpy's global stream: by default continue from wherever it stands now
+            # replay.py:96 draws from numpy's LIVE global stream.  Default (global_state=None): every prioritized
+            # sample() loads np.random's current state, draws on the device and writes the advanced state back, so
+            # the replay and the drop-in uct_search (which consumes the same global stream) never replay each
+            # other's numbers.  An explicit `global_state` gives the replay a private device-resident stream instead
+            # (no host round trip per sample).
+            self._follow_global = global_state is None
             self._global = _DeviceStream(global_state if global_state is not None else _global_numpy_state(),
                                          self.device)
         self._storage: Optional[dict] = None              # field -> tensor [capacity, *item shape]
@@ -164,10 +170,14 @@ class DeviceReplay:
                 if self._scratch is None:
                     self._scratch = (torch.empty(self._capacity + 1, dtype=torch.float32, device=self.device),
                                      torch.empty(self._capacity, dtype=torch.float64, device=self.device))
+                if self._follow_global:
+                    self._global.set(np.random.get_state())
                 _lib.check(lib.mz_replay_sample_prioritized(
                     self.size, batch_size, self._priorities.data_ptr(), self._priority_exponent,
                     self._importance_sampling_exponent, self._global.key.data_ptr(), self._global.pos.data_ptr(),
                     self._scratch[0].data_ptr(), self._scratch[1].data_ptr(), idx.data_ptr(), w.data_ptr(), st))
+                if self._follow_global:
+                    np.random.set_state(self._global.get())
         return self.get(idx), idx, w
 
     def update_priorities(self, indices, priorities) -> None:

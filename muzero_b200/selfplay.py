@@ -195,7 +195,9 @@ class BoardSelfPlay:
         uniq, inv = np.unique(self.steps, return_inverse=True)
         temps = np.array([cfg.visit_softmax_temperature_fn(int(s), self.train_steps) for s in uniq], np.float64)[inv]
         cur = (1 + (self.steps % 2)).astype(np.int32)                   # black moves first, players alternate
-        action, pi, root_value = mz.uct_search_batch(env.obs, self.net, cfg, temps, env.actions_mask, cur, 3 - cur)
+        # plan=: the plan this object seeded (the module-level plan cache may have evicted and rebuilt its entry)
+        action, pi, root_value = mz.uct_search_batch(env.obs, self.net, cfg, temps, env.actions_mask, cur, 3 - cur,
+                                                     plan=self._plan)
         # the reference's actor dies with ValueError('probabilities contain NaN') when every visit of a search went
         # below an illegal first pick (mcts.py:404); same here, before the bad action reaches the environment
         self._plan.pool.check_errors()

@@ -10,7 +10,8 @@ Reference semantics mirrored here (michaelnny/muzero):
 The reference has ONE learner on one device; here every rank computes the loss of its shard of the replay batch and
 the gradients are averaged with ONE flat-bucket all-reduce (the whole model, 29 MB fp32 for the Gomoku net, is a single
 latency-bound NVLink transfer), then every rank applies the identical Adam step, so weights stay in sync and the
-self-play engine on the same rank sees them without a broadcast.  Forward/backward run through PyTorch autograd over
+self-play engine on the same rank sees them without a broadcast.  BatchNorm running statistics (which the inference
+engine folds into its weights) are averaged the same way through a second, small flat bucket.  Forward/backward run through PyTorch autograd over
 the same parameters the inference engine repacks (SURVEY.md §8 e/f-2: fused fwd/bwd kernels are "next").
 
 BatchNorm note: like the reference's `network.train()` (pipeline.py:218) each rank uses ITS shard's batch statistics;
@@ -147,7 +148,8 @@ class DataParallelLearner:
     ~3000 small kernels of the unroll are launch-bound when issued from Python.  ``use_graph=False`` keeps every
     iteration eager; a capture that fails (e.g. a collective backend that cannot be captured) falls back to eager."""
 
-    def __init__(self, network: MuZeroNet, config, device, process_group=None, use_graph: bool = True) -> None:
+    def __init__(self, network: MuZeroNet, config, device, process_group=None, use_graph: bool = True,
+                 data_parallel: bool = True) -> None:
         self.network, self.config, self.device = network, config, torch.device(device)
         # conv nets on CUDA train with NHWC weights / activations: same fp32 (TF32) cuDNN arithmetic without the layout
         # transposes around every convolution (24.8 -> 20.7 ms per 128 x K=5 Gomoku step).  state_dict shapes, the
@@ -158,6 +160,8 @@ class DataParallelLearner:
             network.to(memory_format=torch.channels_last)
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        if not data_parallel:                 # a learner of its own inside a multi-rank job (no collective)
+            self.world = 1
         params = [p for p in network.parameters() if p.requires_grad]
         # one flat gradient bucket; every .grad is a view into it -> the all-reduce needs no packing copies
         self.flat_grad = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=self.device)
@@ -167,6 +171,20 @@ class DataParallelLearner:
             p.grad = self.flat_grad[off:off + p.numel()].as_strided(p.size(), p.stride())
             off += p.numel()
         self.params = params
+        # BatchNorm running statistics are updated from each rank's shard: average them with a second flat bucket so that
+        # every rank's actor folds the SAME statistics into its inference engine and any rank's checkpoint is the model
+        # all ranks used (DDP broadcasts rank 0's buffers instead; the average uses every shard's data)
+        self.flat_buf = None
+        if self.world > 1:
+            bufs = [b for b in network.buffers() if b.dtype.is_floating_point]
+            if bufs:
+                self.flat_buf = torch.zeros(sum(b.numel() for b in bufs), dtype=torch.float32, device=self.device)
+                off = 0
+                for b in bufs:
+                    view = self.flat_buf[off:off + b.numel()].view(b.shape)
+                    view.copy_(b)
+                    b.data = view
+                    off += b.numel()
         self.use_graph = bool(use_graph) and self.device.type == 'cuda'
         # gomoku/run_training.py:110 / classic: Adam(lr_init, weight_decay), MultiStepLR(milestones, lr_decay_rate).
         # Graph mode: step counters and the learning rate live on the device so that a replay sees their updates.
@@ -194,6 +212,9 @@ class DataParallelLearner:
                 e0.record()
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
             self.flat_grad.div_(self.world)
+            if self.flat_buf is not None:
+                dist.all_reduce(self.flat_buf, op=dist.ReduceOp.SUM, group=self.group)
+                self.flat_buf.div_(self.world)
             if time_allreduce and self.device.type == 'cuda':
                 e1.record()
                 torch.cuda.synchronize(self.device)
@@ -239,6 +260,9 @@ class DataParallelLearner:
                 loss, priorities = self._iteration(*inputs, time_allreduce=time_allreduce)
         self.lr_scheduler.step()
         self.train_steps += 1
+        # a graph replay does not advance the parameters' version counters: tell the inference engine explicitly
+        if hasattr(self.network, 'mark_weights_updated'):
+            self.network.mark_weights_updated()
         return float(loss), priorities.cpu().numpy()
 
     def state_dict(self):

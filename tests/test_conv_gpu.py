@@ -298,3 +298,76 @@ def test_atari_batched_vs_torch_fp32():
     report('atari r', r.cpu().numpy(), r_ref.numpy(), TOL_PV)
     report('atari v1', v2.cpu().numpy(), v2_ref.numpy(), TOL_PV)
     report('atari pi1', pi2.cpu().numpy(), pi2_ref.numpy(), TOL_PV)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[3] at its FULL shape: 16 stacked planes, 18 actions, 8 blocks, support 61
+# ---------------------------------------------------------------------------------------------------------------
+ATARI_C4 = dict(input_shape=(16, 96, 96), num_actions=18, num_res_blocks=8, num_planes=128, value_support_size=61,
+                reward_support_size=61)
+
+
+def _chain_vs_recording(net, z, name, label):
+    from test_net_golden_cpu import golden_obs
+    for j in range(2):
+        obs = golden_obs(z, name, j)
+        g = {k: z[f'{name}_{j}_{k}'] for k in ('actions', 'h0', 'pi0', 'v0', 'h', 'r', 'v', 'pi')}
+        o = net.initial_inference(torch.from_numpy(obs)[None].cuda())
+        assert o.hidden_state.shape == g['h0'].shape and o.hidden_state.dtype == np.float32
+        report(f'{label}/{j} h0', o.hidden_state, g['h0'].astype(np.float32), TOL_H)
+        report(f'{label}/{j} pi0', o.pi_probs, g['pi0'], TOL_PV)
+        report(f'{label}/{j} v0', o.value, g['v0'], TOL_PV)
+        h = g['h0'].astype(np.float32)
+        for i, a in enumerate(g['actions']):
+            o = net.recurrent_inference(torch.from_numpy(h)[None].cuda(), torch.tensor([[int(a)]]).cuda())
+            report(f'{label}/{j} h[{i}]', o.hidden_state, g['h'][i].astype(np.float32), TOL_H)
+            report(f'{label}/{j} r[{i}]', o.reward, g['r'][i], TOL_PV)
+            report(f'{label}/{j} v[{i}]', o.value, g['v'][i], TOL_PV)
+            report(f'{label}/{j} pi[{i}]', o.pi_probs, g['pi'][i], TOL_PV)
+            h = g['h'][i].astype(np.float32)
+
+
+def test_atari_c4_full_shape_vs_reference_recording(tile_rows):
+    """MuZeroAtariNet((16, 96, 96), 18, 8, 128, 61, 61) -- the benchmarked shape -- against the reference's own
+    recorded outputs (tests/golden/net_golden_r2.npz): 16-plane observation packing, both stride-2 tcgen05 convs, the
+    full-depth towers, the support-61 heads."""
+    net, _ = build_atari(ATARI_C4, 0)
+    _chain_vs_recording(net, np.load(os.path.join(GOLDEN, 'net_golden_r2.npz')), 'atari_c4', 'atari_c4')
+
+
+def test_atari_c4_search_replays_in_the_oracle_and_rows_match_fp32():
+    """One 64-tree x 50-simulation search with the C4 network: every tree rebuilt bit-for-bit by the CPU oracle from
+    the network outputs the engine produced, and sampled rows of the initial / recurrent inference compared with the
+    fp32 torch restatement of the reference network."""
+    import muzero_b200 as mz
+    from parity_util import check_rows_against_oracle_net, replay_tree_in_oracle
+    net, onet = build_atari(ATARI_C4, 0)
+    cfg = mz.make_atari_config(use_tensorboard=False)
+    cfg.num_simulations = 50
+    B, A, S = 64, 18, 50
+    gen = np.random.RandomState(44)
+    obs = gen.randint(0, 256, size=(B, 16, 96, 96)).astype(np.float32)
+    obs[:, 8:] = ((gen.randint(0, A, size=(B, 8, 1, 1)) + 1) / A).astype(np.float32)
+    mask = np.ones((B, A), dtype=bool)
+    streams = [np.random.RandomState(700 + t) for t in range(B)]
+    plan = mz.mcts.SearchPlan(net, cfg, B)
+    action, pi, rootv = mz.uct_search_batch(obs, net, cfg, 1.0, mask, 1, 1, rng=streams, plan=plan)
+    plan.pool.check_errors()
+    action_h, rootv_h = action.cpu(), rootv.cpu().numpy()
+    noise = plan.noise.cpu().numpy()
+    for t in range(B):
+        rs = np.random.RandomState(700 + t)
+        nz = rs.dirichlet(np.ones(A, dtype=np.float32) * cfg.root_dirichlet_alpha)
+        assert np.array_equal(nz, noise[t])                    # numpy-exact mode: the host drew the noise
+        replay_tree_in_oracle(plan, t, cfg, 1.0, mask[t], (1, 1), action_h, pi, rootv_h, rs, noise=nz)
+        assert rs.get_state()[2] == streams[t].get_state()[2]
+    # initial inference of 4 observations and 64 recurrent rows vs fp32 torch
+    rows4 = [0, 21, 42, 63]
+    h_ref, pi_ref, v_ref = onet.initial_batch(obs[rows4])
+    S1 = S + 1
+    roots = net.hidden_to_reference(plan.pool.hidden.view(B, S1, -1)[rows4, 0]).cpu().numpy()
+    report('c4 root hidden', roots, h_ref.numpy(), TOL_H)
+    report('c4 pi0', plan.pi0[rows4].cpu().numpy(), pi_ref.numpy(), TOL_PV)
+    report('c4 v0', plan.v0[rows4].cpu().numpy(), v_ref.numpy(), TOL_PV)
+    rows = [(int(t), int(k)) for t, k in zip(gen.choice(B, size=64), gen.randint(1, S1, size=64))]
+    check_rows_against_oracle_net(net, onet, plan, rows, TOL_H, TOL_PV)

@@ -387,3 +387,26 @@ def test_fused_and_confined_tree_kernels_equal_the_separate_launches(A, S, board
         got = run(mode)
         for k in want:
             assert np.array_equal(want[k], got[k]), f'{mode}: {k} differs'
+
+
+def test_fresh_pools_are_seeded_and_the_default_batch_call_is_not_degenerate():
+    """mz_pool_create zeroes the MT19937 states and an all-zero state emits 0 forever (NaN Dirichlet noise, constant
+    tie-breaks).  SearchPool seeds every new pool from OS entropy, so uct_search_batch(rng=None) on a plan the caller
+    never touched -- the call INTEGRATION.md shows -- must search with proper noise and distinct streams."""
+    import muzero_b200 as mz
+    dev = _dev()
+    cfg = mz.make_tictactoe_config(use_tensorboard=False)
+    pool = mz.SearchPool(8, 10, cfg, 0, dev)
+    keys = pool.view('RNG_KEY').view(8, 624).cpu().numpy()
+    assert (keys != 0).any(axis=1).all() and len({k.tobytes() for k in keys}) == 8
+    net = mz.MuZeroMLPNet((9, 3, 3), 10, 256, 1, 1, 64).to(dev).eval()
+    mz.mcts._PLANS.clear()
+    obs = np.random.RandomState(0).randint(0, 2, size=(32, 9, 3, 3)).astype(np.float32)
+    a, pi, q = mz.uct_search_batch(obs, net, cfg, 1.0, np.ones((32, 10), bool), 1, 2)
+    plan = mz.mcts._plan_for(net, cfg, 32)
+    plan.pool.check_errors()
+    prior = plan.pool.view('PRIOR').view(32, 10).cpu().numpy()
+    assert np.isfinite(prior).all() and np.allclose(prior.sum(1), 1.0)
+    assert np.isfinite(pi.cpu().numpy()).all() and np.allclose(pi.cpu().numpy().sum(1), 1.0)
+    assert len({p.tobytes() for p in plan.noise.cpu().numpy()}) == 32      # 32 different Dirichlet samples
+    mz.mcts._PLANS.clear()

@@ -174,3 +174,24 @@ def test_self_play_samples_flow_into_replay_and_the_learner():
     rep.update_priorities(idx, prio)
     net.eval()
     sp.play_move()                      # the actor searches with the refreshed weights (engine rebuilt)
+
+
+@pytest.mark.gpu
+def test_prioritized_sampling_follows_numpys_live_global_stream():
+    """replay.py:96 calls the GLOBAL np.random.choice at every sample(): with no `global_state` the device replay must
+    consume np.random's live stream (and leave it advanced), interleaved with other users of that stream."""
+    from muzero_b200.replay import DeviceReplay
+    from muzero_b200.training import Transition
+    _, prios, items = _items(200, 11)
+    rep = DeviceReplay(200, 1.0, 1.0, np.random.RandomState(4))
+    rep.add_batch(Transition(**{f: torch.from_numpy(v).cuda() for f, v in items.items()}), prios)
+    np.random.seed(321)
+    twin = np.random.RandomState(321)
+    for _ in range(3):
+        np.random.random_sample(5); twin.random_sample(5)                    # somebody else draws in between
+        _, idx, w = rep.sample(16)
+        want_idx, want_w = orc.sample_prioritized(prios.astype(np.float32), 200, 16, 1.0, 1.0, twin)
+        assert np.array_equal(idx.cpu().numpy(), want_idx)
+        assert np.array_equal(w.cpu().numpy().view(np.uint32), want_w.view(np.uint32))
+    a, b = np.random.get_state(), twin.get_state()
+    assert np.array_equal(a[1], b[1]) and a[2] == b[2]

@@ -82,7 +82,8 @@ def _dp_worker(rank, world, port, name, out):
     shard = Transition(*[x[lo:hi] for x in tr])
     loss, pri = learner.step(shard, w[lo:hi])
     grads = learner.flat_grad.clone()
-    params = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+    params = torch.cat([p.detach().reshape(-1) for p in net.parameters()] +
+                       [b.detach().reshape(-1).float() for b in net.buffers()])     # BatchNorm statistics included
     gathered = [torch.zeros_like(params) for _ in range(world)]
     dist.all_gather(gathered, params)
     if rank == 0:
@@ -103,7 +104,7 @@ def test_data_parallel_step_world2_gloo(name):
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    # weights identical on both ranks after the step
+    # weights AND BatchNorm running statistics identical on both ranks after the step
     np.testing.assert_array_equal(params[0], params[1])
     # the all-reduced gradient is the mean of the per-shard reference-semantics gradients
     net, B = build(name)
@@ -165,3 +166,31 @@ def test_graphed_training_step_equals_the_eager_one():
         assert abs(float(la.optimizer.param_groups[0]['lr']) - float(lb.optimizer.param_groups[0]['lr'])) < 1e-12
     assert la._graph is not None and lb._graph is None
     assert abs(float(la.optimizer.param_groups[0]['lr']) - cfg.lr_init * cfg.lr_decay_rate) < 1e-9
+
+
+@pytest.mark.gpu
+def test_engine_follows_the_graphed_training_steps():
+    """A CUDA-graph replay never advances the parameters' version counters; the learner tells the network explicitly
+    (MuZeroNet.mark_weights_updated), so inference after graphed steps must run with the NEW weights."""
+    import muzero_b200 as mz
+    from oracle.network_oracle import OracleNet
+    torch.manual_seed(0)
+    kw = dict(input_shape=(9, 3, 3), num_actions=10, num_planes=256, value_support_size=1, reward_support_size=1,
+              hidden_dim=64)
+    net = mz.MuZeroMLPNet(**kw).cuda()
+    cfg = mz.make_tictactoe_config(use_tensorboard=False)
+    learner = DataParallelLearner(net, cfg, 'cuda', use_graph=True)
+    obs = np.random.RandomState(3).randint(0, 2, size=(8, 9, 3, 3)).astype(np.float32)
+    net.eval()
+    _, pi_before, _ = net.initial_inference_batch(torch.from_numpy(obs).cuda())
+    for it in range(8):                                       # 3 eager + 5 replayed iterations
+        tr, w = synthetic_transitions(net, 16, 5, seed=it)
+        learner.step(tr, w)
+    assert learner._graph is not None
+    net.eval()
+    _, pi_after, v_after = net.initial_inference_batch(torch.from_numpy(obs).cuda())
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    _, pi_ref, v_ref = OracleNet('mlp', sd, 10, 1, 1).initial_batch(obs)
+    np.testing.assert_allclose(pi_after.cpu().numpy(), pi_ref.numpy(), rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(v_after.cpu().numpy(), v_ref.numpy().reshape(-1), rtol=2e-4, atol=2e-4)
+    assert float((pi_after - pi_before).abs().max()) > 1e-4   # the weights did move
