@@ -109,9 +109,15 @@ def synthetic_inputs(spec, B: int, seed: int):
         obs = gen.standard_normal((B,) + shape).astype(np.float32)
         obs[:, :, -1] = (gen.randint(0, 2, size=(B, shape[0])) + 1) / 2.0
     else:
-        obs = gen.randint(0, 256, size=(B,) + shape).astype(np.float32)
+        # the Atari observation as the environment produces it (gym_env.py:306-313): k uint8 frames + k constant action
+        # planes (action + 1) / A.  Kept in that compact form (muzero_b200.StackedFrames); .expand() gives the float32
+        # [B, 2k, H, W] tensor the reference builds from it.
+        import torch
+        from muzero_b200 import StackedFrames
         half = shape[0] // 2
-        obs[:, half:] = ((gen.randint(0, A, size=(B, shape[0] - half, 1, 1)) + 1) / A).astype(np.float32)
+        frames = gen.randint(0, 256, size=(B, half) + shape[1:]).astype(np.uint8)
+        planes = ((gen.randint(0, A, size=(B, shape[0] - half)) + 1) / A).astype(np.float32)
+        obs = StackedFrames(torch.from_numpy(frames), torch.from_numpy(planes))
     one = np.ones(B, dtype=np.int32)
     return obs, np.ones((B, A), dtype=bool), one, one
 
@@ -187,6 +193,8 @@ def _cpu_worker_run(args):
     from oracle import mcts_oracle as orc
     spec = _W['spec']
     obs, mask, cur, opp = synthetic_inputs(spec, n, seed + wid)
+    if hasattr(obs, 'expand'):
+        obs = obs.expand().numpy()
     rs = np.random.RandomState(1234 + wid)
     t0 = time.perf_counter()
     for i in range(n):
@@ -289,10 +297,16 @@ def build_search(spec, dev, rank=0, parts=0, cta_limit=0):
     seeds = 1234 + rank * B + np.arange(B)
     plan.pool.seed(seeds)
     obs, mask, cur, opp = synthetic_inputs(spec, B, 99 + rank)
-    obs_h = torch.from_numpy(obs).pin_memory()
     mask_h = torch.from_numpy(mask).pin_memory()
     # inputs resident in HBM for `value`
-    plan.obs.copy_(obs_h.reshape(B, -1)); plan.mask.copy_(mask_h)
+    if isinstance(obs, mz.StackedFrames):
+        obs_h = mz.StackedFrames(obs.frames.pin_memory(), obs.planes.pin_memory())
+        plan.use_frames()
+        plan.frames.copy_(obs_h.frames); plan.planes.copy_(obs_h.planes)
+    else:
+        obs_h = torch.from_numpy(obs).pin_memory()
+        plan.obs.copy_(obs_h.reshape(B, -1))
+    plan.mask.copy_(mask_h)
     plan.players.copy_(torch.from_numpy(np.stack([cur, opp], 1)))
     plan.temps.fill_(1.0)
     return dict(net=net, plan=plan, parts=parts, cta_limit=cta_limit, obs=obs, mask=mask, cur=cur, opp=opp,
@@ -375,7 +389,8 @@ def measure_workload(spec, args, dev, world, rank, steps, warmup, min_seconds=0.
     mean_depth = float(stats1[0] - stats0[0]) / max(1.0, float(stats1[1] - stats0[1]))
     value = world * B * S / (ms_dev / 1000.0)
     e2e_value = world * B * S / (ms_e2e / 1000.0)
-    h2d = obs_h.numel() * obs_h.element_size() + mask_h.numel() + 2 * 4 * B + 8 * B
+    obs_bytes = sum(t.numel() * t.element_size() for t in (obs_h if isinstance(obs_h, tuple) else (obs_h,)))
+    h2d = obs_bytes + mask_h.numel() + 2 * 4 * B + 8 * B
     d2h = sum(t.numel() * t.element_size() for t in out_h)
 
     peaks = {}

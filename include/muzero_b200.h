@@ -184,6 +184,16 @@ int mz_net_destroy(mz_net* net);
 int mz_net_initial(mz_net* net, int32_t batch, const float* obs, void* hidden_out,
                    const int32_t* dst_index, float* pi_probs, float* value, mz_stream stream);
 
+/* initial_inference for MuZeroAtariNet observations in their COMPACT form.  The reference's Atari observation
+ * (gym_env.py:306-313, StackFrameAndAction.observation) is k uint8 frames cast to float32 followed by k constant
+ * action planes (action + 1) / num_actions; uploading that float32 tensor is 4x the bytes of what it encodes.
+ *   frames        u8  [batch, k, h, w]     (k = in_channels / 2)
+ *   plane_values  f32 [batch, k]           the value of each constant plane
+ * Results are identical to mz_net_initial on the expanded float32 observation. */
+int mz_net_initial_frames(mz_net* net, int32_t batch, const uint8_t* frames, const float* plane_values,
+                          void* hidden_out, const int32_t* dst_index, float* pi_probs, float* value,
+                          mz_stream stream);
+
 /* recurrent_inference (network.py:86-111): row i reads slot src_index[i] of
  * hidden_in, applies action[i], writes slot dst_index[i] of hidden_out.
  * pi_probs may be NULL: the search never uses it (mcts.py:386 passes the root

@@ -758,6 +758,32 @@ __global__ void pack_obs_kernel(const float* __restrict__ obs, act_t* __restrict
   }
 }
 
+// The same for an Atari observation handed over in its COMPACT form (gym_env.py:306-313: k uint8 frames cast to float32,
+// then k constant action planes): frames u8 [B][K][H][W] + plane values f32 [B][K] -> the planes pack_obs_kernel would
+// produce from the float32 [B][2K][H][W] observation (0..255 are exact in fp16), at a quarter of the bytes.
+__global__ void pack_frames_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ planes,
+                                   act_t* __restrict__ out, int B, int K, int H, int W, int cpad, int plane_rows, int pad) {
+  const int Wp = W + pad, PB = (H + pad) * Wp;
+  const size_t rows = (size_t)B * PB, n = rows * (cpad / 8);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t P = i % rows;
+    const int g = (int)(i / rows);
+    const int pos = (int)(P % PB), b = (int)(P / PB);
+    const int y = pos / Wp, x = pos % Wp;
+    const bool real = y < H && x < W;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = g * 8 + e;
+      float f = 0.0f;
+      if (real && c < K) f = (float)frames[(((size_t)b * K + c) * H + y) * W + x];
+      else if (real && c < 2 * K) f = fminf(fmaxf(planes[(size_t)b * K + (c - K)], -65504.0f), 65504.0f);
+      v[e] = f;
+    }
+    reinterpret_cast<int4*>(out)[(size_t)g * plane_rows + P] = pack8(v);
+  }
+}
+
 // zeros at the halo positions of a planar buffer (after the SIMT kernels that only write real positions)
 __global__ void zero_halo_kernel(act_t* __restrict__ buf, int B, int H, int W, int cg, int plane_rows) {
   const int Wp = W + 1, PB = (H + 1) * Wp, nh = H + Wp;       // (padded layout only)       // halo positions per board: column W of rows 0..H-1, row H
@@ -1283,11 +1309,16 @@ struct ConvNet : NetImpl {
     return MZ_OK;
   }
 
-  int represent_atari(int batch, const float* obs, act_t* slots, const int32_t* dst_index, cudaStream_t st) {
+  int represent_atari(int batch, const float* obs, const uint8_t* frames, const float* plane_values, act_t* slots,
+                      const int32_t* dst_index, cudaStream_t st) {
     const int Hin = cfg.in_h, Win = cfg.in_w;
     const Geo g0{Hin, Win}, g1{Hin / 2, Win / 2}, g2{Hin / 4, Win / 4}, g3{Hin / 8, Win / 8};
     prof_mark(kProfPack, st);
-    pack_obs_kernel<<<num_sms * 8, 256, 0, st>>>(obs, xobs, batch, cfg.in_channels, Hin, Win, 16, plane_rows_of(g0, batch), grid_pad());
+    if (frames)
+      pack_frames_kernel<<<num_sms * 8, 256, 0, st>>>(frames, plane_values, xobs, batch, cfg.in_channels / 2, Hin, Win, 16,
+                                                      plane_rows_of(g0, batch), grid_pad());
+    else
+      pack_obs_kernel<<<num_sms * 8, 256, 0, st>>>(obs, xobs, batch, cfg.in_channels, Hin, Win, 16, plane_rows_of(g0, batch), grid_pad());
     prof_mark(-1, st);
     MZ_LAUNCH_CHECK("pack_obs_kernel");
     // stride-2 conv + ReLU: one tcgen05 launch at the input resolution whose epilogue stores the even positions on
@@ -1339,7 +1370,7 @@ struct ConvNet : NetImpl {
               cudaStream_t st) override {
     int rc;
     if (atari) {
-      rc = represent_atari(batch, obs, (act_t*)hidden_out, dst_index, st);
+      rc = represent_atari(batch, obs, nullptr, nullptr, (act_t*)hidden_out, dst_index, st);
     } else {
       prof_mark(kProfPack, st);
       pack_obs_kernel<<<num_sms * 4, 256, 0, st>>>(obs, xobs, batch, cfg.in_channels, lat.H, lat.W, in_cg * 8,
@@ -1351,6 +1382,19 @@ struct ConvNet : NetImpl {
       rc = tower(&rep0, rep_blocks, blocks, lat, xobs, nullptr, false, nullptr, nullptr, batch, false, b3,
                  (act_t*)hidden_out, dst_index, st, &fin);
     }
+    if (rc) return rc;
+    if ((rc = predict(batch, pi_probs, value, st))) return rc;
+    return launch_heads(batch, st);
+  }
+
+  int initial_frames(int batch, const uint8_t* frames, const float* plane_values, void* hidden_out,
+                     const int32_t* dst_index, float* pi_probs, float* value, cudaStream_t st) override {
+    if (!atari || (cfg.in_channels & 1)) {
+      set_error("mz_net_initial_frames: compact (uint8 frames + action planes) observations are the MuZeroAtariNet format "
+                "with an even number of stacked planes");
+      return MZ_EINVAL;
+    }
+    int rc = represent_atari(batch, nullptr, frames, plane_values, (act_t*)hidden_out, dst_index, st);
     if (rc) return rc;
     if ((rc = predict(batch, pi_probs, value, st))) return rc;
     return launch_heads(batch, st);

@@ -61,6 +61,15 @@ extern "C" int mz_net_initial(mz_net* net, int32_t batch, const float* obs, void
   return net->impl->initial(batch, obs, hidden_out, dst_index, pi_probs, value, (cudaStream_t)stream);
 }
 
+extern "C" int mz_net_initial_frames(mz_net* net, int32_t batch, const uint8_t* frames, const float* plane_values,
+                                     void* hidden_out, const int32_t* dst_index, float* pi_probs, float* value,
+                                     mz_stream stream) {
+  MZ_CHECK_ARG(net && frames && plane_values && hidden_out && value, "NULL argument");
+  MZ_CHECK_ARG(batch > 0 && batch <= net->max_batch, "batch %d outside (0, %d]", batch, net->max_batch);
+  return net->impl->initial_frames(batch, frames, plane_values, hidden_out, dst_index, pi_probs, value,
+                                   (cudaStream_t)stream);
+}
+
 extern "C" int mz_net_recurrent(mz_net* net, int32_t batch, const void* hidden_in, const int32_t* src_index,
                                 const int32_t* action, void* hidden_out, const int32_t* dst_index, float* reward,
                                 float* value, float* pi_probs, mz_stream stream) {

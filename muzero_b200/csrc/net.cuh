@@ -27,6 +27,10 @@ struct NetImpl {
   }
   virtual int initial(int batch, const float* obs, void* hidden_out, const int32_t* dst_index, float* pi_probs,
                       float* value, cudaStream_t st) = 0;
+  virtual int initial_frames(int, const uint8_t*, const float*, void*, const int32_t*, float*, float*, cudaStream_t) {
+    set_error("mz_net_initial_frames: this network family takes float32 observations");
+    return MZ_EINVAL;
+  }
   virtual int recurrent(int batch, const void* hidden_in, const int32_t* src_index, const int32_t* action,
                         void* hidden_out, const int32_t* dst_index, float* reward, float* value, float* pi_probs,
                         cudaStream_t st) = 0;

@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .network import MuZeroNet
+from .network import MuZeroNet, StackedFrames
 
 
 def pb_c_table(num_simulations: int, pb_c_base: float, pb_c_init: float) -> np.ndarray:
@@ -278,10 +278,22 @@ class SearchPlan:
                 t = torch.full(shape, fill, dtype=dt, device=dev)
             setattr(self, name, t)
         self.root_slots = (torch.arange(B, dtype=torch.int32, device=dev) * (self.S + 1)).contiguous()
+        # compact Atari observations (StackedFrames): uint8 frames + plane values, allocated on first use
+        self.frames = None if buffers is None else buffers.get('frames')
+        self.planes = None if buffers is None else buffers.get('planes')
+        self.obs_mode = 'f32'                    # which observation buffers the next run() reads
         self._graphs = {}
         self._eng = None
         self.launches_per_search = 0
         self.use_graph = True
+
+    def use_frames(self) -> None:
+        """Switch this plan to compact observations (network.StackedFrames): allocates the static frame buffers."""
+        if self.frames is None:
+            c, h, w = self.network.input_shape
+            self.frames = torch.zeros((self.B, c // 2, h, w), dtype=torch.uint8, device=self.dev)
+            self.planes = torch.zeros((self.B, c - c // 2), dtype=torch.float32, device=self.dev)
+        self.obs_mode = 'u8'
 
     def _enqueue(self, noise_mode: str, has_mask: bool, deterministic: bool) -> None:
         """Enqueue one whole search on the current stream (pure C-ABI calls, static pointers)."""
@@ -291,8 +303,13 @@ class SearchPlan:
         stream = _lib.current_stream()
         hidden = pool.hidden.data_ptr() if pool.hidden_bytes else None
         mask_p = self.mask.data_ptr() if has_mask else None
-        _lib.check(lib.mz_net_initial(eng['handle'], self.B, self.obs.data_ptr(), hidden, self.root_slots.data_ptr(),
-                                      self.pi0.data_ptr(), self.v0.data_ptr(), stream))
+        if self.obs_mode == 'u8':
+            _lib.check(lib.mz_net_initial_frames(eng['handle'], self.B, self.frames.data_ptr(), self.planes.data_ptr(),
+                                                 hidden, self.root_slots.data_ptr(), self.pi0.data_ptr(),
+                                                 self.v0.data_ptr(), stream))
+        else:
+            _lib.check(lib.mz_net_initial(eng['handle'], self.B, self.obs.data_ptr(), hidden,
+                                          self.root_slots.data_ptr(), self.pi0.data_ptr(), self.v0.data_ptr(), stream))
         noise_p, eps = None, 0.0
         if noise_mode != 'none':
             eps = cfg.root_exploration_eps
@@ -326,7 +343,7 @@ class SearchPlan:
             if not self.use_graph:
                 self._enqueue(noise_mode, has_mask, deterministic)
                 return
-            key = (noise_mode, has_mask, deterministic)
+            key = (noise_mode, has_mask, deterministic, self.obs_mode)
             g = self._graphs.get(key)
             if g is None:
                 lib = _lib.lib()
@@ -438,6 +455,8 @@ class PipelinedSearchPlan:
         for part in self.parts:
             part.cta_limit = self.cta_limit
         self.pool = _PoolGroup([p.pool for p in self.parts])
+        self.frames = self.planes = None
+        self.obs_mode = 'f32'
         self._streams = [torch.cuda.Stream(device=dev) for _ in range(parts - 1)]
         self._graphs = {}
         self._engs = None
@@ -446,6 +465,18 @@ class PipelinedSearchPlan:
     @property
     def launches_per_search(self) -> int:
         return sum(p.launches_per_search for p in self.parts)
+
+    def use_frames(self) -> None:
+        if self.frames is None:
+            c, h, w = self.network.input_shape
+            self.frames = torch.zeros((self.B, c // 2, h, w), dtype=torch.uint8, device=self.dev)
+            self.planes = torch.zeros((self.B, c - c // 2), dtype=torch.float32, device=self.dev)
+            per = self.B // len(self.parts)
+            for i, part in enumerate(self.parts):
+                part.frames, part.planes = self.frames[i * per:(i + 1) * per], self.planes[i * per:(i + 1) * per]
+        self.obs_mode = 'u8'
+        for part in self.parts:
+            part.obs_mode = 'u8'
 
     def _enqueue_all(self, noise_mode, has_mask, deterministic) -> None:
         """Fork one stream per extra part off the current stream, enqueue every part, join."""
@@ -468,7 +499,7 @@ class PipelinedSearchPlan:
             if not self.use_graph:
                 self._enqueue_all(noise_mode, has_mask, deterministic)
                 return
-            key = (noise_mode, has_mask, deterministic)
+            key = (noise_mode, has_mask, deterministic, self.obs_mode)
             g = self._graphs.get(key)
             if g is None:
                 lib = _lib.lib()
@@ -533,7 +564,8 @@ def uct_search_batch(states, network: MuZeroNet, config, temperature, actions_ma
                      deterministic: bool = False, rng=None, noise=None, plan: Optional[SearchPlan] = None):
     """``uct_search`` for B independent trees at once, everything on the GPU.
 
-    states          [B, *obs] array/tensor (host or device)
+    states          [B, *obs] array/tensor (host or device), or network.StackedFrames (uint8 frames + action-plane
+                    values: the compact form of a MuZeroAtariNet observation, a quarter of the upload)
     temperature     float or float64[B]
     actions_mask    bool[B, A] or None
     current_player / opponent_player   int or int[B]
@@ -549,8 +581,10 @@ def uct_search_batch(states, network: MuZeroNet, config, temperature, actions_ma
 
     Returns (actions int32[B], pi float64[B, A], root_values float64[B]) as CUDA tensors.
     """
-    states = torch.as_tensor(states) if not torch.is_tensor(states) else states
-    B = states.shape[0]
+    compact = isinstance(states, StackedFrames)
+    if not compact:
+        states = torch.as_tensor(states) if not torch.is_tensor(states) else states
+    B = (states.frames if compact else states).shape[0]
     if config.is_board_game:
         assert config.discount == 1.0                                     # mcts.py:349-350
     if np.isscalar(temperature):
@@ -565,7 +599,16 @@ def uct_search_batch(states, network: MuZeroNet, config, temperature, actions_ma
         plan = _plan_for(network, config, B)
     A, dev, pool = plan.A, plan.dev, plan.pool
 
-    plan.obs.copy_(states.reshape(B, -1), non_blocking=True)
+    if compact:
+        plan.use_frames()
+        plan.frames.copy_(torch.as_tensor(states.frames), non_blocking=True)
+        plan.planes.copy_(torch.as_tensor(states.planes), non_blocking=True)
+    else:
+        if plan.obs_mode != 'f32':
+            plan.obs_mode = 'f32'
+            for part in getattr(plan, 'parts', []):
+                part.obs_mode = 'f32'
+        plan.obs.copy_(states.reshape(B, -1), non_blocking=True)
     has_mask = actions_mask is not None
     if has_mask:
         m = actions_mask if torch.is_tensor(actions_mask) else torch.from_numpy(np.asarray(actions_mask, dtype=np.bool_))

@@ -39,6 +39,20 @@ class NetworkOutputs(NamedTuple):
     value: float
 
 
+class StackedFrames(NamedTuple):
+    """An Atari observation batch in the form it is born in (gym_env.py:306-313, StackFrameAndAction.observation):
+    k uint8 frames and the values of the k constant action planes, instead of their float32 expansion [B, 2k, H, W]
+    (which is what the reference uploads: 4x the bytes).  Accepted wherever a MuZeroAtariNet takes observations."""
+    frames: 'torch.Tensor'          # uint8   [B, k, H, W]
+    planes: 'torch.Tensor'          # float32 [B, k]   value of each broadcast action plane, (action + 1) / num_actions
+
+    def expand(self) -> 'torch.Tensor':
+        """The float32 observation [B, 2k, H, W] the reference would build."""
+        f = torch.as_tensor(self.frames)
+        p = torch.as_tensor(self.planes).to(torch.float32)
+        return torch.cat([f.to(torch.float32), p[:, :, None, None].expand(-1, -1, f.shape[2], f.shape[3])], dim=1)
+
+
 # ---------------------------------------------------------------------------
 # parameter containers (attribute names == reference state_dict keys)
 # ---------------------------------------------------------------------------
@@ -212,18 +226,26 @@ class MuZeroNet(nn.Module):
         """``initial_inference`` for a batch, all outputs stay on the device.
 
         Returns (hidden slots [u8, engine layout], pi_probs f32[B,A], value f32[B])."""
-        b = obs.shape[0]
+        frames = isinstance(obs, StackedFrames)
+        b = (obs.frames if frames else obs).shape[0]
         e = self.engine(b)
         dev = e['device']
-        obs = obs.to(device=dev, dtype=torch.float32).reshape(b, -1).contiguous()
         if hidden_out is None:
             hidden_out = self.new_hidden(b)
         pi = torch.empty((b, self.num_actions), dtype=torch.float32, device=dev)
         value = torch.empty((b,), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib().mz_net_initial(e['handle'], b, _lib.ptr(obs), _lib.ptr(hidden_out),
-                                                 _lib.ptr(dst_index), _lib.ptr(pi), _lib.ptr(value),
-                                                 _lib.current_stream()))
+            if frames:
+                f = torch.as_tensor(obs.frames).to(device=dev, dtype=torch.uint8).contiguous()
+                pl = torch.as_tensor(obs.planes).to(device=dev, dtype=torch.float32).contiguous()
+                _lib.check(_lib.lib().mz_net_initial_frames(e['handle'], b, _lib.ptr(f), _lib.ptr(pl),
+                                                            _lib.ptr(hidden_out), _lib.ptr(dst_index), _lib.ptr(pi),
+                                                            _lib.ptr(value), _lib.current_stream()))
+            else:
+                obs = obs.to(device=dev, dtype=torch.float32).reshape(b, -1).contiguous()
+                _lib.check(_lib.lib().mz_net_initial(e['handle'], b, _lib.ptr(obs), _lib.ptr(hidden_out),
+                                                     _lib.ptr(dst_index), _lib.ptr(pi), _lib.ptr(value),
+                                                     _lib.current_stream()))
         return hidden_out, pi, value
 
     @torch.no_grad()
