@@ -68,7 +68,8 @@ struct LayerDesc {
   act_t* out_norm;        // contiguous planes, min-max normalised, or nullptr
   act_t* out_slots;       // indexed slots, normalised, or nullptr
   const int32_t* out_index;
-  int dep;                        // input is produced by the previous layer of this launch
+  int dep0, dep1;                 // layers of THIS launch that produce the input (-1: none / an earlier launch).  Two when
+                                  // the producing conv ran as two 128-column passes (num_planes = 256)
   int fwd;                        // resident launches: 1 = the next layer reads this layer's `out`, 2 = its `out_norm`
   int res_layer;                  // layer of THIS launch that writes the residual buffer (-1: an earlier launch did)
   int in_slots;                   // input is an array of hidden-state slots, not a contiguous buffer
@@ -85,7 +86,11 @@ struct ConvParams {
   int sub;                        // stride-2 layer: only rows with even (y, x) are stored, on the half-size grid
   int out_plane_rows, out_PB, out_Wp;   // geometry of the output buffer when sub is set
   int cg;                         // input channel groups of 8 (Cin_pad / 8), even
-  int N;                          // output channels (multiple of 32, <= 128)
+  int N;                          // output channels of one layer of this launch (multiple of 32, <= 128); wider convs
+                                  // run as several 128-column passes, each its own LayerDesc
+  int n_real;                     // channels < n_real are the network's; the rest pad num_planes up to 32 (zero weights)
+                                  // and are left out of the min-max normalisation
+  int tab_groups;                 // channel groups of a whole action-table entry / hidden-state slot (all passes)
   int relu;
   int num_tiles;
   int TP;                         // tile rows incl. halo, odd
@@ -399,11 +404,12 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
       const bool handed_over = p.resident && l > 0;     // the epilogue of layer l - 1 writes this tile into shared memory
       // dataflow dependency: the three tiles of the previous layer whose rows this tile reads
       long long tw = dbg ? clock64() : 0;
-      if (L.dep && !p.resident) {
-        if (lane < 3) {
-          const int tt = tile - 1 + lane;
-          if (tt >= 0 && tt < p.num_tiles) {
-            const unsigned* f = p.flags + (size_t)(l - 1) * p.num_tiles + tt;
+      if (L.dep0 >= 0 && !p.resident) {
+        if (lane < 6) {
+          const int tt = tile - 1 + lane % 3;
+          const int dl = lane < 3 ? L.dep0 : L.dep1;
+          if (dl >= 0 && tt >= 0 && tt < p.num_tiles) {
+            const unsigned* f = p.flags + (size_t)dl * p.num_tiles + tt;
             unsigned spins = 0;
             while (ld_acquire(f) == 0u) {
               ++spins;
@@ -621,7 +627,7 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
           if (inrange) split_pos(P, p, b, pos, hl);
           const bool valid = !hl;
           const float top = valid ? 65504.0f : 0.0f;
-          const float* tab = (L.tab && valid) ? L.tab + ((size_t)L.action[b] * (kN / 8) * p.PB + pos) * 8 : nullptr;
+          const float* tab = (L.tab && valid) ? L.tab + ((size_t)L.action[b] * p.tab_groups * p.PB + pos) * 8 : nullptr;
           const int4* resp = (L.residual && valid) ? reinterpret_cast<const int4*>(L.residual) + P : nullptr;
           // conv + bias (+ table) (+ residual) + ReLU of one 32-column chunk of this row (one chunk live at a
           // time keeps the register count of the whole kernel low; the normalising layers read TMEM twice)
@@ -661,7 +667,8 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
               float v[32];
               chunk(c, v);
 #pragma unroll
-              for (int e = 0; e < 32; ++e) { mn = fminf(mn, v[e]); mx = fmaxf(mx, v[e]); }
+              for (int e = 0; e < 32; ++e)
+                if (c * 32 + e < p.n_real) { mn = fminf(mn, v[e]); mx = fmaxf(mx, v[e]); }
               if (L.out && inrange) {
                 int4* o = reinterpret_cast<int4*>(L.out) + P;
 #pragma unroll
@@ -687,7 +694,7 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
               int4* os = nullptr;
               if (L.out_slots && inrange) {
                 const size_t slot = L.out_index ? (size_t)L.out_index[b] : (size_t)b;
-                os = reinterpret_cast<int4*>(L.out_slots) + slot * (kN / 8) * p.PB + pos;
+                os = reinterpret_cast<int4*>(L.out_slots) + slot * p.tab_groups * p.PB + pos;
               }
 #pragma unroll 1
               for (int cc = 0; cc < NCW; ++cc) {
@@ -695,7 +702,7 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
                 float v[32];
                 chunk(c, v);
 #pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] = (v[e] - mn) * inv;
+                for (int e = 0; e < 32; ++e) v[e] = (c * 32 + e < p.n_real) ? (v[e] - mn) * inv : 0.0f;
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                   const int4 o4 = pack8(v + 8 * u);
@@ -912,8 +919,9 @@ __global__ void bn_fold_kernel(const float* g, const float* beta, const float* m
 
 // conv weight [N][cin_total][3][3] (first `cin` input channels) * scale[n] -> packed fp16
 // [9 taps][chunks][chunk_g][N][8]
+// (N rows packed; rows >= n_real are zero: the padding of num_planes up to 32, or past the end of a column pass)
 __global__ void pack_conv_kernel(const float* __restrict__ w, const float* __restrict__ scale,
-                                 act_t* __restrict__ out, int N, int cin, int cin_total, int cg) {
+                                 act_t* __restrict__ out, int N, int n_real, int cin, int cin_total, int cg) {
   const int chunk_g = cg < 8 ? cg : 8;
   const size_t total = (size_t)9 * cg * N * 8;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -925,7 +933,7 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, const float* __res
     const int tap = (int)(r / (cg / chunk_g));
     const int c = (ch * chunk_g + gl) * 8 + e;
     float v = 0.0f;
-    if (c < cin) v = w[(((size_t)n * cin_total + c) * 3 + tap / 3) * 3 + tap % 3] * scale[n];
+    if (c < cin && n < n_real) v = w[(((size_t)n * cin_total + c) * 3 + tap / 3) * 3 + tap % 3] * scale[n];
     out[i] = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
   }
 }
@@ -941,7 +949,7 @@ __global__ void scale_rows_kernel(const float* w, const float* scale, float* out
 // 1 iff f % A == action), so their contribution is tab[a][pos][n] = scale[n] * sum over
 // (plane c, tap) of w[n][C + c][tap] * E_a[c][y+ky-1][x+kx-1].
 __global__ void action_table_kernel(const float* __restrict__ w, const float* __restrict__ scale,
-                                    float* __restrict__ tab, int A, int C, int N, int H, int W, int pad) {
+                                    float* __restrict__ tab, int A, int C, int N, int n_real, int H, int W, int pad) {
   const int Wp = W + pad, PB = (H + pad) * Wp, hw = H * W;
   const size_t total = (size_t)A * PB * N;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -953,7 +961,7 @@ __global__ void action_table_kernel(const float* __restrict__ w, const float* __
     const int n = g * 8 + e;
     const int y = pos / Wp, x = pos % Wp;
     float acc = 0.0f;
-    if (y < H && x < W) {
+    if (y < H && x < W && n < n_real) {
       for (int c = 0; c < A; ++c)
         for (int ky = 0; ky < 3; ++ky)
           for (int kx = 0; kx < 3; ++kx) {
@@ -975,35 +983,47 @@ __global__ void action_table_kernel(const float* __restrict__ w, const float* __
 // flops, still 3-4x faster than a SIMT kernel); the pools are plain SIMT kernels; the residual
 // blocks between them go through the tcgen05 kernel at 48x48 / 24x24 / 12x12.
 // ---------------------------------------------------------------------------
-// AvgPool2d(3, stride 2, padding 1), count_include_pad (divide by 9), C = 128: one warp per output
-// position, 4 channels per lane.  Optionally min-max normalises over the channels (util.py:31-36) and
-// also writes the result to indexed hidden-state slots.
+// AvgPool2d(3, stride 2, padding 1), count_include_pad (divide by 9), C = 128 or 256: one warp per output
+// position, 4 channels per lane and 128-channel block.  Optionally min-max normalises over ALL channels
+// (util.py:31-36) and also writes the result to indexed hidden-state slots.
 __global__ void __launch_bounds__(256) avgpool_kernel(const act_t* __restrict__ in, act_t* __restrict__ out,
                                                       act_t* __restrict__ slots, const int32_t* __restrict__ out_index,
                                                       int B, int Hi, int Wi, int normalise, int rows_in, int rows_out,
-                                                      int pad) {
-  constexpr int C = 128;
+                                                      int pad, int C) {
   const int Ho = Hi / 2, Wo = Wi / 2, Wpi = Wi + pad, PBi = (Hi + pad) * Wpi, Wpo = Wo + pad, PBo = (Ho + pad) * Wpo;
   const int lane = threadIdx.x & 31;
-  const int g = lane >> 1, off = (lane & 1) * 4;      // channel-group plane and offset of this lane's 4 channels
+  const int g0 = lane >> 1, off = (lane & 1) * 4;     // channel-group plane and offset of this lane's 4 channels
+  const int nblk = C / 128;                           // 128-channel blocks (<= 2)
   const long long total = (long long)B * PBo;         // halo positions included: they are written as zeros
   for (long long i = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); i < total; i += (long long)gridDim.x * 8) {
     const int b = (int)(i / PBo), pos = (int)(i % PBo), oy = pos / Wpo, ox = pos % Wpo;
-    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     if (oy < Ho && ox < Wo) {
       for (int ky = 0; ky < 3; ++ky)
         for (int kx = 0; kx < 3; ++kx) {
           const int iy = 2 * oy + ky - 1, ix = 2 * ox + kx - 1;
           if (iy < 0 || iy >= Hi || ix < 0 || ix >= Wi) continue;
-          const uint2 v = *reinterpret_cast<const uint2*>(in + ((size_t)g * rows_in + (size_t)b * PBi + (size_t)iy * Wpi + ix) * 8 + off);
-          const float2 f0 = __half22float2(*reinterpret_cast<const act2_t*>(&v.x));
-          const float2 f1 = __half22float2(*reinterpret_cast<const act2_t*>(&v.y));
-          s[0] += f0.x; s[1] += f0.y; s[2] += f1.x; s[3] += f1.y;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            if (k >= nblk) break;
+            const int g = g0 + 16 * k;
+            const uint2 v = *reinterpret_cast<const uint2*>(in + ((size_t)g * rows_in + (size_t)b * PBi + (size_t)iy * Wpi + ix) * 8 + off);
+            const float2 f0 = __half22float2(*reinterpret_cast<const act2_t*>(&v.x));
+            const float2 f1 = __half22float2(*reinterpret_cast<const act2_t*>(&v.y));
+            s[k][0] += f0.x; s[k][1] += f0.y; s[k][2] += f1.x; s[k][3] += f1.y;
+          }
         }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) s[j] *= (1.0f / 9.0f);
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[k][j] *= (1.0f / 9.0f);
       if (normalise) {
-        float mn = fminf(fminf(s[0], s[1]), fminf(s[2], s[3])), mx = fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3]));
+        float mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          if (k < nblk)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { mn = fminf(mn, s[k][j]); mx = fmaxf(mx, s[k][j]); }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
@@ -1011,17 +1031,66 @@ __global__ void __launch_bounds__(256) avgpool_kernel(const act_t* __restrict__ 
         }
         const float inv = 1.0f / ((mx - mn) + 1e-8f);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) s[j] = (s[j] - mn) * inv;
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) s[k][j] = (s[k][j] - mn) * inv;
       }
     }
-    uint2 pk;
-    pk.x = pack2(s[0], s[1]);
-    pk.y = pack2(s[2], s[3]);
-    if (out) *reinterpret_cast<uint2*>(out + ((size_t)g * rows_out + (size_t)b * PBo + pos) * 8 + off) = pk;
-    if (slots) {
-      const size_t board = out_index ? (size_t)out_index[b] : (size_t)b;
-      *reinterpret_cast<uint2*>(slots + ((board * (C / 8) + g) * PBo + pos) * 8 + off) = pk;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (k >= nblk) break;
+      const int g = g0 + 16 * k;
+      uint2 pk;
+      pk.x = pack2(s[k][0], s[k][1]);
+      pk.y = pack2(s[k][2], s[k][3]);
+      if (out) *reinterpret_cast<uint2*>(out + ((size_t)g * rows_out + (size_t)b * PBo + pos) * 8 + off) = pk;
+      if (slots) {
+        const size_t board = out_index ? (size_t)out_index[b] : (size_t)b;
+        *reinterpret_cast<uint2*>(slots + ((board * (C / 8) + g) * PBo + pos) * 8 + off) = pk;
+      }
     }
+  }
+}
+
+// Per-position min-max normalisation over ALL channels (util.py:31-36) of a contiguous planar buffer, for convs wider
+// than one 128-column pass (their halves are written by different layers of a launch, so the normalising epilogue of
+// conv3x3_kernel cannot see the whole row): raw planes -> normalised planes and / or indexed hidden-state slots.
+// One thread per row; the row's 16-byte plane entries are re-read from L1/L2 in the second pass.
+__global__ void normalise_rows_kernel(const act_t* __restrict__ raw, act_t* __restrict__ out, act_t* __restrict__ slots,
+                                      const int32_t* __restrict__ out_index, int Ptot, int PB, int groups, int plane_rows) {
+  const int P = blockIdx.x * blockDim.x + threadIdx.x;
+  if (P >= Ptot) return;
+  const int4* src = reinterpret_cast<const int4*>(raw) + P;
+  float mn = INFINITY, mx = -INFINITY;
+  for (int g = 0; g < groups; ++g) {
+    const int4 r4 = src[(size_t)g * plane_rows];
+    const act2_t* h = reinterpret_cast<const act2_t*>(&r4);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float2 v = __half22float2(h[u]);
+      mn = fminf(mn, fminf(v.x, v.y)); mx = fmaxf(mx, fmaxf(v.x, v.y));
+    }
+  }
+  const float inv = 1.0f / ((mx - mn) + 1e-8f);
+  const int b = P / PB, pos = P - b * PB;
+  int4* on = out ? reinterpret_cast<int4*>(out) + P : nullptr;
+  int4* os = nullptr;
+  if (slots) {
+    const size_t slot = out_index ? (size_t)out_index[b] : (size_t)b;
+    os = reinterpret_cast<int4*>(slots) + slot * groups * PB + pos;
+  }
+  for (int g = 0; g < groups; ++g) {
+    const int4 r4 = src[(size_t)g * plane_rows];
+    const act2_t* h = reinterpret_cast<const act2_t*>(&r4);
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float2 f = __half22float2(h[u]);
+      v[2 * u] = (f.x - mn) * inv; v[2 * u + 1] = (f.y - mn) * inv;
+    }
+    const int4 o4 = pack8(v);
+    if (on) on[(size_t)g * plane_rows] = o4;
+    if (os) os[(size_t)g * PB] = o4;
   }
 }
 
@@ -1029,9 +1098,13 @@ __global__ void __launch_bounds__(256) avgpool_kernel(const act_t* __restrict__ 
 // host side
 // ---------------------------------------------------------------------------
 struct ConvLayer {
-  const act_t* w;
-  const float* bias;
-  int cg;
+  const act_t* w[2];      // packed weights per 128-column pass
+  const float* bias[2];
+  int cg;                 // input channel groups of 8 (padded)
+  int n_out;              // output channels incl. padding: 32, 64, 128 or 256
+  int n_real;             // the network's output channels (< n_out only for num_planes = 16)
+  int passes() const { return n_out > 128 ? 2 : 1; }
+  int n_pass() const { return n_out > 128 ? 128 : n_out; }
 };
 struct Head {
   const float *w1, *b1, *w2, *b2;
@@ -1050,11 +1123,16 @@ struct Geo {
   int Wp() const { return W + grid_pad(); }
   int PB() const { return (H + grid_pad()) * (W + grid_pad()); }
 };
+// channels as the kernels see them: num_planes rounded up to a multiple of 32 (the reference's ResNet Tic-Tac-Toe
+// variant has 16, config.py:126-127); the extra channels have zero weights and zero bias everywhere
+static int padded_planes(int n) { return n < 32 ? 32 : (n + 31) / 32 * 32; }
 
 struct ConvNet : NetImpl {
   mz_net_config cfg;
   Geo lat;                          // latent grid: the board (board games) or 6x6 (Atari)
-  int C, A, blocks, max_batch, num_sms;
+  int C;                            // tower channels incl. padding (hidden-state slots hold C channels)
+  int Creal;                        // the network's num_planes
+  int A, blocks, max_batch, num_sms;
   bool atari;
   int in_cg;                        // channel groups of the packed observation
   ConvLayer rep0, dyn0;
@@ -1074,57 +1152,95 @@ struct ConvNet : NetImpl {
   static int plane_rows_of(const Geo& g, int batch) {
     return (batch * g.PB() + kTileM - 1) / kTileM * kTileM + kPlaneSlack;
   }
-  size_t conv_fixed_smem(const Geo& g, int cg, int rows = kTileM) const {
+  // n = output channels of one pass (the width of a weight stage and of the bias slots)
+  static size_t conv_fixed_smem(const Geo& g, int cg, int n, int rows) {
     const int TP = tp_of(g, rows);
     size_t a = (((size_t)2 * cg * TP * 16) + 127) & ~(size_t)127;
-    return a + (2 * kMaxStages + 10) * 8 + 16 + (size_t)4 * C * 4 + 2048 + 256 + 64;
+    return a + (2 * kMaxStages + 10) * 8 + 16 + (size_t)4 * n * 4 + 2048 + 256 + 64;
   }
-  int conv_stages(const Geo& g, int cg, int rows = kTileM) const {
+  static int conv_stages(const Geo& g, int cg, int n, int rows) {
     const int chunk_g = cg < 8 ? cg : 8;
-    const size_t stage = (size_t)chunk_g * C * 16;
-    const size_t fixed = conv_fixed_smem(g, cg, rows);
+    const size_t stage = (size_t)chunk_g * n * 16;
+    const size_t fixed = conv_fixed_smem(g, cg, n, rows);
     if (fixed + 2 * stage > 227 * 1024) return 0;
     int s = (int)((227 * 1024 - fixed) / stage);
     static const int cap = getenv("MZ_CONV_MAX_STAGES") ? atoi(getenv("MZ_CONV_MAX_STAGES")) : kMaxStages;
     if (s > cap && cap >= 2) s = cap;
     return s > kMaxStages ? kMaxStages : s;
   }
-  size_t conv_smem(const Geo& g, int cg, int rows = kTileM) const {
+  static size_t conv_smem(const Geo& g, int cg, int n, int rows) {
     const int chunk_g = cg < 8 ? cg : 8;
-    return conv_fixed_smem(g, cg, rows) + (size_t)conv_stages(g, cg, rows) * chunk_g * C * 16;
+    return conv_fixed_smem(g, cg, n, rows) + (size_t)conv_stages(g, cg, n, rows) * chunk_g * n * 16;
   }
+  // tile rows a conv with `cg` input groups can use at all: 256-row tiles need 2 x cg x TP x 16 bytes of activations
+  static bool fits(const Geo& g, int cg, int n, int rows) { return conv_stages(g, cg, n, rows) >= 2; }
 
   // ---- layer batching: consecutive convs on the same grid become ONE dataflow launch ----
   ConvParams pend;                 // layers collected so far
   Geo pend_geo{0, 0};
   int pend_cg = 0, pend_batch = 0;
-  bool pend_sub = false;           // the (single) pending layer is a stride-2 conv writing the half-size grid
+  bool pend_sub = false;           // the (single) pending conv is a stride-2 conv writing the half-size grid
+  int pend_prev_first = -1, pend_prev_count = 0;     // LayerDescs of the previous conv of the pending launch
+  const act_t* pend_out_base[kMaxLayers];            // un-offset `out` / `out_norm` of each pending layer + its pass
+  const act_t* pend_norm_base[kMaxLayers];
+  int pend_pass[kMaxLayers];
 
-  int add_layer(const ConvLayer& L, const Geo& g, const act_t* in, const int32_t* in_index, bool in_slots, int batch,
-                const float* tab_, const int32_t* action, const act_t* residual, act_t* out, act_t* out_norm,
-                act_t* out_slots, const int32_t* out_index, cudaStream_t st) {
+  // One convolution = L.passes() LayerDescs (128 output columns each).  `sub`: stride-2 conv, the epilogue keeps the
+  // even positions on the half-size grid (the caller flushes right after it).
+  int add_conv(const ConvLayer& L, const Geo& g, const act_t* in, const int32_t* in_index, bool in_slots, int batch,
+               const float* tab_, const int32_t* action, const act_t* residual, act_t* out, act_t* out_norm,
+               act_t* out_slots, const int32_t* out_index, cudaStream_t st, bool sub = false) {
+    const int np = L.passes();
+    // channels of a pass that take part in the min-max normalisation (all of them unless num_planes was padded)
+    const int eff_real = L.n_real < L.n_out ? L.n_real : L.n_pass();
     if (pend.num_layers > 0 && (pend_cg != L.cg || pend_geo.H != g.H || pend_geo.W != g.W || pend_batch != batch ||
-                                pend.num_layers == kMaxLayers)) {
+                                pend.N != L.n_pass() || pend.n_real != eff_real || pend.tab_groups != L.n_out / 8 ||
+                                pend.num_layers + np > kMaxLayers || sub || pend_sub)) {
       int rc = flush(st);
       if (rc) return rc;
     }
-    LayerDesc& d = pend.L[pend.num_layers];
-    d.in = in; d.in_index = in_index; d.w = L.w; d.bias = L.bias; d.tab = tab_; d.action = action;
-    d.residual = residual; d.out = out; d.out_norm = out_norm; d.out_slots = out_slots; d.out_index = out_index;
-    d.dep = pend.num_layers > 0 ? 1 : 0;
-    d.fwd = 0;
-    d.res_layer = -1;
-    d.in_slots = in_slots ? 1 : 0;
-    pend_geo = g; pend_cg = L.cg; pend_batch = batch;
-    ++pend.num_layers;
+    if (np > 1 && (out_norm || out_slots)) {
+      set_error("internal: a conv wider than one column pass cannot normalise in its epilogue");
+      return MZ_EINVAL;
+    }
+    const size_t PR = (size_t)plane_rows_of(g, batch);
+    const Geo go{g.H / 2, g.W / 2};
+    const size_t PRo = sub ? (size_t)plane_rows_of(go, batch) : PR;
+    const int first = pend.num_layers;
+    for (int h = 0; h < np; ++h) {
+      LayerDesc& d = pend.L[pend.num_layers];
+      const size_t goff = (size_t)h * 16;                    // channel groups before this pass
+      d.in = in; d.in_index = in_index; d.w = L.w[h]; d.bias = L.bias[h];
+      d.tab = tab_ ? tab_ + goff * g.PB() * 8 : nullptr;
+      d.action = action;
+      d.residual = residual ? residual + goff * PR * 8 : nullptr;
+      d.out = out ? out + goff * PRo * 8 : nullptr;
+      d.out_norm = out_norm; d.out_slots = out_slots; d.out_index = out_index;
+      d.dep0 = pend_prev_count > 0 ? pend_prev_first : -1;
+      d.dep1 = pend_prev_count > 1 ? pend_prev_first + 1 : -1;
+      d.fwd = 0;
+      d.res_layer = -1;
+      d.in_slots = in_slots ? 1 : 0;
+      pend_out_base[pend.num_layers] = out; pend_norm_base[pend.num_layers] = out_norm; pend_pass[pend.num_layers] = h;
+      if (residual)                                          // which pending layer wrote this column half of the residual
+        for (int j = pend.num_layers - 1; j >= 0; --j)
+          if (pend_pass[j] == h && (pend_out_base[j] == residual || pend_norm_base[j] == residual)) { d.res_layer = j; break; }
+      ++pend.num_layers;
+    }
+    pend_prev_first = first; pend_prev_count = np;
+    pend_geo = g; pend_cg = L.cg; pend_batch = batch; pend_sub = sub;
+    pend.N = L.n_pass(); pend.n_real = eff_real; pend.tab_groups = L.n_out / 8;
     return MZ_OK;
   }
+
+  void reset_pending() { pend.num_layers = 0; pend_prev_first = -1; pend_prev_count = 0; pend_sub = false; }
 
   int flush(cudaStream_t st) {
     if (pend.num_layers == 0) return MZ_OK;
     ConvParams& p = pend;
     const Geo g = pend_geo;
-    const int batch = pend_batch, cg = pend_cg, nl = p.num_layers;
+    const int batch = pend_batch, cg = pend_cg, nl = p.num_layers, N = p.N;
+    const bool multi_pass = p.tab_groups * 8 > 128;
     p.PB = g.PB(); p.Wp = g.Wp(); p.W = g.W; p.H = g.H; p.B = batch;
     p.Ptot = batch * p.PB;
     p.plane_rows = plane_rows_of(g, batch);
@@ -1133,8 +1249,7 @@ struct ConvNet : NetImpl {
       const Geo go{g.H / 2, g.W / 2};
       p.out_plane_rows = plane_rows_of(go, batch); p.out_PB = go.PB(); p.out_Wp = go.Wp();
     }
-    pend_sub = false;
-    p.cg = cg; p.N = C; p.relu = 1;
+    p.cg = cg; p.relu = 1;
     // Few tiles per SM (small batches / small grids): a multi-layer launch is bound by the dependency chain between
     // layers, so use 128-row tiles whose K range is split over the two MMA warps (half the MMA time per tile).
     // Otherwise 256-row tiles (half the weight traffic per row).
@@ -1142,16 +1257,12 @@ struct ConvNet : NetImpl {
     const int force_rows = force_env ? atoi(force_env) : 0;
     int rows = (nl > 1 && (p.Ptot + kTileM - 1) / kTileM < 2 * num_sms) ? 128 : kTileM;
     if (force_rows == 128 || force_rows == 256) rows = force_rows;
-    for (int i = 0; i < nl; ++i) {          // which layer of this launch produces layer i's residual buffer
-      pend.L[i].res_layer = -1;
-      if (pend.L[i].residual)
-        for (int j = i - 1; j >= 0; --j)
-          if (pend.L[j].out == pend.L[i].residual || pend.L[j].out_norm == pend.L[i].residual) { pend.L[i].res_layer = j; break; }
-    }
     p.masked = grid_pad() == 0;
     // split-K tiles give the second MMA warp the odd weight stages; with one stage per tap its first MMA would be a
     // masked (non-centre) tap and could not initialise its accumulator
     if (p.masked && cg <= 8) rows = kTileM;
+    // 256 input channels: two 256-row activation buffers do not fit shared memory
+    if (!fits(g, cg, N, rows)) rows = rows == kTileM ? 128 : kTileM;
     // RESIDENT launch: when every CTA can own one tile of whole boards for all layers, nothing a tile needs comes from
     // another tile (the halo-free layout masks every tap that leaves a board), so the layers of a tower hand their
     // activations over in shared memory -- no tile flags, no tile loads, no waiting for neighbours after layer 0.
@@ -1162,7 +1273,7 @@ struct ConvNet : NetImpl {
     p.khalf = 0;
     p.tile_stride = rows;
     static const bool no_resident = getenv("MZ_CONV_NO_RESIDENT") != nullptr;
-    if (p.masked && nl > 1 && !p.sub && !no_resident) {
+    if (p.masked && nl > 1 && !p.sub && !no_resident && !multi_pass) {
       bool chain = true;
       for (int i = 0; i + 1 < nl && chain; ++i) {
         LayerDesc& a = pend.L[i];
@@ -1176,6 +1287,7 @@ struct ConvNet : NetImpl {
           const int rr = cand[ci];
           if (force_rows && force_rows != rr) continue;
           if (rr == 128 && cg <= 8) continue;
+          if (!fits(g, cg, N, rr)) continue;
           const int bpt = rr / p.PB;                               // whole boards per tile
           if (bpt < 1) continue;
           if ((batch + bpt - 1) / bpt > sm_cap0) continue;
@@ -1187,26 +1299,26 @@ struct ConvNet : NetImpl {
     }
     p.num_tiles = p.resident ? (p.Ptot + p.tile_stride - 1) / p.tile_stride : (p.Ptot + rows - 1) / rows;
     p.TP = tp_of(g, rows);
-    p.stages = conv_stages(g, cg, rows);
+    p.stages = conv_stages(g, cg, N, rows);
     p.err = err_flag;
-    if (p.stages < 2) { pend.num_layers = 0; set_error("conv tile does not fit shared memory for a %dx%d grid", g.H, g.W); return MZ_EINVAL; }
-    const size_t smem = conv_smem(g, cg, rows);
+    if (p.stages < 2) { reset_pending(); set_error("conv tile does not fit shared memory for a %dx%d grid", g.H, g.W); return MZ_EINVAL; }
+    const size_t smem = conv_smem(g, cg, N, rows);
     const int sm_cap = (cta_limit > 0 && cta_limit < num_sms) ? cta_limit : num_sms;
     const int grid = p.num_tiles < sm_cap ? p.num_tiles : sm_cap;
     p.rot = nl > 1 ? p.num_tiles % grid : 0;
     p.flags = nullptr;
     if (nl > 1 && !p.resident) {
-      if ((size_t)nl * p.num_tiles > flags_cap) { pend.num_layers = 0; set_error("internal: flag buffer too small"); return MZ_EINVAL; }
+      if ((size_t)nl * p.num_tiles > flags_cap) { reset_pending(); set_error("internal: flag buffer too small"); return MZ_EINVAL; }
       p.flags = flags;
       cudaError_t e = cudaMemsetAsync(flags, 0, (size_t)nl * p.num_tiles * sizeof(unsigned), st);
-      if (e != cudaSuccess) { pend.num_layers = 0; set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return MZ_ECUDA; }
+      if (e != cudaSuccess) { reset_pending(); set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return MZ_ECUDA; }
     }
     p.dbg = nullptr;
     static const int ablate = getenv("MZ_CONV_ABLATE") ? atoi(getenv("MZ_CONV_ABLATE")) : 0;
     p.ablate = ablate;
     static const bool debug = getenv("MZ_CONV_DEBUG") != nullptr;
     if (debug) cudaMalloc(&p.dbg, (size_t)grid * 16 * sizeof(long long));
-    prof_mark(kProfConv, st, nl);
+    prof_mark(kProfConv, st, multi_pass ? (nl + 1) / 2 : nl);       // counted in convolutions, not passes
     {
       // Layers of a launch wait on each other's tiles, so every CTA must be resident: a cooperative launch
       // makes the hardware place the grid all at once (two such grids of different streams could otherwise
@@ -1220,18 +1332,18 @@ struct ConvNet : NetImpl {
       lc.attrs = at; lc.numAttrs = 1;
       cudaError_t le;
       if (rows == 256) {
-        if (C == 128) le = cudaLaunchKernelEx(&lc, conv3x3_kernel<128, 256>, p);
-        else if (C == 64) le = cudaLaunchKernelEx(&lc, conv3x3_kernel<64, 256>, p);
+        if (N == 128) le = cudaLaunchKernelEx(&lc, conv3x3_kernel<128, 256>, p);
+        else if (N == 64) le = cudaLaunchKernelEx(&lc, conv3x3_kernel<64, 256>, p);
         else le = cudaLaunchKernelEx(&lc, conv3x3_kernel<32, 256>, p);
       } else {
-        if (C == 128) le = cudaLaunchKernelEx(&lc, conv3x3_kernel<128, 128>, p);
-        else if (C == 64) le = cudaLaunchKernelEx(&lc, conv3x3_kernel<64, 128>, p);
+        if (N == 128) le = cudaLaunchKernelEx(&lc, conv3x3_kernel<128, 128>, p);
+        else if (N == 64) le = cudaLaunchKernelEx(&lc, conv3x3_kernel<64, 128>, p);
         else le = cudaLaunchKernelEx(&lc, conv3x3_kernel<32, 128>, p);
       }
-      if (le != cudaSuccess) { pend.num_layers = 0; set_error("conv3x3_kernel launch: %s", cudaGetErrorString(le)); cudaGetLastError(); return MZ_ECUDA; }
+      if (le != cudaSuccess) { reset_pending(); set_error("conv3x3_kernel launch: %s", cudaGetErrorString(le)); cudaGetLastError(); return MZ_ECUDA; }
     }
     prof_mark(-1, st);
-    pend.num_layers = 0;
+    reset_pending();
     MZ_LAUNCH_CHECK("conv3x3_kernel");
     if (debug) {   // measurement aid: per-role cycle accounting, averaged over CTAs
       cudaDeviceSynchronize();
@@ -1254,7 +1366,7 @@ struct ConvNet : NetImpl {
     HeadParams& p = pend_heads.h[num_pend_heads++];
     p.act = act; p.w1 = h.w1; p.b1 = h.b1; p.w2 = h.w2; p.b2 = h.b2; p.dst = dst;
     p.plane_rows = plane_rows_of(lat, batch);
-    p.C = C; p.H = lat.H; p.W = lat.W; p.pad = grid_pad(); p.mid = h.mid; p.out = h.out; p.kind = h.kind;
+    p.C = Creal; p.H = lat.H; p.W = lat.W; p.pad = grid_pad(); p.mid = h.mid; p.out = h.out; p.kind = h.kind;
     const size_t smem = ((size_t)h.mid * lat.H * lat.W + h.out) * 4;
     if (smem > pend_heads_smem) pend_heads_smem = smem;
   }
@@ -1282,28 +1394,42 @@ struct ConvNet : NetImpl {
     act_t* pp[2] = {b0, b1};
     int which = (in == b0) ? 1 : 0, rc;
     const bool normalise = (norm_out != nullptr) || (slots != nullptr);
+    // convs wider than one column pass cannot normalise in their epilogue: the last layer writes the raw output and
+    // normalise_rows_kernel follows
+    const ConvLayer& last_layer = nblk > 0 ? blk[2 * nblk - 1] : *first;
+    const bool late_norm = normalise && last_layer.passes() > 1;
+    const bool keep_raw = want_raw || late_norm;
     if (first) {
       const bool last = (nblk == 0);
       act_t* dst = (last && raw_dst) ? raw_dst : pp[which];
-      rc = add_layer(*first, g, cur, cur_index, cur_slots, batch, tab_, action, nullptr,
-                       (last && normalise && !want_raw) ? nullptr : dst, last ? norm_out : nullptr,
-                       last ? slots : nullptr, out_index, st);
+      rc = add_conv(*first, g, cur, cur_index, cur_slots, batch, tab_, action, nullptr,
+                    (last && normalise && !keep_raw) ? nullptr : dst, (last && !late_norm) ? norm_out : nullptr,
+                    (last && !late_norm) ? slots : nullptr, out_index, st);
       if (rc) return rc;
       cur = dst; cur_index = nullptr; cur_slots = false; which ^= 1;
     }
     for (int i = 0; i < nblk; ++i) {
       const bool last = (i == nblk - 1);
-      rc = add_layer(blk[2 * i], g, cur, cur_index, cur_slots, batch, nullptr, nullptr, nullptr, b2, nullptr, nullptr, nullptr, st);
+      rc = add_conv(blk[2 * i], g, cur, cur_index, cur_slots, batch, nullptr, nullptr, nullptr, b2, nullptr, nullptr, nullptr, st);
       if (rc) return rc;
       if (cur_slots) { set_error("internal: residual input must be contiguous"); return MZ_EINVAL; }
       act_t* dst = pp[which];
       if (dst == cur) dst = pp[which ^ 1];
       if (last && raw_dst) dst = raw_dst;
-      rc = add_layer(blk[2 * i + 1], g, b2, nullptr, false, batch, nullptr, nullptr, cur,
-                       (last && normalise && !want_raw) ? nullptr : dst, last ? norm_out : nullptr,
-                       last ? slots : nullptr, out_index, st);
+      rc = add_conv(blk[2 * i + 1], g, b2, nullptr, false, batch, nullptr, nullptr, cur,
+                    (last && normalise && !keep_raw) ? nullptr : dst, (last && !late_norm) ? norm_out : nullptr,
+                    (last && !late_norm) ? slots : nullptr, out_index, st);
       if (rc) return rc;
       cur = dst; which ^= 1;
+    }
+    if (late_norm) {
+      if ((rc = flush(st))) return rc;
+      const int Ptot = batch * g.PB();
+      prof_mark(kProfPack, st);
+      normalise_rows_kernel<<<(Ptot + 127) / 128, 128, 0, st>>>(cur, norm_out, slots, out_index, Ptot, g.PB(),
+                                                               last_layer.n_out / 8, plane_rows_of(g, batch));
+      prof_mark(-1, st);
+      MZ_LAUNCH_CHECK("normalise_rows_kernel");
     }
     *final_buf = const_cast<act_t*>(cur);
     return MZ_OK;
@@ -1324,15 +1450,12 @@ struct ConvNet : NetImpl {
     // stride-2 conv + ReLU: one tcgen05 launch at the input resolution whose epilogue stores the even positions on
     // the half-size grid; then the halo of that grid is zeroed
     auto s2 = [&](const ConvLayer& L, const act_t* in, act_t* out, const Geo& gi, const Geo& go) -> int {
-      int rc2 = flush(st);
+      int rc2 = add_conv(L, gi, in, nullptr, false, batch, nullptr, nullptr, nullptr, out, nullptr, nullptr, nullptr, st, true);
       if (rc2) return rc2;
-      rc2 = add_layer(L, gi, in, nullptr, false, batch, nullptr, nullptr, nullptr, out, nullptr, nullptr, nullptr, st);
-      if (rc2) return rc2;
-      pend_sub = true;
       if ((rc2 = flush(st))) return rc2;
       if (grid_pad()) {
         prof_mark(kProfPack, st);
-        zero_halo_kernel<<<num_sms * 4, 256, 0, st>>>(out, batch, go.H, go.W, C / 8, plane_rows_of(go, batch));
+        zero_halo_kernel<<<num_sms * 4, 256, 0, st>>>(out, batch, go.H, go.W, L.n_out / 8, plane_rows_of(go, batch));
         prof_mark(-1, st);
         MZ_LAUNCH_CHECK("zero_halo_kernel");
       }
@@ -1341,7 +1464,7 @@ struct ConvNet : NetImpl {
     auto pool = [&](const act_t* in, act_t* out, act_t* sl, const int32_t* idx, const Geo& gi, const Geo& go, int norm) -> int {
       prof_mark(kProfPack, st);
       avgpool_kernel<<<num_sms * 8, 256, 0, st>>>(in, out, sl, idx, batch, gi.H, gi.W, norm, plane_rows_of(gi, batch),
-                                                  plane_rows_of(go, batch), grid_pad());
+                                                  plane_rows_of(go, batch), grid_pad(), C);
       prof_mark(-1, st);
       MZ_LAUNCH_CHECK("avgpool_kernel");
       return MZ_OK;
@@ -1429,8 +1552,8 @@ struct ConvNet : NetImpl {
 };
 
 static int conv_geometry(const mz_net_config& c, int* H, int* W) {
-  MZ_CHECK_ARG(c.num_planes == 32 || c.num_planes == 64 || c.num_planes == 128,
-               "conv nets need num_planes in {32, 64, 128}, got %d", c.num_planes);
+  MZ_CHECK_ARG(c.num_planes == 16 || c.num_planes == 32 || c.num_planes == 64 || c.num_planes == 128 || c.num_planes == 256,
+               "conv nets need num_planes in {16, 32, 64, 128, 256}, got %d", c.num_planes);
   MZ_CHECK_ARG(c.num_res_blocks >= 0 && c.num_res_blocks <= 32, "num_res_blocks out of range");
   if (c.kind == MZ_NET_BOARD) {
     MZ_CHECK_ARG(c.in_channels > 0 && c.in_channels <= 64, "board nets take 1..64 observation planes, got %d",
@@ -1442,7 +1565,8 @@ static int conv_geometry(const mz_net_config& c, int* H, int* W) {
     // residual stage is 128 wide whatever num_planes says (network.py:324-327)
     MZ_CHECK_ARG(c.in_h == 96 && c.in_w == 96, "MuZeroAtariNet needs 96x96 observations (6x6 latent), got %dx%d",
                  c.in_h, c.in_w);
-    MZ_CHECK_ARG(c.num_planes == 128, "MuZeroAtariNet is built for num_planes == 128, got %d", c.num_planes);
+    MZ_CHECK_ARG(c.num_planes == 128 || c.num_planes == 256, "MuZeroAtariNet is built for num_planes 128 or 256, got %d",
+                 c.num_planes);
     MZ_CHECK_ARG(c.in_channels > 0 && c.in_channels <= 16, "MuZeroAtariNet takes 1..16 stacked planes, got %d",
                  c.in_channels);
     *H = 6; *W = 6;
@@ -1454,7 +1578,7 @@ int conv_hidden_bytes(const mz_net_config& c, int32_t* bytes) {
   int H, W;
   int rc = conv_geometry(c, &H, &W);
   if (rc) return rc;
-  *bytes = (H + grid_pad()) * (W + grid_pad()) * c.num_planes * 2;
+  *bytes = (H + grid_pad()) * (W + grid_pad()) * padded_planes(c.num_planes) * 2;
   return MZ_OK;
 }
 
@@ -1466,12 +1590,12 @@ int conv_arena_bytes(const mz_net_config& c, int max_batch, size_t* bytes) {
   int rc = conv_geometry(c, &H, &W);
   if (rc) return rc;
   const bool atari = c.kind == MZ_NET_ATARI;
-  const int N = c.num_planes, PB = (H + 1) * (W + 1), A = c.num_actions, hw = H * W;
+  const int N = padded_planes(c.num_planes), PB = (H + 1) * (W + 1), A = c.num_actions, hw = H * W;
   size_t t = 0;
   const int nconv_main = 1 + 6 * c.num_res_blocks + (atari ? 12 : 0);   // dyn0 + 2 per block x 3 towers (+ Atari rep)
-  t += conv_w_bytes(obs_cg(c.in_channels), N) + (size_t)nconv_main * conv_w_bytes(N / 8, N);
+  t += conv_w_bytes(obs_cg(c.in_channels), N) + (size_t)nconv_main * (conv_w_bytes(N / 8, N) + 512);
   t += (size_t)(2 + 6 * c.num_res_blocks + 12) * 2 * align_up((size_t)N * 4, 256);     // scale + bias per conv
-  t += 2 * align_up((size_t)9 * 128 * 128 * 2, 256);                                    // stride-2 conv weights
+  t += 2 * align_up((size_t)9 * 128 * 256 * 2, 256);                                    // stride-2 conv weights
   t += align_up((size_t)A * PB * N * 4, 256);                                           // action table
   t += 3 * (align_up((size_t)2 * N * 4, 256) + 2 * 256 + 256);                          // head 1x1 weights/bias/scale
   t += align_up((size_t)c.reward_support * hw * 4, 256) + align_up((size_t)A * 2 * hw * 4, 256) +
@@ -1479,8 +1603,13 @@ int conv_arena_bytes(const mz_net_config& c, int max_batch, size_t* bytes) {
   const size_t big_pb = atari ? (size_t)(c.in_h / 2 + 1) * (c.in_w / 2 + 1) : (size_t)PB;   // largest activation grid
   const size_t obs_pb = atari ? (size_t)(c.in_h + 1) * (c.in_w + 1) : (size_t)PB;
   auto rows = [&](size_t pb) { return ((size_t)max_batch * pb + kTileM - 1) / kTileM * kTileM + kPlaneSlack; };
+  // activation buffers: the largest (grid, channels) product any stage of the net produces (Atari: 128 channels at
+  // 48x48, num_planes at 24x24)
+  const size_t mid_pb = atari ? (size_t)(c.in_h / 4 + 1) * (c.in_w / 4 + 1) : (size_t)PB;
+  size_t act_bytes = rows(mid_pb) * N * 2;
+  if (atari && rows(big_pb) * 128 * 2 > act_bytes) act_bytes = rows(big_pb) * 128 * 2;
   t += align_up(rows(obs_pb) * (atari ? 2 : obs_cg(c.in_channels)) * 16, 256);           // packed observations
-  t += 3 * align_up(rows(big_pb) * N * 2, 256);                                          // b0..b2
+  t += 3 * align_up(act_bytes, 256);                                                     // b0..b2
   t += 2 * align_up(rows(PB) * N * 2, 256);                                              // b3, b4 (latent grid only)
   t += align_up((size_t)kMaxLayers * (((size_t)max_batch * big_pb + 127) / 128) * 4, 256) + 256;   // tile flags (128-row tiles)
   *bytes = t + 8192;
@@ -1493,7 +1622,7 @@ int conv_create(const mz_net_config& c, const float* const* w, int nw, int max_b
   int rc = conv_geometry(c, &H, &W);
   if (rc) return rc;
   const bool atari = c.kind == MZ_NET_ATARI;
-  const int N = c.num_planes, A = c.num_actions, hw = H * W, blocks = c.num_res_blocks;
+  const int Nreal = c.num_planes, N = padded_planes(Nreal), A = c.num_actions, hw = H * W, blocks = c.num_res_blocks;
   const int rep_tensors = atari ? (1 + 20 + 1 + 20 + 20) : (5 + 10 * blocks);
   const int expect = rep_tensors + (5 + 10 * blocks + 7) + (10 * blocks + 14);
   MZ_CHECK_ARG(nw == expect, "%s with %d blocks has %d state_dict tensors, got %d",
@@ -1503,7 +1632,7 @@ int conv_create(const mz_net_config& c, const float* const* w, int nw, int max_b
   if (arena_bytes < need) { set_error("net arena too small: %zu < %zu", arena_bytes, need); return MZ_ENOMEM; }
 
   ConvNet* net = new ConvNet();
-  net->cfg = c; net->lat = Geo{H, W}; net->C = N; net->A = A; net->atari = atari;
+  net->cfg = c; net->lat = Geo{H, W}; net->C = N; net->Creal = Nreal; net->A = A; net->atari = atari;
   net->blocks = blocks; net->max_batch = max_batch;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1516,36 +1645,46 @@ int conv_create(const mz_net_config& c, const float* const* w, int nw, int max_b
   int cur = 0;
   auto next = [&]() { return w[cur++]; };
 
-  // conv (no bias) + BatchNorm -> packed fp16 weights + fp32 bias
-  auto fold_conv = [&](int cin, int cin_total, int cg, ConvLayer* L, float** scale_out) -> int {
-    const float* cw = next();
-    const float *g = next(), *beta = next(), *mean = next(), *var = next();
-    float* scale = (float*)take((size_t)N * 4);
-    float* bias = (float*)take((size_t)N * 4);
-    bn_fold_kernel<<<(N + 127) / 128, 128>>>(g, beta, mean, var, scale, bias, N);
-    MZ_LAUNCH_CHECK("bn_fold_kernel");
-    act_t* wp = (act_t*)take((size_t)9 * cg * N * 16);
-    pack_conv_kernel<<<256, 256>>>(cw, scale, wp, N, cin, cin_total, cg);
-    MZ_LAUNCH_CHECK("pack_conv_kernel");
-    L->w = wp; L->bias = bias; L->cg = cg;
-    if (scale_out) *scale_out = scale;
+  // pack the (scaled) weights of a conv with n_real output channels (cin of cin_total input channels, the first ones)
+  // as one block of n_out rows per 128-column pass
+  auto pack_passes = [&](const float* cw, const float* scale, const float* bias, int n_real, int n_out, int cin,
+                         int cin_total, int cg, ConvLayer* L) -> int {
+    L->cg = cg; L->n_out = n_out; L->n_real = n_real;
+    const int np = L->passes(), npass = L->n_pass();
+    for (int h = 0; h < np; ++h) {
+      act_t* wp = (act_t*)take((size_t)9 * cg * npass * 16);
+      const int rows_real = n_real - h * 128 < npass ? n_real - h * 128 : npass;
+      pack_conv_kernel<<<256, 256>>>(cw + (size_t)h * 128 * cin_total * 9, scale + h * 128, wp, npass, rows_real, cin,
+                                     cin_total, cg);
+      MZ_LAUNCH_CHECK("pack_conv_kernel");
+      L->w[h] = wp; L->bias[h] = bias + h * 128;
+    }
     return MZ_OK;
   };
-  // conv without BatchNorm or bias (the Atari stride-2 convs): scale 1, bias 0
-  float* ones = (float*)take((size_t)N * 4);
-  float* zeros = (float*)take((size_t)N * 4);
-  {
-    std::vector<float> h1((size_t)N, 1.0f);
-    MZ_CUDA(cudaMemcpy(ones, h1.data(), (size_t)N * 4, cudaMemcpyHostToDevice));
-    MZ_CUDA(cudaMemset(zeros, 0, (size_t)N * 4));
-  }
-  auto plain_conv = [&](int cin, int cg, ConvLayer* L) -> int {
+  // conv (no bias) + BatchNorm -> packed fp16 weights + fp32 bias; n_real real output channels padded to n_out
+  auto fold_conv = [&](int cin, int cin_total, int cg, int n_real, int n_out, ConvLayer* L, float** scale_out) -> int {
     const float* cw = next();
-    act_t* wp = (act_t*)take((size_t)9 * cg * N * 16);
-    pack_conv_kernel<<<256, 256>>>(cw, ones, wp, N, cin, cin, cg);
-    MZ_LAUNCH_CHECK("pack_conv_kernel");
-    L->w = wp; L->bias = zeros; L->cg = cg;
-    return MZ_OK;
+    const float *g = next(), *beta = next(), *mean = next(), *var = next();
+    float* scale = (float*)take((size_t)n_out * 4);
+    float* bias = (float*)take((size_t)n_out * 4);
+    MZ_CUDA(cudaMemset(scale, 0, (size_t)n_out * 4));
+    MZ_CUDA(cudaMemset(bias, 0, (size_t)n_out * 4));
+    bn_fold_kernel<<<(n_real + 127) / 128, 128>>>(g, beta, mean, var, scale, bias, n_real);
+    MZ_LAUNCH_CHECK("bn_fold_kernel");
+    if (scale_out) *scale_out = scale;
+    return pack_passes(cw, scale, bias, n_real, n_out, cin, cin_total, cg, L);
+  };
+  // conv without BatchNorm or bias (the Atari stride-2 convs): scale 1, bias 0
+  float* ones = (float*)take((size_t)256 * 4);
+  float* zeros = (float*)take((size_t)256 * 4);
+  {
+    std::vector<float> h1((size_t)256, 1.0f);
+    MZ_CUDA(cudaMemcpy(ones, h1.data(), (size_t)256 * 4, cudaMemcpyHostToDevice));
+    MZ_CUDA(cudaMemset(zeros, 0, (size_t)256 * 4));
+  }
+  auto plain_conv = [&](int cin, int cg, int n_out, ConvLayer* L) -> int {
+    const float* cw = next();
+    return pack_passes(cw, ones, zeros, n_out, n_out, cin, cin, cg, L);
   };
   auto fold_head = [&](int mid, int outn, int kind, Head* h) -> int {
     const float* cw = next();
@@ -1554,8 +1693,8 @@ int conv_create(const mz_net_config& c, const float* const* w, int nw, int max_b
     float* bias = (float*)take(256);
     bn_fold_kernel<<<1, 32>>>(g, beta, mean, var, scale, bias, mid);
     MZ_LAUNCH_CHECK("bn_fold_kernel");
-    float* w1 = (float*)take((size_t)mid * N * 4);
-    scale_rows_kernel<<<(mid * N + 255) / 256, 256>>>(cw, scale, w1, mid, N);
+    float* w1 = (float*)take((size_t)mid * Nreal * 4);
+    scale_rows_kernel<<<(mid * Nreal + 255) / 256, 256>>>(cw, scale, w1, mid, Nreal);
     MZ_LAUNCH_CHECK("scale_rows_kernel");
     const float* lw = next();
     const float* lb = next();
@@ -1569,41 +1708,44 @@ int conv_create(const mz_net_config& c, const float* const* w, int nw, int max_b
 #define MZ_TRY(x) do { int rc__ = (x); if (rc__) { delete net; return rc__; } } while (0)
 
   if (atari) {
-    // representation (network.py:312-353): conv_1, res_blocks_1 x2, conv_2, res_blocks_2 x2, res_blocks_3 x2
-    MZ_TRY(plain_conv(c.in_channels, 2, &net->s2_1));
-    for (int i = 0; i < 4; ++i) MZ_TRY(fold_conv(N, N, N / 8, &net->at_blocks[0][i], nullptr));
-    MZ_TRY(plain_conv(128, N / 8, &net->s2_2));
-    for (int i = 0; i < 4; ++i) MZ_TRY(fold_conv(N, N, N / 8, &net->at_blocks[1][i], nullptr));
-    for (int i = 0; i < 4; ++i) MZ_TRY(fold_conv(N, N, N / 8, &net->at_blocks[2][i], nullptr));
+    // representation (network.py:312-353): conv_1 (-> 128), res_blocks_1 x2 @128, conv_2 (128 -> num_planes),
+    // res_blocks_2 x2, res_blocks_3 x2
+    MZ_TRY(plain_conv(c.in_channels, 2, 128, &net->s2_1));
+    for (int i = 0; i < 4; ++i) MZ_TRY(fold_conv(128, 128, 16, 128, 128, &net->at_blocks[0][i], nullptr));
+    MZ_TRY(plain_conv(128, 16, N, &net->s2_2));
+    for (int i = 0; i < 4; ++i) MZ_TRY(fold_conv(N, N, N / 8, N, N, &net->at_blocks[1][i], nullptr));
+    for (int i = 0; i < 4; ++i) MZ_TRY(fold_conv(N, N, N / 8, N, N, &net->at_blocks[2][i], nullptr));
   } else {
     // representation (network.py:356-393)
-    MZ_TRY(fold_conv(c.in_channels, c.in_channels, net->in_cg, &net->rep0, nullptr));
-    for (int i = 0; i < 2 * blocks; ++i) MZ_TRY(fold_conv(N, N, N / 8, &net->rep_blocks[i], nullptr));
+    MZ_TRY(fold_conv(c.in_channels, c.in_channels, net->in_cg, Nreal, N, &net->rep0, nullptr));
+    for (int i = 0; i < 2 * blocks; ++i) MZ_TRY(fold_conv(Nreal, Nreal, N / 8, Nreal, N, &net->rep_blocks[i], nullptr));
   }
   // dynamics (network.py:396-449): first conv sees C + A channels; the A action planes become a table
   {
     const float* dyn_w = w[cur];
     float* scale = nullptr;
-    MZ_TRY(fold_conv(N, N + A, N / 8, &net->dyn0, &scale));
+    MZ_TRY(fold_conv(Nreal, Nreal + A, N / 8, Nreal, N, &net->dyn0, &scale));
     float* tab = (float*)take((size_t)A * PB * N * 4);
-    action_table_kernel<<<512, 256>>>(dyn_w, scale, tab, A, N, N, H, W, grid_pad());
+    action_table_kernel<<<512, 256>>>(dyn_w, scale, tab, A, Nreal, N, Nreal, H, W, grid_pad());
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("action_table_kernel: %s", cudaGetErrorString(e)); delete net; return MZ_ECUDA; }
     count_launch();
     net->tab = tab;
   }
-  for (int i = 0; i < 2 * blocks; ++i) MZ_TRY(fold_conv(N, N, N / 8, &net->dyn_blocks[i], nullptr));
+  for (int i = 0; i < 2 * blocks; ++i) MZ_TRY(fold_conv(Nreal, Nreal, N / 8, Nreal, N, &net->dyn_blocks[i], nullptr));
   MZ_TRY(fold_head(1, c.reward_support, c.reward_support == 1 ? 0 : 1, &net->h_reward));
   // prediction (network.py:452-498)
-  for (int i = 0; i < 2 * blocks; ++i) MZ_TRY(fold_conv(N, N, N / 8, &net->pred_blocks[i], nullptr));
+  for (int i = 0; i < 2 * blocks; ++i) MZ_TRY(fold_conv(Nreal, Nreal, N / 8, Nreal, N, &net->pred_blocks[i], nullptr));
   MZ_TRY(fold_head(2, A, 2, &net->h_policy));
   MZ_TRY(fold_head(1, c.value_support, c.value_support == 1 ? 0 : 1, &net->h_value));
 #undef MZ_TRY
   const size_t big_pb = atari ? (size_t)(c.in_h / 2 + 1) * (c.in_w / 2 + 1) : (size_t)PB;
+  const size_t mid_pb = atari ? (size_t)(c.in_h / 4 + 1) * (c.in_w / 4 + 1) : (size_t)PB;
   const size_t obs_pb = atari ? (size_t)(c.in_h + 1) * (c.in_w + 1) : (size_t)PB;
   auto rows = [&](size_t pb) { return ((size_t)max_batch * pb + kTileM - 1) / kTileM * kTileM + kPlaneSlack; };
   net->xobs = (act_t*)take(rows(obs_pb) * (atari ? 2 : net->in_cg) * 16);
-  const size_t act_bytes = rows(big_pb) * N * 2;
+  size_t act_bytes = rows(mid_pb) * N * 2;
+  if (atari && rows(big_pb) * 128 * 2 > act_bytes) act_bytes = rows(big_pb) * 128 * 2;
   net->b0 = (act_t*)take(act_bytes);
   net->b1 = (act_t*)take(act_bytes);
   net->b2 = (act_t*)take(act_bytes);
@@ -1613,7 +1755,7 @@ int conv_create(const mz_net_config& c, const float* const* w, int nw, int max_b
   net->flags = (unsigned*)take(net->flags_cap * 4);
   net->err_flag = (int*)take(256);
   cudaMemset(net->err_flag, 0, 4);
-  net->pend.num_layers = 0;
+  net->reset_pending();
   if ((size_t)(p - (char*)arena) > arena_bytes) {
     set_error("internal: net arena overrun (%zu > %zu)", (size_t)(p - (char*)arena), arena_bytes);
     delete net;
@@ -1621,11 +1763,19 @@ int conv_create(const mz_net_config& c, const float* const* w, int nw, int max_b
   }
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { set_error("weight repacking failed: %s", cudaGetErrorString(e)); delete net; return MZ_ECUDA; }
-  if (net->conv_stages(net->lat, N / 8) < 2 || (!atari && net->conv_stages(net->lat, net->in_cg) < 2) ||
-      (atari && (net->conv_stages(Geo{c.in_h / 2, c.in_w / 2}, N / 8) < 2 || net->conv_stages(Geo{c.in_h, c.in_w}, 2) < 2))) {
-    set_error("conv tile does not fit shared memory (grid too wide)");
-    delete net;
-    return MZ_EINVAL;
+  {
+    // every (grid, input groups) combination of this net must fit one of the two tile shapes
+    const int npass = N > 128 ? 128 : N;
+    auto ok = [&](const Geo& g, int cg, int n) { return ConvNet::fits(g, cg, n, kTileM) || ConvNet::fits(g, cg, n, 128); };
+    bool fit = ok(net->lat, N / 8, npass) && (atari || ok(net->lat, net->in_cg, npass));
+    if (atari)
+      fit = fit && ok(Geo{c.in_h, c.in_w}, 2, 128) && ok(Geo{c.in_h / 2, c.in_w / 2}, 16, 128) &&
+            ok(Geo{c.in_h / 4, c.in_w / 4}, N / 8, npass);
+    if (!fit) {
+      set_error("conv tile does not fit shared memory (grid too wide)");
+      delete net;
+      return MZ_EINVAL;
+    }
   }
   const int smem_max = 227 * 1024;
   e = cudaFuncSetAttribute(conv3x3_kernel<128, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);

@@ -384,28 +384,35 @@ class _ConvNet(MuZeroNet):
                                '(self-play always does, pipeline.py:79-80)')
         return super()._engine_tensors()
 
-    # engine layout: fp16 planes of 8 channels, [C/8][(H+pad)*(W+pad)][8], pad = grid_pad (see csrc/conv.cu)
+    # engine layout: fp16 planes of 8 channels, [Cp/8][(H+pad)*(W+pad)][8], pad = grid_pad, Cp = padded_planes
+    # (see csrc/conv.cu)
+    @property
+    def padded_planes(self) -> int:
+        """Channels of a hidden-state slot: num_planes rounded up to a multiple of 32 (the kernels' minimum tile
+        width; the reference's ResNet Tic-Tac-Toe variant has 16 planes, config.py:126-127).  Extra channels are 0."""
+        return max(32, (self.num_planes + 31) // 32 * 32)
+
     def hidden_to_reference(self, slots):
         h, w = self.latent_hw
-        c = self.num_planes
+        c, cp = self.num_planes, self.padded_planes
         pad = self.grid_pad
-        x = slots.view(torch.float16).reshape(slots.shape[0], c // 8, h + pad, w + pad, 8)[:, :, :h, :w, :]
-        return x.permute(0, 1, 4, 2, 3).reshape(slots.shape[0], c, h, w).to(torch.float32).contiguous()
+        x = slots.view(torch.float16).reshape(slots.shape[0], cp // 8, h + pad, w + pad, 8)[:, :, :h, :w, :]
+        return x.permute(0, 1, 4, 2, 3).reshape(slots.shape[0], cp, h, w)[:, :c].to(torch.float32).contiguous()
 
     @property
     def grid_pad(self) -> int:
         """0: boards stored without halo (the conv kernel masks the edge taps); 1: the padded (H+1)x(W+1) layout
         (MZ_CONV_PAD=1).  Read off the engine's slot size so that this module never disagrees with the library."""
         h, w = self.latent_hw
-        return 1 if self.hidden_bytes == (h + 1) * (w + 1) * self.num_planes * 2 else 0
+        return 1 if self.hidden_bytes == (h + 1) * (w + 1) * self.padded_planes * 2 else 0
 
     def hidden_from_reference(self, hid):
         h, w = self.latent_hw
-        c = self.num_planes
+        c, cp = self.num_planes, self.padded_planes
         hid = hid.reshape(-1, c // 8, 8, h, w)
         pad = self.grid_pad
-        out = torch.zeros((hid.shape[0], c // 8, h + pad, w + pad, 8), dtype=torch.float16, device=hid.device)
-        out[:, :, :h, :w, :] = hid.permute(0, 1, 3, 4, 2).to(torch.float16)
+        out = torch.zeros((hid.shape[0], cp // 8, h + pad, w + pad, 8), dtype=torch.float16, device=hid.device)
+        out[:, :c // 8, :h, :w, :] = hid.permute(0, 1, 3, 4, 2).to(torch.float16)
         return out.reshape(hid.shape[0], -1).view(torch.uint8)
 
     def dynamics(self, hidden_state, action):

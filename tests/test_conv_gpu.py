@@ -371,3 +371,84 @@ def test_atari_c4_search_replays_in_the_oracle_and_rows_match_fp32():
     report('c4 v0', plan.v0[rows4].cpu().numpy(), v_ref.numpy(), TOL_PV)
     rows = [(int(t), int(k)) for t, k in zip(gen.choice(B, size=64), gen.randint(1, S1, size=64))]
     check_rows_against_oracle_net(net, onet, plan, rows, TOL_H, TOL_PV)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Every network shape the reference builds: the ResNet Tic-Tac-Toe variant (16 planes,
+# config.py:126-127), the class defaults 256 planes x 16 blocks (network.py:543-549) and the Atari class defaults
+# 256 planes x 16 blocks with support 601 (network.py:504-512)
+# ---------------------------------------------------------------------------------------------------------------
+R2_SHAPES = {
+    'ttt_resnet': ('board', dict(input_shape=(9, 3, 3), num_actions=10, num_res_blocks=2, num_planes=16), 7),
+    'board_256x16': ('board', dict(input_shape=(9, 9, 9), num_actions=82, num_res_blocks=16, num_planes=256), 8),
+    'atari_default': ('atari', dict(input_shape=(4, 96, 96), num_actions=6, num_res_blocks=16, num_planes=256,
+                                    value_support_size=601, reward_support_size=601), 9),
+}
+
+
+def _build_r2(name):
+    kind, kw, seed = R2_SHAPES[name]
+    if kind == 'board':
+        return build_board(kw['input_shape'], kw['num_actions'], kw['num_res_blocks'], kw['num_planes'], seed)
+    return build_atari(kw, seed)
+
+
+@pytest.mark.parametrize('name', list(R2_SHAPES))
+def test_every_reference_network_shape_vs_reference_recording(name):
+    net, _ = _build_r2(name)
+    _chain_vs_recording(net, np.load(os.path.join(GOLDEN, 'net_golden_r2.npz')), name, name)
+
+
+@pytest.mark.parametrize('name,batch,nref', [('ttt_resnet', 1000, 24), ('board_256x16', 300, 6)])
+def test_new_board_shapes_batched_vs_torch_fp32(name, batch, nref):
+    """Multi-tile dataflow launches of the padded (16 -> 32 planes) and the two-pass (256 planes) towers, with slot
+    indirection on both sides, against fp32 torch on a subset of rows."""
+    net, onet = _build_r2(name)
+    kw = R2_SHAPES[name][1]
+    A = kw['num_actions']
+    gen = np.random.RandomState(batch)
+    obs = gen.randint(0, 2, size=(batch,) + kw['input_shape']).astype(np.float32)
+    hid, pi, v = net.initial_inference_batch(torch.from_numpy(obs).cuda())
+    rows = np.sort(gen.choice(batch, size=nref, replace=False))
+    h_ref, pi_ref, v_ref = onet.initial_batch(obs[rows])
+    report(f'{name} h0', net.hidden_to_reference(hid)[rows].cpu().numpy(), h_ref.numpy(), TOL_H)
+    report(f'{name} pi0', pi[rows].cpu().numpy(), pi_ref.numpy(), TOL_PV)
+    report(f'{name} v0', v[rows].cpu().numpy(), v_ref.numpy(), TOL_PV)
+    act = gen.randint(0, A, size=batch)
+    src = torch.arange(batch - 1, -1, -1, dtype=torch.int32).cuda()
+    dst = (torch.arange(batch, dtype=torch.int32) * 2 + 1).cuda()
+    out = net.new_hidden(2 * batch + 1)
+    _, r, pi2, v2 = net.recurrent_inference_batch(hid, torch.from_numpy(act).cuda(), src_index=src, hidden_out=out,
+                                                  dst_index=dst)
+    # row i read slot batch-1-i: reference rows for the sampled OUTPUT rows
+    src_rows = batch - 1 - rows
+    h_in = net.hidden_to_reference(hid)[src_rows].cpu()
+    h2_ref, r_ref, pi2_ref, v2_ref = onet.recurrent_batch(h_in, act[rows])
+    report(f'{name} h1', net.hidden_to_reference(out)[1::2][rows].cpu().numpy(), h2_ref.numpy(), TOL_H)
+    report(f'{name} r', r[rows].cpu().numpy(), r_ref.numpy(), TOL_PV)
+    report(f'{name} v1', v2[rows].cpu().numpy(), v2_ref.numpy(), TOL_PV)
+    report(f'{name} pi1', pi2[rows].cpu().numpy(), pi2_ref.numpy(), TOL_PV)
+    assert (out.view(torch.float16)[0::2] == 0).all()        # untouched slots stay untouched
+    if name == 'ttt_resnet':                                 # channels 16..31 of a slot are the zero padding
+        raw = out.view(torch.float16).reshape(2 * batch + 1, 4, 9, 8)
+        assert (raw[1::2, 2:] == 0).all()
+
+
+def test_resnet_tictactoe_variant_through_the_drop_in_uct_search():
+    """The reference's own smoke configuration (tests/tictactoe/run_training_test.py:30-35: use_mlp_net=False ->
+    MuZeroBoardGameNet(input_shape, num_actions, 2, 16)) through the unchanged uct_search signature."""
+    import muzero_b200 as mz
+    net, _ = _build_r2('ttt_resnet')
+    cfg = mz.make_tictactoe_config(use_mlp_net=False, use_tensorboard=False)
+    assert (cfg.num_planes, cfg.num_res_blocks) == (16, 2)
+    gen = np.random.RandomState(3)
+    obs = gen.randint(0, 2, size=(9, 3, 3)).astype(np.float32)
+    mask = np.ones(10, dtype=bool)
+    np.random.seed(11)
+    a, pi, q = mz.uct_search(obs, net, 'cuda', cfg, 1.0, mask, 1, 2)
+    plan = mz.mcts._plan_for(net, cfg, 1)
+    d = plan.pool.dump_tree(0)
+    np.random.seed(11)
+    stub = ReplayStub(plan.pi0[0].cpu().numpy(), d['R'][1:].astype(np.float32), d['value'][1:], d['parent'], d['move'])
+    a_o, pi_o, q_o = orc.uct_search(obs, stub, 'cpu', cfg, 1.0, mask, 1, 2)
+    assert a == a_o and np.array_equal(bits(pi), bits(pi_o)) and bits(q)[0] == bits(q_o)[0]
