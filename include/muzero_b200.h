@@ -194,6 +194,18 @@ int mz_net_initial_frames(mz_net* net, int32_t batch, const uint8_t* frames, con
                           void* hidden_out, const int32_t* dst_index, float* pi_probs, float* value,
                           mz_stream stream);
 
+/* initial_inference of the B observations of a search WITH the root preparation fused into the policy epilogue
+ * (mcts.py:355-367 in one go): the warp that computes tree t's softmax also draws its Dirichlet noise
+ * (noise_mode 2: from the tree's MT19937 stream, exactly mz_dirichlet; 1: reads `noise`; 0: none), mixes, masks,
+ * renormalises, expands the root and resets MinMaxStats -- bit-identical to mz_net_initial [+ mz_dirichlet] +
+ * mz_search_reset, two launches fewer.  Pass `obs` (f32) or (`frames`, `plane_values`) as in mz_net_initial_frames, the
+ * other NULL.  batch must equal the pool's num_trees; row i is tree i.  In mode 2 the drawn sample is also written to
+ * `noise` (f64 [B, A]). */
+int mz_net_initial_search(mz_net* net, mz_pool* pool, int32_t batch, const float* obs, const uint8_t* frames,
+                          const float* plane_values, void* hidden_out, const int32_t* dst_index, float* pi_probs,
+                          float* value, int32_t noise_mode, double* noise, double alpha, double eps,
+                          const uint8_t* mask, const int32_t* players, mz_stream stream);
+
 /* recurrent_inference (network.py:86-111): row i reads slot src_index[i] of
  * hidden_in, applies action[i], writes slot dst_index[i] of hidden_out.
  * pi_probs may be NULL: the search never uses it (mcts.py:386 passes the root

@@ -64,6 +64,8 @@ PROTOTYPES = {
     'mz_net_destroy': (C.c_int, [_P]),
     'mz_net_initial': (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P]),
     'mz_net_initial_frames': (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
+    'mz_net_initial_search': (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, C.c_int32, _P, C.c_double,
+                                        C.c_double, _P, _P, _P]),
     'mz_net_recurrent': (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'mz_net_set_cta_limit': (C.c_int, [_P, C.c_int32]),
     'mz_net_profile_begin': (C.c_int, [_P]),

@@ -831,6 +831,7 @@ __device__ __forceinline__ float signed_parabolic_f(float x) {
 constexpr int kMaxHeads = 3;
 struct HeadsParams {
   HeadParams h[kMaxHeads];
+  RootSetup root;             // mz_net_initial_search: the policy head's epilogue also prepares the search roots
 };
 
 // grid (boards, heads): all heads of one inference in ONE launch
@@ -902,6 +903,8 @@ __global__ void __launch_bounds__(128) head_kernel(const __grid_constant__ Heads
       if (lane == 0) p.dst[b] = signed_parabolic_f(num / den);
     } else {
       for (int i = lane; i < p.out; i += 32) p.dst[(size_t)b * p.out + i] = expf(lg[i] - m) / den;
+      // fused root preparation: board b is tree b; this lane wrote exactly the actions it reads back
+      if (hp.root.enabled) root_setup_fused(hp.root, b, lane, p.dst + (size_t)b * p.out);
     }
   }
 }
@@ -1372,6 +1375,7 @@ struct ConvNet : NetImpl {
   }
   int launch_heads(int batch, cudaStream_t st) {
     if (num_pend_heads == 0) return MZ_OK;
+    if (pending_root) pend_heads.root = *pending_root; else pend_heads.root.enabled = 0;
     prof_mark(kProfHead, st);
     head_kernel<<<dim3(batch, num_pend_heads), 128, pend_heads_smem, st>>>(pend_heads);
     prof_mark(-1, st);

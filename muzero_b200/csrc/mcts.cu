@@ -8,41 +8,11 @@
 // consume numpy's legacy MT19937 stream with numpy's masked rejection.
 #include "common.cuh"
 #include "rng.cuh"
+#include "pool.cuh"
 #include <vector>
 
 namespace mz {
 
-struct PoolDev {
-  int B, A, S, max_nodes;
-  int board;
-  double discount, dp;
-  Edge* edges;
-  float* qcache;     // f32 [B][max_nodes][A]: Node.child_Q of every edge as select reads it (0 for unvisited edges)
-  double* prior;
-  double* rootW;
-  int* rootN;
-  double* minmax;
-  int* count;
-  int *leaf_parent, *leaf_action, *leaf_depth, *src_slot, *dst_slot;
-  uint32_t* path;
-  int *node_parent, *node_move;
-  float* node_value;
-  uint32_t* rng_key;
-  int* rng_pos;
-  float *reward, *value;
-  int* error;
-  unsigned long long* stats;
-  const double* T;
-  uint8_t* same_player;
-  double* root_reward;
-  uint8_t* f32_prior;
-  double bound_min, bound_max;
-  int has_bounds;
-  unsigned* work;   // {next tree, finished CTAs} of the confined tree kernel
-  int timing;   // MZ_TREE_TIMING: stats[4..6] = min / max block start and max block end of the tree kernels (%globaltimer)
-};
-
-constexpr unsigned kFull = 0xffffffffu;
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -75,49 +45,6 @@ __device__ __forceinline__ Edge load_edge(const Edge* p) {
   e.child = (uint16_t)((uint32_t)r.w >> 16);
   return e;
 }
-__device__ __forceinline__ void store_edge(Edge* p, double W, float reward, uint32_t N, uint32_t child) {
-  int4 r;
-  r.x = __double2loint(W);
-  r.y = __double2hiint(W);
-  r.z = __float_as_int(reward);
-  r.w = (int)((N & 0xffffu) | (child << 16));
-  *reinterpret_cast<int4*>(p) = r;
-}
-
-// ---------------------------------------------------------------------------
-// numpy pairwise summation (np.sum of a contiguous 1-D array), sequential
-// ---------------------------------------------------------------------------
-template <typename T> struct Add;
-template <> struct Add<float>  { static __device__ float  f(float a, float b)   { return __fadd_rn(a, b); } };
-template <> struct Add<double> { static __device__ double f(double a, double b) { return __dadd_rn(a, b); } };
-
-// `a` holds doubles; on the float32 path they are exactly float32 values and T = float.
-template <typename T>
-__device__ T pairwise_sum(const double* a, int n) {
-  if (n < 8) {
-    T res = (T)(-0.0);
-    for (int i = 0; i < n; ++i) res = Add<T>::f(res, (T)a[i]);
-    return res;
-  }
-  if (n <= 128) {
-    T r[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = (T)a[j];
-    int i = 8;
-    for (; i < n - (n % 8); i += 8) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] = Add<T>::f(r[j], (T)a[i + j]);
-    }
-    T res = Add<T>::f(Add<T>::f(Add<T>::f(r[0], r[1]), Add<T>::f(r[2], r[3])),
-                      Add<T>::f(Add<T>::f(r[4], r[5]), Add<T>::f(r[6], r[7])));
-    for (; i < n; ++i) res = Add<T>::f(res, (T)a[i]);
-    return res;
-  }
-  int n2 = n / 2;
-  n2 -= n2 % 8;
-  return Add<T>::f(pairwise_sum<T>(a, n2), pairwise_sum<T>(a + n2, n - n2));
-}
-
 // ---------------------------------------------------------------------------
 // mz_rng_seed: init_genrand(seed) per tree
 // ---------------------------------------------------------------------------
@@ -143,54 +70,9 @@ reset_kernel(PoolDev p, const float* __restrict__ pi, const double* __restrict__
   const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (t >= p.B) return;
-  const int A = p.A;
-  double* P = p.prior + (size_t)t * A;
-  const bool f32p = (noise == nullptr);
-
-  for (int a = lane; a < A; a += 32) {
-    const float pf = pi[(size_t)t * A + a];
-    double pd;
-    if (f32p) {
-      pd = (double)pf;
-    } else {
-      // (1 - eps) * prob is a float32 product (weak python scalar); eps * noise is float64
-      pd = __dadd_rn((double)__fmul_rn(one_minus_eps_f32, pf), __dmul_rn(eps, noise[(size_t)t * A + a]));
-    }
-    if (mask != nullptr && mask[(size_t)t * A + a] == 0) pd = 0.0;
-    P[a] = pd;
-  }
-  __syncwarp();
-  if (mask != nullptr) {
-    // sequential on every lane (identical results), cheaper than a broadcast for A <= a few hundred
-    if (f32p) {
-      const float s = pairwise_sum<float>(P, A);
-      __syncwarp();
-      if (s > 0.0f)
-        for (int a = lane; a < A; a += 32) P[a] = (double)__fdiv_rn((float)P[a], s);
-    } else {
-      const double s = pairwise_sum<double>(P, A);
-      __syncwarp();
-      if (s > 0.0)
-        for (int a = lane; a < A; a += 32) P[a] = __ddiv_rn(P[a], s);
-    }
-  }
-  // root expansion: row 0 zeroed, no children yet
-  Edge* row = p.edges + (size_t)t * p.max_nodes * A;
-  float* qrow = p.qcache + (size_t)t * p.max_nodes * A;
-  for (int a = lane; a < A; a += 32) { store_edge(row + a, 0.0, 0.0f, 0u, kNoChild); qrow[a] = 0.0f; }
-  if (lane == 0) {
-    p.rootW[t] = 0.0;
-    p.rootN[t] = 0;
-    p.minmax[2 * t] = p.has_bounds ? p.bound_min : __longlong_as_double(0x7ff0000000000000LL);
-    p.minmax[2 * t + 1] = p.has_bounds ? p.bound_max : __longlong_as_double(0xfff0000000000000LL);
-    p.count[t] = 1;
-    p.node_parent[(size_t)t * p.max_nodes] = -1;
-    p.node_move[(size_t)t * p.max_nodes] = -1;
-    p.same_player[t] = (players == nullptr) ? 1 : (players[2 * t] == players[2 * t + 1]);
-    p.root_reward[t] = (root_reward == nullptr) ? 0.0 : (double)root_reward[t];
-    p.f32_prior[t] = f32p ? 1 : 0;
-    p.leaf_depth[t] = 0;
-  }
+  const size_t o = (size_t)t * p.A;
+  root_setup_tree(p, t, lane, pi + o, noise ? noise + o : nullptr, eps, one_minus_eps_f32, mask ? mask + o : nullptr,
+                  players ? players + 2 * t : nullptr, root_reward ? root_reward + t : nullptr);
 }
 
 // ---------------------------------------------------------------------------
@@ -961,41 +843,12 @@ root_policy_kernel(PoolDev p, const uint8_t* __restrict__ mask, const double* __
 // ---------------------------------------------------------------------------
 // mz_dirichlet: numpy legacy_standard_gamma / dirichlet on the tree's stream
 // ---------------------------------------------------------------------------
-__device__ double legacy_gamma(WarpRng& rng, double shape) {
-  if (shape == 1.0) return -log(__dsub_rn(1.0, rng.next_double()));
-  if (shape == 0.0) return 0.0;
-  while (true) {
-    const double u = rng.next_double();
-    const double v = -log(__dsub_rn(1.0, rng.next_double()));
-    if (u <= __dsub_rn(1.0, shape)) {
-      const double xx = pow(u, __ddiv_rn(1.0, shape));
-      if (xx <= v) return xx;
-    } else {
-      const double y = -log(__ddiv_rn(__dsub_rn(1.0, u), shape));
-      const double xx = pow(__dadd_rn(__dsub_rn(1.0, shape), __dmul_rn(shape, y)), __ddiv_rn(1.0, shape));
-      if (xx <= __dadd_rn(v, y)) return xx;
-    }
-  }
-}
-
 __global__ void __launch_bounds__(kTreesPerBlock * 32)
 dirichlet_kernel(PoolDev p, double alpha, double* __restrict__ out) {
   const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (t >= p.B) return;
-  WarpRng rng;
-  rng.load(p.rng_key + (size_t)t * 624, p.rng_pos + t, lane);
-  double* o = out + (size_t)t * p.A;
-  double acc = 0.0;
-  for (int a = 0; a < p.A; ++a) {          // every lane runs the identical sequential sampler
-    const double g = legacy_gamma(rng, alpha);
-    acc = __dadd_rn(acc, g);
-    if (lane == 0) o[a] = g;
-  }
-  __syncwarp();
-  const double inv = __ddiv_rn(1.0, acc);
-  for (int a = lane; a < p.A; a += 32) o[a] = __dmul_rn(o[a], inv);
-  rng.store(p.rng_pos + t);
+  dirichlet_tree(p, t, lane, alpha, out + (size_t)t * p.A);
 }
 
 }  // namespace mz
@@ -1067,7 +920,9 @@ int check_cfg(const mz_pool_config* c) {
   return MZ_OK;
 }
 
-PoolDev dev_of(const mz_pool* h) {
+}  // namespace
+namespace mz {
+PoolDev pool_dev(const mz_pool* h) {
   PoolDev d;
   d.B = h->B; d.A = h->A; d.S = h->S; d.max_nodes = h->max_nodes;
   d.board = h->cfg.is_board_game;
@@ -1106,6 +961,9 @@ PoolDev dev_of(const mz_pool* h) {
   d.timing = timing;
   return d;
 }
+}  // namespace mz
+namespace {
+inline PoolDev dev_of(const mz_pool* h) { return pool_dev(h); }
 
 inline int tree_blocks(int B) { return (B + kTreesPerBlock - 1) / kTreesPerBlock; }
 // thread-per-tree kernels: tiny action spaces and enough trees to fill warps (MZ_TREE_THREAD=0/1 overrides)

@@ -229,7 +229,8 @@ __device__ void prediction_heads(const MlpDev& n, const Smem& s, float* pi_probs
 
 __global__ void __launch_bounds__(kThreads)
 mlp_initial_kernel(MlpDev n, int batch, const float* __restrict__ obs, float* __restrict__ hidden_out,
-                   const int32_t* __restrict__ dst_index, float* __restrict__ pi_probs, float* __restrict__ value) {
+                   const int32_t* __restrict__ dst_index, float* __restrict__ pi_probs, float* __restrict__ value,
+                   const __grid_constant__ RootSetup rs) {
   const Smem s = carve(n, mlp_smem);
   const int row0 = blockIdx.x * kRows;
   for (int i = threadIdx.x; i < kRows * s.ldx; i += kThreads) {
@@ -241,6 +242,13 @@ mlp_initial_kernel(MlpDev n, int batch, const float* __restrict__ obs, float* __
   dense(n.rep2_wt, nullptr, n.rep2_b, s.h1, n.P, n.P, n.HD, false, s.hraw, n.HD);
   normalise_and_store(s.hraw, s.hn, n.HD, hidden_out, dst_index, row0, batch);
   prediction_heads(n, s, pi_probs, value, row0, batch);
+  if (rs.enabled) {
+    // fused root preparation (mz_net_initial_search): the warp that wrote row r's softmax (softmax_rows: warp r % 8,
+    // lane i -> actions i, i + 32, ...) draws the tree's Dirichlet noise, mixes, masks, renormalises and resets the tree
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < kRows; r += kThreads / 32)
+      if (row0 + r < batch) root_setup_fused(rs, row0 + r, lane, pi_probs + (size_t)(row0 + r) * n.A);
+  }
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -641,8 +649,10 @@ struct MlpNet : NetImpl {
   int initial(int batch, const float* obs, void* hidden_out, const int32_t* dst_index, float* pi_probs,
               float* value, cudaStream_t st) override {
     prof_mark(kProfMlp, st);
+    RootSetup rs;
+    if (pending_root) rs = *pending_root; else rs.enabled = 0;
     mlp_initial_kernel<<<(batch + kRows - 1) / kRows, kThreads, smem, st>>>(d, batch, obs, (float*)hidden_out,
-                                                                           dst_index, pi_probs, value);
+                                                                           dst_index, pi_probs, value, rs);
     prof_mark(-1, st);
     MZ_LAUNCH_CHECK("mlp_initial_kernel");
     return MZ_OK;

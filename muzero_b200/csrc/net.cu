@@ -70,6 +70,39 @@ extern "C" int mz_net_initial_frames(mz_net* net, int32_t batch, const uint8_t* 
                                    (cudaStream_t)stream);
 }
 
+extern "C" int mz_net_initial_search(mz_net* net, mz_pool* pool, int32_t batch, const float* obs, const uint8_t* frames,
+                                     const float* plane_values, void* hidden_out, const int32_t* dst_index,
+                                     float* pi_probs, float* value, int32_t noise_mode, double* noise, double alpha,
+                                     double eps, const uint8_t* mask, const int32_t* players, mz_stream stream) {
+  MZ_CHECK_ARG(net && pool && hidden_out && pi_probs && value, "NULL argument");
+  MZ_CHECK_ARG((obs != nullptr) != (frames != nullptr), "pass either obs or (frames, plane_values)");
+  MZ_CHECK_ARG(frames == nullptr || plane_values != nullptr, "frames without plane_values");
+  MZ_CHECK_ARG(batch == pool->B && batch <= net->max_batch, "batch %d must equal the pool's %d trees (net max %d)", batch,
+               pool->B, net->max_batch);
+  MZ_CHECK_ARG(net->cfg.num_actions == pool->A, "network has %d actions, pool %d", net->cfg.num_actions, pool->A);
+  MZ_CHECK_ARG(noise_mode >= 0 && noise_mode <= 2, "noise_mode must be 0 (none), 1 (given) or 2 (device draw)");
+  MZ_CHECK_ARG(noise_mode == 0 || noise != nullptr, "noise buffer is NULL");
+  if (noise_mode) {
+    // mcts.py:239-242
+    MZ_CHECK_ARG(eps >= 0.0 && eps <= 1.0, "Expect `eps` to be a float in the range [0.0, 1.0], got %g", eps);
+    if (noise_mode == 2)
+      MZ_CHECK_ARG(alpha > 0.0 && alpha <= 1.0, "Expect `alpha` to be a float in the range (0.0, 1.0], got %g", alpha);
+  }
+  RootSetup rs;
+  rs.pool = pool_dev(pool);
+  rs.enabled = 1;
+  rs.noise_mode = noise_mode; rs.noise = noise; rs.alpha = alpha; rs.eps = noise_mode ? eps : 0.0;
+  rs.one_minus_eps_f32 = (float)(1.0 - rs.eps);
+  rs.mask = mask; rs.players = players;
+  net->impl->pending_root = &rs;
+  const int rc = frames ? net->impl->initial_frames(batch, frames, plane_values, hidden_out, dst_index, pi_probs, value,
+                                                    (cudaStream_t)stream)
+                        : net->impl->initial(batch, obs, hidden_out, dst_index, pi_probs, value, (cudaStream_t)stream);
+  net->impl->pending_root = nullptr;
+  if (rc == MZ_OK) pool->selected = 0;
+  return rc;
+}
+
 extern "C" int mz_net_recurrent(mz_net* net, int32_t batch, const void* hidden_in, const int32_t* src_index,
                                 const int32_t* action, void* hidden_out, const int32_t* dst_index, float* reward,
                                 float* value, float* pi_probs, mz_stream stream) {

@@ -1,6 +1,7 @@
 // Internal interface every network family implements behind the mz_net handle.
 #pragma once
 #include "common.cuh"
+#include "pool.cuh"
 #include <vector>
 
 namespace mz {
@@ -12,6 +13,8 @@ enum ProfClass { kProfConv = 0, kProfHead = 1, kProfPack = 2, kProfMlp = 3, kPro
 struct NetImpl {
   bool profiling = false;
   int cta_limit = 0;                    // persistent kernels use at most this many CTAs (0: one per SM)
+  const RootSetup* pending_root = nullptr;   // set around initial() by mz_net_initial_search: the policy epilogue
+                                             // also prepares the search roots (Dirichlet, mask, renormalise, reset)
   std::vector<cudaEvent_t> prof_ev;     // pairs (begin, end)
   std::vector<int> prof_cls, prof_weight;   // weight: how many layers one launch covers
   void prof_mark(int cls, cudaStream_t st, int weight = 1) {

@@ -221,6 +221,9 @@ def _noise_enabled(config, deterministic: bool) -> bool:
 
 
 _POOLS = {}
+# MZ_NO_FUSED_ROOT=1: initial inference, Dirichlet draw and root reset as three separate launches (the round-1 chain;
+# kept for the test that pins the fused epilogue to it bit for bit)
+_FUSED_ROOT = os.environ.get('MZ_NO_FUSED_ROOT', '0') != '1'
 
 
 def _pool_for(B, A, config, hidden_bytes, device) -> SearchPool:
@@ -303,21 +306,32 @@ class SearchPlan:
         stream = _lib.current_stream()
         hidden = pool.hidden.data_ptr() if pool.hidden_bytes else None
         mask_p = self.mask.data_ptr() if has_mask else None
-        if self.obs_mode == 'u8':
-            _lib.check(lib.mz_net_initial_frames(eng['handle'], self.B, self.frames.data_ptr(), self.planes.data_ptr(),
-                                                 hidden, self.root_slots.data_ptr(), self.pi0.data_ptr(),
-                                                 self.v0.data_ptr(), stream))
+        frames_p = self.frames.data_ptr() if self.obs_mode == 'u8' else None
+        planes_p = self.planes.data_ptr() if self.obs_mode == 'u8' else None
+        obs_p = None if self.obs_mode == 'u8' else self.obs.data_ptr()
+        eps = cfg.root_exploration_eps if noise_mode != 'none' else 0.0
+        # alphas are float32 in the reference (np.ones_like(prob) * alpha)
+        alpha = float(np.float32(cfg.root_dirichlet_alpha)) if noise_mode == 'device' else 0.0
+        noise_p = self.noise.data_ptr() if noise_mode != 'none' else None
+        if _FUSED_ROOT:
+            # initial inference whose policy epilogue draws the noise and prepares the roots (one launch chain, no
+            # separate dirichlet / reset kernels)
+            _lib.check(lib.mz_net_initial_search(eng['handle'], pool.handle, self.B, obs_p, frames_p, planes_p, hidden,
+                                                 self.root_slots.data_ptr(), self.pi0.data_ptr(), self.v0.data_ptr(),
+                                                 {'none': 0, 'given': 1, 'device': 2}[noise_mode], noise_p, alpha,
+                                                 float(eps), mask_p, self.players.data_ptr(), stream))
         else:
-            _lib.check(lib.mz_net_initial(eng['handle'], self.B, self.obs.data_ptr(), hidden,
-                                          self.root_slots.data_ptr(), self.pi0.data_ptr(), self.v0.data_ptr(), stream))
-        noise_p, eps = None, 0.0
-        if noise_mode != 'none':
-            eps = cfg.root_exploration_eps
-            noise_p = self.noise.data_ptr()
-            if noise_mode == 'device':       # alphas are float32 in the reference (np.ones_like(prob) * alpha)
-                _lib.check(lib.mz_dirichlet(pool.handle, float(np.float32(cfg.root_dirichlet_alpha)), noise_p, stream))
-        _lib.check(lib.mz_search_reset(pool.handle, self.pi0.data_ptr(), noise_p, float(eps), mask_p,
-                                       self.players.data_ptr(), None, stream))
+            if self.obs_mode == 'u8':
+                _lib.check(lib.mz_net_initial_frames(eng['handle'], self.B, frames_p, planes_p, hidden,
+                                                     self.root_slots.data_ptr(), self.pi0.data_ptr(),
+                                                     self.v0.data_ptr(), stream))
+            else:
+                _lib.check(lib.mz_net_initial(eng['handle'], self.B, obs_p, hidden, self.root_slots.data_ptr(),
+                                              self.pi0.data_ptr(), self.v0.data_ptr(), stream))
+            if noise_mode == 'device':
+                _lib.check(lib.mz_dirichlet(pool.handle, alpha, noise_p, stream))
+            _lib.check(lib.mz_search_reset(pool.handle, self.pi0.data_ptr(), noise_p, float(eps), mask_p,
+                                           self.players.data_ptr(), None, stream))
         src, dst, act = (pool.view(k).data_ptr() for k in ('SRC_SLOT', 'DST_SLOT', 'LEAF_ACTION'))
         rew, val = pool.view('REWARD').data_ptr(), pool.view('VALUE').data_ptr()
         _lib.check(lib.mz_select(pool.handle, stream))

@@ -214,3 +214,52 @@ def test_public_batch_entry_point_matches_manual_loop():
         assert bits(q)[0] == bits(q_b[t].item())[0]
         assert np.random.get_state()[2] == streams[t].get_state()[2]
         assert np.array_equal(np.random.get_state()[1], streams[t].get_state()[1])
+
+
+@pytest.mark.parametrize('family', ['mlp', 'conv'])
+@pytest.mark.parametrize('noise_mode', ['none', 'given', 'device'])
+def test_fused_root_epilogue_equals_the_separate_launches(family, noise_mode, monkeypatch):
+    """mz_net_initial_search (Dirichlet draw + noise mix + mask + renormalise + root reset fused behind the policy
+    softmax of the initial inference) against mz_net_initial + mz_dirichlet + mz_search_reset: every byte of the
+    pool after the root preparation, the noise, the RNG streams, and the finished search."""
+    import muzero_b200 as mz
+    torch.manual_seed(2)
+    if family == 'mlp':
+        net = mz.MuZeroMLPNet((9, 3, 3), 10, 256, 1, 1, 64).cuda().eval()
+        cfg = mz.make_tictactoe_config(use_tensorboard=False)
+        B, A, shape = 70, 10, (9, 3, 3)
+    else:
+        net = mz.MuZeroBoardGameNet((5, 5, 5), 26, 2, 32).cuda().eval()
+        cfg = mz.make_gomoku_config(use_tensorboard=False)
+        cfg.num_simulations = 12
+        B, A, shape = 37, 26, (5, 5, 5)
+    gen = np.random.RandomState(9)
+    obs = gen.randint(0, 2, size=(B,) + shape).astype(np.float32)
+    mask = gen.rand(B, A) < 0.7
+    mask[:, -1] = True
+    given = gen.dirichlet(np.ones(A) * 0.3, size=B)
+    out = []
+    for fused in (False, True):
+        monkeypatch.setattr(mz.mcts, '_FUSED_ROOT', fused)
+        plan = mz.mcts.SearchPlan(net, cfg, B)
+        plan.use_graph = False
+        plan.pool.seed(np.arange(B) + 31)
+        plan.obs.copy_(torch.from_numpy(obs).reshape(B, -1)); plan.mask.copy_(torch.from_numpy(mask))
+        plan.players.copy_(torch.tensor([[1, 2]] * B, dtype=torch.int32))
+        plan.noise.copy_(torch.from_numpy(given))
+        n0 = mz._lib.lib().mz_launch_count()
+        plan.run(noise_mode, True, False)
+        launches = mz._lib.lib().mz_launch_count() - n0
+        torch.cuda.synchronize()
+        plan.pool.check_errors()
+        names = ('EDGES', 'QCACHE', 'PRIOR', 'MINMAX', 'ROOT_W', 'ROOT_N', 'COUNT', 'NODE_PARENT', 'NODE_MOVE',
+                 'RNG_KEY', 'RNG_POS')
+        state = {k: plan.pool.view(k).cpu().numpy().view(np.uint8).copy() for k in names}
+        state['noise'] = plan.noise.cpu().numpy().view(np.uint8).copy()
+        state['pi'] = plan.pi.cpu().numpy().view(np.uint8).copy()
+        state['action'] = plan.action.cpu().numpy().copy()
+        out.append((state, launches))
+    (sep, n_sep), (fus, n_fus) = out
+    for k in sep:
+        assert np.array_equal(sep[k], fus[k]), f'{family}/{noise_mode}: {k} differs'
+    assert n_fus == n_sep - (2 if noise_mode == 'device' else 1)
