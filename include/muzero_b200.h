@@ -62,7 +62,7 @@ typedef struct mz_pool_config {
 
 /* buffers inside the arena that tests / the host wrapper may look at */
 enum mz_view {
-  MZ_VIEW_EDGES = 0,     /* [B, S+1, A] 16-byte records {f64 W, f32 reward, u16 N, u16 child(0xFFFF=none)} */
+  MZ_VIEW_EDGES = 0,     /* [B, S+1, A] 8-byte HOT records {u32 child << 16 | N (child 0xFFFF = none), f32 child_Q}: statistics of child (node, a) in the PARENT's row -- all the pUCT descent reads; child_Q = Node.child_Q of the edge (float32, min-max normalised; 0 for unvisited edges), refreshed by expand_backup */
   MZ_VIEW_PRIOR,         /* f64 [B, A]   the one prior every node of a tree uses (mcts.py:386)             */
   MZ_VIEW_ROOT_W,        /* f64 [B]                                                                          */
   MZ_VIEW_ROOT_N,        /* i32 [B]                                                                          */
@@ -84,7 +84,8 @@ enum mz_view {
   MZ_VIEW_VALUE,         /* f32 [B]                                                                          */
   MZ_VIEW_ERROR,         /* i32 [1]      sticky device-side error bits (MZ_DEVERR_*)                         */
   MZ_VIEW_STATS,         /* u64 [8]      {sum of select depths, select calls*B, tie-break draws, mt twists, then (MZ_TREE_TIMING only) min / max block start and max block end of the fused tree kernel, ns} */
-  MZ_VIEW_QCACHE,        /* f32 [B, S+1, A] Node.child_Q of every edge (float32, min-max normalised) as the next select reads it; 0 for unvisited edges; refreshed by expand_backup */
+  MZ_VIEW_EDGE_W,        /* f64 [B, S+1, A] Node.W of every edge     (COLD: read and written by the backup only; defined where N > 0) */
+  MZ_VIEW_EDGE_REWARD,   /* f32 [B, S+1, A] Node.reward of every edge (COLD; written once, when the edge's child is expanded)       */
   MZ_VIEW__COUNT
 };
 #define MZ_DEVERR_POOL_FULL   1   /* more than S expansions                       */

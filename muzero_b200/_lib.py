@@ -18,7 +18,7 @@ MZ_NET_MLP, MZ_NET_BOARD, MZ_NET_ATARI = 0, 1, 2
 
 VIEWS = ['EDGES', 'PRIOR', 'ROOT_W', 'ROOT_N', 'MINMAX', 'COUNT', 'LEAF_PARENT', 'LEAF_ACTION', 'LEAF_DEPTH',
          'SRC_SLOT', 'DST_SLOT', 'PATH', 'NODE_PARENT', 'NODE_MOVE', 'NODE_VALUE', 'RNG_KEY', 'RNG_POS', 'HIDDEN', 'REWARD',
-         'VALUE', 'ERROR', 'STATS', 'QCACHE']
+         'VALUE', 'ERROR', 'STATS', 'EDGE_W', 'EDGE_REWARD']
 VIEW = {name: i for i, name in enumerate(VIEWS)}
 
 

@@ -45,18 +45,18 @@ void count_launch(int n = 1);
 constexpr int kWarp = 32;
 constexpr uint16_t kNoChild = 0xFFFF;
 
-// One (node, action) edge of a tree: the statistics of the child that action
-// leads to, stored in the PARENT's row so a warp reads a node's A children
-// with one coalesced 16-byte-per-lane load.  Unvisited child = all zero with
-// child == kNoChild (the reference creates such children eagerly, mcts.py:98-100;
-// N=0, W=0, reward=0 makes lazy creation observationally identical).
-struct __align__(16) Edge {
-  double W;        // total value      (Node.W, float64 in the reference)
-  float reward;    // Node.reward      (float32-representable, network.py:107)
-  uint16_t N;      // Node.N
-  uint16_t child;  // node index of the expanded child, kNoChild if not expanded
-};
-static_assert(sizeof(Edge) == 16, "Edge must be 16 bytes");
+// One (node, action) edge of a tree = the statistics of the child that action leads to, stored in the PARENT's row
+// and split by who reads it:
+//   HOT  (mz_view EDGES, 8 bytes):  .x = child << 16 | N   (u16 node index of the expanded child or kNoChild, u16 Node.N)
+//                                   .y = Node.child_Q of the edge as the next descent needs it (float32 bits, min-max
+//                                        normalised; 0 for an unvisited edge), refreshed by the backup
+//        -- everything the pUCT descent reads: one coalesced 8-byte-per-lane load gives a warp a node's whole child set;
+//   COLD (EDGE_W f64, EDGE_REWARD f32): Node.W and Node.reward, touched by the backup only, for the edges of one path.
+// Unvisited child = N 0, child kNoChild (the reference creates such children eagerly, mcts.py:98-100; N=0, W=0,
+// reward=0 makes lazy creation observationally identical).  The cold words of an edge are DEFINED only once N > 0
+// (the expansion writes them): nothing reads them before, so expanding a node zeroes its hot row only.
+typedef uint2 HotEdge;
+__host__ __device__ inline uint32_t hot_word(uint32_t N, uint32_t child) { return (N & 0xffffu) | (child << 16); }
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

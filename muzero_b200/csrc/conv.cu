@@ -1417,8 +1417,15 @@ struct ConvNet : NetImpl {
       rc = add_conv(blk[2 * i], g, cur, cur_index, cur_slots, batch, nullptr, nullptr, nullptr, b2, nullptr, nullptr, nullptr, st);
       if (rc) return rc;
       if (cur_slots) { set_error("internal: residual input must be contiguous"); return MZ_EINVAL; }
+      // The block's output goes back INTO the buffer its input came from: element (row, channel) of the residual is read
+      // by the very thread that writes the output there, earlier in program order, and every other reader of the old
+      // contents (the block's first conv, tiles t-1..t+1) has published before this tile starts.  Two live buffers per
+      // tower instead of three: two engines' activations (2 x 2 x 21 MB for 1024 Gomoku boards) then fit the 126 MB L2,
+      // where three per engine (126 MB + weights + trees) were evicted to DRAM between a layer's write and its rewrite.
+      static const bool no_inplace = getenv("MZ_CONV_NO_INPLACE") != nullptr;
       act_t* dst = pp[which];
       if (dst == cur) dst = pp[which ^ 1];
+      if (!no_inplace && (cur == b0 || cur == b1 || cur == b3)) dst = const_cast<act_t*>(cur);
       if (last && raw_dst) dst = raw_dst;
       rc = add_conv(blk[2 * i + 1], g, b2, nullptr, false, batch, nullptr, nullptr, cur,
                     (last && normalise && !keep_raw) ? nullptr : dst, (last && !late_norm) ? norm_out : nullptr,

@@ -36,15 +36,6 @@ __device__ __forceinline__ double warp_min_d(double v) {
   return v;
 }
 
-__device__ __forceinline__ Edge load_edge(const Edge* p) {
-  const int4 r = *reinterpret_cast<const int4*>(p);
-  Edge e;
-  e.W = __hiloint2double(r.y, r.x);
-  e.reward = __int_as_float(r.z);
-  e.N = (uint16_t)((uint32_t)r.w & 0xffffu);
-  e.child = (uint16_t)((uint32_t)r.w >> 16);
-  return e;
-}
 // ---------------------------------------------------------------------------
 // mz_rng_seed: init_genrand(seed) per tree
 // ---------------------------------------------------------------------------
@@ -89,21 +80,7 @@ __device__ __forceinline__ float ord2f(uint32_t k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-// pUCT score of one child, bit-for-bit Node.child_Q + Node.child_U (mcts.py:159-200)
-__device__ __forceinline__ float puct_score(double eW, float eR, int cn, double pa, double tN, bool f32p, double dp,
-                                            bool norm, double lo, double range) {
-  const double y = __ddiv_rn(tN, (double)(cn + 1));
-  const float u = f32p ? __fmul_rn((float)pa, __double2float_rn(y)) : __double2float_rn(__dmul_rn(pa, y));
-  float q = 0.0f;
-  if (cn > 0) {
-    double v = __dadd_rn((double)eR, __dmul_rn(dp, __ddiv_rn(eW, (double)cn)));
-    if (norm) v = __ddiv_rn(__dsub_rn(v, lo), range);
-    q = __double2float_rn(v);
-  }
-  return __fadd_rn(q, u);
-}
-
-// Node.child_Q of one edge (mcts.py:159-178) exactly as puct_score computes it, IEEE divisions: evaluated by the
+// Node.child_Q of one edge (mcts.py:159-178), one IEEE instruction per reference operation: evaluated by the
 // BACKUP (off the descent's dependent chain, lanes in parallel) and cached as float32 per edge.  The value depends on
 // the edge's own (W, N, reward) and on the tree's min-max bounds, so the backup refreshes the edges of its path, or
 // every visited edge of the tree when it moved a bound.  Why: while the conv tower of the other sub-batch runs
@@ -137,10 +114,10 @@ __device__ __forceinline__ double div_by_count(double a, int b, double y) {
   if (fastdiv_window(a)) return q1;
   return ieee_div_cold(a, db);
 }
-// (child << 16 | N) of child record `a` of a row -- all the descent needs of a record; "no child" past the last action
-__device__ __forceinline__ uint32_t load_nc(const Edge* row, int a, int A) {
-  uint32_t r = (uint32_t)kNoChild << 16;
-  if (a < A) r = reinterpret_cast<const uint32_t*>(row + a)[3];
+// hot record of child `a` of a row ({child << 16 | N, child_Q}); "no child" past the last action
+__device__ __forceinline__ HotEdge load_hot(const HotEdge* row, int a, int A) {
+  HotEdge r = hot_empty();
+  if (a < A) r = row[a];
   return r;
 }
 
@@ -153,18 +130,11 @@ __device__ __forceinline__ uint32_t load_nc(const Edge* row, int a, int A) {
 // the next level starts without a memory round trip.
 template <int NCH>
 __device__ __forceinline__ void select_tree(const PoolDev& p, const int t, const int lane, const double* sT,
-                                            const double* sR, float* sc) {
+                                            const double* sR, float* sc, unsigned long long* s_stats) {
   const int A = p.A;
-  const Edge* tree = p.edges + (size_t)t * p.max_nodes * A;
-  const float* qtree = p.qcache + (size_t)t * p.max_nodes * A;
+  const HotEdge* tree = p.hot + (size_t)t * p.max_nodes * A;
   const double* __restrict__ P = p.prior + (size_t)t * A;
-  struct { double lo, range; bool norm; } rd = {0.0, 0.0, false};    // generic path only (scores computed in place)
-  if (NCH == 0) {
-    const double lo_ = p.minmax[2 * t], hi_ = p.minmax[2 * t + 1];
-    rd.lo = lo_; rd.norm = hi_ > lo_; rd.range = __dsub_rn(hi_, lo_);
-  }
   const bool f32p = p.f32_prior[t] != 0;
-  const double dp = p.dp;
   uint32_t* pth = p.path + (size_t)t * p.max_nodes;
 
   WarpRng rng;
@@ -181,15 +151,16 @@ __device__ __forceinline__ void select_tree(const PoolDev& p, const int t, const
       const int a = c * 32 + lane;
       pr[c] = (a < A) ? P[a] : 0.0;
       prf[c] = (float)pr[c];
-      cur[c] = load_nc(tree, a, A);
-      curq[c] = (a < A) ? qtree[a] : 0.0f;
+      const HotEdge h = load_hot(tree, a, A);
+      cur[c] = h.x;
+      curq[c] = __uint_as_float(h.y);
     }
   }
 
   int n = 0, Nn = p.rootN[t], depth = 0, act = 0;
   while (true) {
     const double tN = sT[Nn];
-    const Edge* row = tree + (size_t)n * A;
+    const HotEdge* row = tree + (size_t)n * A;
     uint32_t nc_sel;      // (child << 16 | N) of the chosen edge
     if constexpr (NCH > 0) {
       // most-visited expanded child: its row is the likeliest next one
@@ -202,13 +173,12 @@ __device__ __forceinline__ void select_tree(const PoolDev& p, const int t, const
       float nxtq[NC];
       const int spec = (top != 0) ? (int)(top & 0xffffu) : -1;
       if (spec >= 0) {
-        const Edge* srow = tree + (size_t)spec * A;
-        const float* sq = qtree + (size_t)spec * A;
+        const HotEdge* srow = tree + (size_t)spec * A;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-          const int a = c * 32 + lane;
-          nxt[c] = load_nc(srow, a, A);
-          nxtq[c] = (a < A) ? sq[a] : 0.0f;
+          const HotEdge h = load_hot(srow, c * 32 + lane, A);
+          nxt[c] = h.x;
+          nxtq[c] = __uint_as_float(h.y);
         }
       }
       // pUCT score = cached child_Q + child_U; the only float64 work left on the chain is y = tN / (cn + 1) for
@@ -270,21 +240,31 @@ __device__ __forceinline__ void select_tree(const PoolDev& p, const int t, const
 #pragma unroll
           for (int c = 0; c < NCH; ++c) { cur[c] = nxt[c]; curq[c] = nxtq[c]; }
         } else {
-          const Edge* crow = tree + (size_t)child * A;
-          const float* cq = qtree + (size_t)child * A;
+          const HotEdge* crow = tree + (size_t)child * A;
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
-            const int a = c * 32 + lane;
-            cur[c] = load_nc(crow, a, A);
-            curq[c] = (a < A) ? cq[a] : 0.0f;
+            const HotEdge h = load_hot(crow, c * 32 + lane, A);
+            cur[c] = h.x;
+            curq[c] = __uint_as_float(h.y);
           }
         }
       }
     } else {
+      // any A: scores staged in shared memory, same arithmetic (cached child_Q + child_U)
+      const float tNf = __double2float_rn(tN);
       float bestl = -INFINITY;
       for (int a = lane; a < A; a += 32) {
-        const Edge e = load_edge(row + a);
-        const float s = puct_score(e.W, e.reward, (int)e.N, P[a], tN, f32p, dp, rd.norm, rd.lo, rd.range);
+        const HotEdge h = row[a];
+        const int cn = (int)(h.x & 0xffffu);
+        const double pa = P[a];
+        float u;
+        if (cn > 0) {
+          const double y = div_by_count(tN, cn + 1, __ldg(sR + cn + 1));
+          u = f32p ? __fmul_rn((float)pa, __double2float_rn(y)) : __double2float_rn(__dmul_rn(pa, y));
+        } else {
+          u = f32p ? __fmul_rn((float)pa, tNf) : __double2float_rn(__dmul_rn(pa, tN));
+        }
+        const float s = __fadd_rn(__uint_as_float(h.y), u);
         sc[a] = s;
         bestl = fmaxf(bestl, s);
       }
@@ -314,8 +294,7 @@ __device__ __forceinline__ void select_tree(const PoolDev& p, const int t, const
         }
       }
       __syncwarp();
-      const Edge e = load_edge(row + act);
-      nc_sel = ((uint32_t)e.child << 16) | e.N;
+      nc_sel = row[act].x;
     }
     if (lane == 0) pth[depth] = (uint32_t)(n * A + act);
     ++depth;
@@ -331,11 +310,18 @@ __device__ __forceinline__ void select_tree(const PoolDev& p, const int t, const
     p.src_slot[t] = t * p.max_nodes + n;
     const int c = p.count[t];
     p.dst_slot[t] = t * p.max_nodes + (c < p.max_nodes ? c : p.max_nodes - 1);
-    atomicAdd(p.stats + 0, (unsigned long long)depth);
-    atomicAdd(p.stats + 1, 1ULL);
-    if (rng.draws) atomicAdd(p.stats + 2, rng.draws);
-    if (rng.twists) atomicAdd(p.stats + 3, rng.twists);
+    // statistics go to the CTA's shared-memory counters; one global atomic per CTA and counter at the end (4096
+    // same-address global atomics per launch kept the kernel alive for microseconds after the last descent)
+    atomicAdd(s_stats + 0, (unsigned long long)depth);
+    atomicAdd(s_stats + 1, 1ULL);
+    if (rng.draws) atomicAdd(s_stats + 2, rng.draws);
+    if (rng.twists) atomicAdd(s_stats + 3, rng.twists);
   }
+}
+
+__device__ __forceinline__ void flush_stats(const PoolDev& p, const unsigned long long* s_stats) {
+  __syncthreads();
+  if (threadIdx.x < 4 && s_stats[threadIdx.x]) atomicAdd(p.stats + threadIdx.x, s_stats[threadIdx.x]);
 }
 
 template <int NCH>
@@ -348,10 +334,12 @@ select_kernel(PoolDev p) {
   // persistent conv kernel of the other sub-batch (228 KB - 223.75 KB - two 1 KB reservations)
   const double* sR = p.T + (p.S + 2);
   float* sc = reinterpret_cast<float*>(sT + (p.S + 2)) + (size_t)warp * ((p.A + 3) & ~3);
+  __shared__ unsigned long long s_stats[4];
+  if (threadIdx.x < 4) s_stats[threadIdx.x] = 0;
   for (int i = threadIdx.x; i < p.S + 2; i += blockDim.x) sT[i] = p.T[i];
   __syncthreads();
-  if (t >= p.B) return;
-  select_tree<NCH>(p, t, lane, sT, sR, sc);
+  if (t < p.B) select_tree<NCH>(p, t, lane, sT, sR, sc, s_stats);
+  flush_stats(p, s_stats);
 }
 
 // ---------------------------------------------------------------------------
@@ -368,13 +356,15 @@ __device__ __forceinline__ void expand_backup_tree(const PoolDev& p, const int t
     if (lane == 0) atomicOr(p.error, MZ_DEVERR_POOL_FULL);
     return;
   }
-  Edge* tree = p.edges + (size_t)t * p.max_nodes * A;
+  const size_t tbase = (size_t)t * p.max_nodes * A;
+  HotEdge* tree = p.hot + tbase;
+  double* ew = p.ew + tbase;
+  float* er = p.er + tbase;
   const uint32_t* pth = p.path + (size_t)t * p.max_nodes;
 
-  // expand: fresh all-zero row for the new node
-  Edge* crow = tree + (size_t)c * A;
-  float* qtree = p.qcache + (size_t)t * p.max_nodes * A;
-  for (int a = lane; a < A; a += 32) { store_edge(crow + a, 0.0, 0.0f, 0u, kNoChild); qtree[(size_t)c * A + a] = 0.0f; }
+  // expand: fresh hot row for the new node (its cold words stay undefined until an edge is first visited)
+  HotEdge* crow = tree + (size_t)c * A;
+  for (int a = lane; a < A; a += 32) crow[a] = hot_empty();
 
   const float rew = reward_in[t];
   double value = (double)value_in[t];
@@ -385,18 +375,20 @@ __device__ __forceinline__ void expand_backup_tree(const PoolDev& p, const int t
   const double lo0 = lo, hi0 = hi;
 
   const int total = depth + 1;           // leaf ... root
+  // statistics of this lane's edge after the update (last chunk; reused for the child_Q refresh when total <= 32)
+  double Wk = 0.0, Rk = 0.0;
+  uint32_t Nk = 0, eidk = 0xffffffffu;
   for (int base = 0; base < total; base += 32) {
     const int i = base + lane;           // 0 = new leaf, depth = root
     const bool active = i < total;
     const int level = depth - i;
     double W = 0.0, R = 0.0;
-    uint32_t N = 0, child = kNoChild;
-    Edge* ep = nullptr;
+    uint32_t N = 0, child = kNoChild, eid = 0xffffffffu;
     if (active) {
       if (level > 0) {
-        ep = tree + pth[level - 1];
+        eid = pth[level - 1];
         if (i == 0) { R = (double)rew; child = (uint32_t)c; }
-        else { const Edge e = load_edge(ep); W = e.W; R = (double)e.reward; N = e.N; child = e.child; }
+        else { const uint32_t nc = tree[eid].x; W = ew[eid]; R = (double)er[eid]; N = nc & 0xffffu; child = nc >> 16; }
       } else {
         W = p.rootW[t]; N = (uint32_t)p.rootN[t]; R = p.root_reward[t];
       }
@@ -419,8 +411,14 @@ __device__ __forceinline__ void expand_backup_tree(const PoolDev& p, const int t
       const double q = __ddiv_rn(Wn, (double)Nn);
       const double mm = __dadd_rn(R, __dmul_rn(discount, board ? -q : q));
       mm_hi = mm; mm_lo = mm;
-      if (level > 0) store_edge(ep, Wn, (float)R, Nn, child);
-      else { p.rootW[t] = Wn; p.rootN[t] = (int)Nn; }
+      if (level > 0) {
+        ew[eid] = Wn;
+        if (i == 0) er[eid] = rew;                          // Node.reward is written once, at expansion
+        tree[eid].x = hot_word(Nn, child);
+      } else { p.rootW[t] = Wn; p.rootN[t] = (int)Nn; }
+      Wk = Wn; Rk = R; Nk = Nn; eidk = (level > 0) ? eid : 0xffffffffu;
+    } else {
+      eidk = 0xffffffffu;
     }
     hi = fmax(hi, warp_max_d(mm_hi));
     lo = fmin(lo, warp_min_d(mm_lo));
@@ -448,14 +446,15 @@ __device__ __forceinline__ void expand_backup_tree(const PoolDev& p, const int t
       // a bound moved: every cached value of this tree is stale.  Visited edges == expanded nodes 1..c
       for (int k = 1 + lane; k <= c; k += 32) {
         const uint32_t e = (uint32_t)npar[k] * (uint32_t)A + (uint32_t)nmov[k];
-        const Edge r = load_edge(tree + e);
-        qtree[e] = child_q(r.W, r.reward, r.N, dpq, norm, lo, range);
+        tree[e].y = __float_as_uint(child_q(ew[e], er[e], tree[e].x & 0xffffu, dpq, norm, lo, range));
       }
+    } else if (total <= 32) {
+      // the path's statistics are still in registers (one chunk): no reload
+      if (eidk != 0xffffffffu) tree[eidk].y = __float_as_uint(child_q(Wk, (float)Rk, Nk, dpq, norm, lo, range));
     } else {
       for (int k = lane; k < depth; k += 32) {
         const uint32_t e = pth[k];
-        const Edge r = load_edge(tree + e);
-        qtree[e] = child_q(r.W, r.reward, r.N, dpq, norm, lo, range);
+        tree[e].y = __float_as_uint(child_q(ew[e], er[e], tree[e].x & 0xffffu, dpq, norm, lo, range));
       }
     }
   }
@@ -481,18 +480,22 @@ backup_select_kernel(PoolDev p, const float* __restrict__ reward_in, const float
   double* sT = reinterpret_cast<double*>(smem_raw);
   const double* sR = p.T + (p.S + 2);
   float* sc = reinterpret_cast<float*>(sT + (p.S + 2)) + (size_t)warp * ((p.A + 3) & ~3);
+  __shared__ unsigned long long s_stats[4];
+  if (threadIdx.x < 4) s_stats[threadIdx.x] = 0;
   for (int i = threadIdx.x; i < p.S + 2; i += blockDim.x) sT[i] = p.T[i];
   __syncthreads();
-  if (t >= p.B) return;
-  if (p.timing && threadIdx.x == 0) {
-    const unsigned long long t0 = globaltimer_ns();
-    atomicMin(p.stats + 4, t0);
-    atomicMax(p.stats + 5, t0);
+  if (t < p.B) {
+    if (p.timing && threadIdx.x == 0) {
+      const unsigned long long t0 = globaltimer_ns();
+      atomicMin(p.stats + 4, t0);
+      atomicMax(p.stats + 5, t0);
+    }
+    expand_backup_tree(p, t, lane, reward_in, value_in);
+    __syncwarp();
+    select_tree<NCH>(p, t, lane, sT, sR, sc, s_stats);
+    if (p.timing && lane == 0) atomicMax(p.stats + 6, globaltimer_ns());
   }
-  expand_backup_tree(p, t, lane, reward_in, value_in);
-  __syncwarp();
-  select_tree<NCH>(p, t, lane, sT, sR, sc);
-  if (p.timing && lane == 0) atomicMax(p.stats + 6, globaltimer_ns());
+  flush_stats(p, s_stats);
 }
 
 // ---------------------------------------------------------------------------
@@ -508,8 +511,7 @@ constexpr int kThreadBlock = 64;
 __device__ __forceinline__ void select_tree_thread(const PoolDev& p, const int t, const double* sT, const double* sR,
                                                    const unsigned member) {
   const int A = p.A;
-  const Edge* tree = p.edges + (size_t)t * p.max_nodes * A;
-  const float* qtree = p.qcache + (size_t)t * p.max_nodes * A;
+  const HotEdge* tree = p.hot + (size_t)t * p.max_nodes * A;
   const double* __restrict__ P = p.prior + (size_t)t * A;
   const bool f32p = p.f32_prior[t] != 0;
   uint32_t* pth = p.path + (size_t)t * p.max_nodes;
@@ -531,8 +533,9 @@ __device__ __forceinline__ void select_tree_thread(const PoolDev& p, const int t
       nc[a] = (uint32_t)kNoChild << 16;
       s[a] = 0.0f;
       if (a < A) {
-        nc[a] = reinterpret_cast<const uint32_t*>(tree + (size_t)n * A + a)[3];
-        const float q = qtree[(size_t)n * A + a];
+        const HotEdge h = tree[(size_t)n * A + a];
+        nc[a] = h.x;
+        const float q = __uint_as_float(h.y);
         const int cn = (int)(nc[a] & 0xffffu);
         float u;
         if (cn > 0) {
@@ -595,10 +598,12 @@ __device__ __forceinline__ void expand_backup_tree_thread(const PoolDev& p, cons
   const int c = p.count[t];
   if (depth <= 0) return;
   if (c >= p.max_nodes) { atomicOr(p.error, MZ_DEVERR_POOL_FULL); return; }
-  Edge* tree = p.edges + (size_t)t * p.max_nodes * A;
-  float* qtree = p.qcache + (size_t)t * p.max_nodes * A;
+  const size_t tbase = (size_t)t * p.max_nodes * A;
+  HotEdge* tree = p.hot + tbase;
+  double* ew = p.ew + tbase;
+  float* er = p.er + tbase;
   const uint32_t* pth = p.path + (size_t)t * p.max_nodes;
-  for (int a = 0; a < A; ++a) { store_edge(tree + (size_t)c * A + a, 0.0, 0.0f, 0u, kNoChild); qtree[(size_t)c * A + a] = 0.0f; }
+  for (int a = 0; a < A; ++a) tree[(size_t)c * A + a] = hot_empty();
 
   const float rew = reward_in[t];
   double value = (double)value_in[t];
@@ -611,8 +616,9 @@ __device__ __forceinline__ void expand_backup_tree_thread(const PoolDev& p, cons
   // memory round trip each instead of one per level), then the value recurrence runs over them in order
   constexpr int CH = 8;
   for (int base = 0; base <= depth; base += CH) {          // i = 0: new leaf ... i = depth: root
-    uint32_t eid[CH];
-    int4 raw[CH];
+    uint32_t eid[CH], rnc[CH];
+    double rW[CH];
+    float rR[CH];
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
       const int level = depth - (base + j);
@@ -621,7 +627,10 @@ __device__ __forceinline__ void expand_backup_tree_thread(const PoolDev& p, cons
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
       const int i = base + j, level = depth - i;
-      raw[j] = (i > 0 && level > 0) ? *reinterpret_cast<const int4*>(tree + eid[j]) : make_int4(0, 0, 0, 0);
+      const bool ld = (i > 0 && level > 0);
+      rnc[j] = ld ? tree[eid[j]].x : 0u;
+      rW[j] = ld ? ew[eid[j]] : 0.0;
+      rR[j] = ld ? er[eid[j]] : 0.0f;
     }
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
@@ -631,10 +640,7 @@ __device__ __forceinline__ void expand_backup_tree_thread(const PoolDev& p, cons
       uint32_t N = 0, child = kNoChild;
       if (level > 0) {
         if (i == 0) { R = (double)rew; child = (uint32_t)c; }
-        else {
-          W = __hiloint2double(raw[j].y, raw[j].x); R = (double)__int_as_float(raw[j].z);
-          N = (uint32_t)raw[j].w & 0xffffu; child = (uint32_t)raw[j].w >> 16;
-        }
+        else { W = rW[j]; R = (double)rR[j]; N = rnc[j] & 0xffffu; child = rnc[j] >> 16; }
       } else {
         W = p.rootW[t]; N = (uint32_t)p.rootN[t]; R = p.root_reward[t];
       }
@@ -648,8 +654,11 @@ __device__ __forceinline__ void expand_backup_tree_thread(const PoolDev& p, cons
       const double mm = __dadd_rn(R, __dmul_rn(discount, board ? -q : q));
       hi = fmax(hi, mm);
       lo = fmin(lo, mm);
-      if (level > 0) store_edge(tree + eid[j], Wn, (float)R, Nn, child);
-      else { p.rootW[t] = Wn; p.rootN[t] = (int)Nn; }
+      if (level > 0) {
+        ew[eid[j]] = Wn;
+        if (i == 0) er[eid[j]] = rew;
+        tree[eid[j]].x = hot_word(Nn, child);
+      } else { p.rootW[t] = Wn; p.rootN[t] = (int)Nn; }
     }
   }
   int* npar = p.node_parent + (size_t)t * p.max_nodes;
@@ -668,20 +677,25 @@ __device__ __forceinline__ void expand_backup_tree_thread(const PoolDev& p, cons
   // child_Q cache: all visited edges (nodes 1..c) when a bound moved, else the path; same chunking
   const int cnt = moved ? c : depth;
   for (int base = 0; base < cnt; base += CH) {
-    uint32_t eid[CH];
-    int4 raw[CH];
+    uint32_t eid[CH], rnc[CH];
+    double rW[CH];
+    float rR[CH];
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
       const int k = base + j;
       eid[j] = k < cnt ? (moved ? (uint32_t)npar[k + 1] * (uint32_t)A + (uint32_t)nmov[k + 1] : pth[k]) : 0u;
     }
 #pragma unroll
-    for (int j = 0; j < CH; ++j) raw[j] = (base + j < cnt) ? *reinterpret_cast<const int4*>(tree + eid[j]) : make_int4(0, 0, 0, 0);
+    for (int j = 0; j < CH; ++j) {
+      const bool ld = base + j < cnt;
+      rnc[j] = ld ? tree[eid[j]].x : 0u;
+      rW[j] = ld ? ew[eid[j]] : 0.0;
+      rR[j] = ld ? er[eid[j]] : 0.0f;
+    }
 #pragma unroll
     for (int j = 0; j < CH; ++j)
       if (base + j < cnt)
-        qtree[eid[j]] = child_q(__hiloint2double(raw[j].y, raw[j].x), __int_as_float(raw[j].z),
-                                (uint32_t)raw[j].w & 0xffffu, p.dp, norm, lo, range);
+        tree[eid[j]].y = __float_as_uint(child_q(rW[j], rR[j], rnc[j] & 0xffffu, p.dp, norm, lo, range));
   }
 }
 
@@ -715,6 +729,8 @@ backup_select_confined_kernel(PoolDev p, const float* __restrict__ reward_in, co
   const int lane = threadIdx.x & 31;
   double* sT = reinterpret_cast<double*>(smem_raw);
   const double* sR = p.T + (p.S + 2);
+  __shared__ unsigned long long s_stats[4];
+  if (threadIdx.x < 4) s_stats[threadIdx.x] = 0;
   for (int i = threadIdx.x; i < p.S + 2; i += blockDim.x) sT[i] = p.T[i];
   __syncthreads();
   while (true) {
@@ -724,9 +740,9 @@ backup_select_confined_kernel(PoolDev p, const float* __restrict__ reward_in, co
     if (t >= (unsigned)p.B) break;
     expand_backup_tree(p, (int)t, lane, reward_in, value_in);
     __syncwarp();
-    select_tree<NCH>(p, (int)t, lane, sT, sR, nullptr);
+    select_tree<NCH>(p, (int)t, lane, sT, sR, nullptr, s_stats);
   }
-  __syncthreads();
+  flush_stats(p, s_stats);
   if (threadIdx.x == 0) {
     __threadfence();
     if (atomicAdd(p.work + 1, 1u) == gridDim.x - 1) {   // last CTA out: every CTA has left its loop
@@ -764,7 +780,7 @@ root_policy_kernel(PoolDev p, const uint8_t* __restrict__ mask, const double* __
   if (t >= p.B) return;
   const int A = p.A;
   double* x = reinterpret_cast<double*>(smem_raw) + (size_t)warp * A;
-  const Edge* row = p.edges + (size_t)t * p.max_nodes * A;
+  const HotEdge* row = p.hot + (size_t)t * p.max_nodes * A;
   const double T = temperature[t];
 
   int best_v = -1, best_a = 0;
@@ -781,7 +797,7 @@ root_policy_kernel(PoolDev p, const uint8_t* __restrict__ mask, const double* __
     const int a = a0 + lane;
     int v = -1;
     if (a < A) {
-      v = load_edge(row + a).N;
+      v = (int)(row[a].x & 0xffffu);
       if (mask != nullptr && mask[(size_t)t * A + a] == 0) v = 0;
       if (visits_out) visits_out[(size_t)t * A + a] = v;
       x[a] = (T > 0.0) ? (e_int ? pow_int_exact((uint32_t)v, (int)e) : pow((double)v, e)) : (double)v;
@@ -873,7 +889,7 @@ void layout(const mz_pool_config& c, size_t* offs, size_t* sizes, size_t* extra_
   const size_t B = c.num_trees, A = c.num_actions, n = (size_t)c.num_simulations + 1;
   Carve cv;
   auto put = [&](int which, size_t bytes) { offs[which] = cv.take(bytes); sizes[which] = bytes; };
-  put(MZ_VIEW_EDGES, B * n * A * sizeof(Edge));
+  put(MZ_VIEW_EDGES, B * n * A * sizeof(HotEdge));
   put(MZ_VIEW_PRIOR, B * A * 8);
   put(MZ_VIEW_ROOT_W, B * 8);
   put(MZ_VIEW_ROOT_N, B * 4);
@@ -895,7 +911,8 @@ void layout(const mz_pool_config& c, size_t* offs, size_t* sizes, size_t* extra_
   put(MZ_VIEW_VALUE, B * 4);
   put(MZ_VIEW_ERROR, 4);
   put(MZ_VIEW_STATS, 8 * 8);
-  put(MZ_VIEW_QCACHE, B * n * A * 4);
+  put(MZ_VIEW_EDGE_W, B * n * A * 8);
+  put(MZ_VIEW_EDGE_REWARD, B * n * A * 4);
   extra_offs[0] = cv.take((size_t)(c.num_simulations + 2) * 16); // pb_c table, then RN(1/n)
   extra_offs[1] = cv.take(B);                                     // same_player
   extra_offs[2] = cv.take(B * 8);                                 // root_reward
@@ -928,8 +945,9 @@ PoolDev pool_dev(const mz_pool* h) {
   d.board = h->cfg.is_board_game;
   d.discount = h->cfg.discount;
   d.dp = h->cfg.discount * (h->cfg.is_board_game ? -1.0 : 1.0);   // mcts.py:169-174: discount * p
-  d.edges = (Edge*)h->view_ptr[MZ_VIEW_EDGES];
-  d.qcache = (float*)h->view_ptr[MZ_VIEW_QCACHE];
+  d.hot = (HotEdge*)h->view_ptr[MZ_VIEW_EDGES];
+  d.ew = (double*)h->view_ptr[MZ_VIEW_EDGE_W];
+  d.er = (float*)h->view_ptr[MZ_VIEW_EDGE_REWARD];
   d.prior = (double*)h->view_ptr[MZ_VIEW_PRIOR];
   d.rootW = (double*)h->view_ptr[MZ_VIEW_ROOT_W];
   d.rootN = (int*)h->view_ptr[MZ_VIEW_ROOT_N];
@@ -1040,6 +1058,8 @@ extern "C" int mz_pool_create(const mz_pool_config* cfg, const double* pb_c_tabl
     e = cudaMemcpy(h->pb_c_table + (h->S + 2), rcp.data(), rcp.size() * 8, cudaMemcpyHostToDevice);
   }
   if (e == cudaSuccess) e = cudaMemset(h->work, 0, 16);
+  if (e == cudaSuccess) e = cudaMemset(h->view_ptr[MZ_VIEW_EDGE_W], 0, sizes[MZ_VIEW_EDGE_W]);
+  if (e == cudaSuccess) e = cudaMemset(h->view_ptr[MZ_VIEW_EDGE_REWARD], 0, sizes[MZ_VIEW_EDGE_REWARD]);
   if (e == cudaSuccess) e = cudaMemset(h->view_ptr[MZ_VIEW_ERROR], 0, 4);
   if (e == cudaSuccess) e = cudaMemset(h->view_ptr[MZ_VIEW_STATS], 0, 64);
   if (e == cudaSuccess) e = cudaMemset(h->view_ptr[MZ_VIEW_LEAF_DEPTH], 0, sizes[MZ_VIEW_LEAF_DEPTH]);

@@ -12,8 +12,9 @@ struct PoolDev {
   int B, A, S, max_nodes;
   int board;
   double discount, dp;
-  Edge* edges;
-  float* qcache;     // f32 [B][max_nodes][A]: Node.child_Q of every edge as select reads it (0 for unvisited edges)
+  HotEdge* hot;      // [B][max_nodes][A] {child << 16 | N, child_Q}: all the descent reads
+  double* ew;        // f64 [B][max_nodes][A] Node.W        (backup only; defined where N > 0)
+  float* er;         // f32 [B][max_nodes][A] Node.reward   (backup only; defined where N > 0)
   double* prior;
   double* rootW;
   int* rootN;
@@ -42,14 +43,7 @@ PoolDev pool_dev(const mz_pool* h);       // mcts.cu
 
 constexpr unsigned kFull = 0xffffffffu;
 
-__device__ __forceinline__ void store_edge(Edge* p, double W, float reward, uint32_t N, uint32_t child) {
-  int4 r;
-  r.x = __double2loint(W);
-  r.y = __double2hiint(W);
-  r.z = __float_as_int(reward);
-  r.w = (int)((N & 0xffffu) | (child << 16));
-  *reinterpret_cast<int4*>(p) = r;
-}
+__device__ __forceinline__ HotEdge hot_empty() { return make_uint2((uint32_t)kNoChild << 16, 0u); }
 
 // ---------------------------------------------------------------------------
 // numpy pairwise summation (np.sum of a contiguous 1-D array), sequential
@@ -160,9 +154,8 @@ __device__ __forceinline__ void root_setup_tree(const PoolDev& p, int t, int lan
     }
   }
   // root expansion: row 0 zeroed, no children yet
-  Edge* row = p.edges + (size_t)t * p.max_nodes * A;
-  float* qrow = p.qcache + (size_t)t * p.max_nodes * A;
-  for (int a = lane; a < A; a += 32) { store_edge(row + a, 0.0, 0.0f, 0u, kNoChild); qrow[a] = 0.0f; }
+  HotEdge* row = p.hot + (size_t)t * p.max_nodes * A;
+  for (int a = lane; a < A; a += 32) row[a] = hot_empty();
   if (lane == 0) {
     p.rootW[t] = 0.0;
     p.rootN[t] = 0;

@@ -83,7 +83,7 @@ class SearchPool:
 
     # -- typed views into the arena ------------------------------------------
     _VIEW_TYPES = {
-        'EDGES': (torch.uint8, 16), 'PRIOR': (torch.float64, None), 'ROOT_W': (torch.float64, None),
+        'EDGES': (torch.uint8, 8), 'EDGE_W': (torch.float64, None), 'EDGE_REWARD': (torch.float32, None), 'PRIOR': (torch.float64, None), 'ROOT_W': (torch.float64, None),
         'ROOT_N': (torch.int32, None), 'MINMAX': (torch.float64, 2), 'COUNT': (torch.int32, None),
         'LEAF_PARENT': (torch.int32, None), 'LEAF_ACTION': (torch.int32, None), 'LEAF_DEPTH': (torch.int32, None),
         'SRC_SLOT': (torch.int32, None), 'DST_SLOT': (torch.int32, None), 'PATH': (torch.int32, None),
@@ -91,7 +91,6 @@ class SearchPool:
         'RNG_KEY': (torch.int32, 624),
         'RNG_POS': (torch.int32, None), 'HIDDEN': (torch.uint8, None), 'REWARD': (torch.float32, None),
         'VALUE': (torch.float32, None), 'ERROR': (torch.int32, None), 'STATS': (torch.int64, None),
-        'QCACHE': (torch.float32, None),
     }
 
     def view(self, name: str) -> torch.Tensor:
@@ -183,8 +182,13 @@ class SearchPool:
         same shape as ``oracle.mcts_oracle.SearchTrace``."""
         A, n = self.A, self.S + 1
         count = int(self.view('COUNT')[t].cpu())
-        edges = self.view('EDGES').view(self.B, n * A * 16)[t].cpu().numpy()
-        rec = edges.view(np.dtype([('W', '<f8'), ('R', '<f4'), ('N', '<u2'), ('child', '<u2')])).reshape(n, A)
+        hot = self.view('EDGES').view(self.B, n * A * 8)[t].cpu().numpy().view(
+            np.dtype([('N', '<u2'), ('child', '<u2'), ('Q', '<f4')])).reshape(n, A)
+        rec = np.zeros((n, A), dtype=np.dtype([('W', '<f8'), ('R', '<f4'), ('N', '<u2'), ('child', '<u2')]))
+        rec['N'], rec['child'] = hot['N'], hot['child']
+        visited = hot['N'] > 0                            # the cold words of an edge are defined once it was visited
+        rec['W'] = np.where(visited, self.view('EDGE_W').view(self.B, n * A)[t].cpu().numpy().reshape(n, A), 0.0)
+        rec['R'] = np.where(visited, self.view('EDGE_REWARD').view(self.B, n * A)[t].cpu().numpy().reshape(n, A), 0.0)
         parent = self.view('NODE_PARENT').view(self.B, n)[t].cpu().numpy()[:count].copy()
         move = self.view('NODE_MOVE').view(self.B, n)[t].cpu().numpy()[:count].copy()
         N = np.zeros(count, np.int32); W = np.zeros(count, np.float64); R = np.zeros(count, np.float64)

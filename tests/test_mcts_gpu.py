@@ -235,8 +235,10 @@ def test_full_size_properties_and_sampled_replay(B, A, S, alpha):
     pool.check_errors()
     # --- invariants over all trees
     assert (pool.view('COUNT') == S + 1).all() and (pool.view('ROOT_N') == S).all()
-    rec = pool.view('EDGES').view(B, (S + 1) * A, 16).cpu().numpy().view(
-        np.dtype([('W', '<f8'), ('R', '<f4'), ('N', '<u2'), ('child', '<u2')])).reshape(B, S + 1, A)
+    hot = pool.view('EDGES').view(B, (S + 1) * A, 8).cpu().numpy().view(
+        np.dtype([('N', '<u2'), ('child', '<u2'), ('Q', '<f4')])).reshape(B, S + 1, A)
+    rec = {'N': hot['N'], 'child': hot['child'],
+           'W': np.where(hot['N'] > 0, pool.view('EDGE_W').view(B, S + 1, A).cpu().numpy(), 0.0)}
     root_child_visits = rec['N'][:, 0, :].astype(np.int64)
     assert (root_child_visits.sum(1) == S).all()                      # every simulation passes one root child
     has_child = rec['child'] != 0xFFFF
@@ -378,8 +380,8 @@ def test_fused_and_confined_tree_kernels_equal_the_separate_launches(A, S, board
                 pool.expand_backup(r, v)
             torch.cuda.synchronize()
         pool.check_errors()
-        names = ('EDGES', 'QCACHE', 'MINMAX', 'ROOT_W', 'ROOT_N', 'COUNT', 'NODE_PARENT', 'NODE_MOVE', 'RNG_KEY',
-                 'RNG_POS', 'PRIOR')
+        names = ('EDGES', 'EDGE_W', 'EDGE_REWARD', 'MINMAX', 'ROOT_W', 'ROOT_N', 'COUNT', 'NODE_PARENT', 'NODE_MOVE',
+                 'RNG_KEY', 'RNG_POS', 'PRIOR')
         return {k: pool.view(k).cpu().numpy().view(np.uint8).copy() for k in names}
 
     want = run('separate')

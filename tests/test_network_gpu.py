@@ -252,7 +252,7 @@ def test_fused_root_epilogue_equals_the_separate_launches(family, noise_mode, mo
         launches = mz._lib.lib().mz_launch_count() - n0
         torch.cuda.synchronize()
         plan.pool.check_errors()
-        names = ('EDGES', 'QCACHE', 'PRIOR', 'MINMAX', 'ROOT_W', 'ROOT_N', 'COUNT', 'NODE_PARENT', 'NODE_MOVE',
+        names = ('EDGES', 'EDGE_W', 'EDGE_REWARD', 'PRIOR', 'MINMAX', 'ROOT_W', 'ROOT_N', 'COUNT', 'NODE_PARENT', 'NODE_MOVE',
                  'RNG_KEY', 'RNG_POS')
         state = {k: plan.pool.view(k).cpu().numpy().view(np.uint8).copy() for k in names}
         state['noise'] = plan.noise.cpu().numpy().view(np.uint8).copy()
