@@ -263,3 +263,16 @@ def test_fused_root_epilogue_equals_the_separate_launches(family, noise_mode, mo
     for k in sep:
         assert np.array_equal(sep[k], fus[k]), f'{family}/{noise_mode}: {k} differs'
     assert n_fus == n_sep - (2 if noise_mode == 'device' else 1)
+
+
+def test_fp16_networks_rarely_change_a_search():
+    """Search-level effect of fp16 tensor-core inference: 256 Tic-Tac-Toe searches with the
+    checkpoint network, engine vs the oracle search driven by the fp32 torch network on the same inputs, noise and
+    RNG streams.  Bound (measured: see profiles/r2_fp16_search_stats.json): the sampled action differs in <= 5 % of
+    the trees, the mean L1 distance between the visit policies is <= 0.05."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), '..', 'tools'))
+    from fp16_search_stats import search_stats
+    s = search_stats('tictactoe', 256)
+    print(s)
+    assert s['sampled_action_differs'] <= 0.05 and s['mean_l1_visit_policy'] <= 0.05
