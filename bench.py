@@ -480,6 +480,40 @@ def measure_workload(spec, args, dev, world, rank, steps, warmup, min_seconds=0.
                               'frac': ach / tf_peak, 'reference_graph_flops': flops * Bp})
     roofline = dict(roof[dominant])
     roofline.update({'kernel': dominant, 'traffic': None, 'peak_source': peak_src})
+    if spec['kind'] == 'mlp':
+        # what a search of the MLP nets actually launches: ONE persistent kernel for all S simulations
+        # (mz_search_run); the three kernels above are the per-simulation launch chain it replaces, kept as a
+        # diagnostic.  Timed eagerly with CUDA events around the launch.
+        sm = []
+        with torch.cuda.device(dev):
+            for _ in range(max(3, reps)):
+                _lib.check(lib.mz_net_initial_search(eng['handle'], ppool.handle, Bp, pplan.obs.data_ptr(), None, None,
+                                                     hidden, pplan.root_slots.data_ptr(), pplan.pi0.data_ptr(),
+                                                     pplan.v0.data_ptr(), 2, pplan.noise.data_ptr(),
+                                                     float(np.float32(cfg.root_dirichlet_alpha)),
+                                                     float(cfg.root_exploration_eps), pplan.mask.data_ptr(),
+                                                     pplan.players.data_ptr(), stream))
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n0 = lib.mz_launch_count()
+                e0.record()
+                _lib.check(lib.mz_search_run(eng['handle'], ppool.handle, stream))
+                e1.record()
+                n_launch = int(lib.mz_launch_count() - n0)
+                torch.cuda.synchronize()
+                sm.append(e0.elapsed_time(e1))
+        search_ms = min(sm)
+        if n_launch == 1:
+            ab = sum(algorithmic_bytes_per_launch(n, spec, Bp, A, S, mean_depth, pool.hidden_bytes, True) for n in names) * S
+            ach = flops * Bp * S / (search_ms * 1e-3) / 1e12
+            roofline = {'kernel': 'mlp_tc_kernel<search>: one persistent launch per search (thread-per-tree select / backup '
+                                  'around the tcgen05 MLP chain, trees owned by their CTA for all simulations)',
+                        'bound': 'tensor', 'achieved': ach, 'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': ach / tf_peak,
+                        'traffic': None, 'avg_launch_us': search_ms * 1e3, 'us_per_simulation': search_ms * 1e3 / S,
+                        'algorithmic_bytes_per_launch': ab, 'hbm_achieved_gbs': ab / (search_ms * 1e-3) / 1e9,
+                        'hbm_frac': ab / (search_ms * 1e-3) / 1e9 / hbm_peak,
+                        'note': 'latency-bound: 0.18-0.40 MFLOP and a few hundred bytes per row and simulation',
+                        'peak_source': peak_src}
+            roof = {'search_kernel': dict(roofline), 'launch_chain_diagnostic': roof}
     if spec['kind'] != 'mlp' and prof_n[0] > 0:
         # the dominant KERNEL is the tcgen05 3x3 convolution.  One launch runs a whole tower pair as a dataflow
         # of layers (33 convs for a recurrent inference): algorithmic flops per layer = the reference graph's

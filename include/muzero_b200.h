@@ -215,6 +215,20 @@ int mz_net_recurrent(mz_net* net, int32_t batch, const void* hidden_in, const in
                      const int32_t* action, void* hidden_out, const int32_t* dst_index,
                      float* reward, float* value, float* pi_probs, mz_stream stream);
 
+/* All num_simulations simulations of the pool's trees -- select -> recurrent_inference -> expand + backup, the loop of
+ * mcts.py:372-390 -- after the roots were prepared (mz_net_initial_search or mz_search_reset); leaves the pool as the
+ * last mz_expand_backup would.  MuZeroMLPNet with up to 12 actions: ONE launch of a persistent kernel whose CTAs own
+ * their trees for the whole search (the thread that owns row i of a tensor-core tile also runs tree i's descent and
+ * backup; no per-simulation launch, prologue or global round trip for the leaf action / reward / value).  Other
+ * networks: the per-simulation launch chain (mz_select, then S x (mz_net_recurrent, mz_expand_backup[_select])),
+ * enqueued here.  Results are bit-identical either way. */
+int mz_search_run(mz_net* net, mz_pool* pool, mz_stream stream);
+
+/* enable = 0: mz_search_run always enqueues the per-simulation launch chain (scheduling knob, no effect on results;
+ * the parity tests pin the one-launch kernel to the chain bit for bit).  Default: enabled.  MZ_NO_FUSED_SEARCH=1 in
+ * the environment disables it process-wide. */
+int mz_net_set_fused_search(mz_net* net, int32_t enable);
+
 /* Cap the grid of the net's persistent kernels (0 = one CTA per SM).  Two engines that are driven from two
  * streams (sub-batches of one search) can each be given half of the SMs so that their towers run side by side:
  * small batches are bound by the layer-to-layer tile dependencies, not by SM count. */

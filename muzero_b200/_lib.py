@@ -67,6 +67,8 @@ PROTOTYPES = {
     'mz_net_initial_search': (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, C.c_int32, _P, C.c_double,
                                         C.c_double, _P, _P, _P]),
     'mz_net_recurrent': (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'mz_search_run': (C.c_int, [_P, _P, _P]),
+    'mz_net_set_fused_search': (C.c_int, [_P, C.c_int32]),
     'mz_net_set_cta_limit': (C.c_int, [_P, C.c_int32]),
     'mz_net_profile_begin': (C.c_int, [_P]),
     'mz_net_profile_end': (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

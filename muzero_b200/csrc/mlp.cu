@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "net.cuh"
 #include "umma.cuh"
+#include "tree_thread.cuh"
 #include <cuda_fp16.h>
 #include <cstdlib>
 
@@ -375,7 +376,36 @@ __device__ __forceinline__ void gather_tile(const MlpTcParams& p, int tile, int 
   }
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1) mlp_recurrent_tc_kernel(const __grid_constant__ MlpTcParams p) {
+// the same for one row whose slot is already known (persistent search kernel: the thread just selected the leaf)
+__device__ __forceinline__ void gather_row(const float* hidden_in, size_t slot, bool live, int row, uint32_t sIn_a) {
+  const float4* src = reinterpret_cast<const float4*>(hidden_in + slot * 64);
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (live) { a = src[2 * g]; b = src[2 * g + 1]; }
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sIn_a + (uint32_t)(g * 128 + row) * 16),
+                 "r"(pack_h2(a.x, a.y)), "r"(pack_h2(a.z, a.w)), "r"(pack_h2(b.x, b.y)), "r"(pack_h2(b.z, b.w)) : "memory");
+  }
+}
+
+// What the persistent per-search form of the kernel needs besides the network: the pool whose trees it searches.
+struct SearchArgs {
+  PoolDev pool;
+  int sims;                           // simulations to run (the pool's num_simulations)
+};
+
+// kSearch = false: recurrent_inference of `batch` rows (one launch per simulation of the launch-chain search, or a
+// stand-alone network call).
+// kSearch = true: ONE launch per SEARCH.  A CTA owns the trees of its 128-row tiles for all simulations: the thread that
+// owns row i of the tile also owns tree i and runs its pUCT descent and its backup (tree_thread.cuh: thread-per-tree
+// forms of the tree kernels, TA = compile-time bound on the number of actions) around the tensor-core chain
+//   [backup of simulation s-1] -> select -> gather the leaf's parent state -> transition -> reward -> value -> ...
+// so a simulation costs no launch, no prologue (TMEM allocation, bias / action-table staging, barrier set-up happen
+// once per search) and the leaf action, reward and value never leave the thread's registers.  Trees of different
+// CTAs never interact, so there is no inter-CTA synchronisation at all.
+template <bool kSearch, int TA>
+__global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const __grid_constant__ MlpTcParams p,
+                                                               const __grid_constant__ SearchArgs sa) {
   extern __shared__ __align__(1024) unsigned char tsm[];
   unsigned char* sIn = tsm;                       // [8][128][16]  h_in   (fp16, K-major core matrices)
   unsigned char* sRaw = sIn + 16384;              // h_raw
@@ -388,12 +418,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_recurrent_tc_kernel(const _
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar_mma + 1);
   float* sB1 = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_holder + 4) + 15) & ~(uintptr_t)15);   // [4][P] first-layer biases
   float* sTab = sB1 + 4 * p.P;                                      // [A][P] action columns (when they fit)
+  // search form: pb_c table (float64 [S + 2]) and the action each row's thread selected (read by the helper warps)
+  double* sT = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sTab + (p.tab_in_smem ? p.A * (p.P + 4) : 0)) + 15) & ~(uintptr_t)15);
+  int* sAct = reinterpret_cast<int*>(sT + (kSearch ? sa.sims + 2 : 0));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int dbg_n = 0;
   auto stamp = [&]() { if (p.dbg && blockIdx.x == 0 && tid == 0 && dbg_n < 60) p.dbg[dbg_n++] = clock64(); };
   stamp();
   // the first tile's leaf gather (two dependent global round trips) overlaps the staging below and the TMEM allocation
-  const int nsplit = p.nsplit, part = (int)blockIdx.x % nsplit;
+  const int nsplit = kSearch ? 1 : p.nsplit, part = (int)blockIdx.x % nsplit;
+  const int nsims = kSearch ? sa.sims : 1;
   // the nets this CTA runs, in order: everything, or transition + its share of the heads
   uint32_t net_list = 0;              // 4 bits per entry (an indexed array would live in local memory)
   int nn = 0;
@@ -402,7 +436,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_recurrent_tc_kernel(const _
   auto net_at = [&](int ni) { return (int)((net_list >> (4 * ni)) & 15u); };
   const int bpn = 2 * p.chunks;       // weight blocks per net
   const int first_tile = (int)blockIdx.x / nsplit, tile_step = (int)gridDim.x / nsplit;
-  if (tid < 128 && first_tile * kTcRows < p.batch) gather_tile(p, first_tile, tid, smem_u32(sIn));
+  if (!kSearch && tid < 128 && first_tile * kTcRows < p.batch) gather_tile(p, first_tile, tid, smem_u32(sIn));
+  if (kSearch)
+    for (int i = tid; i < sa.sims + 2; i += kTcThreads) sT[i] = sa.pool.T[i];
   // first-layer biases and the action table are read by every row of every tile: stage them once per CTA
   // (from global they cost an exposed L2 round trip per 32-column chunk of every epilogue)
   for (int i = tid; i < p.nnets * p.P; i += kTcThreads) sB1[i] = p.b1[i / p.P][i % p.P];
@@ -430,6 +466,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_recurrent_tc_kernel(const _
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = first_tile; tile < ntiles; tile += tile_step)
+       for (int sim = 0; sim < nsims; ++sim)
         for (int ni = 0; ni < nn; ++ni)
           for (int b = net_at(ni) * bpn; b < (net_at(ni) + 1) * bpn; ++b, ++it) {
             const uint32_t s = it % kTcSlots, ph = (it / kTcSlots) & 1;
@@ -472,16 +509,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_recurrent_tc_kernel(const _
       tc_fence_after();
     };
 
+    TreeThreadStats tstats;
+    const double* sR = kSearch ? sa.pool.T + (sa.sims + 2) : nullptr;      // RN(1/n), read through L1
     for (int tile = first_tile; tile < ntiles; tile += tile_step) {
       const int grow = tile * kTcRows + row;
       const bool live = grow < p.batch;
-      // leaf gather (the CTA's first tile was gathered before the prologue barrier)
-      if (owner && tile != first_tile) gather_tile(p, tile, row, sIn_a);
-      int act = live ? p.action[grow] : 0;
-      act = min(max(act, 0), p.A - 1);
+      float rew_reg = 0.0f, val_reg = 0.0f;       // reward / value of this row's last inference (search form)
+      const int node0 = (kSearch && owner && live) ? sa.pool.count[grow] : 0;     // nodes of the tree so far (1 after a reset)
+     for (int sim = 0; sim < nsims; ++sim) {
+      int act;
+      size_t dst_slot = 0;
+      if constexpr (kSearch) {
+        // tree phase: this thread's tree -- backup of the previous simulation, then the descent of this one
+        act = 0;
+        if (owner) {
+          size_t src_slot = 0;
+          if (live) {
+            if (sim > 0) expand_backup_tree_thread(sa.pool, grow, rew_reg, val_reg);
+            const int2 leaf = select_tree_thread<TA>(sa.pool, grow, sT, sR, tstats);
+            act = leaf.y;
+            src_slot = (size_t)grow * sa.pool.max_nodes + leaf.x;
+            dst_slot = (size_t)grow * sa.pool.max_nodes + min(node0 + sim, sa.pool.max_nodes - 1);
+          }
+          gather_row(p.hidden_in, src_slot, live, row, sIn_a);
+          sAct[row] = act;
+        }
+      } else {
+        // leaf gather (the CTA's first tile was gathered before the prologue barrier)
+        if (owner && tile != first_tile) gather_tile(p, tile, row, sIn_a);
+        act = live ? p.action[grow] : 0;
+      }
       fence_proxy_async();
       tc_fence_before();
       bar128();
+      if (kSearch && !owner) act = sAct[row];
+      act = min(max(act, 0), p.A - 1);
       stamp();
 
       for (int ni = 0; ni < nn; ++ni) {
@@ -566,7 +628,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_recurrent_tc_kernel(const _
                          "r"(pack_h2(h[8 * g + 4], h[8 * g + 5])), "r"(pack_h2(h[8 * g + 6], h[8 * g + 7])) : "memory");
           stamp();
           if (live && part == 0) {
-            const size_t slot = p.dst_index ? (size_t)p.dst_index[grow] : (size_t)grow;
+            const size_t slot = kSearch ? dst_slot : (p.dst_index ? (size_t)p.dst_index[grow] : (size_t)grow);
             float4* dst = reinterpret_cast<float4*>(p.hidden_out + slot * 64);
 #pragma unroll
             for (int g = 0; g < 16; ++g) dst[g] = make_float4(h[4 * g], h[4 * g + 1], h[4 * g + 2], h[4 * g + 3]);
@@ -581,7 +643,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_recurrent_tc_kernel(const _
 #pragma unroll
           for (int e = 0; e < 32; ++e) l[e] = __uint_as_float(r[e]) + (e < S ? __ldg(b2 + e) : 0.0f);
           const float out = support_scalar_regs(l, S);
-          if (live) (net == 1 ? p.reward : p.value)[grow] = out;
+          if (kSearch) { if (net == 1) rew_reg = out; else val_reg = out; }
+          else if (live) (net == 1 ? p.reward : p.value)[grow] = out;
         } else {
           // policy: softmax over A logits spread over Apad TMEM columns (three passes over TMEM)
           float m = -INFINITY, den = 0.0f;
@@ -606,6 +669,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_recurrent_tc_kernel(const _
         tc_fence_before();
         bar128();
         stamp();
+      }
+     }   // simulations
+      if (kSearch && owner && live) expand_backup_tree_thread(sa.pool, grow, rew_reg, val_reg);    // the last simulation
+    }
+    if constexpr (kSearch) {
+      // statistics of this CTA's descents: one atomic per warp and counter
+      if (owner) {
+        unsigned n_live = 0;
+        for (int tile = first_tile; tile < ntiles; tile += tile_step) n_live += (tile * kTcRows + row < p.batch) ? 1u : 0u;
+        const unsigned d = __reduce_add_sync(0xffffffffu, tstats.depth), dr = __reduce_add_sync(0xffffffffu, tstats.draws);
+        const unsigned tw = __reduce_add_sync(0xffffffffu, tstats.twists), nl = __reduce_add_sync(0xffffffffu, n_live);
+        if (lane == 0) {
+          atomicAdd(sa.pool.stats + 0, (unsigned long long)d);
+          atomicAdd(sa.pool.stats + 1, (unsigned long long)nl * (unsigned long long)sa.sims);
+          if (dr) atomicAdd(sa.pool.stats + 2, (unsigned long long)dr);
+          if (tw) atomicAdd(sa.pool.stats + 3, (unsigned long long)tw);
+        }
       }
     }
   }
@@ -646,6 +726,7 @@ struct MlpNet : NetImpl {
   int tc_blocks_no_policy = 0, tc_blocks_policy = 0, num_sms = 148;
   size_t tc_smem = 0;
 
+  int search(mz_pool* pool, cudaStream_t st) override;
   int initial(int batch, const float* obs, void* hidden_out, const int32_t* dst_index, float* pi_probs,
               float* value, cudaStream_t st) override {
     prof_mark(kProfMlp, st);
@@ -673,7 +754,9 @@ struct MlpNet : NetImpl {
       q.dbg = nullptr;
       if (debug) { cudaMalloc(&q.dbg, 64 * sizeof(long long)); cudaMemset(q.dbg, 0, 64 * sizeof(long long)); }
       prof_mark(kProfMlp, st);
-      mlp_recurrent_tc_kernel<<<q.nsplit == 2 ? 2 * ntiles : (ntiles < num_sms ? ntiles : num_sms), kTcThreads, tc_smem, st>>>(q);
+      SearchArgs none;
+      none.sims = 0;
+      mlp_tc_kernel<false, 4><<<q.nsplit == 2 ? 2 * ntiles : (ntiles < num_sms ? ntiles : num_sms), kTcThreads, tc_smem, st>>>(q, none);
       prof_mark(-1, st);
       MZ_LAUNCH_CHECK("mlp_recurrent_tc_kernel");
       if (debug) {   // measurement aid: cycle stamps of CTA 0 (start, prologue, gather, then per net: MMA1, epi1, MMA2, epi2; end)
@@ -695,6 +778,33 @@ struct MlpNet : NetImpl {
     return MZ_OK;
   }
 };
+
+int MlpNet::search(mz_pool* pool, cudaStream_t st) {
+  static const bool off = getenv("MZ_NO_FUSED_SEARCH") != nullptr;
+  if (off || !fused_search || !tc || pool->A != d.A || pool->A > 12 || pool->cfg.hidden_bytes != d.HD * 4) return 1;
+  MlpTcParams q = tcp;
+  q.batch = pool->B;
+  q.hidden_in = (const float*)pool->view_ptr[MZ_VIEW_HIDDEN];
+  q.hidden_out = (float*)pool->view_ptr[MZ_VIEW_HIDDEN];
+  q.src_index = nullptr; q.dst_index = nullptr; q.action = nullptr; q.reward = nullptr; q.value = nullptr; q.pi = nullptr;
+  q.nnets = 3;                       // the search never reads the recurrent policy (mcts.py:386)
+  q.nblk = tc_blocks_no_policy;
+  q.nsplit = 1;
+  q.dbg = nullptr;
+  const size_t smem_need = tc_smem + (size_t)(pool->S + 2) * 8 + kTcRows * sizeof(int) + 64;
+  if (smem_need > 227 * 1024) return 1;
+  SearchArgs sa;
+  sa.pool = pool_dev(pool);
+  sa.sims = pool->S;
+  const int ntiles = (pool->B + kTcRows - 1) / kTcRows;
+  const int grid = ntiles < num_sms ? ntiles : num_sms;
+  prof_mark(kProfMlp, st);
+  if (pool->A <= 4) mlp_tc_kernel<true, 4><<<grid, kTcThreads, smem_need, st>>>(q, sa);
+  else mlp_tc_kernel<true, 12><<<grid, kTcThreads, smem_need, st>>>(q, sa);
+  prof_mark(-1, st);
+  MZ_LAUNCH_CHECK("mlp_tc_kernel<search>");
+  return MZ_OK;
+}
 
 static int mlp_dims(const mz_net_config& c, int* in_dim) {
   MZ_CHECK_ARG(c.hidden_dim > 0 && c.hidden_dim % 4 == 0, "hidden_dim must be a positive multiple of 4, got %d",
@@ -823,7 +933,10 @@ int mlp_create(const mz_net_config& c, const float* const* w, int nw, void* aren
       int dev = 0;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&net->num_sms, cudaDevAttrMultiProcessorCount, dev);
-      MZ_CUDA(cudaFuncSetAttribute(mlp_recurrent_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)net->tc_smem));
+      const int smem_cap = 227 * 1024;
+      MZ_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));
+      MZ_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));
+      MZ_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<true, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));
     }
   }
   net->smem = smem_bytes(d);

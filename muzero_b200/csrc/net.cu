@@ -112,6 +112,41 @@ extern "C" int mz_net_recurrent(mz_net* net, int32_t batch, const void* hidden_i
                               (cudaStream_t)stream);
 }
 
+extern "C" int mz_search_run(mz_net* net, mz_pool* pool, mz_stream stream) {
+  MZ_CHECK_ARG(net && pool, "NULL argument");
+  MZ_CHECK_ARG(pool->cfg.hidden_bytes > 0, "the pool has no hidden-state slots (it was made for an external network)");
+  MZ_CHECK_ARG(pool->B <= net->max_batch, "pool has %d trees, the net was created for batches of at most %d", pool->B,
+               net->max_batch);
+  MZ_CHECK_ARG(net->cfg.num_actions == pool->A, "network has %d actions, pool %d", net->cfg.num_actions, pool->A);
+  int rc = net->impl->search(pool, (cudaStream_t)stream);
+  if (rc <= 0) {
+    if (rc == MZ_OK) pool->selected = 0;
+    return rc;
+  }
+  // launch chain: select, then S x (recurrent inference, expand + backup [+ select of the next simulation])
+  void* hidden = pool->view_ptr[MZ_VIEW_HIDDEN];
+  const int32_t* src = (const int32_t*)pool->view_ptr[MZ_VIEW_SRC_SLOT];
+  const int32_t* dst = (const int32_t*)pool->view_ptr[MZ_VIEW_DST_SLOT];
+  const int32_t* act = (const int32_t*)pool->view_ptr[MZ_VIEW_LEAF_ACTION];
+  float* rew = (float*)pool->view_ptr[MZ_VIEW_REWARD];
+  float* val = (float*)pool->view_ptr[MZ_VIEW_VALUE];
+  if ((rc = mz_select(pool, stream))) return rc;
+  for (int sim = 0; sim < pool->S; ++sim) {
+    // pi_probs = NULL: the search never reads the recurrent policy (mcts.py:386)
+    if ((rc = mz_net_recurrent(net, pool->B, hidden, src, act, hidden, dst, rew, val, nullptr, stream))) return rc;
+    rc = sim + 1 < pool->S ? mz_expand_backup_select(pool, nullptr, nullptr, stream)
+                           : mz_expand_backup(pool, nullptr, nullptr, stream);
+    if (rc) return rc;
+  }
+  return MZ_OK;
+}
+
+extern "C" int mz_net_set_fused_search(mz_net* net, int32_t enable) {
+  MZ_CHECK_ARG(net, "NULL argument");
+  net->impl->fused_search = enable != 0;
+  return MZ_OK;
+}
+
 extern "C" int mz_net_set_cta_limit(mz_net* net, int32_t max_ctas) {
   MZ_CHECK_ARG(net && max_ctas >= 0, "bad argument");
   net->impl->cta_limit = max_ctas;

@@ -13,6 +13,7 @@ enum ProfClass { kProfConv = 0, kProfHead = 1, kProfPack = 2, kProfMlp = 3, kPro
 struct NetImpl {
   bool profiling = false;
   int cta_limit = 0;                    // persistent kernels use at most this many CTAs (0: one per SM)
+  bool fused_search = true;             // mz_search_run may use the one-launch-per-search kernel (mz_net_set_fused_search)
   const RootSetup* pending_root = nullptr;   // set around initial() by mz_net_initial_search: the policy epilogue
                                              // also prepares the search roots (Dirichlet, mask, renormalise, reset)
   std::vector<cudaEvent_t> prof_ev;     // pairs (begin, end)
@@ -34,6 +35,9 @@ struct NetImpl {
     set_error("mz_net_initial_frames: this network family takes float32 observations");
     return MZ_EINVAL;
   }
+  // all simulations of a search in ONE launch (persistent kernel that owns the trees); > 0: this net / pool is not
+  // covered, the caller enqueues the per-simulation launch chain instead
+  virtual int search(mz_pool*, cudaStream_t) { return 1; }
   virtual int recurrent(int batch, const void* hidden_in, const int32_t* src_index, const int32_t* action,
                         void* hidden_out, const int32_t* dst_index, float* reward, float* value, float* pi_probs,
                         cudaStream_t st) = 0;

@@ -336,17 +336,9 @@ class SearchPlan:
                 _lib.check(lib.mz_dirichlet(pool.handle, alpha, noise_p, stream))
             _lib.check(lib.mz_search_reset(pool.handle, self.pi0.data_ptr(), noise_p, float(eps), mask_p,
                                            self.players.data_ptr(), None, stream))
-        src, dst, act = (pool.view(k).data_ptr() for k in ('SRC_SLOT', 'DST_SLOT', 'LEAF_ACTION'))
-        rew, val = pool.view('REWARD').data_ptr(), pool.view('VALUE').data_ptr()
-        _lib.check(lib.mz_select(pool.handle, stream))
-        for sim in range(self.S):
-            # pi_probs = NULL: the search never reads the recurrent policy (mcts.py:386)
-            _lib.check(lib.mz_net_recurrent(eng['handle'], self.B, hidden, src, act, hidden, dst, rew, val, None,
-                                            stream))
-            if sim + 1 < self.S:       # expand+backup of this simulation and select of the next in one launch
-                _lib.check(lib.mz_expand_backup_select(pool.handle, None, None, stream))
-            else:
-                _lib.check(lib.mz_expand_backup(pool.handle, None, None, stream))
+        # the simulation loop (mcts.py:372-390): one persistent launch for the MLP nets, the per-simulation launch
+        # chain otherwise -- the library decides (mz_search_run)
+        _lib.check(lib.mz_search_run(eng['handle'], pool.handle, stream))
         _lib.check(lib.mz_root_policy(pool.handle, mask_p, self.temps.data_ptr(), int(deterministic),
                                       self.action.data_ptr(), self.pi.data_ptr(), self.root_value.data_ptr(),
                                       self.visits.data_ptr(), stream))

@@ -276,3 +276,51 @@ def test_fp16_networks_rarely_change_a_search():
     s = search_stats('tictactoe', 256)
     print(s)
     assert s['sampled_action_differs'] <= 0.05 and s['mean_l1_visit_policy'] <= 0.05
+
+
+@pytest.mark.parametrize('name,B', [('tictactoe', 300), ('cartpole', 200), ('lunarlander', 130), ('tictactoe', 4096)])
+@pytest.mark.parametrize('noise_mode', ['device', 'none'])
+def test_one_launch_search_kernel_equals_the_launch_chain(name, B, noise_mode):
+    """mz_search_run's persistent kernel for the MLP nets (one launch per search; the thread that owns row i of a
+    tensor-core tile runs tree i's descent and backup) against the per-simulation launch chain (warp-per-tree /
+    thread-per-tree tree kernels + one tcgen05 launch per simulation), which the lock-step and replay tests pin to
+    the oracle: trees, statistics, hidden states, RNG streams, policies and actions, byte for byte."""
+    import muzero_b200 as mz
+    from muzero_b200 import _lib
+    net, _, kw = load_mlp(name)
+    cfg = {'tictactoe': mz.make_tictactoe_config, 'cartpole': mz.make_classic_config,
+           'lunarlander': mz.make_classic_config}[name](use_tensorboard=False)
+    A = kw['num_actions']
+    gen = np.random.RandomState(B + A)
+    obs = gen.standard_normal((B,) + kw['input_shape']).astype(np.float32)
+    mask = gen.rand(B, A) < 0.8
+    mask[:, 0] = True
+    board = bool(cfg.is_board_game)
+    out = []
+    for fused in (0, 1):
+        plan = mz.mcts.SearchPlan(net, cfg, B)
+        plan.use_graph = False
+        eng = net.engine(B, plan.instance)
+        _lib.check(_lib.lib().mz_net_set_fused_search(eng['handle'], fused))
+        plan.pool.seed(np.arange(B) + 77)
+        plan.obs.copy_(torch.from_numpy(obs).reshape(B, -1)); plan.mask.copy_(torch.from_numpy(mask))
+        plan.players.copy_(torch.tensor([[1, 2 if board else 1]] * B, dtype=torch.int32))
+        n0 = _lib.lib().mz_launch_count()
+        plan.run(noise_mode, True, False)
+        launches = _lib.lib().mz_launch_count() - n0
+        torch.cuda.synchronize()
+        plan.pool.check_errors()
+        names = ('EDGES', 'EDGE_W', 'EDGE_REWARD', 'PRIOR', 'MINMAX', 'ROOT_W', 'ROOT_N', 'COUNT', 'NODE_PARENT',
+                 'NODE_MOVE', 'NODE_VALUE', 'RNG_KEY', 'RNG_POS', 'HIDDEN', 'PATH')
+        state = {k: plan.pool.view(k).cpu().numpy().view(np.uint8).copy() for k in names}
+        state['pi'] = plan.pi.cpu().numpy().view(np.uint8).copy()
+        state['action'] = plan.action.cpu().numpy().copy()
+        state['root_value'] = plan.root_value.cpu().numpy().view(np.uint8).copy()
+        state['stats'] = plan.pool.view('STATS').cpu().numpy()[:4].copy()
+        out.append((state, launches))
+        _lib.check(_lib.lib().mz_net_set_fused_search(eng['handle'], 1))
+    (chain, n_chain), (fus, n_fus) = out
+    for k in chain:
+        assert np.array_equal(chain[k], fus[k]), f'{name}: {k} differs between the launch chain and the one-launch kernel'
+    S = cfg.num_simulations
+    assert n_chain == n_fus + 2 * S and n_fus <= 4          # initial inference (+ root setup fused), search, root policy
