@@ -277,6 +277,28 @@ def algorithmic_bytes_per_launch(kernel, spec, B, A, S, mean_depth, hidden_bytes
     return per * B
 
 
+def initial_flops(spec):
+    """Multiply-add flops (x2) of ONE initial_inference of the reference graph: representation + prediction nets."""
+    kw = spec['net_kw']
+    A = kw['num_actions']
+    if spec['kind'] == 'mlp':
+        ind = int(np.prod(kw['input_shape'])); P, H = kw['num_planes'], kw['hidden_dim']
+        return 2 * (ind * P + P * H + H * P + P * A + H * P + P * kw['value_support_size'])
+    c, h, w = kw['input_shape']
+    C_, nb = kw['num_planes'], kw['num_res_blocks']
+    conv = lambda ci, co, hh, ww: 2 * 9 * ci * co * hh * ww
+    if spec['kind'] == 'board':
+        rep = conv(c, C_, h, w) + 2 * nb * conv(C_, C_, h, w)
+        lh, lw = h, w
+    else:       # network.py:312-353: conv_1 s2, 2 blocks @48, conv_2 s2, 2 blocks @24, pool, 2 blocks @12, pool
+        rep = conv(c, 128, h // 2, w // 2) + 4 * conv(128, 128, h // 2, w // 2) + conv(128, C_, h // 4, w // 4) + \
+            4 * conv(C_, C_, h // 4, w // 4) + 4 * conv(C_, C_, h // 8, w // 8)
+        lh, lw = 6, 6
+    pred = 2 * nb * conv(C_, C_, lh, lw)
+    heads = 2 * lh * lw * (C_ * 2 + C_ * 1) + 2 * lh * lw * (2 * A + kw.get('value_support_size', 1))
+    return rep + pred + heads
+
+
 def build_search(spec, dev, rank=0, parts=0, cta_limit=0):
     """Network, search plan and synthetic inputs exactly as the bench runs them (tests/test_bench_parity_gpu.py builds
     its plan through this function, so what is parity-checked IS what is timed)."""
@@ -436,16 +458,28 @@ def measure_workload(spec, args, dev, world, rank, steps, warmup, min_seconds=0.
     import ctypes as C
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream().cuda_stream
-        _lib.check(lib.mz_net_profile_begin(eng['handle']))
+        use_frames = pplan.obs_mode == 'u8'
+        prof_ms, prof_n = [0.0] * 5, [0] * 5
+        init_ms = []
+        init_prof = None
         for _ in range(reps):
-            # root part eagerly, then instrumented simulation loop
-            _lib.check(lib.mz_net_initial(eng['handle'], Bp, pplan.obs.data_ptr(), hidden, pplan.root_slots.data_ptr(),
-                                          pplan.pi0.data_ptr(), pplan.v0.data_ptr(), stream))
-            _lib.check(lib.mz_dirichlet(ppool.handle, float(np.float32(cfg.root_dirichlet_alpha)),
-                                        pplan.noise.data_ptr(), stream))
-            _lib.check(lib.mz_search_reset(ppool.handle, pplan.pi0.data_ptr(), pplan.noise.data_ptr(),
-                                           float(cfg.root_exploration_eps), pplan.mask.data_ptr(),
-                                           pplan.players.data_ptr(), None, stream))
+            # root part eagerly (initial inference with the root preparation fused into its policy epilogue), timed
+            # on its own; then the instrumented simulation loop
+            _lib.check(lib.mz_net_profile_begin(eng['handle']))
+            i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            i0.record()
+            _lib.check(lib.mz_net_initial_search(
+                eng['handle'], ppool.handle, Bp, None if use_frames else pplan.obs.data_ptr(),
+                pplan.frames.data_ptr() if use_frames else None, pplan.planes.data_ptr() if use_frames else None, hidden,
+                pplan.root_slots.data_ptr(), pplan.pi0.data_ptr(), pplan.v0.data_ptr(), 2, pplan.noise.data_ptr(),
+                float(np.float32(cfg.root_dirichlet_alpha)), float(cfg.root_exploration_eps), pplan.mask.data_ptr(),
+                pplan.players.data_ptr(), stream))
+            i1.record()
+            ip_ms, ip_n = (C.c_double * 5)(), (C.c_int64 * 5)()
+            _lib.check(lib.mz_net_profile_end(eng['handle'], ip_ms, ip_n))
+            init_ms.append(i0.elapsed_time(i1))
+            init_prof = (list(ip_ms), list(ip_n))
+            _lib.check(lib.mz_net_profile_begin(eng['handle']))
             evs = []
             for _s in range(S):
                 e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -461,9 +495,10 @@ def measure_workload(spec, args, dev, world, rank, steps, warmup, min_seconds=0.
             for e in evs:
                 for i, n in enumerate(names):
                     tot[n] += e[i].elapsed_time(e[i + 1])
-        prof_ms = (C.c_double * 5)()
-        prof_n = (C.c_int64 * 5)()
-        _lib.check(lib.mz_net_profile_end(eng['handle'], prof_ms, prof_n))
+            r_ms, r_n = (C.c_double * 5)(), (C.c_int64 * 5)()
+            _lib.check(lib.mz_net_profile_end(eng['handle'], r_ms, r_n))
+            for i in range(5):
+                prof_ms[i] += r_ms[i]; prof_n[i] += r_n[i]
     launches = reps * S
     avg_ms = {n: tot[n] / launches for n in names}
     share = {n: tot[n] / sum(tot.values()) for n in names}
@@ -548,6 +583,15 @@ def measure_workload(spec, args, dev, world, rank, steps, warmup, min_seconds=0.
                     'share_of_recurrent_inference': prof_ms[0] / max(1e-9, prof_ms[0] + prof_ms[1] + prof_ms[2]),
                     'share_of_sim_loop': prof_ms[0] / max(1e-9, sum(tot.values())), 'peak_source': peak_src}
         roof['head_kernel'] = {'avg_launch_us': 1e3 * prof_ms[1] / max(1, prof_n[1]), 'launches_timed': int(prof_n[1])}
+    # the once-per-search root inference (representation + prediction, root preparation fused into the policy epilogue)
+    fl0 = initial_flops(spec)
+    im = min(init_ms)
+    roof['initial_inference'] = {'avg_launch_us': im * 1e3, 'share_of_search': im / max(1e-9, im + sum(tot.values()) / reps),
+                                 'reference_graph_flops': fl0 * Bp, 'bound': 'tensor',
+                                 'achieved': fl0 * Bp / (im * 1e-3) / 1e12, 'peak': tf_peak, 'unit': 'TFLOP/s',
+                                 'frac': fl0 * Bp / (im * 1e-3) / 1e12 / tf_peak,
+                                 'conv_ms': init_prof[0][0], 'conv_layers': init_prof[1][0], 'pack_pool_ms': init_prof[0][2],
+                                 'head_ms': init_prof[0][1], 'mlp_ms': init_prof[0][3]}
     result['roofline'] = roofline
     result['kernels'] = roof
     del flush

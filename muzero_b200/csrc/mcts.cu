@@ -469,9 +469,9 @@ constexpr int kThreadBlock = 64;
 // mode: 1 select, 2 expand+backup, 3 expand+backup then select
 __global__ void __launch_bounds__(kThreadBlock)
 tree_thread_kernel(PoolDev p, const float* __restrict__ reward_in, const float* __restrict__ value_in, int mode) {
-  double* sT = reinterpret_cast<double*>(smem_raw);
-  const double* sR = p.T + (p.S + 2);
-  for (int i = threadIdx.x; i < p.S + 2; i += blockDim.x) sT[i] = p.T[i];
+  double* sT = reinterpret_cast<double*>(smem_raw);          // pb_c table, then RN(1/n): [2 * (S + 2)]
+  const double* sR = sT + (p.S + 2);
+  for (int i = threadIdx.x; i < 2 * (p.S + 2); i += blockDim.x) sT[i] = p.T[i];
   __syncthreads();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned member = __ballot_sync(kFull, t < p.B);
@@ -915,7 +915,7 @@ extern "C" int mz_select(mz_pool* pool, mz_stream stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const PoolDev d = dev_of(pool);
   if (use_thread_kernels(pool)) {
-    tree_thread_kernel<<<(pool->B + kThreadBlock - 1) / kThreadBlock, kThreadBlock, (size_t)(pool->S + 2) * 8, st>>>(
+    tree_thread_kernel<<<(pool->B + kThreadBlock - 1) / kThreadBlock, kThreadBlock, (size_t)(pool->S + 2) * 16, st>>>(
         d, nullptr, nullptr, 1);
     MZ_LAUNCH_CHECK("tree_thread_kernel");
     pool->selected = 1;
@@ -945,7 +945,7 @@ extern "C" int mz_expand_backup_select(mz_pool* pool, const float* reward, const
   const float* r = reward ? reward : d.reward;
   const float* v = value ? value : d.value;
   if (use_thread_kernels(pool)) {
-    tree_thread_kernel<<<(pool->B + kThreadBlock - 1) / kThreadBlock, kThreadBlock, (size_t)(pool->S + 2) * 8, st>>>(
+    tree_thread_kernel<<<(pool->B + kThreadBlock - 1) / kThreadBlock, kThreadBlock, (size_t)(pool->S + 2) * 16, st>>>(
         d, r, v, 3);
     MZ_LAUNCH_CHECK("tree_thread_kernel");
     pool->selected = 1;
@@ -979,7 +979,7 @@ extern "C" int mz_expand_backup(mz_pool* pool, const float* reward, const float*
   }
   const PoolDev d = dev_of(pool);
   if (use_thread_kernels(pool)) {
-    tree_thread_kernel<<<(pool->B + kThreadBlock - 1) / kThreadBlock, kThreadBlock, (size_t)(pool->S + 2) * 8,
+    tree_thread_kernel<<<(pool->B + kThreadBlock - 1) / kThreadBlock, kThreadBlock, (size_t)(pool->S + 2) * 16,
                          (cudaStream_t)stream>>>(d, reward ? reward : d.reward, value ? value : d.value, 2);
     MZ_LAUNCH_CHECK("tree_thread_kernel");
     pool->selected = 0;

@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const __grid_cons
   float* sTab = sB1 + 4 * p.P;                                      // [A][P] action columns (when they fit)
   // search form: pb_c table (float64 [S + 2]) and the action each row's thread selected (read by the helper warps)
   double* sT = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sTab + (p.tab_in_smem ? p.A * (p.P + 4) : 0)) + 15) & ~(uintptr_t)15);
-  int* sAct = reinterpret_cast<int*>(sT + (kSearch ? sa.sims + 2 : 0));
+  int* sAct = reinterpret_cast<int*>(sT + (kSearch ? 2 * (sa.sims + 2) : 0));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int dbg_n = 0;
   auto stamp = [&]() { if (p.dbg && blockIdx.x == 0 && tid == 0 && dbg_n < 60) p.dbg[dbg_n++] = clock64(); };
@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const __grid_cons
   const int first_tile = (int)blockIdx.x / nsplit, tile_step = (int)gridDim.x / nsplit;
   if (!kSearch && tid < 128 && first_tile * kTcRows < p.batch) gather_tile(p, first_tile, tid, smem_u32(sIn));
   if (kSearch)
-    for (int i = tid; i < sa.sims + 2; i += kTcThreads) sT[i] = sa.pool.T[i];
+    for (int i = tid; i < 2 * (sa.sims + 2); i += kTcThreads) sT[i] = sa.pool.T[i];     // pb_c table, then RN(1/n)
   // first-layer biases and the action table are read by every row of every tile: stage them once per CTA
   // (from global they cost an exposed L2 round trip per 32-column chunk of every epilogue)
   for (int i = tid; i < p.nnets * p.P; i += kTcThreads) sB1[i] = p.b1[i / p.P][i % p.P];
@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const __grid_cons
     };
 
     TreeThreadStats tstats;
-    const double* sR = kSearch ? sa.pool.T + (sa.sims + 2) : nullptr;      // RN(1/n), read through L1
+    const double* sR = sT + (kSearch ? sa.sims + 2 : 0);                   // RN(1/n)
     for (int tile = first_tile; tile < ntiles; tile += tile_step) {
       const int grow = tile * kTcRows + row;
       const bool live = grow < p.batch;
@@ -519,6 +519,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const __grid_cons
      for (int sim = 0; sim < nsims; ++sim) {
       int act;
       size_t dst_slot = 0;
+      if (kSearch) stamp();
       if constexpr (kSearch) {
         // tree phase: this thread's tree -- backup of the previous simulation, then the descent of this one
         act = 0;
@@ -791,7 +792,9 @@ int MlpNet::search(mz_pool* pool, cudaStream_t st) {
   q.nblk = tc_blocks_no_policy;
   q.nsplit = 1;
   q.dbg = nullptr;
-  const size_t smem_need = tc_smem + (size_t)(pool->S + 2) * 8 + kTcRows * sizeof(int) + 64;
+  static const bool debug = getenv("MZ_MLP_DEBUG") != nullptr;
+  if (debug) { cudaMalloc(&q.dbg, 64 * sizeof(long long)); cudaMemset(q.dbg, 0, 64 * sizeof(long long)); }
+  const size_t smem_need = tc_smem + (size_t)(pool->S + 2) * 16 + kTcRows * sizeof(int) + 64;
   if (smem_need > 227 * 1024) return 1;
   SearchArgs sa;
   sa.pool = pool_dev(pool);
@@ -803,6 +806,15 @@ int MlpNet::search(mz_pool* pool, cudaStream_t st) {
   else mlp_tc_kernel<true, 12><<<grid, kTcThreads, smem_need, st>>>(q, sa);
   prof_mark(-1, st);
   MZ_LAUNCH_CHECK("mlp_tc_kernel<search>");
+  if (debug) {   // cycle stamps of CTA 0 / thread 0: start, prologue, then per simulation: sim start, tree phase + gather done, ...
+    cudaDeviceSynchronize();
+    long long h[64];
+    cudaMemcpy(h, q.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(q.dbg);
+    fprintf(stderr, "[mlp search dbg] cycles since start:");
+    for (int i = 1; i < 64 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[0]);
+    fprintf(stderr, "\n");
+  }
   return MZ_OK;
 }
 

@@ -70,12 +70,23 @@ __device__ __forceinline__ int2 select_tree_thread(const PoolDev& p, const int t
   double pr[TA];
   float prf[TA];
 #pragma unroll
-  for (int a = 0; a < TA; ++a) { pr[a] = a < A ? P[a] : 0.0; prf[a] = (float)pr[a]; }
+  for (int a = 0; a < TA; ++a) { pr[a] = P[a < A ? a : 0]; prf[a] = (float)pr[a]; }
 
   int n = 0, Nn = p.rootN[t], depth = 0, act = 0;
   while (true) {
     const double tN = sT[Nn];
     const float tNf = __double2float_rn(tN);
+    // The node's whole child row, then the reciprocals of its visit counts, as two BATCHES of independent,
+    // unconditional loads (index clamped past the last action): one memory round trip each.  Loads left inside the
+    // per-action conditionals are issued one after the other, each waiting for its own L2 round trip -- measured 13 k
+    // cycles per level with 10 actions, against ~1.5 k for the batched form.
+    const HotEdge* row = tree + (size_t)n * A;
+    HotEdge h[TA];
+#pragma unroll
+    for (int a = 0; a < TA; ++a) h[a] = row[a < A ? a : 0];
+    double rcp[TA];
+#pragma unroll
+    for (int a = 0; a < TA; ++a) rcp[a] = sR[(h[a].x & 0xffffu) + 1u];
     uint32_t nc[TA], key = 0;
     float s[TA];
 #pragma unroll
@@ -83,13 +94,12 @@ __device__ __forceinline__ int2 select_tree_thread(const PoolDev& p, const int t
       nc[a] = (uint32_t)kNoChild << 16;
       s[a] = 0.0f;
       if (a < A) {
-        const HotEdge h = tree[(size_t)n * A + a];
-        nc[a] = h.x;
-        const float q = __uint_as_float(h.y);
+        nc[a] = h[a].x;
+        const float q = __uint_as_float(h[a].y);
         const int cn = (int)(nc[a] & 0xffffu);
         float u;
         if (cn > 0) {
-          const double y = div_by_count(tN, cn + 1, __ldg(sR + cn + 1));
+          const double y = div_by_count(tN, cn + 1, rcp[a]);
           u = f32p ? __fmul_rn(prf[a], __double2float_rn(y)) : __double2float_rn(__dmul_rn(pr[a], y));
         } else {
           u = f32p ? __fmul_rn(prf[a], tNf) : __double2float_rn(__dmul_rn(pr[a], tN));
