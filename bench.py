@@ -515,10 +515,10 @@ def measure_workload(spec, args, dev, world, rank, steps, warmup, min_seconds=0.
                               'frac': ach / tf_peak, 'reference_graph_flops': flops * Bp})
     roofline = dict(roof[dominant])
     roofline.update({'kernel': dominant, 'traffic': None, 'peak_source': peak_src})
-    if spec['kind'] == 'mlp':
-        # what a search of the MLP nets actually launches: ONE persistent kernel for all S simulations
-        # (mz_search_run); the three kernels above are the per-simulation launch chain it replaces, kept as a
-        # diagnostic.  Timed eagerly with CUDA events around the launch.
+    if spec['kind'] == 'mlp' and os.environ.get('MZ_FUSED_SEARCH', '0') == '1':
+        # opt-in: ONE persistent kernel for all S simulations (mz_search_run with mz_net_set_fused_search); the three
+        # kernels above are the per-simulation launch chain it replaces.  Timed eagerly with CUDA events around the
+        # launch.
         sm = []
         with torch.cuda.device(dev):
             for _ in range(max(3, reps)):

@@ -43,6 +43,10 @@ typedef void* mz_stream;          /* cudaStream_t                               
 
 const char* mz_last_error(void);
 int mz_version(void);
+/* Programmatic dependent launch between the short kernels of the per-simulation chain (tree kernel <-> tcgen05 MLP
+ * kernel): a kernel's prologue overlaps its predecessor's tail.  Scheduling only, no effect on results.  Default on;
+ * enable = 0 (or MZ_NO_PDL=1 in the environment) launches every kernel the ordinary way. */
+int mz_set_pdl(int enable);
 /* sm count and compute capability of `device`; fails on anything but sm_100. */
 int mz_device_check(int device, int* sm_count, int* cc);
 
@@ -217,16 +221,18 @@ int mz_net_recurrent(mz_net* net, int32_t batch, const void* hidden_in, const in
 
 /* All num_simulations simulations of the pool's trees -- select -> recurrent_inference -> expand + backup, the loop of
  * mcts.py:372-390 -- after the roots were prepared (mz_net_initial_search or mz_search_reset); leaves the pool as the
- * last mz_expand_backup would.  MuZeroMLPNet with up to 12 actions: ONE launch of a persistent kernel whose CTAs own
- * their trees for the whole search (the thread that owns row i of a tensor-core tile also runs tree i's descent and
- * backup; no per-simulation launch, prologue or global round trip for the leaf action / reward / value).  Other
- * networks: the per-simulation launch chain (mz_select, then S x (mz_net_recurrent, mz_expand_backup[_select])),
- * enqueued here.  Results are bit-identical either way. */
+ * last mz_expand_backup would.  Default: the per-simulation launch chain (mz_select, then S x (mz_net_recurrent,
+ * mz_expand_backup[_select])), enqueued here so that a search is three C calls.  With mz_net_set_fused_search(net, 1)
+ * (MuZeroMLPNet, up to 12 actions): ONE launch of a persistent kernel whose CTAs own their trees for the whole search
+ * (the thread that owns row i of a tensor-core tile also runs tree i's descent and backup; no per-simulation launch,
+ * prologue or global round trip for the leaf action / reward / value).  Results are bit-identical either way
+ * (tests/test_network_gpu.py::test_one_launch_search_kernel_equals_the_launch_chain); the one-launch form is opt-in
+ * because it measured SLOWER at the benchmark sizes (a thread-per-tree descent over 10 actions is
+ * ~700 dependent instructions per level on an SM with 4 active warps). */
 int mz_search_run(mz_net* net, mz_pool* pool, mz_stream stream);
 
-/* enable = 0: mz_search_run always enqueues the per-simulation launch chain (scheduling knob, no effect on results;
- * the parity tests pin the one-launch kernel to the chain bit for bit).  Default: enabled.  MZ_NO_FUSED_SEARCH=1 in
- * the environment disables it process-wide. */
+/* enable = 1: mz_search_run uses the one-launch-per-search kernel where it exists (scheduling knob, no effect on
+ * results).  Default 0.  MZ_FUSED_SEARCH=1 in the environment enables it process-wide. */
 int mz_net_set_fused_search(mz_net* net, int32_t enable);
 
 /* Cap the grid of the net's persistent kernels (0 = one CTA per SM).  Two engines that are driven from two

@@ -39,6 +39,7 @@ _P = C.c_void_p
 PROTOTYPES = {
     'mz_last_error': (C.c_char_p, []),
     'mz_version': (C.c_int, []),
+    'mz_set_pdl': (C.c_int, [C.c_int]),
     'mz_device_check': (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'mz_pool_arena_bytes': (C.c_int, [C.POINTER(PoolConfig), C.POINTER(C.c_size_t)]),
     'mz_pool_create': (C.c_int, [C.POINTER(PoolConfig), C.POINTER(C.c_double), _P, C.c_size_t, C.POINTER(_P)]),

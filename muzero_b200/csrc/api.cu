@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <cstdlib>
 
 namespace mz {
 
@@ -15,6 +16,18 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static std::atomic<int> g_pdl{-1};
+bool pdl_enabled() {
+  int v = g_pdl.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("MZ_NO_PDL");
+    v = (e && e[0] == '1') ? 0 : 1;
+    g_pdl.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
+}
+void set_pdl(int on) { g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
+
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 }  // namespace mz
@@ -22,6 +35,8 @@ void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memo
 extern "C" const char* mz_last_error(void) { return mz::g_error; }
 
 extern "C" int mz_version(void) { return 100; }
+
+extern "C" int mz_set_pdl(int enable) { mz::set_pdl(enable); return MZ_OK; }
 
 extern "C" uint64_t mz_launch_count(void) { return mz::g_launches.load(std::memory_order_relaxed); }
 

@@ -13,6 +13,7 @@ namespace mz {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+void set_pdl(int on);
 
 #define MZ_CHECK_ARG(cond, ...)            \
   do {                                     \
@@ -59,6 +60,27 @@ typedef uint2 HotEdge;
 __host__ __device__ inline uint32_t hot_word(uint32_t N, uint32_t child) { return (N & 0xffffu) | (child << 16); }
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Programmatic dependent launch (PDL).  The per-simulation chain of the MLP configurations alternates two short,
+// latency-bound kernels (tree kernel, tcgen05 MLP kernel); with a full kernel boundary between them the second pays the
+// launch latency and its prologue (table staging, TMEM allocation, barrier set-up) after the first has drained.
+// Launched with the programmatic-serialisation attribute a kernel may start while its predecessor still runs; it does
+// everything that does not depend on the predecessor, then pdl_wait() blocks until the predecessor grid has completed
+// and its writes are visible.  pdl_trigger() lets the successor start that early.  Both are no-ops in a kernel that was
+// launched the ordinary way.  MZ_NO_PDL=1 launches everything the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = smem; lc.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  lc.attrs = at; lc.numAttrs = 1;
+  return cudaLaunchKernelEx(&lc, kernel, static_cast<KArgs>(args)...);
+}
 
 }  // namespace mz
 

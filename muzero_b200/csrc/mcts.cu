@@ -293,9 +293,11 @@ select_kernel(PoolDev p) {
   const double* sR = p.T + (p.S + 2);
   float* sc = reinterpret_cast<float*>(sT + (p.S + 2)) + (size_t)warp * ((p.A + 3) & ~3);
   __shared__ unsigned long long s_stats[4];
+  pdl_trigger();
   if (threadIdx.x < 4) s_stats[threadIdx.x] = 0;
   for (int i = threadIdx.x; i < p.S + 2; i += blockDim.x) sT[i] = p.T[i];
   __syncthreads();
+  pdl_wait();
   if (t < p.B) select_tree<NCH>(p, t, lane, sT, sR, sc, s_stats);
   flush_stats(p, s_stats);
 }
@@ -420,6 +422,8 @@ __device__ __forceinline__ void expand_backup_tree(const PoolDev& p, const int t
 
 __global__ void __launch_bounds__(kTreesPerBlock * 32)
 expand_backup_kernel(PoolDev p, const float* __restrict__ reward_in, const float* __restrict__ value_in) {
+  pdl_trigger();
+  pdl_wait();
   const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (t >= p.B) return;
@@ -439,9 +443,11 @@ backup_select_kernel(PoolDev p, const float* __restrict__ reward_in, const float
   const double* sR = p.T + (p.S + 2);
   float* sc = reinterpret_cast<float*>(sT + (p.S + 2)) + (size_t)warp * ((p.A + 3) & ~3);
   __shared__ unsigned long long s_stats[4];
+  pdl_trigger();
   if (threadIdx.x < 4) s_stats[threadIdx.x] = 0;
   for (int i = threadIdx.x; i < p.S + 2; i += blockDim.x) sT[i] = p.T[i];
   __syncthreads();
+  pdl_wait();
   if (t < p.B) {
     if (p.timing && threadIdx.x == 0) {
       const unsigned long long t0 = globaltimer_ns();
@@ -471,8 +477,10 @@ __global__ void __launch_bounds__(kThreadBlock)
 tree_thread_kernel(PoolDev p, const float* __restrict__ reward_in, const float* __restrict__ value_in, int mode) {
   double* sT = reinterpret_cast<double*>(smem_raw);          // pb_c table, then RN(1/n): [2 * (S + 2)]
   const double* sR = sT + (p.S + 2);
+  pdl_trigger();
   for (int i = threadIdx.x; i < 2 * (p.S + 2); i += blockDim.x) sT[i] = p.T[i];
   __syncthreads();
+  pdl_wait();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned member = __ballot_sync(kFull, t < p.B);
   if (t >= p.B) return;
@@ -511,9 +519,11 @@ backup_select_confined_kernel(PoolDev p, const float* __restrict__ reward_in, co
   double* sT = reinterpret_cast<double*>(smem_raw);
   const double* sR = p.T + (p.S + 2);
   __shared__ unsigned long long s_stats[4];
+  pdl_trigger();
   if (threadIdx.x < 4) s_stats[threadIdx.x] = 0;
   for (int i = threadIdx.x; i < p.S + 2; i += blockDim.x) sT[i] = p.T[i];
   __syncthreads();
+  pdl_wait();
   while (true) {
     unsigned t = 0;
     if (lane == 0) t = atomicAdd(p.work, 1u);
@@ -915,17 +925,16 @@ extern "C" int mz_select(mz_pool* pool, mz_stream stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const PoolDev d = dev_of(pool);
   if (use_thread_kernels(pool)) {
-    tree_thread_kernel<<<(pool->B + kThreadBlock - 1) / kThreadBlock, kThreadBlock, (size_t)(pool->S + 2) * 16, st>>>(
-        d, nullptr, nullptr, 1);
+    launch_pdl(tree_thread_kernel, dim3((pool->B + kThreadBlock - 1) / kThreadBlock), dim3(kThreadBlock), (size_t)(pool->S + 2) * 16, st, d, nullptr, nullptr, 1);
     MZ_LAUNCH_CHECK("tree_thread_kernel");
     pool->selected = 1;
     return MZ_OK;
   }
-  if (A <= 32) select_kernel<1><<<grid, block, smem, st>>>(d);
-  else if (A <= 64) select_kernel<2><<<grid, block, smem, st>>>(d);
-  else if (A <= 96) select_kernel<3><<<grid, block, smem, st>>>(d);
-  else if (A <= 128) select_kernel<4><<<grid, block, smem, st>>>(d);
-  else select_kernel<0><<<grid, block, smem, st>>>(d);
+  if (A <= 32) launch_pdl(select_kernel<1>, grid, block, smem, st, d);
+  else if (A <= 64) launch_pdl(select_kernel<2>, grid, block, smem, st, d);
+  else if (A <= 96) launch_pdl(select_kernel<3>, grid, block, smem, st, d);
+  else if (A <= 128) launch_pdl(select_kernel<4>, grid, block, smem, st, d);
+  else launch_pdl(select_kernel<0>, grid, block, smem, st, d);
   MZ_LAUNCH_CHECK("select_kernel");
   pool->selected = 1;
   return MZ_OK;
@@ -945,27 +954,26 @@ extern "C" int mz_expand_backup_select(mz_pool* pool, const float* reward, const
   const float* r = reward ? reward : d.reward;
   const float* v = value ? value : d.value;
   if (use_thread_kernels(pool)) {
-    tree_thread_kernel<<<(pool->B + kThreadBlock - 1) / kThreadBlock, kThreadBlock, (size_t)(pool->S + 2) * 16, st>>>(
-        d, r, v, 3);
+    launch_pdl(tree_thread_kernel, dim3((pool->B + kThreadBlock - 1) / kThreadBlock), dim3(kThreadBlock), (size_t)(pool->S + 2) * 16, st, d, r, v, 3);
     MZ_LAUNCH_CHECK("tree_thread_kernel");
     pool->selected = 1;
     return MZ_OK;
   }
   if (pool->tree_ctas > 0 && A <= 128) {
     const dim3 cgrid(pool->tree_ctas), cblock(kConfinedThreads);
-    if (A <= 32) backup_select_confined_kernel<1><<<cgrid, cblock, kConfinedSmem, st>>>(d, r, v);
-    else if (A <= 64) backup_select_confined_kernel<2><<<cgrid, cblock, kConfinedSmem, st>>>(d, r, v);
-    else if (A <= 96) backup_select_confined_kernel<3><<<cgrid, cblock, kConfinedSmem, st>>>(d, r, v);
-    else backup_select_confined_kernel<4><<<cgrid, cblock, kConfinedSmem, st>>>(d, r, v);
+    if (A <= 32) launch_pdl(backup_select_confined_kernel<1>, cgrid, cblock, (size_t)kConfinedSmem, st, d, r, v);
+    else if (A <= 64) launch_pdl(backup_select_confined_kernel<2>, cgrid, cblock, (size_t)kConfinedSmem, st, d, r, v);
+    else if (A <= 96) launch_pdl(backup_select_confined_kernel<3>, cgrid, cblock, (size_t)kConfinedSmem, st, d, r, v);
+    else launch_pdl(backup_select_confined_kernel<4>, cgrid, cblock, (size_t)kConfinedSmem, st, d, r, v);
     MZ_LAUNCH_CHECK("backup_select_confined_kernel");
     pool->selected = 1;
     return MZ_OK;
   }
-  if (A <= 32) backup_select_kernel<1><<<grid, block, smem, st>>>(d, r, v);
-  else if (A <= 64) backup_select_kernel<2><<<grid, block, smem, st>>>(d, r, v);
-  else if (A <= 96) backup_select_kernel<3><<<grid, block, smem, st>>>(d, r, v);
-  else if (A <= 128) backup_select_kernel<4><<<grid, block, smem, st>>>(d, r, v);
-  else backup_select_kernel<0><<<grid, block, smem, st>>>(d, r, v);
+  if (A <= 32) launch_pdl(backup_select_kernel<1>, grid, block, smem, st, d, r, v);
+  else if (A <= 64) launch_pdl(backup_select_kernel<2>, grid, block, smem, st, d, r, v);
+  else if (A <= 96) launch_pdl(backup_select_kernel<3>, grid, block, smem, st, d, r, v);
+  else if (A <= 128) launch_pdl(backup_select_kernel<4>, grid, block, smem, st, d, r, v);
+  else launch_pdl(backup_select_kernel<0>, grid, block, smem, st, d, r, v);
   MZ_LAUNCH_CHECK("backup_select_kernel");
   pool->selected = 1;
   return MZ_OK;
@@ -979,14 +987,13 @@ extern "C" int mz_expand_backup(mz_pool* pool, const float* reward, const float*
   }
   const PoolDev d = dev_of(pool);
   if (use_thread_kernels(pool)) {
-    tree_thread_kernel<<<(pool->B + kThreadBlock - 1) / kThreadBlock, kThreadBlock, (size_t)(pool->S + 2) * 16,
-                         (cudaStream_t)stream>>>(d, reward ? reward : d.reward, value ? value : d.value, 2);
+    launch_pdl(tree_thread_kernel, dim3((pool->B + kThreadBlock - 1) / kThreadBlock), dim3(kThreadBlock), (size_t)(pool->S + 2) * 16, (cudaStream_t)stream, d, reward ? reward : d.reward, value ? value : d.value, 2);
     MZ_LAUNCH_CHECK("tree_thread_kernel");
     pool->selected = 0;
     return MZ_OK;
   }
-  expand_backup_kernel<<<tree_blocks(pool->B), kTreesPerBlock * 32, 0, (cudaStream_t)stream>>>(
-      d, reward ? reward : d.reward, value ? value : d.value);
+  launch_pdl(expand_backup_kernel, dim3(tree_blocks(pool->B)), dim3(kTreesPerBlock * 32), (size_t)0, (cudaStream_t)stream,
+             d, reward ? reward : d.reward, value ? value : d.value);
   MZ_LAUNCH_CHECK("expand_backup_kernel");
   pool->selected = 0;
   return MZ_OK;

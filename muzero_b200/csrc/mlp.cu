@@ -247,8 +247,14 @@ mlp_initial_kernel(MlpDev n, int batch, const float* __restrict__ obs, float* __
     // fused root preparation (mz_net_initial_search): the warp that wrote row r's softmax (softmax_rows: warp r % 8,
     // lane i -> actions i, i + 32, ...) draws the tree's Dirichlet noise, mixes, masks, renormalises and resets the tree
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (rs.noise_mode == 2 && lane < kRows / (kThreads / 32)) {
+      // the warp's 4 rows draw their Dirichlet samples side by side, one lane each (the sampler is sequential per tree)
+      const int t = row0 + warp + lane * (kThreads / 32);
+      if (t < batch && t < rs.pool.B) dirichlet_tree_thread(rs.pool, t, rs.alpha, rs.noise + (size_t)t * n.A);
+    }
+    __syncwarp();
     for (int r = warp; r < kRows; r += kThreads / 32)
-      if (row0 + r < batch) root_setup_fused(rs, row0 + r, lane, pi_probs + (size_t)(row0 + r) * n.A);
+      if (row0 + r < batch) root_setup_fused(rs, row0 + r, lane, pi_probs + (size_t)(row0 + r) * n.A, true);
   }
 }
 
@@ -436,7 +442,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const __grid_cons
   auto net_at = [&](int ni) { return (int)((net_list >> (4 * ni)) & 15u); };
   const int bpn = 2 * p.chunks;       // weight blocks per net
   const int first_tile = (int)blockIdx.x / nsplit, tile_step = (int)gridDim.x / nsplit;
-  if (!kSearch && tid < 128 && first_tile * kTcRows < p.batch) gather_tile(p, first_tile, tid, smem_u32(sIn));
+  pdl_trigger();          // the next kernel of the chain may start its own prologue now
   if (kSearch)
     for (int i = tid; i < 2 * (sa.sims + 2); i += kTcThreads) sT[i] = sa.pool.T[i];     // pb_c table, then RN(1/n)
   // first-layer biases and the action table are read by every row of every tile: stage them once per CTA
@@ -454,6 +460,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const __grid_cons
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_holder, 512);
+  // everything above is independent of the previous kernel of the stream (programmatic dependent launch: it overlaps
+  // that kernel's tail); the leaf gather below reads what the tree kernel selected
+  pdl_wait();
+  // the first tile's leaf gather (two dependent global round trips) is issued before the prologue barrier
+  if (!kSearch && tid < 128 && first_tile * kTcRows < p.batch) gather_tile(p, first_tile, tid, smem_u32(sIn));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -527,7 +538,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const __grid_cons
           size_t src_slot = 0;
           if (live) {
             if (sim > 0) expand_backup_tree_thread(sa.pool, grow, rew_reg, val_reg);
+            stamp();
             const int2 leaf = select_tree_thread<TA>(sa.pool, grow, sT, sR, tstats);
+            stamp();
             act = leaf.y;
             src_slot = (size_t)grow * sa.pool.max_nodes + leaf.x;
             dst_slot = (size_t)grow * sa.pool.max_nodes + min(node0 + sim, sa.pool.max_nodes - 1);
@@ -757,7 +770,8 @@ struct MlpNet : NetImpl {
       prof_mark(kProfMlp, st);
       SearchArgs none;
       none.sims = 0;
-      mlp_tc_kernel<false, 4><<<q.nsplit == 2 ? 2 * ntiles : (ntiles < num_sms ? ntiles : num_sms), kTcThreads, tc_smem, st>>>(q, none);
+      launch_pdl(mlp_tc_kernel<false, 4>, dim3(q.nsplit == 2 ? 2 * ntiles : (ntiles < num_sms ? ntiles : num_sms)),
+                 dim3(kTcThreads), tc_smem, st, q, none);
       prof_mark(-1, st);
       MZ_LAUNCH_CHECK("mlp_recurrent_tc_kernel");
       if (debug) {   // measurement aid: cycle stamps of CTA 0 (start, prologue, gather, then per net: MMA1, epi1, MMA2, epi2; end)
@@ -781,8 +795,8 @@ struct MlpNet : NetImpl {
 };
 
 int MlpNet::search(mz_pool* pool, cudaStream_t st) {
-  static const bool off = getenv("MZ_NO_FUSED_SEARCH") != nullptr;
-  if (off || !fused_search || !tc || pool->A != d.A || pool->A > 12 || pool->cfg.hidden_bytes != d.HD * 4) return 1;
+  static const bool env_on = getenv("MZ_FUSED_SEARCH") != nullptr && atoi(getenv("MZ_FUSED_SEARCH")) != 0;
+  if (!(fused_search || env_on) || !tc || pool->A != d.A || pool->A > 12 || pool->cfg.hidden_bytes != d.HD * 4) return 1;
   MlpTcParams q = tcp;
   q.batch = pool->B;
   q.hidden_in = (const float*)pool->view_ptr[MZ_VIEW_HIDDEN];

@@ -106,6 +106,10 @@ struct ThreadRng {
     y ^= y >> 18;
     return y;
   }
+  __device__ double next_double() {
+    const uint32_t a = next_u32() >> 5, b = next_u32() >> 6;
+    return __ddiv_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)b), 9007199254740992.0);
+  }
   __device__ uint32_t bounded(uint32_t k) {
     const uint32_t rng = k - 1;
     if (rng == 0) return 0;

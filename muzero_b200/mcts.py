@@ -24,6 +24,24 @@ from . import _lib
 from .network import MuZeroNet, StackedFrames
 
 
+def _capture(enqueue) -> 'torch.cuda.CUDAGraph':
+    """Capture one search into a CUDA graph.  The tree / MLP kernels are launched with the programmatic-dependent-launch
+    attribute (a kernel's prologue overlaps its predecessor's tail); should a driver refuse such launches under stream
+    capture, the library falls back to ordinary launches and the capture is repeated."""
+    try:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            enqueue()
+        return g
+    except Exception:                                           # noqa: BLE001
+        _lib.check(_lib.lib().mz_set_pdl(0))
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            enqueue()
+        return g
+
+
 def pb_c_table(num_simulations: int, pb_c_base: float, pb_c_init: float) -> np.ndarray:
     """The exploration factor of mcts.py:193-195 for every parent visit count,
     evaluated with CPython ``math`` exactly as the reference evaluates it."""
@@ -366,10 +384,7 @@ class SearchPlan:
                 torch.cuda.current_stream().wait_stream(side)
                 torch.cuda.synchronize()
                 # that eager pass WAS this call's search (capture below records, it does not execute)
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._enqueue(noise_mode, has_mask, deterministic)
-                self._graphs[key] = g
+                self._graphs[key] = _capture(lambda: self._enqueue(noise_mode, has_mask, deterministic))
                 return
             g.replay()
 
@@ -522,10 +537,7 @@ class PipelinedSearchPlan:
                         part.launches_per_search = int(lib.mz_launch_count() - n0)
                 torch.cuda.current_stream().wait_stream(side)
                 torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._enqueue_all(noise_mode, has_mask, deterministic)
-                self._graphs[key] = g
+                self._graphs[key] = _capture(lambda: self._enqueue_all(noise_mode, has_mask, deterministic))
                 return
             g.replay()
 

