@@ -774,6 +774,8 @@ PoolDev pool_dev(const mz_pool* h) {
 namespace {
 inline PoolDev dev_of(const mz_pool* h) { return pool_dev(h); }
 
+// early start of the tree kernels only for batches whose kernels leave SMs free (see launch_pdl in mlp.cu)
+inline bool pdl_ok(const mz_pool* pool) { return pool->B <= 8192; }
 inline int tree_blocks(int B) { return (B + kTreesPerBlock - 1) / kTreesPerBlock; }
 // thread-per-tree kernels: tiny action spaces and enough trees to fill warps (MZ_TREE_THREAD=0/1 overrides)
 inline bool use_thread_kernels(const mz_pool* pool) {
@@ -925,16 +927,16 @@ extern "C" int mz_select(mz_pool* pool, mz_stream stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const PoolDev d = dev_of(pool);
   if (use_thread_kernels(pool)) {
-    launch_pdl(tree_thread_kernel, dim3((pool->B + kThreadBlock - 1) / kThreadBlock), dim3(kThreadBlock), (size_t)(pool->S + 2) * 16, st, d, nullptr, nullptr, 1);
+    launch_pdl(pdl_ok(pool), tree_thread_kernel, dim3((pool->B + kThreadBlock - 1) / kThreadBlock), dim3(kThreadBlock), (size_t)(pool->S + 2) * 16, st, d, nullptr, nullptr, 1);
     MZ_LAUNCH_CHECK("tree_thread_kernel");
     pool->selected = 1;
     return MZ_OK;
   }
-  if (A <= 32) launch_pdl(select_kernel<1>, grid, block, smem, st, d);
-  else if (A <= 64) launch_pdl(select_kernel<2>, grid, block, smem, st, d);
-  else if (A <= 96) launch_pdl(select_kernel<3>, grid, block, smem, st, d);
-  else if (A <= 128) launch_pdl(select_kernel<4>, grid, block, smem, st, d);
-  else launch_pdl(select_kernel<0>, grid, block, smem, st, d);
+  if (A <= 32) launch_pdl(pdl_ok(pool), select_kernel<1>, grid, block, smem, st, d);
+  else if (A <= 64) launch_pdl(pdl_ok(pool), select_kernel<2>, grid, block, smem, st, d);
+  else if (A <= 96) launch_pdl(pdl_ok(pool), select_kernel<3>, grid, block, smem, st, d);
+  else if (A <= 128) launch_pdl(pdl_ok(pool), select_kernel<4>, grid, block, smem, st, d);
+  else launch_pdl(pdl_ok(pool), select_kernel<0>, grid, block, smem, st, d);
   MZ_LAUNCH_CHECK("select_kernel");
   pool->selected = 1;
   return MZ_OK;
@@ -954,26 +956,26 @@ extern "C" int mz_expand_backup_select(mz_pool* pool, const float* reward, const
   const float* r = reward ? reward : d.reward;
   const float* v = value ? value : d.value;
   if (use_thread_kernels(pool)) {
-    launch_pdl(tree_thread_kernel, dim3((pool->B + kThreadBlock - 1) / kThreadBlock), dim3(kThreadBlock), (size_t)(pool->S + 2) * 16, st, d, r, v, 3);
+    launch_pdl(pdl_ok(pool), tree_thread_kernel, dim3((pool->B + kThreadBlock - 1) / kThreadBlock), dim3(kThreadBlock), (size_t)(pool->S + 2) * 16, st, d, r, v, 3);
     MZ_LAUNCH_CHECK("tree_thread_kernel");
     pool->selected = 1;
     return MZ_OK;
   }
   if (pool->tree_ctas > 0 && A <= 128) {
     const dim3 cgrid(pool->tree_ctas), cblock(kConfinedThreads);
-    if (A <= 32) launch_pdl(backup_select_confined_kernel<1>, cgrid, cblock, (size_t)kConfinedSmem, st, d, r, v);
-    else if (A <= 64) launch_pdl(backup_select_confined_kernel<2>, cgrid, cblock, (size_t)kConfinedSmem, st, d, r, v);
-    else if (A <= 96) launch_pdl(backup_select_confined_kernel<3>, cgrid, cblock, (size_t)kConfinedSmem, st, d, r, v);
-    else launch_pdl(backup_select_confined_kernel<4>, cgrid, cblock, (size_t)kConfinedSmem, st, d, r, v);
+    if (A <= 32) launch_pdl(pdl_ok(pool), backup_select_confined_kernel<1>, cgrid, cblock, (size_t)kConfinedSmem, st, d, r, v);
+    else if (A <= 64) launch_pdl(pdl_ok(pool), backup_select_confined_kernel<2>, cgrid, cblock, (size_t)kConfinedSmem, st, d, r, v);
+    else if (A <= 96) launch_pdl(pdl_ok(pool), backup_select_confined_kernel<3>, cgrid, cblock, (size_t)kConfinedSmem, st, d, r, v);
+    else launch_pdl(pdl_ok(pool), backup_select_confined_kernel<4>, cgrid, cblock, (size_t)kConfinedSmem, st, d, r, v);
     MZ_LAUNCH_CHECK("backup_select_confined_kernel");
     pool->selected = 1;
     return MZ_OK;
   }
-  if (A <= 32) launch_pdl(backup_select_kernel<1>, grid, block, smem, st, d, r, v);
-  else if (A <= 64) launch_pdl(backup_select_kernel<2>, grid, block, smem, st, d, r, v);
-  else if (A <= 96) launch_pdl(backup_select_kernel<3>, grid, block, smem, st, d, r, v);
-  else if (A <= 128) launch_pdl(backup_select_kernel<4>, grid, block, smem, st, d, r, v);
-  else launch_pdl(backup_select_kernel<0>, grid, block, smem, st, d, r, v);
+  if (A <= 32) launch_pdl(pdl_ok(pool), backup_select_kernel<1>, grid, block, smem, st, d, r, v);
+  else if (A <= 64) launch_pdl(pdl_ok(pool), backup_select_kernel<2>, grid, block, smem, st, d, r, v);
+  else if (A <= 96) launch_pdl(pdl_ok(pool), backup_select_kernel<3>, grid, block, smem, st, d, r, v);
+  else if (A <= 128) launch_pdl(pdl_ok(pool), backup_select_kernel<4>, grid, block, smem, st, d, r, v);
+  else launch_pdl(pdl_ok(pool), backup_select_kernel<0>, grid, block, smem, st, d, r, v);
   MZ_LAUNCH_CHECK("backup_select_kernel");
   pool->selected = 1;
   return MZ_OK;
@@ -987,12 +989,12 @@ extern "C" int mz_expand_backup(mz_pool* pool, const float* reward, const float*
   }
   const PoolDev d = dev_of(pool);
   if (use_thread_kernels(pool)) {
-    launch_pdl(tree_thread_kernel, dim3((pool->B + kThreadBlock - 1) / kThreadBlock), dim3(kThreadBlock), (size_t)(pool->S + 2) * 16, (cudaStream_t)stream, d, reward ? reward : d.reward, value ? value : d.value, 2);
+    launch_pdl(pdl_ok(pool), tree_thread_kernel, dim3((pool->B + kThreadBlock - 1) / kThreadBlock), dim3(kThreadBlock), (size_t)(pool->S + 2) * 16, (cudaStream_t)stream, d, reward ? reward : d.reward, value ? value : d.value, 2);
     MZ_LAUNCH_CHECK("tree_thread_kernel");
     pool->selected = 0;
     return MZ_OK;
   }
-  launch_pdl(expand_backup_kernel, dim3(tree_blocks(pool->B)), dim3(kTreesPerBlock * 32), (size_t)0, (cudaStream_t)stream,
+  launch_pdl(pdl_ok(pool), expand_backup_kernel, dim3(tree_blocks(pool->B)), dim3(kTreesPerBlock * 32), (size_t)0, (cudaStream_t)stream,
              d, reward ? reward : d.reward, value ? value : d.value);
   MZ_LAUNCH_CHECK("expand_backup_kernel");
   pool->selected = 0;

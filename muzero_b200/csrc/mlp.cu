@@ -247,14 +247,8 @@ mlp_initial_kernel(MlpDev n, int batch, const float* __restrict__ obs, float* __
     // fused root preparation (mz_net_initial_search): the warp that wrote row r's softmax (softmax_rows: warp r % 8,
     // lane i -> actions i, i + 32, ...) draws the tree's Dirichlet noise, mixes, masks, renormalises and resets the tree
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (rs.noise_mode == 2 && lane < kRows / (kThreads / 32)) {
-      // the warp's 4 rows draw their Dirichlet samples side by side, one lane each (the sampler is sequential per tree)
-      const int t = row0 + warp + lane * (kThreads / 32);
-      if (t < batch && t < rs.pool.B) dirichlet_tree_thread(rs.pool, t, rs.alpha, rs.noise + (size_t)t * n.A);
-    }
-    __syncwarp();
     for (int r = warp; r < kRows; r += kThreads / 32)
-      if (row0 + r < batch) root_setup_fused(rs, row0 + r, lane, pi_probs + (size_t)(row0 + r) * n.A, true);
+      if (row0 + r < batch) root_setup_fused(rs, row0 + r, lane, pi_probs + (size_t)(row0 + r) * n.A);
   }
 }
 
@@ -770,8 +764,11 @@ struct MlpNet : NetImpl {
       prof_mark(kProfMlp, st);
       SearchArgs none;
       none.sims = 0;
-      launch_pdl(mlp_tc_kernel<false, 4>, dim3(q.nsplit == 2 ? 2 * ntiles : (ntiles < num_sms ? ntiles : num_sms)),
-                 dim3(kTcThreads), tc_smem, st, q, none);
+      // programmatic dependent launch only while the grid leaves SMs free: CTAs of a dependent kernel that start early
+      // sit on their SMs spinning until the predecessor drains, and with one 208 KB CTA per SM on most of the GPU
+      // (CartPole, 128 tiles) they held up the kernels they were waiting for (172 -> 120 M simulations/s)
+      const int grid = q.nsplit == 2 ? 2 * ntiles : (ntiles < num_sms ? ntiles : num_sms);
+      launch_pdl(2 * grid <= num_sms, mlp_tc_kernel<false, 4>, dim3(grid), dim3(kTcThreads), tc_smem, st, q, none);
       prof_mark(-1, st);
       MZ_LAUNCH_CHECK("mlp_recurrent_tc_kernel");
       if (debug) {   // measurement aid: cycle stamps of CTA 0 (start, prologue, gather, then per net: MMA1, epi1, MMA2, epi2; end)

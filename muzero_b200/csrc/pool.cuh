@@ -117,23 +117,6 @@ __device__ __forceinline__ void dirichlet_tree(const PoolDev& p, int t, int lane
   __syncwarp();
 }
 
-// The same sampler run by ONE thread (ThreadRng: same stream, sequential twist): lets the lanes of a warp draw the
-// noise of DIFFERENT trees at once where a warp has several trees to prepare (the MLP root-inference kernel: 4 rows
-// per warp) -- the sampler is sequential in its stream, so a whole warp per tree buys nothing but the twist.
-__device__ __forceinline__ void dirichlet_tree_thread(const PoolDev& p, int t, double alpha, double* o) {
-  ThreadRng rng;
-  rng.load(p.rng_key + (size_t)t * 624, p.rng_pos + t);
-  double acc = 0.0;
-  for (int a = 0; a < p.A; ++a) {
-    const double g = legacy_gamma(rng, alpha);
-    acc = __dadd_rn(acc, g);
-    o[a] = g;
-  }
-  const double inv = __ddiv_rn(1.0, acc);
-  for (int a = 0; a < p.A; ++a) o[a] = __dmul_rn(o[a], inv);
-  rng.store(p.rng_pos + t);
-}
-
 // Root preparation of tree t by one warp (replaces mcts.py:353-367 with 244-246 and 283-299): prior =
 // (1 - eps) * pi + eps * noise (float32 product + float64 product, see reset_kernel's history), masked and
 // renormalised with numpy's pairwise sum; root row zeroed, MinMaxStats reset.  pi / noise / mask point at THIS tree's
@@ -202,15 +185,13 @@ struct RootSetup {
   const int32_t* players;      // i32 [B, 2] or nullptr
 };
 
-// one warp, tree t, pi = this tree's softmax row (global memory, written by this warp); noise_drawn: the Dirichlet
-// sample of mode 2 is already in rs.noise (drawn by dirichlet_tree_thread)
-__device__ __forceinline__ void root_setup_fused(const RootSetup& rs, int t, int lane, const float* pi_row,
-                                                 bool noise_drawn = false) {
+// one warp, tree t, pi = this tree's softmax row (global memory, written by this warp)
+__device__ __forceinline__ void root_setup_fused(const RootSetup& rs, int t, int lane, const float* pi_row) {
   const PoolDev& p = rs.pool;
   if (t >= p.B) return;
   __syncwarp();
   double* nz = rs.noise_mode ? rs.noise + (size_t)t * p.A : nullptr;
-  if (rs.noise_mode == 2 && !noise_drawn) dirichlet_tree(p, t, lane, rs.alpha, nz);
+  if (rs.noise_mode == 2) dirichlet_tree(p, t, lane, rs.alpha, nz);
   root_setup_tree(p, t, lane, pi_row, nz, rs.eps, rs.one_minus_eps_f32,
                   rs.mask ? rs.mask + (size_t)t * p.A : nullptr, rs.players ? rs.players + 2 * t : nullptr, nullptr);
 }
