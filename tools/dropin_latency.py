@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 import muzero_b200 as mz  # noqa: E402
 
-for name in ('cartpole', 'tictactoe', 'gomoku', 'atari'):
+for name in (sys.argv[1:] or ('cartpole', 'tictactoe', 'gomoku', 'atari')):
     spec = bench.workload_spec(name, 1)
     cfg = spec['cfg']
     cls = {'mlp': mz.MuZeroMLPNet, 'board': mz.MuZeroBoardGameNet, 'atari': mz.MuZeroAtariNet}[spec['kind']]
@@ -21,6 +21,8 @@ for name in ('cartpole', 'tictactoe', 'gomoku', 'atari'):
     net.load_state_dict(bench.state_dict_for(spec))
     net = net.cuda().eval()
     obs, mask, cur, opp = bench.synthetic_inputs(spec, 1, 7)
+    if hasattr(obs, 'expand'):
+        obs = obs.expand().numpy()                  # the reference-signature call takes the float32 observation
     np.random.seed(0)
     dev = torch.device('cuda')
     for _ in range(5):
