@@ -299,8 +299,10 @@ int mz_replay_sample_uniform(int64_t size, int32_t batch, uint32_t* rng_key, int
                              float* out_weight, mz_stream stream);
 /* PrioritizedReplay.sample with priority_exponent != 0 (replay.py:93-100): float32 priorities ** exponent / their
  * float32 pairwise sum, np.random.choice(p=...) on the stream passed in (the reference draws from the GLOBAL numpy
- * stream here), importance weights ((1/size) / p[idx]) ** importance_exponent / max.  scratch_probs: f32[size + 1],
- * scratch_cdf: f64[size].  Bit-exact for exponents 1, 2 and 0.5 (numpy's exact paths), powf otherwise.              */
+ * stream here), importance weights ((1/size) / p[idx]) ** importance_exponent / max.  scratch_probs: f32[size + 1026],
+ * scratch_cdf: f64[size + size / 2048 + 1].  Bit-exact for exponents 1, 2 and 0.5 (numpy's exact paths), powf
+ * otherwise.  The float32 pairwise total is evaluated in parallel along numpy's own (fixed) recursion tree; the
+ * float64 running sum by a parallel scan whenever no addition can round (every probability >= 2^-29), else in order. */
 int mz_replay_sample_prioritized(int64_t size, int32_t batch, const float* priorities, float priority_exponent,
                                  float importance_exponent, uint32_t* rng_key, int32_t* rng_pos, float* scratch_probs,
                                  double* scratch_cdf, int64_t* out_index, float* out_weight, mz_stream stream);

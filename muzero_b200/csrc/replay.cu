@@ -94,17 +94,135 @@ __global__ void pow_kernel(const float* __restrict__ prio, float* __restrict__ p
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     pw[i] = np_pow_f32(prio[i], alpha);
 }
-// one thread: the float32 pairwise total and the float64 running sum are inherently ordered (bit-exactness)
-__global__ void total_kernel(const float* __restrict__ pw, long long n, float* total) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) *total = np_pairwise_sum_f32(pw, n);
+// The float32 pairwise total, bit-exact and parallel: numpy's recursion (halves rounded down to a multiple of 8, leaves
+// of at most 128 elements) is a FIXED tree, so its sub-trees can be summed independently.  Thread `path` (kTotalDepth
+// bits, first split = most significant bit) walks the recursion to its node and sums that node's segment with the
+// sequential routine above (which is numpy's recursion on the segment); one thread then combines the partial sums along
+// the top of the same tree.  A node that numpy would not split any further (<= 128 elements) before kTotalDepth splits
+// belongs to the path whose remaining bits are zero.
+constexpr int kTotalDepth = 10;
+__device__ __forceinline__ long long np_split(long long n) { long long n2 = n / 2; return n2 - n2 % 8; }
+__global__ void total_leaves_kernel(const float* __restrict__ pw, long long n, float* __restrict__ partial) {
+  const int path = blockIdx.x * blockDim.x + threadIdx.x;
+  if (path >= (1 << kTotalDepth)) return;
+  long long off = 0, len = n;
+  for (int level = 0; level < kTotalDepth; ++level) {
+    if (len <= 128) {                                     // numpy stops here: owned by the all-zero continuation
+      if (path & ((1 << (kTotalDepth - level)) - 1)) return;
+      break;
+    }
+    const long long n2 = np_split(len);
+    if ((path >> (kTotalDepth - 1 - level)) & 1) { off += n2; len -= n2; } else { len = n2; }
+  }
+  partial[path] = np_pairwise_sum_f32(pw + off, len);
+}
+__global__ void total_combine_kernel(const float* __restrict__ partial, long long n, float* total) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // depth-first walk of the top kTotalDepth levels with an explicit stack (state: 0 enter, 1 left done, 2 right done)
+  struct Frame { long long len; int path, level, state; float left; };
+  Frame st[kTotalDepth + 2];
+  int sp = 0;
+  st[0] = {n, 0, 0, 0, 0.0f};
+  float ret = 0.0f;
+  while (sp >= 0) {
+    Frame& f = st[sp];
+    if (f.state == 0) {
+      if (f.level == kTotalDepth || f.len <= 128) { ret = partial[f.path << (kTotalDepth - f.level)]; --sp; continue; }
+      f.state = 1;
+      st[sp + 1] = {np_split(f.len), f.path << 1, f.level + 1, 0, 0.0f};
+      ++sp;
+    } else if (f.state == 1) {
+      f.left = ret;
+      f.state = 2;
+      st[sp + 1] = {f.len - np_split(f.len), (f.path << 1) | 1, f.level + 1, 0, 0.0f};
+      ++sp;
+    } else {
+      ret = __fadd_rn(f.left, ret);
+      --sp;
+    }
+  }
+  *total = ret;
 }
 __global__ void probs_kernel(float* __restrict__ pw, long long n, const float* total) {
   const float s = *total;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     pw[i] = __fdiv_rn(pw[i], s);
 }
-__global__ void cumsum_kernel(const float* __restrict__ probs, long long n, double* __restrict__ cdf) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// The float64 running sum cdf[i] = cdf[i-1] + p[i] rounds after every addition, which orders it -- unless no addition
+// rounds at all.  Every p[i] is a float32 (24-bit significand) and every partial sum stays below 2, so if each nonzero
+// p[i] is at least 2^-29 all its bits are multiples of 2^-52 = ulp(1.x) and EVERY partial sum is exactly representable:
+// the additions are exact, hence associative, and a parallel scan returns the very doubles the sequential loop does.
+// exact_check_kernel raises a flag when some p[i] is smaller than that (or the total could reach 2); the sequential
+// kernel then runs instead.  (A replay of 10^6 items has p ~ 10^-6 = 2^-20.)
+constexpr int kScanChunk = 2048;       // elements per block
+__global__ void exact_check_kernel(const float* __restrict__ probs, long long n, int* flag) {
+  bool bad = false;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float p = probs[i];
+    bad |= !(p == 0.0f || (p >= 1.862645149230957e-09f && p < 1.0f));      // 2^-29 <= p < 1, or exactly 0
+  }
+  if (__any_sync(kAll, bad) && (threadIdx.x & 31) == 0) atomicExch(flag, 1);
+}
+__global__ void __launch_bounds__(256) scan_block_totals_kernel(const float* __restrict__ probs, long long n,
+                                                                double* __restrict__ block_total, const int* flag) {
+  if (*flag) return;
+  __shared__ double sh[8];
+  const long long base = (long long)blockIdx.x * kScanChunk;
+  double acc = 0.0;
+  for (int j = threadIdx.x; j < kScanChunk; j += 256) {
+    const long long i = base + j;
+    if (i < n) acc += (double)probs[i];                   // exact additions: any order
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kAll, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    block_total[blockIdx.x] = t;
+  }
+}
+__global__ void scan_offsets_kernel(double* __restrict__ block_total, int nblocks, const int* flag) {
+  if (*flag || threadIdx.x != 0 || blockIdx.x != 0) return;
+  double acc = 0.0;
+  for (int b = 0; b < nblocks; ++b) { const double t = block_total[b]; block_total[b] = acc; acc += t; }   // exclusive
+  // the total must stay below 2 for the exactness argument (it is ~1)
+}
+__global__ void __launch_bounds__(256) scan_write_kernel(const float* __restrict__ probs, long long n,
+                                                         const double* __restrict__ block_offset,
+                                                         double* __restrict__ cdf, const int* flag) {
+  if (*flag) return;
+  __shared__ double sh[256];
+  constexpr int PER = kScanChunk / 256;                    // consecutive elements per thread
+  const long long first = (long long)blockIdx.x * kScanChunk + (long long)threadIdx.x * PER;
+  double v[PER];
+  double acc = 0.0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const long long i = first + j;
+    acc += (i < n) ? (double)probs[i] : 0.0;
+    v[j] = acc;
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  // exclusive prefix of the per-thread totals (256 entries: a simple Hillis-Steele scan; every addition is exact)
+  for (int o = 1; o < 256; o <<= 1) {
+    const double add = threadIdx.x >= o ? sh[threadIdx.x - o] : 0.0;
+    __syncthreads();
+    sh[threadIdx.x] += add;
+    __syncthreads();
+  }
+  const double before = block_offset[blockIdx.x] + (threadIdx.x ? sh[threadIdx.x - 1] : 0.0);
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const long long i = first + j;
+    if (i < n) cdf[i] = before + v[j];
+  }
+}
+// sequential form (the general case: some addition may round)
+__global__ void cumsum_kernel(const float* __restrict__ probs, long long n, double* __restrict__ cdf, const int* flag) {
+  if (threadIdx.x != 0 || blockIdx.x != 0 || *flag == 0) return;
   double acc = 0.0;
   long long i = 0;
   for (; i + 4 <= n; i += 4) {          // loads run ahead of the dependent adds
@@ -224,13 +342,30 @@ extern "C" int mz_replay_sample_prioritized(int64_t size, int32_t batch, const f
   cudaStream_t st = (cudaStream_t)stream;
   const long long n = (long long)size;
   float* total = scratch_probs + n;                 // one float past the probabilities
+  // caller-owned scratch (the library allocates nothing): behind the n probabilities and the total come the partial
+  // sums of the parallel pairwise total and the exactness flag; behind the n cdf entries the block offsets of the scan
+  float* partial = total + 1;
+  int* flag = reinterpret_cast<int*>(partial + (1 << kTotalDepth));
+  double* block_total = scratch_cdf + n;
+  const int nblocks = (int)((n + kScanChunk - 1) / kScanChunk);
   pow_kernel<<<blocks_for(n), 256, 0, st>>>(priorities, scratch_probs, n, priority_exponent);
   MZ_LAUNCH_CHECK("pow_kernel");
-  total_kernel<<<1, 32, 0, st>>>(scratch_probs, n, total);
-  MZ_LAUNCH_CHECK("total_kernel");
+  total_leaves_kernel<<<(1 << kTotalDepth) / 128, 128, 0, st>>>(scratch_probs, n, partial);
+  MZ_LAUNCH_CHECK("total_leaves_kernel");
+  total_combine_kernel<<<1, 32, 0, st>>>(partial, n, total);
+  MZ_LAUNCH_CHECK("total_combine_kernel");
   probs_kernel<<<blocks_for(n), 256, 0, st>>>(scratch_probs, n, total);
   MZ_LAUNCH_CHECK("probs_kernel");
-  cumsum_kernel<<<1, 32, 0, st>>>(scratch_probs, n, scratch_cdf);
+  MZ_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  exact_check_kernel<<<blocks_for(n), 256, 0, st>>>(scratch_probs, n, flag);
+  MZ_LAUNCH_CHECK("exact_check_kernel");
+  scan_block_totals_kernel<<<nblocks, 256, 0, st>>>(scratch_probs, n, block_total, flag);
+  MZ_LAUNCH_CHECK("scan_block_totals_kernel");
+  scan_offsets_kernel<<<1, 32, 0, st>>>(block_total, nblocks, flag);
+  MZ_LAUNCH_CHECK("scan_offsets_kernel");
+  scan_write_kernel<<<nblocks, 256, 0, st>>>(scratch_probs, n, block_total, scratch_cdf, flag);
+  MZ_LAUNCH_CHECK("scan_write_kernel");
+  cumsum_kernel<<<1, 32, 0, st>>>(scratch_probs, n, scratch_cdf, flag);
   MZ_LAUNCH_CHECK("cumsum_kernel");
   cdf_norm_kernel<<<blocks_for(n), 256, 0, st>>>(scratch_cdf, n);
   MZ_LAUNCH_CHECK("cdf_norm_kernel");

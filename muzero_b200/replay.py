@@ -168,8 +168,9 @@ class DeviceReplay:
                                                         self._own.pos.data_ptr(), idx.data_ptr(), w.data_ptr(), st))
             else:
                 if self._scratch is None:
-                    self._scratch = (torch.empty(self._capacity + 1, dtype=torch.float32, device=self.device),
-                                     torch.empty(self._capacity, dtype=torch.float64, device=self.device))
+                    self._scratch = (torch.empty(self._capacity + 1026, dtype=torch.float32, device=self.device),
+                                     torch.empty(self._capacity + self._capacity // 2048 + 1, dtype=torch.float64,
+                                                 device=self.device))
                 if self._follow_global:
                     self._global.set(np.random.get_state())
                 _lib.check(lib.mz_replay_sample_prioritized(

@@ -195,3 +195,29 @@ def test_prioritized_sampling_follows_numpys_live_global_stream():
         assert np.array_equal(w.cpu().numpy().view(np.uint32), want_w.view(np.uint32))
     a, b = np.random.get_state(), twin.get_state()
     assert np.array_equal(a[1], b[1]) and a[2] == b[2]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('n,tiny', [(100, False), (5000, False), (200_000, False), (3000, True)])
+def test_parallel_total_and_scan_are_bit_exact(n, tiny):
+    """The prioritized path evaluates numpy's float32 pairwise total in parallel along numpy's own recursion tree and the
+    float64 running sum by a parallel scan when no addition can round (else sequentially: `tiny` plants probabilities
+    below 2^-29).  Indices and weights must equal the oracle's (numpy's) bit for bit at sizes that exercise several
+    levels of the tree / several scan blocks."""
+    from muzero_b200.replay import DeviceReplay
+    from muzero_b200.training import Transition
+    gen = np.random.RandomState(n)
+    prios = (gen.rand(n) * 3 + 1e-3).astype(np.float32)
+    if tiny:
+        prios[::7] = 1e-12
+    k = np.arange(n)
+    items = dict(state=(k % 127).astype(np.int8)[:, None], action=k.astype(np.int32), pi_prob=k.astype(np.float32)[:, None],
+                 value=k.astype(np.float32), reward=k.astype(np.float32))
+    rep = DeviceReplay(n, 1.0, 1.0, np.random.RandomState(1), global_state=np.random.RandomState(2))
+    rep.add_batch(Transition(**{f: torch.from_numpy(v).cuda() for f, v in items.items()}), prios)
+    twin = np.random.RandomState(2)
+    for _ in range(3):
+        _, idx, w = rep.sample(64)
+        want_idx, want_w = orc.sample_prioritized(prios, n, 64, 1.0, 1.0, twin)
+        assert np.array_equal(idx.cpu().numpy(), want_idx)
+        assert np.array_equal(w.cpu().numpy().view(np.uint32), want_w.view(np.uint32))
