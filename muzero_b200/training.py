@@ -178,13 +178,17 @@ class DataParallelLearner:
         if self.world > 1:
             bufs = [b for b in network.buffers() if b.dtype.is_floating_point]
             if bufs:
-                self.flat_buf = torch.zeros(sum(b.numel() for b in bufs), dtype=torch.float32, device=self.device)
+                # every buffer starts on a 256-byte boundary of the bucket: cuDNN's BatchNorm kernels take the running
+                # statistics through vector loads and fault on the 4-byte-aligned views a dense packing would give the
+                # buffers that follow a 1- or 2-channel head BatchNorm
+                pad = lambda n: (n + 63) // 64 * 64
+                self.flat_buf = torch.zeros(sum(pad(b.numel()) for b in bufs), dtype=torch.float32, device=self.device)
                 off = 0
                 for b in bufs:
                     view = self.flat_buf[off:off + b.numel()].view(b.shape)
                     view.copy_(b)
                     b.data = view
-                    off += b.numel()
+                    off += pad(b.numel())
         self.use_graph = bool(use_graph) and self.device.type == 'cuda'
         # gomoku/run_training.py:110 / classic: Adam(lr_init, weight_decay), MultiStepLR(milestones, lr_decay_rate).
         # Graph mode: step counters and the learning rate live on the device so that a replay sees their updates.
