@@ -221,18 +221,21 @@ int mz_net_recurrent(mz_net* net, int32_t batch, const void* hidden_in, const in
 
 /* All num_simulations simulations of the pool's trees -- select -> recurrent_inference -> expand + backup, the loop of
  * mcts.py:372-390 -- after the roots were prepared (mz_net_initial_search or mz_search_reset); leaves the pool as the
- * last mz_expand_backup would.  Default: the per-simulation launch chain (mz_select, then S x (mz_net_recurrent,
- * mz_expand_backup[_select])), enqueued here so that a search is three C calls.  With mz_net_set_fused_search(net, 1)
- * (MuZeroMLPNet, up to 12 actions): ONE launch of a persistent kernel whose CTAs own their trees for the whole search
- * (the thread that owns row i of a tensor-core tile also runs tree i's descent and backup; no per-simulation launch,
- * prologue or global round trip for the leaf action / reward / value).  Results are bit-identical either way
- * (tests/test_network_gpu.py::test_one_launch_search_kernel_equals_the_launch_chain); the one-launch form is opt-in
- * because it measured SLOWER at the benchmark sizes (a thread-per-tree descent over 10 actions is
- * ~700 dependent instructions per level on an SM with 4 active warps). */
+ * last mz_expand_backup would.  Either the per-simulation launch chain (mz_select, then S x (mz_net_recurrent,
+ * mz_expand_backup[_select])), enqueued here so that a search is three C calls, or ONE launch of a persistent kernel
+ * whose CTAs own their trees for the whole search:
+ *   - MuZeroMLPNet, 5..32 actions, at most 32 trees per SM of the device: a CTA of 32 warps owns 32 trees; warp w runs
+ *     tree w's backup and descent, then the CTA runs the tcgen05 chain on the 32 gathered rows (default where it
+ *     applies);
+ *   - MuZeroMLPNet, up to 12 actions, any batch: a CTA owns 128 trees, one thread per tree (only on request: measured
+ *     slower than the chain).
+ * Results are bit-identical in all three forms (tests/test_network_gpu.py::
+ * test_one_launch_search_kernel_equals_the_launch_chain). */
 int mz_search_run(mz_net* net, mz_pool* pool, mz_stream stream);
 
-/* enable = 1: mz_search_run uses the one-launch-per-search kernel where it exists (scheduling knob, no effect on
- * results).  Default 0.  MZ_FUSED_SEARCH=1 in the environment enables it process-wide. */
+/* Which form mz_search_run uses (scheduling knob, no effect on results): -1 (default) one launch where that is the
+ * faster form, 0 always the launch chain, 1 one launch wherever a kernel exists.  MZ_FUSED_SEARCH=0/1 in the
+ * environment overrides it process-wide. */
 int mz_net_set_fused_search(mz_net* net, int32_t enable);
 
 /* Cap the grid of the net's persistent kernels (0 = one CTA per SM).  Two engines that are driven from two

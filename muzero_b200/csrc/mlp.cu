@@ -10,6 +10,7 @@
 #include "net.cuh"
 #include "umma.cuh"
 #include "tree_thread.cuh"
+#include "tree_warp.cuh"
 #include <cuda_fp16.h>
 #include <cstdlib>
 
@@ -703,6 +704,261 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const __grid_cons
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+
+// ---------------------------------------------------------------------------
+// One launch per search, warp per tree (mz_search_run for MuZeroMLPNet with 5..32 actions when the batch fits one wave
+// of 32-tree CTAs): a CTA of 32 warps owns 32 trees for ALL simulations.
+//   tree phase : warp w runs tree w's backup (of the previous simulation) and pUCT descent -- the warp-per-tree code of
+//                the tree kernels (tree_warp.cuh), 32 trees side by side on the SM -- and gathers the leaf's parent
+//                state into row w of the operand tile;
+//   net phase  : the tcgen05 chain of mlp_tc_kernel (transition -> reward -> value, hidden layer in chunks of 256) on a
+//                128-row tile whose first 32 rows are the trees.  Those rows are TMEM lanes 0..31, which only warps with
+//                warp % 4 == 0 can read: the 8 such warps split the 256 columns of the first-layer epilogue (32 each);
+//                thread 0 issues the MMAs and, knowing when a weight slot is free (it waits for its own MMAs), also
+//                issues the TMA loads of the weight ring -- no producer warp.
+// Reward and value go back to the tree warps through shared memory.  Nothing is launched, allocated or staged per
+// simulation and the trees never leave their SM; trees of different CTAs never interact (no inter-CTA synchronisation).
+// ---------------------------------------------------------------------------
+constexpr int kS32Trees = 32;
+constexpr int kS32Threads = 1024;
+
+__global__ void __launch_bounds__(kS32Threads, 1) mlp_search32_kernel(const __grid_constant__ MlpTcParams p,
+                                                                      const __grid_constant__ SearchArgs sa) {
+  extern __shared__ __align__(1024) unsigned char tsm[];
+  unsigned char* sIn = tsm;                       // [8][128][16]  h_in   (fp16, K-major core matrices; rows 0..31 live)
+  unsigned char* sRaw = sIn + 16384;              // h_raw
+  unsigned char* sNorm = sRaw + 16384;            // h' (normalised)
+  unsigned char* sMid = sNorm + 16384;            // [32][128][16] hidden chunk
+  unsigned char* sW = sMid + 65536;               // [kTcSlots][32 KB]
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(sW + kTcSlots * kTcSlotBytes);
+  uint64_t* bar_mma = w_full + kTcSlots;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar_mma + 1);
+  float* sB1 = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_holder + 4) + 15) & ~(uintptr_t)15);   // [3][P]
+  float* sTab = sB1 + 4 * p.P;                    // [A][P + 4] action columns (when they fit)
+  const int tabP = p.P + 4;
+  double* sT = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sTab + (p.tab_in_smem ? p.A * tabP : 0)) + 15) & ~(uintptr_t)15);
+  const double* sR = sT + (sa.sims + 2);          // RN(1/n)
+  float* sRew = reinterpret_cast<float*>(sT + 2 * (sa.sims + 2));   // [32] reward of each tree's last inference
+  float* sVal = sRew + kS32Trees;
+  int* sAct = reinterpret_cast<int*>(sVal + kS32Trees);             // [32] action each tree selected
+  unsigned long long* sDst = reinterpret_cast<unsigned long long*>(sAct + kS32Trees);   // [32] hidden slot of the new node
+  float2* sMM = reinterpret_cast<float2*>(sDst + kS32Trees);        // [2][32] partial (min, max) of the transition output
+  unsigned long long* s_stats = reinterpret_cast<unsigned long long*>(sMM + 2 * kS32Trees);   // [4]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const PoolDev& pool = sa.pool;
+  const int S = sa.sims;
+  // ---- prologue (once per search)
+  for (int i = tid; i < 2 * (S + 2); i += kS32Threads) sT[i] = pool.T[i];
+  for (int i = tid; i < 3 * p.P; i += kS32Threads) sB1[i] = p.b1[i / p.P][i % p.P];
+  if (p.tab_in_smem)
+    for (int i = tid; i < p.A * p.P; i += kS32Threads) sTab[(i / p.P) * tabP + i % p.P] = p.tabA[i];
+  for (int i = tid; i < (3 * 16384 + 65536) / 16; i += kS32Threads)       // operand tiles: rows 32..127 stay zero
+    reinterpret_cast<int4*>(tsm)[i] = make_int4(0, 0, 0, 0);
+  if (tid < 4) s_stats[tid] = 0;
+  if (tid == 0) {
+    for (int s = 0; s < kTcSlots; ++s) mbar_init(&w_full[s], 1);
+    mbar_init(bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_holder, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_holder;
+  const uint32_t sIn_a = smem_u32(sIn), sRaw_a = smem_u32(sRaw), sNorm_a = smem_u32(sNorm), sMid_a = smem_u32(sMid);
+  const int bps = p.nblk;                           // weight blocks per simulation (3 nets x chunks x 2 layers)
+  const int ntiles = (p.batch + kS32Trees - 1) / kS32Trees;
+  int my_tiles = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) ++my_tiles;
+  const long long total_blocks = (long long)my_tiles * S * bps;
+  long long gb = 0;                                 // weight blocks consumed so far (thread 0's view == everyone's)
+  uint32_t mma_ph = 0;
+  // thread 0: fill slot (g % kTcSlots) with block g of the CTA's block stream
+  auto issue_block = [&](long long g) {
+    const int b = (int)(g % bps), s = (int)(g % kTcSlots);
+    mbar_arrive_expect_tx(&w_full[s], p.blk_bytes[b]);
+    bulk_g2s(sW + (size_t)s * kTcSlotBytes, p.wpack + p.blk_off[b], p.blk_bytes[b], &w_full[s]);
+  };
+  if (tid == 0)
+    for (long long g = 0; g < kTcSlots && g < total_blocks; ++g) issue_block(g);
+  // D (+)= A . B^T on the weight block at the head of the stream; the epilogue warps wait for the MMAs, thread 0 then
+  // refills the slot they just released
+  const bool epi = (warp & 3) == 0;                 // warps whose TMEM lane quadrant holds the 32 live rows
+  const int ej = warp >> 2;                         // 0..7: this epilogue warp's 32-column share of 256 columns
+  auto mma_group = [&](uint32_t a_addr, int ksteps, uint32_t dcol, uint32_t N, bool accumulate) {
+    if (tid == 0) {
+      const int s = (int)(gb % kTcSlots);
+      mbar_wait(&w_full[s], (uint32_t)((gb / kTcSlots) & 1));
+      tc_fence_after();
+      const uint32_t idesc = instr_desc_f16(128, N);
+      const uint32_t b_addr = smem_u32(sW) + (uint32_t)s * kTcSlotBytes;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const uint64_t ad = smem_desc(a_addr + (uint32_t)ks * 4096u, 2048, 128);
+        const uint64_t bd = smem_desc(b_addr + (uint32_t)ks * 32u * N, N * 16, 128);
+        mma_f16(tmem + dcol, ad, bd, idesc, (accumulate || ks > 0) ? 1u : 0u);
+      }
+      commit(bar_mma);
+    }
+    if (epi) {
+      mbar_wait(bar_mma, mma_ph);
+      tc_fence_after();
+      if (tid == 0 && gb + kTcSlots < total_blocks) issue_block(gb + kTcSlots);
+    }
+    mma_ph ^= 1;
+    ++gb;
+  };
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int t = tile * kS32Trees + warp;          // this warp's tree
+    const bool live = t < p.batch;
+    const int node0 = live ? pool.count[t] : 0;     // nodes of the tree so far (1 after a reset)
+    for (int sim = 0; sim < S; ++sim) {
+      // ---------------- tree phase: one warp per tree
+      size_t src_slot = 0;
+      if (live) {
+        if (sim > 0) { expand_backup_tree(pool, t, lane, sRew[warp], sVal[warp]); __syncwarp(); }
+        const int2 leaf = select_tree<1>(pool, t, lane, sT, sR, nullptr, s_stats);
+        src_slot = (size_t)t * pool.max_nodes + leaf.x;
+        if (lane == 0) {
+          sAct[warp] = leaf.y;
+          sDst[warp] = (unsigned long long)t * pool.max_nodes + min(node0 + sim, pool.max_nodes - 1);
+        }
+      } else if (lane == 0) {
+        sAct[warp] = 0;
+      }
+      // leaf gather: 64 floats of the parent's state -> row `warp` of the fp16 operand tile (lane l: floats 4l..4l+3)
+      if (lane < 16) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) v = reinterpret_cast<const float4*>(p.hidden_in + src_slot * 64)[lane];
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(sIn_a + (uint32_t)((lane >> 1) * 128 + warp) * 16 + (lane & 1) * 8),
+                     "r"(pack_h2(v.x, v.y)), "r"(pack_h2(v.z, v.w)) : "memory");
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+      // ---------------- net phase
+      const int row = lane;                         // epilogue threads: lane == row of the tile == tree of the tile
+      const uint32_t trow = tmem;                   // TMEM lanes 0..31
+      int act = sAct[row];
+      act = min(max(act, 0), p.A - 1);
+      for (int net = 0; net < 3; ++net) {
+        const uint32_t a_in = net == 0 ? sIn_a : (net == 1 ? sRaw_a : sNorm_a);
+        const uint32_t N2 = net == 0 ? 64u : 32u;
+        const float* b1 = sB1 + net * p.P;
+        const float* tab = net == 0 ? (p.tab_in_smem ? sTab + (size_t)act * tabP : p.tabA + (size_t)act * p.P) : nullptr;
+        for (int c = 0; c < p.chunks; ++c) {
+          mma_group(a_in, 4, 0u, 256u, false);                        // D1 = A_in . W1c^T
+          if (epi) {
+            // epilogue 1: bias (+ action column) + ReLU -> fp16 hidden chunk; this warp's 32 of the 256 columns
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              uint32_t r[16];
+              tmem_ld16(trow + (uint32_t)(ej * 32 + half * 16), r);
+              tmem_ld_wait();
+              const int col0 = c * kTcChunk + ej * 32 + half * 16;
+              float v[16];
+#pragma unroll
+              for (int e = 0; e < 16; e += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(b1 + col0 + e);
+                v[e] = __uint_as_float(r[e]) + b4.x; v[e + 1] = __uint_as_float(r[e + 1]) + b4.y;
+                v[e + 2] = __uint_as_float(r[e + 2]) + b4.z; v[e + 3] = __uint_as_float(r[e + 3]) + b4.w;
+              }
+              if (tab) {
+#pragma unroll
+                for (int e = 0; e < 16; e += 4) {
+                  const float4 t4 = *reinterpret_cast<const float4*>(tab + col0 + e);
+                  v[e] += t4.x; v[e + 1] += t4.y; v[e + 2] += t4.z; v[e + 3] += t4.w;
+                }
+              }
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const float* w = v + 8 * u;
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sMid_a + (uint32_t)((ej * 4 + half * 2 + u) * 128 + row) * 16),
+                             "r"(pack_h2(fmaxf(w[0], 0.f), fmaxf(w[1], 0.f))), "r"(pack_h2(fmaxf(w[2], 0.f), fmaxf(w[3], 0.f))),
+                             "r"(pack_h2(fmaxf(w[4], 0.f), fmaxf(w[5], 0.f))), "r"(pack_h2(fmaxf(w[6], 0.f), fmaxf(w[7], 0.f))) : "memory");
+              }
+            }
+          }
+          fence_proxy_async();
+          tc_fence_before();
+          __syncthreads();
+          tc_fence_after();
+          mma_group(sMid_a, 16, 256u, N2, c > 0);                     // D2 (+)= A_mid . W2c^T
+        }
+        // epilogue 2
+        const float* b2 = p.b2[net];
+        if (net == 0) {
+          // transition output: warps 0 and 4 take 32 of its 64 columns each; h_raw (for the reward net) and its
+          // min-max normalisation (util.py:31-36) over all 64, combined through shared memory
+          if (epi && ej < 2) {
+            float h[32];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              uint32_t r[16];
+              tmem_ld16(trow + 256u + (uint32_t)(ej * 32 + half * 16), r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 16; ++e) h[half * 16 + e] = __uint_as_float(r[e]) + __ldg(b2 + ej * 32 + half * 16 + e);
+            }
+            float mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) { mn = fminf(mn, h[e]); mx = fmaxf(mx, h[e]); }
+            sMM[ej * kS32Trees + row] = make_float2(mn, mx);
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sRaw_a + (uint32_t)((ej * 4 + g) * 128 + row) * 16),
+                           "r"(pack_h2(h[8 * g], h[8 * g + 1])), "r"(pack_h2(h[8 * g + 2], h[8 * g + 3])),
+                           "r"(pack_h2(h[8 * g + 4], h[8 * g + 5])), "r"(pack_h2(h[8 * g + 6], h[8 * g + 7])) : "memory");
+            asm volatile("bar.sync 1, 64;" ::: "memory");              // warps 0 and 4
+            const float2 o = sMM[(ej ^ 1) * kS32Trees + row];
+            mn = fminf(mn, o.x); mx = fmaxf(mx, o.y);
+            // (h - min) * (1 / den), as mlp_tc_kernel does (bit-identical hidden states)
+            const float inv = __fdiv_rn(1.0f, __fadd_rn(__fsub_rn(mx, mn), 1e-8f));
+#pragma unroll
+            for (int e = 0; e < 32; ++e) h[e] = __fmul_rn(__fsub_rn(h[e], mn), inv);
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sNorm_a + (uint32_t)((ej * 4 + g) * 128 + row) * 16),
+                           "r"(pack_h2(h[8 * g], h[8 * g + 1])), "r"(pack_h2(h[8 * g + 2], h[8 * g + 3])),
+                           "r"(pack_h2(h[8 * g + 4], h[8 * g + 5])), "r"(pack_h2(h[8 * g + 6], h[8 * g + 7])) : "memory");
+            if (tile * kS32Trees + row < p.batch) {
+              float4* dst = reinterpret_cast<float4*>(p.hidden_out + sDst[row] * 64 + ej * 32);
+#pragma unroll
+              for (int g = 0; g < 8; ++g) dst[g] = make_float4(h[4 * g], h[4 * g + 1], h[4 * g + 2], h[4 * g + 3]);
+            }
+          }
+        } else if (warp == 0) {
+          float l[32];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t r[16];
+            tmem_ld16(trow + 256u + (uint32_t)(half * 16), r);
+            tmem_ld_wait();
+            const int Sn = net == 1 ? p.Sr : p.Sv;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) l[half * 16 + e] = __uint_as_float(r[e]) + (half * 16 + e < Sn ? __ldg(b2 + half * 16 + e) : 0.0f);
+          }
+          const float out = support_scalar_regs(l, net == 1 ? p.Sr : p.Sv);
+          (net == 1 ? sRew : sVal)[row] = out;
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+      }
+    }   // simulations
+    if (live) expand_backup_tree(pool, t, lane, sRew[warp], sVal[warp]);     // the last simulation
+    __syncthreads();
+  }
+  flush_stats(pool, s_stats);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 // W [out x in_total] fp32 (row-major, PyTorch Linear.weight) -> fp16 block [K/8][N][8]:
 // rows n0 .. n0+N-1 (zero beyond `out`), input columns k0 .. k0+K-1
 __global__ void pack_linear_kernel(const float* __restrict__ w, __half* __restrict__ dst, int out, int in_total, int n0,
@@ -792,8 +1048,11 @@ struct MlpNet : NetImpl {
 };
 
 int MlpNet::search(mz_pool* pool, cudaStream_t st) {
-  static const bool env_on = getenv("MZ_FUSED_SEARCH") != nullptr && atoi(getenv("MZ_FUSED_SEARCH")) != 0;
-  if (!(fused_search || env_on) || !tc || pool->A != d.A || pool->A > 12 || pool->cfg.hidden_bytes != d.HD * 4) return 1;
+  // mode: -1 auto (one launch where it measured faster: the warp-per-tree kernel), 0 launch chain, 1 one launch wherever a
+  // kernel exists.  MZ_FUSED_SEARCH=0/1 in the environment overrides the handle's setting process-wide.
+  static const int env_mode = getenv("MZ_FUSED_SEARCH") ? atoi(getenv("MZ_FUSED_SEARCH")) : -2;
+  const int mode = env_mode >= 0 ? (env_mode != 0) : fused_search;
+  if (mode == 0 || !tc || pool->A != d.A || pool->cfg.hidden_bytes != d.HD * 4) return 1;
   MlpTcParams q = tcp;
   q.batch = pool->B;
   q.hidden_in = (const float*)pool->view_ptr[MZ_VIEW_HIDDEN];
@@ -803,13 +1062,29 @@ int MlpNet::search(mz_pool* pool, cudaStream_t st) {
   q.nblk = tc_blocks_no_policy;
   q.nsplit = 1;
   q.dbg = nullptr;
+  SearchArgs sa;
+  sa.pool = pool_dev(pool);
+  sa.sims = pool->S;
+  // (a) warp per tree, 32 trees per CTA: needs an action row that fills a useful part of a warp and a batch that fits
+  // one wave of CTAs (every CTA runs its trees' whole search)
+  const int ntiles32 = (pool->B + kS32Trees - 1) / kS32Trees;
+  if (pool->A > 4 && pool->A <= 32 && ntiles32 <= num_sms) {
+    const size_t smem32 = tc_smem + (size_t)(pool->S + 2) * 16 + 2048;
+    if (smem32 <= 227 * 1024) {
+      prof_mark(kProfMlp, st);
+      mlp_search32_kernel<<<ntiles32, kS32Threads, smem32, st>>>(q, sa);
+      prof_mark(-1, st);
+      MZ_LAUNCH_CHECK("mlp_search32_kernel");
+      return MZ_OK;
+    }
+  }
+  // (b) thread per tree, 128 trees per CTA: measured slower than the launch chain at every size,
+  // so only on request
+  if (mode != 1 || pool->A > 12) return 1;
   static const bool debug = getenv("MZ_MLP_DEBUG") != nullptr;
   if (debug) { cudaMalloc(&q.dbg, 64 * sizeof(long long)); cudaMemset(q.dbg, 0, 64 * sizeof(long long)); }
   const size_t smem_need = tc_smem + (size_t)(pool->S + 2) * 16 + kTcRows * sizeof(int) + 64;
   if (smem_need > 227 * 1024) return 1;
-  SearchArgs sa;
-  sa.pool = pool_dev(pool);
-  sa.sims = pool->S;
   const int ntiles = (pool->B + kTcRows - 1) / kTcRows;
   const int grid = ntiles < num_sms ? ntiles : num_sms;
   prof_mark(kProfMlp, st);
@@ -960,6 +1235,7 @@ int mlp_create(const mz_net_config& c, const float* const* w, int nw, void* aren
       MZ_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));
       MZ_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));
       MZ_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<true, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));
+      MZ_CUDA(cudaFuncSetAttribute(mlp_search32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));
     }
   }
   net->smem = smem_bytes(d);

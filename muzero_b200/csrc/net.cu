@@ -143,7 +143,7 @@ extern "C" int mz_search_run(mz_net* net, mz_pool* pool, mz_stream stream) {
 
 extern "C" int mz_net_set_fused_search(mz_net* net, int32_t enable) {
   MZ_CHECK_ARG(net, "NULL argument");
-  net->impl->fused_search = enable != 0;
+  net->impl->fused_search = enable < 0 ? -1 : (enable != 0 ? 1 : 0);
   return MZ_OK;
 }
 

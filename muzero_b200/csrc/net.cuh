@@ -13,7 +13,8 @@ enum ProfClass { kProfConv = 0, kProfHead = 1, kProfPack = 2, kProfMlp = 3, kPro
 struct NetImpl {
   bool profiling = false;
   int cta_limit = 0;                    // persistent kernels use at most this many CTAs (0: one per SM)
-  bool fused_search = false;            // mz_search_run uses the one-launch-per-search kernel (mz_net_set_fused_search)
+  int fused_search = -1;                // mz_search_run: -1 one launch per search where it is the faster form, 0 never
+                                        // (launch chain), 1 wherever a one-launch kernel exists (mz_net_set_fused_search)
   const RootSetup* pending_root = nullptr;   // set around initial() by mz_net_initial_search: the policy epilogue
                                              // also prepares the search roots (Dirichlet, mask, renormalise, reset)
   std::vector<cudaEvent_t> prof_ev;     // pairs (begin, end)

@@ -279,13 +279,15 @@ def test_fp16_networks_rarely_change_a_search():
     assert s['sampled_action_differs'] <= 0.05 and s['mean_l1_visit_policy'] <= 0.05
 
 
-@pytest.mark.parametrize('name,B', [('tictactoe', 300), ('cartpole', 200), ('lunarlander', 130), ('tictactoe', 4096)])
+@pytest.mark.parametrize('name,B', [('tictactoe', 300), ('cartpole', 200), ('lunarlander', 130), ('tictactoe', 4096),
+                                    ('tictactoe', 4800)])
 @pytest.mark.parametrize('noise_mode', ['device', 'none'])
 def test_one_launch_search_kernel_equals_the_launch_chain(name, B, noise_mode):
-    """mz_search_run's persistent kernel for the MLP nets (one launch per search; the thread that owns row i of a
-    tensor-core tile runs tree i's descent and backup) against the per-simulation launch chain (warp-per-tree /
-    thread-per-tree tree kernels + one tcgen05 launch per simulation), which the lock-step and replay tests pin to
-    the oracle: trees, statistics, hidden states, RNG streams, policies and actions, byte for byte."""
+    """mz_search_run's persistent kernels for the MLP nets -- one launch per search: 32 trees per CTA with a warp per
+    tree (Tic-Tac-Toe up to 32 trees per SM), or 128 trees per CTA with a thread per tree (the other cases here, on
+    request) -- against the per-simulation launch chain (warp-per-tree / thread-per-tree tree kernels + one tcgen05
+    launch per simulation), which the lock-step and replay tests pin to the oracle: trees, statistics, hidden states,
+    RNG streams, policies and actions, byte for byte."""
     import muzero_b200 as mz
     from muzero_b200 import _lib
     net, _, kw = load_mlp(name)
