@@ -737,7 +737,7 @@ __global__ void __launch_bounds__(kS32Threads, 1) mlp_search32_kernel(const __gr
   float* sTab = sB1 + 4 * p.P;                    // [A][P + 4] action columns (when they fit)
   const int tabP = p.P + 4;
   double* sT = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sTab + (p.tab_in_smem ? p.A * tabP : 0)) + 15) & ~(uintptr_t)15);
-  const double* sR = sT + (sa.sims + 2);          // RN(1/n)
+  const double* sR = sa.pool.T + (sa.sims + 2);   // RN(1/n): select_tree reads it with ld.global.nc (__ldg), so NOT the shared copy
   float* sRew = reinterpret_cast<float*>(sT + 2 * (sa.sims + 2));   // [32] reward of each tree's last inference
   float* sVal = sRew + kS32Trees;
   int* sAct = reinterpret_cast<int*>(sVal + kS32Trees);             // [32] action each tree selected
