@@ -748,6 +748,9 @@ __global__ void __launch_bounds__(kS32Threads, 1) mlp_search32_kernel(const __gr
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const PoolDev& pool = sa.pool;
   const int S = sa.sims;
+  int dbg_n = 0;
+  auto stamp = [&]() { if (p.dbg && blockIdx.x == 0 && tid == 0 && dbg_n < 62) p.dbg[dbg_n++] = clock64(); };
+  stamp();
   // ---- prologue (once per search)
   for (int i = tid; i < 2 * (S + 2); i += kS32Threads) sT[i] = pool.T[i];
   for (int i = tid; i < 3 * p.P; i += kS32Threads) sB1[i] = p.b1[i / p.P][i % p.P];
@@ -788,7 +791,10 @@ __global__ void __launch_bounds__(kS32Threads, 1) mlp_search32_kernel(const __gr
   const bool epi = (warp & 3) == 0;                 // warps whose TMEM lane quadrant holds the 32 live rows
   const int ej = warp >> 2;                         // 0..7: this epilogue warp's 32-column share of 256 columns
   auto mma_group = [&](uint32_t a_addr, int ksteps, uint32_t dcol, uint32_t N, bool accumulate) {
-    if (tid == 0) {
+    if (warp == 0) {
+      // the WHOLE warp walks the issue loop and one lane is elected inside each tcgen05 asm statement: an `if (tid == 0)`
+      // around the MMAs makes ptxas wrap every UTCHMMA in a convergence loop (~100 cycles per MMA, measured 1.6 k cycles
+      // for the 16 MMAs of a second layer that the tensor pipe finishes in 0.5 k)
       const int s = (int)(gb % kTcSlots);
       mbar_wait(&w_full[s], (uint32_t)((gb / kTcSlots) & 1));
       tc_fence_after();
@@ -797,9 +803,9 @@ __global__ void __launch_bounds__(kS32Threads, 1) mlp_search32_kernel(const __gr
       for (int ks = 0; ks < ksteps; ++ks) {
         const uint64_t ad = smem_desc(a_addr + (uint32_t)ks * 4096u, 2048, 128);
         const uint64_t bd = smem_desc(b_addr + (uint32_t)ks * 32u * N, N * 16, 128);
-        mma_f16(tmem + dcol, ad, bd, idesc, (accumulate || ks > 0) ? 1u : 0u);
+        mma_f16_elect(tmem + dcol, ad, bd, idesc, (accumulate || ks > 0) ? 1u : 0u);
       }
-      commit(bar_mma);
+      commit_elect(bar_mma);
     }
     if (epi) {
       mbar_wait(bar_mma, mma_ph);
@@ -815,12 +821,28 @@ __global__ void __launch_bounds__(kS32Threads, 1) mlp_search32_kernel(const __gr
     const bool live = t < p.batch;
     const int node0 = live ? pool.count[t] : 0;     // nodes of the tree so far (1 after a reset)
     for (int sim = 0; sim < S; ++sim) {
+      stamp();
       // ---------------- tree phase: one warp per tree
       size_t src_slot = 0;
       if (live) {
         if (sim > 0) { expand_backup_tree(pool, t, lane, sRew[warp], sVal[warp]); __syncwarp(); }
+        stamp();
         const int2 leaf = select_tree<1>(pool, t, lane, sT, sR, nullptr, s_stats);
+        stamp();
         src_slot = (size_t)t * pool.max_nodes + leaf.x;
+        {
+          // the backup that follows the network reads this path's statistics: pull them into this SM's L1 now, while
+          // the tensor-core chain runs (the trees of a CTA never leave their SM)
+          __syncwarp();                             // lane 0's stores of the path -> every lane
+          const int depth = pool.leaf_depth[t];
+          const size_t tb = (size_t)t * pool.max_nodes * pool.A;
+          if (lane < depth) {
+            const uint32_t e = pool.path[(size_t)t * pool.max_nodes + lane];
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pool.ew + tb + e));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pool.er + tb + e));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pool.hot + tb + e));
+          }
+        }
         if (lane == 0) {
           sAct[warp] = leaf.y;
           sDst[warp] = (unsigned long long)t * pool.max_nodes + min(node0 + sim, pool.max_nodes - 1);
@@ -839,6 +861,7 @@ __global__ void __launch_bounds__(kS32Threads, 1) mlp_search32_kernel(const __gr
       tc_fence_before();
       __syncthreads();
       tc_fence_after();
+      stamp();
       // ---------------- net phase
       const int row = lane;                         // epilogue threads: lane == row of the tile == tree of the tile
       const uint32_t trow = tmem;                   // TMEM lanes 0..31
@@ -851,6 +874,7 @@ __global__ void __launch_bounds__(kS32Threads, 1) mlp_search32_kernel(const __gr
         const float* tab = net == 0 ? (p.tab_in_smem ? sTab + (size_t)act * tabP : p.tabA + (size_t)act * p.P) : nullptr;
         for (int c = 0; c < p.chunks; ++c) {
           mma_group(a_in, 4, 0u, 256u, false);                        // D1 = A_in . W1c^T
+          stamp();
           if (epi) {
             // epilogue 1: bias (+ action column) + ReLU -> fp16 hidden chunk; this warp's 32 of the 256 columns
 #pragma unroll
@@ -886,7 +910,9 @@ __global__ void __launch_bounds__(kS32Threads, 1) mlp_search32_kernel(const __gr
           tc_fence_before();
           __syncthreads();
           tc_fence_after();
+          stamp();
           mma_group(sMid_a, 16, 256u, N2, c > 0);                     // D2 (+)= A_mid . W2c^T
+          stamp();
         }
         // epilogue 2
         const float* b2 = p.b2[net];
@@ -1071,10 +1097,21 @@ int MlpNet::search(mz_pool* pool, cudaStream_t st) {
   if (pool->A > 4 && pool->A <= 32 && ntiles32 <= num_sms) {
     const size_t smem32 = tc_smem + (size_t)(pool->S + 2) * 16 + 2048;
     if (smem32 <= 227 * 1024) {
+      static const bool debug32 = getenv("MZ_MLP_DEBUG") != nullptr;
+      if (debug32) { cudaMalloc(&q.dbg, 64 * sizeof(long long)); cudaMemset(q.dbg, 0, 64 * sizeof(long long)); }
       prof_mark(kProfMlp, st);
       mlp_search32_kernel<<<ntiles32, kS32Threads, smem32, st>>>(q, sa);
       prof_mark(-1, st);
       MZ_LAUNCH_CHECK("mlp_search32_kernel");
+      if (debug32) {   // cycle stamps of CTA 0 / thread 0 (tree 0): start, then per simulation: start, backup done, select done, gather + barrier, per net: MMA1, epilogue 1 + barrier, MMA2
+        cudaDeviceSynchronize();
+        long long h[64];
+        cudaMemcpy(h, q.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        cudaFree(q.dbg);
+        fprintf(stderr, "[mlp search32 dbg] cycles since start:");
+        for (int i = 1; i < 64 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[0]);
+        fprintf(stderr, "\n");
+      }
       return MZ_OK;
     }
   }
