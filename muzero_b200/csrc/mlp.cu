@@ -830,19 +830,6 @@ __global__ void __launch_bounds__(kS32Threads, 1) mlp_search32_kernel(const __gr
         const int2 leaf = select_tree<1>(pool, t, lane, sT, sR, nullptr, s_stats);
         stamp();
         src_slot = (size_t)t * pool.max_nodes + leaf.x;
-        {
-          // the backup that follows the network reads this path's statistics: pull them into this SM's L1 now, while
-          // the tensor-core chain runs (the trees of a CTA never leave their SM)
-          __syncwarp();                             // lane 0's stores of the path -> every lane
-          const int depth = pool.leaf_depth[t];
-          const size_t tb = (size_t)t * pool.max_nodes * pool.A;
-          if (lane < depth) {
-            const uint32_t e = pool.path[(size_t)t * pool.max_nodes + lane];
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(pool.ew + tb + e));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(pool.er + tb + e));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(pool.hot + tb + e));
-          }
-        }
         if (lane == 0) {
           sAct[warp] = leaf.y;
           sDst[warp] = (unsigned long long)t * pool.max_nodes + min(node0 + sim, pool.max_nodes - 1);
