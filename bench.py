@@ -515,10 +515,10 @@ def measure_workload(spec, args, dev, world, rank, steps, warmup, min_seconds=0.
                               'frac': ach / tf_peak, 'reference_graph_flops': flops * Bp})
     roofline = dict(roof[dominant])
     roofline.update({'kernel': dominant, 'traffic': None, 'peak_source': peak_src})
-    if spec['kind'] == 'mlp' and os.environ.get('MZ_FUSED_SEARCH', '0') == '1':
-        # opt-in: ONE persistent kernel for all S simulations (mz_search_run with mz_net_set_fused_search); the three
-        # kernels above are the per-simulation launch chain it replaces.  Timed eagerly with CUDA events around the
-        # launch.
+    if spec['kind'] == 'mlp':
+        # where mz_search_run runs ONE persistent kernel for all S simulations (configuration 2: the warp-per-tree
+        # kernel), that launch is what a search executes; the three kernels above are the per-simulation launch chain it
+        # replaces, kept as a diagnostic.  Timed eagerly with CUDA events around the launch.
         sm = []
         with torch.cuda.device(dev):
             for _ in range(max(3, reps)):
@@ -540,8 +540,8 @@ def measure_workload(spec, args, dev, world, rank, steps, warmup, min_seconds=0.
         if n_launch == 1:
             ab = sum(algorithmic_bytes_per_launch(n, spec, Bp, A, S, mean_depth, pool.hidden_bytes, True) for n in names) * S
             ach = flops * Bp * S / (search_ms * 1e-3) / 1e12
-            roofline = {'kernel': 'mlp_tc_kernel<search>: one persistent launch per search (thread-per-tree select / backup '
-                                  'around the tcgen05 MLP chain, trees owned by their CTA for all simulations)',
+            roofline = {'kernel': 'mlp_search32_kernel / mlp_tc_kernel<search>: one persistent launch per search (select / '
+                                  'backup around the tcgen05 MLP chain, trees owned by their CTA for all simulations)',
                         'bound': 'tensor', 'achieved': ach, 'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': ach / tf_peak,
                         'traffic': None, 'avg_launch_us': search_ms * 1e3, 'us_per_simulation': search_ms * 1e3 / S,
                         'algorithmic_bytes_per_launch': ab, 'hbm_achieved_gbs': ab / (search_ms * 1e-3) / 1e9,
