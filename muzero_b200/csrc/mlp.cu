@@ -19,6 +19,7 @@ using namespace umma;
 
 constexpr int kRows = 32;
 constexpr int kThreads = 256;
+constexpr int kInitThreads = 512;
 
 struct MlpDev {
   int in_dim, A, P, HD, Sv, Sr;
@@ -38,7 +39,7 @@ __device__ void dense_cols(const float* __restrict__ Wt, const float* __restrict
                            int K, int OUT, bool relu, float* out, int ldout, const int* extra_row) {
   constexpr int G = kRows / RPT;
   const int items = OUT * G;
-  for (int idx = threadIdx.x; idx < items; idx += kThreads) {
+  for (int idx = threadIdx.x; idx < items; idx += blockDim.x) {
     const int j = idx % OUT, g = idx / OUT;
     const float* x0 = in + (size_t)g * RPT * ldin;
     float acc[RPT];
@@ -81,7 +82,7 @@ __device__ void dense_cols(const float* __restrict__ Wt, const float* __restrict
 __device__ void dense_tiny(const float* __restrict__ W, const float* __restrict__ bias, const float* in, int ldin,
                            int K, int OUT, float* out, int ldout) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int item = warp; item < kRows * OUT; item += kThreads / 32) {
+  for (int item = warp; item < kRows * OUT; item += blockDim.x / 32) {
     const int r = item / OUT, j = item % OUT;
     float acc = 0.0f;
     for (int k = lane; k < K; k += 32) acc = fmaf(in[(size_t)r * ldin + k], __ldg(W + (size_t)j * K + k), acc);
@@ -93,11 +94,15 @@ __device__ void dense_tiny(const float* __restrict__ W, const float* __restrict_
 
 __device__ void dense(const float* Wt, const float* W, const float* bias, const float* in, int ldin, int K, int OUT,
                       bool relu, float* out, int ldout, const int* extra_row = nullptr) {
+  // rows per thread: as many as still give every thread of the CTA an item (256 threads: 32 for OUT >= 256, 16 for
+  // >= 128, ...; 512 threads: one step fewer).  The summation order of an output element does not depend on it.
+  int rpt = 32;
+  while (rpt > 2 && OUT * (kRows / rpt) < (int)blockDim.x) rpt >>= 1;
   if (OUT < 16 && W != nullptr && !relu && extra_row == nullptr) dense_tiny(W, bias, in, ldin, K, OUT, out, ldout);
-  else if (OUT >= 256) dense_cols<32>(Wt, bias, in, ldin, K, OUT, relu, out, ldout, extra_row);
-  else if (OUT >= 128) dense_cols<16>(Wt, bias, in, ldin, K, OUT, relu, out, ldout, extra_row);
-  else if (OUT >= 64) dense_cols<8>(Wt, bias, in, ldin, K, OUT, relu, out, ldout, extra_row);
-  else if (OUT >= 32) dense_cols<4>(Wt, bias, in, ldin, K, OUT, relu, out, ldout, extra_row);
+  else if (rpt == 32) dense_cols<32>(Wt, bias, in, ldin, K, OUT, relu, out, ldout, extra_row);
+  else if (rpt == 16) dense_cols<16>(Wt, bias, in, ldin, K, OUT, relu, out, ldout, extra_row);
+  else if (rpt == 8) dense_cols<8>(Wt, bias, in, ldin, K, OUT, relu, out, ldout, extra_row);
+  else if (rpt == 4) dense_cols<4>(Wt, bias, in, ldin, K, OUT, relu, out, ldout, extra_row);
   else dense_cols<2>(Wt, bias, in, ldin, K, OUT, relu, out, ldout, extra_row);
   __syncthreads();
 }
@@ -116,7 +121,7 @@ __device__ __forceinline__ float signed_parabolic(float x) {
 // util.py:70-93: softmax over the support, expectation, inverse value transform.  One warp per row.
 __device__ void support_to_scalar(const float* logits, int ld, int S, float* out_global, int row0, int batch) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int r = warp; r < kRows; r += kThreads / 32) {
+  for (int r = warp; r < kRows; r += blockDim.x / 32) {
     if (row0 + r >= batch) continue;
     const float* l = logits + (size_t)r * ld;
     if (S == 1) {                                     // scalar head, network.py:126-134
@@ -147,7 +152,7 @@ __device__ void support_to_scalar(const float* logits, int ld, int S, float* out
 
 __device__ void softmax_rows(const float* logits, int ld, int A, float* out_global, int row0, int batch) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int r = warp; r < kRows; r += kThreads / 32) {
+  for (int r = warp; r < kRows; r += blockDim.x / 32) {
     if (row0 + r >= batch) continue;
     const float* l = logits + (size_t)r * ld;
     float m = -INFINITY;
@@ -167,7 +172,7 @@ __device__ void softmax_rows(const float* logits, int ld, int A, float* out_glob
 __device__ void normalise_and_store(const float* hraw, float* hn, int HD, float* hidden_out,
                                     const int32_t* dst_index, int row0, int batch) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int r = warp; r < kRows; r += kThreads / 32) {
+  for (int r = warp; r < kRows; r += blockDim.x / 32) {
     const float* h = hraw + (size_t)r * HD;
     float mn = INFINITY, mx = -INFINITY;
     for (int i = lane; i < HD; i += 32) { mn = fminf(mn, h[i]); mx = fmaxf(mx, h[i]); }
@@ -229,13 +234,15 @@ __device__ void prediction_heads(const MlpDev& n, const Smem& s, float* pi_probs
   support_to_scalar(s.lg, s.ldl, n.Sv, value, row0, batch);
 }
 
-__global__ void __launch_bounds__(kThreads)
+// kInitThreads = 512: sixteen warps, so that the root preparation fused behind the softmax (root_setup_fused: a
+// sequential Dirichlet sampler per tree) has two rows per warp instead of four
+__global__ void __launch_bounds__(kInitThreads)
 mlp_initial_kernel(MlpDev n, int batch, const float* __restrict__ obs, float* __restrict__ hidden_out,
                    const int32_t* __restrict__ dst_index, float* __restrict__ pi_probs, float* __restrict__ value,
                    const __grid_constant__ RootSetup rs) {
   const Smem s = carve(n, mlp_smem);
   const int row0 = blockIdx.x * kRows;
-  for (int i = threadIdx.x; i < kRows * s.ldx; i += kThreads) {
+  for (int i = threadIdx.x; i < kRows * s.ldx; i += blockDim.x) {
     const int r = i / s.ldx, k = i % s.ldx;
     s.x[i] = (row0 + r < batch && k < n.in_dim) ? obs[(size_t)(row0 + r) * n.in_dim + k] : 0.0f;
   }
@@ -248,7 +255,7 @@ mlp_initial_kernel(MlpDev n, int batch, const float* __restrict__ obs, float* __
     // fused root preparation (mz_net_initial_search): the warp that wrote row r's softmax (softmax_rows: warp r % 8,
     // lane i -> actions i, i + 32, ...) draws the tree's Dirichlet noise, mixes, masks, renormalises and resets the tree
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int r = warp; r < kRows; r += kThreads / 32)
+    for (int r = warp; r < kRows; r += blockDim.x / 32)
       if (row0 + r < batch) root_setup_fused(rs, row0 + r, lane, pi_probs + (size_t)(row0 + r) * n.A);
   }
 }
@@ -261,7 +268,7 @@ mlp_recurrent_kernel(MlpDev n, int batch, const float* __restrict__ hidden_in, c
   const Smem s = carve(n, mlp_smem);
   const int row0 = blockIdx.x * kRows;
   // leaf gather: parent hidden state by slot index + the action as a weight-row index
-  for (int i = threadIdx.x; i < kRows * (n.HD / 4); i += kThreads) {
+  for (int i = threadIdx.x; i < kRows * (n.HD / 4); i += blockDim.x) {
     const int r = i / (n.HD / 4), k4 = i % (n.HD / 4);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (row0 + r < batch) {
@@ -1009,7 +1016,7 @@ struct MlpNet : NetImpl {
     prof_mark(kProfMlp, st);
     RootSetup rs;
     if (pending_root) rs = *pending_root; else rs.enabled = 0;
-    mlp_initial_kernel<<<(batch + kRows - 1) / kRows, kThreads, smem, st>>>(d, batch, obs, (float*)hidden_out,
+    mlp_initial_kernel<<<(batch + kRows - 1) / kRows, kInitThreads, smem, st>>>(d, batch, obs, (float*)hidden_out,
                                                                            dst_index, pi_probs, value, rs);
     prof_mark(-1, st);
     MZ_LAUNCH_CHECK("mlp_initial_kernel");

@@ -8,7 +8,7 @@ for tgt in tree conv_resident conv_dataflow; do
   for tool in memcheck racecheck synccheck; do
     echo "=== compute-sanitizer --tool $tool  python tools/sanitize_target.py $tgt" >> $L
     timeout ${SAN_TIMEOUT:-240} compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_target.py $tgt 2>&1 \
-      | grep -v "^$" | tail -12 >> $L
+      | grep -v "^$" | tail -40 >> $L
     echo "exit ${PIPESTATUS[0]}" >> $L
   done
 done
