@@ -462,3 +462,33 @@ def test_resnet_tictactoe_variant_through_the_drop_in_uct_search():
     stub = ReplayStub(plan.pi0[0].cpu().numpy(), d['R'][1:].astype(np.float32), d['value'][1:], d['parent'], d['move'])
     a_o, pi_o, q_o = orc.uct_search(obs, stub, 'cpu', cfg, 1.0, mask, 1, 2)
     assert a == a_o and np.array_equal(bits(pi), bits(pi_o)) and bits(q)[0] == bits(q_o)[0]
+
+
+def test_stacked_frames_equal_their_float32_expansion():
+    """mz_net_initial_frames / StackedFrames: an Atari observation handed over as uint8 frames + action-plane values
+    (gym_env.py:306-313) must give exactly what its float32 expansion gives -- hidden slots, policy, value, and a whole
+    batched search."""
+    import muzero_b200 as mz
+    net, _ = build_atari(ATARI_SMALL, 5)
+    gen = np.random.RandomState(8)
+    B, A = 9, 6
+    frames = torch.from_numpy(gen.randint(0, 256, size=(B, 2, 96, 96)).astype(np.uint8))
+    planes = torch.from_numpy(((gen.randint(0, A, size=(B, 2)) + 1) / A).astype(np.float32))
+    sf = mz.StackedFrames(frames, planes)
+    full = sf.expand()
+    assert full.shape == (B, 4, 96, 96) and full.dtype == torch.float32
+    h1, pi1, v1 = net.initial_inference_batch(sf)
+    h2, pi2, v2 = net.initial_inference_batch(full.cuda())
+    assert torch.equal(h1, h2) and torch.equal(pi1, pi2) and torch.equal(v1, v2)
+    cfg = mz.make_atari_config(use_tensorboard=False)
+    cfg.num_simulations = 8
+    out = []
+    for obs in (sf, full):
+        plan = mz.mcts.SearchPlan(net, cfg, B)
+        streams = [np.random.RandomState(40 + t) for t in range(B)]
+        a, pi, q = mz.uct_search_batch(obs, net, cfg, 1.0, np.ones((B, A), bool), 1, 1, rng=streams, plan=plan)
+        a2, pi_2, q2 = mz.uct_search_batch(obs, net, cfg, 1.0, np.ones((B, A), bool), 1, 1,
+                                           rng=[np.random.RandomState(40 + t) for t in range(B)], plan=plan)   # graph replay
+        assert torch.equal(a, a2) and torch.equal(pi, pi_2)
+        out.append((a.cpu(), pi.cpu(), q.cpu()))
+    assert all(torch.equal(x, y) for x, y in zip(*out))
