@@ -298,13 +298,14 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
     uint32_t st = 0, st_ph = 0;                 // weight ring slot and its phase parity
     uint32_t b_slot = b_lo0 + sW16;             // descriptor low word of ring slot `st`
     const uint32_t b_first = b_slot;
-    long long t_acc = 0, t_a = 0;
+    long long t_acc = 0, t_a = 0, t_a_pos[3] = {0, 0, 0};
     const long long t_begin = clock64();
     int i = 0;
     for (int l = 0; l < p.num_layers; ++l)
     for (int tile = first_tile(l); tile < p.num_tiles; tile += G, ++i) {
       const int buf = i & 1;
       const uint32_t uph = (i >> 1) & 1;
+      const int pos_in_layer = (tile - first_tile(l)) / G;
       long long tw = dbg ? clock64() : 0;
       mbar_wait(&acc_empty[buf], uph ^ 1);
       long long tw2 = dbg ? clock64() : 0;
@@ -316,7 +317,7 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
         mbar_wait(&a_ready[2 * buf], rdy_ph);                         // low 64 channels of the tile
         if (!p.khalf) mbar_wait(&a_ready[2 * buf + 1], rdy_ph);       // khalf: the high half is awaited before its K chunk
       }
-      if (dbg) t_a += clock64() - tw2;
+      if (dbg) { const long long dt = clock64() - tw2; t_a += dt; t_a_pos[pos_in_layer < 2 ? pos_in_layer : 2] += dt; }
       tc_fence_after();
       const uint32_t a_tile = a_lo0 + sA16 + (uint32_t)buf * (a_bytes >> 4) + (uint32_t)halo + (kSplitK ? 0u : 128u * mhalf);
       const uint32_t dacc = tmem + (uint32_t)(buf * 256) + 128u * mhalf;
@@ -387,6 +388,7 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
     if (dbg && lane == 0 && warp == 1) {
       long long* d = p.dbg + blockIdx.x * 16;
       d[2] = clock64() - t_begin; d[3] = t_acc; d[4] = t_a; d[6] = i;
+      d[12] = t_a_pos[0]; d[13] = t_a_pos[1]; d[14] = t_a_pos[2];
     }
   } else if (warp == 2) {
     // ------------------------------------------------ tile loader: activation rows -> shared memory by bulk copies.
@@ -1356,8 +1358,9 @@ struct ConvNet : NetImpl {
       double a[16] = {0};
       for (int c = 0; c < grid; ++c) for (int k = 0; k < 16; ++k) a[k] += (double)h[(size_t)c * 16 + k] / grid;
       fprintf(stderr, "[conv dbg] %dx%d cg=%d layers=%d items/cta=%.1f | producer total %.0f wait_empty %.0f | mma total %.0f wait_acc %.0f "
-              "wait_a %.0f | loader total %.0f wait_mma %.0f wait_dep %.0f | epilogue total %.0f wait_mma %.0f\n",
-              g.H, g.W, cg, nl, a[6], a[0], a[1], a[2], a[3], a[4], a[7], a[8], a[9], a[10], a[11]);
+              "wait_a %.0f (1st / 2nd / 3rd tile of a layer: %.0f / %.0f / %.0f) | loader total %.0f wait_mma %.0f wait_dep %.0f | "
+              "epilogue total %.0f wait_mma %.0f\n",
+              g.H, g.W, cg, nl, a[6], a[0], a[1], a[2], a[3], a[4], a[12], a[13], a[14], a[7], a[8], a[9], a[10], a[11]);
     }
     return MZ_OK;
   }
