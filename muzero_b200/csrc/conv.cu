@@ -78,9 +78,7 @@ struct LayerDesc {
 struct ConvParams {
   LayerDesc L[kMaxLayers];
   int num_layers;
-  int rot;                        // static schedule: tile t of layer l belongs to CTA (t + l*rot) % grid
-  unsigned int* work;             // dynamic schedule (dataflow launches): CTAs pull (layer, tile) items off this counter in
-                                  // global layer-major order; nullptr = the static schedule
+  int rot;                        // tile t of layer l belongs to CTA (t + l*rot) % grid: rotates who gets the odd tile
   unsigned int* flags;            // [num_layers][num_tiles], zeroed before the launch (nullptr for one layer)
   int* err;                       // dependency wait timed out (should never happen)
   int Ptot, PB, Wp, W, H, B;
@@ -211,14 +209,9 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
   float* s_bias = reinterpret_cast<float*>(tmem_holder + 4);            // [4][N] bias of layer l in slot l & 3, 16-byte aligned
   float2* s_mm = reinterpret_cast<float2*>(s_bias + 4 * p.N);           // [2][128] partial (min, max) per row
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_mm + 2 * 128);       // [2 tiles][2 halves][left,right,top,bottom][4] edge rows
-  // the CTA's item sequence: (layer << 20 | tile) of item k in s_item[k & 7], written by the weight-producer lane (the
-  // role that runs furthest ahead: less than one item before the MMA warps, which are at most two before the
-  // epilogue), published through the counter s_item[8]
-  uint32_t* s_item = s_mask + 2 * 2 * 16;
 
   if (tid == 0) {
     tmem_holder[2] = 0;
-    s_item[8] = 0;
     for (uint32_t s = 0; s < kStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], kSplitK ? 1 : 2); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&a_full[b], 1); mbar_init(&mma_done[b], 2); mbar_init(&acc_empty[b], kEpiThreads);
@@ -235,24 +228,9 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
   // weight-producer lane has seen published (dataflow launches); read by the epilogue before it requests residual rows
   const uint32_t s_res_a = smem_u32(tmem_holder + 2);
 
-  // Every role walks the same (layer, tile) item sequence of this CTA.  The weight-producer lane generates it -- from
-  // the static rotation, or (dataflow launches) by pulling the next item of the launch's layer-major order off a global
-  // counter -- and the other roles read it from the shared-memory ring.  Dynamic order: an item is only ever started
-  // after every item it depends on (tiles t-1, t, t+1 of the previous layer: >= num_tiles - 1 positions earlier in the
-  // order, more than the CTAs in flight) was started by somebody, so no CTA waits for a CTA that waits for it, and no CTA
-  // idles while items are left -- with 324 tiles per layer on 144 CTAs the static rotation gave a quarter of the CTAs a
-  // third tile per layer and the others a bubble (12 % of the MMA warps' time, two thirds of it at their first tile of a
-  // layer).
+  // every role walks the same (layer, tile) item sequence of this CTA
   const int G = (int)gridDim.x;
   auto first_tile = [&](int l) { int t0 = ((int)blockIdx.x - l * p.rot) % G; return t0 < 0 ? t0 + G : t0; };
-  constexpr uint32_t kNoItem = 0xffffffffu;
-  const uint32_t s_item_cnt_a = smem_u32(s_item + 8);
-  // item k of this CTA (blocks until the producer lane has published it); kNoItem: the sequence is over
-  auto get_item = [&](int k) -> uint32_t {
-    uint32_t seen;
-    do { asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(seen) : "r"(s_item_cnt_a) : "memory"); } while (seen <= (uint32_t)k);
-    return *reinterpret_cast<volatile uint32_t*>(s_item + (k & 7));
-  };
   const bool dbg = p.dbg != nullptr;
 
   if (warp == 0) {
@@ -262,25 +240,9 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
       uint32_t it = 0, res_items = 0;
       long long t_wait = 0;
       const long long t_begin = clock64();
-      // static schedule state
-      int sl = 0, stile = first_tile(0);
-      const unsigned total_items = (unsigned)p.num_layers * (unsigned)p.num_tiles;
-      for (int k = 0;; ++k) {
-        // ---- next item of this CTA
-        uint32_t item = kNoItem;
-        if (p.work) {
-          const unsigned g = atomicAdd(p.work, 1u);
-          if (g < total_items) item = ((g / (unsigned)p.num_tiles) << 20) | (g % (unsigned)p.num_tiles);
-        } else {
-          while (sl < p.num_layers && stile >= p.num_tiles) { ++sl; if (sl < p.num_layers) stile = first_tile(sl); }
-          if (sl < p.num_layers) { item = ((uint32_t)sl << 20) | (uint32_t)stile; stile += G; }
-        }
-        s_item[k & 7] = item;
-        asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(s_item_cnt_a), "r"((uint32_t)(k + 1)) : "memory");
-        if (item == kNoItem) break;
-        const int l = (int)(item >> 20), tile = (int)(item & 0xfffffu);
+      for (int l = 0; l < p.num_layers; ++l) {
         const unsigned char* wl = reinterpret_cast<const unsigned char*>(p.L[l].w);
-        {
+        for (int tile = first_tile(l); tile < p.num_tiles; tile += G) {
           if (!p.resident && p.flags) {
             // The epilogue prefetches this item's residual rows (written by layer res_layer, same tile, in general by
             // ANOTHER CTA two layers ago) before its MMAs finish, i.e. possibly before this CTA's loader has acquired
@@ -339,13 +301,11 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
     long long t_acc = 0, t_a = 0, t_a_pos[3] = {0, 0, 0};
     const long long t_begin = clock64();
     int i = 0;
-    for (;; ++i) {
-      const uint32_t item = get_item(i);
-      if (item == kNoItem) break;
-      const int l = (int)(item >> 20), tile = (int)(item & 0xfffffu);
+    for (int l = 0; l < p.num_layers; ++l)
+    for (int tile = first_tile(l); tile < p.num_tiles; tile += G, ++i) {
       const int buf = i & 1;
       const uint32_t uph = (i >> 1) & 1;
-      const int pos_in_layer = p.work ? 0 : (tile - first_tile(l)) / G;
+      const int pos_in_layer = (tile - first_tile(l)) / G;
       long long tw = dbg ? clock64() : 0;
       mbar_wait(&acc_empty[buf], uph ^ 1);
       long long tw2 = dbg ? clock64() : 0;
@@ -438,10 +398,8 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
     long long t_wait = 0, t_dep = 0;
     const long long t_begin = clock64();
     int i = 0, bias_layer = -1;
-    for (;; ++i) {
-      const uint32_t item = get_item(i);
-      if (item == kNoItem) break;
-      const int l = (int)(item >> 20), tile = (int)(item & 0xfffffu);
+    for (int l = 0; l < p.num_layers; ++l)
+    for (int tile = first_tile(l); tile < p.num_tiles; tile += G, ++i) {
       const LayerDesc& L = p.L[l];
       const int buf = i & 1;
       const int r0 = tile * p.tile_stride - halo, r1 = r0 + kRows + 2 * halo;       // tile rows [r0, r1)
@@ -550,10 +508,8 @@ __global__ void __maxnreg__(128) conv3x3_kernel(const __grid_constant__ ConvPara
     long long t_wait = 0;
     const long long t_begin = clock64();
     int k = 0;
-    for (;; ++k) {
-      const uint32_t item = get_item(k);
-      if (item == kNoItem) break;
-      const int l = (int)(item >> 20), tile = (int)(item & 0xfffffu);
+    for (int l = 0; l < p.num_layers; ++l)
+    for (int tile = first_tile(l); tile < p.num_tiles; tile += G, ++k) {
       const LayerDesc& L = p.L[l];
       const bool norm = (L.out_norm != nullptr) || (L.out_slots != nullptr);
       const int buf = k & 1;
@@ -1192,7 +1148,7 @@ struct ConvNet : NetImpl {
   const float* tab;
   Head h_reward, h_policy, h_value;
   act_t *xobs, *b0, *b1, *b2, *b3, *b4;
-  unsigned* flags;                  // tile flags of a dataflow launch; the 64 words before them hold its work counter
+  unsigned* flags;
   size_t flags_cap;
   int* err_flag;
 
@@ -1356,14 +1312,10 @@ struct ConvNet : NetImpl {
     const int grid = p.num_tiles < sm_cap ? p.num_tiles : sm_cap;
     p.rot = nl > 1 ? p.num_tiles % grid : 0;
     p.flags = nullptr;
-    p.work = nullptr;
     if (nl > 1 && !p.resident) {
       if ((size_t)nl * p.num_tiles > flags_cap) { reset_pending(); set_error("internal: flag buffer too small"); return MZ_EINVAL; }
       p.flags = flags;
-      // dynamic (layer, tile) schedule: the counter sits right before the flags, one memset clears both
-      static const bool static_sched = getenv("MZ_CONV_STATIC") != nullptr;
-      if (!static_sched) p.work = flags - 64;
-      cudaError_t e = cudaMemsetAsync(flags - 64, 0, (64 + (size_t)nl * p.num_tiles) * sizeof(unsigned), st);
+      cudaError_t e = cudaMemsetAsync(flags, 0, (size_t)nl * p.num_tiles * sizeof(unsigned), st);
       if (e != cudaSuccess) { reset_pending(); set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return MZ_ECUDA; }
     }
     p.dbg = nullptr;
@@ -1673,7 +1625,7 @@ int conv_arena_bytes(const mz_net_config& c, int max_batch, size_t* bytes) {
   t += align_up(rows(obs_pb) * (atari ? 2 : obs_cg(c.in_channels)) * 16, 256);           // packed observations
   t += 3 * align_up(act_bytes, 256);                                                     // b0..b2
   t += 2 * align_up(rows(PB) * N * 2, 256);                                              // b3, b4 (latent grid only)
-  t += align_up((size_t)kMaxLayers * (((size_t)max_batch * big_pb + 127) / 128) * 4, 256) + 512;   // work counter + tile flags (128-row tiles)
+  t += align_up((size_t)kMaxLayers * (((size_t)max_batch * big_pb + 127) / 128) * 4, 256) + 256;   // tile flags (128-row tiles)
   *bytes = t + 8192;
   return MZ_OK;
 }
@@ -1814,7 +1766,7 @@ int conv_create(const mz_net_config& c, const float* const* w, int nw, int max_b
   net->b3 = (act_t*)take(rows(PB) * N * 2);
   net->b4 = (act_t*)take(rows(PB) * N * 2);
   net->flags_cap = (size_t)kMaxLayers * (((size_t)max_batch * big_pb + 127) / 128);
-  net->flags = (unsigned*)take(256 + net->flags_cap * 4) + 64;
+  net->flags = (unsigned*)take(net->flags_cap * 4);
   net->err_flag = (int*)take(256);
   cudaMemset(net->err_flag, 0, 4);
   net->reset_pending();
