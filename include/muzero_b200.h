@@ -319,6 +319,50 @@ int mz_replay_gather(const void* storage, const int64_t* index, void* rows, int6
 int mz_replay_update_priorities(float* priorities, const int64_t* index, const float* values, int32_t n,
                                 mz_stream stream);
 
+/* ---- training step of the ResNet towers -------------------------------------------------------
+ * Replaces, for MuZeroBoardGameNet with num_planes == 128, what autograd + cuDNN execute for the towers inside
+ * calc_loss (pipeline.py:541-612): network.represent / dynamics / prediction (network.py:353-395, 398-448, 451-500)
+ * up to the tower outputs, forward and backward, in train mode (batch statistics, running-statistics update).
+ * Heads, hidden-state normalisation, losses and the gradient-scale hooks stay with the caller (PyTorch autograd).
+ * All tensors are float32 NCHW device buffers owned by the caller; the handle keeps fp16 / bf16 operand copies and the
+ * saved activations in the caller's arena.  Towers: 0 representation, 1 dynamics, 2 prediction; `call` is the unroll
+ * index (dynamics / prediction are evaluated unroll_steps times per step, each call keeps its own activations).      */
+typedef struct mz_train mz_train;
+typedef struct mz_train_config {
+  int32_t in_channels;      /* observation planes (representation's first conv)                   */
+  int32_t board_h, board_w;
+  int32_t num_actions;      /* <= 128                                                              */
+  int32_t num_planes;       /* 128                                                                 */
+  int32_t num_res_blocks;
+  int32_t batch;
+  int32_t unroll_steps;
+} mz_train_config;
+int mz_train_arena_bytes(const mz_train_config* cfg, size_t* bytes);
+int mz_train_create(const mz_train_config* cfg, void* arena_dev, size_t arena_bytes, mz_train** out);
+int mz_train_destroy(mz_train* t);
+/* 8 device pointers per 3x3 convolution, convolutions in module order (representation conv_block, its res_blocks'
+ * conv_block1 / conv_block2 ..., dynamics conv_block, its res_blocks, prediction res_blocks):
+ * conv weight f32 [128][ci][3][3], its gradient, BatchNorm weight, its gradient, BatchNorm bias, its gradient,
+ * running_mean, running_var.  Gradients are ACCUMULATED (+=) like autograd's: BatchNorm parameters by the tower
+ * backward calls, conv weights by mz_train_end_step.                                                              */
+int mz_train_bind(mz_train* t, void* const* ptrs, int32_t n, mz_stream stream);
+/* once per step before the first tower: re-pack the (updated) weights into operand layouts, clear the statistics   */
+int mz_train_begin_step(mz_train* t, mz_stream stream);
+/* x: observation [B,in_channels,H,W] (tower 0) or hidden state [B,128,H,W]; action i64 [B] (tower 1 only);
+ * out: the tower's output [B,128,H,W] (after the last ReLU, before normalize_hidden_state / the heads)              */
+int mz_train_tower_forward(mz_train* t, int32_t tower, int32_t call, const float* x, const int64_t* action, float* out,
+                           mz_stream stream);
+/* grad_out: dL/d out [B,128,H,W]; grad_in: dL/d x [B,128,H,W] (towers 1, 2; NULL for tower 0)                      */
+int mz_train_tower_backward(mz_train* t, int32_t tower, int32_t call, const float* grad_out, float* grad_in,
+                            mz_stream stream);
+/* after the last tower backward of a step: reduce the split-K partials into the conv weight gradients              */
+int mz_train_end_step(mz_train* t, mz_stream stream);
+/* parity tests: which = 0 tower input planes, 1 raw conv output of `layer`, 2 its activated output, 3 its
+ * statistics f32 [3][128][2] (forward sums | mean, invstd | backward sums).  Planes are 16-bit [groups][plane_rows][8],
+ * row P of the padded (H+1)x(W+1) grid at plane row front_rows + P.                                                */
+int mz_train_debug_view(mz_train* t, int32_t tower, int32_t call, int32_t layer, int32_t which, void** ptr, size_t* bytes,
+                        int32_t* plane_rows, int32_t* front_rows);
+
 /* number of kernels the library has launched since load (bench's gpu_launches) */
 uint64_t mz_launch_count(void);
 

@@ -28,6 +28,12 @@ class PoolConfig(C.Structure):
                 ('bound_min', C.c_double), ('bound_max', C.c_double), ('discount', C.c_double)]
 
 
+class TrainConfig(C.Structure):
+    _fields_ = [('in_channels', C.c_int32), ('board_h', C.c_int32), ('board_w', C.c_int32), ('num_actions', C.c_int32),
+                ('num_planes', C.c_int32), ('num_res_blocks', C.c_int32), ('batch', C.c_int32),
+                ('unroll_steps', C.c_int32)]
+
+
 class NetConfig(C.Structure):
     _fields_ = [('kind', C.c_int32), ('in_channels', C.c_int32), ('in_h', C.c_int32), ('in_w', C.c_int32),
                 ('num_actions', C.c_int32), ('num_planes', C.c_int32), ('num_res_blocks', C.c_int32),
@@ -83,6 +89,16 @@ PROTOTYPES = {
     'mz_targets_mc': (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
     'mz_unroll_sequences': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                       _P, _P]),
+    'mz_train_arena_bytes': (C.c_int, [C.POINTER(TrainConfig), C.POINTER(C.c_size_t)]),
+    'mz_train_create': (C.c_int, [C.POINTER(TrainConfig), _P, C.c_size_t, C.POINTER(_P)]),
+    'mz_train_destroy': (C.c_int, [_P]),
+    'mz_train_bind': (C.c_int, [_P, C.POINTER(_P), C.c_int32, _P]),
+    'mz_train_begin_step': (C.c_int, [_P, _P]),
+    'mz_train_tower_forward': (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    'mz_train_tower_backward': (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P]),
+    'mz_train_end_step': (C.c_int, [_P, _P]),
+    'mz_train_debug_view': (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P), C.POINTER(C.c_size_t),
+                                      C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     'mz_launch_count': (C.c_uint64, []),
 }
 

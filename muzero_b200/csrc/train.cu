@@ -1,0 +1,1050 @@
+// Training forward / backward of the ResNet towers of MuZeroBoardGameNet (network.py:273-300,353-395,398-470) for the
+// K-step unroll of pipeline.py:541-612, on the Blackwell tensor cores.  SURVEY.md 8 f-2.
+//
+// What runs here: every 3x3 convolution of the representation / dynamics / prediction towers -- forward, data
+// gradient and weight gradient as tcgen05 implicit GEMMs -- and the train-mode BatchNorm + ReLU + residual around
+// them, forward and backward.  The 1x1-conv heads, the min-max normalisation of the hidden state, the losses and the
+// two gradient-scale hooks stay PyTorch autograd (muzero_b200/train_engine.py): together < 0.1 % of the flops.
+//
+// Layout: the padded channel-group planes of conv.cu (pad == 1): a board is (H+1)*(W+1) positions, column W and row H
+// are a ZERO halo shared with the next row / board, an activation tensor is C/8 planes of [rows][8 channels] 16-bit.
+// With zeros at the halo every 3x3 tap is an unmasked constant row offset in all three GEMMs:
+//   forward   Y[P][co]    = sum_tap sum_ci  A[P + off(tap)][ci]  * W[co][ci][tap]          M = rows, N = co, K = 9*ci
+//   dgrad     dA[P][ci]   = sum_tap sum_co dY[P + off(tap)][co]  * W[co][ci][8 - tap]      the same kernel, other weights
+//   wgrad     dW[tap][co][ci] = sum_P     dY[P][co] * A[P + off(tap)][ci]                  M = co, N = ci, K = rows
+// For forward / dgrad the planes are the no-swizzle K-major operand layout (as in conv.cu).  For wgrad K runs along
+// the ROWS, and the very same planes are the no-swizzle MN-major operand layout (8 channels contiguous, consecutive
+// K = consecutive 16-byte rows), so both operands are again plain 1-D bulk copies and a tap is a shifted start address.
+// Every plane has `front` zero rows before row 0 and a zero tail, so that no tile needs a special case.
+//
+// Precision: activations and weights fp16 (like the inference engine; MZ_TRAIN_FWD_BF16=1: bf16), gradients bf16
+// (fp32 range, no loss scaling), fp32 accumulation in TMEM, fp32 BatchNorm statistics and parameter gradients.
+#include "common.cuh"
+#include "umma.cuh"
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <cstdlib>
+#include <vector>
+
+namespace mz {
+using namespace umma;
+
+namespace {
+
+constexpr int kC = 128;            // tower width this engine is built for
+constexpr int kFront = 64;         // zero rows before row 0 of every plane (>= W + 2)
+constexpr int kTail = 448;         // zero rows after the last 128-row tile (wgrad splits overshoot by < 16 * splits + halo)
+constexpr int kSplits = 16;        // row splits of a weight-gradient launch
+constexpr int kWgStage = 160;      // rows per wgrad pipeline stage
+constexpr int kConvStagesMax = 8;
+constexpr float kBnEps = 1e-5f, kBnMomentum = 0.1f;
+
+// ---- 16-bit element helpers (runtime element type: 0 = fp16, 1 = bf16) -------------------------------------------
+__device__ __forceinline__ float2 unpack2(uint32_t v, int bf16) {
+  if (bf16) return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
+  return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b, int bf16) {
+  uint32_t d;
+  if (bf16) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    d = *reinterpret_cast<uint32_t*>(&t);
+  } else {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  }
+  return d;
+}
+__device__ __forceinline__ void unpack8(const int4& r, int bf16, float (&v)[8]) {
+  const uint32_t w[4] = {(uint32_t)r.x, (uint32_t)r.y, (uint32_t)r.z, (uint32_t)r.w};
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const float2 f = unpack2(w[u], bf16);
+    v[2 * u] = f.x; v[2 * u + 1] = f.y;
+  }
+}
+__device__ __forceinline__ int4 pack8(const float* v, int bf16) {
+  return make_int4((int)pack2(v[0], v[1], bf16), (int)pack2(v[2], v[3], bf16), (int)pack2(v[4], v[5], bf16),
+                   (int)pack2(v[6], v[7], bf16));
+}
+
+// kind::f16 instruction descriptor with explicit operand formats (0 = fp16, 1 = bf16) and majors (1 = MN-major)
+__host__ __device__ constexpr uint32_t idesc_of(uint32_t M, uint32_t N, uint32_t afmt, uint32_t bfmt, uint32_t mn_major) {
+  return (1u << 4) | (afmt << 7) | (bfmt << 10) | (mn_major << 15) | (mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+struct Geom {
+  int B, H, W, Wp, PB, Ptot, R128, PR;     // PR: rows of one plane incl. front and tail
+};
+
+__device__ __forceinline__ bool is_halo(int P, int PB, int Wp, int W, int H) {
+  const int q = P % PB, y = q / Wp, x = q - y * Wp;
+  return x == W || y == H;
+}
+
+// column sums of a 32 x 32 register tile held as v[32] per lane (lane = row): returns the sum of column `lane`
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float keep = up ? v[i + s] : v[i];
+      const float send = up ? v[i] : v[i + s];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward conv / dgrad: one 128-row tile per CTA, N = 128 output channels, K = 9 taps x cg_in*8 channels
+// ---------------------------------------------------------------------------------------------------------------
+struct TConvParams {
+  const uint16_t* in;       // planes [cg_in][PR][8]
+  const uint16_t* w;        // packed [9][chunks][chunk_g][128][8]
+  uint16_t* out;            // planes [16][PR][8], zeros at halo rows
+  const uint16_t* add;      // optional bf16 planes added to the result (dgrad: the skip connection's gradient)
+  float* stats;             // optional [128][2] += (sum, sum of squares) over the real rows (forward: BatchNorm)
+  int cg_in, chunk_g, chunks;
+  int Ptot, PB, Wp, W, H, PR;
+  int TP, TPs;              // rows of a tile incl. halo / rows of a shared-memory plane (odd)
+  int stages;
+  uint32_t idesc;
+  int out_bf16;
+};
+
+constexpr int kTConvThreads = 192;   // w0 producer, w1 MMA issuer, w2-5 epilogue
+
+__global__ void __launch_bounds__(kTConvThreads) tconv_kernel(const __grid_constant__ TConvParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int halo = p.Wp + 1;
+  const int row0 = blockIdx.x * 128;
+  const uint32_t stage_bytes = (uint32_t)p.chunk_g * kC * 16;
+  const uint32_t a_bytes = (uint32_t)p.cg_in * p.TPs * 16;
+
+  unsigned char* sA = smem;
+  unsigned char* sW = smem + ((a_bytes + 127) & ~127u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)p.stages * stage_bytes);
+  uint64_t* w_full = bars;                           // [stages]
+  uint64_t* w_empty = bars + kConvStagesMax;         // [stages]
+  uint64_t* a_full = bars + 2 * kConvStagesMax;
+  uint64_t* mma_done = a_full + 1;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(mma_done + 1);
+  float* s_stat = reinterpret_cast<float*>(tmem_holder + 2);   // [2][128]
+
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    mbar_init(a_full, 1); mbar_init(mma_done, 1);
+    fence_mbar_init();
+  }
+  for (int i = tid; i < 2 * kC; i += kTConvThreads) s_stat[i] = 0.0f;
+  if (warp == 1) tmem_alloc(tmem_holder, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(a_full, (uint32_t)p.cg_in * p.TP * 16u);
+      for (int g = 0; g < p.cg_in; ++g)
+        bulk_g2s(sA + (size_t)g * p.TPs * 16, p.in + ((size_t)g * p.PR + kFront + row0 - halo) * 8, (uint32_t)p.TP * 16u, a_full);
+      const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.w);
+      const int total = 9 * p.chunks;
+      for (int it = 0; it < total; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        mbar_wait(&w_empty[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&w_full[s], stage_bytes);
+        bulk_g2s(sW + (size_t)s * stage_bytes, wsrc + (size_t)it * stage_bytes, stage_bytes, &w_full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    mbar_wait(a_full, 0);
+    tc_fence_after();
+    const uint32_t sA_a = smem_u32(sA), sW_a = smem_u32(sW);
+    const int ksteps = p.chunk_g / 2;
+    uint32_t acc = 0;
+    int it = 0;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int ky = tap / 3, kx = tap - 3 * ky;
+      const int off = (ky - 1) * p.Wp + (kx - 1);
+      for (int ch = 0; ch < p.chunks; ++ch, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        mbar_wait(&w_full[s], ph);
+        tc_fence_after();
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t a_addr = sA_a + (uint32_t)(((ch * p.chunk_g + 2 * ks) * p.TPs + halo + off) * 16);
+          const uint32_t b_addr = sW_a + (uint32_t)s * stage_bytes + (uint32_t)(2 * ks) * (kC * 16);
+          mma_f16_elect(tmem, smem_desc(a_addr, (uint32_t)p.TPs * 16u, 128), smem_desc(b_addr, kC * 16, 128), p.idesc, acc);
+          acc = 1;
+        }
+        commit_elect(&w_empty[s]);
+      }
+    }
+    commit_elect(mma_done);
+  } else {
+    // ---- epilogue: TMEM lane = tile row; a warp reads the lane quadrant warp % 4
+    const int quad = warp & 3;
+    const int P = row0 + quad * 32 + lane;
+    const bool inr = P < p.Ptot;
+    const bool valid = inr && !is_halo(P, p.PB, p.Wp, p.W, p.H);
+    mbar_wait(mma_done, 0);
+    tc_fence_after();
+    const size_t rowoff = (size_t)kFront + (size_t)P;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), r);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) v[e] = valid ? __uint_as_float(r[e]) : 0.0f;
+      if (p.add && valid) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int4 a4 = __ldg(reinterpret_cast<const int4*>(p.add) + (size_t)(c * 4 + u) * p.PR + rowoff);
+          float f[8];
+          unpack8(a4, 1, f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[8 * u + e] += f[e];
+        }
+      }
+      if (inr) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          reinterpret_cast<int4*>(p.out)[(size_t)(c * 4 + u) * p.PR + rowoff] = pack8(v + 8 * u, p.out_bf16);
+      }
+      if (p.stats) {
+        float sq[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) sq[e] = v[e] * v[e];
+        const float s1 = warp_colsum32(v, lane);
+        const float s2 = warp_colsum32(sq, lane);
+        atomicAdd(&s_stat[c * 32 + lane], s1);
+        atomicAdd(&s_stat[kC + c * 32 + lane], s2);
+      }
+    }
+    if (p.stats) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int et = tid - 64;
+      atomicAdd(p.stats + 2 * et, s_stat[et]);
+      atomicAdd(p.stats + 2 * et + 1, s_stat[kC + et]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 128);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// wgrad: CTA (split s, tap row ky, ci block) accumulates dW[ky*3 + kx][co][ci] for kx = 0..2 over its rows
+// ---------------------------------------------------------------------------------------------------------------
+struct TWgradParams {
+  const uint16_t* dy;       // bf16 planes [16][PR][8]
+  const uint16_t* x;        // planes of the conv's input; ci block b starts at plane b * 16
+  float* partial;           // [ci_blocks][kSplits][9][128][N]
+  int n_groups;             // N / 8 of one ci block
+  int Rs;                   // rows per split, multiple of 16
+  int Wp, PR;
+  int accumulate;           // 0: overwrite the partials (first use in this step), 1: add
+  uint32_t idesc;
+  int swap_strides;         // debug: exchange LBO / SBO of the MN-major descriptors
+};
+
+__global__ void __launch_bounds__(kTConvThreads) twgrad_kernel(const __grid_constant__ TWgradParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int split = blockIdx.x, ky = blockIdx.y, blk = blockIdx.z;
+  const int ng = p.n_groups, N = ng * 8;
+  const uint32_t dy_bytes = 16u * kWgStage * 16u, x_bytes = (uint32_t)ng * (kWgStage + 2) * 16u;
+  const uint32_t st_bytes = dy_bytes + ((x_bytes + 127u) & ~127u);
+  unsigned char* sS = smem;                                        // [2][dY | X]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * (size_t)st_bytes);
+  uint64_t* full = bars;        // [2]
+  uint64_t* empty = bars + 2;   // [2]
+  uint64_t* done = bars + 4;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 5);
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_holder, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_holder;
+  const int nst = (p.Rs + kWgStage - 1) / kWgStage;
+  const int r_base = split * p.Rs;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint16_t* xb = p.x + (size_t)blk * 16 * p.PR * 8;
+      for (int st = 0; st < nst; ++st) {
+        const int s = st & 1;
+        const uint32_t ph = (uint32_t)(st >> 1) & 1u;
+        const int rows = (p.Rs - st * kWgStage) < kWgStage ? (p.Rs - st * kWgStage) : kWgStage;
+        const int r0 = r_base + st * kWgStage;
+        mbar_wait(&empty[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&full[s], 16u * rows * 16u + (uint32_t)ng * (rows + 2) * 16u);
+        unsigned char* d0 = sS + (size_t)s * st_bytes;
+        for (int g = 0; g < 16; ++g)
+          bulk_g2s(d0 + (size_t)g * kWgStage * 16, p.dy + ((size_t)g * p.PR + kFront + r0) * 8, (uint32_t)rows * 16u, &full[s]);
+        const int xr0 = r0 + (ky - 1) * p.Wp - 1;
+        for (int g = 0; g < ng; ++g)
+          bulk_g2s(d0 + dy_bytes + (size_t)g * (kWgStage + 2) * 16, xb + ((size_t)g * p.PR + kFront + xr0) * 8,
+                   (uint32_t)(rows + 2) * 16u, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t base = smem_u32(sS);
+    // MN-major, no swizzle: consecutive K (rows) are consecutive 16-byte units, 8 rows = one 128-byte core matrix;
+    // LBO = distance between core matrices along K (128 B), SBO = distance between 8-channel groups (one plane)
+    uint32_t a_lbo = 128, a_sbo = kWgStage * 16, b_lbo = 128, b_sbo = (kWgStage + 2) * 16;
+    if (p.swap_strides) { uint32_t t = a_lbo; a_lbo = a_sbo; a_sbo = t; t = b_lbo; b_lbo = b_sbo; b_sbo = t; }
+    for (int st = 0; st < nst; ++st) {
+      const int s = st & 1;
+      const uint32_t ph = (uint32_t)(st >> 1) & 1u;
+      const int rows = (p.Rs - st * kWgStage) < kWgStage ? (p.Rs - st * kWgStage) : kWgStage;
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      const uint32_t dy_a = base + (uint32_t)s * st_bytes, x_a = dy_a + dy_bytes;
+      for (int kx = 0; kx < 3; ++kx) {
+        const uint32_t d = tmem + (uint32_t)(kx * N);
+        for (int ks = 0; ks < rows / 16; ++ks) {
+          const uint64_t ad = smem_desc(dy_a + (uint32_t)(ks * 16) * 16u, a_lbo, a_sbo);
+          const uint64_t bd = smem_desc(x_a + (uint32_t)(ks * 16 + kx) * 16u, b_lbo, b_sbo);
+          mma_f16_elect(d, ad, bd, p.idesc, (st > 0 || ks > 0) ? 1u : 0u);
+        }
+      }
+      commit_elect(&empty[s]);
+    }
+    commit_elect(done);
+  } else {
+    const int quad = warp & 3;
+    const int co = quad * 32 + lane;
+    mbar_wait(done, 0);
+    tc_fence_after();
+    for (int kx = 0; kx < 3; ++kx) {
+      float* dst = p.partial + ((((size_t)blk * kSplits + split) * 9 + (ky * 3 + kx)) * kC + co) * N;
+      for (int c = 0; c < N / 16; ++c) {
+        uint32_t r[16];
+        tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(kx * N + c * 16), r);
+        tmem_ld_wait();
+        float4* d4 = reinterpret_cast<float4*>(dst + c * 16);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float4 o = make_float4(__uint_as_float(r[4 * u]), __uint_as_float(r[4 * u + 1]), __uint_as_float(r[4 * u + 2]),
+                                 __uint_as_float(r[4 * u + 3]));
+          if (p.accumulate) {
+            const float4 q = d4[u];
+            o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+          }
+          d4[u] = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// elementwise / reduction kernels on the planes.  Thread = (plane g = blockIdx.y, row P): 8 channels, one 16-byte access
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kEwThreads = 256;
+constexpr int kEwRows = 4;           // rows per thread
+
+struct BnFwdParams {
+  const uint16_t* y;        // raw conv output (fwd type)
+  const uint16_t* res;      // residual (fwd type) or nullptr
+  uint16_t* a;              // relu(bn(y) + res)
+  const float* sums;        // [128][2] from the conv epilogue
+  float* saved;             // [128][2] (mean, invstd) for the backward pass
+  const float *gamma, *beta;
+  float *running_mean, *running_var;
+  int Ptot, PB, Wp, W, H, PR, fbf16;
+  float inv_n, unbias;      // 1 / (B*H*W), n / (n - 1)
+};
+
+__global__ void __launch_bounds__(kEwThreads) bn_fwd_kernel(const BnFwdParams p) {
+  __shared__ float s_scale[8], s_shift[8];
+  const int g = blockIdx.y;
+  if (threadIdx.x < 8) {
+    const int c = g * 8 + threadIdx.x;
+    const float mean = p.sums[2 * c] * p.inv_n;
+    float var = p.sums[2 * c + 1] * p.inv_n - mean * mean;
+    var = var > 0.0f ? var : 0.0f;
+    const float is = rsqrtf(var + kBnEps);
+    const float sc = p.gamma[c] * is;
+    s_scale[threadIdx.x] = sc;
+    s_shift[threadIdx.x] = p.beta[c] - mean * sc;
+    if (blockIdx.x == 0) {
+      p.saved[2 * c] = mean; p.saved[2 * c + 1] = is;
+      p.running_mean[c] = (1.0f - kBnMomentum) * p.running_mean[c] + kBnMomentum * mean;
+      p.running_var[c] = (1.0f - kBnMomentum) * p.running_var[c] + kBnMomentum * var * p.unbias;
+    }
+  }
+  __syncthreads();
+  float sc[8], sh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { sc[e] = s_scale[e]; sh[e] = s_shift[e]; }
+  const size_t plane = (size_t)g * p.PR + kFront;
+#pragma unroll
+  for (int k = 0; k < kEwRows; ++k) {
+    const int P = (blockIdx.x * kEwRows + k) * kEwThreads + threadIdx.x;
+    if (P >= p.Ptot) break;
+    int4 o = make_int4(0, 0, 0, 0);
+    if (!is_halo(P, p.PB, p.Wp, p.W, p.H)) {
+      float v[8];
+      unpack8(__ldg(reinterpret_cast<const int4*>(p.y) + plane + P), p.fbf16, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = v[e] * sc[e] + sh[e];
+      if (p.res) {
+        float r[8];
+        unpack8(__ldg(reinterpret_cast<const int4*>(p.res) + plane + P), p.fbf16, r);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] += r[e];
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.0f);
+      o = pack8(v, p.fbf16);
+    }
+    reinterpret_cast<int4*>(p.a)[plane + P] = o;
+  }
+}
+
+struct BnBwdParams {
+  const uint16_t* g;        // gradient w.r.t. the activated output (bf16)
+  const uint16_t* a;        // the activated output (fwd type): ReLU mask
+  const uint16_t* y;        // raw conv output (fwd type)
+  const float* saved;       // [128][2] mean, invstd
+  float* sums;              // [128][2] (sum dZ, sum dZ * xhat)
+  const float* gamma;
+  float *dgamma, *dbeta;    // += (apply kernel, blockIdx.x == 0)
+  uint16_t* dy;             // gradient w.r.t. the raw conv output (bf16), zeros at halo rows
+  uint16_t* dz;             // optional: the masked gradient itself (the residual branch's share), bf16
+  int Ptot, PB, Wp, W, H, PR, fbf16;
+  float inv_n;
+  int rows_per_cta;         // reduce kernel
+};
+
+__global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(const BnBwdParams p) {
+  const int g = blockIdx.y;
+  float mean[8], is[8], s1[8], s2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    mean[e] = p.saved[2 * (g * 8 + e)]; is[e] = p.saved[2 * (g * 8 + e) + 1];
+    s1[e] = 0.0f; s2[e] = 0.0f;
+  }
+  const size_t plane = (size_t)g * p.PR + kFront;
+  const int r_begin = blockIdx.x * p.rows_per_cta;
+  const int r_end = (r_begin + p.rows_per_cta) < p.Ptot ? (r_begin + p.rows_per_cta) : p.Ptot;
+  for (int P = r_begin + threadIdx.x; P < r_end; P += kEwThreads) {
+    // halo rows: G is zero there, so they add nothing
+    float gv[8], av[8], yv[8];
+    unpack8(__ldg(reinterpret_cast<const int4*>(p.g) + plane + P), 1, gv);
+    unpack8(__ldg(reinterpret_cast<const int4*>(p.a) + plane + P), p.fbf16, av);
+    unpack8(__ldg(reinterpret_cast<const int4*>(p.y) + plane + P), p.fbf16, yv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float dz = av[e] > 0.0f ? gv[e] : 0.0f;
+      s1[e] += dz;
+      s2[e] += dz * (yv[e] - mean[e]) * is[e];
+    }
+  }
+  __shared__ float red[kEwThreads / 32][16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], o);
+      s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], o);
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { red[warp][e] = s1[e]; red[warp][8 + e] = s2[e]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    float t = 0.0f;
+    for (int w = 0; w < kEwThreads / 32; ++w) t += red[w][threadIdx.x];
+    const int e = threadIdx.x & 7, which = threadIdx.x >> 3;
+    atomicAdd(p.sums + 2 * (g * 8 + e) + which, t);
+  }
+}
+
+__global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(const BnBwdParams p) {
+  __shared__ float s_k[8][4];      // mean, invstd, gamma*invstd, and the two batch means
+  __shared__ float s_m[8][2];
+  const int g = blockIdx.y;
+  if (threadIdx.x < 8) {
+    const int c = g * 8 + threadIdx.x;
+    const float S1 = p.sums[2 * c], S2 = p.sums[2 * c + 1];
+    s_k[threadIdx.x][0] = p.saved[2 * c];
+    s_k[threadIdx.x][1] = p.saved[2 * c + 1];
+    s_k[threadIdx.x][2] = p.gamma[c] * p.saved[2 * c + 1];
+    s_m[threadIdx.x][0] = S1 * p.inv_n;
+    s_m[threadIdx.x][1] = S2 * p.inv_n;
+    if (blockIdx.x == 0) { p.dgamma[c] += S2; p.dbeta[c] += S1; }
+  }
+  __syncthreads();
+  float mean[8], is[8], gi[8], m1[8], m2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { mean[e] = s_k[e][0]; is[e] = s_k[e][1]; gi[e] = s_k[e][2]; m1[e] = s_m[e][0]; m2[e] = s_m[e][1]; }
+  const size_t plane = (size_t)g * p.PR + kFront;
+#pragma unroll
+  for (int k = 0; k < kEwRows; ++k) {
+    const int P = (blockIdx.x * kEwRows + k) * kEwThreads + threadIdx.x;
+    if (P >= p.Ptot) break;
+    int4 o = make_int4(0, 0, 0, 0), oz = make_int4(0, 0, 0, 0);
+    if (!is_halo(P, p.PB, p.Wp, p.W, p.H)) {
+      float gv[8], av[8], yv[8], dzv[8], dyv[8];
+      unpack8(__ldg(reinterpret_cast<const int4*>(p.g) + plane + P), 1, gv);
+      unpack8(__ldg(reinterpret_cast<const int4*>(p.a) + plane + P), p.fbf16, av);
+      unpack8(__ldg(reinterpret_cast<const int4*>(p.y) + plane + P), p.fbf16, yv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        dzv[e] = av[e] > 0.0f ? gv[e] : 0.0f;
+        const float xh = (yv[e] - mean[e]) * is[e];
+        dyv[e] = gi[e] * (dzv[e] - m1[e] - xh * m2[e]);
+      }
+      o = pack8(dyv, 1);
+      oz = pack8(dzv, 1);
+    }
+    reinterpret_cast<int4*>(p.dy)[plane + P] = o;
+    if (p.dz) reinterpret_cast<int4*>(p.dz)[plane + P] = oz;
+  }
+}
+
+// float32 [B][C][H][W] -> planes (zeros at halo positions and channels >= C); cg planes are written
+__global__ void nchw_to_planes_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int C, int cg, int Ptot, int PB,
+                                      int Wp, int W, int H, int PR, int bf16) {
+  const int g = blockIdx.y;
+  const int P = blockIdx.x * blockDim.x + threadIdx.x;
+  if (P >= Ptot) return;
+  const int b = P / PB, q = P - b * PB, y = q / Wp, x = q - y * Wp;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = g * 8 + e;
+    v[e] = (c < C && y < H && x < W) ? src[(((size_t)b * C + c) * H + y) * W + x] : 0.0f;
+  }
+  reinterpret_cast<int4*>(dst)[(size_t)g * PR + kFront + P] = pack8(v, bf16);
+}
+
+// planes -> float32 [B][C][H][W]; `mask`: optional planes (fwd type) whose sign gates nothing here (kept simple)
+__global__ void planes_to_nchw_kernel(const uint16_t* __restrict__ src, float* __restrict__ dst, int C, int Ptot, int PB, int Wp,
+                                      int W, int H, int PR, int bf16) {
+  const int g = blockIdx.y;
+  const int P = blockIdx.x * blockDim.x + threadIdx.x;
+  if (P >= Ptot) return;
+  const int b = P / PB, q = P - b * PB, y = q / Wp, x = q - y * Wp;
+  if (y >= H || x >= W) return;
+  float v[8];
+  unpack8(__ldg(reinterpret_cast<const int4*>(src) + (size_t)g * PR + kFront + P), bf16, v);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = g * 8 + e;
+    if (c < C) dst[(((size_t)b * C + c) * H + y) * W + x] = v[e];
+  }
+}
+
+// the action "planes" of DynamicsConvNet.forward (network.py:440-444, quirk C of DESIGN.md): flat element f of the
+// [A*h*w] block is 1 iff f % A == action.  Written as channels 128.. of the dynamics' first-conv input (planes 16..31).
+__global__ void action_planes_kernel(const int64_t* __restrict__ action, uint16_t* __restrict__ dst, int A, int Ptot, int PB, int Wp,
+                                     int W, int H, int PR, int bf16) {
+  const int g = blockIdx.y;                       // 0..15 -> plane 16 + g
+  const int P = blockIdx.x * blockDim.x + threadIdx.x;
+  if (P >= Ptot) return;
+  const int b = P / PB, q = P - b * PB, y = q / Wp, x = q - y * Wp;
+  const int a = (int)action[b];
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = g * 8 + e;
+    float f = 0.0f;
+    if (c < A && y < H && x < W) f = ((c * H * W + y * W + x) % A == a) ? 1.0f : 0.0f;
+    v[e] = f;
+  }
+  reinterpret_cast<int4*>(dst)[(size_t)(16 + g) * PR + kFront + P] = pack8(v, bf16);
+}
+
+// ---- weights ---------------------------------------------------------------------------------------------------
+struct ConvDesc {
+  const float* w;           // [128][ci_total][3][3]
+  float* wgrad;
+  uint16_t* wf;             // forward operand  [9][chunks][chunk_g][128 co][8 ci]
+  uint16_t* wd;             // dgrad operand    [9][2][8][128 ci][8 co] (flipped taps) or nullptr
+  float* partial;           // [ci_blocks][kSplits][9][128][N]
+  int ci_total, cg_in, chunk_g, n_groups, ci_blocks;
+};
+
+__global__ void pack_weights_kernel(const ConvDesc* __restrict__ descs, int fbf16) {
+  const ConvDesc d = descs[blockIdx.y];
+  const int chunks = d.cg_in / d.chunk_g;
+  const size_t nf = (size_t)9 * d.cg_in * kC * 8;
+  const size_t nd = d.wd ? (size_t)9 * 16 * kC * 8 : 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nf + nd; i += (size_t)gridDim.x * blockDim.x) {
+    if (i < nf) {
+      const int e = (int)(i % 8);
+      size_t r = i / 8;
+      const int n = (int)(r % kC); r /= kC;
+      const int gl = (int)(r % d.chunk_g); r /= d.chunk_g;
+      const int ch = (int)(r % chunks);
+      const int tap = (int)(r / chunks);
+      const int c = (ch * d.chunk_g + gl) * 8 + e;
+      const float v = c < d.ci_total ? d.w[((size_t)n * d.ci_total + c) * 9 + tap] : 0.0f;
+      if (fbf16) reinterpret_cast<__nv_bfloat16*>(d.wf)[i] = __float2bfloat16_rn(v);
+      else reinterpret_cast<__half*>(d.wf)[i] = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
+    } else {
+      const size_t j = i - nf;
+      const int e = (int)(j % 8);
+      size_t r = j / 8;
+      const int n = (int)(r % kC); r /= kC;          // ci
+      const int gl = (int)(r % 8); r /= 8;
+      const int ch = (int)(r % 2);
+      const int tap = (int)(r / 2);
+      const int co = (ch * 8 + gl) * 8 + e;
+      reinterpret_cast<__nv_bfloat16*>(d.wd)[j] = __float2bfloat16_rn(d.w[((size_t)co * d.ci_total + n) * 9 + (8 - tap)]);
+    }
+  }
+}
+
+// the parameter's gradient [128][ci_total][3][3] += sum of the row-split partials
+__global__ void wgrad_finalize_kernel(const ConvDesc* __restrict__ descs) {
+  const ConvDesc d = descs[blockIdx.y];
+  const int N = d.n_groups * 8;
+  const size_t per_split = (size_t)9 * kC * N;
+  const size_t total = (size_t)d.ci_blocks * per_split;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int blk = (int)(i / per_split);
+    const size_t r = i - (size_t)blk * per_split;
+    const int n = (int)(r % N), co = (int)((r / N) % kC), tap = (int)(r / ((size_t)N * kC));
+    const int ci = blk * kC + n;
+    if (ci >= d.ci_total) continue;
+    const float* src = d.partial + (size_t)blk * kSplits * per_split + r;
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kSplits; ++k) s += src[(size_t)k * per_split];
+    d.wgrad[((size_t)co * d.ci_total + ci) * 9 + tap] += s;     // autograd semantics: gradients accumulate
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+struct BnPtrs { float *gamma, *dgamma, *beta, *dbeta, *rmean, *rvar; };
+
+struct Layer {              // one conv + BatchNorm of a tower
+  int conv;                 // index into convs[]
+};
+
+}  // namespace
+}  // namespace mz
+
+using namespace mz;
+
+struct mz_train {
+  mz_train_config cfg;
+  Geom g;
+  int fbf16;                               // forward tensors are bf16 (else fp16)
+  int swap_strides;
+  int nconv;                               // convs: rep0, rep blocks (2 each), dyn0, dyn blocks, pred blocks
+  int rep_first, dyn_first, pred_first;    // index of each tower's first conv
+  std::vector<ConvDesc> convs;
+  std::vector<BnPtrs> bn;
+  std::vector<int> touched;                // wgrad partials written in this step
+  ConvDesc* d_convs;
+  bool bound;
+  // arena carving
+  unsigned char* arena;
+  size_t arena_bytes;
+  size_t plane_bytes;                      // one 16-bit plane
+  uint16_t* grad_buf[5];                   // bf16 [16 planes]: G ping/pong, G1, dY, dZ
+  float* stats;                            // [slots][768]: fwd sums | saved (mean, invstd) | bwd sums
+  size_t stats_floats;
+  int n_calls[3];
+  // saved activations: slot(tower, call) -> X, then (Y, A) per layer
+  std::vector<uint16_t*> slot_x;
+  std::vector<std::vector<uint16_t*>> slot_y, slot_a;
+  int smem_conv[3];                        // dynamic shared memory per cg_in case (set at create)
+};
+
+namespace mz {
+namespace {
+
+int tower_layers(const mz_train* t, int tower) { return (tower == 2 ? 0 : 1) + 2 * t->cfg.num_res_blocks; }
+int tower_first_conv(const mz_train* t, int tower) { return tower == 0 ? t->rep_first : (tower == 1 ? t->dyn_first : t->pred_first); }
+int tower_in_groups(const mz_train* t, int tower) { return tower == 0 ? (t->cfg.in_channels + 15) / 16 * 2 : (tower == 1 ? 32 : 16); }
+int slot_of(const mz_train* t, int tower, int call) {
+  int s = 0;
+  for (int k = 0; k < tower; ++k) s += t->n_calls[k];
+  return s + call;
+}
+int stat_slot(const mz_train* t, int tower, int call, int layer) {
+  int s = 0;
+  for (int k = 0; k < tower; ++k) s += t->n_calls[k] * tower_layers(t, k);
+  return s + call * tower_layers(t, tower) + layer;
+}
+
+size_t conv_smem_bytes(const Geom& g, int cg_in, int* stages_out, int* TP_out, int* TPs_out) {
+  const int halo = g.Wp + 1;
+  const int TP = 128 + 2 * halo, TPs = TP | 1;
+  const int chunk_g = cg_in < 8 ? cg_in : 8;
+  const size_t a = (((size_t)cg_in * TPs * 16) + 127) & ~(size_t)127;
+  const size_t stage = (size_t)chunk_g * kC * 16;
+  const size_t fixed = a + (2 * kConvStagesMax + 2) * 8 + 8 + 2 * kC * 4 + 64;
+  int stages = (int)((220 * 1024 - fixed) / stage);
+  const int need = 9 * (cg_in / chunk_g);
+  if (stages > kConvStagesMax) stages = kConvStagesMax;
+  if (stages > need) stages = need;
+  if (stages_out) *stages_out = stages;
+  if (TP_out) *TP_out = TP;
+  if (TPs_out) *TPs_out = TPs;
+  return fixed + (size_t)stages * stage;
+}
+
+size_t wgrad_smem_bytes(int n_groups) {
+  const size_t dy = (size_t)16 * kWgStage * 16, x = ((size_t)n_groups * (kWgStage + 2) * 16 + 127) & ~(size_t)127;
+  return 2 * (dy + x) + 6 * 8 + 16 + 64;
+}
+
+int launch_conv(mz_train* t, const uint16_t* in, int cg_in, const uint16_t* w, uint16_t* out, const uint16_t* add,
+                float* stats, int a_bf16, int w_bf16, int out_bf16, cudaStream_t st) {
+  TConvParams p;
+  const Geom& g = t->g;
+  p.in = in; p.w = w; p.out = out; p.add = add; p.stats = stats;
+  p.cg_in = cg_in; p.chunk_g = cg_in < 8 ? cg_in : 8; p.chunks = cg_in / p.chunk_g;
+  p.Ptot = g.Ptot; p.PB = g.PB; p.Wp = g.Wp; p.W = g.W; p.H = g.H; p.PR = g.PR;
+  const size_t smem = conv_smem_bytes(g, cg_in, &p.stages, &p.TP, &p.TPs);
+  p.idesc = idesc_of(128, kC, (uint32_t)a_bf16, (uint32_t)w_bf16, 0);
+  p.out_bf16 = out_bf16;
+  tconv_kernel<<<g.R128 / 128, kTConvThreads, smem, st>>>(p);
+  MZ_LAUNCH_CHECK("tconv_kernel");
+  return MZ_OK;
+}
+
+int launch_wgrad(mz_train* t, int conv, const uint16_t* dy, const uint16_t* x, cudaStream_t st) {
+  const ConvDesc& d = t->convs[conv];
+  TWgradParams p;
+  const Geom& g = t->g;
+  p.dy = dy; p.x = x; p.partial = d.partial; p.n_groups = d.n_groups;
+  p.Rs = ((g.Ptot + kSplits - 1) / kSplits + 15) / 16 * 16;
+  p.Wp = g.Wp; p.PR = g.PR;
+  p.accumulate = t->touched[conv];
+  p.idesc = idesc_of(128, (uint32_t)d.n_groups * 8, 1, (uint32_t)t->fbf16, 1);
+  p.swap_strides = t->swap_strides;
+  twgrad_kernel<<<dim3(kSplits, 3, d.ci_blocks), kTConvThreads, wgrad_smem_bytes(d.n_groups), st>>>(p);
+  MZ_LAUNCH_CHECK("twgrad_kernel");
+  t->touched[conv] = 1;
+  return MZ_OK;
+}
+
+dim3 ew_grid(const Geom& g, int planes) { return dim3((g.Ptot + kEwThreads * kEwRows - 1) / (kEwThreads * kEwRows), planes); }
+
+int launch_bn_fwd(mz_train* t, int conv, const uint16_t* y, const uint16_t* res, uint16_t* a, float* stat, cudaStream_t st) {
+  const Geom& g = t->g;
+  const BnPtrs& b = t->bn[conv];
+  BnFwdParams p;
+  p.y = y; p.res = res; p.a = a; p.sums = stat; p.saved = stat + 256;
+  p.gamma = b.gamma; p.beta = b.beta; p.running_mean = b.rmean; p.running_var = b.rvar;
+  p.Ptot = g.Ptot; p.PB = g.PB; p.Wp = g.Wp; p.W = g.W; p.H = g.H; p.PR = g.PR; p.fbf16 = t->fbf16;
+  const double n = (double)g.B * g.H * g.W;
+  p.inv_n = (float)(1.0 / n); p.unbias = (float)(n / (n - 1.0));
+  bn_fwd_kernel<<<ew_grid(g, 16), kEwThreads, 0, st>>>(p);
+  MZ_LAUNCH_CHECK("bn_fwd_kernel");
+  return MZ_OK;
+}
+
+int launch_bn_bwd(mz_train* t, int conv, const uint16_t* gin, const uint16_t* a, const uint16_t* y, float* stat, uint16_t* dy,
+                  uint16_t* dz, cudaStream_t st) {
+  const Geom& g = t->g;
+  const BnPtrs& b = t->bn[conv];
+  BnBwdParams p;
+  p.g = gin; p.a = a; p.y = y; p.saved = stat + 256; p.sums = stat + 512; p.gamma = b.gamma; p.dgamma = b.dgamma; p.dbeta = b.dbeta;
+  p.dy = dy; p.dz = dz;
+  p.Ptot = g.Ptot; p.PB = g.PB; p.Wp = g.Wp; p.W = g.W; p.H = g.H; p.PR = g.PR; p.fbf16 = t->fbf16;
+  p.inv_n = (float)(1.0 / ((double)g.B * g.H * g.W));
+  const int nchunk = 9;
+  p.rows_per_cta = (g.Ptot + nchunk - 1) / nchunk;
+  bn_bwd_reduce_kernel<<<dim3(nchunk, 16), kEwThreads, 0, st>>>(p);
+  MZ_LAUNCH_CHECK("bn_bwd_reduce_kernel");
+  bn_bwd_apply_kernel<<<ew_grid(g, 16), kEwThreads, 0, st>>>(p);
+  MZ_LAUNCH_CHECK("bn_bwd_apply_kernel");
+  return MZ_OK;
+}
+
+}  // namespace
+}  // namespace mz
+
+extern "C" {
+
+static int train_layout(const mz_train_config* c, Geom* g, size_t* bytes, mz_train* t) {
+  MZ_CHECK_ARG(c != nullptr, "mz_train: config is NULL");
+  MZ_CHECK_ARG(c->num_planes == kC, "mz_train: the training kernels are built for num_planes = 128 (got %d)", c->num_planes);
+  MZ_CHECK_ARG(c->board_h >= 2 && c->board_w >= 2 && c->board_w + 2 <= kFront, "mz_train: board %dx%d not supported", c->board_h, c->board_w);
+  MZ_CHECK_ARG(c->in_channels >= 1 && c->in_channels <= 128, "mz_train: in_channels %d not supported", c->in_channels);
+  MZ_CHECK_ARG(c->num_actions >= 1 && c->num_actions <= 128, "mz_train: num_actions %d not supported (<= 128)", c->num_actions);
+  MZ_CHECK_ARG(c->num_res_blocks >= 1 && c->num_res_blocks <= 32, "mz_train: num_res_blocks %d not supported", c->num_res_blocks);
+  MZ_CHECK_ARG(c->batch >= 2 && c->unroll_steps >= 1 && c->unroll_steps <= 16, "mz_train: batch %d / unroll_steps %d not supported", c->batch, c->unroll_steps);
+  g->B = c->batch; g->H = c->board_h; g->W = c->board_w; g->Wp = g->W + 1; g->PB = (g->H + 1) * g->Wp;
+  g->Ptot = g->B * g->PB; g->R128 = (g->Ptot + 127) / 128 * 128; g->PR = kFront + g->R128 + kTail;
+  const size_t plane = (size_t)g->PR * 16;
+  const int nb = c->num_res_blocks, T = c->unroll_steps;
+  const int in_cg = (c->in_channels + 15) / 16 * 2;
+  size_t total = 0;
+  auto take = [&](size_t n) { const size_t off = total; total += align_up(n, 256); return off; };
+  // operand copies of the weights + wgrad partials
+  const int nconv = (1 + 2 * nb) + (1 + 2 * nb) + 2 * nb;
+  if (t) { t->convs.resize(nconv); t->bn.resize(nconv); t->touched.assign(nconv, 0); t->nconv = nconv; }
+  int idx = 0;
+  for (int tower = 0; tower < 3; ++tower) {
+    if (t) { if (tower == 0) t->rep_first = idx; else if (tower == 1) t->dyn_first = idx; else t->pred_first = idx; }
+    const int layers = (tower == 2 ? 0 : 1) + 2 * nb;
+    for (int l = 0; l < layers; ++l, ++idx) {
+      const bool first = tower != 2 && l == 0;
+      const int ci_total = first ? (tower == 0 ? c->in_channels : kC + c->num_actions) : kC;
+      const int cg_in = first ? (tower == 0 ? in_cg : 32) : 16;
+      const int chunk_g = cg_in < 8 ? cg_in : 8;
+      const int n_groups = first && tower == 0 ? in_cg : 16;
+      const int ci_blocks = first && tower == 1 ? 2 : 1;
+      const size_t o_wf = take((size_t)9 * cg_in * kC * 16);
+      const bool need_d = !(tower == 0 && l == 0);
+      const size_t o_wd = need_d ? take((size_t)9 * 16 * kC * 16) : 0;
+      const size_t o_p = take((size_t)ci_blocks * kSplits * 9 * kC * n_groups * 8 * 4);
+      if (t) {
+        ConvDesc& d = t->convs[idx];
+        d.w = nullptr; d.wgrad = nullptr;
+        d.wf = reinterpret_cast<uint16_t*>(t->arena + o_wf);
+        d.wd = need_d ? reinterpret_cast<uint16_t*>(t->arena + o_wd) : nullptr;
+        d.partial = reinterpret_cast<float*>(t->arena + o_p);
+        d.ci_total = ci_total; d.cg_in = cg_in; d.chunk_g = chunk_g; d.n_groups = n_groups; d.ci_blocks = ci_blocks;
+      }
+    }
+  }
+  const size_t o_desc = take((size_t)nconv * sizeof(ConvDesc));
+  if (t) t->d_convs = reinterpret_cast<ConvDesc*>(t->arena + o_desc);
+  // gradient work buffers
+  for (int k = 0; k < 5; ++k) {
+    const size_t o = take(16 * plane);
+    if (t) t->grad_buf[k] = reinterpret_cast<uint16_t*>(t->arena + o);
+  }
+  // statistics
+  const int calls[3] = {1, T, T};
+  size_t nstat = 0;
+  for (int tower = 0; tower < 3; ++tower) nstat += (size_t)calls[tower] * ((tower == 2 ? 0 : 1) + 2 * nb);
+  const size_t o_stats = take(nstat * 768 * 4);
+  if (t) { t->stats = reinterpret_cast<float*>(t->arena + o_stats); t->stats_floats = nstat * 768; for (int k = 0; k < 3; ++k) t->n_calls[k] = calls[k]; }
+  // saved activations
+  const int nslots = 1 + 2 * T;
+  if (t) { t->slot_x.resize(nslots); t->slot_y.resize(nslots); t->slot_a.resize(nslots); }
+  int s = 0;
+  for (int tower = 0; tower < 3; ++tower)
+    for (int call = 0; call < calls[tower]; ++call, ++s) {
+      const int xg = tower == 0 ? in_cg : (tower == 1 ? 32 : 16);
+      const size_t ox = take((size_t)xg * plane);
+      if (t) t->slot_x[s] = reinterpret_cast<uint16_t*>(t->arena + ox);
+      const int layers = (tower == 2 ? 0 : 1) + 2 * nb;
+      if (t) { t->slot_y[s].resize(layers); t->slot_a[s].resize(layers); }
+      for (int l = 0; l < layers; ++l) {
+        const size_t oy = take(16 * plane), oa = take(16 * plane);
+        if (t) { t->slot_y[s][l] = reinterpret_cast<uint16_t*>(t->arena + oy); t->slot_a[s][l] = reinterpret_cast<uint16_t*>(t->arena + oa); }
+      }
+    }
+  *bytes = total + 1024;
+  return MZ_OK;
+}
+
+int mz_train_arena_bytes(const mz_train_config* cfg, size_t* bytes) {
+  MZ_CHECK_ARG(bytes != nullptr, "mz_train_arena_bytes: bytes is NULL");
+  Geom g;
+  return train_layout(cfg, &g, bytes, nullptr);
+}
+
+int mz_train_create(const mz_train_config* cfg, void* arena_dev, size_t arena_bytes, mz_train** out) {
+  MZ_CHECK_ARG(out != nullptr && arena_dev != nullptr, "mz_train_create: NULL argument");
+  Geom g;
+  size_t need = 0;
+  int rc = train_layout(cfg, &g, &need, nullptr);
+  if (rc) return rc;
+  if (arena_bytes < need) { set_error("mz_train_create: arena of %zu bytes, %zu needed", arena_bytes, need); return MZ_ENOMEM; }
+  mz_train* t = new mz_train();
+  t->cfg = *cfg; t->g = g;
+  t->arena = static_cast<unsigned char*>(arena_dev); t->arena_bytes = arena_bytes;
+  t->plane_bytes = (size_t)g.PR * 16;
+  t->fbf16 = getenv("MZ_TRAIN_FWD_BF16") ? atoi(getenv("MZ_TRAIN_FWD_BF16")) != 0 : 0;
+  t->swap_strides = getenv("MZ_TRAIN_WGRAD_SWAP") ? atoi(getenv("MZ_TRAIN_WGRAD_SWAP")) != 0 : 0;
+  t->bound = false;
+  rc = train_layout(cfg, &t->g, &need, t);
+  if (rc) { delete t; return rc; }
+  // every plane's front / tail / halo rows must read as zero from the first use on: clear the arena once
+  cudaError_t e = cudaMemset(arena_dev, 0, need);
+  if (e != cudaSuccess) { delete t; set_error("cudaMemset: %s", cudaGetErrorString(e)); return MZ_ECUDA; }
+  const int cgs[3] = {tower_in_groups(t, 0), 16, 32};
+  size_t max_smem = 0;
+  for (int k = 0; k < 3; ++k) { const size_t s = conv_smem_bytes(t->g, cgs[k], nullptr, nullptr, nullptr); if (s > max_smem) max_smem = s; }
+  e = cudaFuncSetAttribute(tconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(twgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_smem_bytes(16));
+  if (e != cudaSuccess) { delete t; set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MZ_ECUDA; }
+  *out = t;
+  return MZ_OK;
+}
+
+int mz_train_destroy(mz_train* t) {
+  delete t;
+  return MZ_OK;
+}
+
+int mz_train_bind(mz_train* t, void* const* ptrs, int32_t n, mz_stream stream) {
+  MZ_CHECK_ARG(t != nullptr && ptrs != nullptr, "mz_train_bind: NULL argument");
+  MZ_CHECK_ARG(n == 8 * t->nconv, "mz_train_bind: %d pointers, %d expected (8 per convolution)", n, 8 * t->nconv);
+  for (int i = 0; i < t->nconv; ++i) {
+    void* const* q = ptrs + 8 * i;
+    for (int k = 0; k < 8; ++k) MZ_CHECK_ARG(q[k] != nullptr, "mz_train_bind: pointer %d of convolution %d is NULL", k, i);
+    t->convs[i].w = static_cast<const float*>(q[0]); t->convs[i].wgrad = static_cast<float*>(q[1]);
+    BnPtrs& b = t->bn[i];
+    b.gamma = static_cast<float*>(q[2]); b.dgamma = static_cast<float*>(q[3]); b.beta = static_cast<float*>(q[4]);
+    b.dbeta = static_cast<float*>(q[5]); b.rmean = static_cast<float*>(q[6]); b.rvar = static_cast<float*>(q[7]);
+  }
+  MZ_CUDA(cudaMemcpyAsync(t->d_convs, t->convs.data(), (size_t)t->nconv * sizeof(ConvDesc), cudaMemcpyHostToDevice,
+                          static_cast<cudaStream_t>(stream)));
+  MZ_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  t->bound = true;
+  return MZ_OK;
+}
+
+int mz_train_begin_step(mz_train* t, mz_stream stream) {
+  MZ_CHECK_ARG(t != nullptr, "mz_train_begin_step: NULL handle");
+  if (!t->bound) { set_error("mz_train_begin_step: mz_train_bind has not been called"); return MZ_ESTATE; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MZ_CUDA(cudaMemsetAsync(t->stats, 0, t->stats_floats * 4, st));
+  pack_weights_kernel<<<dim3(32, t->nconv), 256, 0, st>>>(t->d_convs, t->fbf16);
+  MZ_LAUNCH_CHECK("pack_weights_kernel");
+  std::fill(t->touched.begin(), t->touched.end(), 0);
+  return MZ_OK;
+}
+
+int mz_train_tower_forward(mz_train* t, int32_t tower, int32_t call, const float* x, const int64_t* action, float* out,
+                           mz_stream stream) {
+  MZ_CHECK_ARG(t != nullptr && x != nullptr && out != nullptr, "mz_train_tower_forward: NULL argument");
+  MZ_CHECK_ARG(tower >= 0 && tower < 3 && call >= 0 && call < t->n_calls[tower], "mz_train_tower_forward: tower %d call %d out of range", tower, call);
+  MZ_CHECK_ARG(tower != 1 || action != nullptr, "mz_train_tower_forward: the dynamics tower needs actions");
+  if (!t->bound) { set_error("mz_train_tower_forward: mz_train_bind has not been called"); return MZ_ESTATE; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Geom& g = t->g;
+  const int slot = slot_of(t, tower, call);
+  const int nb = t->cfg.num_res_blocks;
+  const int xg = tower_in_groups(t, tower);
+  const int c_in = tower == 0 ? t->cfg.in_channels : kC;
+  const dim3 cgrid((g.Ptot + 255) / 256, tower == 1 ? 16 : xg);
+  uint16_t* X = t->slot_x[slot];
+  nchw_to_planes_kernel<<<cgrid, 256, 0, st>>>(x, X, c_in, tower == 1 ? 16 : xg, g.Ptot, g.PB, g.Wp, g.W, g.H, g.PR, t->fbf16);
+  MZ_LAUNCH_CHECK("nchw_to_planes_kernel");
+  if (tower == 1) {
+    action_planes_kernel<<<dim3((g.Ptot + 255) / 256, 16), 256, 0, st>>>(action, X, t->cfg.num_actions, g.Ptot, g.PB, g.Wp, g.W, g.H,
+                                                                       g.PR, t->fbf16);
+    MZ_LAUNCH_CHECK("action_planes_kernel");
+  }
+  int conv = tower_first_conv(t, tower), layer = 0, rc;
+  const uint16_t* cur = X;
+  auto stat = [&](int l) { return t->stats + (size_t)stat_slot(t, tower, call, l) * 768; };
+  if (tower != 2) {
+    if ((rc = launch_conv(t, X, xg, t->convs[conv].wf, t->slot_y[slot][0], nullptr, stat(0), t->fbf16, t->fbf16, t->fbf16, st))) return rc;
+    if ((rc = launch_bn_fwd(t, conv, t->slot_y[slot][0], nullptr, t->slot_a[slot][0], stat(0), st))) return rc;
+    cur = t->slot_a[slot][0];
+    ++conv; ++layer;
+  }
+  for (int b = 0; b < nb; ++b) {
+    uint16_t *y1 = t->slot_y[slot][layer], *a1 = t->slot_a[slot][layer], *y2 = t->slot_y[slot][layer + 1], *a2 = t->slot_a[slot][layer + 1];
+    if ((rc = launch_conv(t, cur, 16, t->convs[conv].wf, y1, nullptr, stat(layer), t->fbf16, t->fbf16, t->fbf16, st))) return rc;
+    if ((rc = launch_bn_fwd(t, conv, y1, nullptr, a1, stat(layer), st))) return rc;
+    if ((rc = launch_conv(t, a1, 16, t->convs[conv + 1].wf, y2, nullptr, stat(layer + 1), t->fbf16, t->fbf16, t->fbf16, st))) return rc;
+    if ((rc = launch_bn_fwd(t, conv + 1, y2, cur, a2, stat(layer + 1), st))) return rc;
+    cur = a2;
+    conv += 2; layer += 2;
+  }
+  planes_to_nchw_kernel<<<dim3((g.Ptot + 255) / 256, 16), 256, 0, st>>>(cur, out, kC, g.Ptot, g.PB, g.Wp, g.W, g.H, g.PR, t->fbf16);
+  MZ_LAUNCH_CHECK("planes_to_nchw_kernel");
+  return MZ_OK;
+}
+
+int mz_train_tower_backward(mz_train* t, int32_t tower, int32_t call, const float* grad_out, float* grad_in, mz_stream stream) {
+  MZ_CHECK_ARG(t != nullptr && grad_out != nullptr, "mz_train_tower_backward: NULL argument");
+  MZ_CHECK_ARG(tower >= 0 && tower < 3 && call >= 0 && call < t->n_calls[tower], "mz_train_tower_backward: tower %d call %d out of range", tower, call);
+  MZ_CHECK_ARG(tower == 0 || grad_in != nullptr, "mz_train_tower_backward: grad_in is NULL");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Geom& g = t->g;
+  const int slot = slot_of(t, tower, call);
+  const int nb = t->cfg.num_res_blocks;
+  const int first = tower != 2 ? 1 : 0;
+  uint16_t *G = t->grad_buf[0], *G2 = t->grad_buf[1], *G1 = t->grad_buf[2], *dY = t->grad_buf[3], *dZ = t->grad_buf[4];
+  const dim3 cgrid((g.Ptot + 255) / 256, 16);
+  nchw_to_planes_kernel<<<cgrid, 256, 0, st>>>(grad_out, G, kC, 16, g.Ptot, g.PB, g.Wp, g.W, g.H, g.PR, 1);
+  MZ_LAUNCH_CHECK("nchw_to_planes_kernel");
+  auto stat = [&](int l) { return t->stats + (size_t)stat_slot(t, tower, call, l) * 768; };
+  int rc;
+  for (int b = nb - 1; b >= 0; --b) {
+    const int l1 = first + 2 * b, l2 = l1 + 1;
+    const int c1 = tower_first_conv(t, tower) + l1, c2 = c1 + 1;
+    const uint16_t* a_in = l1 > 0 ? t->slot_a[slot][l1 - 1] : t->slot_x[slot];
+    // second conv of the block: out = relu(bn2(conv2(a1)) + a_in)
+    if ((rc = launch_bn_bwd(t, c2, G, t->slot_a[slot][l2], t->slot_y[slot][l2], stat(l2), dY, dZ, st))) return rc;
+    if ((rc = launch_wgrad(t, c2, dY, t->slot_a[slot][l1], st))) return rc;
+    if ((rc = launch_conv(t, dY, 16, t->convs[c2].wd, G1, nullptr, nullptr, 1, 1, 1, st))) return rc;
+    // first conv: a1 = relu(bn1(conv1(a_in)))
+    if ((rc = launch_bn_bwd(t, c1, G1, t->slot_a[slot][l1], t->slot_y[slot][l1], stat(l1), dY, nullptr, st))) return rc;
+    if ((rc = launch_wgrad(t, c1, dY, a_in, st))) return rc;
+    if ((rc = launch_conv(t, dY, 16, t->convs[c1].wd, G2, dZ, nullptr, 1, 1, 1, st))) return rc;   // + the skip connection's share
+    uint16_t* tmp = G; G = G2; G2 = tmp;
+  }
+  if (first) {
+    const int c0 = tower_first_conv(t, tower);
+    if ((rc = launch_bn_bwd(t, c0, G, t->slot_a[slot][0], t->slot_y[slot][0], stat(0), dY, nullptr, st))) return rc;
+    if ((rc = launch_wgrad(t, c0, dY, t->slot_x[slot], st))) return rc;
+    if (tower == 1) {
+      if ((rc = launch_conv(t, dY, 16, t->convs[c0].wd, G2, nullptr, nullptr, 1, 1, 1, st))) return rc;
+      G = G2;
+    }
+  }
+  if (tower != 0) {
+    planes_to_nchw_kernel<<<cgrid, 256, 0, st>>>(G, grad_in, kC, g.Ptot, g.PB, g.Wp, g.W, g.H, g.PR, 1);
+    MZ_LAUNCH_CHECK("planes_to_nchw_kernel");
+  }
+  return MZ_OK;
+}
+
+int mz_train_end_step(mz_train* t, mz_stream stream) {
+  MZ_CHECK_ARG(t != nullptr, "mz_train_end_step: NULL handle");
+  for (int i = 0; i < t->nconv; ++i)
+    if (!t->touched[i]) { set_error("mz_train_end_step: convolution %d has no weight gradient yet (a tower backward is missing)", i); return MZ_ESTATE; }
+  wgrad_finalize_kernel<<<dim3(64, t->nconv), 256, 0, static_cast<cudaStream_t>(stream)>>>(t->d_convs);
+  MZ_LAUNCH_CHECK("wgrad_finalize_kernel");
+  return MZ_OK;
+}
+
+int mz_train_debug_view(mz_train* t, int32_t tower, int32_t call, int32_t layer, int32_t which, void** ptr, size_t* bytes,
+                        int32_t* plane_rows, int32_t* front_rows) {
+  MZ_CHECK_ARG(t != nullptr && ptr != nullptr && bytes != nullptr, "mz_train_debug_view: NULL argument");
+  MZ_CHECK_ARG(tower >= 0 && tower < 3 && call >= 0 && call < t->n_calls[tower], "mz_train_debug_view: tower %d call %d out of range", tower, call);
+  const int slot = slot_of(t, tower, call);
+  const int layers = tower_layers(t, tower);
+  if (plane_rows) *plane_rows = t->g.PR;
+  if (front_rows) *front_rows = kFront;
+  if (which == 0) { *ptr = t->slot_x[slot]; *bytes = (size_t)tower_in_groups(t, tower) * t->plane_bytes; return MZ_OK; }
+  MZ_CHECK_ARG(layer >= 0 && layer < layers, "mz_train_debug_view: layer %d out of range", layer);
+  if (which == 1) { *ptr = t->slot_y[slot][layer]; *bytes = 16 * t->plane_bytes; return MZ_OK; }
+  if (which == 2) { *ptr = t->slot_a[slot][layer]; *bytes = 16 * t->plane_bytes; return MZ_OK; }
+  if (which == 3) { *ptr = t->stats + (size_t)stat_slot(t, tower, call, layer) * 768; *bytes = 768 * 4; return MZ_OK; }
+  set_error("mz_train_debug_view: unknown view %d", which);
+  return MZ_EINVAL;
+}
+
+}  // extern "C"

@@ -415,7 +415,24 @@ class _ConvNet(MuZeroNet):
         out[:, :c // 8, :h, :w, :] = hid.permute(0, 1, 3, 4, 2).to(torch.float16)
         return out.reshape(hid.shape[0], -1).view(torch.uint8)
 
+    # -- training: the towers run on the hand-written kernels of csrc/train.cu where they apply (train_engine.py) ------
+    unroll_hint = 5          # calc_loss tells the engine how many dynamics / prediction calls a step makes
+
+    def _train_engine(self, x, begin: bool = False):
+        if not (self.training and x.is_cuda):
+            return None
+        from . import train_engine
+        eng = train_engine.engine_for(self, x.shape[0], self.unroll_hint)
+        if eng is None or not (begin or eng.active):
+            return None
+        return eng
+
     def dynamics(self, hidden_state, action):
+        eng = self._train_engine(hidden_state)
+        if eng is not None:
+            from . import train_engine
+            hs = train_engine.tower(eng, 1, hidden_state, action)
+            return normalize_hidden_state(hs), self.dynamics_net.reward_head(hs)
         b, c, h, w = hidden_state.shape
         planes = action_planes(action, self.num_actions, h, w).to(hidden_state.dtype)
         x = torch.cat([hidden_state, planes], dim=1)
@@ -423,7 +440,12 @@ class _ConvNet(MuZeroNet):
         return normalize_hidden_state(hs), self.dynamics_net.reward_head(hs)
 
     def prediction(self, hidden_state):
-        f = self.prediction_net.res_blocks(hidden_state)
+        eng = self._train_engine(hidden_state)
+        if eng is not None:
+            from . import train_engine
+            f = train_engine.tower(eng, 2, hidden_state)
+        else:
+            f = self.prediction_net.res_blocks(hidden_state)
         return self.prediction_net.policy_net(f), self.prediction_net.value_net(f)
 
 
@@ -444,6 +466,10 @@ class MuZeroBoardGameNet(_ConvNet):
         _kaiming(self)
 
     def represent(self, x):
+        eng = self._train_engine(x, begin=True)
+        if eng is not None:
+            from . import train_engine
+            return normalize_hidden_state(train_engine.tower(eng, 0, x))
         return normalize_hidden_state(self.represent_net.res_blocks(self.represent_net.conv_block(x)))
 
 

@@ -105,6 +105,8 @@ def calc_loss_tensors(network: MuZeroNet, state, action, target_value_scalar, ta
     B, T = action.shape
     reward_loss, value_loss, policy_loss = 0, 0, 0
     pred_values = []
+    if hasattr(network, 'unroll_hint'):
+        network.unroll_hint = T                      # sizes the training engine's activation slots (train_engine.py)
     hidden_state = network.represent(state)
     for t in range(T):
         pred_pi_logits, pred_value = network.prediction(hidden_state)
@@ -154,8 +156,11 @@ class DataParallelLearner:
         # conv nets on CUDA train with NHWC weights / activations: same fp32 (TF32) cuDNN arithmetic without the layout
         # transposes around every convolution (24.8 -> 20.7 ms per 128 x K=5 Gomoku step).  state_dict shapes, the
         # engine's weight packing and checkpoints are unaffected (memory format only).  MZ_TRAIN_CHANNELS_LAST=0: NCHW.
+        # Networks the hand-written tower kernels cover (train_engine.py) keep NCHW parameters: the kernels read them.
+        from . import train_engine
+        self.native_towers = (self.device.type == 'cuda' and train_engine._enabled() and train_engine.supported(network))
         self.channels_last = (os.environ.get('MZ_TRAIN_CHANNELS_LAST', '1') != '0' and self.device.type == 'cuda'
-                              and getattr(network, 'latent_hw', (0, 0)) != (0, 0))
+                              and getattr(network, 'latent_hw', (0, 0)) != (0, 0) and not self.native_towers)
         if self.channels_last:
             network.to(memory_format=torch.channels_last)
         self.group = process_group
