@@ -355,6 +355,9 @@ int mz_train_tower_forward(mz_train* t, int32_t tower, int32_t call, const float
 /* grad_out: dL/d out [B,128,H,W]; grad_in: dL/d x [B,128,H,W] (towers 1, 2; NULL for tower 0)                      */
 int mz_train_tower_backward(mz_train* t, int32_t tower, int32_t call, const float* grad_out, float* grad_in,
                             mz_stream stream);
+/* the weight-gradient kernels of the tower backward calls run on a stream of the handle's own, beside the caller's:
+ * make `stream` wait for them (capture-safe; mz_train_end_step does it itself)                                     */
+int mz_train_join(mz_train* t, mz_stream stream);
 /* after the last tower backward of a step: reduce the split-K partials into the conv weight gradients              */
 int mz_train_end_step(mz_train* t, mz_stream stream);
 /* parity tests: which = 0 tower input planes, 1 raw conv output of `layer`, 2 its activated output, 3 its

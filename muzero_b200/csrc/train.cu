@@ -19,6 +19,9 @@
 //
 // Precision: activations and weights fp16 (like the inference engine; MZ_TRAIN_FWD_BF16=1: bf16), gradients bf16
 // (fp32 range, no loss scaling), fp32 accumulation in TMEM, fp32 BatchNorm statistics and parameter gradients.
+// kind::f16 MMAs take fp16 x fp16 or bf16 x bf16 but not a mix (an fp16 x bf16 descriptor raises an illegal-instruction
+// fault), so every activation a weight gradient needs is ALSO kept as a bf16 copy, written by the kernel that produces
+// it: the forward chain keeps fp16's three extra mantissa bits, dW = dY^T A runs bf16 x bf16.
 #include "common.cuh"
 #include "umma.cuh"
 #include <cuda_fp16.h>
@@ -35,7 +38,8 @@ constexpr int kC = 128;            // tower width this engine is built for
 constexpr int kFront = 64;         // zero rows before row 0 of every plane (>= W + 2)
 constexpr int kTail = 448;         // zero rows after the last 128-row tile (wgrad splits overshoot by < 16 * splits + halo)
 constexpr int kSplits = 16;        // row splits of a weight-gradient launch
-constexpr int kWgStage = 160;      // rows per wgrad pipeline stage
+constexpr int kWgStage = 128;      // rows per wgrad pipeline stage
+constexpr int kWgStages = 3;
 constexpr int kConvStagesMax = 8;
 constexpr float kBnEps = 1e-5f, kBnMomentum = 0.1f;
 
@@ -105,12 +109,21 @@ struct TConvParams {
   uint16_t* out;            // planes [16][PR][8], zeros at halo rows
   const uint16_t* add;      // optional bf16 planes added to the result (dgrad: the skip connection's gradient)
   float* stats;             // optional [128][2] += (sum, sum of squares) over the real rows (forward: BatchNorm)
+  // dgrad into a layer that ends in BatchNorm + ReLU: the result G = dL/dA of that layer is turned into
+  // dZ = G * (A > 0) right here (that is all its consumers read) and the layer's BatchNorm-backward sums
+  // (sum dZ, sum dZ * xhat) are taken from the fp32 values -- no separate reduction pass over the tensor
+  const uint16_t* mask_a;   // the layer's activated output A (forward type) or nullptr
+  const uint16_t* mask_y;   // its raw conv output Y (forward type)
+  const float* mask_saved;  // its [128][2] (mean, invstd)
+  float* mask_sums;         // its [128][2] += (sum dZ, sum dZ * xhat)
+  int fbf16;                // forward tensors are bf16
   int cg_in, chunk_g, chunks;
   int Ptot, PB, Wp, W, H, PR;
   int TP, TPs;              // rows of a tile incl. halo / rows of a shared-memory plane (odd)
   int stages;
   uint32_t idesc;
   int out_bf16;
+  int ablate;               // measurement only (MZ_TRAIN_ABLATE): 1 no MMAs, 2 no epilogue loads / stores, 4 no column sums, 8 no weight copies
 };
 
 constexpr int kTConvThreads = 192;   // w0 producer, w1 MMA issuer, w2-5 epilogue
@@ -131,7 +144,8 @@ __global__ void __launch_bounds__(kTConvThreads) tconv_kernel(const __grid_const
   uint64_t* a_full = bars + 2 * kConvStagesMax;
   uint64_t* mma_done = a_full + 1;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(mma_done + 1);
-  float* s_stat = reinterpret_cast<float*>(tmem_holder + 2);   // [2][128]
+  float* s_stat = reinterpret_cast<float*>(tmem_holder + 2);   // [2][128] column sums | [2][128] (mean, invstd) of the masked layer
+  float* s_saved = s_stat + 2 * kC;
 
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
@@ -140,6 +154,7 @@ __global__ void __launch_bounds__(kTConvThreads) tconv_kernel(const __grid_const
   }
   for (int i = tid; i < 2 * kC; i += kTConvThreads) s_stat[i] = 0.0f;
   if (warp == 1) tmem_alloc(tmem_holder, 128);
+  pdl_trigger();            // the next kernel of the chain may set itself up beside this one
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -147,15 +162,25 @@ __global__ void __launch_bounds__(kTConvThreads) tconv_kernel(const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
+      // the weights do not depend on the previous kernel of the chain (they were packed at the start of the step):
+      // fill the ring first, then wait for the predecessor, then fetch the tile it wrote
+      const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.w);
+      const int total = 9 * p.chunks;
+      int it = 0;
+      for (; it < total && it < p.stages; ++it) {
+        if (p.ablate & 8) { mbar_arrive(&w_full[it]); continue; }
+        mbar_arrive_expect_tx(&w_full[it], stage_bytes);
+        bulk_g2s(sW + (size_t)it * stage_bytes, wsrc + (size_t)it * stage_bytes, stage_bytes, &w_full[it]);
+      }
+      pdl_wait();
       mbar_arrive_expect_tx(a_full, (uint32_t)p.cg_in * p.TP * 16u);
       for (int g = 0; g < p.cg_in; ++g)
         bulk_g2s(sA + (size_t)g * p.TPs * 16, p.in + ((size_t)g * p.PR + kFront + row0 - halo) * 8, (uint32_t)p.TP * 16u, a_full);
-      const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.w);
-      const int total = 9 * p.chunks;
-      for (int it = 0; it < total; ++it) {
+      for (; it < total; ++it) {
         const int s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         mbar_wait(&w_empty[s], ph ^ 1u);
+        if (p.ablate & 8) { mbar_arrive(&w_full[s]); continue; }
         mbar_arrive_expect_tx(&w_full[s], stage_bytes);
         bulk_g2s(sW + (size_t)s * stage_bytes, wsrc + (size_t)it * stage_bytes, stage_bytes, &w_full[s]);
       }
@@ -175,11 +200,22 @@ __global__ void __launch_bounds__(kTConvThreads) tconv_kernel(const __grid_const
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         mbar_wait(&w_full[s], ph);
         tc_fence_after();
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint32_t a_addr = sA_a + (uint32_t)(((ch * p.chunk_g + 2 * ks) * p.TPs + halo + off) * 16);
-          const uint32_t b_addr = sW_a + (uint32_t)s * stage_bytes + (uint32_t)(2 * ks) * (kC * 16);
-          mma_f16_elect(tmem, smem_desc(a_addr, (uint32_t)p.TPs * 16u, 128), smem_desc(b_addr, kC * 16, 128), p.idesc, acc);
+        const uint32_t a0 = sA_a + (uint32_t)(((ch * p.chunk_g) * p.TPs + halo + off) * 16);
+        const uint32_t b0 = sW_a + (uint32_t)s * stage_bytes;
+        const uint32_t a_step = (uint32_t)(2 * p.TPs * 16), b_step = 2u * (kC * 16);
+        if (p.ablate & 1) {
+        } else if (ksteps == 4) {   // a 64-channel stage: four K steps under one election
+          mma4_f16_elect(tmem, smem_desc(a0, (uint32_t)p.TPs * 16u, 128), smem_desc(a0 + a_step, (uint32_t)p.TPs * 16u, 128),
+                         smem_desc(a0 + 2 * a_step, (uint32_t)p.TPs * 16u, 128), smem_desc(a0 + 3 * a_step, (uint32_t)p.TPs * 16u, 128),
+                         smem_desc(b0, kC * 16, 128), smem_desc(b0 + b_step, kC * 16, 128), smem_desc(b0 + 2 * b_step, kC * 16, 128),
+                         smem_desc(b0 + 3 * b_step, kC * 16, 128), p.idesc, acc);
           acc = 1;
+        } else {
+          for (int ks = 0; ks < ksteps; ++ks) {
+            mma_f16_elect(tmem, smem_desc(a0 + (uint32_t)ks * a_step, (uint32_t)p.TPs * 16u, 128),
+                          smem_desc(b0 + (uint32_t)ks * b_step, kC * 16, 128), p.idesc, acc);
+            acc = 1;
+          }
         }
         commit_elect(&w_empty[s]);
       }
@@ -191,33 +227,78 @@ __global__ void __launch_bounds__(kTConvThreads) tconv_kernel(const __grid_const
     const int P = row0 + quad * 32 + lane;
     const bool inr = P < p.Ptot;
     const bool valid = inr && !is_halo(P, p.PB, p.Wp, p.W, p.H);
+    const bool mask = p.mask_a != nullptr;
+    const size_t rowoff = (size_t)kFront + (size_t)P;
+    // everything this role reads from global memory was written by earlier kernels of the chain: order it behind them
+    pdl_wait();
+    if (mask) {
+      const int et = tid - 64;
+      s_saved[2 * et] = p.mask_saved[2 * et];
+      s_saved[2 * et + 1] = p.mask_saved[2 * et + 1];
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    // the rows of the skip gradient / of the masked layer's A and Y that belong to 32-column chunk c, requested one chunk
+    // ahead (the first before the MMAs have even finished): their latency never sits on the chain
+    int4 pa[2][4], py[2][4], pd[2][4];
+    auto request = [&](int c, int4 (&a)[4], int4 (&y)[4], int4 (&d)[4]) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const size_t o = (size_t)(c * 4 + u) * p.PR + rowoff;
+        a[u] = (mask && valid && !(p.ablate & 2)) ? __ldcg(reinterpret_cast<const int4*>(p.mask_a) + o) : make_int4(0, 0, 0, 0);
+        y[u] = (mask && valid && !(p.ablate & 2)) ? __ldcg(reinterpret_cast<const int4*>(p.mask_y) + o) : make_int4(0, 0, 0, 0);
+        d[u] = (p.add && valid && !(p.ablate & 2)) ? __ldcg(reinterpret_cast<const int4*>(p.add) + o) : make_int4(0, 0, 0, 0);
+      }
+    };
+    request(0, pa[0], py[0], pd[0]);
     mbar_wait(mma_done, 0);
     tc_fence_after();
-    const size_t rowoff = (size_t)kFront + (size_t)P;
-#pragma unroll 1
+#pragma unroll
     for (int c = 0; c < 4; ++c) {
+      if (c + 1 < 4) request(c + 1, pa[(c + 1) & 1], py[(c + 1) & 1], pd[(c + 1) & 1]);
       uint32_t r[32];
       tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), r);
       tmem_ld_wait();
       float v[32];
 #pragma unroll
       for (int e = 0; e < 32; ++e) v[e] = valid ? __uint_as_float(r[e]) : 0.0f;
-      if (p.add && valid) {
+      if (p.add) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int4 a4 = __ldg(reinterpret_cast<const int4*>(p.add) + (size_t)(c * 4 + u) * p.PR + rowoff);
           float f[8];
-          unpack8(a4, 1, f);
+          unpack8(pd[c & 1][u], 1, f);
 #pragma unroll
           for (int e = 0; e < 8; ++e) v[8 * u + e] += f[e];
         }
       }
-      if (inr) {
+      float zx[32];
+      if (mask) {
+        // v := dZ = G * (A > 0);  zx := dZ * xhat
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float a8[8], y8[8];
+          unpack8(pa[c & 1][u], p.fbf16, a8);
+          unpack8(py[c & 1][u], p.fbf16, y8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int col = c * 32 + 8 * u + e;
+            const float dz = a8[e] > 0.0f ? v[8 * u + e] : 0.0f;
+            v[8 * u + e] = dz;
+            zx[8 * u + e] = dz * (y8[e] - s_saved[2 * col]) * s_saved[2 * col + 1];
+          }
+        }
+      }
+      if (inr && !(p.ablate & 2)) {
 #pragma unroll
         for (int u = 0; u < 4; ++u)
           reinterpret_cast<int4*>(p.out)[(size_t)(c * 4 + u) * p.PR + rowoff] = pack8(v + 8 * u, p.out_bf16);
       }
-      if (p.stats) {
+      if (p.ablate & 4) {
+      } else if (mask) {
+        const float s1 = warp_colsum32(v, lane);
+        const float s2 = warp_colsum32(zx, lane);
+        atomicAdd(&s_stat[c * 32 + lane], s1);
+        atomicAdd(&s_stat[kC + c * 32 + lane], s2);
+      } else if (p.stats) {
         float sq[32];
 #pragma unroll
         for (int e = 0; e < 32; ++e) sq[e] = v[e] * v[e];
@@ -227,11 +308,12 @@ __global__ void __launch_bounds__(kTConvThreads) tconv_kernel(const __grid_const
         atomicAdd(&s_stat[kC + c * 32 + lane], s2);
       }
     }
-    if (p.stats) {
+    float* sums = mask ? p.mask_sums : p.stats;
+    if (sums) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int et = tid - 64;
-      atomicAdd(p.stats + 2 * et, s_stat[et]);
-      atomicAdd(p.stats + 2 * et + 1, s_stat[kC + et]);
+      atomicAdd(sums + 2 * et, s_stat[et]);
+      atomicAdd(sums + 2 * et + 1, s_stat[kC + et]);
     }
   }
   tc_fence_before();
@@ -244,12 +326,13 @@ __global__ void __launch_bounds__(kTConvThreads) tconv_kernel(const __grid_const
 // ---------------------------------------------------------------------------------------------------------------
 struct TWgradParams {
   const uint16_t* dy;       // bf16 planes [16][PR][8]
-  const uint16_t* x;        // planes of the conv's input; ci block b starts at plane b * 16
-  float* partial;           // [ci_blocks][kSplits][9][128][N]
+  const uint16_t* x;        // bf16 planes of the conv's input; ci block b starts at plane b * 16
+  float* partial;           // [ci_blocks][slices][9][N/4][128 co][4]: a warp's lanes (co) store contiguous 16-byte pieces
   int n_groups;             // N / 8 of one ci block
   int Rs;                   // rows per split, multiple of 16
   int Wp, PR;
-  int accumulate;           // 0: overwrite the partials (first use in this step), 1: add
+  int slices, slice0;       // slices of the tensor (calls x kSplits) / first slice of this call: every launch owns its slices,
+                            // nothing is read back (a read-modify-write of 9.4 MB per launch cost more than the MMAs)
   uint32_t idesc;
   int swap_strides;         // debug: exchange LBO / SBO of the MN-major descriptors
 };
@@ -261,15 +344,15 @@ __global__ void __launch_bounds__(kTConvThreads) twgrad_kernel(const __grid_cons
   const int ng = p.n_groups, N = ng * 8;
   const uint32_t dy_bytes = 16u * kWgStage * 16u, x_bytes = (uint32_t)ng * (kWgStage + 2) * 16u;
   const uint32_t st_bytes = dy_bytes + ((x_bytes + 127u) & ~127u);
-  unsigned char* sS = smem;                                        // [2][dY | X]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * (size_t)st_bytes);
-  uint64_t* full = bars;        // [2]
-  uint64_t* empty = bars + 2;   // [2]
-  uint64_t* done = bars + 4;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 5);
+  unsigned char* sS = smem;                                        // [kWgStages][dY | X]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * (size_t)st_bytes);
+  uint64_t* full = bars;                  // [kWgStages]
+  uint64_t* empty = bars + kWgStages;     // [kWgStages]
+  uint64_t* done = bars + 2 * kWgStages;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kWgStages + 1);
 
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kWgStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(done, 1);
     fence_mbar_init();
   }
@@ -285,8 +368,8 @@ __global__ void __launch_bounds__(kTConvThreads) twgrad_kernel(const __grid_cons
     if (lane == 0) {
       const uint16_t* xb = p.x + (size_t)blk * 16 * p.PR * 8;
       for (int st = 0; st < nst; ++st) {
-        const int s = st & 1;
-        const uint32_t ph = (uint32_t)(st >> 1) & 1u;
+        const int s = st % kWgStages;
+        const uint32_t ph = (uint32_t)(st / kWgStages) & 1u;
         const int rows = (p.Rs - st * kWgStage) < kWgStage ? (p.Rs - st * kWgStage) : kWgStage;
         const int r0 = r_base + st * kWgStage;
         mbar_wait(&empty[s], ph ^ 1u);
@@ -307,15 +390,23 @@ __global__ void __launch_bounds__(kTConvThreads) twgrad_kernel(const __grid_cons
     uint32_t a_lbo = 128, a_sbo = kWgStage * 16, b_lbo = 128, b_sbo = (kWgStage + 2) * 16;
     if (p.swap_strides) { uint32_t t = a_lbo; a_lbo = a_sbo; a_sbo = t; t = b_lbo; b_lbo = b_sbo; b_sbo = t; }
     for (int st = 0; st < nst; ++st) {
-      const int s = st & 1;
-      const uint32_t ph = (uint32_t)(st >> 1) & 1u;
+      const int s = st % kWgStages;
+      const uint32_t ph = (uint32_t)(st / kWgStages) & 1u;
       const int rows = (p.Rs - st * kWgStage) < kWgStage ? (p.Rs - st * kWgStage) : kWgStage;
       mbar_wait(&full[s], ph);
       tc_fence_after();
       const uint32_t dy_a = base + (uint32_t)s * st_bytes, x_a = dy_a + dy_bytes;
       for (int kx = 0; kx < 3; ++kx) {
         const uint32_t d = tmem + (uint32_t)(kx * N);
-        for (int ks = 0; ks < rows / 16; ++ks) {
+        int ks = 0;
+        for (; ks + 4 <= rows / 16; ks += 4) {       // four K steps (64 rows) under one election
+          const uint32_t a0 = dy_a + (uint32_t)(ks * 16) * 16u, b0 = x_a + (uint32_t)(ks * 16 + kx) * 16u;
+          mma4_f16_elect(d, smem_desc(a0, a_lbo, a_sbo), smem_desc(a0 + 256, a_lbo, a_sbo), smem_desc(a0 + 512, a_lbo, a_sbo),
+                         smem_desc(a0 + 768, a_lbo, a_sbo), smem_desc(b0, b_lbo, b_sbo), smem_desc(b0 + 256, b_lbo, b_sbo),
+                         smem_desc(b0 + 512, b_lbo, b_sbo), smem_desc(b0 + 768, b_lbo, b_sbo), p.idesc,
+                         (st > 0 || ks > 0) ? 1u : 0u);
+        }
+        for (; ks < rows / 16; ++ks) {
           const uint64_t ad = smem_desc(dy_a + (uint32_t)(ks * 16) * 16u, a_lbo, a_sbo);
           const uint64_t bd = smem_desc(x_a + (uint32_t)(ks * 16 + kx) * 16u, b_lbo, b_sbo);
           mma_f16_elect(d, ad, bd, p.idesc, (st > 0 || ks > 0) ? 1u : 0u);
@@ -327,26 +418,21 @@ __global__ void __launch_bounds__(kTConvThreads) twgrad_kernel(const __grid_cons
   } else {
     const int quad = warp & 3;
     const int co = quad * 32 + lane;
+    // steps j = (tap kx, 16-column chunk c); the partials of step j + 1 are requested while step j is added and stored
+    const int nc = N / 16, steps = 3 * nc;
+    float4* base = reinterpret_cast<float4*>(p.partial) + ((size_t)blk * p.slices + p.slice0 + split) * 9 * (size_t)(N / 4) * kC + co;
     mbar_wait(done, 0);
     tc_fence_after();
-    for (int kx = 0; kx < 3; ++kx) {
-      float* dst = p.partial + ((((size_t)blk * kSplits + split) * 9 + (ky * 3 + kx)) * kC + co) * N;
-      for (int c = 0; c < N / 16; ++c) {
-        uint32_t r[16];
-        tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(kx * N + c * 16), r);
-        tmem_ld_wait();
-        float4* d4 = reinterpret_cast<float4*>(dst + c * 16);
+    for (int j = 0; j < steps; ++j) {
+      const int kx = j / nc, c = j - kx * nc;
+      float4* dst = base + ((size_t)(ky * 3 + kx) * (N / 4) + c * 4) * kC;
+      uint32_t r[16];
+      tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(kx * N + c * 16), r);
+      tmem_ld_wait();
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          float4 o = make_float4(__uint_as_float(r[4 * u]), __uint_as_float(r[4 * u + 1]), __uint_as_float(r[4 * u + 2]),
-                                 __uint_as_float(r[4 * u + 3]));
-          if (p.accumulate) {
-            const float4 q = d4[u];
-            o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
-          }
-          d4[u] = o;
-        }
-      }
+      for (int u = 0; u < 4; ++u)
+        dst[(size_t)u * kC] = make_float4(__uint_as_float(r[4 * u]), __uint_as_float(r[4 * u + 1]), __uint_as_float(r[4 * u + 2]),
+                                          __uint_as_float(r[4 * u + 3]));
     }
   }
   tc_fence_before();
@@ -364,6 +450,7 @@ struct BnFwdParams {
   const uint16_t* y;        // raw conv output (fwd type)
   const uint16_t* res;      // residual (fwd type) or nullptr
   uint16_t* a;              // relu(bn(y) + res)
+  uint16_t* a_b;            // optional bf16 copy (wgrad operand)
   const float* sums;        // [128][2] from the conv epilogue
   float* saved;             // [128][2] (mean, invstd) for the backward pass
   const float *gamma, *beta;
@@ -375,6 +462,8 @@ struct BnFwdParams {
 __global__ void __launch_bounds__(kEwThreads) bn_fwd_kernel(const BnFwdParams p) {
   __shared__ float s_scale[8], s_shift[8];
   const int g = blockIdx.y;
+  pdl_trigger();
+  pdl_wait();
   if (threadIdx.x < 8) {
     const int c = g * 8 + threadIdx.x;
     const float mean = p.sums[2 * c] * p.inv_n;
@@ -399,29 +488,31 @@ __global__ void __launch_bounds__(kEwThreads) bn_fwd_kernel(const BnFwdParams p)
   for (int k = 0; k < kEwRows; ++k) {
     const int P = (blockIdx.x * kEwRows + k) * kEwThreads + threadIdx.x;
     if (P >= p.Ptot) break;
-    int4 o = make_int4(0, 0, 0, 0);
+    int4 o = make_int4(0, 0, 0, 0), ob = o;
     if (!is_halo(P, p.PB, p.Wp, p.W, p.H)) {
       float v[8];
-      unpack8(__ldg(reinterpret_cast<const int4*>(p.y) + plane + P), p.fbf16, v);
+      unpack8(__ldcg(reinterpret_cast<const int4*>(p.y) + plane + P), p.fbf16, v);
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] = v[e] * sc[e] + sh[e];
       if (p.res) {
         float r[8];
-        unpack8(__ldg(reinterpret_cast<const int4*>(p.res) + plane + P), p.fbf16, r);
+        unpack8(__ldcg(reinterpret_cast<const int4*>(p.res) + plane + P), p.fbf16, r);
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] += r[e];
       }
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.0f);
       o = pack8(v, p.fbf16);
+      if (p.a_b) ob = pack8(v, 1);
     }
     reinterpret_cast<int4*>(p.a)[plane + P] = o;
+    if (p.a_b) reinterpret_cast<int4*>(p.a_b)[plane + P] = ob;
   }
 }
 
 struct BnBwdParams {
-  const uint16_t* g;        // gradient w.r.t. the activated output (bf16)
-  const uint16_t* a;        // the activated output (fwd type): ReLU mask
+  const uint16_t* g;        // gradient w.r.t. the activated output (bf16); with a == nullptr it is already dZ
+  const uint16_t* a;        // the activated output (fwd type): ReLU mask, or nullptr
   const uint16_t* y;        // raw conv output (fwd type)
   const float* saved;       // [128][2] mean, invstd
   float* sums;              // [128][2] (sum dZ, sum dZ * xhat)
@@ -448,9 +539,9 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(const BnBwdPa
   for (int P = r_begin + threadIdx.x; P < r_end; P += kEwThreads) {
     // halo rows: G is zero there, so they add nothing
     float gv[8], av[8], yv[8];
-    unpack8(__ldg(reinterpret_cast<const int4*>(p.g) + plane + P), 1, gv);
-    unpack8(__ldg(reinterpret_cast<const int4*>(p.a) + plane + P), p.fbf16, av);
-    unpack8(__ldg(reinterpret_cast<const int4*>(p.y) + plane + P), p.fbf16, yv);
+    unpack8(__ldcg(reinterpret_cast<const int4*>(p.g) + plane + P), 1, gv);
+    unpack8(__ldcg(reinterpret_cast<const int4*>(p.a) + plane + P), p.fbf16, av);
+    unpack8(__ldcg(reinterpret_cast<const int4*>(p.y) + plane + P), p.fbf16, yv);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float dz = av[e] > 0.0f ? gv[e] : 0.0f;
@@ -485,6 +576,8 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(const BnBwdPar
   __shared__ float s_k[8][4];      // mean, invstd, gamma*invstd, and the two batch means
   __shared__ float s_m[8][2];
   const int g = blockIdx.y;
+  pdl_trigger();
+  pdl_wait();
   if (threadIdx.x < 8) {
     const int c = g * 8 + threadIdx.x;
     const float S1 = p.sums[2 * c], S2 = p.sums[2 * c + 1];
@@ -507,12 +600,12 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(const BnBwdPar
     int4 o = make_int4(0, 0, 0, 0), oz = make_int4(0, 0, 0, 0);
     if (!is_halo(P, p.PB, p.Wp, p.W, p.H)) {
       float gv[8], av[8], yv[8], dzv[8], dyv[8];
-      unpack8(__ldg(reinterpret_cast<const int4*>(p.g) + plane + P), 1, gv);
-      unpack8(__ldg(reinterpret_cast<const int4*>(p.a) + plane + P), p.fbf16, av);
-      unpack8(__ldg(reinterpret_cast<const int4*>(p.y) + plane + P), p.fbf16, yv);
+      unpack8(__ldcg(reinterpret_cast<const int4*>(p.g) + plane + P), 1, gv);
+      if (p.a) unpack8(__ldcg(reinterpret_cast<const int4*>(p.a) + plane + P), p.fbf16, av);
+      unpack8(__ldcg(reinterpret_cast<const int4*>(p.y) + plane + P), p.fbf16, yv);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        dzv[e] = av[e] > 0.0f ? gv[e] : 0.0f;
+        dzv[e] = (!p.a || av[e] > 0.0f) ? gv[e] : 0.0f;
         const float xh = (yv[e] - mean[e]) * is[e];
         dyv[e] = gi[e] * (dzv[e] - m1[e] - xh * m2[e]);
       }
@@ -525,8 +618,8 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(const BnBwdPar
 }
 
 // float32 [B][C][H][W] -> planes (zeros at halo positions and channels >= C); cg planes are written
-__global__ void nchw_to_planes_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int C, int cg, int Ptot, int PB,
-                                      int Wp, int W, int H, int PR, int bf16) {
+__global__ void nchw_to_planes_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, uint16_t* __restrict__ dst_b, int C,
+                                      int cg, int Ptot, int PB, int Wp, int W, int H, int PR, int bf16) {
   const int g = blockIdx.y;
   const int P = blockIdx.x * blockDim.x + threadIdx.x;
   if (P >= Ptot) return;
@@ -538,6 +631,7 @@ __global__ void nchw_to_planes_kernel(const float* __restrict__ src, uint16_t* _
     v[e] = (c < C && y < H && x < W) ? src[(((size_t)b * C + c) * H + y) * W + x] : 0.0f;
   }
   reinterpret_cast<int4*>(dst)[(size_t)g * PR + kFront + P] = pack8(v, bf16);
+  if (dst_b) reinterpret_cast<int4*>(dst_b)[(size_t)g * PR + kFront + P] = pack8(v, 1);
 }
 
 // planes -> float32 [B][C][H][W]; `mask`: optional planes (fwd type) whose sign gates nothing here (kept simple)
@@ -549,7 +643,7 @@ __global__ void planes_to_nchw_kernel(const uint16_t* __restrict__ src, float* _
   const int b = P / PB, q = P - b * PB, y = q / Wp, x = q - y * Wp;
   if (y >= H || x >= W) return;
   float v[8];
-  unpack8(__ldg(reinterpret_cast<const int4*>(src) + (size_t)g * PR + kFront + P), bf16, v);
+  unpack8(__ldcg(reinterpret_cast<const int4*>(src) + (size_t)g * PR + kFront + P), bf16, v);
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int c = g * 8 + e;
@@ -559,8 +653,8 @@ __global__ void planes_to_nchw_kernel(const uint16_t* __restrict__ src, float* _
 
 // the action "planes" of DynamicsConvNet.forward (network.py:440-444, quirk C of DESIGN.md): flat element f of the
 // [A*h*w] block is 1 iff f % A == action.  Written as channels 128.. of the dynamics' first-conv input (planes 16..31).
-__global__ void action_planes_kernel(const int64_t* __restrict__ action, uint16_t* __restrict__ dst, int A, int Ptot, int PB, int Wp,
-                                     int W, int H, int PR, int bf16) {
+__global__ void action_planes_kernel(const int64_t* __restrict__ action, uint16_t* __restrict__ dst, uint16_t* __restrict__ dst_b, int A,
+                                     int Ptot, int PB, int Wp, int W, int H, int PR, int bf16) {
   const int g = blockIdx.y;                       // 0..15 -> plane 16 + g
   const int P = blockIdx.x * blockDim.x + threadIdx.x;
   if (P >= Ptot) return;
@@ -575,6 +669,7 @@ __global__ void action_planes_kernel(const int64_t* __restrict__ action, uint16_
     v[e] = f;
   }
   reinterpret_cast<int4*>(dst)[(size_t)(16 + g) * PR + kFront + P] = pack8(v, bf16);
+  if (dst_b) reinterpret_cast<int4*>(dst_b)[(size_t)(16 + g) * PR + kFront + P] = pack8(v, 1);
 }
 
 // ---- weights ---------------------------------------------------------------------------------------------------
@@ -583,8 +678,8 @@ struct ConvDesc {
   float* wgrad;
   uint16_t* wf;             // forward operand  [9][chunks][chunk_g][128 co][8 ci]
   uint16_t* wd;             // dgrad operand    [9][2][8][128 ci][8 co] (flipped taps) or nullptr
-  float* partial;           // [ci_blocks][kSplits][9][128][N]
-  int ci_total, cg_in, chunk_g, n_groups, ci_blocks;
+  float* partial;           // [ci_blocks][slices][9][N/4][128][4]
+  int ci_total, cg_in, chunk_g, n_groups, ci_blocks, slices, tower;
 };
 
 __global__ void pack_weights_kernel(const ConvDesc* __restrict__ descs, int fbf16) {
@@ -619,21 +714,23 @@ __global__ void pack_weights_kernel(const ConvDesc* __restrict__ descs, int fbf1
 }
 
 // the parameter's gradient [128][ci_total][3][3] += sum of the row-split partials
-__global__ void wgrad_finalize_kernel(const ConvDesc* __restrict__ descs) {
+__global__ void wgrad_finalize_kernel(const ConvDesc* __restrict__ descs, int calls0, int calls1, int calls2) {
   const ConvDesc d = descs[blockIdx.y];
+  const int used = (d.tower == 0 ? calls0 : (d.tower == 1 ? calls1 : calls2)) * kSplits;     // slices written in this step
   const int N = d.n_groups * 8;
   const size_t per_split = (size_t)9 * kC * N;
   const size_t total = (size_t)d.ci_blocks * per_split;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int blk = (int)(i / per_split);
-    const size_t r = i - (size_t)blk * per_split;
-    const int n = (int)(r % N), co = (int)((r / N) % kC), tap = (int)(r / ((size_t)N * kC));
+    const size_t r = i - (size_t)blk * per_split;                   // partial layout [tap][N/4][co][4]
+    const int e = (int)(r % 4), co = (int)((r / 4) % kC), q = (int)((r / (4 * kC)) % (N / 4)), tap = (int)(r / ((size_t)N * kC));
+    const int n = q * 4 + e;
     const int ci = blk * kC + n;
     if (ci >= d.ci_total) continue;
-    const float* src = d.partial + (size_t)blk * kSplits * per_split + r;
+    const float* src = d.partial + (size_t)blk * d.slices * per_split + r;
     float s = 0.0f;
-#pragma unroll
-    for (int k = 0; k < kSplits; ++k) s += src[(size_t)k * per_split];
+#pragma unroll 8
+    for (int k = 0; k < used; ++k) s += __ldcs(src + (size_t)k * per_split);
     d.wgrad[((size_t)co * d.ci_total + ci) * 9 + tap] += s;     // autograd semantics: gradients accumulate
   }
 }
@@ -668,14 +765,20 @@ struct mz_train {
   unsigned char* arena;
   size_t arena_bytes;
   size_t plane_bytes;                      // one 16-bit plane
-  uint16_t* grad_buf[5];                   // bf16 [16 planes]: G ping/pong, G1, dY, dZ
+  uint16_t* grad_buf[6];                   // bf16 [16 planes]: four rotating gradient buffers, two dY buffers
   float* stats;                            // [slots][768]: fwd sums | saved (mean, invstd) | bwd sums
   size_t stats_floats;
   int n_calls[3];
   // saved activations: slot(tower, call) -> X, then (Y, A) per layer
-  std::vector<uint16_t*> slot_x;
-  std::vector<std::vector<uint16_t*>> slot_y, slot_a;
-  int smem_conv[3];                        // dynamic shared memory per cg_in case (set at create)
+  std::vector<uint16_t*> slot_x, slot_xb;                    // xb / ab: bf16 copies for wgrad (== x / a when the forward type is bf16)
+  std::vector<std::vector<uint16_t*>> slot_y, slot_a, slot_ab;
+  // weight gradients run on a stream of their own, beside the dgrad / BatchNorm chain: dY alternates between two
+  // buffers, ev_dy[k] = buffer k is written (main -> side), ev_wg[k] = its wgrad has read it (side -> main)
+  int fwd_calls[3];                        // forward calls per tower in this step
+  cudaStream_t side;
+  cudaEvent_t ev_dy[2], ev_wg[2];
+  bool wg_pending[2];
+  int dy_turn;
 };
 
 namespace mz {
@@ -701,7 +804,7 @@ size_t conv_smem_bytes(const Geom& g, int cg_in, int* stages_out, int* TP_out, i
   const int chunk_g = cg_in < 8 ? cg_in : 8;
   const size_t a = (((size_t)cg_in * TPs * 16) + 127) & ~(size_t)127;
   const size_t stage = (size_t)chunk_g * kC * 16;
-  const size_t fixed = a + (2 * kConvStagesMax + 2) * 8 + 8 + 2 * kC * 4 + 64;
+  const size_t fixed = a + (2 * kConvStagesMax + 2) * 8 + 8 + 4 * kC * 4 + 64;
   int stages = (int)((220 * 1024 - fixed) / stage);
   const int need = 9 * (cg_in / chunk_g);
   if (stages > kConvStagesMax) stages = kConvStagesMax;
@@ -714,56 +817,93 @@ size_t conv_smem_bytes(const Geom& g, int cg_in, int* stages_out, int* TP_out, i
 
 size_t wgrad_smem_bytes(int n_groups) {
   const size_t dy = (size_t)16 * kWgStage * 16, x = ((size_t)n_groups * (kWgStage + 2) * 16 + 127) & ~(size_t)127;
-  return 2 * (dy + x) + 6 * 8 + 16 + 64;
+  return kWgStages * (dy + x) + (2 * kWgStages + 2) * 8 + 16 + 64;
+}
+
+struct MaskArgs { const uint16_t *a, *y; float* stat; };      // the layer whose ReLU / BatchNorm-backward sums a dgrad folds in
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_chain(mz_train* t, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  // programmatic dependent launch along the chain: the kernel may start as soon as its predecessor has called
+  // griddepcontrol.launch_dependents (the chain kernels do so at once; after an ordinary kernel -- weight packing, layout
+  // conversion -- it starts when that kernel has completed); everything that touches the predecessor's data sits behind
+  // griddepcontrol.wait, what does not (barrier set-up, TMEM allocation, the weight ring's first fill) runs before it.
+  (void)t;
+  return launch_pdl(true, kernel, grid, block, smem, st, args...);
 }
 
 int launch_conv(mz_train* t, const uint16_t* in, int cg_in, const uint16_t* w, uint16_t* out, const uint16_t* add,
-                float* stats, int a_bf16, int w_bf16, int out_bf16, cudaStream_t st) {
+                float* stats, int a_bf16, int w_bf16, int out_bf16, cudaStream_t st, const MaskArgs* mask = nullptr) {
   TConvParams p;
   const Geom& g = t->g;
   p.in = in; p.w = w; p.out = out; p.add = add; p.stats = stats;
+  p.mask_a = mask ? mask->a : nullptr; p.mask_y = mask ? mask->y : nullptr;
+  p.mask_saved = mask ? mask->stat + 256 : nullptr; p.mask_sums = mask ? mask->stat + 512 : nullptr;
+  p.fbf16 = t->fbf16;
   p.cg_in = cg_in; p.chunk_g = cg_in < 8 ? cg_in : 8; p.chunks = cg_in / p.chunk_g;
   p.Ptot = g.Ptot; p.PB = g.PB; p.Wp = g.Wp; p.W = g.W; p.H = g.H; p.PR = g.PR;
   const size_t smem = conv_smem_bytes(g, cg_in, &p.stages, &p.TP, &p.TPs);
   p.idesc = idesc_of(128, kC, (uint32_t)a_bf16, (uint32_t)w_bf16, 0);
   p.out_bf16 = out_bf16;
-  tconv_kernel<<<g.R128 / 128, kTConvThreads, smem, st>>>(p);
-  MZ_LAUNCH_CHECK("tconv_kernel");
+  static const int ablate = getenv("MZ_TRAIN_ABLATE") ? atoi(getenv("MZ_TRAIN_ABLATE")) : 0;
+  p.ablate = ablate;
+  cudaError_t e = launch_chain(t, tconv_kernel, dim3(g.R128 / 128), dim3(kTConvThreads), smem, st, p);
+  if (e != cudaSuccess) { set_error("tconv_kernel launch: %s", cudaGetErrorString(e)); return MZ_ECUDA; }
+  count_launch();
   return MZ_OK;
 }
 
-int launch_wgrad(mz_train* t, int conv, const uint16_t* dy, const uint16_t* x, cudaStream_t st) {
+// dy = t->dy_buf[k] was just written on `st`: hand it to the side stream's weight-gradient kernel
+int launch_wgrad(mz_train* t, int conv, int call, int k, const uint16_t* dy, const uint16_t* x, cudaStream_t st) {
   const ConvDesc& d = t->convs[conv];
+  MZ_CUDA(cudaEventRecord(t->ev_dy[k], st));
+  MZ_CUDA(cudaStreamWaitEvent(t->side, t->ev_dy[k], 0));
+  st = t->side;
   TWgradParams p;
   const Geom& g = t->g;
   p.dy = dy; p.x = x; p.partial = d.partial; p.n_groups = d.n_groups;
   p.Rs = ((g.Ptot + kSplits - 1) / kSplits + 15) / 16 * 16;
   p.Wp = g.Wp; p.PR = g.PR;
-  p.accumulate = t->touched[conv];
-  p.idesc = idesc_of(128, (uint32_t)d.n_groups * 8, 1, (uint32_t)t->fbf16, 1);
+  p.slices = d.slices; p.slice0 = call * kSplits;
+  p.idesc = idesc_of(128, (uint32_t)d.n_groups * 8, 1, 1, 1);
   p.swap_strides = t->swap_strides;
   twgrad_kernel<<<dim3(kSplits, 3, d.ci_blocks), kTConvThreads, wgrad_smem_bytes(d.n_groups), st>>>(p);
   MZ_LAUNCH_CHECK("twgrad_kernel");
-  t->touched[conv] = 1;
+  MZ_CUDA(cudaEventRecord(t->ev_wg[k], st));
+  t->wg_pending[k] = true;
+  t->touched[conv] += 1;
+  return MZ_OK;
+}
+
+// next dY buffer; the main stream first waits until the weight-gradient kernel that last read it is done
+int next_dy(mz_train* t, cudaStream_t st, int* k_out) {
+  const int k = t->dy_turn;
+  t->dy_turn ^= 1;
+  if (t->wg_pending[k]) { MZ_CUDA(cudaStreamWaitEvent(st, t->ev_wg[k], 0)); t->wg_pending[k] = false; }
+  *k_out = k;
   return MZ_OK;
 }
 
 dim3 ew_grid(const Geom& g, int planes) { return dim3((g.Ptot + kEwThreads * kEwRows - 1) / (kEwThreads * kEwRows), planes); }
 
-int launch_bn_fwd(mz_train* t, int conv, const uint16_t* y, const uint16_t* res, uint16_t* a, float* stat, cudaStream_t st) {
+int launch_bn_fwd(mz_train* t, int conv, const uint16_t* y, const uint16_t* res, uint16_t* a, uint16_t* a_b, float* stat,
+                  cudaStream_t st) {
   const Geom& g = t->g;
   const BnPtrs& b = t->bn[conv];
   BnFwdParams p;
-  p.y = y; p.res = res; p.a = a; p.sums = stat; p.saved = stat + 256;
+  p.y = y; p.res = res; p.a = a; p.a_b = (a_b && a_b != a) ? a_b : nullptr; p.sums = stat; p.saved = stat + 256;
   p.gamma = b.gamma; p.beta = b.beta; p.running_mean = b.rmean; p.running_var = b.rvar;
   p.Ptot = g.Ptot; p.PB = g.PB; p.Wp = g.Wp; p.W = g.W; p.H = g.H; p.PR = g.PR; p.fbf16 = t->fbf16;
   const double n = (double)g.B * g.H * g.W;
   p.inv_n = (float)(1.0 / n); p.unbias = (float)(n / (n - 1.0));
-  bn_fwd_kernel<<<ew_grid(g, 16), kEwThreads, 0, st>>>(p);
-  MZ_LAUNCH_CHECK("bn_fwd_kernel");
+  cudaError_t e = launch_chain(t, bn_fwd_kernel, ew_grid(g, 16), dim3(kEwThreads), 0, st, p);
+  if (e != cudaSuccess) { set_error("bn_fwd_kernel launch: %s", cudaGetErrorString(e)); return MZ_ECUDA; }
+  count_launch();
   return MZ_OK;
 }
 
+// a != nullptr: gin is dL/dA, the ReLU mask and the two sums are taken here (two launches; the top of a tower).
+// a == nullptr: gin is already dZ and the sums were accumulated by the dgrad that produced it (one launch).
 int launch_bn_bwd(mz_train* t, int conv, const uint16_t* gin, const uint16_t* a, const uint16_t* y, float* stat, uint16_t* dy,
                   uint16_t* dz, cudaStream_t st) {
   const Geom& g = t->g;
@@ -775,10 +915,13 @@ int launch_bn_bwd(mz_train* t, int conv, const uint16_t* gin, const uint16_t* a,
   p.inv_n = (float)(1.0 / ((double)g.B * g.H * g.W));
   const int nchunk = 9;
   p.rows_per_cta = (g.Ptot + nchunk - 1) / nchunk;
-  bn_bwd_reduce_kernel<<<dim3(nchunk, 16), kEwThreads, 0, st>>>(p);
-  MZ_LAUNCH_CHECK("bn_bwd_reduce_kernel");
-  bn_bwd_apply_kernel<<<ew_grid(g, 16), kEwThreads, 0, st>>>(p);
-  MZ_LAUNCH_CHECK("bn_bwd_apply_kernel");
+  if (a) {
+    bn_bwd_reduce_kernel<<<dim3(nchunk, 16), kEwThreads, 0, st>>>(p);
+    MZ_LAUNCH_CHECK("bn_bwd_reduce_kernel");
+  }
+  cudaError_t e = launch_chain(t, bn_bwd_apply_kernel, ew_grid(g, 16), dim3(kEwThreads), 0, st, p);
+  if (e != cudaSuccess) { set_error("bn_bwd_apply_kernel launch: %s", cudaGetErrorString(e)); return MZ_ECUDA; }
+  count_launch();
   return MZ_OK;
 }
 
@@ -819,21 +962,22 @@ static int train_layout(const mz_train_config* c, Geom* g, size_t* bytes, mz_tra
       const size_t o_wf = take((size_t)9 * cg_in * kC * 16);
       const bool need_d = !(tower == 0 && l == 0);
       const size_t o_wd = need_d ? take((size_t)9 * 16 * kC * 16) : 0;
-      const size_t o_p = take((size_t)ci_blocks * kSplits * 9 * kC * n_groups * 8 * 4);
+      const int slices = (tower == 0 ? 1 : T) * kSplits;
+      const size_t o_p = take((size_t)ci_blocks * slices * 9 * kC * n_groups * 8 * 4);
       if (t) {
         ConvDesc& d = t->convs[idx];
         d.w = nullptr; d.wgrad = nullptr;
         d.wf = reinterpret_cast<uint16_t*>(t->arena + o_wf);
         d.wd = need_d ? reinterpret_cast<uint16_t*>(t->arena + o_wd) : nullptr;
         d.partial = reinterpret_cast<float*>(t->arena + o_p);
-        d.ci_total = ci_total; d.cg_in = cg_in; d.chunk_g = chunk_g; d.n_groups = n_groups; d.ci_blocks = ci_blocks;
+        d.ci_total = ci_total; d.cg_in = cg_in; d.chunk_g = chunk_g; d.n_groups = n_groups; d.ci_blocks = ci_blocks; d.slices = slices; d.tower = tower;
       }
     }
   }
   const size_t o_desc = take((size_t)nconv * sizeof(ConvDesc));
   if (t) t->d_convs = reinterpret_cast<ConvDesc*>(t->arena + o_desc);
   // gradient work buffers
-  for (int k = 0; k < 5; ++k) {
+  for (int k = 0; k < 6; ++k) {
     const size_t o = take(16 * plane);
     if (t) t->grad_buf[k] = reinterpret_cast<uint16_t*>(t->arena + o);
   }
@@ -845,18 +989,25 @@ static int train_layout(const mz_train_config* c, Geom* g, size_t* bytes, mz_tra
   if (t) { t->stats = reinterpret_cast<float*>(t->arena + o_stats); t->stats_floats = nstat * 768; for (int k = 0; k < 3; ++k) t->n_calls[k] = calls[k]; }
   // saved activations
   const int nslots = 1 + 2 * T;
-  if (t) { t->slot_x.resize(nslots); t->slot_y.resize(nslots); t->slot_a.resize(nslots); }
+  const bool fb = getenv("MZ_TRAIN_FWD_BF16") ? atoi(getenv("MZ_TRAIN_FWD_BF16")) != 0 : false;
+  if (t) { t->slot_x.resize(nslots); t->slot_xb.resize(nslots); t->slot_y.resize(nslots); t->slot_a.resize(nslots); t->slot_ab.resize(nslots); }
   int s = 0;
   for (int tower = 0; tower < 3; ++tower)
     for (int call = 0; call < calls[tower]; ++call, ++s) {
       const int xg = tower == 0 ? in_cg : (tower == 1 ? 32 : 16);
       const size_t ox = take((size_t)xg * plane);
-      if (t) t->slot_x[s] = reinterpret_cast<uint16_t*>(t->arena + ox);
+      const size_t oxb = fb ? ox : take((size_t)xg * plane);
+      if (t) { t->slot_x[s] = reinterpret_cast<uint16_t*>(t->arena + ox); t->slot_xb[s] = reinterpret_cast<uint16_t*>(t->arena + oxb); }
       const int layers = (tower == 2 ? 0 : 1) + 2 * nb;
-      if (t) { t->slot_y[s].resize(layers); t->slot_a[s].resize(layers); }
+      if (t) { t->slot_y[s].resize(layers); t->slot_a[s].resize(layers); t->slot_ab[s].resize(layers); }
       for (int l = 0; l < layers; ++l) {
         const size_t oy = take(16 * plane), oa = take(16 * plane);
-        if (t) { t->slot_y[s][l] = reinterpret_cast<uint16_t*>(t->arena + oy); t->slot_a[s][l] = reinterpret_cast<uint16_t*>(t->arena + oa); }
+        // the tower's last activation feeds no convolution of this tower: no bf16 copy
+        const size_t oab = (fb || l == layers - 1) ? oa : take(16 * plane);
+        if (t) {
+          t->slot_y[s][l] = reinterpret_cast<uint16_t*>(t->arena + oy); t->slot_a[s][l] = reinterpret_cast<uint16_t*>(t->arena + oa);
+          t->slot_ab[s][l] = reinterpret_cast<uint16_t*>(t->arena + oab);
+        }
       }
     }
   *bytes = total + 1024;
@@ -893,12 +1044,36 @@ int mz_train_create(const mz_train_config* cfg, void* arena_dev, size_t arena_by
   for (int k = 0; k < 3; ++k) { const size_t s = conv_smem_bytes(t->g, cgs[k], nullptr, nullptr, nullptr); if (s > max_smem) max_smem = s; }
   e = cudaFuncSetAttribute(tconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(twgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_smem_bytes(16));
+  // The chain alternates kernels that need ~200 KB of shared memory with elementwise kernels that need none; left to
+  // its defaults the driver re-partitions L1 / shared memory at every such boundary, which drains the SMs (measured:
+  // 15 us per conv + BatchNorm pair with every instruction of the conv kernel ablated).  Everything asks for the
+  // maximum carve-out instead.
+  if (!getenv("MZ_TRAIN_NO_CARVEOUT")) {
+    const void* ks[] = {(const void*)tconv_kernel, (const void*)twgrad_kernel, (const void*)bn_fwd_kernel, (const void*)bn_bwd_apply_kernel,
+                        (const void*)bn_bwd_reduce_kernel, (const void*)nchw_to_planes_kernel, (const void*)planes_to_nchw_kernel,
+                        (const void*)action_planes_kernel};
+    for (const void* k : ks)
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  }
   if (e != cudaSuccess) { delete t; set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MZ_ECUDA; }
+  e = cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking);
+  for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+    e = cudaEventCreateWithFlags(&t->ev_dy[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_wg[k], cudaEventDisableTiming);
+  }
+  if (e != cudaSuccess) { delete t; set_error("mz_train_create: stream / event creation: %s", cudaGetErrorString(e)); return MZ_ECUDA; }
+  t->dy_turn = 0;
+  t->wg_pending[0] = t->wg_pending[1] = false;
   *out = t;
   return MZ_OK;
 }
 
 int mz_train_destroy(mz_train* t) {
+  if (t) {
+    cudaStreamSynchronize(t->side);
+    for (int k = 0; k < 2; ++k) { cudaEventDestroy(t->ev_dy[k]); cudaEventDestroy(t->ev_wg[k]); }
+    cudaStreamDestroy(t->side);
+  }
   delete t;
   return MZ_OK;
 }
@@ -929,6 +1104,9 @@ int mz_train_begin_step(mz_train* t, mz_stream stream) {
   pack_weights_kernel<<<dim3(32, t->nconv), 256, 0, st>>>(t->d_convs, t->fbf16);
   MZ_LAUNCH_CHECK("pack_weights_kernel");
   std::fill(t->touched.begin(), t->touched.end(), 0);
+  t->dy_turn = 0;
+  t->wg_pending[0] = t->wg_pending[1] = false;
+  t->fwd_calls[0] = t->fwd_calls[1] = t->fwd_calls[2] = 0;
   return MZ_OK;
 }
 
@@ -942,15 +1120,17 @@ int mz_train_tower_forward(mz_train* t, int32_t tower, int32_t call, const float
   const Geom& g = t->g;
   const int slot = slot_of(t, tower, call);
   const int nb = t->cfg.num_res_blocks;
+  if (call + 1 > t->fwd_calls[tower]) t->fwd_calls[tower] = call + 1;
   const int xg = tower_in_groups(t, tower);
   const int c_in = tower == 0 ? t->cfg.in_channels : kC;
   const dim3 cgrid((g.Ptot + 255) / 256, tower == 1 ? 16 : xg);
   uint16_t* X = t->slot_x[slot];
-  nchw_to_planes_kernel<<<cgrid, 256, 0, st>>>(x, X, c_in, tower == 1 ? 16 : xg, g.Ptot, g.PB, g.Wp, g.W, g.H, g.PR, t->fbf16);
+  uint16_t* Xb = t->slot_xb[slot] != X ? t->slot_xb[slot] : nullptr;
+  nchw_to_planes_kernel<<<cgrid, 256, 0, st>>>(x, X, Xb, c_in, tower == 1 ? 16 : xg, g.Ptot, g.PB, g.Wp, g.W, g.H, g.PR, t->fbf16);
   MZ_LAUNCH_CHECK("nchw_to_planes_kernel");
   if (tower == 1) {
-    action_planes_kernel<<<dim3((g.Ptot + 255) / 256, 16), 256, 0, st>>>(action, X, t->cfg.num_actions, g.Ptot, g.PB, g.Wp, g.W, g.H,
-                                                                       g.PR, t->fbf16);
+    action_planes_kernel<<<dim3((g.Ptot + 255) / 256, 16), 256, 0, st>>>(action, X, Xb, t->cfg.num_actions, g.Ptot, g.PB, g.Wp, g.W,
+                                                                       g.H, g.PR, t->fbf16);
     MZ_LAUNCH_CHECK("action_planes_kernel");
   }
   int conv = tower_first_conv(t, tower), layer = 0, rc;
@@ -958,16 +1138,16 @@ int mz_train_tower_forward(mz_train* t, int32_t tower, int32_t call, const float
   auto stat = [&](int l) { return t->stats + (size_t)stat_slot(t, tower, call, l) * 768; };
   if (tower != 2) {
     if ((rc = launch_conv(t, X, xg, t->convs[conv].wf, t->slot_y[slot][0], nullptr, stat(0), t->fbf16, t->fbf16, t->fbf16, st))) return rc;
-    if ((rc = launch_bn_fwd(t, conv, t->slot_y[slot][0], nullptr, t->slot_a[slot][0], stat(0), st))) return rc;
+    if ((rc = launch_bn_fwd(t, conv, t->slot_y[slot][0], nullptr, t->slot_a[slot][0], t->slot_ab[slot][0], stat(0), st))) return rc;
     cur = t->slot_a[slot][0];
     ++conv; ++layer;
   }
   for (int b = 0; b < nb; ++b) {
     uint16_t *y1 = t->slot_y[slot][layer], *a1 = t->slot_a[slot][layer], *y2 = t->slot_y[slot][layer + 1], *a2 = t->slot_a[slot][layer + 1];
     if ((rc = launch_conv(t, cur, 16, t->convs[conv].wf, y1, nullptr, stat(layer), t->fbf16, t->fbf16, t->fbf16, st))) return rc;
-    if ((rc = launch_bn_fwd(t, conv, y1, nullptr, a1, stat(layer), st))) return rc;
+    if ((rc = launch_bn_fwd(t, conv, y1, nullptr, a1, t->slot_ab[slot][layer], stat(layer), st))) return rc;
     if ((rc = launch_conv(t, a1, 16, t->convs[conv + 1].wf, y2, nullptr, stat(layer + 1), t->fbf16, t->fbf16, t->fbf16, st))) return rc;
-    if ((rc = launch_bn_fwd(t, conv + 1, y2, cur, a2, stat(layer + 1), st))) return rc;
+    if ((rc = launch_bn_fwd(t, conv + 1, y2, cur, a2, t->slot_ab[slot][layer + 1], stat(layer + 1), st))) return rc;
     cur = a2;
     conv += 2; layer += 2;
   }
@@ -985,47 +1165,88 @@ int mz_train_tower_backward(mz_train* t, int32_t tower, int32_t call, const floa
   const int slot = slot_of(t, tower, call);
   const int nb = t->cfg.num_res_blocks;
   const int first = tower != 2 ? 1 : 0;
-  uint16_t *G = t->grad_buf[0], *G2 = t->grad_buf[1], *G1 = t->grad_buf[2], *dY = t->grad_buf[3], *dZ = t->grad_buf[4];
+  const int conv0 = tower_first_conv(t, tower);
+  uint16_t** G = t->grad_buf;              // [0..3] rotate, [4..5] dY
+  uint16_t* dYb[2] = {t->grad_buf[4], t->grad_buf[5]};
   const dim3 cgrid((g.Ptot + 255) / 256, 16);
-  nchw_to_planes_kernel<<<cgrid, 256, 0, st>>>(grad_out, G, kC, 16, g.Ptot, g.PB, g.Wp, g.W, g.H, g.PR, 1);
-  MZ_LAUNCH_CHECK("nchw_to_planes_kernel");
   auto stat = [&](int l) { return t->stats + (size_t)stat_slot(t, tower, call, l) * 768; };
-  int rc;
+  // the gradient w.r.t. the current block output lives in G[cur]; `masked`: it already is dZ = dL/dA * (A > 0) and the
+  // layer's BatchNorm-backward sums are in place (the dgrad that produced it folded both in)
+  int cur = 0, k = 0, rc;
+  bool masked = false;
+  auto other = [&](int a, int b, int c) { for (int i = 0; i < 4; ++i) if (i != a && i != b && i != c) return i; return -1; };
+  nchw_to_planes_kernel<<<cgrid, 256, 0, st>>>(grad_out, G[cur], nullptr, kC, 16, g.Ptot, g.PB, g.Wp, g.W, g.H, g.PR, 1);
+  MZ_LAUNCH_CHECK("nchw_to_planes_kernel");
   for (int b = nb - 1; b >= 0; --b) {
     const int l1 = first + 2 * b, l2 = l1 + 1;
-    const int c1 = tower_first_conv(t, tower) + l1, c2 = c1 + 1;
-    const uint16_t* a_in = l1 > 0 ? t->slot_a[slot][l1 - 1] : t->slot_x[slot];
+    const int c1 = conv0 + l1, c2 = c1 + 1;
+    const uint16_t* a_in_b = l1 > 0 ? t->slot_ab[slot][l1 - 1] : t->slot_xb[slot];
     // second conv of the block: out = relu(bn2(conv2(a1)) + a_in)
-    if ((rc = launch_bn_bwd(t, c2, G, t->slot_a[slot][l2], t->slot_y[slot][l2], stat(l2), dY, dZ, st))) return rc;
-    if ((rc = launch_wgrad(t, c2, dY, t->slot_a[slot][l1], st))) return rc;
-    if ((rc = launch_conv(t, dY, 16, t->convs[c2].wd, G1, nullptr, nullptr, 1, 1, 1, st))) return rc;
+    if ((rc = next_dy(t, st, &k))) return rc;
+    if (!masked) {
+      const int f = other(cur, -1, -1);
+      if ((rc = launch_bn_bwd(t, c2, G[cur], t->slot_a[slot][l2], t->slot_y[slot][l2], stat(l2), dYb[k], G[f], st))) return rc;
+      cur = f;                             // the masked gradient: the skip connection's share
+    } else {
+      if ((rc = launch_bn_bwd(t, c2, G[cur], nullptr, t->slot_y[slot][l2], stat(l2), dYb[k], nullptr, st))) return rc;
+    }
+    if ((rc = launch_wgrad(t, c2, call, k, dYb[k], t->slot_ab[slot][l1], st))) return rc;
+    const int f1 = other(cur, -1, -1);
+    const MaskArgs m1{t->slot_a[slot][l1], t->slot_y[slot][l1], stat(l1)};
+    if ((rc = launch_conv(t, dYb[k], 16, t->convs[c2].wd, G[f1], nullptr, nullptr, 1, 1, 1, st, &m1))) return rc;
     // first conv: a1 = relu(bn1(conv1(a_in)))
-    if ((rc = launch_bn_bwd(t, c1, G1, t->slot_a[slot][l1], t->slot_y[slot][l1], stat(l1), dY, nullptr, st))) return rc;
-    if ((rc = launch_wgrad(t, c1, dY, a_in, st))) return rc;
-    if ((rc = launch_conv(t, dY, 16, t->convs[c1].wd, G2, dZ, nullptr, 1, 1, 1, st))) return rc;   // + the skip connection's share
-    uint16_t* tmp = G; G = G2; G2 = tmp;
+    if ((rc = next_dy(t, st, &k))) return rc;
+    if ((rc = launch_bn_bwd(t, c1, G[f1], nullptr, t->slot_y[slot][l1], stat(l1), dYb[k], nullptr, st))) return rc;
+    if ((rc = launch_wgrad(t, c1, call, k, dYb[k], a_in_b, st))) return rc;
+    const int f2 = other(cur, f1, -1);
+    if (l1 > 0) {                          // a_in is the output of layer l1 - 1 of this tower: fold its ReLU mask and sums in
+      const MaskArgs m0{t->slot_a[slot][l1 - 1], t->slot_y[slot][l1 - 1], stat(l1 - 1)};
+      if ((rc = launch_conv(t, dYb[k], 16, t->convs[c1].wd, G[f2], G[cur], nullptr, 1, 1, 1, st, &m0))) return rc;
+      masked = true;
+    } else {                               // a_in is the tower's input: the plain gradient
+      if ((rc = launch_conv(t, dYb[k], 16, t->convs[c1].wd, G[f2], G[cur], nullptr, 1, 1, 1, st))) return rc;
+      masked = false;
+    }
+    cur = f2;
   }
   if (first) {
-    const int c0 = tower_first_conv(t, tower);
-    if ((rc = launch_bn_bwd(t, c0, G, t->slot_a[slot][0], t->slot_y[slot][0], stat(0), dY, nullptr, st))) return rc;
-    if ((rc = launch_wgrad(t, c0, dY, t->slot_x[slot], st))) return rc;
+    if ((rc = next_dy(t, st, &k))) return rc;
+    if ((rc = launch_bn_bwd(t, conv0, G[cur], nullptr, t->slot_y[slot][0], stat(0), dYb[k], nullptr, st))) return rc;
+    if ((rc = launch_wgrad(t, conv0, call, k, dYb[k], t->slot_xb[slot], st))) return rc;
     if (tower == 1) {
-      if ((rc = launch_conv(t, dY, 16, t->convs[c0].wd, G2, nullptr, nullptr, 1, 1, 1, st))) return rc;
-      G = G2;
+      const int f = other(cur, -1, -1);
+      if ((rc = launch_conv(t, dYb[k], 16, t->convs[conv0].wd, G[f], nullptr, nullptr, 1, 1, 1, st))) return rc;
+      cur = f;
     }
   }
   if (tower != 0) {
-    planes_to_nchw_kernel<<<cgrid, 256, 0, st>>>(G, grad_in, kC, g.Ptot, g.PB, g.Wp, g.W, g.H, g.PR, 1);
+    planes_to_nchw_kernel<<<cgrid, 256, 0, st>>>(G[cur], grad_in, kC, g.Ptot, g.PB, g.Wp, g.W, g.H, g.PR, 1);
     MZ_LAUNCH_CHECK("planes_to_nchw_kernel");
   }
   return MZ_OK;
 }
 
+int mz_train_join(mz_train* t, mz_stream stream) {
+  MZ_CHECK_ARG(t != nullptr, "mz_train_join: NULL handle");
+  for (int k = 0; k < 2; ++k)
+    if (t->wg_pending[k]) { MZ_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), t->ev_wg[k], 0)); t->wg_pending[k] = false; }
+  return MZ_OK;
+}
+
 int mz_train_end_step(mz_train* t, mz_stream stream) {
   MZ_CHECK_ARG(t != nullptr, "mz_train_end_step: NULL handle");
-  for (int i = 0; i < t->nconv; ++i)
-    if (!t->touched[i]) { set_error("mz_train_end_step: convolution %d has no weight gradient yet (a tower backward is missing)", i); return MZ_ESTATE; }
-  wgrad_finalize_kernel<<<dim3(64, t->nconv), 256, 0, static_cast<cudaStream_t>(stream)>>>(t->d_convs);
+  // every tower call of the step must have gone through its backward: the finalize pass sums ALL slices of a tensor
+  for (int i = 0; i < t->nconv; ++i) {
+    const int want = t->fwd_calls[i < t->dyn_first ? 0 : (i < t->pred_first ? 1 : 2)];
+    if (t->touched[i] != want) {
+      set_error("mz_train_end_step: convolution %d has %d of %d weight-gradient passes (a tower backward is missing)", i, t->touched[i], want);
+      return MZ_ESTATE;
+    }
+  }
+  int rc = mz_train_join(t, stream);
+  if (rc) return rc;
+  wgrad_finalize_kernel<<<dim3(64, t->nconv), 256, 0, static_cast<cudaStream_t>(stream)>>>(t->d_convs, t->fwd_calls[0], t->fwd_calls[1],
+                                                                                          t->fwd_calls[2]);
   MZ_LAUNCH_CHECK("wgrad_finalize_kernel");
   return MZ_OK;
 }

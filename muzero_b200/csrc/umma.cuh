@@ -169,6 +169,21 @@ __device__ __forceinline__ void mma4_f16_elect_masked(uint32_t d_tmem, uint64_t 
         "r"(accumulate), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
       : "memory");
 }
+// the same without lane masks (training kernels: padded grid, every tap unmasked)
+__device__ __forceinline__ void mma4_f16_elect(uint32_t d_tmem, uint64_t a0, uint64_t a1, uint64_t a2, uint64_t a3, uint64_t b0,
+                                               uint64_t b1, uint64_t b2, uint64_t b3, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q, t;\n\t"
+      "setp.ne.b32 p, %10, 0;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %5, %9, p;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %6, %9, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %3, %7, %9, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %4, %8, %9, t;\n\t}"
+      ::"r"(d_tmem), "l"(a0), "l"(a1), "l"(a2), "l"(a3), "l"(b0), "l"(b1), "l"(b2), "l"(b3), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void commit_elect(uint64_t* bar) {
   asm volatile(
       "{\n\t.reg .pred q;\n\t"

@@ -131,6 +131,10 @@ class TowerTrainEngine:
         _lib.check(_lib.lib().mz_train_end_step(self.handle, _lib.current_stream()))
         self.active = False
 
+    def join(self) -> None:
+        """The current stream waits for the handle's weight-gradient stream."""
+        _lib.check(_lib.lib().mz_train_join(self.handle, _lib.current_stream()))
+
     def next_call(self, tower: int) -> int:
         k = self.calls[tower]
         limit = 1 if tower == 0 else self.unroll

@@ -201,7 +201,10 @@ class DataParallelLearner:
         # replayed iterations run the same arithmetic.)
         on_cuda = self.device.type == 'cuda'
         lr = torch.tensor(float(config.lr_init), device=self.device) if on_cuda else config.lr_init
-        self.optimizer = torch.optim.Adam(params, lr=lr, weight_decay=config.weight_decay, capturable=on_cuda)
+        # fused=True: one multi-tensor kernel per step.  The capturable foreach flavour divides every parameter by two
+        # 0-dim device scalars with one tiny kernel each -- 330 launches, 1.1 ms of a 14 ms Gomoku step.
+        self.optimizer = torch.optim.Adam(params, lr=lr, weight_decay=config.weight_decay, capturable=on_cuda,
+                                          **({'fused': True} if on_cuda else {}))
         self.lr_scheduler = torch.optim.lr_scheduler.MultiStepLR(self.optimizer, milestones=list(config.lr_milestones),
                                                                  gamma=config.lr_decay_rate)
         self.train_steps = 0
