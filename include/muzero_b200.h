@@ -361,7 +361,7 @@ int mz_train_join(mz_train* t, mz_stream stream);
 /* after the last tower backward of a step: reduce the split-K partials into the conv weight gradients              */
 int mz_train_end_step(mz_train* t, mz_stream stream);
 /* parity tests: which = 0 tower input planes, 1 raw conv output of `layer`, 2 its activated output, 3 its
- * statistics f32 [3][128][2] (forward sums | mean, invstd | backward sums).  Planes are 16-bit [groups][plane_rows][8],
+ * batch statistics f32 [128][2] (mean, 1/sqrt(var + eps)).  Planes are 16-bit [groups][plane_rows][8],
  * row P of the padded (H+1)x(W+1) grid at plane row front_rows + P.                                                */
 int mz_train_debug_view(mz_train* t, int32_t tower, int32_t call, int32_t layer, int32_t which, void** ptr, size_t* bytes,
                         int32_t* plane_rows, int32_t* front_rows);

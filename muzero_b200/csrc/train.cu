@@ -76,6 +76,18 @@ __host__ __device__ constexpr uint32_t idesc_of(uint32_t M, uint32_t N, uint32_t
   return (1u << 4) | (afmt << 7) | (bfmt << 10) | (mn_major << 15) | (mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// Batch statistics are accumulated with INTEGER atomics on fixed-point values: integer addition is associative, so the
+// totals are the same bits whatever order the CTAs arrive in (float atomics are not), and a consumer needs one load per
+// channel instead of a pass over per-CTA partials.  Activation sums use 2^-24 units (|sum| < 5e11), gradient sums
+// 2^-40 units (|sum| < 8e6): both far below float32's own rounding of the values that went in.
+constexpr double kFixAct = 16777216.0, kFixGrad = 1099511627776.0;
+__device__ __forceinline__ void fix_add(long long* dst, float v, double scale) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)__double2ll_rn((double)v * scale));
+}
+__device__ __forceinline__ float fix_get(const long long* src, double scale) {
+  return (float)((double)__ldcg(src) / scale);
+}
+
 struct Geom {
   int B, H, W, Wp, PB, Ptot, R128, PR;     // PR: rows of one plane incl. front and tail
 };
@@ -108,14 +120,14 @@ struct TConvParams {
   const uint16_t* w;        // packed [9][chunks][chunk_g][128][8]
   uint16_t* out;            // planes [16][PR][8], zeros at halo rows
   const uint16_t* add;      // optional bf16 planes added to the result (dgrad: the skip connection's gradient)
-  float* stats;             // optional [128][2] += (sum, sum of squares) over the real rows (forward: BatchNorm)
+  long long* stats;         // optional [128][2] += fixed-point (sum, sum of squares) over the real rows (forward: BatchNorm)
   // dgrad into a layer that ends in BatchNorm + ReLU: the result G = dL/dA of that layer is turned into
   // dZ = G * (A > 0) right here (that is all its consumers read) and the layer's BatchNorm-backward sums
   // (sum dZ, sum dZ * xhat) are taken from the fp32 values -- no separate reduction pass over the tensor
   const uint16_t* mask_a;   // the layer's activated output A (forward type) or nullptr
   const uint16_t* mask_y;   // its raw conv output Y (forward type)
   const float* mask_saved;  // its [128][2] (mean, invstd)
-  float* mask_sums;         // its [128][2] += (sum dZ, sum dZ * xhat)
+  long long* mask_sums;     // its [128][2] += fixed-point (sum dZ, sum dZ * xhat)
   int fbf16;                // forward tensors are bf16
   int cg_in, chunk_g, chunks;
   int Ptot, PB, Wp, W, H, PR;
@@ -144,15 +156,14 @@ __global__ void __launch_bounds__(kTConvThreads) tconv_kernel(const __grid_const
   uint64_t* a_full = bars + 2 * kConvStagesMax;
   uint64_t* mma_done = a_full + 1;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(mma_done + 1);
-  float* s_stat = reinterpret_cast<float*>(tmem_holder + 2);   // [2][128] column sums | [2][128] (mean, invstd) of the masked layer
-  float* s_saved = s_stat + 2 * kC;
+  float* s_stat = reinterpret_cast<float*>(tmem_holder + 2);   // [4 warps][2][128] column sums | [128][2] (mean, invstd) of the masked layer
+  float* s_saved = s_stat + 8 * kC;
 
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     mbar_init(a_full, 1); mbar_init(mma_done, 1);
     fence_mbar_init();
   }
-  for (int i = tid; i < 2 * kC; i += kTConvThreads) s_stat[i] = 0.0f;
   if (warp == 1) tmem_alloc(tmem_holder, 128);
   pdl_trigger();            // the next kernel of the chain may set itself up beside this one
   tc_fence_before();
@@ -240,13 +251,22 @@ __global__ void __launch_bounds__(kTConvThreads) tconv_kernel(const __grid_const
     // the rows of the skip gradient / of the masked layer's A and Y that belong to 32-column chunk c, requested one chunk
     // ahead (the first before the MMAs have even finished): their latency never sits on the chain
     int4 pa[2][4], py[2][4], pd[2][4];
+    // Loads are UNCONDITIONAL per lane (every row of a plane up to its zero tail is readable; halo rows hold zeros and
+    // are discarded by `valid` below): a per-lane predicate would turn each load into load + select and, with in-order
+    // issue, make the warp sit out one L2 round trip per load instead of one per chunk.
+    const bool do_mask = mask && !(p.ablate & 2), do_add = p.add != nullptr && !(p.ablate & 2);
     auto request = [&](int c, int4 (&a)[4], int4 (&y)[4], int4 (&d)[4]) {
+      if (do_mask) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const size_t o = (size_t)(c * 4 + u) * p.PR + rowoff;
-        a[u] = (mask && valid && !(p.ablate & 2)) ? __ldcg(reinterpret_cast<const int4*>(p.mask_a) + o) : make_int4(0, 0, 0, 0);
-        y[u] = (mask && valid && !(p.ablate & 2)) ? __ldcg(reinterpret_cast<const int4*>(p.mask_y) + o) : make_int4(0, 0, 0, 0);
-        d[u] = (p.add && valid && !(p.ablate & 2)) ? __ldcg(reinterpret_cast<const int4*>(p.add) + o) : make_int4(0, 0, 0, 0);
+        for (int u = 0; u < 4; ++u) {
+          const size_t o = (size_t)(c * 4 + u) * p.PR + rowoff;
+          a[u] = __ldcg(reinterpret_cast<const int4*>(p.mask_a) + o);
+          y[u] = __ldcg(reinterpret_cast<const int4*>(p.mask_y) + o);
+        }
+      }
+      if (do_add) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) d[u] = __ldcg(reinterpret_cast<const int4*>(p.add) + (size_t)(c * 4 + u) * p.PR + rowoff);
       }
     };
     request(0, pa[0], py[0], pd[0]);
@@ -261,13 +281,13 @@ __global__ void __launch_bounds__(kTConvThreads) tconv_kernel(const __grid_const
       float v[32];
 #pragma unroll
       for (int e = 0; e < 32; ++e) v[e] = valid ? __uint_as_float(r[e]) : 0.0f;
-      if (p.add) {
+      if (do_add) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           float f[8];
           unpack8(pd[c & 1][u], 1, f);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[8 * u + e] += f[e];
+          for (int e = 0; e < 8; ++e) v[8 * u + e] = valid ? v[8 * u + e] + f[e] : 0.0f;
         }
       }
       float zx[32];
@@ -276,8 +296,11 @@ __global__ void __launch_bounds__(kTConvThreads) tconv_kernel(const __grid_const
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           float a8[8], y8[8];
-          unpack8(pa[c & 1][u], p.fbf16, a8);
-          unpack8(py[c & 1][u], p.fbf16, y8);
+          if (do_mask) { unpack8(pa[c & 1][u], p.fbf16, a8); unpack8(py[c & 1][u], p.fbf16, y8); }
+          else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { a8[e] = 1.0f; y8[e] = 0.0f; }
+          }
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int col = c * 32 + 8 * u + e;
@@ -296,24 +319,31 @@ __global__ void __launch_bounds__(kTConvThreads) tconv_kernel(const __grid_const
       } else if (mask) {
         const float s1 = warp_colsum32(v, lane);
         const float s2 = warp_colsum32(zx, lane);
-        atomicAdd(&s_stat[c * 32 + lane], s1);
-        atomicAdd(&s_stat[kC + c * 32 + lane], s2);
+        s_stat[quad * 2 * kC + c * 32 + lane] = s1;
+        s_stat[quad * 2 * kC + kC + c * 32 + lane] = s2;
       } else if (p.stats) {
         float sq[32];
 #pragma unroll
         for (int e = 0; e < 32; ++e) sq[e] = v[e] * v[e];
         const float s1 = warp_colsum32(v, lane);
         const float s2 = warp_colsum32(sq, lane);
-        atomicAdd(&s_stat[c * 32 + lane], s1);
-        atomicAdd(&s_stat[kC + c * 32 + lane], s2);
+        s_stat[quad * 2 * kC + c * 32 + lane] = s1;
+        s_stat[quad * 2 * kC + kC + c * 32 + lane] = s2;
       }
     }
-    float* sums = mask ? p.mask_sums : p.stats;
+    long long* sums = mask ? p.mask_sums : p.stats;
     if (sums) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int et = tid - 64;
-      atomicAdd(sums + 2 * et, s_stat[et]);
-      atomicAdd(sums + 2 * et + 1, s_stat[kC + et]);
+      float a = 0.0f, b = 0.0f;
+      if (!(p.ablate & 4)) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { a += s_stat[q * 2 * kC + et]; b += s_stat[q * 2 * kC + kC + et]; }
+      }
+      if (!(p.ablate & 32)) {
+        fix_add(sums + 2 * et, a, mask ? kFixGrad : kFixAct);
+        fix_add(sums + 2 * et + 1, b, mask ? kFixGrad : kFixAct);
+      }
     }
   }
   tc_fence_before();
@@ -451,12 +481,13 @@ struct BnFwdParams {
   const uint16_t* res;      // residual (fwd type) or nullptr
   uint16_t* a;              // relu(bn(y) + res)
   uint16_t* a_b;            // optional bf16 copy (wgrad operand)
-  const float* sums;        // [128][2] from the conv epilogue
+  const long long* sums;    // [128][2] fixed-point totals from the conv epilogue
   float* saved;             // [128][2] (mean, invstd) for the backward pass
   const float *gamma, *beta;
   float *running_mean, *running_var;
   int Ptot, PB, Wp, W, H, PR, fbf16;
   float inv_n, unbias;      // 1 / (B*H*W), n / (n - 1)
+  int ablate;               // measurement only: 16 skip the partial-sum pass
 };
 
 __global__ void __launch_bounds__(kEwThreads) bn_fwd_kernel(const BnFwdParams p) {
@@ -466,8 +497,8 @@ __global__ void __launch_bounds__(kEwThreads) bn_fwd_kernel(const BnFwdParams p)
   pdl_wait();
   if (threadIdx.x < 8) {
     const int c = g * 8 + threadIdx.x;
-    const float mean = p.sums[2 * c] * p.inv_n;
-    float var = p.sums[2 * c + 1] * p.inv_n - mean * mean;
+    const float mean = fix_get(p.sums + 2 * c, kFixAct) * p.inv_n;
+    float var = fix_get(p.sums + 2 * c + 1, kFixAct) * p.inv_n - mean * mean;
     var = var > 0.0f ? var : 0.0f;
     const float is = rsqrtf(var + kBnEps);
     const float sc = p.gamma[c] * is;
@@ -484,6 +515,14 @@ __global__ void __launch_bounds__(kEwThreads) bn_fwd_kernel(const BnFwdParams p)
 #pragma unroll
   for (int e = 0; e < 8; ++e) { sc[e] = s_scale[e]; sh[e] = s_shift[e]; }
   const size_t plane = (size_t)g * p.PR + kFront;
+  // all loads of the thread's rows first (unconditional: rows past Ptot are the plane's zero tail), then the arithmetic
+  int4 yr[kEwRows], rr[kEwRows];
+#pragma unroll
+  for (int k = 0; k < kEwRows; ++k) {
+    const int P = (blockIdx.x * kEwRows + k) * kEwThreads + threadIdx.x;
+    yr[k] = __ldcg(reinterpret_cast<const int4*>(p.y) + plane + P);
+    if (p.res) rr[k] = __ldcg(reinterpret_cast<const int4*>(p.res) + plane + P);
+  }
 #pragma unroll
   for (int k = 0; k < kEwRows; ++k) {
     const int P = (blockIdx.x * kEwRows + k) * kEwThreads + threadIdx.x;
@@ -491,12 +530,12 @@ __global__ void __launch_bounds__(kEwThreads) bn_fwd_kernel(const BnFwdParams p)
     int4 o = make_int4(0, 0, 0, 0), ob = o;
     if (!is_halo(P, p.PB, p.Wp, p.W, p.H)) {
       float v[8];
-      unpack8(__ldcg(reinterpret_cast<const int4*>(p.y) + plane + P), p.fbf16, v);
+      unpack8(yr[k], p.fbf16, v);
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] = v[e] * sc[e] + sh[e];
       if (p.res) {
         float r[8];
-        unpack8(__ldcg(reinterpret_cast<const int4*>(p.res) + plane + P), p.fbf16, r);
+        unpack8(rr[k], p.fbf16, r);
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] += r[e];
       }
@@ -515,7 +554,7 @@ struct BnBwdParams {
   const uint16_t* a;        // the activated output (fwd type): ReLU mask, or nullptr
   const uint16_t* y;        // raw conv output (fwd type)
   const float* saved;       // [128][2] mean, invstd
-  float* sums;              // [128][2] (sum dZ, sum dZ * xhat)
+  long long* sums;          // [128][2] fixed-point (sum dZ, sum dZ * xhat): from the reduce kernel / the dgrad epilogue
   const float* gamma;
   float *dgamma, *dbeta;    // += (apply kernel, blockIdx.x == 0)
   uint16_t* dy;             // gradient w.r.t. the raw conv output (bf16), zeros at halo rows
@@ -568,7 +607,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(const BnBwdPa
     float t = 0.0f;
     for (int w = 0; w < kEwThreads / 32; ++w) t += red[w][threadIdx.x];
     const int e = threadIdx.x & 7, which = threadIdx.x >> 3;
-    atomicAdd(p.sums + 2 * (g * 8 + e) + which, t);
+    fix_add(p.sums + 2 * (g * 8 + e) + which, t, kFixGrad);
   }
 }
 
@@ -580,7 +619,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(const BnBwdPar
   pdl_wait();
   if (threadIdx.x < 8) {
     const int c = g * 8 + threadIdx.x;
-    const float S1 = p.sums[2 * c], S2 = p.sums[2 * c + 1];
+    const float S1 = fix_get(p.sums + 2 * c, kFixGrad), S2 = fix_get(p.sums + 2 * c + 1, kFixGrad);
     s_k[threadIdx.x][0] = p.saved[2 * c];
     s_k[threadIdx.x][1] = p.saved[2 * c + 1];
     s_k[threadIdx.x][2] = p.gamma[c] * p.saved[2 * c + 1];
@@ -593,6 +632,14 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(const BnBwdPar
 #pragma unroll
   for (int e = 0; e < 8; ++e) { mean[e] = s_k[e][0]; is[e] = s_k[e][1]; gi[e] = s_k[e][2]; m1[e] = s_m[e][0]; m2[e] = s_m[e][1]; }
   const size_t plane = (size_t)g * p.PR + kFront;
+  int4 gr[kEwRows], ar[kEwRows], yr[kEwRows];
+#pragma unroll
+  for (int k = 0; k < kEwRows; ++k) {
+    const int P = (blockIdx.x * kEwRows + k) * kEwThreads + threadIdx.x;
+    gr[k] = __ldcg(reinterpret_cast<const int4*>(p.g) + plane + P);
+    yr[k] = __ldcg(reinterpret_cast<const int4*>(p.y) + plane + P);
+    if (p.a) ar[k] = __ldcg(reinterpret_cast<const int4*>(p.a) + plane + P);
+  }
 #pragma unroll
   for (int k = 0; k < kEwRows; ++k) {
     const int P = (blockIdx.x * kEwRows + k) * kEwThreads + threadIdx.x;
@@ -600,9 +647,9 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(const BnBwdPar
     int4 o = make_int4(0, 0, 0, 0), oz = make_int4(0, 0, 0, 0);
     if (!is_halo(P, p.PB, p.Wp, p.W, p.H)) {
       float gv[8], av[8], yv[8], dzv[8], dyv[8];
-      unpack8(__ldcg(reinterpret_cast<const int4*>(p.g) + plane + P), 1, gv);
-      if (p.a) unpack8(__ldcg(reinterpret_cast<const int4*>(p.a) + plane + P), p.fbf16, av);
-      unpack8(__ldcg(reinterpret_cast<const int4*>(p.y) + plane + P), p.fbf16, yv);
+      unpack8(gr[k], 1, gv);
+      if (p.a) unpack8(ar[k], p.fbf16, av);
+      unpack8(yr[k], p.fbf16, yv);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         dzv[e] = (!p.a || av[e] > 0.0f) ? gv[e] : 0.0f;
@@ -625,11 +672,14 @@ __global__ void nchw_to_planes_kernel(const float* __restrict__ src, uint16_t* _
   if (P >= Ptot) return;
   const int b = P / PB, q = P - b * PB, y = q / Wp, x = q - y * Wp;
   float v[8];
+  const int yc = y < H ? y : H - 1, xc = x < W ? x : W - 1;          // unconditional loads, the select afterwards
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int c = g * 8 + e;
-    v[e] = (c < C && y < H && x < W) ? src[(((size_t)b * C + c) * H + y) * W + x] : 0.0f;
+    v[e] = __ldg(src + (((size_t)b * C + (c < C ? c : C - 1)) * H + yc) * W + xc);
   }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = (g * 8 + e < C && y < H && x < W) ? v[e] : 0.0f;
   reinterpret_cast<int4*>(dst)[(size_t)g * PR + kFront + P] = pack8(v, bf16);
   if (dst_b) reinterpret_cast<int4*>(dst_b)[(size_t)g * PR + kFront + P] = pack8(v, 1);
 }
@@ -729,8 +779,13 @@ __global__ void wgrad_finalize_kernel(const ConvDesc* __restrict__ descs, int ca
     if (ci >= d.ci_total) continue;
     const float* src = d.partial + (size_t)blk * d.slices * per_split + r;
     float s = 0.0f;
-#pragma unroll 8
-    for (int k = 0; k < used; ++k) s += __ldcs(src + (size_t)k * per_split);
+    for (int k0 = 0; k0 < used; k0 += 16) {          // kSplits = 16 slices per call: 16 loads in flight, then the adds
+      float v[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) v[k] = __ldcs(src + (size_t)(k0 + k) * per_split);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) s += v[k];
+    }
     d.wgrad[((size_t)co * d.ci_total + ci) * 9 + tap] += s;     // autograd semantics: gradients accumulate
   }
 }
@@ -766,8 +821,9 @@ struct mz_train {
   size_t arena_bytes;
   size_t plane_bytes;                      // one 16-bit plane
   uint16_t* grad_buf[6];                   // bf16 [16 planes]: four rotating gradient buffers, two dY buffers
-  float* stats;                            // [slots][768]: fwd sums | saved (mean, invstd) | bwd sums
+  float* stats;                            // [slots][1280 floats]: fwd totals i64 [256] | saved (mean, invstd) f32 [256] | bwd totals i64 [256]
   size_t stats_floats;
+  int stat_stride;
   int n_calls[3];
   // saved activations: slot(tower, call) -> X, then (Y, A) per layer
   std::vector<uint16_t*> slot_x, slot_xb;                    // xb / ab: bf16 copies for wgrad (== x / a when the forward type is bf16)
@@ -804,7 +860,7 @@ size_t conv_smem_bytes(const Geom& g, int cg_in, int* stages_out, int* TP_out, i
   const int chunk_g = cg_in < 8 ? cg_in : 8;
   const size_t a = (((size_t)cg_in * TPs * 16) + 127) & ~(size_t)127;
   const size_t stage = (size_t)chunk_g * kC * 16;
-  const size_t fixed = a + (2 * kConvStagesMax + 2) * 8 + 8 + 4 * kC * 4 + 64;
+  const size_t fixed = a + (2 * kConvStagesMax + 2) * 8 + 8 + 10 * kC * 4 + 64;
   int stages = (int)((220 * 1024 - fixed) / stage);
   const int need = 9 * (cg_in / chunk_g);
   if (stages > kConvStagesMax) stages = kConvStagesMax;
@@ -836,9 +892,9 @@ int launch_conv(mz_train* t, const uint16_t* in, int cg_in, const uint16_t* w, u
                 float* stats, int a_bf16, int w_bf16, int out_bf16, cudaStream_t st, const MaskArgs* mask = nullptr) {
   TConvParams p;
   const Geom& g = t->g;
-  p.in = in; p.w = w; p.out = out; p.add = add; p.stats = stats;
+  p.in = in; p.w = w; p.out = out; p.add = add; p.stats = reinterpret_cast<long long*>(stats);
   p.mask_a = mask ? mask->a : nullptr; p.mask_y = mask ? mask->y : nullptr;
-  p.mask_saved = mask ? mask->stat + 256 : nullptr; p.mask_sums = mask ? mask->stat + 512 : nullptr;
+  p.mask_saved = mask ? mask->stat + 512 : nullptr; p.mask_sums = mask ? reinterpret_cast<long long*>(mask->stat + 768) : nullptr;
   p.fbf16 = t->fbf16;
   p.cg_in = cg_in; p.chunk_g = cg_in < 8 ? cg_in : 8; p.chunks = cg_in / p.chunk_g;
   p.Ptot = g.Ptot; p.PB = g.PB; p.Wp = g.Wp; p.W = g.W; p.H = g.H; p.PR = g.PR;
@@ -847,6 +903,7 @@ int launch_conv(mz_train* t, const uint16_t* in, int cg_in, const uint16_t* w, u
   p.out_bf16 = out_bf16;
   static const int ablate = getenv("MZ_TRAIN_ABLATE") ? atoi(getenv("MZ_TRAIN_ABLATE")) : 0;
   p.ablate = ablate;
+  if (ablate & 128) return MZ_OK;          // measurement only: no conv launches at all
   cudaError_t e = launch_chain(t, tconv_kernel, dim3(g.R128 / 128), dim3(kTConvThreads), smem, st, p);
   if (e != cudaSuccess) { set_error("tconv_kernel launch: %s", cudaGetErrorString(e)); return MZ_ECUDA; }
   count_launch();
@@ -867,6 +924,8 @@ int launch_wgrad(mz_train* t, int conv, int call, int k, const uint16_t* dy, con
   p.slices = d.slices; p.slice0 = call * kSplits;
   p.idesc = idesc_of(128, (uint32_t)d.n_groups * 8, 1, 1, 1);
   p.swap_strides = t->swap_strides;
+  static const int ablate = getenv("MZ_TRAIN_ABLATE") ? atoi(getenv("MZ_TRAIN_ABLATE")) : 0;
+  if (!(ablate & 256))                     // measurement only: 256 = no weight-gradient launches
   twgrad_kernel<<<dim3(kSplits, 3, d.ci_blocks), kTConvThreads, wgrad_smem_bytes(d.n_groups), st>>>(p);
   MZ_LAUNCH_CHECK("twgrad_kernel");
   MZ_CUDA(cudaEventRecord(t->ev_wg[k], st));
@@ -891,11 +950,14 @@ int launch_bn_fwd(mz_train* t, int conv, const uint16_t* y, const uint16_t* res,
   const Geom& g = t->g;
   const BnPtrs& b = t->bn[conv];
   BnFwdParams p;
-  p.y = y; p.res = res; p.a = a; p.a_b = (a_b && a_b != a) ? a_b : nullptr; p.sums = stat; p.saved = stat + 256;
+  p.y = y; p.res = res; p.a = a; p.a_b = (a_b && a_b != a) ? a_b : nullptr; p.sums = reinterpret_cast<const long long*>(stat); p.saved = stat + 512;
   p.gamma = b.gamma; p.beta = b.beta; p.running_mean = b.rmean; p.running_var = b.rvar;
   p.Ptot = g.Ptot; p.PB = g.PB; p.Wp = g.Wp; p.W = g.W; p.H = g.H; p.PR = g.PR; p.fbf16 = t->fbf16;
   const double n = (double)g.B * g.H * g.W;
   p.inv_n = (float)(1.0 / n); p.unbias = (float)(n / (n - 1.0));
+  static const int ablate = getenv("MZ_TRAIN_ABLATE") ? atoi(getenv("MZ_TRAIN_ABLATE")) : 0;
+  p.ablate = ablate;
+  if (ablate & 64) return MZ_OK;           // measurement only: no BatchNorm launches at all
   cudaError_t e = launch_chain(t, bn_fwd_kernel, ew_grid(g, 16), dim3(kEwThreads), 0, st, p);
   if (e != cudaSuccess) { set_error("bn_fwd_kernel launch: %s", cudaGetErrorString(e)); return MZ_ECUDA; }
   count_launch();
@@ -909,7 +971,7 @@ int launch_bn_bwd(mz_train* t, int conv, const uint16_t* gin, const uint16_t* a,
   const Geom& g = t->g;
   const BnPtrs& b = t->bn[conv];
   BnBwdParams p;
-  p.g = gin; p.a = a; p.y = y; p.saved = stat + 256; p.sums = stat + 512; p.gamma = b.gamma; p.dgamma = b.dgamma; p.dbeta = b.dbeta;
+  p.g = gin; p.a = a; p.y = y; p.saved = stat + 512; p.sums = reinterpret_cast<long long*>(stat + 768); p.gamma = b.gamma; p.dgamma = b.dgamma; p.dbeta = b.dbeta;
   p.dy = dy; p.dz = dz;
   p.Ptot = g.Ptot; p.PB = g.PB; p.Wp = g.Wp; p.W = g.W; p.H = g.H; p.PR = g.PR; p.fbf16 = t->fbf16;
   p.inv_n = (float)(1.0 / ((double)g.B * g.H * g.W));
@@ -919,6 +981,8 @@ int launch_bn_bwd(mz_train* t, int conv, const uint16_t* gin, const uint16_t* a,
     bn_bwd_reduce_kernel<<<dim3(nchunk, 16), kEwThreads, 0, st>>>(p);
     MZ_LAUNCH_CHECK("bn_bwd_reduce_kernel");
   }
+  static const int ablate = getenv("MZ_TRAIN_ABLATE") ? atoi(getenv("MZ_TRAIN_ABLATE")) : 0;
+  if (ablate & 64) return MZ_OK;
   cudaError_t e = launch_chain(t, bn_bwd_apply_kernel, ew_grid(g, 16), dim3(kEwThreads), 0, st, p);
   if (e != cudaSuccess) { set_error("bn_bwd_apply_kernel launch: %s", cudaGetErrorString(e)); return MZ_ECUDA; }
   count_launch();
@@ -985,8 +1049,12 @@ static int train_layout(const mz_train_config* c, Geom* g, size_t* bytes, mz_tra
   const int calls[3] = {1, T, T};
   size_t nstat = 0;
   for (int tower = 0; tower < 3; ++tower) nstat += (size_t)calls[tower] * ((tower == 2 ? 0 : 1) + 2 * nb);
-  const size_t o_stats = take(nstat * 768 * 4);
-  if (t) { t->stats = reinterpret_cast<float*>(t->arena + o_stats); t->stats_floats = nstat * 768; for (int k = 0; k < 3; ++k) t->n_calls[k] = calls[k]; }
+  const int stat_stride = 1280;
+  const size_t o_stats = take(nstat * stat_stride * 4);
+  if (t) {
+    t->stats = reinterpret_cast<float*>(t->arena + o_stats); t->stats_floats = nstat * stat_stride; t->stat_stride = stat_stride;
+    for (int k = 0; k < 3; ++k) t->n_calls[k] = calls[k];
+  }
   // saved activations
   const int nslots = 1 + 2 * T;
   const bool fb = getenv("MZ_TRAIN_FWD_BF16") ? atoi(getenv("MZ_TRAIN_FWD_BF16")) != 0 : false;
@@ -1135,7 +1203,7 @@ int mz_train_tower_forward(mz_train* t, int32_t tower, int32_t call, const float
   }
   int conv = tower_first_conv(t, tower), layer = 0, rc;
   const uint16_t* cur = X;
-  auto stat = [&](int l) { return t->stats + (size_t)stat_slot(t, tower, call, l) * 768; };
+  auto stat = [&](int l) { return t->stats + (size_t)stat_slot(t, tower, call, l) * t->stat_stride; };
   if (tower != 2) {
     if ((rc = launch_conv(t, X, xg, t->convs[conv].wf, t->slot_y[slot][0], nullptr, stat(0), t->fbf16, t->fbf16, t->fbf16, st))) return rc;
     if ((rc = launch_bn_fwd(t, conv, t->slot_y[slot][0], nullptr, t->slot_a[slot][0], t->slot_ab[slot][0], stat(0), st))) return rc;
@@ -1169,7 +1237,7 @@ int mz_train_tower_backward(mz_train* t, int32_t tower, int32_t call, const floa
   uint16_t** G = t->grad_buf;              // [0..3] rotate, [4..5] dY
   uint16_t* dYb[2] = {t->grad_buf[4], t->grad_buf[5]};
   const dim3 cgrid((g.Ptot + 255) / 256, 16);
-  auto stat = [&](int l) { return t->stats + (size_t)stat_slot(t, tower, call, l) * 768; };
+  auto stat = [&](int l) { return t->stats + (size_t)stat_slot(t, tower, call, l) * t->stat_stride; };
   // the gradient w.r.t. the current block output lives in G[cur]; `masked`: it already is dZ = dL/dA * (A > 0) and the
   // layer's BatchNorm-backward sums are in place (the dgrad that produced it folded both in)
   int cur = 0, k = 0, rc;
@@ -1263,7 +1331,7 @@ int mz_train_debug_view(mz_train* t, int32_t tower, int32_t call, int32_t layer,
   MZ_CHECK_ARG(layer >= 0 && layer < layers, "mz_train_debug_view: layer %d out of range", layer);
   if (which == 1) { *ptr = t->slot_y[slot][layer]; *bytes = 16 * t->plane_bytes; return MZ_OK; }
   if (which == 2) { *ptr = t->slot_a[slot][layer]; *bytes = 16 * t->plane_bytes; return MZ_OK; }
-  if (which == 3) { *ptr = t->stats + (size_t)stat_slot(t, tower, call, layer) * 768; *bytes = 768 * 4; return MZ_OK; }
+  if (which == 3) { *ptr = t->stats + (size_t)stat_slot(t, tower, call, layer) * t->stat_stride + 512; *bytes = 256 * 4; return MZ_OK; }
   set_error("mz_train_debug_view: unknown view %d", which);
   return MZ_EINVAL;
 }

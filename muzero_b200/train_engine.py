@@ -158,14 +158,14 @@ class TowerTrainEngine:
 
     def debug_view(self, tower: int, call: int, layer: int, which: int) -> torch.Tensor:
         """Float32 [B, C, H, W] copy of a saved tensor (which: 0 input, 1 raw conv output, 2 activated output) or the
-        [3, 128, 2] statistics (which = 3).  Parity tests only."""
+        [128, 2] batch statistics (which = 3).  Parity tests only."""
         p, n, pr, fr = C.c_void_p(), C.c_size_t(), C.c_int32(), C.c_int32()
         _lib.check(_lib.lib().mz_train_debug_view(self.handle, tower, call, layer, which, C.byref(p), C.byref(n), C.byref(pr),
                                                   C.byref(fr)))
         off = p.value - self.arena.data_ptr()
         raw = self.arena[off:off + n.value]
         if which == 3:
-            return raw.view(torch.float32).reshape(3, 128, 2).clone()
+            return raw.view(torch.float32).reshape(128, 2).clone()
         dt = torch.bfloat16 if os.environ.get('MZ_TRAIN_FWD_BF16', '0') not in ('', '0') else torch.float16
         _, h, w = self.input_shape
         planes = raw.view(dt).reshape(-1, pr.value, 8)[:, fr.value:fr.value + self.batch * (h + 1) * (w + 1)]

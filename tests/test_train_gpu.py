@@ -162,10 +162,11 @@ def test_native_training_step_under_the_learner_graph():
                 sb[k].copy_(sa[k])
         loss_a, pa = la.step(tr, w)
         loss_b, pb = lb.step(tr, w)
-        # same kernels, same inputs: only the atomics' summation order differs
-        assert abs(loss_a - loss_b) <= 1e-4 * max(1.0, abs(loss_b)), (it, loss_a, loss_b)
+        # same kernels, same inputs, and nothing in them depends on scheduling (per-tile partial sums are added in a fixed
+        # order, no floating-point atomics): the replayed graph reproduces the eager iteration
+        assert abs(loss_a - loss_b) <= 1e-6 * max(1.0, abs(loss_b)), (it, loss_a, loss_b)
         gmax = float(lb.flat_grad.abs().max())
-        assert float((la.flat_grad - lb.flat_grad).abs().max()) <= 2e-2 * gmax, it
+        assert float((la.flat_grad - lb.flat_grad).abs().max()) <= 1e-5 * gmax, (it, float((la.flat_grad - lb.flat_grad).abs().max()), gmax)
     assert la._graph is not None and lb._graph is None
     assert float((net_a.represent_net.conv_block[0].weight - before).abs().max()) > 1e-5
     net_a.eval()
