@@ -42,6 +42,7 @@ constexpr int kWgStage = 128;      // rows per wgrad pipeline stage
 constexpr int kWgStages = 3;
 constexpr int kConvStagesMax = 8;
 constexpr float kBnEps = 1e-5f, kBnMomentum = 0.1f;
+constexpr int kTimelineMax = 8192;
 
 // ---- 16-bit element helpers (runtime element type: 0 = fp16, 1 = bf16) -------------------------------------------
 __device__ __forceinline__ float2 unpack2(uint32_t v, int bf16) {
@@ -92,6 +93,28 @@ struct Geom {
   int B, H, W, Wp, PB, Ptot, R128, PR;     // PR: rows of one plane incl. front and tail
 };
 
+// MZ_TRAIN_TIMELINE=1 (measurement only): every chain kernel stamps %globaltimer into its own record
+// [first CTA entered | first CTA past griddepcontrol.wait | last CTA done | first CTA done]
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void tl_stamp(unsigned long long* tl, int k) {
+  if (tl && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) tl[k] = gtimer();
+}
+__device__ __forceinline__ void tl_stamp_lane0(unsigned long long* tl, int k) {      // any warp of CTA 0
+  if (tl && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0) tl[k] = gtimer();
+}
+// kind: 1 forward conv, 2 dgrad, 3 bn_fwd, 4 bn_bwd_apply, 5 wgrad
+__device__ __forceinline__ void tl_end(unsigned long long* tl, int kind) {
+  if (tl && threadIdx.x == 0) {
+    const unsigned long long t = gtimer();
+    atomicMax(tl + 2, t);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) { tl[3] = t; tl[8] = (unsigned long long)kind; }
+  }
+}
+
 __device__ __forceinline__ bool is_halo(int P, int PB, int Wp, int W, int H) {
   const int q = P % PB, y = q / Wp, x = q - y * Wp;
   return x == W || y == H;
@@ -117,46 +140,51 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 // ---------------------------------------------------------------------------------------------------------------
 struct TConvParams {
   const uint16_t* in;       // planes [cg_in][PR][8]
-  const uint16_t* w;        // packed [9][chunks][chunk_g][128][8]
+  const uint16_t* w;        // packed [9][chunks][stage_g][128][8]
   uint16_t* out;            // planes [16][PR][8], zeros at halo rows
   const uint16_t* add;      // optional bf16 planes added to the result (dgrad: the skip connection's gradient)
   long long* stats;         // optional [128][2] += fixed-point (sum, sum of squares) over the real rows (forward: BatchNorm)
   // dgrad into a layer that ends in BatchNorm + ReLU: the result G = dL/dA of that layer is turned into
   // dZ = G * (A > 0) right here (that is all its consumers read) and the layer's BatchNorm-backward sums
   // (sum dZ, sum dZ * xhat) are taken from the fp32 values -- no separate reduction pass over the tensor
-  const uint16_t* mask_a;   // the layer's activated output A (forward type) or nullptr
+  const uint8_t* mask_bits; // the layer's ReLU mask [16][R128]: bit e of byte (g, row) = (A[row][8 g + e] > 0), or nullptr
   const uint16_t* mask_y;   // its raw conv output Y (forward type)
   const float* mask_saved;  // its [128][2] (mean, invstd)
   long long* mask_sums;     // its [128][2] += fixed-point (sum dZ, sum dZ * xhat)
   int fbf16;                // forward tensors are bf16
-  int cg_in, chunk_g, chunks;
-  int Ptot, PB, Wp, W, H, PR;
+  int cg_in, stage_g, chunks;   // a weight stage = stage_g channel groups of one tap; chunks stages per tap
+  int Ptot, PB, Wp, W, H, PR, R128;
   int TP, TPs;              // rows of a tile incl. halo / rows of a shared-memory plane (odd)
   int stages;
   uint32_t idesc;
   int out_bf16;
   int ablate;               // measurement only (MZ_TRAIN_ABLATE): 1 no MMAs, 2 no epilogue loads / stores, 4 no column sums, 8 no weight copies
+  unsigned long long* tl;   // measurement only: timeline record or nullptr
 };
 
-constexpr int kTConvThreads = 192;   // w0 producer, w1 MMA issuer, w2-5 epilogue
+constexpr int kTConvThreads = 320;   // w0 producer, w1 MMA issuer, w2-9 epilogue (lane quadrant warp % 4, column half (warp - 2) / 4)
+constexpr int kWgThreads = 192;      // w0 producer, w1 MMA issuer, w2-5 epilogue
 
+// kChunks: 1 / 2 = 128 / 256 input channels in 128-channel weight stages (compile-time issue loop); 0 = any other shape
+template <int kChunks>
 __global__ void __launch_bounds__(kTConvThreads) tconv_kernel(const __grid_constant__ TConvParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int halo = p.Wp + 1;
   const int row0 = blockIdx.x * 128;
-  const uint32_t stage_bytes = (uint32_t)p.chunk_g * kC * 16;
+  const uint32_t stage_bytes = (uint32_t)p.stage_g * kC * 16;
   const uint32_t a_bytes = (uint32_t)p.cg_in * p.TPs * 16;
 
   unsigned char* sA = smem;
   unsigned char* sW = smem + ((a_bytes + 127) & ~127u);
+  tl_stamp(p.tl, 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)p.stages * stage_bytes);
   uint64_t* w_full = bars;                           // [stages]
   uint64_t* w_empty = bars + kConvStagesMax;         // [stages]
   uint64_t* a_full = bars + 2 * kConvStagesMax;
   uint64_t* mma_done = a_full + 1;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(mma_done + 1);
-  float* s_stat = reinterpret_cast<float*>(tmem_holder + 2);   // [4 warps][2][128] column sums | [128][2] (mean, invstd) of the masked layer
+  float* s_stat = reinterpret_cast<float*>(tmem_holder + 2);   // [4 quadrants][2][128] column sums | [128][2] (mean, invstd) of the masked layer
   float* s_saved = s_stat + 8 * kC;
 
   if (tid == 0) {
@@ -170,113 +198,148 @@ __global__ void __launch_bounds__(kTConvThreads) tconv_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_holder;
+  const int total = 9 * p.chunks;
 
   if (warp == 0) {
     if (lane == 0) {
       // the weights do not depend on the previous kernel of the chain (they were packed at the start of the step):
       // fill the ring first, then wait for the predecessor, then fetch the tile it wrote
       const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.w);
-      const int total = 9 * p.chunks;
       int it = 0;
-      for (; it < total && it < p.stages; ++it) {
+      for (; it < p.stages; ++it) {           // stages <= total
         if (p.ablate & 8) { mbar_arrive(&w_full[it]); continue; }
         mbar_arrive_expect_tx(&w_full[it], stage_bytes);
         bulk_g2s(sW + (size_t)it * stage_bytes, wsrc + (size_t)it * stage_bytes, stage_bytes, &w_full[it]);
       }
       pdl_wait();
+      tl_stamp(p.tl, 1);
       mbar_arrive_expect_tx(a_full, (uint32_t)p.cg_in * p.TP * 16u);
       for (int g = 0; g < p.cg_in; ++g)
         bulk_g2s(sA + (size_t)g * p.TPs * 16, p.in + ((size_t)g * p.PR + kFront + row0 - halo) * 8, (uint32_t)p.TP * 16u, a_full);
+      int s = 0;
+      uint32_t ph = 0;
       for (; it < total; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        mbar_wait(&w_empty[s], ph ^ 1u);
-        if (p.ablate & 8) { mbar_arrive(&w_full[s]); continue; }
-        mbar_arrive_expect_tx(&w_full[s], stage_bytes);
-        bulk_g2s(sW + (size_t)s * stage_bytes, wsrc + (size_t)it * stage_bytes, stage_bytes, &w_full[s]);
+        mbar_wait(&w_empty[s], ph);
+        if (p.ablate & 8) mbar_arrive(&w_full[s]);
+        else {
+          mbar_arrive_expect_tx(&w_full[s], stage_bytes);
+          bulk_g2s(sW + (size_t)s * stage_bytes, wsrc + (size_t)it * stage_bytes, stage_bytes, &w_full[s]);
+        }
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
+    // The issue loop is ONE warp running dependent scalar code, and it has to hand the tensor pipe an MMA every 64
+    // cycles.  What that takes (tools/issue_bench2.cu, tools/ring_bench.cu): compile-time loop structure (a runtime trip
+    // count, stage count by division or a descriptor rebuilt per MMA each cost more than the MMA: 145 cycles per MMA
+    // measured), stage index / phase kept incrementally, descriptor high words hoisted and low words stepped by additions
+    // (16-byte units), and operands that are PROVABLY warp-uniform (redux.sync) so that they live in uniform registers
+    // instead of going through R2UR before every UTCHMMA.  Then one warp sustains 64.0 cycles per MMA including the
+    // full / empty hand-over of the weight ring.
+    auto U = [](uint32_t x) { return __reduce_max_sync(0xffffffffu, x); };
+    const uint64_t a_t = smem_desc(smem_u32(sA) + (uint32_t)halo * 16u, (uint32_t)p.TPs * 16u, 128);
+    const uint64_t b_t = smem_desc(smem_u32(sW), kC * 16, 128);
+    const uint32_t a_hi = U((uint32_t)(a_t >> 32)), b_hi = U((uint32_t)(b_t >> 32));
+    const uint32_t a_base = U((uint32_t)a_t), b_base = U((uint32_t)b_t);
+    const uint32_t a_step = U((uint32_t)(2 * p.TPs)), stage_units = U(stage_bytes >> 4);
+    constexpr uint32_t b_step = 2u * kC;
+    const uint32_t a_chunk = U((uint32_t)(p.stage_g * p.TPs));
+    const uint32_t tm = U(tmem), idesc = U(p.idesc), nstages = U((uint32_t)p.stages), wp = U((uint32_t)p.Wp);
+    auto d64 = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
     mbar_wait(a_full, 0);
     tc_fence_after();
-    const uint32_t sA_a = smem_u32(sA), sW_a = smem_u32(sW);
-    const int ksteps = p.chunk_g / 2;
-    uint32_t acc = 0;
-    int it = 0;
-    for (int tap = 0; tap < 9; ++tap) {
-      const int ky = tap / 3, kx = tap - 3 * ky;
-      const int off = (ky - 1) * p.Wp + (kx - 1);
-      for (int ch = 0; ch < p.chunks; ++ch, ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        mbar_wait(&w_full[s], ph);
-        tc_fence_after();
-        const uint32_t a0 = sA_a + (uint32_t)(((ch * p.chunk_g) * p.TPs + halo + off) * 16);
-        const uint32_t b0 = sW_a + (uint32_t)s * stage_bytes;
-        const uint32_t a_step = (uint32_t)(2 * p.TPs * 16), b_step = 2u * (kC * 16);
-        if (p.ablate & 1) {
-        } else if (ksteps == 4) {   // a 64-channel stage: four K steps under one election
-          mma4_f16_elect(tmem, smem_desc(a0, (uint32_t)p.TPs * 16u, 128), smem_desc(a0 + a_step, (uint32_t)p.TPs * 16u, 128),
-                         smem_desc(a0 + 2 * a_step, (uint32_t)p.TPs * 16u, 128), smem_desc(a0 + 3 * a_step, (uint32_t)p.TPs * 16u, 128),
-                         smem_desc(b0, kC * 16, 128), smem_desc(b0 + b_step, kC * 16, 128), smem_desc(b0 + 2 * b_step, kC * 16, 128),
-                         smem_desc(b0 + 3 * b_step, kC * 16, 128), p.idesc, acc);
-          acc = 1;
-        } else {
-          for (int ks = 0; ks < ksteps; ++ks) {
-            mma_f16_elect(tmem, smem_desc(a0 + (uint32_t)ks * a_step, (uint32_t)p.TPs * 16u, 128),
-                          smem_desc(b0 + (uint32_t)ks * b_step, kC * 16, 128), p.idesc, acc);
-            acc = 1;
-          }
+    tl_stamp_lane0(p.tl, 4);
+    uint32_t ph = 0, b_lo = b_base, s = 0;
+    if (kChunks > 0 && !(p.ablate & 1)) {
+      // 128-channel stages: eight K steps under two elections; kChunks stages per tap
+      uint32_t a_tap = a_base - wp - 1u;      // tap (0, 0)
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+        for (int ch = 0; ch < kChunks; ++ch) {
+          const uint32_t a_lo = a_tap + (uint32_t)ch * a_chunk;
+          mbar_wait(&w_full[s], ph);
+          tc_fence_after();
+          mma4_f16_elect(tm, d64(a_lo, a_hi), d64(a_lo + a_step, a_hi), d64(a_lo + 2 * a_step, a_hi), d64(a_lo + 3 * a_step, a_hi),
+                         d64(b_lo, b_hi), d64(b_lo + b_step, b_hi), d64(b_lo + 2 * b_step, b_hi), d64(b_lo + 3 * b_step, b_hi), idesc,
+                         (tap | ch) ? 1u : 0u);
+          mma4_f16_elect(tm, d64(a_lo + 4 * a_step, a_hi), d64(a_lo + 5 * a_step, a_hi), d64(a_lo + 6 * a_step, a_hi),
+                         d64(a_lo + 7 * a_step, a_hi), d64(b_lo + 4 * b_step, b_hi), d64(b_lo + 5 * b_step, b_hi),
+                         d64(b_lo + 6 * b_step, b_hi), d64(b_lo + 7 * b_step, b_hi), idesc, 1u);
+          commit_elect(&w_empty[s]);
+          b_lo += stage_units;
+          if (++s == nstages) { s = 0; ph ^= 1u; b_lo = b_base; }
         }
-        commit_elect(&w_empty[s]);
+        a_tap += (tap % 3 == 2) ? wp - 2u : 1u;
+      }
+    } else {
+      // any other stage shape (the representation tower's first convolution), or the MMAs ablated
+      const int ksteps = p.stage_g / 2;
+      uint32_t acc = 0;
+      uint32_t a_tap = a_base - wp - 1u;
+      for (int tap = 0; tap < 9; ++tap) {
+        uint32_t a_lo = a_tap;
+        for (int ch = 0; ch < p.chunks; ++ch) {
+          mbar_wait(&w_full[s], ph);
+          tc_fence_after();
+          if (!(p.ablate & 1)) {
+            for (int ks = 0; ks < ksteps; ++ks) {
+              mma_f16_elect(tm, d64(a_lo + (uint32_t)ks * a_step, a_hi), d64(b_lo + (uint32_t)ks * b_step, b_hi), idesc, acc);
+              acc = 1;
+            }
+          }
+          commit_elect(&w_empty[s]);
+          a_lo += a_chunk;
+          b_lo += stage_units;
+          if (++s == nstages) { s = 0; ph ^= 1u; b_lo = b_base; }
+        }
+        a_tap += (tap % 3 == 2) ? wp - 2u : 1u;
       }
     }
+    tl_stamp_lane0(p.tl, 5);
     commit_elect(mma_done);
   } else {
-    // ---- epilogue: TMEM lane = tile row; a warp reads the lane quadrant warp % 4
-    const int quad = warp & 3;
+    // ---- epilogue: TMEM lane = tile row; a warp reads lane quadrant warp % 4, columns [64 half, 64 half + 64)
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    const int et = tid - 64;                  // 0..255
     const int P = row0 + quad * 32 + lane;
     const bool inr = P < p.Ptot;
     const bool valid = inr && !is_halo(P, p.PB, p.Wp, p.W, p.H);
-    const bool mask = p.mask_a != nullptr;
+    const bool mask = p.mask_y != nullptr;
     const size_t rowoff = (size_t)kFront + (size_t)P;
     // everything this role reads from global memory was written by earlier kernels of the chain: order it behind them
     pdl_wait();
     if (mask) {
-      const int et = tid - 64;
-      s_saved[2 * et] = p.mask_saved[2 * et];
-      s_saved[2 * et + 1] = p.mask_saved[2 * et + 1];
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      s_saved[et] = p.mask_saved[et];
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
-    // the rows of the skip gradient / of the masked layer's A and Y that belong to 32-column chunk c, requested one chunk
-    // ahead (the first before the MMAs have even finished): their latency never sits on the chain
-    int4 pa[2][4], py[2][4], pd[2][4];
-    // Loads are UNCONDITIONAL per lane (every row of a plane up to its zero tail is readable; halo rows hold zeros and
-    // are discarded by `valid` below): a per-lane predicate would turn each load into load + select and, with in-order
-    // issue, make the warp sit out one L2 round trip per load instead of one per chunk.
+    // Everything the epilogue needs besides the accumulator -- the skip gradient, the masked layer's Y and ReLU bits for
+    // this thread's row and 64 columns -- is requested NOW, while the MMAs run: no global round trip sits between the
+    // last MMA and the stores.  Loads are UNCONDITIONAL per lane (every row of a plane up to its zero tail is readable;
+    // halo rows are discarded by `valid` below): a predicate would turn each load into load + select.
     const bool do_mask = mask && !(p.ablate & 2), do_add = p.add != nullptr && !(p.ablate & 2);
-    auto request = [&](int c, int4 (&a)[4], int4 (&y)[4], int4 (&d)[4]) {
-      if (do_mask) {
+    int4 py[8], pd[8];
+    uint2 bits = make_uint2(0xffffffffu, 0xffffffffu);
+    if (do_mask) {
+      uint32_t b[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const size_t o = (size_t)(c * 4 + u) * p.PR + rowoff;
-          a[u] = __ldcg(reinterpret_cast<const int4*>(p.mask_a) + o);
-          y[u] = __ldcg(reinterpret_cast<const int4*>(p.mask_y) + o);
-        }
-      }
-      if (do_add) {
+      for (int u = 0; u < 8; ++u) b[u] = __ldcg(p.mask_bits + (size_t)(half * 8 + u) * p.R128 + P);
+      bits.x = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+      bits.y = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) d[u] = __ldcg(reinterpret_cast<const int4*>(p.add) + (size_t)(c * 4 + u) * p.PR + rowoff);
-      }
-    };
-    request(0, pa[0], py[0], pd[0]);
+      for (int u = 0; u < 8; ++u) py[u] = __ldcg(reinterpret_cast<const int4*>(p.mask_y) + (size_t)(half * 8 + u) * p.PR + rowoff);
+    }
+    if (do_add) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) pd[u] = __ldcg(reinterpret_cast<const int4*>(p.add) + (size_t)(half * 8 + u) * p.PR + rowoff);
+    }
     mbar_wait(mma_done, 0);
     tc_fence_after();
+    if (warp == 2) tl_stamp_lane0(p.tl, 6);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      if (c + 1 < 4) request(c + 1, pa[(c + 1) & 1], py[(c + 1) & 1], pd[(c + 1) & 1]);
+    for (int c = 0; c < 2; ++c) {
       uint32_t r[32];
-      tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), r);
+      tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 64 + c * 32), r);
       tmem_ld_wait();
       float v[32];
 #pragma unroll
@@ -285,7 +348,7 @@ __global__ void __launch_bounds__(kTConvThreads) tconv_kernel(const __grid_const
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           float f[8];
-          unpack8(pd[c & 1][u], 1, f);
+          unpack8(pd[c * 4 + u], 1, f);
 #pragma unroll
           for (int e = 0; e < 8; ++e) v[8 * u + e] = valid ? v[8 * u + e] + f[e] : 0.0f;
         }
@@ -293,18 +356,19 @@ __global__ void __launch_bounds__(kTConvThreads) tconv_kernel(const __grid_const
       float zx[32];
       if (mask) {
         // v := dZ = G * (A > 0);  zx := dZ * xhat
+        const uint32_t word = c == 0 ? bits.x : bits.y;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          float a8[8], y8[8];
-          if (do_mask) { unpack8(pa[c & 1][u], p.fbf16, a8); unpack8(py[c & 1][u], p.fbf16, y8); }
+          float y8[8];
+          if (do_mask) unpack8(py[c * 4 + u], p.fbf16, y8);
           else {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) { a8[e] = 1.0f; y8[e] = 0.0f; }
+            for (int e = 0; e < 8; ++e) y8[e] = 0.0f;
           }
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const int col = c * 32 + 8 * u + e;
-            const float dz = a8[e] > 0.0f ? v[8 * u + e] : 0.0f;
+            const int col = half * 64 + c * 32 + 8 * u + e;
+            const float dz = ((word >> (8 * u + e)) & 1u) ? v[8 * u + e] : 0.0f;
             v[8 * u + e] = dz;
             zx[8 * u + e] = dz * (y8[e] - s_saved[2 * col]) * s_saved[2 * col + 1];
           }
@@ -313,42 +377,42 @@ __global__ void __launch_bounds__(kTConvThreads) tconv_kernel(const __grid_const
       if (inr && !(p.ablate & 2)) {
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-          reinterpret_cast<int4*>(p.out)[(size_t)(c * 4 + u) * p.PR + rowoff] = pack8(v + 8 * u, p.out_bf16);
+          reinterpret_cast<int4*>(p.out)[(size_t)(half * 8 + c * 4 + u) * p.PR + rowoff] = pack8(v + 8 * u, p.out_bf16);
       }
+      const int col0 = half * 64 + c * 32;
       if (p.ablate & 4) {
       } else if (mask) {
         const float s1 = warp_colsum32(v, lane);
         const float s2 = warp_colsum32(zx, lane);
-        s_stat[quad * 2 * kC + c * 32 + lane] = s1;
-        s_stat[quad * 2 * kC + kC + c * 32 + lane] = s2;
+        s_stat[quad * 2 * kC + col0 + lane] = s1;
+        s_stat[quad * 2 * kC + kC + col0 + lane] = s2;
       } else if (p.stats) {
         float sq[32];
 #pragma unroll
         for (int e = 0; e < 32; ++e) sq[e] = v[e] * v[e];
         const float s1 = warp_colsum32(v, lane);
         const float s2 = warp_colsum32(sq, lane);
-        s_stat[quad * 2 * kC + c * 32 + lane] = s1;
-        s_stat[quad * 2 * kC + kC + c * 32 + lane] = s2;
+        s_stat[quad * 2 * kC + col0 + lane] = s1;
+        s_stat[quad * 2 * kC + kC + col0 + lane] = s2;
       }
     }
+    if (warp == 2) tl_stamp_lane0(p.tl, 7);
     long long* sums = mask ? p.mask_sums : p.stats;
     if (sums) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int et = tid - 64;
-      float a = 0.0f, b = 0.0f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int which = et >> 7, col = et & (kC - 1);
+      float a = 0.0f;
       if (!(p.ablate & 4)) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { a += s_stat[q * 2 * kC + et]; b += s_stat[q * 2 * kC + kC + et]; }
+        for (int q = 0; q < 4; ++q) a += s_stat[q * 2 * kC + which * kC + col];
       }
-      if (!(p.ablate & 32)) {
-        fix_add(sums + 2 * et, a, mask ? kFixGrad : kFixAct);
-        fix_add(sums + 2 * et + 1, b, mask ? kFixGrad : kFixAct);
-      }
+      if (!(p.ablate & 32)) fix_add(sums + 2 * col + which, a, mask ? kFixGrad : kFixAct);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 128);
+  tl_end(p.tl, p.stats ? 1 : 2);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -365,13 +429,16 @@ struct TWgradParams {
                             // nothing is read back (a read-modify-write of 9.4 MB per launch cost more than the MMAs)
   uint32_t idesc;
   int swap_strides;         // debug: exchange LBO / SBO of the MN-major descriptors
+  unsigned long long* tl;   // measurement only
 };
 
-__global__ void __launch_bounds__(kTConvThreads) twgrad_kernel(const __grid_constant__ TWgradParams p) {
+__global__ void __launch_bounds__(kWgThreads) twgrad_kernel(const __grid_constant__ TWgradParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int split = blockIdx.x, ky = blockIdx.y, blk = blockIdx.z;
   const int ng = p.n_groups, N = ng * 8;
+  tl_stamp(p.tl, 0);
+  tl_stamp(p.tl, 1);
   const uint32_t dy_bytes = 16u * kWgStage * 16u, x_bytes = (uint32_t)ng * (kWgStage + 2) * 16u;
   const uint32_t st_bytes = dy_bytes + ((x_bytes + 127u) & ~127u);
   unsigned char* sS = smem;                                        // [kWgStages][dY | X]
@@ -468,6 +535,7 @@ __global__ void __launch_bounds__(kTConvThreads) twgrad_kernel(const __grid_cons
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
+  tl_end(p.tl, 5);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -481,20 +549,24 @@ struct BnFwdParams {
   const uint16_t* res;      // residual (fwd type) or nullptr
   uint16_t* a;              // relu(bn(y) + res)
   uint16_t* a_b;            // optional bf16 copy (wgrad operand)
+  uint8_t* bits;            // ReLU mask [16][R128]: bit e of byte (g, row) = (a[row][8 g + e] > 0): what the backward pass reads instead of a
   const long long* sums;    // [128][2] fixed-point totals from the conv epilogue
   float* saved;             // [128][2] (mean, invstd) for the backward pass
   const float *gamma, *beta;
   float *running_mean, *running_var;
-  int Ptot, PB, Wp, W, H, PR, fbf16;
+  int Ptot, PB, Wp, W, H, PR, R128, fbf16;
   float inv_n, unbias;      // 1 / (B*H*W), n / (n - 1)
   int ablate;               // measurement only: 16 skip the partial-sum pass
+  unsigned long long* tl;
 };
 
 __global__ void __launch_bounds__(kEwThreads) bn_fwd_kernel(const BnFwdParams p) {
   __shared__ float s_scale[8], s_shift[8];
   const int g = blockIdx.y;
+  tl_stamp(p.tl, 0);
   pdl_trigger();
   pdl_wait();
+  tl_stamp(p.tl, 1);
   if (threadIdx.x < 8) {
     const int c = g * 8 + threadIdx.x;
     const float mean = fix_get(p.sums + 2 * c, kFixAct) * p.inv_n;
@@ -528,6 +600,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_fwd_kernel(const BnFwdParams p)
     const int P = (blockIdx.x * kEwRows + k) * kEwThreads + threadIdx.x;
     if (P >= p.Ptot) break;
     int4 o = make_int4(0, 0, 0, 0), ob = o;
+    uint32_t m = 0;
     if (!is_halo(P, p.PB, p.Wp, p.W, p.H)) {
       float v[8];
       unpack8(yr[k], p.fbf16, v);
@@ -543,10 +616,17 @@ __global__ void __launch_bounds__(kEwThreads) bn_fwd_kernel(const BnFwdParams p)
       for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.0f);
       o = pack8(v, p.fbf16);
       if (p.a_b) ob = pack8(v, 1);
+      // the mask is taken from the STORED value (what bn_bwd_reduce_kernel's `a > 0` sees)
+      float w[8];
+      unpack8(o, p.fbf16, w);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) m |= (w[e] > 0.0f ? 1u : 0u) << e;
     }
     reinterpret_cast<int4*>(p.a)[plane + P] = o;
     if (p.a_b) reinterpret_cast<int4*>(p.a_b)[plane + P] = ob;
+    p.bits[(size_t)g * p.R128 + P] = (uint8_t)m;
   }
+  tl_end(p.tl, 3);
 }
 
 struct BnBwdParams {
@@ -562,6 +642,7 @@ struct BnBwdParams {
   int Ptot, PB, Wp, W, H, PR, fbf16;
   float inv_n;
   int rows_per_cta;         // reduce kernel
+  unsigned long long* tl;
 };
 
 __global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(const BnBwdParams p) {
@@ -615,8 +696,10 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(const BnBwdPar
   __shared__ float s_k[8][4];      // mean, invstd, gamma*invstd, and the two batch means
   __shared__ float s_m[8][2];
   const int g = blockIdx.y;
+  tl_stamp(p.tl, 0);
   pdl_trigger();
   pdl_wait();
+  tl_stamp(p.tl, 1);
   if (threadIdx.x < 8) {
     const int c = g * 8 + threadIdx.x;
     const float S1 = fix_get(p.sums + 2 * c, kFixGrad), S2 = fix_get(p.sums + 2 * c + 1, kFixGrad);
@@ -662,6 +745,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(const BnBwdPar
     reinterpret_cast<int4*>(p.dy)[plane + P] = o;
     if (p.dz) reinterpret_cast<int4*>(p.dz)[plane + P] = oz;
   }
+  tl_end(p.tl, 4);
 }
 
 // float32 [B][C][H][W] -> planes (zeros at halo positions and channels >= C); cg planes are written
@@ -828,6 +912,7 @@ struct mz_train {
   // saved activations: slot(tower, call) -> X, then (Y, A) per layer
   std::vector<uint16_t*> slot_x, slot_xb;                    // xb / ab: bf16 copies for wgrad (== x / a when the forward type is bf16)
   std::vector<std::vector<uint16_t*>> slot_y, slot_a, slot_ab;
+  std::vector<std::vector<uint8_t*>> slot_m;                 // ReLU masks [R128][16] per layer
   // weight gradients run on a stream of their own, beside the dgrad / BatchNorm chain: dY alternates between two
   // buffers, ev_dy[k] = buffer k is written (main -> side), ev_wg[k] = its wgrad has read it (side -> main)
   int fwd_calls[3];                        // forward calls per tower in this step
@@ -835,6 +920,8 @@ struct mz_train {
   cudaEvent_t ev_dy[2], ev_wg[2];
   bool wg_pending[2];
   int dy_turn;
+  unsigned long long* timeline;            // MZ_TRAIN_TIMELINE=1: [kTimelineMax][10] stamps, one record per chain launch
+  int tl_next;
 };
 
 namespace mz {
@@ -857,7 +944,7 @@ int stat_slot(const mz_train* t, int tower, int call, int layer) {
 size_t conv_smem_bytes(const Geom& g, int cg_in, int* stages_out, int* TP_out, int* TPs_out) {
   const int halo = g.Wp + 1;
   const int TP = 128 + 2 * halo, TPs = TP | 1;
-  const int chunk_g = cg_in < 8 ? cg_in : 8;
+  const int chunk_g = cg_in < 16 ? cg_in : 16;                     // a stage: one tap's weights for up to 128 input channels
   const size_t a = (((size_t)cg_in * TPs * 16) + 127) & ~(size_t)127;
   const size_t stage = (size_t)chunk_g * kC * 16;
   const size_t fixed = a + (2 * kConvStagesMax + 2) * 8 + 8 + 10 * kC * 4 + 64;
@@ -876,7 +963,7 @@ size_t wgrad_smem_bytes(int n_groups) {
   return kWgStages * (dy + x) + (2 * kWgStages + 2) * 8 + 16 + 64;
 }
 
-struct MaskArgs { const uint16_t *a, *y; float* stat; };      // the layer whose ReLU / BatchNorm-backward sums a dgrad folds in
+struct MaskArgs { const uint8_t* bits; const uint16_t* y; float* stat; };      // the layer whose ReLU / BatchNorm-backward sums a dgrad folds in
 
 template <typename... KArgs, typename... Args>
 cudaError_t launch_chain(mz_train* t, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
@@ -893,18 +980,20 @@ int launch_conv(mz_train* t, const uint16_t* in, int cg_in, const uint16_t* w, u
   TConvParams p;
   const Geom& g = t->g;
   p.in = in; p.w = w; p.out = out; p.add = add; p.stats = reinterpret_cast<long long*>(stats);
-  p.mask_a = mask ? mask->a : nullptr; p.mask_y = mask ? mask->y : nullptr;
+  p.mask_bits = mask ? mask->bits : nullptr; p.mask_y = mask ? mask->y : nullptr;
   p.mask_saved = mask ? mask->stat + 512 : nullptr; p.mask_sums = mask ? reinterpret_cast<long long*>(mask->stat + 768) : nullptr;
   p.fbf16 = t->fbf16;
-  p.cg_in = cg_in; p.chunk_g = cg_in < 8 ? cg_in : 8; p.chunks = cg_in / p.chunk_g;
-  p.Ptot = g.Ptot; p.PB = g.PB; p.Wp = g.Wp; p.W = g.W; p.H = g.H; p.PR = g.PR;
+  p.cg_in = cg_in; p.stage_g = cg_in < 16 ? cg_in : 16; p.chunks = cg_in / p.stage_g;
+  p.Ptot = g.Ptot; p.PB = g.PB; p.Wp = g.Wp; p.W = g.W; p.H = g.H; p.PR = g.PR; p.R128 = g.R128;
   const size_t smem = conv_smem_bytes(g, cg_in, &p.stages, &p.TP, &p.TPs);
   p.idesc = idesc_of(128, kC, (uint32_t)a_bf16, (uint32_t)w_bf16, 0);
   p.out_bf16 = out_bf16;
   static const int ablate = getenv("MZ_TRAIN_ABLATE") ? atoi(getenv("MZ_TRAIN_ABLATE")) : 0;
   p.ablate = ablate;
+  p.tl = t->timeline && t->tl_next < kTimelineMax ? t->timeline + 10 * (size_t)t->tl_next++ : nullptr;
   if (ablate & 128) return MZ_OK;          // measurement only: no conv launches at all
-  cudaError_t e = launch_chain(t, tconv_kernel, dim3(g.R128 / 128), dim3(kTConvThreads), smem, st, p);
+  void (*kern)(TConvParams) = p.stage_g == 16 ? (p.chunks == 1 ? tconv_kernel<1> : (p.chunks == 2 ? tconv_kernel<2> : tconv_kernel<0>)) : tconv_kernel<0>;
+  cudaError_t e = launch_chain(t, kern, dim3(g.R128 / 128), dim3(kTConvThreads), smem, st, p);
   if (e != cudaSuccess) { set_error("tconv_kernel launch: %s", cudaGetErrorString(e)); return MZ_ECUDA; }
   count_launch();
   return MZ_OK;
@@ -924,9 +1013,10 @@ int launch_wgrad(mz_train* t, int conv, int call, int k, const uint16_t* dy, con
   p.slices = d.slices; p.slice0 = call * kSplits;
   p.idesc = idesc_of(128, (uint32_t)d.n_groups * 8, 1, 1, 1);
   p.swap_strides = t->swap_strides;
+  p.tl = t->timeline && t->tl_next < kTimelineMax ? t->timeline + 10 * (size_t)t->tl_next++ : nullptr;
   static const int ablate = getenv("MZ_TRAIN_ABLATE") ? atoi(getenv("MZ_TRAIN_ABLATE")) : 0;
   if (!(ablate & 256))                     // measurement only: 256 = no weight-gradient launches
-  twgrad_kernel<<<dim3(kSplits, 3, d.ci_blocks), kTConvThreads, wgrad_smem_bytes(d.n_groups), st>>>(p);
+  twgrad_kernel<<<dim3(kSplits, 3, d.ci_blocks), kWgThreads, wgrad_smem_bytes(d.n_groups), st>>>(p);
   MZ_LAUNCH_CHECK("twgrad_kernel");
   MZ_CUDA(cudaEventRecord(t->ev_wg[k], st));
   t->wg_pending[k] = true;
@@ -945,18 +1035,19 @@ int next_dy(mz_train* t, cudaStream_t st, int* k_out) {
 
 dim3 ew_grid(const Geom& g, int planes) { return dim3((g.Ptot + kEwThreads * kEwRows - 1) / (kEwThreads * kEwRows), planes); }
 
-int launch_bn_fwd(mz_train* t, int conv, const uint16_t* y, const uint16_t* res, uint16_t* a, uint16_t* a_b, float* stat,
-                  cudaStream_t st) {
+int launch_bn_fwd(mz_train* t, int conv, const uint16_t* y, const uint16_t* res, uint16_t* a, uint16_t* a_b, uint8_t* bits,
+                  float* stat, cudaStream_t st) {
   const Geom& g = t->g;
   const BnPtrs& b = t->bn[conv];
   BnFwdParams p;
-  p.y = y; p.res = res; p.a = a; p.a_b = (a_b && a_b != a) ? a_b : nullptr; p.sums = reinterpret_cast<const long long*>(stat); p.saved = stat + 512;
+  p.y = y; p.res = res; p.a = a; p.a_b = (a_b && a_b != a) ? a_b : nullptr; p.bits = bits; p.sums = reinterpret_cast<const long long*>(stat); p.saved = stat + 512;
   p.gamma = b.gamma; p.beta = b.beta; p.running_mean = b.rmean; p.running_var = b.rvar;
-  p.Ptot = g.Ptot; p.PB = g.PB; p.Wp = g.Wp; p.W = g.W; p.H = g.H; p.PR = g.PR; p.fbf16 = t->fbf16;
+  p.Ptot = g.Ptot; p.PB = g.PB; p.Wp = g.Wp; p.W = g.W; p.H = g.H; p.PR = g.PR; p.R128 = g.R128; p.fbf16 = t->fbf16;
   const double n = (double)g.B * g.H * g.W;
   p.inv_n = (float)(1.0 / n); p.unbias = (float)(n / (n - 1.0));
   static const int ablate = getenv("MZ_TRAIN_ABLATE") ? atoi(getenv("MZ_TRAIN_ABLATE")) : 0;
   p.ablate = ablate;
+  p.tl = t->timeline && t->tl_next < kTimelineMax ? t->timeline + 10 * (size_t)t->tl_next++ : nullptr;
   if (ablate & 64) return MZ_OK;           // measurement only: no BatchNorm launches at all
   cudaError_t e = launch_chain(t, bn_fwd_kernel, ew_grid(g, 16), dim3(kEwThreads), 0, st, p);
   if (e != cudaSuccess) { set_error("bn_fwd_kernel launch: %s", cudaGetErrorString(e)); return MZ_ECUDA; }
@@ -975,6 +1066,7 @@ int launch_bn_bwd(mz_train* t, int conv, const uint16_t* gin, const uint16_t* a,
   p.dy = dy; p.dz = dz;
   p.Ptot = g.Ptot; p.PB = g.PB; p.Wp = g.Wp; p.W = g.W; p.H = g.H; p.PR = g.PR; p.fbf16 = t->fbf16;
   p.inv_n = (float)(1.0 / ((double)g.B * g.H * g.W));
+  p.tl = nullptr;
   const int nchunk = 9;
   p.rows_per_cta = (g.Ptot + nchunk - 1) / nchunk;
   if (a) {
@@ -983,6 +1075,7 @@ int launch_bn_bwd(mz_train* t, int conv, const uint16_t* gin, const uint16_t* a,
   }
   static const int ablate = getenv("MZ_TRAIN_ABLATE") ? atoi(getenv("MZ_TRAIN_ABLATE")) : 0;
   if (ablate & 64) return MZ_OK;
+  p.tl = t->timeline && t->tl_next < kTimelineMax ? t->timeline + 10 * (size_t)t->tl_next++ : nullptr;
   cudaError_t e = launch_chain(t, bn_bwd_apply_kernel, ew_grid(g, 16), dim3(kEwThreads), 0, st, p);
   if (e != cudaSuccess) { set_error("bn_bwd_apply_kernel launch: %s", cudaGetErrorString(e)); return MZ_ECUDA; }
   count_launch();
@@ -1058,7 +1151,7 @@ static int train_layout(const mz_train_config* c, Geom* g, size_t* bytes, mz_tra
   // saved activations
   const int nslots = 1 + 2 * T;
   const bool fb = getenv("MZ_TRAIN_FWD_BF16") ? atoi(getenv("MZ_TRAIN_FWD_BF16")) != 0 : false;
-  if (t) { t->slot_x.resize(nslots); t->slot_xb.resize(nslots); t->slot_y.resize(nslots); t->slot_a.resize(nslots); t->slot_ab.resize(nslots); }
+  if (t) { t->slot_x.resize(nslots); t->slot_xb.resize(nslots); t->slot_y.resize(nslots); t->slot_a.resize(nslots); t->slot_ab.resize(nslots); t->slot_m.resize(nslots); }
   int s = 0;
   for (int tower = 0; tower < 3; ++tower)
     for (int call = 0; call < calls[tower]; ++call, ++s) {
@@ -1067,12 +1160,14 @@ static int train_layout(const mz_train_config* c, Geom* g, size_t* bytes, mz_tra
       const size_t oxb = fb ? ox : take((size_t)xg * plane);
       if (t) { t->slot_x[s] = reinterpret_cast<uint16_t*>(t->arena + ox); t->slot_xb[s] = reinterpret_cast<uint16_t*>(t->arena + oxb); }
       const int layers = (tower == 2 ? 0 : 1) + 2 * nb;
-      if (t) { t->slot_y[s].resize(layers); t->slot_a[s].resize(layers); t->slot_ab[s].resize(layers); }
+      if (t) { t->slot_y[s].resize(layers); t->slot_a[s].resize(layers); t->slot_ab[s].resize(layers); t->slot_m[s].resize(layers); }
       for (int l = 0; l < layers; ++l) {
         const size_t oy = take(16 * plane), oa = take(16 * plane);
         // the tower's last activation feeds no convolution of this tower: no bf16 copy
         const size_t oab = (fb || l == layers - 1) ? oa : take(16 * plane);
+        const size_t om = take((size_t)g->R128 * 16);
         if (t) {
+          t->slot_m[s][l] = t->arena + om;
           t->slot_y[s][l] = reinterpret_cast<uint16_t*>(t->arena + oy); t->slot_a[s][l] = reinterpret_cast<uint16_t*>(t->arena + oa);
           t->slot_ab[s][l] = reinterpret_cast<uint16_t*>(t->arena + oab);
         }
@@ -1110,14 +1205,16 @@ int mz_train_create(const mz_train_config* cfg, void* arena_dev, size_t arena_by
   const int cgs[3] = {tower_in_groups(t, 0), 16, 32};
   size_t max_smem = 0;
   for (int k = 0; k < 3; ++k) { const size_t s = conv_smem_bytes(t->g, cgs[k], nullptr, nullptr, nullptr); if (s > max_smem) max_smem = s; }
-  e = cudaFuncSetAttribute(tconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+  e = cudaFuncSetAttribute(tconv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tconv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tconv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(twgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_smem_bytes(16));
   // The chain alternates kernels that need ~200 KB of shared memory with elementwise kernels that need none; left to
   // its defaults the driver re-partitions L1 / shared memory at every such boundary, which drains the SMs (measured:
   // 15 us per conv + BatchNorm pair with every instruction of the conv kernel ablated).  Everything asks for the
   // maximum carve-out instead.
   if (!getenv("MZ_TRAIN_NO_CARVEOUT")) {
-    const void* ks[] = {(const void*)tconv_kernel, (const void*)twgrad_kernel, (const void*)bn_fwd_kernel, (const void*)bn_bwd_apply_kernel,
+    const void* ks[] = {(const void*)tconv_kernel<0>, (const void*)tconv_kernel<1>, (const void*)tconv_kernel<2>, (const void*)twgrad_kernel, (const void*)bn_fwd_kernel, (const void*)bn_bwd_apply_kernel,
                         (const void*)bn_bwd_reduce_kernel, (const void*)nchw_to_planes_kernel, (const void*)planes_to_nchw_kernel,
                         (const void*)action_planes_kernel};
     for (const void* k : ks)
@@ -1132,6 +1229,12 @@ int mz_train_create(const mz_train_config* cfg, void* arena_dev, size_t arena_by
   if (e != cudaSuccess) { delete t; set_error("mz_train_create: stream / event creation: %s", cudaGetErrorString(e)); return MZ_ECUDA; }
   t->dy_turn = 0;
   t->wg_pending[0] = t->wg_pending[1] = false;
+  t->timeline = nullptr; t->tl_next = 0;
+  if (getenv("MZ_TRAIN_TIMELINE") && atoi(getenv("MZ_TRAIN_TIMELINE"))) {
+    e = cudaMalloc(&t->timeline, (size_t)kTimelineMax * 10 * sizeof(unsigned long long));
+    if (e != cudaSuccess) { delete t; set_error("mz_train_create: timeline buffer: %s", cudaGetErrorString(e)); return MZ_ECUDA; }
+    cudaMemset(t->timeline, 0, (size_t)kTimelineMax * 10 * sizeof(unsigned long long));
+  }
   *out = t;
   return MZ_OK;
 }
@@ -1141,6 +1244,7 @@ int mz_train_destroy(mz_train* t) {
     cudaStreamSynchronize(t->side);
     for (int k = 0; k < 2; ++k) { cudaEventDestroy(t->ev_dy[k]); cudaEventDestroy(t->ev_wg[k]); }
     cudaStreamDestroy(t->side);
+    if (t->timeline) cudaFree(t->timeline);
   }
   delete t;
   return MZ_OK;
@@ -1175,6 +1279,7 @@ int mz_train_begin_step(mz_train* t, mz_stream stream) {
   t->dy_turn = 0;
   t->wg_pending[0] = t->wg_pending[1] = false;
   t->fwd_calls[0] = t->fwd_calls[1] = t->fwd_calls[2] = 0;
+  t->tl_next = 0;
   return MZ_OK;
 }
 
@@ -1206,16 +1311,16 @@ int mz_train_tower_forward(mz_train* t, int32_t tower, int32_t call, const float
   auto stat = [&](int l) { return t->stats + (size_t)stat_slot(t, tower, call, l) * t->stat_stride; };
   if (tower != 2) {
     if ((rc = launch_conv(t, X, xg, t->convs[conv].wf, t->slot_y[slot][0], nullptr, stat(0), t->fbf16, t->fbf16, t->fbf16, st))) return rc;
-    if ((rc = launch_bn_fwd(t, conv, t->slot_y[slot][0], nullptr, t->slot_a[slot][0], t->slot_ab[slot][0], stat(0), st))) return rc;
+    if ((rc = launch_bn_fwd(t, conv, t->slot_y[slot][0], nullptr, t->slot_a[slot][0], t->slot_ab[slot][0], t->slot_m[slot][0], stat(0), st))) return rc;
     cur = t->slot_a[slot][0];
     ++conv; ++layer;
   }
   for (int b = 0; b < nb; ++b) {
     uint16_t *y1 = t->slot_y[slot][layer], *a1 = t->slot_a[slot][layer], *y2 = t->slot_y[slot][layer + 1], *a2 = t->slot_a[slot][layer + 1];
     if ((rc = launch_conv(t, cur, 16, t->convs[conv].wf, y1, nullptr, stat(layer), t->fbf16, t->fbf16, t->fbf16, st))) return rc;
-    if ((rc = launch_bn_fwd(t, conv, y1, nullptr, a1, t->slot_ab[slot][layer], stat(layer), st))) return rc;
+    if ((rc = launch_bn_fwd(t, conv, y1, nullptr, a1, t->slot_ab[slot][layer], t->slot_m[slot][layer], stat(layer), st))) return rc;
     if ((rc = launch_conv(t, a1, 16, t->convs[conv + 1].wf, y2, nullptr, stat(layer + 1), t->fbf16, t->fbf16, t->fbf16, st))) return rc;
-    if ((rc = launch_bn_fwd(t, conv + 1, y2, cur, a2, t->slot_ab[slot][layer + 1], stat(layer + 1), st))) return rc;
+    if ((rc = launch_bn_fwd(t, conv + 1, y2, cur, a2, t->slot_ab[slot][layer + 1], t->slot_m[slot][layer + 1], stat(layer + 1), st))) return rc;
     cur = a2;
     conv += 2; layer += 2;
   }
@@ -1260,7 +1365,7 @@ int mz_train_tower_backward(mz_train* t, int32_t tower, int32_t call, const floa
     }
     if ((rc = launch_wgrad(t, c2, call, k, dYb[k], t->slot_ab[slot][l1], st))) return rc;
     const int f1 = other(cur, -1, -1);
-    const MaskArgs m1{t->slot_a[slot][l1], t->slot_y[slot][l1], stat(l1)};
+    const MaskArgs m1{t->slot_m[slot][l1], t->slot_y[slot][l1], stat(l1)};
     if ((rc = launch_conv(t, dYb[k], 16, t->convs[c2].wd, G[f1], nullptr, nullptr, 1, 1, 1, st, &m1))) return rc;
     // first conv: a1 = relu(bn1(conv1(a_in)))
     if ((rc = next_dy(t, st, &k))) return rc;
@@ -1268,7 +1373,7 @@ int mz_train_tower_backward(mz_train* t, int32_t tower, int32_t call, const floa
     if ((rc = launch_wgrad(t, c1, call, k, dYb[k], a_in_b, st))) return rc;
     const int f2 = other(cur, f1, -1);
     if (l1 > 0) {                          // a_in is the output of layer l1 - 1 of this tower: fold its ReLU mask and sums in
-      const MaskArgs m0{t->slot_a[slot][l1 - 1], t->slot_y[slot][l1 - 1], stat(l1 - 1)};
+      const MaskArgs m0{t->slot_m[slot][l1 - 1], t->slot_y[slot][l1 - 1], stat(l1 - 1)};
       if ((rc = launch_conv(t, dYb[k], 16, t->convs[c1].wd, G[f2], G[cur], nullptr, 1, 1, 1, st, &m0))) return rc;
       masked = true;
     } else {                               // a_in is the tower's input: the plain gradient
@@ -1327,6 +1432,11 @@ int mz_train_debug_view(mz_train* t, int32_t tower, int32_t call, int32_t layer,
   const int layers = tower_layers(t, tower);
   if (plane_rows) *plane_rows = t->g.PR;
   if (front_rows) *front_rows = kFront;
+  if (which == 4) {
+    if (!t->timeline) { set_error("mz_train_debug_view: no timeline (MZ_TRAIN_TIMELINE=1 at creation)"); return MZ_ESTATE; }
+    *ptr = t->timeline; *bytes = (size_t)t->tl_next * 10 * sizeof(unsigned long long);
+    return MZ_OK;
+  }
   if (which == 0) { *ptr = t->slot_x[slot]; *bytes = (size_t)tower_in_groups(t, tower) * t->plane_bytes; return MZ_OK; }
   MZ_CHECK_ARG(layer >= 0 && layer < layers, "mz_train_debug_view: layer %d out of range", layer);
   if (which == 1) { *ptr = t->slot_y[slot][layer]; *bytes = 16 * t->plane_bytes; return MZ_OK; }
