@@ -43,6 +43,8 @@ constexpr int kWgStages = 3;
 constexpr int kConvStagesMax = 8;
 constexpr float kBnEps = 1e-5f, kBnMomentum = 0.1f;
 constexpr int kTimelineMax = 8192;
+constexpr int kDyRing = 6;         // dY buffers in flight between the dgrad / BatchNorm chain and the weight-gradient streams
+constexpr int kSideStreams = 2;    // weight-gradient launches alternate between these: consecutive ones may overlap
 
 // ---- 16-bit element helpers (runtime element type: 0 = fp16, 1 = bf16) -------------------------------------------
 __device__ __forceinline__ float2 unpack2(uint32_t v, int bf16) {
@@ -904,7 +906,7 @@ struct mz_train {
   unsigned char* arena;
   size_t arena_bytes;
   size_t plane_bytes;                      // one 16-bit plane
-  uint16_t* grad_buf[6];                   // bf16 [16 planes]: four rotating gradient buffers, two dY buffers
+  uint16_t* grad_buf[4 + kDyRing];         // bf16 [16 planes]: four rotating gradient buffers, kDyRing dY buffers
   float* stats;                            // [slots][1280 floats]: fwd totals i64 [256] | saved (mean, invstd) f32 [256] | bwd totals i64 [256]
   size_t stats_floats;
   int stat_stride;
@@ -913,13 +915,14 @@ struct mz_train {
   std::vector<uint16_t*> slot_x, slot_xb;                    // xb / ab: bf16 copies for wgrad (== x / a when the forward type is bf16)
   std::vector<std::vector<uint16_t*>> slot_y, slot_a, slot_ab;
   std::vector<std::vector<uint8_t*>> slot_m;                 // ReLU masks [R128][16] per layer
-  // weight gradients run on a stream of their own, beside the dgrad / BatchNorm chain: dY alternates between two
-  // buffers, ev_dy[k] = buffer k is written (main -> side), ev_wg[k] = its wgrad has read it (side -> main)
+  // weight gradients run on streams of their own, beside the dgrad / BatchNorm chain (nothing on the chain reads them):
+  // dY goes through a ring of buffers, ev_dy[k] = buffer k is written (main -> side), ev_wg[k] = its wgrad has read it
+  // (side -> main, waited for only when the ring comes round to k again)
   int fwd_calls[3];                        // forward calls per tower in this step
-  cudaStream_t side;
-  cudaEvent_t ev_dy[2], ev_wg[2];
-  bool wg_pending[2];
-  int dy_turn;
+  cudaStream_t side[kSideStreams];
+  cudaEvent_t ev_dy[kDyRing], ev_wg[kDyRing];
+  bool wg_pending[kDyRing];
+  int dy_turn, side_turn;
   unsigned long long* timeline;            // MZ_TRAIN_TIMELINE=1: [kTimelineMax][10] stamps, one record per chain launch
   int tl_next;
 };
@@ -1003,8 +1006,10 @@ int launch_conv(mz_train* t, const uint16_t* in, int cg_in, const uint16_t* w, u
 int launch_wgrad(mz_train* t, int conv, int call, int k, const uint16_t* dy, const uint16_t* x, cudaStream_t st) {
   const ConvDesc& d = t->convs[conv];
   MZ_CUDA(cudaEventRecord(t->ev_dy[k], st));
-  MZ_CUDA(cudaStreamWaitEvent(t->side, t->ev_dy[k], 0));
-  st = t->side;
+  cudaStream_t side = t->side[t->side_turn];
+  t->side_turn = (t->side_turn + 1) % kSideStreams;
+  MZ_CUDA(cudaStreamWaitEvent(side, t->ev_dy[k], 0));
+  st = side;
   TWgradParams p;
   const Geom& g = t->g;
   p.dy = dy; p.x = x; p.partial = d.partial; p.n_groups = d.n_groups;
@@ -1027,7 +1032,7 @@ int launch_wgrad(mz_train* t, int conv, int call, int k, const uint16_t* dy, con
 // next dY buffer; the main stream first waits until the weight-gradient kernel that last read it is done
 int next_dy(mz_train* t, cudaStream_t st, int* k_out) {
   const int k = t->dy_turn;
-  t->dy_turn ^= 1;
+  t->dy_turn = (k + 1) % kDyRing;
   if (t->wg_pending[k]) { MZ_CUDA(cudaStreamWaitEvent(st, t->ev_wg[k], 0)); t->wg_pending[k] = false; }
   *k_out = k;
   return MZ_OK;
@@ -1134,7 +1139,7 @@ static int train_layout(const mz_train_config* c, Geom* g, size_t* bytes, mz_tra
   const size_t o_desc = take((size_t)nconv * sizeof(ConvDesc));
   if (t) t->d_convs = reinterpret_cast<ConvDesc*>(t->arena + o_desc);
   // gradient work buffers
-  for (int k = 0; k < 6; ++k) {
+  for (int k = 0; k < 4 + kDyRing; ++k) {
     const size_t o = take(16 * plane);
     if (t) t->grad_buf[k] = reinterpret_cast<uint16_t*>(t->arena + o);
   }
@@ -1221,14 +1226,17 @@ int mz_train_create(const mz_train_config* cfg, void* arena_dev, size_t arena_by
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   }
   if (e != cudaSuccess) { delete t; set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MZ_ECUDA; }
-  e = cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking);
-  for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+  for (int k = 0; k < kSideStreams; ++k) t->side[k] = nullptr;
+  for (int k = 0; k < kDyRing; ++k) { t->ev_dy[k] = nullptr; t->ev_wg[k] = nullptr; }
+  e = cudaSuccess;
+  for (int k = 0; k < kSideStreams && e == cudaSuccess; ++k) e = cudaStreamCreateWithFlags(&t->side[k], cudaStreamNonBlocking);
+  for (int k = 0; k < kDyRing && e == cudaSuccess; ++k) {
     e = cudaEventCreateWithFlags(&t->ev_dy[k], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_wg[k], cudaEventDisableTiming);
   }
   if (e != cudaSuccess) { delete t; set_error("mz_train_create: stream / event creation: %s", cudaGetErrorString(e)); return MZ_ECUDA; }
-  t->dy_turn = 0;
-  t->wg_pending[0] = t->wg_pending[1] = false;
+  t->dy_turn = 0; t->side_turn = 0;
+  for (int k = 0; k < kDyRing; ++k) t->wg_pending[k] = false;
   t->timeline = nullptr; t->tl_next = 0;
   if (getenv("MZ_TRAIN_TIMELINE") && atoi(getenv("MZ_TRAIN_TIMELINE"))) {
     e = cudaMalloc(&t->timeline, (size_t)kTimelineMax * 10 * sizeof(unsigned long long));
@@ -1241,9 +1249,9 @@ int mz_train_create(const mz_train_config* cfg, void* arena_dev, size_t arena_by
 
 int mz_train_destroy(mz_train* t) {
   if (t) {
-    cudaStreamSynchronize(t->side);
-    for (int k = 0; k < 2; ++k) { cudaEventDestroy(t->ev_dy[k]); cudaEventDestroy(t->ev_wg[k]); }
-    cudaStreamDestroy(t->side);
+    for (int k = 0; k < kSideStreams; ++k) if (t->side[k]) cudaStreamSynchronize(t->side[k]);
+    for (int k = 0; k < kDyRing; ++k) { if (t->ev_dy[k]) cudaEventDestroy(t->ev_dy[k]); if (t->ev_wg[k]) cudaEventDestroy(t->ev_wg[k]); }
+    for (int k = 0; k < kSideStreams; ++k) if (t->side[k]) cudaStreamDestroy(t->side[k]);
     if (t->timeline) cudaFree(t->timeline);
   }
   delete t;
@@ -1276,8 +1284,7 @@ int mz_train_begin_step(mz_train* t, mz_stream stream) {
   pack_weights_kernel<<<dim3(32, t->nconv), 256, 0, st>>>(t->d_convs, t->fbf16);
   MZ_LAUNCH_CHECK("pack_weights_kernel");
   std::fill(t->touched.begin(), t->touched.end(), 0);
-  t->dy_turn = 0;
-  t->wg_pending[0] = t->wg_pending[1] = false;
+  t->dy_turn = 0;                          // (pending weight-gradient launches keep their events: mz_train_join / next_dy wait for them)
   t->fwd_calls[0] = t->fwd_calls[1] = t->fwd_calls[2] = 0;
   t->tl_next = 0;
   return MZ_OK;
@@ -1339,8 +1346,8 @@ int mz_train_tower_backward(mz_train* t, int32_t tower, int32_t call, const floa
   const int nb = t->cfg.num_res_blocks;
   const int first = tower != 2 ? 1 : 0;
   const int conv0 = tower_first_conv(t, tower);
-  uint16_t** G = t->grad_buf;              // [0..3] rotate, [4..5] dY
-  uint16_t* dYb[2] = {t->grad_buf[4], t->grad_buf[5]};
+  uint16_t** G = t->grad_buf;              // [0..3] rotate, [4..] the dY ring
+  uint16_t** dYb = t->grad_buf + 4;
   const dim3 cgrid((g.Ptot + 255) / 256, 16);
   auto stat = [&](int l) { return t->stats + (size_t)stat_slot(t, tower, call, l) * t->stat_stride; };
   // the gradient w.r.t. the current block output lives in G[cur]; `masked`: it already is dZ = dL/dA * (A > 0) and the
@@ -1401,7 +1408,7 @@ int mz_train_tower_backward(mz_train* t, int32_t tower, int32_t call, const floa
 
 int mz_train_join(mz_train* t, mz_stream stream) {
   MZ_CHECK_ARG(t != nullptr, "mz_train_join: NULL handle");
-  for (int k = 0; k < 2; ++k)
+  for (int k = 0; k < kDyRing; ++k)
     if (t->wg_pending[k]) { MZ_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), t->ev_wg[k], 0)); t->wg_pending[k] = false; }
   return MZ_OK;
 }

@@ -111,6 +111,51 @@ def action_planes(action: torch.Tensor, num_actions: int, h: int, w: int) -> tor
     return ((f % num_actions)[None, :] == action.reshape(b, 1).long()).to(torch.float32).reshape(b, num_actions, h, w)
 
 
+_MOMENTUM_WEIGHTS = {}
+
+
+def _momentum_weights(calls: int, m: float, dtype, device) -> torch.Tensor:
+    """[calls, 1] weights m (1 - m)^(calls - 1 - k) of the calls' statistics in the running average after `calls` updates.
+    Cached per device: a CUDA-graph capture must not see the host-to-device copy that builds it (the learner runs three
+    eager iterations before it captures)."""
+    key = (calls, float(m), dtype, str(device))
+    w = _MOMENTUM_WEIGHTS.get(key)
+    if w is None:
+        w = torch.tensor([m * (1.0 - m) ** (calls - 1 - k) for k in range(calls)], dtype=dtype, device=device)[:, None]
+        _MOMENTUM_WEIGHTS[key] = w
+    return w
+
+
+def head_over_calls(head: nn.Sequential, x: torch.Tensor, calls: int) -> torch.Tensor:
+    """One of the 1x1-conv heads (``_head``: conv, BatchNorm2d, ReLU, Flatten, Linear) applied to the inputs of ``calls``
+    separate forward calls stacked along the batch axis (call-major, [calls * B, C, h, w]) -- the SAME arithmetic as
+    ``calls`` invocations of ``head`` in train mode: every call keeps its own BatchNorm batch statistics (the stack is
+    normalised per (call, channel) over that call's B * h * w values, which is what instance normalisation of the
+    [calls, mid, B, h*w] view computes), and the running statistics receive the calls' updates in order.  One launch per
+    layer instead of one per call: at batch 128 the K-step unroll is bound by kernel count, not by arithmetic."""
+    conv, bn, _, _, lin = head
+    y = F.conv2d(x, conv.weight)
+    tb, mid, h, w = y.shape
+    b = tb // calls
+    y = y.view(calls, b, mid, h * w).transpose(1, 2)                     # [calls, mid, B, hw] (a view for mid == 1)
+    if bn.training:
+        with torch.no_grad():
+            var, mean = torch.var_mean(y, dim=(2, 3), unbiased=False)      # [calls, mid]
+            n = b * h * w
+            m = bn.momentum
+            # running <- (1 - m) running + m stat, applied once per call in call order
+            coef = _momentum_weights(calls, m, y.dtype, y.device)
+            bn.running_mean.mul_((1.0 - m) ** calls).add_((coef * mean).sum(0))
+            bn.running_var.mul_((1.0 - m) ** calls).add_((coef * var).sum(0) * (n / (n - 1.0)))
+            bn.num_batches_tracked += calls
+        z = F.instance_norm(y, None, None, bn.weight, bn.bias, True, 0.0, bn.eps)
+    else:
+        z = F.batch_norm(y.transpose(1, 2).reshape(tb, mid, h * w), bn.running_mean, bn.running_var, bn.weight, bn.bias, False,
+                         0.0, bn.eps).view(calls, b, mid, h * w).transpose(1, 2)
+    z = F.relu(z).transpose(1, 2).reshape(tb, mid * h * w)
+    return lin(z)
+
+
 def normalize_hidden_state(h: torch.Tensor) -> torch.Tensor:
     """util.py:31-36 (torch, used by the autograd/training path only)."""
     lo = h.min(dim=1, keepdim=True)[0]
@@ -438,6 +483,15 @@ class _ConvNet(MuZeroNet):
         x = torch.cat([hidden_state, planes], dim=1)
         hs = self.dynamics_net.res_blocks(self.dynamics_net.conv_block(x))
         return normalize_hidden_state(hs), self.dynamics_net.reward_head(hs)
+
+    def dynamics_tower(self, hidden_state, action):
+        """The dynamics tower's raw output (before normalisation and the reward head) on the autograd modules."""
+        b, c, h, w = hidden_state.shape
+        planes = action_planes(action, self.num_actions, h, w).to(hidden_state.dtype)
+        return self.dynamics_net.res_blocks(self.dynamics_net.conv_block(torch.cat([hidden_state, planes], dim=1)))
+
+    def prediction_tower(self, hidden_state):
+        return self.prediction_net.res_blocks(hidden_state)
 
     def prediction(self, hidden_state):
         eng = self._train_engine(hidden_state)

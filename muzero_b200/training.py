@@ -108,6 +108,15 @@ def calc_loss_tensors(network: MuZeroNet, state, action, target_value_scalar, ta
     if hasattr(network, 'unroll_hint'):
         network.unroll_hint = T                      # sizes the training engine's activation slots (train_engine.py)
     hidden_state = network.represent(state)
+    eng = network._train_engine(hidden_state) if hasattr(network, '_train_engine') else None
+    mode = os.environ.get('MZ_TRAIN_BATCHED_HEADS', '1')    # 0: the reference's loop everywhere; 2: stacked heads for every conv net
+    if eng is not None and mode != '0':
+        from . import train_engine
+        return _calc_loss_stacked(network, lambda h, a: train_engine.tower(eng, 1, h, a), lambda h: train_engine.tower(eng, 2, h),
+                                  hidden_state, action, target_value, target_reward, target_pi_prob, target_value_scalar, weights)
+    if mode == '2' and hasattr(network, 'dynamics_tower'):
+        return _calc_loss_stacked(network, network.dynamics_tower, network.prediction_tower, hidden_state, action, target_value,
+                                  target_reward, target_pi_prob, target_value_scalar, weights)
     for t in range(T):
         pred_pi_logits, pred_value = network.prediction(hidden_state)
         hidden_state, pred_reward = network.dynamics(hidden_state, action[:, t].unsqueeze(1))
@@ -125,6 +134,52 @@ def calc_loss_tensors(network: MuZeroNet, state, action, target_value_scalar, ta
         pv_scalar = pv.squeeze(-1) if network.mse_loss_for_value else \
             logits_to_transformed_expected_value(pv, network.value_support_size).squeeze(-1)
         priorities = (pv_scalar[:, 0] - target_value_scalar[:, 0]).abs()
+    return loss, priorities
+
+
+def _calc_loss_stacked(network, dyn_tower, pred_tower, hidden_state, action, target_value, target_reward, target_pi_prob,
+                       target_value_scalar, weights):
+    """The same loss with the work regrouped for the hand-written tower kernels (train_engine.py): the dynamics chain
+    first (it is the only sequential part: h_0 -> h_1 -> ... ), then the prediction tower on h_0 .. h_{T-1}, then every
+    head ONCE over the T calls' stacked inputs (``head_over_calls``: per-call BatchNorm statistics, running statistics
+    updated in call order) and the losses over [T, B].  Same operands into the same operations as the loop of
+    pipeline.py:579-600 -- only the launch count differs (the heads and losses were 60 % of the kernels of a step)."""
+    from .network import head_over_calls, normalize_hidden_state
+    B, T = action.shape
+    hiddens, raws = [], []
+    for t in range(T):
+        hiddens.append(hidden_state)
+        raw = dyn_tower(hidden_state, action[:, t].unsqueeze(1))
+        raws.append(raw)
+        hidden_state = normalize_hidden_state(raw)
+        hidden_state.register_hook(lambda grad: grad * 0.5)
+    feats = torch.cat([pred_tower(h) for h in hiddens], dim=0)
+    raws = torch.cat(raws, dim=0)
+    pred_net, dyn_net = network.prediction_net, network.dynamics_net
+    pi_logits = head_over_calls(pred_net.policy_net, feats, T)               # [T * B, A]
+    pred_value = head_over_calls(pred_net.value_net, feats, T)               # [T * B, S]
+    pred_reward = head_over_calls(dyn_net.reward_head, raws, T)              # [T * B, S]
+
+    def stacked(target):                                                      # [B, T, ...] -> [T * B, ...]
+        return target.transpose(0, 1).reshape((T * B,) + tuple(target.shape[2:]))
+
+    def per_call(pred, target, mse):
+        if mse:
+            return loss_func(pred.reshape(T * B), stacked(target), True).view(T, B).sum(0)
+        return loss_func(pred, stacked(target), False).view(T, B).sum(0)
+
+    value_loss = per_call(pred_value, target_value, network.mse_loss_for_value)
+    reward_loss = per_call(pred_reward, target_reward, network.mse_loss_for_reward)
+    policy_loss = per_call(pi_logits, target_pi_prob, False)
+    loss = reward_loss + value_loss + policy_loss
+    loss = torch.mean(loss * weights.detach())
+    loss_scale = 1.0 / T
+    loss.register_hook(lambda grad: grad * loss_scale)
+    with torch.no_grad():
+        pv0 = pred_value.detach()[:B]
+        pv_scalar = pv0.squeeze(-1) if network.mse_loss_for_value else \
+            logits_to_transformed_expected_value(pv0, network.value_support_size).squeeze(-1)
+        priorities = (pv_scalar - target_value_scalar[:, 0]).abs()
     return loss, priorities
 
 

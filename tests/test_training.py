@@ -49,6 +49,31 @@ def test_calc_loss_matches_reference_recording(name):
         np.testing.assert_allclose(got, z[f'{name}_grad_{k}'], rtol=1e-4, atol=1e-6, err_msg=k)
 
 
+def test_stacked_heads_equal_the_reference_loop(monkeypatch):
+    """training._calc_loss_stacked (dynamics chain, then the prediction tower, then every head once over the T calls'
+    stacked inputs) against the loop of pipeline.py:579-600 on the same network: recorded loss, gradients and every
+    BatchNorm buffer (per-call batch statistics, running statistics updated in call order)."""
+    import copy
+    z = np.load(os.path.join(GOLDEN, 'train_golden.npz'))
+    net, B = build('board_small')
+    twin = copy.deepcopy(net)
+    tr, w = synthetic_transitions(net, B, 5, seed=77)
+    monkeypatch.setenv('MZ_TRAIN_BATCHED_HEADS', '0')
+    loss_a, pri_a = calc_loss(net, 'cpu', tr, torch.from_numpy(w))
+    loss_a.backward()
+    monkeypatch.setenv('MZ_TRAIN_BATCHED_HEADS', '2')
+    loss_b, pri_b = calc_loss(twin, 'cpu', tr, torch.from_numpy(w))
+    loss_b.backward()
+    assert abs(loss_b.item() - float(z['board_small_loss'])) <= 1e-5 * max(1.0, abs(loss_b.item()))
+    assert abs(loss_a.item() - loss_b.item()) <= 1e-6 * max(1.0, abs(loss_a.item()))
+    np.testing.assert_allclose(pri_b, pri_a, rtol=1e-6, atol=1e-7)
+    for (k, p), (_, q) in zip(net.named_parameters(), twin.named_parameters()):
+        scale = float(p.grad.abs().max()) + 1e-12
+        assert float((p.grad - q.grad).abs().max()) <= 2e-5 * scale, k
+    for (k, a), (_, b) in zip(net.named_buffers(), twin.named_buffers()):
+        torch.testing.assert_close(b.float(), a.float(), rtol=1e-5, atol=1e-7, msg=k)
+
+
 def test_util_known_answer_vectors():
     """The reference's own KAT (tests/util_test.py:25-47): 3.7 -> 0.3/0.7 on bins 3,4; 2.3 -> 0.7/0.3 on bins 2,3."""
     out = transform_to_2hot(torch.tensor([[3.7], [2.3]]), -5, 5, 11)
