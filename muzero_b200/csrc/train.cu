@@ -157,6 +157,8 @@ struct TConvParams {
   int cg_in, stage_g, chunks;   // a weight stage = stage_g channel groups of one tap; chunks stages per tap
   int Ptot, PB, Wp, W, H, PR, R128;
   int TP, TPs;              // rows of a tile incl. halo / rows of a shared-memory plane (odd)
+  int sub_rows, stat_sub;   // several forward calls stacked along the rows: rows per call (a multiple of 128) and the distance
+                            // (floats) between consecutive calls' statistics records -- a tile belongs to call row0 / sub_rows
   int stages;
   uint32_t idesc;
   int out_bf16;
@@ -311,8 +313,9 @@ __global__ void __launch_bounds__(kTConvThreads) tconv_kernel(const __grid_const
     const size_t rowoff = (size_t)kFront + (size_t)P;
     // everything this role reads from global memory was written by earlier kernels of the chain: order it behind them
     pdl_wait();
+    const size_t sub_off = (size_t)(row0 / p.sub_rows) * (size_t)p.stat_sub;      // this tile's call: its statistics record
     if (mask) {
-      s_saved[et] = p.mask_saved[et];
+      s_saved[et] = p.mask_saved[sub_off + et];
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     // Everything the epilogue needs besides the accumulator -- the skip gradient, the masked layer's Y and ReLU bits for
@@ -401,6 +404,7 @@ __global__ void __launch_bounds__(kTConvThreads) tconv_kernel(const __grid_const
     if (warp == 2) tl_stamp_lane0(p.tl, 7);
     long long* sums = mask ? p.mask_sums : p.stats;
     if (sums) {
+      sums += sub_off / 2;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const int which = et >> 7, col = et & (kC - 1);
       float a = 0.0f;
@@ -483,36 +487,47 @@ __global__ void __launch_bounds__(kWgThreads) twgrad_kernel(const __grid_constan
       }
     }
   } else if (warp == 1) {
-    const uint32_t base = smem_u32(sS);
     // MN-major, no swizzle: consecutive K (rows) are consecutive 16-byte units, 8 rows = one 128-byte core matrix;
-    // LBO = distance between core matrices along K (128 B), SBO = distance between 8-channel groups (one plane)
+    // LBO = distance between core matrices along K (128 B), SBO = distance between 8-channel groups (one plane).
+    // Same issue-loop discipline as tconv_kernel: hoisted descriptor words, warp-uniform operands, a compile-time body
+    // for full 128-row stages.
     uint32_t a_lbo = 128, a_sbo = kWgStage * 16, b_lbo = 128, b_sbo = (kWgStage + 2) * 16;
     if (p.swap_strides) { uint32_t t = a_lbo; a_lbo = a_sbo; a_sbo = t; t = b_lbo; b_lbo = b_sbo; b_sbo = t; }
+    auto U = [](uint32_t x) { return __reduce_max_sync(0xffffffffu, x); };
+    auto d64 = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
+    const uint64_t a_t = smem_desc(smem_u32(sS), a_lbo, a_sbo), b_t = smem_desc(smem_u32(sS) + dy_bytes, b_lbo, b_sbo);
+    const uint32_t a_hi = U((uint32_t)(a_t >> 32)), b_hi = U((uint32_t)(b_t >> 32));
+    const uint32_t a_first = U((uint32_t)a_t), b_first = U((uint32_t)b_t), st16 = U(st_bytes >> 4);
+    const uint32_t tm = U(tmem), idesc = U(p.idesc), n_cols = U((uint32_t)N);
+    uint32_t s = 0, ph = 0, a_st = a_first, b_st = b_first;
     for (int st = 0; st < nst; ++st) {
-      const int s = st % kWgStages;
-      const uint32_t ph = (uint32_t)(st / kWgStages) & 1u;
       const int rows = (p.Rs - st * kWgStage) < kWgStage ? (p.Rs - st * kWgStage) : kWgStage;
       mbar_wait(&full[s], ph);
       tc_fence_after();
-      const uint32_t dy_a = base + (uint32_t)s * st_bytes, x_a = dy_a + dy_bytes;
-      for (int kx = 0; kx < 3; ++kx) {
-        const uint32_t d = tmem + (uint32_t)(kx * N);
-        int ks = 0;
-        for (; ks + 4 <= rows / 16; ks += 4) {       // four K steps (64 rows) under one election
-          const uint32_t a0 = dy_a + (uint32_t)(ks * 16) * 16u, b0 = x_a + (uint32_t)(ks * 16 + kx) * 16u;
-          mma4_f16_elect(d, smem_desc(a0, a_lbo, a_sbo), smem_desc(a0 + 256, a_lbo, a_sbo), smem_desc(a0 + 512, a_lbo, a_sbo),
-                         smem_desc(a0 + 768, a_lbo, a_sbo), smem_desc(b0, b_lbo, b_sbo), smem_desc(b0 + 256, b_lbo, b_sbo),
-                         smem_desc(b0 + 512, b_lbo, b_sbo), smem_desc(b0 + 768, b_lbo, b_sbo), p.idesc,
-                         (st > 0 || ks > 0) ? 1u : 0u);
+      if (st == 0) tl_stamp_lane0(p.tl, 4);
+      const uint32_t acc0 = st > 0 ? 1u : 0u;
+      if (rows == kWgStage) {
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {      // eight K steps (16 rows = 16 units each) under two elections per tap
+          const uint32_t d = tm + (uint32_t)kx * n_cols, b0 = b_st + (uint32_t)kx;
+          mma4_f16_elect(d, d64(a_st, a_hi), d64(a_st + 16, a_hi), d64(a_st + 32, a_hi), d64(a_st + 48, a_hi),
+                         d64(b0, b_hi), d64(b0 + 16, b_hi), d64(b0 + 32, b_hi), d64(b0 + 48, b_hi), idesc, acc0);
+          mma4_f16_elect(d, d64(a_st + 64, a_hi), d64(a_st + 80, a_hi), d64(a_st + 96, a_hi), d64(a_st + 112, a_hi),
+                         d64(b0 + 64, b_hi), d64(b0 + 80, b_hi), d64(b0 + 96, b_hi), d64(b0 + 112, b_hi), idesc, 1u);
         }
-        for (; ks < rows / 16; ++ks) {
-          const uint64_t ad = smem_desc(dy_a + (uint32_t)(ks * 16) * 16u, a_lbo, a_sbo);
-          const uint64_t bd = smem_desc(x_a + (uint32_t)(ks * 16 + kx) * 16u, b_lbo, b_sbo);
-          mma_f16_elect(d, ad, bd, p.idesc, (st > 0 || ks > 0) ? 1u : 0u);
+      } else {
+        for (int kx = 0; kx < 3; ++kx) {
+          const uint32_t d = tm + (uint32_t)kx * n_cols;
+          for (int ks = 0; ks < rows / 16; ++ks)
+            mma_f16_elect(d, d64(a_st + (uint32_t)ks * 16u, a_hi), d64(b_st + (uint32_t)(ks * 16 + kx), b_hi), idesc,
+                          (st > 0 || ks > 0) ? 1u : 0u);
         }
       }
       commit_elect(&empty[s]);
+      a_st += st16; b_st += st16;
+      if (++s == (uint32_t)kWgStages) { s = 0; ph ^= 1u; a_st = a_first; b_st = b_first; }
     }
+    tl_stamp_lane0(p.tl, 5);
     commit_elect(done);
   } else {
     const int quad = warp & 3;
@@ -522,6 +537,7 @@ __global__ void __launch_bounds__(kWgThreads) twgrad_kernel(const __grid_constan
     float4* base = reinterpret_cast<float4*>(p.partial) + ((size_t)blk * p.slices + p.slice0 + split) * 9 * (size_t)(N / 4) * kC + co;
     mbar_wait(done, 0);
     tc_fence_after();
+    if (warp == 2) tl_stamp_lane0(p.tl, 6);
     for (int j = 0; j < steps; ++j) {
       const int kx = j / nc, c = j - kx * nc;
       float4* dst = base + ((size_t)(ky * 3 + kx) * (N / 4) + c * 4) * kC;
@@ -533,6 +549,7 @@ __global__ void __launch_bounds__(kWgThreads) twgrad_kernel(const __grid_constan
         dst[(size_t)u * kC] = make_float4(__uint_as_float(r[4 * u]), __uint_as_float(r[4 * u + 1]), __uint_as_float(r[4 * u + 2]),
                                           __uint_as_float(r[4 * u + 3]));
     }
+    if (warp == 2) tl_stamp_lane0(p.tl, 7);
   }
   tc_fence_before();
   __syncthreads();
@@ -557,6 +574,7 @@ struct BnFwdParams {
   const float *gamma, *beta;
   float *running_mean, *running_var;
   int Ptot, PB, Wp, W, H, PR, R128, fbf16;
+  int sub_rows, stat_sub, n_sub;   // stacked calls (blockIdx.z): rows per call, distance between their statistics records (floats)
   float inv_n, unbias;      // 1 / (B*H*W), n / (n - 1)
   int ablate;               // measurement only: 16 skip the partial-sum pass
   unsigned long long* tl;
@@ -564,46 +582,61 @@ struct BnFwdParams {
 
 __global__ void __launch_bounds__(kEwThreads) bn_fwd_kernel(const BnFwdParams p) {
   __shared__ float s_scale[8], s_shift[8];
-  const int g = blockIdx.y;
+  const int g = blockIdx.y, sub = blockIdx.z;
   tl_stamp(p.tl, 0);
   pdl_trigger();
   pdl_wait();
   tl_stamp(p.tl, 1);
+  // the thread's rows are requested FIRST (unconditional: rows past the call's end are the next call's or the plane's zero
+  // tail): their round trip and the one that fetches the statistics overlap instead of following each other
+  const size_t plane = (size_t)g * p.PR + kFront + (size_t)sub * p.sub_rows;
+  int4 yr[kEwRows], rr[kEwRows];
+#pragma unroll
+  for (int k = 0; k < kEwRows; ++k) {
+    const int L = (blockIdx.x * kEwRows + k) * kEwThreads + threadIdx.x;
+    yr[k] = __ldcg(reinterpret_cast<const int4*>(p.y) + plane + L);
+    if (p.res) rr[k] = __ldcg(reinterpret_cast<const int4*>(p.res) + plane + L);
+  }
   if (threadIdx.x < 8) {
     const int c = g * 8 + threadIdx.x;
-    const float mean = fix_get(p.sums + 2 * c, kFixAct) * p.inv_n;
-    float var = fix_get(p.sums + 2 * c + 1, kFixAct) * p.inv_n - mean * mean;
+    const long long* sums = p.sums + (size_t)sub * (p.stat_sub / 2);
+    const float mean = fix_get(sums + 2 * c, kFixAct) * p.inv_n;
+    float var = fix_get(sums + 2 * c + 1, kFixAct) * p.inv_n - mean * mean;
     var = var > 0.0f ? var : 0.0f;
     const float is = rsqrtf(var + kBnEps);
     const float sc = p.gamma[c] * is;
     s_scale[threadIdx.x] = sc;
     s_shift[threadIdx.x] = p.beta[c] - mean * sc;
     if (blockIdx.x == 0) {
-      p.saved[2 * c] = mean; p.saved[2 * c + 1] = is;
-      p.running_mean[c] = (1.0f - kBnMomentum) * p.running_mean[c] + kBnMomentum * mean;
-      p.running_var[c] = (1.0f - kBnMomentum) * p.running_var[c] + kBnMomentum * var * p.unbias;
+      float* saved = p.saved + (size_t)sub * p.stat_sub;
+      saved[2 * c] = mean; saved[2 * c + 1] = is;
+      if (sub == 0) {
+        // the running statistics take the stacked calls' updates one after the other, in call order
+        float rm = p.running_mean[c], rv = p.running_var[c];
+        for (int z = 0; z < p.n_sub; ++z) {
+          const long long* sz = p.sums + (size_t)z * (p.stat_sub / 2);
+          const float mz_ = fix_get(sz + 2 * c, kFixAct) * p.inv_n;
+          float vz = fix_get(sz + 2 * c + 1, kFixAct) * p.inv_n - mz_ * mz_;
+          vz = vz > 0.0f ? vz : 0.0f;
+          rm = (1.0f - kBnMomentum) * rm + kBnMomentum * mz_;
+          rv = (1.0f - kBnMomentum) * rv + kBnMomentum * vz * p.unbias;
+        }
+        p.running_mean[c] = rm; p.running_var[c] = rv;
+      }
     }
   }
   __syncthreads();
   float sc[8], sh[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) { sc[e] = s_scale[e]; sh[e] = s_shift[e]; }
-  const size_t plane = (size_t)g * p.PR + kFront;
-  // all loads of the thread's rows first (unconditional: rows past Ptot are the plane's zero tail), then the arithmetic
-  int4 yr[kEwRows], rr[kEwRows];
 #pragma unroll
   for (int k = 0; k < kEwRows; ++k) {
-    const int P = (blockIdx.x * kEwRows + k) * kEwThreads + threadIdx.x;
-    yr[k] = __ldcg(reinterpret_cast<const int4*>(p.y) + plane + P);
-    if (p.res) rr[k] = __ldcg(reinterpret_cast<const int4*>(p.res) + plane + P);
-  }
-#pragma unroll
-  for (int k = 0; k < kEwRows; ++k) {
-    const int P = (blockIdx.x * kEwRows + k) * kEwThreads + threadIdx.x;
-    if (P >= p.Ptot) break;
+    const int L = (blockIdx.x * kEwRows + k) * kEwThreads + threadIdx.x;
+    if (L >= p.sub_rows) break;
+    const int P = sub * p.sub_rows + L;
     int4 o = make_int4(0, 0, 0, 0), ob = o;
     uint32_t m = 0;
-    if (!is_halo(P, p.PB, p.Wp, p.W, p.H)) {
+    if (P < p.Ptot && !is_halo(P, p.PB, p.Wp, p.W, p.H)) {
       float v[8];
       unpack8(yr[k], p.fbf16, v);
 #pragma unroll
@@ -624,8 +657,8 @@ __global__ void __launch_bounds__(kEwThreads) bn_fwd_kernel(const BnFwdParams p)
 #pragma unroll
       for (int e = 0; e < 8; ++e) m |= (w[e] > 0.0f ? 1u : 0u) << e;
     }
-    reinterpret_cast<int4*>(p.a)[plane + P] = o;
-    if (p.a_b) reinterpret_cast<int4*>(p.a_b)[plane + P] = ob;
+    reinterpret_cast<int4*>(p.a)[plane + L] = o;
+    if (p.a_b) reinterpret_cast<int4*>(p.a_b)[plane + L] = ob;
     p.bits[(size_t)g * p.R128 + P] = (uint8_t)m;
   }
   tl_end(p.tl, 3);
@@ -642,28 +675,30 @@ struct BnBwdParams {
   uint16_t* dy;             // gradient w.r.t. the raw conv output (bf16), zeros at halo rows
   uint16_t* dz;             // optional: the masked gradient itself (the residual branch's share), bf16
   int Ptot, PB, Wp, W, H, PR, fbf16;
+  int sub_rows, stat_sub, n_sub;   // stacked calls (blockIdx.z), as in BnFwdParams
   float inv_n;
   int rows_per_cta;         // reduce kernel
   unsigned long long* tl;
 };
 
 __global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(const BnBwdParams p) {
-  const int g = blockIdx.y;
+  const int g = blockIdx.y, sub = blockIdx.z;
+  const float* saved = p.saved + (size_t)sub * p.stat_sub;
   float mean[8], is[8], s1[8], s2[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    mean[e] = p.saved[2 * (g * 8 + e)]; is[e] = p.saved[2 * (g * 8 + e) + 1];
+    mean[e] = saved[2 * (g * 8 + e)]; is[e] = saved[2 * (g * 8 + e) + 1];
     s1[e] = 0.0f; s2[e] = 0.0f;
   }
-  const size_t plane = (size_t)g * p.PR + kFront;
+  const size_t plane = (size_t)g * p.PR + kFront + (size_t)sub * p.sub_rows;
   const int r_begin = blockIdx.x * p.rows_per_cta;
-  const int r_end = (r_begin + p.rows_per_cta) < p.Ptot ? (r_begin + p.rows_per_cta) : p.Ptot;
-  for (int P = r_begin + threadIdx.x; P < r_end; P += kEwThreads) {
+  const int r_end = (r_begin + p.rows_per_cta) < p.sub_rows ? (r_begin + p.rows_per_cta) : p.sub_rows;
+  for (int L = r_begin + threadIdx.x; L < r_end; L += kEwThreads) {
     // halo rows: G is zero there, so they add nothing
     float gv[8], av[8], yv[8];
-    unpack8(__ldcg(reinterpret_cast<const int4*>(p.g) + plane + P), 1, gv);
-    unpack8(__ldcg(reinterpret_cast<const int4*>(p.a) + plane + P), p.fbf16, av);
-    unpack8(__ldcg(reinterpret_cast<const int4*>(p.y) + plane + P), p.fbf16, yv);
+    unpack8(__ldcg(reinterpret_cast<const int4*>(p.g) + plane + L), 1, gv);
+    unpack8(__ldcg(reinterpret_cast<const int4*>(p.a) + plane + L), p.fbf16, av);
+    unpack8(__ldcg(reinterpret_cast<const int4*>(p.y) + plane + L), p.fbf16, yv);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float dz = av[e] > 0.0f ? gv[e] : 0.0f;
@@ -690,47 +725,58 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(const BnBwdPa
     float t = 0.0f;
     for (int w = 0; w < kEwThreads / 32; ++w) t += red[w][threadIdx.x];
     const int e = threadIdx.x & 7, which = threadIdx.x >> 3;
-    fix_add(p.sums + 2 * (g * 8 + e) + which, t, kFixGrad);
+    fix_add(p.sums + (size_t)sub * (p.stat_sub / 2) + 2 * (g * 8 + e) + which, t, kFixGrad);
   }
 }
 
 __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(const BnBwdParams p) {
   __shared__ float s_k[8][4];      // mean, invstd, gamma*invstd, and the two batch means
   __shared__ float s_m[8][2];
-  const int g = blockIdx.y;
+  const int g = blockIdx.y, sub = blockIdx.z;
   tl_stamp(p.tl, 0);
   pdl_trigger();
   pdl_wait();
   tl_stamp(p.tl, 1);
+  const size_t plane = (size_t)g * p.PR + kFront + (size_t)sub * p.sub_rows;
+  int4 gr[kEwRows], ar[kEwRows], yr[kEwRows];
+#pragma unroll
+  for (int k = 0; k < kEwRows; ++k) {
+    const int L = (blockIdx.x * kEwRows + k) * kEwThreads + threadIdx.x;
+    gr[k] = __ldcg(reinterpret_cast<const int4*>(p.g) + plane + L);
+    yr[k] = __ldcg(reinterpret_cast<const int4*>(p.y) + plane + L);
+    if (p.a) ar[k] = __ldcg(reinterpret_cast<const int4*>(p.a) + plane + L);
+  }
   if (threadIdx.x < 8) {
     const int c = g * 8 + threadIdx.x;
-    const float S1 = fix_get(p.sums + 2 * c, kFixGrad), S2 = fix_get(p.sums + 2 * c + 1, kFixGrad);
-    s_k[threadIdx.x][0] = p.saved[2 * c];
-    s_k[threadIdx.x][1] = p.saved[2 * c + 1];
-    s_k[threadIdx.x][2] = p.gamma[c] * p.saved[2 * c + 1];
+    const long long* sums = p.sums + (size_t)sub * (p.stat_sub / 2);
+    const float* saved = p.saved + (size_t)sub * p.stat_sub;
+    const float S1 = fix_get(sums + 2 * c, kFixGrad), S2 = fix_get(sums + 2 * c + 1, kFixGrad);
+    s_k[threadIdx.x][0] = saved[2 * c];
+    s_k[threadIdx.x][1] = saved[2 * c + 1];
+    s_k[threadIdx.x][2] = p.gamma[c] * saved[2 * c + 1];
     s_m[threadIdx.x][0] = S1 * p.inv_n;
     s_m[threadIdx.x][1] = S2 * p.inv_n;
-    if (blockIdx.x == 0) { p.dgamma[c] += S2; p.dbeta[c] += S1; }
+    if (blockIdx.x == 0 && sub == 0) {      // the parameter gradients take the stacked calls' sums last call first: the
+      float dg = p.dgamma[c], db = p.dbeta[c];   // order in which separate calls' backward passes would run
+      for (int z = p.n_sub - 1; z >= 0; --z) {
+        const long long* sz = p.sums + (size_t)z * (p.stat_sub / 2);
+        dg += fix_get(sz + 2 * c + 1, kFixGrad);
+        db += fix_get(sz + 2 * c, kFixGrad);
+      }
+      p.dgamma[c] = dg; p.dbeta[c] = db;
+    }
   }
   __syncthreads();
   float mean[8], is[8], gi[8], m1[8], m2[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) { mean[e] = s_k[e][0]; is[e] = s_k[e][1]; gi[e] = s_k[e][2]; m1[e] = s_m[e][0]; m2[e] = s_m[e][1]; }
-  const size_t plane = (size_t)g * p.PR + kFront;
-  int4 gr[kEwRows], ar[kEwRows], yr[kEwRows];
 #pragma unroll
   for (int k = 0; k < kEwRows; ++k) {
-    const int P = (blockIdx.x * kEwRows + k) * kEwThreads + threadIdx.x;
-    gr[k] = __ldcg(reinterpret_cast<const int4*>(p.g) + plane + P);
-    yr[k] = __ldcg(reinterpret_cast<const int4*>(p.y) + plane + P);
-    if (p.a) ar[k] = __ldcg(reinterpret_cast<const int4*>(p.a) + plane + P);
-  }
-#pragma unroll
-  for (int k = 0; k < kEwRows; ++k) {
-    const int P = (blockIdx.x * kEwRows + k) * kEwThreads + threadIdx.x;
-    if (P >= p.Ptot) break;
+    const int L = (blockIdx.x * kEwRows + k) * kEwThreads + threadIdx.x;
+    if (L >= p.sub_rows) break;
+    const int P = sub * p.sub_rows + L;
     int4 o = make_int4(0, 0, 0, 0), oz = make_int4(0, 0, 0, 0);
-    if (!is_halo(P, p.PB, p.Wp, p.W, p.H)) {
+    if (P < p.Ptot && !is_halo(P, p.PB, p.Wp, p.W, p.H)) {
       float gv[8], av[8], yv[8], dzv[8], dyv[8];
       unpack8(gr[k], 1, gv);
       if (p.a) unpack8(ar[k], p.fbf16, av);
@@ -744,8 +790,8 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(const BnBwdPar
       o = pack8(dyv, 1);
       oz = pack8(dzv, 1);
     }
-    reinterpret_cast<int4*>(p.dy)[plane + P] = o;
-    if (p.dz) reinterpret_cast<int4*>(p.dz)[plane + P] = oz;
+    reinterpret_cast<int4*>(p.dy)[plane + L] = o;
+    if (p.dz) reinterpret_cast<int4*>(p.dz)[plane + L] = oz;
   }
   tl_end(p.tl, 4);
 }
@@ -923,6 +969,17 @@ struct mz_train {
   cudaEvent_t ev_dy[kDyRing], ev_wg[kDyRing];
   bool wg_pending[kDyRing];
   int dy_turn, side_turn;
+  // Launch context of the tower call in progress: one forward call (n_sub = 1) or several calls of the prediction tower
+  // stacked along the rows (the K unroll steps' predictions do not depend on one another: one launch chain over K * B
+  // boards, every call keeping its own BatchNorm statistics)
+  const Geom* cur_g;
+  int cur_nsub, cur_sub_rows, cur_stat_sub;
+  bool group_ok;                           // rows of one call are a multiple of 256: tiles and weight-gradient splits never straddle calls
+  Geom gg;                                 // geometry of the stacked buffers (plane stride for unroll_steps calls)
+  uint16_t* ggrad_buf[4 + kDyRing];
+  uint16_t *gslot_x, *gslot_xb;
+  std::vector<uint16_t*> gslot_y, gslot_a, gslot_ab;
+  std::vector<uint8_t*> gslot_m;
   unsigned long long* timeline;            // MZ_TRAIN_TIMELINE=1: [kTimelineMax][10] stamps, one record per chain launch
   int tl_next;
 };
@@ -981,7 +1038,8 @@ cudaError_t launch_chain(mz_train* t, void (*kernel)(KArgs...), dim3 grid, dim3 
 int launch_conv(mz_train* t, const uint16_t* in, int cg_in, const uint16_t* w, uint16_t* out, const uint16_t* add,
                 float* stats, int a_bf16, int w_bf16, int out_bf16, cudaStream_t st, const MaskArgs* mask = nullptr) {
   TConvParams p;
-  const Geom& g = t->g;
+  const Geom& g = *t->cur_g;
+  p.sub_rows = t->cur_nsub > 1 ? t->cur_sub_rows : g.R128; p.stat_sub = t->cur_stat_sub;
   p.in = in; p.w = w; p.out = out; p.add = add; p.stats = reinterpret_cast<long long*>(stats);
   p.mask_bits = mask ? mask->bits : nullptr; p.mask_y = mask ? mask->y : nullptr;
   p.mask_saved = mask ? mask->stat + 512 : nullptr; p.mask_sums = mask ? reinterpret_cast<long long*>(mask->stat + 768) : nullptr;
@@ -1011,9 +1069,11 @@ int launch_wgrad(mz_train* t, int conv, int call, int k, const uint16_t* dy, con
   MZ_CUDA(cudaStreamWaitEvent(side, t->ev_dy[k], 0));
   st = side;
   TWgradParams p;
-  const Geom& g = t->g;
+  const Geom& g = *t->cur_g;
+  const int nsub = t->cur_nsub;
   p.dy = dy; p.x = x; p.partial = d.partial; p.n_groups = d.n_groups;
-  p.Rs = ((g.Ptot + kSplits - 1) / kSplits + 15) / 16 * 16;
+  // stacked calls: kSplits splits per call, each inside its call (cur_sub_rows is a multiple of 16 * kSplits)
+  p.Rs = nsub > 1 ? t->cur_sub_rows / kSplits : ((g.Ptot + kSplits - 1) / kSplits + 15) / 16 * 16;
   p.Wp = g.Wp; p.PR = g.PR;
   p.slices = d.slices; p.slice0 = call * kSplits;
   p.idesc = idesc_of(128, (uint32_t)d.n_groups * 8, 1, 1, 1);
@@ -1021,11 +1081,11 @@ int launch_wgrad(mz_train* t, int conv, int call, int k, const uint16_t* dy, con
   p.tl = t->timeline && t->tl_next < kTimelineMax ? t->timeline + 10 * (size_t)t->tl_next++ : nullptr;
   static const int ablate = getenv("MZ_TRAIN_ABLATE") ? atoi(getenv("MZ_TRAIN_ABLATE")) : 0;
   if (!(ablate & 256))                     // measurement only: 256 = no weight-gradient launches
-  twgrad_kernel<<<dim3(kSplits, 3, d.ci_blocks), kWgThreads, wgrad_smem_bytes(d.n_groups), st>>>(p);
+  twgrad_kernel<<<dim3(kSplits * nsub, 3, d.ci_blocks), kWgThreads, wgrad_smem_bytes(d.n_groups), st>>>(p);
   MZ_LAUNCH_CHECK("twgrad_kernel");
   MZ_CUDA(cudaEventRecord(t->ev_wg[k], st));
   t->wg_pending[k] = true;
-  t->touched[conv] += 1;
+  t->touched[conv] += nsub;
   return MZ_OK;
 }
 
@@ -1038,13 +1098,17 @@ int next_dy(mz_train* t, cudaStream_t st, int* k_out) {
   return MZ_OK;
 }
 
-dim3 ew_grid(const Geom& g, int planes) { return dim3((g.Ptot + kEwThreads * kEwRows - 1) / (kEwThreads * kEwRows), planes); }
+dim3 ew_grid(const mz_train* t, int planes) {
+  const int rows = t->cur_nsub > 1 ? t->cur_sub_rows : t->cur_g->Ptot;
+  return dim3((rows + kEwThreads * kEwRows - 1) / (kEwThreads * kEwRows), planes, t->cur_nsub);
+}
 
 int launch_bn_fwd(mz_train* t, int conv, const uint16_t* y, const uint16_t* res, uint16_t* a, uint16_t* a_b, uint8_t* bits,
                   float* stat, cudaStream_t st) {
-  const Geom& g = t->g;
+  const Geom& g = *t->cur_g;
   const BnPtrs& b = t->bn[conv];
   BnFwdParams p;
+  p.n_sub = t->cur_nsub; p.sub_rows = t->cur_nsub > 1 ? t->cur_sub_rows : g.Ptot; p.stat_sub = t->cur_stat_sub;
   p.y = y; p.res = res; p.a = a; p.a_b = (a_b && a_b != a) ? a_b : nullptr; p.bits = bits; p.sums = reinterpret_cast<const long long*>(stat); p.saved = stat + 512;
   p.gamma = b.gamma; p.beta = b.beta; p.running_mean = b.rmean; p.running_var = b.rvar;
   p.Ptot = g.Ptot; p.PB = g.PB; p.Wp = g.Wp; p.W = g.W; p.H = g.H; p.PR = g.PR; p.R128 = g.R128; p.fbf16 = t->fbf16;
@@ -1054,7 +1118,7 @@ int launch_bn_fwd(mz_train* t, int conv, const uint16_t* y, const uint16_t* res,
   p.ablate = ablate;
   p.tl = t->timeline && t->tl_next < kTimelineMax ? t->timeline + 10 * (size_t)t->tl_next++ : nullptr;
   if (ablate & 64) return MZ_OK;           // measurement only: no BatchNorm launches at all
-  cudaError_t e = launch_chain(t, bn_fwd_kernel, ew_grid(g, 16), dim3(kEwThreads), 0, st, p);
+  cudaError_t e = launch_chain(t, bn_fwd_kernel, ew_grid(t, 16), dim3(kEwThreads), 0, st, p);
   if (e != cudaSuccess) { set_error("bn_fwd_kernel launch: %s", cudaGetErrorString(e)); return MZ_ECUDA; }
   count_launch();
   return MZ_OK;
@@ -1064,24 +1128,25 @@ int launch_bn_fwd(mz_train* t, int conv, const uint16_t* y, const uint16_t* res,
 // a == nullptr: gin is already dZ and the sums were accumulated by the dgrad that produced it (one launch).
 int launch_bn_bwd(mz_train* t, int conv, const uint16_t* gin, const uint16_t* a, const uint16_t* y, float* stat, uint16_t* dy,
                   uint16_t* dz, cudaStream_t st) {
-  const Geom& g = t->g;
+  const Geom& g = *t->cur_g;
   const BnPtrs& b = t->bn[conv];
   BnBwdParams p;
+  p.n_sub = t->cur_nsub; p.sub_rows = t->cur_nsub > 1 ? t->cur_sub_rows : g.Ptot; p.stat_sub = t->cur_stat_sub;
   p.g = gin; p.a = a; p.y = y; p.saved = stat + 512; p.sums = reinterpret_cast<long long*>(stat + 768); p.gamma = b.gamma; p.dgamma = b.dgamma; p.dbeta = b.dbeta;
   p.dy = dy; p.dz = dz;
   p.Ptot = g.Ptot; p.PB = g.PB; p.Wp = g.Wp; p.W = g.W; p.H = g.H; p.PR = g.PR; p.fbf16 = t->fbf16;
   p.inv_n = (float)(1.0 / ((double)g.B * g.H * g.W));
   p.tl = nullptr;
   const int nchunk = 9;
-  p.rows_per_cta = (g.Ptot + nchunk - 1) / nchunk;
+  p.rows_per_cta = (p.sub_rows + nchunk - 1) / nchunk;
   if (a) {
-    bn_bwd_reduce_kernel<<<dim3(nchunk, 16), kEwThreads, 0, st>>>(p);
+    bn_bwd_reduce_kernel<<<dim3(nchunk, 16, t->cur_nsub), kEwThreads, 0, st>>>(p);
     MZ_LAUNCH_CHECK("bn_bwd_reduce_kernel");
   }
   static const int ablate = getenv("MZ_TRAIN_ABLATE") ? atoi(getenv("MZ_TRAIN_ABLATE")) : 0;
   if (ablate & 64) return MZ_OK;
   p.tl = t->timeline && t->tl_next < kTimelineMax ? t->timeline + 10 * (size_t)t->tl_next++ : nullptr;
-  cudaError_t e = launch_chain(t, bn_bwd_apply_kernel, ew_grid(g, 16), dim3(kEwThreads), 0, st, p);
+  cudaError_t e = launch_chain(t, bn_bwd_apply_kernel, ew_grid(t, 16), dim3(kEwThreads), 0, st, p);
   if (e != cudaSuccess) { set_error("bn_bwd_apply_kernel launch: %s", cudaGetErrorString(e)); return MZ_ECUDA; }
   count_launch();
   return MZ_OK;
@@ -1178,6 +1243,35 @@ static int train_layout(const mz_train_config* c, Geom* g, size_t* bytes, mz_tra
         }
       }
     }
+  // stacked prediction calls: their own activation slots and gradient buffers with a plane stride for T calls
+  const bool group_ok = T > 1 && g->Ptot % (16 * kSplits) == 0 && !(getenv("MZ_TRAIN_NO_STACK") && atoi(getenv("MZ_TRAIN_NO_STACK")));
+  if (t) t->group_ok = group_ok;
+  if (group_ok) {
+    Geom gg = *g;
+    gg.Ptot = T * g->Ptot; gg.R128 = gg.Ptot; gg.PR = kFront + gg.R128 + kTail;
+    const size_t gplane = (size_t)gg.PR * 16;
+    if (t) t->gg = gg;
+    for (int k = 0; k < 4 + kDyRing; ++k) {
+      const size_t o = take(16 * gplane);
+      if (t) t->ggrad_buf[k] = reinterpret_cast<uint16_t*>(t->arena + o);
+    }
+    const int layers = 2 * nb;
+    const size_t ox = take(16 * gplane);
+    const size_t oxb = fb ? ox : take(16 * gplane);
+    if (t) {
+      t->gslot_x = reinterpret_cast<uint16_t*>(t->arena + ox); t->gslot_xb = reinterpret_cast<uint16_t*>(t->arena + oxb);
+      t->gslot_y.resize(layers); t->gslot_a.resize(layers); t->gslot_ab.resize(layers); t->gslot_m.resize(layers);
+    }
+    for (int l = 0; l < layers; ++l) {
+      const size_t oy = take(16 * gplane), oa = take(16 * gplane);
+      const size_t oab = (fb || l == layers - 1) ? oa : take(16 * gplane);
+      const size_t om = take((size_t)gg.R128 * 16);
+      if (t) {
+        t->gslot_y[l] = reinterpret_cast<uint16_t*>(t->arena + oy); t->gslot_a[l] = reinterpret_cast<uint16_t*>(t->arena + oa);
+        t->gslot_ab[l] = reinterpret_cast<uint16_t*>(t->arena + oab); t->gslot_m[l] = t->arena + om;
+      }
+    }
+  }
   *bytes = total + 1024;
   return MZ_OK;
 }
@@ -1290,22 +1384,45 @@ int mz_train_begin_step(mz_train* t, mz_stream stream) {
   return MZ_OK;
 }
 
-int mz_train_tower_forward(mz_train* t, int32_t tower, int32_t call, const float* x, const int64_t* action, float* out,
-                           mz_stream stream) {
+// the buffers of one tower call (ncalls == 1) or of ncalls stacked prediction calls, and the launch context for them
+struct CallBufs { uint16_t *x, *xb; uint16_t* const* y; uint16_t* const* a; uint16_t* const* ab; uint8_t* const* m; uint16_t** G; };
+
+static int enter_calls(mz_train* t, const char* who, int32_t tower, int32_t call, int32_t ncalls, CallBufs* cb) {
+  MZ_CHECK_ARG(tower >= 0 && tower < 3 && call >= 0 && ncalls >= 1 && call + ncalls <= t->n_calls[tower],
+               "%s: tower %d calls %d..%d out of range", who, tower, call, call + ncalls - 1);
+  t->cur_stat_sub = tower_layers(t, tower) * t->stat_stride;
+  if (ncalls == 1) {
+    const int sl = slot_of(t, tower, call);
+    t->cur_g = &t->g; t->cur_nsub = 1; t->cur_sub_rows = t->g.Ptot;
+    *cb = CallBufs{t->slot_x[sl], t->slot_xb[sl], t->slot_y[sl].data(), t->slot_a[sl].data(), t->slot_ab[sl].data(),
+                   t->slot_m[sl].data(), t->grad_buf};
+    return MZ_OK;
+  }
+  MZ_CHECK_ARG(tower == 2, "%s: only prediction-tower calls can be stacked (tower %d)", who, tower);
+  if (!t->group_ok) { set_error("%s: stacked calls are not available for this shape (rows per call %d)", who, t->g.Ptot); return MZ_ESTATE; }
+  t->gg.Ptot = ncalls * t->g.Ptot; t->gg.R128 = t->gg.Ptot;      // the plane stride gg.PR stays that of unroll_steps calls
+  t->cur_g = &t->gg; t->cur_nsub = ncalls; t->cur_sub_rows = t->g.Ptot;
+  *cb = CallBufs{t->gslot_x, t->gslot_xb, t->gslot_y.data(), t->gslot_a.data(), t->gslot_ab.data(), t->gslot_m.data(), t->ggrad_buf};
+  return MZ_OK;
+}
+
+int mz_train_tower_forward_calls(mz_train* t, int32_t tower, int32_t call, int32_t ncalls, const float* x, const int64_t* action,
+                                 float* out, mz_stream stream) {
   MZ_CHECK_ARG(t != nullptr && x != nullptr && out != nullptr, "mz_train_tower_forward: NULL argument");
-  MZ_CHECK_ARG(tower >= 0 && tower < 3 && call >= 0 && call < t->n_calls[tower], "mz_train_tower_forward: tower %d call %d out of range", tower, call);
   MZ_CHECK_ARG(tower != 1 || action != nullptr, "mz_train_tower_forward: the dynamics tower needs actions");
   if (!t->bound) { set_error("mz_train_tower_forward: mz_train_bind has not been called"); return MZ_ESTATE; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const Geom& g = t->g;
-  const int slot = slot_of(t, tower, call);
+  CallBufs cb;
+  int rc0 = enter_calls(t, "mz_train_tower_forward", tower, call, ncalls, &cb);
+  if (rc0) return rc0;
+  const Geom& g = *t->cur_g;
   const int nb = t->cfg.num_res_blocks;
-  if (call + 1 > t->fwd_calls[tower]) t->fwd_calls[tower] = call + 1;
+  if (call + ncalls > t->fwd_calls[tower]) t->fwd_calls[tower] = call + ncalls;
   const int xg = tower_in_groups(t, tower);
   const int c_in = tower == 0 ? t->cfg.in_channels : kC;
   const dim3 cgrid((g.Ptot + 255) / 256, tower == 1 ? 16 : xg);
-  uint16_t* X = t->slot_x[slot];
-  uint16_t* Xb = t->slot_xb[slot] != X ? t->slot_xb[slot] : nullptr;
+  uint16_t* X = cb.x;
+  uint16_t* Xb = cb.xb != X ? cb.xb : nullptr;
   nchw_to_planes_kernel<<<cgrid, 256, 0, st>>>(x, X, Xb, c_in, tower == 1 ? 16 : xg, g.Ptot, g.PB, g.Wp, g.W, g.H, g.PR, t->fbf16);
   MZ_LAUNCH_CHECK("nchw_to_planes_kernel");
   if (tower == 1) {
@@ -1317,17 +1434,17 @@ int mz_train_tower_forward(mz_train* t, int32_t tower, int32_t call, const float
   const uint16_t* cur = X;
   auto stat = [&](int l) { return t->stats + (size_t)stat_slot(t, tower, call, l) * t->stat_stride; };
   if (tower != 2) {
-    if ((rc = launch_conv(t, X, xg, t->convs[conv].wf, t->slot_y[slot][0], nullptr, stat(0), t->fbf16, t->fbf16, t->fbf16, st))) return rc;
-    if ((rc = launch_bn_fwd(t, conv, t->slot_y[slot][0], nullptr, t->slot_a[slot][0], t->slot_ab[slot][0], t->slot_m[slot][0], stat(0), st))) return rc;
-    cur = t->slot_a[slot][0];
+    if ((rc = launch_conv(t, X, xg, t->convs[conv].wf, cb.y[0], nullptr, stat(0), t->fbf16, t->fbf16, t->fbf16, st))) return rc;
+    if ((rc = launch_bn_fwd(t, conv, cb.y[0], nullptr, cb.a[0], cb.ab[0], cb.m[0], stat(0), st))) return rc;
+    cur = cb.a[0];
     ++conv; ++layer;
   }
   for (int b = 0; b < nb; ++b) {
-    uint16_t *y1 = t->slot_y[slot][layer], *a1 = t->slot_a[slot][layer], *y2 = t->slot_y[slot][layer + 1], *a2 = t->slot_a[slot][layer + 1];
+    uint16_t *y1 = cb.y[layer], *a1 = cb.a[layer], *y2 = cb.y[layer + 1], *a2 = cb.a[layer + 1];
     if ((rc = launch_conv(t, cur, 16, t->convs[conv].wf, y1, nullptr, stat(layer), t->fbf16, t->fbf16, t->fbf16, st))) return rc;
-    if ((rc = launch_bn_fwd(t, conv, y1, nullptr, a1, t->slot_ab[slot][layer], t->slot_m[slot][layer], stat(layer), st))) return rc;
+    if ((rc = launch_bn_fwd(t, conv, y1, nullptr, a1, cb.ab[layer], cb.m[layer], stat(layer), st))) return rc;
     if ((rc = launch_conv(t, a1, 16, t->convs[conv + 1].wf, y2, nullptr, stat(layer + 1), t->fbf16, t->fbf16, t->fbf16, st))) return rc;
-    if ((rc = launch_bn_fwd(t, conv + 1, y2, cur, a2, t->slot_ab[slot][layer + 1], t->slot_m[slot][layer + 1], stat(layer + 1), st))) return rc;
+    if ((rc = launch_bn_fwd(t, conv + 1, y2, cur, a2, cb.ab[layer + 1], cb.m[layer + 1], stat(layer + 1), st))) return rc;
     cur = a2;
     conv += 2; layer += 2;
   }
@@ -1336,18 +1453,25 @@ int mz_train_tower_forward(mz_train* t, int32_t tower, int32_t call, const float
   return MZ_OK;
 }
 
-int mz_train_tower_backward(mz_train* t, int32_t tower, int32_t call, const float* grad_out, float* grad_in, mz_stream stream) {
+int mz_train_tower_forward(mz_train* t, int32_t tower, int32_t call, const float* x, const int64_t* action, float* out,
+                           mz_stream stream) {
+  return mz_train_tower_forward_calls(t, tower, call, 1, x, action, out, stream);
+}
+
+int mz_train_tower_backward_calls(mz_train* t, int32_t tower, int32_t call, int32_t ncalls, const float* grad_out, float* grad_in,
+                                  mz_stream stream) {
   MZ_CHECK_ARG(t != nullptr && grad_out != nullptr, "mz_train_tower_backward: NULL argument");
-  MZ_CHECK_ARG(tower >= 0 && tower < 3 && call >= 0 && call < t->n_calls[tower], "mz_train_tower_backward: tower %d call %d out of range", tower, call);
   MZ_CHECK_ARG(tower == 0 || grad_in != nullptr, "mz_train_tower_backward: grad_in is NULL");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const Geom& g = t->g;
-  const int slot = slot_of(t, tower, call);
+  CallBufs cb;
+  int rc0 = enter_calls(t, "mz_train_tower_backward", tower, call, ncalls, &cb);
+  if (rc0) return rc0;
+  const Geom& g = *t->cur_g;
   const int nb = t->cfg.num_res_blocks;
   const int first = tower != 2 ? 1 : 0;
   const int conv0 = tower_first_conv(t, tower);
-  uint16_t** G = t->grad_buf;              // [0..3] rotate, [4..] the dY ring
-  uint16_t** dYb = t->grad_buf + 4;
+  uint16_t** G = cb.G;                     // [0..3] rotate, [4..] the dY ring
+  uint16_t** dYb = cb.G + 4;
   const dim3 cgrid((g.Ptot + 255) / 256, 16);
   auto stat = [&](int l) { return t->stats + (size_t)stat_slot(t, tower, call, l) * t->stat_stride; };
   // the gradient w.r.t. the current block output lives in G[cur]; `masked`: it already is dZ = dL/dA * (A > 0) and the
@@ -1360,27 +1484,27 @@ int mz_train_tower_backward(mz_train* t, int32_t tower, int32_t call, const floa
   for (int b = nb - 1; b >= 0; --b) {
     const int l1 = first + 2 * b, l2 = l1 + 1;
     const int c1 = conv0 + l1, c2 = c1 + 1;
-    const uint16_t* a_in_b = l1 > 0 ? t->slot_ab[slot][l1 - 1] : t->slot_xb[slot];
+    const uint16_t* a_in_b = l1 > 0 ? cb.ab[l1 - 1] : cb.xb;
     // second conv of the block: out = relu(bn2(conv2(a1)) + a_in)
     if ((rc = next_dy(t, st, &k))) return rc;
     if (!masked) {
       const int f = other(cur, -1, -1);
-      if ((rc = launch_bn_bwd(t, c2, G[cur], t->slot_a[slot][l2], t->slot_y[slot][l2], stat(l2), dYb[k], G[f], st))) return rc;
+      if ((rc = launch_bn_bwd(t, c2, G[cur], cb.a[l2], cb.y[l2], stat(l2), dYb[k], G[f], st))) return rc;
       cur = f;                             // the masked gradient: the skip connection's share
     } else {
-      if ((rc = launch_bn_bwd(t, c2, G[cur], nullptr, t->slot_y[slot][l2], stat(l2), dYb[k], nullptr, st))) return rc;
+      if ((rc = launch_bn_bwd(t, c2, G[cur], nullptr, cb.y[l2], stat(l2), dYb[k], nullptr, st))) return rc;
     }
-    if ((rc = launch_wgrad(t, c2, call, k, dYb[k], t->slot_ab[slot][l1], st))) return rc;
+    if ((rc = launch_wgrad(t, c2, call, k, dYb[k], cb.ab[l1], st))) return rc;
     const int f1 = other(cur, -1, -1);
-    const MaskArgs m1{t->slot_m[slot][l1], t->slot_y[slot][l1], stat(l1)};
+    const MaskArgs m1{cb.m[l1], cb.y[l1], stat(l1)};
     if ((rc = launch_conv(t, dYb[k], 16, t->convs[c2].wd, G[f1], nullptr, nullptr, 1, 1, 1, st, &m1))) return rc;
     // first conv: a1 = relu(bn1(conv1(a_in)))
     if ((rc = next_dy(t, st, &k))) return rc;
-    if ((rc = launch_bn_bwd(t, c1, G[f1], nullptr, t->slot_y[slot][l1], stat(l1), dYb[k], nullptr, st))) return rc;
+    if ((rc = launch_bn_bwd(t, c1, G[f1], nullptr, cb.y[l1], stat(l1), dYb[k], nullptr, st))) return rc;
     if ((rc = launch_wgrad(t, c1, call, k, dYb[k], a_in_b, st))) return rc;
     const int f2 = other(cur, f1, -1);
     if (l1 > 0) {                          // a_in is the output of layer l1 - 1 of this tower: fold its ReLU mask and sums in
-      const MaskArgs m0{t->slot_m[slot][l1 - 1], t->slot_y[slot][l1 - 1], stat(l1 - 1)};
+      const MaskArgs m0{cb.m[l1 - 1], cb.y[l1 - 1], stat(l1 - 1)};
       if ((rc = launch_conv(t, dYb[k], 16, t->convs[c1].wd, G[f2], G[cur], nullptr, 1, 1, 1, st, &m0))) return rc;
       masked = true;
     } else {                               // a_in is the tower's input: the plain gradient
@@ -1391,8 +1515,8 @@ int mz_train_tower_backward(mz_train* t, int32_t tower, int32_t call, const floa
   }
   if (first) {
     if ((rc = next_dy(t, st, &k))) return rc;
-    if ((rc = launch_bn_bwd(t, conv0, G[cur], nullptr, t->slot_y[slot][0], stat(0), dYb[k], nullptr, st))) return rc;
-    if ((rc = launch_wgrad(t, conv0, call, k, dYb[k], t->slot_xb[slot], st))) return rc;
+    if ((rc = launch_bn_bwd(t, conv0, G[cur], nullptr, cb.y[0], stat(0), dYb[k], nullptr, st))) return rc;
+    if ((rc = launch_wgrad(t, conv0, call, k, dYb[k], cb.xb, st))) return rc;
     if (tower == 1) {
       const int f = other(cur, -1, -1);
       if ((rc = launch_conv(t, dYb[k], 16, t->convs[conv0].wd, G[f], nullptr, nullptr, 1, 1, 1, st))) return rc;
@@ -1403,6 +1527,16 @@ int mz_train_tower_backward(mz_train* t, int32_t tower, int32_t call, const floa
     planes_to_nchw_kernel<<<cgrid, 256, 0, st>>>(G[cur], grad_in, kC, g.Ptot, g.PB, g.Wp, g.W, g.H, g.PR, 1);
     MZ_LAUNCH_CHECK("planes_to_nchw_kernel");
   }
+  return MZ_OK;
+}
+
+int mz_train_tower_backward(mz_train* t, int32_t tower, int32_t call, const float* grad_out, float* grad_in, mz_stream stream) {
+  return mz_train_tower_backward_calls(t, tower, call, 1, grad_out, grad_in, stream);
+}
+
+int mz_train_stacked_calls(mz_train* t, int32_t* max_calls) {
+  MZ_CHECK_ARG(t != nullptr && max_calls != nullptr, "mz_train_stacked_calls: NULL argument");
+  *max_calls = t->group_ok ? t->n_calls[2] : 1;
   return MZ_OK;
 }
 

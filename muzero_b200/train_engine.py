@@ -84,6 +84,9 @@ class TowerTrainEngine:
         nb = network.num_res_blocks
         n = [1 + 2 * nb, 1 + 2 * nb, 2 * nb]
         self.counters = [[bn.num_batches_tracked for _, bn in self.modules[sum(n[:k]):sum(n[:k + 1])]] for k in range(3)]
+        mc = C.c_int32()
+        _lib.check(lib.mz_train_stacked_calls(self.handle, C.byref(mc)))
+        self.max_stacked_calls = int(mc.value)      # prediction-tower calls that may run as one launch chain
         self._bound = None
         self.calls = [0, 0, 0]
         self.active = False
@@ -135,13 +138,13 @@ class TowerTrainEngine:
         """The current stream waits for the handle's weight-gradient stream."""
         _lib.check(_lib.lib().mz_train_join(self.handle, _lib.current_stream()))
 
-    def next_call(self, tower: int) -> int:
+    def next_call(self, tower: int, n: int = 1) -> int:
         k = self.calls[tower]
         limit = 1 if tower == 0 else self.unroll
-        if k >= limit:
-            raise RuntimeError(f'training engine built for {self.unroll} unroll steps: tower {tower} called {k + 1} times '
+        if k + n > limit:
+            raise RuntimeError(f'training engine built for {self.unroll} unroll steps: tower {tower} called {k + n} times '
                                'in one step')
-        self.calls[tower] = k + 1
+        self.calls[tower] = k + n
         return k
 
     def forward(self, tower: int, call: int, x: torch.Tensor, action: Optional[torch.Tensor]) -> torch.Tensor:
@@ -154,6 +157,19 @@ class TowerTrainEngine:
         grad_in = torch.empty(self.hidden_shape, dtype=torch.float32, device=self.device) if tower != 0 else None
         _lib.check(_lib.lib().mz_train_tower_backward(self.handle, tower, call, _lib.ptr(grad_out), _lib.ptr(grad_in),
                                                       _lib.current_stream()))
+        return grad_in
+
+    def forward_calls(self, call: int, n: int, x: torch.Tensor) -> torch.Tensor:
+        """n stacked prediction-tower calls (x [n * B, 128, H, W], call-major) as one launch chain."""
+        out = torch.empty((n * self.batch,) + self.hidden_shape[1:], dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib().mz_train_tower_forward_calls(self.handle, 2, call, n, _lib.ptr(x), None, _lib.ptr(out),
+                                                           _lib.current_stream()))
+        return out
+
+    def backward_calls(self, call: int, n: int, grad_out: torch.Tensor) -> torch.Tensor:
+        grad_in = torch.empty((n * self.batch,) + self.hidden_shape[1:], dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib().mz_train_tower_backward_calls(self.handle, 2, call, n, _lib.ptr(grad_out), _lib.ptr(grad_in),
+                                                            _lib.current_stream()))
         return grad_in
 
     def debug_view(self, tower: int, call: int, layer: int, which: int) -> torch.Tensor:
@@ -193,6 +209,32 @@ class _Tower(torch.autograd.Function):
         if ctx.tower == 0:
             eng.end_step()          # every other tower's backward has run: the conv weight gradients are complete
         return grad_in, None, None, None, None, None
+
+
+class _PredictionCalls(torch.autograd.Function):
+    """The prediction tower on n stacked hidden states (n forward calls of the reference) as one launch chain."""
+
+    @staticmethod
+    def forward(ctx, x, anchor, eng, call, n):
+        ctx.eng, ctx.call, ctx.n = eng, call, n
+        return eng.forward_calls(call, n, x)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return ctx.eng.backward_calls(ctx.call, ctx.n, grad_out.contiguous()), None, None, None, None
+
+
+def prediction_calls(eng: TowerTrainEngine, hiddens) -> torch.Tensor:
+    """The prediction tower on every hidden state of the list: [len * B, 128, H, W], call-major.  One launch chain where
+    the engine can stack the calls (``max_stacked_calls``), else one chain per call."""
+    n = len(hiddens)
+    if n > 1 and eng.max_stacked_calls >= n and eng.calls[2] == 0:
+        call = eng.next_call(2, n)
+        x = torch.cat([h.to(dtype=torch.float32) for h in hiddens], dim=0)
+        with torch.no_grad():
+            torch._foreach_add_(eng.counters[2], n)
+        return _PredictionCalls.apply(x, eng.modules[0][0].weight, eng, call, n)
+    return torch.cat([tower(eng, 2, h) for h in hiddens], dim=0)
 
 
 def tower(eng: TowerTrainEngine, which: int, x: torch.Tensor, action: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -112,10 +112,11 @@ def calc_loss_tensors(network: MuZeroNet, state, action, target_value_scalar, ta
     mode = os.environ.get('MZ_TRAIN_BATCHED_HEADS', '1')    # 0: the reference's loop everywhere; 2: stacked heads for every conv net
     if eng is not None and mode != '0':
         from . import train_engine
-        return _calc_loss_stacked(network, lambda h, a: train_engine.tower(eng, 1, h, a), lambda h: train_engine.tower(eng, 2, h),
-                                  hidden_state, action, target_value, target_reward, target_pi_prob, target_value_scalar, weights)
+        return _calc_loss_stacked(network, lambda h, a: train_engine.tower(eng, 1, h, a),
+                                  lambda hs: train_engine.prediction_calls(eng, hs), hidden_state, action, target_value, target_reward, target_pi_prob, target_value_scalar, weights)
     if mode == '2' and hasattr(network, 'dynamics_tower'):
-        return _calc_loss_stacked(network, network.dynamics_tower, network.prediction_tower, hidden_state, action, target_value,
+        return _calc_loss_stacked(network, network.dynamics_tower,
+                                  lambda hs: torch.cat([network.prediction_tower(h) for h in hs], dim=0), hidden_state, action, target_value,
                                   target_reward, target_pi_prob, target_value_scalar, weights)
     for t in range(T):
         pred_pi_logits, pred_value = network.prediction(hidden_state)
@@ -137,7 +138,7 @@ def calc_loss_tensors(network: MuZeroNet, state, action, target_value_scalar, ta
     return loss, priorities
 
 
-def _calc_loss_stacked(network, dyn_tower, pred_tower, hidden_state, action, target_value, target_reward, target_pi_prob,
+def _calc_loss_stacked(network, dyn_tower, pred_towers, hidden_state, action, target_value, target_reward, target_pi_prob,
                        target_value_scalar, weights):
     """The same loss with the work regrouped for the hand-written tower kernels (train_engine.py): the dynamics chain
     first (it is the only sequential part: h_0 -> h_1 -> ... ), then the prediction tower on h_0 .. h_{T-1}, then every
@@ -153,7 +154,7 @@ def _calc_loss_stacked(network, dyn_tower, pred_tower, hidden_state, action, tar
         raws.append(raw)
         hidden_state = normalize_hidden_state(raw)
         hidden_state.register_hook(lambda grad: grad * 0.5)
-    feats = torch.cat([pred_tower(h) for h in hiddens], dim=0)
+    feats = pred_towers(hiddens)                                             # [T * B, C, h, w], call-major
     raws = torch.cat(raws, dim=0)
     pred_net, dyn_net = network.prediction_net, network.dynamics_net
     pi_logits = head_over_calls(pred_net.policy_net, feats, T)               # [T * B, A]

@@ -173,3 +173,45 @@ def test_native_training_step_under_the_learner_graph():
     obs = torch.randint(0, 2, (4, 9, 9, 9), device='cuda').float()
     _, pi, v = net_a.initial_inference_batch(obs)
     assert torch.isfinite(pi).all() and torch.isfinite(v).all()
+
+
+def test_stacked_prediction_calls_equal_separate_calls():
+    """mz_train_tower_forward_calls / _backward_calls (the K prediction calls of an unroll as one launch chain) against K
+    separate calls on the same inputs: per-call BatchNorm statistics, running statistics and parameter gradients in call
+    order.  Nothing in the kernels depends on scheduling (fixed-point statistics, fixed summation orders), so outputs,
+    input gradients, parameter gradients and buffers are the same BITS."""
+    import muzero_b200 as mz
+    from muzero_b200 import train_engine
+    torch.manual_seed(5)
+    K, B = 4, 64                                   # 64 * 100 rows per call: a multiple of 256
+    net = mz.MuZeroBoardGameNet((9, 9, 9), 82, 2, 128).cuda().train()
+    twin = copy.deepcopy(net)
+    gen = torch.Generator(device='cuda').manual_seed(6)
+    obs = torch.randint(0, 2, (B, 9, 9, 9), device='cuda', generator=gen).float()
+    hids = [torch.rand((B, 128, 9, 9), device='cuda', generator=gen) * (k + 1) for k in range(K)]
+    gouts = [torch.randn((B, 128, 9, 9), device='cuda', generator=gen) * (0.5 + k) for k in range(K)]
+    results = []
+    for model, stacked in ((net, True), (twin, False)):
+        eng = train_engine.engine_for(model, B, 5)
+        assert eng.max_stacked_calls >= K
+        xs = [h.clone().requires_grad_(True) for h in hids]
+        rep = train_engine.tower(eng, 0, obs)                       # opens the step
+        if stacked:
+            out = train_engine.prediction_calls(eng, xs)
+            assert eng.calls[2] == K
+        else:
+            out = torch.cat([train_engine.tower(eng, 2, x) for x in xs], dim=0)
+        out.backward(torch.cat(gouts, dim=0))
+        rep.backward(torch.zeros_like(rep))                          # closes the step (weight gradients are finalised)
+        torch.cuda.synchronize()
+        results.append((out.detach(), [x.grad for x in xs], model))
+    (o1, g1, m1), (o2, g2, m2) = results
+    assert torch.equal(o1, o2)
+    for a, b in zip(g1, g2):
+        assert torch.equal(a, b)
+    for (k, p), (_, q) in zip(m1.named_parameters(), m2.named_parameters()):
+        if k.startswith('prediction_net.res_blocks'):
+            assert p.grad is not None and torch.equal(p.grad, q.grad), k
+    for (k, a), (_, b) in zip(m1.named_buffers(), m2.named_buffers()):
+        if k.startswith('prediction_net.res_blocks'):
+            assert torch.equal(a, b), k

@@ -52,7 +52,7 @@ def show(title, rec, names):
         gap = (t1 - prev_end) / 1e3 if prev_end is not None else float('nan')
         name = {1: 'conv', 2: 'dgrad', 3: 'bn_fwd', 4: 'bn_bwd', 5: 'wgrad'}.get(int(kind), '?')
         if name == 'wgrad':
-            print('%-4d %-10s start %9.2f  end %9.2f  (%.2f us) relative to the first record' % (i, name, (t0 - rec[0][0]) / 1e3, (t2 - rec[0][0]) / 1e3, (t2 - t0) / 1e3))
+            print('%-4d %-10s start %9.2f  end %9.2f  (%.2f us) | cta 0: first stage %.2f, MMA issue %.2f, drain %.2f, epilogue %.2f, exit %.2f' % (i, name, (t0 - rec[0][0]) / 1e3, (t2 - rec[0][0]) / 1e3, (t2 - t0) / 1e3, (t4 - t0) / 1e3, (t5 - t4) / 1e3, (t6 - t5) / 1e3, (t7 - t6) / 1e3, (t3 - t7) / 1e3))
             a = tot.setdefault(name, [0, 0.0, 0.0]); a[0] += 1; a[2] += (t2 - t0) / 1e3
             continue
         extra = ''
