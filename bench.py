@@ -675,7 +675,8 @@ def run_engine_arm(args):
 
 def train_step_sample(net, spec, dev, world, batch=128, unroll=5, warmup=6, steps=5):
     """BASELINE.json config 5's second half: the K=5-unroll training step, data-parallel, one flat
-    NCCL all-reduce of the gradients (PyTorch autograd forward/backward)."""
+    NCCL all-reduce of the gradients; the towers' forward / dgrad / wgrad and train-mode BatchNorm run on the
+    hand-written tcgen05 kernels of csrc/train.cu (SURVEY.md section 8 e / f-2)."""
     import copy
     import torch
     import torch.distributed as dist
@@ -764,8 +765,15 @@ def train_step_sample(net, spec, dev, world, batch=128, unroll=5, warmup=6, step
            'samples_per_s': world * batch / (float(ms.item()) / 1e3), 'grad_bytes': nbytes,
            'replay_sample_ms': sample_ms, 'replay_items': replay.size,
            'cuda_graph': bool(learner.use_graph and learner._graph is not None),
-           'impl': 'DeviceReplay.sample (sampling + gather kernels) -> ONE CUDA graph of the PyTorch autograd fwd/bwd, '
-                   'the flat NCCL all-reduce and Adam -> update_priorities'}
+           'native_towers': bool(learner.native_towers),
+           'impl': ('DeviceReplay.sample (sampling + gather kernels) -> ONE CUDA graph of: the towers forward / dgrad / wgrad + '
+                    'train-mode BatchNorm on the tcgen05 kernels of csrc/train.cu (fp16 activations, bf16 gradients, fp32 '
+                    'accumulation; the K prediction calls stacked into one launch chain), heads / losses in PyTorch over the '
+                    'stacked calls, the flat NCCL all-reduce and fused Adam -> update_priorities') if learner.native_towers else
+                   ('DeviceReplay.sample (sampling + gather kernels) -> ONE CUDA graph of the PyTorch autograd fwd/bwd, the flat '
+                    'NCCL all-reduce and Adam -> update_priorities')}
+    if learner.native_towers:
+        out['towers'] = tower_chain_sample(twin, batch, unroll)
     if local_ms is not None:
         out['ms_per_learner_step_no_collective'] = local_ms
         out['ms_per_learner_step_data_parallel'] = dp_only_ms
@@ -776,6 +784,70 @@ def train_step_sample(net, spec, dev, world, batch=128, unroll=5, warmup=6, step
         out['allreduce_bus_gbs'] = 2.0 * (world - 1) / world * nbytes / (a * 1e-3) / 1e9
     del learner, twin, replay
     torch.cuda.empty_cache()
+    return out
+
+
+def tower_chain_sample(net, batch, unroll, reps=10):
+    """The training towers on their own (CUDA events around graph replays of one launch chain): the prediction tower's
+    forward and backward for one call and for the K stacked calls, with the convolution flops they execute."""
+    import torch
+    from muzero_b200 import train_engine
+    eng = train_engine.engine_for(net.train(), batch, unroll)
+    if eng is None:
+        return None
+    c, h, w = eng.hidden_shape[1:]
+    dev = eng.device
+    layers = 2 * net.num_res_blocks
+    flops = lambda calls: calls * batch * h * w * 2.0 * 9 * c * c * layers
+
+    def graphed(fn):
+        s = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(s):
+            fn()
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+        return g
+
+    def timed(g):
+        for _ in range(3):
+            g.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps * 1e3
+
+    out = {'layers': layers, 'batch': batch}
+    with torch.cuda.device(dev):
+        for calls in (1, unroll) if eng.max_stacked_calls >= unroll else (1,):
+            x = torch.rand((calls * batch, c, h, w), device=dev)
+            gr = torch.randn((calls * batch, c, h, w), device=dev)
+
+            def fwd():
+                return eng.forward(2, 0, x, None) if calls == 1 else eng.forward_calls(0, calls, x)
+
+            def bwd():
+                if calls == 1:
+                    eng.backward(2, 0, gr)
+                else:
+                    eng.backward_calls(0, calls, gr)
+                eng.join()
+            eng.begin_step()                 # (weight packing and the statistics reset are not part of a tower's chain)
+            gf = graphed(fwd)
+            tf = timed(gf)
+            gb = graphed(bwd)
+            tb = timed(gb)
+            out['prediction_x%d' % calls] = {
+                'forward_us': tf, 'backward_us': tb, 'forward_tflops': flops(calls) / (tf * 1e-6) / 1e12,
+                'backward_tflops': 2.0 * flops(calls) / (tb * 1e-6) / 1e12,
+                'us_per_layer_forward': tf / layers, 'us_per_layer_backward': tb / layers}
+        eng.begin_step()
+        eng.active = False
     return out
 
 

@@ -37,14 +37,14 @@ namespace {
 constexpr int kC = 128;            // tower width this engine is built for
 constexpr int kFront = 64;         // zero rows before row 0 of every plane (>= W + 2)
 constexpr int kTail = 448;         // zero rows after the last 128-row tile (wgrad splits overshoot by < 16 * splits + halo)
-constexpr int kSplits = 16;        // row splits of a weight-gradient launch
+constexpr int kSplits = 4;         // row splits of a weight-gradient launch
 constexpr int kWgStage = 128;      // rows per wgrad pipeline stage
 constexpr int kWgStages = 3;
 constexpr int kConvStagesMax = 8;
 constexpr float kBnEps = 1e-5f, kBnMomentum = 0.1f;
 constexpr int kTimelineMax = 8192;
 constexpr int kDyRing = 6;         // dY buffers in flight between the dgrad / BatchNorm chain and the weight-gradient streams
-constexpr int kSideStreams = 2;    // weight-gradient launches alternate between these: consecutive ones may overlap
+constexpr int kSideStreams = 3;    // weight-gradient launches alternate between these: consecutive ones may overlap
 
 // ---- 16-bit element helpers (runtime element type: 0 = fp16, 1 = bf16) -------------------------------------------
 __device__ __forceinline__ float2 unpack2(uint32_t v, int bf16) {
@@ -911,12 +911,12 @@ __global__ void wgrad_finalize_kernel(const ConvDesc* __restrict__ descs, int ca
     if (ci >= d.ci_total) continue;
     const float* src = d.partial + (size_t)blk * d.slices * per_split + r;
     float s = 0.0f;
-    for (int k0 = 0; k0 < used; k0 += 16) {          // kSplits = 16 slices per call: 16 loads in flight, then the adds
-      float v[16];
+    for (int k0 = 0; k0 < used; k0 += kSplits) {     // kSplits slices per call: that many loads in flight, then the adds
+      float v[kSplits];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) v[k] = __ldcs(src + (size_t)(k0 + k) * per_split);
+      for (int k = 0; k < kSplits; ++k) v[k] = __ldcs(src + (size_t)(k0 + k) * per_split);
 #pragma unroll
-      for (int k = 0; k < 16; ++k) s += v[k];
+      for (int k = 0; k < kSplits; ++k) s += v[k];
     }
     d.wgrad[((size_t)co * d.ci_total + ci) * 9 + tap] += s;     // autograd semantics: gradients accumulate
   }
@@ -974,7 +974,7 @@ struct mz_train {
   // boards, every call keeping its own BatchNorm statistics)
   const Geom* cur_g;
   int cur_nsub, cur_sub_rows, cur_stat_sub;
-  bool group_ok;                           // rows of one call are a multiple of 256: tiles and weight-gradient splits never straddle calls
+  bool group_ok;                           // rows of one call are a multiple of 128 and of 16 * kSplits: tiles and weight-gradient splits never straddle calls
   Geom gg;                                 // geometry of the stacked buffers (plane stride for unroll_steps calls)
   uint16_t* ggrad_buf[4 + kDyRing];
   uint16_t *gslot_x, *gslot_xb;
@@ -1244,7 +1244,7 @@ static int train_layout(const mz_train_config* c, Geom* g, size_t* bytes, mz_tra
       }
     }
   // stacked prediction calls: their own activation slots and gradient buffers with a plane stride for T calls
-  const bool group_ok = T > 1 && g->Ptot % (16 * kSplits) == 0 && !(getenv("MZ_TRAIN_NO_STACK") && atoi(getenv("MZ_TRAIN_NO_STACK")));
+  const bool group_ok = T > 1 && g->Ptot % 128 == 0 && g->Ptot % (16 * kSplits) == 0 && !(getenv("MZ_TRAIN_NO_STACK") && atoi(getenv("MZ_TRAIN_NO_STACK")));
   if (t) t->group_ok = group_ok;
   if (group_ok) {
     Geom gg = *g;
