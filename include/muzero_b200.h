@@ -359,12 +359,16 @@ int mz_train_tower_backward(mz_train* t, int32_t tower, int32_t call, const floa
  * another, only on the dynamics chain: ncalls of them (calls call .. call + ncalls - 1) run as ONE launch chain over
  * the stacked inputs x [ncalls * B,128,H,W] (call-major).  Every call keeps its own train-mode BatchNorm batch
  * statistics, running statistics and parameter gradients receive the calls' contributions in call order: the same
- * arithmetic as ncalls separate calls.  *max_calls: how many calls may be stacked for this handle (1: none).        */
+ * arithmetic as ncalls separate calls.  *max_calls: how many calls may be stacked for this handle (1: none).
+ * out_norm (optional): the output's per-position min-max normalisation over the channels (util.py:31-36) -- what the
+ * representation and dynamics functions hand on (network.py:353-395, 440-470) -- written by the same pass; out may then
+ * be NULL.  grad_norm (optional): dL/d out_norm, folded into the gradient with respect to the tower's output together
+ * with grad_out (either may be NULL).                                                                               */
 int mz_train_stacked_calls(mz_train* t, int32_t* max_calls);
 int mz_train_tower_forward_calls(mz_train* t, int32_t tower, int32_t call, int32_t ncalls, const float* x, const int64_t* action,
-                                 float* out, mz_stream stream);
-int mz_train_tower_backward_calls(mz_train* t, int32_t tower, int32_t call, int32_t ncalls, const float* grad_out, float* grad_in,
-                                  mz_stream stream);
+                                 float* out, float* out_norm, mz_stream stream);
+int mz_train_tower_backward_calls(mz_train* t, int32_t tower, int32_t call, int32_t ncalls, const float* grad_out,
+                                  const float* grad_norm, float* grad_in, mz_stream stream);
 /* the weight-gradient kernels of the tower backward calls run on a stream of the handle's own, beside the caller's:
  * make `stream` wait for them (capture-safe; mz_train_end_step does it itself)                                     */
 int mz_train_join(mz_train* t, mz_stream stream);

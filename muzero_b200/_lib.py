@@ -97,8 +97,8 @@ PROTOTYPES = {
     'mz_train_tower_forward': (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     'mz_train_tower_backward': (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P]),
     'mz_train_stacked_calls': (C.c_int, [_P, C.POINTER(C.c_int32)]),
-    'mz_train_tower_forward_calls': (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
-    'mz_train_tower_backward_calls': (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
+    'mz_train_tower_forward_calls': (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
+    'mz_train_tower_backward_calls': (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     'mz_train_join': (C.c_int, [_P, _P]),
     'mz_train_end_step': (C.c_int, [_P, _P]),
     'mz_train_debug_view': (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P), C.POINTER(C.c_size_t),

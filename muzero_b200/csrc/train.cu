@@ -833,6 +833,112 @@ __global__ void planes_to_nchw_kernel(const uint16_t* __restrict__ src, float* _
   }
 }
 
+
+// A tower's output for autograd: raw [B][128][H][W] float32 and / or its per-position min-max normalisation over the 128
+// channels (util.py:31-36: (h - lo) / (hi - lo + 1e-8), the float32 operations of the reference on the same values).
+// Thread = row P: sixteen 16-byte loads, channel minimum / maximum in registers, strided float32 stores.
+__global__ void __launch_bounds__(128) tower_out_kernel(const uint16_t* __restrict__ src, float* __restrict__ raw, float* __restrict__ norm,
+                                                        int Ptot, int PB, int Wp, int W, int H, int PR, int bf16) {
+  const int P = blockIdx.x * blockDim.x + threadIdx.x;
+  if (P >= Ptot) return;
+  const int b = P / PB, q = P - b * PB, y = q / Wp, x = q - y * Wp;
+  if (y >= H || x >= W) return;
+  int4 r[16];
+#pragma unroll
+  for (int g = 0; g < 16; ++g) r[g] = __ldcg(reinterpret_cast<const int4*>(src) + (size_t)g * PR + kFront + P);
+  float lo = 3.0e38f, hi = -3.0e38f;
+#pragma unroll
+  for (int g = 0; g < 16; ++g) {
+    float v[8];
+    unpack8(r[g], bf16, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { lo = fminf(lo, v[e]); hi = fmaxf(hi, v[e]); }
+  }
+  const float d = __fadd_rn(__fsub_rn(hi, lo), 1e-8f);
+  const size_t base = (size_t)b * kC * H * W + (size_t)y * W + x, cs = (size_t)H * W;
+#pragma unroll
+  for (int g = 0; g < 16; ++g) {
+    float v[8];
+    unpack8(r[g], bf16, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const size_t o = base + (size_t)(g * 8 + e) * cs;
+      if (raw) raw[o] = v[e];
+      if (norm) norm[o] = __fdiv_rn(__fsub_rn(v[e], lo), d);
+    }
+  }
+}
+
+// The gradient with respect to a tower's output, as bf16 planes, from autograd's two pieces: g_raw = dL/d raw and
+// g_norm = dL/d normalised (either may be missing).  With a = h - lo, d = hi - lo + 1e-8:
+//   dh[c] = g_raw[c] + g_norm[c] / d + [c = argmin] (sum g_norm a / d^2 - sum g_norm / d) - [c = argmax] sum g_norm a / d^2
+// (first index on ties, like a single min / max index of torch; tied minima are ReLU zeros whose gradient the tower's
+// own ReLU mask removes anyway).  h is the tower's saved last activation.
+__global__ void __launch_bounds__(128) tower_gradin_kernel(const float* __restrict__ g_raw, const float* __restrict__ g_norm,
+                                                           const uint16_t* __restrict__ h, uint16_t* __restrict__ dst, int Ptot, int PB,
+                                                           int Wp, int W, int H, int PR, int hbf16) {
+  const int P = blockIdx.x * blockDim.x + threadIdx.x;
+  if (P >= Ptot) return;
+  const int b = P / PB, q = P - b * PB, y = q / Wp, x = q - y * Wp;
+  int4* out = reinterpret_cast<int4*>(dst) + kFront + P;
+  if (y >= H || x >= W) {
+#pragma unroll
+    for (int g = 0; g < 16; ++g) out[(size_t)g * PR] = make_int4(0, 0, 0, 0);
+    return;
+  }
+  const size_t base = (size_t)b * kC * H * W + (size_t)y * W + x, cs = (size_t)H * W;
+  float lo = 0.0f, hi = 0.0f, d = 1.0f, dlo = 0.0f, dhi = 0.0f;
+  int amin = -1, amax = -1;
+  int4 r[16];
+  if (g_norm) {
+#pragma unroll
+    for (int g = 0; g < 16; ++g) r[g] = __ldcg(reinterpret_cast<const int4*>(h) + (size_t)g * PR + kFront + P);
+    lo = 3.0e38f; hi = -3.0e38f;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) {
+      float v[8];
+      unpack8(r[g], hbf16, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (v[e] < lo) { lo = v[e]; amin = g * 8 + e; }
+        if (v[e] > hi) { hi = v[e]; amax = g * 8 + e; }
+      }
+    }
+    d = __fadd_rn(__fsub_rn(hi, lo), 1e-8f);
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) {
+      float v[8];
+      unpack8(r[g], hbf16, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float gn = __ldg(g_norm + base + (size_t)(g * 8 + e) * cs);
+        s1 += gn;
+        s2 += gn * (v[e] - lo);
+      }
+    }
+    const float t = s2 / (d * d);
+    dlo = t - s1 / d;
+    dhi = -t;
+  }
+#pragma unroll
+  for (int g = 0; g < 16; ++g) {
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = g * 8 + e;
+      float v = g_raw ? __ldg(g_raw + base + (size_t)c * cs) : 0.0f;
+      if (g_norm) {
+        v += __ldg(g_norm + base + (size_t)c * cs) / d;
+        if (c == amin) v += dlo;
+        if (c == amax) v += dhi;
+      }
+      o[e] = v;
+    }
+    out[(size_t)g * PR] = pack8(o, 1);
+  }
+}
+
 // the action "planes" of DynamicsConvNet.forward (network.py:440-444, quirk C of DESIGN.md): flat element f of the
 // [A*h*w] block is 1 iff f % A == action.  Written as channels 128.. of the dynamics' first-conv input (planes 16..31).
 __global__ void action_planes_kernel(const int64_t* __restrict__ action, uint16_t* __restrict__ dst, uint16_t* __restrict__ dst_b, int A,
@@ -1407,8 +1513,8 @@ static int enter_calls(mz_train* t, const char* who, int32_t tower, int32_t call
 }
 
 int mz_train_tower_forward_calls(mz_train* t, int32_t tower, int32_t call, int32_t ncalls, const float* x, const int64_t* action,
-                                 float* out, mz_stream stream) {
-  MZ_CHECK_ARG(t != nullptr && x != nullptr && out != nullptr, "mz_train_tower_forward: NULL argument");
+                                 float* out, float* out_norm, mz_stream stream) {
+  MZ_CHECK_ARG(t != nullptr && x != nullptr && (out != nullptr || out_norm != nullptr), "mz_train_tower_forward: NULL argument");
   MZ_CHECK_ARG(tower != 1 || action != nullptr, "mz_train_tower_forward: the dynamics tower needs actions");
   if (!t->bound) { set_error("mz_train_tower_forward: mz_train_bind has not been called"); return MZ_ESTATE; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1448,19 +1554,19 @@ int mz_train_tower_forward_calls(mz_train* t, int32_t tower, int32_t call, int32
     cur = a2;
     conv += 2; layer += 2;
   }
-  planes_to_nchw_kernel<<<dim3((g.Ptot + 255) / 256, 16), 256, 0, st>>>(cur, out, kC, g.Ptot, g.PB, g.Wp, g.W, g.H, g.PR, t->fbf16);
-  MZ_LAUNCH_CHECK("planes_to_nchw_kernel");
+  tower_out_kernel<<<dim3((g.Ptot + 127) / 128), 128, 0, st>>>(cur, out, out_norm, g.Ptot, g.PB, g.Wp, g.W, g.H, g.PR, t->fbf16);
+  MZ_LAUNCH_CHECK("tower_out_kernel");
   return MZ_OK;
 }
 
 int mz_train_tower_forward(mz_train* t, int32_t tower, int32_t call, const float* x, const int64_t* action, float* out,
                            mz_stream stream) {
-  return mz_train_tower_forward_calls(t, tower, call, 1, x, action, out, stream);
+  return mz_train_tower_forward_calls(t, tower, call, 1, x, action, out, nullptr, stream);
 }
 
-int mz_train_tower_backward_calls(mz_train* t, int32_t tower, int32_t call, int32_t ncalls, const float* grad_out, float* grad_in,
-                                  mz_stream stream) {
-  MZ_CHECK_ARG(t != nullptr && grad_out != nullptr, "mz_train_tower_backward: NULL argument");
+int mz_train_tower_backward_calls(mz_train* t, int32_t tower, int32_t call, int32_t ncalls, const float* grad_out,
+                                  const float* grad_norm, float* grad_in, mz_stream stream) {
+  MZ_CHECK_ARG(t != nullptr && (grad_out != nullptr || grad_norm != nullptr), "mz_train_tower_backward: NULL argument");
   MZ_CHECK_ARG(tower == 0 || grad_in != nullptr, "mz_train_tower_backward: grad_in is NULL");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CallBufs cb;
@@ -1479,8 +1585,9 @@ int mz_train_tower_backward_calls(mz_train* t, int32_t tower, int32_t call, int3
   int cur = 0, k = 0, rc;
   bool masked = false;
   auto other = [&](int a, int b, int c) { for (int i = 0; i < 4; ++i) if (i != a && i != b && i != c) return i; return -1; };
-  nchw_to_planes_kernel<<<cgrid, 256, 0, st>>>(grad_out, G[cur], nullptr, kC, 16, g.Ptot, g.PB, g.Wp, g.W, g.H, g.PR, 1);
-  MZ_LAUNCH_CHECK("nchw_to_planes_kernel");
+  tower_gradin_kernel<<<dim3((g.Ptot + 127) / 128), 128, 0, st>>>(grad_out, grad_norm, cb.a[first + 2 * nb - 1], G[cur], g.Ptot, g.PB,
+                                                                  g.Wp, g.W, g.H, g.PR, t->fbf16);
+  MZ_LAUNCH_CHECK("tower_gradin_kernel");
   for (int b = nb - 1; b >= 0; --b) {
     const int l1 = first + 2 * b, l2 = l1 + 1;
     const int c1 = conv0 + l1, c2 = c1 + 1;
@@ -1531,7 +1638,7 @@ int mz_train_tower_backward_calls(mz_train* t, int32_t tower, int32_t call, int3
 }
 
 int mz_train_tower_backward(mz_train* t, int32_t tower, int32_t call, const float* grad_out, float* grad_in, mz_stream stream) {
-  return mz_train_tower_backward_calls(t, tower, call, 1, grad_out, grad_in, stream);
+  return mz_train_tower_backward_calls(t, tower, call, 1, grad_out, nullptr, grad_in, stream);
 }
 
 int mz_train_stacked_calls(mz_train* t, int32_t* max_calls) {

@@ -476,8 +476,8 @@ class _ConvNet(MuZeroNet):
         eng = self._train_engine(hidden_state)
         if eng is not None:
             from . import train_engine
-            hs = train_engine.tower(eng, 1, hidden_state, action)
-            return normalize_hidden_state(hs), self.dynamics_net.reward_head(hs)
+            hs, normalized = train_engine.tower(eng, 1, hidden_state, action, mode=2)
+            return normalized, self.dynamics_net.reward_head(hs)
         b, c, h, w = hidden_state.shape
         planes = action_planes(action, self.num_actions, h, w).to(hidden_state.dtype)
         x = torch.cat([hidden_state, planes], dim=1)
@@ -523,7 +523,7 @@ class MuZeroBoardGameNet(_ConvNet):
         eng = self._train_engine(x, begin=True)
         if eng is not None:
             from . import train_engine
-            return normalize_hidden_state(train_engine.tower(eng, 0, x))
+            return train_engine.tower(eng, 0, x, mode=1)
         return normalize_hidden_state(self.represent_net.res_blocks(self.represent_net.conv_block(x)))
 
 

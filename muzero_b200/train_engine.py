@@ -147,28 +147,33 @@ class TowerTrainEngine:
         self.calls[tower] = k + n
         return k
 
-    def forward(self, tower: int, call: int, x: torch.Tensor, action: Optional[torch.Tensor]) -> torch.Tensor:
-        out = torch.empty(self.hidden_shape, dtype=torch.float32, device=self.device)
-        _lib.check(_lib.lib().mz_train_tower_forward(self.handle, tower, call, _lib.ptr(x), _lib.ptr(action),
-                                                     _lib.ptr(out), _lib.current_stream()))
-        return out
+    def forward(self, tower: int, call: int, x: torch.Tensor, action: Optional[torch.Tensor], raw: bool = True,
+                norm: bool = False):
+        """One tower call: the output [B, 128, H, W] (``raw``) and / or its min-max normalisation (``norm``, util.py:31-36)
+        from the same pass.  Returns the tensor asked for, or the pair (raw, norm)."""
+        out = torch.empty(self.hidden_shape, dtype=torch.float32, device=self.device) if raw else None
+        out_n = torch.empty(self.hidden_shape, dtype=torch.float32, device=self.device) if norm else None
+        _lib.check(_lib.lib().mz_train_tower_forward_calls(self.handle, tower, call, 1, _lib.ptr(x), _lib.ptr(action),
+                                                           _lib.ptr(out), _lib.ptr(out_n), _lib.current_stream()))
+        return (out, out_n) if (raw and norm) else (out if raw else out_n)
 
-    def backward(self, tower: int, call: int, grad_out: torch.Tensor) -> Optional[torch.Tensor]:
+    def backward(self, tower: int, call: int, grad_out: Optional[torch.Tensor],
+                 grad_norm: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
         grad_in = torch.empty(self.hidden_shape, dtype=torch.float32, device=self.device) if tower != 0 else None
-        _lib.check(_lib.lib().mz_train_tower_backward(self.handle, tower, call, _lib.ptr(grad_out), _lib.ptr(grad_in),
-                                                      _lib.current_stream()))
+        _lib.check(_lib.lib().mz_train_tower_backward_calls(self.handle, tower, call, 1, _lib.ptr(grad_out), _lib.ptr(grad_norm),
+                                                            _lib.ptr(grad_in), _lib.current_stream()))
         return grad_in
 
     def forward_calls(self, call: int, n: int, x: torch.Tensor) -> torch.Tensor:
         """n stacked prediction-tower calls (x [n * B, 128, H, W], call-major) as one launch chain."""
         out = torch.empty((n * self.batch,) + self.hidden_shape[1:], dtype=torch.float32, device=self.device)
-        _lib.check(_lib.lib().mz_train_tower_forward_calls(self.handle, 2, call, n, _lib.ptr(x), None, _lib.ptr(out),
+        _lib.check(_lib.lib().mz_train_tower_forward_calls(self.handle, 2, call, n, _lib.ptr(x), None, _lib.ptr(out), None,
                                                            _lib.current_stream()))
         return out
 
     def backward_calls(self, call: int, n: int, grad_out: torch.Tensor) -> torch.Tensor:
         grad_in = torch.empty((n * self.batch,) + self.hidden_shape[1:], dtype=torch.float32, device=self.device)
-        _lib.check(_lib.lib().mz_train_tower_backward_calls(self.handle, 2, call, n, _lib.ptr(grad_out), _lib.ptr(grad_in),
+        _lib.check(_lib.lib().mz_train_tower_backward_calls(self.handle, 2, call, n, _lib.ptr(grad_out), None, _lib.ptr(grad_in),
                                                             _lib.current_stream()))
         return grad_in
 
@@ -194,21 +199,32 @@ _ENGINES = weakref.WeakKeyDictionary()       # network -> {(batch, device): engi
 
 
 class _Tower(torch.autograd.Function):
-    """y = tower(x[, action]); ``anchor`` (a tower parameter) makes the output require grad when x does not."""
+    """y = tower(x[, action]); ``anchor`` (a tower parameter) makes the output require grad when x does not.
+    mode 0: the raw output; 1: its min-max normalisation only (representation); 2: the pair (raw, normalised) (dynamics:
+    the reward head reads the raw output, the next step the normalised one)."""
 
     @staticmethod
-    def forward(ctx, x, anchor, eng, tower, call, action):
-        ctx.eng, ctx.tower, ctx.call = eng, tower, call
-        ctx.needs_in = tower != 0
-        return eng.forward(tower, call, x, action)
+    def forward(ctx, x, anchor, eng, tower, call, action, mode):
+        ctx.eng, ctx.tower, ctx.call, ctx.mode = eng, tower, call, mode
+        ctx.set_materialize_grads(False)
+        return eng.forward(tower, call, x, action, raw=mode != 1, norm=mode != 0)
 
     @staticmethod
-    def backward(ctx, grad_out):
+    def backward(ctx, *grads):
         eng = ctx.eng
-        grad_in = eng.backward(ctx.tower, ctx.call, grad_out.contiguous())
+        if ctx.mode == 0:
+            g_raw, g_norm = grads[0], None
+        elif ctx.mode == 1:
+            g_raw, g_norm = None, grads[0]
+        else:
+            g_raw, g_norm = grads
+        if g_raw is None and g_norm is None:         # nothing downstream used this call: its gradient is zero
+            g_raw = torch.zeros(eng.hidden_shape, dtype=torch.float32, device=eng.device)
+        grad_in = eng.backward(ctx.tower, ctx.call, None if g_raw is None else g_raw.contiguous(),
+                               None if g_norm is None else g_norm.contiguous())
         if ctx.tower == 0:
             eng.end_step()          # every other tower's backward has run: the conv weight gradients are complete
-        return grad_in, None, None, None, None, None
+        return grad_in, None, None, None, None, None, None
 
 
 class _PredictionCalls(torch.autograd.Function):
@@ -237,8 +253,10 @@ def prediction_calls(eng: TowerTrainEngine, hiddens) -> torch.Tensor:
     return torch.cat([tower(eng, 2, h) for h in hiddens], dim=0)
 
 
-def tower(eng: TowerTrainEngine, which: int, x: torch.Tensor, action: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """The representation (0) / dynamics (1) / prediction (2) tower on the training kernels."""
+def tower(eng: TowerTrainEngine, which: int, x: torch.Tensor, action: Optional[torch.Tensor] = None, mode: int = 0):
+    """The representation (0) / dynamics (1) / prediction (2) tower on the training kernels.  mode 0: the tower's output;
+    1: its min-max normalisation (``normalize_hidden_state``) instead; 2: both, as a pair -- from the same kernel pass,
+    forward and backward."""
     if which == 0:
         eng.begin_step()
     call = eng.next_call(which)
@@ -248,7 +266,7 @@ def tower(eng: TowerTrainEngine, which: int, x: torch.Tensor, action: Optional[t
     anchor = eng.modules[0][0].weight
     with torch.no_grad():           # BatchNorm2d.forward counts its train-mode calls
         torch._foreach_add_(eng.counters[which], 1)
-    return _Tower.apply(x, anchor, eng, which, call, action)
+    return _Tower.apply(x, anchor, eng, which, call, action, mode)
 
 
 def engine_for(network, batch: int, unroll_steps: int = 5) -> Optional[TowerTrainEngine]:

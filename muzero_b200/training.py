@@ -29,7 +29,7 @@ import torch
 import torch.distributed as dist
 import torch.nn.functional as F
 
-from .network import MuZeroNet
+from .network import MuZeroNet, normalize_hidden_state
 
 
 class _nullcontext:
@@ -83,6 +83,12 @@ def logits_to_transformed_expected_value(logits: torch.Tensor, support_size: int
     return signed_parabolic(torch.sum(probs * support, dim=-1, keepdim=True))
 
 
+def _half_gradient(grad):
+    """pipeline.py:583 ``register_hook(lambda grad: grad * 0.5)``; the last unrolled state feeds nothing, and a tower
+    function that does not materialise unused gradients hands the hook None for it."""
+    return None if grad is None else grad * 0.5
+
+
 def loss_func(prediction: torch.Tensor, target: torch.Tensor, mse: bool = False) -> torch.Tensor:
     """pipeline.py:615-629."""
     assert prediction.shape == target.shape
@@ -112,16 +118,16 @@ def calc_loss_tensors(network: MuZeroNet, state, action, target_value_scalar, ta
     mode = os.environ.get('MZ_TRAIN_BATCHED_HEADS', '1')    # 0: the reference's loop everywhere; 2: stacked heads for every conv net
     if eng is not None and mode != '0':
         from . import train_engine
-        return _calc_loss_stacked(network, lambda h, a: train_engine.tower(eng, 1, h, a),
+        return _calc_loss_stacked(network, lambda h, a: train_engine.tower(eng, 1, h, a, mode=2),
                                   lambda hs: train_engine.prediction_calls(eng, hs), hidden_state, action, target_value, target_reward, target_pi_prob, target_value_scalar, weights)
     if mode == '2' and hasattr(network, 'dynamics_tower'):
-        return _calc_loss_stacked(network, network.dynamics_tower,
+        return _calc_loss_stacked(network, lambda h, a: (lambda raw: (raw, normalize_hidden_state(raw)))(network.dynamics_tower(h, a)),
                                   lambda hs: torch.cat([network.prediction_tower(h) for h in hs], dim=0), hidden_state, action, target_value,
                                   target_reward, target_pi_prob, target_value_scalar, weights)
     for t in range(T):
         pred_pi_logits, pred_value = network.prediction(hidden_state)
         hidden_state, pred_reward = network.dynamics(hidden_state, action[:, t].unsqueeze(1))
-        hidden_state.register_hook(lambda grad: grad * 0.5)
+        hidden_state.register_hook(_half_gradient)
         value_loss = value_loss + loss_func(pred_value.squeeze(), target_value[:, t], network.mse_loss_for_value)
         reward_loss = reward_loss + loss_func(pred_reward.squeeze(), target_reward[:, t], network.mse_loss_for_reward)
         policy_loss = policy_loss + loss_func(pred_pi_logits, target_pi_prob[:, t])
@@ -145,15 +151,14 @@ def _calc_loss_stacked(network, dyn_tower, pred_towers, hidden_state, action, ta
     head ONCE over the T calls' stacked inputs (``head_over_calls``: per-call BatchNorm statistics, running statistics
     updated in call order) and the losses over [T, B].  Same operands into the same operations as the loop of
     pipeline.py:579-600 -- only the launch count differs (the heads and losses were 60 % of the kernels of a step)."""
-    from .network import head_over_calls, normalize_hidden_state
+    from .network import head_over_calls
     B, T = action.shape
     hiddens, raws = [], []
     for t in range(T):
         hiddens.append(hidden_state)
-        raw = dyn_tower(hidden_state, action[:, t].unsqueeze(1))
+        raw, hidden_state = dyn_tower(hidden_state, action[:, t].unsqueeze(1))     # the tower's output and its normalisation
         raws.append(raw)
-        hidden_state = normalize_hidden_state(raw)
-        hidden_state.register_hook(lambda grad: grad * 0.5)
+        hidden_state.register_hook(_half_gradient)
     feats = pred_towers(hiddens)                                             # [T * B, C, h, w], call-major
     raws = torch.cat(raws, dim=0)
     pred_net, dyn_net = network.prediction_net, network.dynamics_net

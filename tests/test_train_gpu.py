@@ -215,3 +215,47 @@ def test_stacked_prediction_calls_equal_separate_calls():
     for (k, a), (_, b) in zip(m1.named_buffers(), m2.named_buffers()):
         if k.startswith('prediction_net.res_blocks'):
             assert torch.equal(a, b), k
+
+
+def test_fused_hidden_state_normalisation_equals_the_torch_one():
+    """tower(mode=2): the dynamics tower's output AND its min-max normalisation (util.py:31-36) from one kernel pass,
+    with the normalisation's backward folded into the pass that builds the tower's output gradient -- against
+    ``normalize_hidden_state`` applied by PyTorch to the raw output (what the autograd path does).  Forward: the same
+    float32 operations on the same values, so the same bits.  Backward: both paths round the float32 gradient to bf16
+    once; they differ by float32 summation order only (<= 2e-3 relative L2 stated, ~1e-4 measured)."""
+    import muzero_b200 as mz
+    from muzero_b200 import train_engine
+    from muzero_b200.network import normalize_hidden_state
+    torch.manual_seed(9)
+    B = 16
+    net = mz.MuZeroBoardGameNet((9, 9, 9), 82, 2, 128).cuda().train()
+    twin = copy.deepcopy(net)
+    gen = torch.Generator(device='cuda').manual_seed(10)
+    obs = torch.randint(0, 2, (B, 9, 9, 9), device='cuda', generator=gen).float()
+    hid = torch.rand((B, 128, 9, 9), device='cuda', generator=gen)
+    act = torch.randint(0, 82, (B, 1), device='cuda', generator=gen)
+    g_raw = torch.randn((B, 128, 9, 9), device='cuda', generator=gen)
+    g_norm = torch.randn((B, 128, 9, 9), device='cuda', generator=gen) * 3.0
+    got = []
+    for model, fused in ((net, True), (twin, False)):
+        eng = train_engine.engine_for(model, B, 5)
+        x = hid.clone().requires_grad_(True)
+        rep = train_engine.tower(eng, 0, obs, mode=1 if fused else 0)
+        rep_n = rep if fused else normalize_hidden_state(rep)
+        if fused:
+            raw, nrm = train_engine.tower(eng, 1, x, act, mode=2)
+        else:
+            raw = train_engine.tower(eng, 1, x, act)
+            nrm = normalize_hidden_state(raw)
+        torch.autograd.backward([raw, nrm], [g_raw, g_norm])
+        rep_n.backward(g_norm * 0.1)
+        torch.cuda.synchronize()
+        got.append((raw.detach(), nrm.detach(), rep_n.detach(), x.grad, model))
+    (r1, n1, p1, gx1, m1), (r2, n2, p2, gx2, m2) = got
+    assert torch.equal(r1, r2) and torch.equal(n1, n2) and torch.equal(p1, p2)
+    assert float(n1.min()) >= 0.0 and float(n1.max()) <= 1.0
+    assert rel(gx1, gx2) <= 2e-3, rel(gx1, gx2)
+    worst = max(rel(p.grad, q.grad) for (k, p), (_, q) in zip(m1.named_parameters(), m2.named_parameters())
+                if p.grad is not None and (k.startswith('dynamics_net.conv_block') or k.startswith('dynamics_net.res_blocks')
+                                           or k.startswith('represent_net')))
+    assert worst <= 5e-3, worst
