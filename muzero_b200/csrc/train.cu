@@ -836,36 +836,36 @@ __global__ void planes_to_nchw_kernel(const uint16_t* __restrict__ src, float* _
 
 // A tower's output for autograd: raw [B][128][H][W] float32 and / or its per-position min-max normalisation over the 128
 // channels (util.py:31-36: (h - lo) / (hi - lo + 1e-8), the float32 operations of the reference on the same values).
-// Thread = row P: sixteen 16-byte loads, channel minimum / maximum in registers, strided float32 stores.
-__global__ void __launch_bounds__(128) tower_out_kernel(const uint16_t* __restrict__ src, float* __restrict__ raw, float* __restrict__ norm,
-                                                        int Ptot, int PB, int Wp, int W, int H, int PR, int bf16) {
-  const int P = blockIdx.x * blockDim.x + threadIdx.x;
-  if (P >= Ptot) return;
+// Block = 32 rows x 16 channel groups: warp g loads the 32 rows' 16-byte records of plane g (coalesced), the channel
+// minimum / maximum of a row is combined over the 16 warps through shared memory, every thread stores its 8 channels.
+constexpr int kTowerIoThreads = 512;
+
+__global__ void __launch_bounds__(kTowerIoThreads) tower_out_kernel(const uint16_t* __restrict__ src, float* __restrict__ raw,
+                                                                    float* __restrict__ norm, int Ptot, int PB, int Wp, int W, int H,
+                                                                    int PR, int bf16) {
+  __shared__ float s_lo[16][33], s_hi[16][33];
+  const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P = blockIdx.x * 32 + lane;
   const int b = P / PB, q = P - b * PB, y = q / Wp, x = q - y * Wp;
-  if (y >= H || x >= W) return;
-  int4 r[16];
+  const bool real = P < Ptot && y < H && x < W;
+  float v[8];
+  unpack8(__ldcg(reinterpret_cast<const int4*>(src) + (size_t)g * PR + kFront + P), bf16, v);      // rows past Ptot: the zero tail
+  float lo = v[0], hi = v[0];
 #pragma unroll
-  for (int g = 0; g < 16; ++g) r[g] = __ldcg(reinterpret_cast<const int4*>(src) + (size_t)g * PR + kFront + P);
-  float lo = 3.0e38f, hi = -3.0e38f;
+  for (int e = 1; e < 8; ++e) { lo = fminf(lo, v[e]); hi = fmaxf(hi, v[e]); }
+  if (norm) {
+    s_lo[g][lane] = lo; s_hi[g][lane] = hi;
+    __syncthreads();
 #pragma unroll
-  for (int g = 0; g < 16; ++g) {
-    float v[8];
-    unpack8(r[g], bf16, v);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { lo = fminf(lo, v[e]); hi = fmaxf(hi, v[e]); }
+    for (int k = 0; k < 16; ++k) { lo = fminf(lo, s_lo[k][lane]); hi = fmaxf(hi, s_hi[k][lane]); }
   }
+  if (!real) return;
   const float d = __fadd_rn(__fsub_rn(hi, lo), 1e-8f);
-  const size_t base = (size_t)b * kC * H * W + (size_t)y * W + x, cs = (size_t)H * W;
+  const size_t cs = (size_t)H * W, base = (size_t)b * kC * cs + (size_t)y * W + x + (size_t)(g * 8) * cs;
 #pragma unroll
-  for (int g = 0; g < 16; ++g) {
-    float v[8];
-    unpack8(r[g], bf16, v);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const size_t o = base + (size_t)(g * 8 + e) * cs;
-      if (raw) raw[o] = v[e];
-      if (norm) norm[o] = __fdiv_rn(__fsub_rn(v[e], lo), d);
-    }
+  for (int e = 0; e < 8; ++e) {
+    if (raw) raw[base + e * cs] = v[e];
+    if (norm) norm[base + e * cs] = __fdiv_rn(__fsub_rn(v[e], lo), d);
   }
 }
 
@@ -873,70 +873,60 @@ __global__ void __launch_bounds__(128) tower_out_kernel(const uint16_t* __restri
 // g_norm = dL/d normalised (either may be missing).  With a = h - lo, d = hi - lo + 1e-8:
 //   dh[c] = g_raw[c] + g_norm[c] / d + [c = argmin] (sum g_norm a / d^2 - sum g_norm / d) - [c = argmax] sum g_norm a / d^2
 // (first index on ties, like a single min / max index of torch; tied minima are ReLU zeros whose gradient the tower's
-// own ReLU mask removes anyway).  h is the tower's saved last activation.
-__global__ void __launch_bounds__(128) tower_gradin_kernel(const float* __restrict__ g_raw, const float* __restrict__ g_norm,
-                                                           const uint16_t* __restrict__ h, uint16_t* __restrict__ dst, int Ptot, int PB,
-                                                           int Wp, int W, int H, int PR, int hbf16) {
-  const int P = blockIdx.x * blockDim.x + threadIdx.x;
-  if (P >= Ptot) return;
+// own ReLU mask removes anyway).  h is the tower's saved last activation.  Same block shape as tower_out_kernel; the
+// row-wide quantities (lo, hi, their positions, the two sums) are combined over the 16 warps through shared memory.
+__global__ void __launch_bounds__(kTowerIoThreads) tower_gradin_kernel(const float* __restrict__ g_raw, const float* __restrict__ g_norm,
+                                                                       const uint16_t* __restrict__ h, uint16_t* __restrict__ dst,
+                                                                       int Ptot, int PB, int Wp, int W, int H, int PR, int hbf16) {
+  __shared__ float s_lo[16][33], s_hi[16][33], s_1[16][33], s_2[16][33];
+  __shared__ int s_amin[16][33], s_amax[16][33];
+  const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P = blockIdx.x * 32 + lane;
   const int b = P / PB, q = P - b * PB, y = q / Wp, x = q - y * Wp;
-  int4* out = reinterpret_cast<int4*>(dst) + kFront + P;
-  if (y >= H || x >= W) {
+  const bool real = P < Ptot && y < H && x < W;
+  const size_t cs = (size_t)H * W, base = real ? (size_t)b * kC * cs + (size_t)y * W + x + (size_t)(g * 8) * cs : 0;
+  float o[8];
 #pragma unroll
-    for (int g = 0; g < 16; ++g) out[(size_t)g * PR] = make_int4(0, 0, 0, 0);
-    return;
-  }
-  const size_t base = (size_t)b * kC * H * W + (size_t)y * W + x, cs = (size_t)H * W;
-  float lo = 0.0f, hi = 0.0f, d = 1.0f, dlo = 0.0f, dhi = 0.0f;
-  int amin = -1, amax = -1;
-  int4 r[16];
+  for (int e = 0; e < 8; ++e) o[e] = (real && g_raw) ? __ldg(g_raw + base + e * cs) : 0.0f;
   if (g_norm) {
+    float v[8], gn[8];
+    unpack8(__ldcg(reinterpret_cast<const int4*>(h) + (size_t)g * PR + kFront + P), hbf16, v);
 #pragma unroll
-    for (int g = 0; g < 16; ++g) r[g] = __ldcg(reinterpret_cast<const int4*>(h) + (size_t)g * PR + kFront + P);
-    lo = 3.0e38f; hi = -3.0e38f;
+    for (int e = 0; e < 8; ++e) gn[e] = real ? __ldg(g_norm + base + e * cs) : 0.0f;
+    float lo = v[0], hi = v[0];
+    int amin = g * 8, amax = g * 8;
 #pragma unroll
-    for (int g = 0; g < 16; ++g) {
-      float v[8];
-      unpack8(r[g], hbf16, v);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        if (v[e] < lo) { lo = v[e]; amin = g * 8 + e; }
-        if (v[e] > hi) { hi = v[e]; amax = g * 8 + e; }
-      }
+    for (int e = 1; e < 8; ++e) {
+      if (v[e] < lo) { lo = v[e]; amin = g * 8 + e; }
+      if (v[e] > hi) { hi = v[e]; amax = g * 8 + e; }
     }
-    d = __fadd_rn(__fsub_rn(hi, lo), 1e-8f);
+    s_lo[g][lane] = lo; s_hi[g][lane] = hi; s_amin[g][lane] = amin; s_amax[g][lane] = amax;
+    __syncthreads();
+    lo = s_lo[0][lane]; hi = s_hi[0][lane]; amin = s_amin[0][lane]; amax = s_amax[0][lane];
+#pragma unroll
+    for (int k = 1; k < 16; ++k) {          // ascending groups, strict comparisons: the first index wins ties
+      if (s_lo[k][lane] < lo) { lo = s_lo[k][lane]; amin = s_amin[k][lane]; }
+      if (s_hi[k][lane] > hi) { hi = s_hi[k][lane]; amax = s_amax[k][lane]; }
+    }
+    float p1 = 0.0f, p2 = 0.0f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { p1 += gn[e]; p2 += gn[e] * (v[e] - lo); }
+    s_1[g][lane] = p1; s_2[g][lane] = p2;
+    __syncthreads();
     float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
-    for (int g = 0; g < 16; ++g) {
-      float v[8];
-      unpack8(r[g], hbf16, v);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float gn = __ldg(g_norm + base + (size_t)(g * 8 + e) * cs);
-        s1 += gn;
-        s2 += gn * (v[e] - lo);
-      }
-    }
-    const float t = s2 / (d * d);
-    dlo = t - s1 / d;
-    dhi = -t;
-  }
-#pragma unroll
-  for (int g = 0; g < 16; ++g) {
-    float o[8];
+    for (int k = 0; k < 16; ++k) { s1 += s_1[k][lane]; s2 += s_2[k][lane]; }
+    const float d = __fadd_rn(__fsub_rn(hi, lo), 1e-8f);
+    const float t = s2 / (d * d), dlo = t - s1 / d, dhi = -t;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int c = g * 8 + e;
-      float v = g_raw ? __ldg(g_raw + base + (size_t)c * cs) : 0.0f;
-      if (g_norm) {
-        v += __ldg(g_norm + base + (size_t)c * cs) / d;
-        if (c == amin) v += dlo;
-        if (c == amax) v += dhi;
-      }
-      o[e] = v;
+      o[e] += gn[e] / d;
+      if (c == amin) o[e] += dlo;
+      if (c == amax) o[e] += dhi;
     }
-    out[(size_t)g * PR] = pack8(o, 1);
   }
+  if (P < Ptot) reinterpret_cast<int4*>(dst)[(size_t)g * PR + kFront + P] = real ? pack8(o, 1) : make_int4(0, 0, 0, 0);
 }
 
 // the action "planes" of DynamicsConvNet.forward (network.py:440-444, quirk C of DESIGN.md): flat element f of the
@@ -1554,7 +1544,7 @@ int mz_train_tower_forward_calls(mz_train* t, int32_t tower, int32_t call, int32
     cur = a2;
     conv += 2; layer += 2;
   }
-  tower_out_kernel<<<dim3((g.Ptot + 127) / 128), 128, 0, st>>>(cur, out, out_norm, g.Ptot, g.PB, g.Wp, g.W, g.H, g.PR, t->fbf16);
+  tower_out_kernel<<<dim3((g.Ptot + 31) / 32), kTowerIoThreads, 0, st>>>(cur, out, out_norm, g.Ptot, g.PB, g.Wp, g.W, g.H, g.PR, t->fbf16);
   MZ_LAUNCH_CHECK("tower_out_kernel");
   return MZ_OK;
 }
@@ -1585,7 +1575,7 @@ int mz_train_tower_backward_calls(mz_train* t, int32_t tower, int32_t call, int3
   int cur = 0, k = 0, rc;
   bool masked = false;
   auto other = [&](int a, int b, int c) { for (int i = 0; i < 4; ++i) if (i != a && i != b && i != c) return i; return -1; };
-  tower_gradin_kernel<<<dim3((g.Ptot + 127) / 128), 128, 0, st>>>(grad_out, grad_norm, cb.a[first + 2 * nb - 1], G[cur], g.Ptot, g.PB,
+  tower_gradin_kernel<<<dim3((g.Ptot + 31) / 32), kTowerIoThreads, 0, st>>>(grad_out, grad_norm, cb.a[first + 2 * nb - 1], G[cur], g.Ptot, g.PB,
                                                                   g.Wp, g.W, g.H, g.PR, t->fbf16);
   MZ_LAUNCH_CHECK("tower_gradin_kernel");
   for (int b = nb - 1; b >= 0; --b) {
