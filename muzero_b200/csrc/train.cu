@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(kWgThreads) twgrad_kernel(const __grid_constan
 // elementwise / reduction kernels on the planes.  Thread = (plane g = blockIdx.y, row P): 8 channels, one 16-byte access
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kEwThreads = 256;
-constexpr int kEwRows = 4;           // rows per thread
+constexpr int kEwRows = 1;           // rows per thread
 
 struct BnFwdParams {
   const uint16_t* y;        // raw conv output (fwd type)

@@ -1,0 +1,3 @@
+#!/bin/bash
+echo "tower: $(timeout 120 python tools/train_tower_time.py 8 128 20 2>&1 | tail -1 | cut -c50-230)"
+timeout 300 python tools/train_step_target.py 10 1 8 2>&1 | tail -1

@@ -110,6 +110,5 @@ int main(int argc, char** argv) {
   run<false, 8, false, true>("plain, mma4, ring x 8 MMAs", d, grid);
   run<true, 8, false, true>("uniform, mma4, ring x 8 MMAs", d, grid);
   run<true, 8, true, true>("uniform, single-MMA asm, ring x 8 MMAs", d, grid);
-  run<true, 16, false, true>("uniform, mma4, ring x 16 MMAs", d, grid);
   return 0;
 }
