@@ -159,7 +159,7 @@ struct TConvParams {
   int TP, TPs;              // rows of a tile incl. halo / rows of a shared-memory plane (odd)
   int sub_rows, stat_sub;   // several forward calls stacked along the rows: rows per call (a multiple of 128) and the distance
                             // (floats) between consecutive calls' statistics records -- a tile belongs to call row0 / sub_rows
-  int stages;
+  int stages, nbuf;
   uint32_t idesc;
   int out_bf16;
   int ablate;               // measurement only (MZ_TRAIN_ABLATE): 1 no MMAs, 2 no epilogue loads / stores, 4 no column sums, 8 no weight copies
@@ -175,28 +175,33 @@ __global__ void __launch_bounds__(kTConvThreads) tconv_kernel(const __grid_const
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int halo = p.Wp + 1;
-  const int row0 = blockIdx.x * 128;
   const uint32_t stage_bytes = (uint32_t)p.stage_g * kC * 16;
-  const uint32_t a_bytes = (uint32_t)p.cg_in * p.TPs * 16;
+  const uint32_t a_bytes = ((uint32_t)p.cg_in * p.TPs * 16 + 127) & ~127u;
+  // A CTA walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ...  With nbuf == 2 (launches with more tiles than SMs: the
+  // stacked prediction calls) tile buffer and accumulator are double-buffered: tile i + 1 is fetched and its MMAs run
+  // while the epilogue warps are still on tile i, and the weight ring streams on across tiles.
+  const int nbuf = p.nbuf, ntiles = p.R128 / 128, G = (int)gridDim.x;
 
-  unsigned char* sA = smem;
-  unsigned char* sW = smem + ((a_bytes + 127) & ~127u);
+  unsigned char* sA = smem;                                       // [nbuf][cg_in][TPs][16]
+  unsigned char* sW = smem + (size_t)nbuf * a_bytes;
   tl_stamp(p.tl, 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)p.stages * stage_bytes);
   uint64_t* w_full = bars;                           // [stages]
   uint64_t* w_empty = bars + kConvStagesMax;         // [stages]
-  uint64_t* a_full = bars + 2 * kConvStagesMax;
-  uint64_t* mma_done = a_full + 1;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(mma_done + 1);
-  float* s_stat = reinterpret_cast<float*>(tmem_holder + 2);   // [4 quadrants][2][128] column sums | [128][2] (mean, invstd) of the masked layer
-  float* s_saved = s_stat + 8 * kC;
+  uint64_t* a_full = bars + 2 * kConvStagesMax;      // [2] tile fetched
+  uint64_t* a_empty = a_full + 2;                    // [2] the MMAs that read the tile are done
+  uint64_t* mma_done = a_empty + 2;                  // [2] accumulator complete
+  uint64_t* acc_empty = mma_done + 2;                // [2] the epilogue has read the accumulator
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_stat = reinterpret_cast<float*>(tmem_holder + 2);   // [2][4 quadrants][2][128] column sums
+  float* s_saved = s_stat + 2 * 8 * kC;                          // [2][128][2] (mean, invstd) of the masked layer
 
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    mbar_init(a_full, 1); mbar_init(mma_done, 1);
+    for (int k = 0; k < 2; ++k) { mbar_init(&a_full[k], 1); mbar_init(&a_empty[k], 1); mbar_init(&mma_done[k], 1); mbar_init(&acc_empty[k], 256); }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_holder, 128);
+  if (warp == 1) tmem_alloc(tmem_holder, 256);
   pdl_trigger();            // the next kernel of the chain may set itself up beside this one
   tc_fence_before();
   __syncthreads();
@@ -207,29 +212,45 @@ __global__ void __launch_bounds__(kTConvThreads) tconv_kernel(const __grid_const
   if (warp == 0) {
     if (lane == 0) {
       // the weights do not depend on the previous kernel of the chain (they were packed at the start of the step):
-      // fill the ring first, then wait for the predecessor, then fetch the tile it wrote
+      // fill the ring first, then wait for the predecessor, then fetch the tiles it wrote
       const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.w);
-      int it = 0;
-      for (; it < p.stages; ++it) {           // stages <= total
-        if (p.ablate & 8) { mbar_arrive(&w_full[it]); continue; }
-        mbar_arrive_expect_tx(&w_full[it], stage_bytes);
-        bulk_g2s(sW + (size_t)it * stage_bytes, wsrc + (size_t)it * stage_bytes, stage_bytes, &w_full[it]);
-      }
-      pdl_wait();
-      tl_stamp(p.tl, 1);
-      mbar_arrive_expect_tx(a_full, (uint32_t)p.cg_in * p.TP * 16u);
-      for (int g = 0; g < p.cg_in; ++g)
-        bulk_g2s(sA + (size_t)g * p.TPs * 16, p.in + ((size_t)g * p.PR + kFront + row0 - halo) * 8, (uint32_t)p.TP * 16u, a_full);
+      auto fetch_tile = [&](int i, int t) {
+        const int buf = nbuf == 2 ? (i & 1) : 0;
+        if (i >= nbuf) mbar_wait(&a_empty[buf], (uint32_t)((i / nbuf) - 1) & 1u);
+        mbar_arrive_expect_tx(&a_full[buf], (uint32_t)p.cg_in * p.TP * 16u);
+        unsigned char* dstA = sA + (size_t)buf * a_bytes;
+        for (int g = 0; g < p.cg_in; ++g)
+          bulk_g2s(dstA + (size_t)g * p.TPs * 16, p.in + ((size_t)g * p.PR + kFront + t * 128 - halo) * 8, (uint32_t)p.TP * 16u, &a_full[buf]);
+      };
       int s = 0;
       uint32_t ph = 0;
-      for (; it < total; ++it) {
-        mbar_wait(&w_empty[s], ph);
+      bool wrapped = false;                     // the ring has been filled once: from then on a slot must be released first
+      auto next_stage = [&](int it) {
+        if (wrapped) mbar_wait(&w_empty[s], ph);
         if (p.ablate & 8) mbar_arrive(&w_full[s]);
         else {
           mbar_arrive_expect_tx(&w_full[s], stage_bytes);
           bulk_g2s(sW + (size_t)s * stage_bytes, wsrc + (size_t)it * stage_bytes, stage_bytes, &w_full[s]);
         }
-        if (++s == p.stages) { s = 0; ph ^= 1u; }
+        if (++s == p.stages) { s = 0; if (wrapped) ph ^= 1u; wrapped = true; }
+      };
+      int it = 0;
+      for (; it < p.stages; ++it) next_stage(it);          // stages <= total: the first tile's leading stages
+      pdl_wait();
+      tl_stamp(p.tl, 1);
+      if ((int)blockIdx.x < ntiles) fetch_tile(0, (int)blockIdx.x);
+      // The next tile is requested once `stages` stages of this tile have been issued: by then the MMA warp is inside
+      // this tile, so the buffer the next tile goes to (read by the tile before this one) is free without waiting, and
+      // the fetch has the rest of this tile's MMAs to arrive.
+      const int fetch_at = p.stages < total - 1 ? p.stages : total - 1;
+      int i = 0;
+      for (int t = (int)blockIdx.x; t < ntiles; t += G, ++i) {
+        for (; it < total; ++it) {
+          next_stage(it);
+          if (nbuf == 2 && it == fetch_at && t + G < ntiles) fetch_tile(i + 1, t + G);
+        }
+        it = 0;
+        if (nbuf == 1 && t + G < ntiles) fetch_tile(i + 1, t + G);
       }
     }
   } else if (warp == 1) {
@@ -244,180 +265,200 @@ __global__ void __launch_bounds__(kTConvThreads) tconv_kernel(const __grid_const
     const uint64_t a_t = smem_desc(smem_u32(sA) + (uint32_t)halo * 16u, (uint32_t)p.TPs * 16u, 128);
     const uint64_t b_t = smem_desc(smem_u32(sW), kC * 16, 128);
     const uint32_t a_hi = U((uint32_t)(a_t >> 32)), b_hi = U((uint32_t)(b_t >> 32));
-    const uint32_t a_base = U((uint32_t)a_t), b_base = U((uint32_t)b_t);
+    const uint32_t a_base0 = U((uint32_t)a_t), b_base = U((uint32_t)b_t), a_buf_units = U(a_bytes >> 4);
     const uint32_t a_step = U((uint32_t)(2 * p.TPs)), stage_units = U(stage_bytes >> 4);
     constexpr uint32_t b_step = 2u * kC;
     const uint32_t a_chunk = U((uint32_t)(p.stage_g * p.TPs));
-    const uint32_t tm = U(tmem), idesc = U(p.idesc), nstages = U((uint32_t)p.stages), wp = U((uint32_t)p.Wp);
+    const uint32_t tm0 = U(tmem), idesc = U(p.idesc), nstages = U((uint32_t)p.stages), wp = U((uint32_t)p.Wp);
     auto d64 = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
-    mbar_wait(a_full, 0);
-    tc_fence_after();
-    tl_stamp_lane0(p.tl, 4);
     uint32_t ph = 0, b_lo = b_base, s = 0;
-    if (kChunks > 0 && !(p.ablate & 1)) {
-      // 128-channel stages: eight K steps under two elections; kChunks stages per tap
-      uint32_t a_tap = a_base - wp - 1u;      // tap (0, 0)
+    int i = 0;
+    for (int t = (int)blockIdx.x; t < ntiles; t += G, ++i) {
+      const int buf = nbuf == 2 ? (i & 1) : 0;
+      const uint32_t use = (uint32_t)(i / nbuf);
+      mbar_wait(&a_full[buf], use & 1u);
+      if (i >= nbuf) mbar_wait(&acc_empty[buf], (use - 1u) & 1u);
+      tc_fence_after();
+      if (i == 0) tl_stamp_lane0(p.tl, 4);
+      const uint32_t tm = tm0 + (uint32_t)buf * 128u, a_base = a_base0 + (uint32_t)buf * a_buf_units;
+      if (kChunks > 0 && !(p.ablate & 1)) {
+        // 128-channel stages: eight K steps under two elections; kChunks stages per tap
+        uint32_t a_tap = a_base - wp - 1u;      // tap (0, 0)
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
+        for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
-        for (int ch = 0; ch < kChunks; ++ch) {
-          const uint32_t a_lo = a_tap + (uint32_t)ch * a_chunk;
-          mbar_wait(&w_full[s], ph);
-          tc_fence_after();
-          mma4_f16_elect(tm, d64(a_lo, a_hi), d64(a_lo + a_step, a_hi), d64(a_lo + 2 * a_step, a_hi), d64(a_lo + 3 * a_step, a_hi),
-                         d64(b_lo, b_hi), d64(b_lo + b_step, b_hi), d64(b_lo + 2 * b_step, b_hi), d64(b_lo + 3 * b_step, b_hi), idesc,
-                         (tap | ch) ? 1u : 0u);
-          mma4_f16_elect(tm, d64(a_lo + 4 * a_step, a_hi), d64(a_lo + 5 * a_step, a_hi), d64(a_lo + 6 * a_step, a_hi),
-                         d64(a_lo + 7 * a_step, a_hi), d64(b_lo + 4 * b_step, b_hi), d64(b_lo + 5 * b_step, b_hi),
-                         d64(b_lo + 6 * b_step, b_hi), d64(b_lo + 7 * b_step, b_hi), idesc, 1u);
-          commit_elect(&w_empty[s]);
-          b_lo += stage_units;
-          if (++s == nstages) { s = 0; ph ^= 1u; b_lo = b_base; }
-        }
-        a_tap += (tap % 3 == 2) ? wp - 2u : 1u;
-      }
-    } else {
-      // any other stage shape (the representation tower's first convolution), or the MMAs ablated
-      const int ksteps = p.stage_g / 2;
-      uint32_t acc = 0;
-      uint32_t a_tap = a_base - wp - 1u;
-      for (int tap = 0; tap < 9; ++tap) {
-        uint32_t a_lo = a_tap;
-        for (int ch = 0; ch < p.chunks; ++ch) {
-          mbar_wait(&w_full[s], ph);
-          tc_fence_after();
-          if (!(p.ablate & 1)) {
-            for (int ks = 0; ks < ksteps; ++ks) {
-              mma_f16_elect(tm, d64(a_lo + (uint32_t)ks * a_step, a_hi), d64(b_lo + (uint32_t)ks * b_step, b_hi), idesc, acc);
-              acc = 1;
-            }
+          for (int ch = 0; ch < kChunks; ++ch) {
+            const uint32_t a_lo = a_tap + (uint32_t)ch * a_chunk;
+            mbar_wait(&w_full[s], ph);
+            tc_fence_after();
+            mma4_f16_elect(tm, d64(a_lo, a_hi), d64(a_lo + a_step, a_hi), d64(a_lo + 2 * a_step, a_hi), d64(a_lo + 3 * a_step, a_hi),
+                           d64(b_lo, b_hi), d64(b_lo + b_step, b_hi), d64(b_lo + 2 * b_step, b_hi), d64(b_lo + 3 * b_step, b_hi), idesc,
+                           (tap | ch) ? 1u : 0u);
+            mma4_f16_elect(tm, d64(a_lo + 4 * a_step, a_hi), d64(a_lo + 5 * a_step, a_hi), d64(a_lo + 6 * a_step, a_hi),
+                           d64(a_lo + 7 * a_step, a_hi), d64(b_lo + 4 * b_step, b_hi), d64(b_lo + 5 * b_step, b_hi),
+                           d64(b_lo + 6 * b_step, b_hi), d64(b_lo + 7 * b_step, b_hi), idesc, 1u);
+            commit_elect(&w_empty[s]);
+            b_lo += stage_units;
+            if (++s == nstages) { s = 0; ph ^= 1u; b_lo = b_base; }
           }
-          commit_elect(&w_empty[s]);
-          a_lo += a_chunk;
-          b_lo += stage_units;
-          if (++s == nstages) { s = 0; ph ^= 1u; b_lo = b_base; }
+          a_tap += (tap % 3 == 2) ? wp - 2u : 1u;
         }
-        a_tap += (tap % 3 == 2) ? wp - 2u : 1u;
+      } else {
+        // any other stage shape (the representation tower's first convolution), or the MMAs ablated
+        const int ksteps = p.stage_g / 2;
+        uint32_t acc = 0;
+        uint32_t a_tap = a_base - wp - 1u;
+        for (int tap = 0; tap < 9; ++tap) {
+          uint32_t a_lo = a_tap;
+          for (int ch = 0; ch < p.chunks; ++ch) {
+            mbar_wait(&w_full[s], ph);
+            tc_fence_after();
+            if (!(p.ablate & 1)) {
+              for (int ks = 0; ks < ksteps; ++ks) {
+                mma_f16_elect(tm, d64(a_lo + (uint32_t)ks * a_step, a_hi), d64(b_lo + (uint32_t)ks * b_step, b_hi), idesc, acc);
+                acc = 1;
+              }
+            }
+            commit_elect(&w_empty[s]);
+            a_lo += a_chunk;
+            b_lo += stage_units;
+            if (++s == nstages) { s = 0; ph ^= 1u; b_lo = b_base; }
+          }
+          a_tap += (tap % 3 == 2) ? wp - 2u : 1u;
+        }
       }
+      if (i == 0) tl_stamp_lane0(p.tl, 5);
+      commit_elect(&a_empty[buf]);
+      commit_elect(&mma_done[buf]);
     }
-    tl_stamp_lane0(p.tl, 5);
-    commit_elect(mma_done);
   } else {
     // ---- epilogue: TMEM lane = tile row; a warp reads lane quadrant warp % 4, columns [64 half, 64 half + 64)
     const int quad = warp & 3, half = (warp - 2) >> 2;
     const int et = tid - 64;                  // 0..255
-    const int P = row0 + quad * 32 + lane;
-    const bool inr = P < p.Ptot;
-    const bool valid = inr && !is_halo(P, p.PB, p.Wp, p.W, p.H);
     const bool mask = p.mask_y != nullptr;
-    const size_t rowoff = (size_t)kFront + (size_t)P;
     // everything this role reads from global memory was written by earlier kernels of the chain: order it behind them
     pdl_wait();
-    const size_t sub_off = (size_t)(row0 / p.sub_rows) * (size_t)p.stat_sub;      // this tile's call: its statistics record
-    if (mask) {
-      s_saved[et] = p.mask_saved[sub_off + et];
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-    }
-    // Everything the epilogue needs besides the accumulator -- the skip gradient, the masked layer's Y and ReLU bits for
-    // this thread's row and 64 columns -- is requested NOW, while the MMAs run: no global round trip sits between the
-    // last MMA and the stores.  Loads are UNCONDITIONAL per lane (every row of a plane up to its zero tail is readable;
-    // halo rows are discarded by `valid` below): a predicate would turn each load into load + select.
-    const bool do_mask = mask && !(p.ablate & 2), do_add = p.add != nullptr && !(p.ablate & 2);
-    int4 py[8], pd[8];
-    uint2 bits = make_uint2(0xffffffffu, 0xffffffffu);
-    if (do_mask) {
-      uint32_t b[8];
+    int i = 0;
+    for (int t = (int)blockIdx.x; t < ntiles; t += G, ++i) {
+      const int buf = nbuf == 2 ? (i & 1) : 0, sb = i & 1;      // shared-memory scratch alternates in either mode
+      const uint32_t use = (uint32_t)(i / nbuf);
+      const int row0 = t * 128;
+      const int P = row0 + quad * 32 + lane;
+      const bool inr = P < p.Ptot;
+      const bool valid = inr && !is_halo(P, p.PB, p.Wp, p.W, p.H);
+      const size_t rowoff = (size_t)kFront + (size_t)P;
+      float* st_buf = s_stat + sb * 8 * kC;
+      float* sv_buf = s_saved + sb * 2 * kC;
+      const size_t sub_off = (size_t)(row0 / p.sub_rows) * (size_t)p.stat_sub;      // this tile's call: its statistics record
+      if (mask) {
+        sv_buf[et] = p.mask_saved[sub_off + et];
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      // Everything the epilogue needs besides the accumulator -- the skip gradient, the masked layer's Y and ReLU bits for
+      // this thread's row and 64 columns -- is requested NOW, while the MMAs run: no global round trip sits between the
+      // last MMA and the stores.  Loads are UNCONDITIONAL per lane (every row of a plane up to its zero tail is readable;
+      // halo rows are discarded by `valid` below): a predicate would turn each load into load + select.
+      const bool do_mask = mask && !(p.ablate & 2), do_add = p.add != nullptr && !(p.ablate & 2);
+      int4 py[8], pd[8];
+      uint2 bits = make_uint2(0xffffffffu, 0xffffffffu);
+      if (do_mask) {
+        uint32_t bq[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) b[u] = __ldcg(p.mask_bits + (size_t)(half * 8 + u) * p.R128 + P);
-      bits.x = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
-      bits.y = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+        for (int u = 0; u < 8; ++u) bq[u] = __ldcg(p.mask_bits + (size_t)(half * 8 + u) * p.R128 + P);
+        bits.x = bq[0] | (bq[1] << 8) | (bq[2] << 16) | (bq[3] << 24);
+        bits.y = bq[4] | (bq[5] << 8) | (bq[6] << 16) | (bq[7] << 24);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) py[u] = __ldcg(reinterpret_cast<const int4*>(p.mask_y) + (size_t)(half * 8 + u) * p.PR + rowoff);
-    }
-    if (do_add) {
-#pragma unroll
-      for (int u = 0; u < 8; ++u) pd[u] = __ldcg(reinterpret_cast<const int4*>(p.add) + (size_t)(half * 8 + u) * p.PR + rowoff);
-    }
-    mbar_wait(mma_done, 0);
-    tc_fence_after();
-    if (warp == 2) tl_stamp_lane0(p.tl, 6);
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 64 + c * 32), r);
-      tmem_ld_wait();
-      float v[32];
-#pragma unroll
-      for (int e = 0; e < 32; ++e) v[e] = valid ? __uint_as_float(r[e]) : 0.0f;
+        for (int u = 0; u < 8; ++u) py[u] = __ldcg(reinterpret_cast<const int4*>(p.mask_y) + (size_t)(half * 8 + u) * p.PR + rowoff);
+      }
       if (do_add) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          float f[8];
-          unpack8(pd[c * 4 + u], 1, f);
+        for (int u = 0; u < 8; ++u) pd[u] = __ldcg(reinterpret_cast<const int4*>(p.add) + (size_t)(half * 8 + u) * p.PR + rowoff);
+      }
+      mbar_wait(&mma_done[buf], use & 1u);
+      tc_fence_after();
+      if (warp == 2 && i == 0) tl_stamp_lane0(p.tl, 6);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[8 * u + e] = valid ? v[8 * u + e] + f[e] : 0.0f;
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem + (uint32_t)buf * 128u + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 64 + c * 32), r);
+        tmem_ld_wait();
+        if (c == 1) {                          // the accumulator is in registers: the MMAs of the tile after next may have it
+          tc_fence_before();
+          mbar_arrive(&acc_empty[buf]);
+        }
+        float v[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = valid ? __uint_as_float(r[e]) : 0.0f;
+        if (do_add) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float f[8];
+            unpack8(pd[c * 4 + u], 1, f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[8 * u + e] = valid ? v[8 * u + e] + f[e] : 0.0f;
+          }
+        }
+        float zx[32];
+        if (mask) {
+          // v := dZ = G * (A > 0);  zx := dZ * xhat
+          const uint32_t word = c == 0 ? bits.x : bits.y;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float y8[8];
+            if (do_mask) unpack8(py[c * 4 + u], p.fbf16, y8);
+            else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) y8[e] = 0.0f;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int col = half * 64 + c * 32 + 8 * u + e;
+              const float dz = ((word >> (8 * u + e)) & 1u) ? v[8 * u + e] : 0.0f;
+              v[8 * u + e] = dz;
+              zx[8 * u + e] = dz * (y8[e] - sv_buf[2 * col]) * sv_buf[2 * col + 1];
+            }
+          }
+        }
+        if (inr && !(p.ablate & 2)) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            reinterpret_cast<int4*>(p.out)[(size_t)(half * 8 + c * 4 + u) * p.PR + rowoff] = pack8(v + 8 * u, p.out_bf16);
+        }
+        const int col0 = half * 64 + c * 32;
+        if (p.ablate & 4) {
+        } else if (mask) {
+          const float s1 = warp_colsum32(v, lane);
+          const float s2 = warp_colsum32(zx, lane);
+          st_buf[quad * 2 * kC + col0 + lane] = s1;
+          st_buf[quad * 2 * kC + kC + col0 + lane] = s2;
+        } else if (p.stats) {
+          float sq[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) sq[e] = v[e] * v[e];
+          const float s1 = warp_colsum32(v, lane);
+          const float s2 = warp_colsum32(sq, lane);
+          st_buf[quad * 2 * kC + col0 + lane] = s1;
+          st_buf[quad * 2 * kC + kC + col0 + lane] = s2;
         }
       }
-      float zx[32];
-      if (mask) {
-        // v := dZ = G * (A > 0);  zx := dZ * xhat
-        const uint32_t word = c == 0 ? bits.x : bits.y;
+      if (warp == 2 && i == 0) tl_stamp_lane0(p.tl, 7);
+      long long* sums = mask ? p.mask_sums : p.stats;
+      if (sums) {
+        sums += sub_off / 2;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int which = et >> 7, col = et & (kC - 1);
+        float a = 0.0f;
+        if (!(p.ablate & 4)) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          float y8[8];
-          if (do_mask) unpack8(py[c * 4 + u], p.fbf16, y8);
-          else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) y8[e] = 0.0f;
-          }
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int col = half * 64 + c * 32 + 8 * u + e;
-            const float dz = ((word >> (8 * u + e)) & 1u) ? v[8 * u + e] : 0.0f;
-            v[8 * u + e] = dz;
-            zx[8 * u + e] = dz * (y8[e] - s_saved[2 * col]) * s_saved[2 * col + 1];
-          }
+          for (int q = 0; q < 4; ++q) a += st_buf[q * 2 * kC + which * kC + col];
         }
+        if (!(p.ablate & 32)) fix_add(sums + 2 * col + which, a, mask ? kFixGrad : kFixAct);
       }
-      if (inr && !(p.ablate & 2)) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          reinterpret_cast<int4*>(p.out)[(size_t)(half * 8 + c * 4 + u) * p.PR + rowoff] = pack8(v + 8 * u, p.out_bf16);
-      }
-      const int col0 = half * 64 + c * 32;
-      if (p.ablate & 4) {
-      } else if (mask) {
-        const float s1 = warp_colsum32(v, lane);
-        const float s2 = warp_colsum32(zx, lane);
-        s_stat[quad * 2 * kC + col0 + lane] = s1;
-        s_stat[quad * 2 * kC + kC + col0 + lane] = s2;
-      } else if (p.stats) {
-        float sq[32];
-#pragma unroll
-        for (int e = 0; e < 32; ++e) sq[e] = v[e] * v[e];
-        const float s1 = warp_colsum32(v, lane);
-        const float s2 = warp_colsum32(sq, lane);
-        s_stat[quad * 2 * kC + col0 + lane] = s1;
-        s_stat[quad * 2 * kC + kC + col0 + lane] = s2;
-      }
-    }
-    if (warp == 2) tl_stamp_lane0(p.tl, 7);
-    long long* sums = mask ? p.mask_sums : p.stats;
-    if (sums) {
-      sums += sub_off / 2;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const int which = et >> 7, col = et & (kC - 1);
-      float a = 0.0f;
-      if (!(p.ablate & 4)) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) a += s_stat[q * 2 * kC + which * kC + col];
-      }
-      if (!(p.ablate & 32)) fix_add(sums + 2 * col + which, a, mask ? kFixGrad : kFixAct);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 128);
+  if (warp == 1) tmem_dealloc(tmem, 256);
   tl_end(p.tl, p.stats ? 1 : 2);
 }
 
@@ -1070,6 +1111,8 @@ struct mz_train {
   // boards, every call keeping its own BatchNorm statistics)
   const Geom* cur_g;
   int cur_nsub, cur_sub_rows, cur_stat_sub;
+  int num_sms;
+  bool no_persist;                         // MZ_TRAIN_NO_PERSIST=1: one tile per CTA also for the stacked launches
   bool group_ok;                           // rows of one call are a multiple of 128 and of 16 * kSplits: tiles and weight-gradient splits never straddle calls
   Geom gg;                                 // geometry of the stacked buffers (plane stride for unroll_steps calls)
   uint16_t* ggrad_buf[4 + kDyRing];
@@ -1097,13 +1140,13 @@ int stat_slot(const mz_train* t, int tower, int call, int layer) {
   return s + call * tower_layers(t, tower) + layer;
 }
 
-size_t conv_smem_bytes(const Geom& g, int cg_in, int* stages_out, int* TP_out, int* TPs_out) {
+size_t conv_smem_bytes(const Geom& g, int cg_in, int nbuf, int* stages_out, int* TP_out, int* TPs_out) {
   const int halo = g.Wp + 1;
   const int TP = 128 + 2 * halo, TPs = TP | 1;
   const int chunk_g = cg_in < 16 ? cg_in : 16;                     // a stage: one tap's weights for up to 128 input channels
   const size_t a = (((size_t)cg_in * TPs * 16) + 127) & ~(size_t)127;
   const size_t stage = (size_t)chunk_g * kC * 16;
-  const size_t fixed = a + (2 * kConvStagesMax + 2) * 8 + 8 + 10 * kC * 4 + 64;
+  const size_t fixed = (size_t)nbuf * a + (2 * kConvStagesMax + 8) * 8 + 8 + 20 * kC * 4 + 64;
   int stages = (int)((220 * 1024 - fixed) / stage);
   const int need = 9 * (cg_in / chunk_g);
   if (stages > kConvStagesMax) stages = kConvStagesMax;
@@ -1142,7 +1185,9 @@ int launch_conv(mz_train* t, const uint16_t* in, int cg_in, const uint16_t* w, u
   p.fbf16 = t->fbf16;
   p.cg_in = cg_in; p.stage_g = cg_in < 16 ? cg_in : 16; p.chunks = cg_in / p.stage_g;
   p.Ptot = g.Ptot; p.PB = g.PB; p.Wp = g.Wp; p.W = g.W; p.H = g.H; p.PR = g.PR; p.R128 = g.R128;
-  const size_t smem = conv_smem_bytes(g, cg_in, &p.stages, &p.TP, &p.TPs);
+  const int tiles = g.R128 / 128;
+  p.nbuf = (tiles > t->num_sms && cg_in == 16 && !t->no_persist) ? 2 : 1;
+  const size_t smem = conv_smem_bytes(g, cg_in, p.nbuf, &p.stages, &p.TP, &p.TPs);
   p.idesc = idesc_of(128, kC, (uint32_t)a_bf16, (uint32_t)w_bf16, 0);
   p.out_bf16 = out_bf16;
   static const int ablate = getenv("MZ_TRAIN_ABLATE") ? atoi(getenv("MZ_TRAIN_ABLATE")) : 0;
@@ -1150,7 +1195,7 @@ int launch_conv(mz_train* t, const uint16_t* in, int cg_in, const uint16_t* w, u
   p.tl = t->timeline && t->tl_next < kTimelineMax ? t->timeline + 10 * (size_t)t->tl_next++ : nullptr;
   if (ablate & 128) return MZ_OK;          // measurement only: no conv launches at all
   void (*kern)(TConvParams) = p.stage_g == 16 ? (p.chunks == 1 ? tconv_kernel<1> : (p.chunks == 2 ? tconv_kernel<2> : tconv_kernel<0>)) : tconv_kernel<0>;
-  cudaError_t e = launch_chain(t, kern, dim3(g.R128 / 128), dim3(kTConvThreads), smem, st, p);
+  cudaError_t e = launch_chain(t, kern, dim3(p.nbuf == 2 ? t->num_sms : tiles), dim3(kTConvThreads), smem, st, p);
   if (e != cudaSuccess) { set_error("tconv_kernel launch: %s", cudaGetErrorString(e)); return MZ_ECUDA; }
   count_launch();
   return MZ_OK;
@@ -1399,7 +1444,10 @@ int mz_train_create(const mz_train_config* cfg, void* arena_dev, size_t arena_by
   if (e != cudaSuccess) { delete t; set_error("cudaMemset: %s", cudaGetErrorString(e)); return MZ_ECUDA; }
   const int cgs[3] = {tower_in_groups(t, 0), 16, 32};
   size_t max_smem = 0;
-  for (int k = 0; k < 3; ++k) { const size_t s = conv_smem_bytes(t->g, cgs[k], nullptr, nullptr, nullptr); if (s > max_smem) max_smem = s; }
+  for (int k = 0; k < 3; ++k) { const size_t s = conv_smem_bytes(t->g, cgs[k], 1, nullptr, nullptr, nullptr); if (s > max_smem) max_smem = s; }
+  { const size_t s = conv_smem_bytes(t->g, 16, 2, nullptr, nullptr, nullptr); if (s > max_smem) max_smem = s; }
+  { int dev = 0, sms = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); t->num_sms = sms > 0 ? sms : 148; }
+  t->no_persist = getenv("MZ_TRAIN_NO_PERSIST") && atoi(getenv("MZ_TRAIN_NO_PERSIST"));
   e = cudaFuncSetAttribute(tconv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(tconv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(tconv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
