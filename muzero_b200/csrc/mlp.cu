@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "net.cuh"
 #include "umma.cuh"
+#include <type_traits>
 #include "tree_thread.cuh"
 #include "tree_warp.cuh"
 #include <cuda_fp16.h>
@@ -501,21 +502,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const __grid_cons
     auto bar128 = []() { asm volatile("bar.sync 1, 256;" ::: "memory"); };   // all compute warps
     // tid 0 issues `n` K-steps of D(+)= A.B^T on the weight block at the head of the ring, then every thread
     // waits for them (one mbarrier, alternating phase)
-    auto mma_group = [&](uint32_t a_addr, int ksteps, uint32_t dcol, uint32_t N, bool accumulate) {
-      if (tid == 0) {
-        const uint32_t s = wit % kTcSlots, ph = (wit / kTcSlots) & 1;
-        mbar_wait(&w_full[s], ph);
+    // One warp issues the MMAs, and what it executes between two of them is latency the tensor pipe sits out: the K steps
+    // are unrolled four to an election (compile-time count), the descriptors' high words built once per group and their
+    // low words stepped by additions, the ring slot and its phase kept incrementally (csrc/train.cu, tools/issue_bench2.cu).
+    uint32_t slot = 0, slot_ph = 0;
+    auto mma_group = [&](uint32_t a_addr, auto ksteps_c, uint32_t dcol, uint32_t N, bool accumulate) {
+      constexpr int ksteps = decltype(ksteps_c)::value;
+      static_assert(ksteps % 4 == 0, "K steps are issued four to an election");
+      if (warp == 0) {
+        mbar_wait(&w_full[slot], slot_ph);
         tc_fence_after();
         const uint32_t idesc = instr_desc_f16(128, N);
-        const uint32_t b_addr = smem_u32(sW) + s * kTcSlotBytes;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint64_t ad = smem_desc(a_addr + (uint32_t)ks * 4096u, 2048, 128);
-          const uint64_t bd = smem_desc(b_addr + (uint32_t)ks * 32u * N, N * 16, 128);
-          mma_f16(tmem + dcol, ad, bd, idesc, (accumulate || ks > 0) ? 1u : 0u);
-        }
-        commit(&w_empty[s]);
-        commit(bar_mma);
+        const uint64_t at = smem_desc(a_addr, 2048, 128), bt = smem_desc(smem_u32(sW) + slot * kTcSlotBytes, N * 16, 128);
+        const uint32_t a_lo = (uint32_t)at, a_hi = (uint32_t)(at >> 32), b_lo = (uint32_t)bt, b_hi = (uint32_t)(bt >> 32);
+        const uint32_t bs = 2u * N;                  // 32 N bytes per K step, in 16-byte units (A: 4096 bytes = 256 units)
+        auto d64 = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
+#pragma unroll
+        for (int ks = 0; ks < ksteps; ks += 4)
+          mma4_f16_elect(tmem + dcol, d64(a_lo + ks * 256u, a_hi), d64(a_lo + (ks + 1) * 256u, a_hi), d64(a_lo + (ks + 2) * 256u, a_hi),
+                         d64(a_lo + (ks + 3) * 256u, a_hi), d64(b_lo + ks * bs, b_hi), d64(b_lo + (ks + 1) * bs, b_hi),
+                         d64(b_lo + (ks + 2) * bs, b_hi), d64(b_lo + (ks + 3) * bs, b_hi), idesc, (accumulate || ks > 0) ? 1u : 0u);
+        commit_elect(&w_empty[slot]);
+        commit_elect(bar_mma);
       }
+      if (++slot == kTcSlots) { slot = 0; slot_ph ^= 1u; }
       ++wit;
       mbar_wait(bar_mma, mma_ph);
       mma_ph ^= 1;
@@ -569,7 +579,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const __grid_cons
         const float* b1 = sB1 + net * p.P;
         const float* tab = net == 0 ? (p.tab_in_smem ? sTab + (size_t)act * tabP : p.tabA + (size_t)act * p.P) : nullptr;
         for (int c = 0; c < p.chunks; ++c) {
-          mma_group(a_in, 4, 0u, 256u, false);                        // D1 = A_in . W1c^T
+          mma_group(a_in, std::integral_constant<int, 4>{}, 0u, 256u, false);                        // D1 = A_in . W1c^T
           stamp();
           // epilogue 1: bias (+ action column) + ReLU -> fp16 hidden chunk in shared memory
 #pragma unroll 1
@@ -604,7 +614,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mlp_tc_kernel(const __grid_cons
           tc_fence_before();
           bar128();
           stamp();
-          mma_group(sMid_a, 16, 256u, N2, c > 0);                     // D2 (+)= A_mid . W2c^T
+          mma_group(sMid_a, std::integral_constant<int, 16>{}, 256u, N2, c > 0);                     // D2 (+)= A_mid . W2c^T
           stamp();
         }
         // epilogue 2
