@@ -259,3 +259,64 @@ def test_fused_hidden_state_normalisation_equals_the_torch_one():
                 if p.grad is not None and (k.startswith('dynamics_net.conv_block') or k.startswith('dynamics_net.res_blocks')
                                            or k.startswith('represent_net')))
     assert worst <= 5e-3, worst
+
+
+def _native_vs_autograd(batch, unroll, blocks=2, seed=11, accumulate=1):
+    """calc_loss + backward on the training kernels and, on a copy of the network, through fp32 autograd (no TF32)."""
+    import muzero_b200 as mz
+    from muzero_b200 import train_engine
+    from muzero_b200.training import calc_loss, synthetic_transitions
+    torch.manual_seed(seed)
+    net = mz.MuZeroBoardGameNet((9, 9, 9), 82, blocks, 128).cuda().train()
+    twin = copy.deepcopy(net)
+    losses = []
+    for k in range(accumulate):
+        tr, w = synthetic_transitions(net, batch, unroll, seed=seed + 1 + k)
+        wt = torch.from_numpy(w).cuda()
+        loss, _ = calc_loss(net, 'cuda', tr, wt)
+        eng = train_engine.engine_for(net, batch, unroll)
+        assert eng is not None and eng.active
+        loss.backward()
+        prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+        os.environ['MZ_TRAIN_NATIVE'] = '0'
+        try:
+            ref, _ = calc_loss(twin, 'cuda', tr, wt)
+            ref.backward()
+        finally:
+            os.environ.pop('MZ_TRAIN_NATIVE', None)
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+        losses.append((float(loss.detach()), float(ref.detach())))
+    torch.cuda.synchronize()
+    return net, twin, losses, eng
+
+
+@pytest.mark.parametrize('batch,unroll', [(64, 3), (32, 6), (24, 5)])
+def test_calc_loss_native_vs_autograd_other_shapes(batch, unroll):
+    """Unroll lengths other than 5 and batch sizes with (64, 32: rows per call a multiple of 128) and without (24) stacked
+    prediction calls: loss within 2e-3 of fp32 autograd, every gradient's norm within 10 %, BatchNorm buffers within 3e-3."""
+    net, twin, losses, eng = _native_vs_autograd(batch, unroll)
+    assert (eng.max_stacked_calls >= unroll) == (batch * 100 % 128 == 0)
+    for got, want in losses:
+        assert abs(got - want) <= 2e-3 * abs(want), (got, want)
+    for (k, p), (_, q) in zip(net.named_parameters(), twin.named_parameters()):
+        r = float(p.grad.norm()) / (float(q.grad.norm()) + 1e-30)
+        assert 0.9 <= r <= 1.1, (k, r)
+    for (k, a), (_, b) in zip(net.named_buffers(), twin.named_buffers()):
+        if a.dtype.is_floating_point:
+            assert rel(a, b) <= FWD_TOL, (k, rel(a, b))
+        else:
+            assert torch.equal(a, b), k
+
+
+def test_gradients_accumulate_over_two_backward_passes():
+    """Two calc_loss + backward passes without zeroing in between: the kernels add into .grad like autograd does
+    (conv weights through wgrad_finalize_kernel, BatchNorm weights / biases in bn_bwd_apply_kernel)."""
+    net, twin, losses, _ = _native_vs_autograd(32, 5, accumulate=2)
+    single, _, _, _ = _native_vs_autograd(32, 5, accumulate=1)
+    grew = 0
+    for (k, p), (_, q), (_, s) in zip(net.named_parameters(), twin.named_parameters(), single.named_parameters()):
+        r = float(p.grad.norm()) / (float(q.grad.norm()) + 1e-30)
+        assert 0.9 <= r <= 1.1, (k, r)
+        grew += float(p.grad.norm()) > 1.2 * float(s.grad.norm())
+    assert grew >= 0.8 * len(list(net.parameters()))          # the second pass really was added
