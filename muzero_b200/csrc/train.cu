@@ -81,9 +81,10 @@ __host__ __device__ constexpr uint32_t idesc_of(uint32_t M, uint32_t N, uint32_t
 
 // Batch statistics are accumulated with INTEGER atomics on fixed-point values: integer addition is associative, so the
 // totals are the same bits whatever order the CTAs arrive in (float atomics are not), and a consumer needs one load per
-// channel instead of a pass over per-CTA partials.  Activation sums use 2^-24 units (|sum| < 5e11), gradient sums
-// 2^-40 units (|sum| < 8e6): both far below float32's own rounding of the values that went in.
-constexpr double kFixAct = 16777216.0, kFixGrad = 1099511627776.0;
+// channel instead of a pass over per-CTA partials.  Activation sums use 2^-24 units (|sum| < 5e11), their squares 2^-16
+// (sum < 1.4e14: even a tensor saturated at fp16's 65504 fits for 32 000 rows per call), gradient sums 2^-40 units
+// (|sum| < 8e6): all far below float32's own rounding of the values that went in.
+constexpr double kFixAct = 16777216.0, kFixActSq = 65536.0, kFixGrad = 1099511627776.0;
 __device__ __forceinline__ void fix_add(long long* dst, float v, double scale) {
   atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)__double2ll_rn((double)v * scale));
 }
@@ -452,7 +453,7 @@ __global__ void __launch_bounds__(kTConvThreads) tconv_kernel(const __grid_const
 #pragma unroll
           for (int q = 0; q < 4; ++q) a += st_buf[q * 2 * kC + which * kC + col];
         }
-        if (!(p.ablate & 32)) fix_add(sums + 2 * col + which, a, mask ? kFixGrad : kFixAct);
+        if (!(p.ablate & 32)) fix_add(sums + 2 * col + which, a, mask ? kFixGrad : (which ? kFixActSq : kFixAct));
       }
     }
   }
@@ -642,7 +643,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_fwd_kernel(const BnFwdParams p)
     const int c = g * 8 + threadIdx.x;
     const long long* sums = p.sums + (size_t)sub * (p.stat_sub / 2);
     const float mean = fix_get(sums + 2 * c, kFixAct) * p.inv_n;
-    float var = fix_get(sums + 2 * c + 1, kFixAct) * p.inv_n - mean * mean;
+    float var = fix_get(sums + 2 * c + 1, kFixActSq) * p.inv_n - mean * mean;
     var = var > 0.0f ? var : 0.0f;
     const float is = rsqrtf(var + kBnEps);
     const float sc = p.gamma[c] * is;
@@ -657,7 +658,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_fwd_kernel(const BnFwdParams p)
         for (int z = 0; z < p.n_sub; ++z) {
           const long long* sz = p.sums + (size_t)z * (p.stat_sub / 2);
           const float mz_ = fix_get(sz + 2 * c, kFixAct) * p.inv_n;
-          float vz = fix_get(sz + 2 * c + 1, kFixAct) * p.inv_n - mz_ * mz_;
+          float vz = fix_get(sz + 2 * c + 1, kFixActSq) * p.inv_n - mz_ * mz_;
           vz = vz > 0.0f ? vz : 0.0f;
           rm = (1.0f - kBnMomentum) * rm + kBnMomentum * mz_;
           rv = (1.0f - kBnMomentum) * rv + kBnMomentum * vz * p.unbias;
