@@ -673,7 +673,7 @@ def run_engine_arm(args):
         dist.destroy_process_group()
 
 
-def train_step_sample(net, spec, dev, world, batch=128, unroll=5, warmup=6, steps=5):
+def train_step_sample(net, spec, dev, world, batch=128, unroll=5, warmup=6, steps=20):
     """BASELINE.json config 5's second half: the K=5-unroll training step, data-parallel, one flat
     NCCL all-reduce of the gradients; the towers' forward / dgrad / wgrad and train-mode BatchNorm run on the
     hand-written tcgen05 kernels of csrc/train.cu (SURVEY.md section 8 e / f-2)."""
