@@ -774,6 +774,31 @@ def train_step_sample(net, spec, dev, world, batch=128, unroll=5, warmup=6, step
                     'NCCL all-reduce and Adam -> update_priorities')}
     if learner.native_towers:
         out['towers'] = tower_chain_sample(twin, batch, unroll)
+        # roofline of the step's tensor-core work: every 3x3 convolution of the K-step unroll forward, dgrad and wgrad
+        # (algorithmic flops, the padded halo rows the kernels also multiply are not counted) against the measured peak
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            peaks = {}
+        tf_peak = float(peaks.get('bf16_tflops', 1590.0))
+        c, h, w = spec['net_kw']['input_shape']
+        nb, planes, A = twin.num_res_blocks, twin.num_planes, twin.num_actions
+        px = batch * h * w
+        conv = lambda cin: px * 2.0 * 9 * cin * planes
+        rep = conv(c) + 2 * nb * conv(planes)
+        dyn = conv(planes + A) + 2 * nb * conv(planes)
+        pred = 2 * nb * conv(planes)
+        fwd = rep + unroll * (dyn + pred)
+        # backward: dgrad for every convolution whose input needs a gradient (not the representation's first), wgrad for all
+        bwd = 2 * fwd - conv(c)
+        step_s = float(ms.item()) / 1e3
+        out['roofline'] = {'kernel': 'tconv_kernel / twgrad_kernel (tcgen05.mma M128 N128 K16; csrc/train.cu)', 'bound': 'tensor',
+                           'algorithmic_flops_per_step': fwd + bwd, 'achieved': (fwd + bwd) / step_s / 1e12, 'peak': tf_peak,
+                           'unit': 'TFLOP/s', 'frac': (fwd + bwd) / step_s / 1e12 / tf_peak,
+                           'peak_source': 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback (B200_PROFILING.md)',
+                           'note': 'latency-bound: 182 layer-calls of 100 tiles on 148 SMs per direction, each waiting for the '
+                                   'one before it (DESIGN.md section 4, Training towers); the stacked prediction calls run at the '
+                                   'rates under towers.prediction_x%d' % unroll}
     if local_ms is not None:
         out['ms_per_learner_step_no_collective'] = local_ms
         out['ms_per_learner_step_data_parallel'] = dp_only_ms
