@@ -380,6 +380,24 @@ int mz_train_end_step(mz_train* t, mz_stream stream);
 int mz_train_debug_view(mz_train* t, int32_t tower, int32_t call, int32_t layer, int32_t which, void** ptr, size_t* bytes,
                         int32_t* plane_rows, int32_t* front_rows);
 
+/* ---- the learner's optimizer step (pipeline.py:246-252 optimizer.step(); torch.optim.Adam of */
+/* gomoku/run_training.py:110) as ONE launch over all parameter tensors.  tensors: device array, one record per parameter
+ * (parameter, gradient, exp_avg, exp_avg_sq: float32, the same dense layout, n elements) -- the optimizer's own state
+ * tensors, updated in place; chunk_tensor / chunk_start: for every chunk of mz_adam_chunk_elements() elements the
+ * index of its tensor and its first element; step: device scalar holding the ALREADY incremented step count (torch's
+ * capturable per-parameter `step`); lr: device scalar.  L2 weight decay is added to the gradient, like torch.optim.Adam. */
+typedef struct mz_adam_tensor {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  int64_t n;
+} mz_adam_tensor;
+int mz_adam_chunk_elements(void);
+int mz_adam_step(const mz_adam_tensor* tensors_dev, const int32_t* chunk_tensor_dev, const int64_t* chunk_start_dev, int32_t n_chunks,
+                 const float* step_dev, const float* lr_dev, double beta1, double beta2, double eps, double weight_decay,
+                 mz_stream stream);
+
 /* number of kernels the library has launched since load (bench's gpu_launches) */
 uint64_t mz_launch_count(void);
 

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libmuzero_b200.so')
-SOURCES = ['api.cu', 'mcts.cu', 'mlp.cu', 'net.cu', 'conv.cu', 'selfplay.cu', 'replay.cu', 'train.cu']
+SOURCES = ['api.cu', 'mcts.cu', 'mlp.cu', 'net.cu', 'conv.cu', 'selfplay.cu', 'replay.cu', 'train.cu', 'optim.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 

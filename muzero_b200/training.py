@@ -268,6 +268,7 @@ class DataParallelLearner:
                                           **({'fused': True} if on_cuda else {}))
         self.lr_scheduler = torch.optim.lr_scheduler.MultiStepLR(self.optimizer, milestones=list(config.lr_milestones),
                                                                  gamma=config.lr_decay_rate)
+        self._fast_adam = None
         self.train_steps = 0
         self.last_allreduce_ms = None
         self._graph = None
@@ -294,8 +295,62 @@ class DataParallelLearner:
                 self.last_allreduce_ms = e0.elapsed_time(e1)
         if self.config.clip_grad:
             torch.nn.utils.clip_grad_norm_(self.params, self.config.max_grad_norm)
-        self.optimizer.step()
+        self._optimizer_step()
         return loss.detach(), priorities
+
+    # -- optimizer step -----------------------------------------------------------------------------------------------
+    def _optimizer_step(self) -> None:
+        """torch.optim.Adam.step(), or -- once the optimizer's state exists (after its first step) -- the one-launch Adam of
+        csrc/optim.cu on that very state (exp_avg, exp_avg_sq, step tensors of ``self.optimizer.state``, in place): same
+        arithmetic, one kernel over a chunk table instead of five launches of 64 K-element chunks.  MZ_FAST_ADAM=0: torch's."""
+        fast = self._fast_adam
+        if fast is None:
+            fast = self._fast_adam = self._build_fast_adam()
+        if not fast:
+            self.optimizer.step()
+            return
+        from . import _lib
+        torch._foreach_add_(fast['steps'], 1)
+        g = fast['group']
+        _lib.check(_lib.lib().mz_adam_step(fast['tensors'].data_ptr(), fast['chunk_tensor'].data_ptr(), fast['chunk_start'].data_ptr(),
+                                           fast['n_chunks'], fast['steps'][0].data_ptr(), g['lr'].data_ptr(), g['betas'][0],
+                                           g['betas'][1], g['eps'], g['weight_decay'], _lib.current_stream()))
+
+    def _build_fast_adam(self):
+        """Pointer / chunk tables for mz_adam_step, or False where torch's step stays (CPU, no state yet this call, exotic
+        layouts or options).  None is returned until the state exists, so the question is asked again next step."""
+        if self.device.type != 'cuda' or os.environ.get('MZ_FAST_ADAM', '1') == '0' or len(self.optimizer.param_groups) != 1:
+            return False
+        g = self.optimizer.param_groups[0]
+        if g.get('amsgrad') or g.get('maximize') or not torch.is_tensor(g['lr']) or torch.cuda.is_current_stream_capturing():
+            return False if (g.get('amsgrad') or g.get('maximize') or not torch.is_tensor(g['lr'])) else None
+        rows, steps = [], []
+        for p in g['params']:
+            st = self.optimizer.state.get(p)
+            if not st:
+                return None                      # state is created by the optimizer's first step
+            m, v, step = st['exp_avg'], st['exp_avg_sq'], st['step']
+            tensors = (p.data, p.grad, m, v)
+            if any(t.dtype != torch.float32 or t.stride() != p.stride() or t.device != p.device for t in tensors) or \
+                    not (p.is_contiguous() or p.is_contiguous(memory_format=torch.channels_last)) or \
+                    step.dtype != torch.float32 or not step.is_cuda:
+                return False
+            rows.append((p.data_ptr(), p.grad.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel()))
+            steps.append(step)
+        from . import _lib
+        chunk = _lib.lib().mz_adam_chunk_elements()
+        table = np.zeros((len(rows), 5), dtype=np.int64)
+        chunk_tensor, chunk_start = [], []
+        for k, r in enumerate(rows):
+            table[k] = r
+            for start in range(0, r[4], chunk):
+                chunk_tensor.append(k)
+                chunk_start.append(start)
+        dev = self.device
+        return {'group': g, 'steps': steps, 'n_chunks': len(chunk_tensor),
+                'tensors': torch.from_numpy(table).to(dev),               # mz_adam_tensor records: four pointers + n
+                'chunk_tensor': torch.tensor(chunk_tensor, dtype=torch.int32, device=dev),
+                'chunk_start': torch.tensor(chunk_start, dtype=torch.int64, device=dev)}
 
     def _graphed(self, inputs):
         if self._static is None or any(a.shape != b.shape for a, b in zip(self._static, inputs)):

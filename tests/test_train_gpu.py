@@ -320,3 +320,57 @@ def test_gradients_accumulate_over_two_backward_passes():
         assert 0.9 <= r <= 1.1, (k, r)
         grew += float(p.grad.norm()) > 1.2 * float(s.grad.norm())
     assert grew >= 0.8 * len(list(net.parameters()))          # the second pass really was added
+
+
+def test_one_launch_adam_equals_torch_adam(monkeypatch):
+    """DataParallelLearner's optimizer step through csrc/optim.cu (one launch over a chunk table, on the torch optimizer's
+    own exp_avg / exp_avg_sq / step tensors) against torch.optim.Adam(fused=True, capturable=True) on a twin learner fed
+    the SAME gradients (whole training steps cannot be compared this tightly: the PyTorch head kernels are not
+    bit-reproducible, and Adam turns a 1e-8 difference into a different step wherever a gradient is tiny).  Parameters
+    and optimizer state agree to float32 rounding after every step (parameters: to 5e-5 of a step's size, see below),
+    weight decay on."""
+    import muzero_b200 as mz
+    from muzero_b200.training import DataParallelLearner, synthetic_transitions
+    torch.manual_seed(13)
+    net_a = mz.MuZeroBoardGameNet((9, 9, 9), 82, 2, 128).cuda()
+    net_b = copy.deepcopy(net_a)
+    cfg = mz.config.make_gomoku_config(num_training_steps=100, batch_size=32)
+    cfg.weight_decay = 1e-4
+    monkeypatch.setenv('MZ_FAST_ADAM', '1')
+    la = DataParallelLearner(net_a, cfg, 'cuda', use_graph=False)
+    monkeypatch.setenv('MZ_FAST_ADAM', '0')
+    lb = DataParallelLearner(net_b, cfg, 'cuda', use_graph=False)
+    tr, w = synthetic_transitions(net_a, 32, 5, seed=40)
+    monkeypatch.setenv('MZ_FAST_ADAM', '1')
+    la.step(tr, w)                                   # creates the optimizer state (torch's step), real gradients
+    assert la._fast_adam is None
+    lb.flat_grad.copy_(la.flat_grad)
+    with torch.no_grad():                            # the twin starts from the same parameters ...
+        for p, q in zip(net_a.parameters(), net_b.parameters()):
+            q.copy_(p)
+    monkeypatch.setenv('MZ_FAST_ADAM', '0')
+    lb.optimizer.step()                              # ... and gets a state of its own,
+    for p, q in zip(la.params, lb.params):           # which is then made equal to the first learner's
+        for key in ('exp_avg', 'exp_avg_sq', 'step'):
+            lb.optimizer.state[q][key].copy_(la.optimizer.state[p][key])
+        with torch.no_grad():
+            q.copy_(p)
+    gen = torch.Generator(device='cuda').manual_seed(3)
+    for it in range(4):
+        g = torch.randn(la.flat_grad.shape, device='cuda', generator=gen) * (10.0 ** -(2 * it))
+        la.flat_grad.copy_(g)
+        lb.flat_grad.copy_(g)
+        monkeypatch.setenv('MZ_FAST_ADAM', '1')
+        la._optimizer_step()
+        assert isinstance(la._fast_adam, dict)
+        lb.optimizer.step()
+        torch.cuda.synchronize()
+        for (k, p), (_, q) in zip(net_a.named_parameters(), net_b.named_parameters()):
+            # torch forms the bias corrections 1 - beta^step in float32 (1 - 0.998001 loses 3e-5 of its value at step 2),
+            # the kernel in double: the two steps differ by up to ~2e-5 of a step's size (lr = 2e-3)
+            assert float((p - q).abs().max()) <= 2e-6 * float(q.abs().max()) + 1e-7, (it, k, float((p - q).abs().max()))
+            sa, sb = la.optimizer.state[p], lb.optimizer.state[q]
+            assert float(sa['step']) == float(sb['step']) == it + 2
+            for key in ('exp_avg', 'exp_avg_sq'):
+                d, m = float((sa[key] - sb[key]).abs().max()), float(sb[key].abs().max())
+                assert d <= 5e-6 * (m + 1e-30), (it, k, key, d, m)
