@@ -398,6 +398,14 @@ int mz_adam_step(const mz_adam_tensor* tensors_dev, const int32_t* chunk_tensor_
                  const float* step_dev, const float* lr_dev, double beta1, double beta2, double eps, double weight_decay,
                  mz_stream stream);
 
+/* ---- the heads' 1x1 convolutions (network.py:398-470, Conv2d(planes, 1 | 2, kernel_size=1, bias=False)) over stacked tower
+ * outputs: x f32 [n][c][hw], w f32 [m][c] (m <= 4, c <= 256), y f32 [n][m][hw].  Backward: dx f32 [n][c][hw] (written),
+ * dw f32 [m][c] (written: per-block partial sums in `scratch`, mz_head_conv_scratch_bytes, are added in a fixed order). */
+int mz_head_conv_forward(const float* x, const float* w, float* y, int64_t n, int32_t c, int32_t hw, int32_t m, mz_stream stream);
+size_t mz_head_conv_scratch_bytes(int64_t n, int32_t c, int32_t m);
+int mz_head_conv_backward(const float* x, const float* w, const float* dy, float* dx, float* dw, void* scratch, int64_t n, int32_t c,
+                          int32_t hw, int32_t m, mz_stream stream);
+
 /* number of kernels the library has launched since load (bench's gpu_launches) */
 uint64_t mz_launch_count(void);
 

@@ -66,3 +66,135 @@ int mz_adam_step(const mz_adam_tensor* tensors_dev, const int32_t* chunk_tensor_
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// The 1x1 convolutions of the heads (network.py:398-470: Conv2d(planes, 1 or 2, kernel_size=1)) over the K calls'
+// stacked tower outputs: x [N][C][HW] float32 (N = K * B boards), w [M][C], M <= 4.  cuDNN's route for such an output goes
+// through NCHW <-> NHWC transposes of the whole 26 MB input and a split-K weight gradient (~75 us per head and step);
+// these three kernels each stream the tensor once (~8 us).
+// ---------------------------------------------------------------------------------------------------------------
+namespace mz {
+namespace {
+
+constexpr int kHeadMaxM = 4;
+constexpr int kHeadMaxC = 256;
+
+__global__ void __launch_bounds__(256) head_conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y,
+                                                            long long NP, int C, int HW, int M) {
+  __shared__ float s_w[kHeadMaxM * kHeadMaxC];
+  for (int i = threadIdx.x; i < M * C; i += blockDim.x) s_w[i] = w[i];
+  __syncthreads();
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // (board n, position)
+  if (t >= NP) return;
+  const long long n = t / HW;
+  const int pos = (int)(t - n * HW);
+  const float* xp = x + n * (long long)C * HW + pos;
+  float acc[kHeadMaxM] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 8
+  for (int c = 0; c < C; ++c) {
+    const float v = __ldg(xp + (long long)c * HW);
+#pragma unroll
+    for (int m = 0; m < kHeadMaxM; ++m)
+      if (m < M) acc[m] = fmaf(s_w[m * C + c], v, acc[m]);
+  }
+  for (int m = 0; m < M; ++m) y[(n * M + m) * HW + pos] = acc[m];
+}
+
+// dx[n][c][pos] = sum_m w[m][c] dy[n][m][pos]
+__global__ void __launch_bounds__(256) head_conv_dx_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx,
+                                                           long long NP, int C, int HW, int M) {
+  __shared__ float s_w[kHeadMaxM * kHeadMaxC];
+  for (int i = threadIdx.x; i < M * C; i += blockDim.x) s_w[i] = w[i];
+  __syncthreads();
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= NP) return;
+  const long long n = t / HW;
+  const int pos = (int)(t - n * HW);
+  float g[kHeadMaxM] = {0.0f, 0.0f, 0.0f, 0.0f};
+  for (int m = 0; m < M; ++m) g[m] = dy[(n * M + m) * HW + pos];
+  float* dp = dx + n * (long long)C * HW + pos;
+#pragma unroll 8
+  for (int c = 0; c < C; ++c) {
+    float v = 0.0f;
+#pragma unroll
+    for (int m = 0; m < kHeadMaxM; ++m)
+      if (m < M) v = fmaf(s_w[m * C + c], g[m], v);
+    dp[(long long)c * HW] = v;
+  }
+}
+
+// dw[m][c] += sum over this block's boards and all positions of dy[n][m][pos] x[n][c][pos]; thread = channel c.
+// Per-block partials go to `partial` [blocks][M][C]; head_conv_dw_reduce_kernel adds them in block order (no float atomics:
+// the result does not depend on scheduling).
+__global__ void __launch_bounds__(kHeadMaxC) head_conv_dw_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                 float* __restrict__ partial, int N, int C, int HW, int M,
+                                                                 int boards_per_block) {
+  extern __shared__ float s_dy[];                                   // [M][HW] of the current board
+  const int c = threadIdx.x;
+  float acc[kHeadMaxM] = {0.0f, 0.0f, 0.0f, 0.0f};
+  const int n0 = blockIdx.x * boards_per_block;
+  for (int n = n0; n < n0 + boards_per_block && n < N; ++n) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < M * HW; i += blockDim.x) s_dy[i] = dy[(long long)n * M * HW + i];
+    __syncthreads();
+    if (c < C) {
+      const float* xp = x + ((long long)n * C + c) * HW;
+      for (int pos = 0; pos < HW; ++pos) {
+        const float v = __ldg(xp + pos);
+#pragma unroll
+        for (int m = 0; m < kHeadMaxM; ++m)
+          if (m < M) acc[m] = fmaf(s_dy[m * HW + pos], v, acc[m]);
+      }
+    }
+  }
+  if (c < C)
+    for (int m = 0; m < M; ++m) partial[((long long)blockIdx.x * M + m) * C + c] = acc[m];
+}
+
+__global__ void head_conv_dw_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int blocks, int MC) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= MC) return;
+  float s = 0.0f;
+  for (int b = 0; b < blocks; ++b) s += partial[(long long)b * MC + i];
+  dw[i] = s;
+}
+
+}  // namespace
+}  // namespace mz
+
+extern "C" {
+
+int mz_head_conv_forward(const float* x, const float* w, float* y, int64_t n, int32_t c, int32_t hw, int32_t m, mz_stream stream) {
+  MZ_CHECK_ARG(x != nullptr && w != nullptr && y != nullptr, "mz_head_conv_forward: NULL argument");
+  MZ_CHECK_ARG(n > 0 && c > 0 && c <= mz::kHeadMaxC && hw > 0 && m > 0 && m <= mz::kHeadMaxM, "mz_head_conv_forward: shape n=%lld c=%d hw=%d m=%d not supported",
+               (long long)n, c, hw, m);
+  const long long np = (long long)n * hw;
+  mz::head_conv_fwd_kernel<<<(unsigned)((np + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, w, y, np, c, hw, m);
+  MZ_LAUNCH_CHECK("head_conv_fwd_kernel");
+  return MZ_OK;
+}
+
+size_t mz_head_conv_scratch_bytes(int64_t n, int32_t c, int32_t m) {
+  const int64_t blocks = (n + 3) / 4;
+  return (size_t)blocks * (size_t)m * (size_t)c * sizeof(float);
+}
+
+int mz_head_conv_backward(const float* x, const float* w, const float* dy, float* dx, float* dw, void* scratch, int64_t n, int32_t c, int32_t hw,
+                          int32_t m, mz_stream stream) {
+  MZ_CHECK_ARG(x != nullptr && w != nullptr && dy != nullptr && dx != nullptr && dw != nullptr && scratch != nullptr,
+               "mz_head_conv_backward: NULL argument");
+  MZ_CHECK_ARG(n > 0 && c > 0 && c <= mz::kHeadMaxC && hw > 0 && m > 0 && m <= mz::kHeadMaxM && (size_t)m * hw * 4 <= 40 * 1024,
+               "mz_head_conv_backward: shape n=%lld c=%d hw=%d m=%d not supported", (long long)n, c, hw, m);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long np = (long long)n * hw;
+  mz::head_conv_dx_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(dy, w, dx, np, c, hw, m);
+  MZ_LAUNCH_CHECK("head_conv_dx_kernel");
+  const int bpb = 4, blocks = (int)((n + bpb - 1) / bpb);
+  mz::head_conv_dw_kernel<<<blocks, mz::kHeadMaxC, (size_t)m * hw * sizeof(float), st>>>(x, dy, static_cast<float*>(scratch), (int)n, c, hw, m, bpb);
+  MZ_LAUNCH_CHECK("head_conv_dw_kernel");
+  mz::head_conv_dw_reduce_kernel<<<(m * c + 127) / 128, 128, 0, st>>>(static_cast<const float*>(scratch), dw, blocks, m * c);
+  MZ_LAUNCH_CHECK("head_conv_dw_reduce_kernel");
+  return MZ_OK;
+}
+
+}  // extern "C"

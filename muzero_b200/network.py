@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import NamedTuple, Optional, Tuple
 
 import numpy as np
@@ -126,18 +127,50 @@ def _momentum_weights(calls: int, m: float, dtype, device) -> torch.Tensor:
     return w
 
 
-def head_over_calls(head: nn.Sequential, x: torch.Tensor, calls: int) -> torch.Tensor:
-    """One of the 1x1-conv heads (``_head``: conv, BatchNorm2d, ReLU, Flatten, Linear) applied to the inputs of ``calls``
-    separate forward calls stacked along the batch axis (call-major, [calls * B, C, h, w]) -- the SAME arithmetic as
-    ``calls`` invocations of ``head`` in train mode: every call keeps its own BatchNorm batch statistics (the stack is
-    normalised per (call, channel) over that call's B * h * w values, which is what instance normalisation of the
-    [calls, mid, B, h*w] view computes), and the running statistics receive the calls' updates in order.  One launch per
-    layer instead of one per call: at batch 128 the K-step unroll is bound by kernel count, not by arithmetic."""
-    conv, bn, _, _, lin = head
-    y = F.conv2d(x, conv.weight)
+class _HeadConv1x1(torch.autograd.Function):
+    """y = conv2d(x, w) for a 1x1 kernel with at most four output channels on the kernels of csrc/optim.cu
+    (mz_head_conv_forward / _backward): three passes over the input instead of cuDNN's transposes + split-K route."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        n, c, h, wd = x.shape
+        m = w.shape[0]
+        x = x.contiguous()
+        wm = w.reshape(m, c).contiguous()
+        y = torch.empty((n, m, h, wd), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().mz_head_conv_forward(x.data_ptr(), wm.data_ptr(), y.data_ptr(), n, c, h * wd, m, _lib.current_stream()))
+        ctx.save_for_backward(x, wm)
+        ctx.wshape = tuple(w.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wm = ctx.saved_tensors
+        n, c, h, wd = x.shape
+        m = wm.shape[0]
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        dw = torch.empty_like(wm)
+        scratch = torch.empty(_lib.lib().mz_head_conv_scratch_bytes(n, c, m), dtype=torch.uint8, device=x.device)
+        _lib.check(_lib.lib().mz_head_conv_backward(x.data_ptr(), wm.data_ptr(), dy.data_ptr(), dx.data_ptr(), dw.data_ptr(),
+                                                    scratch.data_ptr(), n, c, h * wd, m, _lib.current_stream()))
+        return dx, dw.view(ctx.wshape)
+
+
+def _head_conv(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    if (x.is_cuda and x.dtype == torch.float32 and weight.shape[0] <= 4 and weight.shape[1] <= 256
+            and tuple(weight.shape[2:]) == (1, 1) and os.environ.get('MZ_HEAD_CONV', '1') != '0'):
+        return _HeadConv1x1.apply(x, weight)
+    return F.conv2d(x, weight)
+
+
+def _head_after_conv(head: nn.Sequential, y: torch.Tensor, calls: int) -> torch.Tensor:
+    """BatchNorm (per-call statistics) + ReLU + Flatten + Linear of a head on its 1x1 convolution's output for `calls`
+    stacked calls."""
+    _, bn, _, _, lin = head
     tb, mid, h, w = y.shape
     b = tb // calls
-    y = y.view(calls, b, mid, h * w).transpose(1, 2)                     # [calls, mid, B, hw] (a view for mid == 1)
+    y = y.reshape(calls, b, mid, h * w).transpose(1, 2)                  # [calls, mid, B, hw] (a view for mid == 1)
     if bn.training:
         with torch.no_grad():
             var, mean = torch.var_mean(y, dim=(2, 3), unbiased=False)      # [calls, mid]
@@ -154,6 +187,30 @@ def head_over_calls(head: nn.Sequential, x: torch.Tensor, calls: int) -> torch.T
                          0.0, bn.eps).view(calls, b, mid, h * w).transpose(1, 2)
     z = F.relu(z).transpose(1, 2).reshape(tb, mid * h * w)
     return lin(z)
+
+
+def head_over_calls(head: nn.Sequential, x: torch.Tensor, calls: int) -> torch.Tensor:
+    """One of the 1x1-conv heads (``_head``: conv, BatchNorm2d, ReLU, Flatten, Linear) applied to the inputs of ``calls``
+    separate forward calls stacked along the batch axis (call-major, [calls * B, C, h, w]) -- the SAME arithmetic as
+    ``calls`` invocations of ``head`` in train mode: every call keeps its own BatchNorm batch statistics (the stack is
+    normalised per (call, channel) over that call's B * h * w values, which is what instance normalisation of the
+    [calls, mid, B, h*w] view computes), and the running statistics receive the calls' updates in order.  One launch per
+    layer instead of one per call: at batch 128 the K-step unroll is bound by kernel count, not by arithmetic."""
+    return _head_after_conv(head, _head_conv(x, head[0].weight), calls)
+
+
+def heads_over_calls(heads, x: torch.Tensor, calls: int):
+    """Several heads that read the SAME stacked input (the policy and value heads on the prediction tower's output): their
+    1x1 convolutions run as one convolution with the weights stacked along the output channels -- one pass over the
+    input forward, one input gradient backward instead of one per head and an addition -- then each head continues on
+    its own channels."""
+    mids = [h[0].weight.shape[0] for h in heads]
+    y = _head_conv(x, torch.cat([h[0].weight for h in heads], dim=0))
+    outs, at = [], 0
+    for h, mid in zip(heads, mids):
+        outs.append(_head_after_conv(h, y[:, at:at + mid], calls))
+        at += mid
+    return outs
 
 
 def normalize_hidden_state(h: torch.Tensor) -> torch.Tensor:

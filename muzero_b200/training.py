@@ -151,7 +151,7 @@ def _calc_loss_stacked(network, dyn_tower, pred_towers, hidden_state, action, ta
     head ONCE over the T calls' stacked inputs (``head_over_calls``: per-call BatchNorm statistics, running statistics
     updated in call order) and the losses over [T, B].  Same operands into the same operations as the loop of
     pipeline.py:579-600 -- only the launch count differs (the heads and losses were 60 % of the kernels of a step)."""
-    from .network import head_over_calls
+    from .network import head_over_calls, heads_over_calls
     B, T = action.shape
     hiddens, raws = [], []
     for t in range(T):
@@ -162,8 +162,7 @@ def _calc_loss_stacked(network, dyn_tower, pred_towers, hidden_state, action, ta
     feats = pred_towers(hiddens)                                             # [T * B, C, h, w], call-major
     raws = torch.cat(raws, dim=0)
     pred_net, dyn_net = network.prediction_net, network.dynamics_net
-    pi_logits = head_over_calls(pred_net.policy_net, feats, T)               # [T * B, A]
-    pred_value = head_over_calls(pred_net.value_net, feats, T)               # [T * B, S]
+    pi_logits, pred_value = heads_over_calls([pred_net.policy_net, pred_net.value_net], feats, T)   # [T * B, A], [T * B, S]
     pred_reward = head_over_calls(dyn_net.reward_head, raws, T)              # [T * B, S]
 
     def stacked(target):                                                      # [B, T, ...] -> [T * B, ...]

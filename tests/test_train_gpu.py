@@ -374,3 +374,29 @@ def test_one_launch_adam_equals_torch_adam(monkeypatch):
             for key in ('exp_avg', 'exp_avg_sq'):
                 d, m = float((sa[key] - sb[key]).abs().max()), float(sb[key].abs().max())
                 assert d <= 5e-6 * (m + 1e-30), (it, k, key, d, m)
+
+
+def test_head_conv_kernels_equal_conv2d():
+    """mz_head_conv_forward / _backward (the heads' 1x1 convolutions over stacked tower outputs) against F.conv2d in fp32
+    (no TF32): output, input gradient and weight gradient to float32 summation-order rounding, for the policy (2), value
+    (1) and stacked policy + value (3) shapes."""
+    from muzero_b200.network import _HeadConv1x1
+    prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        gen = torch.Generator(device='cuda').manual_seed(21)
+        for n, c, h, m in ((640, 128, 9, 3), (37, 128, 9, 1), (5, 64, 6, 2), (130, 256, 11, 4)):
+            x = torch.randn((n, c, h, h), device='cuda', generator=gen)
+            w = torch.randn((m, c, 1, 1), device='cuda', generator=gen) * 0.1
+            dy = torch.randn((n, m, h, h), device='cuda', generator=gen)
+            xa, wa = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+            xb, wb = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+            ya = _HeadConv1x1.apply(xa, wa)
+            yb = torch.nn.functional.conv2d(xb, wb)
+            ya.backward(dy)
+            yb.backward(dy)
+            torch.cuda.synchronize()
+            assert rel(ya, yb) <= 2e-6 and rel(xa.grad, xb.grad) <= 2e-6 and rel(wa.grad, wb.grad) <= 2e-5, \
+                (n, c, h, m, rel(ya, yb), rel(xa.grad, xb.grad), rel(wa.grad, wb.grad))
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
