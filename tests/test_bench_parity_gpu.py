@@ -6,6 +6,8 @@ is run the way bench.step_device runs it (plan.run('device', True, False), eager
     policy, root value, RNG end state), fed the network outputs and the noise the engine used;
   * >= 64 sampled (node, action) rows of the recurrent inference (hidden state, reward, value) are compared with the
     fp32 torch restatement of the reference network."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -68,3 +70,20 @@ def test_gomoku_bench_plan_replays_in_the_oracle():
     rows = [(int(t), int(k)) for t, k in zip(gen.choice(B, size=64), gen.randint(1, 201, size=64))]
     check_rows_against_oracle_net(built['net'], onet, plan, rows, TOL_H, TOL_PV)
     bench.release(built)
+
+
+@pytest.mark.parametrize('name,trees,bound_action,bound_visits,bound_l1', [
+    ('tictactoe', 128, 0.03, 0.06, 0.004), ('cartpole', 64, 0.04, 0.08, 0.004), ('gomoku', 4, 0.25, 1.0, 0.03)])
+def test_fp16_networks_rarely_change_a_search(name, trees, bound_action, bound_visits, bound_l1):
+    """How often a whole SEARCH changes because the engine's networks compute in fp16 on the tensor cores: the engine search
+    against the CPU oracle search driven by the fp32 torch restatement of the reference network, same observation, mask
+    and MT19937 stream per tree (tools/fp16_search_stats.py; profiles/r2_fp16_search_stats.json holds the figures at
+    512 / 256 / 32 trees: sampled action 0 %, visit vector 0.8 % / 1.2 % / 62 %, mean L1 of the visit policy 7e-4 / 5e-4 /
+    8e-3).  Bounds: fraction of trees whose sampled action / visit vector differs, mean L1 distance of the visit policies."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools'))
+    import fp16_search_stats
+    st = fp16_search_stats.search_stats(name, trees)
+    assert st['sampled_action_differs'] <= bound_action, st
+    assert st['visit_vector_differs'] <= bound_visits, st
+    assert st['mean_l1_visit_policy'] <= bound_l1, st
