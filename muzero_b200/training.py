@@ -228,8 +228,14 @@ class DataParallelLearner:
         if not data_parallel:                 # a learner of its own inside a multi-rank job (no collective)
             self.world = 1
         params = [p for p in network.parameters() if p.requires_grad]
-        # one flat gradient bucket; every .grad is a view into it -> the all-reduce needs no packing copies
-        self.flat_grad = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=self.device)
+        # ONE flat bucket: the gradients (every .grad is a view into it -> the all-reduce needs no packing copies) followed,
+        # in a data-parallel job, by the BatchNorm running statistics -- a single collective per step
+        n_grad = sum(p.numel() for p in params)
+        pad = lambda n: (n + 63) // 64 * 64
+        bufs = [b for b in network.buffers() if b.dtype.is_floating_point] if self.world > 1 else []
+        n_buf = sum(pad(b.numel()) for b in bufs)
+        self.flat_all = torch.zeros(pad(n_grad) + n_buf, dtype=torch.float32, device=self.device)
+        self.flat_grad = self.flat_all[:n_grad]
         off = 0
         for p in params:
             # same strides as the parameter (NHWC conv weights are a dense permutation): autograd accumulates in place
@@ -240,20 +246,17 @@ class DataParallelLearner:
         # every rank's actor folds the SAME statistics into its inference engine and any rank's checkpoint is the model
         # all ranks used (DDP broadcasts rank 0's buffers instead; the average uses every shard's data)
         self.flat_buf = None
-        if self.world > 1:
-            bufs = [b for b in network.buffers() if b.dtype.is_floating_point]
-            if bufs:
-                # every buffer starts on a 256-byte boundary of the bucket: cuDNN's BatchNorm kernels take the running
-                # statistics through vector loads and fault on the 4-byte-aligned views a dense packing would give the
-                # buffers that follow a 1- or 2-channel head BatchNorm
-                pad = lambda n: (n + 63) // 64 * 64
-                self.flat_buf = torch.zeros(sum(pad(b.numel()) for b in bufs), dtype=torch.float32, device=self.device)
-                off = 0
-                for b in bufs:
-                    view = self.flat_buf[off:off + b.numel()].view(b.shape)
-                    view.copy_(b)
-                    b.data = view
-                    off += pad(b.numel())
+        if bufs:
+            # every buffer starts on a 256-byte boundary of the bucket: cuDNN's BatchNorm kernels take the running
+            # statistics through vector loads and fault on the 4-byte-aligned views a dense packing would give the
+            # buffers that follow a 1- or 2-channel head BatchNorm
+            self.flat_buf = self.flat_all[pad(n_grad):]
+            off = 0
+            for b in bufs:
+                view = self.flat_buf[off:off + b.numel()].view(b.shape)
+                view.copy_(b)
+                b.data = view
+                off += pad(b.numel())
         self.use_graph = bool(use_graph) and self.device.type == 'cuda'
         # gomoku/run_training.py:110 / classic: Adam(lr_init, weight_decay), MultiStepLR(milestones, lr_decay_rate).
         # Graph mode: step counters and the learning rate live on the device so that a replay sees their updates.
@@ -267,6 +270,7 @@ class DataParallelLearner:
                                           **({'fused': True} if on_cuda else {}))
         self.lr_scheduler = torch.optim.lr_scheduler.MultiStepLR(self.optimizer, milestones=list(config.lr_milestones),
                                                                  gamma=config.lr_decay_rate)
+        self._nccl = self.world > 1 and dist.get_backend(self.group) == 'nccl'
         self._fast_adam = None
         self.train_steps = 0
         self.last_allreduce_ms = None
@@ -283,11 +287,12 @@ class DataParallelLearner:
             if time_allreduce and self.device.type == 'cuda':
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
-            self.flat_grad.div_(self.world)
-            if self.flat_buf is not None:
-                dist.all_reduce(self.flat_buf, op=dist.ReduceOp.SUM, group=self.group)
-                self.flat_buf.div_(self.world)
+            # gradients and running statistics in ONE collective; NCCL averages inside it (no division pass over 29 MB)
+            if self._nccl:
+                dist.all_reduce(self.flat_all, op=dist.ReduceOp.AVG, group=self.group)
+            else:
+                dist.all_reduce(self.flat_all, op=dist.ReduceOp.SUM, group=self.group)
+                self.flat_all.div_(self.world)
             if time_allreduce and self.device.type == 'cuda':
                 e1.record()
                 torch.cuda.synchronize(self.device)
