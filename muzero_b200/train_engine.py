@@ -4,8 +4,10 @@ The reference trains with plain PyTorch modules: ``calc_loss`` (pipeline.py:541-
 ``network.dynamics`` and ``network.prediction`` (network.py:113-124) and autograd + cuDNN do the rest.  Here the three
 towers -- every 3x3 convolution with its train-mode BatchNorm, ReLU and residual connection, i.e. all but a rounding
 error of the step's flops -- run as tcgen05 kernels forward AND backward; a tower is one ``torch.autograd.Function``
-whose inputs / outputs are the float32 NCHW tensors the reference's modules exchange, so ``calc_loss`` and everything
-around it (heads, ``normalize_hidden_state``, the losses, the 0.5 and 1/K gradient hooks, the optimizer) is unchanged.
+whose inputs / outputs are the float32 NCHW tensors the reference's modules exchange (optionally with the min-max
+normalisation of ``normalize_hidden_state`` applied by the same pass, forward and backward), so ``calc_loss`` and
+everything around it (the heads' BatchNorm / Linear, the losses, the 0.5 and 1/K gradient hooks) is unchanged.  The K
+prediction calls of an unroll can run as ONE launch chain over the stacked hidden states (``prediction_calls``).
 
 Parameter gradients are written by the kernels straight into ``p.grad`` (accumulated, like autograd's): BatchNorm
 weights / biases during a tower's backward, convolution weights once per step after the representation tower's

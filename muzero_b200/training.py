@@ -8,11 +8,13 @@ Reference semantics mirrored here (michaelnny/muzero):
   replay.py:27-32      Transition(state, action, pi_prob, value, reward)
 
 The reference has ONE learner on one device; here every rank computes the loss of its shard of the replay batch and
-the gradients are averaged with ONE flat-bucket all-reduce (the whole model, 29 MB fp32 for the Gomoku net, is a single
-latency-bound NVLink transfer), then every rank applies the identical Adam step, so weights stay in sync and the
-self-play engine on the same rank sees them without a broadcast.  BatchNorm running statistics (which the inference
-engine folds into its weights) are averaged the same way through a second, small flat bucket.  Forward/backward run through PyTorch autograd over
-the same parameters the inference engine repacks (SURVEY.md §8 e/f-2: fused fwd/bwd kernels are "next").
+the gradients are averaged with ONE flat-bucket all-reduce (the whole model, 29 MB fp32 for the Gomoku net, plus the
+BatchNorm running statistics the inference engine folds into its weights: a single latency-bound NVLink transfer,
+averaged inside NCCL), then every rank applies the identical Adam step (one launch of csrc/optim.cu on
+torch.optim.Adam's own state), so weights stay in sync and the self-play engine on the same rank sees them without a
+broadcast.  Forward / backward: for MuZeroBoardGameNet with 128 planes the three towers run on the tcgen05 kernels of
+csrc/train.cu behind autograd Functions (train_engine.py), the prediction calls of an unroll stacked
+into one launch chain, heads and losses once over the stacked calls; every other network trains through PyTorch autograd.
 
 BatchNorm note: like the reference's `network.train()` (pipeline.py:218) each rank uses ITS shard's batch statistics;
 DP therefore equals "mean of per-shard reference gradients", not the full-batch gradient, for the ResNets (MLP nets
