@@ -510,22 +510,28 @@ __global__ void __launch_bounds__(kWgThreads) twgrad_kernel(const __grid_constan
   const int r_base = split * p.Rs;
 
   if (warp == 0) {
-    if (lane == 0) {
-      const uint16_t* xb = p.x + (size_t)blk * 16 * p.PR * 8;
-      for (int st = 0; st < nst; ++st) {
-        const int s = st % kWgStages;
-        const uint32_t ph = (uint32_t)(st / kWgStages) & 1u;
-        const int rows = (p.Rs - st * kWgStage) < kWgStage ? (p.Rs - st * kWgStage) : kWgStage;
-        const int r0 = r_base + st * kWgStage;
+    // The whole warp produces: lane 0 waits for the slot and posts the byte count, then every lane issues ONE of the
+    // stage's up to 32 plane copies (lanes 0-15: dY planes, 16-31: X planes) -- one instruction for all of them instead of
+    // 32 issued one after the other by a single lane, which took longer than the stage's 24 MMAs.
+    const uint16_t* xb = p.x + (size_t)blk * 16 * p.PR * 8;
+    for (int st = 0; st < nst; ++st) {
+      const int s = st % kWgStages;
+      const uint32_t ph = (uint32_t)(st / kWgStages) & 1u;
+      const int rows = (p.Rs - st * kWgStage) < kWgStage ? (p.Rs - st * kWgStage) : kWgStage;
+      const int r0 = r_base + st * kWgStage;
+      if (lane == 0) {
         mbar_wait(&empty[s], ph ^ 1u);
         mbar_arrive_expect_tx(&full[s], 16u * rows * 16u + (uint32_t)ng * (rows + 2) * 16u);
-        unsigned char* d0 = sS + (size_t)s * st_bytes;
-        for (int g = 0; g < 16; ++g)
-          bulk_g2s(d0 + (size_t)g * kWgStage * 16, p.dy + ((size_t)g * p.PR + kFront + r0) * 8, (uint32_t)rows * 16u, &full[s]);
+      }
+      __syncwarp();
+      unsigned char* d0 = sS + (size_t)s * st_bytes;
+      if (lane < 16) {
+        bulk_g2s(d0 + (size_t)lane * kWgStage * 16, p.dy + ((size_t)lane * p.PR + kFront + r0) * 8, (uint32_t)rows * 16u, &full[s]);
+      } else if (lane - 16 < ng) {
+        const int g = lane - 16;
         const int xr0 = r0 + (ky - 1) * p.Wp - 1;
-        for (int g = 0; g < ng; ++g)
-          bulk_g2s(d0 + dy_bytes + (size_t)g * (kWgStage + 2) * 16, xb + ((size_t)g * p.PR + kFront + xr0) * 8,
-                   (uint32_t)(rows + 2) * 16u, &full[s]);
+        bulk_g2s(d0 + dy_bytes + (size_t)g * (kWgStage + 2) * 16, xb + ((size_t)g * p.PR + kFront + xr0) * 8,
+                 (uint32_t)(rows + 2) * 16u, &full[s]);
       }
     }
   } else if (warp == 1) {
