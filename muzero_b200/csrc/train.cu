@@ -211,48 +211,54 @@ __global__ void __launch_bounds__(kTConvThreads) tconv_kernel(const __grid_const
   const int total = 9 * p.chunks;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // the weights do not depend on the previous kernel of the chain (they were packed at the start of the step):
-      // fill the ring first, then wait for the predecessor, then fetch the tiles it wrote
-      const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.w);
-      auto fetch_tile = [&](int i, int t) {
-        const int buf = nbuf == 2 ? (i & 1) : 0;
+    // The weights do not depend on the previous kernel of the chain (they were packed at the start of the step): fill the
+    // ring first, then wait for the predecessor, then fetch the tiles it wrote.  The whole warp walks this code: lane 0
+    // waits and posts byte counts, and a tile's cg_in plane copies are issued by as many LANES with one instruction
+    // (sixteen copies issued one after the other by a single lane were 0.6 of the 1.2 us between griddepcontrol.wait and
+    // the first MMA).
+    const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.w);
+    auto fetch_tile = [&](int i, int t) {
+      const int buf = nbuf == 2 ? (i & 1) : 0;
+      if (lane == 0) {
         if (i >= nbuf) mbar_wait(&a_empty[buf], (uint32_t)((i / nbuf) - 1) & 1u);
         mbar_arrive_expect_tx(&a_full[buf], (uint32_t)p.cg_in * p.TP * 16u);
-        unsigned char* dstA = sA + (size_t)buf * a_bytes;
-        for (int g = 0; g < p.cg_in; ++g)
-          bulk_g2s(dstA + (size_t)g * p.TPs * 16, p.in + ((size_t)g * p.PR + kFront + t * 128 - halo) * 8, (uint32_t)p.TP * 16u, &a_full[buf]);
-      };
-      int s = 0;
-      uint32_t ph = 0;
-      bool wrapped = false;                     // the ring has been filled once: from then on a slot must be released first
-      auto next_stage = [&](int it) {
+      }
+      __syncwarp();
+      unsigned char* dstA = sA + (size_t)buf * a_bytes;
+      for (int g = lane; g < p.cg_in; g += 32)
+        bulk_g2s(dstA + (size_t)g * p.TPs * 16, p.in + ((size_t)g * p.PR + kFront + t * 128 - halo) * 8, (uint32_t)p.TP * 16u, &a_full[buf]);
+    };
+    int s = 0;
+    uint32_t ph = 0;
+    bool wrapped = false;                     // the ring has been filled once: from then on a slot must be released first
+    auto next_stage = [&](int it) {
+      if (lane == 0) {
         if (wrapped) mbar_wait(&w_empty[s], ph);
         if (p.ablate & 8) mbar_arrive(&w_full[s]);
         else {
           mbar_arrive_expect_tx(&w_full[s], stage_bytes);
           bulk_g2s(sW + (size_t)s * stage_bytes, wsrc + (size_t)it * stage_bytes, stage_bytes, &w_full[s]);
         }
-        if (++s == p.stages) { s = 0; if (wrapped) ph ^= 1u; wrapped = true; }
-      };
-      int it = 0;
-      for (; it < p.stages; ++it) next_stage(it);          // stages <= total: the first tile's leading stages
-      pdl_wait();
-      tl_stamp(p.tl, 1);
-      if ((int)blockIdx.x < ntiles) fetch_tile(0, (int)blockIdx.x);
-      // The next tile is requested once `stages` stages of this tile have been issued: by then the MMA warp is inside
-      // this tile, so the buffer the next tile goes to (read by the tile before this one) is free without waiting, and
-      // the fetch has the rest of this tile's MMAs to arrive.
-      const int fetch_at = p.stages < total - 1 ? p.stages : total - 1;
-      int i = 0;
-      for (int t = (int)blockIdx.x; t < ntiles; t += G, ++i) {
-        for (; it < total; ++it) {
-          next_stage(it);
-          if (nbuf == 2 && it == fetch_at && t + G < ntiles) fetch_tile(i + 1, t + G);
-        }
-        it = 0;
-        if (nbuf == 1 && t + G < ntiles) fetch_tile(i + 1, t + G);
       }
+      if (++s == p.stages) { s = 0; if (wrapped) ph ^= 1u; wrapped = true; }
+    };
+    int it = 0;
+    for (; it < p.stages; ++it) next_stage(it);          // stages <= total: the first tile's leading stages
+    pdl_wait();
+    tl_stamp(p.tl, 1);
+    if ((int)blockIdx.x < ntiles) fetch_tile(0, (int)blockIdx.x);
+    // The next tile is requested once `stages` stages of this tile have been issued: by then the MMA warp is inside
+    // this tile, so the buffer the next tile goes to (read by the tile before this one) is free without waiting, and
+    // the fetch has the rest of this tile's MMAs to arrive.
+    const int fetch_at = p.stages < total - 1 ? p.stages : total - 1;
+    int i = 0;
+    for (int t = (int)blockIdx.x; t < ntiles; t += G, ++i) {
+      for (; it < total; ++it) {
+        next_stage(it);
+        if (nbuf == 2 && it == fetch_at && t + G < ntiles) fetch_tile(i + 1, t + G);
+      }
+      it = 0;
+      if (nbuf == 1 && t + G < ntiles) fetch_tile(i + 1, t + G);
     }
   } else if (warp == 1) {
     // The issue loop is ONE warp running dependent scalar code, and it has to hand the tensor pipe an MMA every 64
