@@ -400,3 +400,28 @@ def test_head_conv_kernels_equal_conv2d():
                 (n, c, h, m, rel(ya, yb), rel(xa.grad, xb.grad), rel(wa.grad, wb.grad))
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def test_reference_learner_loop_on_the_training_kernels():
+    """pipeline.py:232-257 as the reference writes it -- optimizer.zero_grad() (set_to_none, the torch default: the
+    engine finds new gradient tensors every step and re-binds), calc_loss, backward, torch.optim.Adam.step() -- on a
+    network whose towers run on csrc/train.cu: every parameter gets a finite gradient each step and the loss of a fixed
+    batch falls."""
+    import muzero_b200 as mz
+    from muzero_b200 import train_engine
+    from muzero_b200.training import calc_loss, synthetic_transitions
+    torch.manual_seed(0)
+    net = mz.MuZeroBoardGameNet((9, 9, 9), 82, 2, 128).cuda().train()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    tr, w = synthetic_transitions(net, 64, 5, seed=1)
+    wt = torch.from_numpy(w).cuda()
+    losses = []
+    for _ in range(6):
+        opt.zero_grad()
+        loss, _pri = calc_loss(net, 'cuda', tr, wt)
+        assert train_engine.engine_for(net, 64, 5).active
+        loss.backward()
+        assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in net.parameters())
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert losses[-1] < 0.8 * losses[0], losses
