@@ -406,6 +406,20 @@ size_t mz_head_conv_scratch_bytes(int64_t n, int32_t c, int32_t m);
 int mz_head_conv_backward(const float* x, const float* w, const float* dy, float* dx, float* dw, void* scratch, int64_t n, int32_t c,
                           int32_t hw, int32_t m, mz_stream stream);
 
+/* ---- the rest of a head (BatchNorm2d(mid) in train mode + ReLU + Flatten + Linear(mid * hw, o); network.py:398-470) over the
+ * stacked 1x1-convolution outputs y f32 [calls * b][mid][hw] of `calls` forward calls, every call with its own batch statistics
+ * (mid <= 4, mid * hw <= 1024, o <= 128).  forward: saved f32 [calls][mid][3] (mean, 1/sqrt(var + eps), var), z f32
+ * [calls * b][mid * hw] (the activated features, kept for the backward pass), out f32 [calls * b][o]; running_mean / running_var
+ * take the calls' updates in call order.  backward: dout f32 [calls * b][o] -> dy (like y), dgamma / dbeta [mid] (WRITTEN, not
+ * accumulated) and dzr (like z) = dL/dz after the ReLU mask; the Linear layer's own gradients are the plain products
+ * dout^T z and sum(dout) (left to the caller's GEMM); sums f32 [calls][mid][2] is scratch.                                 */
+int mz_head_tail_forward(const float* y, const float* gamma, const float* beta, const float* w, const float* bias, float* running_mean,
+                         float* running_var, float* saved, float* z, float* out, int32_t calls, int32_t b, int32_t mid, int32_t hw, int32_t o,
+                         float eps, float momentum, mz_stream stream);
+int mz_head_tail_backward(const float* dout, const float* y, const float* gamma, const float* w, const float* saved, const float* z, float* dzr,
+                          float* sums, float* dy, float* dgamma, float* dbeta, int32_t calls, int32_t b, int32_t mid, int32_t hw, int32_t o,
+                          mz_stream stream);
+
 /* number of kernels the library has launched since load (bench's gpu_launches) */
 uint64_t mz_launch_count(void);
 

@@ -99,6 +99,8 @@ PROTOTYPES = {
     'mz_head_conv_forward': (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P]),
     'mz_head_conv_scratch_bytes': (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
     'mz_head_conv_backward': (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P]),
+    'mz_head_tail_forward': (C.c_int, [_P] * 10 + [C.c_int32] * 5 + [C.c_float, C.c_float, _P]),
+    'mz_head_tail_backward': (C.c_int, [_P] * 11 + [C.c_int32] * 5 + [_P]),
     'mz_adam_chunk_elements': (C.c_int, []),
     'mz_adam_step': (C.c_int, [_P, _P, _P, C.c_int32, _P, _P, C.c_double, C.c_double, C.c_double, C.c_double, _P]),
     'mz_train_stacked_calls': (C.c_int, [_P, C.POINTER(C.c_int32)]),

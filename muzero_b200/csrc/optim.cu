@@ -198,3 +198,190 @@ int mz_head_conv_backward(const float* x, const float* w, const float* dy, float
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// The rest of a head (network.py:398-470: BatchNorm2d(mid) in train mode, ReLU, Flatten, Linear(mid * hw, O)) over the K
+// calls' stacked 1x1-convolution outputs y [calls * B][mid][hw], every call with its OWN batch statistics -- what
+// network.head_over_calls computes with ~33 small PyTorch kernels per head and step, as six.  mid <= 4, mid * hw <= 1024.
+// Statistics and the Linear weight gradient are summed in fixed orders (no float atomics): results do not depend on
+// scheduling.
+// ---------------------------------------------------------------------------------------------------------------
+namespace mz {
+namespace {
+
+constexpr int kHeadMaxJ = 1024;
+
+constexpr int kStatThreads = 1024;
+__device__ __forceinline__ double block_sum_double(double v, double* red) {        // kStatThreads threads, fixed order
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int w = 0; w < kStatThreads / 32; ++w) s += red[w];
+  return s;
+}
+
+// block (m, call): mean and 1 / sqrt(var + eps) of channel m over the call's B * hw values; saved [calls][mid][3] also keeps
+// the biased variance for the running statistics
+__global__ void __launch_bounds__(kStatThreads) head_bn_stats_kernel(const float* __restrict__ y, float* __restrict__ saved, int B, int mid,
+                                                                     int HW, float eps) {
+  __shared__ double red[kStatThreads / 32];
+  const int m = blockIdx.x, call = blockIdx.y;
+  const long long n0 = (long long)call * B;
+  const int cnt = B * HW;
+  double s = 0.0, q = 0.0;                          // one pass, double accumulators: E[x^2] - mean^2 loses nothing here
+  for (int i = threadIdx.x; i < cnt; i += kStatThreads) {
+    const int b = i / HW, pos = i - b * HW;
+    const double v = (double)y[((n0 + b) * mid + m) * HW + pos];
+    s += v;
+    q += v * v;
+  }
+  const double mean = block_sum_double(s, red) / cnt;
+  double var = block_sum_double(q, red) / cnt - mean * mean;
+  var = var > 0.0 ? var : 0.0;
+  if (threadIdx.x == 0) {
+    float* o = saved + ((size_t)call * mid + m) * 3;
+    o[0] = (float)mean; o[1] = (float)(1.0 / sqrt(var + (double)eps)); o[2] = (float)var;
+  }
+}
+
+// block = board n: z = relu(bn(y)) [J = mid * hw] -> out = W z + b [O]; block 0 also moves the running statistics through
+// the calls' updates in call order
+__global__ void __launch_bounds__(256) head_tail_fwd_kernel(const float* __restrict__ y, const float* __restrict__ saved,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ z,
+                                                            float* __restrict__ out, float* __restrict__ rmean, float* __restrict__ rvar, int B,
+                                                            int calls, int mid, int HW, int O, float momentum) {
+  __shared__ float s_z[kHeadMaxJ];
+  const long long n = blockIdx.x;
+  const int call = (int)(n / B), J = mid * HW;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (n == 0 && threadIdx.x < mid) {
+    const int m = threadIdx.x;
+    const double cnt = (double)B * HW;
+    float rm = rmean[m], rv = rvar[m];
+    for (int c = 0; c < calls; ++c) {
+      const float* sv = saved + ((size_t)c * mid + m) * 3;
+      rm = (1.0f - momentum) * rm + momentum * sv[0];
+      rv = (1.0f - momentum) * rv + momentum * (float)((double)sv[2] * (cnt / (cnt - 1.0)));
+    }
+    rmean[m] = rm; rvar[m] = rv;
+  }
+  for (int j = threadIdx.x; j < J; j += 256) {
+    const int m = j / HW;
+    const float* sv = saved + ((size_t)call * mid + m) * 3;
+    const float v = fmaxf((y[n * J + j] - sv[0]) * sv[1] * gamma[m] + beta[m], 0.0f);
+    s_z[j] = v;
+    z[n * J + j] = v;
+  }
+  __syncthreads();
+  for (int o = warp; o < O; o += 8) {
+    const float* wr = W + (size_t)o * J;
+    float acc = 0.0f;
+    for (int j = lane; j < J; j += 32) acc = fmaf(__ldg(wr + j), s_z[j], acc);
+    for (int k = 16; k > 0; k >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, k);
+    if (lane == 0) out[n * O + o] = acc + bias[o];
+  }
+}
+
+// block = board n: dz = W^T dout, masked by z > 0 -> dzr [J]
+__global__ void __launch_bounds__(256) head_tail_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ W, const float* __restrict__ z,
+                                                            float* __restrict__ dzr, int J, int O) {
+  __shared__ float s_d[128];
+  const long long n = blockIdx.x;
+  for (int o = threadIdx.x; o < O; o += 256) s_d[o] = dout[n * O + o];
+  __syncthreads();
+  for (int j = threadIdx.x; j < J; j += 256) {
+    float acc = 0.0f;
+    for (int o = 0; o < O; ++o) acc = fmaf(__ldg(W + (size_t)o * J + j), s_d[o], acc);
+    dzr[n * J + j] = z[n * J + j] > 0.0f ? acc : 0.0f;
+  }
+}
+
+// block (m, call): S1 = sum dzr, S2 = sum dzr * xhat over the call's B * hw values -> sums [calls][mid][2]
+__global__ void __launch_bounds__(kStatThreads) head_bn_bwd_stats_kernel(const float* __restrict__ dzr, const float* __restrict__ y,
+                                                                         const float* __restrict__ saved, float* __restrict__ sums, int B,
+                                                                         int mid, int HW) {
+  __shared__ double red[kStatThreads / 32];
+  const int m = blockIdx.x, call = blockIdx.y;
+  const long long n0 = (long long)call * B;
+  const int cnt = B * HW;
+  const float* sv = saved + ((size_t)call * mid + m) * 3;
+  const float mean = sv[0], is = sv[1];
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = threadIdx.x; i < cnt; i += kStatThreads) {
+    const int b = i / HW, pos = i - b * HW;
+    const size_t at = ((n0 + b) * mid + m) * HW + pos;
+    const float d = dzr[at];
+    s1 += (double)d;
+    s2 += (double)(d * ((y[at] - mean) * is));
+  }
+  const double t1 = block_sum_double(s1, red);
+  const double t2 = block_sum_double(s2, red);
+  if (threadIdx.x == 0) { sums[((size_t)call * mid + m) * 2] = (float)t1; sums[((size_t)call * mid + m) * 2 + 1] = (float)t2; }
+}
+
+// dy = gamma invstd (dzr - S1 / cnt - xhat S2 / cnt); block 0: dgamma[m] = sum_calls S2, dbeta[m] = sum_calls S1 (call order)
+__global__ void __launch_bounds__(256) head_bn_bwd_apply_kernel(const float* __restrict__ dzr, const float* __restrict__ y,
+                                                                const float* __restrict__ saved, const float* __restrict__ sums,
+                                                                const float* __restrict__ gamma, float* __restrict__ dy, float* __restrict__ dgamma,
+                                                                float* __restrict__ dbeta, long long total, int B, int calls, int mid, int HW) {
+  if (blockIdx.x == 0 && threadIdx.x < mid) {
+    float g = 0.0f, b = 0.0f;
+    for (int c = calls - 1; c >= 0; --c) {            // the order separate calls' backward passes would run in
+      b += sums[((size_t)c * mid + threadIdx.x) * 2];
+      g += sums[((size_t)c * mid + threadIdx.x) * 2 + 1];
+    }
+    dgamma[threadIdx.x] = g; dbeta[threadIdx.x] = b;
+  }
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const long long n = i / ((long long)mid * HW);
+  const int m = (int)((i / HW) % mid), call = (int)(n / B);
+  const float* sv = saved + ((size_t)call * mid + m) * 3;
+  const float* sm = sums + ((size_t)call * mid + m) * 2;
+  const float inv_cnt = 1.0f / ((float)B * HW);
+  const float xh = (y[i] - sv[0]) * sv[1];
+  dy[i] = gamma[m] * sv[1] * (dzr[i] - sm[0] * inv_cnt - xh * sm[1] * inv_cnt);
+}
+
+}  // namespace
+}  // namespace mz
+
+extern "C" {
+
+int mz_head_tail_forward(const float* y, const float* gamma, const float* beta, const float* w, const float* bias, float* running_mean,
+                         float* running_var, float* saved, float* z, float* out, int32_t calls, int32_t b, int32_t mid, int32_t hw, int32_t o,
+                         float eps, float momentum, mz_stream stream) {
+  MZ_CHECK_ARG(y && gamma && beta && w && bias && running_mean && running_var && saved && z && out, "mz_head_tail_forward: NULL argument");
+  MZ_CHECK_ARG(calls > 0 && b > 1 && mid > 0 && mid <= mz::kHeadMaxM && hw > 0 && mid * hw <= mz::kHeadMaxJ && o > 0 && o <= 128,
+               "mz_head_tail_forward: shape calls=%d b=%d mid=%d hw=%d o=%d not supported", calls, b, mid, hw, o);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  mz::head_bn_stats_kernel<<<dim3(mid, calls), mz::kStatThreads, 0, st>>>(y, saved, b, mid, hw, eps);
+  MZ_LAUNCH_CHECK("head_bn_stats_kernel");
+  mz::head_tail_fwd_kernel<<<calls * b, 256, 0, st>>>(y, saved, gamma, beta, w, bias, z, out, running_mean, running_var, b, calls, mid, hw, o, momentum);
+  MZ_LAUNCH_CHECK("head_tail_fwd_kernel");
+  return MZ_OK;
+}
+
+int mz_head_tail_backward(const float* dout, const float* y, const float* gamma, const float* w, const float* saved, const float* z, float* dzr,
+                          float* sums, float* dy, float* dgamma, float* dbeta, int32_t calls, int32_t b, int32_t mid, int32_t hw, int32_t o,
+                          mz_stream stream) {
+  MZ_CHECK_ARG(dout && y && gamma && w && saved && z && dzr && sums && dy && dgamma && dbeta, "mz_head_tail_backward: NULL argument");
+  MZ_CHECK_ARG(calls > 0 && b > 1 && mid > 0 && mid <= mz::kHeadMaxM && hw > 0 && mid * hw <= mz::kHeadMaxJ && o > 0 && o <= 128,
+               "mz_head_tail_backward: shape calls=%d b=%d mid=%d hw=%d o=%d not supported", calls, b, mid, hw, o);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long n = (long long)calls * b;
+  const int J = mid * hw;
+  mz::head_tail_bwd_kernel<<<(unsigned)n, 256, 0, st>>>(dout, w, z, dzr, J, o);
+  MZ_LAUNCH_CHECK("head_tail_bwd_kernel");
+  mz::head_bn_bwd_stats_kernel<<<dim3(mid, calls), mz::kStatThreads, 0, st>>>(dzr, y, saved, sums, b, mid, hw);
+  MZ_LAUNCH_CHECK("head_bn_bwd_stats_kernel");
+  const long long total = n * J;
+  mz::head_bn_bwd_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dzr, y, saved, sums, gamma, dy, dgamma, dbeta, total, b, calls, mid, hw);
+  MZ_LAUNCH_CHECK("head_bn_bwd_apply_kernel");
+  return MZ_OK;
+}
+
+}  // extern "C"

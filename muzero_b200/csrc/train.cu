@@ -4,9 +4,8 @@
 // What runs here: every 3x3 convolution of the representation / dynamics / prediction towers -- forward, data
 // gradient and weight gradient as tcgen05 implicit GEMMs -- the train-mode BatchNorm + ReLU + residual around them,
 // forward and backward, and the min-max normalisation of the hidden state (util.py:31-36) at the tower boundary, forward
-// and backward.  The heads' 1x1 convolutions and the optimizer step are in optim.cu; the heads' BatchNorm / Linear, the
-// losses and the two gradient-scale hooks stay PyTorch autograd (muzero_b200/train_engine.py, training.py): together
-// < 0.1 % of the flops.
+// and backward.  The heads (1x1 convolution, BatchNorm, ReLU, Linear) and the optimizer step are in optim.cu; the losses
+// and the two gradient-scale hooks stay PyTorch autograd (muzero_b200/train_engine.py, training.py).
 //
 // Layout: the padded channel-group planes of conv.cu (pad == 1): a board is (H+1)*(W+1) positions, column W and row H
 // are a ZERO halo shared with the next row / board, an activation tensor is C/8 planes of [rows][8 channels] 16-bit.

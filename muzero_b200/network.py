@@ -164,12 +164,59 @@ def _head_conv(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
     return F.conv2d(x, weight)
 
 
+class _HeadTail(torch.autograd.Function):
+    """BatchNorm2d (train mode, per-call batch statistics) + ReLU + Flatten + Linear of a head over `calls` stacked calls on
+    the kernels of csrc/optim.cu (mz_head_tail_forward / _backward): six launches instead of ~33 small PyTorch kernels."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, weight, bias, running_mean, running_var, calls, eps, momentum):
+        tb, mid, h, w = y.shape
+        o, j = weight.shape
+        y = y.contiguous()
+        dev = y.device
+        saved = torch.empty((calls, mid, 3), dtype=torch.float32, device=dev)
+        z = torch.empty((tb, j), dtype=torch.float32, device=dev)
+        out = torch.empty((tb, o), dtype=torch.float32, device=dev)
+        wc = weight.contiguous()
+        _lib.check(_lib.lib().mz_head_tail_forward(y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), wc.data_ptr(), bias.data_ptr(),
+                                                   running_mean.data_ptr(), running_var.data_ptr(), saved.data_ptr(), z.data_ptr(),
+                                                   out.data_ptr(), calls, tb // calls, mid, h * w, o, eps, momentum,
+                                                   _lib.current_stream()))
+        ctx.save_for_backward(y, gamma, wc, saved, z)
+        ctx.calls = calls
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        y, gamma, wc, saved, z = ctx.saved_tensors
+        tb, mid, h, w = y.shape
+        o, j = wc.shape
+        dev = y.device
+        dout = dout.contiguous()
+        dzr = torch.empty_like(z)
+        sums = torch.empty((ctx.calls, mid, 2), dtype=torch.float32, device=dev)
+        dy = torch.empty_like(y)
+        dgamma = torch.empty_like(gamma)
+        dbeta = torch.empty_like(gamma)
+        _lib.check(_lib.lib().mz_head_tail_backward(dout.data_ptr(), y.data_ptr(), gamma.data_ptr(), wc.data_ptr(), saved.data_ptr(),
+                                                    z.data_ptr(), dzr.data_ptr(), sums.data_ptr(), dy.data_ptr(), dgamma.data_ptr(),
+                                                    dbeta.data_ptr(), ctx.calls, tb // ctx.calls, mid, h * w, o, _lib.current_stream()))
+        # the Linear layer's own gradients: one small GEMM and one column sum
+        return dy, dgamma, dbeta, dout.t().mm(z), dout.sum(0), None, None, None, None, None
+
+
 def _head_after_conv(head: nn.Sequential, y: torch.Tensor, calls: int) -> torch.Tensor:
     """BatchNorm (per-call statistics) + ReLU + Flatten + Linear of a head on its 1x1 convolution's output for `calls`
     stacked calls."""
     _, bn, _, _, lin = head
     tb, mid, h, w = y.shape
     b = tb // calls
+    if (y.is_cuda and bn.training and y.dtype == torch.float32 and mid <= 4 and mid * h * w <= 1024 and lin.out_features <= 128
+            and b >= 2 and lin.bias is not None and bn.momentum is not None and os.environ.get('MZ_HEAD_TAIL', '1') != '0'):
+        out = _HeadTail.apply(y, bn.weight, bn.bias, lin.weight, lin.bias, bn.running_mean, bn.running_var, calls, bn.eps, bn.momentum)
+        with torch.no_grad():
+            bn.num_batches_tracked += calls
+        return out
     y = y.reshape(calls, b, mid, h * w).transpose(1, 2)                  # [calls, mid, B, hw] (a view for mid == 1)
     if bn.training:
         with torch.no_grad():

@@ -425,3 +425,39 @@ def test_reference_learner_loop_on_the_training_kernels():
         opt.step()
         losses.append(float(loss.detach()))
     assert losses[-1] < 0.8 * losses[0], losses
+
+
+@pytest.mark.parametrize('mid,out,calls,batch', [(2, 82, 5, 32), (1, 1, 3, 16), (1, 1, 1, 7)])
+def test_head_tail_kernels_equal_the_torch_head(monkeypatch, mid, out, calls, batch):
+    """mz_head_tail_forward / _backward (a head's train-mode BatchNorm with per-call statistics + ReLU + Flatten + Linear over
+    stacked calls) against the PyTorch form of network.head_over_calls on a twin head: outputs, input gradient, all four
+    parameter gradients and the BatchNorm buffers to float32 rounding (1e-4 relative L2; the two sum in different orders)."""
+    from muzero_b200.network import _head, _head_after_conv
+    torch.manual_seed(31)
+    ha = _head(128, mid, 81, out).cuda().train()
+    with torch.no_grad():
+        ha[1].weight.uniform_(0.5, 1.5)
+        ha[1].bias.uniform_(-0.3, 0.3)
+    hb = copy.deepcopy(ha)
+    gen = torch.Generator(device='cuda').manual_seed(32)
+    y = torch.randn((calls * batch, mid, 9, 9), device='cuda', generator=gen) * 2.0 + 0.5
+    dout = torch.randn((calls * batch, out), device='cuda', generator=gen)
+    ya, yb = y.clone().requires_grad_(True), y.clone().requires_grad_(True)
+    monkeypatch.setenv('MZ_HEAD_TAIL', '1')
+    oa = _head_after_conv(ha, ya, calls)
+    monkeypatch.setenv('MZ_HEAD_TAIL', '0')
+    ob = _head_after_conv(hb, yb, calls)
+    oa.backward(dout)
+    ob.backward(dout)
+    torch.cuda.synchronize()
+    assert rel(oa, ob) <= 1e-5, rel(oa, ob)
+    assert rel(ya.grad, yb.grad) <= 1e-4, rel(ya.grad, yb.grad)
+    for (k, p), (_, q) in zip(ha.named_parameters(), hb.named_parameters()):
+        if p.grad is None and q.grad is None:
+            continue                                  # the 1x1 convolution's weight is not part of the tail
+        assert rel(p.grad, q.grad) <= 1e-4, (k, rel(p.grad, q.grad))
+    for (k, a), (_, b) in zip(ha.named_buffers(), hb.named_buffers()):
+        if a.dtype.is_floating_point:
+            assert rel(a, b) <= 1e-5, (k, rel(a, b))
+        else:
+            assert torch.equal(a, b), k
